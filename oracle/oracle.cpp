@@ -1,0 +1,178 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked, imported or executed by the product path.
+//
+// oracle.cpp: C entry points of the CPU oracle (ctypes-loaded by tests/, __graft_entry__.smoke() and the
+// cpu_baseline / --impl reference legs of bench.py).  PARITY UNPINNED by the reference (no golden vectors, reference
+// not compilable here -- SURVEY.md 8c); pinned by analytic KATs only.
+#include "ot_integrator.h"
+#include "oracle.h"
+#include <thread>
+#include <atomic>
+#include <chrono>
+
+using namespace ot;
+
+extern "C" {
+
+int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, double* film_block, double* film_light,
+                  uint32_t n_threads, oracle_stats* st) {
+    if (!desc || !opts) return -1;
+    if (desc->integrator.type != WTGPU_INTEGRATOR_PLT_PATH) return -4;
+    scene_t sc(desc);
+    const uint32_t W = desc->sensor.width, H = desc->sensor.height, C = desc->sensor.channels;
+    const uint32_t x0 = opts->tile_x0, y0 = opts->tile_y0, x1 = std::min(opts->tile_x1, W), y1 = std::min(opts->tile_y1, H);
+    if (x1 <= x0 || y1 <= y0) return 0;
+    const uint64_t tw = x1 - x0, npix = tw * (y1 - y0);
+    if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (uint32_t)std::min<uint64_t>(n_threads, npix);
+
+    std::vector<film_t> films; films.reserve(n_threads);
+    for (uint32_t t = 0; t < n_threads; ++t) films.emplace_back(sc);
+    std::vector<path_stats_t> stats(n_threads);
+    std::atomic<uint64_t> next{ 0 };
+    const uint64_t chunk = 64;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto worker = [&](uint32_t tid) {
+        plt_path_t integ(sc, films[tid], &stats[tid]);
+        for (;;) {
+            const uint64_t b = next.fetch_add(chunk);
+            if (b >= npix) break;
+            for (uint64_t i = b; i < std::min(npix, b + chunk); ++i) {
+                const uint32_t ex = x0 + (uint32_t)(i % tw), ey = y0 + (uint32_t)(i / tw);
+                for (uint32_t s = opts->sample_begin; s < opts->sample_end; ++s) {
+                    sampler_t smp; smp.seed = opts->seed; smp.pixel = ey * W + ex; smp.sample = s;
+                    integ.integrate(ex, ey, smp);
+                }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < n_threads; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& t : th) t.join();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+
+    for (uint32_t t = 1; t < n_threads; ++t) films[0].merge(films[t]);
+    if (film_block) for (size_t i = 0; i < (size_t)W * H * C * 2; ++i) film_block[i] += films[0].block[i];
+    if (film_light) for (size_t i = 0; i < (size_t)W * H * C; ++i) film_light[i] += films[0].light[i];
+    if (st) {
+        memset(st, 0, sizeof(*st));
+        st->samples = npix * (opts->sample_end - opts->sample_begin);
+        st->seconds = secs; st->threads = n_threads;
+        for (auto& s : stats) {
+            st->segments += s.segments; st->surface += s.surface; st->fsd += s.fsd; st->null_ += s.null; st->splats += s.splats;
+            st->nodes += s.ads.nodes; st->tris += s.ads.tris; st->ray_casts += s.ads.ray_casts; st->cone_casts += s.ads.cone_casts; st->shadow_casts += s.ads.shadow_casts;
+        }
+    }
+    return 0;
+}
+
+int oracle_intersect_rays(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_ray_query* q, wtgpu_ray_hit* out) {
+    ads_t ads(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const ray_t r{ { q[i].o[0], q[i].o[1], q[i].o[2] }, { q[i].d[0], q[i].d[1], q[i].d[2] } };
+        const auto h = intersect_ray(ads, r, { q[i].tmin, q[i].tmax });
+        out[i].tuid = h.tuid; out[i].dist = h.dist; out[i].bary[0] = h.bary.x; out[i].bary[1] = h.bary.y; out[i].front_face = h.front_face;
+    }
+    return 0;
+}
+int oracle_shadow_rays(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_ray_query* q, uint32_t* out) {
+    ads_t ads(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const ray_t r{ { q[i].o[0], q[i].o[1], q[i].o[2] }, { q[i].d[0], q[i].d[1], q[i].d[2] } };
+        out[i] = shadow_ray(ads, r, { q[i].tmin, q[i].tmax }) ? 1u : 0u;
+    }
+    return 0;
+}
+// brute force over all triangles with the scalar Moeller-Trumbore: pins the BVH traversal itself
+int oracle_intersect_rays_bruteforce(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_ray_query* q, wtgpu_ray_hit* out) {
+    ads_t ads(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const ray_t r{ { q[i].o[0], q[i].o[1], q[i].o[2] }, { q[i].d[0], q[i].d[1], q[i].d[2] } };
+        ray_hit_t rec;
+        for (uint32_t t = 0; t < desc->n_tris; ++t) {
+            const auto w = intersect_ray_tri_w(r.o, r.d, ads.tri_a(t), ads.tri_b(t), ads.tri_c(t), { q[i].tmin, q[i].tmax });
+            if (w.result != -inf && w.result < rec.dist) { rec.dist = w.result; rec.tuid = t; rec.bary = { w.baryx, w.baryy }; rec.front_face = dot(ads.tri_n(t), r.d) <= 0; }
+        }
+        out[i].tuid = rec.tuid; out[i].dist = rec.dist; out[i].bary[0] = rec.bary.x; out[i].bary[1] = rec.bary.y; out[i].front_face = rec.front_face;
+    }
+    return 0;
+}
+static elliptic_cone_t cone_of(const wtgpu_cone_query& q) {
+    const ray_t r{ { q.o[0], q.o[1], q.o[2] }, { q.d[0], q.d[1], q.d[2] } };
+    return elliptic_cone_t::make(r, { q.x[0], q.x[1], q.x[2] }, q.x0, q.tan_alpha, 1.f / q.e, q.e);
+}
+int oracle_intersect_cones(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_cone_query* q, wtgpu_cone_hit* out) {
+    ads_t ads(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto rec = intersect_cone(ads, cone_of(q[i]), { q[i].tmin, q[i].tmax }, q[i].z_scale, true);
+        wtgpu_cone_hit& h = out[i];
+        memset(&h, 0, sizeof(h));
+        h.dist = rec.empty() ? inf : rec.dist; h.front_face = rec.front_face;
+        h.n_tris = (uint32_t)rec.tris.size(); h.n_edges = (uint32_t)rec.edges.size();
+        for (uint32_t j = 0; j < std::min<uint32_t>(h.n_tris, WTGPU_MAX_CONE_TRIS); ++j) h.tris[j] = rec.tris[j];
+        for (uint32_t j = 0; j < std::min<uint32_t>(h.n_edges, WTGPU_MAX_CONE_EDGES); ++j) h.edges[j] = rec.edges[j];
+    }
+    return 0;
+}
+// brute-force cone query: distance of the closest triangle over ALL triangles (no BVH, no range shrinking)
+int oracle_cone_closest_bruteforce(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_cone_query* q, float* dist) {
+    ads_t ads(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto cone = cone_of(q[i]);
+        float best = inf;
+        for (uint32_t t = 0; t < desc->n_tris; ++t) {
+            const auto r = intersect_cone_tri(cone, ads.tri_a(t), ads.tri_b(t), ads.tri_c(t), ads.tri_n(t), { q[i].tmin, q[i].tmax });
+            if (r && r->dist < best) best = r->dist;
+        }
+        dist[i] = best;
+    }
+    return 0;
+}
+int oracle_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out) {
+    sampler_t s; s.seed = seed; s.pixel = pixel; s.sample = sample;
+    for (uint32_t i = 0; i < n; ++i) out[i] = s.r();
+    return 0;
+}
+
+// ---- analytic known-answer hooks
+void oracle_svd(const float A[4], float out[6]) {
+    const auto s = SVD(mat2{ A[0], A[1], A[2], A[3] });
+    out[0] = s.Ucos; out[1] = s.Usin; out[2] = s.Vcos; out[3] = s.Vsin; out[4] = s.sigma1; out[5] = s.sigma2;
+}
+void oracle_utdf(float x, float out[2]) { const c_t f = UTDF(x); out[0] = f.real(); out[1] = f.imag(); }
+void oracle_cerfc_rot45(double s, double out[2]) { const auto c = cerfc_rot45(s); out[0] = c.real(); out[1] = c.imag(); }
+void oracle_fresnel(float eta_re, float eta_im, const float w[3], float out[12]) {
+    const auto f = fresnel(c_t{ eta_re, eta_im }, v3{ w[0], w[1], w[2] });
+    out[0] = f.rs.real(); out[1] = f.rs.imag(); out[2] = f.rp.real(); out[3] = f.rp.imag();
+    out[4] = f.ts.real(); out[5] = f.ts.imag(); out[6] = f.tp.real(); out[7] = f.tp.imag();
+    out[8] = f.Ts; out[9] = f.Tp; out[10] = f.Z; out[11] = f.t.z;
+}
+// minimum-uncertainty sourcing: returns sbp (beam_geometry.hpp:43-47) of source_mub_from(length, k)
+float oracle_mub_sbp(float length, float k) {
+    const auto g = sourcing_geometry_t::source_mub_from_length(length, k);
+    const auto e = g.phase_space_extent();
+    const float area_stddev = e.spatial_extent / sqr(beam_cross_section_envelope);
+    const float wv = sqr(e.k * e.tan_alpha / beam_cross_section_envelope);
+    return area_stddev * wv * 1e6f;
+}
+// bsdf sampling energy: mean of weighted_bsdf mean intensity over n samples at incidence wi (albedo estimator)
+float oracle_bsdf_albedo(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], float k, uint32_t n, uint64_t seed) {
+    scene_t sc(desc); bsdf_eval_t be(sc);
+    surface_t s; s.geo = frame_t::canonical(); s.shading = s.geo;
+    const bsdf_query_t q{ &s, k, true };
+    double acc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        sampler_t smp; smp.seed = seed; smp.pixel = 0; smp.sample = i;
+        const auto r = be.sample(bsdf, v3{ wi[0], wi[1], wi[2] }, q, smp);
+        if (r) acc += r->M.mean_intensity();
+    }
+    return (float)(acc / n);
+}
+// cone-through-ellipse / ellipsoid re-fit (for unit parity with the device functions)
+void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], const float o[3], const float d[3], float tan_alpha, float out[8]) {
+    const frame_t f{ { frame[0], frame[1], frame[2] }, { frame[3], frame[4], frame[5] }, { frame[6], frame[7], frame[8] } };
+    const auto c = elliptic_cone_t::cone_through_ellipsoid({ axes[0], axes[1], axes[2] }, f, ray_t{ { o[0], o[1], o[2] }, { d[0], d[1], d[2] } }, tan_alpha);
+    out[0] = c.tangent.x; out[1] = c.tangent.y; out[2] = c.tangent.z; out[3] = c.x0; out[4] = c.e; out[5] = c.one_over_e; out[6] = c.tan_alpha; out[7] = c.z_apex;
+}
+
+} // extern "C"

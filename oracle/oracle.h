@@ -1,0 +1,31 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked, imported or executed by the product path. */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include "../include/wtgpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct oracle_stats {
+    uint64_t samples, segments, surface, fsd, null_, splats;
+    uint64_t nodes, tris, ray_casts, cone_casts, shadow_casts;
+    double seconds; uint32_t threads; uint32_t pad_;
+} oracle_stats;
+/* film_block: double[h][w][c][2], film_light: double[h][w][c]; accumulated into */
+int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, double* film_block, double* film_light, uint32_t n_threads, oracle_stats* st);
+int oracle_intersect_rays(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_ray_query* q, wtgpu_ray_hit* out);
+int oracle_shadow_rays(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_ray_query* q, uint32_t* out);
+int oracle_intersect_rays_bruteforce(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_ray_query* q, wtgpu_ray_hit* out);
+int oracle_intersect_cones(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_cone_query* q, wtgpu_cone_hit* out);
+int oracle_cone_closest_bruteforce(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_cone_query* q, float* dist);
+int oracle_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out);
+void oracle_svd(const float A[4], float out[6]);
+void oracle_utdf(float x, float out[2]);
+void oracle_cerfc_rot45(double s, double out[2]);
+void oracle_fresnel(float eta_re, float eta_im, const float w[3], float out[12]);
+float oracle_mub_sbp(float length, float k);
+float oracle_bsdf_albedo(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], float k, uint32_t n, uint64_t seed);
+void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], const float o[3], const float d[3], float tan_alpha, float out[8]);
+#ifdef __cplusplus
+}
+#endif
+#endif
