@@ -1,0 +1,183 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200 wave_tracer hot path on BASELINE.json's metric (Msamples/sec).
+
+Workload (config.workload): BASELINE.json configs[1], scenes/diffraction_simple/double_slits.xml -D res=1440,spp=1024,pattern=true
+(film 1440x360, 5.31e8 samples), geometry/emitters/sensor restated procedurally (wave_tracer_b200/scenes.py).  The reference file
+selects plt_bdpt; this round's device integrator is plt_path forward + UTD (as double_slits_and_reflectors.xml drives the same
+geometry) -- stated in config.integrator.  A "step" renders the full film at `--spp-per-step` samples per element (sample indices
+[step*S, step*S+S) of the 1024): cost is linear in spp, samples are independent.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N>1; one rank per GPU; NCCL film reduce every step)
+  python bench.py --impl reference ...                     the CPU implementation of the same path (oracle port; the reference
+                                                           itself cannot be built here) on all host cores, bounded sample per step
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+RES, SPP = 1440, 1024
+WORKLOAD = "diffraction_simple/double_slits res=1440 spp=1024 pattern=true (film 1440x360, lambda=0.05mm, procedural restatement)"
+INTEGRATOR = "plt_path forward + UTD FSD, max_depth 16, RR off (reference XML selects plt_bdpt: not implemented on device yet)"
+
+
+def measured_hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.maxmhz = index, [], set(), False, None
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0])); self.maxmhz = float(f[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"): self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_leg(built, seconds_target, threads=0):
+    """Times the oracle (CPU port of the reference path) on a bounded sample: sample index 0.. of every element."""
+    import _oracle
+    t0 = time.time(); _, _, st = _oracle.render(built, spp=1, sample_range=(0, 1), threads=threads); t1 = time.time() - t0
+    n = max(1, min(64, int(seconds_target / max(t1, 1e-3))))
+    _, _, st = _oracle.render(built, spp=n, sample_range=(0, n), threads=threads)
+    return st["samples"] / st["seconds"] / 1e6, st["threads"], f"samples 0..{n - 1} of every element of the 1440x360 film ({st['samples']} samples, {st['seconds']:.1f} s)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--pool", type=int, default=1 << 21)
+    ap.add_argument("--res", type=int, default=RES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sort", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    from wave_tracer_b200 import scenes
+    built = scenes.double_slits(res=a.res, spp=SPP).build()
+    W, H = built.width, built.height
+    config = {"workload": WORKLOAD if a.res == RES else WORKLOAD.replace("1440", str(a.res)), "integrator": INTEGRATOR, "film": [W, H],
+              "spp_per_step": a.spp_per_step, "sampler": "philox4x32-10 counter streams keyed (seed,pixel,sample)",
+              "l2": "path-state pool (%d paths x 0.7 KB) and film exceed the 126 MB L2; no flush needed" % a.pool}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        for s in range(a.warmup + a.steps):
+            v, cores, sample = cpu_leg(built, 8.0)
+            if s >= a.warmup: vals.append(v)
+        v = sum(vals) / len(vals)
+        print(json.dumps({"impl": "reference", "metric": "Msamples/sec", "value": v, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": config, "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from wave_tracer_b200 import GpuScene, _abi
+    from wave_tracer_b200.parallel import render_distributed
+    import ctypes as C
+    import numpy as np
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    gs = GpuScene(built, local)
+    flags = 2 | (1 if a.no_sort else 0)      # WTGPU_RENDER_TIME_KERNELS
+    S = a.spp_per_step
+    # weak scaling: every rank renders S samples per element per step (disjoint sample ranges across ranks)
+    def step(i):
+        base = (i * world + rank) * S
+        dev = torch.device("cuda", local)
+        block = torch.zeros((H, W, 1, 2), dtype=torch.float32, device=dev); light = torch.zeros((H, W, 1), dtype=torch.float32, device=dev)
+        st = gs.render_into(block.data_ptr(), light.data_ptr(), SPP, 0x5EED, (base, base + S), None, True, a.pool, flags, torch.cuda.current_stream().cuda_stream, True)
+        if world > 1:
+            flat = torch.cat([block.reshape(-1), light.reshape(-1)]); dist.reduce(flat, dst=0, op=dist.ReduceOp.SUM)
+        return st
+
+    for i in range(a.warmup):
+        step(i)
+    clk = ClockSampler(local); clk.start()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stats = [step(a.warmup + i) for i in range(a.steps)]
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    clk.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    samples_rank = sum(s["samples"] for s in stats)
+    total_samples = samples_rank * world
+    value = total_samples / (ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (k_traverse): algorithmic bytes from the device counters of the same run
+    core_b, hit_b = 240, 160     # PathCore read + HitRec/key write per segment (16-B chunks: 15 / 10)
+    seg = sum(s["segments"] for s in stats); nodes = sum(s["traverse_nodes"] for s in stats); tris = sum(s["traverse_tris"] for s in stats)
+    trav_ms = sum(s["traverse_ms"] for s in stats); shade_ms = sum(s["shade_ms"] for s in stats)
+    trav_launches = sum(s["iterations"] for s in stats)
+    alg_bytes = seg * (core_b + hit_b + 4) + 256 * nodes + 48 * tris
+    peak, which = measured_hbm_peak()
+    achieved = alg_bytes / max(trav_ms * 1e-3, 1e-12) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_traverse", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
+                "traffic": None, "alg_bytes_per_launch": alg_bytes / max(1, trav_launches), "avg_launch_ms": trav_ms / max(1, trav_launches),
+                "share_of_step": {"k_traverse": trav_ms / ms, "k_shade": shade_ms / ms}}
+
+    if rank == 0:
+        # ---- e2e: through the public API with HOST buffers: scene upload (H2D), render, film read-back (D2H) inside the timed region
+        from wave_tracer_b200 import render
+        h2d = sum(C.sizeof(t) * n for t, n in ((_abi.Node, built.desc.n_nodes), (_abi.Leaf, built.desc.n_leaves), (_abi.Tri, built.desc.n_tris), (_abi.TriMeta, built.desc.n_tris),
+                  (_abi.TriShading, built.desc.n_tris), (_abi.Edge, built.desc.n_edges), (_abi.Shape, built.desc.n_shapes), (_abi.Spectrum, built.desc.n_spectra),
+                  (_abi.Bsdf, built.desc.n_bsdfs), (_abi.Emitter, built.desc.n_emitters), (_abi.KDist, built.desc.n_emitters))) + 4 * (built.desc.n_kdist_data + 1024)
+        d2h = W * H * 3 * 4
+        render(built, spp=SPP, device=local, sample_range=(0, S), pool_size=a.pool, allow_overflow=True)     # warm
+        t0 = time.time(); n_e2e = 0
+        for i in range(max(1, min(a.steps, 3))):
+            _, lgt, st = render(built, spp=SPP, device=local, sample_range=(i * S, i * S + S), pool_size=a.pool, allow_overflow=True)
+            n_e2e += st["samples"]
+        e2e = n_e2e / (time.time() - t0) / 1e6
+        out = {"metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+               "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": int(sum(s["kernel_launches"] for s in stats)), "roofline": roofline, "clocks": clk.summary(),
+               "counters": {k: int(sum(s[k] for s in stats)) for k in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "nodes_visited", "tris_tested", "splats", "capacity_overflows")}}
+        if world == 1 and not a.no_cpu_baseline:
+            v, cores, sample = cpu_leg(built, 12.0)
+            out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

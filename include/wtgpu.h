@@ -285,6 +285,7 @@ typedef struct wtgpu_render_opts {
     void* stream;                   /* cudaStream_t or NULL */
 } wtgpu_render_opts;
 #define WTGPU_RENDER_NO_SORT 1u     /* disable the material sort (for A/B measurement) */
+#define WTGPU_RENDER_TIME_KERNELS 2u /* record CUDA events around every kernel (fills wtgpu_stats::*_ms) */
 
 /* Device counters gathered during wtgpu_render (the quantities the reference exposes in a `profile` build:
  * include/wt/ads/ads_stats.hpp:36-95, include/wt/integrator/stats.hpp:27-82); inputs of the roofline byte count. */
@@ -300,6 +301,8 @@ typedef struct wtgpu_stats {
     uint64_t capacity_overflows;
     uint64_t kernel_launches;
     uint64_t iterations;
+    uint64_t traverse_nodes, traverse_tris;   /* node / triangle fetches of k_traverse alone (roofline of the dominant kernel) */
+    uint64_t shaded_paths;          /* path-vertices processed by k_shade */
     double   gpu_ms;                /* CUDA-event time of the whole call on its stream */
     double   traverse_ms, shade_ms, generate_ms, sort_ms;
 } wtgpu_stats;
@@ -341,6 +344,8 @@ int wtgpu_debug_intersect_cones(wtgpu_scene* scene, uint32_t n, const wtgpu_cone
 
 /* counter-based RNG stream: out[i] = i-th draw of stream (seed, pixel, sample) */
 int wtgpu_debug_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, int device);
+/* sizeof of the i-th ABI struct (order of wave_tracer_b200/_abi.py:ABI_STRUCTS); lets bindings verify their layout */
+uint64_t wtgpu_debug_sizeof(int which);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,22 @@
+import os
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with `pytest -m gpu` on a B200)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_native():
+    # the product library and the oracle are built in-tree (they travel to the GPU box with the snapshot)
+    from wave_tracer_b200 import _abi
+    if not os.path.exists(_abi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    import _oracle
+    _oracle.lib()

@@ -1,0 +1,192 @@
+// dfsd.cuh -- UTD free-space diffraction on the device.
+// Follows src/interaction/fsd/free_space_diffraction.cpp:23-234 and include/wt/interaction/fsd/utd.hpp:26-172 (under /root/reference).
+// The aperture is stored as (interaction geometry, surviving edge ids); wedge parameters are rebuilt from the
+// 96-B ads edge record on use instead of keeping a heap-allocated vector<wedge_edge_t> per path.
+#pragma once
+#include "dscene.cuh"
+
+namespace wt {
+
+constexpr float kUtdMinSinBeta = 1e-3f;
+constexpr float kUtdSigmaScale = 45.f;
+constexpr int kMaxFsdEdges = 24;
+
+struct Aperture {
+    V3 wp; Frame fr; V3 size; V3 wi; float k;
+    uint32_t n; uint32_t edges[kMaxFsdEdges];
+};
+struct Wedge { V3 v; float l; V3 nff, tff, nbf, e; float alpha; uint32_t idx; };
+
+// free_space_diffraction_t ctor body for one edge (free_space_diffraction.cpp:36-78); false: edge does not take part
+WT_D bool wedge_build(const DScene& sc, const Aperture& ap, uint32_t ed, Wedge& w) {
+    const wtgpu_edge E = sc.edges[ed];
+    const V3 n1 = mk3(E.n1), n2 = mk3(E.n2), t1 = mk3(E.t1), t2 = mk3(E.t2), ea = mk3(E.a), eb = mk3(E.b);
+    const bool f1 = dot(ap.wi, n1) > 0.f;
+    w.nff = f1 ? n1 : n2; w.tff = f1 ? t1 : t2; w.nbf = f1 ? n2 : n1;
+    if (dot(ap.wi, w.nff) <= 0.f) return false;
+    V3 v1 = ea, v2 = eb;
+    if (vfinite(ap.size)) {
+        float a, b;
+        intersect_edge_ellipsoid(ea, eb, ap.wp, ap.fr.t, ap.fr.b, ap.size, a, b);
+        a = clampf_(a, 0.f, 1.f); b = clampf_(b, 0.f, 1.f);
+        v1 = mk3(mixf(ea.x, eb.x, a), mixf(ea.y, eb.y, a), mixf(ea.z, eb.z, a));
+        v2 = mk3(mixf(ea.x, eb.x, b), mixf(ea.y, eb.y, b), mixf(ea.z, eb.z, b));
+    }
+    if (veq(v1, v2)) return false;
+    w.v = (v1 + v2) / 2.f; w.l = length(v2 - v1); w.alpha = E.alpha; w.idx = ed;
+    w.e = cross(w.nff, w.tff);
+    return true;
+}
+
+// complex erfc(e^{i pi/4} s), s in [0, sqrt(6)): the only cerfc call of the path (utd.hpp:42; libcerf is a missing submodule).
+// Via Fresnel-integral power series, accumulated in f64 (a handful of calls per diffracting edge; never on the BVH-bound part).
+WT_D void cerfc_rot45(float sf, float& re, float& im) {
+    const double s = (double)sf, s2 = s * s;
+    double Cc = 0.0, Ss = 0.0, term = s;
+    for (int m = 0; m < 64; ++m) {
+        const double c = term / (2.0 * m + 1.0);
+        const int n = m >> 1;
+        if ((m & 1) == 0) Cc += (n & 1) ? -c : c; else Ss += (n & 1) ? -c : c;
+        term *= s2 / (m + 1.0);
+        if (fabs(term) < 1e-20 && m > 4) break;
+    }
+    // erf = (2/sqrt(pi)) e^{i pi/4} (C - i S)
+    const double q = 2.0 / 1.7724538509055160273 * 0.70710678118654752440;
+    const double er = q * (Cc + Ss), ei = q * (Cc - Ss);
+    re = (float)(1.0 - er); im = (float)(-ei);
+}
+WT_D C2 UTDF(float x) {                                         // utd.hpp:36-57
+    const float ax = fabsf(x);
+    C2 res;
+    if (ax < 6.f) {
+        const float sx = sqrtf(ax);
+        float cr, ci; cerfc_rot45(sx, cr, ci);
+        res = ((mkc(1.f, 1.f) * kSqrtPi2) * sx) * cexpi(ax) * mkc(cr, ci);
+    } else {
+        const float r = 1.f / (2.f * ax);
+        const float r2 = r * r, r3 = r2 * r, r4 = r2 * r2;
+        res = mkc(1.f - 3.f * r2 + 75.f * r4, r - 15.f * r3);
+    }
+    return x < 0.f ? cconj(res) : res;
+}
+WT_D float UTDa(float sgn, float phi, float n) {                // utd.hpp:26-31
+    const float N = roundf((sgn * kPi + phi) * kInvTwoPi / n);
+    return 2.f * sqrf(cosf(kPi * n * N - phi / 2.f));
+}
+WT_D float fmod_pos(float a, float b) { return a - b * floorf(a / b); }
+WT_D float cotf_(float x) { return 1.f / tanf(x); }
+
+WT_D bool wedge_diffraction_point(const Wedge& w, V3 src, V3 dst, V3& p) {     // utd.hpp:62-80
+    const float sl = length(mk2(dot(src - w.v, w.tff), dot(src - w.v, w.nff)));
+    const float dl = length(mk2(dot(dst - w.v, w.tff), dot(dst - w.v, w.nff)));
+    const float dist = dot(w.e, src - w.v) + dot(dst - src, w.e) * sl / (sl + dl);
+    if (fabsf(dist) > w.l / 2.f) return false;
+    p = w.v + w.e * dist;
+    return !(veq(p, src) || veq(p, dst));
+}
+WT_D bool wedge_diffraction_point_dir(const Wedge& w, V3 src, V3 wo, V3& p) {  // utd.hpp:85-110
+    const float cb = dot(wo, w.e);
+    const float sb = sqrtf(fmaxf(0.f, 1.f - sqrf(cb)));
+    if (sb < kUtdMinSinBeta) return false;
+    const float sl = length(mk2(dot(src - w.v, w.tff), dot(src - w.v, w.nff)));
+    const V3 prj = w.v + dot(src - w.v, w.e) * w.e;
+    p = prj + sl * (cb / sb) * w.e;
+    if (length2(p - w.v) > sqrf(w.l / 2.f)) return false;
+    return !veq(p, src);
+}
+WT_DN void wedge_UTD(const Wedge& w, float k, V3 wi, V3 wo, float ro, C2& Ds, C2& Dh) {   // utd.hpp:115-172
+    const float n = 2.f - w.alpha * kInvPi;
+    const float sb2 = fmaxf(0.f, 1.f - sqrf(dot(wi, w.e)));
+    const float sb = sqrtf(sb2);
+    const float phii = atan2f(dot(w.nff, wi), dot(w.tff, wi));
+    const float phio = atan2f(dot(w.nff, wo), dot(w.tff, wo));
+    const float kL = k_times_len(k, ro * sb2);
+    const C2 F1 = UTDF(kL * UTDa(1.f, phii - phio, n)), F2 = UTDF(kL * UTDa(-1.f, phii - phio, n));
+    const C2 F3 = UTDF(kL * UTDa(1.f, phii + phio, n)), F4 = UTDF(kL * UTDa(-1.f, phii + phio, n));
+    const C2 D1 = (-cotf_((kPi + (phii - phio)) / (2.f * n))) * F1;
+    const C2 D2 = (-cotf_((kPi - (phii - phio)) / (2.f * n))) * F2;
+    const C2 D3 = (-cotf_((kPi + (phii + phio)) / (2.f * n))) * F3;
+    const C2 D4 = (-cotf_((kPi - (phii + phio)) / (2.f * n))) * F4;
+    const float kro = k_times_len(k, ro);
+    const C2 D = (1.f / (2.f * n * sqrtf(kro) * sb) * kInvSqrtTwoPi) * cexpi(-kPi4);
+    const float t1 = fmod_pos(phii + phio, kPi2), t2 = fmod_pos(phii - phio, kPi2);
+    const bool z = fabsf(t1) < 1e-5f || fabsf(t2) < 1e-5f;
+    const C2 s = z ? mkc(0.f, 0.f) : (D1 + D2) - (D3 + D4);
+    const C2 h = z ? mkc(0.f, 0.f) : (D1 + D2) + (D3 + D4);
+    Ds = (-D) * s; Dh = (-D) * h;
+}
+
+// free_space_diffraction_t::pdf (free_space_diffraction.cpp:152-194)
+WT_DN float fsd_pdf(const DScene& sc, const Aperture& ap, V3 src, V3 wo) {
+    if (ap.n == 0u) return 0.f;
+    float ret = 0.f;
+    for (uint32_t j = 0; j < ap.n; ++j) {
+        Wedge w; if (!wedge_build(sc, ap, ap.edges[j], w)) continue;
+        V3 p; if (!wedge_diffraction_point_dir(w, src, wo, p)) continue;
+        const V3 ui = src - p;
+        if ((dot(wo, w.nff) <= 0.f && dot(wo, w.nbf) <= 0.f) || (dot(ui, w.nff) <= 0.f && dot(ui, w.nbf) <= 0.f)) continue;
+        const float ri = length(src - p);
+        const V3 wi = (src - p) / ri;
+        const float phii = atan2f(dot(w.nff, wi), dot(w.tff, wi)), phio = atan2f(dot(w.nff, wo), dot(w.tff, wo));
+        const float sigma = sqrtf(kUtdSigmaScale / k_times_len(ap.k, ri));
+        float x1 = fabsf(fmod_pos(phio - (kPi + phii), kTwoPi)), x2 = fabsf(fmod_pos(phio - (kPi - phii), kTwoPi));
+        if (x1 > kPi) x1 -= kTwoPi;
+        if (x2 > kPi) x2 -= kTwoPi;
+        ret += kInvSqrtTwoPi / sigma * (expf(-.5f * sqrf(x1 / sigma)) + expf(-.5f * sqrf(x2 / sigma))) / 2.f;
+    }
+    return ret / (float)(ap.n + 1u);
+}
+// free_space_diffraction_t::sample (free_space_diffraction.cpp:84-150); invalid samples carry weight 0
+WT_DN void fsd_sample(const DScene& sc, const Aperture& ap, V3 src, Sampler& smp, V3& wo, float& weight) {
+    wo = mk3(0.f, 0.f, 1.f); weight = 0.f;
+    const int eidx = uniform_int_interval(smp, 0, (int)ap.n + 1);
+    if (eidx == (int)ap.n) { wo = -normalize(src - ap.wp); weight = (float)(ap.n + 1u); return; }
+    Wedge w; if (!wedge_build(sc, ap, ap.edges[eidx], w)) return;
+    const V3 p = w.v + (rnd(smp) - .5f) * w.l * w.e;
+    const V3 ui = src - p;
+    if (dot(ui, w.nff) <= 0.f && dot(ui, w.nbf) <= 0.f) return;
+    const float ri = length(src - p);
+    const V3 wi = (src - p) / ri;
+    const float phii = atan2f(dot(w.nff, wi), dot(w.tff, wi));
+    const float sigma = sqrtf(kUtdSigmaScale / k_times_len(ap.k, ri));
+    const float sm = sigma * normal2d(rnd2(smp)).x;
+    const float phio = (rnd(smp) < .5f ? kPi + phii : kPi - phii) + sm;
+    const float cb = dot(wi, w.e);
+    const float sb = sqrtf(fmaxf(0.f, 1.f - sqrf(cb)));
+    const V3 d = sb * (cosf(phio) * w.tff + sinf(phio) * w.nff) - cb * w.e;
+    if (dot(d, w.nff) <= 0.f && dot(d, w.nbf) <= 0.f) return;
+    if (sb < kUtdMinSinBeta) return;
+    const float dpd = fsd_pdf(sc, ap, src, d);
+    if (dpd == 0.f) return;
+    wo = d; weight = 1.f / dpd;
+}
+
+// plt_path do_fsd (integrator/plt_path/plt_path_detail.hpp:311-346): returns (|ts|^2+|th|^2)/2
+WT_DN float do_fsd(const DScene& sc, const Cone& cone_from_src, const Geo& src_geo, V3 dst, const Aperture& ap, float k, Counters& ctr, uint32_t& edges_fetched) {
+    const V3 src = cone_from_src.o;
+    const Geo dst_geo = geo_point(dst);
+    C2 ts = mkc(0.f, 0.f), th = mkc(0.f, 0.f);
+    for (uint32_t j = 0; j < ap.n; ++j) {
+        Wedge w; if (!wedge_build(sc, ap, ap.edges[j], w)) continue;
+        ++edges_fetched;
+        V3 p; if (!wedge_diffraction_point(w, src, dst, p)) continue;
+        const V3 ui = src - p, uo = dst - p;
+        if ((dot(uo, w.nff) <= 0.f && dot(uo, w.nbf) <= 0.f) || (dot(ui, w.nff) <= 0.f && dot(ui, w.nbf) <= 0.f)) continue;
+        const float ri = length(ui), ro = length(uo);
+        C2 Ds, Dh; wedge_UTD(w, ap.k, ui / ri, uo / ro, ro, Ds, Dh);
+        if (Dh.re == 0.f && Dh.im == 0.f && Ds.re == 0.f && Ds.im == 0.f) continue;
+        const Geo eg = geo_edge(p, w.idx);
+        if (shadow_between(sc, eg, src_geo, ctr) || shadow_between(sc, eg, dst_geo, ctr)) continue;
+        const C2 phase = cexpi(-k_times_len(k, ro + ri));
+        ts = ts + phase * Ds; th = th + phase * Dh;
+    }
+    if (cone_contains(cone_from_src, dst)) {
+        if (!shadow_between(sc, src_geo, dst_geo, ctr)) {
+            const C2 phase = cexpi(-k_times_len(k, length(dst - src)));
+            ts = ts + phase; th = th + phase;
+        }
+    }
+    return (cnorm(ts) + cnorm(th)) / 2.f;
+}
+
+} // namespace wt

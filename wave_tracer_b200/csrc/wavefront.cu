@@ -1,0 +1,777 @@
+// wavefront.cu -- the B200-native wavefront plt_path integrator and its C-ABI (include/wtgpu.h).
+//
+// Replaces the per-pixel recursion  integrator_t::integrate -> plt_path::random_walk
+//   (/root/reference/src/integrator/plt_path.cpp:40-51, include/wt/integrator/plt_path/plt_path_detail.hpp:542-828)
+// driven by scene_renderer_t::render's job loop (/root/reference/src/scene/render.cpp:381-579) with a pool of
+// paths advanced one vertex per iteration:
+//     k_generate   refill dead slots with new samples (emitter/spectrum/sensor sampling: plt_path_detail.hpp:764-828)
+//     k_traverse   traverse() ballistic/diffusive state machine over the 8-wide BVH (integrator/traversal.hpp:94-172),
+//                  primary-triangle pick (plt_path_detail.hpp:253-276), edge collection -> compact hit record + sort key
+//     k_hist/scan/scatter   counting sort of live paths by material key (branch-coherent shading)
+//     k_shade      pending UTD evaluation, NEE / emission / sensing, interaction sampling, beam transform, RR, film splats
+// Path state lives in HBM as structure-of-arrays of 16-B chunks (chunk c of slot s at base[c*pool + s]): every warp-level
+// state access is a run of fully coalesced 512-B transactions.
+#include "dfsd.cuh"
+#include "../../include/wthost.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cmath>
+
+using namespace wt;
+
+// ================================================================================================ state
+constexpr int kMaxHitEdges = kMaxFsdEdges;
+constexpr int kMaxConeTris = WTGPU_MAX_CONE_TRIS;
+
+enum : uint32_t { F_SAMPLED_FSD = 1u, F_HAS_FSD = 2u, F_DPD_DISC = 4u };
+
+struct alignas(16) PathCore {
+    Beam beam;
+    Geo prev_geo;
+    uint32_t flags;
+    float dpd_v, throughput, rspd;
+    uint32_t depth, pixel, sample, rng_d;
+    float ox, oy;
+    float L[4];
+};
+struct alignas(16) PathFsd {
+    Beam prev_beam;
+    Aperture ap;
+};
+enum : uint32_t { H_EMPTY = 1u, H_BALLISTIC = 2u, H_PRIMARY = 4u, H_FRONT = 8u, H_OVERFLOW = 16u };
+struct alignas(16) HitRec {
+    uint32_t flags, primary;
+    float pdist, bx, by, d2i, region_depth;
+    V3 origin;
+    uint32_t n_edges;
+    uint32_t edges[kMaxHitEdges];
+};
+
+template <class T> __host__ __device__ constexpr int chunks_of() { return (int)(sizeof(T) / 16); }
+template <class T> WT_D void soa_load(T& v, const float4* __restrict__ base, uint32_t pool, uint32_t slot) {
+    float4* p = reinterpret_cast<float4*>(&v);
+#pragma unroll
+    for (int c = 0; c < chunks_of<T>(); ++c) p[c] = base[(size_t)c * pool + slot];
+}
+template <class T> WT_D void soa_store(const T& v, float4* __restrict__ base, uint32_t pool, uint32_t slot) {
+    const float4* p = reinterpret_cast<const float4*>(&v);
+#pragma unroll
+    for (int c = 0; c < chunks_of<T>(); ++c) base[(size_t)c * pool + slot] = p[c];
+}
+
+struct DevCounters {
+    unsigned long long samples, segments, ray_casts, cone_casts, shadow_casts, nodes, tris, edges, surface, fsd, null_, splats, overflow, shade_nodes, shade_tris, shaded;
+    unsigned int next_sample_lo; unsigned int pad0;
+    unsigned long long next_sample;     // samples handed out
+    int live;                           // paths alive
+    int n_sorted;                       // live paths in `order`
+};
+
+struct RenderArgs {
+    DScene sc;
+    float4* core; float4* fsd; float4* hit;
+    uint32_t* alive; uint32_t* keys; uint32_t* order; uint32_t* key_count; uint32_t* key_cursor;
+    DevCounters* ctr;
+    float* film_block; float* film_light;
+    uint32_t pool, n_keys;
+    uint32_t seed_lo, seed_hi;
+    uint32_t tile_x0, tile_y0, tile_w, tile_h;
+    uint32_t sample_begin, n_samples;
+    unsigned long long total;
+};
+
+WT_D void flush_counters(DevCounters* g, const Counters& c, bool shade = false) {
+    const unsigned m = __activemask();
+    const unsigned n = __reduce_add_sync(m, c.nodes), t = __reduce_add_sync(m, c.tris), r = __reduce_add_sync(m, c.ray_casts),
+                   cc = __reduce_add_sync(m, c.cone_casts), s = __reduce_add_sync(m, c.shadow_casts);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+        if (n) atomicAdd(shade ? &g->shade_nodes : &g->nodes, (unsigned long long)n);
+        if (t) atomicAdd(shade ? &g->shade_tris : &g->tris, (unsigned long long)t);
+        if (r) atomicAdd(&g->ray_casts, (unsigned long long)r);
+        if (cc) atomicAdd(&g->cone_casts, (unsigned long long)cc);
+        if (s) atomicAdd(&g->shadow_casts, (unsigned long long)s);
+    }
+}
+WT_D void count1(unsigned long long* p, bool pred) {
+    const unsigned m = __activemask();
+    const unsigned n = __reduce_add_sync(m, pred ? 1u : 0u);
+    if (n && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(p, (unsigned long long)n);
+}
+
+// ================================================================================================ generate
+__global__ void __launch_bounds__(128) k_generate(const RenderArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool gen = false;
+    if (slot < a.pool && a.alive[slot] == 0u) {
+        const unsigned long long id = atomicAdd(&a.ctr->next_sample, 1ull);
+        if (id < a.total) {
+            gen = true;
+            const DScene& sc = a.sc;
+            const uint64_t npix = (uint64_t)a.tile_w * a.tile_h;
+            const uint32_t pi = (uint32_t)(id % npix), si = (uint32_t)(id / npix);
+            const uint32_t ex = a.tile_x0 + pi % a.tile_w, ey = a.tile_y0 + pi / a.tile_w;
+            PathCore pc;
+            pc.pixel = ey * sc.sensor.width + ex; pc.sample = a.sample_begin + si;
+            Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = 0;
+            // integrate_backward / integrate_forward preamble (plt_path_detail.hpp:764-828)
+            const int32_t em = sample_emitter(sc, smp);
+            const KSample ks = sample_wavenumber(sc, em, smp);
+            const float k = ks.k;
+            if (sc.integrator.direction == WTGPU_DIRECTION_BACKWARD) {
+                pc.rspd = ks.wpd.disc ? 1.f / ks.wpd.v : 1.f / sum_spectral_pdf(sc, k);
+                const SensorSample ss = sensor_sample(sc, smp, ex, ey, k);
+                pc.beam = ss.beam; pc.ox = ss.el.ox; pc.oy = ss.el.oy;
+            } else {
+                const EmitterSample es = emitter_sample(sc, em, smp, k);
+                pc.rspd = 1.f / sum_spectral_pdf(sc, k);
+                pc.beam = es.beam; pc.ox = pc.oy = 0.f;
+            }
+            pc.prev_geo = geo_point(pc.beam.env.o);
+            pc.flags = F_DPD_DISC; pc.dpd_v = 0.f; pc.throughput = 1.f; pc.depth = 1u; pc.rng_d = smp.d;
+            pc.L[0] = pc.L[1] = pc.L[2] = pc.L[3] = 0.f;
+            soa_store(pc, a.core, a.pool, slot);
+            a.alive[slot] = 1u;
+        }
+    }
+    const unsigned m = __activemask();
+    const unsigned n = __reduce_add_sync(m, gen ? 1u : 0u);
+    if (n && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) { atomicAdd(&a.ctr->live, (int)n); atomicAdd(&a.ctr->samples, (unsigned long long)n); }
+}
+
+// ================================================================================================ traverse
+// integrator::traverse (integrator/traversal.hpp:28-57, 94-172, 276-286)
+struct TravOut { bool empty, ballistic; RayHit ray; ConeResult cone; float region_depth; V3 origin; };
+
+WT_D float min_ballistic_distance(const Cone& env, V3 ro) {
+    if (!veq(ro, env.o)) {
+        const V3 rl = to_local(cone_frame(env), ro - env.o) * mk3(1.f, env.e, 1.f);
+        const float d = (length(mk2(rl.x, rl.y)) - env.x0) / env.ta - rl.z;
+        return max3f(0.f, -rl.z, d);
+    }
+    return 0.f;
+}
+WT_D float max_ballistic_distance(float lambda, uint32_t seg, float mbd) {
+    const unsigned long long B = min(1ull << 16, 8ull << (2u * min(seg, 16u) + 1u));
+    return seg >= 16u ? WT_INF : mbd * 1.05f + lambda * (float)B;
+}
+WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bool force_rt, uint32_t* tris, TravOut& out, Counters& ctr) {
+    env.o = offseted_ray_origin(sc, prev, env.o, env.d);
+    out.origin = env.o; out.region_depth = 0.f;
+    out.cone.n_tris = 0; out.cone.overflow = false; out.cone.dist = WT_INF; out.cone.front = false;
+    if (force_rt || cone_is_ray(env)) {
+        out.ballistic = true;
+        out.empty = !intersect_ray(sc, env.o, env.d, mkr(0.f, WT_INF), out.ray, ctr);
+        return;
+    }
+    const float mbd = min_ballistic_distance(env, env.o);
+    float dist = 0.f;
+    for (uint32_t seg = 0;; ++seg) {
+        const float bd = max_ballistic_distance(lambda, seg, mbd);
+        if (intersect_ray(sc, env.o, env.d, mkr(dist, fminf(WT_INF, dist + bd * 1.001f)), out.ray, ctr)) { out.ballistic = true; out.empty = false; return; }
+        dist += bd;
+        if (bd == WT_INF || dist >= WT_INF) { out.ballistic = true; out.empty = true; return; }
+        const float min_prog = cone_axes(env, dist).x / 2.f;
+        cone_traverse<kMaxConeTris>(sc, env, mkr(dist, WT_INF), kMajorToZ, tris, out.cone, ctr);
+        const bool cempty = out.cone.n_tris == 0u;
+        if (cempty || out.cone.dist - dist >= min_prog) {
+            out.ballistic = false; out.empty = cempty;
+            out.region_depth = cempty ? 0.f : kMajorToZ * cone_axes(env, out.cone.dist).x;
+            return;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr; counters_zero(ctr);
+    bool seg = false, ovf = false;
+    if (slot < a.pool && a.alive[slot]) {
+        const DScene& sc = a.sc;
+        seg = true;
+        PathCore pc; soa_load(pc, a.core, a.pool, slot);
+        uint32_t tris[kMaxConeTris];
+        TravOut tr;
+        const bool force_rt = sc.sensor.ray_trace_only != 0u;
+        traverse(sc, pc.beam.env, pc.prev_geo, wavenum_to_wavelen(pc.beam.k), force_rt, tris, tr, ctr);
+        HitRec h; h.flags = 0u; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.n_edges = 0u;
+        h.origin = tr.origin; h.region_depth = tr.region_depth; h.d2i = 0.f;
+        uint32_t key = a.n_keys - 1u;       // miss
+        if (tr.empty) h.flags |= H_EMPTY;
+        else {
+            const bool is_ballistic = tr.ballistic || cone_is_ray(pc.beam.env);
+            Cone env = pc.beam.env; env.o = tr.origin;
+            const V3 dir = env.d;
+            if (tr.ballistic) {
+                h.flags |= H_BALLISTIC | H_PRIMARY | (tr.ray.front ? H_FRONT : 0u);
+                h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; h.d2i = tr.ray.dist;
+            } else {
+                h.d2i = tr.cone.dist;
+                if (tr.cone.front) h.flags |= H_FRONT;
+                if (tr.cone.overflow) { h.flags |= H_OVERFLOW; ovf = true; }
+                const uint32_t nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
+                // find_closest_triangle (plt_path_detail.hpp:253-276)
+                const Range zr = mkr(h.d2i, h.d2i + h.region_depth);
+                for (uint32_t i = 0; i < nt; ++i) {
+                    const Tri3 t = load_tri(sc, tris[i]);
+                    const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
+                    const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+                    if (rt.hit && rt.dist < h.pdist) { h.primary = tris[i]; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
+                }
+                if (h.primary != WTGPU_INVALID_IDX) h.flags |= H_PRIMARY;
+                if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, h.edges, eo); if (eo) { h.flags |= H_OVERFLOW; ovf = true; } }
+            }
+            // ballistic hit with a finite beam: collect the edges around the hit (plt_path_detail.hpp:656-660)
+            if (is_ballistic && !cone_is_ray(pc.beam.env) && !force_rt) {
+                const float zd = cone_axes(env, h.d2i).x * kMajorToZ;
+                ConeResult cr;
+                cone_traverse<kMaxConeTris>(sc, env, mkr(h.d2i - zd / 2.f, h.d2i + zd / 2.f), 1.f, tris, cr, ctr);
+                bool eo = cr.overflow;
+                h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, min(cr.n_tris, (uint32_t)kMaxConeTris), h.edges, eo);
+                if (eo) { h.flags |= H_OVERFLOW; ovf = true; }
+            }
+            if (h.flags & H_PRIMARY) key = (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
+            else key = h.n_edges ? a.n_keys - 3u : a.n_keys - 2u;
+        }
+        soa_store(h, a.hit, a.pool, slot);
+        a.keys[slot] = key;
+    }
+    flush_counters(a.ctr, ctr);
+    count1(&a.ctr->segments, seg);
+    count1(&a.ctr->overflow, ovf);
+}
+
+// ================================================================================================ material sort (counting sort)
+__global__ void k_hist(const RenderArgs a) {
+    extern __shared__ uint32_t sh[];
+    for (uint32_t i = threadIdx.x; i < a.n_keys; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < a.pool && a.alive[slot]) atomicAdd(&sh[a.keys[slot]], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < a.n_keys; i += blockDim.x) if (sh[i]) atomicAdd(&a.key_count[i], sh[i]);
+}
+__global__ void k_scan(const RenderArgs a) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < a.n_keys; ++i) { const uint32_t c = a.key_count[i]; a.key_cursor[i] = acc; acc += c; a.key_count[i] = 0u; }
+        a.ctr->n_sorted = (int)acc;
+    }
+}
+__global__ void k_scatter(const RenderArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < a.pool && a.alive[slot]) { const uint32_t pos = atomicAdd(&a.key_cursor[a.keys[slot]], 1u); a.order[pos] = slot; }
+}
+__global__ void k_identity_order(const RenderArgs a) {     // WTGPU_RENDER_NO_SORT: live slots in slot order (compaction only)
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < a.pool && a.alive[slot]) { const uint32_t pos = atomicAdd(&a.key_cursor[0], 1u); a.order[pos] = slot; }
+    if (slot == 0) a.ctr->n_sorted = a.ctr->live;
+}
+
+// ================================================================================================ shade
+WT_D float MIS(float p1, float p2) { if (p2 == 0.f) return 1.f; return p1 * p1 / (p1 * p1 + p2 * p2); }
+
+__global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr; counters_zero(ctr);
+    uint32_t n_splat = 0, n_edges_fetched = 0; bool c_surface = false, c_fsd = false, c_null = false, died = false;
+    if (i < (uint32_t)a.ctr->n_sorted) {
+        const DScene& sc = a.sc;
+        const uint32_t slot = a.order[i];
+        PathCore pc; soa_load(pc, a.core, a.pool, slot);
+        HitRec h; soa_load(h, a.hit, a.pool, slot);
+        Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = pc.rng_d;
+        Beam& beam = pc.beam;
+        const bool fwd = beam.fwd;
+        const uint32_t max_depth = sc.integrator.max_depth;
+        bool alive = true;
+        Aperture ap; ap.n = 0u;
+        bool has_new_fsd = false;
+        Beam prev_beam_new;     // beam before this vertex's interaction (becomes prev_vert_beam)
+
+        if (h.flags & H_EMPTY) alive = false;
+        else {
+            const float k = beam.k;
+            const float d2i = h.d2i;
+            const bool is_ballistic = (h.flags & H_BALLISTIC) || cone_is_ray(beam.env);
+            const Frame beam_frame = cone_frame(beam.env);
+            const V3 origin_wp = h.origin;
+            const V3 dir = beam.env.d;
+            const V3 interaction_wp = origin_wp + d2i * dir;
+
+            // ---- evaluate fsd from the previous interaction (plt_path_detail.hpp:591-610)
+            if (pc.flags & F_HAS_FSD) {
+                PathFsd pf; soa_load(pf, a.fsd, a.pool, slot);
+                const float f = do_fsd(sc, pf.prev_beam.env, pc.prev_geo, interaction_wp, pf.ap, k, ctr, n_edges_fetched);
+                pc.flags &= ~F_HAS_FSD;
+                if (pc.flags & F_SAMPLED_FSD) beam_mul(beam, f);
+                else {
+                    beam_transform_region(pf.prev_beam, origin_wp, length(origin_wp - pf.prev_beam.env.o), dir, f);
+                    beam_add(beam, pf.prev_beam);
+                }
+            }
+
+            // ---- surface record of the primary triangle (plt_path_detail.hpp:634-652)
+            const bool has_primary = (h.flags & H_PRIMARY) != 0u;
+            const float region_end = has_primary ? h.pdist : d2i;
+            Surface surf;
+            int32_t bsdf = -1, emitter = -1;
+            if (has_primary) {
+                surf = make_surface(sc, h.primary, mk2(h.bx, h.by), origin_wp + h.pdist * dir);
+                surf.fp = surface_footprint_static(beam, surf, d2i);
+                const wtgpu_shape shp = sc.shapes[sc.tri_meta[h.primary].shape_idx];
+                bsdf = shp.bsdf; emitter = shp.emitter;
+            }
+
+            // ---- construct the fsd aperture from the edges (plt_path_detail.hpp:663-679)
+            if (h.n_edges) {
+                ap.wp = interaction_wp; ap.fr = beam_frame; ap.size = beam_footprint(beam, d2i); ap.wi = -dir; ap.k = k; ap.n = 0u;
+                for (uint32_t j = 0; j < h.n_edges; ++j) { Wedge w; ++n_edges_fetched; if (wedge_build(sc, ap, h.edges[j], w)) ap.edges[ap.n++] = h.edges[j]; }
+                has_new_fsd = ap.n > 0u;
+                c_fsd = true;
+            }
+
+            // ---- NEE (plt_path_detail.hpp:350-424 backward, 468-510 forward)
+            if (!fwd) {
+                if (pc.depth < max_depth && has_primary && !bsdf_is_delta_only(sc, bsdf, k)) {
+                    const EmitterDirect ds = scene_sample_emitter_direct(sc, smp, surf.wp, k);
+                    if (beam_intensity(ds.beam) != 0.f) {
+                        const V3 wiw = -dir, wow = -ds.beam.env.d;
+                        const V3 wi = to_local(surf.shading, wiw), wo = to_local(surf.shading, wow);
+                        const float wig = dot(wiw, surf.geo.n), wog = dot(wow, surf.geo.n);
+                        if (!(wi.z * wig <= 0.f || wo.z * wog <= 0.f)) {
+                            BsdfQuery q; q.k = k; q.fwd = false; q.lobes = 0xffffffffu;
+                            const Mueller f = bsdf_f(sc, bsdf, wi, wo, q);
+                            if (f.m[0] != 0.f) {
+                                const Geo eg = ds.has_surface ? geo_surface(ds.sp, ds.stuid, true) : geo_point(ds.beam.env.o);
+                                if (!shadow_between(sc, geo_surface(surf.wp, surf.tuid, true), eg, ctr)) {
+                                    Beam nb = beam;
+                                    beam_transform_surface(nb, surf, wow, f, 1.f);
+                                    const Stokes sL = integrate_beams(nb, ds.beam);
+                                    float mis = 1.f;
+                                    if (!ds.dpd.disc) mis = MIS(ds.dpd.v * ds.emitter_pdf, bsdf_pdf(sc, bsdf, wi, wo, q));
+                                    for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
+                                }
+                            }
+                        }
+                    }
+                }
+            } else if (pc.depth < max_depth && has_new_fsd && sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE) {
+                const SensorDirect sd = sensor_sample_direct(sc, smp, interaction_wp, k);
+                if ((sd.dpd.disc || sd.dpd.v != 0.f) && beam_intensity(sd.beam) > 0.f) {
+                    const float f = do_fsd(sc, beam.env, pc.prev_geo, sd.beam.env.o, ap, k, ctr, n_edges_fetched);
+                    if (f != 0.f) {
+                        Beam fb = beam;
+                        beam_transform_region(fb, interaction_wp, d2i, -sd.beam.env.d, f);
+                        const Stokes sL = integrate_beams(sd.beam, fb);
+                        n_splat += film_splat(sc, a.film_block, a.film_light, true, sd.el, sL.s[0] * pc.rspd, k);
+                    }
+                }
+            }
+
+            // ---- organic connections: emission (plt_path_detail.hpp:427-465) / sensing (513-540)
+            if (!fwd) {
+                if (has_primary && emitter >= 0) {
+                    const Stokes sL = emitter_Li(sc, emitter, beam, surf);
+                    float mis = 1.f;
+                    if (!(pc.flags & F_DPD_DISC)) {
+                        const wtgpu_emitter E = sc.emitters[emitter];
+                        const float ppd = E.type == WTGPU_EMITTER_AREA ? 1.f / sc.shapes[E.shape].surface_area : 0.f;
+                        const float dn = dot(-dir, surf.geo.n);
+                        const float rdn = dn != 0.f ? 1.f / fabsf(dn) : 0.f;
+                        const float pd_nee = ppd * length2(beam.env.o - surf.wp) * rdn;
+                        mis = MIS(pc.dpd_v, pd_nee * pdf_emitter(sc, emitter));
+                    }
+                    for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
+                }
+            } else {
+                const float maxd = region_end - fmaxf(0.f, dot(dir, origin_wp - beam.env.o));
+                Beam se; Element el;
+                if (sensor_Si(sc, beam, mkr(0.f, maxd), se, el)) {
+                    const Stokes sL = integrate_beams(se, beam);
+                    n_splat += film_splat(sc, a.film_block, a.film_light, true, el, sL.s[0] * pc.rspd, k);
+                }
+            }
+
+            // ---- interactions (plt_path_detail.hpp:156-237, 729-749)
+            bool sampled_null = false;
+            if (has_primary) {
+                BsdfQuery q; q.k = k; q.fwd = fwd; q.lobes = 0xffffffffu;
+                const V3 wiw = -dir;
+                const V3 wi = to_local(surf.shading, wiw);
+                const float wig = dot(wiw, surf.geo.n);
+                if (wig * wi.z <= 0.f) alive = false;
+                else {
+                    const BsdfSample bs = bsdf_sample(sc, bsdf, wi, q, smp);
+                    if (!bs.valid || bs.dpd.v == 0.f) alive = false;
+                    else {
+                        const V3 wow = normalize(to_world(surf.shading, bs.wo));
+                        c_surface = true;
+                        if (dot(wow, surf.geo.n) * bs.wo.z <= 0.f) alive = false;
+                        else {
+                            pc.dpd_v = bs.dpd.v; pc.flags = (pc.flags & ~(F_DPD_DISC | F_SAMPLED_FSD)) | (bs.dpd.disc ? F_DPD_DISC : 0u);
+                            pc.prev_geo = geo_surface(surf.wp, surf.tuid, true);
+                            prev_beam_new = beam;
+                            beam_transform_surface(beam, surf, wow, bs.M, 1.f);
+                            pc.throughput *= 1.f * bs.M.m[0];
+                            if (bs.eta.re != 1.f) pc.throughput /= sqrf(bs.eta.re);
+                        }
+                    }
+                }
+            } else if (has_new_fsd) {
+                V3 wo; float w;
+                fsd_sample(sc, ap, pc.prev_geo.p, smp, wo, w);
+                pc.dpd_v = 0.f; pc.flags = (pc.flags | F_DPD_DISC | F_SAMPLED_FSD);
+                pc.prev_geo = geo_point(interaction_wp);
+                prev_beam_new = beam;
+                beam_transform_region(beam, interaction_wp, d2i, wo, w);
+                pc.throughput *= w;
+            } else {
+                sampled_null = true; c_null = true;
+                beam_transform_restart(beam, interaction_wp, d2i);
+            }
+
+            // ---- continue walk (plt_path_detail.hpp:123-142, 755-757)
+            if (alive) {
+                if (pc.depth >= max_depth) alive = false;
+                else if (beam_intensity(beam) == 0.f) alive = false;
+                else if (!sampled_null && sc.integrator.russian_roulette) {
+                    const float r = pc.throughput < 1.f ? fmaxf(pc.throughput, .5f) : 1.f;
+                    if (rnd(smp) <= r) { const float s = 1.f / r; beam_mul(beam, s); pc.throughput *= s; }
+                    else alive = false;
+                }
+                if (alive && !sampled_null) pc.depth++;
+            }
+        }
+
+        if (alive) {
+            pc.rng_d = smp.d;
+            if (has_new_fsd) {
+                pc.flags |= F_HAS_FSD;
+                PathFsd pf; pf.prev_beam = prev_beam_new; pf.ap = ap;
+                soa_store(pf, a.fsd, a.pool, slot);
+            }
+            soa_store(pc, a.core, a.pool, slot);
+        } else {
+            died = true;
+            if (!fwd) {     // splat_backward (plt_path_detail.hpp:799-800)
+                Element el; el.ex = pc.pixel % sc.sensor.width; el.ey = pc.pixel / sc.sensor.width; el.ox = pc.ox; el.oy = pc.oy;
+                n_splat += film_splat(sc, a.film_block, a.film_light, false, el, pc.L[0] * pc.rspd, pc.beam.k);
+            }
+            a.alive[slot] = 0u;
+        }
+    }
+    flush_counters(a.ctr, ctr, true);
+    count1(&a.ctr->shaded, i < (uint32_t)a.ctr->n_sorted);
+    {
+        const unsigned m = __activemask();
+        const unsigned ns = __reduce_add_sync(m, n_splat), ne = __reduce_add_sync(m, n_edges_fetched), nd = __reduce_add_sync(m, died ? 1u : 0u);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+            if (ns) atomicAdd(&a.ctr->splats, (unsigned long long)ns);
+            if (ne) atomicAdd(&a.ctr->edges, (unsigned long long)ne);
+            if (nd) atomicAdd(&a.ctr->live, -(int)nd);
+        }
+    }
+    count1(&a.ctr->surface, c_surface);
+    count1(&a.ctr->fsd, c_fsd);
+    count1(&a.ctr->null_, c_null);
+}
+
+// ================================================================================================ debug kernels
+__global__ void k_debug_rays(const DScene sc, uint32_t n, const wtgpu_ray_query* q, wtgpu_ray_hit* out, uint32_t* shadow_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Counters ctr; counters_zero(ctr);
+    const V3 o = mk3(q[i].o), d = mk3(q[i].d);
+    if (shadow_out) { shadow_out[i] = shadow_ray(sc, o, d, mkr(q[i].tmin, q[i].tmax), ctr) ? 1u : 0u; return; }
+    RayHit h; intersect_ray(sc, o, d, mkr(q[i].tmin, q[i].tmax), h, ctr);
+    out[i].tuid = h.tuid; out[i].dist = h.dist; out[i].bary[0] = h.bx; out[i].bary[1] = h.by; out[i].front_face = h.front ? 1u : 0u;
+}
+__global__ void k_debug_cones(const DScene sc, uint32_t n, const wtgpu_cone_query* q, wtgpu_cone_hit* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Counters ctr; counters_zero(ctr);
+    const Cone c = mkcone(mk3(q[i].o), mk3(q[i].d), mk3(q[i].x), q[i].x0, q[i].tan_alpha, 1.f / q[i].e, q[i].e);
+    uint32_t tris[kMaxConeTris]; ConeResult r;
+    cone_traverse<kMaxConeTris>(sc, c, mkr(q[i].tmin, q[i].tmax), q[i].z_scale, tris, r, ctr);
+    wtgpu_cone_hit& h = out[i];
+    h.dist = r.dist; h.front_face = r.front ? 1u : 0u; h.n_tris = r.n_tris;
+    const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
+    for (uint32_t j = 0; j < nt; ++j) h.tris[j] = tris[j];
+    bool eo = false; uint32_t edges[WTGPU_MAX_CONE_EDGES];
+    h.n_edges = collect_edges<WTGPU_MAX_CONE_EDGES>(sc, tris, nt, edges, eo);
+    for (uint32_t j = 0; j < h.n_edges; ++j) h.edges[j] = edges[j];
+}
+__global__ void k_debug_rng(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t n, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Sampler s; s.k0 = k0; s.k1 = k1; s.pixel = pixel; s.sample = sample; s.d = i;
+    out[i] = rnd(s);
+}
+
+// ================================================================================================ host side
+static thread_local std::string g_err;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return WTGPU_E_CUDA; } } while (0)
+
+struct wtgpu_scene {
+    int device = 0;
+    DScene d{};
+    std::vector<void*> allocs;
+    wtgpu_sensor sensor{};
+    wtgpu_integrator integ{};
+    // render pool (lazily sized)
+    uint32_t pool = 0;
+    float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
+    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr;
+    DevCounters* ctr = nullptr;
+    uint32_t n_keys = 0;
+    ~wtgpu_scene() {
+        cudaSetDevice(device);
+        for (void* p : allocs) cudaFree(p);
+        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr }) if (p) cudaFree(p);
+    }
+};
+
+template <class T> static int upload(wtgpu_scene* s, const T* src, size_t n, const T** dst) {
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(1, n) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    if (n && src) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = reinterpret_cast<const T*>(p);
+    return WTGPU_OK;
+}
+
+extern "C" {
+
+int wtgpu_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+const char* wtgpu_last_error(void) { return g_err.c_str(); }
+
+uint64_t wtgpu_debug_sizeof(int which) {
+    switch (which) {
+    case 0: return sizeof(wtgpu_node); case 1: return sizeof(wtgpu_leaf); case 2: return sizeof(wtgpu_tri); case 3: return sizeof(wtgpu_tri_meta);
+    case 4: return sizeof(wtgpu_tri_shading); case 5: return sizeof(wtgpu_edge); case 6: return sizeof(wtgpu_shape); case 7: return sizeof(wtgpu_spectrum);
+    case 8: return sizeof(wtgpu_bsdf); case 9: return sizeof(wtgpu_bsdf_bin); case 10: return sizeof(wtgpu_emitter); case 11: return sizeof(wtgpu_kdist);
+    case 12: return sizeof(wtgpu_sensor); case 13: return sizeof(wtgpu_integrator); case 14: return sizeof(wtgpu_scene_desc); case 15: return sizeof(wtgpu_render_opts);
+    case 16: return sizeof(wtgpu_stats); case 17: return sizeof(wtgpu_ray_query); case 18: return sizeof(wtgpu_ray_hit); case 19: return sizeof(wtgpu_cone_query);
+    case 20: return sizeof(wtgpu_cone_hit); case 21: return sizeof(wthost_mesh_desc);
+    }
+    return 0;
+}
+
+int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** out) {
+    if (!desc || !out) { g_err = "null argument"; return WTGPU_E_INVALID; }
+    if (desc->api_version != WTGPU_API_VERSION) { g_err = "api version mismatch"; return WTGPU_E_INVALID; }
+    if (desc->integrator.type != WTGPU_INTEGRATOR_PLT_PATH) { g_err = "integrator type not implemented on the device (plt_path only)"; return WTGPU_E_UNSUPPORTED; }
+    if (desc->sensor.rf_radius > 4) { g_err = "reconstruction filter radius > 4 unsupported"; return WTGPU_E_UNSUPPORTED; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device"; return WTGPU_E_NO_DEVICE; }
+    CK(cudaSetDevice(device));
+    auto* s = new wtgpu_scene(); s->device = device;
+    DScene& d = s->d;
+    int rc = WTGPU_OK;
+#define UP(field, src, n) if ((rc = upload(s, src, n, &d.field)) != WTGPU_OK) { delete s; return rc; }
+    UP(nodes, desc->nodes, desc->n_nodes) UP(leaves, desc->leaves, desc->n_leaves)
+    { const wtgpu_tri* t; if ((rc = upload(s, desc->tris, desc->n_tris, &t)) != WTGPU_OK) { delete s; return rc; } d.tris = reinterpret_cast<const float4*>(t); }
+    UP(tri_meta, desc->tri_meta, desc->n_tris) UP(tri_shading, desc->tri_shading, desc->n_tris) UP(edges, desc->edges, desc->n_edges)
+    UP(shapes, desc->shapes, desc->n_shapes) UP(shape_tri_tuid, desc->shape_tri_tuid, desc->n_shape_tris) UP(shape_tri_cdf, desc->shape_tri_cdf, desc->n_shape_cdf)
+    UP(spectra, desc->spectra, desc->n_spectra) UP(spectrum_data, desc->spectrum_data, desc->n_spectrum_data)
+    UP(bsdfs, desc->bsdfs, desc->n_bsdfs) UP(bsdf_bins, desc->bsdf_bins, desc->n_bsdf_bins)
+    UP(emitters, desc->emitters, desc->n_emitters) UP(emitter_cdf, desc->emitter_cdf, desc->n_emitters + 1) UP(emitter_kdist, desc->emitter_kdist, desc->n_emitters)
+    UP(kdist_data, desc->kdist_data, desc->n_kdist_data)
+    {   // erf table (include/wt/math/erf_lut.hpp:27-32)
+        std::vector<float> lut(1024);
+        for (int i = 0; i < 1024; ++i) lut[i] = std::erf((float)i / 1023.f * 3.5f);
+        UP(erf_lut, lut.data(), lut.size())
+    }
+#undef UP
+    d.root_ptr = desc->root_ptr; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs; d.n_tris = desc->n_tris; d.n_nodes = desc->n_nodes;
+    d.sensor = desc->sensor; d.integrator = desc->integrator;
+    s->sensor = desc->sensor; s->integ = desc->integrator;
+    s->n_keys = desc->n_bsdfs + 3u;
+    *out = s;
+    return WTGPU_OK;
+}
+
+void wtgpu_scene_destroy(wtgpu_scene* s) { delete s; }
+
+static int ensure_pool(wtgpu_scene* s, uint32_t pool) {
+    if (s->pool == pool) return WTGPU_OK;
+    for (void* p : { (void*)s->core, (void*)s->fsd, (void*)s->hit, (void*)s->alive, (void*)s->keys, (void*)s->order, (void*)s->key_count, (void*)s->key_cursor, (void*)s->ctr }) if (p) cudaFree(p);
+    s->core = s->fsd = s->hit = nullptr; s->alive = s->keys = s->order = s->key_count = s->key_cursor = nullptr; s->ctr = nullptr; s->pool = 0;
+    CK(cudaMalloc(&s->core, (size_t)chunks_of<PathCore>() * 16 * pool));
+    CK(cudaMalloc(&s->fsd, (size_t)chunks_of<PathFsd>() * 16 * pool));
+    CK(cudaMalloc(&s->hit, (size_t)chunks_of<HitRec>() * 16 * pool));
+    CK(cudaMalloc(&s->alive, 4ull * pool)); CK(cudaMalloc(&s->keys, 4ull * pool)); CK(cudaMalloc(&s->order, 4ull * pool));
+    CK(cudaMalloc(&s->key_count, 4ull * s->n_keys)); CK(cudaMalloc(&s->key_cursor, 4ull * s->n_keys));
+    CK(cudaMalloc(&s->ctr, sizeof(DevCounters)));
+    s->pool = pool;
+    return WTGPU_OK;
+}
+
+int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, float* film_light, wtgpu_stats* stats) {
+    if (!s || !o) { g_err = "null argument"; return WTGPU_E_INVALID; }
+    CK(cudaSetDevice(s->device));
+    const uint32_t W = s->sensor.width, H = s->sensor.height, C = s->sensor.channels;
+    const uint32_t x1 = std::min(o->tile_x1, W), y1 = std::min(o->tile_y1, H);
+    if (x1 <= o->tile_x0 || y1 <= o->tile_y0 || o->sample_end <= o->sample_begin) { if (stats) memset(stats, 0, sizeof(*stats)); return WTGPU_OK; }
+    cudaStream_t st = (cudaStream_t)o->stream;
+    const unsigned long long total = (unsigned long long)(x1 - o->tile_x0) * (y1 - o->tile_y0) * (o->sample_end - o->sample_begin);
+    uint32_t pool = o->pool_size ? o->pool_size : (1u << 20);
+    pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>(total, 1024ull));
+    pool = (pool + 127u) & ~127u;
+    int rc = ensure_pool(s, pool);
+    if (rc != WTGPU_OK) return rc;
+
+    const size_t nb = (size_t)W * H * C * 2, nl = (size_t)W * H * C;
+    float *dblock = film_block, *dlight = film_light;
+    const bool on_dev = o->film_on_device != 0;
+    if (!on_dev) {
+        CK(cudaMalloc(&dblock, nb * 4)); CK(cudaMalloc(&dlight, nl * 4));
+        CK(cudaMemsetAsync(dblock, 0, nb * 4, st)); CK(cudaMemsetAsync(dlight, 0, nl * 4, st));
+    }
+
+    RenderArgs a;
+    a.sc = s->d; a.core = s->core; a.fsd = s->fsd; a.hit = s->hit; a.alive = s->alive; a.keys = s->keys; a.order = s->order;
+    a.key_count = s->key_count; a.key_cursor = s->key_cursor; a.ctr = s->ctr; a.film_block = dblock; a.film_light = dlight;
+    a.pool = pool; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
+    a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
+    a.sample_begin = o->sample_begin; a.n_samples = o->sample_end - o->sample_begin; a.total = total;
+
+    CK(cudaMemsetAsync(s->alive, 0, 4ull * pool, st));
+    CK(cudaMemsetAsync(s->key_count, 0, 4ull * s->n_keys, st));
+    CK(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
+
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    DevCounters* hctr = nullptr;
+    CK(cudaMallocHost(&hctr, sizeof(DevCounters)));
+    const dim3 blk(128), grd((pool + 127) / 128);
+    const bool nosort = (o->flags & WTGPU_RENDER_NO_SORT) != 0;
+    uint64_t launches = 0, iters = 0;
+    // per-kernel device time: events are only RECORDED inside the loop (no host sync) and resolved after the last iteration
+    const bool time_phases = stats != nullptr && (o->flags & WTGPU_RENDER_TIME_KERNELS) != 0;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() { if (time_phases) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
+    CK(cudaEventRecord(e0, st));
+    for (;;) {
+        mark();
+        k_generate<<<grd, blk, 0, st>>>(a); ++launches; mark();
+        k_traverse<<<grd, blk, 0, st>>>(a); ++launches; mark();
+        if (nosort) {
+            cudaMemsetAsync(s->key_cursor, 0, 4, st);
+            k_identity_order<<<grd, blk, 0, st>>>(a); ++launches;
+        } else {
+            k_hist<<<grd, blk, s->n_keys * 4, st>>>(a);
+            k_scan<<<1, 32, 0, st>>>(a);
+            k_scatter<<<grd, blk, 0, st>>>(a); launches += 3;
+        }
+        mark();
+        k_shade<<<grd, blk, 0, st>>>(a); ++launches; mark();
+        ++iters;
+        CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (hctr->next_sample >= total && hctr->live <= 0) break;
+        if (iters > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
+    }
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    double t_trav = 0, t_shade = 0, t_gen = 0, t_sort = 0;
+    for (size_t i = 0; i + 4 < evs.size(); i += 5) {
+        float f;
+        cudaEventElapsedTime(&f, evs[i], evs[i + 1]); t_gen += f;
+        cudaEventElapsedTime(&f, evs[i + 1], evs[i + 2]); t_trav += f;
+        cudaEventElapsedTime(&f, evs[i + 2], evs[i + 3]); t_sort += f;
+        cudaEventElapsedTime(&f, evs[i + 3], evs[i + 4]); t_shade += f;
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+
+    if (!on_dev) {
+        std::vector<float> tmp(std::max(nb, nl));
+        CK(cudaMemcpy(tmp.data(), dblock, nb * 4, cudaMemcpyDeviceToHost));
+        if (film_block) for (size_t i = 0; i < nb; ++i) film_block[i] += tmp[i];
+        CK(cudaMemcpy(tmp.data(), dlight, nl * 4, cudaMemcpyDeviceToHost));
+        if (film_light) for (size_t i = 0; i < nl; ++i) film_light[i] += tmp[i];
+        cudaFree(dblock); cudaFree(dlight);
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = hctr->samples; stats->segments = hctr->segments; stats->ray_casts = hctr->ray_casts; stats->cone_casts = hctr->cone_casts;
+        stats->shadow_casts = hctr->shadow_casts; stats->nodes_visited = hctr->nodes + hctr->shade_nodes; stats->tris_tested = hctr->tris + hctr->shade_tris;
+        stats->traverse_nodes = hctr->nodes; stats->traverse_tris = hctr->tris; stats->shaded_paths = hctr->shaded; stats->edges_fetched = hctr->edges;
+        stats->surface_interactions = hctr->surface; stats->fsd_interactions = hctr->fsd; stats->null_interactions = hctr->null_; stats->splats = hctr->splats;
+        stats->capacity_overflows = hctr->overflow; stats->kernel_launches = launches; stats->iterations = iters;
+        stats->gpu_ms = ms; stats->traverse_ms = t_trav; stats->shade_ms = t_shade; stats->generate_ms = t_gen; stats->sort_ms = t_sort;
+    }
+    const bool overflowed = hctr->overflow != 0;
+    cudaFreeHost(hctr);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (overflowed) { g_err = "a bounded per-path list (cone triangles / edges) overflowed; results were still produced"; return WTGPU_E_CAPACITY; }
+    return WTGPU_OK;
+}
+
+int wtgpu_develop(const wtgpu_sensor* sensor, uint32_t spp, const float* film_block, const float* film_light, float* out) {
+    if (!sensor || !out) return WTGPU_E_INVALID;
+    const size_t n = (size_t)sensor->width * sensor->height * sensor->channels;
+    const float sl = spp > 0 ? 1.f / (float)spp : 0.f;      // film_storage.hpp:354-358
+    for (size_t i = 0; i < n; ++i) {
+        float v = 0.f;
+        if (film_block) { const float val = film_block[2 * i], w = film_block[2 * i + 1]; v = w > 0.f ? val / w : 0.f; }
+        if (film_light) v += film_light[i] * sl;
+        out[i] = v;
+    }
+    return WTGPU_OK;
+}
+
+int wtgpu_debug_intersect_rays(wtgpu_scene* s, uint32_t n, const wtgpu_ray_query* q, wtgpu_ray_hit* out) {
+    if (!s) return WTGPU_E_INVALID;
+    CK(cudaSetDevice(s->device));
+    wtgpu_ray_query* dq; wtgpu_ray_hit* dh;
+    CK(cudaMalloc(&dq, sizeof(*dq) * n)); CK(cudaMalloc(&dh, sizeof(*dh) * n));
+    CK(cudaMemcpy(dq, q, sizeof(*dq) * n, cudaMemcpyHostToDevice));
+    k_debug_rays<<<(n + 127) / 128, 128>>>(s->d, n, dq, dh, nullptr);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dh, sizeof(*dh) * n, cudaMemcpyDeviceToHost));
+    cudaFree(dq); cudaFree(dh);
+    return WTGPU_OK;
+}
+int wtgpu_debug_shadow_rays(wtgpu_scene* s, uint32_t n, const wtgpu_ray_query* q, uint32_t* out) {
+    if (!s) return WTGPU_E_INVALID;
+    CK(cudaSetDevice(s->device));
+    wtgpu_ray_query* dq; uint32_t* dh;
+    CK(cudaMalloc(&dq, sizeof(*dq) * n)); CK(cudaMalloc(&dh, 4ull * n));
+    CK(cudaMemcpy(dq, q, sizeof(*dq) * n, cudaMemcpyHostToDevice));
+    k_debug_rays<<<(n + 127) / 128, 128>>>(s->d, n, dq, nullptr, dh);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dh, 4ull * n, cudaMemcpyDeviceToHost));
+    cudaFree(dq); cudaFree(dh);
+    return WTGPU_OK;
+}
+int wtgpu_debug_intersect_cones(wtgpu_scene* s, uint32_t n, const wtgpu_cone_query* q, wtgpu_cone_hit* out) {
+    if (!s) return WTGPU_E_INVALID;
+    CK(cudaSetDevice(s->device));
+    wtgpu_cone_query* dq; wtgpu_cone_hit* dh;
+    CK(cudaMalloc(&dq, sizeof(*dq) * n)); CK(cudaMalloc(&dh, sizeof(*dh) * n));
+    CK(cudaMemcpy(dq, q, sizeof(*dq) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dh, 0, sizeof(*dh) * n));
+    k_debug_cones<<<(n + 63) / 64, 64>>>(s->d, n, dq, dh);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dh, sizeof(*dh) * n, cudaMemcpyDeviceToHost));
+    cudaFree(dq); cudaFree(dh);
+    return WTGPU_OK;
+}
+int wtgpu_debug_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, int device) {
+    CK(cudaSetDevice(device));
+    float* d; CK(cudaMalloc(&d, 4ull * n));
+    k_debug_rng<<<(n + 127) / 128, 128>>>((uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, n, d);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, d, 4ull * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return WTGPU_OK;
+}
+
+} // extern "C"

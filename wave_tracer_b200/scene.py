@@ -1,0 +1,503 @@
+"""Host-side scene model mirroring wave_tracer's plugin interface for the hot path, flattened to wtgpu_scene_desc.
+
+Names and parameters follow the reference's scene elements (XML `type=` strings):
+  integrators  plt_path                      (src/integrator/plt_path.cpp:64-94)
+  bsdfs        diffuse, dielectric, surface_spm, twosided, composite, scale (src/bsdf/bsdf_loader.cpp:42-57)
+  profiles     dirac, fractal                (src/interaction/surface_profile/*)
+  emitters     point, spot, directional, area (src/emitter/emitter_loader.cpp)
+  sensors      perspective, virtual_plane    (src/sensor/sensor_loader.cpp)
+  shapes       rectangle, cube, sphere, mesh (src/scene/shape.cpp)
+Geometry preparation (triangles, BVH, edges) is done by the native host library (wthost_ads_build);
+spectra are baked to constants / uniform tables over the sensor's wavenumber range.
+Lengths: metres.  Wavelengths: metres.  Wavenumbers: 1/mm.
+"""
+import ctypes as C
+import math
+import numpy as np
+
+from . import _abi as A
+
+TWO_PI = 2.0 * math.pi
+
+
+def wavelen_to_wavenum(lam_m):
+    """k [1/mm] = 2 pi / lambda (include/wt/math/quantity/math.hpp:25-27)."""
+    return TWO_PI / (lam_m * 1e3)
+
+
+# ------------------------------------------------------------------------------------------------ transforms
+def lookat(origin, target, up=(0, 1, 0)):
+    """transform_t::lookat (include/wt/math/transform/transform.hpp:198-213); returns row-major 4x4 (float64)."""
+    o = np.asarray(origin, np.float64)
+    d = np.asarray(target, np.float64) - o
+    d /= np.linalg.norm(d)
+    l = np.cross(np.asarray(up, np.float64), d)
+    l /= np.linalg.norm(l)
+    u = np.cross(d, l)
+    M = np.eye(4)
+    M[:3, 0], M[:3, 1], M[:3, 2], M[:3, 3] = l, u, d, o
+    return M
+
+
+def translate(v):
+    M = np.eye(4); M[:3, 3] = v; return M
+
+
+def scale(v):
+    M = np.eye(4); M[0, 0], M[1, 1], M[2, 2] = (v, v, v) if np.isscalar(v) else v; return M
+
+
+def rotate(axis, angle_rad):
+    a = np.asarray(axis, np.float64); a /= np.linalg.norm(a)
+    c, s = math.cos(angle_rad), math.sin(angle_rad)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    M = np.eye(4); M[:3, :3] = c * np.eye(3) + s * K + (1 - c) * np.outer(a, a); return M
+
+
+# ------------------------------------------------------------------------------------------------ spectra
+class Spectrum:
+    """spectrum_t / spectrum_real_t (include/wt/spectrum/spectrum.hpp:37-93): value(k) complex, f(k) real."""
+    def value(self, k):  # k: ndarray of 1/mm
+        raise NotImplementedError
+
+
+class Const(Spectrum):
+    def __init__(self, v): self.v = complex(v)
+    def value(self, k): return np.full(np.shape(k), self.v, np.complex128)
+
+
+class Discrete(Spectrum):
+    """spectrum/discrete.hpp: lines (wavelength -> value); f(k) is non-zero only exactly on a line."""
+    def __init__(self, wavelength_m, value=1.0):
+        self.lines = [(np.float32(wavelen_to_wavenum(wavelength_m)), float(value))]
+    def value(self, k):
+        out = np.zeros(np.shape(k), np.complex128)
+        for kl, v in self.lines:
+            out = np.where(np.asarray(k, np.float32) == kl, v, out)
+        return out
+
+
+class Blackbody(Spectrum):
+    """spectrum/blackbody.hpp: Planck spectral radiance per unit wavenumber (arbitrary but fixed normalisation), times scale."""
+    def __init__(self, T, scale=1.0): self.T, self.scale = float(T), float(scale)
+    def value(self, k):
+        k = np.asarray(k, np.float64)
+        lam = TWO_PI / np.maximum(k, 1e-30) * 1e-3          # m
+        h, c, kb = 6.62607015e-34, 2.99792458e8, 1.380649e-23
+        nu = c / lam
+        B = 2 * h * nu ** 3 / c ** 2 / np.expm1(np.minimum(h * nu / (kb * self.T), 700.0))
+        return (self.scale * B * (c / TWO_PI) * 1e3).astype(np.complex128)   # per (1/mm)
+
+
+class Table(Spectrum):
+    """piecewise-linear spectrum over wavelengths (spectrum/piecewise_linear.hpp); zero outside."""
+    def __init__(self, wavelengths_m, values):
+        k = wavelen_to_wavenum(np.asarray(wavelengths_m, np.float64))
+        o = np.argsort(k); self.k, self.v = k[o], np.asarray(values, np.complex128)[o]
+    def value(self, k):
+        k = np.asarray(k, np.float64)
+        re = np.interp(k, self.k, self.v.real, left=0, right=0); im = np.interp(k, self.k, self.v.imag, left=0, right=0)
+        return re + 1j * im
+
+
+class Binned(Spectrum):
+    """composite spectrum (spectrum/composite.hpp): wavelength bins -> spectrum; zero outside all bins."""
+    def __init__(self, bins): self.bins = [(wavelen_to_wavenum(hi), wavelen_to_wavenum(lo), s) for lo, hi, s in bins]
+    def value(self, k):
+        k = np.asarray(k, np.float64); out = np.zeros(k.shape, np.complex128)
+        for kmin, kmax, s in self.bins:
+            m = (k >= kmin) & (k < kmax); out = np.where(m, _as_spectrum(s).value(k), out)
+        return out
+
+
+def _as_spectrum(s):
+    return s if isinstance(s, Spectrum) else Const(s)
+
+
+# ------------------------------------------------------------------------------------------------ bsdfs
+class Bsdf: pass
+
+
+class Diffuse(Bsdf):
+    def __init__(self, reflectance): self.reflectance = _as_spectrum(reflectance)
+
+
+class Dielectric(Bsdf):
+    def __init__(self, IOR, extIOR=1.0, reflection_scale=None, transmission_scale=None):
+        self.IOR, self.extIOR, self.rs, self.ts = _as_spectrum(IOR), _as_spectrum(extIOR), reflection_scale, transmission_scale
+
+
+class Dirac: pass
+
+
+class Fractal:
+    def __init__(self, roughness, gamma=3.0): self.roughness, self.gamma = _as_spectrum(roughness), float(gamma)
+
+
+class SurfaceSPM(Bsdf):
+    def __init__(self, IOR, extIOR=1.0, profile=None, reflection_scale=None, transmission_scale=None):
+        self.IOR, self.extIOR, self.profile = _as_spectrum(IOR), _as_spectrum(extIOR), profile or Dirac()
+        self.rs, self.ts = reflection_scale, transmission_scale
+
+
+class TwoSided(Bsdf):
+    def __init__(self, nested): self.nested = nested
+
+
+class Scale(Bsdf):
+    def __init__(self, scale, nested): self.scale, self.nested = _as_spectrum(scale), nested
+
+
+class Composite(Bsdf):
+    """bins: list of (wavelength_min_m, wavelength_max_m, bsdf) (src/bsdf/composite.cpp:42-95)."""
+    def __init__(self, bins): self.bins = bins
+
+
+# ------------------------------------------------------------------------------------------------ emitters / sensors / shapes
+class Point:
+    def __init__(self, position, radiant_intensity, extent=None, phase_space_extent_scale=1.0):
+        self.position, self.spectrum, self.extent, self.pse = position, _as_spectrum(radiant_intensity), extent, phase_space_extent_scale
+
+
+class Spot:
+    """src/emitter/spot.cpp:82-133: cutoff_angle default 20 deg, beam_width default .75 cutoff."""
+    def __init__(self, to_world, radiant_intensity, cutoff_angle=math.radians(20), beam_width=None, extent=None, phase_space_extent_scale=1.0):
+        self.to_world, self.spectrum = np.asarray(to_world, np.float64), _as_spectrum(radiant_intensity)
+        self.cutoff = float(cutoff_angle); self.falloff = float(beam_width) if beam_width is not None else .75 * self.cutoff
+        self.extent, self.pse = extent, phase_space_extent_scale
+
+
+class Directional:
+    """src/emitter/directional.cpp:86-132: dir = to_world * (0,0,-1) is the direction TO the emitter."""
+    def __init__(self, irradiance, to_world=None, solid_angle=6.794e-5, phase_space_extent_scale=1.0):
+        d = np.array([0, 0, -1.0])
+        if to_world is not None:
+            d = np.asarray(to_world, np.float64)[:3, :3] @ d; d /= np.linalg.norm(d)
+        self.dir, self.spectrum, self.solid_angle, self.pse = d, _as_spectrum(irradiance), solid_angle, phase_space_extent_scale
+
+
+class Area:
+    def __init__(self, radiance, scale=1.0, phase_space_extent_scale=1.0):
+        self.spectrum, self.scale, self.pse = _as_spectrum(radiance), float(scale), phase_space_extent_scale
+
+
+class Film:
+    """film_t (include/wt/sensor/film/film.hpp:116-135, 355-420); response: list of per-channel spectra."""
+    def __init__(self, width, height, response, rfilter_scale=1.0):
+        self.width, self.height, self.response, self.rfilter_scale = int(width), int(height), [_as_spectrum(r) for r in response], float(rfilter_scale)
+
+
+class VirtualPlane:
+    def __init__(self, to_world, extent, film, alpha=None, ray_trace_only=False, samples=1):
+        self.to_world, self.extent, self.film, self.alpha, self.rt, self.samples = np.asarray(to_world, np.float64), extent, film, alpha, ray_trace_only, samples
+
+
+class Perspective:
+    def __init__(self, to_world, fov, film, ray_trace_only=False, samples=1, sourcing_tan_alpha=None, phase_space_extent_scale=1.0):
+        self.to_world, self.fov, self.film, self.rt, self.samples = np.asarray(to_world, np.float64), float(fov), film, ray_trace_only, samples
+        self.sta, self.pse = sourcing_tan_alpha, phase_space_extent_scale
+
+
+class PltPath:
+    def __init__(self, max_depth=1024, direction="backward", fsd=True, russian_roulette=True):
+        self.max_depth, self.direction, self.fsd, self.rr = int(max_depth), direction, bool(fsd), bool(russian_roulette)
+
+
+class Mesh:
+    def __init__(self, positions, indices, normals=None, uvs=None, to_world=None):
+        self.positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        self.indices = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+        self.normals = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+        self.uvs = None if uvs is None else np.ascontiguousarray(uvs, np.float32).reshape(-1, 2)
+        self.to_world = np.eye(4) if to_world is None else np.asarray(to_world, np.float64)
+
+
+def rectangle(p, x, y, to_world=None, tessellation=1):
+    """src/mesh/rectangle.cpp:26-79: 4 vertices + 2 triangles per cell, uv = cell corners."""
+    p, x, y = (np.asarray(v, np.float32) for v in (p, x, y))
+    verts, uvs, tris = [], [], []
+    rt = np.float32(1.0) / np.float32(tessellation)
+    for ix in range(tessellation):
+        for iy in range(tessellation):
+            t = len(verts)
+            u0, v0 = np.float32(ix) * rt, np.float32(iy) * rt
+            u1 = np.float32(1) if ix + 1 == tessellation else np.float32(ix + 1) * rt
+            v1 = np.float32(1) if iy + 1 == tessellation else np.float32(iy + 1) * rt
+            for (u, v) in ((u0, v0), (u1, v0), (u1, v1), (u0, v1)):
+                verts.append(p + u * x + v * y); uvs.append((u, v))
+            tris += [(t, t + 1, t + 2), (t + 2, t + 3, t)]
+    return Mesh(np.array(verts, np.float32), np.array(tris, np.uint32), uvs=np.array(uvs, np.float32), to_world=to_world)
+
+
+def cube(to_world=None):
+    """unit cube [-1,1]^3 with per-face vertices (outward normals)."""
+    faces = [((1, 0, 0), (0, 1, 0), (0, 0, 1)), ((-1, 0, 0), (0, 0, 1), (0, 1, 0)), ((0, 1, 0), (0, 0, 1), (1, 0, 0)),
+             ((0, -1, 0), (1, 0, 0), (0, 0, 1)), ((0, 0, 1), (1, 0, 0), (0, 1, 0)), ((0, 0, -1), (0, 1, 0), (1, 0, 0))]
+    verts, uvs, tris = [], [], []
+    for n, a, b in faces:
+        n, a, b = np.array(n, np.float32), np.array(a, np.float32), np.array(b, np.float32)
+        t = len(verts)
+        for (u, v) in ((-1, -1), (1, -1), (1, 1), (-1, 1)):
+            verts.append(n + u * a + v * b); uvs.append(((u + 1) / 2, (v + 1) / 2))
+        tris += [(t, t + 1, t + 2), (t + 2, t + 3, t)]
+    return Mesh(np.array(verts, np.float32), np.array(tris, np.uint32), uvs=np.array(uvs, np.float32), to_world=to_world)
+
+
+def sphere(radius=1.0, centre=(0, 0, 0), n_lat=16, n_lon=32, to_world=None):
+    verts, normals, uvs, tris = [], [], [], []
+    for i in range(n_lat + 1):
+        th = math.pi * i / n_lat
+        for j in range(n_lon + 1):
+            ph = TWO_PI * j / n_lon
+            n = np.array([math.sin(th) * math.cos(ph), math.sin(th) * math.sin(ph), math.cos(th)])
+            verts.append(np.asarray(centre) + radius * n); normals.append(n); uvs.append((j / n_lon, i / n_lat))
+    for i in range(n_lat):
+        for j in range(n_lon):
+            a, b = i * (n_lon + 1) + j, (i + 1) * (n_lon + 1) + j
+            if i > 0: tris.append((a, b, a + 1))
+            if i < n_lat - 1: tris.append((a + 1, b, b + 1))
+    return Mesh(np.array(verts, np.float32), np.array(tris, np.uint32), normals=np.array(normals, np.float32), uvs=np.array(uvs, np.float32), to_world=to_world)
+
+
+# ------------------------------------------------------------------------------------------------ scene + flattening
+class BuiltScene:
+    """Owns the ctypes wtgpu_scene_desc and everything it points to."""
+    def __init__(self):
+        self.desc = A.SceneDesc()
+        self.keep = []
+        self.ads = None
+    def __del__(self):
+        try:
+            if self.ads is not None: A.lib().wthost_ads_destroy(self.ads)
+        except Exception:
+            pass
+    @property
+    def width(self): return self.desc.sensor.width
+    @property
+    def height(self): return self.desc.sensor.height
+    @property
+    def channels(self): return self.desc.sensor.channels
+
+
+def _arr(ctype, values):
+    a = (ctype * max(1, len(values)))(*values)
+    return a
+
+
+class Scene:
+    def __init__(self):
+        self.integrator = PltPath()
+        self.sensor = None
+        self.shapes = []        # (mesh, bsdf, area_emitter or None)
+        self.emitters = []      # non-area emitters
+
+    def add_shape(self, mesh, bsdf, emitter=None):
+        self.shapes.append((mesh, bsdf, emitter)); return len(self.shapes) - 1
+
+    def add_emitter(self, e):
+        self.emitters.append(e); return e
+
+    # -- sensor wavenumber range (sensitivity_spectrum().wavenumber_range())
+    def _krange(self):
+        ks = []
+        for r in self.sensor.film.response:
+            if isinstance(r, Discrete): ks += [k for k, _ in r.lines]
+            elif isinstance(r, Table): ks += [r.k[0], r.k[-1]]
+            else: raise ValueError("sensor response must be Discrete or Table")
+        return float(min(ks)), float(max(ks))
+
+    def build(self, table_size=256):
+        L = A.lib()
+        out = BuiltScene()
+        d = out.desc
+        d.api_version = 1
+        kmin, kmax = self._krange()
+        mono = kmin == kmax
+
+        spectra, spectrum_data = [], []
+        def bake(s):
+            s = _as_spectrum(s)
+            sp = A.Spectrum()
+            if mono or isinstance(s, Const):
+                v = complex(s.value(np.array([np.float32(kmin)]))[0]) if not isinstance(s, Const) else s.v
+                sp.type, sp.re, sp.im = A.SPECTRUM_CONSTANT, v.real, v.imag
+            else:
+                ks = np.linspace(kmin, kmax, table_size)
+                v = s.value(ks)
+                sp.type, sp.k0, sp.inv_dk, sp.n, sp.offset = A.SPECTRUM_TABLE, kmin, (table_size - 1) / (kmax - kmin), table_size, len(spectrum_data) // 2
+                for c in v: spectrum_data.extend((float(c.real), float(c.imag)))
+            spectra.append(sp); return len(spectra) - 1
+
+        bsdfs, bins = [], []
+        def flat_bsdf(b):
+            n = A.Bsdf(); n.child = -1; n.spec[:] = [-1] * 4; n.prof_spec[:] = [-1] * 2
+            idx = len(bsdfs); bsdfs.append(n)
+            if isinstance(b, Diffuse):
+                n.type = A.BSDF_DIFFUSE; n.spec[0] = bake(b.reflectance)
+            elif isinstance(b, (Dielectric, SurfaceSPM)):
+                n.type = A.BSDF_DIELECTRIC if isinstance(b, Dielectric) else A.BSDF_SURFACE_SPM
+                n.spec[0], n.spec[1] = bake(b.extIOR), bake(b.IOR)
+                if b.rs is not None: n.spec[2] = bake(b.rs)
+                if b.ts is not None: n.spec[3] = bake(b.ts)
+                if isinstance(b, SurfaceSPM):
+                    if isinstance(b.profile, Fractal):
+                        n.profile_type, n.gamma = A.PROFILE_FRACTAL_ROUGHNESS, b.profile.gamma; n.prof_spec[0] = bake(b.profile.roughness)
+                    else:
+                        n.profile_type = A.PROFILE_DIRAC
+            elif isinstance(b, TwoSided):
+                n.type = A.BSDF_TWO_SIDED; n.child = flat_bsdf(b.nested)
+            elif isinstance(b, Scale):
+                n.type = A.BSDF_SCALE; n.spec[0] = bake(b.scale); n.child = flat_bsdf(b.nested)
+            elif isinstance(b, Composite):
+                n.type = A.BSDF_COMPOSITE
+                children = [(wavelen_to_wavenum(hi), wavelen_to_wavenum(lo), flat_bsdf(c)) for lo, hi, c in b.bins]
+                n.bin_first, n.n_bins = len(bins), len(children)
+                for kmn, kmx, c in children:
+                    bb = A.BsdfBin(); bb.kmin, bb.kmax, bb.child = kmn, kmx, c; bins.append(bb)
+            else:
+                raise ValueError(f"unsupported bsdf {type(b)}")
+            return idx
+
+        # ---- emitters (area emitters are appended after the others, in shape order)
+        emitters = []
+        for e in self.emitters:
+            emitters.append((e, -1))
+        meshes = (A.MeshDesc * len(self.shapes))()
+        for si, (mesh, bsdf, em) in enumerate(self.shapes):
+            m = meshes[si]
+            m.n_verts = len(mesh.positions); m.positions = mesh.positions.ctypes.data_as(A.P(A.c_f))
+            m.normals = mesh.normals.ctypes.data_as(A.P(A.c_f)) if mesh.normals is not None else None
+            m.uvs = mesh.uvs.ctypes.data_as(A.P(A.c_f)) if mesh.uvs is not None else None
+            m.n_tris = len(mesh.indices); m.indices = mesh.indices.ctypes.data_as(A.P(A.c_u32))
+            m.to_world[:] = list(np.asarray(mesh.to_world, np.float64).reshape(-1))
+            m.bsdf = flat_bsdf(bsdf)
+            m.emitter = -1
+            if em is not None:
+                m.emitter = len(emitters); emitters.append((em, si))
+            out.keep.append(mesh)
+        ads = C.c_void_p()
+        A.check(L.wthost_ads_build(len(self.shapes), meshes, C.byref(ads)), "wthost_ads_build")
+        out.ads = ads
+        A.check(L.wthost_ads_fill(ads, C.byref(d)), "wthost_ads_fill")
+        out.keep.append(meshes)
+
+        wmin, wmax = np.array(d.world_min[:]), np.array(d.world_max[:])
+        # ---- sensor
+        s = d.sensor
+        film = self.sensor.film
+        s.width, s.height, s.channels = film.width, film.height, len(film.response)
+        stddev = np.float32(.25) * np.float32(film.rfilter_scale)     # beam_source_spatial_stddev * rfilter_scale (film.hpp:417)
+        s.rfilter_stddev = float(stddev)
+        s.rf_radius = int(np.uint32(np.float32(math.ceil(float(stddev * np.float32(3)))) + np.float32(.5)))
+        s.ray_trace_only = 1 if self.sensor.rt else 0
+        s.response[:] = [bake(r) for r in film.response] + [-1] * (4 - len(film.response))
+        M = self.sensor.to_world
+        R = M[:3, :3]
+        if isinstance(self.sensor, VirtualPlane):
+            s.type = A.SENSOR_VIRTUAL_PLANE
+            t, b, n = (R[:, i] / np.linalg.norm(R[:, i]) for i in range(3))
+            ext = np.array(self.sensor.extent, np.float64) * np.array([np.linalg.norm(R[:, 0]), np.linalg.norm(R[:, 1])])
+            centre = M[:3, 3]
+            origin = centre - ext[0] / 2 * t - ext[1] / 2 * b
+            s.frame_t[:], s.frame_b[:], s.frame_n[:], s.origin[:], s.extent[:] = list(t), list(b), list(n), list(origin), list(ext)
+            s.requested_tan_alpha = math.tan(self.sensor.alpha) if self.sensor.alpha is not None else -1.0
+        else:
+            s.type = A.SENSOR_PERSPECTIVE
+            s.pos[:] = list(M[:3, 3]); s.rot[:] = list(R.reshape(-1)); s.inv_rot[:] = list(np.linalg.inv(R).reshape(-1))
+            W, H = film.width, film.height
+            h = 1.0 / math.tan(self.sensor.fov / 2); w = h / (W / H); znear = 0.01
+            Pm = np.zeros((4, 4)); Pm[0, 0], Pm[1, 1], Pm[3, 2], Pm[2, 3] = w, h, 1.0, znear
+            V = scale((.5 * (W - 1), .5 * (H - 1), 1)) @ translate((1, 1, 0)) @ scale((-1, -1, 1))
+            S2C = np.linalg.inv(V @ Pm)
+            s.s2c[:] = list(S2C.reshape(-1)); s.c2s[:] = list((V @ Pm).reshape(-1))
+            if self.sensor.sta is not None:
+                s.sourcing_tan_alpha = self.sensor.sta
+            else:   # pixel_len / image_plane_z (perspective.hpp:147-151)
+                def pos(fx, fy):
+                    p = S2C @ np.array([fx, fy, 1, 1.0]); return p[:3] / p[3]
+                s.sourcing_tan_alpha = float(np.linalg.norm(pos(W, 0) - pos(0, 0)) / W / znear)
+            s.pse_scale = self.sensor.pse
+            s.requested_tan_alpha = -1.0
+
+        # ---- emitters + spectral sampling tables (scene_build_sensor_sampling_data.cpp:40-150, simplified product spectra)
+        em_structs, powers, kdists, kdist_data = [], [], [], []
+        sens = lambda k: sum(_as_spectrum(r).value(k).real for r in film.response)
+        ktab = np.array([kmin], np.float64) if mono else np.linspace(kmin, kmax, 1024)
+        shapes_area = [d.shapes[i].surface_area for i in range(d.n_shapes)]
+        centre = (wmin + wmax) / 2; pr = (wmax - wmin) / 2
+        for e, si in emitters:
+            E = A.Emitter(); E.shape = -1; E.extent = -1.0
+            E.spectrum = bake(e.spectrum); E.pse_scale = e.pse; E.scale = 1.0
+            em_f = e.spectrum.value(ktab).real
+            if isinstance(e, Point):
+                E.type = A.EMITTER_POINT; E.pos[:] = list(e.position); geom = 4 * math.pi
+                if e.extent: E.extent = e.extent
+            elif isinstance(e, Spot):
+                E.type = A.EMITTER_SPOT; Mw = e.to_world; E.pos[:] = list(Mw[:3, 3])
+                E.rot[:] = list(Mw[:3, :3].reshape(-1)); E.inv_rot[:] = list(np.linalg.inv(Mw[:3, :3]).reshape(-1))
+                E.cutoff, E.falloff = e.cutoff, e.falloff
+                if e.extent: E.extent = e.extent
+                geom = TWO_PI * (1 - .5 * (math.cos(e.cutoff) + math.cos(e.falloff)))
+            elif isinstance(e, Directional):
+                E.type = A.EMITTER_DIRECTIONAL; E.dir[:] = list(e.dir)
+                E.tan_alpha = math.tan(math.acos(1 - e.solid_angle / TWO_PI))
+                # set_world_aabb (directional.hpp:56-82)
+                n = e.dir
+                if abs(n[0]) > abs(n[1]):
+                    x = 1 / math.sqrt(n[0] ** 2 + n[2] ** 2); b = np.array([x * n[2], 0, -x * n[0]])
+                else:
+                    x = 1 / math.sqrt(n[1] ** 2 + n[2] ** 2); b = np.array([0, x * n[2], -x * n[1]])
+                t = np.cross(b, n)
+                r2, far = 0.0, 0.0
+                for sy in (-1, 1):
+                    for sz in (-1, 1):
+                        c = np.array([-pr[0], sy * pr[1], sz * pr[2]])
+                        loc = np.array([c @ t, c @ b, c @ n]); r2 = max(r2, loc[0] ** 2 + loc[1] ** 2); far = max(far, abs(loc[2]))
+                E.world_centre[:] = list(centre); E.world_radius = math.sqrt(r2); E.far_dist = 1.01 * far
+                geom = math.pi * r2
+            elif isinstance(e, Area):
+                E.type = A.EMITTER_AREA; E.shape = si; E.scale = e.scale
+                geom = e.scale * shapes_area[si] * math.pi
+            else:
+                raise ValueError(f"unsupported emitter {type(e)}")
+            prod = np.maximum(em_f * sens(ktab), 0)
+            kd = A.KDist(); kd.first = len(kdist_data)
+            if mono:
+                kd.type, kd.n, kd.norm = A.KDIST_DISCRETE, 1, (1.0 / prod[0] if prod[0] > 0 else 0.0)
+                kdist_data += [float(np.float32(kmin)), float(prod[0]), 0.0, 1.0]
+                power = geom * prod[0]
+            else:
+                n = len(ktab); dk = (kmax - kmin) / (n - 1)
+                dcdf = np.concatenate([[0], np.cumsum(dk * (prod[1:] + prod[:-1]) / 2)]); tot = dcdf[-1]
+                kd.type, kd.n, kd.k0, kd.dk, kd.norm = A.KDIST_BINNED, n, kmin, dk, (1 / tot if tot > 0 else 0.0)
+                kdist_data += [float(v) for v in prod] + [float(v / tot if tot > 0 else 0) for v in dcdf]
+                power = geom * tot
+            em_structs.append(E); powers.append(power); kdists.append(kd)
+        if not em_structs:
+            raise ValueError("(scene) no emitters defined")
+        # discrete_distribution_t power cdf, float32 accumulate (discrete_distribution.hpp:45-66)
+        tot = sum(powers); cdf = [np.float32(0)]
+        for p in powers: cdf.append(np.float32(cdf[-1] + np.float32(max(0.0, p / tot if tot > 0 else 0))))
+        cdf = [np.float32(c * (np.float32(1) / cdf[-1])) for c in cdf] if cdf[-1] > 0 else cdf[:-1] + [np.float32(1)]
+
+        # ---- tables into desc
+        def put(name_n, name_p, ctype, values, keepname):
+            arr = _arr(ctype, values); out.keep.append(arr)
+            if name_n: setattr(d, name_n, len(values))
+            setattr(d, name_p, arr)
+        put("n_spectra", "spectra", A.Spectrum, spectra, "spectra")
+        put("n_spectrum_data", "spectrum_data", A.c_f, spectrum_data, "sd")
+        put("n_bsdfs", "bsdfs", A.Bsdf, bsdfs, "bsdfs")
+        put("n_bsdf_bins", "bsdf_bins", A.BsdfBin, bins, "bins")
+        put("n_emitters", "emitters", A.Emitter, em_structs, "em")
+        put(None, "emitter_cdf", A.c_f, [float(c) for c in cdf], "cdf")
+        put(None, "emitter_kdist", A.KDist, kdists, "kd")
+        put("n_kdist_data", "kdist_data", A.c_f, kdist_data, "kdd")
+        # shapes' bsdf/emitter ids were recorded by wthost_ads_build from the mesh descs
+
+        it = d.integrator
+        it.type = A.INTEGRATOR_PLT_PATH
+        it.direction = A.DIRECTION_FORWARD if self.integrator.direction == "forward" else A.DIRECTION_BACKWARD
+        it.max_depth, it.russian_roulette, it.fsd = self.integrator.max_depth, int(self.integrator.rr), int(self.integrator.fsd)
+        out.spp = self.sensor.samples
+        return out

@@ -1,0 +1,59 @@
+"""Procedural restatements of the reference's benchmark scenes (LFS meshes/textures are pointer stubs -- SURVEY.md fact 3).
+
+double_slits(): scenes/diffraction_simple/double_slits.xml + bits/geometry.xml with their default parameters
+(all geometry procedural rectangles), `pattern=true` sensor.  The reference file uses plt_bdpt; the same scene is driven
+here by plt_path forward + UTD as scenes/diffraction_simple/double_slits_and_reflectors.xml does.
+"""
+import math
+import numpy as np
+from .scene import *  # noqa: F401,F403
+
+MM = 1e-3
+
+
+def double_slits(res=1024, spp=32, direction="forward", max_depth=16, fsd=True, screen=True, lam_mm=.05, with_directional=True,
+                 ray_trace_only=False, rr=False):
+    L, Lscale, S, E, extent, D, Hh, Z, W, Wslit = -500.0, 1633.0, 50.0, 5.0, 250.0, 12.0, 20.0, -15.0, .65, .35
+    lam = lam_mm * MM
+    sc = Scene()
+    sc.integrator = PltPath(max_depth=max_depth, direction=direction, fsd=fsd, russian_roulette=rr)
+    film = Film(res, res // 4, [Discrete(lam)], rfilter_scale=.05)
+    sc.sensor = VirtualPlane(lookat((0, 0, (S - .0001) * MM), (0, 0, E * MM), (0, -1, 0)), (extent * MM, extent / 4 * MM), film,
+                             alpha=math.radians(.001), samples=spp, ray_trace_only=ray_trace_only)
+    sc.add_emitter(Spot(lookat((0, 0, L * MM), (0, 0, 0)), Discrete(lam, Lscale), cutoff_angle=math.radians(.2), beam_width=math.radians(.1)))
+    if with_directional:
+        sc.add_emitter(Directional(Blackbody(5750, 1e-6), lookat((-2, 3.5, -1), (0, 0, 0), (1, 0, 0))))
+        sc.add_emitter(Directional(Blackbody(6500, 6e-5), lookat((-1, 4, 1), (0, 0, 0), (1, 0, 0))))
+    um = 1e-6
+    mat_screen = TwoSided(SurfaceSPM(IOR=complex(1, 100), profile=Fractal(.3, gamma=3)))
+    mat_floor = TwoSided(Composite([(300e-9, 800e-9, Diffuse(.5)), (1 * um, 1.0, Diffuse(.1))]))
+    mat_wall = TwoSided(Diffuse(Binned([(300e-9, 800e-9, .539479), (1 * um, 1.0, .9)])))
+    def rect(p, x, y, m):
+        sc.add_shape(rectangle(np.array(p) * MM, np.array(x) * MM, np.array(y) * MM), m)
+    rect((-100, -Hh, S), (200, 0, 0), (0, 2 * Hh, 0), mat_wall)
+    rect((-100, -Hh, L - 100), (200, 0, 0), (0, 0, S - L + 100), mat_floor)
+    if screen:
+        rect((-D / 2, -Hh, Z), (D / 2 - (W + Wslit) / 2, 0, 0), (0, 2 * Hh, 0), mat_screen)
+        rect((-W / 2 + Wslit / 2, -Hh, Z), (W - Wslit, 0, 0), (0, 2 * Hh, 0), mat_screen)
+        rect(((W + Wslit) / 2, -Hh, Z), (D / 2 - (W + Wslit) / 2, 0, 0), (0, 2 * Hh, 0), mat_screen)
+    return sc
+
+
+def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=False, fsd=False, n_sphere=16):
+    """A texture-free, procedural cornell-box variant (scenes/cornell-box/box.xml with its PLY shapes dropped):
+    5 diffuse walls, a dielectric sphere, a rough-conductor cube, a cube area emitter; perspective sensor; plt_path backward."""
+    lam = lam_nm * 1e-9
+    sc = Scene()
+    sc.integrator = PltPath(max_depth=max_depth, direction="backward", fsd=fsd, russian_roulette=True)
+    film = Film(res, res, [Discrete(lam)], rfilter_scale=1.0)
+    sc.sensor = Perspective(lookat((0, 1.0, 3.4), (0, 1.0, 0), (0, 1, 0)), math.radians(40), film, ray_trace_only=ray_trace_only, samples=spp)
+    white, red, green = TwoSided(Diffuse(.6)), TwoSided(Diffuse(.35)), TwoSided(Diffuse(.45))
+    sc.add_shape(rectangle((-1, 0, -1), (2, 0, 0), (0, 0, 2)), white)          # floor
+    sc.add_shape(rectangle((-1, 2, -1), (0, 0, 2), (2, 0, 0)), white)          # ceiling
+    sc.add_shape(rectangle((-1, 0, -1), (0, 2, 0), (2, 0, 0)), white)          # back
+    sc.add_shape(rectangle((-1, 0, -1), (0, 0, 2), (0, 2, 0)), red)            # left
+    sc.add_shape(rectangle((1, 0, -1), (0, 2, 0), (0, 0, 2)), green)           # right
+    sc.add_shape(sphere(.35, (-.4, .35, .2), n_sphere, 2 * n_sphere), Dielectric(1.5))
+    sc.add_shape(cube(translate((.45, .3, -.25)) @ rotate((0, 1, 0), .4) @ scale(.3)), SurfaceSPM(IOR=complex(.2, 3.0), profile=Fractal(.2)))
+    sc.add_shape(cube(translate((0, 1.98, 0)) @ scale((.25, .01, .25))), Diffuse(.0), emitter=Area(Discrete(lam, 1.0), scale=20.0))
+    return sc
