@@ -259,6 +259,13 @@ typedef struct wtgpu_scene_desc {
 
     wtgpu_sensor sensor;
     wtgpu_integrator integrator;
+
+    /* Fraunhofer FSD importance-sampling tables (plt_bdpt): fsd_lut_t (include/wt/interaction/fsd/fraunhofer/fsd_lut.hpp:27-69).
+     * The reference ships them as data/fsd/iCDFa{1,2}{,theta}.fp64 (Git-LFS stubs here): regenerated by the host
+     * (wave_tracer_b200/fsd_lut.py).  icdf_theta*: n entries over u in [0,1] -> theta in [0,pi/2];
+     * icdf*: m x m, row = theta bin, column = u -> radius. */
+    uint32_t fsd_lut_n, fsd_lut_m;
+    const float *fsd_icdf_theta1, *fsd_icdf_theta2, *fsd_icdf1, *fsd_icdf2;
 } wtgpu_scene_desc;
 
 /* ---------------------------------------------------------------------------------------------

@@ -3,7 +3,7 @@
 // oracle.cpp: C entry points of the CPU oracle (ctypes-loaded by tests/, __graft_entry__.smoke() and the
 // cpu_baseline / --impl reference legs of bench.py).  PARITY UNPINNED by the reference (no golden vectors, reference
 // not compilable here -- SURVEY.md 8c); pinned by analytic KATs only.
-#include "ot_integrator.h"
+#include "ot_bdpt.h"
 #include "oracle.h"
 #include <thread>
 #include <atomic>
@@ -11,12 +11,15 @@
 
 using namespace ot;
 
+static bool sc_has_lut(const wtgpu_scene_desc* d) { return d->fsd_lut_n > 1 && d->fsd_lut_m > 1 && d->fsd_icdf_theta1 && d->fsd_icdf1 && d->fsd_icdf_theta2 && d->fsd_icdf2; }
+
 extern "C" {
 
 int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, double* film_block, double* film_light,
                   uint32_t n_threads, oracle_stats* st) {
     if (!desc || !opts) return -1;
-    if (desc->integrator.type != WTGPU_INTEGRATOR_PLT_PATH) return -4;
+    const bool bdpt = desc->integrator.type == WTGPU_INTEGRATOR_PLT_BDPT;
+    if (bdpt && !sc_has_lut(desc) && desc->integrator.fsd && !desc->sensor.ray_trace_only) return -4;
     scene_t sc(desc);
     const uint32_t W = desc->sensor.width, H = desc->sensor.height, C = desc->sensor.channels;
     const uint32_t x0 = opts->tile_x0, y0 = opts->tile_y0, x1 = std::min(opts->tile_x1, W), y1 = std::min(opts->tile_y1, H);
@@ -31,8 +34,10 @@ int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, d
     std::atomic<uint64_t> next{ 0 };
     const uint64_t chunk = 64;
     const auto t_start = std::chrono::steady_clock::now();
+    std::vector<bdpt_stats_t> bstats(n_threads);
     auto worker = [&](uint32_t tid) {
         plt_path_t integ(sc, films[tid], &stats[tid]);
+        plt_bdpt_t binteg(sc, films[tid], &bstats[tid]);
         for (;;) {
             const uint64_t b = next.fetch_add(chunk);
             if (b >= npix) break;
@@ -40,7 +45,7 @@ int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, d
                 const uint32_t ex = x0 + (uint32_t)(i % tw), ey = y0 + (uint32_t)(i / tw);
                 for (uint32_t s = opts->sample_begin; s < opts->sample_end; ++s) {
                     sampler_t smp; smp.seed = opts->seed; smp.pixel = ey * W + ex; smp.sample = s;
-                    integ.integrate(ex, ey, smp);
+                    if (bdpt) binteg.integrate(ex, ey, smp); else integ.integrate(ex, ey, smp);
                 }
             }
         }
@@ -58,6 +63,8 @@ int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, d
         memset(st, 0, sizeof(*st));
         st->samples = npix * (opts->sample_end - opts->sample_begin);
         st->seconds = secs; st->threads = n_threads;
+        for (auto& s : bstats) { st->segments += s.vertices; st->fsd += s.connections; st->splats += s.splats;
+            st->nodes += s.ads.nodes; st->tris += s.ads.tris; st->ray_casts += s.ads.ray_casts; st->cone_casts += s.ads.cone_casts; st->shadow_casts += s.ads.shadow_casts; }
         for (auto& s : stats) {
             st->segments += s.segments; st->surface += s.surface; st->fsd += s.fsd; st->null_ += s.null; st->splats += s.splats;
             st->nodes += s.ads.nodes; st->tris += s.ads.tris; st->ray_casts += s.ads.ray_casts; st->cone_casts += s.ads.cone_casts; st->shadow_casts += s.ads.shadow_casts;
@@ -173,6 +180,11 @@ void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], co
     const frame_t f{ { frame[0], frame[1], frame[2] }, { frame[3], frame[4], frame[5] }, { frame[6], frame[7], frame[8] } };
     const auto c = elliptic_cone_t::cone_through_ellipsoid({ axes[0], axes[1], axes[2] }, f, ray_t{ { o[0], o[1], o[2] }, { d[0], d[1], d[2] } }, tan_alpha);
     out[0] = c.tangent.x; out[1] = c.tangent.y; out[2] = c.tangent.z; out[3] = c.x0; out[4] = c.e; out[5] = c.one_over_e; out[6] = c.tan_alpha; out[7] = c.z_apex;
+}
+
+// integral of the unit-covariance-scaled Gaussian over a triangle (gaussian2d_t::integrate_triangle)
+float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]) {
+    return gaussian2d_t(v2{ sx, sy }).integrate_triangle({ tri[0], tri[1] }, { tri[2], tri[3] }, { tri[4], tri[5] });
 }
 
 } // extern "C"

@@ -111,7 +111,8 @@ class SceneDesc(C.Structure):
                 ("n_bsdfs", c_u32), ("bsdfs", P(Bsdf)), ("n_bsdf_bins", c_u32), ("bsdf_bins", P(BsdfBin)),
                 ("n_emitters", c_u32), ("emitters", P(Emitter)), ("emitter_cdf", P(c_f)), ("emitter_kdist", P(KDist)),
                 ("n_kdist_data", c_u32), ("kdist_data", P(c_f)),
-                ("sensor", Sensor), ("integrator", Integrator)]
+                ("sensor", Sensor), ("integrator", Integrator),
+                ("fsd_lut_n", c_u32), ("fsd_lut_m", c_u32), ("fsd_icdf_theta1", P(c_f)), ("fsd_icdf_theta2", P(c_f)), ("fsd_icdf1", P(c_f)), ("fsd_icdf2", P(c_f))]
 
 
 class RenderOpts(C.Structure):

@@ -67,13 +67,14 @@ struct DevCounters {
     unsigned int next_sample_lo; unsigned int pad0;
     unsigned long long next_sample;     // samples handed out
     int live;                           // paths alive
+    int n_trav;                         // entries of trav_list (paths to traverse this iteration)
     int n_sorted;                       // live paths in `order`
 };
 
 struct RenderArgs {
     DScene sc;
     float4* core; float4* fsd; float4* hit;
-    uint32_t* alive; uint32_t* keys; uint32_t* order; uint32_t* key_count; uint32_t* key_cursor;
+    uint32_t* alive; uint32_t* keys; uint32_t* order; uint32_t* key_count; uint32_t* key_cursor; uint32_t* trav_list;
     DevCounters* ctr;
     float* film_block; float* film_light;
     uint32_t pool, n_keys;
@@ -99,6 +100,17 @@ WT_D void count1(unsigned long long* p, bool pred) {
     const unsigned m = __activemask();
     const unsigned n = __reduce_add_sync(m, pred ? 1u : 0u);
     if (n && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(p, (unsigned long long)n);
+}
+
+// warp-aggregated append of `slot` to a list (one atomic per warp)
+WT_D void list_append(uint32_t* list, int* counter, bool pred, uint32_t slot) {
+    const unsigned m = __ballot_sync(__activemask(), pred);
+    if (!pred) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    list[base + __popc(m & ((1u << lane) - 1u))] = slot;
 }
 
 // ================================================================================================ generate
@@ -136,6 +148,7 @@ __global__ void __launch_bounds__(128) k_generate(const RenderArgs a) {
             a.alive[slot] = 1u;
         }
     }
+    list_append(a.trav_list, &a.ctr->n_trav, gen, slot);
     const unsigned m = __activemask();
     const unsigned n = __reduce_add_sync(m, gen ? 1u : 0u);
     if (n && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) { atomicAdd(&a.ctr->live, (int)n); atomicAdd(&a.ctr->samples, (unsigned long long)n); }
@@ -185,10 +198,11 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
 }
 
 __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     Counters ctr; counters_zero(ctr);
     bool seg = false, ovf = false;
-    if (slot < a.pool && a.alive[slot]) {
+    if (li < (uint32_t)a.ctr->n_trav) {
+        const uint32_t slot = a.trav_list[li];
         const DScene& sc = a.sc;
         seg = true;
         PathCore pc; soa_load(pc, a.core, a.pool, slot);
@@ -248,8 +262,8 @@ __global__ void k_hist(const RenderArgs a) {
     extern __shared__ uint32_t sh[];
     for (uint32_t i = threadIdx.x; i < a.n_keys; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < a.pool && a.alive[slot]) atomicAdd(&sh[a.keys[slot]], 1u);
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li < (uint32_t)a.ctr->n_trav) atomicAdd(&sh[a.keys[a.trav_list[li]]], 1u);
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < a.n_keys; i += blockDim.x) if (sh[i]) atomicAdd(&a.key_count[i], sh[i]);
 }
@@ -261,13 +275,26 @@ __global__ void k_scan(const RenderArgs a) {
     }
 }
 __global__ void k_scatter(const RenderArgs a) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < a.pool && a.alive[slot]) { const uint32_t pos = atomicAdd(&a.key_cursor[a.keys[slot]], 1u); a.order[pos] = slot; }
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = li < (uint32_t)a.ctr->n_trav;
+    uint32_t slot = 0, key = 0;
+    if (act) { slot = a.trav_list[li]; key = a.keys[slot]; }
+    // one atomic per (warp, key): lanes with equal keys elect a leader
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    if (act) {
+        const unsigned peers = __match_any_sync(am, key);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&a.key_cursor[key], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        a.order[base + __popc(peers & ((1u << lane) - 1u))] = slot;
+    }
 }
+__global__ void k_reset_trav(const RenderArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) a.ctr->n_trav = 0; }
 __global__ void k_identity_order(const RenderArgs a) {     // WTGPU_RENDER_NO_SORT: live slots in slot order (compaction only)
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < a.pool && a.alive[slot]) { const uint32_t pos = atomicAdd(&a.key_cursor[0], 1u); a.order[pos] = slot; }
-    if (slot == 0) a.ctr->n_sorted = a.ctr->live;
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li < (uint32_t)a.ctr->n_trav) a.order[li] = a.trav_list[li];
+    if (li == 0) a.ctr->n_sorted = a.ctr->n_trav;
 }
 
 // ================================================================================================ shade
@@ -276,7 +303,7 @@ WT_D float MIS(float p1, float p2) { if (p2 == 0.f) return 1.f; return p1 * p1 /
 __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     Counters ctr; counters_zero(ctr);
-    uint32_t n_splat = 0, n_edges_fetched = 0; bool c_surface = false, c_fsd = false, c_null = false, died = false;
+    uint32_t n_splat = 0, n_edges_fetched = 0, my_slot = 0; bool c_surface = false, c_fsd = false, c_null = false, died = false, survive = false;
     if (i < (uint32_t)a.ctr->n_sorted) {
         const DScene& sc = a.sc;
         const uint32_t slot = a.order[i];
@@ -446,6 +473,8 @@ __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
             }
         }
 
+        survive = alive;
+        my_slot = slot;
         if (alive) {
             pc.rng_d = smp.d;
             if (has_new_fsd) {
@@ -463,6 +492,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
             a.alive[slot] = 0u;
         }
     }
+    list_append(a.trav_list, &a.ctr->n_trav, survive, my_slot);
     flush_counters(a.ctr, ctr, true);
     count1(&a.ctr->shaded, i < (uint32_t)a.ctr->n_sorted);
     {
@@ -524,13 +554,13 @@ struct wtgpu_scene {
     // render pool (lazily sized)
     uint32_t pool = 0;
     float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
-    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr;
+    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr;
     DevCounters* ctr = nullptr;
     uint32_t n_keys = 0;
     ~wtgpu_scene() {
         cudaSetDevice(device);
         for (void* p : allocs) cudaFree(p);
-        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr }) if (p) cudaFree(p);
+        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list }) if (p) cudaFree(p);
     }
 };
 
@@ -599,12 +629,12 @@ void wtgpu_scene_destroy(wtgpu_scene* s) { delete s; }
 
 static int ensure_pool(wtgpu_scene* s, uint32_t pool) {
     if (s->pool == pool) return WTGPU_OK;
-    for (void* p : { (void*)s->core, (void*)s->fsd, (void*)s->hit, (void*)s->alive, (void*)s->keys, (void*)s->order, (void*)s->key_count, (void*)s->key_cursor, (void*)s->ctr }) if (p) cudaFree(p);
-    s->core = s->fsd = s->hit = nullptr; s->alive = s->keys = s->order = s->key_count = s->key_cursor = nullptr; s->ctr = nullptr; s->pool = 0;
+    for (void* p : { (void*)s->core, (void*)s->fsd, (void*)s->hit, (void*)s->alive, (void*)s->keys, (void*)s->order, (void*)s->key_count, (void*)s->key_cursor, (void*)s->ctr, (void*)s->trav_list }) if (p) cudaFree(p);
+    s->core = s->fsd = s->hit = nullptr; s->alive = s->keys = s->order = s->key_count = s->key_cursor = s->trav_list = nullptr; s->ctr = nullptr; s->pool = 0;
     CK(cudaMalloc(&s->core, (size_t)chunks_of<PathCore>() * 16 * pool));
     CK(cudaMalloc(&s->fsd, (size_t)chunks_of<PathFsd>() * 16 * pool));
     CK(cudaMalloc(&s->hit, (size_t)chunks_of<HitRec>() * 16 * pool));
-    CK(cudaMalloc(&s->alive, 4ull * pool)); CK(cudaMalloc(&s->keys, 4ull * pool)); CK(cudaMalloc(&s->order, 4ull * pool));
+    CK(cudaMalloc(&s->alive, 4ull * pool)); CK(cudaMalloc(&s->keys, 4ull * pool)); CK(cudaMalloc(&s->order, 4ull * pool)); CK(cudaMalloc(&s->trav_list, 4ull * pool));
     CK(cudaMalloc(&s->key_count, 4ull * s->n_keys)); CK(cudaMalloc(&s->key_cursor, 4ull * s->n_keys));
     CK(cudaMalloc(&s->ctr, sizeof(DevCounters)));
     s->pool = pool;
@@ -635,7 +665,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
 
     RenderArgs a;
     a.sc = s->d; a.core = s->core; a.fsd = s->fsd; a.hit = s->hit; a.alive = s->alive; a.keys = s->keys; a.order = s->order;
-    a.key_count = s->key_count; a.key_cursor = s->key_cursor; a.ctr = s->ctr; a.film_block = dblock; a.film_light = dlight;
+    a.key_count = s->key_count; a.key_cursor = s->key_cursor; a.trav_list = s->trav_list; a.ctr = s->ctr; a.film_block = dblock; a.film_light = dlight;
     a.pool = pool; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
     a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
     a.sample_begin = o->sample_begin; a.n_samples = o->sample_end - o->sample_begin; a.total = total;
@@ -661,7 +691,6 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         k_generate<<<grd, blk, 0, st>>>(a); ++launches; mark();
         k_traverse<<<grd, blk, 0, st>>>(a); ++launches; mark();
         if (nosort) {
-            cudaMemsetAsync(s->key_cursor, 0, 4, st);
             k_identity_order<<<grd, blk, 0, st>>>(a); ++launches;
         } else {
             k_hist<<<grd, blk, s->n_keys * 4, st>>>(a);
@@ -669,7 +698,8 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             k_scatter<<<grd, blk, 0, st>>>(a); launches += 3;
         }
         mark();
-        k_shade<<<grd, blk, 0, st>>>(a); ++launches; mark();
+        k_reset_trav<<<1, 32, 0, st>>>(a);
+        k_shade<<<grd, blk, 0, st>>>(a); launches += 2; mark();
         ++iters;
         CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
