@@ -187,4 +187,11 @@ float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6])
     return gaussian2d_t(v2{ sx, sy }).integrate_triangle({ tri[0], tri[1] }, { tri[2], tri[3] }, { tri[4], tri[5] });
 }
 
+// |sum_e Psi_e(xi)|^2 for explicit aperture edges (e.x,e.y,v.x,v.y,a_b.re,a_b.im,iab_2.re,iab_2.im each): Fraunhofer ASF (fsd.hpp:127-140)
+float oracle_fraunhofer_asf(uint32_t n, const float* edges, float xix, float xiy) {
+    ffsd::aperture_t ap;
+    for (uint32_t i = 0; i < n; ++i) { const float* e = edges + 8 * i; ap.edges.push_back({ { e[0], e[1] }, { e[2], e[3] }, { e[4], e[5] }, { e[6], e[7] } }); }
+    return ap.ASF_unclamped({ xix, xiy });
+}
+
 } // extern "C"

@@ -10,7 +10,11 @@
 #include <stdint.h>
 
 #define WT_D __device__ __forceinline__
-#define WT_DN __device__ __noinline__
+// "large" device functions.  Force-inlined by default: out-of-line calls pass Beam/Surface/Mueller structs through local memory
+// (ncu r01: 41% of k_shade's stall samples sat on STL); inlining lets the compiler scalarise them.  -DWT_DN=... overrides for A/B runs.
+#ifndef WT_DN
+#define WT_DN __device__ __forceinline__
+#endif
 
 namespace wt {
 

@@ -86,22 +86,22 @@ WT_D Stokes stokes_reorient(const Stokes& S, const Frame& cur, const Frame& nw) 
     return r;
 }
 struct Mueller { float m[16]; };
-WT_D Mueller mu_zero() { Mueller M; for (int i = 0; i < 16; ++i) M.m[i] = 0.f; return M; }
+WT_D Mueller mu_zero() { Mueller M; _Pragma("unroll") for (int i = 0; i < 16; ++i) M.m[i] = 0.f; return M; }
 WT_D Mueller mu_identity() { Mueller M = mu_zero(); M.m[0] = M.m[5] = M.m[10] = M.m[15] = 1.f; return M; }
 WT_D Mueller mu_flip() { Mueller M = mu_zero(); M.m[0] = M.m[5] = 1.f; M.m[10] = M.m[15] = -1.f; return M; }
 WT_D Mueller mu_depol(float s) { Mueller M = mu_zero(); M.m[0] = s; return M; }
-WT_D Mueller mu_scale(const Mueller& A, float s) { Mueller R; for (int i = 0; i < 16; ++i) R.m[i] = A.m[i] * s; return R; }
-WT_D Mueller mu_div(const Mueller& A, float s) { Mueller R; for (int i = 0; i < 16; ++i) R.m[i] = A.m[i] / s; return R; }
-WT_D Mueller mu_add(const Mueller& A, const Mueller& B) { Mueller R; for (int i = 0; i < 16; ++i) R.m[i] = A.m[i] + B.m[i]; return R; }
+WT_D Mueller mu_scale(const Mueller& A, float s) { Mueller R; _Pragma("unroll") for (int i = 0; i < 16; ++i) R.m[i] = A.m[i] * s; return R; }
+WT_D Mueller mu_div(const Mueller& A, float s) { Mueller R; _Pragma("unroll") for (int i = 0; i < 16; ++i) R.m[i] = A.m[i] / s; return R; }
+WT_D Mueller mu_add(const Mueller& A, const Mueller& B) { Mueller R; _Pragma("unroll") for (int i = 0; i < 16; ++i) R.m[i] = A.m[i] + B.m[i]; return R; }
 WT_D Mueller mu_mul(const Mueller& A, const Mueller& B) {     // glm mat4*mat4
     Mueller R;
-    for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r)
+    _Pragma("unroll") for (int c = 0; c < 4; ++c) _Pragma("unroll") for (int r = 0; r < 4; ++r)
         R.m[c * 4 + r] = A.m[r] * B.m[c * 4] + A.m[4 + r] * B.m[c * 4 + 1] + A.m[8 + r] * B.m[c * 4 + 2] + A.m[12 + r] * B.m[c * 4 + 3];
     return R;
 }
 WT_D Stokes mu_apply(const Mueller& M, const Stokes& S) {        // mueller.hpp:130-146
     Stokes r;
-    for (int i = 0; i < 4; ++i) r.s[i] = fmaf(M.m[12 + i], S.s[3], fmaf(M.m[8 + i], S.s[2], fmaf(M.m[4 + i], S.s[1], M.m[i] * S.s[0])));
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) r.s[i] = fmaf(M.m[12 + i], S.s[3], fmaf(M.m[8 + i], S.s[2], fmaf(M.m[4 + i], S.s[1], M.m[i] * S.s[0])));
     return r;
 }
 WT_D Mueller mu_rotation(V2 t1, V2 t2) {                          // mueller.hpp:244-258 (incl. the final transpose)
@@ -233,7 +233,7 @@ WT_D Beam beam_make(bool fwd, V3 o, V3 d, float s, float k, Sourcing sg) {
     return b;
 }
 WT_D void beam_add(Beam& b, const Beam& o) {        // operator+= (beam.hpp:95-98, 200-203)
-    if (b.fwd) { const Stokes r = stokes_reorient(beam_stokes(o), o.frame, b.frame); for (int i = 0; i < 4; ++i) b.M.m[i] += r.s[i]; }
+    if (b.fwd) { const Stokes r = stokes_reorient(beam_stokes(o), o.frame, b.frame); _Pragma("unroll") for (int i = 0; i < 4; ++i) b.M.m[i] += r.s[i]; }
     else b.M = mu_add(b.M, mu_change_incident_frame(o.M, o.frame, b.frame));
 }
 WT_D Footprint surface_footprint_static(const Beam& b, const Surface& s, float z) {    // beam_generic.hpp:171-193
@@ -275,7 +275,7 @@ WT_D void beam_transform_restart(Beam& b, V3 wp, float dist) {   // beam.hpp:464
 WT_D Stokes integrate_beams(const Beam& S, const Beam& I) {       // beam.hpp:562-603
     if (beam_intensity(S) == 0.f || beam_intensity(I) == 0.f) return stokes_zero();
     Stokes r = mu_apply_frames3(S.M, beam_stokes(I), I.frame, S.frame);
-    for (int i = 0; i < 4; ++i) r.s[i] *= S.scale;
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) r.s[i] *= S.scale;
     return r;
 }
 
@@ -780,7 +780,7 @@ WT_D float sum_spectral_pdf(const DScene& sc, float k) {             // scene_se
 
 // ================================================================================================ sensors
 struct Element { uint32_t ex, ey; float ox, oy; };
-WT_D void m4mul(const float* M, const float v[4], float o[4]) { for (int r = 0; r < 4; ++r) o[r] = M[4 * r] * v[0] + M[4 * r + 1] * v[1] + M[4 * r + 2] * v[2] + M[4 * r + 3] * v[3]; }
+WT_D void m4mul(const float* M, const float v[4], float o[4]) { _Pragma("unroll") for (int r = 0; r < 4; ++r) o[r] = M[4 * r] * v[0] + M[4 * r + 1] * v[1] + M[4 * r + 2] * v[2] + M[4 * r + 3] * v[3]; }
 WT_D V3 persp_point_on_sensor(const wtgpu_sensor& s, V2 fp) { const float v[4] = { fp.x, fp.y, 1.f, 1.f }; float p[4]; m4mul(s.s2c, v, p); return mk3(p[0], p[1], p[2]) / p[3]; }
 WT_D V2 persp_point_on_film(const wtgpu_sensor& s, V3 dir) { const V3 p = dir / fabsf(dir.z); const float v[4] = { p.x, p.y, 1.f, 1.f }; float q[4]; m4mul(s.c2s, v, q); return mk2(q[0], q[1]) / q[3]; }
 WT_D V2 persp_extent(const wtgpu_sensor& s) {

@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
                                     const Stokes sL = integrate_beams(nb, ds.beam);
                                     float mis = 1.f;
                                     if (!ds.dpd.disc) mis = MIS(ds.dpd.v * ds.emitter_pdf, bsdf_pdf(sc, bsdf, wi, wo, q));
-                                    for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
+                                    _Pragma("unroll") for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
                                 }
                             }
                         }
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
                         const float pd_nee = ppd * length2(beam.env.o - surf.wp) * rdn;
                         mis = MIS(pc.dpd_v, pd_nee * pdf_emitter(sc, emitter));
                     }
-                    for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
+                    _Pragma("unroll") for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
                 }
             } else {
                 const float maxd = region_end - fmaxf(0.f, dot(dir, origin_wp - beam.env.o));
@@ -557,9 +557,11 @@ struct wtgpu_scene {
     uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr;
     DevCounters* ctr = nullptr;
     uint32_t n_keys = 0;
+    std::vector<cudaEvent_t> ev_pool;   // reused across renders (event creation is not free)
     ~wtgpu_scene() {
         cudaSetDevice(device);
         for (void* p : allocs) cudaFree(p);
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list }) if (p) cudaFree(p);
     }
 };
@@ -683,8 +685,9 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     uint64_t launches = 0, iters = 0;
     // per-kernel device time: events are only RECORDED inside the loop (no host sync) and resolved after the last iteration
     const bool time_phases = stats != nullptr && (o->flags & WTGPU_RENDER_TIME_KERNELS) != 0;
-    std::vector<cudaEvent_t> evs;
-    auto mark = [&]() { if (time_phases) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
+    std::vector<cudaEvent_t>& evs = s->ev_pool;
+    size_t n_ev = 0;
+    auto mark = [&]() { if (time_phases) { if (n_ev == evs.size()) { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); } cudaEventRecord(evs[n_ev++], st); } };
     CK(cudaEventRecord(e0, st));
     for (;;) {
         mark();
@@ -711,14 +714,13 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     double t_trav = 0, t_shade = 0, t_gen = 0, t_sort = 0;
-    for (size_t i = 0; i + 4 < evs.size(); i += 5) {
+    for (size_t i = 0; i + 4 < n_ev; i += 5) {
         float f;
         cudaEventElapsedTime(&f, evs[i], evs[i + 1]); t_gen += f;
         cudaEventElapsedTime(&f, evs[i + 1], evs[i + 2]); t_trav += f;
         cudaEventElapsedTime(&f, evs[i + 2], evs[i + 3]); t_sort += f;
         cudaEventElapsedTime(&f, evs[i + 3], evs[i + 4]); t_shade += f;
     }
-    for (cudaEvent_t e : evs) cudaEventDestroy(e);
 
     if (!on_dev) {
         std::vector<float> tmp(std::max(nb, nl));

@@ -203,6 +203,13 @@ class PltPath:
         self.max_depth, self.direction, self.fsd, self.rr = int(max_depth), direction, bool(fsd), bool(russian_roulette)
 
 
+class PltBdpt:
+    """plt_bdpt options (src/integrator/plt_bdpt.cpp:161-197); lut=(n, m) sizes of the regenerated Fraunhofer sampling tables."""
+    def __init__(self, max_depth=1024, fsd=True, russian_roulette=True, mis=True, sensor_direct_sampling=True, emitter_direct_sampling=True, lut=(2048, 1024)):
+        self.max_depth, self.fsd, self.rr, self.mis = int(max_depth), bool(fsd), bool(russian_roulette), bool(mis)
+        self.sensor_direct, self.emitter_direct, self.lut = bool(sensor_direct_sampling), bool(emitter_direct_sampling), lut
+
+
 class Mesh:
     def __init__(self, positions, indices, normals=None, uvs=None, to_world=None):
         self.positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
@@ -496,8 +503,20 @@ class Scene:
         # shapes' bsdf/emitter ids were recorded by wthost_ads_build from the mesh descs
 
         it = d.integrator
-        it.type = A.INTEGRATOR_PLT_PATH
-        it.direction = A.DIRECTION_FORWARD if self.integrator.direction == "forward" else A.DIRECTION_BACKWARD
         it.max_depth, it.russian_roulette, it.fsd = self.integrator.max_depth, int(self.integrator.rr), int(self.integrator.fsd)
+        if isinstance(self.integrator, PltBdpt):
+            it.type = A.INTEGRATOR_PLT_BDPT
+            it.mis, it.sensor_direct, it.emitter_direct = int(self.integrator.mis), int(self.integrator.sensor_direct), int(self.integrator.emitter_direct)
+            if self.integrator.fsd and not self.sensor.rt:      # plt_bdpt.cpp:189-194: the LUTs are only loaded when not ray tracing
+                from . import fsd_lut
+                n, m = self.integrator.lut
+                t1, t2, c1, c2 = (np.ascontiguousarray(x, np.float32) for x in fsd_lut.build(n, m))
+                out.keep += [t1, t2, c1, c2]
+                d.fsd_lut_n, d.fsd_lut_m = n, m
+                d.fsd_icdf_theta1, d.fsd_icdf_theta2 = t1.ctypes.data_as(A.P(A.c_f)), t2.ctypes.data_as(A.P(A.c_f))
+                d.fsd_icdf1, d.fsd_icdf2 = c1.ctypes.data_as(A.P(A.c_f)), c2.ctypes.data_as(A.P(A.c_f))
+        else:
+            it.type = A.INTEGRATOR_PLT_PATH
+            it.direction = A.DIRECTION_FORWARD if self.integrator.direction == "forward" else A.DIRECTION_BACKWARD
         out.spp = self.sensor.samples
         return out

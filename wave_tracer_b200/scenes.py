@@ -12,11 +12,14 @@ MM = 1e-3
 
 
 def double_slits(res=1024, spp=32, direction="forward", max_depth=16, fsd=True, screen=True, lam_mm=.05, with_directional=True,
-                 ray_trace_only=False, rr=False):
+                 ray_trace_only=False, rr=False, integrator="plt_path", lut=(2048, 1024)):
     L, Lscale, S, E, extent, D, Hh, Z, W, Wslit = -500.0, 1633.0, 50.0, 5.0, 250.0, 12.0, 20.0, -15.0, .65, .35
     lam = lam_mm * MM
     sc = Scene()
-    sc.integrator = PltPath(max_depth=max_depth, direction=direction, fsd=fsd, russian_roulette=rr)
+    if integrator == "plt_bdpt":     # the reference file's own integrator: <integrator type="plt_bdpt"><integer name="max_depth" value="16"/>
+        sc.integrator = PltBdpt(max_depth=max_depth, fsd=fsd, lut=lut)
+    else:
+        sc.integrator = PltPath(max_depth=max_depth, direction=direction, fsd=fsd, russian_roulette=rr)
     film = Film(res, res // 4, [Discrete(lam)], rfilter_scale=.05)
     sc.sensor = VirtualPlane(lookat((0, 0, (S - .0001) * MM), (0, 0, E * MM), (0, -1, 0)), (extent * MM, extent / 4 * MM), film,
                              alpha=math.radians(.001), samples=spp, ray_trace_only=ray_trace_only)
