@@ -1,0 +1,844 @@
+// dbdpt.cuh -- plt_bdpt on the device (included by wavefront.cu after traverse()).
+//
+// Follows src/integrator/plt_bdpt.cpp:43-148, include/wt/integrator/plt_bdpt/{plt_bdpt_detail.hpp,vertex.hpp}, the Fraunhofer FSD
+// (include/wt/interaction/fsd/fraunhofer/*.hpp, src/interaction/fsd/fraunhofer/*.cpp), gaussian2d_t::integrate_triangle
+// (src/math/gaussian2d.cpp:96-192) and clip_triangle_z (include/wt/math/intersect/clip.hpp)   [paths under /root/reference].
+//
+// Execution model (round 1): persistent threads, one sample per thread at a time; the two subpaths' vertices and the
+// Fraunhofer apertures live in a per-thread arena in HBM laid out word-interleaved across threads (word w of thread s at
+// arena[w*P + s]) so that lock-step accesses coalesce.  A wavefront split (walk kernels + connection kernel) is the next step.
+#pragma once
+
+namespace wt {
+
+#define WT_NI __device__ __noinline__      // BDPT is one big per-thread kernel: keep its large pieces out of line (compile time, i-cache)
+
+constexpr float kSqrtPi = 1.77245385090551602730f;
+constexpr float kInvSqrtPi = 0.56418958354775628695f;
+constexpr int kMaxBdptVerts = 18;           // max_depth + 2 vertices per subpath for max_depth <= 16
+constexpr int kMaxFSeg = 48;                // Fraunhofer aperture segments
+constexpr int kMaxFAp = 6;                  // apertures per sample (both subpaths)
+
+WT_D float sincf_(float x) {                // include/wt/math/common.hpp:414-434
+    const float t0 = 1.1920929e-7f, t2 = 0.00034526698300124390839884978618400831996329879769945f, tn = 0.018581361171917516667460937040007436176452688944747f;
+    if (fabsf(x) >= tn) return sinf(x) / x;
+    float r = 1.f;
+    if (fabsf(x) >= t0) { const float x2 = x * x; r -= x2 / 6.f; if (fabsf(x) >= t2) r += (x2 * x2) / 120.f; }
+    return r;
+}
+
+// ---- gaussian2d with x=(1,0), mu=0 (include/wt/math/distribution/gaussian2d.hpp)
+struct G2 { V2 s, rs; float norm; };
+WT_D G2 g2_make(V2 sg) { G2 g; g.s = sg; g.rs = mk2(1.f / sg.x, 1.f / sg.y); g.norm = kInvTwoPi * (1.f / sg.x) * (1.f / sg.y); return g; }
+WT_D bool g2_dirac(const G2& g) { return g.s.x == 0.f || g.s.y == 0.f; }
+WT_D float g2_pdf(const G2& g, V2 p) { const V2 u = p * g.rs; return !g2_dirac(g) ? g.norm * expf(-dot(u, u) / 2.f) : ((p.x == 0.f && p.y == 0.f) ? WT_INF : 0.f); }
+WT_D V2 g2_canon(const G2& g, V2 v) {
+    const V2 p = mk2(dot(mk2(1.f, 0.f), v), dot(mk2(-0.f, 1.f), v));
+    if (!g2_dirac(g)) return p * g.rs;
+    return mk2(p.x == 0.f ? 0.f : WT_INF, p.y == 0.f ? 0.f : WT_INF);
+}
+namespace g2d {     // src/math/gaussian2d.cpp:24-94
+WT_D float Igg0(const DScene& sc, float a, float b, float c, float d) {
+    const float n2 = 1.f / (a + 2.f * c * c), n = sqrtf(n2);
+    return -kSqrtPi / 2.f * n * expf(-2.f * a * sqrf(d - b * c) * n2) * (erf_lut(sc, (a * b + 2.f * c * d) * n) - erf_lut(sc, (a * (1.f + b) + 2.f * c * (c + d)) * n));
+}
+WT_D float Igg1(const DScene& sc, float a, float b, float c, float d) {
+    const float n2 = 1.f / (a + 2.f * c * c), n = sqrtf(n2);
+    return -kSqrtPi / 2.f * n * expf(-2.f * a * sqrf(d - b * c) * n2) * (2.f * erf_lut(sc, a * (d / c - b) * n) + erf_lut(sc, (a * b + 2.f * c * d) * n) + erf_lut(sc, (a * (1.f + b) + 2.f * c * (c + d)) * n));
+}
+WT_D float Ig0(const DScene& sc, float a, float b) { const float n = sqrtf(1.f / a); return -kSqrtPi / 2.f * n * (erf_lut(sc, a * b * n) - erf_lut(sc, a * (1.f + b) * n)); }
+WT_D float Ig1(const DScene& sc, float a, float b, float c, float d) {
+    const float sa = sqrtf(a), n = 1.f / sa, dc = d / c;
+    return -kSqrtPi / 2.f * n * (signf_(b) * erf_lut(sc, sa * fabsf(b)) + signf_(1.f + b) * erf_lut(sc, sa * fabsf(1.f + b)) - 2.f * signf_(b - dc) * erf_lut(sc, sa * fabsf(b - dc)));
+}
+WT_D float Ige(const DScene& sc, float a, float b, float c, float d) {
+    const float dc = d / c;
+    const bool in = c != 0.f && -dc > 0.f && -dc < 1.f;
+    const float sv[4] = { 0.6517755981618476f, 3.250040490513459f, 31.86882707224491f, 778.6613983601425f };
+    const float wv[4] = { 0.2936683276537767f, 0.135758042187825f, 0.05245255757691102f, 0.01673209873360605f };
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float q = sqrtf(sv[i]); const float t = wv[i] * (in ? Igg1(sc, a, b, c * q, d * q) : Igg0(sc, a, b, c * q, d * q)); acc = i == 0 ? t : acc + t; }
+    return ((d != 0.f && c != 0.f) ? signf_(d) : (d == 0.f && c != 0.f) ? signf_(c) : 1.f) * ((in ? Ig1(sc, a, b, c, d) : Ig0(sc, a, b)) - 2.f * acc);
+}
+WT_D bool pit2(V2 p, V2 a, V2 b, V2 c) {        // math/util.hpp:69-82
+    const float s1 = diff_prod(p.x - b.x, a.y - b.y, a.x - b.x, p.y - b.y), s2 = diff_prod(p.x - c.x, b.y - c.y, b.x - c.x, p.y - c.y), s3 = diff_prod(p.x - a.x, c.y - a.y, c.x - a.x, p.y - a.y);
+    const bool neg = s1 < 0.f || s2 < 0.f || s3 < 0.f, pos = s1 > 0.f || s2 > 0.f || s3 > 0.f;
+    return !(neg && pos);
+}
+}
+WT_NI float g2_integrate_triangle(const DScene& sc, const G2& g, V2 a, V2 b, V2 c) {     // src/math/gaussian2d.cpp:96-192
+    if (g2_dirac(g)) {
+        const float A = (a.x * (b.y - c.y) - a.y * (b.x - c.x)) + (b.x * c.y - c.x * b.y);
+        const float sA = signf_(A);
+        const float bx = sA * diff_prod(b.x, c.y, c.x, b.y), by = sA * diff_prod(c.x, a.y, a.x, c.y);
+        return (bx >= 0.f && by >= 0.f && bx + by <= fabsf(A)) ? 1.f : 0.f;
+    }
+    const float L = 3.f;
+    a = g2_canon(g, a); b = g2_canon(g, b); c = g2_canon(g, c);
+    if (min3f(a.x, b.x, c.x) >= L || max3f(a.x, b.x, c.x) <= -L || min3f(a.y, b.y, c.y) >= L || max3f(a.y, b.y, c.y) <= -L) return 0.f;
+    const bool ain = length2(a) <= sqrf(L), bin = length2(b) <= sqrf(L), cin = length2(c) <= sqrf(L);
+    if (!ain && !bin && !cin) {
+        const bool iab = intersect_edge_ellipse_points(a, b, L, L) > 0, iac = intersect_edge_ellipse_points(a, c, L, L) > 0, ibc = intersect_edge_ellipse_points(b, c, L, L) > 0;
+        if (!iab && !iac && !ibc) return g2d::pit2(mk2(0.f, 0.f), a, b, c) ? 1.f : 0.f;
+    }
+    const float min_len = min3f(length2(a - b), length2(a - c), length2(b - c));
+    if (min_len < 1e-3f) {
+        const float delta = .002f;
+        if (b.y < a.y) { const V2 t = a; a = b; b = t; }
+        if (c.y < a.y) { const V2 t = a; a = c; c = t; }
+        const float ab = b.y == a.y ? WT_INF : (b.x - a.x) / (b.y - a.y);
+        const float ac = c.y == a.y ? WT_INF : (c.x - a.x) / (c.y - a.y);
+        const float bc = c.y == b.y ? WT_INF : (c.x - b.x) / (c.y - b.y);
+        float ret = 0.f;
+        for (float y = fmaxf(-L, a.y + delta / 2.f); y < fminf(L, fmaxf(b.y, c.y)); y += delta) {
+            float x0 = y < b.y ? ab * (y - a.y) + a.x : bc * (y - b.y) + b.x;
+            float x1 = y < c.y ? ac * (y - a.y) + a.x : bc * (y - b.y) + b.x;
+            if (x0 > x1) { const float t = x0; x0 = x1; x1 = t; }
+            for (float x = fmaxf(-L, x0) + delta / 2.f; x < fminf(L, x1); x += delta) ret += expf(-(sqrf(x) + sqrf(y)) / 2.f);
+        }
+        return ret * kInvTwoPi * sqrf(delta);
+    }
+    const V2 t0 = b - a, t1 = c - a;         // T = mat2(t0, t1) columns
+    const float detT = t0.x * t1.y - t1.x * t0.y;
+    const float od = 1.f / detT;
+    M2 Ti; Ti.c0x = t1.y * od; Ti.c0y = -t0.y * od; Ti.c1x = -t1.x * od; Ti.c1y = t0.x * od;
+    const V2 mu0 = m2mul(Ti, a);
+    M2 T; T.c0x = t0.x; T.c0y = t0.y; T.c1x = t1.x; T.c1y = t1.y;
+    M2 Tt; Tt.c0x = t0.x; Tt.c0y = t1.x; Tt.c1x = t0.y; Tt.c1y = t1.y;
+    const M2 A = m2mm(Tt, T);
+    const float detA = A.c0x * A.c1y - A.c1x * A.c0y;
+    const float Sxy = A.c0y, Syy = A.c1y;
+    if (Syy <= 0.f || detA <= 0.f) return 0.f;
+    const float denom = 1.f / sqrtf(2.f * Syy);
+    const float pa = detA * sqrf(denom), pb = mu0.x;
+    const float c0 = Sxy * denom, d0 = (Sxy * mu0.x + Syy * mu0.y) * denom, q = .5f / denom;
+    const float I0 = g2d::Ige(sc, pa, pb, c0 - q, d0 + q), I1 = g2d::Ige(sc, pa, pb, c0, d0);
+    return kInvSqrtPi / 2.f * fabsf(detT * denom) * fmaxf(0.f, I0 - I1);
+}
+WT_D G2 wavefront_of(const Beam& b, float d) {       // beam_generic.hpp:130-139 + gaussian_wavefront.hpp:34-40
+    const V3 fp = beam_footprint(b, d);
+    const G2 g = g2_make(mk2(fp.x / kEnvelope, fp.y / kEnvelope));
+    return g2_dirac(g) ? g2_make(mk2(0.f, 0.f)) : g;
+}
+
+// clip_triangle_z (include/wt/math/intersect/clip.hpp:34-88)
+struct Clip { V3 vs[5]; int tris; };
+WT_D void clip_tri(const Clip& c, int idx, V3 o[3]) {
+    if (idx == 0) { o[0] = c.vs[0]; o[1] = c.vs[1]; o[2] = c.vs[2]; } else if (idx == 1) { o[0] = c.vs[2]; o[1] = c.vs[0]; o[2] = c.vs[c.tris == 2 ? 3 : 4]; } else { o[0] = c.vs[4]; o[1] = c.vs[2]; o[2] = c.vs[3]; }
+}
+WT_D Clip clip_triangle_z(V3 a, V3 b, V3 c, Range zr) {
+    const V3 ppmax = mk3(0.f, 0.f, zr.mx), ppmin = mk3(0.f, 0.f, zr.mn), n = mk3(0.f, 0.f, 1.f);
+    V3 tri[3] = { a, b, c };
+    int cls[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cls[i] = tri[i].z > zr.mx ? 1 : tri[i].z < zr.mn ? -1 : 0;
+    Clip r; int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int nx = i == 2 ? 0 : i + 1;
+        if (cls[i] == 0) { if (idx < 5) r.vs[idx++] = tri[i]; }
+        if (cls[nx] != cls[i]) {
+            V3 pt;
+            const bool ok = intersect_edge_plane(tri[i], tri[nx], cls[i] == -1 ? ppmin : (cls[i] == 1 || cls[nx] == 1) ? ppmax : ppmin, n, pt);
+            if (idx < 5) r.vs[idx++] = ok ? pt : (cls[i] != 0 ? tri[i] : tri[nx]);
+            if (cls[nx] != 0 && cls[i] != 0) {
+                V3 p2; const bool ok2 = intersect_edge_plane(tri[i], tri[nx], cls[nx] == 1 ? ppmax : ppmin, n, p2);
+                if (idx < 5) r.vs[idx++] = ok2 ? p2 : tri[nx];
+            }
+        }
+    }
+    r.tris = idx < 3 ? 0 : idx == 3 ? 1 : idx == 4 ? 2 : 3;
+    return r;
+}
+WT_D V2 cone_project_local(const Cone& c, V3 p, float z) {       // elliptic_cone.hpp:205-214
+    const V2 xy = mk2(p.x, p.y);
+    const float scale = (c.ta * z + c.x0) / fabsf(c.ta * p.z + c.x0);
+    return (c.x0 == 0.f && c.ta == 0.f) ? xy : xy * scale;
+}
+
+// ================================================================================================ Fraunhofer FSD
+struct FEdge { V2 e, v; C2 a_b, iab_2; };
+struct FHead { float P0, P0_pdf, psi02, recp_I, k; Frame frame; uint32_t n; };
+constexpr float kPA1 = 0.0049361075794549872500f, kPA2 = 0.21899789398059305541f, kP0s = 0.288675134594813f / 4.f;
+WT_D float falpha1(float x, float y) { return x == 0.f ? 0.f : kInvTwoPi * y / (x * (x * x + y * y)) * (cosf(x / 2.f) - sincf_(x / 2.f)); }
+WT_D float falpha2(float x, float y) { return x == 0.f ? 0.f : kInvTwoPi * y / (x * x + y * y) * sincf_(x / 2.f); }
+WT_D float fchi_e(V2 xi) { const float t = 1.f + 0.830092714835359f * dot(xi, xi), t2 = t * t, t3 = t2 * t; return fmaxf(0.f, 1.f - (3.f / t2 - 2.f / t3)); }
+WT_D float fchi_0(V2 xi) { xi = xi / kP0s; return expf(-.5f * dot(xi, xi)); }
+WT_D V2 fzeta(const FEdge& e, V2 xi) { return mk2(xi.x * e.e.x + xi.y * e.e.y, xi.x * e.e.y + xi.y * (-e.e.x)); }
+WT_D C2 fPsi(const FEdge& e, V2 xi) {
+    const V2 z = fzeta(e, xi);
+    const C2 s = e.a_b * falpha1(z.x, z.y) + e.iab_2 * falpha2(z.x, z.y);
+    const float rho = length2(e.e), th = -dot(e.v, xi);
+    float sn, cs; sincosf(th, &sn, &cs);
+    return mkc(rho * cs, rho * sn) * s;
+}
+WT_D float fPsi2(const FEdge& e, V2 xi) { const V2 z = fzeta(e, xi); return sqrf(length2(e.e)) * cnorm(e.a_b * falpha1(z.x, z.y) + e.iab_2 * falpha2(z.x, z.y)); }
+WT_D float fPj(const FEdge& e) { return sqrf(length2(e.e)) * kPA1 * cnorm(e.a_b) + sqrf(length2(e.e)) * kPA2 * cnorm(e.iab_2); }
+
+// per-thread arena accessor: word w of this thread at base[w*P + slot]
+struct Arena { float* base; uint32_t P, slot; };
+WT_D float& aw(const Arena& A, uint32_t w) { return A.base[(size_t)w * A.P + A.slot]; }
+constexpr uint32_t kVertWords = 72;
+constexpr uint32_t kApWords = 16 + kMaxFSeg * 9;
+constexpr uint32_t kArenaWords = 2 * kMaxBdptVerts * kVertWords + kMaxFAp * kApWords;
+WT_D uint32_t ap_base(int ai) { return 2 * kMaxBdptVerts * kVertWords + (uint32_t)ai * kApWords; }
+WT_D FEdge ap_edge(const Arena& A, int ai, uint32_t j) {
+    const uint32_t b = ap_base(ai) + 16 + j * 9;
+    FEdge e; e.e = mk2(aw(A, b), aw(A, b + 1)); e.v = mk2(aw(A, b + 2), aw(A, b + 3)); e.a_b = mkc(aw(A, b + 4), aw(A, b + 5)); e.iab_2 = mkc(aw(A, b + 6), aw(A, b + 7));
+    return e;
+}
+WT_D float ap_edge_pdf(const Arena& A, int ai, uint32_t j) { return aw(A, ap_base(ai) + 16 + j * 9 + 8); }
+WT_D FHead ap_head(const Arena& A, int ai) {
+    const uint32_t b = ap_base(ai);
+    FHead h; h.P0 = aw(A, b); h.P0_pdf = aw(A, b + 1); h.psi02 = aw(A, b + 2); h.recp_I = aw(A, b + 3); h.k = aw(A, b + 4);
+    h.frame.t = mk3(aw(A, b + 5), aw(A, b + 6), aw(A, b + 7)); h.frame.b = mk3(aw(A, b + 8), aw(A, b + 9), aw(A, b + 10)); h.frame.n = mk3(aw(A, b + 11), aw(A, b + 12), aw(A, b + 13));
+    h.n = __float_as_uint(aw(A, b + 14));
+    return h;
+}
+WT_D float ap_ASF_unclamped(const Arena& A, int ai, uint32_t n, V2 xi) { C2 a = mkc(0.f, 0.f); for (uint32_t j = 0; j < n; ++j) a = a + fPsi(ap_edge(A, ai, j), xi); return cnorm(a); }
+WT_D float ap_ASF(const Arena& A, int ai, const FHead& h, V2 xi) { return ap_ASF_unclamped(A, ai, h.n, xi) * fchi_e(xi) + h.psi02 * fchi_0(xi); }
+WT_D float ap_sampling_density(const Arena& A, int ai, const FHead& h, V2 xi) {
+    float d = 0.f; for (uint32_t j = 0; j < h.n; ++j) d += fPsi2(ap_edge(A, ai, j), xi);
+    return d * fchi_e(xi) + h.P0 * kInvTwoPi / sqrf(kP0s) * fchi_0(xi);
+}
+
+// fraunhofer::free_space_diffraction_t ctor (src/interaction/fsd/fraunhofer/free_space_diffraction.cpp:22-129) into aperture slot `ai`.
+// Returns the number of segments (0: empty aperture); sets overflow when kMaxFSeg is exceeded.
+WT_NI uint32_t fraunhofer_build(const DScene& sc, const Arena& A, int ai, const Frame& frame, float k, float total_power, const Cone& beam,
+                                const uint32_t* edges, uint32_t n_edges, const G2& wf, bool& overflow) {
+    const V2 cse = wf.s * kEnvelope;
+    const float r = fmaxf(cse.x, cse.y);
+    const float max_len = .33f * r;
+    float P_total = 0.f;
+    uint32_t n = 0;
+    const uint32_t b0 = ap_base(ai);
+    for (uint32_t ei = 0; ei < n_edges; ++ei) {
+        const wtgpu_edge E = sc.edges[edges[ei]];
+        if (dot(beam.d, mk3(E.n1)) * dot(beam.d, mk3(E.n2)) >= 0.f) continue;
+        const V3 l1 = to_local(frame, mk3(E.a) - beam.o), l2 = to_local(frame, mk3(E.b) - beam.o);
+        const V2 u1 = mk2(l1.x, l1.y), u2 = mk2(l2.x, l2.y);
+        float t1 = 0.f, t2 = 1.f;
+        const V2 q1 = mk2(u1.x / cse.x, u1.y / cse.y), q2 = mk2(u2.x / cse.x, u2.y / cse.y);
+        if (!(dot(q1, q1) <= 1.f) || !(dot(q2, q2) <= 1.f)) {
+            // intersect_edge_ellipse (misc.hpp:77-127): need points, t1, t2
+            const V2 rs = mk2(1.f / cse.x, 1.f / cse.y);
+            const V2 p0 = u1 * rs, p1 = u2 * rs, d = p1 - p0;
+            const float aa = dot(d, d), bb = 2.f * dot(p0, d), cc = dot(p0, p0) - 1.f;
+            const float det2 = bb * bb - 4.f * aa * cc;
+            if (det2 <= 0.f || aa == 0.f) continue;
+            const float ra = 1.f / aa, det = sqrtf(det2);
+            float s1 = .5f * (-bb - signf_(bb) * det) * ra;
+            float s2 = s1 == 0.f ? -bb * ra : cc * ra / s1;
+            if (s1 > s2) { const float t = s1; s1 = s2; s2 = t; }
+            const bool v1 = s1 >= 0.f && 1.f >= s1, v2 = s2 >= 0.f && 1.f >= s2;
+            if (!v1 && !v2) continue;
+            float rt1 = s1, rt2 = s2;
+            if (!(v1 && v2)) { rt1 = v1 ? s1 : s2; rt2 = v1 ? s2 : s1; }
+            t1 = fmaxf(0.f, rt1); t2 = fminf(1.f, rt2);
+        }
+        const V2 m1 = mk2(mixf(u1.x, u2.x, t1), mixf(u1.y, u2.y, t1)), m2 = mk2(mixf(u1.x, u2.x, t2), mixf(u1.y, u2.y, t2));
+        const float len = length(m1 - m2);
+        const int segments = max(1, int(roundf(len / max_len) + .5f));
+        const float seg = 1.f / (float)segments;
+        V2 v1 = m1;
+        float a = sqrtf(g2_pdf(wf, v1));
+        for (int i = 0; i < segments; ++i) {
+            const float tt = mixf(t1, t2, (float)(i + 1) * seg);
+            const V2 v2 = mk2(mixf(u1.x, u2.x, tt), mixf(u1.y, u2.y, tt));
+            const float b = sqrtf(g2_pdf(wf, v2));
+            if (a > 0.f || b > 0.f) {
+                const V2 v = (v1 + v2) / 2.f, e = v2 - v1;
+                FEdge fe; fe.e = mk2(e.x * 1000.f, e.y * 1000.f); fe.v = mk2(v.x * 1000.f, v.y * 1000.f); fe.a_b = mkc(a - b, 0.f);
+                fe.iab_2 = (mkc(0.f, 1.f) * mkc(a + b, 0.f)) * (1.f / 2.f);
+                // (c_t{0,1}*(ca+cb))/2 : complex / float
+                fe.iab_2 = mkc((0.f * (a + b) - 1.f * 0.f) / 2.f, (0.f * 0.f + 1.f * (a + b)) / 2.f);
+                const float pdf = fPj(fe);
+                if (pdf > 0.f) {
+                    if (n < (uint32_t)kMaxFSeg) {
+                        const uint32_t w = b0 + 16 + n * 9;
+                        aw(A, w) = fe.e.x; aw(A, w + 1) = fe.e.y; aw(A, w + 2) = fe.v.x; aw(A, w + 3) = fe.v.y;
+                        aw(A, w + 4) = fe.a_b.re; aw(A, w + 5) = fe.a_b.im; aw(A, w + 6) = fe.iab_2.re; aw(A, w + 7) = fe.iab_2.im; aw(A, w + 8) = pdf;
+                        ++n; P_total += pdf;
+                    } else overflow = true;
+                }
+            }
+            v1 = v2; a = b;
+        }
+    }
+    const float r0 = 3.f * kP0s;
+    const V2 dirs[8] = { mk2(-kInvSqrtTwo, -kInvSqrtTwo), mk2(-1.f, 0.f), mk2(-kInvSqrtTwo, kInvSqrtTwo), mk2(0.f, 1.f), mk2(kInvSqrtTwo, kInvSqrtTwo), mk2(1.f, 0.f), mk2(kInvSqrtTwo, -kInvSqrtTwo), mk2(0.f, -1.f) };
+    float acc = 0.f;
+    for (int i = 0; i < 8; ++i) acc = acc + ap_ASF_unclamped(A, ai, n, r0 * dirs[i]);
+    const float psi02 = acc / 8.f;
+    const float P0 = (kTwoPi * sqrf(kP0s) * psi02) / sqrf(k);
+    P_total += P0;
+    float P0_pdf;
+    if (P_total > 0.f) { const float rp = 1.f / P_total; P0_pdf = P0 * rp; for (uint32_t j = 0; j < n; ++j) aw(A, b0 + 16 + j * 9 + 8) *= rp; }
+    else { P0_pdf = 1.f; n = 0; }
+    aw(A, b0) = P0; aw(A, b0 + 1) = P0_pdf; aw(A, b0 + 2) = psi02; aw(A, b0 + 3) = total_power > 0.f ? 1.f / total_power : 0.f; aw(A, b0 + 4) = k;
+    aw(A, b0 + 5) = frame.t.x; aw(A, b0 + 6) = frame.t.y; aw(A, b0 + 7) = frame.t.z; aw(A, b0 + 8) = frame.b.x; aw(A, b0 + 9) = frame.b.y; aw(A, b0 + 10) = frame.b.z;
+    aw(A, b0 + 11) = frame.n.x; aw(A, b0 + 12) = frame.n.y; aw(A, b0 + 13) = frame.n.z; aw(A, b0 + 14) = __uint_as_float(n);
+    return n;
+}
+
+// fsd_lut_t (include/wt/interaction/fsd/fraunhofer/fsd_lut.hpp:37-69)
+struct FLut { uint32_t N, M; const float *th1, *th2, *c1, *c2; };
+WT_D float flerp1(float x, const float* tbl, uint32_t S) {
+    x *= (float)(S - 1u);
+    const uint32_t l = min((uint32_t)x, S - 1u), h = min(l + 1u, S - 1u);
+    const float f = x - floorf(x);
+    return f * __ldg(tbl + h) + (1.f - f) * __ldg(tbl + l);
+}
+WT_D V2 flut_sample(const FLut& L, V3 r3, const float* th, const float* cd) {
+    const float theta = flerp1(r3.x, th, L.N);
+    const float tf = theta * 2.f / kPi;
+    float x = tf * (float)(L.M - 1u);
+    const uint32_t l = min((uint32_t)x, L.M - 1u), h = min(l + 1u, L.M - 1u);
+    const float f = x - floorf(x);
+    const float r = fmaxf(0.f, f * flerp1(r3.y, cd + (size_t)h * L.M, L.M) + (1.f - f) * flerp1(r3.y, cd + (size_t)l * L.M, L.M));
+    V2 z = r * mk2(cosf(theta), sinf(theta));
+    const int q = min(3, (int)(r3.z * 4.f));
+    z.x *= (((q + 1) / 2) % 2 == 0 ? 1.f : -1.f);
+    z.y *= ((q / 2) % 2 == 0 ? 1.f : -1.f);
+    return z;
+}
+// fsd_sampler (src/interaction/fsd/fraunhofer/fsd_sampler.cpp:37-113) + free_space_diffraction_t::sample (free_space_diffraction.hpp:68-93)
+WT_NI void fraunhofer_sample(const Arena& A, int ai, const FLut& lut, Sampler& smp, V3& wo, float& dpd, float& weight) {
+    wo = mk3(0.f, 0.f, 1.f); dpd = 0.f; weight = 0.f;
+    const FHead h = ap_head(A, ai);
+    const bool rej = h.n > 1u;
+    const uint32_t max_tries = h.n * 1024u;
+    const float recp_M = 1.f / (float)h.n;
+    for (uint32_t tr = 0; tr < max_tries; ++tr) {
+        // sampleN
+        const float p = rnd(smp) * 1.f;
+        float cdf = 0.f; uint32_t sel = h.n;
+        for (uint32_t i = 0; i < h.n; ++i) { cdf += i == 0 ? h.P0_pdf : ap_edge_pdf(A, ai, i - 1u); if (p < cdf) { sel = i; break; } }
+        V2 xi;
+        if (sel == 0u) xi = kP0s * normal2d(rnd2(smp));
+        else {
+            const FEdge e = ap_edge(A, ai, sel - 1u);
+            const V2 m = mk2(e.e.y, -e.e.x);
+            const float od = 1.f / (e.e.x * m.y - m.x * e.e.y);
+            const float i00 = m.y * od, i01 = -e.e.y * od, i10 = -m.x * od, i11 = e.e.x * od;     // glm::inverse, [col][row]
+            const float Aa = cnorm(e.a_b), Bb = cnorm(e.iab_2);
+            const float pp = rnd(smp) * (Aa + Bb);
+            const V3 r3 = rnd3(smp);
+            const V2 z = pp < Aa ? flut_sample(lut, r3, lut.th1, lut.c1) : flut_sample(lut, r3, lut.th2, lut.c2);
+            xi = mk2(z.x * i00 + z.y * i01, z.x * i10 + z.y * i11);
+        }
+        const float g = ap_sampling_density(A, ai, h, xi), f = ap_ASF(A, ai, h, xi);
+        const bool done = rej ? rnd(smp) * g < f * recp_M : true;
+        if (done) {
+            const float pdf = f * h.recp_I;
+            if (pdf > 0.f) {
+                const V2 zeta = xi / h.k;
+                const V2 wl = mk2(zeta.x / sqrtf(1.f + sqrf(zeta.x)), zeta.y / sqrtf(1.f + sqrf(zeta.y)));
+                const float wo2 = length2(wl);
+                if (wo2 < .85f) { wo = mk3(wl.x, wl.y, sqrtf(1.f - wo2)); dpd = pdf; weight = 1.f; }
+            }
+            return;
+        }
+    }
+}
+WT_D float fraunhofer_pdf(const Arena& A, int ai, const FHead& h, V3 wl) {     // free_space_diffraction.hpp:99-115
+    const float wo2 = length2(mk2(wl.x, wl.y));
+    if (wl.z <= 0.f || wo2 >= .85f) return 0.f;
+    const V2 xi = h.k * mk2(wl.x / sqrtf(1.f - sqrf(wl.x)), wl.y / sqrtf(1.f - sqrf(wl.y)));
+    const float p = ap_ASF(A, ai, h, xi) * h.recp_I;
+    return (0.f <= p && p < 1e+2f) ? p : 0.f;
+}
+
+// ================================================================================================ vertices
+enum : uint32_t { BV_SENSOR = 0u, BV_EMITTER = 1u, BV_SURFACE = 2u, BV_FSD = 3u };
+enum : uint32_t { BG_NONE = 0u, BG_POINT = 1u, BG_SURFACE = 2u, BG_DUMMY = 4u };
+struct BVertex {            // vertex_t (integrator/plt_bdpt/vertex.hpp:49-81)
+    uint32_t type, fwd, delta, ffsd;
+    float pdf_fwd, pdf_bwd, rr;
+    uint32_t gkind; V3 p; uint32_t tuid; V2 bary; Footprint fp; V3 dn;
+    int32_t emitter, bsdf, fsd;
+    uint32_t pad_;
+    Beam beam;
+};
+static_assert(sizeof(BVertex) <= kVertWords * 4, "vertex record too large");
+WT_D void bv_store(const Arena& A, uint32_t idx, const BVertex& v) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+    for (uint32_t i = 0; i < sizeof(BVertex) / 4; ++i) aw(A, idx * kVertWords + i) = __uint_as_float(w[i]);
+}
+WT_D void bv_load(const Arena& A, uint32_t idx, BVertex& v) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+    for (uint32_t i = 0; i < sizeof(BVertex) / 4; ++i) w[i] = __float_as_uint(aw(A, idx * kVertWords + i));
+}
+// word offsets of the scalars the MIS walk touches
+constexpr uint32_t kOffDelta = 2, kOffPdfFwd = 4, kOffPdfBwd = 5, kOffRr = 6;
+WT_D Geo bv_geo(const BVertex& v) { return geo_surface(v.p, v.tuid, v.gkind == BG_SURFACE); }
+WT_D Surface bv_surface(const DScene& sc, const BVertex& v) {
+    if (v.gkind == BG_SURFACE) { Surface s = make_surface(sc, v.tuid, v.bary, v.p); s.fp = v.fp; return s; }
+    return make_dummy_surface(v.dn, v.p);
+}
+
+struct BCtx { const DScene* sc; Arena A; FLut lut; Counters* ctr; bool overflow; };
+WT_D bool bv_area_emitter(const BCtx& c, const BVertex& v) { return v.type == BV_EMITTER && c.sc->emitters[v.emitter].type == WTGPU_EMITTER_AREA; }
+WT_D bool bv_on_surface(const BCtx& c, const BVertex& v) { return v.type == BV_SURFACE || bv_area_emitter(c, v) || (v.type == BV_SENSOR && (v.gkind == BG_SURFACE || v.gkind == BG_DUMMY)); }
+WT_D bool bv_has_srf_normal(const BCtx& c, const BVertex& v) { return v.type == BV_SURFACE || bv_area_emitter(c, v); }
+WT_D V3 bv_ng(const BCtx& c, const BVertex& v) { if (!bv_has_srf_normal(c, v)) return mk3(0.f, 0.f, 1.f); const Tri3 t = load_tri(*c.sc, v.tuid); return t.n; }
+WT_D V3 bv_ns(const BCtx& c, const BVertex& v) { if (!bv_has_srf_normal(c, v)) return mk3(0.f, 0.f, 1.f); return bv_surface(*c.sc, v).shading.n; }
+WT_D int32_t bv_emitter(const BCtx& c, const BVertex& v) { return v.type == BV_EMITTER ? v.emitter : c.sc->shapes[c.sc->tri_meta[v.tuid].shape_idx].emitter; }
+WT_D bool bv_on_emitter(const BCtx& c, const BVertex& v) { return v.type == BV_EMITTER || (v.type == BV_SURFACE && c.sc->shapes[c.sc->tri_meta[v.tuid].shape_idx].emitter >= 0); }
+WT_D bool em_delta_dir(const BCtx& c, int32_t e) { return c.sc->emitters[e].type == WTGPU_EMITTER_DIRECTIONAL; }
+WT_D bool em_delta_pos(const BCtx& c, int32_t e) { const uint32_t t = c.sc->emitters[e].type; return t == WTGPU_EMITTER_POINT || t == WTGPU_EMITTER_SPOT; }
+WT_D bool bv_delta_emitter(const BCtx& c, const BVertex& v) { return v.type == BV_EMITTER && (em_delta_dir(c, v.emitter) || em_delta_pos(c, v.emitter)); }
+WT_D bool sensor_delta_pos(const BCtx& c) { return c.sc->sensor.type == WTGPU_SENSOR_PERSPECTIVE; }
+WT_D bool bv_delta_sensor(const BCtx& c, const BVertex& v) { return v.type == BV_SENSOR && sensor_delta_pos(c); }
+WT_D bool bv_nondelta_interaction(const BVertex& v) { return (v.type == BV_SURFACE || v.type == BV_FSD) && !v.delta; }
+WT_D bool bv_connectible(const BCtx& c, const BVertex& v) {      // vertex.hpp:415-425
+    if (v.type == BV_FSD) return true;
+    if (v.type == BV_EMITTER) return !em_delta_dir(c, v.emitter);
+    if (v.type == BV_SENSOR) return true;
+    return !bsdf_is_delta_only(*c.sc, v.bsdf, v.beam.k);
+}
+WT_D float dir_to_area(const BCtx& c, Pd dpdf, V3 p, const BVertex& next) {     // vertex.hpp:224-243
+    const float dv = dpdf.disc ? 0.f : dpdf.v;
+    if (dv == 0.f) return 0.f;
+    const V3 d = next.p - p;
+    const float d2 = length2(d);
+    if (d2 == 0.f) return WT_INF;
+    float pp = dv * (1.f / d2);
+    if (bv_on_surface(c, next)) pp *= fabsf(dot(bv_ng(c, next), normalize(d)));
+    return pp;
+}
+WT_D float sensor_pdf_direction(const BCtx& c, V3 dir) {         // virtual_plane_sensor.cpp:182-186 / perspective.hpp:326-333
+    const wtgpu_sensor& s = c.sc->sensor;
+    if (s.type == WTGPU_SENSOR_VIRTUAL_PLANE) return cosine_hemisphere_pdf(fmaxf(dot(dir, mk3(s.frame_n)), 0.f));
+    const V3 d = normalize(m3mul(s.inv_rot, dir));
+    return d.z > 1.1920929e-7f ? 1.f / persp_recp_sa(s, d) : 0.f;
+}
+WT_D float sensor_pdf_position(const BCtx& c) { const wtgpu_sensor& s = c.sc->sensor; return s.type == WTGPU_SENSOR_VIRTUAL_PLANE ? 1.f / (s.extent[0] * s.extent[1]) : 0.f; }
+WT_D float pdf_next_from_sensor(const BCtx& c, const BVertex& v, const BVertex& next) {   // vertex.hpp:489-506
+    const V3 dl = next.p - v.p;
+    const float rd2 = 1.f / length2(dl);
+    const V3 d = dl * sqrtf(rd2);
+    float pp = sensor_pdf_direction(c, d) * rd2;
+    if (bv_on_surface(c, next)) pp *= fabsf(dot(bv_ng(c, next), d));
+    return pp;
+}
+WT_D float emitter_pdf_position_density(const BCtx& c, int32_t e) { const wtgpu_emitter E = c.sc->emitters[e]; return E.type == WTGPU_EMITTER_AREA ? 1.f / c.sc->shapes[E.shape].surface_area : 0.f; }
+WT_D float pdf_next_from_emitter(const BCtx& c, const BVertex& v, const BVertex& next) {  // vertex.hpp:522-547
+    const V3 dl = next.p - v.p;
+    const float rd2 = 1.f / length2(dl);
+    const V3 d = dl * sqrtf(rd2);
+    const int32_t em = bv_emitter(c, v);
+    const wtgpu_emitter E = c.sc->emitters[em];
+    if (E.type == WTGPU_EMITTER_DIRECTIONAL) {
+        const Frame fr = orthogonal_frame(mk3(E.dir));
+        const V3 pl = to_local(fr, next.p - mk3(E.world_centre));
+        return length2(mk2(pl.x, pl.y)) <= sqrf(E.world_radius) ? 1.f / (kPi * sqrf(E.world_radius)) : 0.f;
+    }
+    float dd;
+    if (E.type == WTGPU_EMITTER_POINT) dd = kInvFourPi;
+    else if (E.type == WTGPU_EMITTER_SPOT) dd = 1.f / (kTwoPi * (1.f - cosf(E.cutoff)));
+    else dd = cosine_hemisphere_pdf(fmaxf(0.f, dot(d, bv_ng(c, v))));
+    float pp = dd * rd2;
+    if (bv_on_surface(c, next)) pp *= fabsf(dot(bv_ng(c, next), d));
+    return pp;
+}
+WT_D float pdf_emitter_v(const BCtx& c, const BVertex& v) {       // vertex.hpp:549-564
+    const int32_t em = bv_emitter(c, v);
+    if (c.sc->emitters[em].type == WTGPU_EMITTER_DIRECTIONAL) return 0.f;
+    return pdf_emitter(*c.sc, em) * emitter_pdf_position_density(c, em);
+}
+WT_NI float bv_pdf(const BCtx& c, const BVertex& v, const BVertex* prev, const BVertex& next, bool mode_fwd) {   // vertex.hpp:444-487
+    if (v.type == BV_EMITTER) return pdf_next_from_emitter(c, v, next);
+    if (v.type == BV_SENSOR) return pdf_next_from_sensor(c, v, next);
+    const V3 wiw = normalize(prev->p - v.p), wow = normalize(next.p - v.p);
+    Pd pdf = pd_disc(0.f);
+    if (v.type == BV_SURFACE) {
+        const Surface srf = bv_surface(*c.sc, v);
+        BsdfQuery q; q.k = v.beam.k; q.fwd = mode_fwd; q.lobes = 0xffffffffu;
+        pdf = pd_dens(bsdf_pdf(*c.sc, v.bsdf, to_local(srf.shading, wiw), to_local(srf.shading, wow), q));
+    } else {
+        if (!v.ffsd) return 0.f;
+        const FHead h = ap_head(c.A, v.fsd);
+        pdf = pd_dens(fraunhofer_pdf(c.A, v.fsd, h, to_local(h.frame, wow)));
+    }
+    return dir_to_area(c, pdf, v.p, next);
+}
+WT_D float snc_scale(bool fwd, float wig, float wog, float wis, float wos) { return fwd ? fminf(fabsf(wis * wog / (wos * wig)), 1e+2f) : 1.f; }   // integrator/common.hpp:22-33
+// vertex_t::interact (vertex.hpp:330-413)
+WT_NI bool bv_interact(const BCtx& c, const BVertex& v, V3 next_p, bool ignore_fsd, Beam& out) {
+    const DScene& sc = *c.sc;
+    const V3 wiw = -v.beam.env.d;
+    float f = 0.f;
+    if (v.ffsd && !ignore_fsd) { const FHead h = ap_head(c.A, v.fsd); f = fraunhofer_pdf(c.A, v.fsd, h, to_local(h.frame, normalize(next_p - v.p))); }
+    if (v.type == BV_SURFACE) {
+        const Surface srf = bv_surface(sc, v);
+        const V3 wow = normalize(next_p - v.p);
+        const V3 wi = to_local(srf.shading, wiw), wo = to_local(srf.shading, wow);
+        const V3 ng = srf.geo.n, ns = srf.shading.n;
+        const float wig = dot(wiw, ng), wog = dot(wow, ng);
+        if (wig * wi.z <= 0.f || wog * wo.z <= 0.f) return false;
+        BsdfQuery q; q.k = v.beam.k; q.fwd = v.fwd != 0u; q.lobes = 0xffffffffu;
+        Mueller fb = bsdf_f(sc, v.bsdf, wi, wo, q);
+        float scale = 1.f / fabsf(wo.z);
+        if (!veq(ns, ng)) scale *= snc_scale(v.fwd != 0u, wig, wog, wi.z, wo.z);
+        fb = mu_scale(fb, scale);
+        if (f > 0.f) fb = mu_add(fb, mu_scale(mu_identity(), f));
+        if (fb.m[0] == 0.f) return false;
+        out = v.beam;
+        beam_transform_surface(out, srf, wow, fb, 1.f);
+        return true;
+    }
+    if (v.type == BV_FSD) {
+        out = v.beam;
+        beam_transform_region(out, v.p, dot(v.p - v.beam.env.o, v.beam.env.d), normalize(next_p - v.p), f);
+        return true;
+    }
+    return false;
+}
+
+// ================================================================================================ walk
+struct BWalk { Beam beam; bool fwd; Pd pdf_from_prev; float throughput, rr; uint32_t base, n; };   // vertices at [base, base+n)
+
+WT_D bool bd_append(const BCtx& c, BWalk& d, BVertex& v, Pd pdf_fwd, Pd pdf_revr) {     // plt_bdpt_detail.hpp:96-122
+    BVertex prev; bv_load(c.A, d.base + d.n - 1u, prev);
+    if (veq(prev.p, v.p)) return false;
+    const float pa = dir_to_area(c, d.pdf_from_prev, prev.p, v);
+    if (v.fwd) v.pdf_fwd = pa; else v.pdf_bwd = pa;
+    v.beam = d.beam;
+    const float pr = dir_to_area(c, pdf_revr, v.p, prev);
+    // prev.pdf_reversed(): transport backward -> pdf_fwd, forward -> pdf_bwd
+    aw(c.A, (d.base + d.n - 1u) * kVertWords + (prev.fwd ? kOffPdfBwd : kOffPdfFwd)) = pr;
+    d.pdf_from_prev = pdf_fwd;
+    bv_store(c.A, d.base + d.n, v);
+    d.n++;
+    return true;
+}
+
+WT_NI void bd_random_walk(BCtx& c, BWalk& data, Sampler& smp, uint32_t& n_ap, uint64_t& n_vert) {       // plt_bdpt_detail.hpp:421-526
+    const DScene& sc = *c.sc;
+    const uint32_t max_depth = sc.integrator.max_depth;
+    const bool force_rt = sc.sensor.ray_trace_only != 0u;
+    for (;;) {
+        Beam& beam = data.beam;
+        BVertex last; bv_load(c.A, data.base + data.n - 1u, last);
+        uint32_t tris[kMaxConeTris];
+        TravOut tr;
+        traverse(sc, beam.env, bv_geo(last), wavenum_to_wavelen(beam.k), force_rt, tris, tr, *c.ctr);
+        if (tr.empty) return;
+        if (tr.cone.overflow) c.overflow = true;
+        const float beam_dist = tr.ballistic ? tr.ray.dist : tr.cone.dist;
+        const Range zr = mkr(beam_dist, beam_dist + tr.region_depth);
+        const bool is_ballistic = tr.ballistic || cone_is_ray(beam.env);
+        const V3 origin_wp = tr.origin;
+        const V3 dir = beam.env.d;
+        const V3 interaction_wp = origin_wp + zr.mn * dir;
+        const Frame beam_frame = cone_frame(beam.env);
+        const Cone envelope = beam.env;
+        const G2 wf = wavefront_of(beam, beam_dist);
+        const uint32_t nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
+        uint32_t primary = WTGPU_INVALID_IDX; float pdist = WT_INF, pbx = -1.f, pby = -1.f, flux = 0.f;
+        if (is_ballistic) { primary = tr.ray.tuid; pdist = tr.ray.dist; pbx = tr.ray.bx; pby = tr.ray.by; }
+        else {      // find_closest_triangle (:362-419)
+            for (uint32_t i = 0; i < nt; ++i) {
+                const Tri3 t = load_tri(sc, tris[i]);
+                const float tol = cone_intersection_tolerance(origin_wp, t.a, t.b, t.c);
+                const RayTri rt = intersect_ray_tri(origin_wp, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+                if (rt.hit && rt.dist < pdist) { primary = tris[i]; pdist = rt.dist; pbx = rt.bx; pby = rt.by; }
+            }
+            if (primary == WTGPU_INVALID_IDX) {
+                const float csz = (zr.mx + zr.mn) / 2.f;
+                for (uint32_t i = 0; i < nt; ++i) {
+                    const Tri3 t = load_tri(sc, tris[i]);
+                    if ((dot(t.n, -dir) > 0.f) != tr.cone.front) continue;
+                    const Clip cl = clip_triangle_z(to_local(beam_frame, t.a - envelope.o), to_local(beam_frame, t.b - envelope.o), to_local(beam_frame, t.c - envelope.o), zr);
+                    for (int k = 0; k < cl.tris; ++k) {
+                        V3 ct[3]; clip_tri(cl, k, ct);
+                        flux += g2_integrate_triangle(sc, wf, cone_project_local(envelope, ct[0], csz), cone_project_local(envelope, ct[1], csz), cone_project_local(envelope, ct[2], csz));
+                    }
+                }
+            }
+        }
+        bool do_RR = true;
+        if (primary != WTGPU_INVALID_IDX) {     // sample_surface_interaction (:193-270)
+            const float k = beam.k;
+            Surface srf = make_surface(sc, primary, mk2(pbx, pby), origin_wp + envelope.d * pdist);
+            srf.fp = surface_footprint_static(beam, srf, beam_dist);
+            const int32_t bsdf = sc.shapes[sc.tri_meta[primary].shape_idx].bsdf;
+            const V3 ng = srf.geo.n, ns = srf.shading.n;
+            const V3 wiw = -dir;
+            const V3 wi = to_local(srf.shading, wiw);
+            const float wig = dot(wiw, ng);
+            if (wig * wi.z <= 0.f) return;
+            BsdfQuery q; q.k = k; q.fwd = data.fwd; q.lobes = 0xffffffffu;
+            const BsdfSample bs = bsdf_sample(sc, bsdf, wi, q, smp);
+            if (!bs.valid || bs.dpd.v == 0.f) return;
+            const V3 wow = normalize(to_world(srf.shading, bs.wo));
+            const float wog = dot(wow, ng);
+            if (wog * bs.wo.z <= 0.f) return;
+            BsdfQuery qr = q; qr.fwd = !data.fwd;
+            const Pd pdf_revr = pd_dens(bsdf_pdf(sc, bsdf, bs.wo, wi, qr));
+            BVertex v; v.type = BV_SURFACE; v.fwd = data.fwd; v.delta = bs.dpd.disc; v.ffsd = 0u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
+            v.gkind = BG_SURFACE; v.p = srf.wp; v.tuid = primary; v.bary = mk2(pbx, pby); v.fp = srf.fp; v.dn = mk3(0.f, 0.f, 1.f); v.emitter = -1; v.bsdf = bsdf; v.fsd = -1; v.pad_ = 0u;
+            if (!bd_append(c, data, v, bs.dpd, pdf_revr)) return;
+            ++n_vert;
+            float w = 1.f;
+            if (!veq(ns, ng)) w *= snc_scale(data.fwd, wig, wog, wi.z, bs.wo.z);
+            beam_transform_surface(data.beam, srf, wow, bs.M, w);
+            data.throughput *= w * bs.M.m[0];
+            if (!data.fwd && bs.eta.re != 1.f) data.throughput /= sqrf(bs.eta.re);
+        } else if (!is_ballistic && sc.integrator.fsd) {
+            bool eo = false; uint32_t edges[kMaxHitEdges];
+            const uint32_t ne = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo);
+            if (eo) c.overflow = true;
+            if (ne) {       // sample_fraunhofer_fsd_interaction (:288-346)
+                if (n_ap >= (uint32_t)kMaxFAp) { c.overflow = true; return; }
+                const int ai = (int)n_ap;
+                const uint32_t nseg = fraunhofer_build(sc, c.A, ai, beam_frame, beam.k, 1.f - flux, beam.env, edges, ne, wf, c.overflow);
+                if (nseg == 0u) { beam_transform_restart(data.beam, interaction_wp, beam_dist); do_RR = false; }
+                else {
+                    ++n_ap;
+                    V3 wo; float dpd, wgt;
+                    fraunhofer_sample(c.A, ai, c.lut, smp, wo, dpd, wgt);
+                    if (dpd == 0.f || wgt == 0.f) return;
+                    const V3 wow = to_world(beam_frame, wo);
+                    BVertex v; v.type = BV_FSD; v.fwd = data.fwd; v.delta = 0u; v.ffsd = 1u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
+                    v.gkind = BG_POINT; v.p = interaction_wp; v.tuid = WTGPU_INVALID_IDX; v.bary = mk2(0.f, 0.f); v.fp.x = mk2(1.f, 0.f); v.fp.la = v.fp.lb = 0.f; v.dn = mk3(0.f, 0.f, 1.f);
+                    v.emitter = -1; v.bsdf = -1; v.fsd = ai; v.pad_ = 0u;
+                    if (!bd_append(c, data, v, pd_dens(dpd), pd_dens(dpd))) return;
+                    ++n_vert;
+                    beam_transform_region(data.beam, interaction_wp, beam_dist, wow, wgt);
+                    data.throughput *= wgt;
+                }
+            } else { do_RR = false; beam_transform_restart(data.beam, interaction_wp, beam_dist); }
+        } else { do_RR = false; beam_transform_restart(data.beam, interaction_wp, beam_dist); }
+        // continue_walk (:167-182)
+        if (data.n > max_depth + 1u) return;
+        if (do_RR && sc.integrator.russian_roulette) {
+            aw(c.A, (data.base + data.n - 1u) * kVertWords + kOffRr) = data.rr;
+            const float r = data.throughput < 1.f ? fmaxf(data.throughput, .5f) : 1.f;
+            if (rnd(smp) <= r) { const float s = 1.f / r; data.rr *= s; data.throughput *= s; }
+            else return;
+        }
+    }
+}
+
+// ================================================================================================ connections + MIS
+struct BConn { BVertex tmp; bool has_el; Element el; Stokes L; };
+
+WT_D Stokes connect_and_integrate(const BCtx& c, const Beam& db, const Geo& dg, const Beam& eb, const Geo& eg) {   // plt_bdpt_detail.hpp:725-745
+    if (beam_intensity(db) == 0.f || beam_intensity(eb) == 0.f) return stokes_zero();
+    if (shadow_between(*c.sc, dg, eg, *c.ctr)) return stokes_zero();
+    return integrate_beams(db, eb);
+}
+WT_D void tmp_init(BVertex& t, uint32_t type) {
+    t.type = type; t.fwd = type == BV_EMITTER ? 1u : 0u; t.delta = 0u; t.ffsd = 0u; t.pdf_fwd = -1.f; t.pdf_bwd = -1.f; t.rr = 1.f;
+    t.gkind = BG_POINT; t.p = mk3(0.f, 0.f, 0.f); t.tuid = WTGPU_INVALID_IDX; t.bary = mk2(0.f, 0.f); t.fp.x = mk2(1.f, 0.f); t.fp.la = t.fp.lb = 0.f; t.dn = mk3(0.f, 0.f, 1.f);
+    t.emitter = -1; t.bsdf = -1; t.fsd = -1; t.pad_ = 0u;
+}
+WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler& smp, BConn& ret) {       // plt_bdpt_detail.hpp:747-923
+    const DScene& sc = *c.sc;
+    const uint32_t SB = 0u, EB = kMaxBdptVerts;
+    ret.has_el = false; ret.L = stokes_zero(); tmp_init(ret.tmp, BV_SENSOR);
+    const bool virt = sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE;
+    if (s == 0) {
+        BVertex last; bv_load(c.A, SB + t - 1, last);
+        if (bv_on_emitter(c, last)) {
+            Beam QE = last.beam; beam_mul(QE, last.rr);
+            if (last.type == BV_SURFACE) { const Surface srf = bv_surface(sc, last); ret.L = emitter_Li(sc, bv_emitter(c, last), QE, srf); }
+        }
+    } else if (t == 0) {
+        if (virt) {
+            BVertex last, cur; bv_load(c.A, EB + s - 1, last); bv_load(c.A, EB + s - 2, cur);
+            const Beam& beam = last.beam;
+            Beam db; Element el;
+            if (sensor_Si(sc, beam, mkr(0.f, length(last.p - beam.env.o)), db, el)) {
+                ret.has_el = true; ret.el = el;
+                float w = cur.rr;
+                if (bv_on_surface(c, cur) && bv_nondelta_interaction(cur)) w /= fabsf(dot(db.env.d, bv_ns(c, cur)));
+                w /= fabsf(dot(db.env.d, mk3(sc.sensor.frame_n)));
+                beam_mul(db, w);
+                tmp_init(ret.tmp, BV_SENSOR); ret.tmp.pdf_bwd = 0.f; ret.tmp.gkind = BG_DUMMY; ret.tmp.p = db.env.o; ret.tmp.dn = mk3(sc.sensor.frame_n);
+                ret.L = integrate_beams(db, beam);
+            }
+        }
+    } else if (s == 1) {
+        BVertex last; bv_load(c.A, SB + t - 1, last);
+        if (bv_connectible(c, last)) {
+            EmitterDirect ed = scene_sample_emitter_direct(sc, smp, last.p, last.beam.k);
+            if ((ed.dpd.disc || ed.dpd.v != 0.f) && beam_intensity(ed.beam) > 0.f) {
+                float w = last.rr;
+                if (bv_on_surface(c, last)) w *= fabsf(dot(ed.beam.env.d, bv_ns(c, last)));
+                beam_mul(ed.beam, w);
+                tmp_init(ret.tmp, BV_EMITTER); ret.tmp.emitter = ed.emitter;
+                if (ed.has_surface) { ret.tmp.gkind = BG_SURFACE; ret.tmp.p = ed.sp; ret.tmp.tuid = ed.stuid; }
+                else { ret.tmp.gkind = BG_POINT; ret.tmp.p = ed.beam.env.o; }
+                Beam db;
+                if (bv_interact(c, last, ret.tmp.p, false, db)) ret.L = connect_and_integrate(c, db, bv_geo(last), ed.beam, bv_geo(ret.tmp));
+            }
+        }
+    } else if (t == 1) {
+        BVertex last; bv_load(c.A, EB + s - 1, last);
+        if ((virt || last.type != BV_FSD) && bv_connectible(c, last)) {
+            SensorDirect sd = sensor_sample_direct(sc, smp, last.p, last.beam.k);
+            if ((sd.dpd.disc || sd.dpd.v != 0.f) && beam_intensity(sd.beam) > 0.f) {
+                float w = last.rr;
+                if (bv_on_surface(c, last)) w *= fabsf(dot(sd.beam.env.d, bv_ns(c, last)));
+                beam_mul(sd.beam, w);
+                tmp_init(ret.tmp, BV_SENSOR); ret.tmp.p = sd.beam.env.o;
+                if (virt) { ret.tmp.gkind = BG_DUMMY; ret.tmp.dn = mk3(sc.sensor.frame_n); }
+                Beam eb;
+                if (bv_interact(c, last, ret.tmp.p, false, eb)) { ret.L = connect_and_integrate(c, sd.beam, bv_geo(ret.tmp), eb, bv_geo(last)); ret.has_el = true; ret.el = sd.el; }
+            }
+        }
+    } else {
+        BVertex ev, sv; bv_load(c.A, EB + s - 1, ev); bv_load(c.A, SB + t - 1, sv);
+        const V3 dl = ev.p - sv.p;
+        if (bv_connectible(c, ev) && bv_connectible(c, sv) && !(dl.x == 0.f && dl.y == 0.f && dl.z == 0.f)) {
+            Beam eb, db;
+            if (bv_interact(c, ev, sv.p, true, eb) && bv_interact(c, sv, ev.p, true, db)) {
+                const float rd2 = 1.f / length2(dl);
+                const V3 d = dl * sqrtf(rd2);
+                float wev = ev.rr, wsv = sv.rr * rd2;
+                if (bv_on_surface(c, sv)) wev *= fabsf(dot(bv_ns(c, sv), d));
+                if (bv_on_surface(c, ev)) wsv *= fabsf(dot(bv_ns(c, ev), d));
+                beam_mul(db, wsv); beam_mul(eb, wev);
+                ret.L = connect_and_integrate(c, db, bv_geo(sv), eb, bv_geo(ev));
+            }
+        }
+    }
+}
+
+WT_D float area_or_one(float p) { return (isfinite(p) && p > 1.1920929e-7f) ? p : 1.f; }
+WT_NI float bd_mis(BCtx& c, int s, int t, const BConn& cr) {       // plt_bdpt_detail.hpp:604-720
+    if (s + t <= 2) return 1.f;
+    const DScene& sc = *c.sc;
+    const uint32_t SB = 0u, EB = kMaxBdptVerts;
+    float sp_pdf[kMaxBdptVerts], sp_rev[kMaxBdptVerts], ep_pdf[kMaxBdptVerts], ep_rev[kMaxBdptVerts];
+    bool sp_d[kMaxBdptVerts], ep_d[kMaxBdptVerts];
+    for (int i = 0; i < t; ++i) { sp_pdf[i] = aw(c.A, (SB + i) * kVertWords + kOffPdfBwd); sp_rev[i] = aw(c.A, (SB + i) * kVertWords + kOffPdfFwd); sp_d[i] = __float_as_uint(aw(c.A, (SB + i) * kVertWords + kOffDelta)) != 0u; }
+    for (int i = 0; i < s; ++i) { ep_pdf[i] = aw(c.A, (EB + i) * kVertWords + kOffPdfFwd); ep_rev[i] = aw(c.A, (EB + i) * kVertWords + kOffPdfBwd); ep_d[i] = __float_as_uint(aw(c.A, (EB + i) * kVertWords + kOffDelta)) != 0u; }
+    const BVertex& tmp = cr.tmp;
+    const bool virt = sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE;
+    BVertex ev0, sv0;
+    if (s == 0) {
+        BVertex last, prev; bv_load(c.A, SB + t - 1, last); bv_load(c.A, SB + t - 2, prev);
+        sp_rev[t - 1] = pdf_emitter_v(c, last);
+        sp_rev[t - 2] = pdf_next_from_emitter(c, last, prev);
+    } else if (t == 0) {
+        BVertex last, prev; bv_load(c.A, EB + s - 2, prev);
+        if (virt) last = tmp; else bv_load(c.A, EB + s - 1, last);
+        ep_rev[s - 1] = sensor_pdf_position(c);
+        ep_rev[s - 2] = pdf_next_from_sensor(c, last, prev);
+    } else if (s == 1) {
+        BVertex last, lp; bv_load(c.A, SB + t - 1, last); bv_load(c.A, SB + t - 2, lp);
+        sp_rev[t - 1] = pdf_next_from_emitter(c, tmp, last);
+        ep_rev[0] = bv_pdf(c, last, &lp, tmp, false);
+        ep_pdf[0] = pdf_emitter_v(c, tmp);
+    } else if (t == 1) {
+        BVertex last, lp; bv_load(c.A, EB + s - 1, last); bv_load(c.A, EB + s - 2, lp);
+        ep_rev[s - 1] = pdf_next_from_sensor(c, tmp, last);
+        sp_rev[0] = bv_pdf(c, last, &lp, tmp, true);
+        sp_pdf[0] = sensor_pdf_position(c);
+    } else {
+        BVertex e, sv, epv, spv; bv_load(c.A, EB + s - 1, e); bv_load(c.A, SB + t - 1, sv); bv_load(c.A, EB + s - 2, epv); bv_load(c.A, SB + t - 2, spv);
+        ep_rev[s - 1] = bv_pdf(c, sv, &spv, e, false);
+        ep_rev[s - 2] = bv_pdf(c, e, &sv, epv, false);
+        sp_rev[t - 1] = bv_pdf(c, e, &epv, sv, true);
+        sp_rev[t - 2] = bv_pdf(c, sv, &e, spv, true);
+    }
+    if (t > 0) sp_d[t - 1] = false;
+    if (s > 0) ep_d[s - 1] = false;
+    bool delta_emitter = true, delta_sensor = true;
+    if (s == 1) delta_emitter = bv_delta_emitter(c, tmp); else if (s > 1) { bv_load(c.A, EB, ev0); delta_emitter = bv_delta_emitter(c, ev0); }
+    if (t == 1) delta_sensor = bv_delta_sensor(c, tmp); else if (t > 1) { bv_load(c.A, SB, sv0); delta_sensor = bv_delta_sensor(c, sv0); }
+    float sum = 0.f, ri = 1.f;
+    for (int i = t - 1; i >= 0; --i) { ri *= area_or_one(sp_rev[i]) / area_or_one(sp_pdf[i]); if (!sp_d[i] && !(i > 0 ? sp_d[i - 1] : delta_sensor)) sum += ri; }
+    ri = 1.f;
+    for (int i = s - 1; i >= 0; --i) { ri *= area_or_one(ep_rev[i]) / area_or_one(ep_pdf[i]); if (!ep_d[i] && !(i > 0 ? ep_d[i - 1] : delta_emitter)) sum += ri; }
+    return 1.f / (1.f + sum);
+}
+
+struct BdptArgs {
+    DScene sc; FLut lut; float* arena; uint32_t P;
+    DevCounters* ctr; float* film_block; float* film_light;
+    uint32_t seed_lo, seed_hi, tile_x0, tile_y0, tile_w, tile_h, sample_begin;
+    unsigned long long total;
+};
+
+// plt_bdpt_t::integrate (src/integrator/plt_bdpt.cpp:43-148): persistent threads, one sample at a time per thread
+__global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr; counters_zero(ctr);
+    BCtx c; c.sc = &a.sc; c.A.base = a.arena; c.A.P = a.P; c.A.slot = tid; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+    const DScene& sc = a.sc;
+    uint64_t n_samples = 0, n_vert = 0, n_conn = 0; uint32_t n_splat = 0;
+    const uint32_t SB = 0u, EB = kMaxBdptVerts;
+    for (;;) {
+        const unsigned long long id = atomicAdd(&a.ctr->next_sample, 1ull);
+        if (id >= a.total) break;
+        ++n_samples;
+        const uint64_t npix = (uint64_t)a.tile_w * a.tile_h;
+        const uint32_t pi = (uint32_t)(id % npix), si = (uint32_t)(id / npix);
+        const uint32_t ex = a.tile_x0 + pi % a.tile_w, ey = a.tile_y0 + pi / a.tile_w;
+        Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = ey * sc.sensor.width + ex; smp.sample = a.sample_begin + si; smp.d = 0;
+        const int32_t em = sample_emitter(sc, smp);
+        const float em_pdf = pdf_emitter(sc, em);
+        const KSample ks = sample_wavenumber(sc, em, smp);
+        const float k = ks.k;
+        const EmitterSample es = emitter_sample(sc, em, smp, k);
+        const float rspd = ks.wpd.disc ? 1.f / ks.wpd.v : 1.f / sum_spectral_pdf(sc, k);
+        const SensorSample ss = sensor_sample(sc, smp, ex, ey, k);
+        uint32_t n_ap = 0;
+        uint32_t nsv, nev;
+        {   // generate_sensor_subpath (:528-555)
+            BVertex v; tmp_init(v, BV_SENSOR); v.pdf_bwd = ss.ppd.disc ? 0.f : ss.ppd.v; v.beam = ss.beam; v.p = ss.beam.env.o;
+            if (ss.has_surface) { v.gkind = BG_DUMMY; v.dn = mk3(sc.sensor.frame_n); }
+            bv_store(c.A, SB, v);
+            BWalk d; d.beam = ss.beam; d.fwd = false; d.pdf_from_prev = ss.dpd; d.throughput = 1.f; d.rr = 1.f; d.base = SB; d.n = 1u;
+            bd_random_walk(c, d, smp, n_ap, n_vert);
+            nsv = d.n;
+        }
+        {   // generate_emitter_subpath (:557-581)
+            BVertex v; tmp_init(v, BV_EMITTER); v.pdf_fwd = (es.ppd.disc ? 0.f : es.ppd.v) * em_pdf; v.beam = es.beam; v.emitter = em; v.p = es.beam.env.o;
+            if (es.has_surface) { v.gkind = BG_SURFACE; v.tuid = es.s.tuid; v.p = es.s.wp; }
+            bv_store(c.A, EB, v);
+            BWalk d; d.beam = es.beam; d.fwd = true; d.pdf_from_prev = es.dpd; d.throughput = 1.f; d.rr = 1.f; d.base = EB; d.n = 1u;
+            bd_random_walk(c, d, smp, n_ap, n_vert);
+            nev = d.n;
+        }
+        float L0 = 0.f;
+        const int maxd = (int)sc.integrator.max_depth;
+        for (int t = 0; t <= (int)nsv; ++t)
+            for (int s = 0; s <= (int)nev; ++s) {
+                const int depth = t + s - 2;
+                if ((t == 1 && s == 1) || depth < 0) continue;
+                if (!sc.integrator.emitter_direct && s == 1) continue;
+                if (!sc.integrator.sensor_direct && t == 1) continue;
+                if (depth > maxd) break;
+                BConn cr;
+                bd_connect(c, nsv, nev, s, t, smp, cr);
+                ++n_conn;
+                if (cr.L.s[0] <= 0.f) continue;
+                const float mis = sc.integrator.mis ? bd_mis(c, s, t, cr) * rspd : 1.f / ((float)(s + t + 1) * ks.wpd.v);
+                const float flux = cr.L.s[0] * mis;
+                if (t > 1) L0 += flux;
+                else n_splat += film_splat(sc, a.film_block, a.film_light, true, cr.el, flux, k);
+            }
+        n_splat += film_splat(sc, a.film_block, a.film_light, false, ss.el, L0, k);
+    }
+    flush_counters(a.ctr, ctr);
+    {
+        const unsigned m = __activemask();
+        const unsigned ns = __reduce_add_sync(m, n_splat), nv = __reduce_add_sync(m, (unsigned)n_vert), nc = __reduce_add_sync(m, (unsigned)n_conn), nn = __reduce_add_sync(m, (unsigned)n_samples);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+            if (ns) atomicAdd(&a.ctr->splats, (unsigned long long)ns);
+            if (nv) atomicAdd(&a.ctr->segments, (unsigned long long)nv);
+            if (nc) atomicAdd(&a.ctr->shaded, (unsigned long long)nc);
+            if (nn) atomicAdd(&a.ctr->samples, (unsigned long long)nn);
+        }
+    }
+    count1(&a.ctr->overflow, c.overflow);
+}
+
+} // namespace wt

@@ -197,6 +197,8 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
     }
 }
 
+#include "dbdpt.cuh"
+
 __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     Counters ctr; counters_zero(ctr);
@@ -558,11 +560,13 @@ struct wtgpu_scene {
     DevCounters* ctr = nullptr;
     uint32_t n_keys = 0;
     std::vector<cudaEvent_t> ev_pool;   // reused across renders (event creation is not free)
+    wt::FLut lut{};                     // plt_bdpt: Fraunhofer sampling tables
+    float* bdpt_arena = nullptr; uint32_t bdpt_P = 0;
     ~wtgpu_scene() {
         cudaSetDevice(device);
         for (void* p : allocs) cudaFree(p);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
-        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list }) if (p) cudaFree(p);
+        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list, (void*)bdpt_arena }) if (p) cudaFree(p);
     }
 };
 
@@ -596,7 +600,11 @@ uint64_t wtgpu_debug_sizeof(int which) {
 int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** out) {
     if (!desc || !out) { g_err = "null argument"; return WTGPU_E_INVALID; }
     if (desc->api_version != WTGPU_API_VERSION) { g_err = "api version mismatch"; return WTGPU_E_INVALID; }
-    if (desc->integrator.type != WTGPU_INTEGRATOR_PLT_PATH) { g_err = "integrator type not implemented on the device (plt_path only)"; return WTGPU_E_UNSUPPORTED; }
+    if (desc->integrator.type != WTGPU_INTEGRATOR_PLT_PATH && desc->integrator.type != WTGPU_INTEGRATOR_PLT_BDPT) { g_err = "unknown integrator type"; return WTGPU_E_UNSUPPORTED; }
+    const bool bdpt = desc->integrator.type == WTGPU_INTEGRATOR_PLT_BDPT;
+    if (bdpt && desc->integrator.max_depth + 2u > (uint32_t)wt::kMaxBdptVerts) { g_err = "plt_bdpt: max_depth > 16 unsupported"; return WTGPU_E_UNSUPPORTED; }
+    if (bdpt && desc->integrator.fsd && (!desc->fsd_lut_n || !desc->fsd_lut_m || !desc->fsd_icdf1 || !desc->fsd_icdf2 || !desc->fsd_icdf_theta1 || !desc->fsd_icdf_theta2)) {
+        g_err = "plt_bdpt with FSD needs the Fraunhofer sampling tables (fsd_lut_*)"; return WTGPU_E_INVALID; }
     if (desc->sensor.rf_radius > 4) { g_err = "reconstruction filter radius > 4 unsupported"; return WTGPU_E_UNSUPPORTED; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device"; return WTGPU_E_NO_DEVICE; }
@@ -617,6 +625,12 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
         std::vector<float> lut(1024);
         for (int i = 0; i < 1024; ++i) lut[i] = std::erf((float)i / 1023.f * 3.5f);
         UP(erf_lut, lut.data(), lut.size())
+    }
+    if (bdpt && desc->fsd_lut_n) {
+        s->lut.N = desc->fsd_lut_n; s->lut.M = desc->fsd_lut_m;
+        const size_t mm = (size_t)desc->fsd_lut_m * desc->fsd_lut_m;
+        if ((rc = upload(s, desc->fsd_icdf_theta1, desc->fsd_lut_n, &s->lut.th1)) != WTGPU_OK || (rc = upload(s, desc->fsd_icdf_theta2, desc->fsd_lut_n, &s->lut.th2)) != WTGPU_OK ||
+            (rc = upload(s, desc->fsd_icdf1, mm, &s->lut.c1)) != WTGPU_OK || (rc = upload(s, desc->fsd_icdf2, mm, &s->lut.c2)) != WTGPU_OK) { delete s; return rc; }
     }
 #undef UP
     d.root_ptr = desc->root_ptr; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs; d.n_tris = desc->n_tris; d.n_nodes = desc->n_nodes;
@@ -651,7 +665,8 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     if (x1 <= o->tile_x0 || y1 <= o->tile_y0 || o->sample_end <= o->sample_begin) { if (stats) memset(stats, 0, sizeof(*stats)); return WTGPU_OK; }
     cudaStream_t st = (cudaStream_t)o->stream;
     const unsigned long long total = (unsigned long long)(x1 - o->tile_x0) * (y1 - o->tile_y0) * (o->sample_end - o->sample_begin);
-    uint32_t pool = o->pool_size ? o->pool_size : (1u << 20);
+    const bool bdpt = s->integ.type == WTGPU_INTEGRATOR_PLT_BDPT;
+    uint32_t pool = o->pool_size ? o->pool_size : (bdpt ? 148u * 8u * 128u : (1u << 20));
     pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>(total, 1024ull));
     pool = (pool + 127u) & ~127u;
     int rc = ensure_pool(s, pool);
@@ -689,6 +704,20 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     size_t n_ev = 0;
     auto mark = [&]() { if (time_phases) { if (n_ev == evs.size()) { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); } cudaEventRecord(evs[n_ev++], st); } };
     CK(cudaEventRecord(e0, st));
+    if (bdpt) {     // persistent threads, one launch (dbdpt.cuh)
+        if (s->bdpt_P != pool) {
+            if (s->bdpt_arena) cudaFree(s->bdpt_arena);
+            s->bdpt_arena = nullptr; s->bdpt_P = 0;
+            CK(cudaMalloc(&s->bdpt_arena, (size_t)wt::kArenaWords * 4 * pool));
+            s->bdpt_P = pool;
+        }
+        BdptArgs b;
+        b.sc = s->d; b.lut = s->lut; b.arena = s->bdpt_arena; b.P = pool; b.ctr = s->ctr; b.film_block = dblock; b.film_light = dlight;
+        b.seed_lo = a.seed_lo; b.seed_hi = a.seed_hi; b.tile_x0 = a.tile_x0; b.tile_y0 = a.tile_y0; b.tile_w = a.tile_w; b.tile_h = a.tile_h; b.sample_begin = a.sample_begin; b.total = total;
+        k_bdpt<<<pool / 128, blk, 0, st>>>(b); ++launches; ++iters;
+        CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    } else
     for (;;) {
         mark();
         k_generate<<<grd, blk, 0, st>>>(a); ++launches; mark();

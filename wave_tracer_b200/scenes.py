@@ -42,12 +42,13 @@ def double_slits(res=1024, spp=32, direction="forward", max_depth=16, fsd=True, 
     return sc
 
 
-def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=False, fsd=False, n_sphere=16):
+def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=False, fsd=False, n_sphere=16, integrator="plt_path", lut=(512, 256)):
     """A texture-free, procedural cornell-box variant (scenes/cornell-box/box.xml with its PLY shapes dropped):
     5 diffuse walls, a dielectric sphere, a rough-conductor cube, a cube area emitter; perspective sensor; plt_path backward."""
     lam = lam_nm * 1e-9
     sc = Scene()
-    sc.integrator = PltPath(max_depth=max_depth, direction="backward", fsd=fsd, russian_roulette=True)
+    sc.integrator = PltBdpt(max_depth=max_depth, fsd=fsd, lut=lut) if integrator == "plt_bdpt" else \
+        PltPath(max_depth=max_depth, direction="backward", fsd=fsd, russian_roulette=True)
     film = Film(res, res, [Discrete(lam)], rfilter_scale=1.0)
     sc.sensor = Perspective(lookat((0, 1.0, 3.4), (0, 1.0, 0), (0, 1, 0)), math.radians(40), film, ray_trace_only=ray_trace_only, samples=spp)
     white, red, green = TwoSided(Diffuse(.6)), TwoSided(Diffuse(.35)), TwoSided(Diffuse(.45))
