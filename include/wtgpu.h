@@ -278,6 +278,10 @@ typedef struct wtgpu_scene_desc {
  * RNG contract (the reference has no user seed -- seeded_mt19937_64.hpp:31-50 -- so this is ours):
  * a counter-based Philox4x32-10 stream keyed by `seed`, indexed by (pixel linear index, sample index,
  * draw counter); results are invariant to tiling, sample ranges and the number of GPUs.
+ * Draw d of (pixel, sample, stream) is lane d&3 of Philox4x32-10(key = seed, counter = (d>>2, sample, pixel, stream)),
+ * float = (u32 >> 8) * 2^-24.  stream is 0 for plt_path.  plt_bdpt splits a sample into sub-streams (each starting at d = 0) so
+ * that the two subpath walks and every (s,t) strategy are independent: 0 = emitter / wavenumber / source sampling, 1 = sensor
+ * subpath walk, 2 = emitter subpath walk, 3 + 32 t + s = strategy (s,t).
  * ------------------------------------------------------------------------------------------- */
 typedef struct wtgpu_render_opts {
     uint64_t seed;
@@ -292,6 +296,7 @@ typedef struct wtgpu_render_opts {
     void* stream;                   /* cudaStream_t or NULL */
 } wtgpu_render_opts;
 #define WTGPU_RENDER_NO_SORT 1u     /* disable the material sort (for A/B measurement) */
+#define WTGPU_RENDER_BDPT_MEGAKERNEL 4u  /* plt_bdpt: run the one-thread-per-sample cross-check kernel instead of the wavefront */
 #define WTGPU_RENDER_TIME_KERNELS 2u /* record CUDA events around every kernel (fills wtgpu_stats::*_ms) */
 
 /* Device counters gathered during wtgpu_render (the quantities the reference exposes in a `profile` build:

@@ -5,6 +5,13 @@
 //   Fraunhofer free-space diffraction (include/wt/interaction/fsd/fraunhofer/*.hpp, src/interaction/fsd/fraunhofer/*.cpp),
 //   gaussian2d_t::integrate_triangle (src/math/gaussian2d.cpp:96-192), clip_triangle_z (include/wt/math/intersect/clip.hpp).
 #pragma once
+#ifdef OT_DEBUG_COUNTERS
+#include <atomic>
+namespace ot { inline std::atomic<unsigned long long> g_dbg[8]; }
+#define OT_DBG(i, n) (ot::g_dbg[i] += (n))
+#else
+#define OT_DBG(i, n) ((void)0)
+#endif
 #include "ot_integrator.h"
 
 namespace ot {
@@ -90,6 +97,7 @@ inline f_t gaussian2d_t::integrate_triangle(v2 a, v2 b, v2 c) const {
     const f_t min_len = min3(length2(a - b), length2(a - c), length2(b - c));
     if (min_len < 1e-3f) {
         const f_t delta = .002f;
+        OT_DBG(0, 1);
         if (b.y < a.y) std::swap(a, b);
         if (c.y < a.y) std::swap(a, c);
         const f_t ab = b.y == a.y ? inf : (b.x - a.x) / (b.y - a.y);
@@ -100,10 +108,11 @@ inline f_t gaussian2d_t::integrate_triangle(v2 a, v2 b, v2 c) const {
             f_t x0 = y < b.y ? ab * (y - a.y) + a.x : bc * (y - b.y) + b.x;
             f_t x1 = y < c.y ? ac * (y - a.y) + a.x : bc * (y - b.y) + b.x;
             if (x0 > x1) std::swap(x0, x1);
-            for (f_t x = std::max(-L, x0) + delta / 2; x < std::min(L, x1); x += delta) ret += std::exp(-(sqr(x) + sqr(y)) / 2);
+            for (f_t x = std::max(-L, x0) + delta / 2; x < std::min(L, x1); x += delta) { ret += std::exp(-(sqr(x) + sqr(y)) / 2); OT_DBG(1, 1); }
         }
         return ret * inv_two_pi * sqr(delta);
     }
+    OT_DBG(2, 1);
     // analytic approximation: T = mat2(b-a, c-a) (columns)
     const mat2 T{ b - a, c - a };
     const f_t detT = T.m[0][0] * T.m[1][1] - T.m[1][0] * T.m[0][1];
@@ -305,7 +314,9 @@ struct fraunhofer_fsd_t {       // fraunhofer::free_space_diffraction_t
         const bool rej = edge_count > 1;
         const size_t M = edge_count, max_tries = M * 1024ul;
         const f_t recp_M = 1.f / (f_t)M;
+        OT_DBG(3, 1); OT_DBG(5, M);
         for (size_t tr = 0; tr < max_tries; ++tr) {
+            OT_DBG(4, 1);
             const v2 xi = sampleN(s);
             const f_t g = ap.sampling_density(xi), f = ap.ASF(xi);
             const bool done = rej ? s.r() * g < f * recp_M : true;
@@ -751,6 +762,7 @@ struct plt_bdpt_t {
             vertex_t v; v.type = V_SENSOR; v.forward = false; v.pdf_bwd = ss.ppd.density_or_zero(); v.beam = ss.beam; v.has_beam = true;
             v.geo = ss.surface ? geo_t::surface(*ss.surface) : geo_t::point(ss.beam.origin());
             ar.sv.push_back(v);
+            sampler.set_stream(1);
             walk_t d{ ss.beam, false, ss.dpd, 1, 1, &ar.sv, &ar, &sampler };
             random_walk(d);
         }
@@ -758,6 +770,7 @@ struct plt_bdpt_t {
             vertex_t v; v.type = V_EMITTER; v.forward = true; v.pdf_fwd = es.ppd.density_or_zero() * emitter_pdf; v.beam = es.beam; v.has_beam = true; v.emitter = em;
             v.geo = es.surface ? geo_t::surface(*es.surface) : geo_t::point(es.beam.origin());
             ar.ev.push_back(v);
+            sampler.set_stream(2);
             walk_t d{ es.beam, true, es.dpd, 1, 1, &ar.ev, &ar, &sampler };
             random_walk(d);
         }
@@ -770,6 +783,7 @@ struct plt_bdpt_t {
                 if (!emitter_direct && s == 1) continue;
                 if (!sensor_direct && t == 1) continue;
                 if (depth > (int)max_depth) break;
+                sampler.set_stream(3u + 32u * (uint32_t)t + (uint32_t)s);
                 const auto ret = connect_subpaths(ar, s, t, sampler);
                 if (stats) stats->connections++;
                 if (ret.L.intensity() <= 0) continue;

@@ -5,7 +5,10 @@
 // sampler warps of include/wt/sampler/sampler.hpp:78-306.
 //
 // Stream definition: draw number d of stream (seed, pixel, sample) is lane (d&3) of
-// Philox4x32-10(key = (seed_lo, seed_hi), counter = (d>>2, sample, pixel, 0)); float = (u32>>8)*2^-24.
+// Philox4x32-10(key = (seed_lo, seed_hi), counter = (d>>2, sample, pixel, stream)); float = (u32>>8)*2^-24.
+// stream is 0 for plt_path.  plt_bdpt splits a sample into independent sub-streams so that the two subpath walks and every (s,t)
+// connection can run concurrently on the device: 0 = emitter/wavenumber/source sampling, 1 = sensor subpath walk, 2 = emitter
+// subpath walk, 3 + 32 t + s = connection (s,t); each sub-stream starts at d = 0.
 #pragma once
 #include "ot_math.h"
 
@@ -28,19 +31,21 @@ struct sampler_t {
     uint64_t seed = 0;
     uint32_t pixel = 0, sample = 0;
     uint32_t d = 0;
+    uint32_t stream = 0;
     uint32_t cached_block = 0xffffffffu;
     uint32_t cache[4];
 
     uint32_t next_u32() {
         const uint32_t block = d >> 2, lane = d & 3;
         if (block != cached_block) {
-            cache[0] = block; cache[1] = sample; cache[2] = pixel; cache[3] = 0;
+            cache[0] = block; cache[1] = sample; cache[2] = pixel; cache[3] = stream;
             philox4x32_10(cache, (uint32_t)seed, (uint32_t)(seed >> 32));
             cached_block = block;
         }
         ++d;
         return cache[lane];
     }
+    void set_stream(uint32_t s) { stream = s; d = 0; cached_block = 0xffffffffu; }
     f_t r() { return (f_t)(next_u32() >> 8) * (1.0f / 16777216.0f); }
     v2 r2() { const f_t a = r(); const f_t b = r(); return { a, b }; }
     v3 r3() { const f_t a = r(); const f_t b = r(); const f_t c = r(); return { a, b, c }; }

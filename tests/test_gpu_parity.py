@@ -135,28 +135,30 @@ def test_partition_invariance_on_gpu():
     assert np.allclose(ns, full, rtol=1e-4, atol=1e-6 * full.max())
 
 
-@pytest.mark.parametrize("fsd", [False, True])
-def test_bdpt_double_slits_matches_oracle(fsd):
-    """plt_bdpt (both subpaths, all (s,t) connections, MIS; Fraunhofer FSD when fsd) on the double_slits geometry, virtual-plane sensor."""
+@pytest.mark.parametrize("fsd,flags", [(False, 0), (True, 0), (True, 4)])
+def test_bdpt_double_slits_matches_oracle(fsd, flags):
+    """plt_bdpt (both subpaths, all (s,t) connections, MIS; Fraunhofer FSD when fsd) on the double_slits geometry, virtual-plane sensor.
+    flags=0: wavefront driver; flags=4 (WTGPU_RENDER_BDPT_MEGAKERNEL): the one-thread-per-sample cross-check driver."""
     b = scenes.double_slits(res=128, spp=8, with_directional=False, integrator="plt_bdpt", fsd=fsd, lut=(512, 256)).build()
-    blk, lgt, st = render(b, spp=8, allow_overflow=True)
+    blk, lgt, st = render(b, spp=8, allow_overflow=True, flags=flags)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"] == 128 * 32 * 8
     img_g = develop(b, 8, blk, lgt); img_o = develop(b, 8, oblk, olgt)
     assert img_o.sum() > 0
     l2, flux = _film_metrics(img_g, img_o)
-    print("bdpt double_slits fsd=%s: rel-L2 %.3e flux %.3e" % (fsd, l2, flux), st, ost)
+    print("bdpt double_slits fsd=%s flags=%d: rel-L2 %.3e flux %.3e" % (fsd, flags, l2, flux), st["gpu_ms"], st["segments"], ost["segments"], st["shaded_paths"])
     assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
 
 
-def test_bdpt_cornell_matches_oracle():
+@pytest.mark.parametrize("flags", [0, 4])
+def test_bdpt_cornell_matches_oracle(flags):
     """plt_bdpt with a perspective sensor and an area emitter (s=0 emission hits, t=1 sensor connections, NEE, MIS)."""
     b = scenes.cornell_like(res=48, spp=8, integrator="plt_bdpt").build()
-    blk, lgt, st = render(b, spp=8, allow_overflow=True)
+    blk, lgt, st = render(b, spp=8, allow_overflow=True, flags=flags)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"]
     img_g = develop(b, 8, blk, lgt); img_o = develop(b, 8, oblk, olgt)
     assert img_o.mean() > 0
     l2, flux = _film_metrics(img_g, img_o)
-    print("bdpt cornell: rel-L2 %.3e flux %.3e" % (l2, flux))
+    print("bdpt cornell flags=%d: rel-L2 %.3e flux %.3e" % (flags, l2, flux), st["gpu_ms"])
     assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)

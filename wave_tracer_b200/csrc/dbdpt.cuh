@@ -17,7 +17,8 @@ constexpr float kSqrtPi = 1.77245385090551602730f;
 constexpr float kInvSqrtPi = 0.56418958354775628695f;
 constexpr int kMaxBdptVerts = 18;           // max_depth + 2 vertices per subpath for max_depth <= 16
 constexpr int kMaxFSeg = 48;                // Fraunhofer aperture segments
-constexpr int kMaxFAp = 6;                  // apertures per sample (both subpaths)
+constexpr int kMaxFApWalk = 4;              // Fraunhofer apertures per subpath
+constexpr int kMaxFAp = 2 * kMaxFApWalk;
 
 WT_D float sincf_(float x) {                // include/wt/math/common.hpp:414-434
     const float t0 = 1.1920929e-7f, t2 = 0.00034526698300124390839884978618400831996329879769945f, tn = 0.018581361171917516667460937040007436176452688944747f;
@@ -177,9 +178,9 @@ WT_D float fPsi2(const FEdge& e, V2 xi) { const V2 z = fzeta(e, xi); return sqrf
 WT_D float fPj(const FEdge& e) { return sqrf(length2(e.e)) * kPA1 * cnorm(e.a_b) + sqrf(length2(e.e)) * kPA2 * cnorm(e.iab_2); }
 
 // per-thread arena accessor: word w of this thread at base[w*P + slot]
-struct Arena { float* base; uint32_t P, slot; };
-WT_D float& aw(const Arena& A, uint32_t w) { return A.base[(size_t)w * A.P + A.slot]; }
-constexpr uint32_t kVertWords = 72;
+struct Arena { float* base; };       // this sample's records, contiguous (AoS): a vertex or an aperture is read by one thread at a time
+WT_D float& aw(const Arena& A, uint32_t w) { return A.base[w]; }
+constexpr uint32_t kVertWords = 68;
 constexpr uint32_t kApWords = 16 + kMaxFSeg * 9;
 constexpr uint32_t kArenaWords = 2 * kMaxBdptVerts * kVertWords + kMaxFAp * kApWords;
 WT_D uint32_t ap_base(int ai) { return 2 * kMaxBdptVerts * kVertWords + (uint32_t)ai * kApWords; }
@@ -353,7 +354,7 @@ WT_D float fraunhofer_pdf(const Arena& A, int ai, const FHead& h, V3 wl) {     /
 // ================================================================================================ vertices
 enum : uint32_t { BV_SENSOR = 0u, BV_EMITTER = 1u, BV_SURFACE = 2u, BV_FSD = 3u };
 enum : uint32_t { BG_NONE = 0u, BG_POINT = 1u, BG_SURFACE = 2u, BG_DUMMY = 4u };
-struct BVertex {            // vertex_t (integrator/plt_bdpt/vertex.hpp:49-81)
+struct alignas(16) BVertex {            // vertex_t (integrator/plt_bdpt/vertex.hpp:49-81)
     uint32_t type, fwd, delta, ffsd;
     float pdf_fwd, pdf_bwd, rr;
     uint32_t gkind; V3 p; uint32_t tuid; V2 bary; Footprint fp; V3 dn;
@@ -361,14 +362,16 @@ struct BVertex {            // vertex_t (integrator/plt_bdpt/vertex.hpp:49-81)
     uint32_t pad_;
     Beam beam;
 };
-static_assert(sizeof(BVertex) <= kVertWords * 4, "vertex record too large");
+static_assert(sizeof(BVertex) == kVertWords * 4, "vertex record size");
 WT_D void bv_store(const Arena& A, uint32_t idx, const BVertex& v) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-    for (uint32_t i = 0; i < sizeof(BVertex) / 4; ++i) aw(A, idx * kVertWords + i) = __uint_as_float(w[i]);
+    const float4* s = reinterpret_cast<const float4*>(&v); float4* d = reinterpret_cast<float4*>(A.base + idx * kVertWords);
+#pragma unroll
+    for (uint32_t i = 0; i < kVertWords / 4; ++i) d[i] = s[i];
 }
 WT_D void bv_load(const Arena& A, uint32_t idx, BVertex& v) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-    for (uint32_t i = 0; i < sizeof(BVertex) / 4; ++i) w[i] = __float_as_uint(aw(A, idx * kVertWords + i));
+    float4* d = reinterpret_cast<float4*>(&v); const float4* s = reinterpret_cast<const float4*>(A.base + idx * kVertWords);
+#pragma unroll
+    for (uint32_t i = 0; i < kVertWords / 4; ++i) d[i] = s[i];
 }
 // word offsets of the scalars the MIS walk touches
 constexpr uint32_t kOffDelta = 2, kOffPdfFwd = 4, kOffPdfBwd = 5, kOffRr = 6;
@@ -498,7 +501,7 @@ WT_NI bool bv_interact(const BCtx& c, const BVertex& v, V3 next_p, bool ignore_f
 }
 
 // ================================================================================================ walk
-struct BWalk { Beam beam; bool fwd; Pd pdf_from_prev; float throughput, rr; uint32_t base, n; };   // vertices at [base, base+n)
+struct BWalk { Beam beam; bool fwd; Pd pdf_from_prev; float throughput, rr; uint32_t base, n; Geo prev_geo; uint32_t ap0, n_ap; };   // vertices at [base, base+n)
 
 WT_D bool bd_append(const BCtx& c, BWalk& d, BVertex& v, Pd pdf_fwd, Pd pdf_revr) {     // plt_bdpt_detail.hpp:96-122
     BVertex prev; bv_load(c.A, d.base + d.n - 1u, prev);
@@ -512,115 +515,118 @@ WT_D bool bd_append(const BCtx& c, BWalk& d, BVertex& v, Pd pdf_fwd, Pd pdf_revr
     d.pdf_from_prev = pdf_fwd;
     bv_store(c.A, d.base + d.n, v);
     d.n++;
+    d.prev_geo = bv_geo(v);
     return true;
 }
 
-WT_NI void bd_random_walk(BCtx& c, BWalk& data, Sampler& smp, uint32_t& n_ap, uint64_t& n_vert) {       // plt_bdpt_detail.hpp:421-526
-    const DScene& sc = *c.sc;
-    const uint32_t max_depth = sc.integrator.max_depth;
-    const bool force_rt = sc.sensor.ray_trace_only != 0u;
-    for (;;) {
-        Beam& beam = data.beam;
-        BVertex last; bv_load(c.A, data.base + data.n - 1u, last);
-        uint32_t tris[kMaxConeTris];
-        TravOut tr;
-        traverse(sc, beam.env, bv_geo(last), wavenum_to_wavelen(beam.k), force_rt, tris, tr, *c.ctr);
-        if (tr.empty) return;
-        if (tr.cone.overflow) c.overflow = true;
-        const float beam_dist = tr.ballistic ? tr.ray.dist : tr.cone.dist;
-        const Range zr = mkr(beam_dist, beam_dist + tr.region_depth);
-        const bool is_ballistic = tr.ballistic || cone_is_ray(beam.env);
-        const V3 origin_wp = tr.origin;
-        const V3 dir = beam.env.d;
-        const V3 interaction_wp = origin_wp + zr.mn * dir;
-        const Frame beam_frame = cone_frame(beam.env);
-        const Cone envelope = beam.env;
-        const G2 wf = wavefront_of(beam, beam_dist);
-        const uint32_t nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
-        uint32_t primary = WTGPU_INVALID_IDX; float pdist = WT_INF, pbx = -1.f, pby = -1.f, flux = 0.f;
-        if (is_ballistic) { primary = tr.ray.tuid; pdist = tr.ray.dist; pbx = tr.ray.bx; pby = tr.ray.by; }
-        else {      // find_closest_triangle (:362-419)
-            for (uint32_t i = 0; i < nt; ++i) {
-                const Tri3 t = load_tri(sc, tris[i]);
-                const float tol = cone_intersection_tolerance(origin_wp, t.a, t.b, t.c);
-                const RayTri rt = intersect_ray_tri(origin_wp, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
-                if (rt.hit && rt.dist < pdist) { primary = tris[i]; pdist = rt.dist; pbx = rt.bx; pby = rt.by; }
-            }
-            if (primary == WTGPU_INVALID_IDX) {
-                const float csz = (zr.mx + zr.mn) / 2.f;
-                for (uint32_t i = 0; i < nt; ++i) {
-                    const Tri3 t = load_tri(sc, tris[i]);
-                    if ((dot(t.n, -dir) > 0.f) != tr.cone.front) continue;
-                    const Clip cl = clip_triangle_z(to_local(beam_frame, t.a - envelope.o), to_local(beam_frame, t.b - envelope.o), to_local(beam_frame, t.c - envelope.o), zr);
-                    for (int k = 0; k < cl.tris; ++k) {
-                        V3 ct[3]; clip_tri(cl, k, ct);
-                        flux += g2_integrate_triangle(sc, wf, cone_project_local(envelope, ct[0], csz), cone_project_local(envelope, ct[1], csz), cone_project_local(envelope, ct[2], csz));
-                    }
-                }
-            }
-        }
-        bool do_RR = true;
-        if (primary != WTGPU_INVALID_IDX) {     // sample_surface_interaction (:193-270)
-            const float k = beam.k;
-            Surface srf = make_surface(sc, primary, mk2(pbx, pby), origin_wp + envelope.d * pdist);
-            srf.fp = surface_footprint_static(beam, srf, beam_dist);
-            const int32_t bsdf = sc.shapes[sc.tri_meta[primary].shape_idx].bsdf;
-            const V3 ng = srf.geo.n, ns = srf.shading.n;
-            const V3 wiw = -dir;
-            const V3 wi = to_local(srf.shading, wiw);
-            const float wig = dot(wiw, ng);
-            if (wig * wi.z <= 0.f) return;
-            BsdfQuery q; q.k = k; q.fwd = data.fwd; q.lobes = 0xffffffffu;
-            const BsdfSample bs = bsdf_sample(sc, bsdf, wi, q, smp);
-            if (!bs.valid || bs.dpd.v == 0.f) return;
-            const V3 wow = normalize(to_world(srf.shading, bs.wo));
-            const float wog = dot(wow, ng);
-            if (wog * bs.wo.z <= 0.f) return;
-            BsdfQuery qr = q; qr.fwd = !data.fwd;
-            const Pd pdf_revr = pd_dens(bsdf_pdf(sc, bsdf, bs.wo, wi, qr));
-            BVertex v; v.type = BV_SURFACE; v.fwd = data.fwd; v.delta = bs.dpd.disc; v.ffsd = 0u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
-            v.gkind = BG_SURFACE; v.p = srf.wp; v.tuid = primary; v.bary = mk2(pbx, pby); v.fp = srf.fp; v.dn = mk3(0.f, 0.f, 1.f); v.emitter = -1; v.bsdf = bsdf; v.fsd = -1; v.pad_ = 0u;
-            if (!bd_append(c, data, v, bs.dpd, pdf_revr)) return;
-            ++n_vert;
-            float w = 1.f;
-            if (!veq(ns, ng)) w *= snc_scale(data.fwd, wig, wog, wi.z, bs.wo.z);
-            beam_transform_surface(data.beam, srf, wow, bs.M, w);
-            data.throughput *= w * bs.M.m[0];
-            if (!data.fwd && bs.eta.re != 1.f) data.throughput /= sqrf(bs.eta.re);
-        } else if (!is_ballistic && sc.integrator.fsd) {
-            bool eo = false; uint32_t edges[kMaxHitEdges];
-            const uint32_t ne = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo);
-            if (eo) c.overflow = true;
-            if (ne) {       // sample_fraunhofer_fsd_interaction (:288-346)
-                if (n_ap >= (uint32_t)kMaxFAp) { c.overflow = true; return; }
-                const int ai = (int)n_ap;
-                const uint32_t nseg = fraunhofer_build(sc, c.A, ai, beam_frame, beam.k, 1.f - flux, beam.env, edges, ne, wf, c.overflow);
-                if (nseg == 0u) { beam_transform_restart(data.beam, interaction_wp, beam_dist); do_RR = false; }
-                else {
-                    ++n_ap;
-                    V3 wo; float dpd, wgt;
-                    fraunhofer_sample(c.A, ai, c.lut, smp, wo, dpd, wgt);
-                    if (dpd == 0.f || wgt == 0.f) return;
-                    const V3 wow = to_world(beam_frame, wo);
-                    BVertex v; v.type = BV_FSD; v.fwd = data.fwd; v.delta = 0u; v.ffsd = 1u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
-                    v.gkind = BG_POINT; v.p = interaction_wp; v.tuid = WTGPU_INVALID_IDX; v.bary = mk2(0.f, 0.f); v.fp.x = mk2(1.f, 0.f); v.fp.la = v.fp.lb = 0.f; v.dn = mk3(0.f, 0.f, 1.f);
-                    v.emitter = -1; v.bsdf = -1; v.fsd = ai; v.pad_ = 0u;
-                    if (!bd_append(c, data, v, pd_dens(dpd), pd_dens(dpd))) return;
-                    ++n_vert;
-                    beam_transform_region(data.beam, interaction_wp, beam_dist, wow, wgt);
-                    data.throughput *= wgt;
-                }
-            } else { do_RR = false; beam_transform_restart(data.beam, interaction_wp, beam_dist); }
-        } else { do_RR = false; beam_transform_restart(data.beam, interaction_wp, beam_dist); }
-        // continue_walk (:167-182)
-        if (data.n > max_depth + 1u) return;
-        if (do_RR && sc.integrator.russian_roulette) {
-            aw(c.A, (data.base + data.n - 1u) * kVertWords + kOffRr) = data.rr;
-            const float r = data.throughput < 1.f ? fmaxf(data.throughput, .5f) : 1.f;
-            if (rnd(smp) <= r) { const float s = 1.f / r; data.rr *= s; data.throughput *= s; }
-            else return;
+// What one traverse() found, reduced to what the vertex step needs (random_walk :421-470 + find_closest_triangle :362-419)
+struct BHit { bool empty, ballistic, overflow; uint32_t primary; float pdist, bx, by, dist, region_depth, flux; V3 origin; uint32_t n_edges; };
+WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, const uint32_t* tris, uint32_t* edges, BHit& h) {
+    h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u;
+    h.origin = tr.origin; h.region_depth = tr.region_depth; h.dist = 0.f; h.ballistic = true;
+    if (tr.empty) return;
+    if (tr.cone.overflow) h.overflow = true;
+    h.dist = tr.ballistic ? tr.ray.dist : tr.cone.dist;
+    const Range zr = mkr(h.dist, h.dist + tr.region_depth);
+    h.ballistic = tr.ballistic || cone_is_ray(beam.env);
+    const V3 dir = beam.env.d;
+    const uint32_t nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
+    if (h.ballistic) { h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; return; }
+    for (uint32_t i = 0; i < nt; ++i) {
+        const Tri3 t = load_tri(sc, tris[i]);
+        const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
+        const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+        if (rt.hit && rt.dist < h.pdist) { h.primary = tris[i]; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
+    }
+    if (h.primary != WTGPU_INVALID_IDX) return;
+    const Frame beam_frame = cone_frame(beam.env);
+    const G2 wf = wavefront_of(beam, h.dist);
+    const float csz = (zr.mx + zr.mn) / 2.f;
+    for (uint32_t i = 0; i < nt; ++i) {
+        const Tri3 t = load_tri(sc, tris[i]);
+        if ((dot(t.n, -dir) > 0.f) != tr.cone.front) continue;
+        const Clip cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
+        for (int k = 0; k < cl.tris; ++k) {
+            V3 ct[3]; clip_tri(cl, k, ct);
+            h.flux += g2_integrate_triangle(sc, wf, cone_project_local(beam.env, ct[0], csz), cone_project_local(beam.env, ct[1], csz), cone_project_local(beam.env, ct[2], csz));
         }
     }
+    if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo); if (eo) h.overflow = true; }
+}
+
+// One vertex of a subpath: the body of plt_bdpt::random_walk (plt_bdpt_detail.hpp:470-526) after the traverse.  false: the walk ended.
+WT_NI bool bd_walk_step(BCtx& c, BWalk& data, Sampler& smp, const BHit& h, const uint32_t* edges, uint32_t& n_vert) {
+    const DScene& sc = *c.sc;
+    if (h.empty) return false;
+    if (h.overflow) c.overflow = true;
+    Beam& beam = data.beam;
+    const float beam_dist = h.dist;
+    const V3 dir = beam.env.d;
+    const V3 interaction_wp = h.origin + beam_dist * dir;
+    const Frame beam_frame = cone_frame(beam.env);
+    bool do_RR = true;
+    if (h.primary != WTGPU_INVALID_IDX) {     // sample_surface_interaction (:193-270)
+        Surface srf = make_surface(sc, h.primary, mk2(h.bx, h.by), h.origin + dir * h.pdist);
+        srf.fp = surface_footprint_static(beam, srf, beam_dist);
+        const int32_t bsdf = sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
+        const V3 ng = srf.geo.n, ns = srf.shading.n;
+        const V3 wiw = -dir;
+        const V3 wi = to_local(srf.shading, wiw);
+        const float wig = dot(wiw, ng);
+        if (wig * wi.z <= 0.f) return false;
+        BsdfQuery q; q.k = beam.k; q.fwd = data.fwd; q.lobes = 0xffffffffu;
+        const BsdfSample bs = bsdf_sample(sc, bsdf, wi, q, smp);
+        if (!bs.valid || bs.dpd.v == 0.f) return false;
+        const V3 wow = normalize(to_world(srf.shading, bs.wo));
+        const float wog = dot(wow, ng);
+        if (wog * bs.wo.z <= 0.f) return false;
+        BsdfQuery qr = q; qr.fwd = !data.fwd;
+        const Pd pdf_revr = pd_dens(bsdf_pdf(sc, bsdf, bs.wo, wi, qr));
+        BVertex v; v.type = BV_SURFACE; v.fwd = data.fwd; v.delta = bs.dpd.disc; v.ffsd = 0u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
+        v.gkind = BG_SURFACE; v.p = srf.wp; v.tuid = h.primary; v.bary = mk2(h.bx, h.by); v.fp = srf.fp; v.dn = mk3(0.f, 0.f, 1.f); v.emitter = -1; v.bsdf = bsdf; v.fsd = -1; v.pad_ = 0u;
+        if (!bd_append(c, data, v, bs.dpd, pdf_revr)) return false;
+        ++n_vert;
+        float w = 1.f;
+        if (!veq(ns, ng)) w *= snc_scale(data.fwd, wig, wog, wi.z, bs.wo.z);
+        beam_transform_surface(data.beam, srf, wow, bs.M, w);
+        data.throughput *= w * bs.M.m[0];
+        if (!data.fwd && bs.eta.re != 1.f) data.throughput /= sqrf(bs.eta.re);
+    } else if (!h.ballistic && sc.integrator.fsd && h.n_edges) {       // sample_fraunhofer_fsd_interaction (:288-346)
+        if (data.n_ap >= (uint32_t)kMaxFApWalk) { c.overflow = true; return false; }
+        const int ai = (int)(data.ap0 + data.n_ap);
+        const G2 wf = wavefront_of(beam, beam_dist);
+        const uint32_t nseg = fraunhofer_build(sc, c.A, ai, beam_frame, beam.k, 1.f - h.flux, beam.env, edges, h.n_edges, wf, c.overflow);
+        if (nseg == 0u) { beam_transform_restart(data.beam, interaction_wp, beam_dist); do_RR = false; }
+        else {
+            ++data.n_ap;
+            V3 wo; float dpd, wgt;
+            fraunhofer_sample(c.A, ai, c.lut, smp, wo, dpd, wgt);
+            if (dpd == 0.f || wgt == 0.f) return false;
+            const V3 wow = to_world(beam_frame, wo);
+            BVertex v; v.type = BV_FSD; v.fwd = data.fwd; v.delta = 0u; v.ffsd = 1u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
+            v.gkind = BG_POINT; v.p = interaction_wp; v.tuid = WTGPU_INVALID_IDX; v.bary = mk2(0.f, 0.f); v.fp.x = mk2(1.f, 0.f); v.fp.la = v.fp.lb = 0.f; v.dn = mk3(0.f, 0.f, 1.f);
+            v.emitter = -1; v.bsdf = -1; v.fsd = ai; v.pad_ = 0u;
+            if (!bd_append(c, data, v, pd_dens(dpd), pd_dens(dpd))) return false;
+            ++n_vert;
+            beam_transform_region(data.beam, interaction_wp, beam_dist, wow, wgt);
+            data.throughput *= wgt;
+        }
+    } else { do_RR = false; beam_transform_restart(data.beam, interaction_wp, beam_dist); }
+    // continue_walk (:167-182)
+    if (data.n > sc.integrator.max_depth + 1u) return false;
+    if (do_RR && sc.integrator.russian_roulette) {
+        aw(c.A, (data.base + data.n - 1u) * kVertWords + kOffRr) = data.rr;
+        const float r = data.throughput < 1.f ? fmaxf(data.throughput, .5f) : 1.f;
+        if (rnd(smp) <= r) { const float s = 1.f / r; data.rr *= s; data.throughput *= s; }
+        else return false;
+    }
+    return true;
+}
+// key for the material sort of subpath walkers: bsdf id | fsd | null | miss
+WT_D uint32_t bd_hit_key(const DScene& sc, const BHit& h, uint32_t n_keys) {
+    if (h.empty) return n_keys - 1u;
+    if (h.primary != WTGPU_INVALID_IDX) return (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
+    return (!h.ballistic && sc.integrator.fsd && h.n_edges) ? n_keys - 3u : n_keys - 2u;
 }
 
 // ================================================================================================ connections + MIS
@@ -759,86 +765,272 @@ WT_NI float bd_mis(BCtx& c, int s, int t, const BConn& cr) {       // plt_bdpt_d
     return 1.f / (1.f + sum);
 }
 
+// ================================================================================================ sample set-up shared by both drivers
+struct BdSampleInit { uint32_t pixel, sample, ex, ey; float k, rspd, wpd_v; Element el; };
+// plt_bdpt_t::integrate preamble + generate_{sensor,emitter}_subpath heads (src/integrator/plt_bdpt.cpp:54-75; plt_bdpt_detail.hpp:528-581):
+// draws on sub-stream 0, writes vertex 0 of both subpaths, returns the two walk states
+WT_D void bd_init_sample(const BCtx& c, uint32_t seed_lo, uint32_t seed_hi, uint32_t ex, uint32_t ey, uint32_t sample, BdSampleInit& si, BWalk& ws, BWalk& we) {
+    const DScene& sc = *c.sc;
+    Sampler smp; smp.k0 = seed_lo; smp.k1 = seed_hi; smp.pixel = ey * sc.sensor.width + ex; smp.sample = sample; smp.d = 0; smp.stream = 0u;
+    const int32_t em = sample_emitter(sc, smp);
+    const float em_pdf = pdf_emitter(sc, em);
+    const KSample ks = sample_wavenumber(sc, em, smp);
+    const float k = ks.k;
+    const EmitterSample es = emitter_sample(sc, em, smp, k);
+    si.rspd = ks.wpd.disc ? 1.f / ks.wpd.v : 1.f / sum_spectral_pdf(sc, k);
+    const SensorSample ss = sensor_sample(sc, smp, ex, ey, k);
+    si.pixel = smp.pixel; si.sample = sample; si.ex = ex; si.ey = ey; si.k = k; si.wpd_v = ks.wpd.v; si.el = ss.el;
+    {
+        BVertex v; tmp_init(v, BV_SENSOR); v.pdf_bwd = ss.ppd.disc ? 0.f : ss.ppd.v; v.beam = ss.beam; v.p = ss.beam.env.o;
+        if (ss.has_surface) { v.gkind = BG_DUMMY; v.dn = mk3(sc.sensor.frame_n); }
+        bv_store(c.A, 0u, v);
+        ws.beam = ss.beam; ws.fwd = false; ws.pdf_from_prev = ss.dpd; ws.throughput = 1.f; ws.rr = 1.f; ws.base = 0u; ws.n = 1u; ws.prev_geo = bv_geo(v); ws.ap0 = 0u; ws.n_ap = 0u;
+    }
+    {
+        BVertex v; tmp_init(v, BV_EMITTER); v.pdf_fwd = (es.ppd.disc ? 0.f : es.ppd.v) * em_pdf; v.beam = es.beam; v.emitter = em; v.p = es.beam.env.o;
+        if (es.has_surface) { v.gkind = BG_SURFACE; v.tuid = es.s.tuid; v.p = es.s.wp; }
+        bv_store(c.A, (uint32_t)kMaxBdptVerts, v);
+        we.beam = es.beam; we.fwd = true; we.pdf_from_prev = es.dpd; we.throughput = 1.f; we.rr = 1.f; we.base = (uint32_t)kMaxBdptVerts; we.n = 1u; we.prev_geo = bv_geo(v);
+        we.ap0 = (uint32_t)kMaxFApWalk; we.n_ap = 0u;
+    }
+}
+// the (s,t) enumeration of plt_bdpt.cpp:96-110; f(s,t) for every strategy that is evaluated
+template <class F> WT_D void bd_for_each_pair(const DScene& sc, uint32_t nsv, uint32_t nev, F&& f) {
+    const int maxd = (int)sc.integrator.max_depth;
+    for (int t = 0; t <= (int)nsv; ++t)
+        for (int s = 0; s <= (int)nev; ++s) {
+            const int depth = t + s - 2;
+            if ((t == 1 && s == 1) || depth < 0) continue;
+            if (!sc.integrator.emitter_direct && s == 1) continue;
+            if (!sc.integrator.sensor_direct && t == 1) continue;
+            if (depth > maxd) break;
+            f(s, t);
+        }
+}
+// one (s,t) strategy: connect, weight; returns the flux and where it goes (plt_bdpt.cpp:111-140)
+WT_D float bd_eval_pair(BCtx& c, const BdSampleInit& si, uint32_t seed_lo, uint32_t seed_hi, uint32_t nsv, uint32_t nev, int s, int t, BConn& cr) {
+    const DScene& sc = *c.sc;
+    Sampler smp; smp.k0 = seed_lo; smp.k1 = seed_hi; smp.pixel = si.pixel; smp.sample = si.sample; smp.d = 0; smp.stream = 3u + 32u * (uint32_t)t + (uint32_t)s;
+    bd_connect(c, nsv, nev, s, t, smp, cr);
+    if (cr.L.s[0] <= 0.f) return 0.f;
+    const float mis = sc.integrator.mis ? bd_mis(c, s, t, cr) * si.rspd : 1.f / ((float)(s + t + 1) * si.wpd_v);
+    return cr.L.s[0] * mis;
+}
+
+// ================================================================================================ driver 1: one thread per sample (cross-check path)
 struct BdptArgs {
     DScene sc; FLut lut; float* arena; uint32_t P;
     DevCounters* ctr; float* film_block; float* film_light;
     uint32_t seed_lo, seed_hi, tile_x0, tile_y0, tile_w, tile_h, sample_begin;
     unsigned long long total;
 };
-
-// plt_bdpt_t::integrate (src/integrator/plt_bdpt.cpp:43-148): persistent threads, one sample at a time per thread
+WT_D void bd_sample_coords(unsigned long long id, uint32_t tile_x0, uint32_t tile_y0, uint32_t tile_w, uint32_t tile_h, uint32_t sample_begin, uint32_t& ex, uint32_t& ey, uint32_t& sample) {
+    const uint64_t npix = (uint64_t)tile_w * tile_h;
+    const uint32_t pi = (uint32_t)(id % npix), si = (uint32_t)(id / npix);
+    ex = tile_x0 + pi % tile_w; ey = tile_y0 + pi / tile_w; sample = sample_begin + si;
+}
+WT_D void bd_flush_stats(DevCounters* g, uint32_t n_splat, uint32_t n_vert, uint32_t n_conn, uint32_t n_samples, bool overflow) {
+    const unsigned m = __activemask();
+    const unsigned ns = __reduce_add_sync(m, n_splat), nv = __reduce_add_sync(m, n_vert), nc = __reduce_add_sync(m, n_conn), nn = __reduce_add_sync(m, n_samples);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+        if (ns) atomicAdd(&g->splats, (unsigned long long)ns);
+        if (nv) atomicAdd(&g->segments, (unsigned long long)nv);
+        if (nc) atomicAdd(&g->shaded, (unsigned long long)nc);
+        if (nn) atomicAdd(&g->samples, (unsigned long long)nn);
+    }
+    count1(&g->overflow, overflow);
+}
+// plt_bdpt_t::integrate (src/integrator/plt_bdpt.cpp:43-148) start to finish in one thread.  Slow (divergent); kept as an
+// independent second implementation of the same contract for the parity tests (WTGPU_RENDER_BDPT_MEGAKERNEL).
 __global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     Counters ctr; counters_zero(ctr);
-    BCtx c; c.sc = &a.sc; c.A.base = a.arena; c.A.P = a.P; c.A.slot = tid; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+    BCtx c; c.sc = &a.sc; c.A.base = a.arena + (size_t)tid * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
     const DScene& sc = a.sc;
-    uint64_t n_samples = 0, n_vert = 0, n_conn = 0; uint32_t n_splat = 0;
-    const uint32_t SB = 0u, EB = kMaxBdptVerts;
+    uint32_t n_samples = 0, n_vert = 0, n_conn = 0, n_splat = 0;
+    const bool force_rt = sc.sensor.ray_trace_only != 0u;
     for (;;) {
         const unsigned long long id = atomicAdd(&a.ctr->next_sample, 1ull);
         if (id >= a.total) break;
         ++n_samples;
-        const uint64_t npix = (uint64_t)a.tile_w * a.tile_h;
-        const uint32_t pi = (uint32_t)(id % npix), si = (uint32_t)(id / npix);
-        const uint32_t ex = a.tile_x0 + pi % a.tile_w, ey = a.tile_y0 + pi / a.tile_w;
-        Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = ey * sc.sensor.width + ex; smp.sample = a.sample_begin + si; smp.d = 0;
-        const int32_t em = sample_emitter(sc, smp);
-        const float em_pdf = pdf_emitter(sc, em);
-        const KSample ks = sample_wavenumber(sc, em, smp);
-        const float k = ks.k;
-        const EmitterSample es = emitter_sample(sc, em, smp, k);
-        const float rspd = ks.wpd.disc ? 1.f / ks.wpd.v : 1.f / sum_spectral_pdf(sc, k);
-        const SensorSample ss = sensor_sample(sc, smp, ex, ey, k);
-        uint32_t n_ap = 0;
-        uint32_t nsv, nev;
-        {   // generate_sensor_subpath (:528-555)
-            BVertex v; tmp_init(v, BV_SENSOR); v.pdf_bwd = ss.ppd.disc ? 0.f : ss.ppd.v; v.beam = ss.beam; v.p = ss.beam.env.o;
-            if (ss.has_surface) { v.gkind = BG_DUMMY; v.dn = mk3(sc.sensor.frame_n); }
-            bv_store(c.A, SB, v);
-            BWalk d; d.beam = ss.beam; d.fwd = false; d.pdf_from_prev = ss.dpd; d.throughput = 1.f; d.rr = 1.f; d.base = SB; d.n = 1u;
-            bd_random_walk(c, d, smp, n_ap, n_vert);
-            nsv = d.n;
-        }
-        {   // generate_emitter_subpath (:557-581)
-            BVertex v; tmp_init(v, BV_EMITTER); v.pdf_fwd = (es.ppd.disc ? 0.f : es.ppd.v) * em_pdf; v.beam = es.beam; v.emitter = em; v.p = es.beam.env.o;
-            if (es.has_surface) { v.gkind = BG_SURFACE; v.tuid = es.s.tuid; v.p = es.s.wp; }
-            bv_store(c.A, EB, v);
-            BWalk d; d.beam = es.beam; d.fwd = true; d.pdf_from_prev = es.dpd; d.throughput = 1.f; d.rr = 1.f; d.base = EB; d.n = 1u;
-            bd_random_walk(c, d, smp, n_ap, n_vert);
-            nev = d.n;
+        uint32_t ex, ey, sample; bd_sample_coords(id, a.tile_x0, a.tile_y0, a.tile_w, a.tile_h, a.sample_begin, ex, ey, sample);
+        BdSampleInit si; BWalk w[2];
+        bd_init_sample(c, a.seed_lo, a.seed_hi, ex, ey, sample, si, w[0], w[1]);
+        for (int wi = 0; wi < 2; ++wi) {
+            Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = si.pixel; smp.sample = si.sample; smp.d = 0; smp.stream = 1u + (uint32_t)wi;
+            for (;;) {
+                uint32_t tris[kMaxConeTris], edges[kMaxHitEdges];
+                TravOut tr; BHit h;
+                traverse(sc, w[wi].beam.env, w[wi].prev_geo, wavenum_to_wavelen(w[wi].beam.k), force_rt, tris, tr, ctr);
+                bd_resolve_hit(sc, w[wi].beam, tr, tris, edges, h);
+                if (!bd_walk_step(c, w[wi], smp, h, edges, n_vert)) break;
+            }
         }
         float L0 = 0.f;
-        const int maxd = (int)sc.integrator.max_depth;
-        for (int t = 0; t <= (int)nsv; ++t)
-            for (int s = 0; s <= (int)nev; ++s) {
-                const int depth = t + s - 2;
-                if ((t == 1 && s == 1) || depth < 0) continue;
-                if (!sc.integrator.emitter_direct && s == 1) continue;
-                if (!sc.integrator.sensor_direct && t == 1) continue;
-                if (depth > maxd) break;
-                BConn cr;
-                bd_connect(c, nsv, nev, s, t, smp, cr);
-                ++n_conn;
-                if (cr.L.s[0] <= 0.f) continue;
-                const float mis = sc.integrator.mis ? bd_mis(c, s, t, cr) * rspd : 1.f / ((float)(s + t + 1) * ks.wpd.v);
-                const float flux = cr.L.s[0] * mis;
-                if (t > 1) L0 += flux;
-                else n_splat += film_splat(sc, a.film_block, a.film_light, true, cr.el, flux, k);
-            }
-        n_splat += film_splat(sc, a.film_block, a.film_light, false, ss.el, L0, k);
+        const uint32_t nsv = w[0].n, nev = w[1].n;
+        bd_for_each_pair(sc, nsv, nev, [&](int s, int t) {
+            BConn cr;
+            const float flux = bd_eval_pair(c, si, a.seed_lo, a.seed_hi, nsv, nev, s, t, cr);
+            ++n_conn;
+            if (cr.L.s[0] <= 0.f) return;
+            if (t > 1) L0 += flux;
+            else n_splat += film_splat(sc, a.film_block, a.film_light, true, cr.el, flux, si.k);
+        });
+        n_splat += film_splat(sc, a.film_block, a.film_light, false, si.el, L0, si.k);
     }
     flush_counters(a.ctr, ctr);
-    {
-        const unsigned m = __activemask();
-        const unsigned ns = __reduce_add_sync(m, n_splat), nv = __reduce_add_sync(m, (unsigned)n_vert), nc = __reduce_add_sync(m, (unsigned)n_conn), nn = __reduce_add_sync(m, (unsigned)n_samples);
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
-            if (ns) atomicAdd(&a.ctr->splats, (unsigned long long)ns);
-            if (nv) atomicAdd(&a.ctr->segments, (unsigned long long)nv);
-            if (nc) atomicAdd(&a.ctr->shaded, (unsigned long long)nc);
-            if (nn) atomicAdd(&a.ctr->samples, (unsigned long long)nn);
+    bd_flush_stats(a.ctr, n_splat, n_vert, n_conn, n_samples, c.overflow);
+}
+
+// ================================================================================================ driver 2: wavefront
+// Sample slots hold both subpaths' vertices (AoS records in the arena).  The two walks of a sample are independent "walkers"
+// (id = 2 slot + which) that advance one vertex per iteration through  traverse -> material sort -> vertex step; when both have
+// ended, the slot's (s,t) strategies are expanded into a task list and evaluated one strategy per thread; the last strategy to
+// finish splats the sample's block contribution and frees the slot.
+struct alignas(16) BdWalker { Beam beam; Geo prev_geo; float pdf_v; uint32_t pdf_disc; float throughput, rr; uint32_t n, rng_d, n_ap, pad0; };
+struct alignas(16) BdHeader { uint32_t pixel, sample, ex, ey; float k, rspd, wpd_v, ox, oy; uint32_t elx, ely, pad0; };
+struct BdArgs {
+    RenderArgs r;               // sort buffers sized for 2P walkers; r.hit = walker hit records; r.alive = slot flags; r.pool = 2P
+    FLut lut; float* arena; uint32_t P;
+    float4* walkers; float4* headers;
+    int* pending; float* L0; uint32_t* nverts; uint32_t* pairs;
+};
+WT_D void bd_walker_to_state(const BdWalker& w, uint32_t which, BWalk& d) {
+    d.beam = w.beam; d.fwd = which == 1u; d.pdf_from_prev.v = w.pdf_v; d.pdf_from_prev.disc = w.pdf_disc != 0u; d.throughput = w.throughput; d.rr = w.rr;
+    d.base = which * (uint32_t)kMaxBdptVerts; d.n = w.n; d.prev_geo = w.prev_geo; d.ap0 = which * (uint32_t)kMaxFApWalk; d.n_ap = w.n_ap;
+}
+WT_D void bd_state_to_walker(const BWalk& d, uint32_t rng_d, BdWalker& w) {
+    w.beam = d.beam; w.prev_geo = d.prev_geo; w.pdf_v = d.pdf_from_prev.v; w.pdf_disc = d.pdf_from_prev.disc ? 1u : 0u; w.throughput = d.throughput; w.rr = d.rr;
+    w.n = d.n; w.rng_d = rng_d; w.n_ap = d.n_ap; w.pad0 = 0u;
+}
+WT_D void bd_header_to_init(const BdHeader& h, BdSampleInit& si) {
+    si.pixel = h.pixel; si.sample = h.sample; si.ex = h.ex; si.ey = h.ey; si.k = h.k; si.rspd = h.rspd; si.wpd_v = h.wpd_v; si.el.ex = h.elx; si.el.ey = h.ely; si.el.ox = h.ox; si.el.oy = h.oy;
+}
+// last act of a sample: the block splat of the summed t>1 strategies (plt_bdpt.cpp:143-146); frees the slot
+WT_D uint32_t bd_finalize(const BdArgs& a, uint32_t slot, float L0) {
+    BdHeader h; soa_load(h, a.headers, a.P, slot);
+    Element el; el.ex = h.elx; el.ey = h.ely; el.ox = h.ox; el.oy = h.oy;
+    const uint32_t n = film_splat(a.r.sc, a.r.film_block, a.r.film_light, false, el, L0, h.k);
+    a.r.alive[slot] = 0u;
+    atomicSub(&a.r.ctr->live, 1);
+    return n;
+}
+
+__global__ void __launch_bounds__(128) k_bd_generate(const BdArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool gen = false;
+    if (slot < a.P && a.r.alive[slot] == 0u) {
+        const unsigned long long id = atomicAdd(&a.r.ctr->next_sample, 1ull);
+        if (id < a.r.total) {
+            gen = true;
+            Counters ctr; counters_zero(ctr);
+            BCtx c; c.sc = &a.r.sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+            uint32_t ex, ey, sample; bd_sample_coords(id, a.r.tile_x0, a.r.tile_y0, a.r.tile_w, a.r.tile_h, a.r.sample_begin, ex, ey, sample);
+            BdSampleInit si; BWalk w0, w1;
+            bd_init_sample(c, a.r.seed_lo, a.r.seed_hi, ex, ey, sample, si, w0, w1);
+            BdHeader h; h.pixel = si.pixel; h.sample = si.sample; h.ex = ex; h.ey = ey; h.k = si.k; h.rspd = si.rspd; h.wpd_v = si.wpd_v; h.ox = si.el.ox; h.oy = si.el.oy; h.elx = si.el.ex; h.ely = si.el.ey; h.pad0 = 0u;
+            soa_store(h, a.headers, a.P, slot);
+            BdWalker w; bd_state_to_walker(w0, 0u, w); soa_store(w, a.walkers, 2u * a.P, 2u * slot);
+            bd_state_to_walker(w1, 0u, w); soa_store(w, a.walkers, 2u * a.P, 2u * slot + 1u);
+            a.r.alive[slot] = 1u; a.pending[slot] = 2; a.L0[slot] = 0.f;
         }
     }
-    count1(&a.ctr->overflow, c.overflow);
+    list_append(a.r.trav_list, &a.r.ctr->n_trav, gen, 2u * slot);
+    list_append(a.r.trav_list, &a.r.ctr->n_trav, gen, 2u * slot + 1u);
+    const unsigned m = __activemask();
+    const unsigned n = __reduce_add_sync(m, gen ? 1u : 0u);
+    if (n && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) { atomicAdd(&a.r.ctr->live, (int)n); atomicAdd(&a.r.ctr->samples, (unsigned long long)n); }
+}
+
+__global__ void __launch_bounds__(128) k_bd_traverse(const BdArgs a) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr; counters_zero(ctr);
+    bool ovf = false;
+    if (li < (uint32_t)a.r.ctr->n_trav) {
+        const uint32_t wid = a.r.trav_list[li];
+        const DScene& sc = a.r.sc;
+        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+        uint32_t tris[kMaxConeTris];
+        TravOut tr; BHit bh; HitRec h;
+        traverse(sc, w.beam.env, w.prev_geo, wavenum_to_wavelen(w.beam.k), sc.sensor.ray_trace_only != 0u, tris, tr, ctr);
+        bd_resolve_hit(sc, w.beam, tr, tris, h.edges, bh);
+        h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
+        h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
+        ovf = bh.overflow;
+        soa_store(h, a.r.hit, a.r.pool, wid);
+        a.r.keys[wid] = bd_hit_key(sc, bh, a.r.n_keys);
+    }
+    flush_counters(a.r.ctr, ctr);
+    count1(&a.r.ctr->overflow, ovf);
+}
+
+__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->n_pairs = 0; } }
+
+__global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr; counters_zero(ctr);
+    uint32_t n_vert = 0, n_splat = 0, wid = 0; bool survive = false, overflow = false;
+    if (i < (uint32_t)a.r.ctr->n_sorted) {
+        const DScene& sc = a.r.sc;
+        wid = a.r.order[i];
+        const uint32_t slot = wid >> 1, which = wid & 1u;
+        BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+        HitRec h; soa_load(h, a.r.hit, a.r.pool, wid);
+        BdHeader hd; soa_load(hd, a.headers, a.P, slot);
+        BWalk d; bd_walker_to_state(w, which, d);
+        BHit bh; bh.empty = (h.flags & H_EMPTY) != 0u; bh.ballistic = (h.flags & H_BALLISTIC) != 0u; bh.overflow = (h.flags & H_OVERFLOW) != 0u;
+        bh.primary = h.primary; bh.pdist = h.pdist; bh.bx = h.bx; bh.by = h.by; bh.dist = h.d2i; bh.region_depth = h.region_depth; bh.flux = h.flux; bh.origin = h.origin; bh.n_edges = h.n_edges;
+        Sampler smp; smp.k0 = a.r.seed_lo; smp.k1 = a.r.seed_hi; smp.pixel = hd.pixel; smp.sample = hd.sample; smp.d = w.rng_d; smp.stream = 1u + which;
+        survive = bd_walk_step(c, d, smp, bh, h.edges, n_vert);
+        overflow = c.overflow;
+        if (survive) { bd_state_to_walker(d, smp.d, w); soa_store(w, a.walkers, 2u * a.P, wid); }
+        else {
+            a.nverts[wid] = d.n;
+            __threadfence();
+            if (atomicSub(&a.pending[slot], 1) == 1) {      // the sample's second walk just ended: expand its strategies
+                __threadfence();
+                const uint32_t nsv = which == 0u ? d.n : __ldcg(a.nverts + (wid ^ 1u)), nev = which == 1u ? d.n : __ldcg(a.nverts + (wid ^ 1u));
+                int np = 0;
+                bd_for_each_pair(sc, nsv, nev, [&](int, int) { ++np; });
+                if (np == 0) n_splat += bd_finalize(a, slot, 0.f);
+                else {
+                    a.pending[slot] = np;
+                    uint32_t at = (uint32_t)atomicAdd(&a.r.ctr->n_pairs, np);
+                    bd_for_each_pair(sc, nsv, nev, [&](int s, int t) { a.pairs[at++] = slot | ((uint32_t)s << 22) | ((uint32_t)t << 27); });
+                }
+            }
+        }
+    }
+    list_append(a.r.trav_list, &a.r.ctr->n_trav, survive, wid);
+    flush_counters(a.r.ctr, ctr, true);
+    bd_flush_stats(a.r.ctr, n_splat, n_vert, 0u, 0u, overflow);
+}
+
+__global__ void __launch_bounds__(128) k_bd_connect(const BdArgs a) {
+    Counters ctr; counters_zero(ctr);
+    uint32_t n_conn = 0, n_splat = 0; bool overflow = false;
+    const uint32_t np = (uint32_t)a.r.ctr->n_pairs;
+    const DScene& sc = a.r.sc;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        const uint32_t task = a.pairs[i];
+        const uint32_t slot = task & 0x3fffffu; const int s = (int)((task >> 22) & 31u), t = (int)(task >> 27);
+        BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+        BdHeader hd; soa_load(hd, a.headers, a.P, slot);
+        BdSampleInit si; bd_header_to_init(hd, si);
+        const uint32_t nsv = a.nverts[2u * slot], nev = a.nverts[2u * slot + 1u];
+        BConn cr;
+        const float flux = bd_eval_pair(c, si, a.r.seed_lo, a.r.seed_hi, nsv, nev, s, t, cr);
+        ++n_conn; overflow |= c.overflow;
+        if (cr.L.s[0] > 0.f) {
+            if (t > 1) atomicAdd(&a.L0[slot], flux);
+            else n_splat += film_splat(sc, a.r.film_block, a.r.film_light, true, cr.el, flux, si.k);
+        }
+        __threadfence();
+        if (atomicSub(&a.pending[slot], 1) == 1) { __threadfence(); n_splat += bd_finalize(a, slot, atomicAdd(&a.L0[slot], 0.f)); }
+    }
+    flush_counters(a.r.ctr, ctr, true);
+    bd_flush_stats(a.r.ctr, n_splat, 0u, n_conn, 0u, overflow);
 }
 
 } // namespace wt

@@ -8,8 +8,8 @@ namespace wt {
 
 // ================================================================================================ sampler
 // Counter-based stream (include/wtgpu.h "RNG contract"): draw d of (seed, pixel, sample) is lane d&3 of
-// Philox4x32-10(key=seed, ctr=(d>>2, sample, pixel, 0)).  Replaces sampler::uniform_t (include/wt/sampler/uniform.hpp:36-50).
-struct Sampler { uint32_t k0, k1, pixel, sample, d; };
+// Philox4x32-10(key=seed, ctr=(d>>2, sample, pixel, stream)).  Replaces sampler::uniform_t (include/wt/sampler/uniform.hpp:36-50).
+struct Sampler { uint32_t k0, k1, pixel, sample, d, stream; };      // stream: 0 (plt_path); plt_bdpt sub-streams, see include/wtgpu.h
 WT_D uint32_t philox_lane(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t lane) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -22,7 +22,7 @@ WT_D uint32_t philox_lane(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, ui
     return lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3;
 }
 WT_D float rnd(Sampler& s) {
-    const uint32_t u = philox_lane(s.k0, s.k1, s.d >> 2, s.sample, s.pixel, 0u, s.d & 3u);
+    const uint32_t u = philox_lane(s.k0, s.k1, s.d >> 2, s.sample, s.pixel, s.stream, s.d & 3u);
     ++s.d;
     return (float)(u >> 8) * (1.0f / 16777216.0f);
 }

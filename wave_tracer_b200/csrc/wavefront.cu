@@ -47,6 +47,7 @@ struct alignas(16) HitRec {
     float pdist, bx, by, d2i, region_depth;
     V3 origin;
     uint32_t n_edges;
+    float flux;                 // plt_bdpt: Gaussian power over the clipped triangles (no primary hit)
     uint32_t edges[kMaxHitEdges];
 };
 
@@ -69,6 +70,7 @@ struct DevCounters {
     int live;                           // paths alive
     int n_trav;                         // entries of trav_list (paths to traverse this iteration)
     int n_sorted;                       // live paths in `order`
+    int n_pairs;                        // plt_bdpt: (s,t) strategies queued this iteration
 };
 
 struct RenderArgs {
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(128) k_generate(const RenderArgs a) {
             const uint32_t ex = a.tile_x0 + pi % a.tile_w, ey = a.tile_y0 + pi / a.tile_w;
             PathCore pc;
             pc.pixel = ey * sc.sensor.width + ex; pc.sample = a.sample_begin + si;
-            Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = 0;
+            Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = 0; smp.stream = 0u;
             // integrate_backward / integrate_forward preamble (plt_path_detail.hpp:764-828)
             const int32_t em = sample_emitter(sc, smp);
             const KSample ks = sample_wavenumber(sc, em, smp);
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
         TravOut tr;
         const bool force_rt = sc.sensor.ray_trace_only != 0u;
         traverse(sc, pc.beam.env, pc.prev_geo, wavenum_to_wavelen(pc.beam.k), force_rt, tris, tr, ctr);
-        HitRec h; h.flags = 0u; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.n_edges = 0u;
+        HitRec h; h.flags = 0u; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.n_edges = 0u; h.flux = 0.f;
         h.origin = tr.origin; h.region_depth = tr.region_depth; h.d2i = 0.f;
         uint32_t key = a.n_keys - 1u;       // miss
         if (tr.empty) h.flags |= H_EMPTY;
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
         const uint32_t slot = a.order[i];
         PathCore pc; soa_load(pc, a.core, a.pool, slot);
         HitRec h; soa_load(h, a.hit, a.pool, slot);
-        Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = pc.rng_d;
+        Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = pc.rng_d; smp.stream = 0u;
         Beam& beam = pc.beam;
         const bool fwd = beam.fwd;
         const uint32_t max_depth = sc.integrator.max_depth;
@@ -539,7 +541,7 @@ __global__ void k_debug_cones(const DScene sc, uint32_t n, const wtgpu_cone_quer
 __global__ void k_debug_rng(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t n, float* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Sampler s; s.k0 = k0; s.k1 = k1; s.pixel = pixel; s.sample = sample; s.d = i;
+    Sampler s; s.k0 = k0; s.k1 = k1; s.pixel = pixel; s.sample = sample; s.d = i; s.stream = 0u;
     out[i] = rnd(s);
 }
 
@@ -562,10 +564,19 @@ struct wtgpu_scene {
     std::vector<cudaEvent_t> ev_pool;   // reused across renders (event creation is not free)
     wt::FLut lut{};                     // plt_bdpt: Fraunhofer sampling tables
     float* bdpt_arena = nullptr; uint32_t bdpt_P = 0;
+    // plt_bdpt wavefront state (P sample slots, 2P walkers)
+    float4 *bd_walkers = nullptr, *bd_headers = nullptr, *bd_hit = nullptr;
+    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_pairs = nullptr, *bd_alive = nullptr, *bd_keys = nullptr, *bd_order = nullptr, *bd_trav = nullptr;
+    uint32_t bd_wave_P = 0;
+    void free_bd_wave() {
+        for (void* p : { (void*)bd_walkers, (void*)bd_headers, (void*)bd_hit, (void*)bd_pending, (void*)bd_L0, (void*)bd_nverts, (void*)bd_pairs, (void*)bd_alive, (void*)bd_keys, (void*)bd_order, (void*)bd_trav }) if (p) cudaFree(p);
+        bd_walkers = bd_headers = bd_hit = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_pairs = bd_alive = bd_keys = bd_order = bd_trav = nullptr; bd_wave_P = 0;
+    }
     ~wtgpu_scene() {
         cudaSetDevice(device);
         for (void* p : allocs) cudaFree(p);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+        free_bd_wave();
         for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list, (void*)bdpt_arena }) if (p) cudaFree(p);
     }
 };
@@ -666,7 +677,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     cudaStream_t st = (cudaStream_t)o->stream;
     const unsigned long long total = (unsigned long long)(x1 - o->tile_x0) * (y1 - o->tile_y0) * (o->sample_end - o->sample_begin);
     const bool bdpt = s->integ.type == WTGPU_INTEGRATOR_PLT_BDPT;
-    uint32_t pool = o->pool_size ? o->pool_size : (bdpt ? 148u * 8u * 128u : (1u << 20));
+    uint32_t pool = o->pool_size ? o->pool_size : (bdpt ? ((o->flags & WTGPU_RENDER_BDPT_MEGAKERNEL) ? 148u * 8u * 128u : (1u << 18)) : (1u << 20));
     pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>(total, 1024ull));
     pool = (pool + 127u) & ~127u;
     int rc = ensure_pool(s, pool);
@@ -704,7 +715,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     size_t n_ev = 0;
     auto mark = [&]() { if (time_phases) { if (n_ev == evs.size()) { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); } cudaEventRecord(evs[n_ev++], st); } };
     CK(cudaEventRecord(e0, st));
-    if (bdpt) {     // persistent threads, one launch (dbdpt.cuh)
+    if (bdpt && (o->flags & WTGPU_RENDER_BDPT_MEGAKERNEL)) {     // one thread per sample, one launch (dbdpt.cuh driver 1)
         if (s->bdpt_P != pool) {
             if (s->bdpt_arena) cudaFree(s->bdpt_arena);
             s->bdpt_arena = nullptr; s->bdpt_P = 0;
@@ -717,6 +728,46 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         k_bdpt<<<pool / 128, blk, 0, st>>>(b); ++launches; ++iters;
         CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+    } else if (bdpt) {      // wavefront (dbdpt.cuh driver 2)
+        const uint32_t P = pool, W2 = 2u * pool;
+        uint32_t max_pairs = 0;     // strategies per sample: the enumeration of plt_bdpt.cpp:96-110 at full subpath lengths
+        {
+            const int n = (int)s->integ.max_depth + 2, maxd = (int)s->integ.max_depth;
+            for (int t = 0; t <= n; ++t) for (int q = 0; q <= n; ++q) { const int depth = t + q - 2; if ((t == 1 && q == 1) || depth < 0) continue; if (depth > maxd) break; ++max_pairs; }
+        }
+        if (s->bd_wave_P != P) {
+            s->free_bd_wave();
+            if (s->bdpt_P != P) { if (s->bdpt_arena) cudaFree(s->bdpt_arena); s->bdpt_arena = nullptr; s->bdpt_P = 0; CK(cudaMalloc(&s->bdpt_arena, (size_t)wt::kArenaWords * 4 * P)); s->bdpt_P = P; }
+            CK(cudaMalloc(&s->bd_walkers, (size_t)chunks_of<BdWalker>() * 16 * W2)); CK(cudaMalloc(&s->bd_headers, (size_t)chunks_of<BdHeader>() * 16 * P));
+            CK(cudaMalloc(&s->bd_hit, (size_t)chunks_of<HitRec>() * 16 * W2));
+            CK(cudaMalloc(&s->bd_pending, 4ull * P)); CK(cudaMalloc(&s->bd_L0, 4ull * P)); CK(cudaMalloc(&s->bd_nverts, 4ull * W2)); CK(cudaMalloc(&s->bd_alive, 4ull * P));
+            CK(cudaMalloc(&s->bd_keys, 4ull * W2)); CK(cudaMalloc(&s->bd_order, 4ull * W2)); CK(cudaMalloc(&s->bd_trav, 4ull * W2));
+            CK(cudaMalloc(&s->bd_pairs, 4ull * (size_t)P * max_pairs));
+            s->bd_wave_P = P;
+        }
+        if (P > (1u << 22)) { g_err = "plt_bdpt: pool_size > 4M sample slots"; return WTGPU_E_INVALID; }
+        BdArgs b;
+        b.r = a; b.r.hit = s->bd_hit; b.r.alive = s->bd_alive; b.r.keys = s->bd_keys; b.r.order = s->bd_order; b.r.trav_list = s->bd_trav; b.r.pool = W2;
+        b.lut = s->lut; b.arena = s->bdpt_arena; b.P = P; b.walkers = s->bd_walkers; b.headers = s->bd_headers;
+        b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs;
+        CK(cudaMemsetAsync(s->bd_alive, 0, 4ull * P, st));
+        const dim3 gP((P + 127) / 128), gW((W2 + 127) / 128), gC(148 * 8);
+        for (;;) {
+            mark();
+            k_bd_generate<<<gP, blk, 0, st>>>(b); ++launches; mark();
+            k_bd_traverse<<<gW, blk, 0, st>>>(b); ++launches; mark();
+            k_hist<<<gW, blk, s->n_keys * 4, st>>>(b.r);
+            k_scan<<<1, 32, 0, st>>>(b.r);
+            k_scatter<<<gW, blk, 0, st>>>(b.r); launches += 3; mark();
+            k_bd_reset<<<1, 32, 0, st>>>(b);
+            k_bd_shade<<<gW, blk, 0, st>>>(b);
+            k_bd_connect<<<gC, blk, 0, st>>>(b); launches += 3; mark();
+            ++iters;
+            CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (hctr->next_sample >= total && hctr->live <= 0) break;
+            if (iters > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
+        }
     } else
     for (;;) {
         mark();
