@@ -554,10 +554,38 @@ WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, 
     if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo); if (eo) h.overflow = true; }
 }
 
-// One vertex of a subpath: the body of plt_bdpt::random_walk (plt_bdpt_detail.hpp:470-526) after the traverse.  false: the walk ended.
-WT_NI bool bd_walk_step(BCtx& c, BWalk& data, Sampler& smp, const BHit& h, const uint32_t* edges, uint32_t& n_vert) {
+// continue_walk (plt_bdpt_detail.hpp:167-182)
+WT_D bool bd_continue_walk(BCtx& c, BWalk& data, Sampler& smp, bool do_RR) {
     const DScene& sc = *c.sc;
-    if (h.empty) return false;
+    if (data.n > sc.integrator.max_depth + 1u) return false;
+    if (do_RR && sc.integrator.russian_roulette) {
+        aw(c.A, (data.base + data.n - 1u) * kVertWords + kOffRr) = data.rr;
+        const float r = data.throughput < 1.f ? fmaxf(data.throughput, .5f) : 1.f;
+        if (rnd(smp) <= r) { const float s = 1.f / r; data.rr *= s; data.throughput *= s; }
+        else return false;
+    }
+    return true;
+}
+// second half of sample_fraunhofer_fsd_interaction (:318-346): the sampled direction becomes an FSD vertex
+WT_D bool bd_walk_fsd_finish(BCtx& c, BWalk& data, Sampler& smp, int ai, V3 interaction_wp, float beam_dist, V3 wo, float dpd, float wgt, uint32_t& n_vert) {
+    if (dpd == 0.f || wgt == 0.f) return false;
+    const V3 wow = to_world(cone_frame(data.beam.env), wo);
+    BVertex v; v.type = BV_FSD; v.fwd = data.fwd; v.delta = 0u; v.ffsd = 1u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
+    v.gkind = BG_POINT; v.p = interaction_wp; v.tuid = WTGPU_INVALID_IDX; v.bary = mk2(0.f, 0.f); v.fp.x = mk2(1.f, 0.f); v.fp.la = v.fp.lb = 0.f; v.dn = mk3(0.f, 0.f, 1.f);
+    v.emitter = -1; v.bsdf = -1; v.fsd = ai; v.pad_ = 0u;
+    if (!bd_append(c, data, v, pd_dens(dpd), pd_dens(dpd))) return false;
+    ++n_vert;
+    beam_transform_region(data.beam, interaction_wp, beam_dist, wow, wgt);
+    data.throughput *= wgt;
+    return bd_continue_walk(c, data, smp, true);
+}
+enum : int { BD_END = 0, BD_CONTINUE = 1, BD_FSD_DEFERRED = 2 };
+// One vertex of a subpath: the body of plt_bdpt::random_walk (plt_bdpt_detail.hpp:470-526) after the traverse.
+// defer_fsd: stop after the aperture is built (BD_FSD_DEFERRED, aperture index data.ap0 + data.n_ap - 1) so that the caller can run
+// the rejection sampler elsewhere and resume with bd_walk_fsd_finish.
+WT_NI int bd_walk_step(BCtx& c, BWalk& data, Sampler& smp, const BHit& h, const uint32_t* edges, uint32_t& n_vert, bool defer_fsd) {
+    const DScene& sc = *c.sc;
+    if (h.empty) return BD_END;
     if (h.overflow) c.overflow = true;
     Beam& beam = data.beam;
     const float beam_dist = h.dist;
@@ -573,18 +601,18 @@ WT_NI bool bd_walk_step(BCtx& c, BWalk& data, Sampler& smp, const BHit& h, const
         const V3 wiw = -dir;
         const V3 wi = to_local(srf.shading, wiw);
         const float wig = dot(wiw, ng);
-        if (wig * wi.z <= 0.f) return false;
+        if (wig * wi.z <= 0.f) return BD_END;
         BsdfQuery q; q.k = beam.k; q.fwd = data.fwd; q.lobes = 0xffffffffu;
         const BsdfSample bs = bsdf_sample(sc, bsdf, wi, q, smp);
-        if (!bs.valid || bs.dpd.v == 0.f) return false;
+        if (!bs.valid || bs.dpd.v == 0.f) return BD_END;
         const V3 wow = normalize(to_world(srf.shading, bs.wo));
         const float wog = dot(wow, ng);
-        if (wog * bs.wo.z <= 0.f) return false;
+        if (wog * bs.wo.z <= 0.f) return BD_END;
         BsdfQuery qr = q; qr.fwd = !data.fwd;
         const Pd pdf_revr = pd_dens(bsdf_pdf(sc, bsdf, bs.wo, wi, qr));
         BVertex v; v.type = BV_SURFACE; v.fwd = data.fwd; v.delta = bs.dpd.disc; v.ffsd = 0u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
         v.gkind = BG_SURFACE; v.p = srf.wp; v.tuid = h.primary; v.bary = mk2(h.bx, h.by); v.fp = srf.fp; v.dn = mk3(0.f, 0.f, 1.f); v.emitter = -1; v.bsdf = bsdf; v.fsd = -1; v.pad_ = 0u;
-        if (!bd_append(c, data, v, bs.dpd, pdf_revr)) return false;
+        if (!bd_append(c, data, v, bs.dpd, pdf_revr)) return BD_END;
         ++n_vert;
         float w = 1.f;
         if (!veq(ns, ng)) w *= snc_scale(data.fwd, wig, wog, wi.z, bs.wo.z);
@@ -592,35 +620,20 @@ WT_NI bool bd_walk_step(BCtx& c, BWalk& data, Sampler& smp, const BHit& h, const
         data.throughput *= w * bs.M.m[0];
         if (!data.fwd && bs.eta.re != 1.f) data.throughput /= sqrf(bs.eta.re);
     } else if (!h.ballistic && sc.integrator.fsd && h.n_edges) {       // sample_fraunhofer_fsd_interaction (:288-346)
-        if (data.n_ap >= (uint32_t)kMaxFApWalk) { c.overflow = true; return false; }
+        if (data.n_ap >= (uint32_t)kMaxFApWalk) { c.overflow = true; return BD_END; }
         const int ai = (int)(data.ap0 + data.n_ap);
         const G2 wf = wavefront_of(beam, beam_dist);
         const uint32_t nseg = fraunhofer_build(sc, c.A, ai, beam_frame, beam.k, 1.f - h.flux, beam.env, edges, h.n_edges, wf, c.overflow);
         if (nseg == 0u) { beam_transform_restart(data.beam, interaction_wp, beam_dist); do_RR = false; }
         else {
             ++data.n_ap;
+            if (defer_fsd) return BD_FSD_DEFERRED;
             V3 wo; float dpd, wgt;
             fraunhofer_sample(c.A, ai, c.lut, smp, wo, dpd, wgt);
-            if (dpd == 0.f || wgt == 0.f) return false;
-            const V3 wow = to_world(beam_frame, wo);
-            BVertex v; v.type = BV_FSD; v.fwd = data.fwd; v.delta = 0u; v.ffsd = 1u; v.pdf_fwd = v.pdf_bwd = -1.f; v.rr = 1.f;
-            v.gkind = BG_POINT; v.p = interaction_wp; v.tuid = WTGPU_INVALID_IDX; v.bary = mk2(0.f, 0.f); v.fp.x = mk2(1.f, 0.f); v.fp.la = v.fp.lb = 0.f; v.dn = mk3(0.f, 0.f, 1.f);
-            v.emitter = -1; v.bsdf = -1; v.fsd = ai; v.pad_ = 0u;
-            if (!bd_append(c, data, v, pd_dens(dpd), pd_dens(dpd))) return false;
-            ++n_vert;
-            beam_transform_region(data.beam, interaction_wp, beam_dist, wow, wgt);
-            data.throughput *= wgt;
+            return bd_walk_fsd_finish(c, data, smp, ai, interaction_wp, beam_dist, wo, dpd, wgt, n_vert) ? BD_CONTINUE : BD_END;
         }
     } else { do_RR = false; beam_transform_restart(data.beam, interaction_wp, beam_dist); }
-    // continue_walk (:167-182)
-    if (data.n > sc.integrator.max_depth + 1u) return false;
-    if (do_RR && sc.integrator.russian_roulette) {
-        aw(c.A, (data.base + data.n - 1u) * kVertWords + kOffRr) = data.rr;
-        const float r = data.throughput < 1.f ? fmaxf(data.throughput, .5f) : 1.f;
-        if (rnd(smp) <= r) { const float s = 1.f / r; data.rr *= s; data.throughput *= s; }
-        else return false;
-    }
-    return true;
+    return bd_continue_walk(c, data, smp, do_RR) ? BD_CONTINUE : BD_END;
 }
 // key for the material sort of subpath walkers: bsdf id | fsd | null | miss
 WT_D uint32_t bd_hit_key(const DScene& sc, const BHit& h, uint32_t n_keys) {
@@ -863,7 +876,7 @@ __global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
                 TravOut tr; BHit h;
                 traverse(sc, w[wi].beam.env, w[wi].prev_geo, wavenum_to_wavelen(w[wi].beam.k), force_rt, tris, tr, ctr);
                 bd_resolve_hit(sc, w[wi].beam, tr, tris, edges, h);
-                if (!bd_walk_step(c, w[wi], smp, h, edges, n_vert)) break;
+                if (bd_walk_step(c, w[wi], smp, h, edges, n_vert, false) != BD_CONTINUE) break;
             }
         }
         float L0 = 0.f;
@@ -894,6 +907,9 @@ struct BdArgs {
     FLut lut; float* arena; uint32_t P;
     float4* walkers; float4* headers;
     int* pending; float* L0; uint32_t* nverts; uint32_t* pairs;
+    uint32_t* fsd_list; float4* fsd_out;    // walkers waiting for a Fraunhofer direction sample (two lists, ping-pong); its result / carried state
+    uint32_t fl_cur, fl_next, fl_fin;       // list fed by this iteration's vertex step and consumed by its sampler; carry-over list; list being finished
+    float tag, tag_fin;                     // marks results written by this iteration's sampler / by the sampler whose list is being finished
 };
 WT_D void bd_walker_to_state(const BdWalker& w, uint32_t which, BWalk& d) {
     d.beam = w.beam; d.fwd = which == 1u; d.pdf_from_prev.v = w.pdf_v; d.pdf_from_prev.disc = w.pdf_disc != 0u; d.throughput = w.throughput; d.rr = w.rr;
@@ -964,14 +980,39 @@ __global__ void __launch_bounds__(128) k_bd_traverse(const BdArgs a) {
     count1(&a.r.ctr->overflow, ovf);
 }
 
-__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->n_pairs = 0; } }
+__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->n_pairs = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }
+
+// a walk has ended with n vertices: when it is the sample's second, expand the sample's strategies into the task list
+WT_D void bd_walker_done(const BdArgs& a, uint32_t wid, uint32_t n, uint32_t& n_splat) {
+    const uint32_t slot = wid >> 1, which = wid & 1u;
+    a.nverts[wid] = n;
+    __threadfence();
+    if (atomicSub(&a.pending[slot], 1) == 1) {
+        __threadfence();
+        const uint32_t other = __ldcg(a.nverts + (wid ^ 1u));
+        const uint32_t nsv = which == 0u ? n : other, nev = which == 1u ? n : other;
+        int np = 0;
+        bd_for_each_pair(a.r.sc, nsv, nev, [&](int, int) { ++np; });
+        if (np == 0) n_splat += bd_finalize(a, slot, 0.f);
+        else {
+            a.pending[slot] = np;
+            uint32_t at = (uint32_t)atomicAdd(&a.r.ctr->n_pairs, np);
+            bd_for_each_pair(a.r.sc, nsv, nev, [&](int s, int t) { a.pairs[at++] = slot | ((uint32_t)s << 22) | ((uint32_t)t << 27); });
+        }
+    }
+}
+WT_D void bd_hit_to_bhit(const HitRec& h, BHit& bh) {
+    bh.empty = (h.flags & H_EMPTY) != 0u; bh.ballistic = (h.flags & H_BALLISTIC) != 0u; bh.overflow = (h.flags & H_OVERFLOW) != 0u;
+    bh.primary = h.primary; bh.pdist = h.pdist; bh.bx = h.bx; bh.by = h.by; bh.dist = h.d2i; bh.region_depth = h.region_depth; bh.flux = h.flux; bh.origin = h.origin; bh.n_edges = h.n_edges;
+}
 
 __global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     Counters ctr; counters_zero(ctr);
-    uint32_t n_vert = 0, n_splat = 0, wid = 0; bool survive = false, overflow = false;
+    uint32_t n_vert = 0, n_splat = 0, wid = 0; int res = BD_END; bool overflow = false, act = false;
     if (i < (uint32_t)a.r.ctr->n_sorted) {
         const DScene& sc = a.r.sc;
+        act = true;
         wid = a.r.order[i];
         const uint32_t slot = wid >> 1, which = wid & 1u;
         BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
@@ -979,28 +1020,140 @@ __global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
         HitRec h; soa_load(h, a.r.hit, a.r.pool, wid);
         BdHeader hd; soa_load(hd, a.headers, a.P, slot);
         BWalk d; bd_walker_to_state(w, which, d);
-        BHit bh; bh.empty = (h.flags & H_EMPTY) != 0u; bh.ballistic = (h.flags & H_BALLISTIC) != 0u; bh.overflow = (h.flags & H_OVERFLOW) != 0u;
-        bh.primary = h.primary; bh.pdist = h.pdist; bh.bx = h.bx; bh.by = h.by; bh.dist = h.d2i; bh.region_depth = h.region_depth; bh.flux = h.flux; bh.origin = h.origin; bh.n_edges = h.n_edges;
+        BHit bh; bd_hit_to_bhit(h, bh);
         Sampler smp; smp.k0 = a.r.seed_lo; smp.k1 = a.r.seed_hi; smp.pixel = hd.pixel; smp.sample = hd.sample; smp.d = w.rng_d; smp.stream = 1u + which;
-        survive = bd_walk_step(c, d, smp, bh, h.edges, n_vert);
+        res = bd_walk_step(c, d, smp, bh, h.edges, n_vert, true);
         overflow = c.overflow;
-        if (survive) { bd_state_to_walker(d, smp.d, w); soa_store(w, a.walkers, 2u * a.P, wid); }
-        else {
-            a.nverts[wid] = d.n;
-            __threadfence();
-            if (atomicSub(&a.pending[slot], 1) == 1) {      // the sample's second walk just ended: expand its strategies
-                __threadfence();
-                const uint32_t nsv = which == 0u ? d.n : __ldcg(a.nverts + (wid ^ 1u)), nev = which == 1u ? d.n : __ldcg(a.nverts + (wid ^ 1u));
-                int np = 0;
-                bd_for_each_pair(sc, nsv, nev, [&](int, int) { ++np; });
-                if (np == 0) n_splat += bd_finalize(a, slot, 0.f);
-                else {
-                    a.pending[slot] = np;
-                    uint32_t at = (uint32_t)atomicAdd(&a.r.ctr->n_pairs, np);
-                    bd_for_each_pair(sc, nsv, nev, [&](int s, int t) { a.pairs[at++] = slot | ((uint32_t)s << 22) | ((uint32_t)t << 27); });
+        if (res != BD_END) { bd_state_to_walker(d, smp.d, w); soa_store(w, a.walkers, 2u * a.P, wid); }
+        else bd_walker_done(a, wid, d.n, n_splat);
+    }
+    list_append(a.r.trav_list, &a.r.ctr->n_trav, act && res == BD_CONTINUE, wid);
+    if (act && res == BD_FSD_DEFERRED) a.fsd_out[2u * wid + 1u] = make_float4(0.f, 0.f, 0.f, 0.f);      // .w: 0 fresh, 1 carried over, >= 16 sampled (iteration tag)
+    list_append(a.fsd_list + (size_t)a.fl_cur * 2u * a.P, &a.r.ctr->n_fsd_list[a.fl_cur], act && res == BD_FSD_DEFERRED, wid);
+    flush_counters(a.r.ctr, ctr, true);
+    bd_flush_stats(a.r.ctr, n_splat, n_vert, 0u, 0u, overflow);
+}
+
+// fsd_sampler_t::sample (src/interaction/fsd/fraunhofer/fsd_sampler.cpp:81-113) + free_space_diffraction_t::sample (free_space_diffraction.hpp:68-93)
+// for every walker whose aperture was just built.  Rejection sampling takes a geometric number of tries (a few apertures: thousands),
+// each a sum over the aperture's <= 48 segments, and only ~10^4 walkers need it per iteration: the problem is latency, not throughput.
+// So ONE WARP samples one walker: lane l evaluates segments l and l+32 of the current try, and every lane then adds the per-segment
+// terms in segment order (shuffles), which keeps sums, and therefore accept/reject decisions, bit-identical to the sequential
+// fraunhofer_sample.  All control flow is warp-uniform.  Runs on a second stream, overlapped with the next iteration's kernels; its
+// results are picked up one iteration later.  A launch does not wait for stragglers: after `budget` tries a walker is carried over
+// to the next iteration (the stream is counter-based: only the draw index and the try count are kept).
+__global__ void __launch_bounds__(128) k_bd_fsd_sample(const BdArgs a) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int n_tasks = a.r.ctr->n_fsd_list[a.fl_cur];
+    const uint32_t* list = a.fsd_list + (size_t)a.fl_cur * 2u * a.P;
+    uint32_t* carry_list = a.fsd_list + (size_t)a.fl_next * 2u * a.P;
+    const uint32_t budget = n_tasks > 2048 ? 256u : 0xffffffffu;       // tries per walker per launch; unbounded once only stragglers remain
+    for (;;) {
+        int t = 0;
+        if (lane == 0u) t = atomicAdd(&a.r.ctr->fsd_head, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tasks) break;
+        const uint32_t wid = list[t];
+        const uint32_t slot = wid >> 1, which = wid & 1u;
+        Arena A; A.base = a.arena + (size_t)slot * kArenaWords;
+        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+        const uint32_t w_rng_d = w.rng_d, w_n_ap = w.n_ap;
+        BdHeader h; soa_load(h, a.headers, a.P, slot);
+        const int ai = (int)(which * (uint32_t)kMaxFApWalk + w_n_ap - 1u);
+        const FHead hd = ap_head(A, ai);
+        const uint32_t n = hd.n;
+        const float4 st = a.fsd_out[2u * wid + 1u];      // carried over: resume after the tries already spent
+        const bool carried = st.w == 1.f;
+        Sampler smp; smp.k0 = a.r.seed_lo; smp.k1 = a.r.seed_hi; smp.pixel = h.pixel; smp.sample = h.sample; smp.d = carried ? __float_as_uint(st.y) : w_rng_d; smp.stream = 1u + which;
+        uint32_t tries = carried ? __float_as_uint(st.z) : 0u;
+        const bool rej = n > 1u; const uint32_t max_tries = n * 1024u; const float recp_M = 1.f / (float)n;
+        // this lane's segments and selection masses
+        const bool has0 = lane < n, has1 = lane + 32u < n;
+        FEdge e0, e1; e0.e = e0.v = mk2(0.f, 0.f); e0.a_b = e0.iab_2 = mkc(0.f, 0.f); e1 = e0;
+        float pdf0 = 0.f, pdf1 = 0.f;
+        if (has0) { e0 = ap_edge(A, ai, lane); pdf0 = ap_edge_pdf(A, ai, lane); }
+        if (has1) { e1 = ap_edge(A, ai, lane + 32u); pdf1 = ap_edge_pdf(A, ai, lane + 32u); }
+        V3 wo = mk3(0.f, 0.f, 1.f); float dpd = 0.f, wgt = 0.f;
+        bool finished = false;
+        for (uint32_t spent = 0; spent < budget; ++spent) {
+            // sampleN (fsd_sampler.cpp:37-79): entry 0 is the P0 lobe, entry i the segment i-1
+            const float p = rnd(smp) * 1.f;
+            float cdf = 0.f; uint32_t sel = n;
+            for (uint32_t i = 0; i < n; ++i) {
+                const float q0 = __shfl_sync(0xffffffffu, pdf0, (int)((i - 1u) & 31u)), q1 = __shfl_sync(0xffffffffu, pdf1, (int)((i - 1u) & 31u));
+                cdf += i == 0u ? hd.P0_pdf : (i - 1u < 32u ? q0 : q1);
+                if (p < cdf) { sel = i; break; }
+            }
+            V2 xi;
+            if (sel == 0u) xi = kP0s * normal2d(rnd2(smp));
+            else {
+                const FEdge e = ap_edge(A, ai, sel - 1u);
+                const V2 m = mk2(e.e.y, -e.e.x);
+                const float od = 1.f / (e.e.x * m.y - m.x * e.e.y);
+                const float i00 = m.y * od, i01 = -e.e.y * od, i10 = -m.x * od, i11 = e.e.x * od;
+                const float Aa = cnorm(e.a_b), Bb = cnorm(e.iab_2);
+                const float pp = rnd(smp) * (Aa + Bb);
+                const V3 r3 = rnd3(smp);
+                const V2 z = pp < Aa ? flut_sample(a.lut, r3, a.lut.th1, a.lut.c1) : flut_sample(a.lut, r3, a.lut.th2, a.lut.c2);
+                xi = mk2(z.x * i00 + z.y * i01, z.x * i10 + z.y * i11);
+            }
+            // per-segment terms: Psi (complex) and Psi2
+            C2 t0 = mkc(0.f, 0.f), t1 = mkc(0.f, 0.f); float d0 = 0.f, d1 = 0.f;
+            if (has0) { const V2 z = fzeta(e0, xi); const C2 sx = e0.a_b * falpha1(z.x, z.y) + e0.iab_2 * falpha2(z.x, z.y); const float rho = length2(e0.e); float sn, cs; sincosf(-dot(e0.v, xi), &sn, &cs); t0 = mkc(rho * cs, rho * sn) * sx; d0 = sqrf(rho) * cnorm(sx); }
+            if (has1) { const V2 z = fzeta(e1, xi); const C2 sx = e1.a_b * falpha1(z.x, z.y) + e1.iab_2 * falpha2(z.x, z.y); const float rho = length2(e1.e); float sn, cs; sincosf(-dot(e1.v, xi), &sn, &cs); t1 = mkc(rho * cs, rho * sn) * sx; d1 = sqrf(rho) * cnorm(sx); }
+            C2 acc = mkc(0.f, 0.f); float dens = 0.f;
+            for (uint32_t jj = 0; jj < n; ++jj) {
+                const int src = (int)(jj & 31u);
+                const float re = __shfl_sync(0xffffffffu, jj < 32u ? t0.re : t1.re, src), im = __shfl_sync(0xffffffffu, jj < 32u ? t0.im : t1.im, src), dd = __shfl_sync(0xffffffffu, jj < 32u ? d0 : d1, src);
+                acc = acc + mkc(re, im); dens += dd;
+            }
+            const float g = dens * fchi_e(xi) + hd.P0 * kInvTwoPi / sqrf(kP0s) * fchi_0(xi);
+            const float f = cnorm(acc) * fchi_e(xi) + hd.psi02 * fchi_0(xi);
+            const bool done = rej ? rnd(smp) * g < f * recp_M : true;
+            if (done) {
+                const float pdf = f * hd.recp_I;
+                if (pdf > 0.f) {
+                    const V2 zeta = xi / hd.k;
+                    const V2 wl = mk2(zeta.x / sqrtf(1.f + sqrf(zeta.x)), zeta.y / sqrtf(1.f + sqrf(zeta.y)));
+                    const float wo2 = length2(wl);
+                    if (wo2 < .85f) { wo = mk3(wl.x, wl.y, sqrtf(1.f - wo2)); dpd = pdf; wgt = 1.f; }
                 }
+                finished = true; break;
+            }
+            if (++tries == max_tries) { finished = true; break; }
+        }
+        if (lane == 0u) {
+            if (finished) {
+                a.fsd_out[2u * wid] = make_float4(wo.x, wo.y, wo.z, dpd);
+                a.fsd_out[2u * wid + 1u] = make_float4(wgt, __uint_as_float(smp.d), 0.f, a.tag);
+            } else {
+                a.fsd_out[2u * wid + 1u] = make_float4(0.f, __uint_as_float(smp.d), __uint_as_float(tries), 1.f);
+                carry_list[atomicAdd(&a.r.ctr->n_fsd_list[a.fl_next], 1)] = wid;
             }
         }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_bd_fsd_finish(const BdArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ctr; counters_zero(ctr);
+    uint32_t n_vert = 0, n_splat = 0, wid = 0; bool survive = false, overflow = false;
+    if (i < (uint32_t)a.r.ctr->n_fsd_list[a.fl_fin] && a.fsd_out[2u * a.fsd_list[(size_t)a.fl_fin * 2u * a.P + i] + 1u].w == a.tag_fin) {
+        const DScene& sc = a.r.sc;
+        wid = a.fsd_list[(size_t)a.fl_fin * 2u * a.P + i];
+        const uint32_t slot = wid >> 1, which = wid & 1u;
+        BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+        HitRec h; soa_load(h, a.r.hit, a.r.pool, wid);
+        BdHeader hd; soa_load(hd, a.headers, a.P, slot);
+        BWalk d; bd_walker_to_state(w, which, d);
+        const float4 o0 = a.fsd_out[2u * wid], o1 = a.fsd_out[2u * wid + 1u];
+        Sampler smp; smp.k0 = a.r.seed_lo; smp.k1 = a.r.seed_hi; smp.pixel = hd.pixel; smp.sample = hd.sample; smp.d = __float_as_uint(o1.y); smp.stream = 1u + which;
+        const V3 interaction_wp = h.origin + h.d2i * d.beam.env.d;
+        survive = bd_walk_fsd_finish(c, d, smp, (int)(d.ap0 + d.n_ap - 1u), interaction_wp, h.d2i, mk3(o0.x, o0.y, o0.z), o0.w, o1.x, n_vert);
+        overflow = c.overflow;
+        if (survive) { bd_state_to_walker(d, smp.d, w); soa_store(w, a.walkers, 2u * a.P, wid); }
+        else bd_walker_done(a, wid, d.n, n_splat);
     }
     list_append(a.r.trav_list, &a.r.ctr->n_trav, survive, wid);
     flush_counters(a.r.ctr, ctr, true);

@@ -71,6 +71,7 @@ struct DevCounters {
     int n_trav;                         // entries of trav_list (paths to traverse this iteration)
     int n_sorted;                       // live paths in `order`
     int n_pairs;                        // plt_bdpt: (s,t) strategies queued this iteration
+    int n_fsd_list[3], fsd_head;        // plt_bdpt: walkers waiting for a Fraunhofer sample (three rotating lists); work-fetch cursor
 };
 
 struct RenderArgs {
@@ -566,17 +567,21 @@ struct wtgpu_scene {
     float* bdpt_arena = nullptr; uint32_t bdpt_P = 0;
     // plt_bdpt wavefront state (P sample slots, 2P walkers)
     float4 *bd_walkers = nullptr, *bd_headers = nullptr, *bd_hit = nullptr;
-    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_pairs = nullptr, *bd_alive = nullptr, *bd_keys = nullptr, *bd_order = nullptr, *bd_trav = nullptr;
+    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_pairs = nullptr, *bd_alive = nullptr, *bd_keys = nullptr, *bd_order = nullptr, *bd_trav = nullptr, *bd_fsd_list = nullptr; float4* bd_fsd_out = nullptr;
     uint32_t bd_wave_P = 0;
+    cudaStream_t bd_stream = nullptr; cudaEvent_t bd_ev_shade = nullptr, bd_ev_samp = nullptr;   // Fraunhofer sampler overlap
     void free_bd_wave() {
-        for (void* p : { (void*)bd_walkers, (void*)bd_headers, (void*)bd_hit, (void*)bd_pending, (void*)bd_L0, (void*)bd_nverts, (void*)bd_pairs, (void*)bd_alive, (void*)bd_keys, (void*)bd_order, (void*)bd_trav }) if (p) cudaFree(p);
-        bd_walkers = bd_headers = bd_hit = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_pairs = bd_alive = bd_keys = bd_order = bd_trav = nullptr; bd_wave_P = 0;
+        for (void* p : { (void*)bd_walkers, (void*)bd_headers, (void*)bd_hit, (void*)bd_pending, (void*)bd_L0, (void*)bd_nverts, (void*)bd_pairs, (void*)bd_alive, (void*)bd_keys, (void*)bd_order, (void*)bd_trav, (void*)bd_fsd_list, (void*)bd_fsd_out }) if (p) cudaFree(p);
+        bd_walkers = bd_headers = bd_hit = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_pairs = bd_alive = bd_keys = bd_order = bd_trav = bd_fsd_list = nullptr; bd_fsd_out = nullptr; bd_wave_P = 0;
     }
     ~wtgpu_scene() {
         cudaSetDevice(device);
         for (void* p : allocs) cudaFree(p);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         free_bd_wave();
+        if (bd_stream) cudaStreamDestroy(bd_stream);
+        if (bd_ev_shade) cudaEventDestroy(bd_ev_shade);
+        if (bd_ev_samp) cudaEventDestroy(bd_ev_samp);
         for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list, (void*)bdpt_arena }) if (p) cudaFree(p);
     }
 };
@@ -743,16 +748,26 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             CK(cudaMalloc(&s->bd_pending, 4ull * P)); CK(cudaMalloc(&s->bd_L0, 4ull * P)); CK(cudaMalloc(&s->bd_nverts, 4ull * W2)); CK(cudaMalloc(&s->bd_alive, 4ull * P));
             CK(cudaMalloc(&s->bd_keys, 4ull * W2)); CK(cudaMalloc(&s->bd_order, 4ull * W2)); CK(cudaMalloc(&s->bd_trav, 4ull * W2));
             CK(cudaMalloc(&s->bd_pairs, 4ull * (size_t)P * max_pairs));
+            CK(cudaMalloc(&s->bd_fsd_list, 12ull * W2)); CK(cudaMalloc(&s->bd_fsd_out, 32ull * W2));
             s->bd_wave_P = P;
         }
         if (P > (1u << 22)) { g_err = "plt_bdpt: pool_size > 4M sample slots"; return WTGPU_E_INVALID; }
         BdArgs b;
         b.r = a; b.r.hit = s->bd_hit; b.r.alive = s->bd_alive; b.r.keys = s->bd_keys; b.r.order = s->bd_order; b.r.trav_list = s->bd_trav; b.r.pool = W2;
         b.lut = s->lut; b.arena = s->bdpt_arena; b.P = P; b.walkers = s->bd_walkers; b.headers = s->bd_headers;
-        b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs;
+        b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs; b.fsd_list = s->bd_fsd_list; b.fsd_out = s->bd_fsd_out;
+        const bool has_fsd = s->integ.fsd != 0u;
         CK(cudaMemsetAsync(s->bd_alive, 0, 4ull * P, st));
         const dim3 gP((P + 127) / 128), gW((W2 + 127) / 128), gC(148 * 8);
+        if (has_fsd && !s->bd_stream) {
+            CK(cudaStreamCreateWithFlags(&s->bd_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s->bd_ev_shade, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->bd_ev_samp, cudaEventDisableTiming));
+        }
         for (;;) {
+            // Fraunhofer direction sampling of iteration j runs on bd_stream, overlapped with the strategies of j and the walk kernels
+            // of j+1; its walkers rejoin at "finish" in iteration j+1.  Three rotating lists keep producer and consumers apart.
+            b.fl_cur = (uint32_t)(iters % 3ull); b.fl_next = (uint32_t)((iters + 1ull) % 3ull); b.fl_fin = (uint32_t)((iters + 2ull) % 3ull);
+            b.tag = 16.f + (float)(iters % 1024ull); b.tag_fin = 16.f + (float)((iters + 1023ull) % 1024ull);
             mark();
             k_bd_generate<<<gP, blk, 0, st>>>(b); ++launches; mark();
             k_bd_traverse<<<gW, blk, 0, st>>>(b); ++launches; mark();
@@ -760,14 +775,23 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             k_scan<<<1, 32, 0, st>>>(b.r);
             k_scatter<<<gW, blk, 0, st>>>(b.r); launches += 3; mark();
             k_bd_reset<<<1, 32, 0, st>>>(b);
-            k_bd_shade<<<gW, blk, 0, st>>>(b);
-            k_bd_connect<<<gC, blk, 0, st>>>(b); launches += 3; mark();
+            k_bd_shade<<<gW, blk, 0, st>>>(b); launches += 2;
+            if (has_fsd) {
+                CK(cudaEventRecord(s->bd_ev_shade, st));
+                if (iters > 0) { CK(cudaStreamWaitEvent(st, s->bd_ev_samp, 0)); k_bd_fsd_finish<<<gW, blk, 0, st>>>(b); ++launches; }
+                CK(cudaStreamWaitEvent(s->bd_stream, s->bd_ev_shade, 0));
+                CK(cudaMemsetAsync(&s->ctr->fsd_head, 0, sizeof(int), s->bd_stream));
+                k_bd_fsd_sample<<<gC, blk, 0, s->bd_stream>>>(b); ++launches;
+                CK(cudaEventRecord(s->bd_ev_samp, s->bd_stream));
+            }
+            k_bd_connect<<<gC, blk, 0, st>>>(b); ++launches; mark();
             ++iters;
             CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (hctr->next_sample >= total && hctr->live <= 0) break;
             if (iters > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
         }
+        if (has_fsd) CK(cudaStreamSynchronize(s->bd_stream));
     } else
     for (;;) {
         mark();
