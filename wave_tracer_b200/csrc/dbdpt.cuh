@@ -900,6 +900,7 @@ __global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
 // (id = 2 slot + which) that advance one vertex per iteration through  traverse -> material sort -> vertex step; when both have
 // ended, the slot's (s,t) strategies are expanded into a task list and evaluated one strategy per thread; the last strategy to
 // finish splats the sample's block contribution and frees the slot.
+constexpr int kPairClasses = 5;
 struct alignas(16) BdWalker { Beam beam; Geo prev_geo; float pdf_v; uint32_t pdf_disc; float throughput, rr; uint32_t n, rng_d, n_ap, pad0; };
 struct alignas(16) BdHeader { uint32_t pixel, sample, ex, ey; float k, rspd, wpd_v, ox, oy; uint32_t elx, ely, pad0; };
 struct BdArgs {
@@ -908,6 +909,7 @@ struct BdArgs {
     float4* walkers; float4* headers;
     int* pending; float* L0; uint32_t* nverts; uint32_t* pairs;
     uint32_t* fsd_list; float4* fsd_out;    // walkers waiting for a Fraunhofer direction sample (two lists, ping-pong); its result / carried state
+    size_t pair_off[kPairClasses];          // start of each strategy class's segment of `pairs`
     uint32_t fl_cur, fl_next, fl_fin;       // list fed by this iteration's vertex step and consumed by its sampler; carry-over list; list being finished
     float tag, tag_fin;                     // marks results written by this iteration's sampler / by the sampler whose list is being finished
 };
@@ -980,9 +982,12 @@ __global__ void __launch_bounds__(128) k_bd_traverse(const BdArgs a) {
     count1(&a.r.ctr->overflow, ovf);
 }
 
-__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->n_pairs = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }
+__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }
 
-// a walk has ended with n vertices: when it is the sample's second, expand the sample's strategies into the task list
+// Strategy classes = the branches of connect_subpaths (plt_bdpt_detail.hpp:747-923): each class has its own task list and its own
+// launch, so a warp runs one branch (emission hit / sensor hit / emitter-direct / sensor-direct / vertex-vertex).
+WT_D int bd_pair_class(int s, int t) { return s == 0 ? 0 : t == 0 ? 1 : s == 1 ? 2 : t == 1 ? 3 : 4; }
+// a walk has ended with n vertices: when it is the sample's second, expand the sample's strategies into the task lists
 WT_D void bd_walker_done(const BdArgs& a, uint32_t wid, uint32_t n, uint32_t& n_splat) {
     const uint32_t slot = wid >> 1, which = wid & 1u;
     a.nverts[wid] = n;
@@ -996,8 +1001,12 @@ WT_D void bd_walker_done(const BdArgs& a, uint32_t wid, uint32_t n, uint32_t& n_
         if (np == 0) n_splat += bd_finalize(a, slot, 0.f);
         else {
             a.pending[slot] = np;
-            uint32_t at = (uint32_t)atomicAdd(&a.r.ctr->n_pairs, np);
-            bd_for_each_pair(a.r.sc, nsv, nev, [&](int s, int t) { a.pairs[at++] = slot | ((uint32_t)s << 22) | ((uint32_t)t << 27); });
+            int cnt[kPairClasses] = { 0, 0, 0, 0, 0 };
+            bd_for_each_pair(a.r.sc, nsv, nev, [&](int s, int t) { ++cnt[bd_pair_class(s, t)]; });
+            uint32_t at[kPairClasses];
+#pragma unroll
+            for (int c = 0; c < kPairClasses; ++c) at[c] = cnt[c] ? (uint32_t)atomicAdd(&a.r.ctr->n_pairs[c], cnt[c]) : 0u;
+            bd_for_each_pair(a.r.sc, nsv, nev, [&](int s, int t) { const int c = bd_pair_class(s, t); a.pairs[a.pair_off[c] + at[c]++] = slot | ((uint32_t)s << 22) | ((uint32_t)t << 27); });
         }
     }
 }
@@ -1047,13 +1056,17 @@ __global__ void __launch_bounds__(128) k_bd_fsd_sample(const BdArgs a) {
     const int n_tasks = a.r.ctr->n_fsd_list[a.fl_cur];
     const uint32_t* list = a.fsd_list + (size_t)a.fl_cur * 2u * a.P;
     uint32_t* carry_list = a.fsd_list + (size_t)a.fl_next * 2u * a.P;
-    const uint32_t budget = n_tasks > 2048 ? 256u : 0xffffffffu;       // tries per walker per launch; unbounded once only stragglers remain
+    uint32_t budget = n_tasks > 2048 ? 160u : 0xffffffffu;       // tries per WARP per launch; unbounded once only stragglers remain
     for (;;) {
         int t = 0;
         if (lane == 0u) t = atomicAdd(&a.r.ctr->fsd_head, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_tasks) break;
         const uint32_t wid = list[t];
+        if (budget == 0u) {     // out of budget: hand the rest of the list to the next iteration untouched
+            if (lane == 0u) carry_list[atomicAdd(&a.r.ctr->n_fsd_list[a.fl_next], 1)] = wid;
+            continue;
+        }
         const uint32_t slot = wid >> 1, which = wid & 1u;
         Arena A; A.base = a.arena + (size_t)slot * kArenaWords;
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
@@ -1075,7 +1088,7 @@ __global__ void __launch_bounds__(128) k_bd_fsd_sample(const BdArgs a) {
         if (has1) { e1 = ap_edge(A, ai, lane + 32u); pdf1 = ap_edge_pdf(A, ai, lane + 32u); }
         V3 wo = mk3(0.f, 0.f, 1.f); float dpd = 0.f, wgt = 0.f;
         bool finished = false;
-        for (uint32_t spent = 0; spent < budget; ++spent) {
+        for (; budget > 0u; --budget) {
             // sampleN (fsd_sampler.cpp:37-79): entry 0 is the P0 lobe, entry i the segment i-1
             const float p = rnd(smp) * 1.f;
             float cdf = 0.f; uint32_t sel = n;
@@ -1118,9 +1131,9 @@ __global__ void __launch_bounds__(128) k_bd_fsd_sample(const BdArgs a) {
                     const float wo2 = length2(wl);
                     if (wo2 < .85f) { wo = mk3(wl.x, wl.y, sqrtf(1.f - wo2)); dpd = pdf; wgt = 1.f; }
                 }
-                finished = true; break;
+                finished = true; --budget; break;
             }
-            if (++tries == max_tries) { finished = true; break; }
+            if (++tries == max_tries) { finished = true; --budget; break; }
         }
         if (lane == 0u) {
             if (finished) {
@@ -1160,13 +1173,14 @@ __global__ void __launch_bounds__(128) k_bd_fsd_finish(const BdArgs a) {
     bd_flush_stats(a.r.ctr, n_splat, n_vert, 0u, 0u, overflow);
 }
 
-__global__ void __launch_bounds__(128) k_bd_connect(const BdArgs a) {
+template <int CLS> __global__ void __launch_bounds__(128) k_bd_connect(const BdArgs a) {
     Counters ctr; counters_zero(ctr);
     uint32_t n_conn = 0, n_splat = 0; bool overflow = false;
-    const uint32_t np = (uint32_t)a.r.ctr->n_pairs;
+    const uint32_t np = (uint32_t)a.r.ctr->n_pairs[CLS];
+    const uint32_t* pairs = a.pairs + a.pair_off[CLS];
     const DScene& sc = a.r.sc;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
-        const uint32_t task = a.pairs[i];
+        const uint32_t task = pairs[i];
         const uint32_t slot = task & 0x3fffffu; const int s = (int)((task >> 22) & 31u), t = (int)(task >> 27);
         BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
         BdHeader hd; soa_load(hd, a.headers, a.P, slot);

@@ -70,7 +70,7 @@ struct DevCounters {
     int live;                           // paths alive
     int n_trav;                         // entries of trav_list (paths to traverse this iteration)
     int n_sorted;                       // live paths in `order`
-    int n_pairs;                        // plt_bdpt: (s,t) strategies queued this iteration
+    int n_pairs[5];                     // plt_bdpt: (s,t) strategies queued this iteration, per strategy class
     int n_fsd_list[3], fsd_head;        // plt_bdpt: walkers waiting for a Fraunhofer sample (three rotating lists); work-fetch cursor
 };
 
@@ -735,6 +735,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         CK(cudaStreamSynchronize(st));
     } else if (bdpt) {      // wavefront (dbdpt.cuh driver 2)
         const uint32_t P = pool, W2 = 2u * pool;
+        const uint32_t nmaxv = s->integ.max_depth + 3u;
         uint32_t max_pairs = 0;     // strategies per sample: the enumeration of plt_bdpt.cpp:96-110 at full subpath lengths
         {
             const int n = (int)s->integ.max_depth + 2, maxd = (int)s->integ.max_depth;
@@ -747,7 +748,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             CK(cudaMalloc(&s->bd_hit, (size_t)chunks_of<HitRec>() * 16 * W2));
             CK(cudaMalloc(&s->bd_pending, 4ull * P)); CK(cudaMalloc(&s->bd_L0, 4ull * P)); CK(cudaMalloc(&s->bd_nverts, 4ull * W2)); CK(cudaMalloc(&s->bd_alive, 4ull * P));
             CK(cudaMalloc(&s->bd_keys, 4ull * W2)); CK(cudaMalloc(&s->bd_order, 4ull * W2)); CK(cudaMalloc(&s->bd_trav, 4ull * W2));
-            CK(cudaMalloc(&s->bd_pairs, 4ull * (size_t)P * max_pairs));
+            CK(cudaMalloc(&s->bd_pairs, 4ull * (size_t)P * (max_pairs + 4ull * nmaxv)));
             CK(cudaMalloc(&s->bd_fsd_list, 12ull * W2)); CK(cudaMalloc(&s->bd_fsd_out, 32ull * W2));
             s->bd_wave_P = P;
         }
@@ -756,6 +757,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         b.r = a; b.r.hit = s->bd_hit; b.r.alive = s->bd_alive; b.r.keys = s->bd_keys; b.r.order = s->bd_order; b.r.trav_list = s->bd_trav; b.r.pool = W2;
         b.lut = s->lut; b.arena = s->bdpt_arena; b.P = P; b.walkers = s->bd_walkers; b.headers = s->bd_headers;
         b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs; b.fsd_list = s->bd_fsd_list; b.fsd_out = s->bd_fsd_out;
+        for (int c = 0; c < 5; ++c) b.pair_off[c] = (size_t)P * nmaxv * (size_t)c;      // classes 0-3 hold <= max_depth+3 strategies per sample, class 4 the rest
         const bool has_fsd = s->integ.fsd != 0u;
         CK(cudaMemsetAsync(s->bd_alive, 0, 4ull * P, st));
         const dim3 gP((P + 127) / 128), gW((W2 + 127) / 128), gC(148 * 8);
@@ -784,7 +786,8 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
                 k_bd_fsd_sample<<<gC, blk, 0, s->bd_stream>>>(b); ++launches;
                 CK(cudaEventRecord(s->bd_ev_samp, s->bd_stream));
             }
-            k_bd_connect<<<gC, blk, 0, st>>>(b); ++launches; mark();
+            k_bd_connect<0><<<gC, blk, 0, st>>>(b); k_bd_connect<1><<<gC, blk, 0, st>>>(b); k_bd_connect<2><<<gC, blk, 0, st>>>(b);
+            k_bd_connect<3><<<gC, blk, 0, st>>>(b); k_bd_connect<4><<<gC, blk, 0, st>>>(b); launches += 5; mark();
             ++iters;
             CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
