@@ -2,10 +2,10 @@
 """bench.py -- throughput of the B200 wave_tracer hot path on BASELINE.json's metric (Msamples/sec).
 
 Workload (config.workload): BASELINE.json configs[1], scenes/diffraction_simple/double_slits.xml -D res=1440,spp=1024,pattern=true
-(film 1440x360, 5.31e8 samples), geometry/emitters/sensor restated procedurally (wave_tracer_b200/scenes.py).  The reference file
-selects plt_bdpt; this round's device integrator is plt_path forward + UTD (as double_slits_and_reflectors.xml drives the same
-geometry) -- stated in config.integrator.  A "step" renders the full film at `--spp-per-step` samples per element (sample indices
-[step*S, step*S+S) of the 1024): cost is linear in spp, samples are independent.
+(film 1440x360, 5.31e8 samples), geometry/emitters/sensor restated procedurally (wave_tracer_b200/scenes.py), integrator plt_bdpt with
+Fraunhofer FSD, max_depth 16, as the reference file selects (double_slits.xml:42-44).  `--integrator plt_path` runs the same geometry
+with plt_path forward + UTD (as double_slits_and_reflectors.xml does).  A "step" renders the full film at `--spp-per-step` samples per
+element (sample indices [step*S, step*S+S) of the 1024): cost is linear in spp, samples are independent.
 
   python bench.py --gpus N --steps K --warmup W            (torchrun for N>1; one rank per GPU; NCCL film reduce every step)
   python bench.py --impl reference ...                     the CPU implementation of the same path (oracle port; the reference
@@ -25,7 +25,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 RES, SPP = 1440, 1024
 WORKLOAD = "diffraction_simple/double_slits res=1440 spp=1024 pattern=true (film 1440x360, lambda=0.05mm, procedural restatement)"
-INTEGRATOR = "plt_path forward + UTD FSD, max_depth 16, RR off (reference XML selects plt_bdpt: not implemented on device yet)"
+INTEGRATORS = {"plt_bdpt": "plt_bdpt (MIS, emitter+sensor direct), Fraunhofer FSD, max_depth 16 -- the reference file's integrator",
+               "plt_path": "plt_path forward + UTD FSD, max_depth 16, RR off"}
 
 
 def measured_hbm_peak():
@@ -71,8 +72,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--integrator", default="plt_bdpt", choices=["plt_bdpt", "plt_path"])
     ap.add_argument("--spp-per-step", type=int, default=16)
-    ap.add_argument("--pool", type=int, default=1 << 21)
+    ap.add_argument("--pool", type=int, default=0, help="paths (plt_path) / sample slots (plt_bdpt) in flight; 0: 1M / 256k")
     ap.add_argument("--res", type=int, default=RES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sort", action="store_true")
@@ -80,11 +82,13 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     from wave_tracer_b200 import scenes
-    built = scenes.double_slits(res=a.res, spp=SPP).build()
+    bdpt = a.integrator == "plt_bdpt"
+    if a.pool == 0: a.pool = (1 << 18) if bdpt else (1 << 20)
+    built = scenes.double_slits(res=a.res, spp=SPP, integrator=a.integrator, lut=(2048, 1024)).build()
     W, H = built.width, built.height
-    config = {"workload": WORKLOAD if a.res == RES else WORKLOAD.replace("1440", str(a.res)), "integrator": INTEGRATOR, "film": [W, H],
+    config = {"workload": WORKLOAD if a.res == RES else WORKLOAD.replace("1440", str(a.res)), "integrator": INTEGRATORS[a.integrator], "film": [W, H],
               "spp_per_step": a.spp_per_step, "sampler": "philox4x32-10 counter streams keyed (seed,pixel,sample)",
-              "l2": "path-state pool (%d paths x 0.7 KB) and film exceed the 126 MB L2; no flush needed" % a.pool}
+              "l2": ("%d sample slots x 30 KB of subpath vertices/apertures" % a.pool if bdpt else "path-state pool (%d paths x 0.7 KB)" % a.pool) + " exceed the 126 MB L2; no flush needed"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -141,24 +145,35 @@ def main():
     total_samples = samples_rank * world
     value = total_samples / (ms * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (k_traverse): algorithmic bytes from the device counters of the same run
-    core_b, hit_b = 240, 160     # PathCore read + HitRec/key write per segment (16-B chunks: 15 / 10)
-    seg = sum(s["segments"] for s in stats); nodes = sum(s["traverse_nodes"] for s in stats); tris = sum(s["traverse_tris"] for s in stats)
-    trav_ms = sum(s["traverse_ms"] for s in stats); shade_ms = sum(s["shade_ms"] for s in stats)
-    trav_launches = sum(s["iterations"] for s in stats)
-    alg_bytes = seg * (core_b + hit_b + 4) + 256 * nodes + 48 * tris
+    # ---- roofline of the dominant kernel: algorithmic bytes from the device counters of the same run (DESIGN.md "Roofline model")
     peak, which = measured_hbm_peak()
-    achieved = alg_bytes / max(trav_ms * 1e-3, 1e-12) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_traverse", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                "traffic": None, "alg_bytes_per_launch": alg_bytes / max(1, trav_launches), "avg_launch_ms": trav_ms / max(1, trav_launches),
-                "share_of_step": {"k_traverse": trav_ms / ms, "k_shade": shade_ms / ms}}
+    tot = lambda k: sum(s[k] for s in stats)
+    trav_ms, shade_ms, conn_ms, its = tot("traverse_ms"), tot("shade_ms"), tot("connect_ms"), tot("iterations")
+    if bdpt:
+        # k_bd_traverse: walker record read (224 B) + hit record + key + list entry written (144+4+4 B) per walker step, 256 B per node, 48 B per triangle
+        b_trav = tot("walker_steps") * (224 + 152) + 256 * tot("traverse_nodes") + 48 * tot("traverse_tris")
+        # k_bd_connect<*>: task (4 B) + sample header (48 B) + the distinct 272-B vertex records a strategy reads (2,2,2,2,4 by class) + 12 B of
+        # pdf/delta scalars per subpath vertex for MIS (~ 4 vertices) + shadow-ray nodes/triangles + the film/L0 atomic (8 B)
+        strat = [sum(s["strategies"][c] for s in stats) for c in range(5)]
+        b_conn = sum(n * (4 + 48 + u * 272 + 48 + 8) for n, u in zip(strat, (2, 2, 2, 2, 4))) + 256 * (tot("nodes_visited") - tot("traverse_nodes")) + 48 * (tot("tris_tested") - tot("traverse_tris"))
+        kern, kms, kbytes, launches_k = ("k_bd_connect", conn_ms, b_conn, 5 * its) if conn_ms >= trav_ms else ("k_bd_traverse", trav_ms, b_trav, its)
+        share = {"k_bd_traverse": trav_ms / ms, "k_bd_shade(+fsd_finish)": shade_ms / ms, "k_bd_connect": conn_ms / ms}
+    else:
+        core_b, hit_b = 240, 160     # PathCore read + HitRec/key write per segment (16-B chunks: 15 / 10)
+        kbytes = tot("segments") * (core_b + hit_b + 4) + 256 * tot("traverse_nodes") + 48 * tot("traverse_tris")
+        kern, kms, launches_k = "k_traverse", trav_ms, its
+        share = {"k_traverse": trav_ms / ms, "k_shade": shade_ms / ms}
+    achieved = kbytes / max(kms * 1e-3, 1e-12) / 1e9
+    roofline = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
+                "traffic": None, "alg_bytes_per_launch": kbytes / max(1, launches_k), "avg_launch_ms": kms / max(1, launches_k), "share_of_step": share}
 
     if rank == 0:
         # ---- e2e: through the public API with HOST buffers: scene upload (H2D), render, film read-back (D2H) inside the timed region
         from wave_tracer_b200 import render
         h2d = sum(C.sizeof(t) * n for t, n in ((_abi.Node, built.desc.n_nodes), (_abi.Leaf, built.desc.n_leaves), (_abi.Tri, built.desc.n_tris), (_abi.TriMeta, built.desc.n_tris),
                   (_abi.TriShading, built.desc.n_tris), (_abi.Edge, built.desc.n_edges), (_abi.Shape, built.desc.n_shapes), (_abi.Spectrum, built.desc.n_spectra),
-                  (_abi.Bsdf, built.desc.n_bsdfs), (_abi.Emitter, built.desc.n_emitters), (_abi.KDist, built.desc.n_emitters))) + 4 * (built.desc.n_kdist_data + 1024)
+                  (_abi.Bsdf, built.desc.n_bsdfs), (_abi.Emitter, built.desc.n_emitters), (_abi.KDist, built.desc.n_emitters))) + 4 * (built.desc.n_kdist_data + 1024) + \
+            (8 * (built.desc.fsd_lut_n + built.desc.fsd_lut_m ** 2) if bdpt else 0)      # + the Fraunhofer sampling tables
         d2h = W * H * 3 * 4
         render(built, spp=SPP, device=local, sample_range=(0, S), pool_size=a.pool, allow_overflow=True)     # warm
         t0 = time.time(); n_e2e = 0

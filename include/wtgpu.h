@@ -317,6 +317,9 @@ typedef struct wtgpu_stats {
     uint64_t shaded_paths;          /* path-vertices processed by k_shade */
     double   gpu_ms;                /* CUDA-event time of the whole call on its stream */
     double   traverse_ms, shade_ms, generate_ms, sort_ms;
+    double   connect_ms;            /* plt_bdpt: the (s,t) strategy kernels (shade_ms then covers the vertex step only) */
+    uint64_t strategies[5];         /* plt_bdpt: strategies evaluated per class: s=0, t=0, s=1, t=1, vertex-vertex */
+    uint64_t walker_steps;          /* plt_bdpt: subpath-walker traverse() calls */
 } wtgpu_stats;
 
 typedef struct wtgpu_scene wtgpu_scene;

@@ -125,10 +125,10 @@ class Stats(C.Structure):
     _fields_ = [(n, c_u64) for n in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "nodes_visited", "tris_tested", "edges_fetched",
                                      "surface_interactions", "fsd_interactions", "null_interactions", "splats", "capacity_overflows", "kernel_launches", "iterations",
                                      "traverse_nodes", "traverse_tris", "shaded_paths")] + \
-               [(n, c_dbl) for n in ("gpu_ms", "traverse_ms", "shade_ms", "generate_ms", "sort_ms")]
+               [(n, c_dbl) for n in ("gpu_ms", "traverse_ms", "shade_ms", "generate_ms", "sort_ms", "connect_ms")] + [("strategies", c_u64 * 5), ("walker_steps", c_u64)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "strategies" else getattr(self, n)) for n, _ in self._fields_}
 
 
 class RayQuery(C.Structure):

@@ -980,6 +980,7 @@ __global__ void __launch_bounds__(128) k_bd_traverse(const BdArgs a) {
     }
     flush_counters(a.r.ctr, ctr);
     count1(&a.r.ctr->overflow, ovf);
+    count1(&a.r.ctr->walker_steps, li < (uint32_t)a.r.ctr->n_trav);
 }
 
 __global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }
@@ -1198,6 +1199,11 @@ template <int CLS> __global__ void __launch_bounds__(128) k_bd_connect(const BdA
     }
     flush_counters(a.r.ctr, ctr, true);
     bd_flush_stats(a.r.ctr, n_splat, 0u, n_conn, 0u, overflow);
+    {
+        const unsigned m = __activemask();
+        const unsigned nc = __reduce_add_sync(m, n_conn);
+        if (nc && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(&a.r.ctr->strategies[CLS], (unsigned long long)nc);
+    }
 }
 
 } // namespace wt

@@ -71,6 +71,7 @@ struct DevCounters {
     int n_trav;                         // entries of trav_list (paths to traverse this iteration)
     int n_sorted;                       // live paths in `order`
     int n_pairs[5];                     // plt_bdpt: (s,t) strategies queued this iteration, per strategy class
+    unsigned long long strategies[5], walker_steps;
     int n_fsd_list[3], fsd_head;        // plt_bdpt: walkers waiting for a Fraunhofer sample (three rotating lists); work-fetch cursor
 };
 
@@ -786,6 +787,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
                 k_bd_fsd_sample<<<gC, blk, 0, s->bd_stream>>>(b); ++launches;
                 CK(cudaEventRecord(s->bd_ev_samp, s->bd_stream));
             }
+            mark();
             k_bd_connect<0><<<gC, blk, 0, st>>>(b); k_bd_connect<1><<<gC, blk, 0, st>>>(b); k_bd_connect<2><<<gC, blk, 0, st>>>(b);
             k_bd_connect<3><<<gC, blk, 0, st>>>(b); k_bd_connect<4><<<gC, blk, 0, st>>>(b); launches += 5; mark();
             ++iters;
@@ -820,13 +822,15 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     CK(cudaEventSynchronize(e1));
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    double t_trav = 0, t_shade = 0, t_gen = 0, t_sort = 0;
-    for (size_t i = 0; i + 4 < n_ev; i += 5) {
+    double t_trav = 0, t_shade = 0, t_gen = 0, t_sort = 0, t_conn = 0;
+    const size_t per_it = (bdpt && !(o->flags & WTGPU_RENDER_BDPT_MEGAKERNEL)) ? 6 : 5;      // marks per iteration
+    for (size_t i = 0; i + per_it - 1 < n_ev; i += per_it) {
         float f;
         cudaEventElapsedTime(&f, evs[i], evs[i + 1]); t_gen += f;
         cudaEventElapsedTime(&f, evs[i + 1], evs[i + 2]); t_trav += f;
         cudaEventElapsedTime(&f, evs[i + 2], evs[i + 3]); t_sort += f;
         cudaEventElapsedTime(&f, evs[i + 3], evs[i + 4]); t_shade += f;
+        if (per_it == 6) { cudaEventElapsedTime(&f, evs[i + 4], evs[i + 5]); t_conn += f; }
     }
 
     if (!on_dev) {
@@ -844,7 +848,9 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         stats->traverse_nodes = hctr->nodes; stats->traverse_tris = hctr->tris; stats->shaded_paths = hctr->shaded; stats->edges_fetched = hctr->edges;
         stats->surface_interactions = hctr->surface; stats->fsd_interactions = hctr->fsd; stats->null_interactions = hctr->null_; stats->splats = hctr->splats;
         stats->capacity_overflows = hctr->overflow; stats->kernel_launches = launches; stats->iterations = iters;
-        stats->gpu_ms = ms; stats->traverse_ms = t_trav; stats->shade_ms = t_shade; stats->generate_ms = t_gen; stats->sort_ms = t_sort;
+        stats->gpu_ms = ms; stats->traverse_ms = t_trav; stats->shade_ms = t_shade; stats->generate_ms = t_gen; stats->sort_ms = t_sort; stats->connect_ms = t_conn;
+        for (int c = 0; c < 5; ++c) stats->strategies[c] = hctr->strategies[c];
+        stats->walker_steps = hctr->walker_steps;
     }
     const bool overflowed = hctr->overflow != 0;
     cudaFreeHost(hctr);
