@@ -297,6 +297,7 @@ typedef struct wtgpu_render_opts {
 } wtgpu_render_opts;
 #define WTGPU_RENDER_NO_SORT 1u     /* disable the material sort (for A/B measurement) */
 #define WTGPU_RENDER_BDPT_MEGAKERNEL 4u  /* plt_bdpt: run the one-thread-per-sample cross-check kernel instead of the wavefront */
+#define WTGPU_RENDER_THREAD_TRAVERSE 8u  /* plt_bdpt: one thread per beam in traverse() instead of eight lanes per beam (A/B measurement) */
 #define WTGPU_RENDER_TIME_KERNELS 2u /* record CUDA events around every kernel (fills wtgpu_stats::*_ms) */
 
 /* Device counters gathered during wtgpu_render (the quantities the reference exposes in a `profile` build:

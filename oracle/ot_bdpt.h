@@ -9,8 +9,10 @@
 #include <atomic>
 namespace ot { inline std::atomic<unsigned long long> g_dbg[8]; }
 #define OT_DBG(i, n) (ot::g_dbg[i] += (n))
+#define OT_DBG_MAX(i, n) do { unsigned long long o_ = ot::g_dbg[i]; while (o_ < (n) && !ot::g_dbg[i].compare_exchange_weak(o_, (n))) {} } while (0)
 #else
 #define OT_DBG(i, n) ((void)0)
+#define OT_DBG_MAX(i, n) ((void)0)
 #endif
 #include "ot_integrator.h"
 
@@ -97,7 +99,7 @@ inline f_t gaussian2d_t::integrate_triangle(v2 a, v2 b, v2 c) const {
     const f_t min_len = min3(length2(a - b), length2(a - c), length2(b - c));
     if (min_len < 1e-3f) {
         const f_t delta = .002f;
-        OT_DBG(0, 1);
+        OT_DBG(0, 1); unsigned long long dbg_it = 0;
         if (b.y < a.y) std::swap(a, b);
         if (c.y < a.y) std::swap(a, c);
         const f_t ab = b.y == a.y ? inf : (b.x - a.x) / (b.y - a.y);
@@ -108,8 +110,9 @@ inline f_t gaussian2d_t::integrate_triangle(v2 a, v2 b, v2 c) const {
             f_t x0 = y < b.y ? ab * (y - a.y) + a.x : bc * (y - b.y) + b.x;
             f_t x1 = y < c.y ? ac * (y - a.y) + a.x : bc * (y - b.y) + b.x;
             if (x0 > x1) std::swap(x0, x1);
-            for (f_t x = std::max(-L, x0) + delta / 2; x < std::min(L, x1); x += delta) { ret += std::exp(-(sqr(x) + sqr(y)) / 2); OT_DBG(1, 1); }
+            for (f_t x = std::max(-L, x0) + delta / 2; x < std::min(L, x1); x += delta) { ret += std::exp(-(sqr(x) + sqr(y)) / 2); OT_DBG(1, 1); ++dbg_it; }
         }
+        OT_DBG_MAX(6, dbg_it); (void)dbg_it;
         return ret * inv_two_pi * sqr(delta);
     }
     OT_DBG(2, 1);

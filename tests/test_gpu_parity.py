@@ -135,10 +135,11 @@ def test_partition_invariance_on_gpu():
     assert np.allclose(ns, full, rtol=1e-4, atol=1e-6 * full.max())
 
 
-@pytest.mark.parametrize("fsd,flags", [(False, 0), (True, 0), (True, 4)])
+@pytest.mark.parametrize("fsd,flags", [(False, 0), (True, 0), (True, 8), (True, 4)])
 def test_bdpt_double_slits_matches_oracle(fsd, flags):
     """plt_bdpt (both subpaths, all (s,t) connections, MIS; Fraunhofer FSD when fsd) on the double_slits geometry, virtual-plane sensor.
-    flags=0: wavefront driver; flags=4 (WTGPU_RENDER_BDPT_MEGAKERNEL): the one-thread-per-sample cross-check driver."""
+    flags=0: wavefront driver (eight lanes per beam in traverse()); 8: wavefront with one thread per beam; 4 (WTGPU_RENDER_BDPT_MEGAKERNEL):
+    the one-thread-per-sample cross-check driver."""
     b = scenes.double_slits(res=128, spp=8, with_directional=False, integrator="plt_bdpt", fsd=fsd, lut=(512, 256)).build()
     blk, lgt, st = render(b, spp=8, allow_overflow=True, flags=flags)
     oblk, olgt, ost = _oracle.render(b, spp=8)
@@ -150,7 +151,7 @@ def test_bdpt_double_slits_matches_oracle(fsd, flags):
     assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
 
 
-@pytest.mark.parametrize("flags", [0, 4])
+@pytest.mark.parametrize("flags", [0, 8, 4])
 def test_bdpt_cornell_matches_oracle(flags):
     """plt_bdpt with a perspective sensor and an area emitter (s=0 emission hits, t=1 sensor connections, NEE, MIS)."""
     b = scenes.cornell_like(res=48, spp=8, integrator="plt_bdpt").build()

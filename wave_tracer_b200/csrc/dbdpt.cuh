@@ -908,6 +908,7 @@ struct BdArgs {
     FLut lut; float* arena; uint32_t P;
     float4* walkers; float4* headers;
     int* pending; float* L0; uint32_t* nverts; uint32_t* pairs;
+    TravRec* trav_rec; uint32_t* trav_tris;  // group traversal results (per walker), consumed by k_bd_resolve
     uint32_t* fsd_list; float4* fsd_out;    // walkers waiting for a Fraunhofer direction sample (two lists, ping-pong); its result / carried state
     size_t pair_off[kPairClasses];          // start of each strategy class's segment of `pairs`
     uint32_t fl_cur, fl_next, fl_fin;       // list fed by this iteration's vertex step and consumed by its sampler; carry-over list; list being finished
@@ -983,7 +984,55 @@ __global__ void __launch_bounds__(128) k_bd_traverse(const BdArgs a) {
     count1(&a.r.ctr->walker_steps, li < (uint32_t)a.r.ctr->n_trav);
 }
 
-__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }
+// traverse() for every walker of the list, eight lanes per walker (gtrav.cuh)
+__global__ void __launch_bounds__(128) k_bd_gtraverse(const BdArgs a) {
+    __shared__ GShared shm[128 / kGW];
+    Counters ctr; counters_zero(ctr);
+    const DScene& sc = a.r.sc;
+    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, ctr,
+        [&](int i, Cone& env, Geo& prev, float& lambda) {
+            const uint32_t wid = a.r.trav_list[i];
+            BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+            env = w.beam.env; prev = w.prev_geo; lambda = wavenum_to_wavelen(w.beam.k);
+        },
+        [&](int i, const TravRec& r, const uint32_t* tris, const GLane& g) {
+            const uint32_t wid = a.r.trav_list[i];
+            if (g.gl == 0u) a.trav_rec[wid] = r;
+            const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
+            for (uint32_t k = g.gl; k < nt; k += (uint32_t)kGW) a.trav_tris[(size_t)wid * kMaxConeTris + k] = tris[k];
+        });
+    flush_counters(a.r.ctr, ctr);
+}
+// what the vertex step needs from a traversal result: primary triangle, Gaussian power over clipped triangles, edges, sort key
+__global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ovf = false;
+    if (li < (uint32_t)a.r.ctr->n_trav) {
+        const uint32_t wid = a.r.trav_list[li];
+        const DScene& sc = a.r.sc;
+        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+        const TravRec r = a.trav_rec[wid];
+        TravOut tr;
+        tr.empty = (r.flags & TR_EMPTY) != 0u; tr.ballistic = (r.flags & TR_BALLISTIC) != 0u;
+        tr.ray.tuid = r.ray_tuid; tr.ray.dist = r.ray_dist; tr.ray.bx = r.bx; tr.ray.by = r.by; tr.ray.front = (r.flags & TR_RAY_FRONT) != 0u;
+        tr.cone.dist = r.cone_dist; tr.cone.front = (r.flags & TR_CONE_FRONT) != 0u; tr.cone.n_tris = r.n_tris; tr.cone.overflow = (r.flags & TR_OVERFLOW) != 0u;
+        tr.region_depth = r.region_depth; tr.origin = mk3(r.ox, r.oy, r.oz);
+        uint32_t tris[kMaxConeTris];
+        const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
+        for (uint32_t k = 0; k < nt; ++k) tris[k] = a.trav_tris[(size_t)wid * kMaxConeTris + k];
+        BHit bh; HitRec h;
+        bd_resolve_hit(sc, w.beam, tr, tris, h.edges, bh);
+        h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
+        h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
+        ovf = bh.overflow;
+        soa_store(h, a.r.hit, a.r.pool, wid);
+        a.r.keys[wid] = bd_hit_key(sc, bh, a.r.n_keys);
+    }
+    count1(&a.r.ctr->overflow, ovf);
+    count1(&a.r.ctr->walker_steps, li < (uint32_t)a.r.ctr->n_trav);
+}
+
+__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->trav_head = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }
 
 // Strategy classes = the branches of connect_subpaths (plt_bdpt_detail.hpp:747-923): each class has its own task list and its own
 // launch, so a warp runs one branch (emission hit / sensor hit / emitter-direct / sensor-direct / vertex-vertex).

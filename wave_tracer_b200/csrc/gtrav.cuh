@@ -1,0 +1,243 @@
+// gtrav.cuh -- group-cooperative traversal: integrator::traverse (include/wt/integrator/traversal.hpp:94-172) with the 8-wide BVH
+// queries of src/ads/bvh8w.cpp (ray: 469-554, cone: 123-347) executed by EIGHT LANES PER QUERY.  (Included by wavefront.cu.)
+//
+// Why: one thread per beam (dtrav.cuh) leaves a warp running ~2-4 lanes on cone-heavy scenes -- every lane is in a different place
+// of a different query, and a few wide beams take 100x longer than the rest.  Here a group of 8 lanes owns one beam at a time:
+//   * node step: lane i tests child i of the 256-B node (the node's SoA rows are read as 32-B segments), the surviving children
+//     are ranked with shuffles and pushed in the order the sequential insertion sort would leave them;
+//   * leaf step: lane i intersects triangle i of the leaf (ray: of a <=16-triangle subtree); hits are appended with a ballot
+//     prefix, the closest is found with a (distance, lane) min-reduction = the first minimal one in sequential order;
+//   * the stack and the triangle list live in shared memory (1.25 KB per group);
+//   * groups pull beams from the list with an atomic cursor, so a long beam delays only its own group;
+//   * the four groups of a warp run node steps freely but meet before every leaf step, where the expensive cone-triangle code runs.
+// Every decision is taken on the same values, in the same order, as the sequential code: results are bit-identical to dtrav.cuh.
+#pragma once
+
+namespace wt {
+
+constexpr int kGW = 8;
+constexpr int kGStack = 128;
+struct GShared { float tmin[kGStack]; int32_t ptr[kGStack]; uint32_t tris[kMaxConeTris]; };
+
+// what traverse() returns, as stored between the traversal kernel and the per-thread resolve kernel
+struct alignas(16) TravRec { uint32_t flags, ray_tuid; float ray_dist, bx, by, cone_dist; uint32_t n_tris; float region_depth, ox, oy, oz; uint32_t pad_; };
+enum : uint32_t { TR_EMPTY = 1u, TR_BALLISTIC = 2u, TR_CONE_FRONT = 4u, TR_OVERFLOW = 8u, TR_RAY_FRONT = 16u };
+
+struct GLane { unsigned gl, gshift, gmask; };
+WT_D unsigned g_ballot(const GLane& g, bool p) { return (__ballot_sync(g.gmask, p) >> g.gshift) & 0xffu; }
+template <class T> WT_D T g_shfl(const GLane& g, T v, int src) { return __shfl_sync(g.gmask, v, src, kGW); }
+// (value, lane) lexicographic minimum over the lanes with `valid`; returns the winning lane (or -1)
+WT_D int g_argmin(const GLane& g, float v, bool valid) {
+    float bv = valid ? v : WT_INF; int bl = valid ? (int)g.gl : 64;
+#pragma unroll
+    for (int o = 1; o < kGW; o <<= 1) {
+        const float ov = __shfl_xor_sync(g.gmask, bv, o, kGW); const int ol = __shfl_xor_sync(g.gmask, bl, o, kGW);
+        if (ol < 64 && (bl >= 64 || ov < bv || (ov == bv && ol < bl))) { bv = ov; bl = ol; }
+    }
+    return bl < 64 ? bl : -1;
+}
+
+// One group's traversal machine.  All members hold the same value in the 8 lanes of a group.
+struct GTrav {
+    // beam
+    Cone env; float lambda, dist, bd, min_prog; uint32_t seg; int wstate;       // wstate: 0 ray-only, 1 segment ray, 2 segment cone
+    // query
+    int mode, s;                // mode: 1 ray, 2 cone; s: stack size
+    V3 inv; bool nx, ny, nz; Frame frame;
+    Range qrange, crange;       // ray range / cone traversal range; current cone search range
+    RayHit rec; ConeResult res;
+};
+
+WT_D void g_start_ray(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, Range r, Counters& ctr) {
+    t.mode = 1; t.qrange = r; t.rec.tuid = WTGPU_INVALID_IDX; t.rec.dist = WT_INF; t.rec.bx = t.rec.by = -1.f; t.rec.front = false;
+    t.s = 1;
+    if (g.gl == 0u) { sh.tmin[0] = 0.f; sh.ptr[0] = sc.root_ptr; ctr.ray_casts++; }
+    __syncwarp(g.gmask);
+}
+WT_D void g_start_cone(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, Range tr, Counters& ctr) {
+    t.mode = 2; t.qrange = tr; t.res.dist = WT_INF; t.res.front = false; t.res.n_tris = 0u; t.res.overflow = false;
+    t.crange = cone_search_range(t.env, tr, t.res.dist, kMajorToZ);
+    t.s = 1;
+    if (g.gl == 0u) { sh.tmin[0] = 0.f; sh.ptr[0] = sc.root_ptr; ctr.cone_casts++; }
+    __syncwarp(g.gmask);
+}
+// push the children that passed, in the order insertion sort (descending tmin, stable) leaves them (bvh8w.cpp:44-57)
+WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float tmin, int32_t ch, int cap) {
+    const unsigned m = g_ballot(g, push);
+    const int idx = __popc(m & ((1u << g.gl) - 1u));
+    const bool keep = push && t.s + idx < cap;
+    const unsigned km = g_ballot(g, keep);
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < kGW; ++j) {
+        const float tj = g_shfl(g, tmin, j);
+        if (((km >> j) & 1u) && (tj > tmin || (tj == tmin && j < (int)g.gl))) ++rank;
+    }
+    if (keep) { sh.tmin[t.s + rank] = tmin; sh.ptr[t.s + rank] = ch; }
+    t.s += __popc(km);
+    __syncwarp(g.gmask);
+}
+WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, int32_t ptr, Counters& ctr) {
+    const wtgpu_node* __restrict__ n = sc.nodes + (ptr - 1);
+    if (g.gl == 0u) ctr.nodes++;
+    const float mnx = __ldg(&n->minx[g.gl]), mny = __ldg(&n->miny[g.gl]), mnz = __ldg(&n->minz[g.gl]);
+    const float mxx = __ldg(&n->maxx[g.gl]), mxy = __ldg(&n->maxy[g.gl]), mxz = __ldg(&n->maxz[g.gl]);
+    const int32_t ch = __ldg(&n->child[g.gl]);
+    const V3 ro = t.env.o, rd = t.env.d;
+    if (t.mode == 1) {      // intersect_ray_aabb_fast (intersect/ray.hpp:331-351), range {0, closest hit}
+        const float t1x = ((t.nx ? mxx : mnx) - ro.x) * t.inv.x, t2x = ((t.nx ? mnx : mxx) - ro.x) * t.inv.x;
+        const float t1y = ((t.ny ? mxy : mny) - ro.y) * t.inv.y, t2y = ((t.ny ? mny : mxy) - ro.y) * t.inv.y;
+        const float t1z = ((t.nz ? mxz : mnz) - ro.z) * t.inv.z, t2z = ((t.nz ? mnz : mxz) - ro.z) * t.inv.z;
+        const float rmin = vmaxps(vmaxps(vmaxps(t1x, t1y), t1z), 0.f);
+        const float rmax = vminps(vminps(vminps(t2x, t2y), t2z), t.rec.dist);
+        g_push_sorted(g, sh, t, rmin <= rmax && ch != 0, rmin, ch, 64);
+    } else {                // cone_cluster_intersect (bvh8w.cpp:187-230)
+        float omnx = mnx - ro.x, omny = mny - ro.y, omnz = mnz - ro.z;
+        float omxx = mxx - ro.x, omxy = mxy - ro.y, omxz = mxz - ro.z;
+        const float bx = t.nx ? omnx : omxx, by = t.ny ? omny : omxy, bz = t.nz ? omnz : omxz;
+        const float ddb = fmaf(rd.z, bz, fmaf(rd.y, by, rd.x * bx));
+        const float maxz = fminf(fmaxf(ddb, 0.f), t.crange.mx);
+        const float enl = fmaf(maxz, t.env.ta, t.env.x0);
+        omnx -= enl; omny -= enl; omnz -= enl; omxx += enl; omxy += enl; omxz += enl;
+        const float dminx = (t.nx ? omxx : omnx) * t.inv.x, dminy = (t.ny ? omxy : omny) * t.inv.y, dminz = (t.nz ? omxz : omnz) * t.inv.z;
+        const float dmaxx = (t.nx ? omnx : omxx) * t.inv.x, dmaxy = (t.ny ? omny : omxy) * t.inv.y, dmaxz = (t.nz ? omnz : omxz) * t.inv.z;
+        float tmin = 0.f, tmax = dmaxx;
+        tmin = vmaxps(tmin, dminx); tmax = vminps(tmax, dmaxy);
+        tmin = vmaxps(tmin, dminy); tmax = vminps(tmax, dmaxz);
+        tmin = vmaxps(tmin, dminz);
+        const bool ok = tmin <= tmax && tmax >= t.crange.mn && tmin <= t.crange.mx;
+        g_push_sorted(g, sh, t, ok && ch != 0 && !(tmin >= t.crange.mx), tmin, ch, kGStack);
+    }
+}
+// triangles [t0, t0+cnt) against the current query
+WT_D void g_leaf_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, uint32_t t0, uint32_t cnt, Counters& ctr) {
+    const V3 ro = t.env.o, rd = t.env.d;
+    if (t.mode == 1) {      // ray_gather (bvh8w.cpp:394-467)
+        bool hit = false;
+        for (uint32_t base = 0; base < cnt; base += (uint32_t)kGW) {
+            const uint32_t k = base + g.gl; const bool valid = k < cnt; const uint32_t tuid = t0 + k;
+            float z = -WT_INF, bx = 0.f, by = 0.f; bool front = false;
+            if (valid) { const Tri3 tr = load_tri(sc, tuid); ctr.tris++; z = intersect_ray_tri_w(ro, rd, tr.a, tr.b, tr.c, t.qrange, bx, by); front = dot(tr.n, rd) <= 0.f; }
+            const int w = g_argmin(g, z, valid && z != -WT_INF && z < t.rec.dist);
+            if (w >= 0) { t.rec.dist = g_shfl(g, z, w); t.rec.bx = g_shfl(g, bx, w); t.rec.by = g_shfl(g, by, w); t.rec.tuid = g_shfl(g, tuid, w); t.rec.front = g_shfl(g, front ? 1 : 0, w) != 0; hit = true; }
+        }
+        if (hit) while (t.s > 0 && sh.tmin[t.s - 1] >= t.rec.dist) --t.s;
+    } else {                // gather_tris (bvh8w.cpp:123-185)
+        bool found = false;
+        for (uint32_t base = 0; base < cnt; base += (uint32_t)kGW) {
+            const uint32_t k = base + g.gl; const bool valid = k < cnt; const uint32_t tuid = t0 + k;
+            float d = WT_INF; bool front = false;
+            if (valid) { const Tri3 tr = load_tri(sc, tuid); ctr.tris++; d = intersect_cone_tri(t.env, t.frame, tr.a, tr.b, tr.c, tr.n, t.crange); front = dot(tr.n, -rd) > 0.f; }
+            const bool acc = d < WT_INF && !(d > t.crange.mx);
+            const unsigned m = g_ballot(g, acc);
+            if (m) {
+                found = true;
+                const int w = g_argmin(g, d, acc && d < t.res.dist);
+                if (w >= 0) { t.res.dist = g_shfl(g, d, w); t.res.front = g_shfl(g, front ? 1 : 0, w) != 0; }
+                const uint32_t pos = t.res.n_tris + (uint32_t)__popc(m & ((1u << g.gl) - 1u));
+                if (acc && pos < (uint32_t)kMaxConeTris) sh.tris[pos] = tuid;
+                t.res.n_tris += (uint32_t)__popc(m);
+                if (t.res.n_tris > (uint32_t)kMaxConeTris) t.res.overflow = true;
+            }
+        }
+        if (found) {
+            t.crange = cone_search_range(t.env, t.qrange, t.res.dist, kMajorToZ);
+            while (t.s > 0 && sh.tmin[t.s - 1] >= t.crange.mx) --t.s;
+        }
+        __syncwarp(g.gmask);
+    }
+}
+// beam set-up: integrator::traverse up to the first query
+WT_D void g_begin(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, const Cone& env0, const Geo& prev, float lambda, bool force_rt, Counters& ctr) {
+    t.env = env0; t.env.o = offseted_ray_origin(sc, prev, env0.o, env0.d);
+    t.lambda = lambda;
+    const V3 rd = t.env.d;
+    t.inv = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
+    t.nx = signbit(t.inv.x); t.ny = signbit(t.inv.y); t.nz = signbit(t.inv.z);
+    t.frame = cone_frame(t.env);
+    t.res.n_tris = 0u; t.res.overflow = false; t.res.dist = WT_INF; t.res.front = false;
+    if (force_rt || cone_is_ray(t.env)) { t.wstate = 0; g_start_ray(sc, g, sh, t, mkr(0.f, WT_INF), ctr); return; }
+    t.dist = 0.f; t.seg = 0u; t.bd = max_ballistic_distance(lambda, 0u, 0.f);      // calculate_min_ballistic_distance == 0: the ray starts at the envelope's origin
+    t.wstate = 1;
+    g_start_ray(sc, g, sh, t, mkr(t.dist, fminf(WT_INF, t.dist + t.bd * 1.001f)), ctr);
+}
+// the current query has no work left: next query of this beam, or the beam's result (returns true, fills out)
+WT_D bool g_query_done(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, TravRec& out, Counters& ctr) {
+    out.ox = t.env.o.x; out.oy = t.env.o.y; out.oz = t.env.o.z; out.pad_ = 0u; out.region_depth = 0.f;
+    out.n_tris = 0u; out.cone_dist = WT_INF; out.ray_tuid = WTGPU_INVALID_IDX; out.ray_dist = WT_INF; out.bx = out.by = -1.f; out.flags = 0u;
+    if (t.mode == 1) {
+        // ads_t::intersect(ray, range) post-processing (traversal_common.hpp:93-110)
+        bool hit = true;
+        if (!isfinite(t.rec.dist) || t.rec.dist > t.qrange.mx) { t.rec.tuid = WTGPU_INVALID_IDX; t.rec.dist = WT_INF; hit = false; }
+        if (t.wstate == 0 || hit) {
+            out.flags = TR_BALLISTIC | (hit ? 0u : TR_EMPTY) | (t.rec.front ? TR_RAY_FRONT : 0u);
+            out.ray_tuid = t.rec.tuid; out.ray_dist = t.rec.dist; out.bx = t.rec.bx; out.by = t.rec.by;
+            return true;
+        }
+        t.dist += t.bd;
+        if (t.bd == WT_INF || t.dist >= WT_INF) { out.flags = TR_BALLISTIC | TR_EMPTY; return true; }
+        t.min_prog = cone_axes(t.env, t.dist).x / 2.f;
+        t.wstate = 2;
+        g_start_cone(sc, g, sh, t, mkr(t.dist, WT_INF), ctr);
+        return false;
+    }
+    const bool cempty = t.res.n_tris == 0u;
+    if (cempty || t.res.dist - t.dist >= t.min_prog) {
+        out.flags = (cempty ? TR_EMPTY : 0u) | (t.res.front ? TR_CONE_FRONT : 0u) | (t.res.overflow ? TR_OVERFLOW : 0u);
+        out.cone_dist = t.res.dist; out.n_tris = t.res.n_tris;
+        out.region_depth = cempty ? 0.f : kMajorToZ * cone_axes(t.env, t.res.dist).x;
+        // the ray record of the last (missed) ballistic segment stays as traverse() leaves it
+        out.ray_tuid = t.rec.tuid; out.ray_dist = t.rec.dist; out.bx = t.rec.bx; out.by = t.rec.by; if (t.rec.front) out.flags |= TR_RAY_FRONT;
+        return true;
+    }
+    ++t.seg;
+    t.bd = max_ballistic_distance(t.lambda, t.seg, 0.f);
+    t.wstate = 1;
+    g_start_ray(sc, g, sh, t, mkr(t.dist, fminf(WT_INF, t.dist + t.bd * 1.001f)), ctr);
+    return false;
+}
+
+// The driver loop.  fetch(i, env, prev, lambda) loads item i (group-uniformly); emit(i, rec, tris) stores its result.
+template <class Fetch, class Emit>
+WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* shm, bool force_rt, Counters& ctr, Fetch&& fetch, Emit&& emit) {
+    GLane g; g.gl = threadIdx.x & 7u; g.gshift = (threadIdx.x & 31u) & 24u; g.gmask = 0xffu << g.gshift;
+    GShared& sh = shm[threadIdx.x / kGW];
+    GTrav t; t.mode = 0; t.s = 0;
+    bool have = false, done = false; int item = 0;
+    for (;;) {
+        // phase 1: bookkeeping and node steps, until a leaf is on top of this group's stack
+        uint32_t lt0 = 0u, lcnt = 0u; bool leaf = false;
+        for (;;) {
+            if (!have) {
+                if (done) break;
+                int i = 0;
+                if (g.gl == 0u) i = atomicAdd(cursor, 1);
+                i = g_shfl(g, i, 0);
+                if (i >= n_items) { done = true; break; }
+                item = i;
+                Cone env; Geo prev; float lambda;
+                fetch(item, env, prev, lambda);
+                g_begin(sc, g, sh, t, env, prev, lambda, force_rt, ctr);
+                have = true;
+            }
+            if (t.s == 0) {
+                TravRec out;
+                if (g_query_done(sc, g, sh, t, out, ctr)) { emit(item, out, sh.tris, g); have = false; __syncwarp(g.gmask); }
+                continue;
+            }
+            const int32_t top = sh.ptr[t.s - 1];
+            if (top < 0) { const wtgpu_leaf lf = sc.leaves[-top - 1]; lt0 = lf.tris_ptr; lcnt = lf.count; leaf = true; --t.s; break; }
+            if (t.mode == 1) {      // ray_traversal_treat_node_as_leaf_if_triangle_count_lt (bvh8w.cpp:29)
+                const uint2 tr = __ldg(reinterpret_cast<const uint2*>(&sc.nodes[top - 1].tris_start));
+                if (tr.y <= 16u) { if (g.gl == 0u) ctr.nodes++; lt0 = tr.x; lcnt = tr.y; leaf = true; --t.s; break; }
+            }
+            --t.s;
+            g_node_step(sc, g, sh, t, top, ctr);
+        }
+        if (__all_sync(0xffffffffu, done && !have)) break;
+        // phase 2: the groups of the warp do their leaf steps together
+        if (leaf) g_leaf_step(sc, g, sh, t, lt0, lcnt, ctr);
+    }
+}
+
+} // namespace wt

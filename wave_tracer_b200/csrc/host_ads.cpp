@@ -143,6 +143,7 @@ struct builder_t {
         return ex * ey + ey * ez + ez * ex;
     }
 
+    static constexpr uint32_t kLeafMaxTris = 8;
     int build(uint32_t first, uint32_t count) {
         const int ni = (int)nodes.size();
         nodes.emplace_back();
@@ -156,7 +157,9 @@ struct builder_t {
                 }
             n.first = first; n.count = count;
         }
-        if (count < 2) return ni;
+        // Leaves hold up to 8 triangles: the device tests a leaf's triangles with eight lanes at once (gtrav.cuh), and ray queries
+        // already treat subtrees of <= 16 triangles as leaves (bvh8w.cpp:29), so finer leaves would only add node steps.
+        if (count <= kLeafMaxTris) return ni;
 
         // centroid bounds
         double cmn[3] = { 1e300, 1e300, 1e300 }, cmx[3] = { -1e300, -1e300, -1e300 };

@@ -72,6 +72,7 @@ struct DevCounters {
     int n_sorted;                       // live paths in `order`
     int n_pairs[5];                     // plt_bdpt: (s,t) strategies queued this iteration, per strategy class
     unsigned long long strategies[5], walker_steps;
+    int trav_head;                      // work-fetch cursor of the group traversal
     int n_fsd_list[3], fsd_head;        // plt_bdpt: walkers waiting for a Fraunhofer sample (three rotating lists); work-fetch cursor
 };
 
@@ -201,6 +202,7 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
     }
 }
 
+#include "gtrav.cuh"
 #include "dbdpt.cuh"
 
 __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
@@ -568,12 +570,12 @@ struct wtgpu_scene {
     float* bdpt_arena = nullptr; uint32_t bdpt_P = 0;
     // plt_bdpt wavefront state (P sample slots, 2P walkers)
     float4 *bd_walkers = nullptr, *bd_headers = nullptr, *bd_hit = nullptr;
-    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_pairs = nullptr, *bd_alive = nullptr, *bd_keys = nullptr, *bd_order = nullptr, *bd_trav = nullptr, *bd_fsd_list = nullptr; float4* bd_fsd_out = nullptr;
+    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_pairs = nullptr, *bd_alive = nullptr, *bd_keys = nullptr, *bd_order = nullptr, *bd_trav = nullptr, *bd_fsd_list = nullptr, *bd_trav_tris = nullptr; float4* bd_fsd_out = nullptr; TravRec* bd_trav_rec = nullptr;
     uint32_t bd_wave_P = 0;
     cudaStream_t bd_stream = nullptr; cudaEvent_t bd_ev_shade = nullptr, bd_ev_samp = nullptr;   // Fraunhofer sampler overlap
     void free_bd_wave() {
-        for (void* p : { (void*)bd_walkers, (void*)bd_headers, (void*)bd_hit, (void*)bd_pending, (void*)bd_L0, (void*)bd_nverts, (void*)bd_pairs, (void*)bd_alive, (void*)bd_keys, (void*)bd_order, (void*)bd_trav, (void*)bd_fsd_list, (void*)bd_fsd_out }) if (p) cudaFree(p);
-        bd_walkers = bd_headers = bd_hit = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_pairs = bd_alive = bd_keys = bd_order = bd_trav = bd_fsd_list = nullptr; bd_fsd_out = nullptr; bd_wave_P = 0;
+        for (void* p : { (void*)bd_walkers, (void*)bd_headers, (void*)bd_hit, (void*)bd_pending, (void*)bd_L0, (void*)bd_nverts, (void*)bd_pairs, (void*)bd_alive, (void*)bd_keys, (void*)bd_order, (void*)bd_trav, (void*)bd_fsd_list, (void*)bd_fsd_out, (void*)bd_trav_tris, (void*)bd_trav_rec }) if (p) cudaFree(p);
+        bd_walkers = bd_headers = bd_hit = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_pairs = bd_alive = bd_keys = bd_order = bd_trav = bd_fsd_list = bd_trav_tris = nullptr; bd_fsd_out = nullptr; bd_trav_rec = nullptr; bd_wave_P = 0;
     }
     ~wtgpu_scene() {
         cudaSetDevice(device);
@@ -750,6 +752,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             CK(cudaMalloc(&s->bd_pending, 4ull * P)); CK(cudaMalloc(&s->bd_L0, 4ull * P)); CK(cudaMalloc(&s->bd_nverts, 4ull * W2)); CK(cudaMalloc(&s->bd_alive, 4ull * P));
             CK(cudaMalloc(&s->bd_keys, 4ull * W2)); CK(cudaMalloc(&s->bd_order, 4ull * W2)); CK(cudaMalloc(&s->bd_trav, 4ull * W2));
             CK(cudaMalloc(&s->bd_pairs, 4ull * (size_t)P * (max_pairs + 4ull * nmaxv)));
+            CK(cudaMalloc(&s->bd_trav_rec, sizeof(TravRec) * (size_t)W2)); CK(cudaMalloc(&s->bd_trav_tris, 4ull * kMaxConeTris * W2));
             CK(cudaMalloc(&s->bd_fsd_list, 12ull * W2)); CK(cudaMalloc(&s->bd_fsd_out, 32ull * W2));
             s->bd_wave_P = P;
         }
@@ -757,7 +760,8 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         BdArgs b;
         b.r = a; b.r.hit = s->bd_hit; b.r.alive = s->bd_alive; b.r.keys = s->bd_keys; b.r.order = s->bd_order; b.r.trav_list = s->bd_trav; b.r.pool = W2;
         b.lut = s->lut; b.arena = s->bdpt_arena; b.P = P; b.walkers = s->bd_walkers; b.headers = s->bd_headers;
-        b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs; b.fsd_list = s->bd_fsd_list; b.fsd_out = s->bd_fsd_out;
+        b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs; b.fsd_list = s->bd_fsd_list; b.fsd_out = s->bd_fsd_out; b.trav_rec = s->bd_trav_rec; b.trav_tris = s->bd_trav_tris;
+        const bool thread_trav = (o->flags & WTGPU_RENDER_THREAD_TRAVERSE) != 0;
         for (int c = 0; c < 5; ++c) b.pair_off[c] = (size_t)P * nmaxv * (size_t)c;      // classes 0-3 hold <= max_depth+3 strategies per sample, class 4 the rest
         const bool has_fsd = s->integ.fsd != 0u;
         CK(cudaMemsetAsync(s->bd_alive, 0, 4ull * P, st));
@@ -773,7 +777,9 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             b.tag = 16.f + (float)(iters % 1024ull); b.tag_fin = 16.f + (float)((iters + 1023ull) % 1024ull);
             mark();
             k_bd_generate<<<gP, blk, 0, st>>>(b); ++launches; mark();
-            k_bd_traverse<<<gW, blk, 0, st>>>(b); ++launches; mark();
+            if (thread_trav) { k_bd_traverse<<<gW, blk, 0, st>>>(b); ++launches; }
+            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blk, 0, st>>>(b); launches += 2; }
+            mark();
             k_hist<<<gW, blk, s->n_keys * 4, st>>>(b.r);
             k_scan<<<1, 32, 0, st>>>(b.r);
             k_scatter<<<gW, blk, 0, st>>>(b.r); launches += 3; mark();
