@@ -373,6 +373,8 @@ WT_D void bv_load(const Arena& A, uint32_t idx, BVertex& v) {
 #pragma unroll
     for (uint32_t i = 0; i < kVertWords / 4; ++i) d[i] = s[i];
 }
+// read-only view of a stored vertex: fields are fetched from the arena when used (no 272-B local copy)
+WT_D const BVertex& bv_ref(const Arena& A, uint32_t idx) { return *reinterpret_cast<const BVertex*>(A.base + idx * kVertWords); }
 // word offsets of the scalars the MIS walk touches
 constexpr uint32_t kOffDelta = 2, kOffPdfFwd = 4, kOffPdfBwd = 5, kOffRr = 6;
 WT_D Geo bv_geo(const BVertex& v) { return geo_surface(v.p, v.tuid, v.gkind == BG_SURFACE); }
@@ -504,14 +506,15 @@ WT_NI bool bv_interact(const BCtx& c, const BVertex& v, V3 next_p, bool ignore_f
 struct BWalk { Beam beam; bool fwd; Pd pdf_from_prev; float throughput, rr; uint32_t base, n; Geo prev_geo; uint32_t ap0, n_ap; };   // vertices at [base, base+n)
 
 WT_D bool bd_append(const BCtx& c, BWalk& d, BVertex& v, Pd pdf_fwd, Pd pdf_revr) {     // plt_bdpt_detail.hpp:96-122
-    BVertex prev; bv_load(c.A, d.base + d.n - 1u, prev);
+    const BVertex& prev = bv_ref(c.A, d.base + d.n - 1u);
     if (veq(prev.p, v.p)) return false;
     const float pa = dir_to_area(c, d.pdf_from_prev, prev.p, v);
     if (v.fwd) v.pdf_fwd = pa; else v.pdf_bwd = pa;
     v.beam = d.beam;
     const float pr = dir_to_area(c, pdf_revr, v.p, prev);
+    const bool prev_fwd = prev.fwd != 0u;
     // prev.pdf_reversed(): transport backward -> pdf_fwd, forward -> pdf_bwd
-    aw(c.A, (d.base + d.n - 1u) * kVertWords + (prev.fwd ? kOffPdfBwd : kOffPdfFwd)) = pr;
+    aw(c.A, (d.base + d.n - 1u) * kVertWords + (prev_fwd ? kOffPdfBwd : kOffPdfFwd)) = pr;
     d.pdf_from_prev = pdf_fwd;
     bv_store(c.A, d.base + d.n, v);
     d.n++;
@@ -661,14 +664,14 @@ WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler
     ret.has_el = false; ret.L = stokes_zero(); tmp_init(ret.tmp, BV_SENSOR);
     const bool virt = sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE;
     if (s == 0) {
-        BVertex last; bv_load(c.A, SB + t - 1, last);
+        const BVertex& last = bv_ref(c.A, SB + t - 1);
         if (bv_on_emitter(c, last)) {
             Beam QE = last.beam; beam_mul(QE, last.rr);
             if (last.type == BV_SURFACE) { const Surface srf = bv_surface(sc, last); ret.L = emitter_Li(sc, bv_emitter(c, last), QE, srf); }
         }
     } else if (t == 0) {
         if (virt) {
-            BVertex last, cur; bv_load(c.A, EB + s - 1, last); bv_load(c.A, EB + s - 2, cur);
+            const BVertex& last = bv_ref(c.A, EB + s - 1); const BVertex& cur = bv_ref(c.A, EB + s - 2);
             const Beam& beam = last.beam;
             Beam db; Element el;
             if (sensor_Si(sc, beam, mkr(0.f, length(last.p - beam.env.o)), db, el)) {
@@ -682,7 +685,7 @@ WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler
             }
         }
     } else if (s == 1) {
-        BVertex last; bv_load(c.A, SB + t - 1, last);
+        const BVertex& last = bv_ref(c.A, SB + t - 1);
         if (bv_connectible(c, last)) {
             EmitterDirect ed = scene_sample_emitter_direct(sc, smp, last.p, last.beam.k);
             if ((ed.dpd.disc || ed.dpd.v != 0.f) && beam_intensity(ed.beam) > 0.f) {
@@ -697,7 +700,7 @@ WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler
             }
         }
     } else if (t == 1) {
-        BVertex last; bv_load(c.A, EB + s - 1, last);
+        const BVertex& last = bv_ref(c.A, EB + s - 1);
         if ((virt || last.type != BV_FSD) && bv_connectible(c, last)) {
             SensorDirect sd = sensor_sample_direct(sc, smp, last.p, last.beam.k);
             if ((sd.dpd.disc || sd.dpd.v != 0.f) && beam_intensity(sd.beam) > 0.f) {
@@ -711,7 +714,7 @@ WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler
             }
         }
     } else {
-        BVertex ev, sv; bv_load(c.A, EB + s - 1, ev); bv_load(c.A, SB + t - 1, sv);
+        const BVertex& ev = bv_ref(c.A, EB + s - 1); const BVertex& sv = bv_ref(c.A, SB + t - 1);
         const V3 dl = ev.p - sv.p;
         if (bv_connectible(c, ev) && bv_connectible(c, sv) && !(dl.x == 0.f && dl.y == 0.f && dl.z == 0.f)) {
             Beam eb, db;
@@ -739,28 +742,27 @@ WT_NI float bd_mis(BCtx& c, int s, int t, const BConn& cr) {       // plt_bdpt_d
     for (int i = 0; i < s; ++i) { ep_pdf[i] = aw(c.A, (EB + i) * kVertWords + kOffPdfFwd); ep_rev[i] = aw(c.A, (EB + i) * kVertWords + kOffPdfBwd); ep_d[i] = __float_as_uint(aw(c.A, (EB + i) * kVertWords + kOffDelta)) != 0u; }
     const BVertex& tmp = cr.tmp;
     const bool virt = sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE;
-    BVertex ev0, sv0;
     if (s == 0) {
-        BVertex last, prev; bv_load(c.A, SB + t - 1, last); bv_load(c.A, SB + t - 2, prev);
+        const BVertex& last = bv_ref(c.A, SB + t - 1); const BVertex& prev = bv_ref(c.A, SB + t - 2);
         sp_rev[t - 1] = pdf_emitter_v(c, last);
         sp_rev[t - 2] = pdf_next_from_emitter(c, last, prev);
     } else if (t == 0) {
-        BVertex last, prev; bv_load(c.A, EB + s - 2, prev);
-        if (virt) last = tmp; else bv_load(c.A, EB + s - 1, last);
+        const BVertex& prev = bv_ref(c.A, EB + s - 2);
+        const BVertex& last = virt ? tmp : bv_ref(c.A, EB + s - 1);
         ep_rev[s - 1] = sensor_pdf_position(c);
         ep_rev[s - 2] = pdf_next_from_sensor(c, last, prev);
     } else if (s == 1) {
-        BVertex last, lp; bv_load(c.A, SB + t - 1, last); bv_load(c.A, SB + t - 2, lp);
+        const BVertex& last = bv_ref(c.A, SB + t - 1); const BVertex& lp = bv_ref(c.A, SB + t - 2);
         sp_rev[t - 1] = pdf_next_from_emitter(c, tmp, last);
         ep_rev[0] = bv_pdf(c, last, &lp, tmp, false);
         ep_pdf[0] = pdf_emitter_v(c, tmp);
     } else if (t == 1) {
-        BVertex last, lp; bv_load(c.A, EB + s - 1, last); bv_load(c.A, EB + s - 2, lp);
+        const BVertex& last = bv_ref(c.A, EB + s - 1); const BVertex& lp = bv_ref(c.A, EB + s - 2);
         ep_rev[s - 1] = pdf_next_from_sensor(c, tmp, last);
         sp_rev[0] = bv_pdf(c, last, &lp, tmp, true);
         sp_pdf[0] = sensor_pdf_position(c);
     } else {
-        BVertex e, sv, epv, spv; bv_load(c.A, EB + s - 1, e); bv_load(c.A, SB + t - 1, sv); bv_load(c.A, EB + s - 2, epv); bv_load(c.A, SB + t - 2, spv);
+        const BVertex& e = bv_ref(c.A, EB + s - 1); const BVertex& sv = bv_ref(c.A, SB + t - 1); const BVertex& epv = bv_ref(c.A, EB + s - 2); const BVertex& spv = bv_ref(c.A, SB + t - 2);
         ep_rev[s - 1] = bv_pdf(c, sv, &spv, e, false);
         ep_rev[s - 2] = bv_pdf(c, e, &sv, epv, false);
         sp_rev[t - 1] = bv_pdf(c, e, &epv, sv, true);
@@ -769,8 +771,8 @@ WT_NI float bd_mis(BCtx& c, int s, int t, const BConn& cr) {       // plt_bdpt_d
     if (t > 0) sp_d[t - 1] = false;
     if (s > 0) ep_d[s - 1] = false;
     bool delta_emitter = true, delta_sensor = true;
-    if (s == 1) delta_emitter = bv_delta_emitter(c, tmp); else if (s > 1) { bv_load(c.A, EB, ev0); delta_emitter = bv_delta_emitter(c, ev0); }
-    if (t == 1) delta_sensor = bv_delta_sensor(c, tmp); else if (t > 1) { bv_load(c.A, SB, sv0); delta_sensor = bv_delta_sensor(c, sv0); }
+    if (s == 1) delta_emitter = bv_delta_emitter(c, tmp); else if (s > 1) delta_emitter = bv_delta_emitter(c, bv_ref(c.A, EB));
+    if (t == 1) delta_sensor = bv_delta_sensor(c, tmp); else if (t > 1) delta_sensor = bv_delta_sensor(c, bv_ref(c.A, SB));
     float sum = 0.f, ri = 1.f;
     for (int i = t - 1; i >= 0; --i) { ri *= area_or_one(sp_rev[i]) / area_or_one(sp_pdf[i]); if (!sp_d[i] && !(i > 0 ? sp_d[i - 1] : delta_sensor)) sum += ri; }
     ri = 1.f;
@@ -1101,12 +1103,12 @@ __global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
 // fraunhofer_sample.  All control flow is warp-uniform.  Runs on a second stream, overlapped with the next iteration's kernels; its
 // results are picked up one iteration later.  A launch does not wait for stragglers: after `budget` tries a walker is carried over
 // to the next iteration (the stream is counter-based: only the draw index and the try count are kept).
-__global__ void __launch_bounds__(128) k_bd_fsd_sample(const BdArgs a) {
+__global__ void __launch_bounds__(128, 8) k_bd_fsd_sample(const BdArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const int n_tasks = a.r.ctr->n_fsd_list[a.fl_cur];
     const uint32_t* list = a.fsd_list + (size_t)a.fl_cur * 2u * a.P;
     uint32_t* carry_list = a.fsd_list + (size_t)a.fl_next * 2u * a.P;
-    uint32_t budget = n_tasks > 2048 ? 160u : 0xffffffffu;       // tries per WARP per launch; unbounded once only stragglers remain
+    uint32_t budget = n_tasks > 2048 ? 128u : 0xffffffffu;       // tries per WARP per launch; unbounded once only stragglers remain
     for (;;) {
         int t = 0;
         if (lane == 0u) t = atomicAdd(&a.r.ctr->fsd_head, 1);
@@ -1127,28 +1129,32 @@ __global__ void __launch_bounds__(128) k_bd_fsd_sample(const BdArgs a) {
         const uint32_t n = hd.n;
         const float4 st = a.fsd_out[2u * wid + 1u];      // carried over: resume after the tries already spent
         const bool carried = st.w == 1.f;
-        Sampler smp; smp.k0 = a.r.seed_lo; smp.k1 = a.r.seed_hi; smp.pixel = h.pixel; smp.sample = h.sample; smp.d = carried ? __float_as_uint(st.y) : w_rng_d; smp.stream = 1u + which;
+        Sampler smp0; smp0.k0 = a.r.seed_lo; smp0.k1 = a.r.seed_hi; smp0.pixel = h.pixel; smp0.sample = h.sample; smp0.d = carried ? __float_as_uint(st.y) : w_rng_d; smp0.stream = 1u + which;
+        SamplerC smp = samplerc(smp0);
         uint32_t tries = carried ? __float_as_uint(st.z) : 0u;
         const bool rej = n > 1u; const uint32_t max_tries = n * 1024u; const float recp_M = 1.f / (float)n;
-        // this lane's segments and selection masses
+        // this lane's segments
         const bool has0 = lane < n, has1 = lane + 32u < n;
         FEdge e0, e1; e0.e = e0.v = mk2(0.f, 0.f); e0.a_b = e0.iab_2 = mkc(0.f, 0.f); e1 = e0;
-        float pdf0 = 0.f, pdf1 = 0.f;
-        if (has0) { e0 = ap_edge(A, ai, lane); pdf0 = ap_edge_pdf(A, ai, lane); }
-        if (has1) { e1 = ap_edge(A, ai, lane + 32u); pdf1 = ap_edge_pdf(A, ai, lane + 32u); }
+        if (has0) e0 = ap_edge(A, ai, lane);
+        if (has1) e1 = ap_edge(A, ai, lane + 32u);
+        // selection cdf of sampleN (fsd_sampler.cpp:37-79), summed once in the sequential order: entry 0 is the P0 lobe, entry i the
+        // segment i-1; lane l keeps entries l and l+32.  The cdf is non-decreasing, so "first i with p < cdf[i]" = #{i : !(p < cdf[i])}.
+        float c0 = 0.f, c1 = 0.f;
+        {
+            float cdf = 0.f;
+            for (uint32_t i = 0; i < n; ++i) {
+                cdf += i == 0u ? hd.P0_pdf : ap_edge_pdf(A, ai, i - 1u);
+                if ((i & 31u) == lane) { if (i < 32u) c0 = cdf; else c1 = cdf; }
+            }
+        }
         V3 wo = mk3(0.f, 0.f, 1.f); float dpd = 0.f, wgt = 0.f;
         bool finished = false;
         for (; budget > 0u; --budget) {
-            // sampleN (fsd_sampler.cpp:37-79): entry 0 is the P0 lobe, entry i the segment i-1
             const float p = rnd(smp) * 1.f;
-            float cdf = 0.f; uint32_t sel = n;
-            for (uint32_t i = 0; i < n; ++i) {
-                const float q0 = __shfl_sync(0xffffffffu, pdf0, (int)((i - 1u) & 31u)), q1 = __shfl_sync(0xffffffffu, pdf1, (int)((i - 1u) & 31u));
-                cdf += i == 0u ? hd.P0_pdf : (i - 1u < 32u ? q0 : q1);
-                if (p < cdf) { sel = i; break; }
-            }
+            const uint32_t sel = (uint32_t)__popc(__ballot_sync(0xffffffffu, has0 && !(p < c0))) + (uint32_t)__popc(__ballot_sync(0xffffffffu, has1 && !(p < c1)));
             V2 xi;
-            if (sel == 0u) xi = kP0s * normal2d(rnd2(smp));
+            if (sel == 0u) { const float u0 = rnd(smp); const float u1 = rnd(smp); xi = kP0s * normal2d(mk2(u0, u1)); }
             else {
                 const FEdge e = ap_edge(A, ai, sel - 1u);
                 const V2 m = mk2(e.e.y, -e.e.x);
@@ -1156,7 +1162,8 @@ __global__ void __launch_bounds__(128) k_bd_fsd_sample(const BdArgs a) {
                 const float i00 = m.y * od, i01 = -e.e.y * od, i10 = -m.x * od, i11 = e.e.x * od;
                 const float Aa = cnorm(e.a_b), Bb = cnorm(e.iab_2);
                 const float pp = rnd(smp) * (Aa + Bb);
-                const V3 r3 = rnd3(smp);
+                const float r0 = rnd(smp); const float r1 = rnd(smp); const float r2 = rnd(smp);
+                const V3 r3 = mk3(r0, r1, r2);
                 const V2 z = pp < Aa ? flut_sample(a.lut, r3, a.lut.th1, a.lut.c1) : flut_sample(a.lut, r3, a.lut.th2, a.lut.c2);
                 xi = mk2(z.x * i00 + z.y * i01, z.x * i10 + z.y * i11);
             }
@@ -1188,9 +1195,9 @@ __global__ void __launch_bounds__(128) k_bd_fsd_sample(const BdArgs a) {
         if (lane == 0u) {
             if (finished) {
                 a.fsd_out[2u * wid] = make_float4(wo.x, wo.y, wo.z, dpd);
-                a.fsd_out[2u * wid + 1u] = make_float4(wgt, __uint_as_float(smp.d), 0.f, a.tag);
+                a.fsd_out[2u * wid + 1u] = make_float4(wgt, __uint_as_float(smp.s.d), 0.f, a.tag);
             } else {
-                a.fsd_out[2u * wid + 1u] = make_float4(0.f, __uint_as_float(smp.d), __uint_as_float(tries), 1.f);
+                a.fsd_out[2u * wid + 1u] = make_float4(0.f, __uint_as_float(smp.s.d), __uint_as_float(tries), 1.f);
                 carry_list[atomicAdd(&a.r.ctr->n_fsd_list[a.fl_next], 1)] = wid;
             }
         }

@@ -21,6 +21,28 @@ WT_D uint32_t philox_lane(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, ui
     }
     return lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3;
 }
+// the same stream with the four lanes of a Philox block kept between draws (for code that draws many numbers in a row)
+struct SamplerC { Sampler s; uint32_t blk; uint32_t c[4]; };
+WT_D SamplerC samplerc(const Sampler& s) { SamplerC r; r.s = s; r.blk = 0xffffffffu; r.c[0] = r.c[1] = r.c[2] = r.c[3] = 0u; return r; }
+WT_D float rnd(SamplerC& q) {
+    const uint32_t blk = q.s.d >> 2;
+    if (blk != q.blk) {
+        uint32_t c0 = blk, c1 = q.s.sample, c2 = q.s.pixel, c3 = q.s.stream, k0 = q.s.k0, k1 = q.s.k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+            const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+            c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        q.c[0] = c0; q.c[1] = c1; q.c[2] = c2; q.c[3] = c3; q.blk = blk;
+    }
+    const uint32_t lane = q.s.d & 3u;
+    const uint32_t u = lane == 0u ? q.c[0] : lane == 1u ? q.c[1] : lane == 2u ? q.c[2] : q.c[3];
+    ++q.s.d;
+    return (float)(u >> 8) * (1.0f / 16777216.0f);
+}
 WT_D float rnd(Sampler& s) {
     const uint32_t u = philox_lane(s.k0, s.k1, s.d >> 2, s.sample, s.pixel, s.stream, s.d & 3u);
     ++s.d;

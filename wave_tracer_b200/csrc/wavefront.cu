@@ -790,7 +790,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
                 if (iters > 0) { CK(cudaStreamWaitEvent(st, s->bd_ev_samp, 0)); k_bd_fsd_finish<<<gW, blk, 0, st>>>(b); ++launches; }
                 CK(cudaStreamWaitEvent(s->bd_stream, s->bd_ev_shade, 0));
                 CK(cudaMemsetAsync(&s->ctr->fsd_head, 0, sizeof(int), s->bd_stream));
-                k_bd_fsd_sample<<<gC, blk, 0, s->bd_stream>>>(b); ++launches;
+                k_bd_fsd_sample<<<dim3(148 * 16), blk, 0, s->bd_stream>>>(b); ++launches;
                 CK(cudaEventRecord(s->bd_ev_samp, s->bd_stream));
             }
             mark();
