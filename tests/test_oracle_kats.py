@@ -175,3 +175,65 @@ def test_double_slit_fringe_spacing():
     assert abs((right - c) * px_mm - 5.0) < 1.0 and abs((c - left) * px_mm - 5.0) < 1.0
     assert prof[c - 2:c + 3].sum() > 20 * prof[right]        # zero order dominates
     assert st["samples"] == res * (res // 4) * 8
+
+
+# ------------------------------------------------------------------------------------------------ plt_bdpt pieces
+def _bdpt_lib():
+    L = _oracle.lib()
+    L.oracle_fraunhofer_asf.argtypes = [C.c_uint32, C.POINTER(C.c_float), C.c_float, C.c_float]; L.oracle_fraunhofer_asf.restype = C.c_float
+    L.oracle_gaussian_integrate_triangle.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float)]; L.oracle_gaussian_integrate_triangle.restype = C.c_float
+    return L
+
+
+def test_fraunhofer_asf_of_a_rectangle_is_its_fourier_transform():
+    """Edge formulation (fsd.hpp:59-140) with unit field on a closed w x h rectangle: |sum Psi|^2 = |FT of the indicator|^2 / (2 pi)^2
+    = (w h sinc(w xi_x/2) sinc(h xi_y/2))^2 / (4 pi^2)  -- the textbook Fraunhofer pattern, independent of any implementation."""
+    L = _bdpt_lib()
+    w, h = 0.7, 0.3
+    P = [(-w / 2, -h / 2), (w / 2, -h / 2), (w / 2, h / 2), (-w / 2, h / 2)]
+    edges = []
+    for i in range(4):
+        a, b = np.array(P[i]), np.array(P[(i + 1) % 4])
+        e, v = b - a, (a + b) / 2
+        edges += [e[0], e[1], v[0], v[1], 0.0, 0.0, 0.0, 1.0]          # a_b = a-b = 0, iab_2 = i (a+b)/2 = i
+    arr = (C.c_float * len(edges))(*edges)
+    for xi in [(3.0, 2.0), (10.0, -7.0), (0.5, 0.2), (25.0, 3.0), (-4.0, 11.0)]:
+        asf = L.oracle_fraunhofer_asf(4, arr, xi[0], xi[1])
+        ft = w * h * np.sinc(w * xi[0] / 2 / np.pi) * np.sinc(h * xi[1] / 2 / np.pi)
+        assert asf == pytest.approx(ft * ft / (4 * np.pi ** 2), rel=2e-5, abs=1e-12)
+
+
+def test_gaussian_triangle_integral_against_quadrature():
+    """gaussian2d_t::integrate_triangle (src/math/gaussian2d.cpp:96-192, erf-LUT + 4-Gaussian erf approximation) vs brute-force quadrature."""
+    L = _bdpt_lib()
+    rng = np.random.default_rng(1)
+
+    def numint(sx, sy, t, n=1200):
+        a, b, c = [np.array(t[i:i + 2]) for i in (0, 2, 4)]
+        u = (np.arange(n) + .5) / n; U, V = np.meshgrid(u, u); m = U + V < 1
+        pts = a[None, :] + U[m][:, None] * (b - a)[None, :] + V[m][:, None] * (c - a)[None, :]
+        e1, e2 = b - a, c - a
+        area = abs(e1[0] * e2[1] - e1[1] * e2[0]) / 2
+        return (np.exp(-.5 * ((pts[:, 0] / sx) ** 2 + (pts[:, 1] / sy) ** 2)) / (2 * np.pi * sx * sy)).mean() * area
+
+    for _ in range(12):
+        sx, sy = rng.uniform(.5, 2, 2); t = rng.uniform(-3, 3, 6)
+        v = L.oracle_gaussian_integrate_triangle(sx, sy, (C.c_float * 6)(*t))
+        assert v == pytest.approx(numint(sx, sy, list(t)), abs=2.5e-3)
+    # a triangle covering the 3-sigma disc integrates to 1; a far one to 0; a sliver takes the fixed-step quadrature branch
+    assert L.oracle_gaussian_integrate_triangle(1, 1, (C.c_float * 6)(-20, -20, 20, -20, 0, 30)) == pytest.approx(1.0, abs=1e-6)
+    assert L.oracle_gaussian_integrate_triangle(1, 1, (C.c_float * 6)(5, 5, 6, 5, 5, 6)) == 0.0
+    sl = [-1.0, 0.0, 1.0, 0.0, 1.0, 0.02]
+    assert L.oracle_gaussian_integrate_triangle(1, 1, (C.c_float * 6)(*sl)) == pytest.approx(numint(1, 1, sl, n=3000), rel=3e-2)
+
+
+def test_fraunhofer_sampling_tables():
+    """fsd_lut.py: the regenerated iCDF tables are monotone, span the first quadrant, and integrate() reproduces its documented constants."""
+    from wave_tracer_b200 import fsd_lut
+    t1, t2, c1, c2 = fsd_lut.build(128, 64, use_cache=False)
+    for t in (t1, t2):
+        assert t.dtype == np.float32 and np.all(np.diff(t) >= 0) and t[0] >= 0 and t[-1] <= np.pi / 2 + 1e-6
+    for c in (c1, c2):
+        assert c.shape == (64, 64) and np.all(np.diff(c, axis=1) >= -1e-6) and c.min() >= 0
+    assert fsd_lut.integrate(1, n_theta=257) == pytest.approx(0.004827, rel=2e-2)
+    assert fsd_lut.integrate(2, n_theta=257) == pytest.approx(0.16252, rel=2e-2)
