@@ -227,6 +227,16 @@ typedef struct wtgpu_integrator {
     uint32_t mis, sensor_direct, emitter_direct;   /* plt_bdpt only */
 } wtgpu_integrator;
 
+/* ---------------------------------------------------------------------------------------------
+ * sobolld sampler table: one line "d sj aj mk[0..sj)" of data/sobolld/initIrreducibleGF3.dat
+ * (include/wt/sampler/sobolld/irreducible_gf3.hpp:124-158): dimension, degree of the irreducible polynomial over GF(3),
+ * the polynomial's coefficients as a base-3 number (leading coefficient included), initial direction numbers.
+ * ------------------------------------------------------------------------------------------- */
+#define WTGPU_SOBOL_ENTRIES 48u     /* irreducible_gf3.hpp:34 */
+#define WTGPU_SOBOL_DIMS    47u     /* src/sampler/sobolld.cpp:31: sobolls_sampler<47> */
+#define WTGPU_SOBOL_DIGITS  11u     /* irreducible_gf3.hpp:33: batches of 3^11 = 177147 points */
+typedef struct wtgpu_sobol_entry { int32_t d, sj, aj; int32_t mk[32]; int32_t pad_; } wtgpu_sobol_entry;   /* 144 B */
+
 typedef struct wtgpu_scene_desc {
     uint32_t api_version;           /* WTGPU_API_VERSION */
 
@@ -266,6 +276,11 @@ typedef struct wtgpu_scene_desc {
      * icdf*: m x m, row = theta bin, column = u -> radius. */
     uint32_t fsd_lut_n, fsd_lut_m;
     const float *fsd_icdf_theta1, *fsd_icdf_theta2, *fsd_icdf1, *fsd_icdf2;
+
+    /* sobolld scene sampler (src/sampler/sobolld.cpp:29-60): WTGPU_SOBOL_ENTRIES parsed lines of data/sobolld/initIrreducibleGF3.dat
+     * (irreducible_gf3.hpp:124-158; entry 0 is skipped by the reference, dimensions use entries 1..47), or NULL when the scene's
+     * sampler is the uniform one.  Required when wtgpu_render_opts::sampler == WTGPU_SAMPLER_SOBOLLD. */
+    const struct wtgpu_sobol_entry* sobol_table;
 } wtgpu_scene_desc;
 
 /* ---------------------------------------------------------------------------------------------
@@ -282,6 +297,13 @@ typedef struct wtgpu_scene_desc {
  * float = (u32 >> 8) * 2^-24.  stream is 0 for plt_path.  plt_bdpt splits a sample into sub-streams (each starting at d = 0) so
  * that the two subpath walks and every (s,t) strategy are independent: 0 = emitter / wavenumber / source sampling, 1 = sensor
  * subpath walk, 2 = emitter subpath walk, 3 + 32 t + s = strategy (s,t).
+ *
+ * sobolld contract (the reference draws a fresh batch of 3^11 x 47 values per pool thread with random seeds,
+ * src/sampler/sobolld.cpp:53-60, and consumes it as one flat stream, sobolld.hpp:40-48): sample `s` of element `p` owns point
+ * g = p * spp + s of the global sequence; batch b = g / 3^11 is Owen-scrambled with seeds[dim] = lane 0 of
+ * Philox4x32-10(key = seed, counter = (dim, b_lo, b_hi, 0x50B01D)); scene-sampler draw d of that sample is dimension d % 47 of
+ * point g + d / 47 (the reference's flat layout, each sample starting at a point boundary).  Digit arithmetic is bit-exact with
+ * sobolld_sampler.hpp:59-207 (wtgpu_debug_sobol() exposes the integer numerators).
  * ------------------------------------------------------------------------------------------- */
 typedef struct wtgpu_render_opts {
     uint64_t seed;
@@ -291,10 +313,14 @@ typedef struct wtgpu_render_opts {
     int32_t device;                 /* CUDA device ordinal */
     uint32_t film_on_device;        /* film pointers are device pointers */
     uint32_t pool_size;             /* paths in flight (0: default) */
-    uint32_t sampler;               /* 0: philox uniform; 1: sobolld for the scene-sampler dimensions */
+    uint32_t sampler;               /* WTGPU_SAMPLER_*: the scene sampler (scene_t::sampler(), src/scene/loader/loader.cpp:299-300) */
     uint32_t flags;                 /* WTGPU_RENDER_* */
     void* stream;                   /* cudaStream_t or NULL */
 } wtgpu_render_opts;
+#define WTGPU_SAMPLER_UNIFORM 0u    /* sampler::uniform_t -> the Philox stream */
+#define WTGPU_SAMPLER_SOBOLLD 1u    /* sampler::sobolld_t for the scene-sampler draws (emitter / wavenumber / source beam / sensor element:
+                                       plt_path_detail.hpp:772,783; plt_bdpt.cpp:56,70); path sampling stays on the Philox stream, as the
+                                       reference's integrators keep their own uniform_t for it (plt_path_detail.hpp:59-60,146; plt_bdpt.cpp:50-52) */
 #define WTGPU_RENDER_NO_SORT 1u     /* disable the material sort (for A/B measurement) */
 #define WTGPU_RENDER_BDPT_MEGAKERNEL 4u  /* plt_bdpt: run the one-thread-per-sample cross-check kernel instead of the wavefront */
 #define WTGPU_RENDER_THREAD_TRAVERSE 8u  /* plt_bdpt: one thread per beam in traverse() instead of eight lanes per beam (A/B measurement) */
@@ -360,6 +386,8 @@ int wtgpu_debug_intersect_cones(wtgpu_scene* scene, uint32_t n, const wtgpu_cone
 
 /* counter-based RNG stream: out[i] = i-th draw of stream (seed, pixel, sample) */
 int wtgpu_debug_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, int device);
+/* sobolld: numerators (value * 3^11) and floats of dimensions 0..46 of points g0 .. g0+n-1 of the global sequence; out arrays n*47 */
+int wtgpu_debug_sobol(wtgpu_scene* scene, uint64_t seed, uint64_t g0, uint32_t n, uint32_t* out_numerators, float* out_values);
 /* sizeof of the i-th ABI struct (order of wave_tracer_b200/_abi.py:ABI_STRUCTS); lets bindings verify their layout */
 uint64_t wtgpu_debug_sizeof(int which);
 

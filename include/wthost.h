@@ -43,6 +43,12 @@ void wthost_ads_destroy(wthost_ads* ads);
 double wthost_ads_sah_cost(const wthost_ads* ads);
 uint32_t wthost_ads_max_depth(const wthost_ads* ads);
 
+
+/* sobolld: generator matrices of the 47 dimensions derived from the parsed table (the reference's generate_mkgf3 + gen_mat,
+ * include/wt/sampler/sobolld/irreducible_gf3.hpp:103-118, sobolld_sampler.hpp:140-154) in the packed form the device keeps in
+ * constant memory: bit c of ones[dim*11 + j] is set when matrix row 10-j, column c equals 1 (twos: equals 2).  Host only. */
+int wthost_sobol_tables(const wtgpu_sobol_entry* table, uint16_t* ones /* 47*11 */, uint16_t* twos /* 47*11 */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,8 @@ int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, d
     if (!desc || !opts) return -1;
     const bool bdpt = desc->integrator.type == WTGPU_INTEGRATOR_PLT_BDPT;
     if (bdpt && !sc_has_lut(desc) && desc->integrator.fsd && !desc->sensor.ray_trace_only) return -4;
+    std::unique_ptr<sobol_ctx_t> sob;
+    if (opts->sampler == WTGPU_SAMPLER_SOBOLLD) { if (!desc->sobol_table || opts->spp == 0) return -1; sob.reset(new sobol_ctx_t(desc->sobol_table)); }
     scene_t sc(desc);
     const uint32_t W = desc->sensor.width, H = desc->sensor.height, C = desc->sensor.channels;
     const uint32_t x0 = opts->tile_x0, y0 = opts->tile_y0, x1 = std::min(opts->tile_x1, W), y1 = std::min(opts->tile_y1, H);
@@ -45,6 +47,7 @@ int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, d
                 const uint32_t ex = x0 + (uint32_t)(i % tw), ey = y0 + (uint32_t)(i / tw);
                 for (uint32_t s = opts->sample_begin; s < opts->sample_end; ++s) {
                     sampler_t smp; smp.seed = opts->seed; smp.pixel = ey * W + ex; smp.sample = s;
+                    smp.begin_scene_draws(sob.get(), opts->spp);
                     if (bdpt) binteg.integrate(ex, ey, smp); else integ.integrate(ex, ey, smp);
                 }
             }
@@ -70,6 +73,26 @@ int oracle_render(const wtgpu_scene_desc* desc, const wtgpu_render_opts* opts, d
             st->nodes += s.ads.nodes; st->tris += s.ads.tris; st->ray_casts += s.ads.ray_casts; st->cone_casts += s.ads.cone_casts; st->shadow_casts += s.ads.shadow_casts;
         }
     }
+    return 0;
+}
+
+// sobolld: the literal generate_points() of batch `batch` under our seeding contract; out arrays hold n_points*47 values (point-major)
+int oracle_sobol_batch(const wtgpu_sobol_entry* table, uint64_t seed, uint64_t batch, uint32_t n_points, uint32_t* out_numerators, float* out_values) {
+    if (!table) return -1;
+    sobol::gf3_t gf3(table);
+    sobol::sobolls_sampler gen(sobol::N, gf3);
+    uint64_t seeds[sobol::D]; sobol_ctx_t::seeds_for_batch(seed, batch, seeds);
+    std::vector<float> v; std::vector<uint32_t> num;
+    gen.generate_points(seeds, n_points, v, &num);
+    for (size_t i = 0; i < v.size(); ++i) { if (out_values) out_values[i] = v[i]; if (out_numerators) out_numerators[i] = num[i]; }
+    return (int)(v.size() / sobol::D);
+}
+// generator matrices as gen_mat builds them: out[dim][row][col], 47 x 11 x 11 digits
+int oracle_sobol_matrices(const wtgpu_sobol_entry* table, int32_t* out) {
+    if (!table) return -1;
+    sobol::gf3_t gf3(table);
+    sobol::sobolls_sampler gen(sobol::N, gf3);
+    for (size_t d = 0; d < sobol::D; ++d) for (size_t r = 0; r < sobol::N; ++r) for (size_t c = 0; c < sobol::N; ++c) out[(d * sobol::N + r) * sobol::N + c] = (int32_t)gen.matrix[d][r][c];
     return 0;
 }
 

@@ -611,6 +611,7 @@ struct plt_path_t {
         const f_t k = ws.k;
         const f_t recp_spectral_pd = ws.wpd.is_discrete ? 1.f / ws.wpd.v : 1.f / emitters.sum_spectral_pdf_for_all_emitters(k);
         const auto ss = sensor.sample(sampler, ex, ey, k);
+        sampler.end_scene_draws();      // scene->sampler() is used up to here (plt_path_detail.hpp:772,783); the walk has its own uniform sampler (:59-60,146)
         walk_t data; data.beam = ss.beam; data.prev_vert_geo = geo_t::point(ss.beam.origin()); data.sampler = &sampler;
         const stokes_t L = random_walk(data, recp_spectral_pd);
         film.splat(ss.element, L * recp_spectral_pd, k);
@@ -624,6 +625,7 @@ struct plt_path_t {
         const f_t k = ws.k;
         const auto es = emitters.sample(em, sampler, k);
         const f_t recp_spectral_pd = 1.f / emitters.sum_spectral_pdf_for_all_emitters(k);
+        sampler.end_scene_draws();
         walk_t data; data.beam = es.beam; data.prev_vert_geo = geo_t::point(es.beam.origin()); data.sampler = &sampler;
         random_walk(data, recp_spectral_pd);
     }

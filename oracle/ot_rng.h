@@ -11,6 +11,10 @@
 // subpath walk, 3 + 32 t + s = connection (s,t); each sub-stream starts at d = 0.
 #pragma once
 #include "ot_math.h"
+#include "ot_sobol.h"
+#include <map>
+#include <memory>
+#include <mutex>
 
 namespace ot {
 
@@ -27,7 +31,33 @@ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
     }
 }
 
+// The sobolld scene sampler under our seeding contract (include/wtgpu.h "sobolld contract"): whole batches are produced by the
+// literal generate_points() restatement (ot_sobol.h) and cached; a draw indexes the flat point-major batch exactly as
+// sobolld_t::next_sample does (include/wt/sampler/sobolld.hpp:40-48).
+struct sobol_ctx_t {
+    sobol::gf3_t gf3;
+    sobol::sobolls_sampler gen;
+    mutable std::mutex m;
+    mutable std::map<uint64_t, std::shared_ptr<std::vector<float>>> batches;
+    explicit sobol_ctx_t(const wtgpu_sobol_entry* e) : gf3(e), gen(sobol::N, gf3) {}
+    static void seeds_for_batch(uint64_t seed, uint64_t batch, uint64_t* out);
+    std::shared_ptr<std::vector<float>> batch(uint64_t seed, uint64_t b) const {
+        std::lock_guard<std::mutex> l(m);
+        auto it = batches.find(b);
+        if (it != batches.end()) return it->second;
+        uint64_t seeds[sobol::D]; seeds_for_batch(seed, b, seeds);
+        auto v = std::make_shared<std::vector<float>>();
+        gen.generate_points(seeds, (size_t)-1, *v);
+        if (batches.size() >= 4) batches.erase(batches.begin());
+        batches[b] = v;
+        return v;
+    }
+};
+
 struct sampler_t {
+    static constexpr uint32_t sobol_flag = 0x80000000u;
+    const sobol_ctx_t* sob = nullptr;
+    std::shared_ptr<std::vector<float>> sob_batch; uint64_t sob_batch_idx = ~0ull;
     uint64_t seed = 0;
     uint32_t pixel = 0, sample = 0;
     uint32_t d = 0;
@@ -46,13 +76,31 @@ struct sampler_t {
         return cache[lane];
     }
     void set_stream(uint32_t s) { stream = s; d = 0; cached_block = 0xffffffffu; }
-    f_t r() { return (f_t)(next_u32() >> 8) * (1.0f / 16777216.0f); }
+    // scene sampler = sobolld: flag | spp in `stream` (the device carries it the same way, csrc/dscene.cuh rnd())
+    void begin_scene_draws(const sobol_ctx_t* ctx, uint32_t spp) { if (ctx) { sob = ctx; stream = sobol_flag | spp; } }
+    void end_scene_draws() { if (stream & sobol_flag) { stream = 0; cached_block = 0xffffffffu; } }     // path sampling continues on the Philox stream at the same d
+    f_t sobol_r() {
+        const uint64_t g = (uint64_t)pixel * (uint64_t)(stream & ~sobol_flag) + sample + d / sobol::D;
+        const uint32_t dim = d % sobol::D; ++d;
+        const uint64_t npts = sobol::pow3tab[sobol::N], b = g / npts, i = g % npts;
+        if (b != sob_batch_idx) { sob_batch = sob->batch(seed, b); sob_batch_idx = b; }
+        return (*sob_batch)[i * sobol::D + dim];
+    }
+    f_t r() { if (stream & sobol_flag) return sobol_r(); return (f_t)(next_u32() >> 8) * (1.0f / 16777216.0f); }
     v2 r2() { const f_t a = r(); const f_t b = r(); return { a, b }; }
     v3 r3() { const f_t a = r(); const f_t b = r(); const f_t c = r(); return { a, b, c }; }
 
     // sampler.hpp:106-109
     int uniform_int_interval(int start, int end) { return std::min(end - 1, int(r() * (end - start)) + start); }
 };
+
+inline void sobol_ctx_t::seeds_for_batch(uint64_t seed, uint64_t batch, uint64_t* out) {
+    for (uint32_t d = 0; d < sobol::D; ++d) {
+        uint32_t c[4] = { d, (uint32_t)batch, (uint32_t)(batch >> 32), 0x50B01Du };
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        out[d] = c[0];
+    }
+}
 
 // sampler.hpp:139-150
 inline v3 uniform_sphere(v2 u) {

@@ -37,6 +37,8 @@ def lib():
         L.oracle_intersect_cones.argtypes = [C.POINTER(A.SceneDesc), C.c_uint32, C.POINTER(A.ConeQuery), C.POINTER(A.ConeHit)]
         L.oracle_cone_closest_bruteforce.argtypes = [C.POINTER(A.SceneDesc), C.c_uint32, C.POINTER(A.ConeQuery), C.POINTER(C.c_float)]
         L.oracle_rng.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+        L.oracle_sobol_batch.argtypes = [C.POINTER(A.SobolEntry), C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.oracle_sobol_matrices.argtypes = [C.POINTER(A.SobolEntry), C.POINTER(C.c_int32)]
         L.oracle_svd.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.oracle_utdf.argtypes = [C.c_float, C.POINTER(C.c_float)]
         L.oracle_cerfc_rot45.argtypes = [C.c_double, C.POINTER(C.c_double)]
@@ -52,6 +54,7 @@ def render(built, spp=None, seed=0x5EED, sample_range=None, tile=None, threads=0
     spp = spp or built.spp
     o = A.RenderOpts()
     o.seed, o.spp = seed, spp
+    o.sampler = getattr(built, "sampler", 0)
     o.sample_begin, o.sample_end = sample_range if sample_range else (0, spp)
     o.tile_x0, o.tile_y0, o.tile_x1, o.tile_y1 = tile if tile else (0, 0, built.width, built.height)
     W, H, Cn = built.width, built.height, built.channels

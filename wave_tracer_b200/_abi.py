@@ -9,6 +9,7 @@ import os
 
 c_f, c_u32, c_i32, c_u64, c_dbl = C.c_float, C.c_uint32, C.c_int32, C.c_uint64, C.c_double
 INVALID_IDX = 0xFFFFFFFF
+SAMPLER_UNIFORM, SAMPLER_SOBOLLD = 0, 1
 
 
 class Node(C.Structure):
@@ -100,6 +101,10 @@ class Integrator(C.Structure):
 P = C.POINTER
 
 
+class SobolEntry(C.Structure):
+    _fields_ = [("d", c_i32), ("sj", c_i32), ("aj", c_i32), ("mk", c_i32 * 32), ("pad_", c_i32)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("api_version", c_u32),
                 ("n_nodes", c_u32), ("nodes", P(Node)), ("n_leaves", c_u32), ("leaves", P(Leaf)), ("root_ptr", c_i32),
@@ -112,7 +117,8 @@ class SceneDesc(C.Structure):
                 ("n_emitters", c_u32), ("emitters", P(Emitter)), ("emitter_cdf", P(c_f)), ("emitter_kdist", P(KDist)),
                 ("n_kdist_data", c_u32), ("kdist_data", P(c_f)),
                 ("sensor", Sensor), ("integrator", Integrator),
-                ("fsd_lut_n", c_u32), ("fsd_lut_m", c_u32), ("fsd_icdf_theta1", P(c_f)), ("fsd_icdf_theta2", P(c_f)), ("fsd_icdf1", P(c_f)), ("fsd_icdf2", P(c_f))]
+                ("fsd_lut_n", c_u32), ("fsd_lut_m", c_u32), ("fsd_icdf_theta1", P(c_f)), ("fsd_icdf_theta2", P(c_f)), ("fsd_icdf1", P(c_f)), ("fsd_icdf2", P(c_f)),
+                ("sobol_table", P(SobolEntry))]
 
 
 class RenderOpts(C.Structure):
@@ -156,7 +162,7 @@ class MeshDesc(C.Structure):
 
 
 ABI_STRUCTS = [Node, Leaf, Tri, TriMeta, TriShading, Edge, Shape, Spectrum, Bsdf, BsdfBin, Emitter, KDist, Sensor, Integrator,
-               SceneDesc, RenderOpts, Stats, RayQuery, RayHit, ConeQuery, ConeHit, MeshDesc]
+               SceneDesc, RenderOpts, Stats, RayQuery, RayHit, ConeQuery, ConeHit, MeshDesc, SobolEntry]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwt_b200.so")
@@ -183,6 +189,8 @@ def lib():
     L.wtgpu_debug_shadow_rays.argtypes = [C.c_void_p, c_u32, P(RayQuery), P(c_u32)]
     L.wtgpu_debug_intersect_cones.argtypes = [C.c_void_p, c_u32, P(ConeQuery), P(ConeHit)]
     L.wtgpu_debug_rng.argtypes = [c_u64, c_u32, c_u32, c_u32, P(c_f), C.c_int]
+    L.wtgpu_debug_sobol.argtypes = [C.c_void_p, c_u64, c_u64, c_u32, P(c_u32), P(c_f)]
+    L.wthost_sobol_tables.argtypes = [P(SobolEntry), P(C.c_uint16), P(C.c_uint16)]
     L.wtgpu_debug_sizeof.argtypes = [C.c_int]
     L.wtgpu_debug_sizeof.restype = C.c_uint64
     L.wthost_ads_build.argtypes = [c_u32, P(MeshDesc), P(C.c_void_p)]
@@ -198,7 +206,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_render", "wtgpu_develop",
-                    "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_sizeof",
+                    "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_sobol", "wtgpu_debug_sizeof", "wthost_sobol_tables",
                     "wthost_ads_build", "wthost_ads_fill", "wthost_ads_destroy", "wthost_ads_sah_cost", "wthost_ads_max_depth"]
 
 

@@ -786,7 +786,7 @@ struct BdSampleInit { uint32_t pixel, sample, ex, ey; float k, rspd, wpd_v; Elem
 // draws on sub-stream 0, writes vertex 0 of both subpaths, returns the two walk states
 WT_D void bd_init_sample(const BCtx& c, uint32_t seed_lo, uint32_t seed_hi, uint32_t ex, uint32_t ey, uint32_t sample, BdSampleInit& si, BWalk& ws, BWalk& we) {
     const DScene& sc = *c.sc;
-    Sampler smp; smp.k0 = seed_lo; smp.k1 = seed_hi; smp.pixel = ey * sc.sensor.width + ex; smp.sample = sample; smp.d = 0; smp.stream = 0u;
+    Sampler smp; smp.k0 = seed_lo; smp.k1 = seed_hi; smp.pixel = ey * sc.sensor.width + ex; smp.sample = sample; smp.d = 0; smp.stream = sc.scene_stream;
     const int32_t em = sample_emitter(sc, smp);
     const float em_pdf = pdf_emitter(sc, em);
     const KSample ks = sample_wavenumber(sc, em, smp);

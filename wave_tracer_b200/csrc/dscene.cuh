@@ -3,6 +3,7 @@
 // Each block cites the reference code whose behaviour it reproduces (paths relative to /root/reference).
 #pragma once
 #include "dtrav.cuh"
+#include "dsobol.cuh"
 
 namespace wt {
 
@@ -44,6 +45,8 @@ WT_D float rnd(SamplerC& q) {
     return (float)(u >> 8) * (1.0f / 16777216.0f);
 }
 WT_D float rnd(Sampler& s) {
+    // scene sampler = sobolld (include/wtgpu.h "sobolld contract"): stream carries the flag and the sensor's spp
+    if (s.stream & kSobolStreamFlag) return sobol_draw(s.k0, s.k1, (uint64_t)s.pixel * (uint64_t)(s.stream & ~kSobolStreamFlag) + s.sample, s.d++);
     const uint32_t u = philox_lane(s.k0, s.k1, s.d >> 2, s.sample, s.pixel, s.stream, s.d & 3u);
     ++s.d;
     return (float)(u >> 8) * (1.0f / 16777216.0f);

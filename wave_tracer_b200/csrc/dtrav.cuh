@@ -24,6 +24,7 @@ struct DScene {
     wtgpu_sensor sensor;
     wtgpu_integrator integrator;
     const float* erf_lut;             // 1024-entry erf table (include/wt/math/erf_lut.hpp)
+    uint32_t scene_stream;            // Sampler::stream of the scene-sampler draws: 0 (uniform) or kSobolStreamFlag | spp (sobolld); set per render
 };
 
 struct Counters {       // per-thread, flushed with one atomic per counter per warp

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) k_generate(const RenderArgs a) {
             const uint32_t ex = a.tile_x0 + pi % a.tile_w, ey = a.tile_y0 + pi / a.tile_w;
             PathCore pc;
             pc.pixel = ey * sc.sensor.width + ex; pc.sample = a.sample_begin + si;
-            Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = 0; smp.stream = 0u;
+            Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = 0; smp.stream = sc.scene_stream;
             // integrate_backward / integrate_forward preamble (plt_path_detail.hpp:764-828)
             const int32_t em = sample_emitter(sc, smp);
             const KSample ks = sample_wavenumber(sc, em, smp);
@@ -542,6 +542,13 @@ __global__ void k_debug_cones(const DScene sc, uint32_t n, const wtgpu_cone_quer
     h.n_edges = collect_edges<WTGPU_MAX_CONE_EDGES>(sc, tris, nt, edges, eo);
     for (uint32_t j = 0; j < h.n_edges; ++j) h.edges[j] = edges[j];
 }
+// sobolld: dimensions 0..46 of points g0 .. g0+n-1 (one thread per value)
+__global__ void k_debug_sobol(uint32_t k0, uint32_t k1, unsigned long long g0, uint32_t n, uint32_t* num, float* val) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * WTGPU_SOBOL_DIMS) return;
+    const uint32_t u = sobol_numerator(k0, k1, g0 + i / WTGPU_SOBOL_DIMS, i % WTGPU_SOBOL_DIMS);
+    num[i] = u; val[i] = sobol_value(u);
+}
 __global__ void k_debug_rng(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t n, float* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -566,6 +573,7 @@ struct wtgpu_scene {
     DevCounters* ctr = nullptr;
     uint32_t n_keys = 0;
     std::vector<cudaEvent_t> ev_pool;   // reused across renders (event creation is not free)
+    bool has_sobol = false;             // sobolld generator matrices are in constant memory of this device
     wt::FLut lut{};                     // plt_bdpt: Fraunhofer sampling tables
     float* bdpt_arena = nullptr; uint32_t bdpt_P = 0;
     // plt_bdpt wavefront state (P sample slots, 2P walkers)
@@ -589,6 +597,42 @@ struct wtgpu_scene {
     }
 };
 
+// Generator matrices of the sobolld sampler from the parsed table, as row masks for dsobol.cuh.
+// Direction numbers m_1..m_11 of a dimension are kept as base-3 digit vectors v[c][t] (digit t of m_{c+1}); the first s_j come from the
+// table, the rest from the recurrence over GF(3) of irreducible_gf3.hpp:103-118 written digit-wise:
+//     v[c][t] = v[c-deg][t] + sum_{j=1..deg} g_j * v[c-j][t-j]   (mod 3),   g_j = -a_{deg-j}  (the reference's convert_to_gf3 = {0,2,1}).
+// gen_mat (sobolld_sampler.hpp:140-154) then puts digit (c - r) of m_{c+1} at row r, column c (upper triangular).
+static bool sobol_build_tables(const wtgpu_sobol_entry* e, wt::SobolTables& t, std::string& why) {
+    const int M = (int)WTGPU_SOBOL_DIGITS;
+    memset(&t, 0, sizeof(t));
+    for (int dim = 0; dim < (int)WTGPU_SOBOL_DIMS; ++dim) {
+        const wtgpu_sobol_entry& en = e[dim + 1];       // entry 0 is skipped by the reference (sobolld_sampler.hpp:50-52: d+1)
+        const int deg = en.sj;
+        if (en.d == 0 || deg < 1 || deg + 1 > M) { why = "sobol table: bad entry " + std::to_string(dim + 1); return false; }
+        int poly[16] = { 0 };
+        { int a = en.aj; for (int i = 0; i <= deg; ++i) { poly[i] = a % 3; a /= 3; } if (a != 0 || poly[deg] == 0) { why = "sobol table: polynomial/degree mismatch in entry " + std::to_string(dim + 1); return false; } }
+        int v[WTGPU_SOBOL_DIGITS][WTGPU_SOBOL_DIGITS] = {};
+        for (int c = 0; c < deg; ++c) {
+            int m = en.mk[c], lim = 1; for (int q = 0; q <= c; ++q) lim *= 3;
+            if (m <= 0 || m >= lim) { why = "sobol table: direction number out of range in entry " + std::to_string(dim + 1); return false; }
+            for (int q = 0; q <= c; ++q) { v[c][q] = m % 3; m /= 3; }
+        }
+        for (int c = deg; c < M; ++c)
+            for (int q = 0; q <= c; ++q) {
+                int acc = v[c - deg][q];
+                for (int j = 1; j <= deg; ++j) if (q >= j) acc += ((3 - poly[deg - j]) % 3) * v[c - j][q - j];
+                v[c][q] = acc % 3;
+            }
+        for (int j = 0; j < M; ++j) {
+            const int r = M - 1 - j;                    // output digit j reads matrix row M-1-j (sobolld_sampler.hpp:170)
+            uint16_t o1 = 0, o2 = 0;
+            for (int c = r; c < M; ++c) { const int x = v[c][c - r]; if (x == 1) o1 |= (uint16_t)(1u << c); else if (x == 2) o2 |= (uint16_t)(1u << c); }
+            t.ones[dim][j] = o1; t.twos[dim][j] = o2;
+        }
+    }
+    return true;
+}
+
 template <class T> static int upload(wtgpu_scene* s, const T* src, size_t n, const T** dst) {
     void* p = nullptr;
     const size_t bytes = std::max<size_t>(1, n) * sizeof(T);
@@ -611,7 +655,7 @@ uint64_t wtgpu_debug_sizeof(int which) {
     case 8: return sizeof(wtgpu_bsdf); case 9: return sizeof(wtgpu_bsdf_bin); case 10: return sizeof(wtgpu_emitter); case 11: return sizeof(wtgpu_kdist);
     case 12: return sizeof(wtgpu_sensor); case 13: return sizeof(wtgpu_integrator); case 14: return sizeof(wtgpu_scene_desc); case 15: return sizeof(wtgpu_render_opts);
     case 16: return sizeof(wtgpu_stats); case 17: return sizeof(wtgpu_ray_query); case 18: return sizeof(wtgpu_ray_hit); case 19: return sizeof(wtgpu_cone_query);
-    case 20: return sizeof(wtgpu_cone_hit); case 21: return sizeof(wthost_mesh_desc);
+    case 20: return sizeof(wtgpu_cone_hit); case 21: return sizeof(wthost_mesh_desc); case 22: return sizeof(wtgpu_sobol_entry);
     }
     return 0;
 }
@@ -652,6 +696,14 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
             (rc = upload(s, desc->fsd_icdf1, mm, &s->lut.c1)) != WTGPU_OK || (rc = upload(s, desc->fsd_icdf2, mm, &s->lut.c2)) != WTGPU_OK) { delete s; return rc; }
     }
 #undef UP
+    if (desc->sobol_table) {
+        wt::SobolTables tb; std::string why;
+        if (!sobol_build_tables(desc->sobol_table, tb, why)) { g_err = why; delete s; return WTGPU_E_INVALID; }
+        cudaError_t e_ = cudaMemcpyToSymbol(wt::c_sobol, &tb, sizeof(tb));
+        if (e_ != cudaSuccess) { g_err = std::string("cudaMemcpyToSymbol(c_sobol): ") + cudaGetErrorString(e_); delete s; return WTGPU_E_CUDA; }
+        s->has_sobol = true;
+    }
+    d.scene_stream = 0u;
     d.root_ptr = desc->root_ptr; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs; d.n_tris = desc->n_tris; d.n_nodes = desc->n_nodes;
     d.sensor = desc->sensor; d.integrator = desc->integrator;
     s->sensor = desc->sensor; s->integ = desc->integrator;
@@ -682,6 +734,12 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     const uint32_t W = s->sensor.width, H = s->sensor.height, C = s->sensor.channels;
     const uint32_t x1 = std::min(o->tile_x1, W), y1 = std::min(o->tile_y1, H);
     if (x1 <= o->tile_x0 || y1 <= o->tile_y0 || o->sample_end <= o->sample_begin) { if (stats) memset(stats, 0, sizeof(*stats)); return WTGPU_OK; }
+    if (o->sampler == WTGPU_SAMPLER_SOBOLLD) {
+        if (!s->has_sobol) { g_err = "sampler = sobolld needs wtgpu_scene_desc::sobol_table"; return WTGPU_E_INVALID; }
+        if (o->spp == 0u || (o->spp & kSobolStreamFlag)) { g_err = "sampler = sobolld: spp out of range"; return WTGPU_E_INVALID; }
+        s->d.scene_stream = kSobolStreamFlag | o->spp;
+    } else if (o->sampler == WTGPU_SAMPLER_UNIFORM) s->d.scene_stream = 0u;
+    else { g_err = "unknown sampler"; return WTGPU_E_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)o->stream;
     const unsigned long long total = (unsigned long long)(x1 - o->tile_x0) * (y1 - o->tile_y0) * (o->sample_end - o->sample_begin);
     const bool bdpt = s->integ.type == WTGPU_INTEGRATOR_PLT_BDPT;
@@ -915,6 +973,28 @@ int wtgpu_debug_intersect_cones(wtgpu_scene* s, uint32_t n, const wtgpu_cone_que
     cudaFree(dq); cudaFree(dh);
     return WTGPU_OK;
 }
+int wthost_sobol_tables(const wtgpu_sobol_entry* table, uint16_t* ones, uint16_t* twos) {
+    if (!table || !ones || !twos) { g_err = "null argument"; return WTGPU_E_INVALID; }
+    wt::SobolTables tb; std::string why;
+    if (!sobol_build_tables(table, tb, why)) { g_err = why; return WTGPU_E_INVALID; }
+    memcpy(ones, tb.ones, sizeof(tb.ones)); memcpy(twos, tb.twos, sizeof(tb.twos));
+    return WTGPU_OK;
+}
+
+int wtgpu_debug_sobol(wtgpu_scene* s, uint64_t seed, uint64_t g0, uint32_t n, uint32_t* out_num, float* out_val) {
+    if (!s || !out_num || !out_val) { g_err = "null argument"; return WTGPU_E_INVALID; }
+    if (!s->has_sobol) { g_err = "scene has no sobol table"; return WTGPU_E_INVALID; }
+    CK(cudaSetDevice(s->device));
+    const size_t m = (size_t)n * WTGPU_SOBOL_DIMS;
+    if (m == 0) return WTGPU_OK;
+    uint32_t* dn; float* dv; CK(cudaMalloc(&dn, 4 * m)); CK(cudaMalloc(&dv, 4 * m));
+    k_debug_sobol<<<(unsigned)((m + 127) / 128), 128>>>((uint32_t)seed, (uint32_t)(seed >> 32), g0, n, dn, dv);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out_num, dn, 4 * m, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(out_val, dv, 4 * m, cudaMemcpyDeviceToHost));
+    cudaFree(dn); cudaFree(dv);
+    return WTGPU_OK;
+}
+
 int wtgpu_debug_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, int device) {
     CK(cudaSetDevice(device));
     float* d; CK(cudaMalloc(&d, 4ull * n));

@@ -35,6 +35,7 @@ class GpuScene:
         o.tile_x0, o.tile_y0, o.tile_x1, o.tile_y1 = tile if tile else (0, 0, b.width, b.height)
         o.device, o.film_on_device, o.pool_size, o.flags = self.device, int(on_device), pool_size, flags
         o.stream = stream
+        o.sampler = getattr(b, "sampler", 0)
         st = A.Stats()
         rc = A.lib().wtgpu_render(self.handle, C.byref(o), block_ptr, light_ptr, C.byref(st))
         if rc == -5 and allow_overflow:

@@ -110,6 +110,25 @@ class Binned(Spectrum):
         return out
 
 
+class ITU(Spectrum):
+    """Complex IOR of an ITU-R P.2040-2 (table 3) material: sqrt(eps_r - i sigma / (eps0 omega)), eps_r = a f^b, sigma = c f^d, f in GHz
+    (src/spectrum/util/spectrum_from_ITU.cpp:31-55, table :78-170).  Zero outside the material's frequency range."""
+    TABLE = {"vacuum": [(1, 0, 0, 0, 0, float("inf"))], "concrete": [(5.24, 0, 0.0462, 0.7822, 1, 100)], "brick": [(3.91, 0, 0.0238, 0.16, 1, 40)],
+             "plasterboard": [(2.73, 0, 0.0085, 0.9395, 1, 100)], "wood": [(1.99, 0, 0.0047, 1.0718, 0.001, 100)],
+             "glass": [(6.31, 0, 0.0036, 1.3394, 0.1, 100), (5.79, 0, 0.0004, 1.658, 220, 450)], "chipboard": [(2.58, 0, 0.0217, 0.78, 1, 100)],
+             "plywood": [(2.71, 0, 0.33, 0, 1, 40)], "marble": [(7.074, 0, 0.0055, 0.9262, 1, 60)], "metal": [(1, 0, 1e7, 0, 1, 100)]}
+    def __init__(self, material): self.params = self.TABLE[material]
+    def value(self, k):
+        k = np.asarray(k, np.float64); c0, eps0 = 2.99792458e8, 8.8541878128e-12
+        omega = k * 1e3 * c0; f_ghz = omega / TWO_PI * 1e-9
+        out = np.zeros(k.shape, np.complex128)
+        for a, b, c, d, f0, f1 in self.params:
+            eps = a * (f_ghz ** b if b else 1.0); sig = c * (f_ghz ** d if d else 1.0)
+            v = np.sqrt(eps - 1j * sig / (eps0 * np.maximum(omega, 1e-300)))
+            out = np.where((f_ghz >= f0 * (1 - 1e-6)) & (f_ghz <= f1 * (1 + 1e-6)), v, out)      # endpoints inclusive up to f32 rounding of k
+        return out
+
+
 def _as_spectrum(s):
     return s if isinstance(s, Spectrum) else Const(s)
 
@@ -250,6 +269,13 @@ def cube(to_world=None):
     return Mesh(np.array(verts, np.float32), np.array(tris, np.uint32), uvs=np.array(uvs, np.float32), to_world=to_world)
 
 
+def box(lo, hi, to_world=None):
+    """axis-aligned box [lo, hi] as a transformed cube (src/mesh/cube.cpp): 12 triangles, face normals."""
+    lo, hi = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+    M = translate((lo + hi) / 2) @ scale(tuple((hi - lo) / 2))
+    return cube(M if to_world is None else to_world @ M)
+
+
 def sphere(radius=1.0, centre=(0, 0, 0), n_lat=16, n_lon=32, to_world=None):
     verts, normals, uvs, tris = [], [], [], []
     for i in range(n_lat + 1):
@@ -273,6 +299,7 @@ class BuiltScene:
         self.desc = A.SceneDesc()
         self.keep = []
         self.ads = None
+        self.sampler = 0        # WTGPU_SAMPLER_*
     def __del__(self):
         try:
             if self.ads is not None: A.lib().wthost_ads_destroy(self.ads)
@@ -291,8 +318,17 @@ def _arr(ctype, values):
     return a
 
 
+class Sobolld:
+    """<sampler type="sobolld"> (src/sampler/sobolld.cpp:84-99): the scene sampler; `table` = parsed initIrreducibleGF3.dat entries
+    (wave_tracer_b200/sobol.py), default: the real file if `path` holds one, else the stand-in table."""
+    def __init__(self, table=None, path=None):
+        from . import sobol
+        self.table = table if table is not None else sobol.table_for(path)
+
+
 class Scene:
     def __init__(self):
+        self.sampler = None     # None: sampler::uniform_t (src/scene/loader/loader.cpp:299-300); or Sobolld()
         self.integrator = PltPath()
         self.sensor = None
         self.shapes = []        # (mesh, bsdf, area_emitter or None)
@@ -519,4 +555,10 @@ class Scene:
             it.type = A.INTEGRATOR_PLT_PATH
             it.direction = A.DIRECTION_FORWARD if self.integrator.direction == "forward" else A.DIRECTION_BACKWARD
         out.spp = self.sensor.samples
+        out.sampler = A.SAMPLER_UNIFORM
+        if isinstance(self.sampler, Sobolld):
+            from . import sobol
+            arr = sobol.to_abi(self.sampler.table); out.keep.append(arr)
+            d.sobol_table = arr
+            out.sampler = A.SAMPLER_SOBOLLD
         return out
