@@ -27,6 +27,14 @@ RES, SPP = 1440, 1024
 WORKLOAD = "diffraction_simple/double_slits res=1440 spp=1024 pattern=true (film 1440x360, lambda=0.05mm, procedural restatement)"
 INTEGRATORS = {"plt_bdpt": "plt_bdpt (MIS, emitter+sensor direct), Fraunhofer FSD, max_depth 16 -- the reference file's integrator",
                "plt_path": "plt_path forward + UTD FSD, max_depth 16, RR off"}
+# --workload: the default is BASELINE.json configs[1]; the others are the remaining GPU configs restated procedurally (their meshes are LFS stubs)
+WORKLOADS = {
+    "double_slits": dict(res=1440, integrator=None, name=WORKLOAD),
+    "etoile": dict(res=720, integrator="plt_path", name="sionna_etoile/etoile res=720 spp=1024 wavelength=10GHz (film 720x540; plt_path forward + UTD, max_depth 16, RR off; "
+                   "SYNTHETIC geometry: ground plane + 562 extruded boxes (6746 triangles) on a seeded street plan, the file's ITU materials, emitter and sensor)"),
+    "cornell": dict(res=1440, integrator="plt_bdpt", name="cornell-box/box res=1440 spp=1024 (film 1440x1440; plt_bdpt max_depth 8; SYNTHETIC: texture-free procedural variant -- 5 walls, "
+                    "dielectric sphere, rough-conductor cube, cube area emitter; monochromatic 550 nm)"),
+}
 
 
 def measured_hbm_peak():
@@ -63,7 +71,7 @@ def cpu_leg(built, seconds_target, threads=0):
     t0 = time.time(); _, _, st = _oracle.render(built, spp=1, sample_range=(0, 1), threads=threads); t1 = time.time() - t0
     n = max(1, min(64, int(seconds_target / max(t1, 1e-3))))
     _, _, st = _oracle.render(built, spp=n, sample_range=(0, n), threads=threads)
-    return st["samples"] / st["seconds"] / 1e6, st["threads"], f"samples 0..{n - 1} of every element of the 1440x360 film ({st['samples']} samples, {st['seconds']:.1f} s)"
+    return st["samples"] / st["seconds"] / 1e6, st["threads"], f"samples 0..{n - 1} of every element of the {built.width}x{built.height} film ({st['samples']} samples, {st['seconds']:.1f} s)"
 
 
 def main():
@@ -72,10 +80,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--integrator", default="plt_bdpt", choices=["plt_bdpt", "plt_path"])
+    ap.add_argument("--workload", default="double_slits", choices=list(WORKLOADS))
+    ap.add_argument("--integrator", default=None, choices=["plt_bdpt", "plt_path"])
+    ap.add_argument("--sampler", default="uniform", choices=["uniform", "sobolld"], help="the scene sampler (sobolld: stand-in table, see wave_tracer_b200/sobol.py)")
     ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--pool", type=int, default=0, help="paths (plt_path) / sample slots (plt_bdpt) in flight; 0: 1M / 256k")
-    ap.add_argument("--res", type=int, default=RES)
+    ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sort", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="extra WTGPU_RENDER_* flags (A/B measurements)")
@@ -83,12 +93,25 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     from wave_tracer_b200 import scenes
+    wl = WORKLOADS[a.workload]
+    a.integrator = a.integrator or wl["integrator"] or "plt_bdpt"
+    a.res = a.res or wl["res"]
     bdpt = a.integrator == "plt_bdpt"
     if a.pool == 0: a.pool = (1 << 18) if bdpt else (1 << 20)
-    built = scenes.double_slits(res=a.res, spp=SPP, integrator=a.integrator, lut=(2048, 1024)).build()
+    if a.workload == "double_slits":
+        sc = scenes.double_slits(res=a.res, spp=SPP, integrator=a.integrator, lut=(2048, 1024)); integ_desc = INTEGRATORS[a.integrator]
+    elif a.workload == "etoile":
+        sc = scenes.etoile_like(res=a.res, spp=SPP); integ_desc = "plt_path forward + UTD FSD, max_depth 16, RR off -- the reference file's integrator"
+    else:
+        sc = scenes.cornell_like(res=a.res, spp=SPP, integrator=a.integrator, fsd=bdpt, lut=(2048, 1024)); integ_desc = a.integrator + ", max_depth 8"
+        if a.spp_per_step == 16: a.spp_per_step = 2
+    if a.sampler == "sobolld":
+        from wave_tracer_b200.scene import Sobolld
+        sc.sampler = Sobolld()
+    built = sc.build()
     W, H = built.width, built.height
-    config = {"workload": WORKLOAD if a.res == RES else WORKLOAD.replace("1440", str(a.res)), "integrator": INTEGRATORS[a.integrator], "film": [W, H],
-              "spp_per_step": a.spp_per_step, "sampler": "philox4x32-10 counter streams keyed (seed,pixel,sample)",
+    config = {"workload": wl["name"] if a.res == wl["res"] else wl["name"].replace(str(wl["res"]), str(a.res)), "integrator": integ_desc, "film": [W, H],
+              "spp_per_step": a.spp_per_step, "sampler": "philox4x32-10 counter streams keyed (seed,pixel,sample)" + ("; scene sampler sobolld (stand-in table)" if a.sampler == "sobolld" else ""),
               "l2": ("%d sample slots x 30 KB of subpath vertices/apertures" % a.pool if bdpt else "path-state pool (%d paths x 0.7 KB)" % a.pool) + " exceed the 126 MB L2; no flush needed"}
 
     if a.impl == "reference":

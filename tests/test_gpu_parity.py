@@ -120,6 +120,22 @@ def test_cornell_backward_film_matches_oracle():
     assert np.allclose(blk[..., 1], oblk[..., 1], rtol=1e-4, atol=1e-5)          # filter weights: sample placement identical
 
 
+def test_etoile_like_forward_utd_matches_oracle():
+    """BASELINE configs[3] restated (wave_tracer_b200/scenes.py etoile_like): plt_path forward, RR off, UTD free-space diffraction off 6.7k building
+    edges at 10 GHz, ITU surface_spm materials, point emitter, virtual-plane coverage sensor.  UTD sums run over up to 48 edges per vertex, so the
+    capacity counters must stay at zero here."""
+    b = scenes.etoile_like(res=96, spp=4).build()
+    blk, lgt, st = render(b, spp=4)
+    oblk, olgt, ost = _oracle.render(b, spp=4)
+    assert st["samples"] == ost["samples"] == 96 * 72 * 4 and st["capacity_overflows"] == 0
+    assert olgt.sum() > 0
+    l2, flux = _film_metrics(lgt, olgt)
+    print("etoile_like: rel-L2 %.3e flux %.3e" % (l2, flux), st["gpu_ms"], st["segments"], ost["segments"])
+    assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
+    for kg, ko in (("segments", "segments"), ("surface_interactions", "surface"), ("fsd_interactions", "fsd"), ("null_interactions", "null_")):
+        assert abs(st[kg] - ost[ko]) <= 2e-3 * max(1, ost[ko]), (kg, st[kg], ost[ko])
+
+
 def test_partition_invariance_on_gpu():
     """Sample-range / tile partitions give the same film as one call (RNG keyed by (pixel, sample))."""
     b = scenes.double_slits(res=128, spp=8, with_directional=False).build()

@@ -67,3 +67,19 @@ def test_double_slit_scene_matches_reference_geometry():
     assert d.n_tris == 10 and d.n_shapes == 5 and d.n_emitters == 3
     xs = sorted({round(v * 1e3, 4) for i in range(d.n_tris) for v in (d.tris[i].ax, d.tris[i].bx, d.tris[i].cx) if abs(d.tris[i].az + 0.015) < 1e-6})
     assert xs == [-6.0, -0.5, -0.15, 0.15, 0.5, 6.0]
+
+
+def test_etoile_like_scene_builds_and_itu_iors():
+    """The etoile restatement: 563 shapes (ground + 562 boxes), ITU complex IORs at 10 GHz against hand values of
+    sqrt(eps_r - i sigma/(eps0 omega)) (ITU-R P.2040-2 table 3 as in src/spectrum/util/spectrum_from_ITU.cpp:78-170)."""
+    from wave_tracer_b200.scene import ITU, wavelen_to_wavenum
+    b = scenes.etoile_like(res=64, spp=1).build()
+    d = b.desc
+    assert d.n_shapes == 563 and d.n_tris == 2 + 562 * 12 and d.n_emitters == 1 and (b.width, b.height) == (64, 48)
+    assert d.integrator.type == 0 and d.integrator.direction == 1 and d.integrator.russian_roulette == 0 and d.integrator.max_depth == 16
+    k = np.array([wavelen_to_wavenum(2.99792458e8 / 10e9)])
+    for name, (eps, sig) in {"concrete": (5.24, 0.0462 * 10 ** 0.7822), "marble": (7.074, 0.0055 * 10 ** 0.9262), "wood": (1.99, 0.0047 * 10 ** 1.0718)}.items():
+        want = np.sqrt(eps - 1j * sig / (8.8541878128e-12 * 2 * math.pi * 10e9))
+        assert abs(ITU(name).value(k)[0] - want) < 1e-6 * abs(want)
+    n = ITU("metal").value(k)[0]
+    assert n.real > 1e3 and abs(n.real + n.imag) / n.real < 1e-3          # good conductor: n ~ (1 - i) sqrt(sigma / (2 eps0 omega))
