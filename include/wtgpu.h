@@ -323,7 +323,7 @@ typedef struct wtgpu_render_opts {
                                        reference's integrators keep their own uniform_t for it (plt_path_detail.hpp:59-60,146; plt_bdpt.cpp:50-52) */
 #define WTGPU_RENDER_NO_SORT 1u     /* disable the material sort (for A/B measurement) */
 #define WTGPU_RENDER_BDPT_MEGAKERNEL 4u  /* plt_bdpt: run the one-thread-per-sample cross-check kernel instead of the wavefront */
-#define WTGPU_RENDER_THREAD_TRAVERSE 8u  /* plt_bdpt: one thread per beam in traverse() instead of eight lanes per beam (A/B measurement) */
+#define WTGPU_RENDER_THREAD_TRAVERSE 8u  /* one thread per beam in traverse() instead of eight lanes per beam (A/B measurement; bit-identical results) */
 #define WTGPU_RENDER_TIME_KERNELS 2u /* record CUDA events around every kernel (fills wtgpu_stats::*_ms) */
 
 /* Device counters gathered during wtgpu_render (the quantities the reference exposes in a `profile` build:
@@ -374,7 +374,7 @@ typedef struct wtgpu_cone_query {
     float tmin, tmax;
     float z_scale;                  /* intersect_opts_t::z_search_range_scale */
 } wtgpu_cone_query;
-#define WTGPU_MAX_CONE_TRIS  64
+#define WTGPU_MAX_CONE_TRIS  128
 #define WTGPU_MAX_CONE_EDGES 48
 typedef struct wtgpu_cone_hit {
     float dist; uint32_t front_face;

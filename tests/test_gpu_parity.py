@@ -136,6 +136,23 @@ def test_etoile_like_forward_utd_matches_oracle():
         assert abs(st[kg] - ost[ko]) <= 2e-3 * max(1, ost[ko]), (kg, st[kg], ost[ko])
 
 
+@pytest.mark.parametrize("scene", ["double_slits", "etoile", "cornell"])
+def test_plt_path_group_traverse_equals_thread_traverse(scene):
+    """k_gtraverse + k_resolve (eight lanes per beam) take the same decisions as the one-thread-per-beam k_traverse: identical structural
+    counters, films equal up to the order of the f32 atomics."""
+    b = {"double_slits": lambda: scenes.double_slits(res=256, spp=4, with_directional=True), "etoile": lambda: scenes.etoile_like(res=96, spp=4),
+         "cornell": lambda: scenes.cornell_like(res=48, spp=4, fsd=True)}[scene]().build()
+    gs = GpuScene(b, 0)
+    blk0, lgt0, st0 = render(b, spp=4, gpu_scene=gs, allow_overflow=True)
+    blk1, lgt1, st1 = render(b, spp=4, gpu_scene=gs, allow_overflow=True, flags=8)
+    for k in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "nodes_visited", "tris_tested", "surface_interactions", "fsd_interactions",
+              "null_interactions", "splats", "capacity_overflows", "edges_fetched"):
+        assert st0[k] == st1[k], (k, st0[k], st1[k])
+    for x, y in ((blk0, blk1), (lgt0, lgt1)):
+        assert np.allclose(x, y, rtol=1e-4, atol=1e-6 * max(1e-30, float(np.abs(y).max())))
+    gs.close()
+
+
 def test_partition_invariance_on_gpu():
     """Sample-range / tile partitions give the same film as one call (RNG keyed by (pixel, sample))."""
     b = scenes.double_slits(res=128, spp=8, with_directional=False).build()

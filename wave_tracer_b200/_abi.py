@@ -145,7 +145,7 @@ class RayHit(C.Structure):
     _fields_ = [("tuid", c_u32), ("dist", c_f), ("bary", c_f * 2), ("front_face", c_u32)]
 
 
-MAX_CONE_TRIS, MAX_CONE_EDGES = 64, 48
+MAX_CONE_TRIS, MAX_CONE_EDGES = 128, 48
 
 
 class ConeQuery(C.Structure):

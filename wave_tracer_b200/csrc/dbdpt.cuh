@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(128) k_bd_traverse(const BdArgs a) {
         h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
         h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
         ovf = bh.overflow;
-        soa_store(h, a.r.hit, a.r.pool, wid);
+        hit_store(h, a.r.hit, a.r.pool, wid);
         a.r.keys[wid] = bd_hit_key(sc, bh, a.r.n_keys);
     }
     flush_counters(a.r.ctr, ctr);
@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(128) k_bd_gtraverse(const BdArgs a) {
     __shared__ GShared shm[128 / kGW];
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.r.sc;
-    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, ctr,
+    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr,
         [&](int i, Cone& env, Geo& prev, float& lambda) {
             const uint32_t wid = a.r.trav_list[i];
             BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
@@ -1027,7 +1027,7 @@ __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
         h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
         h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
         ovf = bh.overflow;
-        soa_store(h, a.r.hit, a.r.pool, wid);
+        hit_store(h, a.r.hit, a.r.pool, wid);
         a.r.keys[wid] = bd_hit_key(sc, bh, a.r.n_keys);
     }
     count1(&a.r.ctr->overflow, ovf);
@@ -1078,7 +1078,7 @@ __global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
         const uint32_t slot = wid >> 1, which = wid & 1u;
         BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
-        HitRec h; soa_load(h, a.r.hit, a.r.pool, wid);
+        HitRec h; hit_load(h, a.r.hit, a.r.pool, wid);
         BdHeader hd; soa_load(hd, a.headers, a.P, slot);
         BWalk d; bd_walker_to_state(w, which, d);
         BHit bh; bd_hit_to_bhit(h, bh);
@@ -1096,108 +1096,181 @@ __global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
 }
 
 // fsd_sampler_t::sample (src/interaction/fsd/fraunhofer/fsd_sampler.cpp:81-113) + free_space_diffraction_t::sample (free_space_diffraction.hpp:68-93)
-// for every walker whose aperture was just built.  Rejection sampling takes a geometric number of tries (a few apertures: thousands),
-// each a sum over the aperture's <= 48 segments, and only ~10^4 walkers need it per iteration: the problem is latency, not throughput.
-// So ONE WARP samples one walker: lane l evaluates segments l and l+32 of the current try, and every lane then adds the per-segment
-// terms in segment order (shuffles), which keeps sums, and therefore accept/reject decisions, bit-identical to the sequential
-// fraunhofer_sample.  All control flow is warp-uniform.  Runs on a second stream, overlapped with the next iteration's kernels; its
-// results are picked up one iteration later.  A launch does not wait for stragglers: after `budget` tries a walker is carried over
-// to the next iteration (the stream is counter-based: only the draw index and the try count are kept).
-__global__ void __launch_bounds__(128, 8) k_bd_fsd_sample(const BdArgs a) {
+// for every walker whose aperture was just built.  Rejection sampling takes a geometric number of tries (mean = the segment count, ~21 on
+// double_slits; a few apertures: thousands), each try a sum over the aperture's <= 48 segments.
+//
+// ONE WARP samples one walker, EIGHT TRIES AT A TIME (speculatively: tries are independent given where their draws start):
+//   1. the draw index of try t+1 depends on try t only through "did try t pick the P0 lobe" (3 draws) "or a segment" (5 draws), i.e. on one
+//      comparison of try t's first draw: a window of Philox blocks is computed lane-parallel and the eight start indices follow from a
+//      short scan over it;
+//   2. lane t generates the candidate xi of try t (selection by binary search of the cdf in shared memory, LUT lookup) from its own
+//      position of the stream -- the expensive warp-uniform part of a try is done for eight tries at the cost of one;
+//   3. the 8 x n (try, segment) terms Psi, |Psi|^2 are spread over the 32 lanes and written to shared memory;
+//   4. lane t adds the n terms of try t IN SEGMENT ORDER (sums, and therefore accept/reject decisions, are bit-identical to the sequential
+//      fraunhofer_sample), evaluates the acceptance test with try t's last draw; the first accepting try in sequence order wins.
+// Tries evaluated past the accepted one are discarded (~3.5 of ~21 on average).  Runs on a second stream, overlapped with the next
+// iteration's kernels; its results are picked up one iteration later.  A launch does not wait for stragglers: after `budget` tries a
+// walker is carried over to the next iteration (the stream is counter-based: only the draw index and the try count are kept).
+constexpr int kFsdK = 8;                    // speculative tries per batch
+constexpr int kFsdRow = kMaxFSeg + 1;       // padded row of the term arrays (bank-conflict free for the per-try sums)
+struct FsdShared { float4 ea[kMaxFSeg], eb[kMaxFSeg]; float cdf[kMaxFSeg + 1]; float re[kFsdK][kFsdRow], im[kFsdK][kFsdRow], dd[kFsdK][kFsdRow]; };
+__global__ void __launch_bounds__(128, 6) k_bd_fsd_sample(const BdArgs a) {
+    __shared__ FsdShared shm[4];
+    FsdShared& sh = shm[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     const int n_tasks = a.r.ctr->n_fsd_list[a.fl_cur];
     const uint32_t* list = a.fsd_list + (size_t)a.fl_cur * 2u * a.P;
     uint32_t* carry_list = a.fsd_list + (size_t)a.fl_next * 2u * a.P;
-    uint32_t budget = n_tasks > 2048 ? 128u : 0xffffffffu;       // tries per WARP per launch; unbounded once only stragglers remain
+    int budget = n_tasks > 2048 ? 128 : 0x7fffffff;       // tries per WARP per launch; unbounded once only stragglers remain
     for (;;) {
         int t = 0;
         if (lane == 0u) t = atomicAdd(&a.r.ctr->fsd_head, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_tasks) break;
         const uint32_t wid = list[t];
-        if (budget == 0u) {     // out of budget: hand the rest of the list to the next iteration untouched
+        if (budget <= 0) {      // out of budget: hand the rest of the list to the next iteration untouched
             if (lane == 0u) carry_list[atomicAdd(&a.r.ctr->n_fsd_list[a.fl_next], 1)] = wid;
             continue;
         }
         const uint32_t slot = wid >> 1, which = wid & 1u;
         Arena A; A.base = a.arena + (size_t)slot * kArenaWords;
-        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
-        const uint32_t w_rng_d = w.rng_d, w_n_ap = w.n_ap;
+        uint32_t w_rng_d, w_n_ap;
+        { BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid); w_rng_d = w.rng_d; w_n_ap = w.n_ap; }
         BdHeader h; soa_load(h, a.headers, a.P, slot);
         const int ai = (int)(which * (uint32_t)kMaxFApWalk + w_n_ap - 1u);
         const FHead hd = ap_head(A, ai);
         const uint32_t n = hd.n;
         const float4 st = a.fsd_out[2u * wid + 1u];      // carried over: resume after the tries already spent
         const bool carried = st.w == 1.f;
-        Sampler smp0; smp0.k0 = a.r.seed_lo; smp0.k1 = a.r.seed_hi; smp0.pixel = h.pixel; smp0.sample = h.sample; smp0.d = carried ? __float_as_uint(st.y) : w_rng_d; smp0.stream = 1u + which;
-        SamplerC smp = samplerc(smp0);
+        uint32_t d_base = carried ? __float_as_uint(st.y) : w_rng_d;
         uint32_t tries = carried ? __float_as_uint(st.z) : 0u;
         const bool rej = n > 1u; const uint32_t max_tries = n * 1024u; const float recp_M = 1.f / (float)n;
-        // this lane's segments
-        const bool has0 = lane < n, has1 = lane + 32u < n;
-        FEdge e0, e1; e0.e = e0.v = mk2(0.f, 0.f); e0.a_b = e0.iab_2 = mkc(0.f, 0.f); e1 = e0;
-        if (has0) e0 = ap_edge(A, ai, lane);
-        if (has1) e1 = ap_edge(A, ai, lane + 32u);
-        // selection cdf of sampleN (fsd_sampler.cpp:37-79), summed once in the sequential order: entry 0 is the P0 lobe, entry i the
-        // segment i-1; lane l keeps entries l and l+32.  The cdf is non-decreasing, so "first i with p < cdf[i]" = #{i : !(p < cdf[i])}.
-        float c0 = 0.f, c1 = 0.f;
-        {
-            float cdf = 0.f;
-            for (uint32_t i = 0; i < n; ++i) {
-                cdf += i == 0u ? hd.P0_pdf : ap_edge_pdf(A, ai, i - 1u);
-                if ((i & 31u) == lane) { if (i < 32u) c0 = cdf; else c1 = cdf; }
-            }
+        // stage the aperture: segments, and the selection cdf of sampleN (fsd_sampler.cpp:37-79) summed in the sequential order
+        // (entry 0 is the P0 lobe, entry i the segment i-1; non-decreasing, so "first i with p < cdf[i]" = #{i : !(p < cdf[i])})
+        __syncwarp();
+        for (uint32_t j = lane; j < n; j += 32u) {
+            const FEdge e = ap_edge(A, ai, j);
+            sh.ea[j] = make_float4(e.e.x, e.e.y, e.v.x, e.v.y); sh.eb[j] = make_float4(e.a_b.re, e.a_b.im, e.iab_2.re, e.iab_2.im);
         }
+        if (lane == 0u) { float cdf = 0.f; for (uint32_t i = 0; i < n; ++i) { cdf += i == 0u ? hd.P0_pdf : ap_edge_pdf(A, ai, i - 1u); sh.cdf[i] = cdf; } }
+        __syncwarp();
+        const float cdf0 = hd.P0_pdf;       // == sh.cdf[0] (0 + P0_pdf)
         V3 wo = mk3(0.f, 0.f, 1.f); float dpd = 0.f, wgt = 0.f;
-        bool finished = false;
-        for (; budget > 0u; --budget) {
-            const float p = rnd(smp) * 1.f;
-            const uint32_t sel = (uint32_t)__popc(__ballot_sync(0xffffffffu, has0 && !(p < c0))) + (uint32_t)__popc(__ballot_sync(0xffffffffu, has1 && !(p < c1)));
-            V2 xi;
-            if (sel == 0u) { const float u0 = rnd(smp); const float u1 = rnd(smp); xi = kP0s * normal2d(mk2(u0, u1)); }
-            else {
-                const FEdge e = ap_edge(A, ai, sel - 1u);
-                const V2 m = mk2(e.e.y, -e.e.x);
-                const float od = 1.f / (e.e.x * m.y - m.x * e.e.y);
-                const float i00 = m.y * od, i01 = -e.e.y * od, i10 = -m.x * od, i11 = e.e.x * od;
-                const float Aa = cnorm(e.a_b), Bb = cnorm(e.iab_2);
-                const float pp = rnd(smp) * (Aa + Bb);
-                const float r0 = rnd(smp); const float r1 = rnd(smp); const float r2 = rnd(smp);
-                const V3 r3 = mk3(r0, r1, r2);
-                const V2 z = pp < Aa ? flut_sample(a.lut, r3, a.lut.th1, a.lut.c1) : flut_sample(a.lut, r3, a.lut.th2, a.lut.c2);
-                xi = mk2(z.x * i00 + z.y * i01, z.x * i10 + z.y * i11);
-            }
-            // per-segment terms: Psi (complex) and Psi2
-            C2 t0 = mkc(0.f, 0.f), t1 = mkc(0.f, 0.f); float d0 = 0.f, d1 = 0.f;
-            if (has0) { const V2 z = fzeta(e0, xi); const C2 sx = e0.a_b * falpha1(z.x, z.y) + e0.iab_2 * falpha2(z.x, z.y); const float rho = length2(e0.e); float sn, cs; sincosf(-dot(e0.v, xi), &sn, &cs); t0 = mkc(rho * cs, rho * sn) * sx; d0 = sqrf(rho) * cnorm(sx); }
-            if (has1) { const V2 z = fzeta(e1, xi); const C2 sx = e1.a_b * falpha1(z.x, z.y) + e1.iab_2 * falpha2(z.x, z.y); const float rho = length2(e1.e); float sn, cs; sincosf(-dot(e1.v, xi), &sn, &cs); t1 = mkc(rho * cs, rho * sn) * sx; d1 = sqrf(rho) * cnorm(sx); }
-            C2 acc = mkc(0.f, 0.f); float dens = 0.f;
-            for (uint32_t jj = 0; jj < n; ++jj) {
-                const int src = (int)(jj & 31u);
-                const float re = __shfl_sync(0xffffffffu, jj < 32u ? t0.re : t1.re, src), im = __shfl_sync(0xffffffffu, jj < 32u ? t0.im : t1.im, src), dd = __shfl_sync(0xffffffffu, jj < 32u ? d0 : d1, src);
-                acc = acc + mkc(re, im); dens += dd;
-            }
-            const float g = dens * fchi_e(xi) + hd.P0 * kInvTwoPi / sqrf(kP0s) * fchi_0(xi);
-            const float f = cnorm(acc) * fchi_e(xi) + hd.psi02 * fchi_0(xi);
-            const bool done = rej ? rnd(smp) * g < f * recp_M : true;
-            if (done) {
-                const float pdf = f * hd.recp_I;
-                if (pdf > 0.f) {
-                    const V2 zeta = xi / hd.k;
-                    const V2 wl = mk2(zeta.x / sqrtf(1.f + sqrf(zeta.x)), zeta.y / sqrtf(1.f + sqrf(zeta.y)));
-                    const float wo2 = length2(wl);
-                    if (wo2 < .85f) { wo = mk3(wl.x, wl.y, sqrtf(1.f - wo2)); dpd = pdf; wgt = 1.f; }
+        bool finished = n == 0u;            // an empty aperture makes no try (max_tries == 0)
+        uint32_t d_final = d_base;
+        while (!finished && budget > 0) {
+            const uint32_t kv = min((uint32_t)kFsdK, max_tries - tries);      // tries of this batch
+            // 1. start index of every try: window of 13 Philox blocks (8 tries x <= 6 draws), then the scan
+            const uint32_t blk0 = d_base >> 2;
+            uint32_t c0, c1, c2, c3;
+            {
+                uint32_t x0 = blk0 + lane, x1 = h.sample, x2 = h.pixel, x3 = 1u + which, k0 = a.r.seed_lo, k1 = a.r.seed_hi;
+#pragma unroll
+                for (int r = 0; r < 10; ++r) {
+                    const uint32_t h0 = __umulhi(0xD2511F53u, x0), l0 = 0xD2511F53u * x0;
+                    const uint32_t h1 = __umulhi(0xCD9E8D57u, x2), l1 = 0xCD9E8D57u * x2;
+                    const uint32_t n0 = h1 ^ x1 ^ k0, n2 = h0 ^ x3 ^ k1;
+                    x0 = n0; x1 = l1; x2 = n2; x3 = l0;
+                    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
                 }
-                finished = true; --budget; break;
+                c0 = x0; c1 = x1; c2 = x2; c3 = x3;
             }
-            if (++tries == max_tries) { finished = true; --budget; break; }
+            uint32_t my_d = d_base, dt = d_base;
+#pragma unroll
+            for (int q = 0; q < kFsdK; ++q) {
+                if (lane == (unsigned)q) my_d = dt;
+                const uint32_t word = dt & 3u;
+                const uint32_t mine = word == 0u ? c0 : word == 1u ? c1 : word == 2u ? c2 : c3;
+                const uint32_t u = __shfl_sync(0xffffffffu, mine, (int)((dt >> 2) - blk0));
+                const float p = (float)(u >> 8) * (1.0f / 16777216.0f) * 1.f;
+                dt += (p < cdf0 && n > 0u ? 3u : 5u) + (rej ? 1u : 0u);
+            }
+            // 2. lane t: candidate of try t
+            Sampler sm0; sm0.k0 = a.r.seed_lo; sm0.k1 = a.r.seed_hi; sm0.pixel = h.pixel; sm0.sample = h.sample; sm0.d = my_d; sm0.stream = 1u + which;
+            SamplerC smp = samplerc(sm0);
+            V2 xi = mk2(0.f, 0.f);
+            const bool mine_valid = lane < kv;
+            if (mine_valid) {
+                const float p = rnd(smp) * 1.f;
+                uint32_t lo = 0u, hi = n;               // sel = #{i < n : !(p < cdf[i])}
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (!(p < sh.cdf[mid])) lo = mid + 1u; else hi = mid; }
+                const uint32_t sel = lo;
+                if (sel == 0u) { const float u0 = rnd(smp); const float u1 = rnd(smp); xi = kP0s * normal2d(mk2(u0, u1)); }
+                else {
+                    const float4 ea = sh.ea[sel - 1u], eb = sh.eb[sel - 1u];
+                    const V2 ee = mk2(ea.x, ea.y);
+                    const V2 m = mk2(ee.y, -ee.x);
+                    const float od = 1.f / (ee.x * m.y - m.x * ee.y);
+                    const float i00 = m.y * od, i01 = -ee.y * od, i10 = -m.x * od, i11 = ee.x * od;
+                    const float Aa = cnorm(mkc(eb.x, eb.y)), Bb = cnorm(mkc(eb.z, eb.w));
+                    const float pp = rnd(smp) * (Aa + Bb);
+                    const float r0 = rnd(smp); const float r1 = rnd(smp); const float r2 = rnd(smp);
+                    const V3 r3 = mk3(r0, r1, r2);
+                    const V2 z = pp < Aa ? flut_sample(a.lut, r3, a.lut.th1, a.lut.c1) : flut_sample(a.lut, r3, a.lut.th2, a.lut.c2);
+                    xi = mk2(z.x * i00 + z.y * i01, z.x * i10 + z.y * i11);
+                }
+            }
+            // 3. the kv x n (try, segment) terms, spread over the warp
+            {
+                const uint32_t items = kv * n;
+                uint32_t tt = 0u, jj = lane;
+                for (uint32_t base = 0u; base < items; base += 32u) {
+                    while (jj >= n && tt < kv) { jj -= n; ++tt; }
+                    const bool act = tt < kv;
+                    const float xx = __shfl_sync(0xffffffffu, xi.x, (int)(act ? tt : 0u)), xy = __shfl_sync(0xffffffffu, xi.y, (int)(act ? tt : 0u));
+                    if (act) {
+                        const float4 ea = sh.ea[jj], eb = sh.eb[jj];
+                        FEdge e; e.e = mk2(ea.x, ea.y); e.v = mk2(ea.z, ea.w); e.a_b = mkc(eb.x, eb.y); e.iab_2 = mkc(eb.z, eb.w);
+                        const V2 x2 = mk2(xx, xy);
+                        const V2 z = fzeta(e, x2);
+                        const C2 sx = e.a_b * falpha1(z.x, z.y) + e.iab_2 * falpha2(z.x, z.y);
+                        const float rho = length2(e.e);
+                        float sn, cs; sincosf(-dot(e.v, x2), &sn, &cs);
+                        const C2 tm = mkc(rho * cs, rho * sn) * sx;
+                        sh.re[tt][jj] = tm.re; sh.im[tt][jj] = tm.im; sh.dd[tt][jj] = sqrf(rho) * cnorm(sx);
+                    }
+                    jj += 32u;
+                }
+            }
+            __syncwarp();
+            // 4. lane t: sums in segment order, acceptance test
+            bool done = false; float f = 0.f;
+            if (mine_valid) {
+                C2 acc = mkc(0.f, 0.f); float dens = 0.f;
+                for (uint32_t j = 0; j < n; ++j) { acc = acc + mkc(sh.re[lane][j], sh.im[lane][j]); dens += sh.dd[lane][j]; }
+                const float g = dens * fchi_e(xi) + hd.P0 * kInvTwoPi / sqrf(kP0s) * fchi_0(xi);
+                f = cnorm(acc) * fchi_e(xi) + hd.psi02 * fchi_0(xi);
+                done = rej ? rnd(smp) * g < f * recp_M : true;
+            }
+            __syncwarp();
+            const unsigned dm = __ballot_sync(0xffffffffu, done);
+            if (dm) {
+                const int win = __ffs(dm) - 1;
+                if ((int)lane == win) {
+                    const float pdf = f * hd.recp_I;
+                    if (pdf > 0.f) {
+                        const V2 zeta = xi / hd.k;
+                        const V2 wl = mk2(zeta.x / sqrtf(1.f + sqrf(zeta.x)), zeta.y / sqrtf(1.f + sqrf(zeta.y)));
+                        const float wo2 = length2(wl);
+                        if (wo2 < .85f) { wo = mk3(wl.x, wl.y, sqrtf(1.f - wo2)); dpd = pdf; wgt = 1.f; }
+                    }
+                }
+                wo.x = __shfl_sync(0xffffffffu, wo.x, win); wo.y = __shfl_sync(0xffffffffu, wo.y, win); wo.z = __shfl_sync(0xffffffffu, wo.z, win);
+                dpd = __shfl_sync(0xffffffffu, dpd, win); wgt = __shfl_sync(0xffffffffu, wgt, win);
+                d_final = __shfl_sync(0xffffffffu, smp.s.d, win);
+                finished = true; budget -= win + 1;
+            } else {
+                d_final = __shfl_sync(0xffffffffu, smp.s.d, (int)kv - 1);
+                d_base = d_final; tries += kv; budget -= (int)kv;
+                if (tries == max_tries) finished = true;
+            }
         }
         if (lane == 0u) {
             if (finished) {
                 a.fsd_out[2u * wid] = make_float4(wo.x, wo.y, wo.z, dpd);
-                a.fsd_out[2u * wid + 1u] = make_float4(wgt, __uint_as_float(smp.s.d), 0.f, a.tag);
+                a.fsd_out[2u * wid + 1u] = make_float4(wgt, __uint_as_float(d_final), 0.f, a.tag);
             } else {
-                a.fsd_out[2u * wid + 1u] = make_float4(0.f, __uint_as_float(smp.s.d), __uint_as_float(tries), 1.f);
+                a.fsd_out[2u * wid + 1u] = make_float4(0.f, __uint_as_float(d_final), __uint_as_float(tries), 1.f);
                 carry_list[atomicAdd(&a.r.ctr->n_fsd_list[a.fl_next], 1)] = wid;
             }
         }
@@ -1214,7 +1287,7 @@ __global__ void __launch_bounds__(128) k_bd_fsd_finish(const BdArgs a) {
         const uint32_t slot = wid >> 1, which = wid & 1u;
         BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
-        HitRec h; soa_load(h, a.r.hit, a.r.pool, wid);
+        HitRec h; hit_load(h, a.r.hit, a.r.pool, wid);
         BdHeader hd; soa_load(hd, a.headers, a.P, slot);
         BWalk d; bd_walker_to_state(w, which, d);
         const float4 o0 = a.fsd_out[2u * wid], o1 = a.fsd_out[2u * wid + 1u];

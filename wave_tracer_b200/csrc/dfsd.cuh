@@ -9,7 +9,7 @@ namespace wt {
 
 constexpr float kUtdMinSinBeta = 1e-3f;
 constexpr float kUtdSigmaScale = 45.f;
-constexpr int kMaxFsdEdges = 24;
+constexpr int kMaxFsdEdges = 48;     // edges of one UTD aperture (a per-path bound; overflows are counted and reported, never silent)
 
 struct Aperture {
     V3 wp; Frame fr; V3 size; V3 wi; float k;

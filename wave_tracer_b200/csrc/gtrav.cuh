@@ -40,7 +40,8 @@ WT_D int g_argmin(const GLane& g, float v, bool valid) {
 // One group's traversal machine.  All members hold the same value in the 8 lanes of a group.
 struct GTrav {
     // beam
-    Cone env; float lambda, dist, bd, min_prog; uint32_t seg; int wstate;       // wstate: 0 ray-only, 1 segment ray, 2 segment cone
+    Cone env; float lambda, dist, bd, min_prog; uint32_t seg; int wstate;       // wstate: 0 ray-only, 1 segment ray, 2 segment cone, 3 edge query around a ballistic hit
+    float zs; bool edge_query;  // z_search_range_scale of the current cone query; plt_path: follow a ballistic hit of a finite beam with the edge query
     // query
     int mode, s;                // mode: 1 ray, 2 cone; s: stack size
     V3 inv; bool nx, ny, nz; Frame frame;
@@ -56,7 +57,7 @@ WT_D void g_start_ray(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, R
 }
 WT_D void g_start_cone(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, Range tr, Counters& ctr) {
     t.mode = 2; t.qrange = tr; t.res.dist = WT_INF; t.res.front = false; t.res.n_tris = 0u; t.res.overflow = false;
-    t.crange = cone_search_range(t.env, tr, t.res.dist, kMajorToZ);
+    t.crange = cone_search_range(t.env, tr, t.res.dist, t.zs);
     t.s = 1;
     if (g.gl == 0u) { sh.tmin[0] = 0.f; sh.ptr[0] = sc.root_ptr; ctr.cone_casts++; }
     __syncwarp(g.gmask);
@@ -141,16 +142,16 @@ WT_D void g_leaf_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, u
             }
         }
         if (found) {
-            t.crange = cone_search_range(t.env, t.qrange, t.res.dist, kMajorToZ);
+            t.crange = cone_search_range(t.env, t.qrange, t.res.dist, t.zs);
             while (t.s > 0 && sh.tmin[t.s - 1] >= t.crange.mx) --t.s;
         }
         __syncwarp(g.gmask);
     }
 }
 // beam set-up: integrator::traverse up to the first query
-WT_D void g_begin(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, const Cone& env0, const Geo& prev, float lambda, bool force_rt, Counters& ctr) {
+WT_D void g_begin(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, const Cone& env0, const Geo& prev, float lambda, bool force_rt, bool edge_query, Counters& ctr) {
     t.env = env0; t.env.o = offseted_ray_origin(sc, prev, env0.o, env0.d);
-    t.lambda = lambda;
+    t.lambda = lambda; t.zs = kMajorToZ; t.edge_query = edge_query;
     const V3 rd = t.env.d;
     t.inv = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
     t.nx = signbit(t.inv.x); t.ny = signbit(t.inv.y); t.nz = signbit(t.inv.z);
@@ -169,6 +170,14 @@ WT_D bool g_query_done(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, 
         // ads_t::intersect(ray, range) post-processing (traversal_common.hpp:93-110)
         bool hit = true;
         if (!isfinite(t.rec.dist) || t.rec.dist > t.qrange.mx) { t.rec.tuid = WTGPU_INVALID_IDX; t.rec.dist = WT_INF; hit = false; }
+        if (t.edge_query && t.wstate == 1 && hit) {
+            // plt_path only: a ballistic hit of a finite beam is followed by a cone query around the hit, +-zdist/2, z scale 1, whose triangles
+            // are only used to collect edges (plt_path_detail.hpp:656-660).  The ray record is kept in t.rec.
+            const float zd = cone_axes(t.env, t.rec.dist).x * kMajorToZ;
+            t.wstate = 3; t.zs = 1.f;
+            g_start_cone(sc, g, sh, t, mkr(t.rec.dist - zd / 2.f, t.rec.dist + zd / 2.f), ctr);
+            return false;
+        }
         if (t.wstate == 0 || hit) {
             out.flags = TR_BALLISTIC | (hit ? 0u : TR_EMPTY) | (t.rec.front ? TR_RAY_FRONT : 0u);
             out.ray_tuid = t.rec.tuid; out.ray_dist = t.rec.dist; out.bx = t.rec.bx; out.by = t.rec.by;
@@ -180,6 +189,12 @@ WT_D bool g_query_done(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, 
         t.wstate = 2;
         g_start_cone(sc, g, sh, t, mkr(t.dist, WT_INF), ctr);
         return false;
+    }
+    if (t.wstate == 3) {        // edge query done: the ballistic hit, plus the triangles around it
+        out.flags = TR_BALLISTIC | (t.rec.front ? TR_RAY_FRONT : 0u) | (t.res.overflow ? TR_OVERFLOW : 0u);
+        out.ray_tuid = t.rec.tuid; out.ray_dist = t.rec.dist; out.bx = t.rec.bx; out.by = t.rec.by;
+        out.n_tris = t.res.n_tris;
+        return true;
     }
     const bool cempty = t.res.n_tris == 0u;
     if (cempty || t.res.dist - t.dist >= t.min_prog) {
@@ -199,7 +214,7 @@ WT_D bool g_query_done(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, 
 
 // The driver loop.  fetch(i, env, prev, lambda) loads item i (group-uniformly); emit(i, rec, tris) stores its result.
 template <class Fetch, class Emit>
-WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* shm, bool force_rt, Counters& ctr, Fetch&& fetch, Emit&& emit) {
+WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* shm, bool force_rt, bool edge_query, Counters& ctr, Fetch&& fetch, Emit&& emit) {
     GLane g; g.gl = threadIdx.x & 7u; g.gshift = (threadIdx.x & 31u) & 24u; g.gmask = 0xffu << g.gshift;
     GShared& sh = shm[threadIdx.x / kGW];
     GTrav t; t.mode = 0; t.s = 0;
@@ -217,7 +232,7 @@ WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* sh
                 item = i;
                 Cone env; Geo prev; float lambda;
                 fetch(item, env, prev, lambda);
-                g_begin(sc, g, sh, t, env, prev, lambda, force_rt, ctr);
+                g_begin(sc, g, sh, t, env, prev, lambda, force_rt, edge_query, ctr);
                 have = true;
             }
             if (t.s == 0) {

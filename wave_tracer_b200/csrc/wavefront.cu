@@ -51,6 +51,7 @@ struct alignas(16) HitRec {
     uint32_t edges[kMaxHitEdges];
 };
 
+static_assert(offsetof(HitRec, edges) == 48, "HitRec header is three 16-B chunks");
 template <class T> __host__ __device__ constexpr int chunks_of() { return (int)(sizeof(T) / 16); }
 template <class T> WT_D void soa_load(T& v, const float4* __restrict__ base, uint32_t pool, uint32_t slot) {
     float4* p = reinterpret_cast<float4*>(&v);
@@ -61,6 +62,20 @@ template <class T> WT_D void soa_store(const T& v, float4* __restrict__ base, ui
     const float4* p = reinterpret_cast<const float4*>(&v);
 #pragma unroll
     for (int c = 0; c < chunks_of<T>(); ++c) base[(size_t)c * pool + slot] = p[c];
+}
+
+// HitRec moves its edge list only as far as it is filled: 3 header chunks + ceil(n_edges / 4) edge chunks
+WT_D void hit_store(const HitRec& v, float4* __restrict__ base, uint32_t pool, uint32_t slot) {
+    const float4* p = reinterpret_cast<const float4*>(&v);
+    const int nc = 3 + (int)((min(v.n_edges, (uint32_t)kMaxHitEdges) + 3u) >> 2);
+    for (int c = 0; c < nc; ++c) base[(size_t)c * pool + slot] = p[c];
+}
+WT_D void hit_load(HitRec& v, const float4* __restrict__ base, uint32_t pool, uint32_t slot) {
+    float4* p = reinterpret_cast<float4*>(&v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = base[(size_t)c * pool + slot];
+    const int nc = 3 + (int)((min(v.n_edges, (uint32_t)kMaxHitEdges) + 3u) >> 2);
+    for (int c = 3; c < nc; ++c) p[c] = base[(size_t)c * pool + slot];
 }
 
 struct DevCounters {
@@ -76,8 +91,10 @@ struct DevCounters {
     int n_fsd_list[3], fsd_head;        // plt_bdpt: walkers waiting for a Fraunhofer sample (three rotating lists); work-fetch cursor
 };
 
+namespace wt { struct TravRec; }
 struct RenderArgs {
     DScene sc;
+    wt::TravRec* trav_rec; uint32_t* trav_tris;      // results of the group traversal (gtrav.cuh), per slot
     float4* core; float4* fsd; float4* hit;
     uint32_t* alive; uint32_t* keys; uint32_t* order; uint32_t* key_count; uint32_t* key_cursor; uint32_t* trav_list;
     DevCounters* ctr;
@@ -257,10 +274,84 @@ __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
             if (h.flags & H_PRIMARY) key = (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
             else key = h.n_edges ? a.n_keys - 3u : a.n_keys - 2u;
         }
-        soa_store(h, a.hit, a.pool, slot);
+        hit_store(h, a.hit, a.pool, slot);
         a.keys[slot] = key;
     }
     flush_counters(a.ctr, ctr);
+    count1(&a.ctr->segments, seg);
+    count1(&a.ctr->overflow, ovf);
+}
+
+// traverse() for every path of the list, eight lanes per beam (gtrav.cuh), including the edge query that follows a ballistic hit of a
+// finite beam; k_resolve then builds the hit record per thread.  Bit-identical to k_traverse (WTGPU_RENDER_THREAD_TRAVERSE selects that one).
+__global__ void __launch_bounds__(128) k_gtraverse(const RenderArgs a) {
+    __shared__ GShared shm[128 / kGW];
+    Counters ctr; counters_zero(ctr);
+    const DScene& sc = a.sc;
+    g_traverse_all(sc, a.ctr->n_trav, &a.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr,
+        [&](int i, Cone& env, Geo& prev, float& lambda) {
+            const uint32_t slot = a.trav_list[i];
+            PathCore pc; soa_load(pc, a.core, a.pool, slot);
+            env = pc.beam.env; prev = pc.prev_geo; lambda = wavenum_to_wavelen(pc.beam.k);
+        },
+        [&](int i, const TravRec& r, const uint32_t* tris, const GLane& g) {
+            const uint32_t slot = a.trav_list[i];
+            if (g.gl == 0u) a.trav_rec[slot] = r;
+            const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
+            for (uint32_t k = g.gl; k < nt; k += (uint32_t)kGW) a.trav_tris[(size_t)slot * kMaxConeTris + k] = tris[k];
+        });
+    flush_counters(a.ctr, ctr);
+}
+// primary-triangle pick (plt_path_detail.hpp:253-276), edge collection, sort key: the per-thread tail of k_traverse
+__global__ void __launch_bounds__(128) k_resolve(const RenderArgs a) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    bool seg = false, ovf = false;
+    if (li < (uint32_t)a.ctr->n_trav) {
+        const uint32_t slot = a.trav_list[li];
+        const DScene& sc = a.sc;
+        seg = true;
+        const TravRec r = a.trav_rec[slot];
+        const uint32_t* __restrict__ tris = a.trav_tris + (size_t)slot * kMaxConeTris;
+        const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
+        const V3 origin = mk3(r.ox, r.oy, r.oz);
+        // the beam's mean direction: floats 3..5 of PathCore (beam.env = {o, d, ...}), i.e. chunk 0 .w and chunk 1 .xy
+        static_assert(offsetof(PathCore, beam) == 0 && offsetof(Beam, env) == 0 && offsetof(Cone, d) == 12 && sizeof(V3) == 12, "PathCore layout");
+        const float4 c0 = a.core[slot], c1 = a.core[(size_t)a.pool + slot];
+        const V3 dir = mk3(c0.w, c1.x, c1.y);
+        HitRec h; h.flags = 0u; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.n_edges = 0u; h.flux = 0.f;
+        h.origin = origin; h.region_depth = r.region_depth; h.d2i = 0.f;
+        uint32_t key = a.n_keys - 1u;       // miss
+        if (r.flags & TR_EMPTY) h.flags |= H_EMPTY;
+        else {
+            if (r.flags & TR_OVERFLOW) { h.flags |= H_OVERFLOW; ovf = true; }
+            if (r.flags & TR_BALLISTIC) {
+                h.flags |= H_BALLISTIC | H_PRIMARY | ((r.flags & TR_RAY_FRONT) ? H_FRONT : 0u);
+                h.primary = r.ray_tuid; h.pdist = r.ray_dist; h.bx = r.bx; h.by = r.by; h.d2i = r.ray_dist;
+            } else {
+                h.d2i = r.cone_dist;
+                if (r.flags & TR_CONE_FRONT) h.flags |= H_FRONT;
+                const Range zr = mkr(h.d2i, h.d2i + h.region_depth);
+                for (uint32_t i = 0; i < nt; ++i) {
+                    const uint32_t tu = tris[i];
+                    const Tri3 t = load_tri(sc, tu);
+                    const float tol = cone_intersection_tolerance(origin, t.a, t.b, t.c);
+                    const RayTri rt = intersect_ray_tri(origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+                    if (rt.hit && rt.dist < h.pdist) { h.primary = tu; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
+                }
+                if (h.primary != WTGPU_INVALID_IDX) h.flags |= H_PRIMARY;
+            }
+            // cone segment: edges of the returned triangles when FSD is on; ballistic hit: edges of the edge query's triangles (always, as k_traverse)
+            if (((r.flags & TR_BALLISTIC) || sc.integrator.fsd) && nt) {
+                bool eo = false;
+                h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, h.edges, eo);
+                if (eo) { h.flags |= H_OVERFLOW; ovf = true; }
+            }
+            if (h.flags & H_PRIMARY) key = (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
+            else key = h.n_edges ? a.n_keys - 3u : a.n_keys - 2u;
+        }
+        hit_store(h, a.hit, a.pool, slot);
+        a.keys[slot] = key;
+    }
     count1(&a.ctr->segments, seg);
     count1(&a.ctr->overflow, ovf);
 }
@@ -298,7 +389,7 @@ __global__ void k_scatter(const RenderArgs a) {
         a.order[base + __popc(peers & ((1u << lane) - 1u))] = slot;
     }
 }
-__global__ void k_reset_trav(const RenderArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) a.ctr->n_trav = 0; }
+__global__ void k_reset_trav(const RenderArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.ctr->n_trav = 0; a.ctr->trav_head = 0; } }
 __global__ void k_identity_order(const RenderArgs a) {     // WTGPU_RENDER_NO_SORT: live slots in slot order (compaction only)
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li < (uint32_t)a.ctr->n_trav) a.order[li] = a.trav_list[li];
@@ -316,7 +407,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
         const DScene& sc = a.sc;
         const uint32_t slot = a.order[i];
         PathCore pc; soa_load(pc, a.core, a.pool, slot);
-        HitRec h; soa_load(h, a.hit, a.pool, slot);
+        HitRec h; hit_load(h, a.hit, a.pool, slot);
         Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = pc.rng_d; smp.stream = 0u;
         Beam& beam = pc.beam;
         const bool fwd = beam.fwd;
@@ -569,7 +660,8 @@ struct wtgpu_scene {
     // render pool (lazily sized)
     uint32_t pool = 0;
     float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
-    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr;
+    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr, *trav_tris = nullptr;
+    TravRec* trav_rec = nullptr;
     DevCounters* ctr = nullptr;
     uint32_t n_keys = 0;
     std::vector<cudaEvent_t> ev_pool;   // reused across renders (event creation is not free)
@@ -593,7 +685,7 @@ struct wtgpu_scene {
         if (bd_stream) cudaStreamDestroy(bd_stream);
         if (bd_ev_shade) cudaEventDestroy(bd_ev_shade);
         if (bd_ev_samp) cudaEventDestroy(bd_ev_samp);
-        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list, (void*)bdpt_arena }) if (p) cudaFree(p);
+        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list, (void*)bdpt_arena, (void*)trav_rec, (void*)trav_tris }) if (p) cudaFree(p);
     }
 };
 
@@ -716,8 +808,9 @@ void wtgpu_scene_destroy(wtgpu_scene* s) { delete s; }
 
 static int ensure_pool(wtgpu_scene* s, uint32_t pool) {
     if (s->pool == pool) return WTGPU_OK;
-    for (void* p : { (void*)s->core, (void*)s->fsd, (void*)s->hit, (void*)s->alive, (void*)s->keys, (void*)s->order, (void*)s->key_count, (void*)s->key_cursor, (void*)s->ctr, (void*)s->trav_list }) if (p) cudaFree(p);
-    s->core = s->fsd = s->hit = nullptr; s->alive = s->keys = s->order = s->key_count = s->key_cursor = s->trav_list = nullptr; s->ctr = nullptr; s->pool = 0;
+    for (void* p : { (void*)s->core, (void*)s->fsd, (void*)s->hit, (void*)s->alive, (void*)s->keys, (void*)s->order, (void*)s->key_count, (void*)s->key_cursor, (void*)s->ctr, (void*)s->trav_list, (void*)s->trav_rec, (void*)s->trav_tris }) if (p) cudaFree(p);
+    s->core = s->fsd = s->hit = nullptr; s->alive = s->keys = s->order = s->key_count = s->key_cursor = s->trav_list = s->trav_tris = nullptr; s->trav_rec = nullptr; s->ctr = nullptr; s->pool = 0;
+    if (s->integ.type == WTGPU_INTEGRATOR_PLT_PATH) { CK(cudaMalloc(&s->trav_rec, sizeof(TravRec) * (size_t)pool)); CK(cudaMalloc(&s->trav_tris, 4ull * kMaxConeTris * pool)); }
     CK(cudaMalloc(&s->core, (size_t)chunks_of<PathCore>() * 16 * pool));
     CK(cudaMalloc(&s->fsd, (size_t)chunks_of<PathFsd>() * 16 * pool));
     CK(cudaMalloc(&s->hit, (size_t)chunks_of<HitRec>() * 16 * pool));
@@ -759,6 +852,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
 
     RenderArgs a;
     a.sc = s->d; a.core = s->core; a.fsd = s->fsd; a.hit = s->hit; a.alive = s->alive; a.keys = s->keys; a.order = s->order;
+    a.trav_rec = s->trav_rec; a.trav_tris = s->trav_tris;
     a.key_count = s->key_count; a.key_cursor = s->key_cursor; a.trav_list = s->trav_list; a.ctr = s->ctr; a.film_block = dblock; a.film_light = dlight;
     a.pool = pool; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
     a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
@@ -865,7 +959,9 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     for (;;) {
         mark();
         k_generate<<<grd, blk, 0, st>>>(a); ++launches; mark();
-        k_traverse<<<grd, blk, 0, st>>>(a); ++launches; mark();
+        if (o->flags & WTGPU_RENDER_THREAD_TRAVERSE) { k_traverse<<<grd, blk, 0, st>>>(a); ++launches; }
+        else { k_gtraverse<<<dim3(148 * 8), blk, 0, st>>>(a); k_resolve<<<grd, blk, 0, st>>>(a); launches += 2; }
+        mark();
         if (nosort) {
             k_identity_order<<<grd, blk, 0, st>>>(a); ++launches;
         } else {
