@@ -324,6 +324,7 @@ typedef struct wtgpu_render_opts {
 #define WTGPU_RENDER_NO_SORT 1u     /* disable the material sort (for A/B measurement) */
 #define WTGPU_RENDER_BDPT_MEGAKERNEL 4u  /* plt_bdpt: run the one-thread-per-sample cross-check kernel instead of the wavefront */
 #define WTGPU_RENDER_THREAD_TRAVERSE 8u  /* one thread per beam in traverse() instead of eight lanes per beam (A/B measurement; bit-identical results) */
+#define WTGPU_RENDER_GROUP_TRAVERSE 16u  /* force eight lanes per beam (default: chosen by scene size for plt_path, always for plt_bdpt) */
 #define WTGPU_RENDER_TIME_KERNELS 2u /* record CUDA events around every kernel (fills wtgpu_stats::*_ms) */
 
 /* Device counters gathered during wtgpu_render (the quantities the reference exposes in a `profile` build:
@@ -355,6 +356,9 @@ int wtgpu_device_count(void);
 const char* wtgpu_last_error(void);
 int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** out);
 void wtgpu_scene_destroy(wtgpu_scene* scene);
+/* Device blocks >= 1 MiB released by a destroyed scene / finished render are kept for reuse by the next one (path pools are GBs);
+ * wtgpu_trim() returns them to the driver. */
+void wtgpu_trim(void);
 int wtgpu_render(wtgpu_scene* scene, const wtgpu_render_opts* opts,
                  float* film_block, float* film_light, wtgpu_stats* stats);
 /* out[h][w][c] = block value/weight + light/spp ; host pointers */

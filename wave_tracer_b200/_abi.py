@@ -183,6 +183,7 @@ def lib():
     L.wtgpu_scene_create.argtypes = [P(SceneDesc), C.c_int, P(C.c_void_p)]
     L.wtgpu_scene_destroy.argtypes = [C.c_void_p]
     L.wtgpu_scene_destroy.restype = None
+    L.wtgpu_trim.argtypes = []; L.wtgpu_trim.restype = None
     L.wtgpu_render.argtypes = [C.c_void_p, P(RenderOpts), C.c_void_p, C.c_void_p, P(Stats)]
     L.wtgpu_develop.argtypes = [P(Sensor), c_u32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.wtgpu_debug_intersect_rays.argtypes = [C.c_void_p, c_u32, P(RayQuery), P(RayHit)]
@@ -205,7 +206,7 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_render", "wtgpu_develop",
+EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_trim", "wtgpu_render", "wtgpu_develop",
                     "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_sobol", "wtgpu_debug_sizeof", "wthost_sobol_tables",
                     "wthost_ads_build", "wthost_ads_fill", "wthost_ads_destroy", "wthost_ads_sah_cost", "wthost_ads_max_depth"]
 

@@ -18,7 +18,8 @@ struct Aperture {
 struct Wedge { V3 v; float l; V3 nff, tff, nbf, e; float alpha; uint32_t idx; };
 
 // free_space_diffraction_t ctor body for one edge (free_space_diffraction.cpp:36-78); false: edge does not take part
-WT_D bool wedge_build(const DScene& sc, const Aperture& ap, uint32_t ed, Wedge& w) {
+struct ApHead { V3 wp; Frame fr; V3 size; V3 wi; float k; };        // an Aperture without its edge list
+template <class AP> WT_D bool wedge_build(const DScene& sc, const AP& ap, uint32_t ed, Wedge& w) {
     const wtgpu_edge E = sc.edges[ed];
     const V3 n1 = mk3(E.n1), n2 = mk3(E.n2), t1 = mk3(E.t1), t2 = mk3(E.t2), ea = mk3(E.a), eb = mk3(E.b);
     const bool f1 = dot(ap.wi, n1) > 0.f;
@@ -182,6 +183,99 @@ WT_DN float do_fsd(const DScene& sc, const Cone& cone_from_src, const Geo& src_g
     }
     if (cone_contains(cone_from_src, dst)) {
         if (!shadow_between(sc, src_geo, dst_geo, ctr)) {
+            const C2 phase = cexpi(-k_times_len(k, length(dst - src)));
+            ts = ts + phase; th = th + phase;
+        }
+    }
+    return (cnorm(ts) + cnorm(th)) / 2.f;
+}
+
+// ------------------------------------------------------------------------------------------------ do_fsd, one warp for its 32 paths
+// do_fsd per thread runs a loop over <= 48 edges in which most edges fail a cheap geometric test and a few reach the expensive part
+// (four UTD transition functions + two shadow rays): the warp ends up executing the expensive part one or two lanes at a time
+// (ncu: 1.2 active threads per instruction on the etoile-like scene).  Here the warp's 32 paths are served together:
+//   filter   every lane walks ITS path's edges through the cheap tests (wedge_build, diffraction point, side tests) in lockstep and appends
+//            the survivors to a shared (owner lane, edge) list;
+//   evaluate whenever 32 items are queued, every lane evaluates one item -- UTD coefficients, both shadow rays, phase -- with the owner's
+//            inputs fetched by shuffles;
+//   reduce   every owner adds its items' terms in list order, which is its own edge order: sums are bit-identical to the sequential loop.
+// All 32 lanes must call (need = false for lanes without a request).
+struct UtdShared { uint32_t item[64]; float4 res[32]; uint32_t ok[32]; };
+WT_D V3 shfl3(V3 v, int src) { return mk3(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src)); }
+__device__ __noinline__ float warp_do_fsd(const DScene& sc, UtdShared& sh, bool need, const Cone& cone_from_src, const Geo& src_geo, V3 dst, const Aperture& ap, float k,
+                        Counters& ctr, uint32_t& edges_fetched) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (!__ballot_sync(0xffffffffu, need)) return 0.f;
+    const V3 src = cone_from_src.o;
+    const uint32_t n = need ? ap.n : 0u;
+    const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
+    C2 ts = mkc(0.f, 0.f), th = mkc(0.f, 0.f);
+    uint32_t cnt = 0u;
+    auto evaluate = [&](uint32_t m) {
+        const bool has = lane < m;
+        const uint32_t it = sh.item[has ? lane : 0u];
+        const int owner = (int)(it >> 26); const uint32_t ed = it & 0x3ffffffu;
+        ApHead ah; ah.wp = shfl3(ap.wp, owner); ah.fr.t = shfl3(ap.fr.t, owner); ah.fr.b = shfl3(ap.fr.b, owner); ah.fr.n = shfl3(ap.fr.n, owner);
+        ah.size = shfl3(ap.size, owner); ah.wi = shfl3(ap.wi, owner); ah.k = __shfl_sync(0xffffffffu, ap.k, owner);
+        const V3 osrc = shfl3(src, owner), odst = shfl3(dst, owner);
+        Geo osg; osg.kind = __shfl_sync(0xffffffffu, src_geo.kind, owner); osg.p = shfl3(src_geo.p, owner); osg.id = __shfl_sync(0xffffffffu, src_geo.id, owner);
+        const float ok_ = __shfl_sync(0xffffffffu, k, owner);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f); uint32_t okf = 0u;
+        if (has) {
+            Wedge w; V3 p;
+            if (wedge_build(sc, ah, ed, w) && wedge_diffraction_point(w, osrc, odst, p)) {      // passed in the filter: recomputed, not re-decided
+                const V3 ui = osrc - p, uo = odst - p;
+                const float ri = length(ui), ro = length(uo);
+                C2 Ds, Dh; wedge_UTD(w, ah.k, ui / ri, uo / ro, ro, Ds, Dh);
+                if (!(Dh.re == 0.f && Dh.im == 0.f && Ds.re == 0.f && Ds.im == 0.f)) {
+                    const Geo eg = geo_edge(p, w.idx);
+                    if (!(shadow_between(sc, eg, osg, ctr) || shadow_between(sc, eg, geo_point(odst), ctr))) {
+                        const C2 phase = cexpi(-k_times_len(ok_, ro + ri));
+                        const C2 a = phase * Ds, b = phase * Dh;
+                        r = make_float4(a.re, a.im, b.re, b.im); okf = 1u;
+                    }
+                }
+            }
+        }
+        sh.res[lane] = r; sh.ok[lane] = okf;
+        __syncwarp();
+        for (uint32_t q = 0; q < m; ++q) {
+            if ((sh.item[q] >> 26) == lane && sh.ok[q]) { const float4 v = sh.res[q]; ts = ts + mkc(v.x, v.y); th = th + mkc(v.z, v.w); }
+        }
+        __syncwarp();
+    };
+    for (uint32_t j = 0; j < nmax; ++j) {
+        bool pass = false; uint32_t ed = 0u;
+        if (j < n) {
+            ed = ap.edges[j];
+            Wedge w;
+            if (wedge_build(sc, ap, ed, w)) {
+                ++edges_fetched;
+                V3 p;
+                if (wedge_diffraction_point(w, src, dst, p)) {
+                    const V3 ui = src - p, uo = dst - p;
+                    pass = !((dot(uo, w.nff) <= 0.f && dot(uo, w.nbf) <= 0.f) || (dot(ui, w.nff) <= 0.f && dot(ui, w.nbf) <= 0.f));
+                }
+            }
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+        if (pass) sh.item[cnt + (uint32_t)__popc(pm & ((1u << lane) - 1u))] = (lane << 26) | ed;
+        cnt += (uint32_t)__popc(pm);
+        __syncwarp();
+        if (cnt >= 32u) {
+            evaluate(32u);
+            const uint32_t rest = cnt - 32u;
+            const uint32_t mv = lane < rest ? sh.item[32u + lane] : 0u;
+            __syncwarp();
+            if (lane < rest) sh.item[lane] = mv;
+            cnt = rest;
+            __syncwarp();
+        }
+    }
+    if (cnt) evaluate(cnt);
+    if (!need) return 0.f;
+    if (cone_contains(cone_from_src, dst)) {
+        if (!shadow_between(sc, src_geo, geo_point(dst), ctr)) {
             const C2 phase = cexpi(-k_times_len(k, length(dst - src)));
             ts = ts + phase; th = th + phase;
         }

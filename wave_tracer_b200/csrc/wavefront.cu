@@ -366,12 +366,35 @@ __global__ void k_hist(const RenderArgs a) {
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < a.n_keys; i += blockDim.x) if (sh[i]) atomicAdd(&a.key_count[i], sh[i]);
 }
-__global__ void k_scan(const RenderArgs a) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t acc = 0;
-        for (uint32_t i = 0; i < a.n_keys; ++i) { const uint32_t c = a.key_count[i]; a.key_cursor[i] = acc; acc += c; a.key_count[i] = 0u; }
-        a.ctr->n_sorted = (int)acc;
+// exclusive scan of the key histogram by one block (keys = bsdf nodes + 3: a scene with hundreds of materials has thousands)
+__global__ void __launch_bounds__(1024) k_scan(const RenderArgs a) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    const uint32_t lane = threadIdx.x & 31u, wrp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < a.n_keys; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t c = i < a.n_keys ? a.key_count[i] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+        if (lane == 31u) warp_tot[wrp] = incl;
+        __syncthreads();
+        if (wrp == 0u) {
+            uint32_t w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0u, wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if ((int)lane >= o) wi += v; }
+            warp_tot[lane] = wi - w;        // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_tot[wrp] + incl - c;
+        if (i < a.n_keys) { a.key_cursor[i] = excl; a.key_count[i] = 0u; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1u) carry = excl + c;      // total so far
+        __syncthreads();
     }
+    if (threadIdx.x == 0) a.ctr->n_sorted = (int)carry;
 }
 __global__ void k_scatter(const RenderArgs a) {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,186 +422,196 @@ __global__ void k_identity_order(const RenderArgs a) {     // WTGPU_RENDER_NO_SO
 // ================================================================================================ shade
 WT_D float MIS(float p1, float p2) { if (p2 == 0.f) return 1.f; return p1 * p1 / (p1 * p1 + p2 * p2); }
 
-__global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
+// One thread per path; the two do_fsd evaluations of a vertex (pending UTD of the previous vertex, forward NEE through the new aperture) are
+// served by the whole warp at convergent points (warp_do_fsd, dfsd.cuh), so the kernel body is written as flat phases.
+__global__ void __launch_bounds__(128, 3) k_shade(const RenderArgs a) {
+    __shared__ UtdShared utd_sh[4];
+    UtdShared& ush = utd_sh[threadIdx.x >> 5];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const DScene& sc = a.sc;
     Counters ctr; counters_zero(ctr);
     uint32_t n_splat = 0, n_edges_fetched = 0, my_slot = 0; bool c_surface = false, c_fsd = false, c_null = false, died = false, survive = false;
-    if (i < (uint32_t)a.ctr->n_sorted) {
-        const DScene& sc = a.sc;
-        const uint32_t slot = a.order[i];
-        PathCore pc; soa_load(pc, a.core, a.pool, slot);
-        HitRec h; hit_load(h, a.hit, a.pool, slot);
-        Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = pc.rng_d; smp.stream = 0u;
-        Beam& beam = pc.beam;
-        const bool fwd = beam.fwd;
-        const uint32_t max_depth = sc.integrator.max_depth;
-        bool alive = true;
-        Aperture ap; ap.n = 0u;
-        bool has_new_fsd = false;
-        Beam prev_beam_new;     // beam before this vertex's interaction (becomes prev_vert_beam)
+    const bool act = i < (uint32_t)a.ctr->n_sorted;
+    bool proc = false, alive = true;
+    uint32_t slot = 0;
+    PathCore pc; HitRec h; PathFsd pf; Aperture ap; ap.n = 0u;
+    Sampler smp;
+    bool has_new_fsd = false;
+    Beam prev_beam_new;     // beam before this vertex's interaction (becomes prev_vert_beam)
+    if (act) {
+        slot = a.order[i];
+        soa_load(pc, a.core, a.pool, slot);
+        hit_load(h, a.hit, a.pool, slot);
+        smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = pc.rng_d; smp.stream = 0u;
+        if (h.flags & H_EMPTY) alive = false; else proc = true;
+    }
+    Beam& beam = pc.beam;
+    const bool fwd = act ? beam.fwd : false;
+    const uint32_t max_depth = sc.integrator.max_depth;
+    const float k = proc ? beam.k : 0.f;
+    const float d2i = proc ? h.d2i : 0.f;
+    const V3 origin_wp = proc ? h.origin : mk3(0.f, 0.f, 0.f);
+    const V3 dir = proc ? beam.env.d : mk3(0.f, 0.f, 1.f);
+    const V3 interaction_wp = origin_wp + d2i * dir;
 
-        if (h.flags & H_EMPTY) alive = false;
+    // ---- evaluate fsd from the previous interaction (plt_path_detail.hpp:591-610)
+    const bool need1 = proc && (pc.flags & F_HAS_FSD);
+    if (need1) soa_load(pf, a.fsd, a.pool, slot);
+    const float f1 = warp_do_fsd(sc, ush, need1, pf.prev_beam.env, pc.prev_geo, interaction_wp, pf.ap, k, ctr, n_edges_fetched);
+    if (need1) {
+        pc.flags &= ~F_HAS_FSD;
+        if (pc.flags & F_SAMPLED_FSD) beam_mul(beam, f1);
         else {
-            const float k = beam.k;
-            const float d2i = h.d2i;
-            const bool is_ballistic = (h.flags & H_BALLISTIC) || cone_is_ray(beam.env);
-            const Frame beam_frame = cone_frame(beam.env);
-            const V3 origin_wp = h.origin;
-            const V3 dir = beam.env.d;
-            const V3 interaction_wp = origin_wp + d2i * dir;
+            beam_transform_region(pf.prev_beam, origin_wp, length(origin_wp - pf.prev_beam.env.o), dir, f1);
+            beam_add(beam, pf.prev_beam);
+        }
+    }
 
-            // ---- evaluate fsd from the previous interaction (plt_path_detail.hpp:591-610)
-            if (pc.flags & F_HAS_FSD) {
-                PathFsd pf; soa_load(pf, a.fsd, a.pool, slot);
-                const float f = do_fsd(sc, pf.prev_beam.env, pc.prev_geo, interaction_wp, pf.ap, k, ctr, n_edges_fetched);
-                pc.flags &= ~F_HAS_FSD;
-                if (pc.flags & F_SAMPLED_FSD) beam_mul(beam, f);
-                else {
-                    beam_transform_region(pf.prev_beam, origin_wp, length(origin_wp - pf.prev_beam.env.o), dir, f);
-                    beam_add(beam, pf.prev_beam);
-                }
-            }
+    // ---- surface record of the primary triangle (plt_path_detail.hpp:634-652)
+    const bool has_primary = proc && (h.flags & H_PRIMARY) != 0u;
+    const float region_end = has_primary ? h.pdist : d2i;
+    Surface surf;
+    int32_t bsdf = -1, emitter = -1;
+    bool need2 = false; SensorDirect sd;
+    if (proc) {
+        const Frame beam_frame = cone_frame(beam.env);
+        if (has_primary) {
+            surf = make_surface(sc, h.primary, mk2(h.bx, h.by), origin_wp + h.pdist * dir);
+            surf.fp = surface_footprint_static(beam, surf, d2i);
+            const wtgpu_shape shp = sc.shapes[sc.tri_meta[h.primary].shape_idx];
+            bsdf = shp.bsdf; emitter = shp.emitter;
+        }
 
-            // ---- surface record of the primary triangle (plt_path_detail.hpp:634-652)
-            const bool has_primary = (h.flags & H_PRIMARY) != 0u;
-            const float region_end = has_primary ? h.pdist : d2i;
-            Surface surf;
-            int32_t bsdf = -1, emitter = -1;
-            if (has_primary) {
-                surf = make_surface(sc, h.primary, mk2(h.bx, h.by), origin_wp + h.pdist * dir);
-                surf.fp = surface_footprint_static(beam, surf, d2i);
-                const wtgpu_shape shp = sc.shapes[sc.tri_meta[h.primary].shape_idx];
-                bsdf = shp.bsdf; emitter = shp.emitter;
-            }
+        // ---- construct the fsd aperture from the edges (plt_path_detail.hpp:663-679)
+        if (h.n_edges) {
+            ap.wp = interaction_wp; ap.fr = beam_frame; ap.size = beam_footprint(beam, d2i); ap.wi = -dir; ap.k = k; ap.n = 0u;
+            for (uint32_t j = 0; j < h.n_edges; ++j) { Wedge w; ++n_edges_fetched; if (wedge_build(sc, ap, h.edges[j], w)) ap.edges[ap.n++] = h.edges[j]; }
+            has_new_fsd = ap.n > 0u;
+            c_fsd = true;
+        }
 
-            // ---- construct the fsd aperture from the edges (plt_path_detail.hpp:663-679)
-            if (h.n_edges) {
-                ap.wp = interaction_wp; ap.fr = beam_frame; ap.size = beam_footprint(beam, d2i); ap.wi = -dir; ap.k = k; ap.n = 0u;
-                for (uint32_t j = 0; j < h.n_edges; ++j) { Wedge w; ++n_edges_fetched; if (wedge_build(sc, ap, h.edges[j], w)) ap.edges[ap.n++] = h.edges[j]; }
-                has_new_fsd = ap.n > 0u;
-                c_fsd = true;
-            }
-
-            // ---- NEE (plt_path_detail.hpp:350-424 backward, 468-510 forward)
-            if (!fwd) {
-                if (pc.depth < max_depth && has_primary && !bsdf_is_delta_only(sc, bsdf, k)) {
-                    const EmitterDirect ds = scene_sample_emitter_direct(sc, smp, surf.wp, k);
-                    if (beam_intensity(ds.beam) != 0.f) {
-                        const V3 wiw = -dir, wow = -ds.beam.env.d;
-                        const V3 wi = to_local(surf.shading, wiw), wo = to_local(surf.shading, wow);
-                        const float wig = dot(wiw, surf.geo.n), wog = dot(wow, surf.geo.n);
-                        if (!(wi.z * wig <= 0.f || wo.z * wog <= 0.f)) {
-                            BsdfQuery q; q.k = k; q.fwd = false; q.lobes = 0xffffffffu;
-                            const Mueller f = bsdf_f(sc, bsdf, wi, wo, q);
-                            if (f.m[0] != 0.f) {
-                                const Geo eg = ds.has_surface ? geo_surface(ds.sp, ds.stuid, true) : geo_point(ds.beam.env.o);
-                                if (!shadow_between(sc, geo_surface(surf.wp, surf.tuid, true), eg, ctr)) {
-                                    Beam nb = beam;
-                                    beam_transform_surface(nb, surf, wow, f, 1.f);
-                                    const Stokes sL = integrate_beams(nb, ds.beam);
-                                    float mis = 1.f;
-                                    if (!ds.dpd.disc) mis = MIS(ds.dpd.v * ds.emitter_pdf, bsdf_pdf(sc, bsdf, wi, wo, q));
-                                    _Pragma("unroll") for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
-                                }
+        // ---- NEE (plt_path_detail.hpp:350-424 backward, 468-510 forward)
+        if (!fwd) {
+            if (pc.depth < max_depth && has_primary && !bsdf_is_delta_only(sc, bsdf, k)) {
+                const EmitterDirect ds = scene_sample_emitter_direct(sc, smp, surf.wp, k);
+                if (beam_intensity(ds.beam) != 0.f) {
+                    const V3 wiw = -dir, wow = -ds.beam.env.d;
+                    const V3 wi = to_local(surf.shading, wiw), wo = to_local(surf.shading, wow);
+                    const float wig = dot(wiw, surf.geo.n), wog = dot(wow, surf.geo.n);
+                    if (!(wi.z * wig <= 0.f || wo.z * wog <= 0.f)) {
+                        BsdfQuery q; q.k = k; q.fwd = false; q.lobes = 0xffffffffu;
+                        const Mueller f = bsdf_f(sc, bsdf, wi, wo, q);
+                        if (f.m[0] != 0.f) {
+                            const Geo eg = ds.has_surface ? geo_surface(ds.sp, ds.stuid, true) : geo_point(ds.beam.env.o);
+                            if (!shadow_between(sc, geo_surface(surf.wp, surf.tuid, true), eg, ctr)) {
+                                Beam nb = beam;
+                                beam_transform_surface(nb, surf, wow, f, 1.f);
+                                const Stokes sL = integrate_beams(nb, ds.beam);
+                                float mis = 1.f;
+                                if (!ds.dpd.disc) mis = MIS(ds.dpd.v * ds.emitter_pdf, bsdf_pdf(sc, bsdf, wi, wo, q));
+                                _Pragma("unroll") for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
                             }
                         }
                     }
                 }
-            } else if (pc.depth < max_depth && has_new_fsd && sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE) {
-                const SensorDirect sd = sensor_sample_direct(sc, smp, interaction_wp, k);
-                if ((sd.dpd.disc || sd.dpd.v != 0.f) && beam_intensity(sd.beam) > 0.f) {
-                    const float f = do_fsd(sc, beam.env, pc.prev_geo, sd.beam.env.o, ap, k, ctr, n_edges_fetched);
-                    if (f != 0.f) {
-                        Beam fb = beam;
-                        beam_transform_region(fb, interaction_wp, d2i, -sd.beam.env.d, f);
-                        const Stokes sL = integrate_beams(sd.beam, fb);
-                        n_splat += film_splat(sc, a.film_block, a.film_light, true, sd.el, sL.s[0] * pc.rspd, k);
-                    }
-                }
             }
+        } else if (pc.depth < max_depth && has_new_fsd && sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE) {
+            sd = sensor_sample_direct(sc, smp, interaction_wp, k);
+            need2 = (sd.dpd.disc || sd.dpd.v != 0.f) && beam_intensity(sd.beam) > 0.f;
+        }
+    }
+    const float f2 = warp_do_fsd(sc, ush, need2, beam.env, pc.prev_geo, sd.beam.env.o, ap, k, ctr, n_edges_fetched);
+    if (need2 && f2 != 0.f) {
+        Beam fb = beam;
+        beam_transform_region(fb, interaction_wp, d2i, -sd.beam.env.d, f2);
+        const Stokes sL = integrate_beams(sd.beam, fb);
+        n_splat += film_splat(sc, a.film_block, a.film_light, true, sd.el, sL.s[0] * pc.rspd, k);
+    }
 
-            // ---- organic connections: emission (plt_path_detail.hpp:427-465) / sensing (513-540)
-            if (!fwd) {
-                if (has_primary && emitter >= 0) {
-                    const Stokes sL = emitter_Li(sc, emitter, beam, surf);
-                    float mis = 1.f;
-                    if (!(pc.flags & F_DPD_DISC)) {
-                        const wtgpu_emitter E = sc.emitters[emitter];
-                        const float ppd = E.type == WTGPU_EMITTER_AREA ? 1.f / sc.shapes[E.shape].surface_area : 0.f;
-                        const float dn = dot(-dir, surf.geo.n);
-                        const float rdn = dn != 0.f ? 1.f / fabsf(dn) : 0.f;
-                        const float pd_nee = ppd * length2(beam.env.o - surf.wp) * rdn;
-                        mis = MIS(pc.dpd_v, pd_nee * pdf_emitter(sc, emitter));
-                    }
-                    _Pragma("unroll") for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
+    if (proc) {
+        // ---- organic connections: emission (plt_path_detail.hpp:427-465) / sensing (513-540)
+        if (!fwd) {
+            if (has_primary && emitter >= 0) {
+                const Stokes sL = emitter_Li(sc, emitter, beam, surf);
+                float mis = 1.f;
+                if (!(pc.flags & F_DPD_DISC)) {
+                    const wtgpu_emitter E = sc.emitters[emitter];
+                    const float ppd = E.type == WTGPU_EMITTER_AREA ? 1.f / sc.shapes[E.shape].surface_area : 0.f;
+                    const float dn = dot(-dir, surf.geo.n);
+                    const float rdn = dn != 0.f ? 1.f / fabsf(dn) : 0.f;
+                    const float pd_nee = ppd * length2(beam.env.o - surf.wp) * rdn;
+                    mis = MIS(pc.dpd_v, pd_nee * pdf_emitter(sc, emitter));
                 }
-            } else {
-                const float maxd = region_end - fmaxf(0.f, dot(dir, origin_wp - beam.env.o));
-                Beam se; Element el;
-                if (sensor_Si(sc, beam, mkr(0.f, maxd), se, el)) {
-                    const Stokes sL = integrate_beams(se, beam);
-                    n_splat += film_splat(sc, a.film_block, a.film_light, true, el, sL.s[0] * pc.rspd, k);
-                }
+                _Pragma("unroll") for (int c = 0; c < 4; ++c) pc.L[c] += sL.s[c] * mis;
             }
-
-            // ---- interactions (plt_path_detail.hpp:156-237, 729-749)
-            bool sampled_null = false;
-            if (has_primary) {
-                BsdfQuery q; q.k = k; q.fwd = fwd; q.lobes = 0xffffffffu;
-                const V3 wiw = -dir;
-                const V3 wi = to_local(surf.shading, wiw);
-                const float wig = dot(wiw, surf.geo.n);
-                if (wig * wi.z <= 0.f) alive = false;
-                else {
-                    const BsdfSample bs = bsdf_sample(sc, bsdf, wi, q, smp);
-                    if (!bs.valid || bs.dpd.v == 0.f) alive = false;
-                    else {
-                        const V3 wow = normalize(to_world(surf.shading, bs.wo));
-                        c_surface = true;
-                        if (dot(wow, surf.geo.n) * bs.wo.z <= 0.f) alive = false;
-                        else {
-                            pc.dpd_v = bs.dpd.v; pc.flags = (pc.flags & ~(F_DPD_DISC | F_SAMPLED_FSD)) | (bs.dpd.disc ? F_DPD_DISC : 0u);
-                            pc.prev_geo = geo_surface(surf.wp, surf.tuid, true);
-                            prev_beam_new = beam;
-                            beam_transform_surface(beam, surf, wow, bs.M, 1.f);
-                            pc.throughput *= 1.f * bs.M.m[0];
-                            if (bs.eta.re != 1.f) pc.throughput /= sqrf(bs.eta.re);
-                        }
-                    }
-                }
-            } else if (has_new_fsd) {
-                V3 wo; float w;
-                fsd_sample(sc, ap, pc.prev_geo.p, smp, wo, w);
-                pc.dpd_v = 0.f; pc.flags = (pc.flags | F_DPD_DISC | F_SAMPLED_FSD);
-                pc.prev_geo = geo_point(interaction_wp);
-                prev_beam_new = beam;
-                beam_transform_region(beam, interaction_wp, d2i, wo, w);
-                pc.throughput *= w;
-            } else {
-                sampled_null = true; c_null = true;
-                beam_transform_restart(beam, interaction_wp, d2i);
-            }
-
-            // ---- continue walk (plt_path_detail.hpp:123-142, 755-757)
-            if (alive) {
-                if (pc.depth >= max_depth) alive = false;
-                else if (beam_intensity(beam) == 0.f) alive = false;
-                else if (!sampled_null && sc.integrator.russian_roulette) {
-                    const float r = pc.throughput < 1.f ? fmaxf(pc.throughput, .5f) : 1.f;
-                    if (rnd(smp) <= r) { const float s = 1.f / r; beam_mul(beam, s); pc.throughput *= s; }
-                    else alive = false;
-                }
-                if (alive && !sampled_null) pc.depth++;
+        } else {
+            const float maxd = region_end - fmaxf(0.f, dot(dir, origin_wp - beam.env.o));
+            Beam se; Element el;
+            if (sensor_Si(sc, beam, mkr(0.f, maxd), se, el)) {
+                const Stokes sL = integrate_beams(se, beam);
+                n_splat += film_splat(sc, a.film_block, a.film_light, true, el, sL.s[0] * pc.rspd, k);
             }
         }
 
+        // ---- interactions (plt_path_detail.hpp:156-237, 729-749)
+        bool sampled_null = false;
+        if (has_primary) {
+            BsdfQuery q; q.k = k; q.fwd = fwd; q.lobes = 0xffffffffu;
+            const V3 wiw = -dir;
+            const V3 wi = to_local(surf.shading, wiw);
+            const float wig = dot(wiw, surf.geo.n);
+            if (wig * wi.z <= 0.f) alive = false;
+            else {
+                const BsdfSample bs = bsdf_sample(sc, bsdf, wi, q, smp);
+                if (!bs.valid || bs.dpd.v == 0.f) alive = false;
+                else {
+                    const V3 wow = normalize(to_world(surf.shading, bs.wo));
+                    c_surface = true;
+                    if (dot(wow, surf.geo.n) * bs.wo.z <= 0.f) alive = false;
+                    else {
+                        pc.dpd_v = bs.dpd.v; pc.flags = (pc.flags & ~(F_DPD_DISC | F_SAMPLED_FSD)) | (bs.dpd.disc ? F_DPD_DISC : 0u);
+                        pc.prev_geo = geo_surface(surf.wp, surf.tuid, true);
+                        prev_beam_new = beam;
+                        beam_transform_surface(beam, surf, wow, bs.M, 1.f);
+                        pc.throughput *= 1.f * bs.M.m[0];
+                        if (bs.eta.re != 1.f) pc.throughput /= sqrf(bs.eta.re);
+                    }
+                }
+            }
+        } else if (has_new_fsd) {
+            V3 wo; float w;
+            fsd_sample(sc, ap, pc.prev_geo.p, smp, wo, w);
+            pc.dpd_v = 0.f; pc.flags = (pc.flags | F_DPD_DISC | F_SAMPLED_FSD);
+            pc.prev_geo = geo_point(interaction_wp);
+            prev_beam_new = beam;
+            beam_transform_region(beam, interaction_wp, d2i, wo, w);
+            pc.throughput *= w;
+        } else {
+            sampled_null = true; c_null = true;
+            beam_transform_restart(beam, interaction_wp, d2i);
+        }
+
+        // ---- continue walk (plt_path_detail.hpp:123-142, 755-757)
+        if (alive) {
+            if (pc.depth >= max_depth) alive = false;
+            else if (beam_intensity(beam) == 0.f) alive = false;
+            else if (!sampled_null && sc.integrator.russian_roulette) {
+                const float r = pc.throughput < 1.f ? fmaxf(pc.throughput, .5f) : 1.f;
+                if (rnd(smp) <= r) { const float s = 1.f / r; beam_mul(beam, s); pc.throughput *= s; }
+                else alive = false;
+            }
+            if (alive && !sampled_null) pc.depth++;
+        }
+    }
+
+    if (act) {
         survive = alive;
         my_slot = slot;
         if (alive) {
             pc.rng_d = smp.d;
             if (has_new_fsd) {
                 pc.flags |= F_HAS_FSD;
-                PathFsd pf; pf.prev_beam = prev_beam_new; pf.ap = ap;
+                pf.prev_beam = prev_beam_new; pf.ap = ap;
                 soa_store(pf, a.fsd, a.pool, slot);
             }
             soa_store(pc, a.core, a.pool, slot);
@@ -593,7 +626,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderArgs a) {
     }
     list_append(a.trav_list, &a.ctr->n_trav, survive, my_slot);
     flush_counters(a.ctr, ctr, true);
-    count1(&a.ctr->shaded, i < (uint32_t)a.ctr->n_sorted);
+    count1(&a.ctr->shaded, act);
     {
         const unsigned m = __activemask();
         const unsigned ns = __reduce_add_sync(m, n_splat), ne = __reduce_add_sync(m, n_edges_fetched), nd = __reduce_add_sync(m, died ? 1u : 0u);
@@ -651,6 +684,56 @@ __global__ void k_debug_rng(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t s
 static thread_local std::string g_err;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return WTGPU_E_CUDA; } } while (0)
 
+// Device block cache.  Path pools are GBs (a plt_bdpt pool of 2^18 sample slots is ~8 GB); a host that renders through
+// scene create -> render -> destroy repeatedly (one call per sensor, per frame, per bench step) must not pay cudaMalloc/cudaFree of
+// those every time.  Freed blocks >= 1 MiB are kept per (device, size) and handed back on the next request of the same size;
+// wtgpu_trim() releases them.  Blocks carry no state: every user initialises what it reads.
+#include <map>
+#include <mutex>
+#include <unordered_map>
+namespace {
+struct BlockCache {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void*> idle;
+    std::unordered_map<void*, std::pair<int, size_t>> live;
+    size_t idle_bytes = 0;
+};
+BlockCache g_blocks;
+constexpr size_t kCacheMinBlock = 1ull << 20, kCacheMaxIdle = 48ull << 30;
+cudaError_t wt_malloc_impl(void** p, size_t bytes) {
+    int dev = 0; cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> l(g_blocks.m);
+        auto it = g_blocks.idle.find({ dev, bytes });
+        if (it != g_blocks.idle.end()) { *p = it->second; g_blocks.idle.erase(it); g_blocks.idle_bytes -= bytes; g_blocks.live[*p] = { dev, bytes }; return cudaSuccess; }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {     // out of memory with idle blocks around: drop them and retry once
+        std::vector<void*> drop;
+        { std::lock_guard<std::mutex> l(g_blocks.m); for (auto& kv : g_blocks.idle) drop.push_back(kv.second); g_blocks.idle.clear(); g_blocks.idle_bytes = 0; }
+        for (void* q : drop) cudaFree(q);
+        cudaGetLastError();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> l(g_blocks.m); g_blocks.live[*p] = { dev, bytes }; }
+    return e;
+}
+template <class T> cudaError_t wt_malloc(T** p, size_t bytes) { return wt_malloc_impl(reinterpret_cast<void**>(p), bytes); }
+void wt_free(void* p) {
+    if (!p) return;
+    std::pair<int, size_t> info{ -1, 0 };
+    {
+        std::lock_guard<std::mutex> l(g_blocks.m);
+        auto it = g_blocks.live.find(p);
+        if (it != g_blocks.live.end()) { info = it->second; g_blocks.live.erase(it); }
+        if (info.first >= 0 && info.second >= kCacheMinBlock && g_blocks.idle_bytes + info.second <= kCacheMaxIdle) {
+            g_blocks.idle.insert({ info, p }); g_blocks.idle_bytes += info.second; return;
+        }
+    }
+    cudaFree(p);
+}
+}
+
 struct wtgpu_scene {
     int device = 0;
     DScene d{};
@@ -674,18 +757,18 @@ struct wtgpu_scene {
     uint32_t bd_wave_P = 0;
     cudaStream_t bd_stream = nullptr; cudaEvent_t bd_ev_shade = nullptr, bd_ev_samp = nullptr;   // Fraunhofer sampler overlap
     void free_bd_wave() {
-        for (void* p : { (void*)bd_walkers, (void*)bd_headers, (void*)bd_hit, (void*)bd_pending, (void*)bd_L0, (void*)bd_nverts, (void*)bd_pairs, (void*)bd_alive, (void*)bd_keys, (void*)bd_order, (void*)bd_trav, (void*)bd_fsd_list, (void*)bd_fsd_out, (void*)bd_trav_tris, (void*)bd_trav_rec }) if (p) cudaFree(p);
+        for (void* p : { (void*)bd_walkers, (void*)bd_headers, (void*)bd_hit, (void*)bd_pending, (void*)bd_L0, (void*)bd_nverts, (void*)bd_pairs, (void*)bd_alive, (void*)bd_keys, (void*)bd_order, (void*)bd_trav, (void*)bd_fsd_list, (void*)bd_fsd_out, (void*)bd_trav_tris, (void*)bd_trav_rec }) if (p) wt_free(p);
         bd_walkers = bd_headers = bd_hit = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_pairs = bd_alive = bd_keys = bd_order = bd_trav = bd_fsd_list = bd_trav_tris = nullptr; bd_fsd_out = nullptr; bd_trav_rec = nullptr; bd_wave_P = 0;
     }
     ~wtgpu_scene() {
         cudaSetDevice(device);
-        for (void* p : allocs) cudaFree(p);
+        for (void* p : allocs) wt_free(p);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         free_bd_wave();
         if (bd_stream) cudaStreamDestroy(bd_stream);
         if (bd_ev_shade) cudaEventDestroy(bd_ev_shade);
         if (bd_ev_samp) cudaEventDestroy(bd_ev_samp);
-        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list, (void*)bdpt_arena, (void*)trav_rec, (void*)trav_tris }) if (p) cudaFree(p);
+        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list, (void*)bdpt_arena, (void*)trav_rec, (void*)trav_tris }) if (p) wt_free(p);
     }
 };
 
@@ -728,7 +811,7 @@ static bool sobol_build_tables(const wtgpu_sobol_entry* e, wt::SobolTables& t, s
 template <class T> static int upload(wtgpu_scene* s, const T* src, size_t n, const T** dst) {
     void* p = nullptr;
     const size_t bytes = std::max<size_t>(1, n) * sizeof(T);
-    CK(cudaMalloc(&p, bytes));
+    CK(wt_malloc(&p, bytes));
     s->allocs.push_back(p);
     if (n && src) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
     *dst = reinterpret_cast<const T*>(p);
@@ -760,6 +843,7 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
     if (bdpt && desc->integrator.max_depth + 2u > (uint32_t)wt::kMaxBdptVerts) { g_err = "plt_bdpt: max_depth > 16 unsupported"; return WTGPU_E_UNSUPPORTED; }
     if (bdpt && desc->integrator.fsd && (!desc->fsd_lut_n || !desc->fsd_lut_m || !desc->fsd_icdf1 || !desc->fsd_icdf2 || !desc->fsd_icdf_theta1 || !desc->fsd_icdf_theta2)) {
         g_err = "plt_bdpt with FSD needs the Fraunhofer sampling tables (fsd_lut_*)"; return WTGPU_E_INVALID; }
+    if (desc->n_edges >= (1u << 26)) { g_err = "more than 2^26 edges unsupported"; return WTGPU_E_UNSUPPORTED; }
     if (desc->sensor.rf_radius > 4) { g_err = "reconstruction filter radius > 4 unsupported"; return WTGPU_E_UNSUPPORTED; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device"; return WTGPU_E_NO_DEVICE; }
@@ -806,17 +890,25 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
 
 void wtgpu_scene_destroy(wtgpu_scene* s) { delete s; }
 
+void wtgpu_trim(void) {
+    std::vector<std::pair<int, void*>> drop;
+    { std::lock_guard<std::mutex> l(g_blocks.m); for (auto& kv : g_blocks.idle) drop.push_back({ kv.first.first, kv.second }); g_blocks.idle.clear(); g_blocks.idle_bytes = 0; }
+    int cur = 0; cudaGetDevice(&cur);
+    for (auto& d : drop) { cudaSetDevice(d.first); cudaFree(d.second); }
+    cudaSetDevice(cur);
+}
+
 static int ensure_pool(wtgpu_scene* s, uint32_t pool) {
     if (s->pool == pool) return WTGPU_OK;
-    for (void* p : { (void*)s->core, (void*)s->fsd, (void*)s->hit, (void*)s->alive, (void*)s->keys, (void*)s->order, (void*)s->key_count, (void*)s->key_cursor, (void*)s->ctr, (void*)s->trav_list, (void*)s->trav_rec, (void*)s->trav_tris }) if (p) cudaFree(p);
+    for (void* p : { (void*)s->core, (void*)s->fsd, (void*)s->hit, (void*)s->alive, (void*)s->keys, (void*)s->order, (void*)s->key_count, (void*)s->key_cursor, (void*)s->ctr, (void*)s->trav_list, (void*)s->trav_rec, (void*)s->trav_tris }) if (p) wt_free(p);
     s->core = s->fsd = s->hit = nullptr; s->alive = s->keys = s->order = s->key_count = s->key_cursor = s->trav_list = s->trav_tris = nullptr; s->trav_rec = nullptr; s->ctr = nullptr; s->pool = 0;
-    if (s->integ.type == WTGPU_INTEGRATOR_PLT_PATH) { CK(cudaMalloc(&s->trav_rec, sizeof(TravRec) * (size_t)pool)); CK(cudaMalloc(&s->trav_tris, 4ull * kMaxConeTris * pool)); }
-    CK(cudaMalloc(&s->core, (size_t)chunks_of<PathCore>() * 16 * pool));
-    CK(cudaMalloc(&s->fsd, (size_t)chunks_of<PathFsd>() * 16 * pool));
-    CK(cudaMalloc(&s->hit, (size_t)chunks_of<HitRec>() * 16 * pool));
-    CK(cudaMalloc(&s->alive, 4ull * pool)); CK(cudaMalloc(&s->keys, 4ull * pool)); CK(cudaMalloc(&s->order, 4ull * pool)); CK(cudaMalloc(&s->trav_list, 4ull * pool));
-    CK(cudaMalloc(&s->key_count, 4ull * s->n_keys)); CK(cudaMalloc(&s->key_cursor, 4ull * s->n_keys));
-    CK(cudaMalloc(&s->ctr, sizeof(DevCounters)));
+    if (s->integ.type == WTGPU_INTEGRATOR_PLT_PATH) { CK(wt_malloc(&s->trav_rec, sizeof(TravRec) * (size_t)pool)); CK(wt_malloc(&s->trav_tris, 4ull * kMaxConeTris * pool)); }
+    CK(wt_malloc(&s->core, (size_t)chunks_of<PathCore>() * 16 * pool));
+    CK(wt_malloc(&s->fsd, (size_t)chunks_of<PathFsd>() * 16 * pool));
+    CK(wt_malloc(&s->hit, (size_t)chunks_of<HitRec>() * 16 * pool));
+    CK(wt_malloc(&s->alive, 4ull * pool)); CK(wt_malloc(&s->keys, 4ull * pool)); CK(wt_malloc(&s->order, 4ull * pool)); CK(wt_malloc(&s->trav_list, 4ull * pool));
+    CK(wt_malloc(&s->key_count, 4ull * s->n_keys)); CK(wt_malloc(&s->key_cursor, 4ull * s->n_keys));
+    CK(wt_malloc(&s->ctr, sizeof(DevCounters)));
     s->pool = pool;
     return WTGPU_OK;
 }
@@ -846,7 +938,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     float *dblock = film_block, *dlight = film_light;
     const bool on_dev = o->film_on_device != 0;
     if (!on_dev) {
-        CK(cudaMalloc(&dblock, nb * 4)); CK(cudaMalloc(&dlight, nl * 4));
+        CK(wt_malloc(&dblock, nb * 4)); CK(wt_malloc(&dlight, nl * 4));
         CK(cudaMemsetAsync(dblock, 0, nb * 4, st)); CK(cudaMemsetAsync(dlight, 0, nl * 4, st));
     }
 
@@ -862,6 +954,9 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     CK(cudaMemsetAsync(s->key_count, 0, 4ull * s->n_keys, st));
     CK(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
 
+    // traverse(): eight lanes per beam pay off when queries are long (cone queries over real geometry); on a handful of triangles one thread
+    // per beam is faster (measured: double_slits plt_path 99 vs 52 Msamples/s; etoile-like 6 vs 16).  Both give bit-identical results.
+    const bool use_thread_trav = (o->flags & WTGPU_RENDER_THREAD_TRAVERSE) ? true : (o->flags & WTGPU_RENDER_GROUP_TRAVERSE) ? false : (!bdpt && s->d.n_tris < 128u);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     DevCounters* hctr = nullptr;
@@ -877,9 +972,9 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     CK(cudaEventRecord(e0, st));
     if (bdpt && (o->flags & WTGPU_RENDER_BDPT_MEGAKERNEL)) {     // one thread per sample, one launch (dbdpt.cuh driver 1)
         if (s->bdpt_P != pool) {
-            if (s->bdpt_arena) cudaFree(s->bdpt_arena);
+            if (s->bdpt_arena) wt_free(s->bdpt_arena);
             s->bdpt_arena = nullptr; s->bdpt_P = 0;
-            CK(cudaMalloc(&s->bdpt_arena, (size_t)wt::kArenaWords * 4 * pool));
+            CK(wt_malloc(&s->bdpt_arena, (size_t)wt::kArenaWords * 4 * pool));
             s->bdpt_P = pool;
         }
         BdptArgs b;
@@ -898,14 +993,14 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         }
         if (s->bd_wave_P != P) {
             s->free_bd_wave();
-            if (s->bdpt_P != P) { if (s->bdpt_arena) cudaFree(s->bdpt_arena); s->bdpt_arena = nullptr; s->bdpt_P = 0; CK(cudaMalloc(&s->bdpt_arena, (size_t)wt::kArenaWords * 4 * P)); s->bdpt_P = P; }
-            CK(cudaMalloc(&s->bd_walkers, (size_t)chunks_of<BdWalker>() * 16 * W2)); CK(cudaMalloc(&s->bd_headers, (size_t)chunks_of<BdHeader>() * 16 * P));
-            CK(cudaMalloc(&s->bd_hit, (size_t)chunks_of<HitRec>() * 16 * W2));
-            CK(cudaMalloc(&s->bd_pending, 4ull * P)); CK(cudaMalloc(&s->bd_L0, 4ull * P)); CK(cudaMalloc(&s->bd_nverts, 4ull * W2)); CK(cudaMalloc(&s->bd_alive, 4ull * P));
-            CK(cudaMalloc(&s->bd_keys, 4ull * W2)); CK(cudaMalloc(&s->bd_order, 4ull * W2)); CK(cudaMalloc(&s->bd_trav, 4ull * W2));
-            CK(cudaMalloc(&s->bd_pairs, 4ull * (size_t)P * (max_pairs + 4ull * nmaxv)));
-            CK(cudaMalloc(&s->bd_trav_rec, sizeof(TravRec) * (size_t)W2)); CK(cudaMalloc(&s->bd_trav_tris, 4ull * kMaxConeTris * W2));
-            CK(cudaMalloc(&s->bd_fsd_list, 12ull * W2)); CK(cudaMalloc(&s->bd_fsd_out, 32ull * W2));
+            if (s->bdpt_P != P) { if (s->bdpt_arena) wt_free(s->bdpt_arena); s->bdpt_arena = nullptr; s->bdpt_P = 0; CK(wt_malloc(&s->bdpt_arena, (size_t)wt::kArenaWords * 4 * P)); s->bdpt_P = P; }
+            CK(wt_malloc(&s->bd_walkers, (size_t)chunks_of<BdWalker>() * 16 * W2)); CK(wt_malloc(&s->bd_headers, (size_t)chunks_of<BdHeader>() * 16 * P));
+            CK(wt_malloc(&s->bd_hit, (size_t)chunks_of<HitRec>() * 16 * W2));
+            CK(wt_malloc(&s->bd_pending, 4ull * P)); CK(wt_malloc(&s->bd_L0, 4ull * P)); CK(wt_malloc(&s->bd_nverts, 4ull * W2)); CK(wt_malloc(&s->bd_alive, 4ull * P));
+            CK(wt_malloc(&s->bd_keys, 4ull * W2)); CK(wt_malloc(&s->bd_order, 4ull * W2)); CK(wt_malloc(&s->bd_trav, 4ull * W2));
+            CK(wt_malloc(&s->bd_pairs, 4ull * (size_t)P * (max_pairs + 4ull * nmaxv)));
+            CK(wt_malloc(&s->bd_trav_rec, sizeof(TravRec) * (size_t)W2)); CK(wt_malloc(&s->bd_trav_tris, 4ull * kMaxConeTris * W2));
+            CK(wt_malloc(&s->bd_fsd_list, 12ull * W2)); CK(wt_malloc(&s->bd_fsd_out, 32ull * W2));
             s->bd_wave_P = P;
         }
         if (P > (1u << 22)) { g_err = "plt_bdpt: pool_size > 4M sample slots"; return WTGPU_E_INVALID; }
@@ -913,7 +1008,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         b.r = a; b.r.hit = s->bd_hit; b.r.alive = s->bd_alive; b.r.keys = s->bd_keys; b.r.order = s->bd_order; b.r.trav_list = s->bd_trav; b.r.pool = W2;
         b.lut = s->lut; b.arena = s->bdpt_arena; b.P = P; b.walkers = s->bd_walkers; b.headers = s->bd_headers;
         b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs; b.fsd_list = s->bd_fsd_list; b.fsd_out = s->bd_fsd_out; b.trav_rec = s->bd_trav_rec; b.trav_tris = s->bd_trav_tris;
-        const bool thread_trav = (o->flags & WTGPU_RENDER_THREAD_TRAVERSE) != 0;
+        const bool thread_trav = use_thread_trav;
         for (int c = 0; c < 5; ++c) b.pair_off[c] = (size_t)P * nmaxv * (size_t)c;      // classes 0-3 hold <= max_depth+3 strategies per sample, class 4 the rest
         const bool has_fsd = s->integ.fsd != 0u;
         CK(cudaMemsetAsync(s->bd_alive, 0, 4ull * P, st));
@@ -933,7 +1028,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blk, 0, st>>>(b); launches += 2; }
             mark();
             k_hist<<<gW, blk, s->n_keys * 4, st>>>(b.r);
-            k_scan<<<1, 32, 0, st>>>(b.r);
+            k_scan<<<1, 1024, 0, st>>>(b.r);
             k_scatter<<<gW, blk, 0, st>>>(b.r); launches += 3; mark();
             k_bd_reset<<<1, 32, 0, st>>>(b);
             k_bd_shade<<<gW, blk, 0, st>>>(b); launches += 2;
@@ -959,14 +1054,14 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     for (;;) {
         mark();
         k_generate<<<grd, blk, 0, st>>>(a); ++launches; mark();
-        if (o->flags & WTGPU_RENDER_THREAD_TRAVERSE) { k_traverse<<<grd, blk, 0, st>>>(a); ++launches; }
+        if (use_thread_trav) { k_traverse<<<grd, blk, 0, st>>>(a); ++launches; }
         else { k_gtraverse<<<dim3(148 * 8), blk, 0, st>>>(a); k_resolve<<<grd, blk, 0, st>>>(a); launches += 2; }
         mark();
         if (nosort) {
             k_identity_order<<<grd, blk, 0, st>>>(a); ++launches;
         } else {
             k_hist<<<grd, blk, s->n_keys * 4, st>>>(a);
-            k_scan<<<1, 32, 0, st>>>(a);
+            k_scan<<<1, 1024, 0, st>>>(a);
             k_scatter<<<grd, blk, 0, st>>>(a); launches += 3;
         }
         mark();
@@ -999,7 +1094,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         if (film_block) for (size_t i = 0; i < nb; ++i) film_block[i] += tmp[i];
         CK(cudaMemcpy(tmp.data(), dlight, nl * 4, cudaMemcpyDeviceToHost));
         if (film_light) for (size_t i = 0; i < nl; ++i) film_light[i] += tmp[i];
-        cudaFree(dblock); cudaFree(dlight);
+        wt_free(dblock); wt_free(dlight);
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -1036,37 +1131,37 @@ int wtgpu_debug_intersect_rays(wtgpu_scene* s, uint32_t n, const wtgpu_ray_query
     if (!s) return WTGPU_E_INVALID;
     CK(cudaSetDevice(s->device));
     wtgpu_ray_query* dq; wtgpu_ray_hit* dh;
-    CK(cudaMalloc(&dq, sizeof(*dq) * n)); CK(cudaMalloc(&dh, sizeof(*dh) * n));
+    CK(wt_malloc(&dq, sizeof(*dq) * n)); CK(wt_malloc(&dh, sizeof(*dh) * n));
     CK(cudaMemcpy(dq, q, sizeof(*dq) * n, cudaMemcpyHostToDevice));
     k_debug_rays<<<(n + 127) / 128, 128>>>(s->d, n, dq, dh, nullptr);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, dh, sizeof(*dh) * n, cudaMemcpyDeviceToHost));
-    cudaFree(dq); cudaFree(dh);
+    wt_free(dq); wt_free(dh);
     return WTGPU_OK;
 }
 int wtgpu_debug_shadow_rays(wtgpu_scene* s, uint32_t n, const wtgpu_ray_query* q, uint32_t* out) {
     if (!s) return WTGPU_E_INVALID;
     CK(cudaSetDevice(s->device));
     wtgpu_ray_query* dq; uint32_t* dh;
-    CK(cudaMalloc(&dq, sizeof(*dq) * n)); CK(cudaMalloc(&dh, 4ull * n));
+    CK(wt_malloc(&dq, sizeof(*dq) * n)); CK(wt_malloc(&dh, 4ull * n));
     CK(cudaMemcpy(dq, q, sizeof(*dq) * n, cudaMemcpyHostToDevice));
     k_debug_rays<<<(n + 127) / 128, 128>>>(s->d, n, dq, nullptr, dh);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, dh, 4ull * n, cudaMemcpyDeviceToHost));
-    cudaFree(dq); cudaFree(dh);
+    wt_free(dq); wt_free(dh);
     return WTGPU_OK;
 }
 int wtgpu_debug_intersect_cones(wtgpu_scene* s, uint32_t n, const wtgpu_cone_query* q, wtgpu_cone_hit* out) {
     if (!s) return WTGPU_E_INVALID;
     CK(cudaSetDevice(s->device));
     wtgpu_cone_query* dq; wtgpu_cone_hit* dh;
-    CK(cudaMalloc(&dq, sizeof(*dq) * n)); CK(cudaMalloc(&dh, sizeof(*dh) * n));
+    CK(wt_malloc(&dq, sizeof(*dq) * n)); CK(wt_malloc(&dh, sizeof(*dh) * n));
     CK(cudaMemcpy(dq, q, sizeof(*dq) * n, cudaMemcpyHostToDevice));
     CK(cudaMemset(dh, 0, sizeof(*dh) * n));
     k_debug_cones<<<(n + 63) / 64, 64>>>(s->d, n, dq, dh);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, dh, sizeof(*dh) * n, cudaMemcpyDeviceToHost));
-    cudaFree(dq); cudaFree(dh);
+    wt_free(dq); wt_free(dh);
     return WTGPU_OK;
 }
 int wthost_sobol_tables(const wtgpu_sobol_entry* table, uint16_t* ones, uint16_t* twos) {
@@ -1083,21 +1178,21 @@ int wtgpu_debug_sobol(wtgpu_scene* s, uint64_t seed, uint64_t g0, uint32_t n, ui
     CK(cudaSetDevice(s->device));
     const size_t m = (size_t)n * WTGPU_SOBOL_DIMS;
     if (m == 0) return WTGPU_OK;
-    uint32_t* dn; float* dv; CK(cudaMalloc(&dn, 4 * m)); CK(cudaMalloc(&dv, 4 * m));
+    uint32_t* dn; float* dv; CK(wt_malloc(&dn, 4 * m)); CK(wt_malloc(&dv, 4 * m));
     k_debug_sobol<<<(unsigned)((m + 127) / 128), 128>>>((uint32_t)seed, (uint32_t)(seed >> 32), g0, n, dn, dv);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out_num, dn, 4 * m, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(out_val, dv, 4 * m, cudaMemcpyDeviceToHost));
-    cudaFree(dn); cudaFree(dv);
+    wt_free(dn); wt_free(dv);
     return WTGPU_OK;
 }
 
 int wtgpu_debug_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, int device) {
     CK(cudaSetDevice(device));
-    float* d; CK(cudaMalloc(&d, 4ull * n));
+    float* d; CK(wt_malloc(&d, 4ull * n));
     k_debug_rng<<<(n + 127) / 128, 128>>>((uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, n, d);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, d, 4ull * n, cudaMemcpyDeviceToHost));
-    cudaFree(d);
+    wt_free(d);
     return WTGPU_OK;
 }
 

@@ -372,7 +372,10 @@ class Scene:
             spectra.append(sp); return len(spectra) - 1
 
         bsdfs, bins = [], []
+        flat_ids = {}          # a bsdf object shared between shapes (the XML's <ref id=...>) is flattened once
         def flat_bsdf(b):
+            if id(b) in flat_ids: return flat_ids[id(b)]
+            flat_ids[id(b)] = len(bsdfs)
             n = A.Bsdf(); n.child = -1; n.spec[:] = [-1] * 4; n.prof_spec[:] = [-1] * 2
             idx = len(bsdfs); bsdfs.append(n)
             if isinstance(b, Diffuse):
