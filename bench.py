@@ -88,6 +88,7 @@ def main():
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sort", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true", help="do not record per-kernel CUDA events in the timed region (A/B of the instrumentation cost)")
     ap.add_argument("--flags", type=int, default=0, help="extra WTGPU_RENDER_* flags (A/B measurements)")
     a = ap.parse_args()
 
@@ -138,7 +139,7 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     gs = GpuScene(built, local)
-    flags = 2 | (1 if a.no_sort else 0) | a.flags      # WTGPU_RENDER_TIME_KERNELS
+    flags = (0 if a.no_kernel_timing else 2) | (1 if a.no_sort else 0) | a.flags      # WTGPU_RENDER_TIME_KERNELS
     S = a.spp_per_step
     # weak scaling: every rank renders S samples per element per step (disjoint sample ranges across ranks)
     def step(i):
