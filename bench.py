@@ -181,16 +181,24 @@ def main():
         # pdf/delta scalars per subpath vertex for MIS (~ 4 vertices) + shadow-ray nodes/triangles + the film/L0 atomic (8 B)
         strat = [sum(s["strategies"][c] for s in stats) for c in range(5)]
         b_conn = sum(n * (4 + 48 + u * 272 + 48 + 8) for n, u in zip(strat, (2, 2, 2, 2, 4))) + 256 * (tot("nodes_visited") - tot("traverse_nodes")) + 48 * (tot("tris_tested") - tot("traverse_tris"))
-        kern, kms, kbytes, launches_k = ("k_bd_connect", conn_ms, b_conn, 5 * its) if conn_ms >= trav_ms else ("k_bd_traverse", trav_ms, b_trav, its)
+        # a "launch" of k_bd_connect = the five class launches of one iteration; of k_bd_traverse = k_bd_gtraverse + k_bd_resolve
+        kern, kms, kbytes, launches_k = ("k_bd_connect", conn_ms, b_conn, its) if conn_ms >= trav_ms else ("k_bd_traverse", trav_ms, b_trav, its)
         share = {"k_bd_traverse": trav_ms / ms, "k_bd_shade(+fsd_finish)": shade_ms / ms, "k_bd_connect": conn_ms / ms}
     else:
         core_b, hit_b = 240, 160     # PathCore read + HitRec/key write per segment (16-B chunks: 15 / 10)
         kbytes = tot("segments") * (core_b + hit_b + 4) + 256 * tot("traverse_nodes") + 48 * tot("traverse_tris")
         kern, kms, launches_k = "k_traverse", trav_ms, its
         share = {"k_traverse": trav_ms / ms, "k_shade": shade_ms / ms}
+    # DRAM traffic of one launch of that kernel from the committed `ncu --set full` capture of this command (profiles/ncu_traffic.json)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(a.workload, {}).get(kern)
+        if tj and a.res == wl["res"]: traffic, traffic_src = tj["bytes"], tj["capture"]
+    except Exception:
+        pass
     achieved = kbytes / max(kms * 1e-3, 1e-12) / 1e9
     roofline = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                "traffic": None, "alg_bytes_per_launch": kbytes / max(1, launches_k), "avg_launch_ms": kms / max(1, launches_k), "share_of_step": share}
+                "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": kbytes / max(1, launches_k), "avg_launch_ms": kms / max(1, launches_k), "share_of_step": share}
 
     if rank == 0:
         # ---- e2e: through the public API with HOST buffers: scene upload (H2D), render, film read-back (D2H) inside the timed region

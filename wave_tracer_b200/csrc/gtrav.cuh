@@ -213,59 +213,48 @@ WT_D bool g_query_done(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, 
 }
 
 // The driver loop.  fetch(i, env, prev, lambda) loads item i (group-uniformly); emit(i, rec, tris) stores its result.
-//
-// The four groups of a warp are independent state machines, but they share one instruction stream: left to themselves (a per-group loop
-// with breaks) they end up executing ONE GROUP AT A TIME (ncu r01s2: 8.2 active threads per instruction in this kernel).  So the loop below
-// is warp-uniform: every iteration each group that has no leaf pending pops its stack top and either takes a node step -- all such groups
-// in the same instructions -- or parks the leaf; when every live group has a leaf parked, the leaf steps (the expensive cone-triangle
-// code) run together.  Transitions (next query of a beam, emit + fetch of the next beam) run in their own warp-uniform loop.
+// (A fully warp-uniform variant -- one pop per group per iteration, node steps of all groups in the same instructions -- was measured 8 %
+// SLOWER on the etoile-like scene and on double_slits, profiles/r01s2_notes.md: the lanes idle inside the cone-triangle test, whose
+// early-outs differ per triangle, not between the groups.)
 template <class Fetch, class Emit>
 WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* shm, bool force_rt, bool edge_query, Counters& ctr, Fetch&& fetch, Emit&& emit) {
     GLane g; g.gl = threadIdx.x & 7u; g.gshift = (threadIdx.x & 31u) & 24u; g.gmask = 0xffu << g.gshift;
     GShared& sh = shm[threadIdx.x / kGW];
     GTrav t; t.mode = 0; t.s = 0;
-    bool have = false, done = false, leaf = false; int item = 0;
-    uint32_t lt0 = 0u, lcnt = 0u;
+    bool have = false, done = false; int item = 0;
     for (;;) {
-        // transitions: a group without a beam fetches one; a group whose query ran dry moves to the beam's next query or emits the result
-        while (__any_sync(0xffffffffu, !done && !leaf && (!have || t.s == 0))) {
-            if (!done && !leaf && !have) {
+        // phase 1: bookkeeping and node steps, until a leaf is on top of this group's stack
+        uint32_t lt0 = 0u, lcnt = 0u; bool leaf = false;
+        for (;;) {
+            if (!have) {
+                if (done) break;
                 int i = 0;
                 if (g.gl == 0u) i = atomicAdd(cursor, 1);
                 i = g_shfl(g, i, 0);
-                if (i >= n_items) done = true;
-                else {
-                    item = i;
-                    Cone env; Geo prev; float lambda;
-                    fetch(item, env, prev, lambda);
-                    g_begin(sc, g, sh, t, env, prev, lambda, force_rt, edge_query, ctr);
-                    have = true;
-                }
-            } else if (!done && !leaf && t.s == 0) {
+                if (i >= n_items) { done = true; break; }
+                item = i;
+                Cone env; Geo prev; float lambda;
+                fetch(item, env, prev, lambda);
+                g_begin(sc, g, sh, t, env, prev, lambda, force_rt, edge_query, ctr);
+                have = true;
+            }
+            if (t.s == 0) {
                 TravRec out;
                 if (g_query_done(sc, g, sh, t, out, ctr)) { emit(item, out, sh.tris, g); have = false; __syncwarp(g.gmask); }
+                continue;
             }
-        }
-        if (__all_sync(0xffffffffu, done)) break;
-        // one pop per group that has no leaf parked
-        bool node = false; int32_t top = 0;
-        if (have && !leaf) {
-            top = sh.ptr[t.s - 1]; --t.s;
-            if (top < 0) { const wtgpu_leaf lf = sc.leaves[-top - 1]; lt0 = lf.tris_ptr; lcnt = lf.count; leaf = true; }
-            else {
-                node = true;
-                if (t.mode == 1) {      // ray_traversal_treat_node_as_leaf_if_triangle_count_lt (bvh8w.cpp:29)
-                    const uint2 tr = __ldg(reinterpret_cast<const uint2*>(&sc.nodes[top - 1].tris_start));
-                    if (tr.y <= 16u) { if (g.gl == 0u) ctr.nodes++; lt0 = tr.x; lcnt = tr.y; leaf = true; node = false; }
-                }
+            const int32_t top = sh.ptr[t.s - 1];
+            if (top < 0) { const wtgpu_leaf lf = sc.leaves[-top - 1]; lt0 = lf.tris_ptr; lcnt = lf.count; leaf = true; --t.s; break; }
+            if (t.mode == 1) {      // ray_traversal_treat_node_as_leaf_if_triangle_count_lt (bvh8w.cpp:29)
+                const uint2 tr = __ldg(reinterpret_cast<const uint2*>(&sc.nodes[top - 1].tris_start));
+                if (tr.y <= 16u) { if (g.gl == 0u) ctr.nodes++; lt0 = tr.x; lcnt = tr.y; leaf = true; --t.s; break; }
             }
+            --t.s;
+            g_node_step(sc, g, sh, t, top, ctr);
         }
-        if (__any_sync(0xffffffffu, node)) { if (node) g_node_step(sc, g, sh, t, top, ctr); }
-        // leaf steps once every live group has one parked (a group that is done, or that still walks nodes, holds the others back at most
-        // until its own next leaf)
-        if (__all_sync(0xffffffffu, leaf || done)) {
-            if (leaf) { g_leaf_step(sc, g, sh, t, lt0, lcnt, ctr); leaf = false; }
-        }
+        if (__all_sync(0xffffffffu, done && !have)) break;
+        // phase 2: the groups of the warp do their leaf steps together
+        if (leaf) g_leaf_step(sc, g, sh, t, lt0, lcnt, ctr);
     }
 }
 
