@@ -153,7 +153,8 @@ def main():
 
     for i in range(a.warmup):
         step(i)
-    clk = ClockSampler(local); clk.start()
+    clk = ClockSampler(local)
+    if not os.environ.get("WT_BENCH_NO_CLOCKS"): clk.start()     # (diagnostic switch: is the nvidia-smi polling perturbing the run?)
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -200,24 +201,46 @@ def main():
     roofline = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
                 "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": kbytes / max(1, launches_k), "avg_launch_ms": kms / max(1, launches_k), "share_of_step": share}
 
+    # ---- e2e: through the public API with HOST inputs and outputs inside the timed region, at N GPUs: every step uploads the scene tables
+    # (H2D), renders this rank's sample range, reduces the films to rank 0 (N>1) and reads the film back to the host (D2H).
+    # N=1 is the plain C-ABI call with host film buffers (wtgpu_render does the copies); N>1 is wave_tracer_b200.parallel.
+    from wave_tracer_b200 import render
+    h2d = sum(C.sizeof(t) * n for t, n in ((_abi.Node, built.desc.n_nodes), (_abi.Leaf, built.desc.n_leaves), (_abi.Tri, built.desc.n_tris), (_abi.TriMeta, built.desc.n_tris),
+              (_abi.TriShading, built.desc.n_tris), (_abi.Edge, built.desc.n_edges), (_abi.Shape, built.desc.n_shapes), (_abi.Spectrum, built.desc.n_spectra),
+              (_abi.Bsdf, built.desc.n_bsdfs), (_abi.Emitter, built.desc.n_emitters), (_abi.KDist, built.desc.n_emitters))) + 4 * (built.desc.n_kdist_data + 1024) + \
+        (8 * (built.desc.fsd_lut_n + built.desc.fsd_lut_m ** 2) if bdpt else 0)      # + the Fraunhofer sampling tables
+    d2h = W * H * 3 * 4
+    def e2e_step(i):
+        base = (i * world + rank) * S
+        if world == 1:
+            return render(built, spp=SPP, device=local, sample_range=(base, base + S), pool_size=a.pool, allow_overflow=True)[2]["samples"]
+        g = GpuScene(built, local)
+        dev = torch.device("cuda", local)
+        block = torch.zeros((H, W, 1, 2), dtype=torch.float32, device=dev); light = torch.zeros((H, W, 1), dtype=torch.float32, device=dev)
+        st = g.render_into(block.data_ptr(), light.data_ptr(), SPP, 0x5EED, (base, base + S), None, True, a.pool, 0, torch.cuda.current_stream().cuda_stream, True)
+        flat = torch.cat([block.reshape(-1), light.reshape(-1)]); dist.reduce(flat, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0: flat.cpu()
+        g.close()
+        return st["samples"]
+    e2e_step(0)     # warm
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time(); n_e2e = 0
+    for i in range(max(1, min(a.steps, 3))):
+        n_e2e += e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    e2e_s = time.time() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e = n_e2e * world / e2e_s / 1e6
+
     if rank == 0:
-        # ---- e2e: through the public API with HOST buffers: scene upload (H2D), render, film read-back (D2H) inside the timed region
-        from wave_tracer_b200 import render
-        h2d = sum(C.sizeof(t) * n for t, n in ((_abi.Node, built.desc.n_nodes), (_abi.Leaf, built.desc.n_leaves), (_abi.Tri, built.desc.n_tris), (_abi.TriMeta, built.desc.n_tris),
-                  (_abi.TriShading, built.desc.n_tris), (_abi.Edge, built.desc.n_edges), (_abi.Shape, built.desc.n_shapes), (_abi.Spectrum, built.desc.n_spectra),
-                  (_abi.Bsdf, built.desc.n_bsdfs), (_abi.Emitter, built.desc.n_emitters), (_abi.KDist, built.desc.n_emitters))) + 4 * (built.desc.n_kdist_data + 1024) + \
-            (8 * (built.desc.fsd_lut_n + built.desc.fsd_lut_m ** 2) if bdpt else 0)      # + the Fraunhofer sampling tables
-        d2h = W * H * 3 * 4
-        render(built, spp=SPP, device=local, sample_range=(0, S), pool_size=a.pool, allow_overflow=True)     # warm
-        t0 = time.time(); n_e2e = 0
-        for i in range(max(1, min(a.steps, 3))):
-            _, lgt, st = render(built, spp=SPP, device=local, sample_range=(i * S, i * S + S), pool_size=a.pool, allow_overflow=True)
-            n_e2e += st["samples"]
-        e2e = n_e2e / (time.time() - t0) / 1e6
         out = {"metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": int(sum(s["kernel_launches"] for s in stats)), "roofline": roofline, "clocks": clk.summary(),
+               "phases_ms_per_step": {k: tot(k) / a.steps for k in ("gpu_ms", "generate_ms", "traverse_ms", "sort_ms", "shade_ms", "connect_ms")} | {"iterations": its / a.steps},
                "counters": {k: int(sum(s[k] for s in stats)) for k in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "nodes_visited", "tris_tested", "splats", "capacity_overflows")}}
         if world == 1 and not a.no_cpu_baseline:
             v, cores, sample = cpu_leg(built, 12.0)

@@ -325,6 +325,7 @@ typedef struct wtgpu_render_opts {
 #define WTGPU_RENDER_BDPT_MEGAKERNEL 4u  /* plt_bdpt: run the one-thread-per-sample cross-check kernel instead of the wavefront */
 #define WTGPU_RENDER_THREAD_TRAVERSE 8u  /* one thread per beam in traverse() instead of eight lanes per beam (A/B measurement; bit-identical results) */
 #define WTGPU_RENDER_GROUP_TRAVERSE 16u  /* force eight lanes per beam (default: chosen by scene size for plt_path, always for plt_bdpt) */
+#define WTGPU_RENDER_NO_RAY_CULL 32u /* ray queries walk every node along the infinite ray, as bvh8w.cpp:469-554 does, instead of culling children outside the query range (A/B; same results) */
 #define WTGPU_RENDER_TIME_KERNELS 2u /* record CUDA events around every kernel (fills wtgpu_stats::*_ms) */
 
 /* Device counters gathered during wtgpu_render (the quantities the reference exposes in a `profile` build:

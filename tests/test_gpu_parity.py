@@ -165,6 +165,25 @@ def test_plt_path_group_traverse_equals_thread_traverse(scene):
     gs.close()
 
 
+@pytest.mark.parametrize("scene", ["double_slits", "etoile", "cornell_bdpt"])
+def test_ray_range_culling_changes_no_result(scene):
+    """Ray queries cull children outside the query range (dtrav.cuh RayCull); WTGPU_RENDER_NO_RAY_CULL walks the infinite ray as bvh8w.cpp:469-554
+    does.  Same hits => identical structural counters (only the node / triangle visit counts drop), films equal up to the order of the f32 atomics."""
+    b = {"double_slits": lambda: scenes.double_slits(res=256, spp=4, with_directional=True), "etoile": lambda: scenes.etoile_like(res=96, spp=4),
+         "cornell_bdpt": lambda: scenes.cornell_like(res=48, spp=4, fsd=True, integrator="plt_bdpt", lut=(512, 256))}[scene]().build()
+    gs = GpuScene(b, 0)
+    blk0, lgt0, st0 = render(b, spp=4, gpu_scene=gs, allow_overflow=True, flags=0)
+    blk1, lgt1, st1 = render(b, spp=4, gpu_scene=gs, allow_overflow=True, flags=32)     # WTGPU_RENDER_NO_RAY_CULL
+    for k in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "surface_interactions", "fsd_interactions", "null_interactions", "splats",
+              "capacity_overflows", "edges_fetched"):
+        assert st0[k] == st1[k], (k, st0[k], st1[k])
+    assert st0["nodes_visited"] <= st1["nodes_visited"] and st0["tris_tested"] <= st1["tris_tested"]
+    print("ray culling %s: nodes %d -> %d, tris %d -> %d, gpu_ms %.2f -> %.2f" % (scene, st1["nodes_visited"], st0["nodes_visited"], st1["tris_tested"], st0["tris_tested"], st1["gpu_ms"], st0["gpu_ms"]))
+    for x, y in ((blk0, blk1), (lgt0, lgt1)):
+        assert np.linalg.norm(x.astype(np.float64) - y) <= 1e-5 * np.linalg.norm(y.astype(np.float64)) + 1e-30
+    gs.close()
+
+
 def test_partition_invariance_on_gpu():
     """Sample-range / tile partitions give the same film as one call (RNG keyed by (pixel, sample))."""
     b = scenes.double_slits(res=128, spp=8, with_directional=False).build()

@@ -25,7 +25,21 @@ struct DScene {
     wtgpu_integrator integrator;
     const float* erf_lut;             // 1024-entry erf table (include/wt/math/erf_lut.hpp)
     uint32_t scene_stream;            // Sampler::stream of the scene-sampler draws: 0 (uniform) or kSobolStreamFlag | spp (sobolld); set per render
+    float ray_cull_abs;               // absolute slack of the ray-query range culling (RayCull below); +inf disables the culling; set per render
 };
+
+// Range culling of RAY queries.  bvh8w.cpp:469-554 tests nodes against {0, closest hit} only, so a ray cast over a short range (a
+// ballistic segment of traverse(), a shadow ray) still walks every node along the infinite ray and rejects the triangles one by one
+// (intersect_ray_tri's range check).  A child whose slab interval [rmin, rmax] lies outside the query range cannot contain an accepted
+// hit, so it is not pushed: same hits, same order of the remaining stack, far fewer node visits.  The slack covers the rounding of the
+// two distance computations (slab vs. watertight ray-triangle: a few ulp of the largest vertex distance): 1e-4 relative + 1e-5 x the
+// largest |coordinate| of the scene.
+struct RayCull { float mn, mx; };
+WT_D RayCull ray_cull(const DScene& sc, Range r) {
+    RayCull c; c.mx = r.mx + (1e-4f * r.mx + sc.ray_cull_abs); c.mn = r.mn - (1e-4f * fabsf(r.mn) + sc.ray_cull_abs);
+    return c;
+}
+WT_D bool ray_cull_keep(const RayCull& c, float rmin, float rmax) { return !(rmin > c.mx) && !(rmax < c.mn); }
 
 struct Counters {       // per-thread, flushed with one atomic per counter per warp
     uint32_t nodes, tris, ray_casts, cone_casts, shadow_casts;
@@ -75,6 +89,7 @@ WT_DN bool ray_traverse(const DScene& sc, V3 ro, V3 rd, Range range, RayHit& rec
     rec.tuid = WTGPU_INVALID_IDX; rec.dist = WT_INF; rec.bx = rec.by = -1.f; rec.front = false;
     const V3 inv = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
     const bool nx = signbit(inv.x), ny = signbit(inv.y), nz = signbit(inv.z);
+    const RayCull cull = ray_cull(sc, range);
     StackEnt stack[64];
     int s = 1;
     stack[0].tmin = 0.f; stack[0].ptr = sc.root_ptr;
@@ -109,7 +124,7 @@ WT_DN bool ray_traverse(const DScene& sc, V3 ro, V3 rd, Range range, RayHit& rec
                         const float t1z = ((nz ? amxz[i] : amnz[i]) - ro.z) * inv.z, t2z = ((nz ? amnz[i] : amxz[i]) - ro.z) * inv.z;
                         const float rmin = vmaxps(vmaxps(vmaxps(t1x, t1y), t1z), 0.f);
                         const float rmax = vminps(vminps(vminps(t2x, t2y), t2z), rec.dist);
-                        if (rmin <= rmax && ach[i] != 0 && s < 64) { stack[s].tmin = rmin; stack[s].ptr = ach[i]; ++s; }
+                        if (rmin <= rmax && ach[i] != 0 && ray_cull_keep(cull, rmin, rmax) && s < 64) { stack[s].tmin = rmin; stack[s].ptr = ach[i]; ++s; }
                     }
                 }
                 stack_sort(stack + begin, s - begin);

@@ -46,11 +46,12 @@ struct GTrav {
     int mode, s;                // mode: 1 ray, 2 cone; s: stack size
     V3 inv; bool nx, ny, nz; Frame frame;
     Range qrange, crange;       // ray range / cone traversal range; current cone search range
+    RayCull cull;               // range culling bounds of the current ray query (dtrav.cuh)
     RayHit rec; ConeResult res;
 };
 
 WT_D void g_start_ray(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, Range r, Counters& ctr) {
-    t.mode = 1; t.qrange = r; t.rec.tuid = WTGPU_INVALID_IDX; t.rec.dist = WT_INF; t.rec.bx = t.rec.by = -1.f; t.rec.front = false;
+    t.mode = 1; t.qrange = r; t.cull = ray_cull(sc, r); t.rec.tuid = WTGPU_INVALID_IDX; t.rec.dist = WT_INF; t.rec.bx = t.rec.by = -1.f; t.rec.front = false;
     t.s = 1;
     if (g.gl == 0u) { sh.tmin[0] = 0.f; sh.ptr[0] = sc.root_ptr; ctr.ray_casts++; }
     __syncwarp(g.gmask);
@@ -91,7 +92,7 @@ WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, i
         const float t1z = ((t.nz ? mxz : mnz) - ro.z) * t.inv.z, t2z = ((t.nz ? mnz : mxz) - ro.z) * t.inv.z;
         const float rmin = vmaxps(vmaxps(vmaxps(t1x, t1y), t1z), 0.f);
         const float rmax = vminps(vminps(vminps(t2x, t2y), t2z), t.rec.dist);
-        g_push_sorted(g, sh, t, rmin <= rmax && ch != 0, rmin, ch, 64);
+        g_push_sorted(g, sh, t, rmin <= rmax && ch != 0 && ray_cull_keep(t.cull, rmin, rmax), rmin, ch, 64);
     } else {                // cone_cluster_intersect (bvh8w.cpp:187-230)
         float omnx = mnx - ro.x, omny = mny - ro.y, omnz = mnz - ro.z;
         float omxx = mxx - ro.x, omxy = mxy - ro.y, omxz = mxz - ro.z;

@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 #include <cmath>
+#include <limits>
 
 using namespace wt;
 
@@ -740,6 +741,7 @@ struct wtgpu_scene {
     std::vector<void*> allocs;
     wtgpu_sensor sensor{};
     wtgpu_integrator integ{};
+    float ray_cull_abs = 0.f;
     // render pool (lazily sized)
     uint32_t pool = 0;
     float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
@@ -880,6 +882,12 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
         s->has_sobol = true;
     }
     d.scene_stream = 0u;
+    {   // slack of the ray-query range culling (dtrav.cuh RayCull): 1e-5 x the largest |coordinate| of the scene
+        float mabs = 0.f;
+        for (uint32_t i = 0; i < desc->n_tris; ++i) { const float* v = &desc->tris[i].ax; for (int k = 0; k < 12; ++k) if ((k & 3) != 3) mabs = std::max(mabs, std::fabs(v[k])); }
+        s->ray_cull_abs = 1e-5f * mabs;
+        d.ray_cull_abs = s->ray_cull_abs;
+    }
     d.root_ptr = desc->root_ptr; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs; d.n_tris = desc->n_tris; d.n_nodes = desc->n_nodes;
     d.sensor = desc->sensor; d.integrator = desc->integrator;
     s->sensor = desc->sensor; s->integ = desc->integrator;
@@ -942,6 +950,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         CK(cudaMemsetAsync(dblock, 0, nb * 4, st)); CK(cudaMemsetAsync(dlight, 0, nl * 4, st));
     }
 
+    s->d.ray_cull_abs = (o->flags & WTGPU_RENDER_NO_RAY_CULL) ? std::numeric_limits<float>::infinity() : s->ray_cull_abs;
     RenderArgs a;
     a.sc = s->d; a.core = s->core; a.fsd = s->fsd; a.hit = s->hit; a.alive = s->alive; a.keys = s->keys; a.order = s->order;
     a.trav_rec = s->trav_rec; a.trav_tris = s->trav_tris;
