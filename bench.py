@@ -44,25 +44,36 @@ def measured_hbm_peak():
         return 6650.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
+class ClockSampler:
+    """SM clocks and throttle reasons DURING the timed region: ONE long-running `nvidia-smi -lms 200` (B200_PROFILING.md's clocks line), started before
+    and terminated after.  (Spawning a fresh nvidia-smi every 200 ms -- NVML init enumerates the whole box each time -- stalled this
+    process's launches: the polling itself cost 5-40 % of a step, measured as e2e > value in profiles/r01s3_*.)"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.maxmhz = index, [], set(), False, None
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [x.strip() for x in out.split(",")]
-                self.samples.append(float(f[0])); self.maxmhz = float(f[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                    if v.lower().startswith("active"): self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.2)
+        self.index, self.proc, self.stop_flag = index, None, False
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
     def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons)}
+        samples, reasons, maxmhz = [], set(), None
+        if self.proc is not None:
+            try:
+                self.proc.terminate(); out, _ = self.proc.communicate(timeout=10)
+            except Exception:
+                out = ""
+            for line in out.splitlines():
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    samples.append(float(f[0])); maxmhz = float(f[1])
+                except Exception:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"): reasons.add(name)
+        s = sorted(samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": maxmhz, "reasons": sorted(reasons), "n_samples": len(s)}
 
 
 def cpu_leg(built, seconds_target, threads=0):
@@ -151,10 +162,10 @@ def main():
             flat = torch.cat([block.reshape(-1), light.reshape(-1)]); dist.reduce(flat, dst=0, op=dist.ReduceOp.SUM)
         return st
 
+    clk = ClockSampler(local)
+    if not os.environ.get("WT_BENCH_NO_CLOCKS"): clk.start()     # started before the warm-up so that its NVML start-up is over when the timed region begins
     for i in range(a.warmup):
         step(i)
-    clk = ClockSampler(local)
-    if not os.environ.get("WT_BENCH_NO_CLOCKS"): clk.start()     # (diagnostic switch: is the nvidia-smi polling perturbing the run?)
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -163,7 +174,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
-    clk.stop_flag = True
+    clocks = clk.summary()
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
@@ -239,7 +250,7 @@ def main():
         out = {"metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": int(sum(s["kernel_launches"] for s in stats)), "roofline": roofline, "clocks": clk.summary(),
+               "gpu_launches": int(sum(s["kernel_launches"] for s in stats)), "roofline": roofline, "clocks": clocks,
                "phases_ms_per_step": {k: tot(k) / a.steps for k in ("gpu_ms", "generate_ms", "traverse_ms", "sort_ms", "shade_ms", "connect_ms")} | {"iterations": its / a.steps},
                "counters": {k: int(sum(s[k] for s in stats)) for k in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "nodes_visited", "tris_tested", "splats", "capacity_overflows")}}
         if world == 1 and not a.no_cpu_baseline:

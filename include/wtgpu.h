@@ -132,9 +132,10 @@ typedef struct wtgpu_spectrum {
 #define WTGPU_BSDF_MASK        6u   /* src/bsdf/mask.cpp         child, spec[0]=mask (constant only)       */
 
 #define WTGPU_PROFILE_DIRAC             0u  /* interaction/surface_profile/dirac.hpp    */
-#define WTGPU_PROFILE_GAUSSIAN          1u  /* interaction/surface_profile/gaussian.hpp : prof_spec[0]=sigma2, [1]=rms (mm) */
+#define WTGPU_PROFILE_GAUSSIAN          1u  /* interaction/surface_profile/gaussian.hpp:80-255, roughness-parametrised: prof_spec[0]=roughness */
 #define WTGPU_PROFILE_FRACTAL_ROUGHNESS 2u  /* interaction/surface_profile/fractal.hpp  : prof_spec[0]=roughness */
 #define WTGPU_PROFILE_FRACTAL_T         3u  /* fractal.hpp: prof_spec[0]=T (mm^2), prof_spec[1]=sigma_h (1/mm) */
+#define WTGPU_PROFILE_GAUSSIAN_SIGMA    4u  /* gaussian.hpp, sigma-parametrised: prof_spec[0]=sigma (1/mm, surface_profile.hpp:41) */
 typedef struct wtgpu_bsdf {
     uint32_t type;
     int32_t child;

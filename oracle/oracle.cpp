@@ -198,6 +198,31 @@ float oracle_bsdf_albedo(const wtgpu_scene_desc* desc, int32_t bsdf, const float
     }
     return (float)(acc / n);
 }
+// surface-profile unit checks (surface_profile.hpp interface: alpha / psd / pdf / sample)
+void oracle_profile_eval(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], const float wo[3], float k, float out[3]) {
+    scene_t sc(desc); bsdf_eval_t be(sc);
+    const wtgpu_bsdf& b = be.node(bsdf);
+    const v3 i{ wi[0], wi[1], wi[2] }, o{ wo[0], wo[1], wo[2] };
+    out[0] = be.profile_alpha(b, i, o, k); out[1] = be.profile_psd(b, i, o, k); out[2] = be.profile_pdf(b, i, o, k);
+}
+// n samples at incidence wi: out[0] = mean psd/pdf, out[1] / out[2] = largest relative deviation of pdf(wi, wo) / psd(wi, wo) evaluated at the
+// sampled direction from the values the sampler returned, out[3] = fraction of samples outside the unit disk (clamped to grazing)
+void oracle_profile_check(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], float k, uint32_t n, uint64_t seed, float out[4]) {
+    scene_t sc(desc); bsdf_eval_t be(sc);
+    const wtgpu_bsdf& b = be.node(bsdf);
+    const v3 i{ wi[0], wi[1], wi[2] };
+    double acc = 0, dpdf = 0, dpsd = 0, outside = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+        sampler_t smp; smp.seed = seed; smp.pixel = 0; smp.sample = j;
+        const auto r = be.profile_sample(b, i, k, smp);
+        if (r.pdf > 0) acc += r.psd / r.pdf;
+        if (dot(v2{ r.wo.x, r.wo.y }, v2{ r.wo.x, r.wo.y }) > 1) { outside += 1; continue; }
+        const f_t pdf = be.profile_pdf(b, i, r.wo, k), psd = be.profile_psd(b, i, r.wo, k);
+        if (r.pdf > 0) dpdf = std::max(dpdf, (double)std::fabs(pdf - r.pdf) / r.pdf);
+        if (r.psd > 0) dpsd = std::max(dpsd, (double)std::fabs(psd - r.psd) / r.psd);
+    }
+    out[0] = (float)(acc / n); out[1] = (float)dpdf; out[2] = (float)dpsd; out[3] = (float)(outside / n);
+}
 // cone-through-ellipse / ellipsoid re-fit (for unit parity with the device functions)
 void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], const float o[3], const float d[3], float tan_alpha, float out[8]) {
     const frame_t f{ { frame[0], frame[1], frame[2] }, { frame[3], frame[4], frame[5] }, { frame[6], frame[7], frame[8] } };

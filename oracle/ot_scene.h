@@ -162,24 +162,78 @@ struct bsdf_eval_t {
         const f_t f = 1 / pw;
         return p.sigma2_norm * (inv_two_pi * k * k * (gamma - 1) * p.T * f);
     }
+    // ---- gaussian profile (include/wt/interaction/surface_profile/gaussian.hpp:28-255)
+    static bool is_gaussian(const wtgpu_bsdf& b) { return b.profile_type == WTGPU_PROFILE_GAUSSIAN || b.profile_type == WTGPU_PROFILE_GAUSSIAN_SIGMA; }
+    struct gaussian_params_t { f_t sigma2, sigma2_norm, alpha; };
+    gaussian_params_t gaussian_params(const wtgpu_bsdf& b, f_t k) const {     // gaussian.hpp:95-119
+        f_t sigma2, alpha;
+        if (b.profile_type == WTGPU_PROFILE_GAUSSIAN) {
+            const f_t roughness = sc.spectrum_f(b.prof_spec[0], k);
+            sigma2 = 1 / fractal_details::roughness_to_T(roughness);
+            alpha = fractal_details::roughness_to_alpha(roughness);
+        } else {
+            sigma2 = sqr(sc.spectrum_f(b.prof_spec[0], k));
+            alpha = sigma2;
+        }
+        return { sigma2, 1 / (1 - std::exp(-(k * k / 2 / sigma2))), alpha };
+    }
+    f_t gaussian_psd(const gaussian_params_t& p, v2 z, f_t k) const {          // gaussian.hpp:121-130
+        const f_t z2 = dot(z, z);
+        const f_t e = std::exp(-(z2 / 2 / p.sigma2));
+        return e <= std::numeric_limits<f_t>::epsilon() ? 0.f : p.sigma2_norm * (inv_two_pi / p.sigma2 * k * k * e);
+    }
+    static f_t boxmueller_max_phi(f_t r, f_t l) {                               // gaussian.hpp:43-49, 70-76
+        const f_t eps = std::numeric_limits<f_t>::epsilon();
+        return (r < eps || l < eps) ? pi : std::max(1e-2f, std::acos(clampf((sqr(r) + sqr(l) - 1) / (2 * r * l), -1, 1)));
+    }
+    // truncated Box-Mueller transform (gaussian.hpp:28-56); returns the point and its pdf
+    static std::pair<v2, f_t> sample_boxmueller_truncated(v2 sample, v2 mean, f_t sigma2) {
+        const f_t eps = std::numeric_limits<f_t>::epsilon();
+        const f_t l = std::sqrt(std::min(1.f, dot(mean, mean)));
+        const f_t coso = std::sqrt(std::max(0.f, 1 - dot(mean, mean)));
+        const f_t phi_i = (mean.x != 0 || mean.y != 0) ? std::atan2(mean.y, mean.x) : 0.f;
+        const f_t s = std::exp(-.5f * sqr(1 + l) / sigma2);
+        const f_t x = (1 - s) * std::max(eps, sample.x) + s;
+        const f_t r = std::sqrt(-2 * sigma2 * std::log(x));
+        const f_t max_phi = boxmueller_max_phi(r, l);
+        const f_t phi = phi_i + pi + max_phi * (2 * sample.y - 1);
+        const v2 p = r * v2{ std::cos(phi), std::sin(phi) };
+        const f_t pdf = .5f * x / (max_phi * sigma2) * coso;
+        return { p + mean, pdf };
+    }
+    static f_t boxmueller_truncated_pdf(v2 wo, v2 mean, f_t sigma2) {          // gaussian.hpp:58-79
+        const f_t l = std::sqrt(std::min(1.f, dot(mean, mean)));
+        const f_t coso = std::sqrt(std::max(0.f, 1 - dot(mean, mean)));
+        wo = wo - mean;
+        const f_t r2 = dot(wo, wo);
+        const f_t x = std::exp(-.5f * r2 / sigma2);
+        const f_t r = std::sqrt(r2);
+        const f_t max_phi = boxmueller_max_phi(r, l);
+        return .5f * x / (max_phi * sigma2) * coso;
+    }
     bool profile_is_delta_only(const wtgpu_bsdf& b, f_t k) const {
         if (b.profile_type == WTGPU_PROFILE_DIRAC) return true;
         return sc.spectrum_f(b.prof_spec[0], k) == 0;      // mean_value(k)==0 (fractal.hpp:161-169)
     }
     f_t profile_alpha(const wtgpu_bsdf& b, v3 wi, v3 wo, f_t k) const {
         if (b.profile_type == WTGPU_PROFILE_DIRAC) return 1;
-        const auto p = fractal_params(b, k);
-        const f_t a = sqr((std::fabs(wi.z) + std::fabs(wo.z)) * k) * p.alpha;
+        const f_t palpha = is_gaussian(b) ? gaussian_params(b, k).alpha : fractal_params(b, k).alpha;     // gaussian.hpp:162-169 == fractal.hpp
+        const f_t a = sqr((std::fabs(wi.z) + std::fabs(wo.z)) * k) * palpha;
         return std::exp(-a);
     }
     f_t profile_psd(const wtgpu_bsdf& b, v3 wi, v3 wo, f_t k) const {
         if (b.profile_type == WTGPU_PROFILE_DIRAC) return 0;
-        const auto p = fractal_params(b, k);
         const v2 z = k * (v2{ wi.x, wi.y } + v2{ wo.x, wo.y });
+        if (is_gaussian(b)) return gaussian_psd(gaussian_params(b, k), z, k);       // gaussian.hpp:197-205
+        const auto p = fractal_params(b, k);
         return fractal_psd(b, p, z, k);
     }
     f_t profile_pdf(const wtgpu_bsdf& b, v3 wi, v3 wo, f_t k) const {
         if (b.profile_type == WTGPU_PROFILE_DIRAC) return 0;
+        if (is_gaussian(b)) {                                                       // gaussian.hpp:240-250
+            const f_t s2 = gaussian_params(b, k).sigma2 / (k * k);
+            return boxmueller_truncated_pdf(v2{ wo.x, wo.y }, v2{ -wi.x, -wi.y }, s2);
+        }
         const auto p = fractal_params(b, k);
         const v2 zeta_k = v2{ wi.x, wi.y } + v2{ wo.x, wo.y };
         const f_t f_k = length(zeta_k);
@@ -193,6 +247,16 @@ struct bsdf_eval_t {
     struct profile_sample_t { v3 wo; f_t pdf, psd, weight; };
     profile_sample_t profile_sample(const wtgpu_bsdf& b, v3 wi, f_t k, sampler_t& sampler) const {
         if (b.profile_type == WTGPU_PROFILE_DIRAC) return { { 0, 0, 1 }, 0, 0, 0 };
+        if (is_gaussian(b)) {                                                       // gaussian.hpp:210-235
+            const auto p = gaussian_params(b, k);
+            const f_t s2 = p.sigma2 / (k * k);
+            const v2 mean = v2{ -wi.x, -wi.y };
+            const auto smp = sample_boxmueller_truncated(sampler.r2(), mean, s2);
+            const v2 wo2 = smp.first;
+            const f_t psd = gaussian_psd(p, k * (wo2 - mean), k);
+            const f_t z = std::sqrt(std::max(0.f, 1 - dot(wo2, wo2)));
+            return { { wo2.x, wo2.y, wi.z >= 0 ? z : -z }, smp.second, psd, psd / smp.second };
+        }
         const f_t gamma = b.gamma;
         const auto p = fractal_params(b, k);
         const f_t s = std::sqrt(std::max(0.f, 1 - sqr(wi.z)));

@@ -46,6 +46,8 @@ def lib():
         L.oracle_mub_sbp.argtypes = [C.c_float, C.c_float]; L.oracle_mub_sbp.restype = C.c_float
         L.oracle_bsdf_albedo.argtypes = [C.POINTER(A.SceneDesc), C.c_int32, C.POINTER(C.c_float), C.c_float, C.c_uint32, C.c_uint64]
         L.oracle_bsdf_albedo.restype = C.c_float
+        L.oracle_profile_eval.argtypes = [C.POINTER(A.SceneDesc), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
+        L.oracle_profile_check.argtypes = [C.POINTER(A.SceneDesc), C.c_int32, C.POINTER(C.c_float), C.c_float, C.c_uint32, C.c_uint64, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 

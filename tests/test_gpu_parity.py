@@ -107,9 +107,13 @@ def test_double_slits_film_matches_oracle(direction, rt):
         assert abs(st[kg] - ost[ko]) <= 1e-3 * max(1, ost[ko]), (kg, st[kg], ost[ko])
 
 
-def test_cornell_backward_film_matches_oracle():
-    """plt_path backward (NEE + emission MIS + RR; diffuse / dielectric / surface_spm) on the procedural cornell variant."""
-    b = scenes.cornell_like(res=48, spp=8).build()
+@pytest.mark.parametrize("profile", ["fractal", "gaussian_roughness", "gaussian_sigma"])
+def test_cornell_backward_film_matches_oracle(profile):
+    """plt_path backward (NEE + emission MIS + RR; diffuse / dielectric / surface_spm) on the procedural cornell variant; the rough-conductor
+    cube carries a fractal or a gaussian surface profile (interaction/surface_profile/{fractal,gaussian}.hpp)."""
+    from wave_tracer_b200 import Gaussian
+    prof = {"fractal": None, "gaussian_roughness": Gaussian(roughness=.3), "gaussian_sigma": Gaussian(sigma=6000.0)}[profile]
+    b = scenes.cornell_like(res=48, spp=8, cube_profile=prof).build()
     blk, lgt, st = render(b, spp=8, allow_overflow=True)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"]

@@ -237,3 +237,66 @@ def test_fraunhofer_sampling_tables():
         assert c.shape == (64, 64) and np.all(np.diff(c, axis=1) >= -1e-6) and c.min() >= 0
     assert fsd_lut.integrate(1, n_theta=257) == pytest.approx(0.004827, rel=2e-2)
     assert fsd_lut.integrate(2, n_theta=257) == pytest.approx(0.16252, rel=2e-2)
+
+
+def _spm_scene(profile, lam=5.5e-7):
+    from wave_tracer_b200 import Scene, PltPath, Film, VirtualPlane, Spot, Discrete, SurfaceSPM, rectangle, lookat
+    sc = Scene(); sc.integrator = PltPath(max_depth=2, direction="forward")
+    sc.sensor = VirtualPlane(lookat((0, 0, 1), (0, 0, 0), (0, 1, 0)), (1, 1), Film(8, 8, [Discrete(lam)]))
+    sc.add_emitter(Spot(lookat((0, 0, -1), (0, 0, 0)), Discrete(lam, 1.0)))
+    sc.add_shape(rectangle((0, 0, 0), (1, 0, 0), (0, 1, 0)), SurfaceSPM(complex(1.5, 2.0), profile=profile))
+    b = sc.build()
+    k = b.desc.emitter_kdist[0]
+    return b, b.desc.kdist_data[k.first]
+
+
+@pytest.mark.parametrize("kind,value", [("roughness", .3), ("roughness", .05), ("sigma", 4000.0)])
+def test_gaussian_profile_kats(kind, value):
+    """surface_profile type="gaussian" (gaussian.hpp): (i) the PSD is normalised over the disk of propagating directions at normal incidence,
+    int_{|wo_xy|<=1} psd d^2wo = 1 -- that is what sigma2_normalized (gaussian.hpp:87-89) is for; (ii) the sampler's pdf/psd equal pdf()/psd()
+    evaluated at the sampled direction; (iii) at normal incidence psd/pdf is the constant sigma2_norm = 1/(1 - exp(-k^2/(2 sigma^2))): the
+    truncated Box-Mueller pdf (gaussian.hpp:28-56) is the un-truncated Gaussian density, a reference quirk that is preserved; (iv) alpha follows exp(-((|wi.z|+|wo.z|) k)^2 alpha) (gaussian.hpp:162-169)."""
+    from wave_tracer_b200 import Gaussian
+    b, k = _spm_scene(Gaussian(**{kind: value}))
+    L = _oracle.lib()
+    n = 400
+    xs = (np.arange(n) + .5) / n * 2 - 1
+    tot = 0.0
+    wi = np.array([0, 0, 1], np.float32)
+    out = (C.c_float * 3)()
+    # polar quadrature concentrated where the lobe lives: r = t^2 substitution
+    nr, nphi = 4000, 8
+    ts = (np.arange(nr) + .5) / nr
+    sig2 = None
+    for t in ts:
+        r = t ** 4; dr = 4 * t ** 3 / nr
+        wo = np.array([r, 0, math.sqrt(max(0.0, 1 - r * r))], np.float32)
+        L.oracle_profile_eval(C.byref(b.desc), 0, _f(wi), _f(wo), k, out)
+        tot += out[1] * 2 * math.pi * r * dr
+    assert tot == pytest.approx(1.0, rel=2e-2), tot
+    chk = (C.c_float * 4)()
+    L.oracle_profile_check(C.byref(b.desc), 0, _f(wi), k, 20000, 3, chk)
+    if kind == "roughness":
+        a2 = min(value, .75) ** 2; meank = 2 * math.pi / 550e-6
+        sigma2 = 1.0 / min(70.0 ** 2, (1 - a2) / (4 * meank ** 2 * a2))
+    else: sigma2 = value ** 2
+    s2n = 1.0 / (1.0 - math.exp(-k * k / 2 / sigma2))
+    assert chk[0] == pytest.approx(s2n, rel=2e-2) and chk[1] < 2e-3 and chk[2] < 2e-3 and chk[3] == 0.0, (list(chk), s2n)
+    wi2 = np.array([.5, .3, math.sqrt(1 - .34)], np.float32)
+    L.oracle_profile_check(C.byref(b.desc), 0, _f(wi2), k, 20000, 5, chk)
+    assert chk[1] < 2e-2 and chk[2] < 2e-3, list(chk)
+    # alpha
+    wo = np.array([.1, -.2, math.sqrt(1 - .05)], np.float32)
+    L.oracle_profile_eval(C.byref(b.desc), 0, _f(wi2), _f(wo), k, out)
+    if kind == "roughness": pa = (value / 9.0) ** 2
+    else: pa = value ** 2
+    assert out[0] == pytest.approx(math.exp(-(((abs(wi2[2]) + abs(wo[2])) * k) ** 2) * pa), rel=1e-3, abs=1e-30)
+
+
+def test_gaussian_profile_bsdf_energy_bounded():
+    """surface_spm over a gaussian profile: the sampled, weighted BSDF of a lossless-ish conductor stays an energy-bounded estimator."""
+    from wave_tracer_b200 import Gaussian
+    b, k = _spm_scene(Gaussian(roughness=.3))
+    wi = np.array([.3, .2, math.sqrt(1 - .13)], np.float32)
+    a = _oracle.lib().oracle_bsdf_albedo(C.byref(b.desc), 0, _f(wi), k, 20000, 1)
+    assert 0.2 < a < 1.05, a

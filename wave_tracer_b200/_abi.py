@@ -50,7 +50,7 @@ class Spectrum(C.Structure):
 
 
 BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_SURFACE_SPM, BSDF_TWO_SIDED, BSDF_COMPOSITE, BSDF_SCALE, BSDF_MASK = range(7)
-PROFILE_DIRAC, PROFILE_GAUSSIAN, PROFILE_FRACTAL_ROUGHNESS, PROFILE_FRACTAL_T = range(4)
+PROFILE_DIRAC, PROFILE_GAUSSIAN, PROFILE_FRACTAL_ROUGHNESS, PROFILE_FRACTAL_T, PROFILE_GAUSSIAN_SIGMA = range(5)
 
 
 class Bsdf(C.Structure):
@@ -166,6 +166,8 @@ ABI_STRUCTS = [Node, Leaf, Tri, TriMeta, TriShading, Edge, Shape, Spectrum, Bsdf
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwt_b200.so")
+if os.environ.get("WT_B200_LIB"):      # A/B builds of the same sources (tools/gpu_session_*.sh); still the CUDA library, never a fallback
+    LIB_PATH = os.path.abspath(os.environ["WT_B200_LIB"])
 _lib = None
 
 

@@ -420,11 +420,12 @@ WT_DN float intersect_cone_tri(const Cone& cone, const Frame& frame, V3 a, V3 b,
     V3 vs[3];
     vs[0] = to_local(frame, a - o); vs[1] = to_local(frame, b - o); vs[2] = to_local(frame, c - o);
     const V3 ln = to_local(frame, n);
+    // (the z-range rejection is taken before the containment tests: same result, less work for the triangles a leaf step rejects)
+    const float closest_z = min3f(vs[0].z, vs[1].z, vs[2].z), farthest_z = max3f(vs[0].z, vs[1].z, vs[2].z);
+    if (farthest_z < range.mn || closest_z > range.mx) return WT_INF;
     bool in[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) in[i] = cone_contains_local_w(cone, vs[i], range);
-    const float closest_z = min3f(vs[0].z, vs[1].z, vs[2].z), farthest_z = max3f(vs[0].z, vs[1].z, vs[2].z);
-    if (farthest_z < range.mn || closest_z > range.mx) return WT_INF;
 #pragma unroll
     for (int i = 0; i < 3; ++i) if (in[i] && vs[i].z == closest_z) return closest_z;
     const ConePlane icp = intersect_cone_plane(cone, ln, dot(vs[0], ln), range, true);

@@ -420,22 +420,60 @@ WT_D float fractal_psd(const wtgpu_bsdf& b, const FractalP& p, V2 z, float k) {
     const float pw = gamma == 3.f ? (x * x) : powf(x, (gamma + 1.f) / 2.f);
     return p.s2n * (kInvTwoPi * k * k * (gamma - 1.f) * p.T * (1.f / pw));
 }
+// ---- gaussian profile (include/wt/interaction/surface_profile/gaussian.hpp:28-255)
+WT_D bool is_gaussian_profile(const wtgpu_bsdf& b) { return b.profile_type == WTGPU_PROFILE_GAUSSIAN || b.profile_type == WTGPU_PROFILE_GAUSSIAN_SIGMA; }
+struct GaussP { float sigma2, s2n, alpha; };
+WT_D GaussP gaussian_params(const DScene& sc, const wtgpu_bsdf& b, float k) {      // gaussian.hpp:95-119
+    GaussP p;
+    if (b.profile_type == WTGPU_PROFILE_GAUSSIAN) {
+        const float rough = spectrum_f(sc, b.prof_spec[0], k);
+        const float meank = kTwoPi / 550e-6f;
+        const float a2 = sqrf(clampf_(rough, 0.f, .75f));
+        p.sigma2 = 1.f / fminf(70.f * 70.f, (1.f - a2) / (4.f * sqrf(meank) * a2));
+        p.alpha = sqrf(rough / 9.f);
+    } else {
+        p.sigma2 = sqrf(spectrum_f(sc, b.prof_spec[0], k));
+        p.alpha = p.sigma2;
+    }
+    p.s2n = 1.f / (1.f - expf(-(k * k / 2.f / p.sigma2)));
+    return p;
+}
+WT_D float gaussian_psd(const GaussP& p, V2 z, float k) {                          // gaussian.hpp:121-130
+    const float z2 = dot(z, z);
+    const float e = expf(-(z2 / 2.f / p.sigma2));
+    return e <= 1.1920929e-7f ? 0.f : p.s2n * (kInvTwoPi / p.sigma2 * k * k * e);
+}
+WT_D float boxmueller_max_phi(float r, float l) {                                   // gaussian.hpp:43-49, 70-76
+    const float eps = 1.1920929e-7f;
+    return (r < eps || l < eps) ? kPi : fmaxf(1e-2f, acosf(clampf_((sqrf(r) + sqrf(l) - 1.f) / (2.f * r * l), -1.f, 1.f)));
+}
+WT_D float boxmueller_truncated_pdf(V2 wo, V2 mean, float sigma2) {               // gaussian.hpp:58-79
+    const float l = sqrtf(fminf(1.f, dot(mean, mean)));
+    const float coso = sqrtf(fmaxf(0.f, 1.f - dot(mean, mean)));
+    wo = wo - mean;
+    const float r2 = dot(wo, wo);
+    const float x = expf(-.5f * r2 / sigma2);
+    const float r = sqrtf(r2);
+    return .5f * x / (boxmueller_max_phi(r, l) * sigma2) * coso;
+}
 WT_D bool profile_delta_only(const DScene& sc, const wtgpu_bsdf& b, float k) {
     if (b.profile_type == WTGPU_PROFILE_DIRAC) return true;
     return spectrum_f(sc, b.prof_spec[0], k) == 0.f;
 }
 WT_D float profile_alpha(const DScene& sc, const wtgpu_bsdf& b, V3 wi, V3 wo, float k) {
     if (b.profile_type == WTGPU_PROFILE_DIRAC) return 1.f;
-    const FractalP p = fractal_params(sc, b, k);
-    return expf(-(sqrf((fabsf(wi.z) + fabsf(wo.z)) * k) * p.alpha));
+    const float palpha = is_gaussian_profile(b) ? gaussian_params(sc, b, k).alpha : fractal_params(sc, b, k).alpha;
+    return expf(-(sqrf((fabsf(wi.z) + fabsf(wo.z)) * k) * palpha));
 }
 WT_D float profile_psd(const DScene& sc, const wtgpu_bsdf& b, V3 wi, V3 wo, float k) {
     if (b.profile_type == WTGPU_PROFILE_DIRAC) return 0.f;
+    if (is_gaussian_profile(b)) return gaussian_psd(gaussian_params(sc, b, k), k * (mk2(wi.x, wi.y) + mk2(wo.x, wo.y)), k);
     const FractalP p = fractal_params(sc, b, k);
     return fractal_psd(b, p, k * (mk2(wi.x, wi.y) + mk2(wo.x, wo.y)), k);
 }
 WT_D float profile_pdf(const DScene& sc, const wtgpu_bsdf& b, V3 wi, V3 wo, float k) {   // fractal.hpp:205-226
     if (b.profile_type == WTGPU_PROFILE_DIRAC) return 0.f;
+    if (is_gaussian_profile(b)) return boxmueller_truncated_pdf(mk2(wo.x, wo.y), mk2(-wi.x, -wi.y), gaussian_params(sc, b, k).sigma2 / (k * k));   // gaussian.hpp:240-250
     const FractalP p = fractal_params(sc, b, k);
     const V2 zk = mk2(wi.x, wi.y) + mk2(wo.x, wo.y);
     const float fk = length(zk);
@@ -449,6 +487,27 @@ struct ProfSample { V3 wo; float pdf, psd; };
 WT_D ProfSample profile_sample(const DScene& sc, const wtgpu_bsdf& b, V3 wi, float k, Sampler& smp) {   // surface_profile/fractal.cpp:27-69
     ProfSample r;
     if (b.profile_type == WTGPU_PROFILE_DIRAC) { r.wo = mk3(0.f, 0.f, 1.f); r.pdf = r.psd = 0.f; return r; }
+    if (is_gaussian_profile(b)) {       // gaussian.hpp:210-235 with the truncated Box-Mueller transform of 28-56
+        const GaussP p = gaussian_params(sc, b, k);
+        const float s2 = p.sigma2 / (k * k), eps = 1.1920929e-7f;
+        const V2 mean = mk2(-wi.x, -wi.y);
+        const V2 u2 = rnd2(smp);
+        const float l = sqrtf(fminf(1.f, dot(mean, mean)));
+        const float coso = sqrtf(fmaxf(0.f, 1.f - dot(mean, mean)));
+        const float phi_i = (mean.x != 0.f || mean.y != 0.f) ? atan2f(mean.y, mean.x) : 0.f;
+        const float s = expf(-.5f * sqrf(1.f + l) / s2);
+        const float x = (1.f - s) * fmaxf(eps, u2.x) + s;
+        const float rr = sqrtf(-2.f * s2 * logf(x));
+        const float max_phi = boxmueller_max_phi(rr, l);
+        const float phi = phi_i + kPi + max_phi * (2.f * u2.y - 1.f);
+        const V2 pt = rr * mk2(cosf(phi), sinf(phi));
+        const V2 wo2 = pt + mean;
+        r.pdf = .5f * x / (max_phi * s2) * coso;
+        r.psd = gaussian_psd(p, k * (wo2 - mean), k);
+        const float z = sqrtf(fmaxf(0.f, 1.f - dot(wo2, wo2)));
+        r.wo = mk3(wo2.x, wo2.y, wi.z >= 0.f ? z : -z);
+        return r;
+    }
     const float gamma = b.gamma;
     const FractalP p = fractal_params(sc, b, k);
     const float s = sqrtf(fmaxf(0.f, 1.f - sqrf(wi.z)));

@@ -285,7 +285,10 @@ __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
 
 // traverse() for every path of the list, eight lanes per beam (gtrav.cuh), including the edge query that follows a ballistic hit of a
 // finite beam; k_resolve then builds the hit record per thread.  Bit-identical to k_traverse (WTGPU_RENDER_THREAD_TRAVERSE selects that one).
-__global__ void __launch_bounds__(128) k_gtraverse(const RenderArgs a) {
+#ifndef WT_GT_MINB
+#define WT_GT_MINB 5      // 96 registers: 5 blocks/SM; measured against 4 (119 regs), 6 (80, spills) and 8 (64, spills): profiles/r01s3_variants.txt
+#endif
+__global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs a) {
     __shared__ GShared shm[128 / kGW];
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.sc;
@@ -750,6 +753,7 @@ struct wtgpu_scene {
     DevCounters* ctr = nullptr;
     uint32_t n_keys = 0;
     std::vector<cudaEvent_t> ev_pool;   // reused across renders (event creation is not free)
+    DevCounters* hctr = nullptr; cudaEvent_t ev_begin = nullptr, ev_end = nullptr;     // pinned read-back of the counters + the render's timing events: made once (cudaMallocHost / cudaFreeHost per render cost 5-150 ms of driver time, profiles/r01s3_phases.txt)
     bool has_sobol = false;             // sobolld generator matrices are in constant memory of this device
     wt::FLut lut{};                     // plt_bdpt: Fraunhofer sampling tables
     float* bdpt_arena = nullptr; uint32_t bdpt_P = 0;
@@ -766,6 +770,9 @@ struct wtgpu_scene {
         cudaSetDevice(device);
         for (void* p : allocs) wt_free(p);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+        if (hctr) cudaFreeHost(hctr);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
         free_bd_wave();
         if (bd_stream) cudaStreamDestroy(bd_stream);
         if (bd_ev_shade) cudaEventDestroy(bd_ev_shade);
@@ -950,6 +957,15 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         CK(cudaMemsetAsync(dblock, 0, nb * 4, st)); CK(cudaMemsetAsync(dlight, 0, nl * 4, st));
     }
 
+    {   // the group-traversal kernels keep their stacks in shared memory (24.5 KB per block): ask for the large shared-memory carve-out so that the
+        // register file, not the L1/shared split, bounds the resident blocks
+        static bool once = false;
+        if (!once) {
+            cudaFuncSetAttribute(k_gtraverse, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(wt::k_bd_gtraverse, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            once = true;
+        }
+    }
     s->d.ray_cull_abs = (o->flags & WTGPU_RENDER_NO_RAY_CULL) ? std::numeric_limits<float>::infinity() : s->ray_cull_abs;
     RenderArgs a;
     a.sc = s->d; a.core = s->core; a.fsd = s->fsd; a.hit = s->hit; a.alive = s->alive; a.keys = s->keys; a.order = s->order;
@@ -966,10 +982,9 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     // traverse(): eight lanes per beam pay off when queries are long (cone queries over real geometry); on a handful of triangles one thread
     // per beam is faster (measured: double_slits plt_path 99 vs 52 Msamples/s; etoile-like 6 vs 16).  Both give bit-identical results.
     const bool use_thread_trav = (o->flags & WTGPU_RENDER_THREAD_TRAVERSE) ? true : (o->flags & WTGPU_RENDER_GROUP_TRAVERSE) ? false : (!bdpt && s->d.n_tris < 128u);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    DevCounters* hctr = nullptr;
-    CK(cudaMallocHost(&hctr, sizeof(DevCounters)));
+    if (!s->hctr) { CK(cudaMallocHost(&s->hctr, sizeof(DevCounters))); CK(cudaEventCreate(&s->ev_begin)); CK(cudaEventCreate(&s->ev_end)); }
+    const cudaEvent_t e0 = s->ev_begin, e1 = s->ev_end;
+    DevCounters* const hctr = s->hctr;
     const dim3 blk(128), grd((pool + 127) / 128);
     const bool nosort = (o->flags & WTGPU_RENDER_NO_SORT) != 0;
     uint64_t launches = 0, iters = 0;
@@ -1034,7 +1049,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             mark();
             k_bd_generate<<<gP, blk, 0, st>>>(b); ++launches; mark();
             if (thread_trav) { k_bd_traverse<<<gW, blk, 0, st>>>(b); ++launches; }
-            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blk, 0, st>>>(b); launches += 2; }
+            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<dim3((W2 * (uint32_t)kGW + 127u) / 128u), blk, 0, st>>>(b); launches += 2; }
             mark();
             k_hist<<<gW, blk, s->n_keys * 4, st>>>(b.r);
             k_scan<<<1, 1024, 0, st>>>(b.r);
@@ -1117,8 +1132,6 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         stats->walker_steps = hctr->walker_steps;
     }
     const bool overflowed = hctr->overflow != 0;
-    cudaFreeHost(hctr);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (overflowed) { g_err = "a bounded per-path list (cone triangles / edges) overflowed; results were still produced"; return WTGPU_E_CAPACITY; }
     return WTGPU_OK;
 }

@@ -3,7 +3,7 @@
 Names and parameters follow the reference's scene elements (XML `type=` strings):
   integrators  plt_path                      (src/integrator/plt_path.cpp:64-94)
   bsdfs        diffuse, dielectric, surface_spm, twosided, composite, scale (src/bsdf/bsdf_loader.cpp:42-57)
-  profiles     dirac, fractal                (src/interaction/surface_profile/*)
+  profiles     dirac, fractal, gaussian              (src/interaction/surface_profile/*)
   emitters     point, spot, directional, area (src/emitter/emitter_loader.cpp)
   sensors      perspective, virtual_plane    (src/sensor/sensor_loader.cpp)
   shapes       rectangle, cube, sphere, mesh (src/scene/shape.cpp)
@@ -151,6 +151,14 @@ class Dirac: pass
 
 class Fractal:
     def __init__(self, roughness, gamma=3.0): self.roughness, self.gamma = _as_spectrum(roughness), float(gamma)
+
+
+class Gaussian:
+    """surface_profile type="gaussian" (interaction/surface_profile/gaussian.hpp): exactly one of `roughness` (perceptual) or `sigma` (1/mm)."""
+    def __init__(self, roughness=None, sigma=None):
+        if (roughness is None) == (sigma is None): raise ValueError("gaussian surface profile: either 'roughness' or 'sigma' must be provided")   # gaussian.cpp:55-56
+        self.roughness = None if roughness is None else _as_spectrum(roughness)
+        self.sigma = None if sigma is None else _as_spectrum(sigma)
 
 
 class SurfaceSPM(Bsdf):
@@ -388,6 +396,9 @@ class Scene:
                 if isinstance(b, SurfaceSPM):
                     if isinstance(b.profile, Fractal):
                         n.profile_type, n.gamma = A.PROFILE_FRACTAL_ROUGHNESS, b.profile.gamma; n.prof_spec[0] = bake(b.profile.roughness)
+                    elif isinstance(b.profile, Gaussian):
+                        if b.profile.roughness is not None: n.profile_type = A.PROFILE_GAUSSIAN; n.prof_spec[0] = bake(b.profile.roughness)
+                        else: n.profile_type = A.PROFILE_GAUSSIAN_SIGMA; n.prof_spec[0] = bake(b.profile.sigma)
                     else:
                         n.profile_type = A.PROFILE_DIRAC
             elif isinstance(b, TwoSided):

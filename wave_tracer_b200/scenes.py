@@ -42,7 +42,7 @@ def double_slits(res=1024, spp=32, direction="forward", max_depth=16, fsd=True, 
     return sc
 
 
-def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=False, fsd=False, n_sphere=16, integrator="plt_path", lut=(512, 256)):
+def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=False, fsd=False, n_sphere=16, integrator="plt_path", lut=(512, 256), cube_profile=None):
     """A texture-free, procedural cornell-box variant (scenes/cornell-box/box.xml with its PLY shapes dropped):
     5 diffuse walls, a dielectric sphere, a rough-conductor cube, a cube area emitter; perspective sensor; plt_path backward."""
     lam = lam_nm * 1e-9
@@ -58,7 +58,7 @@ def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=Fals
     sc.add_shape(rectangle((-1, 0, -1), (0, 0, 2), (0, 2, 0)), red)            # left
     sc.add_shape(rectangle((1, 0, -1), (0, 2, 0), (0, 0, 2)), green)           # right
     sc.add_shape(sphere(.35, (-.4, .35, .2), n_sphere, 2 * n_sphere), Dielectric(1.5))
-    sc.add_shape(cube(translate((.45, .3, -.25)) @ rotate((0, 1, 0), .4) @ scale(.3)), SurfaceSPM(IOR=complex(.2, 3.0), profile=Fractal(.2)))
+    sc.add_shape(cube(translate((.45, .3, -.25)) @ rotate((0, 1, 0), .4) @ scale(.3)), SurfaceSPM(IOR=complex(.2, 3.0), profile=cube_profile or Fractal(.2)))
     sc.add_shape(cube(translate((0, 1.98, 0)) @ scale((.25, .01, .25))), Diffuse(.0), emitter=Area(Discrete(lam, 1.0), scale=20.0))
     return sc
 
