@@ -3,6 +3,8 @@
 // oracle.cpp: C entry points of the CPU oracle (ctypes-loaded by tests/, __graft_entry__.smoke() and the
 // cpu_baseline / --impl reference legs of bench.py).  PARITY UNPINNED by the reference (no golden vectors, reference
 // not compilable here -- SURVEY.md 8c); pinned by analytic KATs only.
+#include <cstdlib>
+#include <cstdio>
 #include "ot_bdpt.h"
 #include "oracle.h"
 #include <thread>
@@ -222,6 +224,110 @@ void oracle_profile_check(const wtgpu_scene_desc* desc, int32_t bsdf, const floa
         if (r.psd > 0) dpsd = std::max(dpsd, (double)std::fabs(psd - r.psd) / r.psd);
     }
     out[0] = (float)(acc / n); out[1] = (float)dpdf; out[2] = (float)dpsd; out[3] = (float)(outside / n);
+}
+// ---- checks of the two result-preserving shortcuts the PRODUCT takes and the reference does not (restated here as predicates):
+// (1) the separating-axis rejection in front of the cone-triangle test (csrc/dmath.cuh intersect_cone_tri) and
+// (2) the range culling of ray-query children (csrc/dtrav.cuh RayCull).  Each fuzzer draws random configurations, biased towards the
+// borderline ones, and counts the cases where the shortcut would drop something the literal reference test accepts (must be 0).
+static bool product_cone_quick_reject(const elliptic_cone_t& cone, v3 a, v3 b, v3 c, range_t range) {
+    if (cone.is_ray() || !(cone.tan_alpha >= 0)) return false;
+    const frame_t frame = cone.frame();
+    const v3 o = cone.o();
+    const v3 vs[3] = { frame.to_local(a - o), frame.to_local(b - o), frame.to_local(c - o) };
+    const f_t closest_z = min3(vs[0].z, vs[1].z, vs[2].z), farthest_z = max3(vs[0].z, vs[1].z, vs[2].z);
+    if (farthest_z < range.min || closest_z > range.max) return true;
+    const f_t r = std::fma(std::min(farthest_z, range.max), cone.tan_alpha, cone.x0);
+    if (!(r > 0 && r < inf)) return false;
+    const f_t u0 = vs[0].x, u1 = vs[1].x, u2 = vs[2].x, v0 = vs[0].y * cone.e, v1 = vs[1].y * cone.e, v2 = vs[2].y * cone.e;
+    const f_t ext = std::max(std::max(max3(std::fabs(u0), std::fabs(u1), std::fabs(u2)), max3(std::fabs(v0), std::fabs(v1), std::fabs(v2))), std::max(std::fabs(closest_z), std::fabs(farthest_z)));
+    const f_t bb = r + (1e-3f * r + 1e-5f * ext), bd = 1.41421356f * r + (2e-3f * r + 2e-5f * ext);
+    const f_t p0 = u0 + v0, p1 = u1 + v1, p2 = u2 + v2, q0 = u0 - v0, q1 = u1 - v1, q2 = u2 - v2;
+    return min3(u0, u1, u2) > bb || max3(u0, u1, u2) < -bb || min3(v0, v1, v2) > bb || max3(v0, v1, v2) < -bb ||
+           min3(p0, p1, p2) > bd || max3(p0, p1, p2) < -bd || min3(q0, q1, q2) > bd || max3(q0, q1, q2) < -bd;
+}
+struct fuzz_rng_t { uint64_t s; f_t u() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (f_t)((s >> 40) & 0xffffff) / 16777216.f; } f_t sym() { return 2 * u() - 1; } };
+// out[0] = cases, out[1] = rejected by the shortcut, out[2] = accepted by the literal test, out[3] = VIOLATIONS (rejected but accepted)
+void oracle_fuzz_cone_quick_reject(uint32_t n, uint64_t seed, uint64_t out[4]) {
+    fuzz_rng_t g{ seed * 2654435761ull + 12345 };
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const f_t scale = std::pow(10.f, -3 + 5 * g.u());                       // scene scales 1 mm .. 100 m
+        const v3 d = normalize(v3{ g.sym(), g.sym(), g.sym() + 1e-3f });
+        const v3 o = scale * v3{ g.sym(), g.sym(), g.sym() };
+        const f_t ta = g.u() < .1f ? 0.f : std::pow(10.f, -4 + 4 * g.u());
+        const f_t x0 = g.u() < .2f ? 0.f : scale * std::pow(10.f, -4 + 3 * g.u());
+        if (ta == 0 && x0 == 0) continue;
+        const f_t ecc = g.u() < .5f ? 0.f : .95f * g.u();
+        const frame_t of = frame_t::build_orthogonal_frame(d);
+        const f_t phi = 6.2831853f * g.u();
+        const v3 x = std::cos(phi) * of.t + std::sin(phi) * of.b;
+        const auto cone = elliptic_cone_t::make_ecc(ray_t{ o, d }, x, ta, ecc, x0);
+        const f_t z = scale * (g.u() < .1f ? 100 * g.u() : 3 * g.u());
+        range_t range{ 0, inf };
+        const f_t ru = g.u();
+        if (ru < .3f) range = { z * g.u(), z * (1 + g.u()) }; else if (ru < .5f) range = { z * .5f * g.u(), inf };
+        // triangle near the cone boundary at depth z: centre at (1 +- spread) radii from the axis, size from tiny to huge
+        const f_t rad = ta * z + x0;
+        const f_t psi = 6.2831853f * g.u();
+        const f_t off = rad * (g.u() < .6f ? 1 + .2f * g.sym() : 3 * g.u());
+        const f_t size = std::max(rad, 1e-6f * scale) * std::pow(10.f, -2 + 4 * g.u());
+        const frame_t cf = cone.frame();
+        const v3 ctr = o + z * d + off * (std::cos(psi) * cf.t + std::sin(psi) * cf.b / std::max(cone.e, 1e-3f));
+        const v3 a = ctr + size * v3{ g.sym(), g.sym(), g.sym() }, b = ctr + size * v3{ g.sym(), g.sym(), g.sym() }, c = ctr + size * v3{ g.sym(), g.sym(), g.sym() };
+        const v3 nn = cross(b - a, c - a);
+        if (length(nn) == 0) continue;
+        // triangles that collapse at f32 resolution (edges below ~1000 ulp of their distance from the cone's origin) are left out: there the literal
+        // test's answer is a rounding artifact (it reports hits for zero-area triangles well outside the cone)
+        if (size < 1e-4f * length(ctr - o)) continue;
+        const v3 tn = normalize(nn);
+        ++out[0];
+        const bool rej = product_cone_quick_reject(cone, a, b, c, range);
+        const bool acc = intersect_cone_tri(cone, a, b, c, tn, range).has_value();
+        out[1] += rej; out[2] += acc; out[3] += (rej && acc);
+        if (rej && acc && getenv("ORACLE_FUZZ_VERBOSE")) {
+            const auto r = intersect_cone_tri(cone, a, b, c, tn, range);
+            const frame_t fr = cone.frame();
+            const v3 la = fr.to_local(a - o), lb = fr.to_local(b - o), lc = fr.to_local(c - o);
+            fprintf(stderr, "violation: ta %g x0 %g e %g range [%g,%g] dist %g | a (%g %g %g) b (%g %g %g) c (%g %g %g) rad@z %g size %g\n", cone.tan_alpha, cone.x0, cone.e, range.min, range.max, r->dist,
+                    la.x, la.y, la.z, lb.x, lb.y, lb.z, lc.x, lc.y, lc.z, rad, size);
+        }
+    }
+}
+// ray culling: random triangles and rays, the child's box is the triangle's AABB (what a leaf's parent stores); a violation is a triangle
+// the literal ray test accepts within the range while the slab interval of its box, widened by the slack, misses the range
+void oracle_fuzz_ray_cull(uint32_t n, uint64_t seed, uint64_t out[4]) {
+    fuzz_rng_t g{ seed * 2654435761ull + 999 };
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const f_t scale = std::pow(10.f, -3 + 5 * g.u());
+        const v3 o = scale * v3{ g.sym(), g.sym(), g.sym() };
+        v3 d = normalize(v3{ g.sym(), g.sym(), g.sym() });
+        if (g.u() < .2f) d = normalize(v3{ d.x, d.y * 1e-4f, d.z });                 // near axis-aligned
+        const f_t t = scale * std::pow(10.f, -4 + 5 * g.u());
+        const f_t size = scale * std::pow(10.f, -3 + 4 * g.u());
+        const v3 ctr = o + t * d;
+        v3 a = ctr + size * v3{ g.sym(), g.sym(), g.sym() }, b = ctr + size * v3{ g.sym(), g.sym(), g.sym() }, c = ctr + size * v3{ g.sym(), g.sym(), g.sym() };
+        if (g.u() < .3f) { a.y = b.y = c.y = ctr.y; }                                 // flat (axis-aligned) triangles: degenerate boxes
+        // range with an end near the hit distance
+        const f_t ru = g.u();
+        range_t range = ru < .4f ? range_t{ 0, t * (1 + 1e-3f * g.sym()) } : ru < .8f ? range_t{ t * (1 + 1e-3f * g.sym()), t * 4 } : range_t{ t * .5f, t * (1 + 1e-5f * g.sym()) };
+        const f_t mabs = std::max(std::max(max3(std::fabs(a.x), std::fabs(a.y), std::fabs(a.z)), max3(std::fabs(b.x), std::fabs(b.y), std::fabs(b.z))),
+                                  std::max(max3(std::fabs(c.x), std::fabs(c.y), std::fabs(c.z)), max3(std::fabs(o.x), std::fabs(o.y), std::fabs(o.z))));
+        const f_t cull_abs = 1e-5f * mabs;                                             // wtgpu_scene_create: 1e-5 x largest |coordinate| of the scene (>= this)
+        const v3 mn{ min3(a.x, b.x, c.x), min3(a.y, b.y, c.y), min3(a.z, b.z, c.z) }, mx{ max3(a.x, b.x, c.x), max3(a.y, b.y, c.y), max3(a.z, b.z, c.z) };
+        const v3 inv{ 1 / d.x, 1 / d.y, 1 / d.z };
+        auto vmax = [](f_t p, f_t q) { return p > q ? p : q; }; auto vmin = [](f_t p, f_t q) { return p < q ? p : q; };
+        const bool nx = std::signbit(inv.x), ny = std::signbit(inv.y), nz = std::signbit(inv.z);
+        const f_t t1x = ((nx ? mx.x : mn.x) - o.x) * inv.x, t2x = ((nx ? mn.x : mx.x) - o.x) * inv.x;
+        const f_t t1y = ((ny ? mx.y : mn.y) - o.y) * inv.y, t2y = ((ny ? mn.y : mx.y) - o.y) * inv.y;
+        const f_t t1z = ((nz ? mx.z : mn.z) - o.z) * inv.z, t2z = ((nz ? mn.z : mx.z) - o.z) * inv.z;
+        const f_t rmin = vmax(vmax(vmax(t1x, t1y), t1z), 0.f), rmax = vmin(vmin(vmin(t2x, t2y), t2z), inf);
+        const f_t cmx = range.max + (1e-4f * range.max + cull_abs), cmn = range.min - (1e-4f * std::fabs(range.min) + cull_abs);
+        const bool pushed = rmin <= rmax;
+        const bool kept = pushed && !(rmin > cmx) && !(rmax < cmn);
+        const bool acc = intersect_ray_tri_w(o, d, a, b, c, range).result != -inf;
+        ++out[0]; out[1] += (pushed && !kept); out[2] += acc; out[3] += (acc && pushed && !kept);
+    }
 }
 // cone-through-ellipse / ellipsoid re-fit (for unit parity with the device functions)
 void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], const float o[3], const float d[3], float tan_alpha, float out[8]) {

@@ -28,6 +28,8 @@ float oracle_mub_sbp(float length, float k);
 float oracle_bsdf_albedo(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], float k, uint32_t n, uint64_t seed);
 void oracle_profile_eval(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], const float wo[3], float k, float out[3]);
 void oracle_profile_check(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], float k, uint32_t n, uint64_t seed, float out[4]);
+void oracle_fuzz_cone_quick_reject(uint32_t n, uint64_t seed, uint64_t out[4]);
+void oracle_fuzz_ray_cull(uint32_t n, uint64_t seed, uint64_t out[4]);
 void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], const float o[3], const float d[3], float tan_alpha, float out[8]);
 float oracle_fraunhofer_asf(uint32_t n, const float* edges, float xix, float xiy);
 float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]);

@@ -300,3 +300,17 @@ def test_gaussian_profile_bsdf_energy_bounded():
     wi = np.array([.3, .2, math.sqrt(1 - .13)], np.float32)
     a = _oracle.lib().oracle_bsdf_albedo(C.byref(b.desc), 0, _f(wi), k, 20000, 1)
     assert 0.2 < a < 1.05, a
+
+
+def test_product_shortcuts_drop_nothing_the_reference_accepts():
+    """The product takes two shortcuts the reference does not: ray-query children outside the query range are not pushed (csrc/dtrav.cuh RayCull)
+    and a separating-axis rejection precedes the cone-triangle test (csrc/dmath.cuh).  oracle.cpp restates both as predicates and fuzzes them
+    against the literal reference tests on configurations biased towards the borderline (range ends within 1e-5..1e-3 of the hit distance,
+    triangles straddling the cone's boundary, scales 1 mm .. 100 m): no accepted triangle may be dropped."""
+    L = _oracle.lib()
+    out = (C.c_uint64 * 4)()
+    for seed in (1, 2, 3):
+        L.oracle_fuzz_cone_quick_reject(1500000, seed, out)
+        assert out[0] > 1000000 and out[1] > 100000 and out[2] > 100000 and out[3] == 0, list(out)
+        L.oracle_fuzz_ray_cull(1500000, seed, out)
+        assert out[1] > 10000 and out[2] > 10000 and out[3] == 0, list(out)

@@ -557,69 +557,6 @@ WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, 
     if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo); if (eo) h.overflow = true; }
 }
 
-// bd_resolve_hit by the EIGHT LANES OF A GROUP (gtrav.cuh): lane l takes triangles l, l+8, ... of the cone list.
-//   * primary pick: every lane keeps its first minimum, a (distance, list index) min-reduction gives the first minimum of the whole list;
-//   * Gaussian power: the <= 3 clipped pieces of eight triangles are integrated in parallel and added to the flux in list order through
-//     shuffles -- the same additions, in the same order, as the loop of bd_resolve_hit, so the result is bit-identical;
-//   * the edge set stays with lane 0 (collect_edges is an ordered insertion).
-// All members of h except the edge list hold the same value in the 8 lanes.
-WT_D void g_bd_resolve_hit(const DScene& sc, const GLane& g, const Beam& beam, const TravOut& tr, const uint32_t* __restrict__ tris, BHit& h) {
-    h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u;
-    h.origin = tr.origin; h.region_depth = tr.region_depth; h.dist = 0.f; h.ballistic = true;
-    if (tr.empty) return;
-    if (tr.cone.overflow) h.overflow = true;
-    h.dist = tr.ballistic ? tr.ray.dist : tr.cone.dist;
-    const Range zr = mkr(h.dist, h.dist + tr.region_depth);
-    h.ballistic = tr.ballistic || cone_is_ray(beam.env);
-    const V3 dir = beam.env.d;
-    const uint32_t nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
-    if (h.ballistic) { h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; return; }
-    {
-        float bd = WT_INF, bbx = -1.f, bby = -1.f; uint32_t bi = 0xffffffffu, bt = WTGPU_INVALID_IDX;
-        for (uint32_t i = g.gl; i < nt; i += (uint32_t)kGW) {
-            const uint32_t tuid = __ldg(tris + i);
-            const Tri3 t = load_tri(sc, tuid);
-            const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
-            const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
-            if (rt.hit && rt.dist < bd) { bd = rt.dist; bi = i; bt = tuid; bbx = rt.bx; bby = rt.by; }
-        }
-#pragma unroll
-        for (int o = 1; o < kGW; o <<= 1) {
-            const float od = __shfl_xor_sync(g.gmask, bd, o, kGW); const uint32_t oi = __shfl_xor_sync(g.gmask, bi, o, kGW);
-            const uint32_t ot = __shfl_xor_sync(g.gmask, bt, o, kGW); const float ox = __shfl_xor_sync(g.gmask, bbx, o, kGW), oy = __shfl_xor_sync(g.gmask, bby, o, kGW);
-            if (oi != 0xffffffffu && (bi == 0xffffffffu || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; bt = ot; bbx = ox; bby = oy; }
-        }
-        if (bi != 0xffffffffu) { h.primary = bt; h.pdist = bd; h.bx = bbx; h.by = bby; return; }
-    }
-    const Frame beam_frame = cone_frame(beam.env);
-    const G2 wf = wavefront_of(beam, h.dist);
-    const float csz = (zr.mx + zr.mn) / 2.f;
-    for (uint32_t base = 0; base < nt; base += (uint32_t)kGW) {
-        const uint32_t i = base + g.gl;
-        int cnt = 0; float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-        if (i < nt) {
-            const Tri3 t = load_tri(sc, __ldg(tris + i));
-            if ((dot(t.n, -dir) > 0.f) == tr.cone.front) {
-                const Clip cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
-                cnt = cl.tris;
-                for (int k = 0; k < cl.tris; ++k) {
-                    V3 ct[3]; clip_tri(cl, k, ct);
-                    const float v = g2_integrate_triangle(sc, wf, cone_project_local(beam.env, ct[0], csz), cone_project_local(beam.env, ct[1], csz), cone_project_local(beam.env, ct[2], csz));
-                    if (k == 0) v0 = v; else if (k == 1) v1 = v; else v2 = v;
-                }
-            }
-        }
-#pragma unroll
-        for (int l = 0; l < kGW; ++l) {
-            const int c = g_shfl(g, cnt, l);
-            const float a0 = g_shfl(g, v0, l), a1 = g_shfl(g, v1, l), a2 = g_shfl(g, v2, l);
-            if (c > 0) h.flux += a0;
-            if (c > 1) h.flux += a1;
-            if (c > 2) h.flux += a2;
-        }
-    }
-}
-
 // continue_walk (plt_bdpt_detail.hpp:167-182)
 WT_D bool bd_continue_walk(BCtx& c, BWalk& data, Sampler& smp, bool do_RR) {
     const DScene& sc = *c.sc;
@@ -1071,15 +1008,11 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
         });
     flush_counters(a.r.ctr, ctr);
 }
-// what the vertex step needs from a traversal result: primary triangle, Gaussian power over clipped triangles, edges, sort key.
-// Eight lanes per walker (g_bd_resolve_hit): one thread per walker ran 3-4 of 32 lanes (profiles/r01s2_ncu_sass_hotspots_2.txt) because a
-// diffusive walker loops over up to 128 triangles while a ballistic one has nothing to do.
+// what the vertex step needs from a traversal result: primary triangle, Gaussian power over clipped triangles, edges, sort key
 __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
-    GLane g; g.gl = threadIdx.x & 7u; g.gshift = (threadIdx.x & 31u) & 24u; g.gmask = 0xffu << g.gshift;
-    const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) / (uint32_t)kGW;
-    const bool active = li < (uint32_t)a.r.ctr->n_trav;
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     bool ovf = false;
-    if (active) {
+    if (li < (uint32_t)a.r.ctr->n_trav) {
         const uint32_t wid = a.r.trav_list[li];
         const DScene& sc = a.r.sc;
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
@@ -1089,22 +1022,19 @@ __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
         tr.ray.tuid = r.ray_tuid; tr.ray.dist = r.ray_dist; tr.ray.bx = r.bx; tr.ray.by = r.by; tr.ray.front = (r.flags & TR_RAY_FRONT) != 0u;
         tr.cone.dist = r.cone_dist; tr.cone.front = (r.flags & TR_CONE_FRONT) != 0u; tr.cone.n_tris = r.n_tris; tr.cone.overflow = (r.flags & TR_OVERFLOW) != 0u;
         tr.region_depth = r.region_depth; tr.origin = mk3(r.ox, r.oy, r.oz);
-        const uint32_t* tris = a.trav_tris + (size_t)wid * kMaxConeTris;
-        BHit bh;
-        g_bd_resolve_hit(sc, g, w.beam, tr, tris, bh);
-        if (g.gl == 0u) {
-            HitRec h;
-            const bool edge_set = !bh.empty && !bh.ballistic && bh.primary == WTGPU_INVALID_IDX && sc.integrator.fsd;
-            if (edge_set) { bool eo = false; bh.n_edges = collect_edges<kMaxHitEdges>(sc, tris, min(r.n_tris, (uint32_t)kMaxConeTris), h.edges, eo); if (eo) bh.overflow = true; }
-            h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
-            h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
-            ovf = bh.overflow;
-            hit_store(h, a.r.hit, a.r.pool, wid);
-            a.r.keys[wid] = bd_hit_key(sc, bh, a.r.n_keys);
-        }
+        uint32_t tris[kMaxConeTris];
+        const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
+        for (uint32_t k = 0; k < nt; ++k) tris[k] = a.trav_tris[(size_t)wid * kMaxConeTris + k];
+        BHit bh; HitRec h;
+        bd_resolve_hit(sc, w.beam, tr, tris, h.edges, bh);
+        h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
+        h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
+        ovf = bh.overflow;
+        hit_store(h, a.r.hit, a.r.pool, wid);
+        a.r.keys[wid] = bd_hit_key(sc, bh, a.r.n_keys);
     }
     count1(&a.r.ctr->overflow, ovf);
-    count1(&a.r.ctr->walker_steps, active && g.gl == 0u);
+    count1(&a.r.ctr->walker_steps, li < (uint32_t)a.r.ctr->n_trav);
 }
 
 __global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->trav_head = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }

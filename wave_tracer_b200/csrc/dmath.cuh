@@ -423,6 +423,23 @@ WT_DN float intersect_cone_tri(const Cone& cone, const Frame& frame, V3 a, V3 b,
     // (the z-range rejection is taken before the containment tests: same result, less work for the triangles a leaf step rejects)
     const float closest_z = min3f(vs[0].z, vs[1].z, vs[2].z), farthest_z = max3f(vs[0].z, vs[1].z, vs[2].z);
     if (farthest_z < range.mn || closest_z > range.mx) return WT_INF;
+#ifndef WT_NO_CONE_QUICK_REJECT
+    // Separating-axis rejection (ours; the reference goes straight to the plane and edge tests).  Inside the z slab the cone's cross-section is
+    // contained in |x| <= r, |e y| <= r, |x +- e y| <= sqrt(2) r with r = tan(alpha) z1 + x0 at the far end z1 of the slab; a triangle whose three
+    // vertices lie beyond one of these lines -- by a slack of 1e-3 r + 1e-5 x its own extent, orders of magnitude above the rounding of
+    // the tests it skips -- cannot touch the cone, and every later stage would report "no intersection".
+    if (cone.ta >= 0.f) {
+        const float r = fmaf(fminf(farthest_z, range.mx), cone.ta, cone.x0);
+        if (r > 0.f && r < WT_INF) {
+            const float u0 = vs[0].x, u1 = vs[1].x, u2 = vs[2].x, v0 = vs[0].y * cone.e, v1 = vs[1].y * cone.e, v2 = vs[2].y * cone.e;
+            const float ext = fmaxf(fmaxf(max3f(fabsf(u0), fabsf(u1), fabsf(u2)), max3f(fabsf(v0), fabsf(v1), fabsf(v2))), fmaxf(fabsf(closest_z), fabsf(farthest_z)));
+            const float b = r + (1e-3f * r + 1e-5f * ext), bd = 1.41421356f * r + (2e-3f * r + 2e-5f * ext);
+            const float p0 = u0 + v0, p1 = u1 + v1, p2 = u2 + v2, q0 = u0 - v0, q1 = u1 - v1, q2 = u2 - v2;
+            if (min3f(u0, u1, u2) > b || max3f(u0, u1, u2) < -b || min3f(v0, v1, v2) > b || max3f(v0, v1, v2) < -b ||
+                min3f(p0, p1, p2) > bd || max3f(p0, p1, p2) < -bd || min3f(q0, q1, q2) > bd || max3f(q0, q1, q2) < -bd) return WT_INF;
+        }
+    }
+#endif
     bool in[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) in[i] = cone_contains_local_w(cone, vs[i], range);

@@ -1049,7 +1049,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             mark();
             k_bd_generate<<<gP, blk, 0, st>>>(b); ++launches; mark();
             if (thread_trav) { k_bd_traverse<<<gW, blk, 0, st>>>(b); ++launches; }
-            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<dim3((W2 * (uint32_t)kGW + 127u) / 128u), blk, 0, st>>>(b); launches += 2; }
+            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blk, 0, st>>>(b); launches += 2; }
             mark();
             k_hist<<<gW, blk, s->n_keys * 4, st>>>(b.r);
             k_scan<<<1, 1024, 0, st>>>(b.r);

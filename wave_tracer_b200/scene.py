@@ -106,7 +106,8 @@ class Binned(Spectrum):
     def value(self, k):
         k = np.asarray(k, np.float64); out = np.zeros(k.shape, np.complex128)
         for kmin, kmax, s in self.bins:
-            m = (k >= kmin) & (k < kmax); out = np.where(m, _as_spectrum(s).value(k), out)
+            m = (k >= kmin) & (k < kmax)
+            if m.any(): out[m] = _as_spectrum(s).value(k[m])       # a bin's spectrum is only asked about its own range
         return out
 
 
@@ -407,7 +408,10 @@ class Scene:
                 n.type = A.BSDF_SCALE; n.spec[0] = bake(b.scale); n.child = flat_bsdf(b.nested)
             elif isinstance(b, Composite):
                 n.type = A.BSDF_COMPOSITE
-                children = [(wavelen_to_wavenum(hi), wavelen_to_wavenum(lo), flat_bsdf(c)) for lo, hi, c in b.bins]
+                # bins that cannot be selected at any wavenumber the sensor queries are dropped (composite.hpp:64-70 picks a bin by k; k stays
+                # inside the sensor's range): their spectra need not be defined there (e.g. rgb reflectances in a microwave scene)
+                live = [(lo, hi, c) for lo, hi, c in b.bins if wavelen_to_wavenum(hi) <= kmax and kmin < wavelen_to_wavenum(lo)]
+                children = [(wavelen_to_wavenum(hi), wavelen_to_wavenum(lo), flat_bsdf(c)) for lo, hi, c in live]
                 n.bin_first, n.n_bins = len(bins), len(children)
                 for kmn, kmx, c in children:
                     bb = A.BsdfBin(); bb.kmin, bb.kmax, bb.child = kmn, kmx, c; bins.append(bb)

@@ -23,7 +23,8 @@ def double_slits(res=1024, spp=32, direction="forward", max_depth=16, fsd=True, 
     film = Film(res, res // 4, [Discrete(lam)], rfilter_scale=.05)
     sc.sensor = VirtualPlane(lookat((0, 0, (S - .0001) * MM), (0, 0, E * MM), (0, -1, 0)), (extent * MM, extent / 4 * MM), film,
                              alpha=math.radians(.001), samples=spp, ray_trace_only=ray_trace_only)
-    sc.add_emitter(Spot(lookat((0, 0, L * MM), (0, 0, 0)), Discrete(lam, Lscale), cutoff_angle=math.radians(.2), beam_width=math.radians(.1)))
+    # the file's <lookat> has no `up`: the loader takes the tangent of build_orthogonal_frame(dir) = (1,0,0) for dir = +z (transform_loader.cpp:74-76)
+    sc.add_emitter(Spot(lookat((0, 0, L * MM), (0, 0, 0), (1, 0, 0)), Discrete(lam, Lscale), cutoff_angle=math.radians(.2), beam_width=math.radians(.1)))
     if with_directional:
         sc.add_emitter(Directional(Blackbody(5750, 1e-6), lookat((-2, 3.5, -1), (0, 0, 0), (1, 0, 0))))
         sc.add_emitter(Directional(Blackbody(6500, 6e-5), lookat((-1, 4, 1), (0, 0, 0), (1, 0, 0))))

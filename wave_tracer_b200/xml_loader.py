@@ -1,0 +1,475 @@
+"""Scene XML front-end: reads the reference's scene files (the format of /root/reference/scenes/**.xml, loaded there by
+src/scene/loader/loader.cpp + src/scene/loader/xml/loader.cpp) into the host scene model of scene.py, so that a file written
+for wave_tracer renders through wtgpu_render unchanged.
+
+What is covered is what the procedural BASELINE scene needs (scenes/diffraction_simple/double_slits.xml + bits/geometry.xml) and the
+procedural parts of the others; anything else raises SceneXmlError naming the element -- nothing is skipped silently:
+
+  <default name value> + -D overrides, `$name` substitution (loader.cpp:69-86, 369-411: textual, before any parsing)
+  <include path>                     a fragment with several top-level elements
+  expressions                        "( ... )" / bare arithmetic with + - * / ^ comparisons && || ! true false (the reference evaluates
+                                     them with tinyexpr-plusplus); quantities "expr unit" with mm/cm/m/um/nm/km, deg/rad, K, Hz..GHz
+  <integrator type=plt_path|plt_bdpt> integer max_depth, boolean FSD / russian_roulette / MIS / *_direct_sampling, string direction
+  <sensor type=virtual_plane|perspective> boolean enabled / ray_trace_only, transform to_world, quantity extent / alpha / fov,
+                                     integer samples, <film type=array> (width, height, rfilter_scale, <response type=monochromatic>)
+  <emitter type=spot|point|directional|area>
+  <bsdf type=twosided|diffuse|dielectric|surface_spm|composite|scale> (+ id / <ref id>), <surface_profile type=dirac|fractal|gaussian>
+  <spectrum constant=|rgb=|blackbody=|type=discrete|composite|piecewise_linear(uniform)>
+  <shape type=rectangle|cube|sphere> point p/x/y, transform to_world, boolean enabled, nested bsdf / ref / area emitter
+
+`rgb=` spectra (the reference upsamples RGB to a spectrum) are represented by an object that refuses to be evaluated: the microwave /
+single-wavelength BASELINE scenes only carry them in composite bins the sensor never queries.
+"""
+import ast
+import math
+import os
+import re
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+from . import scene as S
+
+
+class SceneXmlError(RuntimeError):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------ expressions and quantities
+_UNITS = {
+    "m": ("len", 1.0), "mm": ("len", 1e-3), "cm": ("len", 1e-2), "um": ("len", 1e-6), "µm": ("len", 1e-6), "nm": ("len", 1e-9), "km": ("len", 1e3),
+    "°": ("ang", math.pi / 180), "deg": ("ang", math.pi / 180), "rad": ("ang", 1.0),
+    "K": ("temp", 1.0),
+    "Hz": ("freq", 1.0), "kHz": ("freq", 1e3), "MHz": ("freq", 1e6), "GHz": ("freq", 1e9), "THz": ("freq", 1e12),
+}
+_C0 = 2.99792458e8
+_ALLOWED = (ast.Expression, ast.BinOp, ast.UnaryOp, ast.BoolOp, ast.Compare, ast.Constant, ast.Add, ast.Sub, ast.Mult, ast.Div, ast.Pow, ast.Mod,
+            ast.USub, ast.UAdd, ast.Not, ast.And, ast.Or, ast.Eq, ast.NotEq, ast.Lt, ast.LtE, ast.Gt, ast.GtE, ast.Call, ast.Name, ast.Load)
+_FUNCS = {"sqrt": math.sqrt, "sin": math.sin, "cos": math.cos, "tan": math.tan, "abs": abs, "min": min, "max": max, "floor": math.floor, "ceil": math.ceil,
+          "exp": math.exp, "log": math.log, "pow": pow, "pi": math.pi, "true": True, "false": False}
+
+
+def evaluate(expr):
+    """A value expression after `$` substitution: number, or arithmetic / boolean expression in tinyexpr syntax."""
+    e = expr.strip()
+    if e == "":
+        raise SceneXmlError("empty expression")
+    py = e.replace("&&", " and ").replace("||", " or ").replace("^", "**")
+    py = re.sub(r"!(?!=)", " not ", py)
+    py = re.sub(r"(?<![\w.])\.(\d)", r"0.\1", py)          # ".05" -> "0.05"
+    py = re.sub(r"(?<![\w.])0+(\d)", r"\1", py)             # leading zeros are not octal
+    try:
+        tree = ast.parse(py, mode="eval")
+    except SyntaxError as ex:
+        raise SceneXmlError(f"cannot parse expression {expr!r}") from ex
+    for n in ast.walk(tree):
+        if not isinstance(n, _ALLOWED):
+            raise SceneXmlError(f"unsupported construct in expression {expr!r}")
+        if isinstance(n, ast.Name) and n.id not in _FUNCS:
+            raise SceneXmlError(f"unknown identifier {n.id!r} in expression {expr!r}")
+    return eval(compile(tree, "<scene-xml>", "eval"), {"__builtins__": {}}, dict(_FUNCS))
+
+
+def _split_top(s, sep=","):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch == "(": depth += 1
+        elif ch == ")": depth -= 1
+        if ch == sep and depth == 0:
+            out.append(cur); cur = ""
+        else:
+            cur += ch
+    out.append(cur)
+    return [x.strip() for x in out]
+
+
+_QRE = re.compile(r"^(?P<expr>.*?)(?P<unit>(?:[A-Za-zµ]+|°))?$", re.S)
+
+
+def quantity(s, kind=None):
+    """"($S-.0001) mm" -> SI float (metres / radians / kelvin / hertz).  kind: expected dimension or None (dimensionless allowed)."""
+    s = s.strip()
+    m = re.match(r"^(.*?)\s*([A-Za-zµ°]+)$", s, re.S)
+    unit = None
+    if m and m.group(2) in _UNITS and m.group(1).strip() != "":
+        body, unit = m.group(1).strip(), m.group(2)
+    else:
+        body = s
+    v = float(evaluate(body))
+    if unit is None:
+        if kind in ("len", "ang", "temp", "freq") and v != 0.0:
+            raise SceneXmlError(f"quantity {s!r} needs a unit")
+        return v
+    dim, f = _UNITS[unit]
+    if kind == "wavelength" and dim == "freq":
+        return _C0 / (v * f)
+    if kind == "wavelength":
+        kind = "len"
+    if kind is not None and dim != kind:
+        raise SceneXmlError(f"quantity {s!r}: expected a {kind} unit")
+    return v * f
+
+
+def qvec(s, kind=None, n=None):
+    v = [quantity(p, kind) for p in _split_top(s)]
+    if n is not None and len(v) != n:
+        raise SceneXmlError(f"expected {n} components in {s!r}")
+    return v
+
+
+def qrange(s, kind):
+    a, b = s.split("..")
+    return quantity(a, kind), quantity(b, kind)
+
+
+def boolean(s):
+    v = evaluate(s)
+    return bool(v)
+
+
+def integer(s):
+    v = evaluate(s)
+    return int(v)          # "$res/4": truncation, as the reference's integer parser does for an integral quotient
+
+
+def complex_value(s):
+    """"(1,100i)" / "1.5" / "(.2,3i)" (spectrum constant=...)."""
+    t = s.strip()
+    m = re.match(r"^\(\s*([^,]+)\s*,\s*([^)]+?)i\s*\)$", t)
+    if m:
+        return complex(float(evaluate(m.group(1))), float(evaluate(m.group(2))))
+    return complex(float(evaluate(t)), 0.0)
+
+
+# ------------------------------------------------------------------------------------------------ the document
+class RGBSpectrum(S.Spectrum):
+    """`rgb="r,g,b"`: the reference upsamples to a spectrum (src/spectrum/rgb.cpp); not restated -- evaluating it is an error."""
+    def __init__(self, rgb): self.rgb = rgb
+    def value(self, k):
+        if np.size(k) == 0: return np.zeros(np.shape(k), np.complex128)
+        raise SceneXmlError("rgb spectra are not supported at the wavenumbers this sensor queries")
+
+
+def _subst(text, defines):
+    def rep(m):
+        name = m.group(1)
+        if name not in defines:
+            raise SceneXmlError(f'unknown define "${name}"')
+        return defines[name]
+    return re.sub(r"\$([A-Za-z0-9_]+)", rep, text)
+
+
+def _parse_file(path):
+    txt = open(path, encoding="utf-8").read()
+    # pugixml (the reference's parser) accepts a bare `&` and `<` inside attribute values ("$a==true && $b==false", "$x<3"); expat does not
+    txt = re.sub(r"&(?!(?:amp|lt|gt|quot|apos|#\d+|#x[0-9a-fA-F]+);)", "&amp;", txt)
+    txt = re.sub(r'"[^"<>]*<[^"<>]*"', lambda m: m.group(0).replace("<", "&lt;"), txt)
+    try:
+        return ET.fromstring(txt)
+    except ET.ParseError:
+        body = re.sub(r"<\?xml[^>]*\?>", "", txt)             # an <include> fragment: several top-level elements
+        return ET.fromstring("<fragment>" + body + "</fragment>")
+
+
+class _Loader:
+    def __init__(self, path, defines):
+        self.dir = os.path.dirname(os.path.abspath(path))
+        self.root = _parse_file(path)
+        if self.root.tag != "scene":
+            raise SceneXmlError("root element must be <scene>")
+        self._expand_includes(self.root, self.dir)
+        self.defines = {k: str(v) for k, v in (defines or {}).items()}
+        for d in self.root.findall("default"):
+            self.defines.setdefault(d.attrib["name"], d.attrib["value"])
+        for el in self.root.iter():
+            for k, v in list(el.attrib.items()):
+                if "$" in v:
+                    el.attrib[k] = _subst(v, self.defines)
+        self.bsdfs = {}
+
+    def _expand_includes(self, node, base):
+        for i, ch in enumerate(list(node)):
+            if ch.tag == "include":
+                p = os.path.join(base, ch.attrib["path"])
+                frag = _parse_file(p)
+                self._expand_includes(frag, os.path.dirname(p))
+                idx = list(node).index(ch)
+                node.remove(ch)
+                for j, sub in enumerate(list(frag) if frag.tag == "fragment" else [frag]):
+                    node.insert(idx + j, sub)
+            else:
+                self._expand_includes(ch, base)
+
+    # ---- helpers
+    @staticmethod
+    def _named(node, tag, name):
+        for ch in node.findall(tag):
+            if ch.attrib.get("name") == name:
+                return ch
+        return None
+
+    def _enabled(self, node):
+        b = self._named(node, "boolean", "enabled")
+        return True if b is None else boolean(b.attrib["value"])
+
+    def _bool(self, node, name, default):
+        b = self._named(node, "boolean", name)
+        return default if b is None else boolean(b.attrib["value"])
+
+    def _int(self, node, name, default):
+        b = self._named(node, "integer", name)
+        return default if b is None else integer(b.attrib["value"])
+
+    def _float(self, node, name, default):
+        b = self._named(node, "float", name)
+        return default if b is None else float(evaluate(b.attrib["value"]))
+
+    def _quantity(self, node, name, kind, default=None):
+        b = self._named(node, "quantity", name)
+        return default if b is None else quantity(b.attrib["value"], kind)
+
+    def transform(self, node):
+        """src/math/transform_loader.cpp:60-125."""
+        if node is None:
+            return np.eye(4)
+        la = node.find("lookat")
+        if la is not None:
+            origin = np.array(qvec(la.attrib["origin"], "len", 3)) if "origin" in la.attrib else np.zeros(3)
+            target = np.array(qvec(la.attrib["target"], "len", 3)) if "target" in la.attrib else np.array([0, 0, 1.0])
+            d = target - origin; d = d / np.linalg.norm(d)
+            if "up" in la.attrib:
+                up = np.array(qvec(la.attrib["up"], None, 3), np.float64)
+            else:       # frame_t::build_orthogonal_frame(dir).t  (include/wt/math/frame.hpp:158-174)
+                n = d
+                if abs(n[0]) > abs(n[1]): x = 1 / math.sqrt(n[0] ** 2 + n[2] ** 2); b = np.array([x * n[2], 0, -x * n[0]])
+                else: x = 1 / math.sqrt(n[1] ** 2 + n[2] ** 2); b = np.array([0, x * n[2], -x * n[1]])
+                up = np.cross(b, n) + 0.0          # (+0.0: no negative zeros in the frame)
+            if 1 - abs(float(np.dot(up / np.linalg.norm(up), d))) < 1e-5:
+                raise SceneXmlError("degenerate 'lookat' transform")
+            return S.lookat(origin, target, up)
+        M = np.eye(4)
+        for it in node:
+            if it.tag == "translate":
+                M = S.translate([quantity(it.attrib.get(a, "0"), "len") for a in "xyz"]) @ M
+            elif it.tag == "scale":
+                if "value" in it.attrib: v = float(evaluate(it.attrib["value"])); M = S.scale((v, v, v)) @ M
+                else: M = S.scale([float(evaluate(it.attrib.get(a, "1"))) for a in "xyz"]) @ M
+            elif it.tag == "rotate":
+                M = S.rotate([float(evaluate(it.attrib.get(a, "0"))) for a in "xyz"], quantity(it.attrib["angle"], "ang")) @ M
+            elif it.tag == "matrix":
+                vals = [float(evaluate(x)) for x in re.split(r"[,\s]+", it.attrib["value"].strip())]
+                M = np.array(vals, np.float64).reshape(4, 4) @ M
+            else:
+                raise SceneXmlError(f"<transform>: unsupported child <{it.tag}>")
+        return M
+
+    # ---- spectra
+    def spectrum(self, node):
+        a = node.attrib
+        scale = self._float(node, "scale", 1.0)
+        if "constant" in a:
+            v = complex_value(a["constant"]) * scale
+            return S.Const(v)
+        if "rgb" in a:
+            return RGBSpectrum(qvec(a["rgb"], None, 3))
+        if "blackbody" in a:
+            return S.Blackbody(quantity(a["blackbody"], "temp"), scale)
+        t = a.get("type")
+        if t == "discrete":
+            return S.Discrete(quantity(a["wavelength"], "wavelength"), float(evaluate(a.get("value", "1"))) * scale)
+        if t == "composite":
+            bins = []
+            for b in node.findall("bin"):
+                lo, hi = qrange(b.attrib["wavelength_range"], "wavelength")
+                sub = b.find("spectrum")
+                if sub is None: raise SceneXmlError("composite spectrum: <bin> without <spectrum>")
+                bins.append((lo, hi, self.spectrum(sub)))
+            return S.Binned(bins)
+        raise SceneXmlError(f"<spectrum>: unsupported form {dict(a)}")
+
+    def _spectrum_child(self, node, name, default=None):
+        ch = self._named(node, "spectrum", name)
+        return default if ch is None else self.spectrum(ch)
+
+    # ---- bsdfs
+    def surface_profile(self, node):
+        if node is None:
+            return S.Dirac()
+        t = node.attrib.get("type")
+        if t == "dirac":
+            return S.Dirac()
+        if t == "fractal":
+            r = self._spectrum_child(node, "roughness")
+            if r is None: raise SceneXmlError("fractal surface_profile: only the roughness parametrisation is supported")
+            return S.Fractal(r, gamma=self._float(node, "gamma", 3.0))
+        if t == "gaussian":
+            r = self._spectrum_child(node, "roughness")
+            if r is not None: return S.Gaussian(roughness=r)
+            q = self._named(node, "quantity", "sigma")
+            if q is None: raise SceneXmlError("gaussian surface_profile: either 'roughness' or 'sigma' must be provided")
+            # rms_t is 1/mm (surface_profile.hpp:41): "<value> 1/mm" is not a unit this loader parses; accept a bare number in 1/mm
+            return S.Gaussian(sigma=float(evaluate(q.attrib["value"].replace("1/mm", "").replace("/mm", ""))))
+        raise SceneXmlError(f"<surface_profile type={t!r}> is not supported")
+
+    def bsdf(self, node):
+        t = node.attrib.get("type")
+        nested = [self.bsdf(ch) for ch in node.findall("bsdf")] + [self._ref(ch) for ch in node.findall("ref")]
+        if t == "twosided":
+            if len(nested) != 1: raise SceneXmlError("twosided bsdf needs exactly one nested bsdf")
+            out = S.TwoSided(nested[0])
+        elif t == "diffuse":
+            out = S.Diffuse(self._spectrum_child(node, "reflectance", S.Const(.5)))
+        elif t in ("dielectric", "surface_spm"):
+            ior = self._spectrum_child(node, "IOR")
+            if ior is None: raise SceneXmlError(f"{t} bsdf: 'IOR' spectrum must be provided")
+            ext = self._spectrum_child(node, "extIOR", S.Const(1.0))
+            rs, ts = self._spectrum_child(node, "reflection_scale"), self._spectrum_child(node, "transmission_scale")
+            if t == "dielectric": out = S.Dielectric(ior, ext, rs, ts)
+            else: out = S.SurfaceSPM(ior, ext, self.surface_profile(node.find("surface_profile")), rs, ts)
+        elif t == "composite":
+            bins = []
+            for b in node.findall("bin"):
+                lo, hi = qrange(b.attrib["wavelength_range"], "wavelength")
+                subs = [self.bsdf(ch) for ch in b.findall("bsdf")] + [self._ref(ch) for ch in b.findall("ref")]
+                if len(subs) != 1: raise SceneXmlError("composite bsdf: each <bin> needs exactly one bsdf")
+                bins.append((lo, hi, subs[0]))
+            out = S.Composite(bins)
+        elif t == "scale":
+            if len(nested) != 1: raise SceneXmlError("scale bsdf needs exactly one nested bsdf")
+            out = S.Scale(self._spectrum_child(node, "scale", S.Const(1.0)), nested[0])
+        else:
+            raise SceneXmlError(f"<bsdf type={t!r}> is not supported")
+        if "id" in node.attrib:
+            self.bsdfs[node.attrib["id"]] = out
+        return out
+
+    def _ref(self, node):
+        i = node.attrib["id"]
+        if i not in self.bsdfs:
+            raise SceneXmlError(f'<ref id="{i}">: unknown id')
+        return self.bsdfs[i]
+
+    # ---- integrator / sensor / emitters / shapes
+    def integrator(self, node, lut):
+        t = node.attrib.get("type")
+        md = self._int(node, "max_depth", 1024)
+        fsd = self._bool(node, "FSD", True)
+        rr = self._bool(node, "russian_roulette", True)
+        if t == "plt_path":
+            d = self._named(node, "string", "direction")
+            return S.PltPath(max_depth=md, direction=d.attrib["value"] if d is not None else "backward", fsd=fsd, russian_roulette=rr)
+        if t == "plt_bdpt":
+            return S.PltBdpt(max_depth=md, fsd=fsd, russian_roulette=rr, mis=self._bool(node, "MIS", True),
+                             sensor_direct_sampling=self._bool(node, "sensor_direct_sampling", True),
+                             emitter_direct_sampling=self._bool(node, "emitter_direct_sampling", True), lut=lut)
+        raise SceneXmlError(f"<integrator type={t!r}> is not supported")
+
+    def film(self, node):
+        if node is None or node.attrib.get("type") != "array":
+            raise SceneXmlError("sensor needs a <film type=\"array\">")
+        resp = node.find("response")
+        if resp is None or resp.attrib.get("type") != "monochromatic":
+            raise SceneXmlError("only <response type=\"monochromatic\"> films are supported (RGB responses need the XYZ tables)")
+        sp = resp.find("spectrum")
+        return S.Film(self._int(node, "width", 0), self._int(node, "height", 0), [self.spectrum(sp)], rfilter_scale=self._float(node, "rfilter_scale", 1.0))
+
+    def sensor(self, node):
+        t = node.attrib.get("type")
+        tw = self.transform(self._named(node, "transform", "to_world"))
+        film = self.film(node.find("film"))
+        spp = self._int(node, "samples", 1)
+        rt = self._bool(node, "ray_trace_only", False)
+        if t == "virtual_plane":
+            ext = self._named(node, "quantity", "extent")
+            if ext is None: raise SceneXmlError("virtual_plane sensor: 'extent' must be provided")
+            return S.VirtualPlane(tw, tuple(qvec(ext.attrib["value"], "len", 2)), film, alpha=self._quantity(node, "alpha", "ang"), ray_trace_only=rt, samples=spp)
+        if t == "perspective":
+            return S.Perspective(tw, self._quantity(node, "fov", "ang"), film, ray_trace_only=rt, samples=spp)
+        raise SceneXmlError(f"<sensor type={t!r}> is not supported")
+
+    def emitter(self, node):
+        t = node.attrib.get("type")
+        tw_node = self._named(node, "transform", "to_world")
+        pse = self._float(node, "phase_space_extent_scale", 1.0)
+        if t == "spot":
+            kw = {}
+            c = self._quantity(node, "cutoff_angle", "ang"); b = self._quantity(node, "beam_width", "ang")
+            if c is not None: kw["cutoff_angle"] = c
+            if b is not None: kw["beam_width"] = b
+            return S.Spot(self.transform(tw_node), self._spectrum_child(node, "radiant_intensity"), phase_space_extent_scale=pse, **kw)
+        if t == "point":
+            p = self._named(node, "point", "position")
+            pos = [quantity(p.attrib.get(a, "0"), "len") for a in "xyz"] if p is not None else [0, 0, 0]
+            return S.Point(pos, self._spectrum_child(node, "radiant_intensity"), phase_space_extent_scale=pse)
+        if t == "directional":
+            return S.Directional(self._spectrum_child(node, "irradiance"), self.transform(tw_node) if tw_node is not None else None, phase_space_extent_scale=pse)
+        if t == "area":
+            return S.Area(self._spectrum_child(node, "radiance"), scale=self._float(node, "scale", 1.0), phase_space_extent_scale=pse)
+        raise SceneXmlError(f"<emitter type={t!r}> is not supported")
+
+    def shape(self, node):
+        t = node.attrib.get("type")
+        tw_node = self._named(node, "transform", "to_world")
+        tw = self.transform(tw_node) if tw_node is not None else None
+        def pt(name):
+            p = self._named(node, "point", name)
+            if p is None: raise SceneXmlError(f"{t} shape: point '{name}' must be provided")
+            return np.array([quantity(p.attrib.get(a, "0"), "len") for a in "xyz"])
+        if t == "rectangle":
+            mesh = S.rectangle(pt("p"), pt("x"), pt("y"), to_world=tw)
+        elif t == "cube":
+            mesh = S.cube(tw)
+        elif t == "sphere":
+            r = self._quantity(node, "radius", "len", 1.0)
+            c = self._named(node, "point", "center")
+            centre = [quantity(c.attrib.get(a, "0"), "len") for a in "xyz"] if c is not None else (0, 0, 0)
+            mesh = S.sphere(r, centre, to_world=tw)
+        else:
+            raise SceneXmlError(f"<shape type={t!r}> is not supported (ply/obj meshes are Git-LFS stubs in the reference tree)")
+        bs = [self.bsdf(ch) for ch in node.findall("bsdf")] + [self._ref(ch) for ch in node.findall("ref")]
+        if len(bs) != 1: raise SceneXmlError("a shape needs exactly one bsdf (nested or <ref>)")
+        em = node.find("emitter")
+        return mesh, bs[0], (self.emitter(em) if em is not None else None)
+
+    def build(self, lut=(2048, 1024), sensor_id=None):
+        sc = S.Scene()
+        root = self.root
+        integ = root.find("integrator")
+        if integ is None: raise SceneXmlError("no <integrator>")
+        sc.integrator = self.integrator(integ, lut)
+        sensors = [s for s in root.findall("sensor") if self._enabled(s) and (sensor_id is None or s.attrib.get("id") == sensor_id)]
+        if len(sensors) != 1:
+            raise SceneXmlError(f"{len(sensors)} enabled sensors; exactly one is rendered per call (select with sensor_id)")
+        sc.sensor = self.sensor(sensors[0])
+        for b in root.findall("bsdf"):
+            self.bsdf(b)
+        for e in root.findall("emitter"):
+            if self._enabled(e): sc.add_emitter(self.emitter(e))
+        for sh in root.findall("shape"):
+            if not self._enabled(sh): continue
+            mesh, bsdf, em = self.shape(sh)
+            sc.add_shape(mesh, bsdf, emitter=em)
+        known = {"default", "integrator", "sensor", "bsdf", "emitter", "shape", "sampler"}
+        for ch in root:
+            if ch.tag not in known:
+                raise SceneXmlError(f"unsupported top-level element <{ch.tag}>")
+        smp = root.find("sampler")
+        if smp is not None:
+            t = smp.attrib.get("type")
+            if t in ("sobolld", "sobol"): sc.sampler = S.Sobolld()
+            elif t not in ("uniform", "independent"): raise SceneXmlError(f"<sampler type={t!r}> is not supported")
+        return sc
+
+
+def load_scene(path, defines=None, lut=(2048, 1024), sensor_id=None):
+    """`wave_tracer render scene.xml -D k=v,...` front half: returns a scene.Scene (call .build() for the wtgpu_scene_desc tables)."""
+    return _Loader(path, defines).build(lut=lut, sensor_id=sensor_id)
+
+
+def parse_defines(s):
+    """"res=1440,spp=1024" -> dict (the CLI's -D option, src/main.cpp)."""
+    out = {}
+    for kv in (s or "").split(","):
+        if kv.strip():
+            k, v = kv.split("=", 1); out[k.strip()] = v.strip()
+    return out
