@@ -130,24 +130,25 @@ WT_D void clip_tri(const Clip& c, int idx, V3 o[3]) {
 }
 WT_D Clip clip_triangle_z(V3 a, V3 b, V3 c, Range zr) {
     const V3 ppmax = mk3(0.f, 0.f, zr.mx), ppmin = mk3(0.f, 0.f, zr.mn), n = mk3(0.f, 0.f, 1.f);
-    V3 tri[3] = { a, b, c };
-    int cls[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) cls[i] = tri[i].z > zr.mx ? 1 : tri[i].z < zr.mn ? -1 : 0;
+    // the three edges go through ONE copy of the clipping code (vertices rotate through registers): same edges, same order, a third of the code
+    V3 ti = a, tn = b, tl = c;
+    auto zcls = [&](const V3& v) { return v.z > zr.mx ? 1 : v.z < zr.mn ? -1 : 0; };
+    int ci = zcls(a), cn = zcls(b), cl = zcls(c);
     Clip r; int idx = 0;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 3; ++i) {
-        const int nx = i == 2 ? 0 : i + 1;
-        if (cls[i] == 0) { if (idx < 5) r.vs[idx++] = tri[i]; }
-        if (cls[nx] != cls[i]) {
+        if (ci == 0) { if (idx < 5) r.vs[idx++] = ti; }
+        if (cn != ci) {
             V3 pt;
-            const bool ok = intersect_edge_plane(tri[i], tri[nx], cls[i] == -1 ? ppmin : (cls[i] == 1 || cls[nx] == 1) ? ppmax : ppmin, n, pt);
-            if (idx < 5) r.vs[idx++] = ok ? pt : (cls[i] != 0 ? tri[i] : tri[nx]);
-            if (cls[nx] != 0 && cls[i] != 0) {
-                V3 p2; const bool ok2 = intersect_edge_plane(tri[i], tri[nx], cls[nx] == 1 ? ppmax : ppmin, n, p2);
-                if (idx < 5) r.vs[idx++] = ok2 ? p2 : tri[nx];
+            const bool ok = intersect_edge_plane(ti, tn, ci == -1 ? ppmin : (ci == 1 || cn == 1) ? ppmax : ppmin, n, pt);
+            if (idx < 5) r.vs[idx++] = ok ? pt : (ci != 0 ? ti : tn);
+            if (cn != 0 && ci != 0) {
+                V3 p2; const bool ok2 = intersect_edge_plane(ti, tn, cn == 1 ? ppmax : ppmin, n, p2);
+                if (idx < 5) r.vs[idx++] = ok2 ? p2 : tn;
             }
         }
+        const V3 tv = ti; ti = tn; tn = tl; tl = tv;
+        const int tc = ci; ci = cn; cn = cl; cl = tc;
     }
     r.tris = idx < 3 ? 0 : idx == 3 ? 1 : idx == 4 ? 2 : 3;
     return r;
@@ -658,18 +659,21 @@ WT_D void tmp_init(BVertex& t, uint32_t type) {
     t.gkind = BG_POINT; t.p = mk3(0.f, 0.f, 0.f); t.tuid = WTGPU_INVALID_IDX; t.bary = mk2(0.f, 0.f); t.fp.x = mk2(1.f, 0.f); t.fp.la = t.fp.lb = 0.f; t.dn = mk3(0.f, 0.f, 1.f);
     t.emitter = -1; t.bsdf = -1; t.fsd = -1; t.pad_ = 0u;
 }
+// CLS = strategy class of (s,t) (bd_pair_class: the branch taken below), or -1 to choose at run time.  The wavefront driver launches one
+// kernel per class; compiling only that class's branch into it keeps each kernel's code small (these kernels stall on instruction fetch).
+template <int CLS>
 WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler& smp, BConn& ret) {       // plt_bdpt_detail.hpp:747-923
     const DScene& sc = *c.sc;
     const uint32_t SB = 0u, EB = kMaxBdptVerts;
     ret.has_el = false; ret.L = stokes_zero(); tmp_init(ret.tmp, BV_SENSOR);
     const bool virt = sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE;
-    if (s == 0) {
+    if ((CLS < 0 && s == 0) || CLS == 0) {
         const BVertex& last = bv_ref(c.A, SB + t - 1);
         if (bv_on_emitter(c, last)) {
             Beam QE = last.beam; beam_mul(QE, last.rr);
             if (last.type == BV_SURFACE) { const Surface srf = bv_surface(sc, last); ret.L = emitter_Li(sc, bv_emitter(c, last), QE, srf); }
         }
-    } else if (t == 0) {
+    } else if ((CLS < 0 && t == 0) || CLS == 1) {
         if (virt) {
             const BVertex& last = bv_ref(c.A, EB + s - 1); const BVertex& cur = bv_ref(c.A, EB + s - 2);
             const Beam& beam = last.beam;
@@ -684,7 +688,7 @@ WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler
                 ret.L = integrate_beams(db, beam);
             }
         }
-    } else if (s == 1) {
+    } else if ((CLS < 0 && s == 1) || CLS == 2) {
         const BVertex& last = bv_ref(c.A, SB + t - 1);
         if (bv_connectible(c, last)) {
             EmitterDirect ed = scene_sample_emitter_direct(sc, smp, last.p, last.beam.k);
@@ -699,7 +703,7 @@ WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler
                 if (bv_interact(c, last, ret.tmp.p, false, db)) ret.L = connect_and_integrate(c, db, bv_geo(last), ed.beam, bv_geo(ret.tmp));
             }
         }
-    } else if (t == 1) {
+    } else if ((CLS < 0 && t == 1) || CLS == 3) {
         const BVertex& last = bv_ref(c.A, EB + s - 1);
         if ((virt || last.type != BV_FSD) && bv_connectible(c, last)) {
             SensorDirect sd = sensor_sample_direct(sc, smp, last.p, last.beam.k);
@@ -823,10 +827,11 @@ template <class F> WT_D void bd_for_each_pair(const DScene& sc, uint32_t nsv, ui
         }
 }
 // one (s,t) strategy: connect, weight; returns the flux and where it goes (plt_bdpt.cpp:111-140)
+template <int CLS = -1>
 WT_D float bd_eval_pair(BCtx& c, const BdSampleInit& si, uint32_t seed_lo, uint32_t seed_hi, uint32_t nsv, uint32_t nev, int s, int t, BConn& cr) {
     const DScene& sc = *c.sc;
     Sampler smp; smp.k0 = seed_lo; smp.k1 = seed_hi; smp.pixel = si.pixel; smp.sample = si.sample; smp.d = 0; smp.stream = 3u + 32u * (uint32_t)t + (uint32_t)s;
-    bd_connect(c, nsv, nev, s, t, smp, cr);
+    bd_connect<CLS>(c, nsv, nev, s, t, smp, cr);
     if (cr.L.s[0] <= 0.f) return 0.f;
     const float mis = sc.integrator.mis ? bd_mis(c, s, t, cr) * si.rspd : 1.f / ((float)(s + t + 1) * si.wpd_v);
     return cr.L.s[0] * mis;
@@ -1320,7 +1325,7 @@ template <int CLS> __global__ void __launch_bounds__(128) k_bd_connect(const BdA
         BdSampleInit si; bd_header_to_init(hd, si);
         const uint32_t nsv = a.nverts[2u * slot], nev = a.nverts[2u * slot + 1u];
         BConn cr;
-        const float flux = bd_eval_pair(c, si, a.r.seed_lo, a.r.seed_hi, nsv, nev, s, t, cr);
+        const float flux = bd_eval_pair<CLS>(c, si, a.r.seed_lo, a.r.seed_hi, nsv, nev, s, t, cr);
         ++n_conn; overflow |= c.overflow;
         if (cr.L.s[0] > 0.f) {
             if (t > 1) atomicAdd(&a.L0[slot], flux);

@@ -448,15 +448,17 @@ WT_DN float intersect_cone_tri(const Cone& cone, const Frame& frame, V3 a, V3 b,
     const ConePlane icp = intersect_cone_plane(cone, ln, dot(vs[0], ln), range, true);
     if (!rempty(icp.range) && point_in_triangle(icp.nearp, vs[0], vs[1], vs[2])) return icp.range.mn;
     bool hasp = false; float pz = 0.f;
-#pragma unroll
+    // one copy of the cone-edge test instead of three (the vertices rotate through registers; same edges, same order): the unrolled form
+    // was ~700 SASS instructions of kernels whose dominant stall is instruction fetch (etoile-like k_gtraverse 111 -> 91 ms/step, profiles/r01s3_phases.txt session O)
+    V3 ea = vs[0], eb = vs[1], ec = vs[2]; bool ia = in[0], ib = in[1], ic = in[2];
+#pragma unroll 1
     for (int i = 0; i < 3; ++i) {
-        const int j = i == 2 ? 0 : i + 1;
-        const V3 ea = vs[i], eb = vs[j];
-        if (in[i] && in[j]) continue;
-        if (ea.z > range.mx && eb.z > range.mx) continue;
-        if (ea.z < range.mn && eb.z < range.mn) continue;
-        V3 cp;
-        if (intersect_cone_edge_local(cone, ea, eb, range, cp) && (!hasp || pz > cp.z)) { pz = cp.z; hasp = true; }
+        if (!(ia && ib) && !(ea.z > range.mx && eb.z > range.mx) && !(ea.z < range.mn && eb.z < range.mn)) {
+            V3 cp;
+            if (intersect_cone_edge_local(cone, ea, eb, range, cp) && (!hasp || pz > cp.z)) { pz = cp.z; hasp = true; }
+        }
+        const V3 tv = ea; ea = eb; eb = ec; ec = tv;
+        const bool tb = ia; ia = ib; ib = ic; ic = tb;
     }
     return hasp ? pz : WT_INF;
 }

@@ -108,7 +108,7 @@ WT_DN bool ray_traverse(const DScene& sc, V3 ro, V3 rd, Range range, RayHit& rec
             } else {
                 const int begin = s;
                 const float4* __restrict__ q = reinterpret_cast<const float4*>(n);
-#pragma unroll
+#pragma unroll 1        // two passes over four children instead of eight unrolled slab tests: this function is inlined at every shadow-ray site (etoile-like k_shade -8 %)
                 for (int h = 0; h < 2; ++h) {
                     const float4 mnx = __ldg(q + 0 + h), mny = __ldg(q + 2 + h), mnz = __ldg(q + 4 + h);
                     const float4 mxx = __ldg(q + 6 + h), mxy = __ldg(q + 8 + h), mxz = __ldg(q + 10 + h);
@@ -242,10 +242,9 @@ WT_D uint32_t collect_edges(const DScene& sc, const uint32_t* tris, uint32_t n_t
     uint32_t n = 0;
     for (uint32_t i = 0; i < n_tris; ++i) {
         const wtgpu_tri_meta m = sc.tri_meta[tris[i]];
-        const uint32_t es[3] = { m.edge_ab, m.edge_bc, m.edge_ca };
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint32_t e = es[k];
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {       // (one copy of the insertion: code size)
+            const uint32_t e = k == 0 ? m.edge_ab : k == 1 ? m.edge_bc : m.edge_ca;
             if (e == WTGPU_INVALID_IDX) continue;
             uint32_t pos = 0;
             while (pos < n && edges[pos] < e) ++pos;

@@ -17,7 +17,9 @@ namespace wt {
 
 constexpr int kGW = 8;
 constexpr int kGStack = 128;
-struct GShared { float tmin[kGStack]; int32_t ptr[kGStack]; uint32_t tris[kMaxConeTris]; };
+struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; uint32_t tris[kMaxConeTris];
+    float key[kGW];
+};
 
 // what traverse() returns, as stored between the traversal kernel and the per-thread resolve kernel
 struct alignas(16) TravRec { uint32_t flags, ray_tuid; float ray_dist, bx, by, cone_dist; uint32_t n_tris; float region_depth, ox, oy, oz; uint32_t pad_; };
@@ -70,11 +72,17 @@ WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float 
     const bool keep = push && t.s + idx < cap;
     const unsigned km = g_ballot(g, keep);
     int rank = 0;
+    // the eight keys go through shared memory (one store, two 16-B loads) instead of eight shuffles (fewer instructions in the hottest loop: etoile-like k_gtraverse 111 -> 96 ms/step); lanes that do not push publish -inf
+    sh.key[g.gl] = keep ? tmin : -WT_INF;
+    __syncwarp(g.gmask);
+    {
+        const float4 k0 = *reinterpret_cast<const float4*>(&sh.key[0]), k1 = *reinterpret_cast<const float4*>(&sh.key[4]);
+        const float kk[8] = { k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w };
 #pragma unroll
-    for (int j = 0; j < kGW; ++j) {
-        const float tj = g_shfl(g, tmin, j);
-        if (((km >> j) & 1u) && (tj > tmin || (tj == tmin && j < (int)g.gl))) ++rank;
+        for (int j = 0; j < kGW; ++j) rank += (kk[j] > tmin || (kk[j] == tmin && j < (int)g.gl)) ? 1 : 0;
     }
+    __syncwarp(g.gmask);
+
     if (keep) { sh.tmin[t.s + rank] = tmin; sh.ptr[t.s + rank] = ch; }
     t.s += __popc(km);
     __syncwarp(g.gmask);
@@ -86,13 +94,14 @@ WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, i
     const float mxx = __ldg(&n->maxx[g.gl]), mxy = __ldg(&n->maxy[g.gl]), mxz = __ldg(&n->maxz[g.gl]);
     const int32_t ch = __ldg(&n->child[g.gl]);
     const V3 ro = t.env.o, rd = t.env.d;
+    bool push; float key; int cap;       // (one copy of the ranked push for both query kinds: code size is what bounds this kernel)
     if (t.mode == 1) {      // intersect_ray_aabb_fast (intersect/ray.hpp:331-351), range {0, closest hit}
         const float t1x = ((t.nx ? mxx : mnx) - ro.x) * t.inv.x, t2x = ((t.nx ? mnx : mxx) - ro.x) * t.inv.x;
         const float t1y = ((t.ny ? mxy : mny) - ro.y) * t.inv.y, t2y = ((t.ny ? mny : mxy) - ro.y) * t.inv.y;
         const float t1z = ((t.nz ? mxz : mnz) - ro.z) * t.inv.z, t2z = ((t.nz ? mnz : mxz) - ro.z) * t.inv.z;
         const float rmin = vmaxps(vmaxps(vmaxps(t1x, t1y), t1z), 0.f);
         const float rmax = vminps(vminps(vminps(t2x, t2y), t2z), t.rec.dist);
-        g_push_sorted(g, sh, t, rmin <= rmax && ch != 0 && ray_cull_keep(t.cull, rmin, rmax), rmin, ch, 64);
+        push = rmin <= rmax && ch != 0 && ray_cull_keep(t.cull, rmin, rmax); key = rmin; cap = 64;
     } else {                // cone_cluster_intersect (bvh8w.cpp:187-230)
         float omnx = mnx - ro.x, omny = mny - ro.y, omnz = mnz - ro.z;
         float omxx = mxx - ro.x, omxy = mxy - ro.y, omxz = mxz - ro.z;
@@ -108,8 +117,9 @@ WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, i
         tmin = vmaxps(tmin, dminy); tmax = vminps(tmax, dmaxz);
         tmin = vmaxps(tmin, dminz);
         const bool ok = tmin <= tmax && tmax >= t.crange.mn && tmin <= t.crange.mx;
-        g_push_sorted(g, sh, t, ok && ch != 0 && !(tmin >= t.crange.mx), tmin, ch, kGStack);
+        push = ok && ch != 0 && !(tmin >= t.crange.mx); key = tmin; cap = kGStack;
     }
+    g_push_sorted(g, sh, t, push, key, ch, cap);
 }
 // triangles [t0, t0+cnt) against the current query
 WT_D void g_leaf_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, uint32_t t0, uint32_t cnt, Counters& ctr) {
