@@ -52,13 +52,16 @@ WT_D float Ig1(const DScene& sc, float a, float b, float c, float d) {
     const float sa = sqrtf(a), n = 1.f / sa, dc = d / c;
     return -kSqrtPi / 2.f * n * (signf_(b) * erf_lut(sc, sa * fabsf(b)) + signf_(1.f + b) * erf_lut(sc, sa * fabsf(1.f + b)) - 2.f * signf_(b - dc) * erf_lut(sc, sa * fabsf(b - dc)));
 }
-WT_D float Ige(const DScene& sc, float a, float b, float c, float d) {
+// Out of line and rolled: inlined twice with its four-term loop unrolled this was 16 copies of Igg0/Igg1 (~2500 SASS instructions), and
+// k_bd_resolve -- which runs it with 2-3 lanes per warp -- stalled 6.3 cycles per issue on instruction fetch (profiles/r01s3_ncu_full_digest.txt).
+// Scalar arguments and result: the call moves nothing through local memory.  Same terms, same order of additions.
+__device__ __noinline__ float Ige(const DScene& sc, float a, float b, float c, float d) {
     const float dc = d / c;
     const bool in = c != 0.f && -dc > 0.f && -dc < 1.f;
     const float sv[4] = { 0.6517755981618476f, 3.250040490513459f, 31.86882707224491f, 778.6613983601425f };
     const float wv[4] = { 0.2936683276537767f, 0.135758042187825f, 0.05245255757691102f, 0.01673209873360605f };
     float acc = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) { const float q = sqrtf(sv[i]); const float t = wv[i] * (in ? Igg1(sc, a, b, c * q, d * q) : Igg0(sc, a, b, c * q, d * q)); acc = i == 0 ? t : acc + t; }
     return ((d != 0.f && c != 0.f) ? signf_(d) : (d == 0.f && c != 0.f) ? signf_(c) : 1.f) * ((in ? Ig1(sc, a, b, c, d) : Ig0(sc, a, b)) - 2.f * acc);
 }

@@ -72,6 +72,7 @@ WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float 
     const bool keep = push && t.s + idx < cap;
     const unsigned km = g_ballot(g, keep);
     int rank = 0;
+    if (__popc(km) > 1) {       // (group-uniform) nothing to order when at most one child passed (etoile-like k_gtraverse -6 %)
     // the eight keys go through shared memory (one store, two 16-B loads) instead of eight shuffles (fewer instructions in the hottest loop: etoile-like k_gtraverse 111 -> 96 ms/step); lanes that do not push publish -inf
     sh.key[g.gl] = keep ? tmin : -WT_INF;
     __syncwarp(g.gmask);
@@ -82,6 +83,7 @@ WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float 
         for (int j = 0; j < kGW; ++j) rank += (kk[j] > tmin || (kk[j] == tmin && j < (int)g.gl)) ? 1 : 0;
     }
     __syncwarp(g.gmask);
+    }
 
     if (keep) { sh.tmin[t.s + rank] = tmin; sh.ptr[t.s + rank] = ch; }
     t.s += __popc(km);
