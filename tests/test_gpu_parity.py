@@ -231,3 +231,20 @@ def test_bdpt_cornell_matches_oracle(flags):
     l2, flux = _film_metrics(img_g, img_o)
     print("bdpt cornell flags=%d: rel-L2 %.3e flux %.3e" % (flags, l2, flux), st["gpu_ms"])
     assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
+
+
+def test_xml_scene_film_matches_oracle():
+    """A scene file in the reference's XML format (tests/data/slit_bench.xml + its include: plt_path forward + UTD past a slit in a gaussian-profile
+    conductor) goes through xml_loader -> wtgpu_scene_desc -> wtgpu_render and matches the oracle on the same tables.
+    (The profile is sigma-parametrised on purpose: with the perceptual-roughness form at this 0.08 mm wavelength sigma^2/k^2 ~ 5e3 and the
+    reference's truncated Box-Mueller takes log((1-s) u + s) with s = 1 - 2e-4, so one ulp of expf moves a sampled direction by 1e-4; floor-bounce
+    paths through the 0.9 mm slit then decorrelate between libm implementations -- tools/xml_diag.py, profiles/r01s3_xml_diag.log.)"""
+    import os
+    from wave_tracer_b200 import xml_loader
+    b = xml_loader.load_scene(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "slit_bench.xml"), {"res": "192", "spp": "8"}).build()
+    blk, lgt, st = render(b, spp=8, allow_overflow=True)
+    oblk, olgt, ost = _oracle.render(b, spp=8)
+    assert st["samples"] == ost["samples"] == 192 * 64 * 8 and olgt.sum() > 0
+    l2, flux = _film_metrics(lgt, olgt)
+    print("xml slit_bench: rel-L2 %.3e flux %.3e" % (l2, flux), st["segments"], ost["segments"])
+    assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)

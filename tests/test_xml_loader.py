@@ -36,7 +36,7 @@ def _slit_bench_api(res=96, spp=4, lam_mm=.08, gap=.9, Zs=-12.0, with_floor=True
     film = Film(res, res // 3, [Discrete(lam)], rfilter_scale=.1)
     sc.sensor = VirtualPlane(lookat((0, 0, (40 - .001) * MM), (0, 0, 2 * MM), (0, -1, 0)), (200 * MM, 200 / 3 * MM), film, alpha=math.radians(.002), samples=spp)
     sc.add_emitter(Spot(lookat((0, 0, -400 * MM), (0, 0, 0), (1, 0, 0)), Discrete(lam, 900.0), cutoff_angle=math.radians(.3), beam_width=math.radians(.15)))
-    mat_screen = TwoSided(SurfaceSPM(IOR=complex(1, 80), profile=Gaussian(roughness=.25)))
+    mat_screen = TwoSided(SurfaceSPM(IOR=complex(1, 80), profile=Gaussian(sigma=50.0)))
     mat_floor = TwoSided(Composite([(1e-6, 1.0, Diffuse(.15))]))
     mat_wall = TwoSided(Diffuse(Binned([(300e-9, 800e-9, .5), (1e-6, 1.0, .85)])))
     def rect(p, x, y, m): sc.add_shape(rectangle(np.array(p) * MM, np.array(x) * MM, np.array(y) * MM), m)

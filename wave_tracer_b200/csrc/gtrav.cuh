@@ -227,8 +227,8 @@ WT_D bool g_query_done(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, 
 
 // The driver loop.  fetch(i, env, prev, lambda) loads item i (group-uniformly); emit(i, rec, tris) stores its result.
 // (A fully warp-uniform variant -- one pop per group per iteration, node steps of all groups in the same instructions -- was measured 8 %
-// SLOWER on the etoile-like scene and on double_slits, profiles/r01s2_notes.md: the lanes idle inside the cone-triangle test, whose
-// early-outs differ per triangle, not between the groups.)
+// SLOWER on the etoile-like scene and on double_slits, and again 6-9 % slower after the code-size work removed the instruction-fetch
+// stall (profiles/r01s3_phases.txt, session V): a group that reaches its leaf early idles through the others' node steps.)
 template <class Fetch, class Emit>
 WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* shm, bool force_rt, bool edge_query, Counters& ctr, Fetch&& fetch, Emit&& emit) {
     GLane g; g.gl = threadIdx.x & 7u; g.gshift = (threadIdx.x & 31u) & 24u; g.gmask = 0xffu << g.gshift;

@@ -15,6 +15,7 @@
 #include "../../include/wthost.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@ using namespace wt;
 // ================================================================================================ state
 constexpr int kMaxHitEdges = kMaxFsdEdges;
 constexpr int kMaxConeTris = WTGPU_MAX_CONE_TRIS;
+constexpr unsigned kBlockT = 128u;
 
 enum : uint32_t { F_SAMPLED_FSD = 1u, F_HAS_FSD = 2u, F_DPD_DISC = 4u };
 
@@ -985,7 +987,12 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     if (!s->hctr) { CK(cudaMallocHost(&s->hctr, sizeof(DevCounters))); CK(cudaEventCreate(&s->ev_begin)); CK(cudaEventCreate(&s->ev_end)); }
     const cudaEvent_t e0 = s->ev_begin, e1 = s->ev_end;
     DevCounters* const hctr = s->hctr;
-    const dim3 blk(128), grd((pool + 127) / 128);
+    // Block size of the one-thread-per-item kernels (generate / resolve / sort / shade / connect).  Their warps run for very different times (a
+    // path with thousands of UTD edges next to paths that die at once), and a block's slots are only handed on when its LAST warp retires:
+    // with one warp per block a finished warp is replaced immediately.  (The group-traversal and Fraunhofer-sampler kernels keep 128: their
+    // shared-memory layout is per 128 threads and they pull work from a cursor anyway.)  WT_BLOCK_T overrides for A/B runs.
+    static const unsigned bt = []() { const char* e = getenv("WT_BLOCK_T"); const unsigned v = e ? (unsigned)atoi(e) : kBlockT; return (v == 32u || v == 64u || v == 128u) ? v : kBlockT; }();
+    const dim3 blk(128), blkT(bt), grd((pool + bt - 1) / bt);
     const bool nosort = (o->flags & WTGPU_RENDER_NO_SORT) != 0;
     uint64_t launches = 0, iters = 0;
     // per-kernel device time: events are only RECORDED inside the loop (no host sync) and resolved after the last iteration
@@ -1036,7 +1043,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         for (int c = 0; c < 5; ++c) b.pair_off[c] = (size_t)P * nmaxv * (size_t)c;      // classes 0-3 hold <= max_depth+3 strategies per sample, class 4 the rest
         const bool has_fsd = s->integ.fsd != 0u;
         CK(cudaMemsetAsync(s->bd_alive, 0, 4ull * P, st));
-        const dim3 gP((P + 127) / 128), gW((W2 + 127) / 128), gC(148 * 8);
+        const dim3 gP((P + bt - 1) / bt), gW((W2 + bt - 1) / bt), gC(148 * 8), gCT(148 * 8 * (128 / bt));
         if (has_fsd && !s->bd_stream) {
             CK(cudaStreamCreateWithFlags(&s->bd_stream, cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&s->bd_ev_shade, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->bd_ev_samp, cudaEventDisableTiming));
@@ -1047,26 +1054,26 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
             b.fl_cur = (uint32_t)(iters % 3ull); b.fl_next = (uint32_t)((iters + 1ull) % 3ull); b.fl_fin = (uint32_t)((iters + 2ull) % 3ull);
             b.tag = 16.f + (float)(iters % 1024ull); b.tag_fin = 16.f + (float)((iters + 1023ull) % 1024ull);
             mark();
-            k_bd_generate<<<gP, blk, 0, st>>>(b); ++launches; mark();
-            if (thread_trav) { k_bd_traverse<<<gW, blk, 0, st>>>(b); ++launches; }
-            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blk, 0, st>>>(b); launches += 2; }
+            k_bd_generate<<<gP, blkT, 0, st>>>(b); ++launches; mark();
+            if (thread_trav) { k_bd_traverse<<<gW, blkT, 0, st>>>(b); ++launches; }
+            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blkT, 0, st>>>(b); launches += 2; }
             mark();
-            k_hist<<<gW, blk, s->n_keys * 4, st>>>(b.r);
+            k_hist<<<gW, blkT, s->n_keys * 4, st>>>(b.r);
             k_scan<<<1, 1024, 0, st>>>(b.r);
-            k_scatter<<<gW, blk, 0, st>>>(b.r); launches += 3; mark();
+            k_scatter<<<gW, blkT, 0, st>>>(b.r); launches += 3; mark();
             k_bd_reset<<<1, 32, 0, st>>>(b);
-            k_bd_shade<<<gW, blk, 0, st>>>(b); launches += 2;
+            k_bd_shade<<<gW, blkT, 0, st>>>(b); launches += 2;
             if (has_fsd) {
                 CK(cudaEventRecord(s->bd_ev_shade, st));
-                if (iters > 0) { CK(cudaStreamWaitEvent(st, s->bd_ev_samp, 0)); k_bd_fsd_finish<<<gW, blk, 0, st>>>(b); ++launches; }
+                if (iters > 0) { CK(cudaStreamWaitEvent(st, s->bd_ev_samp, 0)); k_bd_fsd_finish<<<gW, blkT, 0, st>>>(b); ++launches; }
                 CK(cudaStreamWaitEvent(s->bd_stream, s->bd_ev_shade, 0));
                 CK(cudaMemsetAsync(&s->ctr->fsd_head, 0, sizeof(int), s->bd_stream));
                 k_bd_fsd_sample<<<dim3(148 * 16), blk, 0, s->bd_stream>>>(b); ++launches;
                 CK(cudaEventRecord(s->bd_ev_samp, s->bd_stream));
             }
             mark();
-            k_bd_connect<0><<<gC, blk, 0, st>>>(b); k_bd_connect<1><<<gC, blk, 0, st>>>(b); k_bd_connect<2><<<gC, blk, 0, st>>>(b);
-            k_bd_connect<3><<<gC, blk, 0, st>>>(b); k_bd_connect<4><<<gC, blk, 0, st>>>(b); launches += 5; mark();
+            k_bd_connect<0><<<gCT, blkT, 0, st>>>(b); k_bd_connect<1><<<gCT, blkT, 0, st>>>(b); k_bd_connect<2><<<gCT, blkT, 0, st>>>(b);
+            k_bd_connect<3><<<gCT, blkT, 0, st>>>(b); k_bd_connect<4><<<gCT, blkT, 0, st>>>(b); launches += 5; mark();
             ++iters;
             CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -1077,20 +1084,20 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     } else
     for (;;) {
         mark();
-        k_generate<<<grd, blk, 0, st>>>(a); ++launches; mark();
-        if (use_thread_trav) { k_traverse<<<grd, blk, 0, st>>>(a); ++launches; }
-        else { k_gtraverse<<<dim3(148 * 8), blk, 0, st>>>(a); k_resolve<<<grd, blk, 0, st>>>(a); launches += 2; }
+        k_generate<<<grd, blkT, 0, st>>>(a); ++launches; mark();
+        if (use_thread_trav) { k_traverse<<<grd, blkT, 0, st>>>(a); ++launches; }
+        else { k_gtraverse<<<dim3(148 * 8), blk, 0, st>>>(a); k_resolve<<<grd, blkT, 0, st>>>(a); launches += 2; }
         mark();
         if (nosort) {
-            k_identity_order<<<grd, blk, 0, st>>>(a); ++launches;
+            k_identity_order<<<grd, blkT, 0, st>>>(a); ++launches;
         } else {
-            k_hist<<<grd, blk, s->n_keys * 4, st>>>(a);
+            k_hist<<<grd, blkT, s->n_keys * 4, st>>>(a);
             k_scan<<<1, 1024, 0, st>>>(a);
-            k_scatter<<<grd, blk, 0, st>>>(a); launches += 3;
+            k_scatter<<<grd, blkT, 0, st>>>(a); launches += 3;
         }
         mark();
         k_reset_trav<<<1, 32, 0, st>>>(a);
-        k_shade<<<grd, blk, 0, st>>>(a); launches += 2; mark();
+        k_shade<<<grd, blkT, 0, st>>>(a); launches += 2; mark();
         ++iters;
         CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
