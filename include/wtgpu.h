@@ -120,7 +120,7 @@ typedef struct wtgpu_spectrum {
 } wtgpu_spectrum;
 
 /* ---------------------------------------------------------------------------------------------
- * BSDFs.  bsdf_t implementations (include/wt/bsdf/*.hpp, src/bsdf/*.cpp) flattened to a node array;
+ * BSDFs.  bsdf_t implementations (include/wt/bsdf/<all>.hpp, src/bsdf/<all>.cpp) flattened to a node array;
  * wrappers reference their nested node by index.
  * ------------------------------------------------------------------------------------------- */
 #define WTGPU_BSDF_DIFFUSE     0u   /* src/bsdf/diffuse.cpp      spec[0]=reflectance                       */
@@ -149,7 +149,7 @@ typedef struct wtgpu_bsdf {
 typedef struct wtgpu_bsdf_bin { float kmin, kmax; int32_t child; uint32_t pad_; } wtgpu_bsdf_bin;
 
 /* ---------------------------------------------------------------------------------------------
- * Emitters (include/wt/emitter/{point,spot,directional,area}.hpp, src/emitter/*.cpp).
+ * Emitters (include/wt/emitter/{point,spot,directional,area}.hpp, src/emitter/<all>.cpp).
  * ------------------------------------------------------------------------------------------- */
 #define WTGPU_EMITTER_POINT       0u
 #define WTGPU_EMITTER_SPOT        1u
