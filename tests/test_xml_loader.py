@@ -96,3 +96,45 @@ def test_reference_double_slits_xml_equals_procedural_restatement():
     assert bytes(d1.sensor) == bytes(d2.sensor) and bytes(d1.integrator) == bytes(d2.integrator)
     o1 = _oracle.render(b1, spp=4, threads=1); o2 = _oracle.render(b2, spp=4, threads=1)
     assert o1[1].sum() > 0 and np.array_equal(o1[0], o2[0]) and np.array_equal(o1[1], o2[1])
+
+
+REF_ETOILE = "/root/reference/scenes/sionna_etoile/etoile.xml"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ETOILE), reason="reference tree not mounted (GPU box)")
+def test_reference_etoile_xml_matches_the_restatement_outside_its_meshes():
+    """BASELINE configs[3]: every shape of etoile.xml is a PLY mesh (Git-LFS stubs) -- missing_meshes="skip" lists all 563 and loads the rest.
+    Integrator, coverage sensor, the 10 GHz point emitter and the five ITU materials equal what scenes.etoile_like() restates; the file's three
+    optical emitters (D65 / D55 illuminants) carry no power at the sensor's wavenumber."""
+    from wave_tracer_b200 import TwoSided, Composite, SurfaceSPM, ITU, Diffuse, Const, Point, Directional
+    sc = xml_loader.load_scene(REF_ETOILE, {"res": "720", "spp": "1024", "wavelength": "10GHz"}, missing_meshes="skip")
+    ref = scenes.etoile_like(res=720, spp=1024)
+    assert len(sc.skipped_shapes) == 563 and sc.skipped_shapes[0] == ("mesh-Plane", "meshes/Plane.ply") and len(sc.shapes) == 0
+    assert vars(sc.integrator) == vars(ref.integrator)
+    s, r = sc.sensor, ref.sensor
+    assert type(s) is type(r) and np.array_equal(s.to_world, r.to_world) and tuple(s.extent) == tuple(r.extent) and s.alpha == r.alpha and s.samples == r.samples and s.rt == r.rt
+    assert (s.film.width, s.film.height, s.film.rfilter_scale) == (r.film.width, r.film.height, r.film.rfilter_scale) and s.film.response[0].lines == r.film.response[0].lines
+    e, q = sc.emitters[0], ref.emitters[0]
+    assert isinstance(e, Point) and tuple(e.position) == tuple(q.position) and e.spectrum.lines == q.spectrum.lines and e.pse == q.pse
+    assert len(sc.emitters) == 4 and isinstance(sc.emitters[2], Directional)
+    k = np.array([s.film.response[0].lines[0][0]], np.float64)
+    for extra in sc.emitters[1:]:
+        assert np.all(extra.spectrum.value(k) == 0)
+    for m in ("marble", "metal", "brick", "wood", "concrete"):
+        b = sc.xml_bsdfs["mat-itu_" + m]
+        assert isinstance(b, TwoSided) and isinstance(b.nested, Composite) and len(b.nested.bins) == 2
+        lo, hi, radio = b.nested.bins[1]
+        assert (lo, hi) == (pytest.approx(.1e-3), pytest.approx(1.0)) and isinstance(radio, SurfaceSPM) and isinstance(radio.IOR, ITU) and radio.IOR.params == ITU.TABLE[m]
+        assert isinstance(radio.ts, Const) and radio.ts.v == 0
+    with pytest.raises(xml_loader.SceneXmlError, match="missing_meshes"):
+        xml_loader.load_scene(REF_ETOILE, {"wavelength": "10GHz"})
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not mounted (GPU box)")
+def test_reference_double_slits_and_reflectors_xml_loads():
+    """The plt_path-forward sibling of BASELINE configs[1] (what `bench.py --integrator plt_path` restates) loads and renders on the oracle."""
+    sc = xml_loader.load_scene(os.path.join(os.path.dirname(REF), "double_slits_and_reflectors.xml"), {"res": "64", "spp": "2"})
+    assert type(sc.integrator).__name__ == "PltPath" and sc.integrator.direction == "forward"
+    b = sc.build()
+    o = _oracle.render(b, spp=2, threads=1)
+    assert o[2]["samples"] == 64 * 16 * 2 and o[1].sum() > 0

@@ -14,7 +14,7 @@ procedural parts of the others; anything else raises SceneXmlError naming the el
                                      integer samples, <film type=array> (width, height, rfilter_scale, <response type=monochromatic>)
   <emitter type=spot|point|directional|area>
   <bsdf type=twosided|diffuse|dielectric|surface_spm|composite|scale> (+ id / <ref id>), <surface_profile type=dirac|fractal|gaussian>
-  <spectrum constant=|rgb=|blackbody=|type=discrete|composite|piecewise_linear(uniform)>
+  <spectrum constant=|rgb=|blackbody=|ITU=|emitter=(illuminant)|type=discrete|composite>
   <shape type=rectangle|cube|sphere> point p/x/y, transform to_world, boolean enabled, nested bsdf / ref / area emitter
 
 `rgb=` spectra (the reference upsamples RGB to a spectrum) are represented by an object that refuses to be evaluated: the microwave /
@@ -150,6 +150,18 @@ class RGBSpectrum(S.Spectrum):
         raise SceneXmlError("rgb spectra are not supported at the wavenumbers this sensor queries")
 
 
+class IlluminantSpectrum(S.Spectrum):
+    """`emitter="D65"` etc. (CIE standard illuminants, tabulated over the visible range in the reference's data/): zero outside 300-830 nm, which is
+    all a microwave sensor ever asks; evaluating it inside the visible range is an error (the tables are not restated)."""
+    def __init__(self, name, scale=1.0): self.name, self.scale = name, scale
+    def value(self, k):
+        k = np.asarray(k, np.float64)
+        kvis_lo, kvis_hi = S.wavelen_to_wavenum(830e-9), S.wavelen_to_wavenum(300e-9)
+        if np.any((k >= kvis_lo) & (k <= kvis_hi)):
+            raise SceneXmlError(f"illuminant {self.name} is not tabulated: only sensors outside the visible range can carry it")
+        return np.zeros(k.shape, np.complex128)
+
+
 def _subst(text, defines):
     def rep(m):
         name = m.group(1)
@@ -172,7 +184,8 @@ def _parse_file(path):
 
 
 class _Loader:
-    def __init__(self, path, defines):
+    def __init__(self, path, defines, missing_meshes="error"):
+        self.missing_meshes, self.skipped = missing_meshes, []
         self.dir = os.path.dirname(os.path.abspath(path))
         self.root = _parse_file(path)
         if self.root.tag != "scene":
@@ -201,6 +214,13 @@ class _Loader:
                 self._expand_includes(ch, base)
 
     # ---- helpers
+    @staticmethod
+    def _point(p):
+        """<point name=... x= y= z=/> or <point name=... value="x, y, z"/> (lengths)."""
+        if "value" in p.attrib:
+            return [float(v) for v in qvec(p.attrib["value"], "len", 3)]
+        return [quantity(p.attrib.get(a, "0"), "len") for a in "xyz"]
+
     @staticmethod
     def _named(node, tag, name):
         for ch in node.findall(tag):
@@ -250,7 +270,7 @@ class _Loader:
         M = np.eye(4)
         for it in node:
             if it.tag == "translate":
-                M = S.translate([quantity(it.attrib.get(a, "0"), "len") for a in "xyz"]) @ M
+                M = S.translate(self._point(it)) @ M
             elif it.tag == "scale":
                 if "value" in it.attrib: v = float(evaluate(it.attrib["value"])); M = S.scale((v, v, v)) @ M
                 else: M = S.scale([float(evaluate(it.attrib.get(a, "1"))) for a in "xyz"]) @ M
@@ -274,6 +294,12 @@ class _Loader:
             return RGBSpectrum(qvec(a["rgb"], None, 3))
         if "blackbody" in a:
             return S.Blackbody(quantity(a["blackbody"], "temp"), scale)
+        if "ITU" in a:
+            if a["ITU"] not in S.ITU.TABLE: raise SceneXmlError(f'<spectrum ITU="{a["ITU"]}">: unknown ITU-R P.2040 material')
+            if scale != 1.0: raise SceneXmlError("scaled ITU spectra are not supported")
+            return S.ITU(a["ITU"])
+        if "emitter" in a:
+            return IlluminantSpectrum(a["emitter"], scale)
         t = a.get("type")
         if t == "discrete":
             return S.Discrete(quantity(a["wavelength"], "wavelength"), float(evaluate(a.get("value", "1"))) * scale)
@@ -399,7 +425,7 @@ class _Loader:
             return S.Spot(self.transform(tw_node), self._spectrum_child(node, "radiant_intensity"), phase_space_extent_scale=pse, **kw)
         if t == "point":
             p = self._named(node, "point", "position")
-            pos = [quantity(p.attrib.get(a, "0"), "len") for a in "xyz"] if p is not None else [0, 0, 0]
+            pos = self._point(p) if p is not None else [0, 0, 0]
             return S.Point(pos, self._spectrum_child(node, "radiant_intensity"), phase_space_extent_scale=pse)
         if t == "directional":
             return S.Directional(self._spectrum_child(node, "irradiance"), self.transform(tw_node) if tw_node is not None else None, phase_space_extent_scale=pse)
@@ -414,7 +440,7 @@ class _Loader:
         def pt(name):
             p = self._named(node, "point", name)
             if p is None: raise SceneXmlError(f"{t} shape: point '{name}' must be provided")
-            return np.array([quantity(p.attrib.get(a, "0"), "len") for a in "xyz"])
+            return np.array(self._point(p))
         if t == "rectangle":
             mesh = S.rectangle(pt("p"), pt("x"), pt("y"), to_world=tw)
         elif t == "cube":
@@ -422,10 +448,16 @@ class _Loader:
         elif t == "sphere":
             r = self._quantity(node, "radius", "len", 1.0)
             c = self._named(node, "point", "center")
-            centre = [quantity(c.attrib.get(a, "0"), "len") for a in "xyz"] if c is not None else (0, 0, 0)
+            centre = self._point(c) if c is not None else (0, 0, 0)
             mesh = S.sphere(r, centre, to_world=tw)
+        elif t in ("ply", "obj") and self.missing_meshes == "skip":
+            fn = self._named(node, "string", "filename") or self._named(node, "path", "filename")
+            self.skipped.append((node.attrib.get("id", "?"), fn.attrib.get("value") if fn is not None else "?"))
+            for ch in node.findall("bsdf"): self.bsdf(ch)          # nested materials may carry ids other shapes refer to
+            return None
         else:
-            raise SceneXmlError(f"<shape type={t!r}> is not supported (ply/obj meshes are Git-LFS stubs in the reference tree)")
+            raise SceneXmlError(f"<shape type={t!r}> is not supported (ply/obj meshes are Git-LFS stubs in the reference tree; "
+                                "missing_meshes=\"skip\" loads the rest of the scene and lists them)")
         bs = [self.bsdf(ch) for ch in node.findall("bsdf")] + [self._ref(ch) for ch in node.findall("ref")]
         if len(bs) != 1: raise SceneXmlError("a shape needs exactly one bsdf (nested or <ref>)")
         em = node.find("emitter")
@@ -434,9 +466,9 @@ class _Loader:
     def build(self, lut=(2048, 1024), sensor_id=None):
         sc = S.Scene()
         root = self.root
-        integ = root.find("integrator")
-        if integ is None: raise SceneXmlError("no <integrator>")
-        sc.integrator = self.integrator(integ, lut)
+        integs = [i for i in root.findall("integrator") if self._enabled(i)]
+        if len(integs) != 1: raise SceneXmlError(f"{len(integs)} enabled <integrator> elements; exactly one is needed")
+        sc.integrator = self.integrator(integs[0], lut)
         sensors = [s for s in root.findall("sensor") if self._enabled(s) and (sensor_id is None or s.attrib.get("id") == sensor_id)]
         if len(sensors) != 1:
             raise SceneXmlError(f"{len(sensors)} enabled sensors; exactly one is rendered per call (select with sensor_id)")
@@ -447,7 +479,9 @@ class _Loader:
             if self._enabled(e): sc.add_emitter(self.emitter(e))
         for sh in root.findall("shape"):
             if not self._enabled(sh): continue
-            mesh, bsdf, em = self.shape(sh)
+            r = self.shape(sh)
+            if r is None: continue
+            mesh, bsdf, em = r
             sc.add_shape(mesh, bsdf, emitter=em)
         known = {"default", "integrator", "sensor", "bsdf", "emitter", "shape", "sampler"}
         for ch in root:
@@ -458,12 +492,15 @@ class _Loader:
             t = smp.attrib.get("type")
             if t in ("sobolld", "sobol"): sc.sampler = S.Sobolld()
             elif t not in ("uniform", "independent"): raise SceneXmlError(f"<sampler type={t!r}> is not supported")
+        sc.xml_bsdfs = dict(self.bsdfs)             # materials by id, as <ref> resolves them
+        sc.skipped_shapes = list(self.skipped)      # (id, file) of mesh shapes left out under missing_meshes="skip"
         return sc
 
 
-def load_scene(path, defines=None, lut=(2048, 1024), sensor_id=None):
-    """`wave_tracer render scene.xml -D k=v,...` front half: returns a scene.Scene (call .build() for the wtgpu_scene_desc tables)."""
-    return _Loader(path, defines).build(lut=lut, sensor_id=sensor_id)
+def load_scene(path, defines=None, lut=(2048, 1024), sensor_id=None, missing_meshes="error"):
+    """`wave_tracer render scene.xml -D k=v,...` front half: returns a scene.Scene (call .build() for the wtgpu_scene_desc tables).
+    missing_meshes="skip": ply/obj shapes (Git-LFS stubs in the reference tree) are left out and listed in scene.skipped_shapes."""
+    return _Loader(path, defines, missing_meshes).build(lut=lut, sensor_id=sensor_id)
 
 
 def parse_defines(s):
