@@ -55,8 +55,15 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import atexit
+            atexit.register(self._kill)             # never leave the poller behind, whatever ends this process
         except Exception:
             self.proc = None
+    def _kill(self):
+        try:
+            if self.proc is not None and self.proc.poll() is None: self.proc.kill()
+        except Exception:
+            pass
     def summary(self):
         samples, reasons, maxmhz = [], set(), None
         if self.proc is not None:
