@@ -89,6 +89,19 @@ int oracle_sobol_batch(const wtgpu_sobol_entry* table, uint64_t seed, uint64_t b
     for (size_t i = 0; i < v.size(); ++i) { if (out_values) out_values[i] = v[i]; if (out_numerators) out_numerators[i] = num[i]; }
     return (int)(v.size() / sobol::D);
 }
+// the same with explicit per-dimension seeds (what the reference draws from its RNG), and the seeds our contract derives for a batch:
+// the hooks that let tests/test_sobol.py put the restatement next to the reference's own code (oracle/_ref/libref_sobol.so)
+int oracle_sobol_points_with_seeds(const wtgpu_sobol_entry* table, const uint64_t* seeds, uint32_t n_points, uint32_t* out_numerators, float* out_values) {
+    if (!table || !seeds) return -1;
+    sobol::gf3_t gf3(table);
+    sobol::sobolls_sampler gen(sobol::N, gf3);
+    uint64_t sd[sobol::D]; for (size_t i = 0; i < sobol::D; ++i) sd[i] = seeds[i];
+    std::vector<float> v; std::vector<uint32_t> num;
+    gen.generate_points(sd, n_points, v, &num);
+    for (size_t i = 0; i < v.size(); ++i) { if (out_values) out_values[i] = v[i]; if (out_numerators) out_numerators[i] = num[i]; }
+    return (int)(v.size() / sobol::D);
+}
+void oracle_sobol_seeds(uint64_t seed, uint64_t batch, uint64_t* out) { sobol_ctx_t::seeds_for_batch(seed, batch, out); }
 // generator matrices as gen_mat builds them: out[dim][row][col], 47 x 11 x 11 digits
 int oracle_sobol_matrices(const wtgpu_sobol_entry* table, int32_t* out) {
     if (!table) return -1;

@@ -18,6 +18,8 @@ int oracle_intersect_rays_bruteforce(const wtgpu_scene_desc* desc, uint32_t n, c
 int oracle_intersect_cones(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_cone_query* q, wtgpu_cone_hit* out);
 int oracle_cone_closest_bruteforce(const wtgpu_scene_desc* desc, uint32_t n, const wtgpu_cone_query* q, float* dist);
 int oracle_sobol_batch(const wtgpu_sobol_entry* table, uint64_t seed, uint64_t batch, uint32_t n_points, uint32_t* out_numerators, float* out_values);
+int oracle_sobol_points_with_seeds(const wtgpu_sobol_entry* table, const uint64_t* seeds, uint32_t n_points, uint32_t* out_numerators, float* out_values);
+void oracle_sobol_seeds(uint64_t seed, uint64_t batch, uint64_t* out /* 47 */);
 int oracle_sobol_matrices(const wtgpu_sobol_entry* table, int32_t* out);
 int oracle_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out);
 void oracle_svd(const float A[4], float out[6]);

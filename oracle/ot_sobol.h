@@ -8,6 +8,9 @@
 // All of it is integer arithmetic: the device generator (wave_tracer_b200/csrc/dsobol.cuh, which computes a point directly
 // from its index instead of incrementally) must reproduce the digit values BIT-EXACTLY (tests/test_sobol.py).
 //
+// PINNED against the reference's own code: those three headers compile unmodified into oracle/_ref/libref_sobol.so (oracle/ref_sobol.cpp, `make ref`)
+// and tests/test_sobol.py::test_oracle_sobol_equals_the_reference_code compares matrices and points bit for bit.
+//
 // The table data/sobolld/initIrreducibleGF3.dat is a Git-LFS pointer stub in the reference tree: the table is
 // an input here (wtgpu_sobol_entry[48]), so the index / digit / scramble math is pinned for any table.
 #pragma once

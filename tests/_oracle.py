@@ -50,6 +50,8 @@ def lib():
         L.oracle_profile_check.argtypes = [C.POINTER(A.SceneDesc), C.c_int32, C.POINTER(C.c_float), C.c_float, C.c_uint32, C.c_uint64, C.POINTER(C.c_float)]
         L.oracle_fuzz_cone_quick_reject.argtypes = [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]
         L.oracle_fuzz_ray_cull.argtypes = [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.oracle_sobol_points_with_seeds.argtypes = [C.POINTER(A.SobolEntry), C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.oracle_sobol_seeds.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 

@@ -6,6 +6,7 @@ properties the construction guarantees for ANY valid table: each dimension of a 
 numerators (a (0,11,1)-net), consecutive blocks of 3^m points stratify 3^m intervals, and the scrambling is a pure function of
 (seed, dimension, batch)."""
 import ctypes as C
+import os
 import numpy as np
 import pytest
 
@@ -126,3 +127,57 @@ def test_gpu_render_with_sobolld_matches_oracle(integrator):
     assert st["samples"] == ost["samples"]
     num = np.linalg.norm(blk.astype(np.float64) - oblk); den = np.linalg.norm(oblk)
     assert den > 0 and num / den <= 5e-3, num / den         # rel-L2 tolerance of the uniform-sampler parity tests (f32 path math + f32 film atomics vs f64 film)
+
+
+# ------------------------------------------------------------------------------------------------ pinned against the reference's own code
+REF_SOBOL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_sobol.so")
+
+
+def _write_dat(path, table):
+    """initIrreducibleGF3.dat layout (irreducible_gf3.hpp:124-158): a header line starting with 'd', then one line `d sj aj mk...` per entry."""
+    with open(path, "w") as f:
+        f.write("d sj aj mk\n")
+        for d, sj, aj, mk in table:
+            f.write(" ".join(str(v) for v in [d, sj, aj] + list(mk)) + "\n")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SOBOL), reason="oracle/_ref/libref_sobol.so is built from /root/reference (this container only)")
+def test_oracle_sobol_equals_the_reference_code(tmp_path):
+    """The restatement (oracle/ot_sobol.h) against the REFERENCE'S OWN sobolld headers, compiled unmodified into oracle/_ref/libref_sobol.so
+    (oracle/ref_sobol.cpp + two shim headers): the table file goes through the reference's parser, generator matrices and 3^8 points x 47
+    dimensions are compared BIT FOR BIT, for the seeds of our batch contract and for arbitrary ones.  Together with the golden fixture
+    (tests/golden: oracle numerators for seed 0x5EED, batch 0) and the GPU test of the device generator against the oracle, this pins the
+    Sobol index / digit / scramble math end to end."""
+    R = C.CDLL(REF_SOBOL)
+    R.ref_sobol_points.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_float)]
+    R.ref_sobol_matrices.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
+    L = _oracle.lib()
+    table = sobol.default_table()
+    dat = str(tmp_path / "initIrreducibleGF3.dat"); _write_dat(dat, table)
+    assert sobol.load_table(dat) == [(d, sj, aj, list(mk)) for d, sj, aj, mk in table]
+    abi = sobol.to_abi(table)
+    m_ref = np.zeros(47 * 11 * 11, np.int32); m_or = np.zeros_like(m_ref)
+    assert R.ref_sobol_matrices(dat.encode(), m_ref.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    assert L.oracle_sobol_matrices(abi, m_or.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    assert np.array_equal(m_ref, m_or) and m_ref.any()
+    n = 3 ** 8
+    rng = np.random.default_rng(11)
+    seed_sets = []
+    s0 = np.zeros(47, np.uint64); L.oracle_sobol_seeds(0x5EED, 0, s0.ctypes.data_as(C.POINTER(C.c_uint64))); seed_sets.append(s0)
+    s1 = np.zeros(47, np.uint64); L.oracle_sobol_seeds(0x5EED, 3, s1.ctypes.data_as(C.POINTER(C.c_uint64))); seed_sets.append(s1)
+    seed_sets.append(rng.integers(0, 2 ** 32, 47, dtype=np.uint64))          # what the reference feeds it: uniform_int_distribution<unsigned>
+    seed_sets.append(rng.integers(0, 2 ** 63, 47, dtype=np.uint64))
+    for seeds in seed_sets:
+        seeds = np.ascontiguousarray(seeds, np.uint64)
+        v_ref = np.zeros(n * 47, np.float32); v_or = np.zeros(n * 47, np.float32); num = np.zeros(n * 47, np.uint32)
+        assert R.ref_sobol_points(dat.encode(), seeds.ctypes.data_as(C.POINTER(C.c_uint64)), n, v_ref.ctypes.data_as(C.POINTER(C.c_float))) == n
+        assert L.oracle_sobol_points_with_seeds(abi, seeds.ctypes.data_as(C.POINTER(C.c_uint64)), n, num.ctypes.data_as(C.POINTER(C.c_uint32)), v_or.ctypes.data_as(C.POINTER(C.c_float))) == n
+        assert np.array_equal(v_ref.view(np.uint32), v_or.view(np.uint32))                  # bit-identical floats
+        assert np.array_equal(np.float32(num) / np.float32(3 ** 11), v_ref)                 # value = numerator / 3^M (integer3.hpp:48-50)
+        assert len(np.unique(v_ref.reshape(n, 47)[:, 0])) == n                              # a (0,8,1)-net in base 3: all first coordinates distinct
+    # the frozen golden numerators (oracle, seed 0x5EED, batch 0) are what the reference code produces for those seeds
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden.npz"))
+    g = G["sobol/numerators_seed5EED_batch0_81pts"]
+    v_ref = np.zeros(81 * 47, np.float32)
+    assert R.ref_sobol_points(dat.encode(), np.ascontiguousarray(seed_sets[0]).ctypes.data_as(C.POINTER(C.c_uint64)), 81, v_ref.ctypes.data_as(C.POINTER(C.c_float))) == 81
+    assert np.array_equal(np.float32(g) / np.float32(3 ** 11), v_ref.reshape(81, 47))
