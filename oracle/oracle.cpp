@@ -192,6 +192,17 @@ void oracle_fresnel(float eta_re, float eta_im, const float w[3], float out[12])
     out[4] = f.ts.real(); out[5] = f.ts.imag(); out[6] = f.tp.real(); out[7] = f.tp.imag();
     out[8] = f.Ts; out[9] = f.Tp; out[10] = f.Z; out[11] = f.t.z;
 }
+void oracle_fresnel_full(float eta_re, float eta_im, const float w[3], float out[16]) {
+    const auto f = fresnel(c_t{ eta_re, eta_im }, v3{ w[0], w[1], w[2] });
+    out[0] = f.rs.real(); out[1] = f.rs.imag(); out[2] = f.rp.real(); out[3] = f.rp.imag();
+    out[4] = f.ts.real(); out[5] = f.ts.imag(); out[6] = f.tp.real(); out[7] = f.tp.imag();
+    out[8] = f.Ts; out[9] = f.Tp; out[10] = f.Z; out[11] = f.t.x; out[12] = f.t.y; out[13] = f.t.z; out[14] = f.eta_12.real(); out[15] = f.eta_12.imag();
+}
+void oracle_fresnel_reflection(float eta_re, float eta_im, const float w[3], float out[4]) {
+    const auto f = fresnel_reflection(c_t{ eta_re, eta_im }, v3{ w[0], w[1], w[2] });
+    out[0] = f.rs.real(); out[1] = f.rs.imag(); out[2] = f.rp.real(); out[3] = f.rp.imag();
+}
+void oracle_reflect(const float w[3], float out[3]) { const v3 r = reflect(v3{ w[0], w[1], w[2] }); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
 // minimum-uncertainty sourcing: returns sbp (beam_geometry.hpp:43-47) of source_mub_from(length, k)
 float oracle_mub_sbp(float length, float k) {
     const auto g = sourcing_geometry_t::source_mub_from_length(length, k);
@@ -359,6 +370,15 @@ float oracle_fraunhofer_asf(uint32_t n, const float* edges, float xix, float xiy
     ffsd::aperture_t ap;
     for (uint32_t i = 0; i < n; ++i) { const float* e = edges + 8 * i; ap.edges.push_back({ { e[0], e[1] }, { e[2], e[3] }, { e[4], e[5] }, { e[6], e[7] } }); }
     return ap.ASF_unclamped({ xix, xiy });
+}
+
+// everything fsd.hpp defines, for one aperture and one xi -- same layout as oracle/ref_fsd.cpp's ref_fsd_eval
+void oracle_fsd_eval(uint32_t n, const float* edges, float P0v, float psi02, float xix, float xiy, float out[9]) {
+    ffsd::aperture_t ap; ap.P0 = P0v; ap.psi02 = psi02;
+    for (uint32_t i = 0; i < n; ++i) { const float* e = edges + 8 * i; ap.edges.push_back({ { e[0], e[1] }, { e[2], e[3] }, { e[4], e[5] }, { e[6], e[7] } }); }
+    const v2 xi{ xix, xiy };
+    out[0] = ap.ASF_unclamped(xi); out[1] = ap.ASF(xi); out[2] = ap.sampling_density(xi); out[3] = ffsd::chi_e(xi); out[4] = ffsd::chi_0(xi);
+    out[5] = n ? ffsd::Pj(ap.edges[0]) : 0.f; out[6] = two_pi * sqr(ffsd::P0_sigma) * ap.psi02; out[7] = ffsd::alpha1(xi.x, xi.y); out[8] = ffsd::alpha2(xi.x, xi.y);
 }
 
 } // extern "C"

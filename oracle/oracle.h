@@ -26,6 +26,9 @@ void oracle_svd(const float A[4], float out[6]);
 void oracle_utdf(float x, float out[2]);
 void oracle_cerfc_rot45(double s, double out[2]);
 void oracle_fresnel(float eta_re, float eta_im, const float w[3], float out[12]);
+void oracle_fresnel_full(float eta_re, float eta_im, const float w[3], float out[16]);
+void oracle_fresnel_reflection(float eta_re, float eta_im, const float w[3], float out[4]);
+void oracle_reflect(const float w[3], float out[3]);
 float oracle_mub_sbp(float length, float k);
 float oracle_bsdf_albedo(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], float k, uint32_t n, uint64_t seed);
 void oracle_profile_eval(const wtgpu_scene_desc* desc, int32_t bsdf, const float wi[3], const float wo[3], float k, float out[3]);
@@ -34,6 +37,7 @@ void oracle_fuzz_cone_quick_reject(uint32_t n, uint64_t seed, uint64_t out[4]);
 void oracle_fuzz_ray_cull(uint32_t n, uint64_t seed, uint64_t out[4]);
 void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], const float o[3], const float d[3], float tan_alpha, float out[8]);
 float oracle_fraunhofer_asf(uint32_t n, const float* edges, float xix, float xiy);
+void oracle_fsd_eval(uint32_t n, const float* edges, float P0v, float psi02, float xix, float xiy, float out[9]);
 float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]);
 #ifdef __cplusplus
 }

@@ -1,17 +1,76 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.
-// Build shim for oracle/_ref: stands in for /root/reference/include/wt/math/common.hpp (glm / mp-units) with the handful of names the
-// reference's sobolld_sampler.hpp uses: f_t (the f32 build, CMakeLists.txt:214-216), limits<>, m::pow / ceil / log / min.
+// Build shim for oracle/_ref: stands in for /root/reference/include/wt/math/common.hpp (an umbrella over glm and mp-units, both absent here --
+// SURVEY.md 8c) with just the names the reference headers compiled into oracle/_ref use, so that those headers compile UNMODIFIED from where
+// they lie.  Everything here has textbook semantics (std::complex, a 3-float vector, std::sqrt ...) except m::dot, which is the fma chain of
+// the reference's include/wt/math/vecmath.hpp:21-66 as ot_math.h restates it.  The formulas under test are the reference's own text.
 #pragma once
 #include <cmath>
 #include <cstddef>
+#include <complex>
 #include <limits>
 #include <algorithm>
 namespace wt {
-using f_t = float;
+using f_t = float;                                   // the f32 build (CMakeLists.txt:214-216)
+using c_t = std::complex<f_t>;
 template <typename T> using limits = std::numeric_limits<T>;
+
+// glm::vec2 / glm::mat2 as fsd.hpp uses them: mat2(c0, c1) takes COLUMNS; vec * mat is the row vector times the matrix,
+// (v.x*m[0].x + v.y*m[0].y, v.x*m[1].x + v.y*m[1].y) (glm/detail/type_mat2x2.inl), plain multiply-adds
+struct vec2_t {
+    f_t x{}, y{};
+    constexpr vec2_t() = default;
+    constexpr vec2_t(f_t x_, f_t y_) : x(x_), y(y_) {}
+    constexpr vec2_t& operator/=(f_t s) { x /= s; y /= s; return *this; }
+};
+struct mat2_t {
+    vec2_t c[2];
+    constexpr mat2_t(vec2_t c0, vec2_t c1) : c{ c0, c1 } {}
+};
+constexpr vec2_t operator*(vec2_t v, const mat2_t& m) { return { v.x * m.c[0].x + v.y * m.c[0].y, v.x * m.c[1].x + v.y * m.c[1].y }; }
+namespace u::ang { inline constexpr f_t rad = 1; }      // mp-units' radian: angles are plain f_t here
+
+struct vec3_t {
+    f_t x{}, y{}, z{};
+    constexpr vec3_t() = default;
+    constexpr vec3_t(f_t x_, f_t y_, f_t z_) : x(x_), y(y_), z(z_) {}
+};
+constexpr vec3_t operator+(vec3_t a, vec3_t b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+constexpr vec3_t operator-(vec3_t a, vec3_t b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+constexpr vec3_t operator*(f_t s, vec3_t a) { return { s * a.x, s * a.y, s * a.z }; }
+constexpr vec3_t operator*(vec3_t a, f_t s) { return { a.x * s, a.y * s, a.z * s }; }
+// unit vector (include/wt/math/unit_vector/unit_vector.hpp): a vec3 with explicit construction from one
+struct dir3_t : vec3_t {
+    constexpr dir3_t() = default;
+    constexpr dir3_t(f_t x_, f_t y_, f_t z_) : vec3_t(x_, y_, z_) {}
+    constexpr explicit dir3_t(const vec3_t& v) : vec3_t(v) {}
+    constexpr dir3_t operator-() const { return dir3_t{ -x, -y, -z }; }
+};
+
 namespace m {
 template <typename T> constexpr T pow(T base, std::size_t e) noexcept { T r = 1; for (std::size_t i = 0; i < e; ++i) r *= base; return r; }
-using std::ceil; using std::log;
+using std::ceil; using std::log; using std::abs;
 template <typename T> constexpr T min(T a, T b) noexcept { return std::min(a, b); }
+template <typename T> constexpr T max(T a, T b) noexcept { return std::max(a, b); }
+template <typename T> constexpr T sqr(T v) noexcept { return v * v; }
+inline f_t sqrt(f_t v) noexcept { return std::sqrt(v); }
+inline c_t sqrt(c_t v) noexcept { return std::sqrt(v); }                 // common.hpp:38-40: glm::sqrt(c) == std::sqrt
+inline constexpr f_t two_pi = f_t(2. * 3.141592653589793238462643383279502884);            // math/defs.hpp:40
+inline constexpr f_t inv_two_pi = f_t(0.318309886183790671537767526745028724 / 2.);        // math/defs.hpp:49
+inline f_t cos(f_t v) noexcept { return std::cos(v); }
+inline f_t exp(f_t v) noexcept { return std::exp(v); }
+// common.hpp:414-434 ("From boost")
+inline f_t sinc(const f_t x) noexcept {
+    constexpr f_t taylor_0_bound = std::numeric_limits<f_t>::epsilon();
+    constexpr f_t taylor_2_bound = static_cast<f_t>(0.00034526698300124390839884978618400831996329879769945L);
+    constexpr f_t taylor_n_bound = static_cast<f_t>(0.018581361171917516667460937040007436176452688944747L);
+    if (std::abs(x) >= taylor_n_bound) return std::sin(x) / x;
+    f_t result = 1;
+    if (std::abs(x) >= taylor_0_bound) { const f_t x2 = x * x; result -= x2 / f_t(6); if (std::abs(x) >= taylor_2_bound) result += (x2 * x2) / f_t(120); }
+    return result;
+}
+inline f_t dot(const vec2_t& a, const vec2_t& b) noexcept { return std::fma(a.y, b.y, a.x * b.x); }                          // vecmath.hpp:21-66
+inline f_t length2(const vec2_t& v) noexcept { return dot(v, v); }
+inline f_t dot(const vec3_t& a, const vec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }   // vecmath.hpp:21-66
+inline dir3_t normalize(const vec3_t& v) noexcept { const f_t l = std::sqrt(dot(v, v)); return dir3_t{ v.x / l, v.y / l, v.z / l }; }
 }
 }

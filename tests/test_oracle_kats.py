@@ -2,6 +2,7 @@
 and cannot be compiled here -> parity is UNPINNED by the reference; these are the pins we do have:
 physics identities, brute-force cross-checks of the BVH traversal, scipy for the complex error function."""
 import ctypes as C
+import os
 import math
 import numpy as np
 import pytest
@@ -314,3 +315,76 @@ def test_product_shortcuts_drop_nothing_the_reference_accepts():
         assert out[0] > 1000000 and out[1] > 100000 and out[2] > 100000 and out[3] == 0, list(out)
         L.oracle_fuzz_ray_cull(1500000, seed, out)
         assert out[1] > 10000 and out[2] > 10000 and out[3] == 0, list(out)
+
+
+REF_FRESNEL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_fresnel.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FRESNEL), reason="oracle/_ref/libref_fresnel.so is built from /root/reference (this container only)")
+def test_fresnel_equals_the_reference_code():
+    """ot_polar.h's reflect / refract / fresnel / fresnel_reflection against the REFERENCE'S OWN include/wt/interaction/fresnel.hpp, compiled
+    unmodified into oracle/_ref/libref_fresnel.so (oracle/ref_fresnel.cpp over the shim headers): dielectrics on both sides of the interface,
+    total internal reflection, grazing and normal incidence, index-matched media, absorbing conductors.  Same f32 operations in the same
+    order: the results are required to be BIT-IDENTICAL."""
+    R = C.CDLL(REF_FRESNEL); L = _oracle.lib()
+    fp = C.POINTER(C.c_float)
+    for lib, names in ((R, ("ref_fresnel", "ref_fresnel_reflection", "ref_reflect")), (L, ("oracle_fresnel_full", "oracle_fresnel_reflection", "oracle_reflect"))):
+        getattr(lib, names[0]).argtypes = [C.c_float, C.c_float, fp, fp]; getattr(lib, names[1]).argtypes = [C.c_float, C.c_float, fp, fp]; getattr(lib, names[2]).argtypes = [fp, fp]
+        for n in names: getattr(lib, n).restype = None
+    rng = np.random.default_rng(5)
+    cases = []
+    for _ in range(4000):
+        w = rng.normal(size=3); w /= np.linalg.norm(w)
+        r = rng.random()
+        if r < .1: w = np.array([math.sqrt(1 - 1e-8), 1e-4, 0.0]) * (1 if rng.random() < .5 else -1)          # grazing
+        elif r < .15: w = np.array([0.0, 0.0, 1.0 if rng.random() < .5 else -1.0])                              # normal
+        elif r < .2: w = np.array([w[0], w[1], 0.0]); w /= np.linalg.norm(w)                                    # in the surface
+        eta = complex(1 + 2 * rng.random(), 0.0)
+        r2 = rng.random()
+        if r2 < .1: eta = complex(1.0, 0.0)
+        elif r2 < .4: eta = complex(.2 + 3 * rng.random(), 6 * rng.random())                                    # conductors
+        elif r2 < .5: eta = complex(1 / (1 + rng.random()), 0.0)
+        cases.append((eta, w.astype(np.float32)))
+    a16, b16, a4, b4, a3, b3 = (np.zeros(n, np.float32) for n in (16, 16, 4, 4, 3, 3))
+    n_tir = n_trans = 0
+    for eta, w in cases:
+        wp = w.ctypes.data_as(fp)
+        R.ref_fresnel(eta.real, eta.imag, wp, a16.ctypes.data_as(fp)); L.oracle_fresnel_full(eta.real, eta.imag, wp, b16.ctypes.data_as(fp))
+        assert np.array_equal(a16.view(np.uint32), b16.view(np.uint32)), (eta, w, a16, b16)
+        R.ref_fresnel_reflection(eta.real, eta.imag, wp, a4.ctypes.data_as(fp)); L.oracle_fresnel_reflection(eta.real, eta.imag, wp, b4.ctypes.data_as(fp))
+        assert np.array_equal(a4.view(np.uint32), b4.view(np.uint32)), (eta, w, a4, b4)
+        R.ref_reflect(wp, a3.ctypes.data_as(fp)); L.oracle_reflect(wp, b3.ctypes.data_as(fp))
+        assert np.array_equal(a3.view(np.uint32), b3.view(np.uint32))
+        n_tir += a16[8] == 0 and a16[9] == 0; n_trans += a16[8] > 0
+    assert n_tir > 50 and n_trans > 1000
+
+
+REF_FSD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_fsd.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FSD), reason="oracle/_ref/libref_fsd.so is built from /root/reference (this container only)")
+def test_fraunhofer_formulas_equal_the_reference_code():
+    """ot_bdpt.h's Fraunhofer FSD formulas (alpha1, alpha2, chi_e, chi_0, Psi via ASF_unclamped, Psi2 via sampling_density, ASF, P0, Pj) against
+    the REFERENCE'S OWN include/wt/interaction/fsd/fraunhofer/fsd.hpp, compiled unmodified into oracle/_ref/libref_fsd.so: random apertures of
+    1..24 edges, xi from 1e-4 to 30 (both sinc branches, the chi_e clamp).  Required: BIT-IDENTICAL f32 results."""
+    R = C.CDLL(REF_FSD); L = _oracle.lib()
+    fp = C.POINTER(C.c_float)
+    for f in (R.ref_fsd_eval, L.oracle_fsd_eval):
+        f.argtypes = [C.c_uint32, fp, C.c_float, C.c_float, C.c_float, C.c_float, fp]; f.restype = None
+    rng = np.random.default_rng(9)
+    a, b = np.zeros(9, np.float32), np.zeros(9, np.float32)
+    nz = 0
+    for it in range(3000):
+        n = int(rng.integers(1, 25))
+        scale = 10.0 ** rng.uniform(-2, 1)
+        edges = (rng.normal(size=(n, 8)) * np.array([scale, scale, scale, scale, 1, 1, 1, 1])).astype(np.float32)
+        if it % 7 == 0: edges[0, 0] = 0.0          # an edge along y: zeta.x can vanish -> the x == 0 branches of alpha1 / alpha2
+        mag = 10.0 ** rng.uniform(-4, 1.5); ang = rng.uniform(0, 2 * math.pi)
+        xi = np.float32([mag * math.cos(ang), mag * math.sin(ang)])
+        if it % 11 == 0: xi[0] = 0.0
+        P0v, psi02 = np.float32(rng.random()), np.float32(rng.random() * 3)
+        ep = np.ascontiguousarray(edges).ctypes.data_as(fp)
+        R.ref_fsd_eval(n, ep, P0v, psi02, xi[0], xi[1], a.ctypes.data_as(fp)); L.oracle_fsd_eval(n, ep, P0v, psi02, xi[0], xi[1], b.ctypes.data_as(fp))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (it, n, xi, a, b)
+        nz += a[0] > 0
+    assert nz > 2500
