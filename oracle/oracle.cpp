@@ -381,4 +381,10 @@ void oracle_fsd_eval(uint32_t n, const float* edges, float P0v, float psi02, flo
     out[5] = n ? ffsd::Pj(ap.edges[0]) : 0.f; out[6] = two_pi * sqr(ffsd::P0_sigma) * ap.psi02; out[7] = ffsd::alpha1(xi.x, xi.y); out[8] = ffsd::alpha2(xi.x, xi.y);
 }
 
+// ffsd::lut_t::sample for caller-supplied tables (theta: n, icdf: m x m); rand: cnt x 3, out: cnt x 2 -- same layout as oracle/ref_fsd_lut.cpp
+void oracle_fsd_lut_sample(uint32_t n, uint32_t m, const float* theta, const float* icdf, uint32_t cnt, const float* rand, float* out) {
+    const ffsd::lut_t lut{ n, m, theta, theta, icdf, icdf };
+    for (uint32_t i = 0; i < cnt; ++i) { const v2 z = lut.sample(v3{ rand[3 * i], rand[3 * i + 1], rand[3 * i + 2] }, theta, icdf); out[2 * i] = z.x; out[2 * i + 1] = z.y; }
+}
+
 } // extern "C"

@@ -38,6 +38,7 @@ void oracle_fuzz_ray_cull(uint32_t n, uint64_t seed, uint64_t out[4]);
 void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], const float o[3], const float d[3], float tan_alpha, float out[8]);
 float oracle_fraunhofer_asf(uint32_t n, const float* edges, float xix, float xiy);
 void oracle_fsd_eval(uint32_t n, const float* edges, float P0v, float psi02, float xix, float xiy, float out[9]);
+void oracle_fsd_lut_sample(uint32_t n, uint32_t m, const float* theta, const float* icdf, uint32_t cnt, const float* rand, float* out);
 float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]);
 #ifdef __cplusplus
 }

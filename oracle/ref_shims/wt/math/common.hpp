@@ -26,6 +26,7 @@ struct mat2_t {
     vec2_t c[2];
     constexpr mat2_t(vec2_t c0, vec2_t c1) : c{ c0, c1 } {}
 };
+constexpr vec2_t operator*(f_t s, vec2_t v) { return { s * v.x, s * v.y }; }
 constexpr vec2_t operator*(vec2_t v, const mat2_t& m) { return { v.x * m.c[0].x + v.y * m.c[0].y, v.x * m.c[1].x + v.y * m.c[1].y }; }
 namespace u::ang { inline constexpr f_t rad = 1; }      // mp-units' radian: angles are plain f_t here
 
@@ -56,7 +57,10 @@ inline f_t sqrt(f_t v) noexcept { return std::sqrt(v); }
 inline c_t sqrt(c_t v) noexcept { return std::sqrt(v); }                 // common.hpp:38-40: glm::sqrt(c) == std::sqrt
 inline constexpr f_t two_pi = f_t(2. * 3.141592653589793238462643383279502884);            // math/defs.hpp:40
 inline constexpr f_t inv_two_pi = f_t(0.318309886183790671537767526745028724 / 2.);        // math/defs.hpp:49
+inline constexpr f_t pi = f_t(3.141592653589793238462643383279502884);                     // math/defs.hpp
 inline f_t cos(f_t v) noexcept { return std::cos(v); }
+inline f_t sin(f_t v) noexcept { return std::sin(v); }
+inline f_t fract(f_t v) noexcept { return v - std::floor(v); }                              // common.hpp:228 glm::fract
 inline f_t exp(f_t v) noexcept { return std::exp(v); }
 // common.hpp:414-434 ("From boost")
 inline f_t sinc(const f_t x) noexcept {

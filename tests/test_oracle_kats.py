@@ -388,3 +388,33 @@ def test_fraunhofer_formulas_equal_the_reference_code():
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (it, n, xi, a, b)
         nz += a[0] > 0
     assert nz > 2500
+
+
+REF_FSD_LUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_fsd_lut.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FSD_LUT), reason="oracle/_ref/libref_fsd_lut.so is built from /root/reference (this container only)")
+def test_fraunhofer_lut_sampling_equals_the_reference_code():
+    """ot_bdpt.h's lut_t::sample (linear + bilinear table look-up, quadrant choice) against the REFERENCE'S OWN fsd_lut_t::sample
+    (include/wt/interaction/fsd/fraunhofer/fsd_lut.hpp:35-69, compiled unmodified into oracle/_ref/libref_fsd_lut.so) at the reference's table
+    sizes (2048, 3072 x 3072), tables filled with a smooth synthetic inverse CDF, 20 000 random triples incl. the ends of [0,1].  BIT-IDENTICAL."""
+    R = C.CDLL(REF_FSD_LUT); L = _oracle.lib()
+    fp = C.POINTER(C.c_float)
+    R.ref_fsd_lut_n.restype = C.c_uint32; R.ref_fsd_lut_m.restype = C.c_uint32
+    n, m = R.ref_fsd_lut_n(), R.ref_fsd_lut_m()
+    assert (n, m) == (2048, 3072)
+    R.ref_fsd_lut_sample.argtypes = [fp, fp, C.c_uint32, fp, fp]; R.ref_fsd_lut_sample.restype = None
+    L.oracle_fsd_lut_sample.argtypes = [C.c_uint32, C.c_uint32, fp, fp, C.c_uint32, fp, fp]; L.oracle_fsd_lut_sample.restype = None
+    u = np.linspace(0, 1, n, dtype=np.float64)
+    theta = (np.pi / 2 * u ** 1.3).astype(np.float32)                                   # monotone [0, pi/2]
+    rows = np.linspace(0, 1, m)[:, None]; cols = np.linspace(0, 1, m)[None, :]
+    icdf = ((1 + 3 * rows) * np.tan(1.4 * cols) - .01).astype(np.float32)              # radius grows with u, a few slightly negative entries (the max(0, .) clamp)
+    rng = np.random.default_rng(3)
+    cnt = 20000
+    rand = rng.random((cnt, 3)).astype(np.float32)
+    rand[:50] = np.float32([[0, 0, 0]] * 10 + [[1, 1, 1]] * 10 + [[.999999, 0, .25]] * 10 + [[0, 1, .5]] * 10 + [[.5, .5, .75]] * 10)
+    a = np.zeros((cnt, 2), np.float32); b = np.zeros((cnt, 2), np.float32)
+    R.ref_fsd_lut_sample(theta.ctypes.data_as(fp), np.ascontiguousarray(icdf).ctypes.data_as(fp), cnt, rand.ctypes.data_as(fp), a.ctypes.data_as(fp))
+    L.oracle_fsd_lut_sample(n, m, theta.ctypes.data_as(fp), np.ascontiguousarray(icdf).ctypes.data_as(fp), cnt, rand.ctypes.data_as(fp), b.ctypes.data_as(fp))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert (a[:, 0] > 0).sum() > 4000 and (a[:, 0] < 0).sum() > 4000 and (a[:, 1] < 0).sum() > 4000       # all four quadrants
