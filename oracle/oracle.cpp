@@ -387,4 +387,25 @@ void oracle_fsd_lut_sample(uint32_t n, uint32_t m, const float* theta, const flo
     for (uint32_t i = 0; i < cnt; ++i) { const v2 z = lut.sample(v3{ rand[3 * i], rand[3 * i + 1], rand[3 * i + 2] }, theta, icdf); out[2 * i] = z.x; out[2 * i + 1] = z.y; }
 }
 
+// fraunhofer_fsd_t::sample_rejection on a caller-supplied aperture and tables with a scripted number sequence -- same layout as
+// oracle/ref_fsd_sampler.cpp's ref_fsd_sampler_sample; out: xi.x, xi.y, pdf, weight, numbers consumed
+void oracle_fsd_sampler_sample(uint32_t n, uint32_t m, const float* th1, const float* th2, const float* c1, const float* c2, uint32_t n_edges, const float* edges,
+                               const float* edge_pdfs, float P0v, float P0_pdf, float psi02, float recp_I, const float* script, uint32_t n_script, uint32_t n_samples, float* out) {
+    const ffsd::lut_t lut{ n, m, th1, th2, c1, c2 };
+    fraunhofer_fsd_t fs(fraunhofer_fsd_t::for_test_t{}, &lut);
+    fs.ap.P0 = P0v; fs.ap.P0_pdf = P0_pdf; fs.ap.psi02 = psi02; fs.ap.recp_I = recp_I;
+    for (uint32_t i = 0; i < n_edges; ++i) { const float* e = edges + 8 * i; fs.ap.edges.push_back({ { e[0], e[1] }, { e[2], e[3] }, { e[4], e[5] }, { e[6], e[7] } }); fs.ap.edge_pdfs.push_back(edge_pdfs[i]); }
+    sampler_t smp; smp.script = script; smp.script_n = n_script;
+    for (uint32_t s = 0; s < n_samples; ++s) {
+        const auto r = fs.sample_rejection(smp);
+        out[5 * s] = r.xi.x; out[5 * s + 1] = r.xi.y; out[5 * s + 2] = r.pdf; out[5 * s + 3] = r.weight; out[5 * s + 4] = (float)smp.d;
+    }
+}
+// the warps of sampler.hpp:139-286 on explicit (u1, u2) -- same layout as ref_sampler_warps (uniform_hemisphere has no caller on the path: not restated)
+void oracle_sampler_warps(float u1, float u2, float solid_angle, float out[13]) {
+    const v2 u{ u1, u2 };
+    const v3 a = cosine_hemisphere(u); const v2 b = concentric_disk(u); const v3 c = uniform_sphere(u); const v3 d = uniform_cone(solid_angle, u); const v2 e = normal2d(u);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = b.x; out[4] = b.y; out[5] = c.x; out[6] = c.y; out[7] = c.z; out[8] = d.x; out[9] = d.y; out[10] = d.z; out[11] = e.x; out[12] = e.y;
+}
+
 } // extern "C"

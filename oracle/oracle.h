@@ -39,6 +39,9 @@ void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], co
 float oracle_fraunhofer_asf(uint32_t n, const float* edges, float xix, float xiy);
 void oracle_fsd_eval(uint32_t n, const float* edges, float P0v, float psi02, float xix, float xiy, float out[9]);
 void oracle_fsd_lut_sample(uint32_t n, uint32_t m, const float* theta, const float* icdf, uint32_t cnt, const float* rand, float* out);
+void oracle_fsd_sampler_sample(uint32_t n, uint32_t m, const float* th1, const float* th2, const float* c1, const float* c2, uint32_t n_edges, const float* edges,
+                               const float* edge_pdfs, float P0v, float P0_pdf, float psi02, float recp_I, const float* script, uint32_t n_script, uint32_t n_samples, float* out);
+void oracle_sampler_warps(float u1, float u2, float solid_angle, float out[13]);
 float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]);
 #ifdef __cplusplus
 }

@@ -236,6 +236,8 @@ struct fraunhofer_fsd_t {       // fraunhofer::free_space_diffraction_t
     ffsd::aperture_t ap; f_t k; frame_t frame; const ffsd::lut_t* lut;
     static constexpr f_t wo2_cutoff = .85f;
     bool empty() const { return ap.edges.empty(); }
+    struct for_test_t {};
+    fraunhofer_fsd_t(for_test_t, const ffsd::lut_t* l) : k(1), frame(frame_t::canonical()), lut(l) {}      // aperture filled by the caller (oracle.cpp test hooks)
 
     // src/interaction/fsd/fraunhofer/free_space_diffraction.cpp:22-129 (fsd_unit = 1 mm; lengths arrive in metres)
     fraunhofer_fsd_t(const scene_t& sc, const ffsd::lut_t* l, const frame_t& fr, f_t k_, f_t total_power, const elliptic_cone_t& beam,

@@ -86,7 +86,12 @@ struct sampler_t {
         if (b != sob_batch_idx) { sob_batch = sob->batch(seed, b); sob_batch_idx = b; }
         return (*sob_batch)[i * sobol::D + dim];
     }
-    f_t r() { if (stream & sobol_flag) return sobol_r(); return (f_t)(next_u32() >> 8) * (1.0f / 16777216.0f); }
+    // test hook: replay a scripted sequence instead of the Philox stream (lets tests compare the ORDER of draws with the reference's own code)
+    const float* script = nullptr; uint32_t script_n = 0;
+    f_t r() {
+        if (script) { const f_t v = d < script_n ? script[d] : .5f; ++d; return v; }
+        if (stream & sobol_flag) return sobol_r(); return (f_t)(next_u32() >> 8) * (1.0f / 16777216.0f);
+    }
     v2 r2() { const f_t a = r(); const f_t b = r(); return { a, b }; }
     v3 r3() { const f_t a = r(); const f_t b = r(); const f_t c = r(); return { a, b, c }; }
 

@@ -4,6 +4,7 @@
 // they lie.  Everything here has textbook semantics (std::complex, a 3-float vector, std::sqrt ...) except m::dot, which is the fma chain of
 // the reference's include/wt/math/vecmath.hpp:21-66 as ot_math.h restates it.  The formulas under test are the reference's own text.
 #pragma once
+#include <cassert>
 #include <cmath>
 #include <cstddef>
 #include <complex>
@@ -27,8 +28,11 @@ struct mat2_t {
     constexpr mat2_t(vec2_t c0, vec2_t c1) : c{ c0, c1 } {}
 };
 constexpr vec2_t operator*(f_t s, vec2_t v) { return { s * v.x, s * v.y }; }
+constexpr vec2_t operator-(vec2_t a, vec2_t b) { return { a.x - b.x, a.y - b.y }; }
 constexpr vec2_t operator*(vec2_t v, const mat2_t& m) { return { v.x * m.c[0].x + v.y * m.c[0].y, v.x * m.c[1].x + v.y * m.c[1].y }; }
 namespace u::ang { inline constexpr f_t rad = 1; }      // mp-units' radian: angles are plain f_t here
+using angle_t = f_t;
+struct vec4_t { f_t x{}, y{}, z{}, w{}; };
 
 struct vec3_t {
     f_t x{}, y{}, z{};
@@ -57,6 +61,13 @@ inline f_t sqrt(f_t v) noexcept { return std::sqrt(v); }
 inline c_t sqrt(c_t v) noexcept { return std::sqrt(v); }                 // common.hpp:38-40: glm::sqrt(c) == std::sqrt
 inline constexpr f_t two_pi = f_t(2. * 3.141592653589793238462643383279502884);            // math/defs.hpp:40
 inline constexpr f_t inv_two_pi = f_t(0.318309886183790671537767526745028724 / 2.);        // math/defs.hpp:49
+inline constexpr f_t pi_2 = f_t(3.141592653589793238462643383279502884 / 2.), pi_4 = f_t(3.141592653589793238462643383279502884 / 4.);   // math/defs.hpp
+inline constexpr f_t inv_pi = f_t(0.318309886183790671537767526745028724), inv_four_pi = f_t(0.318309886183790671537767526745028724 / 4.);
+// glm::inverse(mat2) (glm/detail/func_matrix.inl compute_inverse<2,2>): one reciprocal of the determinant, then four products
+inline mat2_t inverse(const mat2_t& m) noexcept {
+    const f_t ood = f_t(1) / (m.c[0].x * m.c[1].y - m.c[1].x * m.c[0].y);
+    return mat2_t{ vec2_t{ m.c[1].y * ood, -m.c[0].y * ood }, vec2_t{ -m.c[1].x * ood, m.c[0].x * ood } };
+}
 inline constexpr f_t pi = f_t(3.141592653589793238462643383279502884);                     // math/defs.hpp
 inline f_t cos(f_t v) noexcept { return std::cos(v); }
 inline f_t sin(f_t v) noexcept { return std::sin(v); }

@@ -418,3 +418,58 @@ def test_fraunhofer_lut_sampling_equals_the_reference_code():
     L.oracle_fsd_lut_sample(n, m, theta.ctypes.data_as(fp), np.ascontiguousarray(icdf).ctypes.data_as(fp), cnt, rand.ctypes.data_as(fp), b.ctypes.data_as(fp))
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert (a[:, 0] > 0).sum() > 4000 and (a[:, 0] < 0).sum() > 4000 and (a[:, 1] < 0).sum() > 4000       # all four quadrants
+
+
+REF_FSD_SAMPLER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_fsd_sampler.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FSD_SAMPLER), reason="oracle/_ref/libref_fsd_sampler.so is built from /root/reference (this container only)")
+def test_sampler_warps_equal_the_reference_code():
+    """ot_rng.h's cosine_hemisphere / concentric_disk / uniform_sphere / uniform_cone / normal2d against the REFERENCE'S OWN
+    include/wt/sampler/sampler.hpp (compiled unmodified into oracle/_ref/libref_fsd_sampler.so): bit-identical on 20 000 (u1, u2)."""
+    R = C.CDLL(REF_FSD_SAMPLER); L = _oracle.lib()
+    fp = C.POINTER(C.c_float)
+    R.ref_sampler_warps.argtypes = [C.c_float, C.c_float, C.c_float, fp]; R.ref_sampler_warps.restype = None
+    L.oracle_sampler_warps.argtypes = [C.c_float, C.c_float, C.c_float, fp]; L.oracle_sampler_warps.restype = None
+    rng = np.random.default_rng(21)
+    a, b = np.zeros(16, np.float32), np.zeros(13, np.float32)
+    us = rng.random((20000, 2)).astype(np.float32)
+    us[:8] = np.float32([[0, 0], [.5, .5], [1 - 2 ** -24, 0], [0, 1 - 2 ** -24], [.5, 0], [0, .5], [.25, .75], [.75, .25]])
+    for u1, u2 in us:
+        sa = np.float32(rng.random() * 2 * math.pi)
+        R.ref_sampler_warps(u1, u2, sa, a.ctypes.data_as(fp)); L.oracle_sampler_warps(u1, u2, sa, b.ctypes.data_as(fp))
+        assert np.array_equal(a[:13].view(np.uint32), b.view(np.uint32)), (u1, u2, sa, a, b)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FSD_SAMPLER), reason="oracle/_ref/libref_fsd_sampler.so is built from /root/reference (this container only)")
+def test_fraunhofer_rejection_sampler_equals_the_reference_code():
+    """ot_bdpt.h's sampleN / sample_rejection against the REFERENCE'S OWN translation unit src/interaction/fsd/fraunhofer/fsd_sampler.cpp (compiled
+    unmodified, with the reference's sampler.hpp, fsd.hpp and fsd_lut.hpp): both replay the same scripted number sequence, so the test sees the
+    sampled xi, the pdf AND how many numbers each sample consumed -- i.e. the order and count of the reference's random draws (edge choice,
+    lobe choice, table triple, acceptance test), for single-edge apertures (no rejection) and apertures of 2..12 edges.  BIT-IDENTICAL."""
+    R = C.CDLL(REF_FSD_SAMPLER); L = _oracle.lib()
+    fp = C.POINTER(C.c_float)
+    R.ref_fsd_sampler_sample.argtypes = [fp, fp, fp, fp, C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, fp, C.c_uint32, C.c_uint32, fp]; R.ref_fsd_sampler_sample.restype = None
+    L.oracle_fsd_sampler_sample.argtypes = [C.c_uint32, C.c_uint32, fp, fp, fp, fp, C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, fp, C.c_uint32, C.c_uint32, fp]; L.oracle_fsd_sampler_sample.restype = None
+    n, m = 2048, 3072
+    u = np.linspace(0, 1, n)
+    th1 = (np.pi / 2 * u ** 1.3).astype(np.float32); th2 = (np.pi / 2 * u ** .8).astype(np.float32)
+    rows = np.linspace(0, 1, m)[:, None]; cols = np.linspace(0, 1, m)[None, :]
+    c1 = np.ascontiguousarray(((1 + 3 * rows) * np.tan(1.4 * cols)).astype(np.float32)); c2 = np.ascontiguousarray(((2 + rows) * 6 * cols ** 2).astype(np.float32))
+    P = lambda x: x.ctypes.data_as(fp)
+    rng = np.random.default_rng(17)
+    n_samples, consumed_all = 6, []
+    for it in range(60):
+        ne = 1 if it % 6 == 0 else int(rng.integers(2, 13))
+        edges = (rng.normal(size=(ne, 8)) * np.array([3, 3, 2, 2, 1, 1, 1, 1])).astype(np.float32)
+        w = rng.random(ne + 1); w /= w.sum()
+        P0_pdf, edge_pdfs = np.float32(w[0]), np.ascontiguousarray(w[1:].astype(np.float32))
+        script = rng.random(20000).astype(np.float32)
+        a = np.zeros(5 * n_samples, np.float32); b = np.zeros(5 * n_samples, np.float32)
+        args = (ne, P(np.ascontiguousarray(edges)), P(edge_pdfs), np.float32(.3), P0_pdf, np.float32(.7), np.float32(1.3), P(script), len(script), n_samples)
+        R.ref_fsd_sampler_sample(P(th1), P(th2), P(c1), P(c2), *args, P(a))
+        L.oracle_fsd_sampler_sample(n, m, P(th1), P(th2), P(c1), P(c2), *args, P(b))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (it, ne, a, b)
+        consumed_all.append(a[4::5].copy())
+        if ne == 1: assert a[4] in (3.0, 5.0)       # one edge: edge choice + (normal2d pair | lobe choice + table triple), no acceptance draw
+    assert max(c[-1] for c in consumed_all) > 60        # rejections did happen
