@@ -408,4 +408,6 @@ void oracle_sampler_warps(float u1, float u2, float solid_angle, float out[13]) 
     out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = b.x; out[4] = b.y; out[5] = c.x; out[6] = c.y; out[7] = c.z; out[8] = d.x; out[9] = d.y; out[10] = d.z; out[11] = e.x; out[12] = e.y;
 }
 
+float oracle_erf_lut(float x) { return erf_lut()(x); }
+
 } // extern "C"

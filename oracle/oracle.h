@@ -42,6 +42,7 @@ void oracle_fsd_lut_sample(uint32_t n, uint32_t m, const float* theta, const flo
 void oracle_fsd_sampler_sample(uint32_t n, uint32_t m, const float* th1, const float* th2, const float* c1, const float* c2, uint32_t n_edges, const float* edges,
                                const float* edge_pdfs, float P0v, float P0_pdf, float psi02, float recp_I, const float* script, uint32_t n_script, uint32_t n_samples, float* out);
 void oracle_sampler_warps(float u1, float u2, float solid_angle, float out[13]);
+float oracle_erf_lut(float x);
 float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]);
 #ifdef __cplusplus
 }

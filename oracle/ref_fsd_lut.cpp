@@ -16,7 +16,11 @@
 
 using lut_t = wt::fraunhofer::fsd_sampler::fsd_lut_t;
 
+#include <wt/math/erf_lut.hpp>
+
 extern "C" {
+// the 1024-entry erf table of include/wt/math/erf_lut.hpp:20-55 (used by gaussian2d_t::integrate_triangle and the film's reconstruction filter)
+float ref_erf_lut(float x) { return wt::m::erf_lut(x); }
 unsigned ref_fsd_lut_n(void) { return (unsigned)lut_t::Nsamples; }
 unsigned ref_fsd_lut_m(void) { return (unsigned)lut_t::Msamples; }
 // theta: 2048 floats; icdf: 3072 x 3072 floats (row = theta bin); rand: n x 3; out: n x 2

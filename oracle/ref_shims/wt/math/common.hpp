@@ -71,7 +71,10 @@ inline mat2_t inverse(const mat2_t& m) noexcept {
 inline constexpr f_t pi = f_t(3.141592653589793238462643383279502884);                     // math/defs.hpp
 inline f_t cos(f_t v) noexcept { return std::cos(v); }
 inline f_t sin(f_t v) noexcept { return std::sin(v); }
-inline f_t fract(f_t v) noexcept { return v - std::floor(v); }                              // common.hpp:228 glm::fract
+inline f_t fract(f_t v) noexcept { return v - std::floor(v); }
+inline f_t sign(f_t t) noexcept { return f_t((f_t(0) < t) - (t < f_t(0))); }                   // common.hpp:128-131 glm::sign
+// common.hpp:257-264: the end points are returned exactly, otherwise glm::mix = a (1 - x) + b x
+inline f_t mix(f_t a, f_t b, f_t x) noexcept { if (x == f_t(0)) return a; if (x == f_t(1)) return b; return a * (f_t(1) - x) + b * x; }                              // common.hpp:228 glm::fract
 inline f_t exp(f_t v) noexcept { return std::exp(v); }
 // common.hpp:414-434 ("From boost")
 inline f_t sinc(const f_t x) noexcept {

@@ -473,3 +473,17 @@ def test_fraunhofer_rejection_sampler_equals_the_reference_code():
         consumed_all.append(a[4::5].copy())
         if ne == 1: assert a[4] in (3.0, 5.0)       # one edge: edge choice + (normal2d pair | lobe choice + table triple), no acceptance draw
     assert max(c[-1] for c in consumed_all) > 60        # rejections did happen
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FSD_LUT), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_erf_lut_equals_the_reference_code():
+    """ot_scene.h's erf_lut_t (the 1024-entry table behind gaussian2d_t::integrate_triangle and the film's reconstruction-filter weights) against
+    the REFERENCE'S OWN include/wt/math/erf_lut.hpp: bit-identical on 200 000 arguments in [-5, 5], the table knots and the ends."""
+    R = C.CDLL(REF_FSD_LUT); L = _oracle.lib()
+    R.ref_erf_lut.argtypes = [C.c_float]; R.ref_erf_lut.restype = C.c_float
+    L.oracle_erf_lut.argtypes = [C.c_float]; L.oracle_erf_lut.restype = C.c_float
+    rng = np.random.default_rng(2)
+    xs = np.concatenate([rng.uniform(-5, 5, 200000), np.arange(1024) / 1023 * 3.5, [0, -0.0, 3.5, -3.5, 3.4999998, 1e-8, -1e-8, 1e9, -1e9]]).astype(np.float32)
+    a = np.float32([R.ref_erf_lut(float(x)) for x in xs]); b = np.float32([L.oracle_erf_lut(float(x)) for x in xs])
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert abs(R.ref_erf_lut(1.0) - math.erf(1.0)) < 2e-6
