@@ -364,6 +364,11 @@ void oracle_cone_through_ellipsoid(const float axes[3], const float frame[9], co
 float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]) {
     return gaussian2d_t(v2{ sx, sy }).integrate_triangle({ tri[0], tri[1] }, { tri[2], tri[3] }, { tri[4], tri[5] });
 }
+// the same for n triangles (tri: n x 6) -- same layout as oracle/ref_gaussian2d.cpp's ref_gaussian_integrate_triangles
+void oracle_gaussian_integrate_triangles(float sx, float sy, uint32_t n, const float* tri, float* out) {
+    const gaussian2d_t g(v2{ sx, sy });
+    for (uint32_t i = 0; i < n; ++i) { const float* t = tri + 6 * i; out[i] = g.integrate_triangle({ t[0], t[1] }, { t[2], t[3] }, { t[4], t[5] }); }
+}
 
 // |sum_e Psi_e(xi)|^2 for explicit aperture edges (e.x,e.y,v.x,v.y,a_b.re,a_b.im,iab_2.re,iab_2.im each): Fraunhofer ASF (fsd.hpp:127-140)
 float oracle_fraunhofer_asf(uint32_t n, const float* edges, float xix, float xiy) {

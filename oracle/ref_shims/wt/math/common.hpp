@@ -22,15 +22,44 @@ struct vec2_t {
     constexpr vec2_t() = default;
     constexpr vec2_t(f_t x_, f_t y_) : x(x_), y(y_) {}
     constexpr vec2_t& operator/=(f_t s) { x /= s; y /= s; return *this; }
-};
-struct mat2_t {
-    vec2_t c[2];
-    constexpr mat2_t(vec2_t c0, vec2_t c1) : c{ c0, c1 } {}
+    constexpr f_t& operator[](std::size_t i) { return i == 0 ? x : y; }
+    constexpr const f_t& operator[](std::size_t i) const { return i == 0 ? x : y; }
 };
 constexpr vec2_t operator*(f_t s, vec2_t v) { return { s * v.x, s * v.y }; }
+constexpr vec2_t operator*(vec2_t v, f_t s) { return { v.x * s, v.y * s }; }
+constexpr vec2_t operator*(vec2_t a, vec2_t b) { return { a.x * b.x, a.y * b.y }; }
+constexpr vec2_t operator/(f_t s, vec2_t v) { return { s / v.x, s / v.y }; }
+constexpr vec2_t operator/(vec2_t v, f_t s) { return { v.x / s, v.y / s }; }
+constexpr vec2_t operator+(vec2_t a, vec2_t b) { return { a.x + b.x, a.y + b.y }; }
 constexpr vec2_t operator-(vec2_t a, vec2_t b) { return { a.x - b.x, a.y - b.y }; }
+constexpr vec2_t operator-(vec2_t a) { return { -a.x, -a.y }; }
+constexpr bool operator==(vec2_t a, vec2_t b) { return a.x == b.x && a.y == b.y; }
+struct dir2_t : vec2_t {        // unit vector in the plane
+    constexpr dir2_t() = default;
+    constexpr dir2_t(f_t x_, f_t y_) : vec2_t(x_, y_) {}
+    constexpr explicit dir2_t(const vec2_t& v) : vec2_t(v) {}
+};
+// glm::mat2: column-major; mat2(c0, c1) / mat2(x0, y0, x1, y1) take COLUMNS; m[i] is column i; vec * mat = row vector times matrix,
+// mat * vec = matrix times column vector, mat * mat the usual product (glm/detail/type_mat2x2.inl: plain multiply-adds in this order)
+struct mat2_t {
+    vec2_t c[2];
+    constexpr mat2_t() : c{ { 1, 0 }, { 0, 1 } } {}
+    constexpr mat2_t(vec2_t c0, vec2_t c1) : c{ c0, c1 } {}
+    constexpr mat2_t(f_t x0, f_t y0, f_t x1, f_t y1) : c{ { x0, y0 }, { x1, y1 } } {}
+    constexpr vec2_t& operator[](std::size_t i) { return c[i]; }
+    constexpr const vec2_t& operator[](std::size_t i) const { return c[i]; }
+};
 constexpr vec2_t operator*(vec2_t v, const mat2_t& m) { return { v.x * m.c[0].x + v.y * m.c[0].y, v.x * m.c[1].x + v.y * m.c[1].y }; }
+constexpr vec2_t operator*(const mat2_t& m, vec2_t v) { return { m.c[0].x * v.x + m.c[1].x * v.y, m.c[0].y * v.x + m.c[1].y * v.y }; }
+constexpr mat2_t operator*(const mat2_t& a, const mat2_t& b) {
+    return { a.c[0].x * b.c[0].x + a.c[1].x * b.c[0].y, a.c[0].y * b.c[0].x + a.c[1].y * b.c[0].y,
+             a.c[0].x * b.c[1].x + a.c[1].x * b.c[1].y, a.c[0].y * b.c[1].x + a.c[1].y * b.c[1].y };
+}
+constexpr mat2_t operator+(const mat2_t& a, const mat2_t& b) { return { a.c[0] + b.c[0], a.c[1] + b.c[1] }; }
+constexpr mat2_t operator*(const mat2_t& a, f_t s) { return { a.c[0] * s, a.c[1] * s }; }
+constexpr mat2_t operator*(f_t s, const mat2_t& a) { return { a.c[0] * s, a.c[1] * s }; }
 namespace u::ang { inline constexpr f_t rad = 1; }      // mp-units' radian: angles are plain f_t here
+namespace u { inline constexpr f_t m = 1; }             // mp-units' metre: lengths are plain f_t here
 using angle_t = f_t;
 struct vec4_t { f_t x{}, y{}, z{}, w{}; };
 
@@ -72,6 +101,19 @@ inline constexpr f_t pi = f_t(3.141592653589793238462643383279502884);          
 inline f_t cos(f_t v) noexcept { return std::cos(v); }
 inline f_t sin(f_t v) noexcept { return std::sin(v); }
 inline f_t fract(f_t v) noexcept { return v - std::floor(v); }
+inline constexpr f_t inf = std::numeric_limits<f_t>::infinity();
+inline constexpr f_t sqrt_pi = f_t(1.772453850905516027298167483341145183), inv_sqrt_pi = f_t(0.564189583547756286948079451560772586);   // math/defs.hpp
+template <typename T> constexpr T min(T a, T b, T c) noexcept { return std::min(a, std::min(b, c)); }
+template <typename T> constexpr T max(T a, T b, T c) noexcept { return std::max(a, std::max(b, c)); }
+inline bool isfinite(f_t v) noexcept { return std::isfinite(v); }
+inline f_t pow(f_t b, f_t e) noexcept { return std::pow(b, e); }
+inline f_t determinant(const mat2_t& m) noexcept { return m.c[0].x * m.c[1].y - m.c[1].x * m.c[0].y; }          // glm::determinant
+inline mat2_t transpose(const mat2_t& m) noexcept { return mat2_t{ m.c[0].x, m.c[1].x, m.c[0].y, m.c[1].y }; }
+inline vec2_t iszero(vec2_t v) noexcept { return { f_t(v.x == 0), f_t(v.y == 0) }; }
+inline bool all(vec2_t v) noexcept { return v.x != 0 && v.y != 0; }
+namespace eft {     // math/eft/eft.hpp: compensated a*b - c*d (Kahan), as ot_math.h restates it
+inline f_t diff_prod(f_t a, f_t b, f_t c, f_t d) noexcept { const f_t cd = c * d; const f_t r = std::fma(a, b, -cd); return r + std::fma(-c, d, cd); }
+}
 inline f_t sign(f_t t) noexcept { return f_t((f_t(0) < t) - (t < f_t(0))); }                   // common.hpp:128-131 glm::sign
 // common.hpp:257-264: the end points are returned exactly, otherwise glm::mix = a (1 - x) + b x
 inline f_t mix(f_t a, f_t b, f_t x) noexcept { if (x == f_t(0)) return a; if (x == f_t(1)) return b; return a * (f_t(1) - x) + b * x; }                              // common.hpp:228 glm::fract

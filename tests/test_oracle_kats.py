@@ -487,3 +487,35 @@ def test_erf_lut_equals_the_reference_code():
     a = np.float32([R.ref_erf_lut(float(x)) for x in xs]); b = np.float32([L.oracle_erf_lut(float(x)) for x in xs])
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert abs(R.ref_erf_lut(1.0) - math.erf(1.0)) < 2e-6
+
+
+REF_GAUSSIAN2D = os.path.join(os.path.dirname(REF_FSD_LUT), "libref_gaussian2d.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GAUSSIAN2D), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_gaussian_triangle_integral_equals_the_reference_code():
+    """ot_bdpt.h's gaussian2d_t::integrate_triangle (the weight of every aperture triangle in a BDPT connection, SURVEY.md 8 row a13) against the
+    REFERENCE'S OWN src/math/gaussian2d.cpp + distribution/gaussian2d.hpp compiled unmodified (oracle/ref_gaussian2d.cpp): bit-identical on
+    120 000 triangles -- isotropic, anisotropic both ways, sub-millimetre and large footprints, triangles around the mean, far from it,
+    containing the 3-sigma disc, straddling it by an edge only, and slivers."""
+    R = C.CDLL(REF_GAUSSIAN2D); L = _oracle.lib()
+    fp = C.POINTER(C.c_float)
+    for f in (R.ref_gaussian_integrate_triangles, L.oracle_gaussian_integrate_triangles):
+        f.argtypes = [C.c_float, C.c_float, C.c_uint32, fp, fp]; f.restype = None
+    rng = np.random.default_rng(5)
+    n = 20000
+    inside = 0
+    for (sx, sy), scale, spread in (((1, 1), 1, 1), ((0.3, 2.0), 2, 1), ((5, 0.1), 5, 1), ((1e-3, 1e-3), 3e-3, 1), ((40, 7), 60, 1), ((1, 1), 0.2, 8)):
+        ctr = rng.normal(size=(n, 1, 2)) * scale * spread
+        tri = (ctr + rng.normal(size=(n, 3, 2)) * scale * rng.uniform(0.05, 3, size=(n, 1, 1)))
+        tri[: n // 20] *= 40                                   # huge triangles: many contain the whole 3-sigma disc
+        tri[n // 20: n // 10, 2] = tri[n // 20: n // 10, 0] + (tri[n // 20: n // 10, 1] - tri[n // 20: n // 10, 0]) * 0.5 + 1e-4 * scale   # slivers
+        tri = np.ascontiguousarray(tri.astype(np.float32).reshape(n, 6))
+        a = np.zeros(n, np.float32); b = np.zeros(n, np.float32)
+        R.ref_gaussian_integrate_triangles(sx, sy, n, tri.ctypes.data_as(fp), a.ctypes.data_as(fp))
+        L.oracle_gaussian_integrate_triangles(sx, sy, n, tri.ctypes.data_as(fp), b.ctypes.data_as(fp))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ((sx, sy), np.nonzero(a.view(np.uint32) != b.view(np.uint32))[0][:5])
+        assert np.all(np.isfinite(a)) and a.min() >= -1e-3 and a.max() <= 1 + 1e-3
+        assert (a > 0).sum() > n // 3 and (a == 0).sum() > 50
+        inside += int((a > 0.98).sum())
+    assert inside > 1000                                    # the "disc inside the triangle" branches were taken
