@@ -370,6 +370,21 @@ void oracle_gaussian_integrate_triangles(float sx, float sy, uint32_t n, const f
     for (uint32_t i = 0; i < n; ++i) { const float* t = tri + 6 * i; out[i] = g.integrate_triangle({ t[0], t[1] }, { t[2], t[3] }, { t[4], t[5] }); }
 }
 
+// clip_triangle_z + clip_ret_t::triangle for n triangles -- same layout as oracle/ref_clip.cpp's ref_clip_triangles
+void oracle_clip_triangles(uint32_t n, const float* tri, const float* zr, int* ntris, float* polygon, float* pieces) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* t = tri + 9 * i;
+        const auto r = clip_triangle_z({ t[0], t[1], t[2] }, { t[3], t[4], t[5] }, { t[6], t[7], t[8] }, range_t{ zr[2 * i], zr[2 * i + 1] });
+        ntris[i] = r.tris;
+        for (int k = 0; k < 5; ++k) { const bool used = r.tris > 0 && k < r.tris + 2; polygon[15 * i + 3 * k] = used ? r.vs[k].x : 0; polygon[15 * i + 3 * k + 1] = used ? r.vs[k].y : 0; polygon[15 * i + 3 * k + 2] = used ? r.vs[k].z : 0; }
+        for (int j = 0; j < 3; ++j) {
+            if (j >= r.tris) { for (int k = 0; k < 9; ++k) pieces[27 * i + 9 * j + k] = 0; continue; }
+            v3 p[3]; r.triangle(j, p);
+            for (int k = 0; k < 3; ++k) { pieces[27 * i + 9 * j + 3 * k] = p[k].x; pieces[27 * i + 9 * j + 3 * k + 1] = p[k].y; pieces[27 * i + 9 * j + 3 * k + 2] = p[k].z; }
+        }
+    }
+}
+
 // |sum_e Psi_e(xi)|^2 for explicit aperture edges (e.x,e.y,v.x,v.y,a_b.re,a_b.im,iab_2.re,iab_2.im each): Fraunhofer ASF (fsd.hpp:127-140)
 float oracle_fraunhofer_asf(uint32_t n, const float* edges, float xix, float xiy) {
     ffsd::aperture_t ap;

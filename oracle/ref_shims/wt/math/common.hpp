@@ -72,6 +72,7 @@ constexpr vec3_t operator+(vec3_t a, vec3_t b) { return { a.x + b.x, a.y + b.y, 
 constexpr vec3_t operator-(vec3_t a, vec3_t b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
 constexpr vec3_t operator*(f_t s, vec3_t a) { return { s * a.x, s * a.y, s * a.z }; }
 constexpr vec3_t operator*(vec3_t a, f_t s) { return { a.x * s, a.y * s, a.z * s }; }
+using pqvec3_t = vec3_t;        // mp-units' vector of lengths: plain floats here
 // unit vector (include/wt/math/unit_vector/unit_vector.hpp): a vec3 with explicit construction from one
 struct dir3_t : vec3_t {
     constexpr dir3_t() = default;

@@ -1,6 +1,8 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.  Build shim for oracle/_ref: intersect_edge_circle of include/wt/math/intersect/misc.hpp:77-134 (the real header
-// is written over mp-units quantities), restated on plain floats: only the `points` count is used by src/math/gaussian2d.cpp.
+// is written over mp-units quantities), restated on plain floats: only the `points` count is used by src/math/gaussian2d.cpp; and
+// intersect_edge_plane (:163-180), which math/intersect/clip.hpp calls.
 #pragma once
+#include <optional>
 #include <utility>
 #include <wt/math/common.hpp>
 namespace wt::intersect {
@@ -20,5 +22,14 @@ inline intersect_edge_circle_ret_t intersect_edge_circle(const vec2_t& point0, c
     intersect_edge_circle_ret_t ret; ret.t1 = t1; ret.t2 = t2;
     ret.points = (u1valid ? 1 : 0) + (u2valid ? 1 : 0);
     return ret;
+}
+inline std::optional<pqvec3_t> intersect_edge_plane(const pqvec3_t& p0, const pqvec3_t& p1, const pqvec3_t& pp, const dir3_t& n) noexcept {
+    const auto d0 = m::dot(pp - p0, n), d1 = m::dot(pp - p1, n);
+    const auto E = p1 - p0;
+    const auto E_dot_N = m::dot(E, n);
+    if (m::sign(d0) == m::sign(d1) || E_dot_N == 0) return std::nullopt;
+    const auto d = d0 / E_dot_N;
+    if (d >= 0 && 1 >= d) return p0 + d * E;
+    return std::nullopt;
 }
 }

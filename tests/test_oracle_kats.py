@@ -519,3 +519,32 @@ def test_gaussian_triangle_integral_equals_the_reference_code():
         assert (a > 0).sum() > n // 3 and (a == 0).sum() > 50
         inside += int((a > 0.98).sum())
     assert inside > 1000                                    # the "disc inside the triangle" branches were taken
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GAUSSIAN2D), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_triangle_clip_equals_the_reference_code():
+    """ot_bdpt.h's clip_triangle_z / clip_ret_t::triangle (every aperture triangle of a BDPT connection is clipped to the beam's depth range
+    before the wavefront is integrated over the pieces) against the REFERENCE'S OWN include/wt/math/intersect/clip.hpp
+    compiled unmodified (oracle/ref_clip.cpp): piece count, polygon vertices in order and the fan triangles bit-identical on 200 000 triangles,
+    with vertices exactly on a clip plane, edges parallel to it, and empty slabs."""
+    R = C.CDLL(REF_GAUSSIAN2D); L = _oracle.lib()
+    fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
+    rng = np.random.default_rng(3); n = 200000
+    tri = rng.normal(size=(n, 9)).astype(np.float32)
+    zr = np.sort(rng.normal(size=(n, 2)).astype(np.float32) * rng.choice([0.1, 1, 3], size=(n, 1)).astype(np.float32), axis=1)
+    m = rng.random(n) < 0.15; tri[m, 2] = zr[m, 0]             # a vertex on the near plane
+    m = rng.random(n) < 0.15; tri[m, 5] = zr[m, 1]             # a vertex on the far plane
+    m = rng.random(n) < 0.05; tri[m, 8] = tri[m, 2]            # an edge parallel to the planes
+    m = rng.random(n) < 0.03; zr[m, 1] = zr[m, 0]              # an empty slab
+    zr = np.ascontiguousarray(zr)
+    out = []
+    for lib, name in ((R, "ref_clip_triangles"), (L, "oracle_clip_triangles")):
+        f = getattr(lib, name); f.argtypes = [C.c_uint32, fp, fp, ip, fp, fp]; f.restype = None
+        nt = np.zeros(n, np.int32); poly = np.zeros((n, 15), np.float32); pcs = np.zeros((n, 27), np.float32)
+        f(n, tri.ctypes.data_as(fp), zr.ctypes.data_as(fp), nt.ctypes.data_as(ip), poly.ctypes.data_as(fp), pcs.ctypes.data_as(fp))
+        out.append((nt, poly, pcs))
+    (nt_a, poly_a, pcs_a), (nt_b, poly_b, pcs_b) = out
+    assert np.array_equal(nt_a, nt_b)
+    assert np.array_equal(poly_a.view(np.uint32), poly_b.view(np.uint32))
+    assert np.array_equal(pcs_a.view(np.uint32), pcs_b.view(np.uint32))
+    assert np.bincount(nt_a, minlength=4).min() > 5000          # 0, 1, 2 and 3 pieces all occur
