@@ -184,6 +184,7 @@ void oracle_svd(const float A[4], float out[6]) {
     const auto s = SVD(mat2{ A[0], A[1], A[2], A[3] });
     out[0] = s.Ucos; out[1] = s.Usin; out[2] = s.Vcos; out[3] = s.Vsin; out[4] = s.sigma1; out[5] = s.sigma2;
 }
+void oracle_svd_n(uint32_t n, const float* A, float* out) { for (uint32_t i = 0; i < n; ++i) oracle_svd(A + 4 * i, out + 6 * i); }
 void oracle_utdf(float x, float out[2]) { const c_t f = UTDF(x); out[0] = f.real(); out[1] = f.imag(); }
 void oracle_cerfc_rot45(double s, double out[2]) { const auto c = cerfc_rot45(s); out[0] = c.real(); out[1] = c.imag(); }
 void oracle_fresnel(float eta_re, float eta_im, const float w[3], float out[12]) {

@@ -23,6 +23,7 @@ void oracle_sobol_seeds(uint64_t seed, uint64_t batch, uint64_t* out /* 47 */);
 int oracle_sobol_matrices(const wtgpu_sobol_entry* table, int32_t* out);
 int oracle_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out);
 void oracle_svd(const float A[4], float out[6]);
+void oracle_svd_n(uint32_t n, const float* A, float* out);
 void oracle_utdf(float x, float out[2]);
 void oracle_cerfc_rot45(double s, double out[2]);
 void oracle_fresnel(float eta_re, float eta_im, const float w[3], float out[12]);

@@ -4,6 +4,8 @@
 // they lie.  Everything here has textbook semantics (std::complex, a 3-float vector, std::sqrt ...) except m::dot, which is the fma chain of
 // the reference's include/wt/math/vecmath.hpp:21-66 as ot_math.h restates it.  The formulas under test are the reference's own text.
 #pragma once
+#include <wt/util/concepts.hpp>
+#include <concepts>
 #include <cassert>
 #include <cmath>
 #include <cstddef>
@@ -72,6 +74,11 @@ constexpr vec3_t operator+(vec3_t a, vec3_t b) { return { a.x + b.x, a.y + b.y, 
 constexpr vec3_t operator-(vec3_t a, vec3_t b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
 constexpr vec3_t operator*(f_t s, vec3_t a) { return { s * a.x, s * a.y, s * a.z }; }
 constexpr vec3_t operator*(vec3_t a, f_t s) { return { a.x * s, a.y * s, a.z * s }; }
+// names math/linalg.hpp's one template (solve_linear_system2x2, not on the path and never instantiated here) is parsed against
+template <int N, typename T> using vec = vec2_t;
+template <typename T> using vec2 = vec2_t;
+template <typename T> using mat2 = mat2_t;
+template <typename T> using limits = std::numeric_limits<T>;
 using pqvec3_t = vec3_t;        // mp-units' vector of lengths: plain floats here
 // unit vector (include/wt/math/unit_vector/unit_vector.hpp): a vec3 with explicit construction from one
 struct dir3_t : vec3_t {
@@ -114,6 +121,7 @@ inline vec2_t iszero(vec2_t v) noexcept { return { f_t(v.x == 0), f_t(v.y == 0) 
 inline bool all(vec2_t v) noexcept { return v.x != 0 && v.y != 0; }
 namespace eft {     // math/eft/eft.hpp: compensated a*b - c*d (Kahan), as ot_math.h restates it
 inline f_t diff_prod(f_t a, f_t b, f_t c, f_t d) noexcept { const f_t cd = c * d; const f_t r = std::fma(a, b, -cd); return r + std::fma(-c, d, cd); }
+inline f_t sum_prod(f_t a, f_t b, f_t c, f_t d) noexcept { return diff_prod(a, b, -c, d); }          // eft.hpp:153-159
 }
 inline f_t sign(f_t t) noexcept { return f_t((f_t(0) < t) - (t < f_t(0))); }                   // common.hpp:128-131 glm::sign
 // common.hpp:257-264: the end points are returned exactly, otherwise glm::mix = a (1 - x) + b x
