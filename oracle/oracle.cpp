@@ -185,6 +185,31 @@ void oracle_svd(const float A[4], float out[6]) {
     out[0] = s.Ucos; out[1] = s.Usin; out[2] = s.Vcos; out[3] = s.Vsin; out[4] = s.sigma1; out[5] = s.sigma2;
 }
 void oracle_svd_n(uint32_t n, const float* A, float* out) { for (uint32_t i = 0; i < n; ++i) oracle_svd(A + 4 * i, out + 6 * i); }
+// wedge_edge_t::UTD and ::diffraction_point for n wedges -- same layouts as oracle/ref_utd.cpp (wedge: v[3] l nff[3] tff[3] nbf[3] alpha; q: k wi[3] wo[3] ro)
+static wedge_edge_t wedge_from(const float* w) {
+    wedge_edge_t e{}; e.v = { w[0], w[1], w[2] }; e.l = w[3]; e.nff = { w[4], w[5], w[6] }; e.tff = { w[7], w[8], w[9] }; e.nbf = { w[10], w[11], w[12] }; e.alpha = w[13];
+    return e;
+}
+void oracle_utd(uint32_t n, const float* wedge, const float* q, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = q + 8 * i; float* o = out + 4 * i;
+        const auto r = wedge_from(wedge + 14 * i).UTD(a[0], v3{ a[1], a[2], a[3] }, v3{ a[4], a[5], a[6] }, a[7]);
+        o[0] = r.Ds.real(); o[1] = r.Ds.imag(); o[2] = r.Dh.real(); o[3] = r.Dh.imag();
+    }
+}
+void oracle_utd_diffraction_points(uint32_t n, const float* wedge, const float* pts, int* found, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = pts + 9 * i; float* o = out + 6 * i;
+        const auto e = wedge_from(wedge + 14 * i);
+        const auto p = e.diffraction_point(v3{ a[0], a[1], a[2] }, v3{ a[3], a[4], a[5] });
+        const auto d = e.diffraction_point_dir(v3{ a[0], a[1], a[2] }, v3{ a[6], a[7], a[8] });
+        found[2 * i] = p ? 1 : 0; found[2 * i + 1] = d ? 1 : 0;
+        for (int k = 0; k < 6; ++k) o[k] = 0;
+        if (p) { o[0] = p->x; o[1] = p->y; o[2] = p->z; }
+        if (d) { o[3] = d->x; o[4] = d->y; o[5] = d->z; }
+    }
+}
+void oracle_utdf_n(uint32_t n, const float* x, float* out) { for (uint32_t i = 0; i < n; ++i) { const c_t f = UTDF(x[i]); out[2 * i] = f.real(); out[2 * i + 1] = f.imag(); } }
 void oracle_utdf(float x, float out[2]) { const c_t f = UTDF(x); out[0] = f.real(); out[1] = f.imag(); }
 void oracle_cerfc_rot45(double s, double out[2]) { const auto c = cerfc_rot45(s); out[0] = c.real(); out[1] = c.imag(); }
 void oracle_fresnel(float eta_re, float eta_im, const float w[3], float out[12]) {

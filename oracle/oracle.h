@@ -25,6 +25,9 @@ int oracle_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float
 void oracle_svd(const float A[4], float out[6]);
 void oracle_svd_n(uint32_t n, const float* A, float* out);
 void oracle_utdf(float x, float out[2]);
+void oracle_utdf_n(uint32_t n, const float* x, float* out);
+void oracle_utd(uint32_t n, const float* wedge, const float* q, float* out);
+void oracle_utd_diffraction_points(uint32_t n, const float* wedge, const float* pts, int* found, float* out);
 void oracle_cerfc_rot45(double s, double out[2]);
 void oracle_fresnel(float eta_re, float eta_im, const float w[3], float out[12]);
 void oracle_fresnel_full(float eta_re, float eta_im, const float w[3], float out[16]);

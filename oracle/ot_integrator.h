@@ -129,13 +129,29 @@ inline std::complex<double> cerfc_rot45(double s) {
     return 1.0 - erf;
 }
 
+// erfc(z) for a general complex z with |z| < 2.5: Maclaurin series of erf in double precision (terms peak below e^6, so ~1e-13 absolute).
+// UTDF's argument is NOT exactly on the 45-degree ray: the reference forms exp(i pi/4) * sqrt(x) in complex<float> (utd.hpp:42) and libcerf
+// takes that f32-rounded point; evaluating on the exact ray instead moves F by up to 6e-7 relative (found by the pin against the reference's
+// own utd.hpp, tests/test_oracle_kats.py::test_utd_equals_the_reference_code).
+inline std::complex<double> cerfc_series(std::complex<double> z) {
+    const std::complex<double> z2 = z * z;
+    std::complex<double> term = z, sum = z;     // term = (-1)^n z^(2n+1) / n!
+    for (int n = 1; n < 200; ++n) {
+        term *= -z2 / (double)n;
+        sum += term / (2.0 * n + 1.0);
+        if (std::abs(term) < 1e-30 && n > 4) break;
+    }
+    return 1.0 - (2.0 / 1.7724538509055160273) * sum;
+}
+
 // utd.hpp:36-57
 inline c_t UTDF(f_t x) {
     const f_t absx = std::fabs(x);
     c_t result;
     if (absx < 6) {
         const f_t sqrt_x = std::sqrt(absx);
-        const std::complex<double> ce = cerfc_rot45((double)sqrt_x);
+        const c_t zf = std::exp(c_t{ 0, pi_4 }) * sqrt_x;
+        const std::complex<double> ce = cerfc_series(std::complex<double>(zf.real(), zf.imag()));
         const c_t cerf{ (f_t)ce.real(), (f_t)ce.imag() };
         result = c_t{ 1, 1 } * sqrt_pi_2 * sqrt_x * std::exp(c_t{ 0, absx }) * cerf;
     } else {

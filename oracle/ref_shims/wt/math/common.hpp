@@ -74,11 +74,23 @@ constexpr vec3_t operator+(vec3_t a, vec3_t b) { return { a.x + b.x, a.y + b.y, 
 constexpr vec3_t operator-(vec3_t a, vec3_t b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
 constexpr vec3_t operator*(f_t s, vec3_t a) { return { s * a.x, s * a.y, s * a.z }; }
 constexpr vec3_t operator*(vec3_t a, f_t s) { return { a.x * s, a.y * s, a.z * s }; }
+constexpr bool operator==(const vec3_t& a, const vec3_t& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 // names math/linalg.hpp's one template (solve_linear_system2x2, not on the path and never instantiated here) is parsed against
 template <int N, typename T> using vec = vec2_t;
 template <typename T> using vec2 = vec2_t;
 template <typename T> using mat2 = mat2_t;
 template <typename T> using limits = std::numeric_limits<T>;
+using pqvec2_t = vec2_t;
+using length_t = f_t;           // metres
+using angle_t = f_t;            // radians
+// mp-units semantics the pinned UTD code relies on: a wavenumber is held in 1/mm and lengths in m, so the dimensionless number k * l taken
+// with u::to_num is (k * l) scaled by the unit ratio m/mm = 1000 (one f32 product by 1000 after the product of the two numerical values)
+struct wavenumber_t { f_t per_mm; };
+struct wavenumber_length_t { f_t mm_per_m_scaled; };
+constexpr wavenumber_length_t operator*(wavenumber_t k, length_t l) { return { k.per_mm * l }; }
+template <typename T> concept Angle = std::is_floating_point_v<T>;
+template <typename T> concept Wavenumber = std::is_same_v<T, wavenumber_t>;
+namespace u { constexpr f_t to_num(f_t v) { return v; } constexpr f_t to_num(wavenumber_length_t v) { return v.mm_per_m_scaled * f_t(1000); } }
 using pqvec3_t = vec3_t;        // mp-units' vector of lengths: plain floats here
 // unit vector (include/wt/math/unit_vector/unit_vector.hpp): a vec3 with explicit construction from one
 struct dir3_t : vec3_t {
@@ -123,6 +135,12 @@ namespace eft {     // math/eft/eft.hpp: compensated a*b - c*d (Kahan), as ot_ma
 inline f_t diff_prod(f_t a, f_t b, f_t c, f_t d) noexcept { const f_t cd = c * d; const f_t r = std::fma(a, b, -cd); return r + std::fma(-c, d, cd); }
 inline f_t sum_prod(f_t a, f_t b, f_t c, f_t d) noexcept { return diff_prod(a, b, -c, d); }          // eft.hpp:153-159
 }
+inline constexpr f_t sqrt_pi_2 = f_t(1.253314137315500251207882642405522627), inv_sqrt_two_pi = f_t(0.398942280401432677939946059934381868);  // math/defs.hpp
+inline f_t round(f_t v) noexcept { return std::round(v); }                                      // common.hpp:104-106 glm::round
+inline f_t atan2(f_t y, f_t x) noexcept { return std::atan2(y, x); }                            // quantity/math.hpp:213-216
+inline f_t cot(f_t a) noexcept { return f_t(1) / std::tan(a); }                                 // quantity/math.hpp:199-202
+inline f_t mod(f_t a, f_t b) noexcept { return a - b * std::floor(a / b); }                      // quantity/math.hpp:84-88 glm::mod
+inline bool isfinite(const c_t& v) noexcept { return std::isfinite(v.real()) && std::isfinite(v.imag()); }
 inline f_t sign(f_t t) noexcept { return f_t((f_t(0) < t) - (t < f_t(0))); }                   // common.hpp:128-131 glm::sign
 // common.hpp:257-264: the end points are returned exactly, otherwise glm::mix = a (1 - x) + b x
 inline f_t mix(f_t a, f_t b, f_t x) noexcept { if (x == f_t(0)) return a; if (x == f_t(1)) return b; return a * (f_t(1) - x) + b * x; }                              // common.hpp:228 glm::fract
@@ -140,6 +158,12 @@ inline f_t sinc(const f_t x) noexcept {
 inline f_t dot(const vec2_t& a, const vec2_t& b) noexcept { return std::fma(a.y, b.y, a.x * b.x); }                          // vecmath.hpp:21-66
 inline f_t length2(const vec2_t& v) noexcept { return dot(v, v); }
 inline f_t dot(const vec3_t& a, const vec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }   // vecmath.hpp:21-66
+inline f_t length2(const vec3_t& v) noexcept { return dot(v, v); }
+inline f_t length(const vec2_t& v) noexcept { return std::sqrt(length2(v)); }                    // vecmath.hpp:38-44
+inline f_t length(const vec3_t& v) noexcept { return std::sqrt(length2(v)); }
+inline vec3_t cross(const vec3_t& x, const vec3_t& y) noexcept {                                 // vecmath.hpp:53-64
+    return { eft::diff_prod(x.y, y.z, x.z, y.y), eft::diff_prod(x.z, y.x, x.x, y.z), eft::diff_prod(x.x, y.y, x.y, y.x) };
+}
 inline dir3_t normalize(const vec3_t& v) noexcept { const f_t l = std::sqrt(dot(v, v)); return dir3_t{ v.x / l, v.y / l, v.z / l }; }
 }
 }

@@ -575,3 +575,58 @@ def test_svd_equals_the_reference_code():
     # max(|R00|, |R10|) == 1 -- the quirk is part of the path's arithmetic and both sides reproduce it; U and V are rotations regardless
     g = slice(6 * k, n)
     assert np.allclose(a[g, 0] ** 2 + a[g, 1] ** 2, 1, atol=1e-5) and np.allclose(a[g, 2] ** 2 + a[g, 3] ** 2, 1, atol=1e-5)
+
+
+REF_UTD = os.path.join(os.path.dirname(REF_FSD_LUT), "libref_utd.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_UTD), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_utd_equals_the_reference_code():
+    """ot_integrator.h's UTD (UTDa, the transition function UTDF, the soft / hard wedge coefficients and both Fermat-point searches: what
+    plt_path's free-space diffraction evaluates per edge and sample) against the REFERENCE'S OWN
+    include/wt/interaction/fsd/utd.hpp compiled unmodified (oracle/ref_utd.cpp).  libcerf is an empty submodule: the reference code gets its
+    cerfc from scipy.special.erfc here (complex128, independent of the oracle's series).  Bit-identical: F on 25 000 arguments either side of
+    the |x| = 6 switch, Ds / Dh on 20 000 (wedge, k, wi, wo, r) with wavelengths from 0.1 um to 30 cm, half planes, directions exactly on the
+    shadow boundary and grazing the edge, and the Fermat points with their found / not-found decisions."""
+    import scipy.special as sp
+    R = C.CDLL(REF_UTD); L = _oracle.lib(); fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
+    CB = C.CFUNCTYPE(None, C.c_double, C.c_double, C.POINTER(C.c_double))
+    calls = [0]
+    def cerfc(re, im, out):
+        v = sp.erfc(complex(re, im)); out[0] = v.real; out[1] = v.imag; calls[0] += 1
+    cb = CB(cerfc); R.ref_set_cerfc.argtypes = [CB]; R.ref_set_cerfc(cb)
+    rng = np.random.default_rng(7)
+
+    x = np.concatenate([rng.uniform(-8, 8, 20000), 10.0 ** rng.uniform(-8, 3, 5000), [0, -0.0, 6, -6, 5.9999995]]).astype(np.float32); n = len(x)
+    a = np.zeros((n, 2), np.float32); b = a.copy()
+    R.ref_utdf.argtypes = [C.c_uint32, fp, fp]; L.oracle_utdf_n.argtypes = [C.c_uint32, fp, fp]
+    R.ref_utdf(n, x.ctypes.data_as(fp), a.ctypes.data_as(fp)); L.oracle_utdf_n(n, x.ctypes.data_as(fp), b.ctypes.data_as(fp))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and calls[0] > 15000
+
+    unit = lambda v: v / np.linalg.norm(v, axis=-1, keepdims=True)
+    n = 20000
+    nff = unit(rng.normal(size=(n, 3))); tff = unit(np.cross(nff, rng.normal(size=(n, 3)))); e = np.cross(nff, tff)
+    alpha = rng.uniform(0.02, np.pi - 0.02, n); alpha[:2000] = 0.0
+    nbf = unit(-np.cos(alpha)[:, None] * nff - np.sin(alpha)[:, None] * tff)
+    wedge = np.ascontiguousarray(np.concatenate([rng.normal(size=(n, 3)), rng.uniform(0.01, 2, size=(n, 1)), nff, tff, nbf, alpha[:, None]], axis=1).astype(np.float32))
+    k = 2 * np.pi / (10.0 ** rng.uniform(-4, 2.5, n))                               # 1/mm
+    wi = unit(rng.normal(size=(n, 3))); wo = unit(rng.normal(size=(n, 3)))
+    wo[:1500] = -wi[:1500]                                                          # shadow boundary
+    wi[1500:2500] = unit(e[1500:2500] * rng.uniform(0.9, 1, size=(1000, 1)) + 0.05 * rng.normal(size=(1000, 3)))   # grazing the edge
+    ro = 10.0 ** rng.uniform(-3, 1.5, n)
+    q = np.ascontiguousarray(np.concatenate([k[:, None], wi, wo, ro[:, None]], axis=1).astype(np.float32))
+    a = np.zeros((n, 16), np.float32); b = np.zeros((n, 4), np.float32)
+    R.ref_utd.argtypes = [C.c_uint32, fp, fp, fp]; L.oracle_utd.argtypes = [C.c_uint32, fp, fp, fp]
+    R.ref_utd(n, wedge.ctypes.data_as(fp), q.ctypes.data_as(fp), a.ctypes.data_as(fp)); L.oracle_utd(n, wedge.ctypes.data_as(fp), q.ctypes.data_as(fp), b.ctypes.data_as(fp))
+    assert np.all(np.isfinite(a)) and np.array_equal(a[:, :4].view(np.uint32), b.view(np.uint32))
+    assert 500 < (a[:, :4] == 0).all(axis=1).sum() < n // 4                        # the |mod(phi, pi/2)| < 1e-5 zeroing happened, and is rare
+    for f in (a[:, 4:7], a[:, 7:10], a[:, 10:13], a[:, 13:16]): assert np.allclose(np.linalg.norm(f[2500:], axis=1), 1, atol=1e-4)
+
+    pts = np.ascontiguousarray(np.concatenate([wedge[:, :3] + rng.normal(size=(n, 3)) * rng.choice([0.3, 3], size=(n, 1)),
+                                               wedge[:, :3] + rng.normal(size=(n, 3)) * rng.choice([0.3, 3], size=(n, 1)), wo], axis=1).astype(np.float32))
+    fa = np.zeros((n, 2), np.int32); fb = fa.copy(); pa = np.zeros((n, 6), np.float32); pb = pa.copy()
+    for lib, name, f_, p_ in ((R, "ref_utd_diffraction_points", fa, pa), (L, "oracle_utd_diffraction_points", fb, pb)):
+        f = getattr(lib, name); f.argtypes = [C.c_uint32, fp, fp, ip, fp]
+        f(n, wedge.ctypes.data_as(fp), pts.ctypes.data_as(fp), f_.ctypes.data_as(ip), p_.ctypes.data_as(fp))
+    assert np.array_equal(fa, fb) and np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
+    assert 0.2 < fa[:, 0].mean() < 0.9 and 0.1 < fa[:, 1].mean() < 0.9
