@@ -396,6 +396,14 @@ void oracle_gaussian_integrate_triangles(float sx, float sy, uint32_t n, const f
     for (uint32_t i = 0; i < n; ++i) { const float* t = tri + 6 * i; out[i] = g.integrate_triangle({ t[0], t[1] }, { t[2], t[3] }, { t[4], t[5] }); }
 }
 
+void oracle_gaussian_pdf(float sx, float sy, uint32_t n, const float* pts, float* out) {
+    const gaussian2d_t g(v2{ sx, sy });
+    for (uint32_t i = 0; i < n; ++i) {
+        const v2 p{ pts[2 * i], pts[2 * i + 1] };
+        const v2 c = g.to_canonical(p);
+        out[3 * i] = g.pdf(p); out[3 * i + 1] = c.x; out[3 * i + 2] = c.y;
+    }
+}
 // clip_triangle_z + clip_ret_t::triangle for n triangles -- same layout as oracle/ref_clip.cpp's ref_clip_triangles
 void oracle_clip_triangles(uint32_t n, const float* tri, const float* zr, int* ntris, float* polygon, float* pieces) {
     for (uint32_t i = 0; i < n; ++i) {

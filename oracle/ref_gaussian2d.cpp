@@ -18,4 +18,13 @@ void ref_gaussian_integrate_triangles(float sx, float sy, unsigned n, const floa
         out[i] = g.integrate_triangle(wt::vec2_t{ t[0], t[1] }, wt::vec2_t{ t[2], t[3] }, wt::vec2_t{ t[4], t[5] });
     }
 }
+// pdf and the canonical-space map (gaussian2d.hpp:96-101, :190-197) that amplitude_magnitude() of the wavefront evaluates; pts: n x 2; out: n x 3
+void ref_gaussian_pdf(float sx, float sy, unsigned n, const float* pts, float* out) {
+    const wt::gaussian2d_t g(wt::vec2_t{ sx, sy });
+    for (unsigned i = 0; i < n; ++i) {
+        const wt::vec2_t p{ pts[2 * i], pts[2 * i + 1] };
+        const auto c = g.to_canonical(p);
+        out[3 * i] = g.pdf(p); out[3 * i + 1] = c.x; out[3 * i + 2] = c.y;
+    }
+}
 }

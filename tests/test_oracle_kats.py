@@ -519,6 +519,14 @@ def test_gaussian_triangle_integral_equals_the_reference_code():
         assert (a > 0).sum() > n // 3 and (a == 0).sum() > 50
         inside += int((a > 0.98).sum())
     assert inside > 1000                                    # the "disc inside the triangle" branches were taken
+    # pdf and the canonical-space map (gaussian2d.hpp:96-101, :190-197: the wavefront's amplitude_magnitude) on 4 x 50 000 points
+    for f in (R.ref_gaussian_pdf, L.oracle_gaussian_pdf): f.argtypes = [C.c_float, C.c_float, C.c_uint32, fp, fp]; f.restype = None
+    n = 50000
+    for sx, sy in ((1, 1), (0.3, 2), (1e-3, 4e-3), (40, 7)):
+        pts = np.ascontiguousarray((rng.normal(size=(n, 2)) * [sx, sy] * rng.uniform(0, 6, size=(n, 1))).astype(np.float32)); pts[:10] = 0
+        a = np.zeros((n, 3), np.float32); b = a.copy()
+        R.ref_gaussian_pdf(sx, sy, n, pts.ctypes.data_as(fp), a.ctypes.data_as(fp)); L.oracle_gaussian_pdf(sx, sy, n, pts.ctypes.data_as(fp), b.ctypes.data_as(fp))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
 @pytest.mark.skipif(not os.path.exists(REF_GAUSSIAN2D), reason="oracle/_ref is built from /root/reference (this container only)")
