@@ -396,6 +396,14 @@ void oracle_gaussian_integrate_triangles(float sx, float sy, uint32_t n, const f
     for (uint32_t i = 0; i < n; ++i) { const float* t = tri + 6 * i; out[i] = g.integrate_triangle({ t[0], t[1] }, { t[2], t[3] }, { t[4], t[5] }); }
 }
 
+// ot_scene.h's look-ups on caller-supplied tables -- same layouts as oracle/ref_distributions.cpp
+void oracle_binned_eval(uint32_t n, const float* ys, const float* dcdf, float k0, float dk, float norm, uint32_t m, const float* v, float* icdf, const float* x, float* value, float* pdf) {
+    for (uint32_t i = 0; i < m; ++i) {
+        const v2 r = binned_icdf(ys, dcdf, n, k0, dk, v[i]); icdf[2 * i] = r.x; icdf[2 * i + 1] = r.y;
+        value[i] = binned_value(ys, n, k0, dk, x[i]); pdf[i] = value[i] * norm;
+    }
+}
+void oracle_discrete_icdf(uint32_t n, const float* dcdf, uint32_t m, const float* v, int* idx) { for (uint32_t i = 0; i < m; ++i) idx[i] = (int)discrete_icdf(dcdf, n, v[i]); }
 void oracle_gaussian_pdf(float sx, float sy, uint32_t n, const float* pts, float* out) {
     const gaussian2d_t g(v2{ sx, sy });
     for (uint32_t i = 0; i < n; ++i) {

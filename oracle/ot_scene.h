@@ -455,6 +455,36 @@ struct emitter_direct_sample_t { int32_t emitter = -1; f_t emitter_pdf = 0; pd_t
 
 inline v3 mat3_mul(const float* M, v3 v) { return { M[0] * v.x + M[1] * v.y + M[2] * v.z, M[3] * v.x + M[4] * v.y + M[5] * v.z, M[6] * v.x + M[7] * v.y + M[8] * v.z }; }
 
+// discrete_distribution_t::icdf (discrete_distribution.hpp:130-136): lower_bound, -1, clamp, skip empty bins.  dcdf has n + 1 entries.
+inline int64_t discrete_icdf(const float* dcdf, uint32_t n, f_t v) {
+    const float* it = std::lower_bound(dcdf, dcdf + n + 1, v);
+    int64_t idx = std::min<int64_t>(std::max<int64_t>((it - dcdf) - 1, 0), (int64_t)n - 1);
+    for (; idx < (int64_t)n - 1 && dcdf[idx + 1] - dcdf[idx] == 0; ++idx) {}
+    return idx;
+}
+// binned_piecewise_linear_distribution_t::icdf (binned_piecewise_linear_distribution.hpp:251-280) -> (x, y); sample() = (x, y*norm) (:285-292).
+// The reference walks from a binned guess to the bracketing knot; a binary search finds the same bracket.  ys, dcdf: n entries each.
+inline v2 binned_icdf(const float* ys, const float* dcdf, uint32_t n, f_t k0, f_t dk, f_t v) {
+    const float* it = std::upper_bound(dcdf, dcdf + n, v);
+    uint32_t idx = (uint32_t)std::min<int64_t>(std::max<int64_t>((it - dcdf) - 1, 0), (int64_t)n - 2);
+    while (idx + 1 < n - 1 && v > dcdf[idx + 1]) ++idx;
+    const f_t f = (v - dcdf[idx]) / (dcdf[idx + 1] - dcdf[idx]);
+    const f_t a = ys[idx], b = ys[idx + 1];
+    if (a == b) return { ((f_t)idx + f) * dk, a };     // sic: no xrange.min offset (line 270)
+    const f_t mm = mix(sqr(a), sqr(b), f);
+    const f_t dd = std::sqrt(mm);
+    const f_t t = clampf((a - dd) / (a - b), 0, 1);
+    return { mix(k0 + (f_t)idx * dk, k0 + (f_t)(idx + 1) * dk, t), mix(a, b, t) };
+}
+// binned value(x) (binned_piecewise_linear_distribution.hpp:196-205)
+inline f_t binned_value(const float* ys, uint32_t n, f_t k0, f_t dk, f_t k) {
+    const f_t bin = (k - k0) * (1.f / dk);
+    if (bin < 0 || bin > (f_t)(n - 1)) return 0;
+    const size_t ii = (size_t)bin;
+    const f_t fr = bin - std::floor(bin);
+    return mix(ys[ii], ys[std::min<size_t>(n - 1, ii + 1)], fr);
+}
+
 struct emitters_t {
     const scene_t& sc;
     explicit emitters_t(const scene_t& s) : sc(s) {}
@@ -642,15 +672,7 @@ struct emitters_t {
     }
 
     // ---- scene-level sampling (scene.hpp:96-200, scene_sensor.cpp:19-59)
-    int32_t sample_emitter(sampler_t& sampler) const {
-        const uint32_t n = sc.d->n_emitters;
-        const float* cdf = sc.d->emitter_cdf;
-        const f_t v = sampler.r();
-        const float* it = std::lower_bound(cdf, cdf + n + 1, v);
-        int64_t idx = std::min<int64_t>(std::max<int64_t>((it - cdf) - 1, 0), (int64_t)n - 1);
-        for (; idx < (int64_t)n - 1 && cdf[idx + 1] - cdf[idx] == 0; ++idx) {}
-        return (int32_t)idx;
-    }
+    int32_t sample_emitter(sampler_t& sampler) const { return (int32_t)discrete_icdf(sc.d->emitter_cdf, sc.d->n_emitters, sampler.r()); }
     f_t pdf_emitter(int32_t i) const { return sc.d->emitter_cdf[i + 1] - sc.d->emitter_cdf[i]; }
 
     struct wavenumber_sample_t { f_t k; pd_t wpd; };
@@ -663,25 +685,11 @@ struct emitters_t {
         if (kd.type == WTGPU_KDIST_DISCRETE) {
             // discrete_distribution_t<vec2_t>::icdf/sample (discrete_distribution.hpp:258-272)
             const float* ks = data; const float* ys = data + n; const float* dcdf = data + 2 * n;
-            const float* it = std::lower_bound(dcdf, dcdf + n + 1, v);
-            int64_t idx = std::min<int64_t>(std::max<int64_t>((it - dcdf) - 1, 0), (int64_t)n - 1);
-            for (; idx < (int64_t)n - 1 && dcdf[idx + 1] - dcdf[idx] == 0; ++idx) {}
+            const int64_t idx = discrete_icdf(dcdf, n, v);
             return { ks[idx], pd_t::discrete(ys[idx] * kd.norm) };
         }
-        // binned_piecewise_linear_distribution_t::icdf/sample (binned_piecewise_linear_distribution.hpp:251-292).
-        // The reference walks from a binned guess to the bracketing knot; a binary search finds the same bracket.
-        const float* ys = data; const float* dcdf = data + n;
-        const float* it = std::upper_bound(dcdf, dcdf + n, v);
-        uint32_t idx = (uint32_t)std::min<int64_t>(std::max<int64_t>((it - dcdf) - 1, 0), (int64_t)n - 2);
-        while (idx + 1 < n - 1 && v > dcdf[idx + 1]) ++idx;
-        const f_t f = (v - dcdf[idx]) / (dcdf[idx + 1] - dcdf[idx]);
-        const f_t a = ys[idx], b = ys[idx + 1];
-        if (a == b) return { ((f_t)idx + f) * kd.dk, pd_t::density(a * kd.norm) };     // sic: no xrange.min offset (line 270)
-        const f_t mm = mix(sqr(a), sqr(b), f);
-        const f_t dd = std::sqrt(mm);
-        const f_t t = clampf((a - dd) / (a - b), 0, 1);
-        const f_t x = mix(kd.k0 + (f_t)idx * kd.dk, kd.k0 + (f_t)(idx + 1) * kd.dk, t);
-        return { x, pd_t::density(mix(a, b, t) * kd.norm) };
+        const v2 xy = binned_icdf(data, data + n, n, kd.k0, kd.dk, v);
+        return { xy.x, pd_t::density(xy.y * kd.norm) };
     }
     // emitter_sampling_data_t::pdf_wavenumber (scene_sensor.hpp:63-70)
     f_t pdf_wavenumber(int32_t i, f_t k) const {
@@ -695,12 +703,7 @@ struct emitters_t {
             const size_t idx = it - ks;
             return dcdf[idx + 1] - dcdf[idx];
         }
-        // binned value(x)*norm (binned_piecewise_linear_distribution.hpp:196-205,241-244)
-        const f_t bin = (k - kd.k0) * (1.f / kd.dk);
-        if (bin < 0 || bin > (f_t)(n - 1)) return 0;
-        const size_t ii = (size_t)bin;
-        const f_t fr = bin - std::floor(bin);
-        return mix(data[ii], data[std::min<size_t>(n - 1, ii + 1)], fr) * kd.norm;
+        return binned_value(data, n, kd.k0, kd.dk, k) * kd.norm;       // pdf = value(x)*norm (binned_piecewise_linear_distribution.hpp:241-244)
     }
     f_t sum_spectral_pdf_for_all_emitters(f_t k) const {                // scene_sensor.hpp:115-123
         f_t s = 0;

@@ -4,6 +4,7 @@
 // they lie.  Everything here has textbook semantics (std::complex, a 3-float vector, std::sqrt ...) except m::dot, which is the fma chain of
 // the reference's include/wt/math/vecmath.hpp:21-66 as ot_math.h restates it.  The formulas under test are the reference's own text.
 #pragma once
+#include <type_traits>
 #include <wt/util/concepts.hpp>
 #include <concepts>
 #include <cassert>
@@ -144,6 +145,16 @@ inline bool isfinite(const c_t& v) noexcept { return std::isfinite(v.real()) && 
 inline f_t sign(f_t t) noexcept { return f_t((f_t(0) < t) - (t < f_t(0))); }                   // common.hpp:128-131 glm::sign
 // common.hpp:257-264: the end points are returned exactly, otherwise glm::mix = a (1 - x) + b x
 inline f_t mix(f_t a, f_t b, f_t x) noexcept { if (x == f_t(0)) return a; if (x == f_t(1)) return b; return a * (f_t(1) - x) + b * x; }                              // common.hpp:228 glm::fract
+// glm::clamp = min(max(v, lo), hi) (common.hpp:238-243); clamp01 (:508-511)
+template <typename T> constexpr T clamp(const T& v, const std::type_identity_t<T>& lo, const std::type_identity_t<T>& hi) noexcept { return std::min(std::max(v, lo), hi); }
+template <typename T> constexpr T clamp01(const T& v) noexcept { return clamp<T>(v, 0, 1); }
+inline double sqrt(double v) noexcept { return std::sqrt(v); }
+inline double sqr(double v) noexcept { return v * v; }
+inline bool isfinite(double v) noexcept { return std::isfinite(v); }
+inline vec2_t mix(const vec2_t& a, const vec2_t& b, f_t x) noexcept {        // common.hpp:264-271: glm::mix on a vector = a (1 - x) + b x per component
+    if (x == f_t(0)) return a; if (x == f_t(1)) return b;
+    return { a.x * (f_t(1) - x) + b.x * x, a.y * (f_t(1) - x) + b.y * x };
+}
 inline f_t exp(f_t v) noexcept { return std::exp(v); }
 // common.hpp:414-434 ("From boost")
 inline f_t sinc(const f_t x) noexcept {

@@ -1,8 +1,22 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.  Build shim for oracle/_ref: the closed interval of include/wt/math/range.hpp (a template over mp-units
-// quantities and the wide-vector types), as far as math/intersect/clip.hpp reads it: two bounds.
+// quantities, inclusiveness and the wide-vector types), as far as the pinned headers use it: math/intersect/clip.hpp reads the two bounds, the
+// 1-D distributions use length / contains / all / & / == (range.hpp:64-69, :141-158) and m::mix(range, t) (:309-314).
 #pragma once
+#include <limits>
 #include <wt/math/common.hpp>
 namespace wt {
-template <typename T = f_t> struct range_t { T min, max; };
+template <typename T = f_t> struct range_t {
+    T min, max;
+    constexpr T length() const noexcept { return max - min; }
+    constexpr bool empty() const noexcept { return !(min <= max); }
+    constexpr bool contains(T pt) const noexcept { return (pt < max && min < pt) || pt == min || pt == max; }
+    constexpr range_t operator&(const range_t& o) const noexcept { return { m::max(min, o.min), m::min(max, o.max) }; }
+    constexpr bool operator==(const range_t& o) const noexcept { return (min == o.min && max == o.max) || (empty() && o.empty()); }
+    constexpr bool operator!=(const range_t& o) const noexcept { return !(*this == o); }
+    static constexpr range_t all() noexcept { return { -std::numeric_limits<T>::infinity(), +std::numeric_limits<T>::infinity() }; }
+};
 template <typename T = f_t> using pqrange_t = range_t<T>;     // lengths are plain f_t here
+namespace m {
+template <typename S, typename T> constexpr S mix(const range_t<S>& r, const T& x) noexcept { if (x == T(0)) return r.min; if (x == T(1)) return r.max; return m::mix(r.min, r.max, S(x)); }
+}
 }

@@ -638,3 +638,50 @@ def test_utd_equals_the_reference_code():
         f(n, wedge.ctypes.data_as(fp), pts.ctypes.data_as(fp), f_.ctypes.data_as(ip), p_.ctypes.data_as(fp))
     assert np.array_equal(fa, fb) and np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
     assert 0.2 < fa[:, 0].mean() < 0.9 and 0.1 < fa[:, 1].mean() < 0.9
+
+
+REF_DISTRIBUTIONS = os.path.join(os.path.dirname(REF_FSD_LUT), "libref_distributions.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DISTRIBUTIONS), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_spectrum_distributions_equal_the_reference_code():
+    """The tabulated 1-D distributions every sample goes through against the REFERENCE'S OWN
+    binned_piecewise_linear_distribution.hpp and discrete_distribution.hpp compiled unmodified (oracle/ref_distributions.cpp), bit for bit:
+    (1) the tables the host layer bakes (scene.bake_binned_spectrum / bake_discrete_cdf) against the reference constructors' members -- f32
+    running sums, grid step, total, normalisation; (2) ot_scene.h's binned_icdf (a binary search where the reference walks from a binned
+    guess), binned_value / pdf and discrete_icdf against the reference's icdf / value / pdf, on 40 000 arguments per table incl. 0, 1, zero
+    knots, flat runs (the a == b branch, which returns x without the range offset) and empty stretches of the cdf."""
+    from wave_tracer_b200.scene import bake_binned_spectrum, bake_discrete_cdf
+    R = C.CDLL(REF_DISTRIBUTIONS); L = _oracle.lib(); fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int); up = C.POINTER(C.c_uint32)
+    R.ref_binned_build.argtypes = [C.c_uint32, fp, C.c_float, C.c_float, fp, up, fp]
+    R.ref_binned_eval.argtypes = [C.c_uint32, fp, C.c_float, C.c_float, C.c_uint32, fp, fp, fp, fp, fp]
+    L.oracle_binned_eval.argtypes = [C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_uint32, fp, fp, fp, fp, fp]
+    R.ref_discrete.argtypes = [C.c_uint32, fp, fp, C.c_uint32, fp, ip]; L.oracle_discrete_icdf.argtypes = [C.c_uint32, fp, C.c_uint32, fp, ip]
+    P = lambda a: a.ctypes.data_as(fp)
+    rng = np.random.default_rng(4)
+    for n, (kmin, kmax) in ((2, (1., 3.)), (16, (7000., 16000.)), (64, (0.01, 0.09)), (257, (9000., 15000.)), (1024, (11423.97, 15707.96))):
+        ys = np.float32(rng.uniform(0, 1, n) ** 3 * rng.choice([1e-3, 1, 50]))
+        if n > 8: ys[rng.integers(0, n, n // 8)] = 0; ys[5:9] = ys[5]
+        if n == 64: ys[10:30] = 0
+        d = np.zeros(n, np.float32); b = np.zeros(4 * n, np.uint32); s = np.zeros(4, np.float32)
+        R.ref_binned_build(n, P(ys), kmin, kmax, P(d), b.ctypes.data_as(up), P(s))
+        y2, dcdf, dx, norm, tot = bake_binned_spectrum(ys.astype(np.float64), kmin, kmax)
+        assert np.array_equal(y2, ys) and np.array_equal(dcdf.view(np.uint32), d.view(np.uint32)) and (dx, norm, tot) == (s[0], s[3], s[2])
+        m = 40000
+        v = np.concatenate([rng.random(m - 6), [0, 1, 0.5, 1e-8, 0.99999994, 0.25]]).astype(np.float32)
+        x = (kmin + (kmax - kmin) * rng.uniform(-0.05, 1.05, m)).astype(np.float32); x[:3] = [kmin, kmax, (kmin + kmax) / 2]
+        A_ = [np.zeros((m, 2), np.float32), np.zeros(m, np.float32), np.zeros(m, np.float32)]; B_ = [a.copy() for a in A_]
+        R.ref_binned_eval(n, P(ys), kmin, kmax, m, P(v), P(A_[0]), P(x), P(A_[1]), P(A_[2]))
+        L.oracle_binned_eval(n, P(ys), P(dcdf), kmin, float(dx), float(norm), m, P(v), P(B_[0]), P(x), P(B_[1]), P(B_[2]))
+        for a, o in zip(A_, B_): assert np.all(np.isfinite(a)) and np.array_equal(a.view(np.uint32), o.view(np.uint32)), n
+        assert (A_[1] > 0).sum() > m // 3 and (A_[1] == 0).sum() > 100
+    for n in (1, 2, 5, 37, 400):
+        dens = np.float32(rng.uniform(0, 1, n) ** 4 * rng.choice([1e-4, 1, 1e3]))
+        if n > 4: dens[rng.integers(0, n, n // 3)] = 0; dens[0] = 0; dens[-1] = 0
+        if n == 2: dens[:] = 0                                                      # no mass at all: dcdf.back() = 1
+        m = 20000; v = np.concatenate([rng.random(m - 5), [0, 1, 0.5, 1e-8, 0.99999994]]).astype(np.float32)
+        d = np.zeros(n + 1, np.float32); ia = np.zeros(m, np.int32); ib = ia.copy()
+        R.ref_discrete(n, P(dens), P(d), m, P(v), ia.ctypes.data_as(ip))
+        pc = bake_discrete_cdf(dens)
+        L.oracle_discrete_icdf(n, P(pc), m, P(v), ib.ctypes.data_as(ip))
+        assert np.array_equal(pc.view(np.uint32), d.view(np.uint32)) and np.array_equal(ia, ib), n

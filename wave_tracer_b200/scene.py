@@ -55,6 +55,31 @@ def rotate(axis, angle_rad):
 
 
 # ------------------------------------------------------------------------------------------------ spectra
+def bake_binned_spectrum(values, kmin, kmax):
+    """The tables of binned_piecewise_linear_distribution_t's constructor (binned_piecewise_linear_distribution.hpp:36-63) in ITS arithmetic:
+    f32 grid step, f32 running trapezoid sum in index order, one f32 reciprocal of the total, f32 products.  Returns (ys, dcdf, dx, norm, sum),
+    bit-identical with the reference's members (DESIGN.md 7's pin table, row `binned_piecewise_linear_distribution.hpp`)."""
+    f = np.float32
+    ys = np.asarray(values, f); n = len(ys)
+    dx = f(f(kmax) - f(kmin)) / f(n - 1)
+    terms = (dx * (ys[1:] + ys[:-1])).astype(f) / f(2)
+    dcdf = np.concatenate([np.zeros(1, f), np.add.accumulate(terms, dtype=f)]).astype(f)       # accumulate is strictly sequential
+    tot = dcdf[-1]
+    norm = f(1) / tot if tot > 0 else f(0)
+    return ys, (dcdf * norm).astype(f), dx, norm, tot
+
+
+def bake_discrete_cdf(densities):
+    """discrete_distribution_t's constructor (discrete_distribution.hpp:45-66) in its arithmetic: f32 running sum of max(0, density) in index
+    order, one f32 reciprocal of the total, f32 products; a distribution without mass gets dcdf.back() = 1.  n + 1 entries."""
+    f = np.float32
+    d = np.maximum(np.asarray(densities, f), f(0))
+    cdf = np.concatenate([np.zeros(1, f), np.add.accumulate(d, dtype=f)]).astype(f)
+    if cdf[-1] > 0: return (cdf * (f(1) / cdf[-1])).astype(f)
+    cdf[-1] = 1
+    return cdf
+
+
 class Spectrum:
     """spectrum_t / spectrum_real_t (include/wt/spectrum/spectrum.hpp:37-93): value(k) complex, f(k) real."""
     def value(self, k):  # k: ndarray of 1/mm
@@ -528,18 +553,17 @@ class Scene:
                 kdist_data += [float(np.float32(kmin)), float(prod[0]), 0.0, 1.0]
                 power = geom * prod[0]
             else:
-                n = len(ktab); dk = (kmax - kmin) / (n - 1)
-                dcdf = np.concatenate([[0], np.cumsum(dk * (prod[1:] + prod[:-1]) / 2)]); tot = dcdf[-1]
-                kd.type, kd.n, kd.k0, kd.dk, kd.norm = A.KDIST_BINNED, n, kmin, dk, (1 / tot if tot > 0 else 0.0)
-                kdist_data += [float(v) for v in prod] + [float(v / tot if tot > 0 else 0) for v in dcdf]
-                power = geom * tot
+                n = len(ktab)
+                ys, dcdf, dk, norm, tot = bake_binned_spectrum(prod, kmin, kmax)
+                kd.type, kd.n, kd.k0, kd.dk, kd.norm = A.KDIST_BINNED, n, kmin, float(dk), float(norm)
+                kdist_data += [float(v) for v in ys] + [float(v) for v in dcdf]
+                power = geom * float(tot)
             em_structs.append(E); powers.append(power); kdists.append(kd)
         if not em_structs:
             raise ValueError("(scene) no emitters defined")
         # discrete_distribution_t power cdf, float32 accumulate (discrete_distribution.hpp:45-66)
-        tot = sum(powers); cdf = [np.float32(0)]
-        for p in powers: cdf.append(np.float32(cdf[-1] + np.float32(max(0.0, p / tot if tot > 0 else 0))))
-        cdf = [np.float32(c * (np.float32(1) / cdf[-1])) for c in cdf] if cdf[-1] > 0 else cdf[:-1] + [np.float32(1)]
+        tot = sum(powers)
+        cdf = list(bake_discrete_cdf([p / tot if tot > 0 else 0 for p in powers]))
 
         # ---- tables into desc
         def put(name_n, name_p, ctype, values, keepname):
