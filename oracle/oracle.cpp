@@ -403,6 +403,7 @@ void oracle_binned_eval(uint32_t n, const float* ys, const float* dcdf, float k0
         value[i] = binned_value(ys, n, k0, dk, x[i]); pdf[i] = value[i] * norm;
     }
 }
+void oracle_gaussian1d_integrate(float sigma, uint32_t n, const float* mn, const float* mx, float* out) { for (uint32_t i = 0; i < n; ++i) out[i] = gaussian1d_integrate(sigma, mn[i], mx[i]); }
 void oracle_discrete_icdf(uint32_t n, const float* dcdf, uint32_t m, const float* v, int* idx) { for (uint32_t i = 0; i < m; ++i) idx[i] = (int)discrete_icdf(dcdf, n, v[i]); }
 void oracle_gaussian_pdf(float sx, float sy, uint32_t n, const float* pts, float* out) {
     const gaussian2d_t g(v2{ sx, sy });

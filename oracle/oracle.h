@@ -49,6 +49,7 @@ void oracle_sampler_warps(float u1, float u2, float solid_angle, float out[13]);
 float oracle_erf_lut(float x);
 float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]);
 void oracle_binned_eval(uint32_t n, const float* ys, const float* dcdf, float k0, float dk, float norm, uint32_t m, const float* v, float* icdf, const float* x, float* value, float* pdf);
+void oracle_gaussian1d_integrate(float sigma, uint32_t n, const float* mn, const float* mx, float* out);
 void oracle_discrete_icdf(uint32_t n, const float* dcdf, uint32_t m, const float* v, int* idx);
 void oracle_gaussian_pdf(float sx, float sy, uint32_t n, const float* pts, float* out);
 void oracle_clip_triangles(uint32_t n, const float* tri, const float* zr, int* ntris, float* polygon, float* pieces);

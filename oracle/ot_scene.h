@@ -914,6 +914,12 @@ struct erf_lut_t {
 inline const erf_lut_t& erf_lut() { static erf_lut_t l; return l; }
 
 // film_t / film_storage_t (sensor/film/film.hpp:214-340, film_storage.hpp:196-291): double accumulation
+// gaussian1d_t::integrate over a range (math/distribution/gaussian1d.hpp:100-106), mu = 0: the reconstruction filter's mass over one pixel
+inline f_t gaussian1d_integrate(f_t sigma, f_t mn, f_t mx) {
+    if (sigma == 0) return (mn <= 0 && 0 <= mx) ? 1.f : 0.f;
+    const f_t n = inv_sqrt_two * (1.f / sigma);
+    return (erf_lut()(mx * n) - erf_lut()(mn * n)) / 2;
+}
 struct film_t {
     const scene_t& sc;
     uint32_t W, H, C;
@@ -925,11 +931,7 @@ struct film_t {
         r((int)s.d->sensor.rf_radius), sigma(s.d->sensor.rfilter_stddev), block((size_t)W * H * C * 2, 0.0), light((size_t)W * H * C, 0.0) {}
 
     // gaussian1d_t::integrate (math/distribution/gaussian1d.hpp:100-106), mu = 0
-    f_t rf_integrate(f_t mn, f_t mx) const {
-        if (sigma == 0) return (mn <= 0 && 0 <= mx) ? 1.f : 0.f;
-        const f_t n = inv_sqrt_two * (1.f / sigma);
-        return (erf_lut()(mx * n) - erf_lut()(mn * n)) / 2;
-    }
+    f_t rf_integrate(f_t mn, f_t mx) const { return gaussian1d_integrate(sigma, mn, mx); }
     // film.hpp:308-340; weights ordered x-major (for_range: last dimension fastest)
     f_t weights(f_t ox, f_t oy, f_t* w) const {
         const int Wd = 2 * r + 1;

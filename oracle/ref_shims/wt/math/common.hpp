@@ -136,6 +136,7 @@ namespace eft {     // math/eft/eft.hpp: compensated a*b - c*d (Kahan), as ot_ma
 inline f_t diff_prod(f_t a, f_t b, f_t c, f_t d) noexcept { const f_t cd = c * d; const f_t r = std::fma(a, b, -cd); return r + std::fma(-c, d, cd); }
 inline f_t sum_prod(f_t a, f_t b, f_t c, f_t d) noexcept { return diff_prod(a, b, -c, d); }          // eft.hpp:153-159
 }
+inline constexpr f_t inv_sqrt_two = f_t(1. / 1.41421356237309504880168872420969808);                   // math/defs.hpp:57
 inline constexpr f_t sqrt_pi_2 = f_t(1.253314137315500251207882642405522627), inv_sqrt_two_pi = f_t(0.398942280401432677939946059934381868);  // math/defs.hpp
 inline f_t round(f_t v) noexcept { return std::round(v); }                                      // common.hpp:104-106 glm::round
 inline f_t atan2(f_t y, f_t x) noexcept { return std::atan2(y, x); }                            // quantity/math.hpp:213-216

@@ -685,3 +685,13 @@ def test_spectrum_distributions_equal_the_reference_code():
         pc = bake_discrete_cdf(dens)
         L.oracle_discrete_icdf(n, P(pc), m, P(v), ib.ctypes.data_as(ip))
         assert np.array_equal(pc.view(np.uint32), d.view(np.uint32)) and np.array_equal(ia, ib), n
+    # gaussian1d_t::integrate (gaussian1d.hpp:100-106): the film's reconstruction-filter mass over one pixel (a20), incl. the Dirac filter
+    for f in (R.ref_gaussian1d_integrate, L.oracle_gaussian1d_integrate): f.argtypes = [C.c_float, C.c_uint32, fp, fp, fp]
+    n = 100000
+    for sigma in (0.5, 0.25, 1.3, 0.0):
+        c = rng.uniform(-4, 4, n); mn = (c - 0.5).astype(np.float32); mx = (c + 0.5).astype(np.float32)
+        mn[:5] = [0, -0.5, 0.5, -1e-9, 0]; mx[:5] = [0, 0.5, 1.5, 1e-9, 1]
+        a = np.zeros(n, np.float32); b = a.copy()
+        R.ref_gaussian1d_integrate(sigma, n, P(mn), P(mx), P(a)); L.oracle_gaussian1d_integrate(sigma, n, P(mn), P(mx), P(b))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), sigma
+    assert abs(a[1] - 1.0) < 1e-6                    # sigma = 0: all the mass in the pixel that holds the sample
