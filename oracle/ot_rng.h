@@ -90,7 +90,8 @@ struct sampler_t {
     const float* script = nullptr; uint32_t script_n = 0;
     f_t r() {
         if (script) { const f_t v = d < script_n ? script[d] : .5f; ++d; return v; }
-        if (stream & sobol_flag) return sobol_r(); return (f_t)(next_u32() >> 8) * (1.0f / 16777216.0f);
+        if (stream & sobol_flag) return sobol_r();
+        return (f_t)(next_u32() >> 8) * (1.0f / 16777216.0f);
     }
     v2 r2() { const f_t a = r(); const f_t b = r(); return { a, b }; }
     v3 r3() { const f_t a = r(); const f_t b = r(); const f_t c = r(); return { a, b, c }; }
