@@ -136,13 +136,14 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        vals = []
+        vals = []; step_ms = []
         for s in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
             v, cores, sample = cpu_leg(built, 8.0)
-            if s >= a.warmup: vals.append(v)
+            if s >= a.warmup: vals.append(v); step_ms.append((time.perf_counter() - t0) * 1e3)
         v = sum(vals) / len(vals)
         print(json.dumps({"impl": "reference", "metric": "Msamples/sec", "value": v, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                          "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "ms_per_step": sum(step_ms) / len(step_ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": config, "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
                           "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
