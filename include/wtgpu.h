@@ -392,6 +392,10 @@ int wtgpu_debug_intersect_cones(wtgpu_scene* scene, uint32_t n, const wtgpu_cone
 
 /* counter-based RNG stream: out[i] = i-th draw of stream (seed, pixel, sample) */
 int wtgpu_debug_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out, int device);
+/* the portable elementary functions of wave_tracer_b200/csrc/pmath.h evaluated on the device (they replace the host libm the reference calls through
+ * m::sin ..., include/wt/math/common.hpp, and return the same bits on host and device): fn 0 sin, 1 cos, 2 tan, 3 exp, 4 log, 5 pow(x,y), 6 atan2(x,y),
+ * 7 acos, 8 hypot(x,y), 9 / 10 real / imaginary part of the UTD transition function UTDF(x) (interaction/fsd/utd.hpp:36-57); y may be NULL for unary fn */
+int wtgpu_debug_pmath(int fn, uint32_t n, const float* x, const float* y, float* out, int device);
 /* sobolld: numerators (value * 3^11) and floats of dimensions 0..46 of points g0 .. g0+n-1 of the global sequence; out arrays n*47 */
 int wtgpu_debug_sobol(wtgpu_scene* scene, uint64_t seed, uint64_t g0, uint32_t n, uint32_t* out_numerators, float* out_values);
 /* sizeof of the i-th ABI struct (order of wave_tracer_b200/_abi.py:ABI_STRUCTS); lets bindings verify their layout */

@@ -472,5 +472,17 @@ void oracle_sampler_warps(float u1, float u2, float solid_angle, float out[13]) 
 }
 
 float oracle_erf_lut(float x) { return erf_lut()(x); }
+// pmath.h on the host (fn as wtgpu_debug_pmath); in the glibc build (OT_PORTABLE_LIBM=0) the same entry evaluates the host libm through lm::
+void oracle_pmath(int fn, uint32_t n, const float* x, const float* y, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float a = x[i], b = y ? y[i] : 0.f; float r = 0.f;
+        switch (fn) {
+        case 0: r = lm::sin(a); break; case 1: r = lm::cos(a); break; case 2: r = lm::tan(a); break; case 3: r = lm::exp(a); break;
+        case 4: r = lm::log(a); break; case 5: r = lm::pow(a, b); break; case 6: r = lm::atan2(a, b); break; case 7: r = lm::acos(a); break;
+        case 8: r = lm::hypot(a, b); break; case 9: r = UTDF(a).real(); break; case 10: r = UTDF(a).imag(); break;
+        }
+        out[i] = r;
+    }
+}
 
 } // extern "C"

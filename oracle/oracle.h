@@ -47,6 +47,7 @@ void oracle_fsd_sampler_sample(uint32_t n, uint32_t m, const float* th1, const f
                                const float* edge_pdfs, float P0v, float P0_pdf, float psi02, float recp_I, const float* script, uint32_t n_script, uint32_t n_samples, float* out);
 void oracle_sampler_warps(float u1, float u2, float solid_angle, float out[13]);
 float oracle_erf_lut(float x);
+void oracle_pmath(int fn, uint32_t n, const float* x, const float* y, float* out);
 float oracle_gaussian_integrate_triangle(float sx, float sy, const float tri[6]);
 void oracle_binned_eval(uint32_t n, const float* ys, const float* dcdf, float k0, float dk, float norm, uint32_t m, const float* v, float* icdf, const float* x, float* value, float* pdf);
 void oracle_gaussian1d_integrate(float sigma, uint32_t n, const float* mn, const float* mx, float* out);

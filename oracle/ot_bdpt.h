@@ -24,7 +24,7 @@ static constexpr f_t inv_sqrt_pi = 0.56418958354775628695f;
 // boost-style sinc (include/wt/math/common.hpp:414-434)
 inline f_t sinc(f_t x) {
     const f_t t0 = std::numeric_limits<f_t>::epsilon(), t2 = 0.00034526698300124390839884978618400831996329879769945f, tn = 0.018581361171917516667460937040007436176452688944747f;
-    if (std::fabs(x) >= tn) return std::sin(x) / x;
+    if (std::fabs(x) >= tn) return lm::sin(x) / x;
     f_t r = 1;
     if (std::fabs(x) >= t0) { const f_t x2 = x * x; r -= x2 / 6.f; if (std::fabs(x) >= t2) r += (x2 * x2) / 120.f; }
     return r;
@@ -38,7 +38,7 @@ struct gaussian2d_t {
     bool is_dirac() const { return sigma.x == 0 || sigma.y == 0; }
     f_t pdf(v2 p) const {
         const v2 u = p * recp_sigma;
-        return !is_dirac() ? norm * std::exp(-dot(u, u) / 2) : ((p.x == 0 && p.y == 0) ? inf : 0.f);
+        return !is_dirac() ? norm * lm::exp(-dot(u, u) / 2) : ((p.x == 0 && p.y == 0) ? inf : 0.f);
     }
     v2 to_canonical(v2 v) const {
         const v2 p{ dot(v2{ 1, 0 }, v), dot(v2{ -0.f, 1 }, v) };
@@ -52,11 +52,11 @@ namespace g2d {      // src/math/gaussian2d.cpp:24-94
 inline f_t erf_(f_t x) { return erf_lut()(x); }
 inline f_t I_gauss_gauss0(f_t a, f_t b, f_t c, f_t d) {
     const f_t n2 = 1 / (a + 2 * c * c), n = std::sqrt(n2);
-    return -sqrt_pi / 2 * n * std::exp(-2 * a * sqr(d - b * c) * n2) * (erf_((a * b + 2 * c * d) * n) - erf_((a * (1 + b) + 2 * c * (c + d)) * n));
+    return -sqrt_pi / 2 * n * lm::exp(-2 * a * sqr(d - b * c) * n2) * (erf_((a * b + 2 * c * d) * n) - erf_((a * (1 + b) + 2 * c * (c + d)) * n));
 }
 inline f_t I_gauss_gauss1(f_t a, f_t b, f_t c, f_t d) {
     const f_t n2 = 1 / (a + 2 * c * c), n = std::sqrt(n2);
-    return -sqrt_pi / 2 * n * std::exp(-2 * a * sqr(d - b * c) * n2) * (2 * erf_(a * (d / c - b) * n) + erf_((a * b + 2 * c * d) * n) + erf_((a * (1 + b) + 2 * c * (c + d)) * n));
+    return -sqrt_pi / 2 * n * lm::exp(-2 * a * sqr(d - b * c) * n2) * (2 * erf_(a * (d / c - b) * n) + erf_((a * b + 2 * c * d) * n) + erf_((a * (1 + b) + 2 * c * (c + d)) * n));
 }
 inline f_t I_gauss0(f_t a, f_t b) { const f_t n = std::sqrt(1 / a); return -sqrt_pi / 2 * n * (erf_(a * b * n) - erf_(a * (1 + b) * n)); }
 inline f_t I_gauss1(f_t a, f_t b, f_t c, f_t d) {
@@ -110,7 +110,7 @@ inline f_t gaussian2d_t::integrate_triangle(v2 a, v2 b, v2 c) const {
             f_t x0 = y < b.y ? ab * (y - a.y) + a.x : bc * (y - b.y) + b.x;
             f_t x1 = y < c.y ? ac * (y - a.y) + a.x : bc * (y - b.y) + b.x;
             if (x0 > x1) std::swap(x0, x1);
-            for (f_t x = std::max(-L, x0) + delta / 2; x < std::min(L, x1); x += delta) { ret += std::exp(-(sqr(x) + sqr(y)) / 2); OT_DBG(1, 1); ++dbg_it; }
+            for (f_t x = std::max(-L, x0) + delta / 2; x < std::min(L, x1); x += delta) { ret += lm::exp(-(sqr(x) + sqr(y)) / 2); OT_DBG(1, 1); ++dbg_it; }
         }
         OT_DBG_MAX(6, dbg_it); (void)dbg_it;
         return ret * inv_two_pi * sqr(delta);
@@ -178,16 +178,16 @@ inline clip_ret_t clip_triangle_z(v3 a, v3 b, v3 c, range_t zr) {
 namespace ffsd {
 struct edge_t { v2 e, v; c_t a_b, iab_2; };
 static constexpr f_t PA1 = 0.0049361075794549872500f, PA2 = 0.21899789398059305541f, P0_sigma = 0.288675134594813f / 4;
-inline f_t alpha1(f_t x, f_t y) { return x == 0 ? 0.f : inv_two_pi * y / (x * (x * x + y * y)) * (std::cos(x / 2) - sinc(x / 2)); }
+inline f_t alpha1(f_t x, f_t y) { return x == 0 ? 0.f : inv_two_pi * y / (x * (x * x + y * y)) * (lm::cos(x / 2) - sinc(x / 2)); }
 inline f_t alpha2(f_t x, f_t y) { return x == 0 ? 0.f : inv_two_pi * y / (x * x + y * y) * sinc(x / 2); }
 inline f_t chi_e(v2 xi) { const f_t chi = 0.830092714835359f; const f_t t = 1 + chi * dot(xi, xi), t2 = t * t, t3 = t2 * t; return std::max(0.f, 1 - (3 / t2 - 2 / t3)); }
-inline f_t chi_0(v2 xi) { xi = xi / P0_sigma; return std::exp(-.5f * dot(xi, xi)); }
+inline f_t chi_0(v2 xi) { xi = xi / P0_sigma; return lm::exp(-.5f * dot(xi, xi)); }
 // zeta = xi * Xi, Xi = mat2(e, m) columns, row-vector times matrix: (dot(xi,e), dot(xi,m)), m = (e.y,-e.x) (fsd.hpp:27-33, 108)
 inline v2 zeta_of(const edge_t& e, v2 xi) { return { xi.x * e.e.x + xi.y * e.e.y, xi.x * e.e.y + xi.y * (-e.e.x) }; }
 inline c_t Psi(const edge_t& e, v2 xi) {
     const v2 z = zeta_of(e, xi);
     const c_t a1 = e.a_b * alpha1(z.x, z.y), a2 = e.iab_2 * alpha2(z.x, z.y);
-    return std::polar<f_t>(length2(e.e), -dot(e.v, xi)) * (a1 + a2);
+    return lm::polar(length2(e.e), -dot(e.v, xi)) * (a1 + a2);
 }
 inline f_t Psi2(const edge_t& e, v2 xi) {
     const v2 z = zeta_of(e, xi);
@@ -223,7 +223,7 @@ struct lut_t {
         const f_t theta = lerp1(r3.x, th, N);
         const f_t tf = theta * 2 / pi;
         const f_t r = std::max(0.f, lerp2(tf, r3.y, cd));
-        v2 z = r * v2{ std::cos(theta), std::sin(theta) };
+        v2 z = r * v2{ lm::cos(theta), lm::sin(theta) };
         const int q = std::min(3, (int)(r3.z * 4));
         z.x *= (((q + 1) / 2) % 2 == 0 ? 1.f : -1.f);
         z.y *= ((q / 2) % 2 == 0 ? 1.f : -1.f);

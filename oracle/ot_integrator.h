@@ -150,10 +150,10 @@ inline c_t UTDF(f_t x) {
     c_t result;
     if (absx < 6) {
         const f_t sqrt_x = std::sqrt(absx);
-        const c_t zf = std::exp(c_t{ 0, pi_4 }) * sqrt_x;
+        const c_t zf = lm::expi(pi_4) * sqrt_x;
         const std::complex<double> ce = cerfc_series(std::complex<double>(zf.real(), zf.imag()));
         const c_t cerf{ (f_t)ce.real(), (f_t)ce.imag() };
-        result = c_t{ 1, 1 } * sqrt_pi_2 * sqrt_x * std::exp(c_t{ 0, absx }) * cerf;
+        result = c_t{ 1, 1 } * sqrt_pi_2 * sqrt_x * lm::expi(absx) * cerf;
     } else {
         const f_t r = 1 / (2 * absx);
         const f_t r2 = r * r, r3 = r2 * r, r4 = r2 * r2;
@@ -164,7 +164,7 @@ inline c_t UTDF(f_t x) {
 // utd.hpp:26-31
 inline f_t UTDa(int sgn, f_t phi, f_t n) {
     const f_t N = std::round((f_t)(sgn * pi + phi) * inv_two_pi / n);
-    return 2 * sqr(std::cos(pi * n * N - phi / 2));
+    return 2 * sqr(lm::cos(pi * n * N - phi / 2));
 }
 inline f_t fmod_pos(f_t a, f_t b) { return a - b * std::floor(a / b); }    // glm::mod
 
@@ -205,20 +205,20 @@ struct wedge_edge_t {       // interaction/fsd/common.hpp
         const f_t n = 2 - alpha * inv_pi;
         const f_t sin_beta2 = std::max(0.f, 1 - sqr(dot(wi, ee)));
         const f_t sin_beta = std::sqrt(sin_beta2);
-        const f_t phii = std::atan2(dot(nff, wi), dot(tff, wi));
-        const f_t phio = std::atan2(dot(nff, wo), dot(tff, wo));
+        const f_t phii = lm::atan2(dot(nff, wi), dot(tff, wi));
+        const f_t phio = lm::atan2(dot(nff, wo), dot(tff, wo));
         const f_t Li = ro * sin_beta2;
         const f_t a1 = UTDa(+1, phii - phio, n), a2 = UTDa(-1, phii - phio, n);
         const f_t a3 = UTDa(+1, phii + phio, n), a4 = UTDa(-1, phii + phio, n);
         const f_t kL = k_times_len(k, Li);
         const c_t F1 = UTDF(kL * a1), F2 = UTDF(kL * a2), F3 = UTDF(kL * a3), F4 = UTDF(kL * a4);
-        auto cot = [](f_t x) { return 1.f / std::tan(x); };
+        auto cot = [](f_t x) { return 1.f / lm::tan(x); };
         const c_t D1 = -cot((pi + (phii - phio)) / (2 * n)) * F1;
         const c_t D2 = -cot((pi - (phii - phio)) / (2 * n)) * F2;
         const c_t D3 = -cot((pi + (phii + phio)) / (2 * n)) * F3;
         const c_t D4 = -cot((pi - (phii + phio)) / (2 * n)) * F4;
         const f_t kro = k_times_len(k, ro);
-        const c_t D = (1 / (2 * n * std::sqrt(kro) * sin_beta) * inv_sqrt_two_pi) * std::exp(c_t{ 0, -pi_4 });
+        const c_t D = (1 / (2 * n * std::sqrt(kro) * sin_beta) * inv_sqrt_two_pi) * lm::expi(-pi_4);
         const f_t t1 = fmod_pos(phii + phio, pi_2);
         const f_t t2 = fmod_pos(phii - phio, pi_2);
         const bool z = std::fabs(t1) < 1e-5f || std::fabs(t2) < 1e-5f;
@@ -288,15 +288,15 @@ struct fsd_t {      // free_space_diffraction_t
             if ((dot(wo, edge.nff) <= 0 && dot(wo, edge.nbf) <= 0) || (dot(ui, edge.nff) <= 0 && dot(ui, edge.nbf) <= 0)) continue;
             const f_t ri = length(src - *p);
             const v3 wi = (src - *p) / ri;
-            const f_t phii = std::atan2(dot(edge.nff, wi), dot(edge.tff, wi));
-            const f_t phio = std::atan2(dot(edge.nff, wo), dot(edge.tff, wo));
+            const f_t phii = lm::atan2(dot(edge.nff, wi), dot(edge.tff, wi));
+            const f_t phio = lm::atan2(dot(edge.nff, wo), dot(edge.tff, wo));
             const f_t sigma = std::sqrt(utd_IS_sigma_scale / k_times_len(k, ri));
             const f_t mean_phi1 = pi + phii, mean_phi2 = pi - phii;
             f_t x1 = std::fabs(fmod_pos(phio - mean_phi1, two_pi));
             f_t x2 = std::fabs(fmod_pos(phio - mean_phi2, two_pi));
             if (x1 > pi) x1 -= two_pi;
             if (x2 > pi) x2 -= two_pi;
-            const f_t apd = inv_sqrt_two_pi / sigma * (std::exp(-.5f * sqr(x1 / sigma)) + std::exp(-.5f * sqr(x2 / sigma))) / 2;
+            const f_t apd = inv_sqrt_two_pi / sigma * (lm::exp(-.5f * sqr(x1 / sigma)) + lm::exp(-.5f * sqr(x2 / sigma))) / 2;
             ret += apd;
         }
         return ret / (f_t)(edges.size() + 1);
@@ -315,7 +315,7 @@ struct fsd_t {      // free_space_diffraction_t
         if (dot(ui, edge.nff) <= 0 && dot(ui, edge.nbf) <= 0) return {};
         const f_t ri = length(src - p);
         const v3 wi = (src - p) / ri;
-        const f_t phii = std::atan2(dot(edge.nff, wi), dot(edge.tff, wi));
+        const f_t phii = lm::atan2(dot(edge.nff, wi), dot(edge.tff, wi));
         const f_t sigma = std::sqrt(utd_IS_sigma_scale / k_times_len(k, ri));
         const f_t smp = sigma * normal2d(sampler.r2()).x;
         const f_t mean_phi1 = pi + phii, mean_phi2 = pi - phii;
@@ -323,7 +323,7 @@ struct fsd_t {      // free_space_diffraction_t
         const v3 e = edge.e();
         const f_t cos_beta = dot(wi, e);
         const f_t sin_beta = std::sqrt(std::max(0.f, 1 - sqr(cos_beta)));
-        const v3 wo = sin_beta * (std::cos(phio) * edge.tff + std::sin(phio) * edge.nff) - cos_beta * e;
+        const v3 wo = sin_beta * (lm::cos(phio) * edge.tff + lm::sin(phio) * edge.nff) - cos_beta * e;
         if (dot(wo, edge.nff) <= 0 && dot(wo, edge.nbf) <= 0) return {};
         if (sin_beta < utd_min_sin_beta) return {};
         const f_t dpd = pdf(src, wo);
@@ -384,13 +384,13 @@ struct plt_path_t {
             const geo_t eintr = geo_t::on_edge(f.edge_idx, f.p);
             if (shadow(sc, eintr, src_geo, ctr()) || shadow(sc, eintr, dst_geo, ctr())) continue;
             const f_t dd = f.ro + f.ri;
-            const c_t phase = std::exp(c_t{ 0, -k_times_len(k, dd) });
+            const c_t phase = lm::expi(-k_times_len(k, dd));
             ts += phase * f.utd.Ds; th += phase * f.utd.Dh;
         }
         if (cone_from_src.contains(dst)) {
             if (!shadow(sc, src_geo, dst_geo, ctr())) {
                 const f_t dd = length(dst - src);
-                const c_t phase = std::exp(c_t{ 0, -k_times_len(k, dd) });
+                const c_t phase = lm::expi(-k_times_len(k, dd));
                 ts += phase; th += phase;
             }
         }

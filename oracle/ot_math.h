@@ -34,6 +34,58 @@ static constexpr f_t inv_sqrt_two = 0.70710678118654752440f;
 static constexpr f_t inv_sqrt_two_pi = 0.39894228040143267794f;
 static constexpr f_t sqrt_pi_2 = 1.25331413731550025121f;   // sqrt(pi/2)
 
+// ---- elementary functions.  OT_PORTABLE_LIBM=1 (liboracle.so, what the GPU is compared with): the portable binary64-internal functions of
+// wave_tracer_b200/csrc/pmath.h, which return the same bits on the host and on the device -- so that device-vs-oracle differences are the
+// code's, not the math library's (the path is ill-conditioned in libm ulps: a phase is k*L ~ 1e5..1e8 rad).  OT_PORTABLE_LIBM=0
+// (liboracle_glibc.so): the host libm through std::, exactly as the reference calls it (m::sin ... -> std::sin, include/wt/math/common.hpp);
+// this build is the one pinned bit for bit against the reference's own translation units (tests/test_oracle_kats.py) and is compared with
+// the portable build in tests/test_pmath.py (films agree to the f32 conditioning of the path, functions to <= 1 ulp).
+#ifndef OT_PORTABLE_LIBM
+#define OT_PORTABLE_LIBM 1
+#endif
+} // namespace ot
+#if OT_PORTABLE_LIBM
+#include "../wave_tracer_b200/csrc/pmath.h"
+#endif
+namespace ot {
+namespace lm {
+#if OT_PORTABLE_LIBM
+inline f_t sin(f_t x) { return pm::sinf(x); }
+inline f_t cos(f_t x) { return pm::cosf(x); }
+inline f_t tan(f_t x) { return pm::tanf(x); }
+inline f_t exp(f_t x) { return pm::expf(x); }
+inline f_t log(f_t x) { return pm::logf(x); }
+inline f_t pow(f_t x, f_t y) { return pm::powf(x, y); }
+inline f_t atan2(f_t y, f_t x) { return pm::atan2f(y, x); }
+inline f_t acos(f_t x) { return pm::acosf(x); }
+inline f_t hypot(f_t a, f_t b) { return pm::hypotf(a, b); }
+inline c_t expi(f_t x) { f_t s, c; pm::sincosf(x, &s, &c); return { c, s }; }                       // std::exp(c_t{0, x})
+inline c_t polar(f_t rho, f_t th) { f_t s, c; pm::sincosf(th, &s, &c); return { rho * c, rho * s }; }   // std::polar
+inline f_t cabs(c_t z) { return pm::hypotf(z.real(), z.imag()); }
+inline c_t csqrt(c_t z) {       // principal square root, the formula of the device's csqrt_ (glibc csqrtf without its over/underflow scaling)
+    if (z.real() == 0 && z.imag() == 0) return { 0, 0 };
+    const f_t r = pm::hypotf(z.real(), z.imag());
+    const f_t t = std::sqrt(0.5f * (r + std::fabs(z.real())));
+    if (z.real() >= 0) return { t, z.imag() / (2 * t) };
+    return { std::fabs(z.imag()) / (2 * t), z.imag() >= 0 ? t : -t };
+}
+#else
+inline f_t sin(f_t x) { return std::sin(x); }
+inline f_t cos(f_t x) { return std::cos(x); }
+inline f_t tan(f_t x) { return std::tan(x); }
+inline f_t exp(f_t x) { return std::exp(x); }
+inline f_t log(f_t x) { return std::log(x); }
+inline f_t pow(f_t x, f_t y) { return std::pow(x, y); }
+inline f_t atan2(f_t y, f_t x) { return std::atan2(y, x); }
+inline f_t acos(f_t x) { return std::acos(x); }
+inline f_t hypot(f_t a, f_t b) { return std::hypot(a, b); }
+inline c_t expi(f_t x) { return std::exp(c_t{ 0, x }); }
+inline c_t polar(f_t rho, f_t th) { return std::polar<f_t>(rho, th); }
+inline f_t cabs(c_t z) { return std::abs(z); }
+inline c_t csqrt(c_t z) { return std::sqrt(z); }
+#endif
+}
+
 inline f_t sqr(f_t x) { return x * x; }
 inline f_t sign(f_t t) { return f_t(t > 0) - f_t(t < 0); }             // glm::sign
 inline f_t mix(f_t a, f_t b, f_t x) {                                   // math/common.hpp:258-264

@@ -134,7 +134,7 @@ inline fresnel_ret_t fresnel(c_t eta_12, v3 w, v3 n = { 0, 0, 1 }) {      // fre
     const c_t rp = (abs_cosi - e * cost) / (abs_cosi + e * cost);
     const c_t ts = rs + c_t{ 1, 0 };
     const c_t tp = (rp + c_t{ 1, 0 }) * e;
-    const f_t Z = std::abs(cost / (e * abs_cosi));
+    const f_t Z = lm::cabs(cost / (e * abs_cosi));
     return { refr.t, e, Z, rs, rp, ts, tp, std::min(1.f, Z * std::norm(ts)), std::min(1.f, Z * std::norm(tp)) };
 }
 struct fresnel_conductor_ret_t { c_t rs, rp; };
@@ -142,7 +142,7 @@ inline fresnel_conductor_ret_t fresnel_reflection(c_t eta_12, v3 w, v3 n = { 0, 
     const f_t wn = dot(w, n);
     if (eta_12 == c_t{ 1, 0 } || wn < 0) return { 0, 0 };
     const c_t t2 = c_t{ 1, 0 } - (1 - sqr(wn)) * (eta_12 * eta_12);
-    const c_t t = std::sqrt(t2);
+    const c_t t = lm::csqrt(t2);
     const c_t i{ wn, 0 };
     return { (eta_12 * i - t) / (eta_12 * i + t), (i - eta_12 * t) / (i + eta_12 * t) };
 }

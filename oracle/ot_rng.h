@@ -113,7 +113,7 @@ inline v3 uniform_sphere(v2 u) {
     const f_t z = 1 - 2 * u.x;
     const f_t rr = std::sqrt(std::max(0.f, 1 - sqr(z)));
     const f_t phi = two_pi * u.y;
-    return { rr * std::cos(phi), rr * std::sin(phi), z };
+    return { rr * lm::cos(phi), rr * lm::sin(phi), z };
 }
 // sampler.hpp:164-181
 inline v2 concentric_disk(v2 u) {
@@ -122,7 +122,7 @@ inline v2 concentric_disk(v2 u) {
     if (offset.x == 0 && offset.y == 0) { rr = 0; theta = 0; }
     else if (std::fabs(offset.x) > std::fabs(offset.y)) { rr = offset.x; theta = pi_4 * (offset.y / offset.x); }
     else { rr = offset.y; theta = pi_2 - pi_4 * (offset.x / offset.y); }
-    return rr * v2{ std::cos(theta), std::sin(theta) };
+    return rr * v2{ lm::cos(theta), lm::sin(theta) };
 }
 // sampler.hpp:197-203
 inline v3 cosine_hemisphere(v2 u) {
@@ -137,14 +137,14 @@ inline v3 uniform_cone(f_t solid_angle, v2 u) {
     const f_t cos_theta = 1 + u.x * (cos_theta_max - 1);
     const f_t sin_theta = std::sqrt(std::max(0.f, 1 - sqr(cos_theta)));
     const f_t phi = two_pi * u.y;
-    return { std::cos(phi) * sin_theta, std::sin(phi) * sin_theta, cos_theta };
+    return { lm::cos(phi) * sin_theta, lm::sin(phi) * sin_theta, cos_theta };
 }
 inline f_t uniform_cone_pdf(f_t solid_angle) { return 1.f / solid_angle; }
 // sampler.hpp:253-260
 inline v2 normal2d(v2 u) {
-    const f_t r = std::sqrt(-2 * std::log(1 - u.x));
+    const f_t r = std::sqrt(-2 * lm::log(1 - u.x));
     const f_t theta = two_pi * u.y;
-    return { r * std::cos(theta), r * std::sin(theta) };
+    return { r * lm::cos(theta), r * lm::sin(theta) };
 }
 // sampler.hpp:281-286
 inline v2 uniform_triangle(v2 u) { if (u.x + u.y > 1) u = v2{ 1, 1 } - u; return u; }

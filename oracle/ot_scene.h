@@ -143,7 +143,7 @@ struct bsdf_eval_t {
         const f_t gamma = b.gamma;
         auto sigma2_normalized = [&](f_t T) {
             const f_t x = 1 + k * k * T;
-            const f_t p = gamma == 3 ? x : std::pow(x, (gamma - 1) / 2);
+            const f_t p = gamma == 3 ? x : lm::pow(x, (gamma - 1) / 2);
             return 1 / (1 - 1.f / p);
         };
         if (b.profile_type == WTGPU_PROFILE_FRACTAL_ROUGHNESS) {
@@ -158,7 +158,7 @@ struct bsdf_eval_t {
     f_t fractal_psd(const wtgpu_bsdf& b, const fractal_params_t& p, v2 z, f_t k) const {
         const f_t gamma = b.gamma;
         const f_t x = 1 + p.T * dot(z, z);
-        const f_t pw = gamma == 3 ? (x * x) : std::pow(x, (gamma + 1) / 2);
+        const f_t pw = gamma == 3 ? (x * x) : lm::pow(x, (gamma + 1) / 2);
         const f_t f = 1 / pw;
         return p.sigma2_norm * (inv_two_pi * k * k * (gamma - 1) * p.T * f);
     }
@@ -175,29 +175,29 @@ struct bsdf_eval_t {
             sigma2 = sqr(sc.spectrum_f(b.prof_spec[0], k));
             alpha = sigma2;
         }
-        return { sigma2, 1 / (1 - std::exp(-(k * k / 2 / sigma2))), alpha };
+        return { sigma2, 1 / (1 - lm::exp(-(k * k / 2 / sigma2))), alpha };
     }
     f_t gaussian_psd(const gaussian_params_t& p, v2 z, f_t k) const {          // gaussian.hpp:121-130
         const f_t z2 = dot(z, z);
-        const f_t e = std::exp(-(z2 / 2 / p.sigma2));
+        const f_t e = lm::exp(-(z2 / 2 / p.sigma2));
         return e <= std::numeric_limits<f_t>::epsilon() ? 0.f : p.sigma2_norm * (inv_two_pi / p.sigma2 * k * k * e);
     }
     static f_t boxmueller_max_phi(f_t r, f_t l) {                               // gaussian.hpp:43-49, 70-76
         const f_t eps = std::numeric_limits<f_t>::epsilon();
-        return (r < eps || l < eps) ? pi : std::max(1e-2f, std::acos(clampf((sqr(r) + sqr(l) - 1) / (2 * r * l), -1, 1)));
+        return (r < eps || l < eps) ? pi : std::max(1e-2f, lm::acos(clampf((sqr(r) + sqr(l) - 1) / (2 * r * l), -1, 1)));
     }
     // truncated Box-Mueller transform (gaussian.hpp:28-56); returns the point and its pdf
     static std::pair<v2, f_t> sample_boxmueller_truncated(v2 sample, v2 mean, f_t sigma2) {
         const f_t eps = std::numeric_limits<f_t>::epsilon();
         const f_t l = std::sqrt(std::min(1.f, dot(mean, mean)));
         const f_t coso = std::sqrt(std::max(0.f, 1 - dot(mean, mean)));
-        const f_t phi_i = (mean.x != 0 || mean.y != 0) ? std::atan2(mean.y, mean.x) : 0.f;
-        const f_t s = std::exp(-.5f * sqr(1 + l) / sigma2);
+        const f_t phi_i = (mean.x != 0 || mean.y != 0) ? lm::atan2(mean.y, mean.x) : 0.f;
+        const f_t s = lm::exp(-.5f * sqr(1 + l) / sigma2);
         const f_t x = (1 - s) * std::max(eps, sample.x) + s;
-        const f_t r = std::sqrt(-2 * sigma2 * std::log(x));
+        const f_t r = std::sqrt(-2 * sigma2 * lm::log(x));
         const f_t max_phi = boxmueller_max_phi(r, l);
         const f_t phi = phi_i + pi + max_phi * (2 * sample.y - 1);
-        const v2 p = r * v2{ std::cos(phi), std::sin(phi) };
+        const v2 p = r * v2{ lm::cos(phi), lm::sin(phi) };
         const f_t pdf = .5f * x / (max_phi * sigma2) * coso;
         return { p + mean, pdf };
     }
@@ -206,7 +206,7 @@ struct bsdf_eval_t {
         const f_t coso = std::sqrt(std::max(0.f, 1 - dot(mean, mean)));
         wo = wo - mean;
         const f_t r2 = dot(wo, wo);
-        const f_t x = std::exp(-.5f * r2 / sigma2);
+        const f_t x = lm::exp(-.5f * r2 / sigma2);
         const f_t r = std::sqrt(r2);
         const f_t max_phi = boxmueller_max_phi(r, l);
         return .5f * x / (max_phi * sigma2) * coso;
@@ -219,7 +219,7 @@ struct bsdf_eval_t {
         if (b.profile_type == WTGPU_PROFILE_DIRAC) return 1;
         const f_t palpha = is_gaussian(b) ? gaussian_params(b, k).alpha : fractal_params(b, k).alpha;     // gaussian.hpp:162-169 == fractal.hpp
         const f_t a = sqr((std::fabs(wi.z) + std::fabs(wo.z)) * k) * palpha;
-        return std::exp(-a);
+        return lm::exp(-a);
     }
     f_t profile_psd(const wtgpu_bsdf& b, v3 wi, v3 wo, f_t k) const {
         if (b.profile_type == WTGPU_PROFILE_DIRAC) return 0;
@@ -238,7 +238,7 @@ struct bsdf_eval_t {
         const v2 zeta_k = v2{ wi.x, wi.y } + v2{ wo.x, wo.y };
         const f_t f_k = length(zeta_k);
         const f_t s = std::sqrt(std::max(0.f, 1 - sqr(wi.z)));
-        const f_t phi_max = (f_k == 0 || s == 0) ? pi : std::acos(clampf((sqr(f_k) + sqr(s) - 1) / (2 * f_k * s), -1, 1));
+        const f_t phi_max = (f_k == 0 || s == 0) ? pi : lm::acos(clampf((sqr(f_k) + sqr(s) - 1) / (2 * f_k * s), -1, 1));
         const v2 zeta = zeta_k * k;
         const f_t psd = fractal_psd(b, p, zeta, k);
         const f_t w = inv_pi * phi_max;
@@ -260,16 +260,16 @@ struct bsdf_eval_t {
         const f_t gamma = b.gamma;
         const auto p = fractal_params(b, k);
         const f_t s = std::sqrt(std::max(0.f, 1 - sqr(wi.z)));
-        const f_t phi_i = s > 0 ? std::atan2(wi.y, wi.x) : 0.f;
+        const f_t phi_i = s > 0 ? lm::atan2(wi.y, wi.x) : 0.f;
         const f_t sqrtT = std::sqrt(p.T);
         const v2 u2 = sampler.r2();
         const f_t k2T = sqr(k) * p.T;
-        const f_t M = 1 - std::pow(1 + k2T * sqr(1 + s), -(gamma - 1) / 2);
-        const f_t f = std::sqrt(std::pow(1 - M * u2.x, -2 / (gamma - 1)) - 1) / sqrtT;
+        const f_t M = 1 - lm::pow(1 + k2T * sqr(1 + s), -(gamma - 1) / 2);
+        const f_t f = std::sqrt(lm::pow(1 - M * u2.x, -2 / (gamma - 1)) - 1) / sqrtT;
         const f_t f_k = f / k;
-        const f_t phi_max = (f == 0 || s == 0) ? pi : std::acos(clampf((sqr(f_k) + sqr(s) - 1) / (2 * f_k * s), -1, 1));
+        const f_t phi_max = (f == 0 || s == 0) ? pi : lm::acos(clampf((sqr(f_k) + sqr(s) - 1) / (2 * f_k * s), -1, 1));
         const f_t phi_f = phi_i + (2 * u2.y - 1) * phi_max;
-        const v2 vf = f * v2{ std::cos(phi_f), std::sin(phi_f) };
+        const v2 vf = f * v2{ lm::cos(phi_f), lm::sin(phi_f) };
         const v2 zeta = vf;
         const v2 zeta_k = zeta / k;
         const v2 wo = zeta_k - v2{ wi.x, wi.y };
@@ -503,14 +503,14 @@ struct emitters_t {
         }
         const f_t extent = (e.type != WTGPU_EMITTER_AREA && e.extent > 0) ? e.extent : 10.f * wavenum_to_wavelen(k);
         auto se = sourcing_geometry_t::source_mub_from_length(extent, k).phase_space_extent().enlarge(e.pse_scale);
-        if (e.type == WTGPU_EMITTER_SPOT) se.tan_alpha = std::min(se.tan_alpha, std::tan(e.falloff));
+        if (e.type == WTGPU_EMITTER_SPOT) se.tan_alpha = std::min(se.tan_alpha, lm::tan(e.falloff));
         return sourcing_geometry_t::source(se);
     }
     f_t spot_falloff(const wtgpu_emitter& e, v3 local_dir) const {       // spot.hpp:76-81
         const f_t cos_theta = local_dir.z;
-        if (cos_theta <= std::cos(e.cutoff)) return 0;
-        if (cos_theta >= std::cos(e.falloff)) return 1;
-        return (e.cutoff - std::acos(cos_theta)) * (1.f / (e.cutoff - e.falloff));
+        if (cos_theta <= lm::cos(e.cutoff)) return 0;
+        if (cos_theta >= lm::cos(e.falloff)) return 1;
+        return (e.cutoff - lm::acos(cos_theta)) * (1.f / (e.cutoff - e.falloff));
     }
     f_t area_radiance(const wtgpu_emitter& e, f_t k) const { return e.scale * sc.spectrum_f(e.spectrum, k); }   // area.hpp:104-117
     // area_t::Le (area.hpp:170-180)
@@ -545,7 +545,7 @@ struct emitters_t {
             return { b, pd_t::discrete(1), pd_t::density(inv_four_pi), std::nullopt };
         }
         case WTGPU_EMITTER_SPOT: {      // spot.cpp:29-46
-            const f_t cutoff_sa = two_pi * (1 - std::cos(e.cutoff));
+            const f_t cutoff_sa = two_pi * (1 - lm::cos(e.cutoff));
             const v3 local_wo = uniform_cone(cutoff_sa, sampler.r2());
             const v3 wo = normalize(mat3_mul(e.rot, local_wo));
             const f_t w = spot_falloff(e, local_wo);
@@ -592,7 +592,7 @@ struct emitters_t {
         const wtgpu_emitter& e = em(i);
         switch (e.type) {
         case WTGPU_EMITTER_POINT: return inv_four_pi;
-        case WTGPU_EMITTER_SPOT: return uniform_cone_pdf(two_pi * (1 - std::cos(e.cutoff)));
+        case WTGPU_EMITTER_SPOT: return uniform_cone_pdf(two_pi * (1 - lm::cos(e.cutoff)));
         case WTGPU_EMITTER_AREA: return cosine_hemisphere_pdf(std::max(0.f, dot(dir, surface->ng())));
         default: return 0;
         }

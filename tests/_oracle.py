@@ -9,7 +9,8 @@ from wave_tracer_b200 import _abi as A
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")                 # elementary functions from pmath.h (same bits as the device): GPU parity, CPU baseline
+LIB_GLIBC = os.path.join(ORACLE_DIR, "liboracle_glibc.so")     # host libm as the reference calls it: the pins against the reference's own code
 
 
 class OracleStats(C.Structure):
@@ -18,10 +19,20 @@ class OracleStats(C.Structure):
 
 
 _lib = None
+_lib_glibc = None
 
 
 def build():
     subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+
+
+def lib_glibc():
+    global _lib_glibc
+    if _lib_glibc is None:
+        if not os.path.exists(LIB_GLIBC):
+            build()
+        _lib_glibc = _bind(C.CDLL(LIB_GLIBC))
+    return _lib_glibc
 
 
 def lib():
@@ -29,7 +40,14 @@ def lib():
     if _lib is None:
         if not os.path.exists(LIB):
             build()
-        L = C.CDLL(LIB)
+        _lib = _bind(C.CDLL(LIB))
+    return _lib
+
+
+def _bind(L):
+    if True:
+        if True:
+            pass
         L.oracle_render.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(A.RenderOpts), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(OracleStats)]
         L.oracle_intersect_rays.argtypes = [C.POINTER(A.SceneDesc), C.c_uint32, C.POINTER(A.RayQuery), C.POINTER(A.RayHit)]
         L.oracle_intersect_rays_bruteforce.argtypes = L.oracle_intersect_rays.argtypes
@@ -52,11 +70,11 @@ def lib():
         L.oracle_fuzz_ray_cull.argtypes = [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]
         L.oracle_sobol_points_with_seeds.argtypes = [C.POINTER(A.SobolEntry), C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.oracle_sobol_seeds.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
-        _lib = L
-    return _lib
+        L.oracle_pmath.argtypes = [C.c_int, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    return L
 
 
-def render(built, spp=None, seed=0x5EED, sample_range=None, tile=None, threads=0):
+def render(built, spp=None, seed=0x5EED, sample_range=None, tile=None, threads=0, glibc=False):
     spp = spp or built.spp
     o = A.RenderOpts()
     o.seed, o.spp = seed, spp
@@ -66,7 +84,7 @@ def render(built, spp=None, seed=0x5EED, sample_range=None, tile=None, threads=0
     W, H, Cn = built.width, built.height, built.channels
     block = np.zeros((H, W, Cn, 2), np.float64); light = np.zeros((H, W, Cn), np.float64)
     st = OracleStats()
-    rc = lib().oracle_render(C.byref(built.desc), C.byref(o), block.ctypes.data_as(C.c_void_p), light.ctypes.data_as(C.c_void_p), threads, C.byref(st))
+    rc = (lib_glibc() if glibc else lib()).oracle_render(C.byref(built.desc), C.byref(o), block.ctypes.data_as(C.c_void_p), light.ctypes.data_as(C.c_void_p), threads, C.byref(st))
     if rc != 0:
         raise RuntimeError(f"oracle_render failed: {rc}")
     return block, light, {n: getattr(st, n) for n, _ in st._fields_}

@@ -326,7 +326,7 @@ def test_fresnel_equals_the_reference_code():
     unmodified into oracle/_ref/libref_fresnel.so (oracle/ref_fresnel.cpp over the shim headers): dielectrics on both sides of the interface,
     total internal reflection, grazing and normal incidence, index-matched media, absorbing conductors.  Same f32 operations in the same
     order: the results are required to be BIT-IDENTICAL."""
-    R = C.CDLL(REF_FRESNEL); L = _oracle.lib()
+    R = C.CDLL(REF_FRESNEL); L = _oracle.lib_glibc()
     fp = C.POINTER(C.c_float)
     for lib, names in ((R, ("ref_fresnel", "ref_fresnel_reflection", "ref_reflect")), (L, ("oracle_fresnel_full", "oracle_fresnel_reflection", "oracle_reflect"))):
         getattr(lib, names[0]).argtypes = [C.c_float, C.c_float, fp, fp]; getattr(lib, names[1]).argtypes = [C.c_float, C.c_float, fp, fp]; getattr(lib, names[2]).argtypes = [fp, fp]
@@ -367,7 +367,7 @@ def test_fraunhofer_formulas_equal_the_reference_code():
     """ot_bdpt.h's Fraunhofer FSD formulas (alpha1, alpha2, chi_e, chi_0, Psi via ASF_unclamped, Psi2 via sampling_density, ASF, P0, Pj) against
     the REFERENCE'S OWN include/wt/interaction/fsd/fraunhofer/fsd.hpp, compiled unmodified into oracle/_ref/libref_fsd.so: random apertures of
     1..24 edges, xi from 1e-4 to 30 (both sinc branches, the chi_e clamp).  Required: BIT-IDENTICAL f32 results."""
-    R = C.CDLL(REF_FSD); L = _oracle.lib()
+    R = C.CDLL(REF_FSD); L = _oracle.lib_glibc()
     fp = C.POINTER(C.c_float)
     for f in (R.ref_fsd_eval, L.oracle_fsd_eval):
         f.argtypes = [C.c_uint32, fp, C.c_float, C.c_float, C.c_float, C.c_float, fp]; f.restype = None
@@ -398,7 +398,7 @@ def test_fraunhofer_lut_sampling_equals_the_reference_code():
     """ot_bdpt.h's lut_t::sample (linear + bilinear table look-up, quadrant choice) against the REFERENCE'S OWN fsd_lut_t::sample
     (include/wt/interaction/fsd/fraunhofer/fsd_lut.hpp:35-69, compiled unmodified into oracle/_ref/libref_fsd_lut.so) at the reference's table
     sizes (2048, 3072 x 3072), tables filled with a smooth synthetic inverse CDF, 20 000 random triples incl. the ends of [0,1].  BIT-IDENTICAL."""
-    R = C.CDLL(REF_FSD_LUT); L = _oracle.lib()
+    R = C.CDLL(REF_FSD_LUT); L = _oracle.lib_glibc()
     fp = C.POINTER(C.c_float)
     R.ref_fsd_lut_n.restype = C.c_uint32; R.ref_fsd_lut_m.restype = C.c_uint32
     n, m = R.ref_fsd_lut_n(), R.ref_fsd_lut_m()
@@ -427,7 +427,7 @@ REF_FSD_SAMPLER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(_
 def test_sampler_warps_equal_the_reference_code():
     """ot_rng.h's cosine_hemisphere / concentric_disk / uniform_sphere / uniform_cone / normal2d against the REFERENCE'S OWN
     include/wt/sampler/sampler.hpp (compiled unmodified into oracle/_ref/libref_fsd_sampler.so): bit-identical on 20 000 (u1, u2)."""
-    R = C.CDLL(REF_FSD_SAMPLER); L = _oracle.lib()
+    R = C.CDLL(REF_FSD_SAMPLER); L = _oracle.lib_glibc()
     fp = C.POINTER(C.c_float)
     R.ref_sampler_warps.argtypes = [C.c_float, C.c_float, C.c_float, fp]; R.ref_sampler_warps.restype = None
     L.oracle_sampler_warps.argtypes = [C.c_float, C.c_float, C.c_float, fp]; L.oracle_sampler_warps.restype = None
@@ -447,7 +447,7 @@ def test_fraunhofer_rejection_sampler_equals_the_reference_code():
     unmodified, with the reference's sampler.hpp, fsd.hpp and fsd_lut.hpp): both replay the same scripted number sequence, so the test sees the
     sampled xi, the pdf AND how many numbers each sample consumed -- i.e. the order and count of the reference's random draws (edge choice,
     lobe choice, table triple, acceptance test), for single-edge apertures (no rejection) and apertures of 2..12 edges.  BIT-IDENTICAL."""
-    R = C.CDLL(REF_FSD_SAMPLER); L = _oracle.lib()
+    R = C.CDLL(REF_FSD_SAMPLER); L = _oracle.lib_glibc()
     fp = C.POINTER(C.c_float)
     R.ref_fsd_sampler_sample.argtypes = [fp, fp, fp, fp, C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, fp, C.c_uint32, C.c_uint32, fp]; R.ref_fsd_sampler_sample.restype = None
     L.oracle_fsd_sampler_sample.argtypes = [C.c_uint32, C.c_uint32, fp, fp, fp, fp, C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, fp, C.c_uint32, C.c_uint32, fp]; L.oracle_fsd_sampler_sample.restype = None
@@ -479,7 +479,7 @@ def test_fraunhofer_rejection_sampler_equals_the_reference_code():
 def test_erf_lut_equals_the_reference_code():
     """ot_scene.h's erf_lut_t (the 1024-entry table behind gaussian2d_t::integrate_triangle and the film's reconstruction-filter weights) against
     the REFERENCE'S OWN include/wt/math/erf_lut.hpp: bit-identical on 200 000 arguments in [-5, 5], the table knots and the ends."""
-    R = C.CDLL(REF_FSD_LUT); L = _oracle.lib()
+    R = C.CDLL(REF_FSD_LUT); L = _oracle.lib_glibc()
     R.ref_erf_lut.argtypes = [C.c_float]; R.ref_erf_lut.restype = C.c_float
     L.oracle_erf_lut.argtypes = [C.c_float]; L.oracle_erf_lut.restype = C.c_float
     rng = np.random.default_rng(2)
@@ -498,7 +498,7 @@ def test_gaussian_triangle_integral_equals_the_reference_code():
     REFERENCE'S OWN src/math/gaussian2d.cpp + distribution/gaussian2d.hpp compiled unmodified (oracle/ref_gaussian2d.cpp): bit-identical on
     120 000 triangles -- isotropic, anisotropic both ways, sub-millimetre and large footprints, triangles around the mean, far from it,
     containing the 3-sigma disc, straddling it by an edge only, and slivers."""
-    R = C.CDLL(REF_GAUSSIAN2D); L = _oracle.lib()
+    R = C.CDLL(REF_GAUSSIAN2D); L = _oracle.lib_glibc()
     fp = C.POINTER(C.c_float)
     for f in (R.ref_gaussian_integrate_triangles, L.oracle_gaussian_integrate_triangles):
         f.argtypes = [C.c_float, C.c_float, C.c_uint32, fp, fp]; f.restype = None
@@ -535,7 +535,7 @@ def test_triangle_clip_equals_the_reference_code():
     before the wavefront is integrated over the pieces) against the REFERENCE'S OWN include/wt/math/intersect/clip.hpp
     compiled unmodified (oracle/ref_clip.cpp): piece count, polygon vertices in order and the fan triangles bit-identical on 200 000 triangles,
     with vertices exactly on a clip plane, edges parallel to it, and empty slabs."""
-    R = C.CDLL(REF_GAUSSIAN2D); L = _oracle.lib()
+    R = C.CDLL(REF_GAUSSIAN2D); L = _oracle.lib_glibc()
     fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
     rng = np.random.default_rng(3); n = 200000
     tri = rng.normal(size=(n, 9)).astype(np.float32)
@@ -563,7 +563,7 @@ def test_svd_equals_the_reference_code():
     """ot_math.h's 2x2 QR / SVD (every beam-footprint transform goes through it) against the REFERENCE'S OWN
     include/wt/math/linalg.hpp compiled unmodified (oracle/ref_linalg.cpp): all six outputs bit-identical on 300 000 matrices spanning eight
     decades of scale -- general, triangular both ways, diagonal, anti-diagonal, rank one, zero, and rotation-scale (equal singular values)."""
-    R = C.CDLL(REF_GAUSSIAN2D); L = _oracle.lib(); fp = C.POINTER(C.c_float)
+    R = C.CDLL(REF_GAUSSIAN2D); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
     rng = np.random.default_rng(11); n = 300000; k = n // 10
     A = (rng.normal(size=(n, 4)) * 10.0 ** rng.uniform(-4, 4, size=(n, 1))).astype(np.float32)
     A[:k, 2] = 0
@@ -597,7 +597,7 @@ def test_utd_equals_the_reference_code():
     the |x| = 6 switch, Ds / Dh on 20 000 (wedge, k, wi, wo, r) with wavelengths from 0.1 um to 30 cm, half planes, directions exactly on the
     shadow boundary and grazing the edge, and the Fermat points with their found / not-found decisions."""
     import scipy.special as sp
-    R = C.CDLL(REF_UTD); L = _oracle.lib(); fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
+    R = C.CDLL(REF_UTD); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
     CB = C.CFUNCTYPE(None, C.c_double, C.c_double, C.POINTER(C.c_double))
     calls = [0]
     def cerfc(re, im, out):
@@ -652,7 +652,7 @@ def test_spectrum_distributions_equal_the_reference_code():
     guess), binned_value / pdf and discrete_icdf against the reference's icdf / value / pdf, on 40 000 arguments per table incl. 0, 1, zero
     knots, flat runs (the a == b branch, which returns x without the range offset) and empty stretches of the cdf."""
     from wave_tracer_b200.scene import bake_binned_spectrum, bake_discrete_cdf
-    R = C.CDLL(REF_DISTRIBUTIONS); L = _oracle.lib(); fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int); up = C.POINTER(C.c_uint32)
+    R = C.CDLL(REF_DISTRIBUTIONS); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int); up = C.POINTER(C.c_uint32)
     R.ref_binned_build.argtypes = [C.c_uint32, fp, C.c_float, C.c_float, fp, up, fp]
     R.ref_binned_eval.argtypes = [C.c_uint32, fp, C.c_float, C.c_float, C.c_uint32, fp, fp, fp, fp, fp]
     L.oracle_binned_eval.argtypes = [C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_uint32, fp, fp, fp, fp, fp]

@@ -192,6 +192,7 @@ def lib():
     L.wtgpu_debug_shadow_rays.argtypes = [C.c_void_p, c_u32, P(RayQuery), P(c_u32)]
     L.wtgpu_debug_intersect_cones.argtypes = [C.c_void_p, c_u32, P(ConeQuery), P(ConeHit)]
     L.wtgpu_debug_rng.argtypes = [c_u64, c_u32, c_u32, c_u32, P(c_f), C.c_int]
+    L.wtgpu_debug_pmath.argtypes = [C.c_int, c_u32, P(c_f), P(c_f), P(c_f), C.c_int]
     L.wtgpu_debug_sobol.argtypes = [C.c_void_p, c_u64, c_u64, c_u32, P(c_u32), P(c_f)]
     L.wthost_sobol_tables.argtypes = [P(SobolEntry), P(C.c_uint16), P(C.c_uint16)]
     L.wtgpu_debug_sizeof.argtypes = [C.c_int]
@@ -209,7 +210,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_trim", "wtgpu_render", "wtgpu_develop",
-                    "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_sobol", "wtgpu_debug_sizeof", "wthost_sobol_tables",
+                    "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_pmath", "wtgpu_debug_sobol", "wtgpu_debug_sizeof", "wthost_sobol_tables",
                     "wthost_ads_build", "wthost_ads_fill", "wthost_ads_destroy", "wthost_ads_sah_cost", "wthost_ads_max_depth"]
 
 

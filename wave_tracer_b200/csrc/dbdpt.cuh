@@ -22,7 +22,7 @@ constexpr int kMaxFAp = 2 * kMaxFApWalk;
 
 WT_D float sincf_(float x) {                // include/wt/math/common.hpp:414-434
     const float t0 = 1.1920929e-7f, t2 = 0.00034526698300124390839884978618400831996329879769945f, tn = 0.018581361171917516667460937040007436176452688944747f;
-    if (fabsf(x) >= tn) return sinf(x) / x;
+    if (fabsf(x) >= tn) return pm::sinf(x) / x;
     float r = 1.f;
     if (fabsf(x) >= t0) { const float x2 = x * x; r -= x2 / 6.f; if (fabsf(x) >= t2) r += (x2 * x2) / 120.f; }
     return r;
@@ -32,7 +32,7 @@ WT_D float sincf_(float x) {                // include/wt/math/common.hpp:414-43
 struct G2 { V2 s, rs; float norm; };
 WT_D G2 g2_make(V2 sg) { G2 g; g.s = sg; g.rs = mk2(1.f / sg.x, 1.f / sg.y); g.norm = kInvTwoPi * (1.f / sg.x) * (1.f / sg.y); return g; }
 WT_D bool g2_dirac(const G2& g) { return g.s.x == 0.f || g.s.y == 0.f; }
-WT_D float g2_pdf(const G2& g, V2 p) { const V2 u = p * g.rs; return !g2_dirac(g) ? g.norm * expf(-dot(u, u) / 2.f) : ((p.x == 0.f && p.y == 0.f) ? WT_INF : 0.f); }
+WT_D float g2_pdf(const G2& g, V2 p) { const V2 u = p * g.rs; return !g2_dirac(g) ? g.norm * pm::expf(-dot(u, u) / 2.f) : ((p.x == 0.f && p.y == 0.f) ? WT_INF : 0.f); }
 WT_D V2 g2_canon(const G2& g, V2 v) {
     const V2 p = mk2(dot(mk2(1.f, 0.f), v), dot(mk2(-0.f, 1.f), v));
     if (!g2_dirac(g)) return p * g.rs;
@@ -41,11 +41,11 @@ WT_D V2 g2_canon(const G2& g, V2 v) {
 namespace g2d {     // src/math/gaussian2d.cpp:24-94
 WT_D float Igg0(const DScene& sc, float a, float b, float c, float d) {
     const float n2 = 1.f / (a + 2.f * c * c), n = sqrtf(n2);
-    return -kSqrtPi / 2.f * n * expf(-2.f * a * sqrf(d - b * c) * n2) * (erf_lut(sc, (a * b + 2.f * c * d) * n) - erf_lut(sc, (a * (1.f + b) + 2.f * c * (c + d)) * n));
+    return -kSqrtPi / 2.f * n * pm::expf(-2.f * a * sqrf(d - b * c) * n2) * (erf_lut(sc, (a * b + 2.f * c * d) * n) - erf_lut(sc, (a * (1.f + b) + 2.f * c * (c + d)) * n));
 }
 WT_D float Igg1(const DScene& sc, float a, float b, float c, float d) {
     const float n2 = 1.f / (a + 2.f * c * c), n = sqrtf(n2);
-    return -kSqrtPi / 2.f * n * expf(-2.f * a * sqrf(d - b * c) * n2) * (2.f * erf_lut(sc, a * (d / c - b) * n) + erf_lut(sc, (a * b + 2.f * c * d) * n) + erf_lut(sc, (a * (1.f + b) + 2.f * c * (c + d)) * n));
+    return -kSqrtPi / 2.f * n * pm::expf(-2.f * a * sqrf(d - b * c) * n2) * (2.f * erf_lut(sc, a * (d / c - b) * n) + erf_lut(sc, (a * b + 2.f * c * d) * n) + erf_lut(sc, (a * (1.f + b) + 2.f * c * (c + d)) * n));
 }
 WT_D float Ig0(const DScene& sc, float a, float b) { const float n = sqrtf(1.f / a); return -kSqrtPi / 2.f * n * (erf_lut(sc, a * b * n) - erf_lut(sc, a * (1.f + b) * n)); }
 WT_D float Ig1(const DScene& sc, float a, float b, float c, float d) {
@@ -99,7 +99,7 @@ WT_NI float g2_integrate_triangle(const DScene& sc, const G2& g, V2 a, V2 b, V2 
             float x0 = y < b.y ? ab * (y - a.y) + a.x : bc * (y - b.y) + b.x;
             float x1 = y < c.y ? ac * (y - a.y) + a.x : bc * (y - b.y) + b.x;
             if (x0 > x1) { const float t = x0; x0 = x1; x1 = t; }
-            for (float x = fmaxf(-L, x0) + delta / 2.f; x < fminf(L, x1); x += delta) ret += expf(-(sqrf(x) + sqrf(y)) / 2.f);
+            for (float x = fmaxf(-L, x0) + delta / 2.f; x < fminf(L, x1); x += delta) ret += pm::expf(-(sqrf(x) + sqrf(y)) / 2.f);
         }
         return ret * kInvTwoPi * sqrf(delta);
     }
@@ -166,16 +166,16 @@ WT_D V2 cone_project_local(const Cone& c, V3 p, float z) {       // elliptic_con
 struct FEdge { V2 e, v; C2 a_b, iab_2; };
 struct FHead { float P0, P0_pdf, psi02, recp_I, k; Frame frame; uint32_t n; };
 constexpr float kPA1 = 0.0049361075794549872500f, kPA2 = 0.21899789398059305541f, kP0s = 0.288675134594813f / 4.f;
-WT_D float falpha1(float x, float y) { return x == 0.f ? 0.f : kInvTwoPi * y / (x * (x * x + y * y)) * (cosf(x / 2.f) - sincf_(x / 2.f)); }
+WT_D float falpha1(float x, float y) { return x == 0.f ? 0.f : kInvTwoPi * y / (x * (x * x + y * y)) * (pm::cosf(x / 2.f) - sincf_(x / 2.f)); }
 WT_D float falpha2(float x, float y) { return x == 0.f ? 0.f : kInvTwoPi * y / (x * x + y * y) * sincf_(x / 2.f); }
 WT_D float fchi_e(V2 xi) { const float t = 1.f + 0.830092714835359f * dot(xi, xi), t2 = t * t, t3 = t2 * t; return fmaxf(0.f, 1.f - (3.f / t2 - 2.f / t3)); }
-WT_D float fchi_0(V2 xi) { xi = xi / kP0s; return expf(-.5f * dot(xi, xi)); }
+WT_D float fchi_0(V2 xi) { xi = xi / kP0s; return pm::expf(-.5f * dot(xi, xi)); }
 WT_D V2 fzeta(const FEdge& e, V2 xi) { return mk2(xi.x * e.e.x + xi.y * e.e.y, xi.x * e.e.y + xi.y * (-e.e.x)); }
 WT_D C2 fPsi(const FEdge& e, V2 xi) {
     const V2 z = fzeta(e, xi);
     const C2 s = e.a_b * falpha1(z.x, z.y) + e.iab_2 * falpha2(z.x, z.y);
     const float rho = length2(e.e), th = -dot(e.v, xi);
-    float sn, cs; sincosf(th, &sn, &cs);
+    float sn, cs; pm::sincosf(th, &sn, &cs);
     return mkc(rho * cs, rho * sn) * s;
 }
 WT_D float fPsi2(const FEdge& e, V2 xi) { const V2 z = fzeta(e, xi); return sqrf(length2(e.e)) * cnorm(e.a_b * falpha1(z.x, z.y) + e.iab_2 * falpha2(z.x, z.y)); }
@@ -302,7 +302,7 @@ WT_D V2 flut_sample(const FLut& L, V3 r3, const float* th, const float* cd) {
     const uint32_t l = min((uint32_t)x, L.M - 1u), h = min(l + 1u, L.M - 1u);
     const float f = x - floorf(x);
     const float r = fmaxf(0.f, f * flerp1(r3.y, cd + (size_t)h * L.M, L.M) + (1.f - f) * flerp1(r3.y, cd + (size_t)l * L.M, L.M));
-    V2 z = r * mk2(cosf(theta), sinf(theta));
+    V2 z = r * mk2(pm::cosf(theta), pm::sinf(theta));
     const int q = min(3, (int)(r3.z * 4.f));
     z.x *= (((q + 1) / 2) % 2 == 0 ? 1.f : -1.f);
     z.y *= ((q / 2) % 2 == 0 ? 1.f : -1.f);
@@ -446,7 +446,7 @@ WT_D float pdf_next_from_emitter(const BCtx& c, const BVertex& v, const BVertex&
     }
     float dd;
     if (E.type == WTGPU_EMITTER_POINT) dd = kInvFourPi;
-    else if (E.type == WTGPU_EMITTER_SPOT) dd = 1.f / (kTwoPi * (1.f - cosf(E.cutoff)));
+    else if (E.type == WTGPU_EMITTER_SPOT) dd = 1.f / (kTwoPi * (1.f - pm::cosf(E.cutoff)));
     else dd = cosine_hemisphere_pdf(fmaxf(0.f, dot(d, bv_ng(c, v))));
     float pp = dd * rd2;
     if (bv_on_surface(c, next)) pp *= fabsf(dot(bv_ng(c, next), d));
@@ -1236,7 +1236,7 @@ __global__ void __launch_bounds__(128, 6) k_bd_fsd_sample(const BdArgs a) {
                         const V2 z = fzeta(e, x2);
                         const C2 sx = e.a_b * falpha1(z.x, z.y) + e.iab_2 * falpha2(z.x, z.y);
                         const float rho = length2(e.e);
-                        float sn, cs; sincosf(-dot(e.v, x2), &sn, &cs);
+                        float sn, cs; pm::sincosf(-dot(e.v, x2), &sn, &cs);
                         const C2 tm = mkc(rho * cs, rho * sn) * sx;
                         sh.re[tt][jj] = tm.re; sh.im[tt][jj] = tm.im; sh.dd[tt][jj] = sqrf(rho) * cnorm(sx);
                     }

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include "pmath.h"
 
 #define WT_D __device__ __forceinline__
 // "large" device functions.  Force-inlined by default: out-of-line calls pass Beam/Surface/Mueller structs through local memory
@@ -88,7 +89,7 @@ WT_D float eft_dot3(V3 a, V3 b) {        // eft.hpp:170-183
     return d + err;
 }
 
-// ---- complex helpers (std::complex<float> semantics, Smith-free direct formulas; scaled division)
+// ---- complex helpers (std::complex<float> semantics as compiled by g++ 13 / libgcc: naive product, binary64 quotient)
 WT_D C2 mkc(float re, float im) { C2 c; c.re = re; c.im = im; return c; }
 WT_D C2 operator+(C2 a, C2 b) { return mkc(a.re + b.re, a.im + b.im); }
 WT_D C2 operator-(C2 a, C2 b) { return mkc(a.re - b.re, a.im - b.im); }
@@ -98,18 +99,18 @@ WT_D C2 operator*(C2 a, float s) { return mkc(a.re * s, a.im * s); }
 WT_D C2 operator*(float s, C2 a) { return mkc(a.re * s, a.im * s); }
 WT_D C2 cconj(C2 a) { return mkc(a.re, -a.im); }
 WT_D float cnorm(C2 a) { return a.re * a.re + a.im * a.im; }
-WT_D float cabsf_(C2 a) { return hypotf(a.re, a.im); }
+WT_D float cabsf_(C2 a) { return pm::hypotf(a.re, a.im); }
 WT_D C2 operator/(C2 a, C2 b) {
-    // scaled like libgcc's __divsc3 fast path
-    const float s = fmaxf(fabsf(b.re), fabsf(b.im));
-    const float br = b.re / s, bi = b.im / s;
-    const float den = br * br + bi * bi;
-    return mkc(((a.re * br + a.im * bi) / den) / s, ((a.im * br - a.re * bi) / den) / s);
+    // std::complex<float> division = libgcc's __divsc3, which since GCC 12 evaluates in binary64 (libgcc2.c, L_divsc3: "float is handled by
+    // using double arithmetic"): products exact, one rounding per sum and quotient, then to float.  Bit-identical to the oracle's c_t / c_t.
+    const double c = (double)b.re, d = (double)b.im;
+    const double den = c * c + d * d;
+    return mkc((float)(((double)a.re * c + (double)a.im * d) / den), (float)(((double)a.im * c - (double)a.re * d) / den));
 }
-WT_D C2 cexpi(float phase) { float s, c; sincosf(phase, &s, &c); return mkc(c, s); }
+WT_D C2 cexpi(float phase) { float s, c; pm::sincosf(phase, &s, &c); return mkc(c, s); }
 WT_D C2 csqrt_(C2 z) {
     if (z.re == 0.f && z.im == 0.f) return mkc(0.f, 0.f);
-    const float r = hypotf(z.re, z.im);
+    const float r = pm::hypotf(z.re, z.im);
     const float t = sqrtf(0.5f * (r + fabsf(z.re)));
     if (z.re >= 0.f) return mkc(t, z.im / (2.f * t));
     return mkc(fabsf(z.im) / (2.f * t), z.im >= 0.f ? t : -t);

@@ -56,14 +56,14 @@ WT_D V3 rnd3(Sampler& s) { const float a = rnd(s); const float b = rnd(s); const
 WT_D int uniform_int_interval(Sampler& s, int start, int end) { return min(end - 1, int(rnd(s) * (end - start)) + start); }
 
 // warps (include/wt/sampler/sampler.hpp:139-286)
-WT_D V3 uniform_sphere(V2 u) { const float z = 1.f - 2.f * u.x; const float rr = sqrtf(fmaxf(0.f, 1.f - sqrf(z))); const float phi = kTwoPi * u.y; return mk3(rr * cosf(phi), rr * sinf(phi), z); }
+WT_D V3 uniform_sphere(V2 u) { const float z = 1.f - 2.f * u.x; const float rr = sqrtf(fmaxf(0.f, 1.f - sqrf(z))); const float phi = kTwoPi * u.y; return mk3(rr * pm::cosf(phi), rr * pm::sinf(phi), z); }
 WT_D V2 concentric_disk(V2 u) {
     const V2 o = 2.f * u - mk2(1.f, 1.f);
     float rr, th;
     if (o.x == 0.f && o.y == 0.f) { rr = 0.f; th = 0.f; }
     else if (fabsf(o.x) > fabsf(o.y)) { rr = o.x; th = kPi4 * (o.y / o.x); }
     else { rr = o.y; th = kPi2 - kPi4 * (o.x / o.y); }
-    return rr * mk2(cosf(th), sinf(th));
+    return rr * mk2(pm::cosf(th), pm::sinf(th));
 }
 WT_D V3 cosine_hemisphere(V2 u) { const V2 d = concentric_disk(u); return mk3(d.x, d.y, sqrtf(fmaxf(0.f, 1.f - sqrf(d.x) - sqrf(d.y)))); }
 WT_D float cosine_hemisphere_pdf(float c) { return kInvPi * c; }
@@ -72,9 +72,9 @@ WT_D V3 uniform_cone(float sa, V2 u) {
     const float ct = 1.f + u.x * (ctm - 1.f);
     const float st = sqrtf(fmaxf(0.f, 1.f - sqrf(ct)));
     const float phi = kTwoPi * u.y;
-    return mk3(cosf(phi) * st, sinf(phi) * st, ct);
+    return mk3(pm::cosf(phi) * st, pm::sinf(phi) * st, ct);
 }
-WT_D V2 normal2d(V2 u) { const float r = sqrtf(-2.f * logf(1.f - u.x)); const float th = kTwoPi * u.y; return mk2(r * cosf(th), r * sinf(th)); }
+WT_D V2 normal2d(V2 u) { const float r = sqrtf(-2.f * pm::logf(1.f - u.x)); const float th = kTwoPi * u.y; return mk2(r * pm::cosf(th), r * pm::sinf(th)); }
 WT_D V2 uniform_triangle(V2 u) { if (u.x + u.y > 1.f) u = mk2(1.f, 1.f) - u; return u; }
 
 // sampling density with discrete flag (include/wt/sampler/density.hpp)
@@ -410,14 +410,14 @@ WT_D FractalP fractal_params(const DScene& sc, const wtgpu_bsdf& b, float k) {  
         p.alpha = sqrf(spectrum_f(sc, b.prof_spec[1], k));
     }
     const float x = 1.f + k * k * p.T;
-    const float pw = gamma == 3.f ? x : powf(x, (gamma - 1.f) / 2.f);
+    const float pw = gamma == 3.f ? x : pm::powf(x, (gamma - 1.f) / 2.f);
     p.s2n = 1.f / (1.f - 1.f / pw);
     return p;
 }
 WT_D float fractal_psd(const wtgpu_bsdf& b, const FractalP& p, V2 z, float k) {
     const float gamma = b.gamma;
     const float x = 1.f + p.T * dot(z, z);
-    const float pw = gamma == 3.f ? (x * x) : powf(x, (gamma + 1.f) / 2.f);
+    const float pw = gamma == 3.f ? (x * x) : pm::powf(x, (gamma + 1.f) / 2.f);
     return p.s2n * (kInvTwoPi * k * k * (gamma - 1.f) * p.T * (1.f / pw));
 }
 // ---- gaussian profile (include/wt/interaction/surface_profile/gaussian.hpp:28-255)
@@ -435,24 +435,24 @@ WT_D GaussP gaussian_params(const DScene& sc, const wtgpu_bsdf& b, float k) {   
         p.sigma2 = sqrf(spectrum_f(sc, b.prof_spec[0], k));
         p.alpha = p.sigma2;
     }
-    p.s2n = 1.f / (1.f - expf(-(k * k / 2.f / p.sigma2)));
+    p.s2n = 1.f / (1.f - pm::expf(-(k * k / 2.f / p.sigma2)));
     return p;
 }
 WT_D float gaussian_psd(const GaussP& p, V2 z, float k) {                          // gaussian.hpp:121-130
     const float z2 = dot(z, z);
-    const float e = expf(-(z2 / 2.f / p.sigma2));
+    const float e = pm::expf(-(z2 / 2.f / p.sigma2));
     return e <= 1.1920929e-7f ? 0.f : p.s2n * (kInvTwoPi / p.sigma2 * k * k * e);
 }
 WT_D float boxmueller_max_phi(float r, float l) {                                   // gaussian.hpp:43-49, 70-76
     const float eps = 1.1920929e-7f;
-    return (r < eps || l < eps) ? kPi : fmaxf(1e-2f, acosf(clampf_((sqrf(r) + sqrf(l) - 1.f) / (2.f * r * l), -1.f, 1.f)));
+    return (r < eps || l < eps) ? kPi : fmaxf(1e-2f, pm::acosf(clampf_((sqrf(r) + sqrf(l) - 1.f) / (2.f * r * l), -1.f, 1.f)));
 }
 WT_D float boxmueller_truncated_pdf(V2 wo, V2 mean, float sigma2) {               // gaussian.hpp:58-79
     const float l = sqrtf(fminf(1.f, dot(mean, mean)));
     const float coso = sqrtf(fmaxf(0.f, 1.f - dot(mean, mean)));
     wo = wo - mean;
     const float r2 = dot(wo, wo);
-    const float x = expf(-.5f * r2 / sigma2);
+    const float x = pm::expf(-.5f * r2 / sigma2);
     const float r = sqrtf(r2);
     return .5f * x / (boxmueller_max_phi(r, l) * sigma2) * coso;
 }
@@ -463,7 +463,7 @@ WT_D bool profile_delta_only(const DScene& sc, const wtgpu_bsdf& b, float k) {
 WT_D float profile_alpha(const DScene& sc, const wtgpu_bsdf& b, V3 wi, V3 wo, float k) {
     if (b.profile_type == WTGPU_PROFILE_DIRAC) return 1.f;
     const float palpha = is_gaussian_profile(b) ? gaussian_params(sc, b, k).alpha : fractal_params(sc, b, k).alpha;
-    return expf(-(sqrf((fabsf(wi.z) + fabsf(wo.z)) * k) * palpha));
+    return pm::expf(-(sqrf((fabsf(wi.z) + fabsf(wo.z)) * k) * palpha));
 }
 WT_D float profile_psd(const DScene& sc, const wtgpu_bsdf& b, V3 wi, V3 wo, float k) {
     if (b.profile_type == WTGPU_PROFILE_DIRAC) return 0.f;
@@ -478,7 +478,7 @@ WT_D float profile_pdf(const DScene& sc, const wtgpu_bsdf& b, V3 wi, V3 wo, floa
     const V2 zk = mk2(wi.x, wi.y) + mk2(wo.x, wo.y);
     const float fk = length(zk);
     const float s = sqrtf(fmaxf(0.f, 1.f - sqrf(wi.z)));
-    const float phi_max = (fk == 0.f || s == 0.f) ? kPi : acosf(clampf_((sqrf(fk) + sqrf(s) - 1.f) / (2.f * fk * s), -1.f, 1.f));
+    const float phi_max = (fk == 0.f || s == 0.f) ? kPi : pm::acosf(clampf_((sqrf(fk) + sqrf(s) - 1.f) / (2.f * fk * s), -1.f, 1.f));
     const float psd = fractal_psd(b, p, zk * k, k);
     const float w = kInvPi * phi_max;
     return w > 1e-2f ? 1.f / w * fabsf(wo.z) * psd : 0.f;
@@ -494,13 +494,13 @@ WT_D ProfSample profile_sample(const DScene& sc, const wtgpu_bsdf& b, V3 wi, flo
         const V2 u2 = rnd2(smp);
         const float l = sqrtf(fminf(1.f, dot(mean, mean)));
         const float coso = sqrtf(fmaxf(0.f, 1.f - dot(mean, mean)));
-        const float phi_i = (mean.x != 0.f || mean.y != 0.f) ? atan2f(mean.y, mean.x) : 0.f;
-        const float s = expf(-.5f * sqrf(1.f + l) / s2);
+        const float phi_i = (mean.x != 0.f || mean.y != 0.f) ? pm::atan2f(mean.y, mean.x) : 0.f;
+        const float s = pm::expf(-.5f * sqrf(1.f + l) / s2);
         const float x = (1.f - s) * fmaxf(eps, u2.x) + s;
-        const float rr = sqrtf(-2.f * s2 * logf(x));
+        const float rr = sqrtf(-2.f * s2 * pm::logf(x));
         const float max_phi = boxmueller_max_phi(rr, l);
         const float phi = phi_i + kPi + max_phi * (2.f * u2.y - 1.f);
-        const V2 pt = rr * mk2(cosf(phi), sinf(phi));
+        const V2 pt = rr * mk2(pm::cosf(phi), pm::sinf(phi));
         const V2 wo2 = pt + mean;
         r.pdf = .5f * x / (max_phi * s2) * coso;
         r.psd = gaussian_psd(p, k * (wo2 - mean), k);
@@ -511,16 +511,16 @@ WT_D ProfSample profile_sample(const DScene& sc, const wtgpu_bsdf& b, V3 wi, flo
     const float gamma = b.gamma;
     const FractalP p = fractal_params(sc, b, k);
     const float s = sqrtf(fmaxf(0.f, 1.f - sqrf(wi.z)));
-    const float phi_i = s > 0.f ? atan2f(wi.y, wi.x) : 0.f;
+    const float phi_i = s > 0.f ? pm::atan2f(wi.y, wi.x) : 0.f;
     const float sqrtT = sqrtf(p.T);
     const V2 u2 = rnd2(smp);
     const float k2T = sqrf(k) * p.T;
-    const float Mv = 1.f - powf(1.f + k2T * sqrf(1.f + s), -(gamma - 1.f) / 2.f);
-    const float f = sqrtf(powf(1.f - Mv * u2.x, -2.f / (gamma - 1.f)) - 1.f) / sqrtT;
+    const float Mv = 1.f - pm::powf(1.f + k2T * sqrf(1.f + s), -(gamma - 1.f) / 2.f);
+    const float f = sqrtf(pm::powf(1.f - Mv * u2.x, -2.f / (gamma - 1.f)) - 1.f) / sqrtT;
     const float fk = f / k;
-    const float phi_max = (f == 0.f || s == 0.f) ? kPi : acosf(clampf_((sqrf(fk) + sqrf(s) - 1.f) / (2.f * fk * s), -1.f, 1.f));
+    const float phi_max = (f == 0.f || s == 0.f) ? kPi : pm::acosf(clampf_((sqrf(fk) + sqrf(s) - 1.f) / (2.f * fk * s), -1.f, 1.f));
     const float phi_f = phi_i + (2.f * u2.y - 1.f) * phi_max;
-    const V2 zeta = f * mk2(cosf(phi_f), sinf(phi_f));
+    const V2 zeta = f * mk2(pm::cosf(phi_f), pm::sinf(phi_f));
     const V2 wo = zeta / k - mk2(wi.x, wi.y);
     const float z = sqrtf(fmaxf(0.f, 1.f - dot(wo, wo)));
     r.psd = fractal_psd(b, p, zeta, k);
@@ -684,14 +684,14 @@ WT_D Sourcing emitter_sourcing(const wtgpu_emitter& e, float k) {    // point.hp
     const float extent = (e.type != WTGPU_EMITTER_AREA && e.extent > 0.f) ? e.extent : 10.f * wavenum_to_wavelen(k);
     float se = extent * extent, ta = mub_tan_alpha(extent, k);
     enlarge(se, ta, e.pse_scale);
-    if (e.type == WTGPU_EMITTER_SPOT) ta = fminf(ta, tanf(e.falloff));
+    if (e.type == WTGPU_EMITTER_SPOT) ta = fminf(ta, pm::tanf(e.falloff));
     return source_extent(se, ta);
 }
 WT_D float spot_falloff(const wtgpu_emitter& e, V3 ld) {           // spot.hpp:76-81
     const float ct = ld.z;
-    if (ct <= cosf(e.cutoff)) return 0.f;
-    if (ct >= cosf(e.falloff)) return 1.f;
-    return (e.cutoff - acosf(ct)) * (1.f / (e.cutoff - e.falloff));
+    if (ct <= pm::cosf(e.cutoff)) return 0.f;
+    if (ct >= pm::cosf(e.falloff)) return 1.f;
+    return (e.cutoff - pm::acosf(ct)) * (1.f / (e.cutoff - e.falloff));
 }
 WT_D Beam area_Le(const DScene& sc, const wtgpu_emitter& e, V3 o, V3 d, float k, const Surface& s) {  // area.hpp:104-117,170-180
     const float rad = e.scale * spectrum_f(sc, e.spectrum, k);
@@ -727,7 +727,7 @@ WT_DN EmitterSample emitter_sample(const DScene& sc, int32_t i, Sampler& smp, fl
         beam_mul(r.beam, kFourPi);
         r.ppd = pd_disc(1.f); r.dpd = pd_dens(kInvFourPi);
     } else if (e.type == WTGPU_EMITTER_SPOT) {      // spot.cpp:29-46
-        const float csa = kTwoPi * (1.f - cosf(e.cutoff));
+        const float csa = kTwoPi * (1.f - pm::cosf(e.cutoff));
         const V3 lwo = uniform_cone(csa, rnd2(smp));
         const V3 wo = normalize(m3mul(e.rot, lwo));
         const float w = spot_falloff(e, lwo);

@@ -686,6 +686,20 @@ __global__ void k_debug_rng(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t s
     out[i] = rnd(s);
 }
 
+// pmath.h on the device, one thread per argument: fn 0 sin 1 cos 2 tan 3 exp 4 log 5 pow(x,y) 6 atan2(x,y) 7 acos 8 hypot(x,y) 9/10 Re/Im UTDF(x)
+__global__ void k_debug_pmath(int fn, uint32_t n, const float* x, const float* y, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = x[i], b = y ? y[i] : 0.f;
+    float r = 0.f;
+    switch (fn) {
+    case 0: r = pm::sinf(a); break; case 1: r = pm::cosf(a); break; case 2: r = pm::tanf(a); break; case 3: r = pm::expf(a); break;
+    case 4: r = pm::logf(a); break; case 5: r = pm::powf(a, b); break; case 6: r = pm::atan2f(a, b); break; case 7: r = pm::acosf(a); break;
+    case 8: r = pm::hypotf(a, b); break; case 9: r = UTDF(a).re; break; case 10: r = UTDF(a).im; break;
+    }
+    out[i] = r;
+}
+
 // ================================================================================================ host side
 static thread_local std::string g_err;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return WTGPU_E_CUDA; } } while (0)
@@ -1212,6 +1226,21 @@ int wtgpu_debug_sobol(wtgpu_scene* s, uint64_t seed, uint64_t g0, uint32_t n, ui
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out_num, dn, 4 * m, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(out_val, dv, 4 * m, cudaMemcpyDeviceToHost));
     wt_free(dn); wt_free(dv);
+    return WTGPU_OK;
+}
+
+int wtgpu_debug_pmath(int fn, uint32_t n, const float* x, const float* y, float* out, int device) {
+    if (!x || !out || fn < 0 || fn > 10) { g_err = "bad argument"; return WTGPU_E_INVALID; }
+    if (n == 0) return WTGPU_OK;
+    CK(cudaSetDevice(device));
+    float *dx, *dy = nullptr, *dout;
+    CK(wt_malloc(&dx, 4ull * n)); CK(wt_malloc(&dout, 4ull * n));
+    CK(cudaMemcpy(dx, x, 4ull * n, cudaMemcpyHostToDevice));
+    if (y) { CK(wt_malloc(&dy, 4ull * n)); CK(cudaMemcpy(dy, y, 4ull * n, cudaMemcpyHostToDevice)); }
+    k_debug_pmath<<<(n + 127) / 128, 128>>>(fn, n, dx, dy, dout);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dout, 4ull * n, cudaMemcpyDeviceToHost));
+    wt_free(dx); wt_free(dout); if (dy) wt_free(dy);
     return WTGPU_OK;
 }
 
