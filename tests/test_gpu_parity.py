@@ -86,25 +86,40 @@ def test_cone_traversal_lists_exact(cornell):
     assert mism <= n // 1000, f"{mism} of {n} cone queries returned a different triangle/edge list"
 
 
+# The parity gate of BASELINE.md 3.4 / SURVEY 8c: per-pixel rel-L2 <= 1e-3 and mean relative error <= 2e-4 against the oracle's f64 film at equal
+# seeds.  Device and oracle share the elementary functions (pmath.h) and the IEEE op order, so what is left is the f32 film accumulation (atomics,
+# in any order) against the oracle's f64 sums: measured 1e-7 .. 1e-5 (profiles/r02_parity.txt).
+L2_GATE, MEAN_GATE = 1e-3, 2e-4
+
+
 def _film_metrics(g, o):
     g = g.astype(np.float64); num = np.linalg.norm(g - o); den = np.linalg.norm(o)
     return num / max(den, 1e-300), abs(g.sum() - o.sum()) / max(abs(o.sum()), 1e-300)
 
 
+def _mean_rel(g, o):
+    lit = np.abs(o) > 0
+    return float((np.abs(g.astype(np.float64) - o)[lit] / np.abs(o[lit])).mean()) if lit.any() else 0.0
+
+
+def _gate(g, o, what=""):
+    l2, flux = _film_metrics(g, o); mr = _mean_rel(g, o)
+    assert l2 <= L2_GATE and flux <= MEAN_GATE and mr <= MEAN_GATE, (what, l2, flux, mr)
+    return l2, flux, mr
+
+
 @pytest.mark.parametrize("direction,rt", [("forward", False), ("forward", True)])
 def test_double_slits_film_matches_oracle(direction, rt):
-    """plt_path forward + UTD on double_slits geometry: per-element film within f32 tolerance of the oracle (equal streams).
-    Tolerances: rel-L2 <= 2e-3, total flux <= 5e-4 (f32 path math + f32 atomic accumulation vs f64 film in the oracle)."""
+    """plt_path forward + UTD on double_slits geometry: per-element film within the parity gate of the oracle (equal streams)."""
     b = scenes.double_slits(res=256, spp=8, with_directional=True, ray_trace_only=rt).build()
     blk, lgt, st = render(b, spp=8, allow_overflow=True)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"] == 256 * 64 * 8
     assert olgt.sum() > 0
-    l2, flux = _film_metrics(lgt, olgt)
-    assert l2 <= 2e-3 and flux <= 5e-4, (l2, flux)
-    # structural counters agree to a vanishing fraction (divergent paths would show up here first)
+    _gate(lgt, olgt, "double_slits %s rt=%s" % (direction, rt))
+    # same decisions everywhere: the structural counters are identical
     for kg, ko in (("segments", "segments"), ("surface_interactions", "surface"), ("null_interactions", "null_"), ("ray_casts", "ray_casts"), ("cone_casts", "cone_casts")):
-        assert abs(st[kg] - ost[ko]) <= 1e-3 * max(1, ost[ko]), (kg, st[kg], ost[ko])
+        assert st[kg] == ost[ko], (kg, st[kg], ost[ko])
 
 
 @pytest.mark.parametrize("profile", ["fractal", "gaussian_roughness", "gaussian_sigma"])
@@ -119,8 +134,7 @@ def test_cornell_backward_film_matches_oracle(profile):
     assert st["samples"] == ost["samples"]
     img_g = develop(b, 8, blk, lgt); img_o = develop(b, 8, oblk, olgt)
     assert img_o.mean() > 0
-    l2, flux = _film_metrics(img_g, img_o)
-    assert l2 <= 5e-3 and flux <= 1e-3, (l2, flux)
+    _gate(img_g, img_o, "cornell backward " + profile)
     assert np.allclose(blk[..., 1], oblk[..., 1], rtol=1e-4, atol=1e-5)          # filter weights: sample placement identical
 
 
@@ -130,26 +144,22 @@ def test_etoile_like_forward_matches_oracle(rt):
     emitter, virtual-plane coverage sensor; rt=True is the reference's --ray-tracing mode (no diffraction), rt=False adds UTD free-space
     diffraction off the 6.7k building edges.
 
-    Tolerances.  rt=True: the usual rel-L2 <= 5e-3, flux <= 2e-3.  rt=False: the film is sparse with a huge dynamic range (5 % of the elements
-    are lit at 4 spp, one path carries ~1 % of the film's L2 norm), and a path takes thousands of UTD edge decisions with shadow rays grazing
-    building faces: a handful of the ~7000 paths branch differently from the oracle's (CUDA libm vs glibc in the last ulp; <= 4 capacity
-    overflows).  Measured on B200 over four seeds (profiles/r01s2_etoile_diag.log): 11-29 of ~340 lit elements differ, rel-L2 6e-3 .. 1.6e-2,
-    flux 2e-4 .. 2e-3, structural counters within 3e-4.  So: elementwise agreement to 1e-3 on >= 90 % of the lit elements, rel-L2 <= 2.5e-2,
-    total flux <= 3e-3, counters <= 1e-3."""
+    Round 1 needed rel-L2 <= 2.5e-2 here (a path takes thousands of UTD edge decisions and CUDA's libm differs from glibc in the last ulp);
+    with the shared elementary functions every decision is the oracle's: identical counters, the plain parity gate."""
     b = scenes.etoile_like(res=96, spp=4, ray_trace_only=rt).build()
     blk, lgt, st = render(b, spp=4, allow_overflow=True)
     oblk, olgt, ost = _oracle.render(b, spp=4)
     print("etoile_like rt=%s capacity overflows:" % rt, st["capacity_overflows"], "of", st["segments"], "segments")
-    assert st["samples"] == ost["samples"] == 96 * 72 * 4 and st["capacity_overflows"] <= 2e-4 * st["segments"]
+    assert st["samples"] == ost["samples"] == 96 * 72 * 4
     assert olgt.sum() > 0
     l2, flux = _film_metrics(lgt, olgt)
     lit = olgt > 0
     agree = np.abs(lgt.astype(np.float64) - olgt)[lit] <= 1e-3 * olgt[lit]
     print("etoile_like rt=%s: rel-L2 %.3e flux %.3e lit %d agree %.4f" % (rt, l2, flux, lit.sum(), agree.mean()), st["gpu_ms"], st["segments"], ost["segments"])
-    if rt: assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
-    else: assert agree.mean() >= 0.90 and l2 <= 2.5e-2 and flux <= 3e-3, (agree.mean(), l2, flux)
+    _gate(lgt, olgt, "etoile rt=%s" % rt)
+    assert agree.mean() >= 0.999
     for kg, ko in (("segments", "segments"), ("surface_interactions", "surface"), ("fsd_interactions", "fsd"), ("null_interactions", "null_")):
-        assert abs(st[kg] - ost[ko]) <= 1e-3 * max(1, ost[ko]), (kg, st[kg], ost[ko])
+        assert st[kg] == ost[ko], (kg, st[kg], ost[ko])
 
 
 @pytest.mark.parametrize("scene", ["double_slits", "etoile", "cornell"])
@@ -216,7 +226,7 @@ def test_bdpt_double_slits_matches_oracle(fsd, flags):
     assert img_o.sum() > 0
     l2, flux = _film_metrics(img_g, img_o)
     print("bdpt double_slits fsd=%s flags=%d: rel-L2 %.3e flux %.3e" % (fsd, flags, l2, flux), st["gpu_ms"], st["segments"], ost["segments"], st["shaded_paths"])
-    assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
+    assert l2 <= L2_GATE and flux <= MEAN_GATE and _mean_rel(img_g, img_o) <= MEAN_GATE, (l2, flux)
 
 
 @pytest.mark.parametrize("flags", [0, 8, 4])
@@ -230,7 +240,60 @@ def test_bdpt_cornell_matches_oracle(flags):
     assert img_o.mean() > 0
     l2, flux = _film_metrics(img_g, img_o)
     print("bdpt cornell flags=%d: rel-L2 %.3e flux %.3e" % (flags, l2, flux), st["gpu_ms"])
-    assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
+    assert l2 <= L2_GATE and flux <= MEAN_GATE and _mean_rel(img_g, img_o) <= MEAN_GATE, (l2, flux)
+
+
+def _report(name, b, st, ost, img_g, img_o):
+    l2, flux = _film_metrics(img_g, img_o)
+    lit = np.abs(img_o) > 0
+    rel = np.abs(img_g.astype(np.float64) - img_o)[lit] / np.abs(img_o[lit])
+    print("%s: rel-L2 %.3e flux %.3e mean-rel %.3e max-rel %.3e overflows %d gpu_ms %.1f segments %d/%d" %
+          (name, l2, flux, rel.mean() if rel.size else 0.0, rel.max() if rel.size else 0.0, st["capacity_overflows"], st["gpu_ms"], st["segments"], ost["segments"]))
+    return l2, flux, (rel.mean() if rel.size else 0.0)
+
+
+@pytest.mark.parametrize("flags", [0, 4])
+def test_bdpt_cornell_with_fraunhofer_fsd_matches_oracle(flags):
+    """plt_bdpt WITH Fraunhofer FSD on non-slit geometry: the tessellated sphere and the cubes put diffracting edges inside
+    the beams' footprints -- aperture construction from cone-query edge lists, rejection sampling, FSD vertices in connections and MIS."""
+    b = scenes.cornell_like(res=40, spp=4, integrator="plt_bdpt", fsd=True, lut=(512, 256), n_sphere=8).build()
+    blk, lgt, st = render(b, spp=4, allow_overflow=True, flags=flags)
+    oblk, olgt, ost = _oracle.render(b, spp=4)
+    assert st["samples"] == ost["samples"]
+    img_g = develop(b, 4, blk, lgt); img_o = develop(b, 4, oblk, olgt)
+    l2, flux, mrel = _report("bdpt cornell fsd=True flags=%d" % flags, b, st, ost, img_g, img_o)
+    assert ost["fsd"] > 0 and img_o.mean() > 0
+    assert l2 <= L2_GATE and flux <= MEAN_GATE and mrel <= MEAN_GATE, (l2, flux, mrel)
+
+
+def test_cornell_backward_with_utd_matches_oracle():
+    """plt_path BACKWARD + UTD: pending-FSD evaluation at the next vertex, edge apertures on real geometry, NEE / emission MIS."""
+    b = scenes.cornell_like(res=40, spp=4, fsd=True, n_sphere=8).build()
+    blk, lgt, st = render(b, spp=4, allow_overflow=True)
+    oblk, olgt, ost = _oracle.render(b, spp=4)
+    assert st["samples"] == ost["samples"]
+    img_g = develop(b, 4, blk, lgt); img_o = develop(b, 4, oblk, olgt)
+    l2, flux, mrel = _report("plt_path cornell backward fsd=True", b, st, ost, img_g, img_o)
+    assert ost["fsd"] > 0 and img_o.mean() > 0
+    assert l2 <= L2_GATE and flux <= MEAN_GATE and mrel <= MEAN_GATE, (l2, flux, mrel)
+
+
+@pytest.mark.parametrize("integrator", ["plt_path", "plt_bdpt"])
+def test_rgb_polychromatic_film_matches_oracle(integrator):
+    """Three-channel film over the visible spectrum: binned product-spectrum wavenumber sampling, tabulated reflectances,
+    film_t::splat's per-channel response->f(channel, k) (film.hpp:254-288)."""
+    b = scenes.cornell_like(res=40, spp=4, rgb=True, integrator=integrator, n_sphere=8).build()
+    assert b.channels == 3
+    blk, lgt, st = render(b, spp=4, allow_overflow=True)
+    oblk, olgt, ost = _oracle.render(b, spp=4)
+    assert st["samples"] == ost["samples"] and blk.shape == (40, 40, 3, 2)
+    img_g = develop(b, 4, blk, lgt); img_o = develop(b, 4, oblk, olgt)
+    assert (img_o.mean(axis=(0, 1)) > 0).all()
+    l2, flux, mrel = _report("rgb cornell %s" % integrator, b, st, ost, img_g, img_o)
+    for c in range(3):
+        lc, fc = _film_metrics(img_g[..., c], img_o[..., c])
+        assert lc <= L2_GATE and fc <= MEAN_GATE and _mean_rel(img_g[..., c], img_o[..., c]) <= MEAN_GATE, (c, lc, fc)
+    assert np.allclose(blk[..., 1], oblk[..., 1], rtol=1e-4, atol=1e-5)
 
 
 def test_xml_scene_film_matches_oracle():
@@ -247,4 +310,4 @@ def test_xml_scene_film_matches_oracle():
     assert st["samples"] == ost["samples"] == 192 * 64 * 8 and olgt.sum() > 0
     l2, flux = _film_metrics(lgt, olgt)
     print("xml slit_bench: rel-L2 %.3e flux %.3e" % (l2, flux), st["segments"], ost["segments"])
-    assert l2 <= 5e-3 and flux <= 2e-3, (l2, flux)
+    assert l2 <= L2_GATE and flux <= MEAN_GATE and _mean_rel(lgt, olgt) <= MEAN_GATE, (l2, flux)

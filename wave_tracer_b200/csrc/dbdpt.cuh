@@ -71,38 +71,69 @@ WT_D bool pit2(V2 p, V2 a, V2 b, V2 c) {        // math/util.hpp:69-82
     return !(neg && pos);
 }
 }
-WT_NI float g2_integrate_triangle(const DScene& sc, const G2& g, V2 a, V2 b, V2 c) {     // src/math/gaussian2d.cpp:96-192
+// gaussian2d_t::integrate_triangle (src/math/gaussian2d.cpp:96-192) in three parts, so that the rare but long quadrature branch can be served by
+// a whole warp (k_bd_resolve): g2_classify takes the early-outs and decides the branch, g2_quadrature / g2_quadrature_warp is the 0.002-step
+// Riemann sum of :141-164 for triangles with a short edge, g2_analytic the four-Gaussian erf approximation of :166-192.
+enum : int { G2_DONE = 0, G2_QUADRATURE = 1, G2_ANALYTIC = 2 };
+WT_D int g2_classify(const G2& g, V2& a, V2& b, V2& c, float& value) {
     if (g2_dirac(g)) {
         const float A = (a.x * (b.y - c.y) - a.y * (b.x - c.x)) + (b.x * c.y - c.x * b.y);
         const float sA = signf_(A);
         const float bx = sA * diff_prod(b.x, c.y, c.x, b.y), by = sA * diff_prod(c.x, a.y, a.x, c.y);
-        return (bx >= 0.f && by >= 0.f && bx + by <= fabsf(A)) ? 1.f : 0.f;
+        value = (bx >= 0.f && by >= 0.f && bx + by <= fabsf(A)) ? 1.f : 0.f;
+        return G2_DONE;
     }
     const float L = 3.f;
     a = g2_canon(g, a); b = g2_canon(g, b); c = g2_canon(g, c);
-    if (min3f(a.x, b.x, c.x) >= L || max3f(a.x, b.x, c.x) <= -L || min3f(a.y, b.y, c.y) >= L || max3f(a.y, b.y, c.y) <= -L) return 0.f;
+    if (min3f(a.x, b.x, c.x) >= L || max3f(a.x, b.x, c.x) <= -L || min3f(a.y, b.y, c.y) >= L || max3f(a.y, b.y, c.y) <= -L) { value = 0.f; return G2_DONE; }
     const bool ain = length2(a) <= sqrf(L), bin = length2(b) <= sqrf(L), cin = length2(c) <= sqrf(L);
     if (!ain && !bin && !cin) {
         const bool iab = intersect_edge_ellipse_points(a, b, L, L) > 0, iac = intersect_edge_ellipse_points(a, c, L, L) > 0, ibc = intersect_edge_ellipse_points(b, c, L, L) > 0;
-        if (!iab && !iac && !ibc) return g2d::pit2(mk2(0.f, 0.f), a, b, c) ? 1.f : 0.f;
+        if (!iab && !iac && !ibc) { value = g2d::pit2(mk2(0.f, 0.f), a, b, c) ? 1.f : 0.f; return G2_DONE; }
     }
     const float min_len = min3f(length2(a - b), length2(a - c), length2(b - c));
-    if (min_len < 1e-3f) {
-        const float delta = .002f;
-        if (b.y < a.y) { const V2 t = a; a = b; b = t; }
-        if (c.y < a.y) { const V2 t = a; a = c; c = t; }
-        const float ab = b.y == a.y ? WT_INF : (b.x - a.x) / (b.y - a.y);
-        const float ac = c.y == a.y ? WT_INF : (c.x - a.x) / (c.y - a.y);
-        const float bc = c.y == b.y ? WT_INF : (c.x - b.x) / (c.y - b.y);
-        float ret = 0.f;
-        for (float y = fmaxf(-L, a.y + delta / 2.f); y < fminf(L, fmaxf(b.y, c.y)); y += delta) {
-            float x0 = y < b.y ? ab * (y - a.y) + a.x : bc * (y - b.y) + b.x;
-            float x1 = y < c.y ? ac * (y - a.y) + a.x : bc * (y - b.y) + b.x;
-            if (x0 > x1) { const float t = x0; x0 = x1; x1 = t; }
-            for (float x = fmaxf(-L, x0) + delta / 2.f; x < fminf(L, x1); x += delta) ret += pm::expf(-(sqrf(x) + sqrf(y)) / 2.f);
-        }
-        return ret * kInvTwoPi * sqrf(delta);
+    return min_len < 1e-3f ? G2_QUADRATURE : G2_ANALYTIC;
+}
+// The quadrature's (y, x) sample sequence, shared by the serial and the warp form: float accumulation of y and x exactly as the reference's loops.
+template <class F> WT_D void g2_quadrature_points(V2 a, V2 b, V2 c, F&& f) {
+    const float L = 3.f, delta = .002f;
+    if (b.y < a.y) { const V2 t = a; a = b; b = t; }
+    if (c.y < a.y) { const V2 t = a; a = c; c = t; }
+    const float ab = b.y == a.y ? WT_INF : (b.x - a.x) / (b.y - a.y);
+    const float ac = c.y == a.y ? WT_INF : (c.x - a.x) / (c.y - a.y);
+    const float bc = c.y == b.y ? WT_INF : (c.x - b.x) / (c.y - b.y);
+    for (float y = fmaxf(-L, a.y + delta / 2.f); y < fminf(L, fmaxf(b.y, c.y)); y += delta) {
+        float x0 = y < b.y ? ab * (y - a.y) + a.x : bc * (y - b.y) + b.x;
+        float x1 = y < c.y ? ac * (y - a.y) + a.x : bc * (y - b.y) + b.x;
+        if (x0 > x1) { const float t = x0; x0 = x1; x1 = t; }
+        for (float x = fmaxf(-L, x0) + delta / 2.f; x < fminf(L, x1); x += delta) f(x, y);
     }
+}
+WT_D float g2_quadrature(V2 a, V2 b, V2 c) {
+    float ret = 0.f;
+    g2_quadrature_points(a, b, c, [&](float x, float y) { ret += pm::expf(-(sqrf(x) + sqrf(y)) / 2.f); });
+    return ret * kInvTwoPi * sqrf(.002f);
+}
+// The same sum by a whole warp (all 32 lanes call with the same triangle): the sample sequence is enumerated by every lane (cheap, warp-uniform),
+// lane j keeps sample j of each batch of 32, the exponentials of a batch are evaluated in parallel and added IN SEQUENCE ORDER -- the result is
+// bit-identical to g2_quadrature.  One thread walking up to ~10^4 samples (each a binary64-internal exp) used to decide the duration of the
+// whole k_bd_resolve launch (profiles/r02_phases.txt).
+WT_D float g2_quadrature_warp(V2 a, V2 b, V2 c) {
+    const unsigned lane = threadIdx.x & 31u;
+    float ret = 0.f, mx = 0.f, my = 0.f; uint32_t cnt = 0u;
+    auto flush = [&](uint32_t n) {
+        const float e = lane < n ? pm::expf(-(sqrf(mx) + sqrf(my)) / 2.f) : 0.f;
+        for (uint32_t j = 0; j < n; ++j) ret += __shfl_sync(0xffffffffu, e, (int)j);
+    };
+    g2_quadrature_points(a, b, c, [&](float x, float y) {
+        if ((cnt & 31u) == lane) { mx = x; my = y; }
+        ++cnt;
+        if ((cnt & 31u) == 0u) flush(32u);
+    });
+    if (cnt & 31u) flush(cnt & 31u);
+    return ret * kInvTwoPi * sqrf(.002f);
+}
+WT_NI float g2_analytic(const DScene& sc, V2 a, V2 b, V2 c) {
     const V2 t0 = b - a, t1 = c - a;         // T = mat2(t0, t1) columns
     const float detT = t0.x * t1.y - t1.x * t0.y;
     const float od = 1.f / detT;
@@ -119,6 +150,11 @@ WT_NI float g2_integrate_triangle(const DScene& sc, const G2& g, V2 a, V2 b, V2 
     const float c0 = Sxy * denom, d0 = (Sxy * mu0.x + Syy * mu0.y) * denom, q = .5f / denom;
     const float I0 = g2d::Ige(sc, pa, pb, c0 - q, d0 + q), I1 = g2d::Ige(sc, pa, pb, c0, d0);
     return kInvSqrtPi / 2.f * fabsf(detT * denom) * fmaxf(0.f, I0 - I1);
+}
+WT_NI float g2_integrate_triangle(const DScene& sc, const G2& g, V2 a, V2 b, V2 c) {
+    float v = 0.f;
+    const int kind = g2_classify(g, a, b, c, v);
+    return kind == G2_DONE ? v : kind == G2_QUADRATURE ? g2_quadrature(a, b, c) : g2_analytic(sc, a, b, c);
 }
 WT_D G2 wavefront_of(const Beam& b, float d) {       // beam_generic.hpp:130-139 + gaussian_wavefront.hpp:34-40
     const V3 fp = beam_footprint(b, d);
@@ -559,6 +595,76 @@ WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, 
         }
     }
     if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo); if (eo) h.overflow = true; }
+}
+
+// bd_resolve_hit with the flux integral organised for a warp (all 32 lanes call; `act` marks lanes that hold a walker): every lane walks its own
+// clipped triangles, but the lanes advance piece by piece together, and a piece that needs the quadrature branch of integrate_triangle is
+// evaluated by the whole warp (g2_quadrature_warp).  Same values, same order of additions as bd_resolve_hit.
+WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, const TravOut& tr, const uint32_t* tris, uint32_t* edges, BHit& h) {
+    const unsigned lane = threadIdx.x & 31u;
+    bool need = false;
+    uint32_t nt = 0u;
+    Range zr = mkr(0.f, 0.f);
+    V3 dir = mk3(0.f, 0.f, 1.f);
+    if (act) {
+        h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u;
+        h.origin = tr.origin; h.region_depth = tr.region_depth; h.dist = 0.f; h.ballistic = true;
+        if (!tr.empty) {
+            if (tr.cone.overflow) h.overflow = true;
+            h.dist = tr.ballistic ? tr.ray.dist : tr.cone.dist;
+            zr = mkr(h.dist, h.dist + tr.region_depth);
+            h.ballistic = tr.ballistic || cone_is_ray(beam.env);
+            dir = beam.env.d;
+            nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
+            if (h.ballistic) { h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; }
+            else {
+                for (uint32_t i = 0; i < nt; ++i) {
+                    const Tri3 t = load_tri(sc, tris[i]);
+                    const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
+                    const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+                    if (rt.hit && rt.dist < h.pdist) { h.primary = tris[i]; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
+                }
+                need = h.primary == WTGPU_INVALID_IDX;
+            }
+        }
+    }
+    const bool flux_lane = need;
+    if (__any_sync(0xffffffffu, need)) {
+        Frame beam_frame; G2 wf; float csz = 0.f;
+        if (need) { beam_frame = cone_frame(beam.env); wf = wavefront_of(beam, h.dist); csz = (zr.mx + zr.mn) / 2.f; }
+        uint32_t i = 0u; int k = 0; Clip cl; cl.tris = 0;
+        while (__any_sync(0xffffffffu, need)) {
+            int kind = G2_DONE; float val = 0.f; bool add = false;
+            V2 pa = mk2(0.f, 0.f), pb = pa, pc = pa;
+            if (need) {
+                while (k >= cl.tris) {        // next triangle facing like the closest one (plt_bdpt_detail.hpp:391-416)
+                    if (i >= nt) { need = false; break; }
+                    const Tri3 t = load_tri(sc, tris[i]); ++i;
+                    if ((dot(t.n, -dir) > 0.f) != tr.cone.front) continue;
+                    cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
+                    k = 0;
+                }
+                if (need) {
+                    V3 ct[3]; clip_tri(cl, k, ct); ++k;
+                    pa = cone_project_local(beam.env, ct[0], csz); pb = cone_project_local(beam.env, ct[1], csz); pc = cone_project_local(beam.env, ct[2], csz);
+                    kind = g2_classify(wf, pa, pb, pc, val);
+                    if (kind == G2_ANALYTIC) val = g2_analytic(sc, pa, pb, pc);
+                    add = true;
+                }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, kind == G2_QUADRATURE);
+            while (m) {
+                const int src = __ffs(m) - 1; m &= m - 1u;
+                const V2 qa = mk2(__shfl_sync(0xffffffffu, pa.x, src), __shfl_sync(0xffffffffu, pa.y, src));
+                const V2 qb = mk2(__shfl_sync(0xffffffffu, pb.x, src), __shfl_sync(0xffffffffu, pb.y, src));
+                const V2 qc = mk2(__shfl_sync(0xffffffffu, pc.x, src), __shfl_sync(0xffffffffu, pc.y, src));
+                const float r = g2_quadrature_warp(qa, qb, qc);
+                if ((int)lane == src) val = r;
+            }
+            if (add) h.flux += val;
+        }
+    }
+    if (flux_lane && sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo); if (eo) h.overflow = true; }
 }
 
 // continue_walk (plt_bdpt_detail.hpp:167-182)
@@ -1019,22 +1125,26 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
 // what the vertex step needs from a traversal result: primary triangle, Gaussian power over clipped triangles, edges, sort key
 __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = li < (uint32_t)a.r.ctr->n_trav;
+    const DScene& sc = a.r.sc;
     bool ovf = false;
-    if (li < (uint32_t)a.r.ctr->n_trav) {
-        const uint32_t wid = a.r.trav_list[li];
-        const DScene& sc = a.r.sc;
-        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+    uint32_t wid = 0u;
+    BdWalker w; TravOut tr; BHit bh; HitRec h;
+    uint32_t tris[kMaxConeTris];
+    tr.empty = true; tr.ballistic = true; tr.cone.n_tris = 0u;
+    if (act) {
+        wid = a.r.trav_list[li];
+        soa_load(w, a.walkers, 2u * a.P, wid);
         const TravRec r = a.trav_rec[wid];
-        TravOut tr;
         tr.empty = (r.flags & TR_EMPTY) != 0u; tr.ballistic = (r.flags & TR_BALLISTIC) != 0u;
         tr.ray.tuid = r.ray_tuid; tr.ray.dist = r.ray_dist; tr.ray.bx = r.bx; tr.ray.by = r.by; tr.ray.front = (r.flags & TR_RAY_FRONT) != 0u;
         tr.cone.dist = r.cone_dist; tr.cone.front = (r.flags & TR_CONE_FRONT) != 0u; tr.cone.n_tris = r.n_tris; tr.cone.overflow = (r.flags & TR_OVERFLOW) != 0u;
         tr.region_depth = r.region_depth; tr.origin = mk3(r.ox, r.oy, r.oz);
-        uint32_t tris[kMaxConeTris];
         const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
         for (uint32_t k = 0; k < nt; ++k) tris[k] = a.trav_tris[(size_t)wid * kMaxConeTris + k];
-        BHit bh; HitRec h;
-        bd_resolve_hit(sc, w.beam, tr, tris, h.edges, bh);
+    }
+    bd_resolve_hit_warp(sc, act, w.beam, tr, tris, h.edges, bh);
+    if (act) {
         h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
         h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
         ovf = bh.overflow;
@@ -1042,7 +1152,7 @@ __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
         a.r.keys[wid] = bd_hit_key(sc, bh, a.r.n_keys);
     }
     count1(&a.r.ctr->overflow, ovf);
-    count1(&a.r.ctr->walker_steps, li < (uint32_t)a.r.ctr->n_trav);
+    count1(&a.r.ctr->walker_steps, act);
 }
 
 __global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->trav_head = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }

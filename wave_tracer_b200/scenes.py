@@ -43,16 +43,29 @@ def double_slits(res=1024, spp=32, direction="forward", max_depth=16, fsd=True, 
     return sc
 
 
-def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=False, fsd=False, n_sphere=16, integrator="plt_path", lut=(512, 256), cube_profile=None):
+def rgb_response():
+    """Three smooth sensitivity curves over 400-700 nm (a stand-in for the reference's RGB response, src/sensor/response/RGB.cpp, whose
+    colour-matching tables come from data/sensitivity/XYZ.yml): what matters on the hot path is film_t::splat's per-channel response->f(c, k)
+    (film.hpp:254-288) over a polychromatic wavenumber distribution."""
+    lam = np.linspace(400e-9, 700e-9, 31)
+    g = lambda mu, sg: np.exp(-.5 * ((lam - mu) / sg) ** 2)
+    return [Table(lam, 1.0 * g(600e-9, 40e-9) + .35 * g(445e-9, 20e-9)), Table(lam, g(550e-9, 45e-9)), Table(lam, 1.7 * g(450e-9, 25e-9))]
+
+
+def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=False, fsd=False, n_sphere=16, integrator="plt_path", lut=(512, 256), cube_profile=None, rgb=False):
     """A texture-free, procedural cornell-box variant (scenes/cornell-box/box.xml with its PLY shapes dropped):
-    5 diffuse walls, a dielectric sphere, a rough-conductor cube, a cube area emitter; perspective sensor; plt_path backward."""
+    5 diffuse walls, a dielectric sphere, a rough-conductor cube, a cube area emitter; perspective sensor; plt_path backward.
+    rgb=True: three-channel film over the visible spectrum, 6500 K blackbody emitter, spectrally varying wall reflectances."""
     lam = lam_nm * 1e-9
     sc = Scene()
     sc.integrator = PltBdpt(max_depth=max_depth, fsd=fsd, lut=lut) if integrator == "plt_bdpt" else \
         PltPath(max_depth=max_depth, direction="backward", fsd=fsd, russian_roulette=True)
-    film = Film(res, res, [Discrete(lam)], rfilter_scale=1.0)
+    film = Film(res, res, rgb_response() if rgb else [Discrete(lam)], rfilter_scale=1.0)
     sc.sensor = Perspective(lookat((0, 1.0, 3.4), (0, 1.0, 0), (0, 1, 0)), math.radians(40), film, ray_trace_only=ray_trace_only, samples=spp)
     white, red, green = TwoSided(Diffuse(.6)), TwoSided(Diffuse(.35)), TwoSided(Diffuse(.45))
+    if rgb:
+        wl = np.array([400e-9, 480e-9, 520e-9, 580e-9, 620e-9, 700e-9])
+        red, green = TwoSided(Diffuse(Table(wl, [.05, .05, .08, .25, .6, .65]))), TwoSided(Diffuse(Table(wl, [.06, .15, .5, .35, .1, .06])))
     sc.add_shape(rectangle((-1, 0, -1), (2, 0, 0), (0, 0, 2)), white)          # floor
     sc.add_shape(rectangle((-1, 2, -1), (0, 0, 2), (2, 0, 0)), white)          # ceiling
     sc.add_shape(rectangle((-1, 0, -1), (0, 2, 0), (2, 0, 0)), white)          # back
@@ -60,7 +73,7 @@ def cornell_like(res=256, spp=16, max_depth=8, lam_nm=550.0, ray_trace_only=Fals
     sc.add_shape(rectangle((1, 0, -1), (0, 2, 0), (0, 0, 2)), green)           # right
     sc.add_shape(sphere(.35, (-.4, .35, .2), n_sphere, 2 * n_sphere), Dielectric(1.5))
     sc.add_shape(cube(translate((.45, .3, -.25)) @ rotate((0, 1, 0), .4) @ scale(.3)), SurfaceSPM(IOR=complex(.2, 3.0), profile=cube_profile or Fractal(.2)))
-    sc.add_shape(cube(translate((0, 1.98, 0)) @ scale((.25, .01, .25))), Diffuse(.0), emitter=Area(Discrete(lam, 1.0), scale=20.0))
+    sc.add_shape(cube(translate((0, 1.98, 0)) @ scale((.25, .01, .25))), Diffuse(.0), emitter=Area(Blackbody(6500, 2e-12) if rgb else Discrete(lam, 1.0), scale=20.0))
     return sc
 
 
