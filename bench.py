@@ -165,7 +165,7 @@ def main():
         base = (i * world + rank) * S
         dev = torch.device("cuda", local)
         block = torch.zeros((H, W, 1, 2), dtype=torch.float32, device=dev); light = torch.zeros((H, W, 1), dtype=torch.float32, device=dev)
-        st = gs.render_into(block.data_ptr(), light.data_ptr(), SPP, 0x5EED, (base, base + S), None, True, a.pool, flags, torch.cuda.current_stream().cuda_stream, True)
+        st = gs.render_into(block.data_ptr(), light.data_ptr(), SPP, 0x5EED, (base, base + S), None, True, a.pool, flags, torch.cuda.current_stream().cuda_stream)
         if world > 1:
             flat = torch.cat([block.reshape(-1), light.reshape(-1)]); dist.reduce(flat, dst=0, op=dist.ReduceOp.SUM)
         return st
@@ -232,11 +232,11 @@ def main():
     def e2e_step(i):
         base = (i * world + rank) * S
         if world == 1:
-            return render(built, spp=SPP, device=local, sample_range=(base, base + S), pool_size=a.pool, allow_overflow=True)[2]["samples"]
+            return render(built, spp=SPP, device=local, sample_range=(base, base + S), pool_size=a.pool)[2]["samples"]
         g = GpuScene(built, local)
         dev = torch.device("cuda", local)
         block = torch.zeros((H, W, 1, 2), dtype=torch.float32, device=dev); light = torch.zeros((H, W, 1), dtype=torch.float32, device=dev)
-        st = g.render_into(block.data_ptr(), light.data_ptr(), SPP, 0x5EED, (base, base + S), None, True, a.pool, 0, torch.cuda.current_stream().cuda_stream, True)
+        st = g.render_into(block.data_ptr(), light.data_ptr(), SPP, 0x5EED, (base, base + S), None, True, a.pool, 0, torch.cuda.current_stream().cuda_stream)
         flat = torch.cat([block.reshape(-1), light.reshape(-1)]); dist.reduce(flat, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0: flat.cpu()
         g.close()

@@ -36,7 +36,7 @@ static Rect rectangle(const double pd[3], const double xd[3], const double yd[3]
 }
 static void identity16(double m[16]) { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0; }
 
-#define CHECK(call) do { const int rc_ = (call); if (rc_ != WTGPU_OK && rc_ != WTGPU_E_CAPACITY) { std::fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, wtgpu_last_error()); return 2; } } while (0)
+#define CHECK(call) do { const int rc_ = (call); if (rc_ != WTGPU_OK) { std::fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, wtgpu_last_error()); return 2; } } while (0)
 
 int main(int argc, char** argv) {
     const uint32_t res = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 96u, spp = argc > 2 ? (uint32_t)std::atoi(argv[2]) : 4u;

@@ -39,7 +39,8 @@ extern "C" {
 #define WTGPU_E_CUDA          -2   /* CUDA runtime error (message in wtgpu_last_error)   */
 #define WTGPU_E_NO_DEVICE     -3   /* no CUDA device / extension built without a GPU     */
 #define WTGPU_E_UNSUPPORTED   -4   /* feature in the description not implemented         */
-#define WTGPU_E_CAPACITY      -5   /* a bounded per-path list overflowed (reported, never silent) */
+#define WTGPU_E_CAPACITY      -5   /* a per-path list could not be grown to the length the scene needs (out of device memory), or a BVH
+                                      traversal stack of the reference's depth (64 / 128) was full: reported, never silent */
 
 #define WTGPU_INVALID_IDX 0xffffffffu
 
@@ -297,7 +298,7 @@ typedef struct wtgpu_scene_desc {
  * Draw d of (pixel, sample, stream) is lane d&3 of Philox4x32-10(key = seed, counter = (d>>2, sample, pixel, stream)),
  * float = (u32 >> 8) * 2^-24.  stream is 0 for plt_path.  plt_bdpt splits a sample into sub-streams (each starting at d = 0) so
  * that the two subpath walks and every (s,t) strategy are independent: 0 = emitter / wavenumber / source sampling, 1 = sensor
- * subpath walk, 2 = emitter subpath walk, 3 + 32 t + s = strategy (s,t).
+ * subpath walk, 2 = emitter subpath walk, 3 + 4096 t + s = strategy (s,t).
  *
  * sobolld contract (the reference draws a fresh batch of 3^11 x 47 values per pool thread with random seeds,
  * src/sampler/sobolld.cpp:53-60, and consumes it as one flat stream, sobolld.hpp:40-48): sample `s` of element `p` owns point
@@ -340,7 +341,7 @@ typedef struct wtgpu_stats {
     uint64_t edges_fetched;
     uint64_t surface_interactions, fsd_interactions, null_interactions;
     uint64_t splats;                /* film taps written */
-    uint64_t capacity_overflows;
+    uint64_t capacity_overflows;    /* lists that did not fit their row in the FINAL pass: 0 on success (see `passes`) */
     uint64_t kernel_launches;
     uint64_t iterations;
     uint64_t traverse_nodes, traverse_tris;   /* node / triangle fetches of k_traverse alone (roofline of the dominant kernel) */
@@ -350,6 +351,15 @@ typedef struct wtgpu_stats {
     double   connect_ms;            /* plt_bdpt: the (s,t) strategy kernels (shade_ms then covers the vertex step only) */
     uint64_t strategies[5];         /* plt_bdpt: strategies evaluated per class: s=0, t=0, s=1, t=1, vertex-vertex */
     uint64_t walker_steps;          /* plt_bdpt: subpath-walker traverse() calls */
+    /* Capacity growth.  Cone-query triangle lists, edge sets, aperture segments, apertures and subpath vertices are std::vector / std::set of any
+     * length in the reference (traversal_common.hpp:116-149); here they are rows of device arrays whose lengths belong to the scene handle.  A pass
+     * over the samples that finds a longer list is discarded, the rows are re-sized to what it measured, and the pass is repeated (`passes` > 1);
+     * the handle keeps the lengths for the next render.  Results therefore never depend on a capacity. */
+    uint32_t passes;                /* passes over the samples this call took (1: every list fitted) */
+    uint32_t pool_used;             /* paths / sample slots in flight (smaller than asked when long rows would not fit in device memory) */
+    uint32_t cap_tris, cap_edges, cap_segments, cap_apertures, cap_vertices;   /* row lengths after this call */
+    uint32_t pad_;
+    uint64_t stack_drops;           /* children a full BVH traversal stack dropped (bvh8w.cpp's stack depths); non-zero => WTGPU_E_CAPACITY */
 } wtgpu_stats;
 
 typedef struct wtgpu_scene wtgpu_scene;
@@ -363,6 +373,10 @@ void wtgpu_scene_destroy(wtgpu_scene* scene);
 void wtgpu_trim(void);
 int wtgpu_render(wtgpu_scene* scene, const wtgpu_render_opts* opts,
                  float* film_block, float* film_light, wtgpu_stats* stats);
+/* row lengths of the per-path lists of a scene handle, {cone triangles, edges, aperture segments, apertures per subpath, vertices per subpath}:
+ * read them / preset them (e.g. from a previous run of the same scene, to skip the measuring pass; or tiny, to test the growth) */
+int wtgpu_get_capacities(wtgpu_scene* scene, uint32_t out[5]);
+int wtgpu_set_capacities(wtgpu_scene* scene, const uint32_t in[5]);
 /* out[h][w][c] = block value/weight + light/spp ; host pointers */
 int wtgpu_develop(const wtgpu_sensor* sensor, uint32_t spp,
                   const float* film_block, const float* film_light, float* out);

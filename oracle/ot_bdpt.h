@@ -788,7 +788,7 @@ struct plt_bdpt_t {
                 if (!emitter_direct && s == 1) continue;
                 if (!sensor_direct && t == 1) continue;
                 if (depth > (int)max_depth) break;
-                sampler.set_stream(3u + 32u * (uint32_t)t + (uint32_t)s);
+                sampler.set_stream(3u + 4096u * (uint32_t)t + (uint32_t)s);
                 const auto ret = connect_subpaths(ar, s, t, sampler);
                 if (stats) stats->connections++;
                 if (ret.L.intensity() <= 0) continue;

@@ -46,7 +46,7 @@ def test_gpu_matches_golden_films(name):
     from wave_tracer_b200 import render
     mk, spp = CASES[name]
     b = mk().build()
-    blk, lgt, st = render(b, spp=spp, seed=0x5EED, allow_overflow=True)
+    blk, lgt, st = render(b, spp=spp, seed=0x5EED)
     gold_c = dict(zip(COUNTERS, G[name + "/counters"]))
     assert st["samples"] == gold_c["samples"]
     for g, o in ((blk.astype(np.float64), G[name + "/block"]), (lgt.astype(np.float64), G[name + "/light"])):

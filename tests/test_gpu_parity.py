@@ -102,6 +102,10 @@ def _mean_rel(g, o):
     return float((np.abs(g.astype(np.float64) - o)[lit] / np.abs(o[lit])).mean()) if lit.any() else 0.0
 
 
+def _no_overflow(st):
+    assert st["capacity_overflows"] == 0 and st["stack_drops"] == 0, (st["capacity_overflows"], st["stack_drops"])
+
+
 def _gate(g, o, what=""):
     l2, flux = _film_metrics(g, o); mr = _mean_rel(g, o)
     assert l2 <= L2_GATE and flux <= MEAN_GATE and mr <= MEAN_GATE, (what, l2, flux, mr)
@@ -112,7 +116,8 @@ def _gate(g, o, what=""):
 def test_double_slits_film_matches_oracle(direction, rt):
     """plt_path forward + UTD on double_slits geometry: per-element film within the parity gate of the oracle (equal streams)."""
     b = scenes.double_slits(res=256, spp=8, with_directional=True, ray_trace_only=rt).build()
-    blk, lgt, st = render(b, spp=8, allow_overflow=True)
+    blk, lgt, st = render(b, spp=8)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"] == 256 * 64 * 8
     assert olgt.sum() > 0
@@ -129,7 +134,8 @@ def test_cornell_backward_film_matches_oracle(profile):
     from wave_tracer_b200 import Gaussian
     prof = {"fractal": None, "gaussian_roughness": Gaussian(roughness=.3), "gaussian_sigma": Gaussian(sigma=6000.0)}[profile]
     b = scenes.cornell_like(res=48, spp=8, cube_profile=prof).build()
-    blk, lgt, st = render(b, spp=8, allow_overflow=True)
+    blk, lgt, st = render(b, spp=8)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"]
     img_g = develop(b, 8, blk, lgt); img_o = develop(b, 8, oblk, olgt)
@@ -147,7 +153,8 @@ def test_etoile_like_forward_matches_oracle(rt):
     Round 1 needed rel-L2 <= 2.5e-2 here (a path takes thousands of UTD edge decisions and CUDA's libm differs from glibc in the last ulp);
     with the shared elementary functions every decision is the oracle's: identical counters, the plain parity gate."""
     b = scenes.etoile_like(res=96, spp=4, ray_trace_only=rt).build()
-    blk, lgt, st = render(b, spp=4, allow_overflow=True)
+    blk, lgt, st = render(b, spp=4)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=4)
     print("etoile_like rt=%s capacity overflows:" % rt, st["capacity_overflows"], "of", st["segments"], "segments")
     assert st["samples"] == ost["samples"] == 96 * 72 * 4
@@ -169,8 +176,8 @@ def test_plt_path_group_traverse_equals_thread_traverse(scene):
     b = {"double_slits": lambda: scenes.double_slits(res=256, spp=4, with_directional=True), "etoile": lambda: scenes.etoile_like(res=96, spp=4),
          "cornell": lambda: scenes.cornell_like(res=48, spp=4, fsd=True)}[scene]().build()
     gs = GpuScene(b, 0)
-    blk0, lgt0, st0 = render(b, spp=4, gpu_scene=gs, allow_overflow=True, flags=16)     # WTGPU_RENDER_GROUP_TRAVERSE
-    blk1, lgt1, st1 = render(b, spp=4, gpu_scene=gs, allow_overflow=True, flags=8)      # WTGPU_RENDER_THREAD_TRAVERSE
+    blk0, lgt0, st0 = render(b, spp=4, gpu_scene=gs, flags=16)     # WTGPU_RENDER_GROUP_TRAVERSE
+    blk1, lgt1, st1 = render(b, spp=4, gpu_scene=gs, flags=8)      # WTGPU_RENDER_THREAD_TRAVERSE
     for k in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "nodes_visited", "tris_tested", "surface_interactions", "fsd_interactions",
               "null_interactions", "splats", "capacity_overflows", "edges_fetched"):
         assert st0[k] == st1[k], (k, st0[k], st1[k])
@@ -186,8 +193,8 @@ def test_ray_range_culling_changes_no_result(scene):
     b = {"double_slits": lambda: scenes.double_slits(res=256, spp=4, with_directional=True), "etoile": lambda: scenes.etoile_like(res=96, spp=4),
          "cornell_bdpt": lambda: scenes.cornell_like(res=48, spp=4, fsd=True, integrator="plt_bdpt", lut=(512, 256))}[scene]().build()
     gs = GpuScene(b, 0)
-    blk0, lgt0, st0 = render(b, spp=4, gpu_scene=gs, allow_overflow=True, flags=0)
-    blk1, lgt1, st1 = render(b, spp=4, gpu_scene=gs, allow_overflow=True, flags=32)     # WTGPU_RENDER_NO_RAY_CULL
+    blk0, lgt0, st0 = render(b, spp=4, gpu_scene=gs, flags=0)
+    blk1, lgt1, st1 = render(b, spp=4, gpu_scene=gs, flags=32)     # WTGPU_RENDER_NO_RAY_CULL
     for k in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "surface_interactions", "fsd_interactions", "null_interactions", "splats",
               "capacity_overflows", "edges_fetched"):
         assert st0[k] == st1[k], (k, st0[k], st1[k])
@@ -202,14 +209,14 @@ def test_partition_invariance_on_gpu():
     """Sample-range / tile partitions give the same film as one call (RNG keyed by (pixel, sample))."""
     b = scenes.double_slits(res=128, spp=8, with_directional=False).build()
     gs = GpuScene(b, 0)
-    _, full, _ = render(b, spp=8, gpu_scene=gs, allow_overflow=True)
-    _, a, _ = render(b, spp=8, sample_range=(0, 3), gpu_scene=gs, allow_overflow=True)
-    _, c, _ = render(b, spp=8, sample_range=(3, 8), gpu_scene=gs, allow_overflow=True)
+    _, full, _ = render(b, spp=8, gpu_scene=gs)
+    _, a, _ = render(b, spp=8, sample_range=(0, 3), gpu_scene=gs)
+    _, c, _ = render(b, spp=8, sample_range=(3, 8), gpu_scene=gs)
     assert np.allclose(a + c, full, rtol=1e-4, atol=1e-6 * full.max())
-    _, t1, _ = render(b, spp=8, tile=(0, 0, 64, 32), gpu_scene=gs, allow_overflow=True)
-    _, t2, _ = render(b, spp=8, tile=(64, 0, 128, 32), gpu_scene=gs, allow_overflow=True)
+    _, t1, _ = render(b, spp=8, tile=(0, 0, 64, 32), gpu_scene=gs)
+    _, t2, _ = render(b, spp=8, tile=(64, 0, 128, 32), gpu_scene=gs)
     assert np.allclose(t1 + t2, full, rtol=1e-4, atol=1e-6 * full.max())
-    _, ns, _ = render(b, spp=8, gpu_scene=gs, flags=1, allow_overflow=True)          # material sort off: same result
+    _, ns, _ = render(b, spp=8, gpu_scene=gs, flags=1)          # material sort off: same result
     assert np.allclose(ns, full, rtol=1e-4, atol=1e-6 * full.max())
 
 
@@ -219,7 +226,8 @@ def test_bdpt_double_slits_matches_oracle(fsd, flags):
     flags=0: wavefront driver (eight lanes per beam in traverse()); 8: wavefront with one thread per beam; 4 (WTGPU_RENDER_BDPT_MEGAKERNEL):
     the one-thread-per-sample cross-check driver."""
     b = scenes.double_slits(res=128, spp=8, with_directional=False, integrator="plt_bdpt", fsd=fsd, lut=(512, 256)).build()
-    blk, lgt, st = render(b, spp=8, allow_overflow=True, flags=flags)
+    blk, lgt, st = render(b, spp=8, flags=flags)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"] == 128 * 32 * 8
     img_g = develop(b, 8, blk, lgt); img_o = develop(b, 8, oblk, olgt)
@@ -233,7 +241,8 @@ def test_bdpt_double_slits_matches_oracle(fsd, flags):
 def test_bdpt_cornell_matches_oracle(flags):
     """plt_bdpt with a perspective sensor and an area emitter (s=0 emission hits, t=1 sensor connections, NEE, MIS)."""
     b = scenes.cornell_like(res=48, spp=8, integrator="plt_bdpt").build()
-    blk, lgt, st = render(b, spp=8, allow_overflow=True, flags=flags)
+    blk, lgt, st = render(b, spp=8, flags=flags)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"]
     img_g = develop(b, 8, blk, lgt); img_o = develop(b, 8, oblk, olgt)
@@ -257,7 +266,8 @@ def test_bdpt_cornell_with_fraunhofer_fsd_matches_oracle(flags):
     """plt_bdpt WITH Fraunhofer FSD on non-slit geometry: the tessellated sphere and the cubes put diffracting edges inside
     the beams' footprints -- aperture construction from cone-query edge lists, rejection sampling, FSD vertices in connections and MIS."""
     b = scenes.cornell_like(res=40, spp=4, integrator="plt_bdpt", fsd=True, lut=(512, 256), n_sphere=8).build()
-    blk, lgt, st = render(b, spp=4, allow_overflow=True, flags=flags)
+    blk, lgt, st = render(b, spp=4, flags=flags)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=4)
     assert st["samples"] == ost["samples"]
     img_g = develop(b, 4, blk, lgt); img_o = develop(b, 4, oblk, olgt)
@@ -269,7 +279,8 @@ def test_bdpt_cornell_with_fraunhofer_fsd_matches_oracle(flags):
 def test_cornell_backward_with_utd_matches_oracle():
     """plt_path BACKWARD + UTD: pending-FSD evaluation at the next vertex, edge apertures on real geometry, NEE / emission MIS."""
     b = scenes.cornell_like(res=40, spp=4, fsd=True, n_sphere=8).build()
-    blk, lgt, st = render(b, spp=4, allow_overflow=True)
+    blk, lgt, st = render(b, spp=4)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=4)
     assert st["samples"] == ost["samples"]
     img_g = develop(b, 4, blk, lgt); img_o = develop(b, 4, oblk, olgt)
@@ -284,7 +295,8 @@ def test_rgb_polychromatic_film_matches_oracle(integrator):
     film_t::splat's per-channel response->f(channel, k) (film.hpp:254-288)."""
     b = scenes.cornell_like(res=40, spp=4, rgb=True, integrator=integrator, n_sphere=8).build()
     assert b.channels == 3
-    blk, lgt, st = render(b, spp=4, allow_overflow=True)
+    blk, lgt, st = render(b, spp=4)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=4)
     assert st["samples"] == ost["samples"] and blk.shape == (40, 40, 3, 2)
     img_g = develop(b, 4, blk, lgt); img_o = develop(b, 4, oblk, olgt)
@@ -296,6 +308,63 @@ def test_rgb_polychromatic_film_matches_oracle(integrator):
     assert np.allclose(blk[..., 1], oblk[..., 1], rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("integrator", ["plt_path", "plt_bdpt", "plt_bdpt_mega"])
+def test_list_capacities_grow_and_never_change_a_result(integrator):
+    """The reference's cone-query triangle lists, edge sets, Fraunhofer segments / apertures and subpath vertices are unbounded containers
+    (traversal_common.hpp:116-149).  Device rows start tiny here (8 triangles, 4 edges, 4 segments, 1 aperture, 3 vertices per subpath): the
+    render must notice, re-size them (passes > 1), end with zero overflows, and give the film of a render whose rows were long from the start --
+    and the oracle's."""
+    bd = integrator != "plt_path"
+    b = scenes.cornell_like(res=32, spp=4, fsd=True, n_sphere=12, integrator="plt_bdpt" if bd else "plt_path", lut=(512, 256)).build()
+    flags = 4 if integrator == "plt_bdpt_mega" else 0
+    gs = GpuScene(b, 0)
+    caps0 = gs.capacities()
+    blk0, lgt0, st0 = render(b, spp=4, gpu_scene=gs, flags=flags)
+    assert st0["capacity_overflows"] == 0 and st0["stack_drops"] == 0
+    gs2 = GpuScene(b, 0)
+    gs2.set_capacities([8, 4, 4, 1, 3])
+    blk1, lgt1, st1 = render(b, spp=4, gpu_scene=gs2, flags=flags)
+    caps1 = gs2.capacities()
+    print("capacity growth %s: default caps %s (passes %d) | from [8,4,4,1,3]: passes %d -> %s" % (integrator, gs.capacities(), st0["passes"], st1["passes"], caps1))
+    assert st1["passes"] > 1 and st1["capacity_overflows"] == 0
+    assert caps1[0] > 8 and caps1[1] > 4 and (not bd or (caps1[2] > 4 and caps1[4] > 3))
+    for k in ("samples", "segments", "ray_casts", "cone_casts", "surface_interactions", "fsd_interactions", "null_interactions", "splats"):
+        assert st0[k] == st1[k], (k, st0[k], st1[k])
+    for x, y in ((blk0, blk1), (lgt0, lgt1)):
+        assert np.linalg.norm(x.astype(np.float64) - y) <= 1e-5 * np.linalg.norm(y.astype(np.float64)) + 1e-30
+    # a second render with the grown rows needs one pass
+    _, _, st2 = render(b, spp=4, gpu_scene=gs2, flags=flags)
+    assert st2["passes"] == 1 and st2["capacity_overflows"] == 0
+    oblk, olgt, ost = _oracle.render(b, spp=4)
+    _gate(develop(b, 4, blk1, lgt1), develop(b, 4, oblk, olgt), "capacity growth " + integrator)
+    gs.close(); gs2.close()
+
+
+def test_bdpt_default_max_depth_renders():
+    """plt_bdpt's default max_depth is 1024 (plt_bdpt.cpp:169); subpath vertex rows start at 18 and grow only if Russian roulette lets a walk get there."""
+    from wave_tracer_b200 import PltBdpt
+    sc = scenes.cornell_like(res=24, spp=4, integrator="plt_bdpt", n_sphere=6); sc.integrator = PltBdpt(fsd=False)
+    assert sc.integrator.max_depth == 1024
+    b = sc.build()
+    blk, lgt, st = render(b, spp=4)
+    _no_overflow(st)
+    oblk, olgt, ost = _oracle.render(b, spp=4)
+    print("bdpt max_depth 1024: passes %d vertex rows %d" % (st["passes"], st["cap_vertices"]))
+    assert st["samples"] == ost["samples"] and st["capacity_overflows"] == 0
+    _gate(develop(b, 4, blk, lgt), develop(b, 4, oblk, olgt), "bdpt default max_depth")
+
+
+def test_bdpt_ray_tracing_mode_needs_no_fraunhofer_tables():
+    """--ray-tracing with plt_bdpt: the reference does not even load the FSD tables (plt_bdpt.cpp:189-194) -- ADVICE r1."""
+    b = scenes.double_slits(res=64, spp=4, with_directional=False, ray_trace_only=True, integrator="plt_bdpt").build()
+    assert b.desc.fsd_lut_n == 0
+    blk, lgt, st = render(b, spp=4)
+    _no_overflow(st)
+    oblk, olgt, ost = _oracle.render(b, spp=4)
+    assert st["samples"] == ost["samples"]
+    _gate(develop(b, 4, blk, lgt), develop(b, 4, oblk, olgt), "bdpt rt")
+
+
 def test_xml_scene_film_matches_oracle():
     """A scene file in the reference's XML format (tests/data/slit_bench.xml + its include: plt_path forward + UTD past a slit in a gaussian-profile
     conductor) goes through xml_loader -> wtgpu_scene_desc -> wtgpu_render and matches the oracle on the same tables.
@@ -305,7 +374,8 @@ def test_xml_scene_film_matches_oracle():
     import os
     from wave_tracer_b200 import xml_loader
     b = xml_loader.load_scene(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "slit_bench.xml"), {"res": "192", "spp": "8"}).build()
-    blk, lgt, st = render(b, spp=8, allow_overflow=True)
+    blk, lgt, st = render(b, spp=8)
+    _no_overflow(st)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     assert st["samples"] == ost["samples"] == 192 * 64 * 8 and olgt.sum() > 0
     l2, flux = _film_metrics(lgt, olgt)

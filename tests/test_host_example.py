@@ -61,7 +61,7 @@ def test_cxx_host_example_film_equals_python_layer(tmp_path):
     assert r.returncode == 0, (r.stdout, r.stderr)
     img_c = np.fromfile(out, np.float32).reshape(res // 3, res, 1)
     b = _python_twin(res, spp).build()
-    blk, lgt, st = render(b, spp=spp, seed=0x5EED, allow_overflow=True)
+    blk, lgt, st = render(b, spp=spp, seed=0x5EED)
     img_p = develop(b, spp, blk, lgt)
     print(r.stdout.strip(), "| python sum %.9e" % img_p.sum())
     assert img_p.sum() > 0 and st["samples"] == res * (res // 3) * spp

@@ -122,7 +122,7 @@ def test_gpu_render_with_sobolld_matches_oracle(integrator):
     from wave_tracer_b200.scene import Sobolld
     sc = scenes.cornell_like(res=32, spp=8, max_depth=5, n_sphere=6, integrator=integrator); sc.sampler = Sobolld()
     built = sc.build()
-    blk, lgt, st = render(built, spp=8, device=0, allow_overflow=True)
+    blk, lgt, st = render(built, spp=8, device=0)
     oblk, olgt, ost = _oracle.render(built, spp=8)
     assert st["samples"] == ost["samples"]
     num = np.linalg.norm(blk.astype(np.float64) - oblk); den = np.linalg.norm(oblk)

@@ -9,5 +9,5 @@ if scene == "ds":
 else:
     b = scenes.cornell_like(res=res, spp=1024, integrator="plt_bdpt").build()
 gs = GpuScene(b, 0)
-_, _, st = render(b, spp=1024, sample_range=(0, spp), gpu_scene=gs, allow_overflow=True)
+_, _, st = render(b, spp=1024, sample_range=(0, spp), gpu_scene=gs)
 print(st["gpu_ms"], st["samples"])

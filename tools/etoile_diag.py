@@ -10,7 +10,7 @@ b = scenes.etoile_like(res=96, spp=4).build()
 gs = GpuScene(b, 0)
 for seed in (0x5EED, 1, 2, 3):
     for flags in (0, 8):
-        blk, lgt, st = render(b, spp=4, seed=seed, gpu_scene=gs, allow_overflow=True, flags=flags)
+        blk, lgt, st = render(b, spp=4, seed=seed, gpu_scene=gs, flags=flags)
         oblk, olgt, ost = _oracle.render(b, spp=4, seed=seed)
         d = lgt.astype(np.float64) - olgt
         l2 = np.linalg.norm(d) / np.linalg.norm(olgt)

@@ -36,7 +36,7 @@ cases = {
 }
 for name, kw in cases.items():
     b = mk(**kw).build()
-    blk, lgt, st = render(b, spp=8, allow_overflow=True)
+    blk, lgt, st = render(b, spp=8)
     oblk, olgt, ost = _oracle.render(b, spp=8)
     g = lgt.astype(np.float64)
     l2 = np.linalg.norm(g - olgt) / max(np.linalg.norm(olgt), 1e-300); fl = abs(g.sum() - olgt.sum()) / max(abs(olgt.sum()), 1e-300)

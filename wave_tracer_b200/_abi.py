@@ -131,7 +131,8 @@ class Stats(C.Structure):
     _fields_ = [(n, c_u64) for n in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "nodes_visited", "tris_tested", "edges_fetched",
                                      "surface_interactions", "fsd_interactions", "null_interactions", "splats", "capacity_overflows", "kernel_launches", "iterations",
                                      "traverse_nodes", "traverse_tris", "shaded_paths")] + \
-               [(n, c_dbl) for n in ("gpu_ms", "traverse_ms", "shade_ms", "generate_ms", "sort_ms", "connect_ms")] + [("strategies", c_u64 * 5), ("walker_steps", c_u64)]
+               [(n, c_dbl) for n in ("gpu_ms", "traverse_ms", "shade_ms", "generate_ms", "sort_ms", "connect_ms")] + [("strategies", c_u64 * 5), ("walker_steps", c_u64)] + \
+               [(n, c_u32) for n in ("passes", "pool_used", "cap_tris", "cap_edges", "cap_segments", "cap_apertures", "cap_vertices", "pad_")] + [("stack_drops", c_u64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "strategies" else getattr(self, n)) for n, _ in self._fields_}
@@ -187,6 +188,8 @@ def lib():
     L.wtgpu_scene_destroy.restype = None
     L.wtgpu_trim.argtypes = []; L.wtgpu_trim.restype = None
     L.wtgpu_render.argtypes = [C.c_void_p, P(RenderOpts), C.c_void_p, C.c_void_p, P(Stats)]
+    L.wtgpu_get_capacities.argtypes = [C.c_void_p, P(c_u32)]
+    L.wtgpu_set_capacities.argtypes = [C.c_void_p, P(c_u32)]
     L.wtgpu_develop.argtypes = [P(Sensor), c_u32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.wtgpu_debug_intersect_rays.argtypes = [C.c_void_p, c_u32, P(RayQuery), P(RayHit)]
     L.wtgpu_debug_shadow_rays.argtypes = [C.c_void_p, c_u32, P(RayQuery), P(c_u32)]
@@ -209,7 +212,7 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_trim", "wtgpu_render", "wtgpu_develop",
+EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_trim", "wtgpu_render", "wtgpu_get_capacities", "wtgpu_set_capacities", "wtgpu_develop",
                     "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_pmath", "wtgpu_debug_sobol", "wtgpu_debug_sizeof", "wthost_sobol_tables",
                     "wthost_ads_build", "wthost_ads_fill", "wthost_ads_destroy", "wthost_ads_sah_cost", "wthost_ads_max_depth"]
 

@@ -15,10 +15,9 @@ namespace wt {
 
 constexpr float kSqrtPi = 1.77245385090551602730f;
 constexpr float kInvSqrtPi = 0.56418958354775628695f;
-constexpr int kMaxBdptVerts = 18;           // max_depth + 2 vertices per subpath for max_depth <= 16
-constexpr int kMaxFSeg = 48;                // Fraunhofer aperture segments
-constexpr int kMaxFApWalk = 4;              // Fraunhofer apertures per subpath
-constexpr int kMaxFAp = 2 * kMaxFApWalk;
+constexpr int kFsdChunk = 48;               // Fraunhofer aperture segments staged in shared memory at a time by the sampler kernel
+// Per-sample record sizes are run-time (dtrav.cuh Caps): cap.verts vertices per subpath (max_depth + 2), cap.ap_walk apertures per subpath of
+// cap.seg segments each.  Defaults (wavefront.cu): 4 apertures of 48 segments; grown by wtgpu_render when a sample needs more.
 
 WT_D float sincf_(float x) {                // include/wt/math/common.hpp:414-434
     const float t0 = 1.1920929e-7f, t2 = 0.00034526698300124390839884978618400831996329879769945f, tn = 0.018581361171917516667460937040007436176452688944747f;
@@ -218,20 +217,23 @@ WT_D float fPsi2(const FEdge& e, V2 xi) { const V2 z = fzeta(e, xi); return sqrf
 WT_D float fPj(const FEdge& e) { return sqrf(length2(e.e)) * kPA1 * cnorm(e.a_b) + sqrf(length2(e.e)) * kPA2 * cnorm(e.iab_2); }
 
 // per-thread arena accessor: word w of this thread at base[w*P + slot]
-struct Arena { float* base; };       // this sample's records, contiguous (AoS): a vertex or an aperture is read by one thread at a time
-WT_D float& aw(const Arena& A, uint32_t w) { return A.base[w]; }
+// this sample's records, contiguous (AoS): a vertex or an aperture is read by one thread at a time.  Layout: 2 x cap.verts vertices (sensor
+// subpath, emitter subpath), then 2 x cap.ap_walk apertures of ap_words = 16 + 9 cap.seg words.
+struct Arena { float* base; uint32_t ap0, ap_words; };
 constexpr uint32_t kVertWords = 68;
-constexpr uint32_t kApWords = 16 + kMaxFSeg * 9;
-constexpr uint32_t kArenaWords = 2 * kMaxBdptVerts * kVertWords + kMaxFAp * kApWords;
-WT_D uint32_t ap_base(int ai) { return 2 * kMaxBdptVerts * kVertWords + (uint32_t)ai * kApWords; }
+WT_D float& aw(const Arena& A, uint32_t w) { return A.base[w]; }
+WT_D Arena mk_arena(const DScene& sc, float* arena, uint32_t slot) {
+    Arena A; A.base = arena + (size_t)slot * sc.cap.arena_words; A.ap0 = 2u * sc.cap.verts * kVertWords; A.ap_words = sc.cap.ap_words; return A;
+}
+WT_D uint32_t ap_base(const Arena& A, int ai) { return A.ap0 + (uint32_t)ai * A.ap_words; }
 WT_D FEdge ap_edge(const Arena& A, int ai, uint32_t j) {
-    const uint32_t b = ap_base(ai) + 16 + j * 9;
+    const uint32_t b = ap_base(A, ai) + 16 + j * 9;
     FEdge e; e.e = mk2(aw(A, b), aw(A, b + 1)); e.v = mk2(aw(A, b + 2), aw(A, b + 3)); e.a_b = mkc(aw(A, b + 4), aw(A, b + 5)); e.iab_2 = mkc(aw(A, b + 6), aw(A, b + 7));
     return e;
 }
-WT_D float ap_edge_pdf(const Arena& A, int ai, uint32_t j) { return aw(A, ap_base(ai) + 16 + j * 9 + 8); }
+WT_D float ap_edge_pdf(const Arena& A, int ai, uint32_t j) { return aw(A, ap_base(A, ai) + 16 + j * 9 + 8); }
 WT_D FHead ap_head(const Arena& A, int ai) {
-    const uint32_t b = ap_base(ai);
+    const uint32_t b = ap_base(A, ai);
     FHead h; h.P0 = aw(A, b); h.P0_pdf = aw(A, b + 1); h.psi02 = aw(A, b + 2); h.recp_I = aw(A, b + 3); h.k = aw(A, b + 4);
     h.frame.t = mk3(aw(A, b + 5), aw(A, b + 6), aw(A, b + 7)); h.frame.b = mk3(aw(A, b + 8), aw(A, b + 9), aw(A, b + 10)); h.frame.n = mk3(aw(A, b + 11), aw(A, b + 12), aw(A, b + 13));
     h.n = __float_as_uint(aw(A, b + 14));
@@ -245,15 +247,15 @@ WT_D float ap_sampling_density(const Arena& A, int ai, const FHead& h, V2 xi) {
 }
 
 // fraunhofer::free_space_diffraction_t ctor (src/interaction/fsd/fraunhofer/free_space_diffraction.cpp:22-129) into aperture slot `ai`.
-// Returns the number of segments (0: empty aperture); sets overflow when kMaxFSeg is exceeded.
+// Returns the number of segments (0: empty aperture); an aperture of more than sc.cap.seg segments sets overflow and reports its size in need_seg.
 WT_NI uint32_t fraunhofer_build(const DScene& sc, const Arena& A, int ai, const Frame& frame, float k, float total_power, const Cone& beam,
-                                const uint32_t* edges, uint32_t n_edges, const G2& wf, bool& overflow) {
+                                const uint32_t* edges, uint32_t n_edges, const G2& wf, bool& overflow, uint32_t& need_seg) {
     const V2 cse = wf.s * kEnvelope;
     const float r = fmaxf(cse.x, cse.y);
     const float max_len = .33f * r;
     float P_total = 0.f;
-    uint32_t n = 0;
-    const uint32_t b0 = ap_base(ai);
+    uint32_t n = 0, n_all = 0;
+    const uint32_t b0 = ap_base(A, ai);
     for (uint32_t ei = 0; ei < n_edges; ++ei) {
         const wtgpu_edge E = sc.edges[edges[ei]];
         if (dot(beam.d, mk3(E.n1)) * dot(beam.d, mk3(E.n2)) >= 0.f) continue;
@@ -296,7 +298,8 @@ WT_NI uint32_t fraunhofer_build(const DScene& sc, const Arena& A, int ai, const 
                 fe.iab_2 = mkc((0.f * (a + b) - 1.f * 0.f) / 2.f, (0.f * 0.f + 1.f * (a + b)) / 2.f);
                 const float pdf = fPj(fe);
                 if (pdf > 0.f) {
-                    if (n < (uint32_t)kMaxFSeg) {
+                    ++n_all;
+                    if (n < sc.cap.seg) {
                         const uint32_t w = b0 + 16 + n * 9;
                         aw(A, w) = fe.e.x; aw(A, w + 1) = fe.e.y; aw(A, w + 2) = fe.v.x; aw(A, w + 3) = fe.v.y;
                         aw(A, w + 4) = fe.a_b.re; aw(A, w + 5) = fe.a_b.im; aw(A, w + 6) = fe.iab_2.re; aw(A, w + 7) = fe.iab_2.im; aw(A, w + 8) = pdf;
@@ -307,6 +310,7 @@ WT_NI uint32_t fraunhofer_build(const DScene& sc, const Arena& A, int ai, const 
             v1 = v2; a = b;
         }
     }
+    if (n_all > sc.cap.seg) need_seg = max(need_seg, n_all);
     const float r0 = 3.f * kP0s;
     const V2 dirs[8] = { mk2(-kInvSqrtTwo, -kInvSqrtTwo), mk2(-1.f, 0.f), mk2(-kInvSqrtTwo, kInvSqrtTwo), mk2(0.f, 1.f), mk2(kInvSqrtTwo, kInvSqrtTwo), mk2(1.f, 0.f), mk2(kInvSqrtTwo, -kInvSqrtTwo), mk2(0.f, -1.f) };
     float acc = 0.f;
@@ -423,7 +427,10 @@ WT_D Surface bv_surface(const DScene& sc, const BVertex& v) {
     return make_dummy_surface(v.dn, v.p);
 }
 
-struct BCtx { const DScene* sc; Arena A; FLut lut; Counters* ctr; bool overflow; };
+struct BCtx { const DScene* sc; Arena A; FLut lut; Counters* ctr; bool overflow; uint32_t need_seg, need_ap, need_verts; };
+WT_D BCtx mk_bctx(const DScene& sc, float* arena, uint32_t slot, const FLut& lut, Counters* ctr) {
+    BCtx c; c.sc = &sc; c.A = mk_arena(sc, arena, slot); c.lut = lut; c.ctr = ctr; c.overflow = false; c.need_seg = 0u; c.need_ap = 0u; c.need_verts = 0u; return c;
+}
 WT_D bool bv_area_emitter(const BCtx& c, const BVertex& v) { return v.type == BV_EMITTER && c.sc->emitters[v.emitter].type == WTGPU_EMITTER_AREA; }
 WT_D bool bv_on_surface(const BCtx& c, const BVertex& v) { return v.type == BV_SURFACE || bv_area_emitter(c, v) || (v.type == BV_SENSOR && (v.gkind == BG_SURFACE || v.gkind == BG_DUMMY)); }
 WT_D bool bv_has_srf_normal(const BCtx& c, const BVertex& v) { return v.type == BV_SURFACE || bv_area_emitter(c, v); }
@@ -563,9 +570,9 @@ WT_D bool bd_append(const BCtx& c, BWalk& d, BVertex& v, Pd pdf_fwd, Pd pdf_revr
 }
 
 // What one traverse() found, reduced to what the vertex step needs (random_walk :421-470 + find_closest_triangle :362-419)
-struct BHit { bool empty, ballistic, overflow; uint32_t primary; float pdist, bx, by, dist, region_depth, flux; V3 origin; uint32_t n_edges; };
+struct BHit { bool empty, ballistic, overflow; uint32_t primary; float pdist, bx, by, dist, region_depth, flux; V3 origin; uint32_t n_edges, need_edges; };
 WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, const uint32_t* tris, uint32_t* edges, BHit& h) {
-    h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u;
+    h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u; h.need_edges = 0u;
     h.origin = tr.origin; h.region_depth = tr.region_depth; h.dist = 0.f; h.ballistic = true;
     if (tr.empty) return;
     if (tr.cone.overflow) h.overflow = true;
@@ -573,7 +580,7 @@ WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, 
     const Range zr = mkr(h.dist, h.dist + tr.region_depth);
     h.ballistic = tr.ballistic || cone_is_ray(beam.env);
     const V3 dir = beam.env.d;
-    const uint32_t nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
+    const uint32_t nt = min(tr.cone.n_tris, sc.cap.tris);
     if (h.ballistic) { h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; return; }
     for (uint32_t i = 0; i < nt; ++i) {
         const Tri3 t = load_tri(sc, tris[i]);
@@ -594,7 +601,7 @@ WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, 
             h.flux += g2_integrate_triangle(sc, wf, cone_project_local(beam.env, ct[0], csz), cone_project_local(beam.env, ct[1], csz), cone_project_local(beam.env, ct[2], csz));
         }
     }
-    if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo); if (eo) h.overflow = true; }
+    if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tris, nt, edges, sc.cap.edges, eo); if (eo) { h.overflow = true; h.need_edges = 3u * nt; } }
 }
 
 // bd_resolve_hit with the flux integral organised for a warp (all 32 lanes call; `act` marks lanes that hold a walker): every lane walks its own
@@ -607,7 +614,7 @@ WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, cons
     Range zr = mkr(0.f, 0.f);
     V3 dir = mk3(0.f, 0.f, 1.f);
     if (act) {
-        h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u;
+        h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u; h.need_edges = 0u;
         h.origin = tr.origin; h.region_depth = tr.region_depth; h.dist = 0.f; h.ballistic = true;
         if (!tr.empty) {
             if (tr.cone.overflow) h.overflow = true;
@@ -615,7 +622,7 @@ WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, cons
             zr = mkr(h.dist, h.dist + tr.region_depth);
             h.ballistic = tr.ballistic || cone_is_ray(beam.env);
             dir = beam.env.d;
-            nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
+            nt = min(tr.cone.n_tris, sc.cap.tris);
             if (h.ballistic) { h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; }
             else {
                 for (uint32_t i = 0; i < nt; ++i) {
@@ -664,13 +671,14 @@ WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, cons
             if (add) h.flux += val;
         }
     }
-    if (flux_lane && sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, edges, eo); if (eo) h.overflow = true; }
+    if (flux_lane && sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tris, nt, edges, sc.cap.edges, eo); if (eo) { h.overflow = true; h.need_edges = 3u * nt; } }
 }
 
 // continue_walk (plt_bdpt_detail.hpp:167-182)
 WT_D bool bd_continue_walk(BCtx& c, BWalk& data, Sampler& smp, bool do_RR) {
     const DScene& sc = *c.sc;
     if (data.n > sc.integrator.max_depth + 1u) return false;
+    if (data.n >= sc.cap.verts) { c.overflow = true; c.need_verts = max(c.need_verts, 2u * sc.cap.verts); return false; }      // the subpath's vertex row is full (capacity growth)
     if (do_RR && sc.integrator.russian_roulette) {
         aw(c.A, (data.base + data.n - 1u) * kVertWords + kOffRr) = data.rr;
         const float r = data.throughput < 1.f ? fmaxf(data.throughput, .5f) : 1.f;
@@ -733,10 +741,10 @@ WT_NI int bd_walk_step(BCtx& c, BWalk& data, Sampler& smp, const BHit& h, const 
         data.throughput *= w * bs.M.m[0];
         if (!data.fwd && bs.eta.re != 1.f) data.throughput /= sqrf(bs.eta.re);
     } else if (!h.ballistic && sc.integrator.fsd && h.n_edges) {       // sample_fraunhofer_fsd_interaction (:288-346)
-        if (data.n_ap >= (uint32_t)kMaxFApWalk) { c.overflow = true; return BD_END; }
+        if (data.n_ap >= sc.cap.ap_walk) { c.overflow = true; c.need_ap = max(c.need_ap, 2u * sc.cap.ap_walk); return BD_END; }
         const int ai = (int)(data.ap0 + data.n_ap);
         const G2 wf = wavefront_of(beam, beam_dist);
-        const uint32_t nseg = fraunhofer_build(sc, c.A, ai, beam_frame, beam.k, 1.f - h.flux, beam.env, edges, h.n_edges, wf, c.overflow);
+        const uint32_t nseg = fraunhofer_build(sc, c.A, ai, beam_frame, beam.k, 1.f - h.flux, beam.env, edges, h.n_edges, wf, c.overflow, c.need_seg);
         if (nseg == 0u) { beam_transform_restart(data.beam, interaction_wp, beam_dist); do_RR = false; }
         else {
             ++data.n_ap;
@@ -773,7 +781,7 @@ WT_D void tmp_init(BVertex& t, uint32_t type) {
 template <int CLS>
 WT_NI void bd_connect(BCtx& c, uint32_t nsv, uint32_t nev, int s, int t, Sampler& smp, BConn& ret) {       // plt_bdpt_detail.hpp:747-923
     const DScene& sc = *c.sc;
-    const uint32_t SB = 0u, EB = kMaxBdptVerts;
+    const uint32_t SB = 0u, EB = sc.cap.verts;
     ret.has_el = false; ret.L = stokes_zero(); tmp_init(ret.tmp, BV_SENSOR);
     const bool virt = sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE;
     if ((CLS < 0 && s == 0) || CLS == 0) {
@@ -848,48 +856,55 @@ WT_D float area_or_one(float p) { return (isfinite(p) && p > 1.1920929e-7f) ? p 
 WT_NI float bd_mis(BCtx& c, int s, int t, const BConn& cr) {       // plt_bdpt_detail.hpp:604-720
     if (s + t <= 2) return 1.f;
     const DScene& sc = *c.sc;
-    const uint32_t SB = 0u, EB = kMaxBdptVerts;
-    float sp_pdf[kMaxBdptVerts], sp_rev[kMaxBdptVerts], ep_pdf[kMaxBdptVerts], ep_rev[kMaxBdptVerts];
-    bool sp_d[kMaxBdptVerts], ep_d[kMaxBdptVerts];
-    for (int i = 0; i < t; ++i) { sp_pdf[i] = aw(c.A, (SB + i) * kVertWords + kOffPdfBwd); sp_rev[i] = aw(c.A, (SB + i) * kVertWords + kOffPdfFwd); sp_d[i] = __float_as_uint(aw(c.A, (SB + i) * kVertWords + kOffDelta)) != 0u; }
-    for (int i = 0; i < s; ++i) { ep_pdf[i] = aw(c.A, (EB + i) * kVertWords + kOffPdfFwd); ep_rev[i] = aw(c.A, (EB + i) * kVertWords + kOffPdfBwd); ep_d[i] = __float_as_uint(aw(c.A, (EB + i) * kVertWords + kOffDelta)) != 0u; }
+    const uint32_t SB = 0u, EB = sc.cap.verts;
+    // The reference copies the subpaths' area pdfs into scratch vectors and overwrites the entries the connection changes (:621-690): the
+    // reverse pdfs of the last two vertices of each subpath, and vertex 0's forward pdf when it is the sampled endpoint.  Here the overrides
+    // are kept as scalars and every other entry is read from the vertex records where it is used: no per-thread arrays, any path length.
+    int sr_i1 = -1, sr_i2 = -1, er_i1 = -1, er_i2 = -1;
+    float sr_v1 = 0.f, sr_v2 = 0.f, er_v1 = 0.f, er_v2 = 0.f, sp0 = 0.f, ep0 = 0.f;
+    bool sp0_set = false, ep0_set = false;
     const BVertex& tmp = cr.tmp;
     const bool virt = sc.sensor.type == WTGPU_SENSOR_VIRTUAL_PLANE;
     if (s == 0) {
         const BVertex& last = bv_ref(c.A, SB + t - 1); const BVertex& prev = bv_ref(c.A, SB + t - 2);
-        sp_rev[t - 1] = pdf_emitter_v(c, last);
-        sp_rev[t - 2] = pdf_next_from_emitter(c, last, prev);
+        sr_i1 = t - 1; sr_v1 = pdf_emitter_v(c, last);
+        sr_i2 = t - 2; sr_v2 = pdf_next_from_emitter(c, last, prev);
     } else if (t == 0) {
         const BVertex& prev = bv_ref(c.A, EB + s - 2);
         const BVertex& last = virt ? tmp : bv_ref(c.A, EB + s - 1);
-        ep_rev[s - 1] = sensor_pdf_position(c);
-        ep_rev[s - 2] = pdf_next_from_sensor(c, last, prev);
+        er_i1 = s - 1; er_v1 = sensor_pdf_position(c);
+        er_i2 = s - 2; er_v2 = pdf_next_from_sensor(c, last, prev);
     } else if (s == 1) {
         const BVertex& last = bv_ref(c.A, SB + t - 1); const BVertex& lp = bv_ref(c.A, SB + t - 2);
-        sp_rev[t - 1] = pdf_next_from_emitter(c, tmp, last);
-        ep_rev[0] = bv_pdf(c, last, &lp, tmp, false);
-        ep_pdf[0] = pdf_emitter_v(c, tmp);
+        sr_i1 = t - 1; sr_v1 = pdf_next_from_emitter(c, tmp, last);
+        er_i1 = 0; er_v1 = bv_pdf(c, last, &lp, tmp, false);
+        ep0_set = true; ep0 = pdf_emitter_v(c, tmp);
     } else if (t == 1) {
         const BVertex& last = bv_ref(c.A, EB + s - 1); const BVertex& lp = bv_ref(c.A, EB + s - 2);
-        ep_rev[s - 1] = pdf_next_from_sensor(c, tmp, last);
-        sp_rev[0] = bv_pdf(c, last, &lp, tmp, true);
-        sp_pdf[0] = sensor_pdf_position(c);
+        er_i1 = s - 1; er_v1 = pdf_next_from_sensor(c, tmp, last);
+        sr_i1 = 0; sr_v1 = bv_pdf(c, last, &lp, tmp, true);
+        sp0_set = true; sp0 = sensor_pdf_position(c);
     } else {
         const BVertex& e = bv_ref(c.A, EB + s - 1); const BVertex& sv = bv_ref(c.A, SB + t - 1); const BVertex& epv = bv_ref(c.A, EB + s - 2); const BVertex& spv = bv_ref(c.A, SB + t - 2);
-        ep_rev[s - 1] = bv_pdf(c, sv, &spv, e, false);
-        ep_rev[s - 2] = bv_pdf(c, e, &sv, epv, false);
-        sp_rev[t - 1] = bv_pdf(c, e, &epv, sv, true);
-        sp_rev[t - 2] = bv_pdf(c, sv, &e, spv, true);
+        er_i1 = s - 1; er_v1 = bv_pdf(c, sv, &spv, e, false);
+        er_i2 = s - 2; er_v2 = bv_pdf(c, e, &sv, epv, false);
+        sr_i1 = t - 1; sr_v1 = bv_pdf(c, e, &epv, sv, true);
+        sr_i2 = t - 2; sr_v2 = bv_pdf(c, sv, &e, spv, true);
     }
-    if (t > 0) sp_d[t - 1] = false;
-    if (s > 0) ep_d[s - 1] = false;
+    auto word = [&](uint32_t v, uint32_t off) { return aw(c.A, v * kVertWords + off); };
+    auto sp_pdf = [&](int i) { return (i == 0 && sp0_set) ? sp0 : word(SB + i, kOffPdfBwd); };
+    auto sp_rev = [&](int i) { return i == sr_i1 ? sr_v1 : i == sr_i2 ? sr_v2 : word(SB + i, kOffPdfFwd); };
+    auto sp_d = [&](int i) { return i == t - 1 ? false : __float_as_uint(word(SB + i, kOffDelta)) != 0u; };
+    auto ep_pdf = [&](int i) { return (i == 0 && ep0_set) ? ep0 : word(EB + i, kOffPdfFwd); };
+    auto ep_rev = [&](int i) { return i == er_i1 ? er_v1 : i == er_i2 ? er_v2 : word(EB + i, kOffPdfBwd); };
+    auto ep_d = [&](int i) { return i == s - 1 ? false : __float_as_uint(word(EB + i, kOffDelta)) != 0u; };
     bool delta_emitter = true, delta_sensor = true;
     if (s == 1) delta_emitter = bv_delta_emitter(c, tmp); else if (s > 1) delta_emitter = bv_delta_emitter(c, bv_ref(c.A, EB));
     if (t == 1) delta_sensor = bv_delta_sensor(c, tmp); else if (t > 1) delta_sensor = bv_delta_sensor(c, bv_ref(c.A, SB));
     float sum = 0.f, ri = 1.f;
-    for (int i = t - 1; i >= 0; --i) { ri *= area_or_one(sp_rev[i]) / area_or_one(sp_pdf[i]); if (!sp_d[i] && !(i > 0 ? sp_d[i - 1] : delta_sensor)) sum += ri; }
+    for (int i = t - 1; i >= 0; --i) { ri *= area_or_one(sp_rev(i)) / area_or_one(sp_pdf(i)); if (!sp_d(i) && !(i > 0 ? sp_d(i - 1) : delta_sensor)) sum += ri; }
     ri = 1.f;
-    for (int i = s - 1; i >= 0; --i) { ri *= area_or_one(ep_rev[i]) / area_or_one(ep_pdf[i]); if (!ep_d[i] && !(i > 0 ? ep_d[i - 1] : delta_emitter)) sum += ri; }
+    for (int i = s - 1; i >= 0; --i) { ri *= area_or_one(ep_rev(i)) / area_or_one(ep_pdf(i)); if (!ep_d(i) && !(i > 0 ? ep_d(i - 1) : delta_emitter)) sum += ri; }
     return 1.f / (1.f + sum);
 }
 
@@ -917,9 +932,9 @@ WT_D void bd_init_sample(const BCtx& c, uint32_t seed_lo, uint32_t seed_hi, uint
     {
         BVertex v; tmp_init(v, BV_EMITTER); v.pdf_fwd = (es.ppd.disc ? 0.f : es.ppd.v) * em_pdf; v.beam = es.beam; v.emitter = em; v.p = es.beam.env.o;
         if (es.has_surface) { v.gkind = BG_SURFACE; v.tuid = es.s.tuid; v.p = es.s.wp; }
-        bv_store(c.A, (uint32_t)kMaxBdptVerts, v);
-        we.beam = es.beam; we.fwd = true; we.pdf_from_prev = es.dpd; we.throughput = 1.f; we.rr = 1.f; we.base = (uint32_t)kMaxBdptVerts; we.n = 1u; we.prev_geo = bv_geo(v);
-        we.ap0 = (uint32_t)kMaxFApWalk; we.n_ap = 0u;
+        bv_store(c.A, sc.cap.verts, v);
+        we.beam = es.beam; we.fwd = true; we.pdf_from_prev = es.dpd; we.throughput = 1.f; we.rr = 1.f; we.base = sc.cap.verts; we.n = 1u; we.prev_geo = bv_geo(v);
+        we.ap0 = sc.cap.ap_walk; we.n_ap = 0u;
     }
 }
 // the (s,t) enumeration of plt_bdpt.cpp:96-110; f(s,t) for every strategy that is evaluated
@@ -939,7 +954,7 @@ template <class F> WT_D void bd_for_each_pair(const DScene& sc, uint32_t nsv, ui
 template <int CLS = -1>
 WT_D float bd_eval_pair(BCtx& c, const BdSampleInit& si, uint32_t seed_lo, uint32_t seed_hi, uint32_t nsv, uint32_t nev, int s, int t, BConn& cr) {
     const DScene& sc = *c.sc;
-    Sampler smp; smp.k0 = seed_lo; smp.k1 = seed_hi; smp.pixel = si.pixel; smp.sample = si.sample; smp.d = 0; smp.stream = 3u + 32u * (uint32_t)t + (uint32_t)s;
+    Sampler smp; smp.k0 = seed_lo; smp.k1 = seed_hi; smp.pixel = si.pixel; smp.sample = si.sample; smp.d = 0; smp.stream = 3u + 4096u * (uint32_t)t + (uint32_t)s;
     bd_connect<CLS>(c, nsv, nev, s, t, smp, cr);
     if (cr.L.s[0] <= 0.f) return 0.f;
     const float mis = sc.integrator.mis ? bd_mis(c, s, t, cr) * si.rspd : 1.f / ((float)(s + t + 1) * si.wpd_v);
@@ -949,6 +964,7 @@ WT_D float bd_eval_pair(BCtx& c, const BdSampleInit& si, uint32_t seed_lo, uint3
 // ================================================================================================ driver 1: one thread per sample (cross-check path)
 struct BdptArgs {
     DScene sc; FLut lut; float* arena; uint32_t P;
+    uint32_t* trav_tris; uint32_t* hit_edges;      // per-thread rows (sc.cap.tris / sc.cap.edges entries)
     DevCounters* ctr; float* film_block; float* film_light;
     uint32_t seed_lo, seed_hi, tile_x0, tile_y0, tile_w, tile_h, sample_begin;
     unsigned long long total;
@@ -957,6 +973,11 @@ WT_D void bd_sample_coords(unsigned long long id, uint32_t tile_x0, uint32_t til
     const uint64_t npix = (uint64_t)tile_w * tile_h;
     const uint32_t pi = (uint32_t)(id % npix), si = (uint32_t)(id / npix);
     ex = tile_x0 + pi % tile_w; ey = tile_y0 + pi / tile_w; sample = sample_begin + si;
+}
+WT_D void bd_flush_need(DevCounters* g, const BCtx& c) {
+    if (c.need_seg) need_max(&g->need_seg, c.need_seg);
+    if (c.need_ap) need_max(&g->need_ap, c.need_ap);
+    if (c.need_verts) need_max(&g->need_verts, c.need_verts);
 }
 WT_D void bd_flush_stats(DevCounters* g, uint32_t n_splat, uint32_t n_vert, uint32_t n_conn, uint32_t n_samples, bool overflow) {
     const unsigned m = __activemask();
@@ -974,8 +995,9 @@ WT_D void bd_flush_stats(DevCounters* g, uint32_t n_splat, uint32_t n_vert, uint
 __global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     Counters ctr; counters_zero(ctr);
-    BCtx c; c.sc = &a.sc; c.A.base = a.arena + (size_t)tid * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
     const DScene& sc = a.sc;
+    BCtx c = mk_bctx(sc, a.arena, tid, a.lut, &ctr);
+    uint32_t* tris = a.trav_tris + (size_t)tid * sc.cap.tris; uint32_t* edges = a.hit_edges + (size_t)tid * sc.cap.edges;
     uint32_t n_samples = 0, n_vert = 0, n_conn = 0, n_splat = 0;
     const bool force_rt = sc.sensor.ray_trace_only != 0u;
     for (;;) {
@@ -988,10 +1010,11 @@ __global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
         for (int wi = 0; wi < 2; ++wi) {
             Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = si.pixel; smp.sample = si.sample; smp.d = 0; smp.stream = 1u + (uint32_t)wi;
             for (;;) {
-                uint32_t tris[kMaxConeTris], edges[kMaxHitEdges];
                 TravOut tr; BHit h;
                 traverse(sc, w[wi].beam.env, w[wi].prev_geo, wavenum_to_wavelen(w[wi].beam.k), force_rt, tris, tr, ctr);
+                if (tr.cone.overflow) need_max(&a.ctr->need_tris, tr.cone.n_tris);
                 bd_resolve_hit(sc, w[wi].beam, tr, tris, edges, h);
+                if (h.need_edges) need_max(&a.ctr->need_edges, h.need_edges);
                 if (bd_walk_step(c, w[wi], smp, h, edges, n_vert, false) != BD_CONTINUE) break;
             }
         }
@@ -1008,6 +1031,7 @@ __global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
         n_splat += film_splat(sc, a.film_block, a.film_light, false, si.el, L0, si.k);
     }
     flush_counters(a.ctr, ctr);
+    bd_flush_need(a.ctr, c);
     bd_flush_stats(a.ctr, n_splat, n_vert, n_conn, n_samples, c.overflow);
 }
 
@@ -1023,16 +1047,16 @@ struct BdArgs {
     RenderArgs r;               // sort buffers sized for 2P walkers; r.hit = walker hit records; r.alive = slot flags; r.pool = 2P
     FLut lut; float* arena; uint32_t P;
     float4* walkers; float4* headers;
-    int* pending; float* L0; uint32_t* nverts; uint32_t* pairs;
+    int* pending; float* L0; uint32_t* nverts; unsigned long long* pairs;      // pairs: strategy tasks, slot | s << 32 | t << 48
     TravRec* trav_rec; uint32_t* trav_tris;  // group traversal results (per walker), consumed by k_bd_resolve
     uint32_t* fsd_list; float4* fsd_out;    // walkers waiting for a Fraunhofer direction sample (two lists, ping-pong); its result / carried state
     size_t pair_off[kPairClasses];          // start of each strategy class's segment of `pairs`
     uint32_t fl_cur, fl_next, fl_fin;       // list fed by this iteration's vertex step and consumed by its sampler; carry-over list; list being finished
     float tag, tag_fin;                     // marks results written by this iteration's sampler / by the sampler whose list is being finished
 };
-WT_D void bd_walker_to_state(const BdWalker& w, uint32_t which, BWalk& d) {
+WT_D void bd_walker_to_state(const DScene& sc, const BdWalker& w, uint32_t which, BWalk& d) {
     d.beam = w.beam; d.fwd = which == 1u; d.pdf_from_prev.v = w.pdf_v; d.pdf_from_prev.disc = w.pdf_disc != 0u; d.throughput = w.throughput; d.rr = w.rr;
-    d.base = which * (uint32_t)kMaxBdptVerts; d.n = w.n; d.prev_geo = w.prev_geo; d.ap0 = which * (uint32_t)kMaxFApWalk; d.n_ap = w.n_ap;
+    d.base = which * sc.cap.verts; d.n = w.n; d.prev_geo = w.prev_geo; d.ap0 = which * sc.cap.ap_walk; d.n_ap = w.n_ap;
 }
 WT_D void bd_state_to_walker(const BWalk& d, uint32_t rng_d, BdWalker& w) {
     w.beam = d.beam; w.prev_geo = d.prev_geo; w.pdf_v = d.pdf_from_prev.v; w.pdf_disc = d.pdf_from_prev.disc ? 1u : 0u; w.throughput = d.throughput; w.rr = d.rr;
@@ -1059,7 +1083,7 @@ __global__ void __launch_bounds__(128) k_bd_generate(const BdArgs a) {
         if (id < a.r.total) {
             gen = true;
             Counters ctr; counters_zero(ctr);
-            BCtx c; c.sc = &a.r.sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+            BCtx c = mk_bctx(a.r.sc, a.arena, slot, a.lut, &ctr);
             uint32_t ex, ey, sample; bd_sample_coords(id, a.r.tile_x0, a.r.tile_y0, a.r.tile_w, a.r.tile_h, a.r.sample_begin, ex, ey, sample);
             BdSampleInit si; BWalk w0, w1;
             bd_init_sample(c, a.r.seed_lo, a.r.seed_hi, ex, ey, sample, si, w0, w1);
@@ -1085,10 +1109,12 @@ __global__ void __launch_bounds__(128) k_bd_traverse(const BdArgs a) {
         const uint32_t wid = a.r.trav_list[li];
         const DScene& sc = a.r.sc;
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
-        uint32_t tris[kMaxConeTris];
+        uint32_t* tris = a.trav_tris + (size_t)wid * sc.cap.tris;
         TravOut tr; BHit bh; HitRec h;
         traverse(sc, w.beam.env, w.prev_geo, wavenum_to_wavelen(w.beam.k), sc.sensor.ray_trace_only != 0u, tris, tr, ctr);
-        bd_resolve_hit(sc, w.beam, tr, tris, h.edges, bh);
+        if (tr.cone.overflow) need_max(&a.r.ctr->need_tris, tr.cone.n_tris);
+        bd_resolve_hit(sc, w.beam, tr, tris, a.r.hit_edges + (size_t)wid * sc.cap.edges, bh);
+        if (bh.need_edges) need_max(&a.r.ctr->need_edges, bh.need_edges);
         h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
         h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
         ovf = bh.overflow;
@@ -1109,16 +1135,14 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.r.sc;
     g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr,
-        [&](int i, Cone& env, Geo& prev, float& lambda) {
+        [&](int i, Cone& env, Geo& prev, float& lambda, uint32_t*& tris_out) {
             const uint32_t wid = a.r.trav_list[i];
             BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
             env = w.beam.env; prev = w.prev_geo; lambda = wavenum_to_wavelen(w.beam.k);
+            tris_out = a.trav_tris + (size_t)wid * sc.cap.tris;
         },
-        [&](int i, const TravRec& r, const uint32_t* tris, const GLane& g) {
-            const uint32_t wid = a.r.trav_list[i];
-            if (g.gl == 0u) a.trav_rec[wid] = r;
-            const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
-            for (uint32_t k = g.gl; k < nt; k += (uint32_t)kGW) a.trav_tris[(size_t)wid * kMaxConeTris + k] = tris[k];
+        [&](int i, const TravRec& r, const GLane& g) {
+            if (g.gl == 0u) { a.trav_rec[a.r.trav_list[i]] = r; if (r.flags & TR_OVERFLOW) need_max(&a.r.ctr->need_tris, r.n_tris); }
         });
     flush_counters(a.r.ctr, ctr);
 }
@@ -1130,7 +1154,7 @@ __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
     bool ovf = false;
     uint32_t wid = 0u;
     BdWalker w; TravOut tr; BHit bh; HitRec h;
-    uint32_t tris[kMaxConeTris];
+    const uint32_t* tris = nullptr; uint32_t* edges = nullptr;
     tr.empty = true; tr.ballistic = true; tr.cone.n_tris = 0u;
     if (act) {
         wid = a.r.trav_list[li];
@@ -1140,11 +1164,11 @@ __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
         tr.ray.tuid = r.ray_tuid; tr.ray.dist = r.ray_dist; tr.ray.bx = r.bx; tr.ray.by = r.by; tr.ray.front = (r.flags & TR_RAY_FRONT) != 0u;
         tr.cone.dist = r.cone_dist; tr.cone.front = (r.flags & TR_CONE_FRONT) != 0u; tr.cone.n_tris = r.n_tris; tr.cone.overflow = (r.flags & TR_OVERFLOW) != 0u;
         tr.region_depth = r.region_depth; tr.origin = mk3(r.ox, r.oy, r.oz);
-        const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
-        for (uint32_t k = 0; k < nt; ++k) tris[k] = a.trav_tris[(size_t)wid * kMaxConeTris + k];
+        tris = a.trav_tris + (size_t)wid * sc.cap.tris; edges = a.r.hit_edges + (size_t)wid * sc.cap.edges;
     }
-    bd_resolve_hit_warp(sc, act, w.beam, tr, tris, h.edges, bh);
+    bd_resolve_hit_warp(sc, act, w.beam, tr, tris, edges, bh);
     if (act) {
+        if (bh.need_edges) need_max(&a.r.ctr->need_edges, bh.need_edges);
         h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
         h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
         ovf = bh.overflow;
@@ -1179,13 +1203,13 @@ WT_D void bd_walker_done(const BdArgs& a, uint32_t wid, uint32_t n, uint32_t& n_
             uint32_t at[kPairClasses];
 #pragma unroll
             for (int c = 0; c < kPairClasses; ++c) at[c] = cnt[c] ? (uint32_t)atomicAdd(&a.r.ctr->n_pairs[c], cnt[c]) : 0u;
-            bd_for_each_pair(a.r.sc, nsv, nev, [&](int s, int t) { const int c = bd_pair_class(s, t); a.pairs[a.pair_off[c] + at[c]++] = slot | ((uint32_t)s << 22) | ((uint32_t)t << 27); });
+            bd_for_each_pair(a.r.sc, nsv, nev, [&](int s, int t) { const int c = bd_pair_class(s, t); a.pairs[a.pair_off[c] + at[c]++] = (unsigned long long)slot | ((unsigned long long)s << 32) | ((unsigned long long)t << 48); });
         }
     }
 }
 WT_D void bd_hit_to_bhit(const HitRec& h, BHit& bh) {
     bh.empty = (h.flags & H_EMPTY) != 0u; bh.ballistic = (h.flags & H_BALLISTIC) != 0u; bh.overflow = (h.flags & H_OVERFLOW) != 0u;
-    bh.primary = h.primary; bh.pdist = h.pdist; bh.bx = h.bx; bh.by = h.by; bh.dist = h.d2i; bh.region_depth = h.region_depth; bh.flux = h.flux; bh.origin = h.origin; bh.n_edges = h.n_edges;
+    bh.primary = h.primary; bh.pdist = h.pdist; bh.bx = h.bx; bh.by = h.by; bh.dist = h.d2i; bh.region_depth = h.region_depth; bh.flux = h.flux; bh.origin = h.origin; bh.n_edges = h.n_edges; bh.need_edges = 0u;
 }
 
 __global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
@@ -1197,15 +1221,15 @@ __global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
         act = true;
         wid = a.r.order[i];
         const uint32_t slot = wid >> 1, which = wid & 1u;
-        BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+        BCtx c = mk_bctx(sc, a.arena, slot, a.lut, &ctr);
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
         HitRec h; hit_load(h, a.r.hit, a.r.pool, wid);
         BdHeader hd; soa_load(hd, a.headers, a.P, slot);
-        BWalk d; bd_walker_to_state(w, which, d);
+        BWalk d; bd_walker_to_state(sc, w, which, d);
         BHit bh; bd_hit_to_bhit(h, bh);
         Sampler smp; smp.k0 = a.r.seed_lo; smp.k1 = a.r.seed_hi; smp.pixel = hd.pixel; smp.sample = hd.sample; smp.d = w.rng_d; smp.stream = 1u + which;
-        res = bd_walk_step(c, d, smp, bh, h.edges, n_vert, true);
-        overflow = c.overflow;
+        res = bd_walk_step(c, d, smp, bh, a.r.hit_edges + (size_t)wid * sc.cap.edges, n_vert, true);
+        overflow = c.overflow; bd_flush_need(a.r.ctr, c);
         if (res != BD_END) { bd_state_to_walker(d, smp.d, w); soa_store(w, a.walkers, 2u * a.P, wid); }
         else bd_walker_done(a, wid, d.n, n_splat);
     }
@@ -1233,8 +1257,10 @@ __global__ void __launch_bounds__(128) k_bd_shade(const BdArgs a) {
 // iteration's kernels; its results are picked up one iteration later.  A launch does not wait for stragglers: after `budget` tries a
 // walker is carried over to the next iteration (the stream is counter-based: only the draw index and the try count are kept).
 constexpr int kFsdK = 8;                    // speculative tries per batch
-constexpr int kFsdRow = kMaxFSeg + 1;       // padded row of the term arrays (bank-conflict free for the per-try sums)
-struct FsdShared { float4 ea[kMaxFSeg], eb[kMaxFSeg]; float cdf[kMaxFSeg + 1]; float re[kFsdK][kFsdRow], im[kFsdK][kFsdRow], dd[kFsdK][kFsdRow]; };
+constexpr int kFsdRow = kFsdChunk + 1;      // padded row of the term arrays (bank-conflict free for the per-try sums)
+// Shared-memory staging holds kFsdChunk segments.  An aperture with more (rare: a beam footprint over finely tessellated geometry) is walked
+// chunk by chunk -- the per-try sums still run over the segments in order -- and its selection cdf is scanned from the aperture record in HBM.
+struct FsdShared { float4 ea[kFsdChunk], eb[kFsdChunk]; float cdf[kFsdChunk + 1]; float re[kFsdK][kFsdRow], im[kFsdK][kFsdRow], dd[kFsdK][kFsdRow]; };
 __global__ void __launch_bounds__(128, 6) k_bd_fsd_sample(const BdArgs a) {
     __shared__ FsdShared shm[4];
     FsdShared& sh = shm[threadIdx.x >> 5];
@@ -1254,11 +1280,11 @@ __global__ void __launch_bounds__(128, 6) k_bd_fsd_sample(const BdArgs a) {
             continue;
         }
         const uint32_t slot = wid >> 1, which = wid & 1u;
-        Arena A; A.base = a.arena + (size_t)slot * kArenaWords;
+        const Arena A = mk_arena(a.r.sc, a.arena, slot);
         uint32_t w_rng_d, w_n_ap;
         { BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid); w_rng_d = w.rng_d; w_n_ap = w.n_ap; }
         BdHeader h; soa_load(h, a.headers, a.P, slot);
-        const int ai = (int)(which * (uint32_t)kMaxFApWalk + w_n_ap - 1u);
+        const int ai = (int)(which * a.r.sc.cap.ap_walk + w_n_ap - 1u);
         const FHead hd = ap_head(A, ai);
         const uint32_t n = hd.n;
         const float4 st = a.fsd_out[2u * wid + 1u];      // carried over: resume after the tries already spent
@@ -1268,12 +1294,17 @@ __global__ void __launch_bounds__(128, 6) k_bd_fsd_sample(const BdArgs a) {
         const bool rej = n > 1u; const uint32_t max_tries = n * 1024u; const float recp_M = 1.f / (float)n;
         // stage the aperture: segments, and the selection cdf of sampleN (fsd_sampler.cpp:37-79) summed in the sequential order
         // (entry 0 is the P0 lobe, entry i the segment i-1; non-decreasing, so "first i with p < cdf[i]" = #{i : !(p < cdf[i])})
-        __syncwarp();
-        for (uint32_t j = lane; j < n; j += 32u) {
-            const FEdge e = ap_edge(A, ai, j);
-            sh.ea[j] = make_float4(e.e.x, e.e.y, e.v.x, e.v.y); sh.eb[j] = make_float4(e.a_b.re, e.a_b.im, e.iab_2.re, e.iab_2.im);
-        }
-        if (lane == 0u) { float cdf = 0.f; for (uint32_t i = 0; i < n; ++i) { cdf += i == 0u ? hd.P0_pdf : ap_edge_pdf(A, ai, i - 1u); sh.cdf[i] = cdf; } }
+        const bool small = n <= (uint32_t)kFsdChunk;
+        auto stage = [&](uint32_t j0) {         // segments [j0, j0 + kFsdChunk) into shared memory
+            __syncwarp();
+            for (uint32_t j = j0 + lane; j < min(n, j0 + (uint32_t)kFsdChunk); j += 32u) {
+                const FEdge e = ap_edge(A, ai, j);
+                sh.ea[j - j0] = make_float4(e.e.x, e.e.y, e.v.x, e.v.y); sh.eb[j - j0] = make_float4(e.a_b.re, e.a_b.im, e.iab_2.re, e.iab_2.im);
+            }
+            __syncwarp();
+        };
+        stage(0u);
+        if (small && lane == 0u) { float cdf = 0.f; for (uint32_t i = 0; i < n; ++i) { cdf += i == 0u ? hd.P0_pdf : ap_edge_pdf(A, ai, i - 1u); sh.cdf[i] = cdf; } }
         __syncwarp();
         const float cdf0 = hd.P0_pdf;       // == sh.cdf[0] (0 + P0_pdf)
         V3 wo = mk3(0.f, 0.f, 1.f); float dpd = 0.f, wgt = 0.f;
@@ -1313,12 +1344,14 @@ __global__ void __launch_bounds__(128, 6) k_bd_fsd_sample(const BdArgs a) {
             const bool mine_valid = lane < kv;
             if (mine_valid) {
                 const float p = rnd(smp) * 1.f;
-                uint32_t lo = 0u, hi = n;               // sel = #{i < n : !(p < cdf[i])}
-                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (!(p < sh.cdf[mid])) lo = mid + 1u; else hi = mid; }
-                const uint32_t sel = lo;
+                uint32_t sel;                           // sel = #{i < n : !(p < cdf[i])}, cdf summed in sequence (fsd_sampler.cpp:37-79)
+                if (small) { uint32_t lo = 0u, hi = n; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (!(p < sh.cdf[mid])) lo = mid + 1u; else hi = mid; } sel = lo; }
+                else { float cdf = 0.f; sel = n; for (uint32_t i = 0; i < n; ++i) { cdf += i == 0u ? hd.P0_pdf : ap_edge_pdf(A, ai, i - 1u); if (p < cdf) { sel = i; break; } } }
                 if (sel == 0u) { const float u0 = rnd(smp); const float u1 = rnd(smp); xi = kP0s * normal2d(mk2(u0, u1)); }
                 else {
-                    const float4 ea = sh.ea[sel - 1u], eb = sh.eb[sel - 1u];
+                    float4 ea, eb;
+                    if (small) { ea = sh.ea[sel - 1u]; eb = sh.eb[sel - 1u]; }
+                    else { const FEdge e = ap_edge(A, ai, sel - 1u); ea = make_float4(e.e.x, e.e.y, e.v.x, e.v.y); eb = make_float4(e.a_b.re, e.a_b.im, e.iab_2.re, e.iab_2.im); }
                     const V2 ee = mk2(ea.x, ea.y);
                     const V2 m = mk2(ee.y, -ee.x);
                     const float od = 1.f / (ee.x * m.y - m.x * ee.y);
@@ -1331,34 +1364,39 @@ __global__ void __launch_bounds__(128, 6) k_bd_fsd_sample(const BdArgs a) {
                     xi = mk2(z.x * i00 + z.y * i01, z.x * i10 + z.y * i11);
                 }
             }
-            // 3. the kv x n (try, segment) terms, spread over the warp
-            {
-                const uint32_t items = kv * n;
-                uint32_t tt = 0u, jj = lane;
-                for (uint32_t base = 0u; base < items; base += 32u) {
-                    while (jj >= n && tt < kv) { jj -= n; ++tt; }
-                    const bool act = tt < kv;
-                    const float xx = __shfl_sync(0xffffffffu, xi.x, (int)(act ? tt : 0u)), xy = __shfl_sync(0xffffffffu, xi.y, (int)(act ? tt : 0u));
-                    if (act) {
-                        const float4 ea = sh.ea[jj], eb = sh.eb[jj];
-                        FEdge e; e.e = mk2(ea.x, ea.y); e.v = mk2(ea.z, ea.w); e.a_b = mkc(eb.x, eb.y); e.iab_2 = mkc(eb.z, eb.w);
-                        const V2 x2 = mk2(xx, xy);
-                        const V2 z = fzeta(e, x2);
-                        const C2 sx = e.a_b * falpha1(z.x, z.y) + e.iab_2 * falpha2(z.x, z.y);
-                        const float rho = length2(e.e);
-                        float sn, cs; pm::sincosf(-dot(e.v, x2), &sn, &cs);
-                        const C2 tm = mkc(rho * cs, rho * sn) * sx;
-                        sh.re[tt][jj] = tm.re; sh.im[tt][jj] = tm.im; sh.dd[tt][jj] = sqrf(rho) * cnorm(sx);
+            // 3. + 4.  per chunk of staged segments: the kv x nc (try, segment) terms spread over the warp, then lane t adds try t's terms IN
+            // SEGMENT ORDER to its running sums; after the last chunk, the acceptance test
+            C2 acc = mkc(0.f, 0.f); float dens = 0.f;
+            for (uint32_t j0 = 0u; j0 < n; j0 += (uint32_t)kFsdChunk) {
+                const uint32_t nc = min(n - j0, (uint32_t)kFsdChunk);
+                if (!small) stage(j0);
+                {
+                    const uint32_t items = kv * nc;
+                    uint32_t tt = 0u, jj = lane;
+                    for (uint32_t base = 0u; base < items; base += 32u) {
+                        while (jj >= nc && tt < kv) { jj -= nc; ++tt; }
+                        const bool act = tt < kv;
+                        const float xx = __shfl_sync(0xffffffffu, xi.x, (int)(act ? tt : 0u)), xy = __shfl_sync(0xffffffffu, xi.y, (int)(act ? tt : 0u));
+                        if (act) {
+                            const float4 ea = sh.ea[jj], eb = sh.eb[jj];
+                            FEdge e; e.e = mk2(ea.x, ea.y); e.v = mk2(ea.z, ea.w); e.a_b = mkc(eb.x, eb.y); e.iab_2 = mkc(eb.z, eb.w);
+                            const V2 x2 = mk2(xx, xy);
+                            const V2 z = fzeta(e, x2);
+                            const C2 sx = e.a_b * falpha1(z.x, z.y) + e.iab_2 * falpha2(z.x, z.y);
+                            const float rho = length2(e.e);
+                            float sn, cs; pm::sincosf(-dot(e.v, x2), &sn, &cs);
+                            const C2 tm = mkc(rho * cs, rho * sn) * sx;
+                            sh.re[tt][jj] = tm.re; sh.im[tt][jj] = tm.im; sh.dd[tt][jj] = sqrf(rho) * cnorm(sx);
+                        }
+                        jj += 32u;
                     }
-                    jj += 32u;
                 }
+                __syncwarp();
+                if (mine_valid) for (uint32_t j = 0; j < nc; ++j) { acc = acc + mkc(sh.re[lane][j], sh.im[lane][j]); dens += sh.dd[lane][j]; }
+                __syncwarp();
             }
-            __syncwarp();
-            // 4. lane t: sums in segment order, acceptance test
             bool done = false; float f = 0.f;
             if (mine_valid) {
-                C2 acc = mkc(0.f, 0.f); float dens = 0.f;
-                for (uint32_t j = 0; j < n; ++j) { acc = acc + mkc(sh.re[lane][j], sh.im[lane][j]); dens += sh.dd[lane][j]; }
                 const float g = dens * fchi_e(xi) + hd.P0 * kInvTwoPi / sqrf(kP0s) * fchi_0(xi);
                 f = cnorm(acc) * fchi_e(xi) + hd.psi02 * fchi_0(xi);
                 done = rej ? rnd(smp) * g < f * recp_M : true;
@@ -1406,16 +1444,16 @@ __global__ void __launch_bounds__(128) k_bd_fsd_finish(const BdArgs a) {
         const DScene& sc = a.r.sc;
         wid = a.fsd_list[(size_t)a.fl_fin * 2u * a.P + i];
         const uint32_t slot = wid >> 1, which = wid & 1u;
-        BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+        BCtx c = mk_bctx(sc, a.arena, slot, a.lut, &ctr);
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
         HitRec h; hit_load(h, a.r.hit, a.r.pool, wid);
         BdHeader hd; soa_load(hd, a.headers, a.P, slot);
-        BWalk d; bd_walker_to_state(w, which, d);
+        BWalk d; bd_walker_to_state(sc, w, which, d);
         const float4 o0 = a.fsd_out[2u * wid], o1 = a.fsd_out[2u * wid + 1u];
         Sampler smp; smp.k0 = a.r.seed_lo; smp.k1 = a.r.seed_hi; smp.pixel = hd.pixel; smp.sample = hd.sample; smp.d = __float_as_uint(o1.y); smp.stream = 1u + which;
         const V3 interaction_wp = h.origin + h.d2i * d.beam.env.d;
         survive = bd_walk_fsd_finish(c, d, smp, (int)(d.ap0 + d.n_ap - 1u), interaction_wp, h.d2i, mk3(o0.x, o0.y, o0.z), o0.w, o1.x, n_vert);
-        overflow = c.overflow;
+        overflow = c.overflow; bd_flush_need(a.r.ctr, c);
         if (survive) { bd_state_to_walker(d, smp.d, w); soa_store(w, a.walkers, 2u * a.P, wid); }
         else bd_walker_done(a, wid, d.n, n_splat);
     }
@@ -1428,12 +1466,12 @@ template <int CLS> __global__ void __launch_bounds__(128) k_bd_connect(const BdA
     Counters ctr; counters_zero(ctr);
     uint32_t n_conn = 0, n_splat = 0; bool overflow = false;
     const uint32_t np = (uint32_t)a.r.ctr->n_pairs[CLS];
-    const uint32_t* pairs = a.pairs + a.pair_off[CLS];
+    const unsigned long long* pairs = a.pairs + a.pair_off[CLS];
     const DScene& sc = a.r.sc;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
-        const uint32_t task = pairs[i];
-        const uint32_t slot = task & 0x3fffffu; const int s = (int)((task >> 22) & 31u), t = (int)(task >> 27);
-        BCtx c; c.sc = &sc; c.A.base = a.arena + (size_t)slot * kArenaWords; c.lut = a.lut; c.ctr = &ctr; c.overflow = false;
+        const unsigned long long task = pairs[i];
+        const uint32_t slot = (uint32_t)task; const int s = (int)((task >> 32) & 0xffffull), t = (int)(task >> 48);
+        BCtx c = mk_bctx(sc, a.arena, slot, a.lut, &ctr);
         BdHeader hd; soa_load(hd, a.headers, a.P, slot);
         BdSampleInit si; bd_header_to_init(hd, si);
         const uint32_t nsv = a.nverts[2u * slot], nev = a.nverts[2u * slot + 1u];

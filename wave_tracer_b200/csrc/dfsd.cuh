@@ -9,16 +9,16 @@ namespace wt {
 
 constexpr float kUtdMinSinBeta = 1e-3f;
 constexpr float kUtdSigmaScale = 45.f;
-constexpr int kMaxFsdEdges = 48;     // edges of one UTD aperture (a per-path bound; overflows are counted and reported, never silent)
-
+// The aperture of a UTD vertex: interaction geometry + the ids of the edges that take part.  The edge list is a row of an HBM array
+// (sc.cap.edges entries per path, two rows per path: the aperture a path carries from its previous vertex and the one it builds now).
+struct ApHead { V3 wp; Frame fr; V3 size; V3 wi; float k; };        // an Aperture without its edge list
 struct Aperture {
     V3 wp; Frame fr; V3 size; V3 wi; float k;
-    uint32_t n; uint32_t edges[kMaxFsdEdges];
+    uint32_t n; uint32_t* edges;
 };
 struct Wedge { V3 v; float l; V3 nff, tff, nbf, e; float alpha; uint32_t idx; };
 
 // free_space_diffraction_t ctor body for one edge (free_space_diffraction.cpp:36-78); false: edge does not take part
-struct ApHead { V3 wp; Frame fr; V3 size; V3 wi; float k; };        // an Aperture without its edge list
 template <class AP> WT_D bool wedge_build(const DScene& sc, const AP& ap, uint32_t ed, Wedge& w) {
     const wtgpu_edge E = sc.edges[ed];
     const V3 n1 = mk3(E.n1), n2 = mk3(E.n2), t1 = mk3(E.t1), t2 = mk3(E.t2), ea = mk3(E.a), eb = mk3(E.b);

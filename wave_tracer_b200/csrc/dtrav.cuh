@@ -11,6 +11,19 @@
 
 namespace wt {
 
+// Capacities of the per-path variable-length lists.  The reference keeps them in std::vector / std::set (traversal_common.hpp:116-149,
+// fraunhofer/free_space_diffraction.cpp:22-129, vertex arenas of plt_bdpt.cpp:59-67); here they are rows of HBM arrays whose length is a RUN-TIME
+// property of the scene handle: a render that finds a list longer than its row records how long it had to be (DevCounters::need_*), and
+// wtgpu_render re-sizes the rows and renders again -- a two-pass count / fill at the granularity of the render call, so results never depend on a
+// capacity (wavefront.cu, "capacity growth").
+struct Caps {
+    uint32_t tris;          // triangles a cone query returns (row of trav_tris)
+    uint32_t edges;         // edges around a vertex (rows of hit_edges / the UTD aperture's edge list)
+    uint32_t seg;           // segments of a Fraunhofer aperture
+    uint32_t ap_walk;       // Fraunhofer apertures per subpath
+    uint32_t verts;         // vertices per subpath (plt_bdpt: max_depth + 2)
+    uint32_t ap_words, arena_words;     // derived: words per aperture record, per sample slot (dbdpt.cuh)
+};
 struct DScene {
     const wtgpu_node* nodes; const wtgpu_leaf* leaves; int32_t root_ptr;
     const float4* tris;               // 3 float4 per triangle
@@ -26,6 +39,7 @@ struct DScene {
     const float* erf_lut;             // 1024-entry erf table (include/wt/math/erf_lut.hpp)
     uint32_t scene_stream;            // Sampler::stream of the scene-sampler draws: 0 (uniform) or kSobolStreamFlag | spp (sobolld); set per render
     float ray_cull_abs;               // absolute slack of the ray-query range culling (RayCull below); +inf disables the culling; set per render
+    Caps cap;                         // set per render
 };
 
 // Range culling of RAY queries.  bvh8w.cpp:469-554 tests nodes against {0, closest hit} only, so a ray cast over a short range (a
@@ -43,8 +57,9 @@ WT_D bool ray_cull_keep(const RayCull& c, float rmin, float rmax) { return !(rmi
 
 struct Counters {       // per-thread, flushed with one atomic per counter per warp
     uint32_t nodes, tris, ray_casts, cone_casts, shadow_casts;
+    uint32_t stack_drops;   // children a full traversal stack could not take (the reference's stacks are as deep: 64 ray / 128 cone, bvh8w.cpp:305-307 exits in a debug build)
 };
-WT_D void counters_zero(Counters& c) { c.nodes = c.tris = c.ray_casts = c.cone_casts = c.shadow_casts = 0; }
+WT_D void counters_zero(Counters& c) { c.nodes = c.tris = c.ray_casts = c.cone_casts = c.shadow_casts = c.stack_drops = 0; }
 
 struct Tri3 { V3 a, b, c, n; };
 WT_D Tri3 load_tri(const DScene& sc, uint32_t tuid) {
@@ -124,7 +139,7 @@ WT_DN bool ray_traverse(const DScene& sc, V3 ro, V3 rd, Range range, RayHit& rec
                         const float t1z = ((nz ? amxz[i] : amnz[i]) - ro.z) * inv.z, t2z = ((nz ? amnz[i] : amxz[i]) - ro.z) * inv.z;
                         const float rmin = vmaxps(vmaxps(vmaxps(t1x, t1y), t1z), 0.f);
                         const float rmax = vminps(vminps(vminps(t2x, t2y), t2z), rec.dist);
-                        if (rmin <= rmax && ach[i] != 0 && ray_cull_keep(cull, rmin, rmax) && s < 64) { stack[s].tmin = rmin; stack[s].ptr = ach[i]; ++s; }
+                        if (rmin <= rmax && ach[i] != 0 && ray_cull_keep(cull, rmin, rmax)) { if (s < 64) { stack[s].tmin = rmin; stack[s].ptr = ach[i]; ++s; } else ctr.stack_drops++; }
                     }
                 }
                 stack_sort(stack + begin, s - begin);
@@ -153,7 +168,7 @@ WT_D bool shadow_ray(const DScene& sc, V3 ro, V3 rd, Range range, Counters& ctr)
 }
 
 // ---- cone query.  Results: closest distance, front-face flag of the closest triangle, the triangle list in traversal order.
-struct ConeResult { float dist; bool front; uint32_t n_tris; bool overflow; };
+struct ConeResult { float dist; bool front; uint32_t n_tris; bool overflow; };      // n_tris counts every accepted triangle, also those beyond the row
 
 WT_D Range cone_search_range(const Cone& cone, Range searchrange, float intr_dist, float z_scale) {    // traversal_common.hpp:78-84
     const float dist = fmaxf(searchrange.mn, intr_dist);
@@ -161,8 +176,7 @@ WT_D Range cone_search_range(const Cone& cone, Range searchrange, float intr_dis
     return rand_(mkr(searchrange.mn, fminf(searchrange.mx, dist + zd)), mkr(0.f, WT_INF));
 }
 
-template <int MAXT>
-WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_range, float z_scale, uint32_t* tri_out, ConeResult& res, Counters& ctr) {
+WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_range, float z_scale, uint32_t* tri_out, uint32_t max_tris, ConeResult& res, Counters& ctr) {
     ctr.cone_casts++;
     res.dist = WT_INF; res.front = false; res.n_tris = 0; res.overflow = false;
     Range range = cone_search_range(cone, traversal_range, res.dist, z_scale);
@@ -187,7 +201,7 @@ WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_ran
                     if (d > range.mx) continue;
                     if (d < res.dist) { res.dist = d; res.front = dot(tr.n, -rd) > 0.f; }
                     found = true;
-                    if (res.n_tris < MAXT) tri_out[res.n_tris] = tuid; else res.overflow = true;
+                    if (res.n_tris < max_tris) tri_out[res.n_tris] = tuid; else res.overflow = true;
                     res.n_tris++;
                 }
             }
@@ -227,7 +241,7 @@ WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_ran
                     const bool ok = tmin <= tmax && tmax >= range.mn && tmin <= range.mx;
                     if (!ok || ach[i] == 0) continue;
                     if (tmin >= range.mx) continue;
-                    if (s < 128) { stack[s].tmin = tmin; stack[s].ptr = ach[i]; ++s; }
+                    if (s < 128) { stack[s].tmin = tmin; stack[s].ptr = ach[i]; ++s; } else ctr.stack_drops++;
                 }
             }
             stack_sort(stack + begin, s - begin);
@@ -237,8 +251,7 @@ WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_ran
 
 // edges of a triangle list, deduplicated and sorted ascending (the iteration order of std::set<tuid_t>,
 // traversal_common.hpp:124-146)
-template <int MAXE>
-WT_D uint32_t collect_edges(const DScene& sc, const uint32_t* tris, uint32_t n_tris, uint32_t* edges, bool& overflow) {
+WT_D uint32_t collect_edges(const DScene& sc, const uint32_t* tris, uint32_t n_tris, uint32_t* edges, uint32_t max_edges, bool& overflow) {
     uint32_t n = 0;
     for (uint32_t i = 0; i < n_tris; ++i) {
         const wtgpu_tri_meta m = sc.tri_meta[tris[i]];
@@ -249,7 +262,7 @@ WT_D uint32_t collect_edges(const DScene& sc, const uint32_t* tris, uint32_t n_t
             uint32_t pos = 0;
             while (pos < n && edges[pos] < e) ++pos;
             if (pos < n && edges[pos] == e) continue;
-            if (n >= MAXE) { overflow = true; continue; }
+            if (n >= max_edges) { overflow = true; continue; }
             for (uint32_t j = n; j > pos; --j) edges[j] = edges[j - 1];
             edges[pos] = e; ++n;
         }

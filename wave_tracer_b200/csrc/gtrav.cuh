@@ -7,7 +7,8 @@
 //     are ranked with shuffles and pushed in the order the sequential insertion sort would leave them;
 //   * leaf step: lane i intersects triangle i of the leaf (ray: of a <=16-triangle subtree); hits are appended with a ballot
 //     prefix, the closest is found with a (distance, lane) min-reduction = the first minimal one in sequential order;
-//   * the stack and the triangle list live in shared memory (1.25 KB per group);
+//   * the stack lives in shared memory (1 KB per group); accepted triangles go straight to the beam's row of the result array in HBM, whose
+//     length is a run-time capacity (dtrav.cuh Caps) -- the count keeps running past it, so a too-short row is known exactly;
 //   * groups pull beams from the list with an atomic cursor, so a long beam delays only its own group;
 //   * the four groups of a warp run node steps freely but meet before every leaf step, where the expensive cone-triangle code runs.
 // Every decision is taken on the same values, in the same order, as the sequential code: results are bit-identical to dtrav.cuh.
@@ -17,9 +18,7 @@ namespace wt {
 
 constexpr int kGW = 8;
 constexpr int kGStack = 128;
-struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; uint32_t tris[kMaxConeTris];
-    float key[kGW];
-};
+struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; float key[kGW]; };
 
 // what traverse() returns, as stored between the traversal kernel and the per-thread resolve kernel
 struct alignas(16) TravRec { uint32_t flags, ray_tuid; float ray_dist, bx, by, cone_dist; uint32_t n_tris; float region_depth, ox, oy, oz; uint32_t pad_; };
@@ -50,6 +49,7 @@ struct GTrav {
     Range qrange, crange;       // ray range / cone traversal range; current cone search range
     RayCull cull;               // range culling bounds of the current ray query (dtrav.cuh)
     RayHit rec; ConeResult res;
+    uint32_t* tris_out;         // the beam's row of the triangle-list array (sc.cap.tris entries)
 };
 
 WT_D void g_start_ray(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, Range r, Counters& ctr) {
@@ -66,11 +66,12 @@ WT_D void g_start_cone(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, 
     __syncwarp(g.gmask);
 }
 // push the children that passed, in the order insertion sort (descending tmin, stable) leaves them (bvh8w.cpp:44-57)
-WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float tmin, int32_t ch, int cap) {
+WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float tmin, int32_t ch, int cap, Counters& ctr) {
     const unsigned m = g_ballot(g, push);
     const int idx = __popc(m & ((1u << g.gl) - 1u));
     const bool keep = push && t.s + idx < cap;
     const unsigned km = g_ballot(g, keep);
+    if (km != m && g.gl == 0u) ctr.stack_drops += (uint32_t)(__popc(m) - __popc(km));
     int rank = 0;
     if (__popc(km) > 1) {       // (group-uniform) nothing to order when at most one child passed (etoile-like k_gtraverse -6 %)
     // the eight keys go through shared memory (one store, two 16-B loads) instead of eight shuffles (fewer instructions in the hottest loop: etoile-like k_gtraverse 111 -> 96 ms/step); lanes that do not push publish -inf
@@ -121,7 +122,7 @@ WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, i
         const bool ok = tmin <= tmax && tmax >= t.crange.mn && tmin <= t.crange.mx;
         push = ok && ch != 0 && !(tmin >= t.crange.mx); key = tmin; cap = kGStack;
     }
-    g_push_sorted(g, sh, t, push, key, ch, cap);
+    g_push_sorted(g, sh, t, push, key, ch, cap, ctr);
 }
 // triangles [t0, t0+cnt) against the current query
 WT_D void g_leaf_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, uint32_t t0, uint32_t cnt, Counters& ctr) {
@@ -149,9 +150,9 @@ WT_D void g_leaf_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, u
                 const int w = g_argmin(g, d, acc && d < t.res.dist);
                 if (w >= 0) { t.res.dist = g_shfl(g, d, w); t.res.front = g_shfl(g, front ? 1 : 0, w) != 0; }
                 const uint32_t pos = t.res.n_tris + (uint32_t)__popc(m & ((1u << g.gl) - 1u));
-                if (acc && pos < (uint32_t)kMaxConeTris) sh.tris[pos] = tuid;
+                if (acc && pos < sc.cap.tris) t.tris_out[pos] = tuid;
                 t.res.n_tris += (uint32_t)__popc(m);
-                if (t.res.n_tris > (uint32_t)kMaxConeTris) t.res.overflow = true;
+                if (t.res.n_tris > sc.cap.tris) t.res.overflow = true;
             }
         }
         if (found) {
@@ -225,7 +226,7 @@ WT_D bool g_query_done(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, 
     return false;
 }
 
-// The driver loop.  fetch(i, env, prev, lambda) loads item i (group-uniformly); emit(i, rec, tris) stores its result.
+// The driver loop.  fetch(i, env, prev, lambda, tris_out) loads item i (group-uniformly) and names its triangle-list row; emit(i, rec, g) stores its result.
 // (A fully warp-uniform variant -- one pop per group per iteration, node steps of all groups in the same instructions -- was measured 8 %
 // SLOWER on the etoile-like scene and on double_slits, and again 6-9 % slower after the code-size work removed the instruction-fetch
 // stall (profiles/r01s3_phases.txt, session V): a group that reaches its leaf early idles through the others' node steps.)
@@ -247,13 +248,13 @@ WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* sh
                 if (i >= n_items) { done = true; break; }
                 item = i;
                 Cone env; Geo prev; float lambda;
-                fetch(item, env, prev, lambda);
+                fetch(item, env, prev, lambda, t.tris_out);
                 g_begin(sc, g, sh, t, env, prev, lambda, force_rt, edge_query, ctr);
                 have = true;
             }
             if (t.s == 0) {
                 TravRec out;
-                if (g_query_done(sc, g, sh, t, out, ctr)) { emit(item, out, sh.tris, g); have = false; __syncwarp(g.gmask); }
+                if (g_query_done(sc, g, sh, t, out, ctr)) { emit(item, out, g); have = false; __syncwarp(g.gmask); }
                 continue;
             }
             const int32_t top = sh.ptr[t.s - 1];

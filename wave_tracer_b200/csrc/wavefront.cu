@@ -14,6 +14,7 @@
 #include "dfsd.cuh"
 #include "../../include/wthost.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,8 +26,6 @@
 using namespace wt;
 
 // ================================================================================================ state
-constexpr int kMaxHitEdges = kMaxFsdEdges;
-constexpr int kMaxConeTris = WTGPU_MAX_CONE_TRIS;
 constexpr unsigned kBlockT = 128u;
 
 enum : uint32_t { F_SAMPLED_FSD = 1u, F_HAS_FSD = 2u, F_DPD_DISC = 4u };
@@ -40,21 +39,19 @@ struct alignas(16) PathCore {
     float ox, oy;
     float L[4];
 };
-struct alignas(16) PathFsd {
+struct alignas(16) PathFsd {     // what a path keeps of its previous vertex's aperture: the edge ids are in its row of RenderArgs::ap_edges
     Beam prev_beam;
-    Aperture ap;
+    ApHead ap; uint32_t n;
 };
 enum : uint32_t { H_EMPTY = 1u, H_BALLISTIC = 2u, H_PRIMARY = 4u, H_FRONT = 8u, H_OVERFLOW = 16u };
 struct alignas(16) HitRec {
     uint32_t flags, primary;
     float pdist, bx, by, d2i, region_depth;
     V3 origin;
-    uint32_t n_edges;
+    uint32_t n_edges;           // edge ids: the path's row of RenderArgs::hit_edges
     float flux;                 // plt_bdpt: Gaussian power over the clipped triangles (no primary hit)
-    uint32_t edges[kMaxHitEdges];
 };
-
-static_assert(offsetof(HitRec, edges) == 48, "HitRec header is three 16-B chunks");
+static_assert(sizeof(HitRec) == 48, "HitRec is three 16-B chunks");
 template <class T> __host__ __device__ constexpr int chunks_of() { return (int)(sizeof(T) / 16); }
 template <class T> WT_D void soa_load(T& v, const float4* __restrict__ base, uint32_t pool, uint32_t slot) {
     float4* p = reinterpret_cast<float4*>(&v);
@@ -67,19 +64,8 @@ template <class T> WT_D void soa_store(const T& v, float4* __restrict__ base, ui
     for (int c = 0; c < chunks_of<T>(); ++c) base[(size_t)c * pool + slot] = p[c];
 }
 
-// HitRec moves its edge list only as far as it is filled: 3 header chunks + ceil(n_edges / 4) edge chunks
-WT_D void hit_store(const HitRec& v, float4* __restrict__ base, uint32_t pool, uint32_t slot) {
-    const float4* p = reinterpret_cast<const float4*>(&v);
-    const int nc = 3 + (int)((min(v.n_edges, (uint32_t)kMaxHitEdges) + 3u) >> 2);
-    for (int c = 0; c < nc; ++c) base[(size_t)c * pool + slot] = p[c];
-}
-WT_D void hit_load(HitRec& v, const float4* __restrict__ base, uint32_t pool, uint32_t slot) {
-    float4* p = reinterpret_cast<float4*>(&v);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) p[c] = base[(size_t)c * pool + slot];
-    const int nc = 3 + (int)((min(v.n_edges, (uint32_t)kMaxHitEdges) + 3u) >> 2);
-    for (int c = 3; c < nc; ++c) p[c] = base[(size_t)c * pool + slot];
-}
+WT_D void hit_store(const HitRec& v, float4* __restrict__ base, uint32_t pool, uint32_t slot) { soa_store(v, base, pool, slot); }
+WT_D void hit_load(HitRec& v, const float4* __restrict__ base, uint32_t pool, uint32_t slot) { soa_load(v, base, pool, slot); }
 
 struct DevCounters {
     unsigned long long samples, segments, ray_casts, cone_casts, shadow_casts, nodes, tris, edges, surface, fsd, null_, splats, overflow, shade_nodes, shade_tris, shaded;
@@ -92,12 +78,18 @@ struct DevCounters {
     unsigned long long strategies[5], walker_steps;
     int trav_head;                      // work-fetch cursor of the group traversal
     int n_fsd_list[3], fsd_head;        // plt_bdpt: walkers waiting for a Fraunhofer sample (three rotating lists); work-fetch cursor
+    // capacity growth (dtrav.cuh Caps): the longest list a too-short row was asked to hold (0: every list fitted)
+    unsigned int need_tris, need_edges, need_seg, need_ap, need_verts;
+    unsigned long long stack_drops;
 };
+WT_D void need_max(unsigned int* p, uint32_t v) { if (v > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(p, v); }
 
 namespace wt { struct TravRec; }
 struct RenderArgs {
     DScene sc;
-    wt::TravRec* trav_rec; uint32_t* trav_tris;      // results of the group traversal (gtrav.cuh), per slot
+    wt::TravRec* trav_rec; uint32_t* trav_tris;      // results of traverse(), per slot; trav_tris: sc.cap.tris triangle ids per slot
+    uint32_t* hit_edges;                              // sc.cap.edges edge ids per slot: the edges around the vertex (HitRec::n_edges of them)
+    uint32_t* ap_edges; uint32_t it_parity;           // plt_path: 2 x pool rows of sc.cap.edges: UTD aperture edge lists (this iteration's row set: it_parity)
     float4* core; float4* fsd; float4* hit;
     uint32_t* alive; uint32_t* keys; uint32_t* order; uint32_t* key_count; uint32_t* key_cursor; uint32_t* trav_list;
     DevCounters* ctr;
@@ -120,6 +112,7 @@ WT_D void flush_counters(DevCounters* g, const Counters& c, bool shade = false) 
         if (cc) atomicAdd(&g->cone_casts, (unsigned long long)cc);
         if (s) atomicAdd(&g->shadow_casts, (unsigned long long)s);
     }
+    if (c.stack_drops) atomicAdd(&g->stack_drops, (unsigned long long)c.stack_drops);
 }
 WT_D void count1(unsigned long long* p, bool pred) {
     const unsigned m = __activemask();
@@ -212,7 +205,7 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
         dist += bd;
         if (bd == WT_INF || dist >= WT_INF) { out.ballistic = true; out.empty = true; return; }
         const float min_prog = cone_axes(env, dist).x / 2.f;
-        cone_traverse<kMaxConeTris>(sc, env, mkr(dist, WT_INF), kMajorToZ, tris, out.cone, ctr);
+        cone_traverse(sc, env, mkr(dist, WT_INF), kMajorToZ, tris, sc.cap.tris, out.cone, ctr);
         const bool cempty = out.cone.n_tris == 0u;
         if (cempty || out.cone.dist - dist >= min_prog) {
             out.ballistic = false; out.empty = cempty;
@@ -234,7 +227,8 @@ __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
         const DScene& sc = a.sc;
         seg = true;
         PathCore pc; soa_load(pc, a.core, a.pool, slot);
-        uint32_t tris[kMaxConeTris];
+        uint32_t* tris = a.trav_tris + (size_t)slot * sc.cap.tris;
+        uint32_t* edges = a.hit_edges + (size_t)slot * sc.cap.edges;
         TravOut tr;
         const bool force_rt = sc.sensor.ray_trace_only != 0u;
         traverse(sc, pc.beam.env, pc.prev_geo, wavenum_to_wavelen(pc.beam.k), force_rt, tris, tr, ctr);
@@ -252,8 +246,8 @@ __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
             } else {
                 h.d2i = tr.cone.dist;
                 if (tr.cone.front) h.flags |= H_FRONT;
-                if (tr.cone.overflow) { h.flags |= H_OVERFLOW; ovf = true; }
-                const uint32_t nt = min(tr.cone.n_tris, (uint32_t)kMaxConeTris);
+                if (tr.cone.overflow) { h.flags |= H_OVERFLOW; ovf = true; need_max(&a.ctr->need_tris, tr.cone.n_tris); }
+                const uint32_t nt = min(tr.cone.n_tris, sc.cap.tris);
                 // find_closest_triangle (plt_path_detail.hpp:253-276)
                 const Range zr = mkr(h.d2i, h.d2i + h.region_depth);
                 for (uint32_t i = 0; i < nt; ++i) {
@@ -263,16 +257,18 @@ __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
                     if (rt.hit && rt.dist < h.pdist) { h.primary = tris[i]; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
                 }
                 if (h.primary != WTGPU_INVALID_IDX) h.flags |= H_PRIMARY;
-                if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, h.edges, eo); if (eo) { h.flags |= H_OVERFLOW; ovf = true; } }
+                if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tris, nt, edges, sc.cap.edges, eo); if (eo) { h.flags |= H_OVERFLOW; ovf = true; need_max(&a.ctr->need_edges, 3u * nt); } }
             }
             // ballistic hit with a finite beam: collect the edges around the hit (plt_path_detail.hpp:656-660)
             if (is_ballistic && !cone_is_ray(pc.beam.env) && !force_rt) {
                 const float zd = cone_axes(env, h.d2i).x * kMajorToZ;
                 ConeResult cr;
-                cone_traverse<kMaxConeTris>(sc, env, mkr(h.d2i - zd / 2.f, h.d2i + zd / 2.f), 1.f, tris, cr, ctr);
-                bool eo = cr.overflow;
-                h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, min(cr.n_tris, (uint32_t)kMaxConeTris), h.edges, eo);
-                if (eo) { h.flags |= H_OVERFLOW; ovf = true; }
+                cone_traverse(sc, env, mkr(h.d2i - zd / 2.f, h.d2i + zd / 2.f), 1.f, tris, sc.cap.tris, cr, ctr);
+                if (cr.overflow) need_max(&a.ctr->need_tris, cr.n_tris);
+                bool eo = false;
+                h.n_edges = collect_edges(sc, tris, min(cr.n_tris, sc.cap.tris), edges, sc.cap.edges, eo);
+                if (eo) need_max(&a.ctr->need_edges, 3u * min(cr.n_tris, sc.cap.tris));
+                if (eo || cr.overflow) { h.flags |= H_OVERFLOW; ovf = true; }
             }
             if (h.flags & H_PRIMARY) key = (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
             else key = h.n_edges ? a.n_keys - 3u : a.n_keys - 2u;
@@ -295,16 +291,14 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs 
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.sc;
     g_traverse_all(sc, a.ctr->n_trav, &a.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr,
-        [&](int i, Cone& env, Geo& prev, float& lambda) {
+        [&](int i, Cone& env, Geo& prev, float& lambda, uint32_t*& tris_out) {
             const uint32_t slot = a.trav_list[i];
             PathCore pc; soa_load(pc, a.core, a.pool, slot);
             env = pc.beam.env; prev = pc.prev_geo; lambda = wavenum_to_wavelen(pc.beam.k);
+            tris_out = a.trav_tris + (size_t)slot * sc.cap.tris;
         },
-        [&](int i, const TravRec& r, const uint32_t* tris, const GLane& g) {
-            const uint32_t slot = a.trav_list[i];
-            if (g.gl == 0u) a.trav_rec[slot] = r;
-            const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
-            for (uint32_t k = g.gl; k < nt; k += (uint32_t)kGW) a.trav_tris[(size_t)slot * kMaxConeTris + k] = tris[k];
+        [&](int i, const TravRec& r, const GLane& g) {
+            if (g.gl == 0u) { a.trav_rec[a.trav_list[i]] = r; if (r.flags & TR_OVERFLOW) need_max(&a.ctr->need_tris, r.n_tris); }
         });
     flush_counters(a.ctr, ctr);
 }
@@ -317,8 +311,9 @@ __global__ void __launch_bounds__(128) k_resolve(const RenderArgs a) {
         const DScene& sc = a.sc;
         seg = true;
         const TravRec r = a.trav_rec[slot];
-        const uint32_t* __restrict__ tris = a.trav_tris + (size_t)slot * kMaxConeTris;
-        const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
+        const uint32_t* __restrict__ tris = a.trav_tris + (size_t)slot * sc.cap.tris;
+        uint32_t* edges = a.hit_edges + (size_t)slot * sc.cap.edges;
+        const uint32_t nt = min(r.n_tris, sc.cap.tris);
         const V3 origin = mk3(r.ox, r.oy, r.oz);
         // the beam's mean direction: floats 3..5 of PathCore (beam.env = {o, d, ...}), i.e. chunk 0 .w and chunk 1 .xy
         static_assert(offsetof(PathCore, beam) == 0 && offsetof(Beam, env) == 0 && offsetof(Cone, d) == 12 && sizeof(V3) == 12, "PathCore layout");
@@ -349,8 +344,8 @@ __global__ void __launch_bounds__(128) k_resolve(const RenderArgs a) {
             // cone segment: edges of the returned triangles when FSD is on; ballistic hit: edges of the edge query's triangles (always, as k_traverse)
             if (((r.flags & TR_BALLISTIC) || sc.integrator.fsd) && nt) {
                 bool eo = false;
-                h.n_edges = collect_edges<kMaxHitEdges>(sc, tris, nt, h.edges, eo);
-                if (eo) { h.flags |= H_OVERFLOW; ovf = true; }
+                h.n_edges = collect_edges(sc, tris, nt, edges, sc.cap.edges, eo);
+                if (eo) { h.flags |= H_OVERFLOW; ovf = true; need_max(&a.ctr->need_edges, 3u * nt); }
             }
             if (h.flags & H_PRIMARY) key = (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
             else key = h.n_edges ? a.n_keys - 3u : a.n_keys - 2u;
@@ -440,7 +435,8 @@ __global__ void __launch_bounds__(128, 3) k_shade(const RenderArgs a) {
     const bool act = i < (uint32_t)a.ctr->n_sorted;
     bool proc = false, alive = true;
     uint32_t slot = 0;
-    PathCore pc; HitRec h; PathFsd pf; Aperture ap; ap.n = 0u;
+    PathCore pc; HitRec h; PathFsd pf; Aperture ap, apo; ap.n = 0u; ap.edges = nullptr; apo.n = 0u; apo.edges = nullptr;
+    const uint32_t* hedges = nullptr;
     Sampler smp;
     bool has_new_fsd = false;
     Beam prev_beam_new;     // beam before this vertex's interaction (becomes prev_vert_beam)
@@ -448,6 +444,9 @@ __global__ void __launch_bounds__(128, 3) k_shade(const RenderArgs a) {
         slot = a.order[i];
         soa_load(pc, a.core, a.pool, slot);
         hit_load(h, a.hit, a.pool, slot);
+        hedges = a.hit_edges + (size_t)slot * sc.cap.edges;
+        ap.edges = a.ap_edges + ((size_t)a.it_parity * a.pool + slot) * sc.cap.edges;             // the aperture this vertex may build
+        apo.edges = a.ap_edges + ((size_t)(a.it_parity ^ 1u) * a.pool + slot) * sc.cap.edges;     // the one the path carries from its previous vertex
         smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = pc.pixel; smp.sample = pc.sample; smp.d = pc.rng_d; smp.stream = 0u;
         if (h.flags & H_EMPTY) alive = false; else proc = true;
     }
@@ -462,8 +461,8 @@ __global__ void __launch_bounds__(128, 3) k_shade(const RenderArgs a) {
 
     // ---- evaluate fsd from the previous interaction (plt_path_detail.hpp:591-610)
     const bool need1 = proc && (pc.flags & F_HAS_FSD);
-    if (need1) soa_load(pf, a.fsd, a.pool, slot);
-    const float f1 = warp_do_fsd(sc, ush, need1, pf.prev_beam.env, pc.prev_geo, interaction_wp, pf.ap, k, ctr, n_edges_fetched);
+    if (need1) { soa_load(pf, a.fsd, a.pool, slot); apo.wp = pf.ap.wp; apo.fr = pf.ap.fr; apo.size = pf.ap.size; apo.wi = pf.ap.wi; apo.k = pf.ap.k; apo.n = pf.n; }
+    const float f1 = warp_do_fsd(sc, ush, need1, pf.prev_beam.env, pc.prev_geo, interaction_wp, apo, k, ctr, n_edges_fetched);
     if (need1) {
         pc.flags &= ~F_HAS_FSD;
         if (pc.flags & F_SAMPLED_FSD) beam_mul(beam, f1);
@@ -491,7 +490,7 @@ __global__ void __launch_bounds__(128, 3) k_shade(const RenderArgs a) {
         // ---- construct the fsd aperture from the edges (plt_path_detail.hpp:663-679)
         if (h.n_edges) {
             ap.wp = interaction_wp; ap.fr = beam_frame; ap.size = beam_footprint(beam, d2i); ap.wi = -dir; ap.k = k; ap.n = 0u;
-            for (uint32_t j = 0; j < h.n_edges; ++j) { Wedge w; ++n_edges_fetched; if (wedge_build(sc, ap, h.edges[j], w)) ap.edges[ap.n++] = h.edges[j]; }
+            for (uint32_t j = 0; j < h.n_edges; ++j) { Wedge w; ++n_edges_fetched; const uint32_t ed = hedges[j]; if (wedge_build(sc, ap, ed, w)) ap.edges[ap.n++] = ed; }
             has_new_fsd = ap.n > 0u;
             c_fsd = true;
         }
@@ -617,7 +616,7 @@ __global__ void __launch_bounds__(128, 3) k_shade(const RenderArgs a) {
             pc.rng_d = smp.d;
             if (has_new_fsd) {
                 pc.flags |= F_HAS_FSD;
-                pf.prev_beam = prev_beam_new; pf.ap = ap;
+                pf.prev_beam = prev_beam_new; pf.ap.wp = ap.wp; pf.ap.fr = ap.fr; pf.ap.size = ap.size; pf.ap.wi = ap.wi; pf.ap.k = ap.k; pf.n = ap.n;
                 soa_store(pf, a.fsd, a.pool, slot);
             }
             soa_store(pc, a.core, a.pool, slot);
@@ -662,14 +661,14 @@ __global__ void k_debug_cones(const DScene sc, uint32_t n, const wtgpu_cone_quer
     if (i >= n) return;
     Counters ctr; counters_zero(ctr);
     const Cone c = mkcone(mk3(q[i].o), mk3(q[i].d), mk3(q[i].x), q[i].x0, q[i].tan_alpha, 1.f / q[i].e, q[i].e);
-    uint32_t tris[kMaxConeTris]; ConeResult r;
-    cone_traverse<kMaxConeTris>(sc, c, mkr(q[i].tmin, q[i].tmax), q[i].z_scale, tris, r, ctr);
+    uint32_t tris[WTGPU_MAX_CONE_TRIS]; ConeResult r;
+    cone_traverse(sc, c, mkr(q[i].tmin, q[i].tmax), q[i].z_scale, tris, WTGPU_MAX_CONE_TRIS, r, ctr);
     wtgpu_cone_hit& h = out[i];
     h.dist = r.dist; h.front_face = r.front ? 1u : 0u; h.n_tris = r.n_tris;
-    const uint32_t nt = min(r.n_tris, (uint32_t)kMaxConeTris);
+    const uint32_t nt = min(r.n_tris, (uint32_t)WTGPU_MAX_CONE_TRIS);
     for (uint32_t j = 0; j < nt; ++j) h.tris[j] = tris[j];
     bool eo = false; uint32_t edges[WTGPU_MAX_CONE_EDGES];
-    h.n_edges = collect_edges<WTGPU_MAX_CONE_EDGES>(sc, tris, nt, edges, eo);
+    h.n_edges = collect_edges(sc, tris, nt, edges, WTGPU_MAX_CONE_EDGES, eo);
     for (uint32_t j = 0; j < h.n_edges; ++j) h.edges[j] = edges[j];
 }
 // sobolld: dimensions 0..46 of points g0 .. g0+n-1 (one thread per value)
@@ -761,26 +760,30 @@ struct wtgpu_scene {
     wtgpu_sensor sensor{};
     wtgpu_integrator integ{};
     float ray_cull_abs = 0.f;
-    // render pool (lazily sized)
-    uint32_t pool = 0;
+    uint32_t n_keys = 0;
+    // capacities of the per-path lists (dtrav.cuh Caps): grown by wtgpu_render when a render needed more; kept for the next render
+    Caps caps{};
+    // render pool: sized lazily for (pool, caps); every buffer of it is in pool_allocs
+    uint32_t pool = 0; Caps pool_caps{}; uint32_t pool_kind = 0;
+    std::vector<void*> pool_allocs;
     float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
-    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr, *trav_tris = nullptr;
+    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr, *trav_tris = nullptr, *hit_edges = nullptr, *ap_edges = nullptr;
     TravRec* trav_rec = nullptr;
     DevCounters* ctr = nullptr;
-    uint32_t n_keys = 0;
+    // plt_bdpt (P sample slots, 2P walkers)
+    float* bdpt_arena = nullptr;
+    float4 *bd_walkers = nullptr, *bd_headers = nullptr, *bd_fsd_out = nullptr;
+    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_fsd_list = nullptr; unsigned long long* bd_pairs = nullptr;
     std::vector<cudaEvent_t> ev_pool;   // reused across renders (event creation is not free)
     DevCounters* hctr = nullptr; cudaEvent_t ev_begin = nullptr, ev_end = nullptr;     // pinned read-back of the counters + the render's timing events: made once (cudaMallocHost / cudaFreeHost per render cost 5-150 ms of driver time, profiles/r01s3_phases.txt)
     bool has_sobol = false;             // sobolld generator matrices are in constant memory of this device
     wt::FLut lut{};                     // plt_bdpt: Fraunhofer sampling tables
-    float* bdpt_arena = nullptr; uint32_t bdpt_P = 0;
-    // plt_bdpt wavefront state (P sample slots, 2P walkers)
-    float4 *bd_walkers = nullptr, *bd_headers = nullptr, *bd_hit = nullptr;
-    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_pairs = nullptr, *bd_alive = nullptr, *bd_keys = nullptr, *bd_order = nullptr, *bd_trav = nullptr, *bd_fsd_list = nullptr, *bd_trav_tris = nullptr; float4* bd_fsd_out = nullptr; TravRec* bd_trav_rec = nullptr;
-    uint32_t bd_wave_P = 0;
     cudaStream_t bd_stream = nullptr; cudaEvent_t bd_ev_shade = nullptr, bd_ev_samp = nullptr;   // Fraunhofer sampler overlap
-    void free_bd_wave() {
-        for (void* p : { (void*)bd_walkers, (void*)bd_headers, (void*)bd_hit, (void*)bd_pending, (void*)bd_L0, (void*)bd_nverts, (void*)bd_pairs, (void*)bd_alive, (void*)bd_keys, (void*)bd_order, (void*)bd_trav, (void*)bd_fsd_list, (void*)bd_fsd_out, (void*)bd_trav_tris, (void*)bd_trav_rec }) if (p) wt_free(p);
-        bd_walkers = bd_headers = bd_hit = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_pairs = bd_alive = bd_keys = bd_order = bd_trav = bd_fsd_list = bd_trav_tris = nullptr; bd_fsd_out = nullptr; bd_trav_rec = nullptr; bd_wave_P = 0;
+    void free_pool() {
+        for (void* p : pool_allocs) wt_free(p);
+        pool_allocs.clear(); pool = 0;
+        core = fsd = hit = nullptr; alive = keys = order = key_count = key_cursor = trav_list = trav_tris = hit_edges = ap_edges = nullptr; trav_rec = nullptr; ctr = nullptr;
+        bdpt_arena = nullptr; bd_walkers = bd_headers = bd_fsd_out = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_fsd_list = nullptr; bd_pairs = nullptr;
     }
     ~wtgpu_scene() {
         cudaSetDevice(device);
@@ -789,13 +792,14 @@ struct wtgpu_scene {
         if (hctr) cudaFreeHost(hctr);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
-        free_bd_wave();
+        free_pool();
         if (bd_stream) cudaStreamDestroy(bd_stream);
         if (bd_ev_shade) cudaEventDestroy(bd_ev_shade);
         if (bd_ev_samp) cudaEventDestroy(bd_ev_samp);
-        for (void* p : { (void*)core, (void*)fsd, (void*)hit, (void*)alive, (void*)keys, (void*)order, (void*)key_count, (void*)key_cursor, (void*)ctr, (void*)trav_list, (void*)bdpt_arena, (void*)trav_rec, (void*)trav_tris }) if (p) wt_free(p);
     }
 };
+static void caps_derive(Caps& c) { c.ap_words = 16u + 9u * c.seg; c.arena_words = 2u * c.verts * wt::kVertWords + 2u * c.ap_walk * c.ap_words; }
+static bool caps_equal(const Caps& a, const Caps& b) { return a.tris == b.tris && a.edges == b.edges && a.seg == b.seg && a.ap_walk == b.ap_walk && a.verts == b.verts; }
 
 // Generator matrices of the sobolld sampler from the parsed table, as row masks for dsobol.cuh.
 // Direction numbers m_1..m_11 of a dimension are kept as base-3 digit vectors v[c][t] (digit t of m_{c+1}); the first s_j come from the
@@ -865,8 +869,11 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
     if (desc->api_version != WTGPU_API_VERSION) { g_err = "api version mismatch"; return WTGPU_E_INVALID; }
     if (desc->integrator.type != WTGPU_INTEGRATOR_PLT_PATH && desc->integrator.type != WTGPU_INTEGRATOR_PLT_BDPT) { g_err = "unknown integrator type"; return WTGPU_E_UNSUPPORTED; }
     const bool bdpt = desc->integrator.type == WTGPU_INTEGRATOR_PLT_BDPT;
-    if (bdpt && desc->integrator.max_depth + 2u > (uint32_t)wt::kMaxBdptVerts) { g_err = "plt_bdpt: max_depth > 16 unsupported"; return WTGPU_E_UNSUPPORTED; }
-    if (bdpt && desc->integrator.fsd && (!desc->fsd_lut_n || !desc->fsd_lut_m || !desc->fsd_icdf1 || !desc->fsd_icdf2 || !desc->fsd_icdf_theta1 || !desc->fsd_icdf_theta2)) {
+    if (desc->integrator.max_depth == 0u || desc->integrator.max_depth > 4000u) { g_err = "integrator max_depth out of range (1..4000)"; return WTGPU_E_INVALID; }
+    for (uint32_t i = 0; i < desc->n_bsdfs; ++i)
+        if (desc->bsdfs[i].type > WTGPU_BSDF_SCALE) { g_err = "bsdf type " + std::to_string(desc->bsdfs[i].type) + " (mask / normalmap / bumpmap: need textures) is not implemented on the device"; return WTGPU_E_UNSUPPORTED; }
+    // plt_bdpt.cpp:189-194: the Fraunhofer sampling tables are only needed (and only loaded by the reference) when the sensor is not ray-tracing only
+    if (bdpt && desc->integrator.fsd && !desc->sensor.ray_trace_only && (!desc->fsd_lut_n || !desc->fsd_lut_m || !desc->fsd_icdf1 || !desc->fsd_icdf2 || !desc->fsd_icdf_theta1 || !desc->fsd_icdf_theta2)) {
         g_err = "plt_bdpt with FSD needs the Fraunhofer sampling tables (fsd_lut_*)"; return WTGPU_E_INVALID; }
     if (desc->n_edges >= (1u << 26)) { g_err = "more than 2^26 edges unsupported"; return WTGPU_E_UNSUPPORTED; }
     if (desc->sensor.rf_radius > 4) { g_err = "reconstruction filter radius > 4 unsupported"; return WTGPU_E_UNSUPPORTED; }
@@ -915,6 +922,17 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
     d.sensor = desc->sensor; d.integrator = desc->integrator;
     s->sensor = desc->sensor; s->integ = desc->integrator;
     s->n_keys = desc->n_bsdfs + 3u;
+    // initial list capacities; a render that needs more grows them (wtgpu_render).  plt_bdpt keeps max_depth + 2 vertices per subpath, but
+    // with Russian roulette long subpaths are rare: start at 18 (max_depth 16, the reference scenes' setting) and grow on demand.
+    s->caps.tris = 128u; s->caps.edges = 48u; s->caps.seg = 48u; s->caps.ap_walk = 4u;
+    s->caps.verts = bdpt ? std::min(desc->integrator.max_depth + 2u, 18u) : 0u;
+    if (const char* e = getenv("WT_CAPS")) {    // "tris,edges,seg,ap_walk,verts": initial capacities (tests start tiny to exercise the growth)
+        unsigned v[5] = { s->caps.tris, s->caps.edges, s->caps.seg, s->caps.ap_walk, s->caps.verts };
+        sscanf(e, "%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4]);
+        s->caps.tris = std::max(8u, v[0]); s->caps.edges = std::max(4u, v[1]); s->caps.seg = std::max(4u, v[2]); s->caps.ap_walk = std::max(1u, v[3]);
+        if (bdpt) s->caps.verts = std::min(desc->integrator.max_depth + 2u, std::max(3u, v[4]));
+    }
+    caps_derive(s->caps);
     *out = s;
     return WTGPU_OK;
 }
@@ -929,18 +947,169 @@ void wtgpu_trim(void) {
     cudaSetDevice(cur);
 }
 
-static int ensure_pool(wtgpu_scene* s, uint32_t pool) {
-    if (s->pool == pool) return WTGPU_OK;
-    for (void* p : { (void*)s->core, (void*)s->fsd, (void*)s->hit, (void*)s->alive, (void*)s->keys, (void*)s->order, (void*)s->key_count, (void*)s->key_cursor, (void*)s->ctr, (void*)s->trav_list, (void*)s->trav_rec, (void*)s->trav_tris }) if (p) wt_free(p);
-    s->core = s->fsd = s->hit = nullptr; s->alive = s->keys = s->order = s->key_count = s->key_cursor = s->trav_list = s->trav_tris = nullptr; s->trav_rec = nullptr; s->ctr = nullptr; s->pool = 0;
-    if (s->integ.type == WTGPU_INTEGRATOR_PLT_PATH) { CK(wt_malloc(&s->trav_rec, sizeof(TravRec) * (size_t)pool)); CK(wt_malloc(&s->trav_tris, 4ull * kMaxConeTris * pool)); }
-    CK(wt_malloc(&s->core, (size_t)chunks_of<PathCore>() * 16 * pool));
-    CK(wt_malloc(&s->fsd, (size_t)chunks_of<PathFsd>() * 16 * pool));
-    CK(wt_malloc(&s->hit, (size_t)chunks_of<HitRec>() * 16 * pool));
-    CK(wt_malloc(&s->alive, 4ull * pool)); CK(wt_malloc(&s->keys, 4ull * pool)); CK(wt_malloc(&s->order, 4ull * pool)); CK(wt_malloc(&s->trav_list, 4ull * pool));
-    CK(wt_malloc(&s->key_count, 4ull * s->n_keys)); CK(wt_malloc(&s->key_cursor, 4ull * s->n_keys));
-    CK(wt_malloc(&s->ctr, sizeof(DevCounters)));
-    s->pool = pool;
+// kinds of pool: what the render at hand needs
+enum : uint32_t { POOL_PATH = 1u, POOL_BDPT_WAVE = 2u, POOL_BDPT_MEGA = 3u };
+static uint32_t bdpt_max_pairs(uint32_t verts, uint32_t max_depth) {     // strategies per sample: the enumeration of plt_bdpt.cpp:96-110 at full subpath lengths
+    uint32_t n_pairs = 0;
+    const int n = (int)verts, maxd = (int)max_depth;
+    for (int t = 0; t <= n; ++t) for (int q = 0; q <= n; ++q) { const int depth = t + q - 2; if ((t == 1 && q == 1) || depth < 0) continue; if (depth > maxd) break; ++n_pairs; }
+    return n_pairs;
+}
+static size_t pool_bytes(const wtgpu_scene* s, uint32_t kind, uint32_t pool, const Caps& c) {
+    const size_t P = pool;
+    if (kind == POOL_PATH) return P * (16ull * (chunks_of<PathCore>() + chunks_of<PathFsd>() + chunks_of<HitRec>()) + sizeof(TravRec) + 4ull * c.tris + 12ull * c.edges + 16ull);
+    if (kind == POOL_BDPT_MEGA) return P * (4ull * c.arena_words + 4ull * c.tris + 4ull * c.edges);
+    const size_t W2 = 2 * P;
+    return P * (4ull * c.arena_words + 16ull * chunks_of<BdHeader>() + 8ull * (bdpt_max_pairs(c.verts, s->integ.max_depth) + 4ull * (c.verts + 1u)) + 16ull) +
+           W2 * (16ull * (chunks_of<BdWalker>() + chunks_of<HitRec>()) + sizeof(TravRec) + 4ull * c.tris + 4ull * c.edges + 12ull + 32ull + 16ull);
+}
+static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool) {
+    if (s->pool == pool && s->pool_kind == kind && caps_equal(s->pool_caps, s->caps)) return WTGPU_OK;
+    s->free_pool();
+    const Caps& c = s->caps;
+    int rc = WTGPU_OK;
+    auto get = [&](auto** p, size_t bytes) { if (rc != WTGPU_OK) return; cudaError_t e = wt_malloc(p, std::max<size_t>(bytes, 16)); if (e != cudaSuccess) { g_err = std::string("device allocation of the path pool: ") + cudaGetErrorString(e); cudaGetLastError(); rc = WTGPU_E_CUDA; *p = nullptr; } else s->pool_allocs.push_back((void*)*p); };
+    const size_t P = pool;
+    get(&s->ctr, sizeof(DevCounters));
+    get(&s->key_count, 4ull * s->n_keys); get(&s->key_cursor, 4ull * s->n_keys);
+    if (kind == POOL_PATH) {
+        get(&s->trav_rec, sizeof(TravRec) * P); get(&s->trav_tris, 4ull * c.tris * P); get(&s->hit_edges, 4ull * c.edges * P); get(&s->ap_edges, 8ull * c.edges * P);
+        get(&s->core, (size_t)chunks_of<PathCore>() * 16 * P); get(&s->fsd, (size_t)chunks_of<PathFsd>() * 16 * P); get(&s->hit, (size_t)chunks_of<HitRec>() * 16 * P);
+        get(&s->alive, 4ull * P); get(&s->keys, 4ull * P); get(&s->order, 4ull * P); get(&s->trav_list, 4ull * P);
+    } else if (kind == POOL_BDPT_MEGA) {
+        get(&s->bdpt_arena, 4ull * c.arena_words * P); get(&s->trav_tris, 4ull * c.tris * P); get(&s->hit_edges, 4ull * c.edges * P);
+    } else {
+        const size_t W2 = 2 * P;
+        get(&s->bdpt_arena, 4ull * c.arena_words * P);
+        get(&s->bd_walkers, (size_t)chunks_of<BdWalker>() * 16 * W2); get(&s->bd_headers, (size_t)chunks_of<BdHeader>() * 16 * P); get(&s->hit, (size_t)chunks_of<HitRec>() * 16 * W2);
+        get(&s->bd_pending, 4ull * P); get(&s->bd_L0, 4ull * P); get(&s->bd_nverts, 4ull * W2); get(&s->alive, 4ull * P);
+        get(&s->keys, 4ull * W2); get(&s->order, 4ull * W2); get(&s->trav_list, 4ull * W2);
+        get(&s->bd_pairs, 8ull * P * (bdpt_max_pairs(c.verts, s->integ.max_depth) + 4ull * (c.verts + 1u)));
+        get(&s->trav_rec, sizeof(TravRec) * W2); get(&s->trav_tris, 4ull * c.tris * W2); get(&s->hit_edges, 4ull * c.edges * W2);
+        get(&s->bd_fsd_list, 12ull * W2); get(&s->bd_fsd_out, 32ull * W2);
+    }
+    if (rc != WTGPU_OK) { s->free_pool(); return rc; }
+    s->pool = pool; s->pool_kind = kind; s->pool_caps = s->caps;
+    return WTGPU_OK;
+}
+
+__global__ void k_film_add(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+// One pass over the samples with the scene handle's current capacities, into the device films dblock / dlight.  The counters are left in s->hctr.
+static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t pool, uint32_t kind, float* dblock, float* dlight, unsigned long long total, uint32_t x1, uint32_t y1,
+                       bool use_thread_trav, bool time_phases, size_t& n_ev, uint64_t& launches, uint64_t& iters) {
+    cudaStream_t st = (cudaStream_t)o->stream;
+    const bool bdpt = kind != POOL_PATH;
+    s->d.cap = s->caps;
+    RenderArgs a;
+    a.sc = s->d; a.core = s->core; a.fsd = s->fsd; a.hit = s->hit; a.alive = s->alive; a.keys = s->keys; a.order = s->order;
+    a.trav_rec = s->trav_rec; a.trav_tris = s->trav_tris; a.hit_edges = s->hit_edges; a.ap_edges = s->ap_edges; a.it_parity = 0u;
+    a.key_count = s->key_count; a.key_cursor = s->key_cursor; a.trav_list = s->trav_list; a.ctr = s->ctr; a.film_block = dblock; a.film_light = dlight;
+    a.pool = pool; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
+    a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
+    a.sample_begin = o->sample_begin; a.n_samples = o->sample_end - o->sample_begin; a.total = total;
+
+    if (s->alive) CK(cudaMemsetAsync(s->alive, 0, 4ull * pool, st));
+    CK(cudaMemsetAsync(s->key_count, 0, 4ull * s->n_keys, st));
+    CK(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
+    DevCounters* const hctr = s->hctr;
+    // Block size of the one-thread-per-item kernels (generate / resolve / sort / shade / connect).  Their warps run for very different times (a
+    // path with thousands of UTD edges next to paths that die at once), and a block's slots are only handed on when its LAST warp retires:
+    // with one warp per block a finished warp is replaced immediately.  (The group-traversal and Fraunhofer-sampler kernels keep 128: their
+    // shared-memory layout is per 128 threads and they pull work from a cursor anyway.)  WT_BLOCK_T overrides for A/B runs.
+    static const unsigned bt = []() { const char* e = getenv("WT_BLOCK_T"); const unsigned v = e ? (unsigned)atoi(e) : kBlockT; return (v == 32u || v == 64u || v == 128u) ? v : kBlockT; }();
+    int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
+    const dim3 blk(128), blkT(bt), grd((pool + bt - 1) / bt);
+    const bool nosort = (o->flags & WTGPU_RENDER_NO_SORT) != 0;
+    std::vector<cudaEvent_t>& evs = s->ev_pool;
+    auto mark = [&]() { if (time_phases) { if (n_ev == evs.size()) { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); } cudaEventRecord(evs[n_ev++], st); } };
+    if (kind == POOL_BDPT_MEGA) {     // one thread per sample, one launch (dbdpt.cuh driver 1)
+        BdptArgs b;
+        b.sc = s->d; b.lut = s->lut; b.arena = s->bdpt_arena; b.P = pool; b.trav_tris = s->trav_tris; b.hit_edges = s->hit_edges; b.ctr = s->ctr; b.film_block = dblock; b.film_light = dlight;
+        b.seed_lo = a.seed_lo; b.seed_hi = a.seed_hi; b.tile_x0 = a.tile_x0; b.tile_y0 = a.tile_y0; b.tile_w = a.tile_w; b.tile_h = a.tile_h; b.sample_begin = a.sample_begin; b.total = total;
+        k_bdpt<<<pool / 128, blk, 0, st>>>(b); ++launches; ++iters;
+        CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    } else if (bdpt) {      // wavefront (dbdpt.cuh driver 2)
+        const uint32_t P = pool, W2 = 2u * pool;
+        const uint32_t nmaxv = s->caps.verts + 1u;
+        BdArgs b;
+        b.r = a; b.r.pool = W2;
+        b.lut = s->lut; b.arena = s->bdpt_arena; b.P = P; b.walkers = s->bd_walkers; b.headers = s->bd_headers;
+        b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs; b.fsd_list = s->bd_fsd_list; b.fsd_out = s->bd_fsd_out; b.trav_rec = s->trav_rec; b.trav_tris = s->trav_tris;
+        for (int c = 0; c < 5; ++c) b.pair_off[c] = (size_t)P * nmaxv * (size_t)c;      // classes 0-3 hold <= cap.verts + 1 strategies per sample, class 4 the rest
+        const bool has_fsd = s->integ.fsd != 0u && !s->sensor.ray_trace_only;
+        const dim3 gP((P + bt - 1) / bt), gW((W2 + bt - 1) / bt), gC(n_sm * 8), gCT(n_sm * 8 * (128 / bt));
+        if (has_fsd && !s->bd_stream) {
+            CK(cudaStreamCreateWithFlags(&s->bd_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s->bd_ev_shade, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->bd_ev_samp, cudaEventDisableTiming));
+        }
+        const uint64_t it0 = iters;
+        for (;;) {
+            // Fraunhofer direction sampling of iteration j runs on bd_stream, overlapped with the strategies of j and the walk kernels
+            // of j+1; its walkers rejoin at "finish" in iteration j+1.  Three rotating lists keep producer and consumers apart.
+            const uint64_t it = iters - it0;
+            b.fl_cur = (uint32_t)(it % 3ull); b.fl_next = (uint32_t)((it + 1ull) % 3ull); b.fl_fin = (uint32_t)((it + 2ull) % 3ull);
+            b.tag = 16.f + (float)(it % 1024ull); b.tag_fin = 16.f + (float)((it + 1023ull) % 1024ull);
+            mark();
+            k_bd_generate<<<gP, blkT, 0, st>>>(b); ++launches; mark();
+            if (use_thread_trav) { k_bd_traverse<<<gW, blkT, 0, st>>>(b); ++launches; }
+            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blkT, 0, st>>>(b); launches += 2; }
+            mark();
+            k_hist<<<gW, blkT, s->n_keys * 4, st>>>(b.r);
+            k_scan<<<1, 1024, 0, st>>>(b.r);
+            k_scatter<<<gW, blkT, 0, st>>>(b.r); launches += 3; mark();
+            k_bd_reset<<<1, 32, 0, st>>>(b);
+            k_bd_shade<<<gW, blkT, 0, st>>>(b); launches += 2;
+            if (has_fsd) {
+                CK(cudaEventRecord(s->bd_ev_shade, st));
+                if (it > 0) { CK(cudaStreamWaitEvent(st, s->bd_ev_samp, 0)); k_bd_fsd_finish<<<gW, blkT, 0, st>>>(b); ++launches; }
+                CK(cudaStreamWaitEvent(s->bd_stream, s->bd_ev_shade, 0));
+                CK(cudaMemsetAsync(&s->ctr->fsd_head, 0, sizeof(int), s->bd_stream));
+                k_bd_fsd_sample<<<dim3(n_sm * 16), blk, 0, s->bd_stream>>>(b); ++launches;
+                CK(cudaEventRecord(s->bd_ev_samp, s->bd_stream));
+            }
+            mark();
+            k_bd_connect<0><<<gCT, blkT, 0, st>>>(b); k_bd_connect<1><<<gCT, blkT, 0, st>>>(b); k_bd_connect<2><<<gCT, blkT, 0, st>>>(b);
+            k_bd_connect<3><<<gCT, blkT, 0, st>>>(b); k_bd_connect<4><<<gCT, blkT, 0, st>>>(b); launches += 5; mark();
+            ++iters;
+            CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (hctr->next_sample >= total && hctr->live <= 0) break;
+            if (iters - it0 > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
+        }
+        if (has_fsd) CK(cudaStreamSynchronize(s->bd_stream));
+        CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        const uint64_t it0 = iters;
+        for (;;) {
+            a.it_parity = (uint32_t)((iters - it0) & 1ull);
+            mark();
+            k_generate<<<grd, blkT, 0, st>>>(a); ++launches; mark();
+            if (use_thread_trav) { k_traverse<<<grd, blkT, 0, st>>>(a); ++launches; }
+            else { k_gtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_resolve<<<grd, blkT, 0, st>>>(a); launches += 2; }
+            mark();
+            if (nosort) {
+                k_identity_order<<<grd, blkT, 0, st>>>(a); ++launches;
+            } else {
+                k_hist<<<grd, blkT, s->n_keys * 4, st>>>(a);
+                k_scan<<<1, 1024, 0, st>>>(a);
+                k_scatter<<<grd, blkT, 0, st>>>(a); launches += 3;
+            }
+            mark();
+            k_reset_trav<<<1, 32, 0, st>>>(a);
+            k_shade<<<grd, blkT, 0, st>>>(a); launches += 2; mark();
+            ++iters;
+            CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (hctr->next_sample >= total && hctr->live <= 0) break;
+            if (iters - it0 > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
+        }
+    }
+    CK(cudaGetLastError());
     return WTGPU_OK;
 }
 
@@ -959,171 +1128,82 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     cudaStream_t st = (cudaStream_t)o->stream;
     const unsigned long long total = (unsigned long long)(x1 - o->tile_x0) * (y1 - o->tile_y0) * (o->sample_end - o->sample_begin);
     const bool bdpt = s->integ.type == WTGPU_INTEGRATOR_PLT_BDPT;
-    uint32_t pool = o->pool_size ? o->pool_size : (bdpt ? ((o->flags & WTGPU_RENDER_BDPT_MEGAKERNEL) ? 148u * 8u * 128u : (1u << 18)) : (1u << 20));
+    const uint32_t kind = !bdpt ? POOL_PATH : (o->flags & WTGPU_RENDER_BDPT_MEGAKERNEL) ? POOL_BDPT_MEGA : POOL_BDPT_WAVE;
+    int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
+    uint32_t pool = o->pool_size ? o->pool_size : (kind == POOL_BDPT_MEGA ? (uint32_t)n_sm * 8u * 128u : kind == POOL_BDPT_WAVE ? (1u << 18) : (1u << 20));
+    if (pool > (1u << 22) && bdpt) { g_err = "plt_bdpt: pool_size > 4M sample slots"; return WTGPU_E_INVALID; }
     pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>(total, 1024ull));
     pool = (pool + 127u) & ~127u;
-    int rc = ensure_pool(s, pool);
-    if (rc != WTGPU_OK) return rc;
 
-    const size_t nb = (size_t)W * H * C * 2, nl = (size_t)W * H * C;
-    float *dblock = film_block, *dlight = film_light;
-    const bool on_dev = o->film_on_device != 0;
-    if (!on_dev) {
-        CK(wt_malloc(&dblock, nb * 4)); CK(wt_malloc(&dlight, nl * 4));
-        CK(cudaMemsetAsync(dblock, 0, nb * 4, st)); CK(cudaMemsetAsync(dlight, 0, nl * 4, st));
-    }
-
-    {   // the group-traversal kernels keep their stacks in shared memory (24.5 KB per block): ask for the large shared-memory carve-out so that the
-        // register file, not the L1/shared split, bounds the resident blocks
-        static bool once = false;
-        if (!once) {
+    {   // the group-traversal kernels keep their stacks in shared memory: ask for the large shared-memory carve-out so that the register file, not
+        // the L1/shared split, bounds the resident blocks (per device: a process may drive several)
+        static std::mutex m; static std::vector<int> done;
+        std::lock_guard<std::mutex> l(m);
+        if (std::find(done.begin(), done.end(), s->device) == done.end()) {
             cudaFuncSetAttribute(k_gtraverse, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(wt::k_bd_gtraverse, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            once = true;
+            done.push_back(s->device);
         }
     }
     s->d.ray_cull_abs = (o->flags & WTGPU_RENDER_NO_RAY_CULL) ? std::numeric_limits<float>::infinity() : s->ray_cull_abs;
-    RenderArgs a;
-    a.sc = s->d; a.core = s->core; a.fsd = s->fsd; a.hit = s->hit; a.alive = s->alive; a.keys = s->keys; a.order = s->order;
-    a.trav_rec = s->trav_rec; a.trav_tris = s->trav_tris;
-    a.key_count = s->key_count; a.key_cursor = s->key_cursor; a.trav_list = s->trav_list; a.ctr = s->ctr; a.film_block = dblock; a.film_light = dlight;
-    a.pool = pool; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
-    a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
-    a.sample_begin = o->sample_begin; a.n_samples = o->sample_end - o->sample_begin; a.total = total;
-
-    CK(cudaMemsetAsync(s->alive, 0, 4ull * pool, st));
-    CK(cudaMemsetAsync(s->key_count, 0, 4ull * s->n_keys, st));
-    CK(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
-
     // traverse(): eight lanes per beam pay off when queries are long (cone queries over real geometry); on a handful of triangles one thread
     // per beam is faster (measured: double_slits plt_path 99 vs 52 Msamples/s; etoile-like 6 vs 16).  Both give bit-identical results.
     const bool use_thread_trav = (o->flags & WTGPU_RENDER_THREAD_TRAVERSE) ? true : (o->flags & WTGPU_RENDER_GROUP_TRAVERSE) ? false : (!bdpt && s->d.n_tris < 128u);
     if (!s->hctr) { CK(cudaMallocHost(&s->hctr, sizeof(DevCounters))); CK(cudaEventCreate(&s->ev_begin)); CK(cudaEventCreate(&s->ev_end)); }
-    const cudaEvent_t e0 = s->ev_begin, e1 = s->ev_end;
     DevCounters* const hctr = s->hctr;
-    // Block size of the one-thread-per-item kernels (generate / resolve / sort / shade / connect).  Their warps run for very different times (a
-    // path with thousands of UTD edges next to paths that die at once), and a block's slots are only handed on when its LAST warp retires:
-    // with one warp per block a finished warp is replaced immediately.  (The group-traversal and Fraunhofer-sampler kernels keep 128: their
-    // shared-memory layout is per 128 threads and they pull work from a cursor anyway.)  WT_BLOCK_T overrides for A/B runs.
-    static const unsigned bt = []() { const char* e = getenv("WT_BLOCK_T"); const unsigned v = e ? (unsigned)atoi(e) : kBlockT; return (v == 32u || v == 64u || v == 128u) ? v : kBlockT; }();
-    const dim3 blk(128), blkT(bt), grd((pool + bt - 1) / bt);
-    const bool nosort = (o->flags & WTGPU_RENDER_NO_SORT) != 0;
-    uint64_t launches = 0, iters = 0;
-    // per-kernel device time: events are only RECORDED inside the loop (no host sync) and resolved after the last iteration
+
+    // The films of this call are accumulated in scratch device buffers and added to the caller's at the end: a pass that finds a list longer
+    // than its row (capacity growth, below) is discarded and repeated, and must not have touched the caller's film.
+    const size_t nb = (size_t)W * H * C * 2, nl = (size_t)W * H * C;
+    const bool on_dev = o->film_on_device != 0;
+    float *dblock = nullptr, *dlight = nullptr;
+    struct Scratch { float*& a; float*& b; ~Scratch() { if (a) wt_free(a); if (b) wt_free(b); } } scratch{ dblock, dlight };
+    CK(wt_malloc(&dblock, nb * 4)); CK(wt_malloc(&dlight, nl * 4));
+
     const bool time_phases = stats != nullptr && (o->flags & WTGPU_RENDER_TIME_KERNELS) != 0;
-    std::vector<cudaEvent_t>& evs = s->ev_pool;
-    size_t n_ev = 0;
-    auto mark = [&]() { if (time_phases) { if (n_ev == evs.size()) { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); } cudaEventRecord(evs[n_ev++], st); } };
-    CK(cudaEventRecord(e0, st));
-    if (bdpt && (o->flags & WTGPU_RENDER_BDPT_MEGAKERNEL)) {     // one thread per sample, one launch (dbdpt.cuh driver 1)
-        if (s->bdpt_P != pool) {
-            if (s->bdpt_arena) wt_free(s->bdpt_arena);
-            s->bdpt_arena = nullptr; s->bdpt_P = 0;
-            CK(wt_malloc(&s->bdpt_arena, (size_t)wt::kArenaWords * 4 * pool));
-            s->bdpt_P = pool;
-        }
-        BdptArgs b;
-        b.sc = s->d; b.lut = s->lut; b.arena = s->bdpt_arena; b.P = pool; b.ctr = s->ctr; b.film_block = dblock; b.film_light = dlight;
-        b.seed_lo = a.seed_lo; b.seed_hi = a.seed_hi; b.tile_x0 = a.tile_x0; b.tile_y0 = a.tile_y0; b.tile_w = a.tile_w; b.tile_h = a.tile_h; b.sample_begin = a.sample_begin; b.total = total;
-        k_bdpt<<<pool / 128, blk, 0, st>>>(b); ++launches; ++iters;
-        CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-    } else if (bdpt) {      // wavefront (dbdpt.cuh driver 2)
-        const uint32_t P = pool, W2 = 2u * pool;
-        const uint32_t nmaxv = s->integ.max_depth + 3u;
-        uint32_t max_pairs = 0;     // strategies per sample: the enumeration of plt_bdpt.cpp:96-110 at full subpath lengths
-        {
-            const int n = (int)s->integ.max_depth + 2, maxd = (int)s->integ.max_depth;
-            for (int t = 0; t <= n; ++t) for (int q = 0; q <= n; ++q) { const int depth = t + q - 2; if ((t == 1 && q == 1) || depth < 0) continue; if (depth > maxd) break; ++max_pairs; }
-        }
-        if (s->bd_wave_P != P) {
-            s->free_bd_wave();
-            if (s->bdpt_P != P) { if (s->bdpt_arena) wt_free(s->bdpt_arena); s->bdpt_arena = nullptr; s->bdpt_P = 0; CK(wt_malloc(&s->bdpt_arena, (size_t)wt::kArenaWords * 4 * P)); s->bdpt_P = P; }
-            CK(wt_malloc(&s->bd_walkers, (size_t)chunks_of<BdWalker>() * 16 * W2)); CK(wt_malloc(&s->bd_headers, (size_t)chunks_of<BdHeader>() * 16 * P));
-            CK(wt_malloc(&s->bd_hit, (size_t)chunks_of<HitRec>() * 16 * W2));
-            CK(wt_malloc(&s->bd_pending, 4ull * P)); CK(wt_malloc(&s->bd_L0, 4ull * P)); CK(wt_malloc(&s->bd_nverts, 4ull * W2)); CK(wt_malloc(&s->bd_alive, 4ull * P));
-            CK(wt_malloc(&s->bd_keys, 4ull * W2)); CK(wt_malloc(&s->bd_order, 4ull * W2)); CK(wt_malloc(&s->bd_trav, 4ull * W2));
-            CK(wt_malloc(&s->bd_pairs, 4ull * (size_t)P * (max_pairs + 4ull * nmaxv)));
-            CK(wt_malloc(&s->bd_trav_rec, sizeof(TravRec) * (size_t)W2)); CK(wt_malloc(&s->bd_trav_tris, 4ull * kMaxConeTris * W2));
-            CK(wt_malloc(&s->bd_fsd_list, 12ull * W2)); CK(wt_malloc(&s->bd_fsd_out, 32ull * W2));
-            s->bd_wave_P = P;
-        }
-        if (P > (1u << 22)) { g_err = "plt_bdpt: pool_size > 4M sample slots"; return WTGPU_E_INVALID; }
-        BdArgs b;
-        b.r = a; b.r.hit = s->bd_hit; b.r.alive = s->bd_alive; b.r.keys = s->bd_keys; b.r.order = s->bd_order; b.r.trav_list = s->bd_trav; b.r.pool = W2;
-        b.lut = s->lut; b.arena = s->bdpt_arena; b.P = P; b.walkers = s->bd_walkers; b.headers = s->bd_headers;
-        b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs; b.fsd_list = s->bd_fsd_list; b.fsd_out = s->bd_fsd_out; b.trav_rec = s->bd_trav_rec; b.trav_tris = s->bd_trav_tris;
-        const bool thread_trav = use_thread_trav;
-        for (int c = 0; c < 5; ++c) b.pair_off[c] = (size_t)P * nmaxv * (size_t)c;      // classes 0-3 hold <= max_depth+3 strategies per sample, class 4 the rest
-        const bool has_fsd = s->integ.fsd != 0u;
-        CK(cudaMemsetAsync(s->bd_alive, 0, 4ull * P, st));
-        const dim3 gP((P + bt - 1) / bt), gW((W2 + bt - 1) / bt), gC(148 * 8), gCT(148 * 8 * (128 / bt));
-        if (has_fsd && !s->bd_stream) {
-            CK(cudaStreamCreateWithFlags(&s->bd_stream, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&s->bd_ev_shade, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->bd_ev_samp, cudaEventDisableTiming));
-        }
-        for (;;) {
-            // Fraunhofer direction sampling of iteration j runs on bd_stream, overlapped with the strategies of j and the walk kernels
-            // of j+1; its walkers rejoin at "finish" in iteration j+1.  Three rotating lists keep producer and consumers apart.
-            b.fl_cur = (uint32_t)(iters % 3ull); b.fl_next = (uint32_t)((iters + 1ull) % 3ull); b.fl_fin = (uint32_t)((iters + 2ull) % 3ull);
-            b.tag = 16.f + (float)(iters % 1024ull); b.tag_fin = 16.f + (float)((iters + 1023ull) % 1024ull);
-            mark();
-            k_bd_generate<<<gP, blkT, 0, st>>>(b); ++launches; mark();
-            if (thread_trav) { k_bd_traverse<<<gW, blkT, 0, st>>>(b); ++launches; }
-            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blkT, 0, st>>>(b); launches += 2; }
-            mark();
-            k_hist<<<gW, blkT, s->n_keys * 4, st>>>(b.r);
-            k_scan<<<1, 1024, 0, st>>>(b.r);
-            k_scatter<<<gW, blkT, 0, st>>>(b.r); launches += 3; mark();
-            k_bd_reset<<<1, 32, 0, st>>>(b);
-            k_bd_shade<<<gW, blkT, 0, st>>>(b); launches += 2;
-            if (has_fsd) {
-                CK(cudaEventRecord(s->bd_ev_shade, st));
-                if (iters > 0) { CK(cudaStreamWaitEvent(st, s->bd_ev_samp, 0)); k_bd_fsd_finish<<<gW, blkT, 0, st>>>(b); ++launches; }
-                CK(cudaStreamWaitEvent(s->bd_stream, s->bd_ev_shade, 0));
-                CK(cudaMemsetAsync(&s->ctr->fsd_head, 0, sizeof(int), s->bd_stream));
-                k_bd_fsd_sample<<<dim3(148 * 16), blk, 0, s->bd_stream>>>(b); ++launches;
-                CK(cudaEventRecord(s->bd_ev_samp, s->bd_stream));
-            }
-            mark();
-            k_bd_connect<0><<<gCT, blkT, 0, st>>>(b); k_bd_connect<1><<<gCT, blkT, 0, st>>>(b); k_bd_connect<2><<<gCT, blkT, 0, st>>>(b);
-            k_bd_connect<3><<<gCT, blkT, 0, st>>>(b); k_bd_connect<4><<<gCT, blkT, 0, st>>>(b); launches += 5; mark();
-            ++iters;
-            CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (hctr->next_sample >= total && hctr->live <= 0) break;
-            if (iters > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
-        }
-        if (has_fsd) CK(cudaStreamSynchronize(s->bd_stream));
-    } else
+    uint64_t launches = 0, iters = 0; size_t n_ev = 0;
+    uint32_t passes = 0;
+    CK(cudaEventRecord(s->ev_begin, st));
+    // ---- capacity growth: two-pass count / fill at the granularity of the render.  The reference keeps cone-query results, edge sets,
+    // aperture segments and subpath vertices in std::vector / std::set of any length; here they are rows of HBM arrays.  A pass records the longest
+    // list any too-short row was asked to hold; the rows are re-sized and the pass repeated, so a result never depends on a capacity.  The
+    // capacities stay with the scene handle: the next render of this scene starts with rows that fitted.
     for (;;) {
-        mark();
-        k_generate<<<grd, blkT, 0, st>>>(a); ++launches; mark();
-        if (use_thread_trav) { k_traverse<<<grd, blkT, 0, st>>>(a); ++launches; }
-        else { k_gtraverse<<<dim3(148 * 8), blk, 0, st>>>(a); k_resolve<<<grd, blkT, 0, st>>>(a); launches += 2; }
-        mark();
-        if (nosort) {
-            k_identity_order<<<grd, blkT, 0, st>>>(a); ++launches;
-        } else {
-            k_hist<<<grd, blkT, s->n_keys * 4, st>>>(a);
-            k_scan<<<1, 1024, 0, st>>>(a);
-            k_scatter<<<grd, blkT, 0, st>>>(a); launches += 3;
+        size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+        uint32_t use_pool = pool;
+        if (!(s->pool == pool && s->pool_kind == kind && caps_equal(s->pool_caps, s->caps))) {
+            s->free_pool();
+            cudaMemGetInfo(&free_b, &total_b);
+            while (use_pool > 4096u && pool_bytes(s, kind, use_pool, s->caps) > (size_t)(0.85 * (double)free_b) + 0) use_pool = ((use_pool / 2u) + 127u) & ~127u;     // long rows: fewer paths in flight
         }
-        mark();
-        k_reset_trav<<<1, 32, 0, st>>>(a);
-        k_shade<<<grd, blkT, 0, st>>>(a); launches += 2; mark();
-        ++iters;
-        CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (hctr->next_sample >= total && hctr->live <= 0) break;
-        if (iters > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
+        int rc = ensure_pool(s, kind, use_pool);
+        if (rc != WTGPU_OK) return rc;
+        pool = use_pool;
+        CK(cudaMemsetAsync(dblock, 0, nb * 4, st)); CK(cudaMemsetAsync(dlight, 0, nl * 4, st));
+        n_ev = 0;
+        rc = render_pass(s, o, pool, kind, dblock, dlight, total, x1, y1, use_thread_trav, time_phases, n_ev, launches, iters);
+        if (rc != WTGPU_OK) return rc;
+        ++passes;
+        if (hctr->overflow == 0) break;
+        Caps nc = s->caps;
+        auto grow = [](uint32_t cur, uint32_t need) { return need > cur ? std::max((need + 31u) & ~31u, cur + cur / 2u) : cur; };
+        nc.tris = grow(nc.tris, hctr->need_tris); nc.edges = grow(nc.edges, hctr->need_edges); nc.seg = grow(nc.seg, hctr->need_seg);
+        nc.ap_walk = std::min(grow(nc.ap_walk, hctr->need_ap), std::max(s->integ.max_depth, 1u));
+        if (bdpt) nc.verts = std::min(grow(nc.verts, hctr->need_verts), s->integ.max_depth + 2u);
+        caps_derive(nc);
+        if (caps_equal(nc, s->caps) || passes >= 12u) {
+            g_err = "a per-path list outgrew its capacity and could not be grown further (tris " + std::to_string(hctr->need_tris) + ", edges " + std::to_string(hctr->need_edges) +
+                    ", segments " + std::to_string(hctr->need_seg) + ", apertures " + std::to_string(hctr->need_ap) + ", vertices " + std::to_string(hctr->need_verts) + ")";
+            return WTGPU_E_CAPACITY;
+        }
+        s->caps = nc;
     }
-    CK(cudaEventRecord(e1, st));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaGetLastError());
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    CK(cudaEventRecord(s->ev_end, st));
+    CK(cudaEventSynchronize(s->ev_end));
+    float ms = 0; cudaEventElapsedTime(&ms, s->ev_begin, s->ev_end);
     double t_trav = 0, t_shade = 0, t_gen = 0, t_sort = 0, t_conn = 0;
-    const size_t per_it = (bdpt && !(o->flags & WTGPU_RENDER_BDPT_MEGAKERNEL)) ? 6 : 5;      // marks per iteration
+    std::vector<cudaEvent_t>& evs = s->ev_pool;
+    const size_t per_it = (kind == POOL_BDPT_WAVE) ? 6 : 5;      // marks per iteration
     for (size_t i = 0; i + per_it - 1 < n_ev; i += per_it) {
         float f;
         cudaEventElapsedTime(&f, evs[i], evs[i + 1]); t_gen += f;
@@ -1133,13 +1213,16 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         if (per_it == 6) { cudaEventElapsedTime(&f, evs[i + 4], evs[i + 5]); t_conn += f; }
     }
 
-    if (!on_dev) {
+    if (on_dev) {
+        if (film_block) k_film_add<<<dim3(n_sm * 4), 256, 0, st>>>(film_block, dblock, nb);
+        if (film_light) k_film_add<<<dim3(n_sm * 4), 256, 0, st>>>(film_light, dlight, nl);
+        CK(cudaStreamSynchronize(st));
+    } else {
         std::vector<float> tmp(std::max(nb, nl));
         CK(cudaMemcpy(tmp.data(), dblock, nb * 4, cudaMemcpyDeviceToHost));
         if (film_block) for (size_t i = 0; i < nb; ++i) film_block[i] += tmp[i];
         CK(cudaMemcpy(tmp.data(), dlight, nl * 4, cudaMemcpyDeviceToHost));
         if (film_light) for (size_t i = 0; i < nl; ++i) film_light[i] += tmp[i];
-        wt_free(dblock); wt_free(dlight);
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -1151,9 +1234,27 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         stats->gpu_ms = ms; stats->traverse_ms = t_trav; stats->shade_ms = t_shade; stats->generate_ms = t_gen; stats->sort_ms = t_sort; stats->connect_ms = t_conn;
         for (int c = 0; c < 5; ++c) stats->strategies[c] = hctr->strategies[c];
         stats->walker_steps = hctr->walker_steps;
+        stats->passes = passes; stats->stack_drops = hctr->stack_drops; stats->pool_used = pool;
+        stats->cap_tris = s->caps.tris; stats->cap_edges = s->caps.edges; stats->cap_segments = s->caps.seg; stats->cap_apertures = s->caps.ap_walk; stats->cap_vertices = s->caps.verts;
     }
-    const bool overflowed = hctr->overflow != 0;
-    if (overflowed) { g_err = "a bounded per-path list (cone triangles / edges) overflowed; results were still produced"; return WTGPU_E_CAPACITY; }
+    if (hctr->stack_drops) {
+        g_err = "a BVH traversal stack (64 entries for rays, 128 for cones, as bvh8w.cpp's) was full " + std::to_string((unsigned long long)hctr->stack_drops) + " times and dropped children: the tree is too deep for the reference's traversal";
+        return WTGPU_E_CAPACITY;
+    }
+    return WTGPU_OK;
+}
+
+int wtgpu_get_capacities(wtgpu_scene* s, uint32_t out[5]) {
+    if (!s || !out) { g_err = "null argument"; return WTGPU_E_INVALID; }
+    out[0] = s->caps.tris; out[1] = s->caps.edges; out[2] = s->caps.seg; out[3] = s->caps.ap_walk; out[4] = s->caps.verts;
+    return WTGPU_OK;
+}
+int wtgpu_set_capacities(wtgpu_scene* s, const uint32_t in[5]) {
+    if (!s || !in) { g_err = "null argument"; return WTGPU_E_INVALID; }
+    const bool bdpt = s->integ.type == WTGPU_INTEGRATOR_PLT_BDPT;
+    s->caps.tris = std::max(8u, in[0]); s->caps.edges = std::max(4u, in[1]); s->caps.seg = std::max(4u, in[2]); s->caps.ap_walk = std::max(1u, in[3]);
+    s->caps.verts = bdpt ? std::min(s->integ.max_depth + 2u, std::max(3u, in[4])) : 0u;
+    caps_derive(s->caps);
     return WTGPU_OK;
 }
 

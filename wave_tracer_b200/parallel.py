@@ -37,6 +37,18 @@ def render_distributed(gpu_scene, spp, seed=0x5EED, pool_size=0, flags=0):
     light = torch.zeros((b.height, b.width, b.channels), dtype=torch.float32, device=dev)
     s0, s1 = partition_samples(spp, rank, world)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    st = gpu_scene.render_into(block.data_ptr(), light.data_ptr(), spp, seed, (s0, s1), None, True, pool_size, flags, stream)
+    # A rank must never leave for an exception while the others wait in the collective: the status is agreed on first.
+    st, err = None, None
+    try:
+        st = gpu_scene.render_into(block.data_ptr(), light.data_ptr(), spp, seed, (s0, s1), None, True, pool_size, flags, stream)
+    except Exception as e:      # noqa: BLE001 -- reported on every rank below
+        err = e
+    if world > 1:
+        bad = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) and err is None:
+            err = RuntimeError("wtgpu_render failed on another rank")
+    if err is not None:
+        raise err
     block, light = reduce_films(block, light)
     return block, light, st

@@ -27,7 +27,14 @@ class GpuScene:
         try: self.close()
         except Exception: pass
 
-    def render_into(self, block_ptr, light_ptr, spp, seed=0x5EED, sample_range=None, tile=None, on_device=False, pool_size=0, flags=0, stream=None, allow_overflow=False):
+    def capacities(self):
+        """Row lengths of the per-path lists {cone triangles, edges, aperture segments, apertures per subpath, vertices per subpath} (include/wtgpu.h)."""
+        out = (C.c_uint32 * 5)(); A.check(A.lib().wtgpu_get_capacities(self.handle, out), "wtgpu_get_capacities"); return list(out)
+
+    def set_capacities(self, caps):
+        A.check(A.lib().wtgpu_set_capacities(self.handle, (C.c_uint32 * 5)(*caps)), "wtgpu_set_capacities")
+
+    def render_into(self, block_ptr, light_ptr, spp, seed=0x5EED, sample_range=None, tile=None, on_device=False, pool_size=0, flags=0, stream=None):
         b = self.built
         o = A.RenderOpts()
         o.seed, o.spp = seed, spp
@@ -37,20 +44,17 @@ class GpuScene:
         o.stream = stream
         o.sampler = getattr(b, "sampler", 0)
         st = A.Stats()
-        rc = A.lib().wtgpu_render(self.handle, C.byref(o), block_ptr, light_ptr, C.byref(st))
-        if rc == -5 and allow_overflow:
-            rc = 0
-        A.check(rc, "wtgpu_render")
+        A.check(A.lib().wtgpu_render(self.handle, C.byref(o), block_ptr, light_ptr, C.byref(st)), "wtgpu_render")
         return st.as_dict()
 
 
-def render(built, spp=None, seed=0x5EED, device=0, sample_range=None, tile=None, pool_size=0, flags=0, gpu_scene=None, allow_overflow=False):
+def render(built, spp=None, seed=0x5EED, device=0, sample_range=None, tile=None, pool_size=0, flags=0, gpu_scene=None):
     """Host-buffer render through the C-ABI (host<->device copies inside the call).  Returns (film_block, film_light, stats)."""
     spp = spp or built.spp
     gs = gpu_scene or GpuScene(built, device)
     W, H, Cn = built.width, built.height, built.channels
     block = np.zeros((H, W, Cn, 2), np.float32); light = np.zeros((H, W, Cn), np.float32)
-    st = gs.render_into(block.ctypes.data_as(C.c_void_p), light.ctypes.data_as(C.c_void_p), spp, seed, sample_range, tile, False, pool_size, flags, None, allow_overflow)
+    st = gs.render_into(block.ctypes.data_as(C.c_void_p), light.ctypes.data_as(C.c_void_p), spp, seed, sample_range, tile, False, pool_size, flags, None)
     if gpu_scene is None:
         gs.close()
     return block, light, st
