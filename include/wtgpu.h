@@ -328,7 +328,8 @@ typedef struct wtgpu_render_opts {
 #define WTGPU_RENDER_THREAD_TRAVERSE 8u  /* one thread per beam in traverse() instead of eight lanes per beam (A/B measurement; bit-identical results) */
 #define WTGPU_RENDER_GROUP_TRAVERSE 16u  /* force eight lanes per beam (default: chosen by scene size for plt_path, always for plt_bdpt) */
 #define WTGPU_RENDER_NO_RAY_CULL 32u /* ray queries walk every node along the infinite ray, as bvh8w.cpp:469-554 does, instead of culling children outside the query range (A/B; same results) */
-#define WTGPU_RENDER_TIME_KERNELS 2u /* record CUDA events around every kernel (fills wtgpu_stats::*_ms) */
+#define WTGPU_RENDER_TIME_KERNELS 2u /* record CUDA events around every kernel (fills wtgpu_stats::*_ms); runs ONE sub-pool so that kernels do not overlap */
+#define WTGPU_RENDER_ONE_SUBPOOL 64u /* one wavefront at a time instead of four side by side (A/B measurement; same results) */
 
 /* Device counters gathered during wtgpu_render (the quantities the reference exposes in a `profile` build:
  * include/wt/ads/ads_stats.hpp:36-95, include/wt/integrator/stats.hpp:27-82); inputs of the roofline byte count. */
@@ -357,8 +358,9 @@ typedef struct wtgpu_stats {
      * the handle keeps the lengths for the next render.  Results therefore never depend on a capacity. */
     uint32_t passes;                /* passes over the samples this call took (1: every list fitted) */
     uint32_t pool_used;             /* paths / sample slots in flight (smaller than asked when long rows would not fit in device memory) */
-    uint32_t cap_tris, cap_edges, cap_segments, cap_apertures, cap_vertices;   /* row lengths after this call */
-    uint32_t pad_;
+    uint32_t cap_tris, cap_edges, cap_segments, cap_apertures, cap_vertices;   /* capacities after this call: entries of the shared cone-triangle-list
+                                       arena (lists longer than 128 triangles continue there; it is recycled every iteration), then the row lengths */
+    uint32_t subpools;              /* independent wavefronts the call ran side by side (1 under WTGPU_RENDER_TIME_KERNELS) */
     uint64_t stack_drops;           /* children a full BVH traversal stack dropped (bvh8w.cpp's stack depths); non-zero => WTGPU_E_CAPACITY */
 } wtgpu_stats;
 
@@ -373,7 +375,7 @@ void wtgpu_scene_destroy(wtgpu_scene* scene);
 void wtgpu_trim(void);
 int wtgpu_render(wtgpu_scene* scene, const wtgpu_render_opts* opts,
                  float* film_block, float* film_light, wtgpu_stats* stats);
-/* row lengths of the per-path lists of a scene handle, {cone triangles, edges, aperture segments, apertures per subpath, vertices per subpath}:
+/* capacities of the per-path lists of a scene handle, {cone-triangle-list arena entries, edges, aperture segments, apertures per subpath, vertices per subpath}:
  * read them / preset them (e.g. from a previous run of the same scene, to skip the measuring pass; or tiny, to test the growth) */
 int wtgpu_get_capacities(wtgpu_scene* scene, uint32_t out[5]);
 int wtgpu_set_capacities(wtgpu_scene* scene, const uint32_t in[5]);

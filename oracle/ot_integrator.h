@@ -75,6 +75,9 @@ inline traversal_result_t traverse(const scene_t& sc, const elliptic_cone_t& env
         if (ballistic_dist == inf || dist >= distance) { res.origin = ray.o; res.ballistic = true; res.empty = true; return res; }
         const f_t min_df_prog = envelope.axes(dist).x / 2.f;
         auto df = intersect_cone(sc.ads, envelope, { dist, distance }, z_search_range, detect_edges, ctr);
+#ifdef ORACLE_CONE_HOOK
+        ORACLE_CONE_HOOK(envelope, dist, df);
+#endif
         if (df.empty() || df.dist - dist >= min_df_prog) {
             res.origin = envelope.o(); res.ballistic = false;
             res.empty = df.empty();

@@ -311,7 +311,7 @@ def test_rgb_polychromatic_film_matches_oracle(integrator):
 @pytest.mark.parametrize("integrator", ["plt_path", "plt_bdpt", "plt_bdpt_mega"])
 def test_list_capacities_grow_and_never_change_a_result(integrator):
     """The reference's cone-query triangle lists, edge sets, Fraunhofer segments / apertures and subpath vertices are unbounded containers
-    (traversal_common.hpp:116-149).  Device rows start tiny here (8 triangles, 4 edges, 4 segments, 1 aperture, 3 vertices per subpath): the
+    (traversal_common.hpp:116-149).  Device capacities start tiny here (a 1024-entry triangle-list arena, 4 edges, 4 segments, 1 aperture, 3 vertices per subpath): the
     render must notice, re-size them (passes > 1), end with zero overflows, and give the film of a render whose rows were long from the start --
     and the oracle's."""
     bd = integrator != "plt_path"
@@ -322,12 +322,12 @@ def test_list_capacities_grow_and_never_change_a_result(integrator):
     blk0, lgt0, st0 = render(b, spp=4, gpu_scene=gs, flags=flags)
     assert st0["capacity_overflows"] == 0 and st0["stack_drops"] == 0
     gs2 = GpuScene(b, 0)
-    gs2.set_capacities([8, 4, 4, 1, 3])
+    gs2.set_capacities([1024, 4, 4, 1, 3])
     blk1, lgt1, st1 = render(b, spp=4, gpu_scene=gs2, flags=flags)
     caps1 = gs2.capacities()
-    print("capacity growth %s: default caps %s (passes %d) | from [8,4,4,1,3]: passes %d -> %s" % (integrator, gs.capacities(), st0["passes"], st1["passes"], caps1))
+    print("capacity growth %s: default caps %s (passes %d) | from [1024,4,4,1,3]: passes %d -> %s" % (integrator, gs.capacities(), st0["passes"], st1["passes"], caps1))
     assert st1["passes"] > 1 and st1["capacity_overflows"] == 0
-    assert caps1[0] > 8 and caps1[1] > 4 and (not bd or (caps1[2] > 4 and caps1[4] > 3))
+    assert caps1[0] > 1024 and caps1[1] > 4 and (not bd or (caps1[2] > 4 and caps1[4] > 3))
     for k in ("samples", "segments", "ray_casts", "cone_casts", "surface_interactions", "fsd_interactions", "null_interactions", "splats"):
         assert st0[k] == st1[k], (k, st0[k], st1[k])
     for x, y in ((blk0, blk1), (lgt0, lgt1)):

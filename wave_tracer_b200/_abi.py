@@ -132,7 +132,7 @@ class Stats(C.Structure):
                                      "surface_interactions", "fsd_interactions", "null_interactions", "splats", "capacity_overflows", "kernel_launches", "iterations",
                                      "traverse_nodes", "traverse_tris", "shaded_paths")] + \
                [(n, c_dbl) for n in ("gpu_ms", "traverse_ms", "shade_ms", "generate_ms", "sort_ms", "connect_ms")] + [("strategies", c_u64 * 5), ("walker_steps", c_u64)] + \
-               [(n, c_u32) for n in ("passes", "pool_used", "cap_tris", "cap_edges", "cap_segments", "cap_apertures", "cap_vertices", "pad_")] + [("stack_drops", c_u64)]
+               [(n, c_u32) for n in ("passes", "pool_used", "cap_tris", "cap_edges", "cap_segments", "cap_apertures", "cap_vertices", "subpools")] + [("stack_drops", c_u64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "strategies" else getattr(self, n)) for n, _ in self._fields_}

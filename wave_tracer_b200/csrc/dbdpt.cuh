@@ -571,29 +571,29 @@ WT_D bool bd_append(const BCtx& c, BWalk& d, BVertex& v, Pd pdf_fwd, Pd pdf_revr
 
 // What one traverse() found, reduced to what the vertex step needs (random_walk :421-470 + find_closest_triangle :362-419)
 struct BHit { bool empty, ballistic, overflow; uint32_t primary; float pdist, bx, by, dist, region_depth, flux; V3 origin; uint32_t n_edges, need_edges; };
-WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, const uint32_t* tris, uint32_t* edges, BHit& h) {
+WT_D void bd_hit_init(BHit& h, const Beam& beam, const TravOut& tr, Range& zr) {
     h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u; h.need_edges = 0u;
     h.origin = tr.origin; h.region_depth = tr.region_depth; h.dist = 0.f; h.ballistic = true;
+    zr = mkr(0.f, 0.f);
     if (tr.empty) return;
     if (tr.cone.overflow) h.overflow = true;
     h.dist = tr.ballistic ? tr.ray.dist : tr.cone.dist;
-    const Range zr = mkr(h.dist, h.dist + tr.region_depth);
+    zr = mkr(h.dist, h.dist + tr.region_depth);
     h.ballistic = tr.ballistic || cone_is_ray(beam.env);
+    if (h.ballistic) { h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; }
+}
+// one thread, start to finish (the cross-check drivers)
+WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, const TriList& tl, uint32_t* edges, BHit& h) {
+    Range zr; bd_hit_init(h, beam, tr, zr);
+    if (tr.empty || h.ballistic) return;
     const V3 dir = beam.env.d;
-    const uint32_t nt = min(tr.cone.n_tris, sc.cap.tris);
-    if (h.ballistic) { h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; return; }
-    for (uint32_t i = 0; i < nt; ++i) {
-        const Tri3 t = load_tri(sc, tris[i]);
-        const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
-        const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
-        if (rt.hit && rt.dist < h.pdist) { h.primary = tris[i]; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
-    }
+    find_closest(sc, tl, tr.origin, dir, zr, h.primary, h.pdist, h.bx, h.by);
     if (h.primary != WTGPU_INVALID_IDX) return;
     const Frame beam_frame = cone_frame(beam.env);
     const G2 wf = wavefront_of(beam, h.dist);
     const float csz = (zr.mx + zr.mn) / 2.f;
-    for (uint32_t i = 0; i < nt; ++i) {
-        const Tri3 t = load_tri(sc, tris[i]);
+    for (uint32_t i = 0; i < tl.n; ++i) {
+        const Tri3 t = load_tri(sc, tri_at(tl, i));
         if ((dot(t.n, -dir) > 0.f) != tr.cone.front) continue;
         const Clip cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
         for (int k = 0; k < cl.tris; ++k) {
@@ -601,38 +601,23 @@ WT_D void bd_resolve_hit(const DScene& sc, const Beam& beam, const TravOut& tr, 
             h.flux += g2_integrate_triangle(sc, wf, cone_project_local(beam.env, ct[0], csz), cone_project_local(beam.env, ct[1], csz), cone_project_local(beam.env, ct[2], csz));
         }
     }
-    if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tris, nt, edges, sc.cap.edges, eo); if (eo) { h.overflow = true; h.need_edges = 3u * nt; } }
+    if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tl, edges, sc.cap.edges, eo); if (eo) { h.overflow = true; h.need_edges = 3u * tl.n; } }
 }
 
 // bd_resolve_hit with the flux integral organised for a warp (all 32 lanes call; `act` marks lanes that hold a walker): every lane walks its own
 // clipped triangles, but the lanes advance piece by piece together, and a piece that needs the quadrature branch of integrate_triangle is
 // evaluated by the whole warp (g2_quadrature_warp).  Same values, same order of additions as bd_resolve_hit.
-WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, const TravOut& tr, const uint32_t* tris, uint32_t* edges, BHit& h) {
+WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, const TravOut& tr, const TriList& tl, uint32_t* edges, BHit& h) {
     const unsigned lane = threadIdx.x & 31u;
     bool need = false;
-    uint32_t nt = 0u;
     Range zr = mkr(0.f, 0.f);
     V3 dir = mk3(0.f, 0.f, 1.f);
     if (act) {
-        h.empty = tr.empty; h.overflow = false; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.flux = 0.f; h.n_edges = 0u; h.need_edges = 0u;
-        h.origin = tr.origin; h.region_depth = tr.region_depth; h.dist = 0.f; h.ballistic = true;
-        if (!tr.empty) {
-            if (tr.cone.overflow) h.overflow = true;
-            h.dist = tr.ballistic ? tr.ray.dist : tr.cone.dist;
-            zr = mkr(h.dist, h.dist + tr.region_depth);
-            h.ballistic = tr.ballistic || cone_is_ray(beam.env);
+        bd_hit_init(h, beam, tr, zr);
+        if (!tr.empty && !h.ballistic) {
             dir = beam.env.d;
-            nt = min(tr.cone.n_tris, sc.cap.tris);
-            if (h.ballistic) { h.primary = tr.ray.tuid; h.pdist = tr.ray.dist; h.bx = tr.ray.bx; h.by = tr.ray.by; }
-            else {
-                for (uint32_t i = 0; i < nt; ++i) {
-                    const Tri3 t = load_tri(sc, tris[i]);
-                    const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
-                    const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
-                    if (rt.hit && rt.dist < h.pdist) { h.primary = tris[i]; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
-                }
-                need = h.primary == WTGPU_INVALID_IDX;
-            }
+            find_closest(sc, tl, tr.origin, dir, zr, h.primary, h.pdist, h.bx, h.by);
+            need = h.primary == WTGPU_INVALID_IDX;
         }
     }
     const bool flux_lane = need;
@@ -645,8 +630,8 @@ WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, cons
             V2 pa = mk2(0.f, 0.f), pb = pa, pc = pa;
             if (need) {
                 while (k >= cl.tris) {        // next triangle facing like the closest one (plt_bdpt_detail.hpp:391-416)
-                    if (i >= nt) { need = false; break; }
-                    const Tri3 t = load_tri(sc, tris[i]); ++i;
+                    if (i >= tl.n) { need = false; break; }
+                    const Tri3 t = load_tri(sc, tri_at(tl, i)); ++i;
                     if ((dot(t.n, -dir) > 0.f) != tr.cone.front) continue;
                     cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
                     k = 0;
@@ -671,7 +656,65 @@ WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, cons
             if (add) h.flux += val;
         }
     }
-    if (flux_lane && sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tris, nt, edges, sc.cap.edges, eo); if (eo) { h.overflow = true; h.need_edges = 3u * nt; } }
+    if (flux_lane && sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tl, edges, sc.cap.edges, eo); if (eo) { h.overflow = true; h.need_edges = 3u * tl.n; } }
+}
+
+// One WARP resolves one walker whose cone query returned a long triangle list (all lanes call with the same arguments; every lane ends with the
+// same BHit): closest triangle by an ordered warp minimum; the Gaussian power 32 triangles at a time -- lane l clips and integrates triangle
+// base + l (its <= 3 pieces; quadrature pieces by the whole warp), and the piece values are then added IN LIST ORDER; the edge set through
+// the scratch bitmap.  Bit-identical to bd_resolve_hit.
+WT_D void bd_resolve_hit_big(const DScene& sc, const Beam& beam, const TravOut& tr, const TriList& tl, uint32_t* edges, uint32_t* edge_bits, BHit& h) {
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    Range zr; bd_hit_init(h, beam, tr, zr);
+    if (tr.empty || h.ballistic) return;
+    const V3 dir = beam.env.d;
+    w_find_closest(sc, tl, tr.origin, dir, zr, h.primary, h.pdist, h.bx, h.by);
+    if (h.primary != WTGPU_INVALID_IDX) return;
+    const Frame beam_frame = cone_frame(beam.env);
+    const G2 wf = wavefront_of(beam, h.dist);
+    const float csz = (zr.mx + zr.mn) / 2.f;
+    float flux = 0.f;
+    for (uint32_t base = 0u; base < tl.n; base += 32u) {
+        const uint32_t i = base + lane;
+        Clip cl; cl.tris = 0;
+        if (i < tl.n) {
+            const Tri3 t = load_tri(sc, tri_at(tl, i));
+            if ((dot(t.n, -dir) > 0.f) == tr.cone.front)
+                cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
+        }
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {       // piece k of every lane's triangle
+            int kind = G2_DONE; float val = 0.f; V2 pa = mk2(0.f, 0.f), pb = pa, pc = pa;
+            if (k < cl.tris) {
+                V3 ct[3]; clip_tri(cl, k, ct);
+                pa = cone_project_local(beam.env, ct[0], csz); pb = cone_project_local(beam.env, ct[1], csz); pc = cone_project_local(beam.env, ct[2], csz);
+                kind = g2_classify(wf, pa, pb, pc, val);
+                if (kind == G2_ANALYTIC) val = g2_analytic(sc, pa, pb, pc);
+            }
+            unsigned m = __ballot_sync(FULL, kind == G2_QUADRATURE);
+            while (m) {
+                const int src = __ffs(m) - 1; m &= m - 1u;
+                const V2 qa = mk2(__shfl_sync(FULL, pa.x, src), __shfl_sync(FULL, pa.y, src));
+                const V2 qb = mk2(__shfl_sync(FULL, pb.x, src), __shfl_sync(FULL, pb.y, src));
+                const V2 qc = mk2(__shfl_sync(FULL, pc.x, src), __shfl_sync(FULL, pc.y, src));
+                const float r = g2_quadrature_warp(qa, qb, qc);
+                if ((int)lane == src) val = r;
+            }
+            if (k == 0) v0 = val; else if (k == 1) v1 = val; else v2 = val;
+        }
+        // ordered accumulation: triangle base, base + 1, ... ; pieces 0, 1, 2 of each
+        const unsigned any = __ballot_sync(FULL, cl.tris > 0);
+        unsigned rest = any;
+        while (rest) {
+            const int l = __ffs(rest) - 1; rest &= rest - 1u;
+            const int c = __shfl_sync(FULL, cl.tris, l);
+            const float a0 = __shfl_sync(FULL, v0, l), a1 = __shfl_sync(FULL, v1, l), a2 = __shfl_sync(FULL, v2, l);
+            flux += a0; if (c > 1) flux += a1; if (c > 2) flux += a2;
+        }
+    }
+    h.flux = flux;
+    if (sc.integrator.fsd) { bool eo = false; uint32_t need = 0u; h.n_edges = w_collect_edges(sc, tl, edges, sc.cap.edges, edge_bits, eo, need); if (eo) { h.overflow = true; h.need_edges = need; } }
 }
 
 // continue_walk (plt_bdpt_detail.hpp:167-182)
@@ -964,7 +1007,7 @@ WT_D float bd_eval_pair(BCtx& c, const BdSampleInit& si, uint32_t seed_lo, uint3
 // ================================================================================================ driver 1: one thread per sample (cross-check path)
 struct BdptArgs {
     DScene sc; FLut lut; float* arena; uint32_t P;
-    uint32_t* trav_tris; uint32_t* hit_edges;      // per-thread rows (sc.cap.tris / sc.cap.edges entries)
+    uint32_t* trav_tris; uint32_t* hit_edges;      // per-thread rows (kTriRow / sc.cap.edges entries)
     DevCounters* ctr; float* film_block; float* film_light;
     uint32_t seed_lo, seed_hi, tile_x0, tile_y0, tile_w, tile_h, sample_begin;
     unsigned long long total;
@@ -997,7 +1040,7 @@ __global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.sc;
     BCtx c = mk_bctx(sc, a.arena, tid, a.lut, &ctr);
-    uint32_t* tris = a.trav_tris + (size_t)tid * sc.cap.tris; uint32_t* edges = a.hit_edges + (size_t)tid * sc.cap.edges;
+    uint32_t* edges = a.hit_edges + (size_t)tid * sc.cap.edges;
     uint32_t n_samples = 0, n_vert = 0, n_conn = 0, n_splat = 0;
     const bool force_rt = sc.sensor.ray_trace_only != 0u;
     for (;;) {
@@ -1011,9 +1054,10 @@ __global__ void __launch_bounds__(128) k_bdpt(const BdptArgs a) {
             Sampler smp; smp.k0 = a.seed_lo; smp.k1 = a.seed_hi; smp.pixel = si.pixel; smp.sample = si.sample; smp.d = 0; smp.stream = 1u + (uint32_t)wi;
             for (;;) {
                 TravOut tr; BHit h;
-                traverse(sc, w[wi].beam.env, w[wi].prev_geo, wavenum_to_wavelen(w[wi].beam.k), force_rt, tris, tr, ctr);
-                if (tr.cone.overflow) need_max(&a.ctr->need_tris, tr.cone.n_tris);
-                bd_resolve_hit(sc, w[wi].beam, tr, tris, edges, h);
+                // (one launch: the triangle-list arena is not recycled here -- this cross-check driver is for small scenes; the arena grows to the whole render's demand)
+                TriWriter tw = tri_writer(sc, a.trav_tris, tid);
+                traverse(sc, w[wi].beam.env, w[wi].prev_geo, wavenum_to_wavelen(w[wi].beam.k), force_rt, tw, tr, ctr);
+                bd_resolve_hit(sc, w[wi].beam, tr, tri_list(sc, a.trav_tris, tid, tr.cone.n_tris, tr.cone.overflow), edges, h);
                 if (h.need_edges) need_max(&a.ctr->need_edges, h.need_edges);
                 if (bd_walk_step(c, w[wi], smp, h, edges, n_vert, false) != BD_CONTINUE) break;
             }
@@ -1079,7 +1123,7 @@ __global__ void __launch_bounds__(128) k_bd_generate(const BdArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool gen = false;
     if (slot < a.P && a.r.alive[slot] == 0u) {
-        const unsigned long long id = atomicAdd(&a.r.ctr->next_sample, 1ull);
+        const unsigned long long id = atomicAdd(&a.r.ctr->next_sample, 1ull) * a.r.n_parts + a.r.part;
         if (id < a.r.total) {
             gen = true;
             Counters ctr; counters_zero(ctr);
@@ -1109,11 +1153,10 @@ __global__ void __launch_bounds__(128) k_bd_traverse(const BdArgs a) {
         const uint32_t wid = a.r.trav_list[li];
         const DScene& sc = a.r.sc;
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
-        uint32_t* tris = a.trav_tris + (size_t)wid * sc.cap.tris;
+        TriWriter tw = tri_writer(sc, a.trav_tris, wid);
         TravOut tr; BHit bh; HitRec h;
-        traverse(sc, w.beam.env, w.prev_geo, wavenum_to_wavelen(w.beam.k), sc.sensor.ray_trace_only != 0u, tris, tr, ctr);
-        if (tr.cone.overflow) need_max(&a.r.ctr->need_tris, tr.cone.n_tris);
-        bd_resolve_hit(sc, w.beam, tr, tris, a.r.hit_edges + (size_t)wid * sc.cap.edges, bh);
+        traverse(sc, w.beam.env, w.prev_geo, wavenum_to_wavelen(w.beam.k), sc.sensor.ray_trace_only != 0u, tw, tr, ctr);
+        bd_resolve_hit(sc, w.beam, tr, tri_list(sc, a.trav_tris, wid, tr.cone.n_tris, tr.cone.overflow), a.r.hit_edges + (size_t)wid * sc.cap.edges, bh);
         if (bh.need_edges) need_max(&a.r.ctr->need_edges, bh.need_edges);
         h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
         h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
@@ -1134,52 +1177,92 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
     __shared__ GShared shm[128 / kGW];
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.r.sc;
-    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr,
-        [&](int i, Cone& env, Geo& prev, float& lambda, uint32_t*& tris_out) {
+    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr, a.r.big_list, &a.r.ctr->n_big,
+        [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
             const uint32_t wid = a.r.trav_list[i];
             BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
             env = w.beam.env; prev = w.prev_geo; lambda = wavenum_to_wavelen(w.beam.k);
-            tris_out = a.trav_tris + (size_t)wid * sc.cap.tris;
+            tw = tri_writer(sc, a.trav_tris, wid);
         },
-        [&](int i, const TravRec& r, const GLane& g) {
-            if (g.gl == 0u) { a.trav_rec[a.r.trav_list[i]] = r; if (r.flags & TR_OVERFLOW) need_max(&a.r.ctr->need_tris, r.n_tris); }
-        });
+        [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.r.trav_list[i]] = r; });
+    flush_counters(a.r.ctr, ctr);
+}
+// the walkers k_bd_gtraverse handed over (cone queries over > kBigQuery triangles): one warp per walker (gtrav.cuh w_traverse_all)
+__global__ void __launch_bounds__(128, 4) k_bd_wtraverse(const BdArgs a) {
+    __shared__ GShared shm[4];
+    Counters ctr; counters_zero(ctr);
+    const DScene& sc = a.r.sc;
+    w_traverse_all(sc, a.r.ctr->n_big, a.r.big_list, &a.r.ctr->big_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr,
+        [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
+            const uint32_t wid = a.r.trav_list[i];
+            BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+            env = w.beam.env; prev = w.prev_geo; lambda = wavenum_to_wavelen(w.beam.k);
+            tw = tri_writer(sc, a.trav_tris, wid);
+        },
+        [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.r.trav_list[i]] = r; });
     flush_counters(a.r.ctr, ctr);
 }
 // what the vertex step needs from a traversal result: primary triangle, Gaussian power over clipped triangles, edges, sort key
+WT_D void bd_trav_out(const TravRec& r, TravOut& tr) {
+    tr.empty = (r.flags & TR_EMPTY) != 0u; tr.ballistic = (r.flags & TR_BALLISTIC) != 0u;
+    tr.ray.tuid = r.ray_tuid; tr.ray.dist = r.ray_dist; tr.ray.bx = r.bx; tr.ray.by = r.by; tr.ray.front = (r.flags & TR_RAY_FRONT) != 0u;
+    tr.cone.dist = r.cone_dist; tr.cone.front = (r.flags & TR_CONE_FRONT) != 0u; tr.cone.n_tris = r.n_tris; tr.cone.overflow = (r.flags & TR_OVERFLOW) != 0u;
+    tr.region_depth = r.region_depth; tr.origin = mk3(r.ox, r.oy, r.oz);
+}
+WT_D void bd_store_hit(const BdArgs& a, uint32_t wid, const BHit& bh) {
+    HitRec h;
+    h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
+    h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
+    hit_store(h, a.r.hit, a.r.pool, wid);
+    a.r.keys[wid] = bd_hit_key(a.r.sc, bh, a.r.n_keys);
+    if (bh.need_edges) need_max(&a.r.ctr->need_edges, bh.need_edges);
+}
 __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = li < (uint32_t)a.r.ctr->n_trav;
+    bool act = li < (uint32_t)a.r.ctr->n_trav;
     const DScene& sc = a.r.sc;
     bool ovf = false;
     uint32_t wid = 0u;
-    BdWalker w; TravOut tr; BHit bh; HitRec h;
-    const uint32_t* tris = nullptr; uint32_t* edges = nullptr;
+    BdWalker w; TravOut tr; BHit bh;
+    TriList tl; tl.row = nullptr; tl.spill = nullptr; tl.ext = nullptr; tl.n = 0u;
+    uint32_t* edges = nullptr;
     tr.empty = true; tr.ballistic = true; tr.cone.n_tris = 0u;
     if (act) {
         wid = a.r.trav_list[li];
-        soa_load(w, a.walkers, 2u * a.P, wid);
         const TravRec r = a.trav_rec[wid];
-        tr.empty = (r.flags & TR_EMPTY) != 0u; tr.ballistic = (r.flags & TR_BALLISTIC) != 0u;
-        tr.ray.tuid = r.ray_tuid; tr.ray.dist = r.ray_dist; tr.ray.bx = r.bx; tr.ray.by = r.by; tr.ray.front = (r.flags & TR_RAY_FRONT) != 0u;
-        tr.cone.dist = r.cone_dist; tr.cone.front = (r.flags & TR_CONE_FRONT) != 0u; tr.cone.n_tris = r.n_tris; tr.cone.overflow = (r.flags & TR_OVERFLOW) != 0u;
-        tr.region_depth = r.region_depth; tr.origin = mk3(r.ox, r.oy, r.oz);
-        tris = a.trav_tris + (size_t)wid * sc.cap.tris; edges = a.r.hit_edges + (size_t)wid * sc.cap.edges;
+        bd_trav_out(r, tr);
+        tl = tri_list(sc, a.trav_tris, wid, r.n_tris, tr.cone.overflow);
+        if (tl.n > kBigQuery && !tr.empty && !tr.ballistic) { a.r.big_res_list[atomicAdd(&a.r.ctr->n_big_res, 1)] = li; act = false; }    // a long list: to the warp-per-walker kernel
+        else { soa_load(w, a.walkers, 2u * a.P, wid); edges = a.r.hit_edges + (size_t)wid * sc.cap.edges; }
     }
-    bd_resolve_hit_warp(sc, act, w.beam, tr, tris, edges, bh);
-    if (act) {
-        if (bh.need_edges) need_max(&a.r.ctr->need_edges, bh.need_edges);
-        h.flags = (bh.empty ? H_EMPTY : 0u) | (bh.ballistic ? H_BALLISTIC : 0u) | (bh.overflow ? H_OVERFLOW : 0u) | (bh.primary != WTGPU_INVALID_IDX ? H_PRIMARY : 0u);
-        h.primary = bh.primary; h.pdist = bh.pdist; h.bx = bh.bx; h.by = bh.by; h.d2i = bh.dist; h.region_depth = bh.region_depth; h.origin = bh.origin; h.n_edges = bh.n_edges; h.flux = bh.flux;
-        ovf = bh.overflow;
-        hit_store(h, a.r.hit, a.r.pool, wid);
-        a.r.keys[wid] = bd_hit_key(sc, bh, a.r.n_keys);
-    }
+    bd_resolve_hit_warp(sc, act, w.beam, tr, tl, edges, bh);
+    if (act) { ovf = bh.overflow; bd_store_hit(a, wid, bh); }
     count1(&a.r.ctr->overflow, ovf);
     count1(&a.r.ctr->walker_steps, act);
 }
+__global__ void __launch_bounds__(128) k_bd_resolve_big(const BdArgs a, uint32_t bit_words) {
+    const unsigned lane = threadIdx.x & 31u;
+    const DScene& sc = a.r.sc;
+    uint32_t* bits = a.r.edge_bits + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * bit_words;
+    unsigned long long n_step = 0, n_ovf = 0;
+    for (;;) {
+        int i = 0;
+        if (lane == 0u) i = atomicAdd(&a.r.ctr->big_res_head, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= a.r.ctr->n_big_res) break;
+        const uint32_t wid = a.r.trav_list[a.r.big_res_list[i]];
+        const TravRec r = a.trav_rec[wid];
+        TravOut tr; bd_trav_out(r, tr);
+        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+        BHit bh;
+        bd_resolve_hit_big(sc, w.beam, tr, tri_list(sc, a.trav_tris, wid, r.n_tris, tr.cone.overflow), a.r.hit_edges + (size_t)wid * sc.cap.edges, bits, bh);
+        if (lane == 0u) { bd_store_hit(a, wid, bh); ++n_step; n_ovf += bh.overflow ? 1u : 0u; }
+        __syncwarp();
+    }
+    if (lane == 0u) { if (n_step) atomicAdd(&a.r.ctr->walker_steps, n_step); if (n_ovf) atomicAdd(&a.r.ctr->overflow, n_ovf); }
+}
 
-__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->trav_head = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; } }
+__global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->trav_head = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; reset_iteration_lists(a.r.ctr); } }
 
 // Strategy classes = the branches of connect_subpaths (plt_bdpt_detail.hpp:747-923): each class has its own task list and its own
 // launch, so a warp runs one branch (emission hit / sensor hit / emitter-direct / sensor-direct / vertex-vertex).

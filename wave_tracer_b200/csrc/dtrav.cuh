@@ -17,7 +17,8 @@ namespace wt {
 // wtgpu_render re-sizes the rows and renders again -- a two-pass count / fill at the granularity of the render call, so results never depend on a
 // capacity (wavefront.cu, "capacity growth").
 struct Caps {
-    uint32_t tris;          // triangles a cone query returns (row of trav_tris)
+    uint32_t tris;          // triangles of a cone query kept in the path's own row (kTriRow); longer lists continue in extents of the spill arena
+    uint32_t spill_words;   // size of the spill arena (entries), shared by all paths of an iteration
     uint32_t edges;         // edges around a vertex (rows of hit_edges / the UTD aperture's edge list)
     uint32_t seg;           // segments of a Fraunhofer aperture
     uint32_t ap_walk;       // Fraunhofer apertures per subpath
@@ -33,14 +34,52 @@ struct DScene {
     const wtgpu_spectrum* spectra; const float* spectrum_data;
     const wtgpu_bsdf* bsdfs; const wtgpu_bsdf_bin* bsdf_bins;
     const wtgpu_emitter* emitters; const float* emitter_cdf; const wtgpu_kdist* emitter_kdist; const float* kdist_data;
-    uint32_t n_emitters, n_bsdfs, n_tris, n_nodes;
+    uint32_t n_emitters, n_bsdfs, n_tris, n_nodes, n_edges_total;
     wtgpu_sensor sensor;
     wtgpu_integrator integrator;
     const float* erf_lut;             // 1024-entry erf table (include/wt/math/erf_lut.hpp)
     uint32_t scene_stream;            // Sampler::stream of the scene-sampler draws: 0 (uniform) or kSobolStreamFlag | spp (sobolld); set per render
     float ray_cull_abs;               // absolute slack of the ray-query range culling (RayCull below); +inf disables the culling; set per render
     Caps cap;                         // set per render
+    // spill arena of the cone-query triangle lists (TriList below): entries, bump cursor (reset every iteration), extent tables (kTriExt per path)
+    uint32_t* spill; unsigned int* spill_head; uint32_t* spill_ext;
 };
+
+// ---- triangle lists of cone queries.  The reference returns a std::vector<tuid_t> of any length (traversal_common.hpp:116-149); most hold a few
+// triangles, a few hold 10^5 (a beam several millimetres wide over a finely tessellated mesh).  A list lives for one iteration (written by the
+// traversal kernel, read by the resolve kernel): its first kTriRow entries are in the path's own row, the rest in extents of doubling size
+// (256, 512, 1024, ...) bump-allocated from one arena that is reset every iteration; the path's extent table gives O(1) random access.
+constexpr uint32_t kTriRow = 128u, kTriExt0 = 256u, kTriExt = 22u;
+struct TriList { const uint32_t* row; const uint32_t* spill; const uint32_t* ext; uint32_t n; };
+WT_D void tri_locate(uint32_t i, uint32_t& e, uint32_t& off) {     // entry i >= kTriRow -> extent, offset
+    const uint32_t j = i - kTriRow;
+    e = 31u - (uint32_t)__clz(j / kTriExt0 + 1u);
+    off = j - kTriExt0 * ((1u << e) - 1u);
+}
+WT_D uint32_t tri_at(const TriList& l, uint32_t i) {
+    if (i < kTriRow) return l.row[i];
+    uint32_t e, off; tri_locate(i, e, off);
+    return l.spill[l.ext[e] + off];
+}
+// writer side: `alloc_end` entries are backed by storage; reserve() extends it (one thread does the bump allocation), put() stores entry i
+struct TriWriter { uint32_t* row; uint32_t* ext; uint32_t n_ext, alloc_end; bool fail; };
+WT_D void tw_begin(TriWriter& w) { w.n_ext = 0u; w.alloc_end = kTriRow; w.fail = false; }       // (extents of an abandoned list stay allocated until the iteration ends)
+// called by ONE thread: back entries [0, upto) with storage
+WT_D void tw_reserve(const DScene& sc, TriWriter& w, uint32_t upto) {
+    while (upto > w.alloc_end && !w.fail) {
+        if (!w.ext) { w.fail = true; break; }
+        const uint32_t size = kTriExt0 << w.n_ext;
+        const uint32_t base = atomicAdd(sc.spill_head, size);      // (the cursor keeps counting past the arena's end: it measures the demand)
+        if (w.n_ext >= kTriExt || base > sc.cap.spill_words || size > sc.cap.spill_words - base) { w.fail = true; break; }
+        w.ext[w.n_ext++] = base; w.alloc_end += size;
+    }
+}
+WT_D void tw_put(const DScene& sc, const TriWriter& w, uint32_t i, uint32_t tuid) {
+    if (i < kTriRow) { w.row[i] = tuid; return; }
+    if (i >= w.alloc_end) return;
+    uint32_t e, off; tri_locate(i, e, off);
+    sc.spill[w.ext[e] + off] = tuid;
+}
 
 // Range culling of RAY queries.  bvh8w.cpp:469-554 tests nodes against {0, closest hit} only, so a ray cast over a short range (a
 // ballistic segment of traverse(), a shadow ray) still walks every node along the infinite ray and rejects the triangles one by one
@@ -176,9 +215,10 @@ WT_D Range cone_search_range(const Cone& cone, Range searchrange, float intr_dis
     return rand_(mkr(searchrange.mn, fminf(searchrange.mx, dist + zd)), mkr(0.f, WT_INF));
 }
 
-WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_range, float z_scale, uint32_t* tri_out, uint32_t max_tris, ConeResult& res, Counters& ctr) {
+WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_range, float z_scale, TriWriter& tw, ConeResult& res, Counters& ctr) {
     ctr.cone_casts++;
     res.dist = WT_INF; res.front = false; res.n_tris = 0; res.overflow = false;
+    tw_begin(tw);
     Range range = cone_search_range(cone, traversal_range, res.dist, z_scale);
     const Frame frame = cone_frame(cone);
     const V3 ro = cone.o, rd = cone.d;
@@ -201,7 +241,8 @@ WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_ran
                     if (d > range.mx) continue;
                     if (d < res.dist) { res.dist = d; res.front = dot(tr.n, -rd) > 0.f; }
                     found = true;
-                    if (res.n_tris < max_tris) tri_out[res.n_tris] = tuid; else res.overflow = true;
+                    tw_reserve(sc, tw, res.n_tris + 1u);
+                    if (tw.fail) res.overflow = true; else tw_put(sc, tw, res.n_tris, tuid);
                     res.n_tris++;
                 }
             }
@@ -251,10 +292,10 @@ WT_DN void cone_traverse(const DScene& sc, const Cone& cone, Range traversal_ran
 
 // edges of a triangle list, deduplicated and sorted ascending (the iteration order of std::set<tuid_t>,
 // traversal_common.hpp:124-146)
-WT_D uint32_t collect_edges(const DScene& sc, const uint32_t* tris, uint32_t n_tris, uint32_t* edges, uint32_t max_edges, bool& overflow) {
+WT_D uint32_t collect_edges(const DScene& sc, const TriList& tris, uint32_t* edges, uint32_t max_edges, bool& overflow) {
     uint32_t n = 0;
-    for (uint32_t i = 0; i < n_tris; ++i) {
-        const wtgpu_tri_meta m = sc.tri_meta[tris[i]];
+    for (uint32_t i = 0; i < tris.n; ++i) {
+        const wtgpu_tri_meta m = sc.tri_meta[tri_at(tris, i)];
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {       // (one copy of the insertion: code size)
             const uint32_t e = k == 0 ? m.edge_ab : k == 1 ? m.edge_bc : m.edge_ca;

@@ -79,7 +79,9 @@ struct DevCounters {
     int trav_head;                      // work-fetch cursor of the group traversal
     int n_fsd_list[3], fsd_head;        // plt_bdpt: walkers waiting for a Fraunhofer sample (three rotating lists); work-fetch cursor
     // capacity growth (dtrav.cuh Caps): the longest list a too-short row was asked to hold (0: every list fitted)
-    unsigned int need_tris, need_edges, need_seg, need_ap, need_verts;
+    unsigned int need_spill, need_edges, need_seg, need_ap, need_verts;
+    unsigned int spill_head;            // bump cursor of the triangle-list arena (dtrav.cuh TriList); reset every iteration
+    int n_big, big_head, n_big_res, big_res_head;      // beams handed to the warp-per-beam traversal / resolve kernels this iteration; their work cursors
     unsigned long long stack_drops;
 };
 WT_D void need_max(unsigned int* p, uint32_t v) { if (v > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(p, v); }
@@ -87,7 +89,9 @@ WT_D void need_max(unsigned int* p, uint32_t v) { if (v > *reinterpret_cast<vola
 namespace wt { struct TravRec; }
 struct RenderArgs {
     DScene sc;
-    wt::TravRec* trav_rec; uint32_t* trav_tris;      // results of traverse(), per slot; trav_tris: sc.cap.tris triangle ids per slot
+    wt::TravRec* trav_rec; uint32_t* trav_tris;      // results of traverse(), per slot; trav_tris: the first kTriRow triangle ids of the slot's cone-query list (dtrav.cuh TriList)
+    uint32_t* big_list; uint32_t* big_res_list;       // items (indices into trav_list) handed to the warp-per-beam kernels
+    uint32_t* edge_bits;                              // scratch bitmaps (one bit per edge of the scene) of the warp-per-beam resolve kernel, one per resident warp
     uint32_t* hit_edges;                              // sc.cap.edges edge ids per slot: the edges around the vertex (HitRec::n_edges of them)
     uint32_t* ap_edges; uint32_t it_parity;           // plt_path: 2 x pool rows of sc.cap.edges: UTD aperture edge lists (this iteration's row set: it_parity)
     float4* core; float4* fsd; float4* hit;
@@ -99,6 +103,7 @@ struct RenderArgs {
     uint32_t tile_x0, tile_y0, tile_w, tile_h;
     uint32_t sample_begin, n_samples;
     unsigned long long total;
+    uint32_t part, n_parts;     // this sub-pool renders the samples whose linear id is part (mod n_parts)
 };
 
 WT_D void flush_counters(DevCounters* g, const Counters& c, bool shade = false) {
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(128) k_generate(const RenderArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool gen = false;
     if (slot < a.pool && a.alive[slot] == 0u) {
-        const unsigned long long id = atomicAdd(&a.ctr->next_sample, 1ull);
+        const unsigned long long id = atomicAdd(&a.ctr->next_sample, 1ull) * a.n_parts + a.part;
         if (id < a.total) {
             gen = true;
             const DScene& sc = a.sc;
@@ -188,7 +193,7 @@ WT_D float max_ballistic_distance(float lambda, uint32_t seg, float mbd) {
     const unsigned long long B = min(1ull << 16, 8ull << (2u * min(seg, 16u) + 1u));
     return seg >= 16u ? WT_INF : mbd * 1.05f + lambda * (float)B;
 }
-WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bool force_rt, uint32_t* tris, TravOut& out, Counters& ctr) {
+WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bool force_rt, TriWriter& tw, TravOut& out, Counters& ctr) {
     env.o = offseted_ray_origin(sc, prev, env.o, env.d);
     out.origin = env.o; out.region_depth = 0.f;
     out.cone.n_tris = 0; out.cone.overflow = false; out.cone.dist = WT_INF; out.cone.front = false;
@@ -205,7 +210,7 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
         dist += bd;
         if (bd == WT_INF || dist >= WT_INF) { out.ballistic = true; out.empty = true; return; }
         const float min_prog = cone_axes(env, dist).x / 2.f;
-        cone_traverse(sc, env, mkr(dist, WT_INF), kMajorToZ, tris, sc.cap.tris, out.cone, ctr);
+        cone_traverse(sc, env, mkr(dist, WT_INF), kMajorToZ, tw, out.cone, ctr);
         const bool cempty = out.cone.n_tris == 0u;
         if (cempty || out.cone.dist - dist >= min_prog) {
             out.ballistic = false; out.empty = cempty;
@@ -213,6 +218,84 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
             return;
         }
     }
+}
+
+WT_D void reset_iteration_lists(DevCounters* c) {        // the triangle-list arena and the hand-over lists live for one iteration
+    need_max(&c->need_spill, c->spill_head);
+    c->spill_head = 0u; c->n_big = 0; c->big_head = 0; c->n_big_res = 0; c->big_res_head = 0;
+}
+// the triangle-list writer / reader of path `slot` (rows of kTriRow entries + the slot's extent table)
+WT_D TriWriter tri_writer(const DScene& sc, uint32_t* trav_tris, uint32_t slot) { TriWriter w; w.row = trav_tris + (size_t)slot * kTriRow; w.ext = sc.spill_ext + (size_t)slot * kTriExt; tw_begin(w); return w; }
+WT_D TriList tri_list(const DScene& sc, const uint32_t* trav_tris, uint32_t slot, uint32_t n, bool overflow) {
+    TriList l; l.row = trav_tris + (size_t)slot * kTriRow; l.spill = sc.spill; l.ext = sc.spill_ext + (size_t)slot * kTriExt; l.n = overflow ? min(n, kTriRow) : n; return l;
+}
+
+// find_closest_triangle (plt_path_detail.hpp:253-276 / plt_bdpt_detail.hpp:362-390): the first triangle of the list, in list order, with the smallest hit distance
+WT_D void find_closest(const DScene& sc, const TriList& tl, V3 origin, V3 dir, Range zr, uint32_t& primary, float& pdist, float& bx, float& by) {
+    for (uint32_t i = 0; i < tl.n; ++i) {
+        const uint32_t tu = tri_at(tl, i);
+        const Tri3 t = load_tri(sc, tu);
+        const float tol = cone_intersection_tolerance(origin, t.a, t.b, t.c);
+        const RayTri rt = intersect_ray_tri(origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+        if (rt.hit && rt.dist < pdist) { primary = tu; pdist = rt.dist; bx = rt.bx; by = rt.by; }
+    }
+}
+// the same by a whole warp (all lanes call with the same arguments and get the same result): lane l takes entries l, l + 32, ...; the
+// (distance, list index) minimum over the lanes is the sequential loop's pick
+WT_D void w_find_closest(const DScene& sc, const TriList& tl, V3 origin, V3 dir, Range zr, uint32_t& primary, float& pdist, float& bx, float& by) {
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    float bd = WT_INF, bbx = -1.f, bby = -1.f; uint32_t bi = 0xffffffffu, btu = WTGPU_INVALID_IDX;
+    for (uint32_t i = lane; i < tl.n; i += 32u) {
+        const uint32_t tu = tri_at(tl, i);
+        const Tri3 t = load_tri(sc, tu);
+        const float tol = cone_intersection_tolerance(origin, t.a, t.b, t.c);
+        const RayTri rt = intersect_ray_tri(origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+        if (rt.hit && rt.dist < pdist && rt.dist < bd) { bd = rt.dist; bi = i; btu = tu; bbx = rt.bx; bby = rt.by; }
+    }
+    float rd = bd; uint32_t ri = bi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float od = __shfl_xor_sync(FULL, rd, o); const uint32_t oi = __shfl_xor_sync(FULL, ri, o);
+        if (oi != 0xffffffffu && (ri == 0xffffffffu || od < rd || (od == rd && oi < ri))) { rd = od; ri = oi; }
+    }
+    if (ri == 0xffffffffu) return;
+    const int src = __ffs(__ballot_sync(FULL, bi == ri)) - 1;
+    primary = __shfl_sync(FULL, btu, src); pdist = rd; bx = __shfl_sync(FULL, bbx, src); by = __shfl_sync(FULL, bby, src);
+}
+// edges of a triangle list, deduplicated and ascending (collect_edges), by a whole warp through a scratch bitmap with one bit per edge of the
+// scene (all zero on entry and on return).  Returns the number stored; `need` = the number there are.
+WT_D uint32_t w_collect_edges(const DScene& sc, const TriList& tl, uint32_t* edges, uint32_t max_edges, uint32_t* bits, bool& overflow, uint32_t& need) {
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (uint32_t i = lane; i < tl.n; i += 32u) {
+        const wtgpu_tri_meta m = sc.tri_meta[tri_at(tl, i)];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t e = k == 0 ? m.edge_ab : k == 1 ? m.edge_bc : m.edge_ca;
+            if (e == WTGPU_INVALID_IDX) continue;
+            atomicOr(bits + (e >> 5), 1u << (e & 31u)); lo = min(lo, e >> 5); hi = max(hi, e >> 5);
+        }
+    }
+    lo = __reduce_min_sync(FULL, lo); hi = __reduce_max_sync(FULL, hi);
+    __threadfence_block(); __syncwarp();
+    uint32_t count = 0u;
+    if (lo != 0xffffffffu)
+        for (uint32_t w0 = lo; w0 <= hi; w0 += 32u) {
+            const uint32_t w = w0 + lane;
+            uint32_t v = w <= hi ? __ldcg(bits + w) : 0u;
+            if (v) bits[w] = 0u;
+            const uint32_t c = (uint32_t)__popc(v);
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += u; }
+            uint32_t pos = count + incl - c;
+            while (v) { const uint32_t b = (uint32_t)__ffs(v) - 1u; v &= v - 1u; if (pos < max_edges) edges[pos] = w * 32u + b; ++pos; }
+            count += __shfl_sync(FULL, incl, 31);
+        }
+    __syncwarp();
+    need = count;
+    if (count > max_edges) { overflow = true; return max_edges; }
+    return count;
 }
 
 #include "gtrav.cuh"
@@ -227,11 +310,11 @@ __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
         const DScene& sc = a.sc;
         seg = true;
         PathCore pc; soa_load(pc, a.core, a.pool, slot);
-        uint32_t* tris = a.trav_tris + (size_t)slot * sc.cap.tris;
+        TriWriter tw = tri_writer(sc, a.trav_tris, slot);
         uint32_t* edges = a.hit_edges + (size_t)slot * sc.cap.edges;
         TravOut tr;
         const bool force_rt = sc.sensor.ray_trace_only != 0u;
-        traverse(sc, pc.beam.env, pc.prev_geo, wavenum_to_wavelen(pc.beam.k), force_rt, tris, tr, ctr);
+        traverse(sc, pc.beam.env, pc.prev_geo, wavenum_to_wavelen(pc.beam.k), force_rt, tw, tr, ctr);
         HitRec h; h.flags = 0u; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.n_edges = 0u; h.flux = 0.f;
         h.origin = tr.origin; h.region_depth = tr.region_depth; h.d2i = 0.f;
         uint32_t key = a.n_keys - 1u;       // miss
@@ -246,28 +329,29 @@ __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
             } else {
                 h.d2i = tr.cone.dist;
                 if (tr.cone.front) h.flags |= H_FRONT;
-                if (tr.cone.overflow) { h.flags |= H_OVERFLOW; ovf = true; need_max(&a.ctr->need_tris, tr.cone.n_tris); }
-                const uint32_t nt = min(tr.cone.n_tris, sc.cap.tris);
+                if (tr.cone.overflow) { h.flags |= H_OVERFLOW; ovf = true; }
+                const TriList tl = tri_list(sc, a.trav_tris, slot, tr.cone.n_tris, tr.cone.overflow);
                 // find_closest_triangle (plt_path_detail.hpp:253-276)
                 const Range zr = mkr(h.d2i, h.d2i + h.region_depth);
-                for (uint32_t i = 0; i < nt; ++i) {
-                    const Tri3 t = load_tri(sc, tris[i]);
+                for (uint32_t i = 0; i < tl.n; ++i) {
+                    const uint32_t tu = tri_at(tl, i);
+                    const Tri3 t = load_tri(sc, tu);
                     const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
                     const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
-                    if (rt.hit && rt.dist < h.pdist) { h.primary = tris[i]; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
+                    if (rt.hit && rt.dist < h.pdist) { h.primary = tu; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
                 }
                 if (h.primary != WTGPU_INVALID_IDX) h.flags |= H_PRIMARY;
-                if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tris, nt, edges, sc.cap.edges, eo); if (eo) { h.flags |= H_OVERFLOW; ovf = true; need_max(&a.ctr->need_edges, 3u * nt); } }
+                if (sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tl, edges, sc.cap.edges, eo); if (eo) { h.flags |= H_OVERFLOW; ovf = true; need_max(&a.ctr->need_edges, 3u * tl.n); } }
             }
             // ballistic hit with a finite beam: collect the edges around the hit (plt_path_detail.hpp:656-660)
             if (is_ballistic && !cone_is_ray(pc.beam.env) && !force_rt) {
                 const float zd = cone_axes(env, h.d2i).x * kMajorToZ;
                 ConeResult cr;
-                cone_traverse(sc, env, mkr(h.d2i - zd / 2.f, h.d2i + zd / 2.f), 1.f, tris, sc.cap.tris, cr, ctr);
-                if (cr.overflow) need_max(&a.ctr->need_tris, cr.n_tris);
+                cone_traverse(sc, env, mkr(h.d2i - zd / 2.f, h.d2i + zd / 2.f), 1.f, tw, cr, ctr);
+                const TriList tl = tri_list(sc, a.trav_tris, slot, cr.n_tris, cr.overflow);
                 bool eo = false;
-                h.n_edges = collect_edges(sc, tris, min(cr.n_tris, sc.cap.tris), edges, sc.cap.edges, eo);
-                if (eo) need_max(&a.ctr->need_edges, 3u * min(cr.n_tris, sc.cap.tris));
+                h.n_edges = collect_edges(sc, tl, edges, sc.cap.edges, eo);
+                if (eo) need_max(&a.ctr->need_edges, 3u * tl.n);
                 if (eo || cr.overflow) { h.flags |= H_OVERFLOW; ovf = true; }
             }
             if (h.flags & H_PRIMARY) key = (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
@@ -290,71 +374,101 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs 
     __shared__ GShared shm[128 / kGW];
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.sc;
-    g_traverse_all(sc, a.ctr->n_trav, &a.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr,
-        [&](int i, Cone& env, Geo& prev, float& lambda, uint32_t*& tris_out) {
+    g_traverse_all(sc, a.ctr->n_trav, &a.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr, a.big_list, &a.ctr->n_big,
+        [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
             const uint32_t slot = a.trav_list[i];
             PathCore pc; soa_load(pc, a.core, a.pool, slot);
             env = pc.beam.env; prev = pc.prev_geo; lambda = wavenum_to_wavelen(pc.beam.k);
-            tris_out = a.trav_tris + (size_t)slot * sc.cap.tris;
+            tw = tri_writer(sc, a.trav_tris, slot);
         },
-        [&](int i, const TravRec& r, const GLane& g) {
-            if (g.gl == 0u) { a.trav_rec[a.trav_list[i]] = r; if (r.flags & TR_OVERFLOW) need_max(&a.ctr->need_tris, r.n_tris); }
-        });
+        [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
     flush_counters(a.ctr, ctr);
 }
-// primary-triangle pick (plt_path_detail.hpp:253-276), edge collection, sort key: the per-thread tail of k_traverse
+// the beams k_gtraverse handed over (cone queries over > kBigQuery triangles): one warp per beam (gtrav.cuh w_traverse_all)
+__global__ void __launch_bounds__(128, 4) k_wtraverse(const RenderArgs a) {
+    __shared__ GShared shm[4];
+    Counters ctr; counters_zero(ctr);
+    const DScene& sc = a.sc;
+    w_traverse_all(sc, a.ctr->n_big, a.big_list, &a.ctr->big_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr,
+        [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
+            const uint32_t slot = a.trav_list[i];
+            PathCore pc; soa_load(pc, a.core, a.pool, slot);
+            env = pc.beam.env; prev = pc.prev_geo; lambda = wavenum_to_wavelen(pc.beam.k);
+            tw = tri_writer(sc, a.trav_tris, slot);
+        },
+        [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
+    flush_counters(a.ctr, ctr);
+}
+// primary-triangle pick (plt_path_detail.hpp:253-276), edge collection, sort key: the per-thread tail of k_traverse.
+// WARP = false: one thread per path (lists of more than kBigQuery triangles are deferred to big_res_list); WARP = true: one warp per deferred path.
+template <bool WARP> WT_D void path_resolve(const RenderArgs& a, uint32_t li, uint32_t* edge_bits, bool& seg, bool& ovf) {
+    const uint32_t slot = a.trav_list[li];
+    const DScene& sc = a.sc;
+    const unsigned lane = threadIdx.x & 31u;
+    const TravRec r = a.trav_rec[slot];
+    const bool tr_ovf = (r.flags & TR_OVERFLOW) != 0u;
+    const TriList tl = tri_list(sc, a.trav_tris, slot, r.n_tris, tr_ovf);
+    if (!WARP && tl.n > kBigQuery && !(r.flags & TR_EMPTY)) { a.big_res_list[atomicAdd(&a.ctr->n_big_res, 1)] = li; return; }
+    seg = !WARP || lane == 0u;
+    uint32_t* edges = a.hit_edges + (size_t)slot * sc.cap.edges;
+    const V3 origin = mk3(r.ox, r.oy, r.oz);
+    // the beam's mean direction: floats 3..5 of PathCore (beam.env = {o, d, ...}), i.e. chunk 0 .w and chunk 1 .xy
+    static_assert(offsetof(PathCore, beam) == 0 && offsetof(Beam, env) == 0 && offsetof(Cone, d) == 12 && sizeof(V3) == 12, "PathCore layout");
+    const float4 c0 = a.core[slot], c1 = a.core[(size_t)a.pool + slot];
+    const V3 dir = mk3(c0.w, c1.x, c1.y);
+    HitRec h; h.flags = 0u; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.n_edges = 0u; h.flux = 0.f;
+    h.origin = origin; h.region_depth = r.region_depth; h.d2i = 0.f;
+    uint32_t key = a.n_keys - 1u;       // miss
+    bool o2 = false;
+    if (r.flags & TR_EMPTY) h.flags |= H_EMPTY;
+    else {
+        if (tr_ovf) { h.flags |= H_OVERFLOW; o2 = true; }
+        if (r.flags & TR_BALLISTIC) {
+            h.flags |= H_BALLISTIC | H_PRIMARY | ((r.flags & TR_RAY_FRONT) ? H_FRONT : 0u);
+            h.primary = r.ray_tuid; h.pdist = r.ray_dist; h.bx = r.bx; h.by = r.by; h.d2i = r.ray_dist;
+        } else {
+            h.d2i = r.cone_dist;
+            if (r.flags & TR_CONE_FRONT) h.flags |= H_FRONT;
+            const Range zr = mkr(h.d2i, h.d2i + h.region_depth);
+            if (WARP) w_find_closest(sc, tl, origin, dir, zr, h.primary, h.pdist, h.bx, h.by);
+            else find_closest(sc, tl, origin, dir, zr, h.primary, h.pdist, h.bx, h.by);
+            if (h.primary != WTGPU_INVALID_IDX) h.flags |= H_PRIMARY;
+        }
+        // cone segment: edges of the returned triangles when FSD is on; ballistic hit: edges of the edge query's triangles (always, as k_traverse)
+        if (((r.flags & TR_BALLISTIC) || sc.integrator.fsd) && tl.n) {
+            bool eo = false; uint32_t need = 0u;
+            if (WARP) h.n_edges = w_collect_edges(sc, tl, edges, sc.cap.edges, edge_bits, eo, need);
+            else { h.n_edges = collect_edges(sc, tl, edges, sc.cap.edges, eo); need = 3u * tl.n; }
+            if (eo) { h.flags |= H_OVERFLOW; o2 = true; if (!WARP || lane == 0u) need_max(&a.ctr->need_edges, need); }
+        }
+        if (h.flags & H_PRIMARY) key = (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
+        else key = h.n_edges ? a.n_keys - 3u : a.n_keys - 2u;
+    }
+    if (!WARP || lane == 0u) { hit_store(h, a.hit, a.pool, slot); a.keys[slot] = key; ovf = o2; }
+}
 __global__ void __launch_bounds__(128) k_resolve(const RenderArgs a) {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     bool seg = false, ovf = false;
-    if (li < (uint32_t)a.ctr->n_trav) {
-        const uint32_t slot = a.trav_list[li];
-        const DScene& sc = a.sc;
-        seg = true;
-        const TravRec r = a.trav_rec[slot];
-        const uint32_t* __restrict__ tris = a.trav_tris + (size_t)slot * sc.cap.tris;
-        uint32_t* edges = a.hit_edges + (size_t)slot * sc.cap.edges;
-        const uint32_t nt = min(r.n_tris, sc.cap.tris);
-        const V3 origin = mk3(r.ox, r.oy, r.oz);
-        // the beam's mean direction: floats 3..5 of PathCore (beam.env = {o, d, ...}), i.e. chunk 0 .w and chunk 1 .xy
-        static_assert(offsetof(PathCore, beam) == 0 && offsetof(Beam, env) == 0 && offsetof(Cone, d) == 12 && sizeof(V3) == 12, "PathCore layout");
-        const float4 c0 = a.core[slot], c1 = a.core[(size_t)a.pool + slot];
-        const V3 dir = mk3(c0.w, c1.x, c1.y);
-        HitRec h; h.flags = 0u; h.primary = WTGPU_INVALID_IDX; h.pdist = WT_INF; h.bx = h.by = -1.f; h.n_edges = 0u; h.flux = 0.f;
-        h.origin = origin; h.region_depth = r.region_depth; h.d2i = 0.f;
-        uint32_t key = a.n_keys - 1u;       // miss
-        if (r.flags & TR_EMPTY) h.flags |= H_EMPTY;
-        else {
-            if (r.flags & TR_OVERFLOW) { h.flags |= H_OVERFLOW; ovf = true; }
-            if (r.flags & TR_BALLISTIC) {
-                h.flags |= H_BALLISTIC | H_PRIMARY | ((r.flags & TR_RAY_FRONT) ? H_FRONT : 0u);
-                h.primary = r.ray_tuid; h.pdist = r.ray_dist; h.bx = r.bx; h.by = r.by; h.d2i = r.ray_dist;
-            } else {
-                h.d2i = r.cone_dist;
-                if (r.flags & TR_CONE_FRONT) h.flags |= H_FRONT;
-                const Range zr = mkr(h.d2i, h.d2i + h.region_depth);
-                for (uint32_t i = 0; i < nt; ++i) {
-                    const uint32_t tu = tris[i];
-                    const Tri3 t = load_tri(sc, tu);
-                    const float tol = cone_intersection_tolerance(origin, t.a, t.b, t.c);
-                    const RayTri rt = intersect_ray_tri(origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
-                    if (rt.hit && rt.dist < h.pdist) { h.primary = tu; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by; }
-                }
-                if (h.primary != WTGPU_INVALID_IDX) h.flags |= H_PRIMARY;
-            }
-            // cone segment: edges of the returned triangles when FSD is on; ballistic hit: edges of the edge query's triangles (always, as k_traverse)
-            if (((r.flags & TR_BALLISTIC) || sc.integrator.fsd) && nt) {
-                bool eo = false;
-                h.n_edges = collect_edges(sc, tris, nt, edges, sc.cap.edges, eo);
-                if (eo) { h.flags |= H_OVERFLOW; ovf = true; need_max(&a.ctr->need_edges, 3u * nt); }
-            }
-            if (h.flags & H_PRIMARY) key = (uint32_t)sc.shapes[sc.tri_meta[h.primary].shape_idx].bsdf;
-            else key = h.n_edges ? a.n_keys - 3u : a.n_keys - 2u;
-        }
-        hit_store(h, a.hit, a.pool, slot);
-        a.keys[slot] = key;
-    }
+    if (li < (uint32_t)a.ctr->n_trav) path_resolve<false>(a, li, nullptr, seg, ovf);
     count1(&a.ctr->segments, seg);
     count1(&a.ctr->overflow, ovf);
+}
+// the paths k_resolve deferred: one warp per path (closest triangle by a warp-wide ordered minimum, edge set through a scratch bitmap)
+__global__ void __launch_bounds__(128) k_resolve_big(const RenderArgs a, uint32_t bit_words) {
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t* bits = a.edge_bits + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * bit_words;
+    unsigned long long n_seg = 0, n_ovf = 0;
+    for (;;) {
+        int i = 0;
+        if (lane == 0u) i = atomicAdd(&a.ctr->big_res_head, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= a.ctr->n_big_res) break;
+        bool seg = false, ovf = false;
+        path_resolve<true>(a, a.big_res_list[i], bits, seg, ovf);
+        n_seg += seg ? 1u : 0u; n_ovf += ovf ? 1u : 0u;
+        __syncwarp();
+    }
+    if (lane == 0u) { if (n_seg) atomicAdd(&a.ctr->segments, n_seg); if (n_ovf) atomicAdd(&a.ctr->overflow, n_ovf); }
 }
 
 // ================================================================================================ material sort (counting sort)
@@ -413,7 +527,7 @@ __global__ void k_scatter(const RenderArgs a) {
         a.order[base + __popc(peers & ((1u << lane) - 1u))] = slot;
     }
 }
-__global__ void k_reset_trav(const RenderArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.ctr->n_trav = 0; a.ctr->trav_head = 0; } }
+__global__ void k_reset_trav(const RenderArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.ctr->n_trav = 0; a.ctr->trav_head = 0; reset_iteration_lists(a.ctr); } }
 __global__ void k_identity_order(const RenderArgs a) {     // WTGPU_RENDER_NO_SORT: live slots in slot order (compaction only)
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li < (uint32_t)a.ctr->n_trav) a.order[li] = a.trav_list[li];
@@ -661,14 +775,17 @@ __global__ void k_debug_cones(const DScene sc, uint32_t n, const wtgpu_cone_quer
     if (i >= n) return;
     Counters ctr; counters_zero(ctr);
     const Cone c = mkcone(mk3(q[i].o), mk3(q[i].d), mk3(q[i].x), q[i].x0, q[i].tan_alpha, 1.f / q[i].e, q[i].e);
+    static_assert(WTGPU_MAX_CONE_TRIS == kTriRow, "the debug entry point returns the row part of a triangle list");
     uint32_t tris[WTGPU_MAX_CONE_TRIS]; ConeResult r;
-    cone_traverse(sc, c, mkr(q[i].tmin, q[i].tmax), q[i].z_scale, tris, WTGPU_MAX_CONE_TRIS, r, ctr);
+    TriWriter tw; tw.row = tris; tw.ext = nullptr;      // (no extents: a longer list only counts on)
+    cone_traverse(sc, c, mkr(q[i].tmin, q[i].tmax), q[i].z_scale, tw, r, ctr);
     wtgpu_cone_hit& h = out[i];
     h.dist = r.dist; h.front_face = r.front ? 1u : 0u; h.n_tris = r.n_tris;
     const uint32_t nt = min(r.n_tris, (uint32_t)WTGPU_MAX_CONE_TRIS);
     for (uint32_t j = 0; j < nt; ++j) h.tris[j] = tris[j];
     bool eo = false; uint32_t edges[WTGPU_MAX_CONE_EDGES];
-    h.n_edges = collect_edges(sc, tris, nt, edges, WTGPU_MAX_CONE_EDGES, eo);
+    TriList tl; tl.row = tris; tl.spill = nullptr; tl.ext = nullptr; tl.n = nt;
+    h.n_edges = collect_edges(sc, tl, edges, WTGPU_MAX_CONE_EDGES, eo);
     for (uint32_t j = 0; j < h.n_edges; ++j) h.edges[j] = edges[j];
 }
 // sobolld: dimensions 0..46 of points g0 .. g0+n-1 (one thread per value)
@@ -753,6 +870,37 @@ void wt_free(void* p) {
 }
 }
 
+// One sub-pool of paths in flight, with its own stream(s) and counters.  A render runs several side by side (wtgpu_render, "sub-pools"): each
+// advances its own wavefront -- one vertex per iteration for its paths -- and while one sub-pool's launch drains its stragglers (a handful of
+// beams over 10^5 triangles, a path with thousands of diffracting edges), the kernels of the others keep the SMs busy.
+struct Pool {
+    uint32_t size = 0;
+    std::vector<void*> allocs;
+    float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
+    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr, *trav_tris = nullptr, *hit_edges = nullptr, *ap_edges = nullptr;
+    uint32_t *spill = nullptr, *spill_ext = nullptr, *big_list = nullptr, *big_res_list = nullptr, *edge_bits = nullptr;
+    TravRec* trav_rec = nullptr;
+    DevCounters* ctr = nullptr;
+    // plt_bdpt (P sample slots, 2P walkers)
+    float* bdpt_arena = nullptr;
+    float4 *bd_walkers = nullptr, *bd_headers = nullptr, *bd_fsd_out = nullptr;
+    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_fsd_list = nullptr; unsigned long long* bd_pairs = nullptr;
+    // host side: made once per handle (cudaMallocHost / event creation per render cost 5-150 ms of driver time, profiles/r01s3_phases.txt)
+    DevCounters* hctr = nullptr;
+    cudaStream_t st = nullptr, st_fsd = nullptr; cudaEvent_t ev_iter = nullptr, ev_shade = nullptr, ev_samp = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> evs; size_t n_ev = 0;     // per-kernel timing marks (WTGPU_RENDER_TIME_KERNELS)
+    // state of the render in progress
+    uint64_t iters = 0; unsigned long long total = 0; bool in_flight = false, done = false;
+    void free_buffers() { for (void* p : allocs) wt_free(p); allocs.clear(); size = 0; }
+    void destroy() {
+        free_buffers();
+        if (hctr) cudaFreeHost(hctr);
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
+        for (cudaEvent_t e : { ev_iter, ev_shade, ev_samp, ev_done }) if (e) cudaEventDestroy(e);
+        if (st) cudaStreamDestroy(st);
+        if (st_fsd) cudaStreamDestroy(st_fsd);
+    }
+};
 struct wtgpu_scene {
     int device = 0;
     DScene d{};
@@ -763,43 +911,24 @@ struct wtgpu_scene {
     uint32_t n_keys = 0;
     // capacities of the per-path lists (dtrav.cuh Caps): grown by wtgpu_render when a render needed more; kept for the next render
     Caps caps{};
-    // render pool: sized lazily for (pool, caps); every buffer of it is in pool_allocs
-    uint32_t pool = 0; Caps pool_caps{}; uint32_t pool_kind = 0;
-    std::vector<void*> pool_allocs;
-    float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
-    uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr, *trav_tris = nullptr, *hit_edges = nullptr, *ap_edges = nullptr;
-    TravRec* trav_rec = nullptr;
-    DevCounters* ctr = nullptr;
-    // plt_bdpt (P sample slots, 2P walkers)
-    float* bdpt_arena = nullptr;
-    float4 *bd_walkers = nullptr, *bd_headers = nullptr, *bd_fsd_out = nullptr;
-    int* bd_pending = nullptr; float* bd_L0 = nullptr; uint32_t *bd_nverts = nullptr, *bd_fsd_list = nullptr; unsigned long long* bd_pairs = nullptr;
-    std::vector<cudaEvent_t> ev_pool;   // reused across renders (event creation is not free)
-    DevCounters* hctr = nullptr; cudaEvent_t ev_begin = nullptr, ev_end = nullptr;     // pinned read-back of the counters + the render's timing events: made once (cudaMallocHost / cudaFreeHost per render cost 5-150 ms of driver time, profiles/r01s3_phases.txt)
+    // the sub-pools: sized lazily for (paths in flight, number of sub-pools, kind of render, caps)
+    std::vector<Pool> pools; uint32_t pool = 0, pool_parts = 0; Caps pool_caps{}; uint32_t pool_kind = 0;
+    uint32_t bit_words = 0, big_blocks = 0;
+    DevCounters total_ctr{};            // the sub-pools' counters of the last pass, summed (needs: maximum)
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     bool has_sobol = false;             // sobolld generator matrices are in constant memory of this device
     wt::FLut lut{};                     // plt_bdpt: Fraunhofer sampling tables
-    cudaStream_t bd_stream = nullptr; cudaEvent_t bd_ev_shade = nullptr, bd_ev_samp = nullptr;   // Fraunhofer sampler overlap
-    void free_pool() {
-        for (void* p : pool_allocs) wt_free(p);
-        pool_allocs.clear(); pool = 0;
-        core = fsd = hit = nullptr; alive = keys = order = key_count = key_cursor = trav_list = trav_tris = hit_edges = ap_edges = nullptr; trav_rec = nullptr; ctr = nullptr;
-        bdpt_arena = nullptr; bd_walkers = bd_headers = bd_fsd_out = nullptr; bd_pending = nullptr; bd_L0 = nullptr; bd_nverts = bd_fsd_list = nullptr; bd_pairs = nullptr;
-    }
+    void free_pool() { for (Pool& p : pools) p.free_buffers(); pool = 0; }
     ~wtgpu_scene() {
         cudaSetDevice(device);
         for (void* p : allocs) wt_free(p);
-        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
-        if (hctr) cudaFreeHost(hctr);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
-        free_pool();
-        if (bd_stream) cudaStreamDestroy(bd_stream);
-        if (bd_ev_shade) cudaEventDestroy(bd_ev_shade);
-        if (bd_ev_samp) cudaEventDestroy(bd_ev_samp);
+        for (Pool& p : pools) p.destroy();
     }
 };
 static void caps_derive(Caps& c) { c.ap_words = 16u + 9u * c.seg; c.arena_words = 2u * c.verts * wt::kVertWords + 2u * c.ap_walk * c.ap_words; }
-static bool caps_equal(const Caps& a, const Caps& b) { return a.tris == b.tris && a.edges == b.edges && a.seg == b.seg && a.ap_walk == b.ap_walk && a.verts == b.verts; }
+static bool caps_equal(const Caps& a, const Caps& b) { return a.spill_words == b.spill_words && a.edges == b.edges && a.seg == b.seg && a.ap_walk == b.ap_walk && a.verts == b.verts; }
 
 // Generator matrices of the sobolld sampler from the parsed table, as row masks for dsobol.cuh.
 // Direction numbers m_1..m_11 of a dimension are kept as base-3 digit vectors v[c][t] (digit t of m_{c+1}); the first s_j come from the
@@ -918,20 +1047,15 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
         s->ray_cull_abs = 1e-5f * mabs;
         d.ray_cull_abs = s->ray_cull_abs;
     }
+    d.n_edges_total = desc->n_edges;
     d.root_ptr = desc->root_ptr; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs; d.n_tris = desc->n_tris; d.n_nodes = desc->n_nodes;
     d.sensor = desc->sensor; d.integrator = desc->integrator;
     s->sensor = desc->sensor; s->integ = desc->integrator;
     s->n_keys = desc->n_bsdfs + 3u;
     // initial list capacities; a render that needs more grows them (wtgpu_render).  plt_bdpt keeps max_depth + 2 vertices per subpath, but
     // with Russian roulette long subpaths are rare: start at 18 (max_depth 16, the reference scenes' setting) and grow on demand.
-    s->caps.tris = 128u; s->caps.edges = 48u; s->caps.seg = 48u; s->caps.ap_walk = 4u;
+    s->caps.tris = wt::kTriRow; s->caps.spill_words = 16u << 20; s->caps.edges = 48u; s->caps.seg = 48u; s->caps.ap_walk = 4u;
     s->caps.verts = bdpt ? std::min(desc->integrator.max_depth + 2u, 18u) : 0u;
-    if (const char* e = getenv("WT_CAPS")) {    // "tris,edges,seg,ap_walk,verts": initial capacities (tests start tiny to exercise the growth)
-        unsigned v[5] = { s->caps.tris, s->caps.edges, s->caps.seg, s->caps.ap_walk, s->caps.verts };
-        sscanf(e, "%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4]);
-        s->caps.tris = std::max(8u, v[0]); s->caps.edges = std::max(4u, v[1]); s->caps.seg = std::max(4u, v[2]); s->caps.ap_walk = std::max(1u, v[3]);
-        if (bdpt) s->caps.verts = std::min(desc->integrator.max_depth + 2u, std::max(3u, v[4]));
-    }
     caps_derive(s->caps);
     *out = s;
     return WTGPU_OK;
@@ -955,41 +1079,66 @@ static uint32_t bdpt_max_pairs(uint32_t verts, uint32_t max_depth) {     // stra
     for (int t = 0; t <= n; ++t) for (int q = 0; q <= n; ++q) { const int depth = t + q - 2; if ((t == 1 && q == 1) || depth < 0) continue; if (depth > maxd) break; ++n_pairs; }
     return n_pairs;
 }
-static size_t pool_bytes(const wtgpu_scene* s, uint32_t kind, uint32_t pool, const Caps& c) {
+static size_t pool_bytes(const wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t parts, const Caps& c) {
     const size_t P = pool;
-    if (kind == POOL_PATH) return P * (16ull * (chunks_of<PathCore>() + chunks_of<PathFsd>() + chunks_of<HitRec>()) + sizeof(TravRec) + 4ull * c.tris + 12ull * c.edges + 16ull);
-    if (kind == POOL_BDPT_MEGA) return P * (4ull * c.arena_words + 4ull * c.tris + 4ull * c.edges);
+    const size_t row = 4ull * (wt::kTriRow + wt::kTriExt) + 8ull, shared = (size_t)parts * (4ull * c.spill_words + 16ull * s->bit_words * s->big_blocks);      // triangle-list row + extent table + hand-over lists; per sub-pool: the arena, scratch bitmaps
+    if (kind == POOL_PATH) return shared + P * (16ull * (chunks_of<PathCore>() + chunks_of<PathFsd>() + chunks_of<HitRec>()) + sizeof(TravRec) + row + 12ull * c.edges + 16ull);
+    if (kind == POOL_BDPT_MEGA) return shared + P * (4ull * c.arena_words + row + 4ull * c.edges);
     const size_t W2 = 2 * P;
-    return P * (4ull * c.arena_words + 16ull * chunks_of<BdHeader>() + 8ull * (bdpt_max_pairs(c.verts, s->integ.max_depth) + 4ull * (c.verts + 1u)) + 16ull) +
-           W2 * (16ull * (chunks_of<BdWalker>() + chunks_of<HitRec>()) + sizeof(TravRec) + 4ull * c.tris + 4ull * c.edges + 12ull + 32ull + 16ull);
+    return shared + P * (4ull * c.arena_words + 16ull * chunks_of<BdHeader>() + 8ull * (bdpt_max_pairs(c.verts, s->integ.max_depth) + 4ull * (c.verts + 1u)) + 16ull) +
+           W2 * (16ull * (chunks_of<BdWalker>() + chunks_of<HitRec>()) + sizeof(TravRec) + row + 4ull * c.edges + 12ull + 32ull + 16ull);
 }
-static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool) {
-    if (s->pool == pool && s->pool_kind == kind && caps_equal(s->pool_caps, s->caps)) return WTGPU_OK;
+static void bitmap_geometry(wtgpu_scene* s) {
+    int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
+    s->bit_words = (s->d.n_edges_total + 31u) / 32u + 1u;
+    s->big_blocks = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)n_sm * 4, (256ull << 20) / (16ull * s->bit_words)));     // 4 warps per block; <= 256 MiB of bitmaps per sub-pool
+}
+// `pool` paths in flight in all, split over `parts` sub-pools
+static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t parts) {
+    if (s->pool == pool && s->pool_parts == parts && s->pool_kind == kind && caps_equal(s->pool_caps, s->caps)) return WTGPU_OK;
     s->free_pool();
+    if (s->pools.size() < parts) s->pools.resize(parts);
     const Caps& c = s->caps;
-    int rc = WTGPU_OK;
-    auto get = [&](auto** p, size_t bytes) { if (rc != WTGPU_OK) return; cudaError_t e = wt_malloc(p, std::max<size_t>(bytes, 16)); if (e != cudaSuccess) { g_err = std::string("device allocation of the path pool: ") + cudaGetErrorString(e); cudaGetLastError(); rc = WTGPU_E_CUDA; *p = nullptr; } else s->pool_allocs.push_back((void*)*p); };
-    const size_t P = pool;
-    get(&s->ctr, sizeof(DevCounters));
-    get(&s->key_count, 4ull * s->n_keys); get(&s->key_cursor, 4ull * s->n_keys);
-    if (kind == POOL_PATH) {
-        get(&s->trav_rec, sizeof(TravRec) * P); get(&s->trav_tris, 4ull * c.tris * P); get(&s->hit_edges, 4ull * c.edges * P); get(&s->ap_edges, 8ull * c.edges * P);
-        get(&s->core, (size_t)chunks_of<PathCore>() * 16 * P); get(&s->fsd, (size_t)chunks_of<PathFsd>() * 16 * P); get(&s->hit, (size_t)chunks_of<HitRec>() * 16 * P);
-        get(&s->alive, 4ull * P); get(&s->keys, 4ull * P); get(&s->order, 4ull * P); get(&s->trav_list, 4ull * P);
-    } else if (kind == POOL_BDPT_MEGA) {
-        get(&s->bdpt_arena, 4ull * c.arena_words * P); get(&s->trav_tris, 4ull * c.tris * P); get(&s->hit_edges, 4ull * c.edges * P);
-    } else {
-        const size_t W2 = 2 * P;
-        get(&s->bdpt_arena, 4ull * c.arena_words * P);
-        get(&s->bd_walkers, (size_t)chunks_of<BdWalker>() * 16 * W2); get(&s->bd_headers, (size_t)chunks_of<BdHeader>() * 16 * P); get(&s->hit, (size_t)chunks_of<HitRec>() * 16 * W2);
-        get(&s->bd_pending, 4ull * P); get(&s->bd_L0, 4ull * P); get(&s->bd_nverts, 4ull * W2); get(&s->alive, 4ull * P);
-        get(&s->keys, 4ull * W2); get(&s->order, 4ull * W2); get(&s->trav_list, 4ull * W2);
-        get(&s->bd_pairs, 8ull * P * (bdpt_max_pairs(c.verts, s->integ.max_depth) + 4ull * (c.verts + 1u)));
-        get(&s->trav_rec, sizeof(TravRec) * W2); get(&s->trav_tris, 4ull * c.tris * W2); get(&s->hit_edges, 4ull * c.edges * W2);
-        get(&s->bd_fsd_list, 12ull * W2); get(&s->bd_fsd_out, 32ull * W2);
+    const uint32_t psize = ((pool / parts) + 127u) & ~127u;
+    for (uint32_t k = 0; k < parts; ++k) {
+        Pool& q = s->pools[k];
+        int rc = WTGPU_OK;
+        auto get = [&](auto** p, size_t bytes) { if (rc != WTGPU_OK) return; cudaError_t e = wt_malloc(p, std::max<size_t>(bytes, 16)); if (e != cudaSuccess) { g_err = std::string("device allocation of the path pool: ") + cudaGetErrorString(e); cudaGetLastError(); rc = WTGPU_E_CUDA; *p = nullptr; } else q.allocs.push_back((void*)*p); };
+        const size_t P = psize;
+        get(&q.ctr, sizeof(DevCounters));
+        get(&q.key_count, 4ull * s->n_keys); get(&q.key_cursor, 4ull * s->n_keys);
+        {   // triangle-list arena, extent tables and hand-over lists (one row per path / walker / thread); scratch edge bitmaps of the warp-per-beam resolve
+            const size_t rows = kind == POOL_BDPT_WAVE ? 2 * P : P;
+            get(&q.spill, 4ull * c.spill_words); get(&q.spill_ext, 4ull * wt::kTriExt * rows); get(&q.big_list, 4ull * rows); get(&q.big_res_list, 4ull * rows);
+            get(&q.edge_bits, 16ull * s->bit_words * s->big_blocks);
+            if (rc == WTGPU_OK) { cudaError_t e = cudaMemset(q.edge_bits, 0, 16ull * s->bit_words * s->big_blocks); if (e != cudaSuccess) { g_err = "cudaMemset(edge bitmaps)"; rc = WTGPU_E_CUDA; } }
+        }
+        if (kind == POOL_PATH) {
+            get(&q.trav_rec, sizeof(TravRec) * P); get(&q.trav_tris, 4ull * wt::kTriRow * P); get(&q.hit_edges, 4ull * c.edges * P); get(&q.ap_edges, 8ull * c.edges * P);
+            get(&q.core, (size_t)chunks_of<PathCore>() * 16 * P); get(&q.fsd, (size_t)chunks_of<PathFsd>() * 16 * P); get(&q.hit, (size_t)chunks_of<HitRec>() * 16 * P);
+            get(&q.alive, 4ull * P); get(&q.keys, 4ull * P); get(&q.order, 4ull * P); get(&q.trav_list, 4ull * P);
+        } else if (kind == POOL_BDPT_MEGA) {
+            get(&q.bdpt_arena, 4ull * c.arena_words * P); get(&q.trav_tris, 4ull * wt::kTriRow * P); get(&q.hit_edges, 4ull * c.edges * P);
+        } else {
+            const size_t W2 = 2 * P;
+            get(&q.bdpt_arena, 4ull * c.arena_words * P);
+            get(&q.bd_walkers, (size_t)chunks_of<BdWalker>() * 16 * W2); get(&q.bd_headers, (size_t)chunks_of<BdHeader>() * 16 * P); get(&q.hit, (size_t)chunks_of<HitRec>() * 16 * W2);
+            get(&q.bd_pending, 4ull * P); get(&q.bd_L0, 4ull * P); get(&q.bd_nverts, 4ull * W2); get(&q.alive, 4ull * P);
+            get(&q.keys, 4ull * W2); get(&q.order, 4ull * W2); get(&q.trav_list, 4ull * W2);
+            get(&q.bd_pairs, 8ull * P * (bdpt_max_pairs(c.verts, s->integ.max_depth) + 4ull * (c.verts + 1u)));
+            get(&q.trav_rec, sizeof(TravRec) * W2); get(&q.trav_tris, 4ull * wt::kTriRow * W2); get(&q.hit_edges, 4ull * c.edges * W2);
+            get(&q.bd_fsd_list, 12ull * W2); get(&q.bd_fsd_out, 32ull * W2);
+        }
+        if (rc == WTGPU_OK && !q.hctr) {
+            if (cudaMallocHost(&q.hctr, sizeof(DevCounters)) != cudaSuccess || cudaStreamCreateWithFlags(&q.st, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&q.st_fsd, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_iter, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&q.ev_shade, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_samp, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming) != cudaSuccess) { g_err = "creating the sub-pool's streams / events failed"; rc = WTGPU_E_CUDA; }
+        }
+        if (rc != WTGPU_OK) { s->free_pool(); return rc; }
+        q.size = psize;
     }
-    if (rc != WTGPU_OK) { s->free_pool(); return rc; }
-    s->pool = pool; s->pool_kind = kind; s->pool_caps = s->caps;
+    s->pool = pool; s->pool_parts = parts; s->pool_kind = kind; s->pool_caps = s->caps;
     return WTGPU_OK;
 }
 
@@ -997,101 +1146,109 @@ __global__ void k_film_add(float* __restrict__ dst, const float* __restrict__ sr
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
 }
 
-// One pass over the samples with the scene handle's current capacities, into the device films dblock / dlight.  The counters are left in s->hctr.
-static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t pool, uint32_t kind, float* dblock, float* dlight, unsigned long long total, uint32_t x1, uint32_t y1,
-                       bool use_thread_trav, bool time_phases, size_t& n_ev, uint64_t& launches, uint64_t& iters) {
-    cudaStream_t st = (cudaStream_t)o->stream;
+// One pass over the samples with the scene handle's current capacities, into the device films dblock / dlight: every sub-pool advances its own
+// wavefront on its own stream; the host hands a sub-pool its next iteration as soon as the previous one's counters are back.  The summed
+// counters are left in s->total_ctr.
+static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind, float* dblock, float* dlight, unsigned long long total, uint32_t x1, uint32_t y1,
+                       bool use_thread_trav, bool time_phases, uint64_t& launches, uint64_t& iters_total) {
+    cudaStream_t user = (cudaStream_t)o->stream;
     const bool bdpt = kind != POOL_PATH;
+    const uint32_t parts = s->pool_parts;
     s->d.cap = s->caps;
-    RenderArgs a;
-    a.sc = s->d; a.core = s->core; a.fsd = s->fsd; a.hit = s->hit; a.alive = s->alive; a.keys = s->keys; a.order = s->order;
-    a.trav_rec = s->trav_rec; a.trav_tris = s->trav_tris; a.hit_edges = s->hit_edges; a.ap_edges = s->ap_edges; a.it_parity = 0u;
-    a.key_count = s->key_count; a.key_cursor = s->key_cursor; a.trav_list = s->trav_list; a.ctr = s->ctr; a.film_block = dblock; a.film_light = dlight;
-    a.pool = pool; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
-    a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
-    a.sample_begin = o->sample_begin; a.n_samples = o->sample_end - o->sample_begin; a.total = total;
-
-    if (s->alive) CK(cudaMemsetAsync(s->alive, 0, 4ull * pool, st));
-    CK(cudaMemsetAsync(s->key_count, 0, 4ull * s->n_keys, st));
-    CK(cudaMemsetAsync(s->ctr, 0, sizeof(DevCounters), st));
-    DevCounters* const hctr = s->hctr;
     // Block size of the one-thread-per-item kernels (generate / resolve / sort / shade / connect).  Their warps run for very different times (a
     // path with thousands of UTD edges next to paths that die at once), and a block's slots are only handed on when its LAST warp retires:
     // with one warp per block a finished warp is replaced immediately.  (The group-traversal and Fraunhofer-sampler kernels keep 128: their
     // shared-memory layout is per 128 threads and they pull work from a cursor anyway.)  WT_BLOCK_T overrides for A/B runs.
     static const unsigned bt = []() { const char* e = getenv("WT_BLOCK_T"); const unsigned v = e ? (unsigned)atoi(e) : kBlockT; return (v == 32u || v == 64u || v == 128u) ? v : kBlockT; }();
     int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
-    const dim3 blk(128), blkT(bt), grd((pool + bt - 1) / bt);
+    const dim3 blk(128), blkT(bt);
     const bool nosort = (o->flags & WTGPU_RENDER_NO_SORT) != 0;
-    std::vector<cudaEvent_t>& evs = s->ev_pool;
-    auto mark = [&]() { if (time_phases) { if (n_ev == evs.size()) { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); } cudaEventRecord(evs[n_ev++], st); } };
-    if (kind == POOL_BDPT_MEGA) {     // one thread per sample, one launch (dbdpt.cuh driver 1)
-        BdptArgs b;
-        b.sc = s->d; b.lut = s->lut; b.arena = s->bdpt_arena; b.P = pool; b.trav_tris = s->trav_tris; b.hit_edges = s->hit_edges; b.ctr = s->ctr; b.film_block = dblock; b.film_light = dlight;
-        b.seed_lo = a.seed_lo; b.seed_hi = a.seed_hi; b.tile_x0 = a.tile_x0; b.tile_y0 = a.tile_y0; b.tile_w = a.tile_w; b.tile_h = a.tile_h; b.sample_begin = a.sample_begin; b.total = total;
-        k_bdpt<<<pool / 128, blk, 0, st>>>(b); ++launches; ++iters;
-        CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-    } else if (bdpt) {      // wavefront (dbdpt.cuh driver 2)
-        const uint32_t P = pool, W2 = 2u * pool;
-        const uint32_t nmaxv = s->caps.verts + 1u;
-        BdArgs b;
-        b.r = a; b.r.pool = W2;
-        b.lut = s->lut; b.arena = s->bdpt_arena; b.P = P; b.walkers = s->bd_walkers; b.headers = s->bd_headers;
-        b.pending = s->bd_pending; b.L0 = s->bd_L0; b.nverts = s->bd_nverts; b.pairs = s->bd_pairs; b.fsd_list = s->bd_fsd_list; b.fsd_out = s->bd_fsd_out; b.trav_rec = s->trav_rec; b.trav_tris = s->trav_tris;
-        for (int c = 0; c < 5; ++c) b.pair_off[c] = (size_t)P * nmaxv * (size_t)c;      // classes 0-3 hold <= cap.verts + 1 strategies per sample, class 4 the rest
-        const bool has_fsd = s->integ.fsd != 0u && !s->sensor.ray_trace_only;
-        const dim3 gP((P + bt - 1) / bt), gW((W2 + bt - 1) / bt), gC(n_sm * 8), gCT(n_sm * 8 * (128 / bt));
-        if (has_fsd && !s->bd_stream) {
-            CK(cudaStreamCreateWithFlags(&s->bd_stream, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&s->bd_ev_shade, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->bd_ev_samp, cudaEventDisableTiming));
-        }
-        const uint64_t it0 = iters;
-        for (;;) {
-            // Fraunhofer direction sampling of iteration j runs on bd_stream, overlapped with the strategies of j and the walk kernels
-            // of j+1; its walkers rejoin at "finish" in iteration j+1.  Three rotating lists keep producer and consumers apart.
-            const uint64_t it = iters - it0;
+    const bool has_fsd = kind == POOL_BDPT_WAVE && s->integ.fsd != 0u && !s->sensor.ray_trace_only;
+    const dim3 gBig(s->big_blocks);
+
+    // the sub-pools start after whatever the caller queued on its stream
+    CK(cudaEventRecord(s->ev_begin, user));
+    std::vector<RenderArgs> args(parts);
+    for (uint32_t k = 0; k < parts; ++k) {
+        Pool& q = s->pools[k];
+        CK(cudaStreamWaitEvent(q.st, s->ev_begin, 0));
+        DScene d = s->d; d.spill = q.spill; d.spill_ext = q.spill_ext; d.spill_head = &q.ctr->spill_head;
+        RenderArgs& a = args[k];
+        a.sc = d; a.core = q.core; a.fsd = q.fsd; a.hit = q.hit; a.alive = q.alive; a.keys = q.keys; a.order = q.order;
+        a.trav_rec = q.trav_rec; a.trav_tris = q.trav_tris; a.hit_edges = q.hit_edges; a.ap_edges = q.ap_edges; a.it_parity = 0u;
+        a.big_list = q.big_list; a.big_res_list = q.big_res_list; a.edge_bits = q.edge_bits;
+        a.key_count = q.key_count; a.key_cursor = q.key_cursor; a.trav_list = q.trav_list; a.ctr = q.ctr; a.film_block = dblock; a.film_light = dlight;
+        a.pool = q.size; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
+        a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
+        a.sample_begin = o->sample_begin; a.n_samples = o->sample_end - o->sample_begin; a.total = total; a.part = k; a.n_parts = parts;
+        q.total = total > k ? (total - k + parts - 1) / parts : 0ull;       // samples with id = k (mod parts)
+        q.iters = 0; q.in_flight = false; q.done = false; q.n_ev = 0;
+        if (q.alive) CK(cudaMemsetAsync(q.alive, 0, 4ull * q.size, q.st));
+        CK(cudaMemsetAsync(q.key_count, 0, 4ull * s->n_keys, q.st));
+        CK(cudaMemsetAsync(q.ctr, 0, sizeof(DevCounters), q.st));
+    }
+    auto mark = [&](Pool& q) { if (time_phases) { if (q.n_ev == q.evs.size()) { cudaEvent_t e; cudaEventCreate(&e); q.evs.push_back(e); } cudaEventRecord(q.evs[q.n_ev++], q.st); } };
+
+    // one wavefront iteration of sub-pool k, queued on its stream; ends with the counters' read-back and an event
+    auto launch_iteration = [&](uint32_t k) -> int {
+        Pool& q = s->pools[k];
+        RenderArgs& a = args[k];
+        cudaStream_t st = q.st;
+        const uint32_t pool = q.size;
+        const dim3 grd((pool + bt - 1) / bt);
+        if (kind == POOL_BDPT_MEGA) {     // one thread per sample, one launch (dbdpt.cuh driver 1)
+            BdptArgs b;
+            b.sc = a.sc; b.lut = s->lut; b.arena = q.bdpt_arena; b.P = pool; b.trav_tris = q.trav_tris; b.hit_edges = q.hit_edges; b.ctr = q.ctr; b.film_block = dblock; b.film_light = dlight;
+            b.seed_lo = a.seed_lo; b.seed_hi = a.seed_hi; b.tile_x0 = a.tile_x0; b.tile_y0 = a.tile_y0; b.tile_w = a.tile_w; b.tile_h = a.tile_h; b.sample_begin = a.sample_begin; b.total = total;
+            k_bdpt<<<pool / 128, blk, 0, st>>>(b); ++launches;
+        } else if (bdpt) {      // wavefront (dbdpt.cuh driver 2)
+            const uint32_t P = pool, W2 = 2u * pool;
+            const uint32_t nmaxv = s->caps.verts + 1u;
+            BdArgs b;
+            b.r = a; b.r.pool = W2;
+            b.lut = s->lut; b.arena = q.bdpt_arena; b.P = P; b.walkers = q.bd_walkers; b.headers = q.bd_headers;
+            b.pending = q.bd_pending; b.L0 = q.bd_L0; b.nverts = q.bd_nverts; b.pairs = q.bd_pairs; b.fsd_list = q.bd_fsd_list; b.fsd_out = q.bd_fsd_out; b.trav_rec = q.trav_rec; b.trav_tris = q.trav_tris;
+            for (int c = 0; c < 5; ++c) b.pair_off[c] = (size_t)P * nmaxv * (size_t)c;      // classes 0-3 hold <= cap.verts + 1 strategies per sample, class 4 the rest
+            const dim3 gP((P + bt - 1) / bt), gW((W2 + bt - 1) / bt), gC(n_sm * 8), gCT(n_sm * 8 * (128 / bt));
+            // Fraunhofer direction sampling of iteration j runs on the sub-pool's second stream, overlapped with the strategies of j and the walk
+            // kernels of j+1; its walkers rejoin at "finish" in iteration j+1.  Three rotating lists keep producer and consumers apart.
+            const uint64_t it = q.iters;
             b.fl_cur = (uint32_t)(it % 3ull); b.fl_next = (uint32_t)((it + 1ull) % 3ull); b.fl_fin = (uint32_t)((it + 2ull) % 3ull);
             b.tag = 16.f + (float)(it % 1024ull); b.tag_fin = 16.f + (float)((it + 1023ull) % 1024ull);
-            mark();
-            k_bd_generate<<<gP, blkT, 0, st>>>(b); ++launches; mark();
+            mark(q);
+            k_bd_generate<<<gP, blkT, 0, st>>>(b); ++launches; mark(q);
             if (use_thread_trav) { k_bd_traverse<<<gW, blkT, 0, st>>>(b); ++launches; }
-            else { k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_resolve<<<gW, blkT, 0, st>>>(b); launches += 2; }
-            mark();
+            else {
+                k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_wtraverse<<<gC, blk, 0, st>>>(b);
+                k_bd_resolve<<<gW, blkT, 0, st>>>(b); k_bd_resolve_big<<<gBig, blk, 0, st>>>(b, s->bit_words); launches += 4;
+            }
+            mark(q);
             k_hist<<<gW, blkT, s->n_keys * 4, st>>>(b.r);
             k_scan<<<1, 1024, 0, st>>>(b.r);
-            k_scatter<<<gW, blkT, 0, st>>>(b.r); launches += 3; mark();
+            k_scatter<<<gW, blkT, 0, st>>>(b.r); launches += 3; mark(q);
             k_bd_reset<<<1, 32, 0, st>>>(b);
             k_bd_shade<<<gW, blkT, 0, st>>>(b); launches += 2;
             if (has_fsd) {
-                CK(cudaEventRecord(s->bd_ev_shade, st));
-                if (it > 0) { CK(cudaStreamWaitEvent(st, s->bd_ev_samp, 0)); k_bd_fsd_finish<<<gW, blkT, 0, st>>>(b); ++launches; }
-                CK(cudaStreamWaitEvent(s->bd_stream, s->bd_ev_shade, 0));
-                CK(cudaMemsetAsync(&s->ctr->fsd_head, 0, sizeof(int), s->bd_stream));
-                k_bd_fsd_sample<<<dim3(n_sm * 16), blk, 0, s->bd_stream>>>(b); ++launches;
-                CK(cudaEventRecord(s->bd_ev_samp, s->bd_stream));
+                CK(cudaEventRecord(q.ev_shade, st));
+                if (it > 0) { CK(cudaStreamWaitEvent(st, q.ev_samp, 0)); k_bd_fsd_finish<<<gW, blkT, 0, st>>>(b); ++launches; }
+                CK(cudaStreamWaitEvent(q.st_fsd, q.ev_shade, 0));
+                CK(cudaMemsetAsync(&q.ctr->fsd_head, 0, sizeof(int), q.st_fsd));
+                k_bd_fsd_sample<<<dim3(n_sm * 16), blk, 0, q.st_fsd>>>(b); ++launches;
+                CK(cudaEventRecord(q.ev_samp, q.st_fsd));
             }
-            mark();
+            mark(q);
             k_bd_connect<0><<<gCT, blkT, 0, st>>>(b); k_bd_connect<1><<<gCT, blkT, 0, st>>>(b); k_bd_connect<2><<<gCT, blkT, 0, st>>>(b);
-            k_bd_connect<3><<<gCT, blkT, 0, st>>>(b); k_bd_connect<4><<<gCT, blkT, 0, st>>>(b); launches += 5; mark();
-            ++iters;
-            CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (hctr->next_sample >= total && hctr->live <= 0) break;
-            if (iters - it0 > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
-        }
-        if (has_fsd) CK(cudaStreamSynchronize(s->bd_stream));
-        CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-    } else {
-        const uint64_t it0 = iters;
-        for (;;) {
-            a.it_parity = (uint32_t)((iters - it0) & 1ull);
-            mark();
-            k_generate<<<grd, blkT, 0, st>>>(a); ++launches; mark();
+            k_bd_connect<3><<<gCT, blkT, 0, st>>>(b); k_bd_connect<4><<<gCT, blkT, 0, st>>>(b); launches += 5; mark(q);
+        } else {
+            a.it_parity = (uint32_t)(q.iters & 1ull);
+            mark(q);
+            k_generate<<<grd, blkT, 0, st>>>(a); ++launches; mark(q);
             if (use_thread_trav) { k_traverse<<<grd, blkT, 0, st>>>(a); ++launches; }
-            else { k_gtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_resolve<<<grd, blkT, 0, st>>>(a); launches += 2; }
-            mark();
+            else {
+                k_gtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_wtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a);
+                k_resolve<<<grd, blkT, 0, st>>>(a); k_resolve_big<<<gBig, blk, 0, st>>>(a, s->bit_words); launches += 4;
+            }
+            mark(q);
             if (nosort) {
                 k_identity_order<<<grd, blkT, 0, st>>>(a); ++launches;
             } else {
@@ -1099,15 +1256,65 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t pool
                 k_scan<<<1, 1024, 0, st>>>(a);
                 k_scatter<<<grd, blkT, 0, st>>>(a); launches += 3;
             }
-            mark();
+            mark(q);
             k_reset_trav<<<1, 32, 0, st>>>(a);
-            k_shade<<<grd, blkT, 0, st>>>(a); launches += 2; mark();
-            ++iters;
-            CK(cudaMemcpyAsync(hctr, s->ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (hctr->next_sample >= total && hctr->live <= 0) break;
-            if (iters - it0 > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
+            k_shade<<<grd, blkT, 0, st>>>(a); launches += 2; mark(q);
         }
+        ++q.iters; ++iters_total;
+        CK(cudaMemcpyAsync(q.hctr, q.ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(q.ev_iter, st));
+        q.in_flight = true;
+        return WTGPU_OK;
+    };
+
+    uint32_t remaining = 0;
+    for (uint32_t k = 0; k < parts; ++k) {
+        if (s->pools[k].total == 0ull) { s->pools[k].done = true; continue; }
+        ++remaining;
+        const int rc = launch_iteration(k); if (rc != WTGPU_OK) return rc;
+    }
+    uint32_t rr = 0;
+    while (remaining) {
+        bool progressed = false;
+        for (uint32_t j = 0; j < parts; ++j) {
+            const uint32_t k = (rr + j) % parts;
+            Pool& q = s->pools[k];
+            if (!q.in_flight) continue;
+            const cudaError_t e = cudaEventQuery(q.ev_iter);
+            if (e == cudaErrorNotReady) continue;
+            CK(e);
+            q.in_flight = false; progressed = true;
+            const bool finished = kind == POOL_BDPT_MEGA || (q.hctr->next_sample >= q.total && q.hctr->live <= 0);
+            if (finished) { q.done = true; --remaining; continue; }
+            if (q.iters > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
+            const int rc = launch_iteration(k); if (rc != WTGPU_OK) return rc;
+        }
+        if (!progressed) {      // nothing ready: sleep on the next sub-pool in turn
+            for (uint32_t j = 0; j < parts; ++j) { const uint32_t k = (rr + j) % parts; if (s->pools[k].in_flight) { CK(cudaEventSynchronize(s->pools[k].ev_iter)); break; } }
+        }
+        rr = (rr + 1u) % parts;
+    }
+    // all sub-pools done: final counters, and the caller's stream continues after them
+    DevCounters& T = s->total_ctr; memset(&T, 0, sizeof(T));
+    for (uint32_t k = 0; k < parts; ++k) {
+        Pool& q = s->pools[k];
+        if (q.total == 0ull) continue;
+        if (has_fsd) CK(cudaStreamSynchronize(q.st_fsd));
+        CK(cudaMemcpyAsync(q.hctr, q.ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, q.st));
+        CK(cudaEventRecord(q.ev_done, q.st));
+        CK(cudaStreamWaitEvent(user, q.ev_done, 0));
+    }
+    for (uint32_t k = 0; k < parts; ++k) {
+        Pool& q = s->pools[k];
+        if (q.total == 0ull) continue;
+        CK(cudaStreamSynchronize(q.st));
+        const DevCounters& c = *q.hctr;
+        T.samples += c.samples; T.segments += c.segments; T.ray_casts += c.ray_casts; T.cone_casts += c.cone_casts; T.shadow_casts += c.shadow_casts; T.nodes += c.nodes; T.tris += c.tris;
+        T.edges += c.edges; T.surface += c.surface; T.fsd += c.fsd; T.null_ += c.null_; T.splats += c.splats; T.overflow += c.overflow; T.shade_nodes += c.shade_nodes; T.shade_tris += c.shade_tris;
+        T.shaded += c.shaded; T.walker_steps += c.walker_steps; T.stack_drops += c.stack_drops;
+        for (int i = 0; i < 5; ++i) T.strategies[i] += c.strategies[i];
+        T.need_spill = std::max(T.need_spill, std::max(c.need_spill, c.spill_head)); T.need_edges = std::max(T.need_edges, c.need_edges); T.need_seg = std::max(T.need_seg, c.need_seg);
+        T.need_ap = std::max(T.need_ap, c.need_ap); T.need_verts = std::max(T.need_verts, c.need_verts);
     }
     CK(cudaGetLastError());
     return WTGPU_OK;
@@ -1134,6 +1341,12 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     if (pool > (1u << 22) && bdpt) { g_err = "plt_bdpt: pool_size > 4M sample slots"; return WTGPU_E_INVALID; }
     pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>(total, 1024ull));
     pool = (pool + 127u) & ~127u;
+    const bool time_phases = stats != nullptr && (o->flags & WTGPU_RENDER_TIME_KERNELS) != 0;
+    // Sub-pools (Pool above): 4 independent wavefronts side by side once there are enough paths to share out.  Per-kernel timing
+    // (WTGPU_RENDER_TIME_KERNELS) wants one kernel at a time on the device: a single sub-pool.  WT_SUBPOOLS overrides for A/B runs.
+    uint32_t parts = (kind == POOL_BDPT_MEGA || time_phases) ? 1u : (pool >= (1u << 16) ? 4u : pool >= (1u << 14) ? 2u : 1u);
+    if (o->flags & WTGPU_RENDER_ONE_SUBPOOL) parts = 1u;
+    if (const char* e = getenv("WT_SUBPOOLS")) { const int v = atoi(e); if (v >= 1 && v <= 16 && kind != POOL_BDPT_MEGA) parts = (uint32_t)v; }
 
     {   // the group-traversal kernels keep their stacks in shared memory: ask for the large shared-memory carve-out so that the register file, not
         // the L1/shared split, bounds the resident blocks (per device: a process may drive several)
@@ -1149,8 +1362,8 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     // traverse(): eight lanes per beam pay off when queries are long (cone queries over real geometry); on a handful of triangles one thread
     // per beam is faster (measured: double_slits plt_path 99 vs 52 Msamples/s; etoile-like 6 vs 16).  Both give bit-identical results.
     const bool use_thread_trav = (o->flags & WTGPU_RENDER_THREAD_TRAVERSE) ? true : (o->flags & WTGPU_RENDER_GROUP_TRAVERSE) ? false : (!bdpt && s->d.n_tris < 128u);
-    if (!s->hctr) { CK(cudaMallocHost(&s->hctr, sizeof(DevCounters))); CK(cudaEventCreate(&s->ev_begin)); CK(cudaEventCreate(&s->ev_end)); }
-    DevCounters* const hctr = s->hctr;
+    if (!s->ev_begin) { CK(cudaEventCreate(&s->ev_begin)); CK(cudaEventCreate(&s->ev_end)); }
+    if (!s->bit_words) bitmap_geometry(s);
 
     // The films of this call are accumulated in scratch device buffers and added to the caller's at the end: a pass that finds a list longer
     // than its row (capacity growth, below) is discarded and repeated, and must not have touched the caller's film.
@@ -1160,57 +1373,62 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
     struct Scratch { float*& a; float*& b; ~Scratch() { if (a) wt_free(a); if (b) wt_free(b); } } scratch{ dblock, dlight };
     CK(wt_malloc(&dblock, nb * 4)); CK(wt_malloc(&dlight, nl * 4));
 
-    const bool time_phases = stats != nullptr && (o->flags & WTGPU_RENDER_TIME_KERNELS) != 0;
-    uint64_t launches = 0, iters = 0; size_t n_ev = 0;
+    uint64_t launches = 0, iters = 0;
     uint32_t passes = 0;
-    CK(cudaEventRecord(s->ev_begin, st));
+    cudaEvent_t t0 = nullptr, t1 = nullptr;     // the call's device time on the caller's stream
+    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    struct Ev { cudaEvent_t& a; cudaEvent_t& b; ~Ev() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg{ t0, t1 };
+    CK(cudaEventRecord(t0, st));
+    const DevCounters* hctr = &s->total_ctr;
     // ---- capacity growth: two-pass count / fill at the granularity of the render.  The reference keeps cone-query results, edge sets,
-    // aperture segments and subpath vertices in std::vector / std::set of any length; here they are rows of HBM arrays.  A pass records the longest
-    // list any too-short row was asked to hold; the rows are re-sized and the pass repeated, so a result never depends on a capacity.  The
-    // capacities stay with the scene handle: the next render of this scene starts with rows that fitted.
+    // aperture segments and subpath vertices in std::vector / std::set of any length; here they are rows of HBM arrays (and, for the triangle
+    // lists, extents of an arena).  A pass records the longest list any too-short row was asked to hold; the rows are re-sized and the pass
+    // repeated, so a result never depends on a capacity.  The capacities stay with the scene handle: the next render starts with rows that fitted.
     for (;;) {
-        size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
         uint32_t use_pool = pool;
-        if (!(s->pool == pool && s->pool_kind == kind && caps_equal(s->pool_caps, s->caps))) {
+        if (!(s->pool == pool && s->pool_parts == parts && s->pool_kind == kind && caps_equal(s->pool_caps, s->caps))) {
             s->free_pool();
-            cudaMemGetInfo(&free_b, &total_b);
-            while (use_pool > 4096u && pool_bytes(s, kind, use_pool, s->caps) > (size_t)(0.85 * (double)free_b) + 0) use_pool = ((use_pool / 2u) + 127u) & ~127u;     // long rows: fewer paths in flight
+            size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+            while (use_pool > 4096u && pool_bytes(s, kind, use_pool, parts, s->caps) > (size_t)(0.85 * (double)free_b)) use_pool = ((use_pool / 2u) + 127u) & ~127u;     // long rows: fewer paths in flight
         }
-        int rc = ensure_pool(s, kind, use_pool);
+        int rc = ensure_pool(s, kind, use_pool, parts);
         if (rc != WTGPU_OK) return rc;
         pool = use_pool;
         CK(cudaMemsetAsync(dblock, 0, nb * 4, st)); CK(cudaMemsetAsync(dlight, 0, nl * 4, st));
-        n_ev = 0;
-        rc = render_pass(s, o, pool, kind, dblock, dlight, total, x1, y1, use_thread_trav, time_phases, n_ev, launches, iters);
+        rc = render_pass(s, o, kind, dblock, dlight, total, x1, y1, use_thread_trav, time_phases, launches, iters);
         if (rc != WTGPU_OK) return rc;
         ++passes;
         if (hctr->overflow == 0) break;
         Caps nc = s->caps;
         auto grow = [](uint32_t cur, uint32_t need) { return need > cur ? std::max((need + 31u) & ~31u, cur + cur / 2u) : cur; };
-        nc.tris = grow(nc.tris, hctr->need_tris); nc.edges = grow(nc.edges, hctr->need_edges); nc.seg = grow(nc.seg, hctr->need_seg);
+        // the triangle-list arena: the bump cursor kept counting past its end, so the largest demand of an iteration is known
+        if (hctr->need_spill > nc.spill_words) nc.spill_words = (uint32_t)std::min<unsigned long long>(0xfff00000ull, (unsigned long long)hctr->need_spill + hctr->need_spill / 4u + (1u << 20));
+        nc.edges = grow(nc.edges, hctr->need_edges); nc.seg = grow(nc.seg, hctr->need_seg);
         nc.ap_walk = std::min(grow(nc.ap_walk, hctr->need_ap), std::max(s->integ.max_depth, 1u));
         if (bdpt) nc.verts = std::min(grow(nc.verts, hctr->need_verts), s->integ.max_depth + 2u);
         caps_derive(nc);
         if (caps_equal(nc, s->caps) || passes >= 12u) {
-            g_err = "a per-path list outgrew its capacity and could not be grown further (tris " + std::to_string(hctr->need_tris) + ", edges " + std::to_string(hctr->need_edges) +
+            g_err = "a per-path list outgrew its capacity and could not be grown further (triangle-list arena " + std::to_string(hctr->need_spill) + ", edges " + std::to_string(hctr->need_edges) +
                     ", segments " + std::to_string(hctr->need_seg) + ", apertures " + std::to_string(hctr->need_ap) + ", vertices " + std::to_string(hctr->need_verts) + ")";
             return WTGPU_E_CAPACITY;
         }
         s->caps = nc;
     }
-    CK(cudaEventRecord(s->ev_end, st));
-    CK(cudaEventSynchronize(s->ev_end));
-    float ms = 0; cudaEventElapsedTime(&ms, s->ev_begin, s->ev_end);
+    CK(cudaEventRecord(t1, st));
+    CK(cudaEventSynchronize(t1));
+    float ms = 0; cudaEventElapsedTime(&ms, t0, t1);
     double t_trav = 0, t_shade = 0, t_gen = 0, t_sort = 0, t_conn = 0;
-    std::vector<cudaEvent_t>& evs = s->ev_pool;
-    const size_t per_it = (kind == POOL_BDPT_WAVE) ? 6 : 5;      // marks per iteration
-    for (size_t i = 0; i + per_it - 1 < n_ev; i += per_it) {
-        float f;
-        cudaEventElapsedTime(&f, evs[i], evs[i + 1]); t_gen += f;
-        cudaEventElapsedTime(&f, evs[i + 1], evs[i + 2]); t_trav += f;
-        cudaEventElapsedTime(&f, evs[i + 2], evs[i + 3]); t_sort += f;
-        cudaEventElapsedTime(&f, evs[i + 3], evs[i + 4]); t_shade += f;
-        if (per_it == 6) { cudaEventElapsedTime(&f, evs[i + 4], evs[i + 5]); t_conn += f; }
+    if (time_phases) {
+        const Pool& q = s->pools[0];
+        const size_t per_it = (kind == POOL_BDPT_WAVE) ? 6 : 5;      // marks per iteration
+        for (size_t i = 0; i + per_it - 1 < q.n_ev; i += per_it) {
+            float f;
+            cudaEventElapsedTime(&f, q.evs[i], q.evs[i + 1]); t_gen += f;
+            cudaEventElapsedTime(&f, q.evs[i + 1], q.evs[i + 2]); t_trav += f;
+            cudaEventElapsedTime(&f, q.evs[i + 2], q.evs[i + 3]); t_sort += f;
+            cudaEventElapsedTime(&f, q.evs[i + 3], q.evs[i + 4]); t_shade += f;
+            if (per_it == 6) { cudaEventElapsedTime(&f, q.evs[i + 4], q.evs[i + 5]); t_conn += f; }
+        }
     }
 
     if (on_dev) {
@@ -1234,8 +1452,8 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         stats->gpu_ms = ms; stats->traverse_ms = t_trav; stats->shade_ms = t_shade; stats->generate_ms = t_gen; stats->sort_ms = t_sort; stats->connect_ms = t_conn;
         for (int c = 0; c < 5; ++c) stats->strategies[c] = hctr->strategies[c];
         stats->walker_steps = hctr->walker_steps;
-        stats->passes = passes; stats->stack_drops = hctr->stack_drops; stats->pool_used = pool;
-        stats->cap_tris = s->caps.tris; stats->cap_edges = s->caps.edges; stats->cap_segments = s->caps.seg; stats->cap_apertures = s->caps.ap_walk; stats->cap_vertices = s->caps.verts;
+        stats->passes = passes; stats->stack_drops = hctr->stack_drops; stats->pool_used = pool; stats->subpools = parts;
+        stats->cap_tris = s->caps.spill_words; stats->cap_edges = s->caps.edges; stats->cap_segments = s->caps.seg; stats->cap_apertures = s->caps.ap_walk; stats->cap_vertices = s->caps.verts;
     }
     if (hctr->stack_drops) {
         g_err = "a BVH traversal stack (64 entries for rays, 128 for cones, as bvh8w.cpp's) was full " + std::to_string((unsigned long long)hctr->stack_drops) + " times and dropped children: the tree is too deep for the reference's traversal";
@@ -1246,13 +1464,13 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
 
 int wtgpu_get_capacities(wtgpu_scene* s, uint32_t out[5]) {
     if (!s || !out) { g_err = "null argument"; return WTGPU_E_INVALID; }
-    out[0] = s->caps.tris; out[1] = s->caps.edges; out[2] = s->caps.seg; out[3] = s->caps.ap_walk; out[4] = s->caps.verts;
+    out[0] = s->caps.spill_words; out[1] = s->caps.edges; out[2] = s->caps.seg; out[3] = s->caps.ap_walk; out[4] = s->caps.verts;
     return WTGPU_OK;
 }
 int wtgpu_set_capacities(wtgpu_scene* s, const uint32_t in[5]) {
     if (!s || !in) { g_err = "null argument"; return WTGPU_E_INVALID; }
     const bool bdpt = s->integ.type == WTGPU_INTEGRATOR_PLT_BDPT;
-    s->caps.tris = std::max(8u, in[0]); s->caps.edges = std::max(4u, in[1]); s->caps.seg = std::max(4u, in[2]); s->caps.ap_walk = std::max(1u, in[3]);
+    s->caps.tris = wt::kTriRow; s->caps.spill_words = std::max(1024u, in[0]); s->caps.edges = std::max(4u, in[1]); s->caps.seg = std::max(4u, in[2]); s->caps.ap_walk = std::max(1u, in[3]);
     s->caps.verts = bdpt ? std::min(s->integ.max_depth + 2u, std::max(3u, in[4])) : 0u;
     caps_derive(s->caps);
     return WTGPU_OK;

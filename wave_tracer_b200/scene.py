@@ -155,6 +155,57 @@ class ITU(Spectrum):
         return out
 
 
+_SPECTRA = None
+
+
+def spectra_db():
+    """wave_tracer_b200/data/spectra.npz: the tabulated physical data the reference scenes name (refractive indices of data/ior, the emission
+    spectrum box.xml uses, the CIE colour-matching functions), extracted by tools/extract_reference_spectra.py."""
+    global _SPECTRA
+    if _SPECTRA is None:
+        import os
+        _SPECTRA = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "spectra.npz"))
+    return _SPECTRA
+
+
+def Material(name):
+    """<spectrum name="IOR" material="Au"/>: complex refractive index n + i k, piecewise linear in wavenumber (src/spectrum/util/spectrum_from_db.cpp:60-200)."""
+    db = spectra_db()
+    if f"ior/{name}/n" not in db: raise ValueError(f"material {name!r} is not in the spectra fixture (tools/extract_reference_spectra.py)")
+    return Table(db[f"ior/{name}/lam_um"].astype(np.float64) * 1e-6, db[f"ior/{name}/n"].astype(np.float64) + 1j * db[f"ior/{name}/k"].astype(np.float64))
+
+
+class Scaled(Spectrum):
+    def __init__(self, s, scale): self.s, self.scale = _as_spectrum(s), float(scale)
+    def value(self, k): return self.s.value(k) * self.scale
+
+
+def Emission(name, scale=1.0):
+    """<spectrum emitter="2534_CFL_Tensor_Twister">: a tabulated lamp spectrum of data/emission (LSPDD), times scale."""
+    db = spectra_db()
+    if f"emission/{name}/value" not in db: raise ValueError(f"emission spectrum {name!r} is not in the spectra fixture")
+    return Scaled(Table(db[f"emission/{name}/lam_nm"].astype(np.float64) * 1e-9, db[f"emission/{name}/value"].astype(np.float64)), scale)
+
+
+def rgb_response(colourspace="CIE", white_point="D55"):
+    """<response type="RGB">: f(channel, k) = max(0, (M xyz(k))[channel]) with the CIE colour-matching functions and the XYZ -> RGB matrix of the
+    colourspace, Bradford-adapted to the white point (src/sensor/response/RGB.cpp:30-42; spectrum/colourspace/RGB/RGB.hpp:39-130;
+    whitepoint.hpp:28-61).  Returns three Table spectra."""
+    M = {"CIE": ("E", [[2.3706743, -0.9000405, -0.4706338], [-0.5138850, 1.4253036, 0.0885814], [0.0052982, -0.0146949, 1.0093968]]),
+         "sRGB": ("D65", [[3.2404542, -1.5371385, -0.4985314], [-0.9692660, 1.8760108, 0.0415560], [0.0556434, -0.2040259, 1.0572252]])}[colourspace]
+    W = {"D50": (0.96422, 1.0, 0.82521), "D55": (0.95682, 1.0, 0.92149), "D65": (0.95047, 1.0, 1.08883), "D75": (0.94972, 1.0, 1.22638), "E": (1.0, 1.0, 1.0)}
+    X2R = np.array(M[1])
+    if M[0] != white_point:      # Bradford chromatic adaptation
+        MA = np.array([[0.8951, 0.2664, -0.1614], [-0.7502, 1.7135, 0.0367], [0.0389, -0.0685, 1.0296]])
+        iMA = np.array([[0.9869929, -0.1470543, 0.1599627], [0.4323053, 0.5183603, 0.0492912], [-0.0085287, 0.0400428, 0.9684867]])
+        rs, rd = MA @ np.array(W[M[0]]), MA @ np.array(W[white_point])
+        X2R = X2R @ (iMA @ np.diag(rd / rs) @ MA)
+    db = spectra_db()
+    lam = db["XYZ/lam_nm"].astype(np.float64) * 1e-9
+    rgb = np.maximum(db["XYZ/xyz"].astype(np.float64) @ X2R.T, 0.0)
+    return [Table(lam, rgb[:, c]) for c in range(3)]
+
+
 def _as_spectrum(s):
     return s if isinstance(s, Spectrum) else Const(s)
 
@@ -324,6 +375,162 @@ def sphere(radius=1.0, centre=(0, 0, 0), n_lat=16, n_lon=32, to_world=None):
             if i > 0: tris.append((a, b, a + 1))
             if i < n_lat - 1: tris.append((a + 1, b, b + 1))
     return Mesh(np.array(verts, np.float32), np.array(tris, np.uint32), normals=np.array(normals, np.float32), uvs=np.array(uvs, np.float32), to_world=to_world)
+
+
+def square(length, to_world=None, tessellation=1):
+    """<shape type="rectangle"> with `length`: a square in the local xy-plane centred at the origin (src/mesh/rectangle.cpp:74-89)."""
+    return rectangle((-length / 2, -length / 2, 0), (length, 0, 0), (0, length, 0), to_world=to_world, tessellation=tessellation)
+
+
+def cube_len(length=2.0, to_world=None):
+    """<shape type="cube"> with `length` (default 2 m): side `length`, centred at the origin (src/mesh/cube.cpp)."""
+    M = scale(length / 2)
+    return cube(M if to_world is None else np.asarray(to_world, np.float64) @ M)
+
+
+def prism(length=1.0, height=1.0, angle=math.pi / 2, to_world=None):
+    """<shape type="prism">: triangular prism along z, base on y = 0 of width height*tan(angle/2), apex at y = height (src/mesh/prism.cpp): 8 triangles."""
+    hx, hz = .5 * height * math.tan(angle / 2), .5 * length
+    A0, B0, C0 = (-hx, 0, -hz), (hx, 0, -hz), (0, height, -hz)
+    A1, B1, C1 = (-hx, 0, hz), (hx, 0, hz), (0, height, hz)
+    verts, tris = [], []
+    def face(ps, uv):
+        t = len(verts); verts.extend(ps)
+        if len(ps) == 3: tris.append((t, t + 1, t + 2))
+        else: tris.extend([(t, t + 1, t + 2), (t + 2, t + 3, t)])
+    face([A0, C0, B0], None); face([A1, B1, C1], None)          # end caps (outward: -z, +z)
+    face([A1, C1, C0, A0], None); face([B0, C0, C1, B1], None)  # slanted sides
+    face([A1, A0, B0, B1], None)                                # base
+    return Mesh(np.array(verts, np.float32), np.array(tris, np.uint32), to_world=to_world)
+
+
+def icosphere(radius=1.0, centre=(0, 0, 0), tessellation=32, to_world=None, displace=None):
+    """<shape type="sphere">: an icosahedron subdivided round(log2(tessellation/3)) times, per-face vertices with radial normals
+    (src/mesh/sphere.cpp:20-94, icosahedron.cpp): 20 * 4^r triangles (1280 at the default tessellation 32).
+    displace(unit_dirs) -> radii: optional radial displacement (procedural stand-ins for scanned meshes); normals are then recomputed per face."""
+    a, b = 1.0, 2.0 / (1.0 + math.sqrt(5.0))
+    V = np.array([(0, b, -a), (b, a, 0), (-b, a, 0), (0, b, a), (0, -b, a), (-a, 0, b), (0, -b, -a), (a, 0, -b), (a, 0, b), (-a, 0, -b), (b, -a, 0), (-b, -a, 0)], np.float64)
+    V /= np.linalg.norm(V, axis=1, keepdims=True)
+    F = np.array([(2, 1, 0), (1, 2, 3), (5, 4, 3), (4, 8, 3), (7, 6, 0), (6, 9, 0), (11, 10, 4), (10, 11, 6), (9, 5, 2), (5, 9, 11), (8, 7, 1), (7, 8, 10),
+                  (2, 5, 3), (8, 1, 3), (9, 2, 0), (1, 7, 0), (11, 9, 6), (7, 10, 6), (5, 11, 4), (10, 8, 4)], np.int64)
+    tri = V[F]                                                   # (20, 3, 3)
+    rec = int(max(0.0, math.log2(tessellation / 3.0)) + .5)
+    for _ in range(rec):
+        p0, p1, p2 = tri[:, 0], tri[:, 1], tri[:, 2]
+        p01, p02, p12 = (p0 + p1) / 2, (p0 + p2) / 2, (p1 + p2) / 2
+        tri = np.concatenate([np.stack([p0, p01, p02], 1), np.stack([p01, p1, p12], 1), np.stack([p01, p12, p02], 1), np.stack([p02, p12, p2], 1)], 0)
+    n = tri.reshape(-1, 3); n = n / np.linalg.norm(n, axis=1, keepdims=True)
+    r = radius if displace is None else radius * np.asarray(displace(n), np.float64)[:, None]
+    pos = n * r + np.asarray(centre, np.float64)
+    idx = np.arange(len(pos), dtype=np.uint32).reshape(-1, 3)
+    normals = n
+    if displace is not None:
+        fn = np.cross(pos[idx[:, 1]] - pos[idx[:, 0]], pos[idx[:, 2]] - pos[idx[:, 0]]); fn /= np.maximum(np.linalg.norm(fn, axis=1, keepdims=True), 1e-30)
+        normals = np.repeat(fn, 3, axis=0)
+    return Mesh(pos.astype(np.float32), idx, normals=normals.astype(np.float32), to_world=to_world)
+
+
+def blob(radius, centre, n_tris, seed=1, roughness=.35, to_world=None):
+    """SYNTHETIC stand-in for a scanned mesh (the reference's dragon / bunny PLYs are Git-LFS stubs): an icosphere of ~n_tris triangles whose
+    radius is modulated by a few seeded low-frequency lobes -- a closed, smooth-shaded, non-convex surface with the triangle budget of the original."""
+    rec = max(0, int(round(math.log(max(n_tris, 20) / 20.0, 4))))
+    rng = np.random.default_rng(seed)
+    dirs = rng.normal(size=(9, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    amp, freq, ph = rng.uniform(.3, 1.0, 9) * roughness / 3, rng.integers(2, 6, 9), rng.uniform(0, TWO_PI, 9)
+    def displace(n):
+        d = np.ones(len(n))
+        for a, f, p, w in zip(amp, freq, ph, dirs): d += a * np.sin(f * np.arccos(np.clip(n @ w, -1, 1)) + p)
+        return np.maximum(d, .3)
+    return icosphere(radius, centre, tessellation=3 * 2 ** rec, to_world=to_world, displace=displace)
+
+
+def cylinder(p0, p1, radius, tessellation=32, to_world=None):
+    """<shape type="cylinder">: an open tube from p0 to p1, 2 * tessellation triangles, radial normals (src/mesh/cylinder.cpp)."""
+    p0, p1 = np.asarray(p0, np.float64), np.asarray(p1, np.float64)
+    v = p1 - p0; L = np.linalg.norm(v); n = v / L
+    if abs(n[0]) > abs(n[1]): x = 1 / math.sqrt(n[0] ** 2 + n[2] ** 2); b = np.array([x * n[2], 0, -x * n[0]])
+    else: x = 1 / math.sqrt(n[1] ** 2 + n[2] ** 2); b = np.array([0, x * n[2], -x * n[1]])
+    t = np.cross(b, n)
+    verts, normals, uvs, tris = [], [], [], []
+    for i in range(tessellation):
+        phi = TWO_PI * i / tessellation; c, s_ = math.cos(phi), math.sin(phi)
+        d = c * t + s_ * b
+        verts += [p0 + radius * d, p0 + radius * d + L * n]; normals += [d, d]; uvs += [(i / tessellation, 0), (i / tessellation, 1)]
+        i0, i1, i2 = 2 * i, 2 * i + 1, (2 * i + 2) % (2 * tessellation); i3 = i2 + 1
+        tris += [(i0, i2, i1), (i1, i2, i3)]
+    return Mesh(np.array(verts, np.float32), np.array(tris, np.uint32), normals=np.array(normals, np.float32), uvs=np.array(uvs, np.float32), to_world=to_world)
+
+
+def lens(radius, centre, R1, R2, thickness=0.0, tessellation=50, to_world=None):
+    """<shape type="lens">: two spherical caps of curvature R1 / R2 (in units of 1/radius; 0: flat; sign: convex / concave) facing -x / +x, rim radius
+    `radius`, joined by a cylindrical edge when the edge thickness is positive (src/mesh/lens.cpp).  Rings are spaced as (i/n)^0.8 like the
+    reference's; ~4 tessellation^2 triangles."""
+    Rl = radius / R1 if R1 != 0 else math.inf
+    Rr = radius / R2 if R2 != 0 else math.inf
+    x1 = math.copysign(math.sqrt(Rl * Rl - radius * radius), Rl) if math.isfinite(Rl) else 0.0
+    x2 = -math.copysign(math.sqrt(Rr * Rr - radius * radius), Rr) if math.isfinite(Rr) else 0.0
+    ET = x1 - x2 - (Rl if math.isfinite(Rl) else 0.0) - (Rr if math.isfinite(Rr) else 0.0) + thickness
+    if thickness == 0 and R1 <= 0 and R2 <= 0: ET += radius / 1000
+    verts, normals, tris = [], [], []
+    def cap(R, xc, sign, shift):
+        start = len(verts)
+        nt = tessellation if math.isfinite(R) else 1
+        apex = np.array([xc - sign * (R if math.isfinite(R) else 0.0) + shift, 0, 0]) if sign < 0 else np.array([xc + (R if math.isfinite(R) else 0.0) + shift, 0, 0])
+        verts.append(apex); normals.append(np.array([sign, 0, 0], np.float64))
+        for i in range(nt):
+            h = radius * min(1.0, ((i + 1) / nt) ** .8)
+            for j in range(tessellation):
+                phi = TWO_PI * j / tessellation
+                cp = np.array([0, math.cos(phi) * h, math.sin(phi) * h])
+                if math.isfinite(R):
+                    c0 = np.array([xc, 0, 0]); n = cp - c0; n /= np.linalg.norm(n)
+                    if R < 0: n = -n
+                    p = c0 + n * R + np.array([shift, 0, 0])
+                else:
+                    n = np.array([sign, 0, 0], np.float64); p = cp + np.array([shift, 0, 0])
+                verts.append(p); normals.append(n)
+        for i in range(nt):
+            for j in range(tessellation):
+                jp = j - 1 if j > 0 else tessellation - 1
+                cur, prv = start + 1 + i * tessellation + j, start + 1 + i * tessellation + jp
+                if i == 0: t = (start, cur, prv)
+                else:
+                    a0, a1 = start + 1 + (i - 1) * tessellation + jp, start + 1 + (i - 1) * tessellation + j
+                    tris.append((a0, a1, prv) if sign < 0 else (a1, a0, prv)); t = (prv, a1, cur) if sign < 0 else (a1, prv, cur)
+                tris.append(t if sign < 0 or i > 0 else (start, prv, cur))
+    cap(Rl, x1, -1, 0.0)
+    cap(Rr, x2, +1, ET)
+    if ET > 0:
+        e0 = len(verts)
+        for j in range(tessellation):
+            phi = TWO_PI * j / tessellation; n = np.array([0, math.cos(phi), math.sin(phi)])
+            verts += [n * radius, n * radius + np.array([ET, 0, 0])]; normals += [n, n]
+        for j in range(tessellation):
+            p0 = 2 * j - 2 if j > 0 else 2 * tessellation - 2
+            tris += [(e0 + p0 + 1, e0 + p0, e0 + 2 * j), (e0 + 2 * j + 1, e0 + p0 + 1, e0 + 2 * j)]
+    V = np.array(verts, np.float64) + np.asarray(centre, np.float64)
+    return Mesh(V.astype(np.float32), np.array(tris, np.uint32), normals=np.array(normals, np.float32), to_world=to_world)
+
+
+def star_prism(outer=1.0, inner=.5, depth=.1, points=6, to_world=None):
+    """SYNTHETIC stand-in for box.xml's star_big.ply ("star of david", loaded with face normals): a flat `points`-pointed star in the local yz-plane,
+    extruded along x by `depth`: 4 * 2 * points triangles, face normals (sharp edges everywhere -- it is the scene's diffracting screen)."""
+    ang = np.arange(2 * points) * math.pi / points
+    rad = np.where(np.arange(2 * points) % 2 == 0, outer, inner)
+    ring = np.stack([np.zeros_like(ang), rad * np.cos(ang), rad * np.sin(ang)], 1)
+    verts, tris = [], []
+    def tri(a, b, c):
+        t = len(verts); verts.extend([a, b, c]); tris.append((t, t + 1, t + 2))
+    for side, x in ((-1, -depth / 2), (1, depth / 2)):
+        c = np.array([x, 0, 0])
+        for i in range(2 * points):
+            a, b = ring[i] + c, ring[(i + 1) % (2 * points)] + c
+            tri(c, a, b) if side > 0 else tri(c, b, a)
+    for i in range(2 * points):
+        a, b = ring[i], ring[(i + 1) % (2 * points)]
+        a0, b0, a1, b1 = a + [-depth / 2, 0, 0], b + [-depth / 2, 0, 0], a + [depth / 2, 0, 0], b + [depth / 2, 0, 0]
+        tri(a0, b1, a1); tri(a0, b0, b1)
+    return Mesh(np.array(verts, np.float32), np.array(tris, np.uint32), to_world=to_world)
 
 
 # ------------------------------------------------------------------------------------------------ scene + flattening

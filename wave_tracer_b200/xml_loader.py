@@ -184,7 +184,8 @@ def _parse_file(path):
 
 
 class _Loader:
-    def __init__(self, path, defines, missing_meshes="error"):
+    def __init__(self, path, defines, missing_meshes="error", standins=None, bitmap_standin=.5):
+        self.standin_specs, self.standins, self.bitmap_standin = dict(standins or {}), [], float(bitmap_standin)
         self.missing_meshes, self.skipped = missing_meshes, []
         self.dir = os.path.dirname(os.path.abspath(path))
         self.root = _parse_file(path)
@@ -277,7 +278,7 @@ class _Loader:
             elif it.tag == "rotate":
                 M = S.rotate([float(evaluate(it.attrib.get(a, "0"))) for a in "xyz"], quantity(it.attrib["angle"], "ang")) @ M
             elif it.tag == "matrix":
-                vals = [float(evaluate(x)) for x in re.split(r"[,\s]+", it.attrib["value"].strip())]
+                vals = [quantity(x, "len") if re.search(r"[a-zA-Z]\s*$", x) else float(evaluate(x)) for x in _split_top(it.attrib["value"].strip())]       # "0, 1, 0, 0cm, ..."
                 M = np.array(vals, np.float64).reshape(4, 4) @ M
             else:
                 raise SceneXmlError(f"<transform>: unsupported child <{it.tag}>")
@@ -298,7 +299,12 @@ class _Loader:
             if a["ITU"] not in S.ITU.TABLE: raise SceneXmlError(f'<spectrum ITU="{a["ITU"]}">: unknown ITU-R P.2040 material')
             if scale != 1.0: raise SceneXmlError("scaled ITU spectra are not supported")
             return S.ITU(a["ITU"])
+        if "material" in a:        # refractive index database (data/ior/<name>.yml): complex IOR
+            try: m = S.Material(a["material"])
+            except ValueError as ex: raise SceneXmlError(str(ex)) from ex
+            return m if scale == 1.0 else S.Scaled(m, scale)
         if "emitter" in a:
+            if f'emission/{a["emitter"]}/value' in S.spectra_db(): return S.Emission(a["emitter"], scale)
             return IlluminantSpectrum(a["emitter"], scale)
         t = a.get("type")
         if t == "discrete":
@@ -313,8 +319,30 @@ class _Loader:
             return S.Binned(bins)
         raise SceneXmlError(f"<spectrum>: unsupported form {dict(a)}")
 
+    def texture(self, node):
+        """texture_t (include/wt/texture/texture.hpp) reduced to what the device evaluates: a spectrum.  constant and scale textures are exact;
+        a bitmap is replaced by its stand-in mean value (the reference's PNG / EXR files are Git-LFS stubs): `bitmap_standin` (default 0.5)."""
+        t = node.attrib.get("type", "constant")
+        if t == "constant":
+            sp = node.find("spectrum")
+            return self.spectrum(sp) if sp is not None else S.Const(float(evaluate(node.attrib.get("value", "1"))))
+        if t == "scale":
+            sc = self._spectrum_child(node, "scale", S.Const(1.0))
+            inner = [self.texture(ch) for ch in node.findall("texture")]
+            if len(inner) != 1: raise SceneXmlError("scale texture needs exactly one nested texture")
+            if not isinstance(sc, S.Const): raise SceneXmlError("scale texture: only constant scales are supported")
+            return S.Scaled(inner[0], sc.v.real)
+        if t == "bitmap":
+            pth = node.find("path")
+            self.standins.append(("texture", pth.attrib.get("value") if pth is not None else "?", f"constant {self.bitmap_standin}"))
+            return S.Const(self.bitmap_standin)
+        raise SceneXmlError(f"<texture type={t!r}> is not supported")
+
     def _spectrum_child(self, node, name, default=None):
         ch = self._named(node, "spectrum", name)
+        if ch is None:
+            tx = self._named(node, "texture", name)
+            if tx is not None: return self.texture(tx)
         return default if ch is None else self.spectrum(ch)
 
     # ---- bsdfs
@@ -340,7 +368,10 @@ class _Loader:
     def bsdf(self, node):
         t = node.attrib.get("type")
         nested = [self.bsdf(ch) for ch in node.findall("bsdf")] + [self._ref(ch) for ch in node.findall("ref")]
-        if t == "twosided":
+        if t is None and "scale" in node.attrib:       # <bsdf scale=".1"> ... </bsdf>  (src/bsdf/bsdf_loader.cpp:36-53)
+            if len(nested) != 1: raise SceneXmlError("scale bsdf needs exactly one nested bsdf")
+            out = S.Scale(S.Const(float(evaluate(node.attrib["scale"]))), nested[0])
+        elif t == "twosided":
             if len(nested) != 1: raise SceneXmlError("twosided bsdf needs exactly one nested bsdf")
             out = S.TwoSided(nested[0])
         elif t == "diffuse":
@@ -394,10 +425,16 @@ class _Loader:
         if node is None or node.attrib.get("type") != "array":
             raise SceneXmlError("sensor needs a <film type=\"array\">")
         resp = node.find("response")
-        if resp is None or resp.attrib.get("type") != "monochromatic":
-            raise SceneXmlError("only <response type=\"monochromatic\"> films are supported (RGB responses need the XYZ tables)")
-        sp = resp.find("spectrum")
-        return S.Film(self._int(node, "width", 0), self._int(node, "height", 0), [self.spectrum(sp)], rfilter_scale=self._float(node, "rfilter_scale", 1.0))
+        rt = resp.attrib.get("type") if resp is not None else None
+        if rt == "monochromatic":
+            channels = [self.spectrum(resp.find("spectrum"))]
+        elif rt == "RGB":       # src/sensor/response/RGB.cpp: defaults sRGB / D65
+            cs = self._named(resp, "string", "colourspace"); wp = self._named(resp, "string", "white_point")
+            try: channels = S.rgb_response(cs.attrib["value"] if cs is not None else "sRGB", wp.attrib["value"] if wp is not None else "D65")
+            except KeyError as ex: raise SceneXmlError(f"RGB response: unsupported colourspace / white point {ex}") from ex
+        else:
+            raise SceneXmlError(f"<response type={rt!r}> is not supported (monochromatic, RGB)")
+        return S.Film(self._int(node, "width", 0), self._int(node, "height", 0), channels, rfilter_scale=self._float(node, "rfilter_scale", 1.0))
 
     def sensor(self, node):
         t = node.attrib.get("type")
@@ -441,15 +478,41 @@ class _Loader:
             p = self._named(node, "point", name)
             if p is None: raise SceneXmlError(f"{t} shape: point '{name}' must be provided")
             return np.array(self._point(p))
-        if t == "rectangle":
-            mesh = S.rectangle(pt("p"), pt("x"), pt("y"), to_world=tw)
+        def centre_of(name="center"):
+            c = self._named(node, "point", name)
+            return self._point(c) if c is not None else (0, 0, 0)
+        if t == "rectangle":        # src/scene/shape.cpp:196-227
+            ln = self._quantity(node, "length", "len")
+            tess = self._int(node, "tessellation", 1)
+            mesh = S.square(ln, to_world=tw, tessellation=tess) if ln is not None else S.rectangle(pt("p"), pt("x"), pt("y"), to_world=tw, tessellation=tess)
         elif t == "cube":
-            mesh = S.cube(tw)
+            mesh = S.cube_len(self._quantity(node, "length", "len", 2.0), tw)
+        elif t == "prism":
+            mesh = S.prism(self._quantity(node, "length", "len", 1.0), self._quantity(node, "height", "len", 1.0), self._quantity(node, "angle", "ang", math.pi / 2), to_world=tw)
         elif t == "sphere":
-            r = self._quantity(node, "radius", "len", 1.0)
-            c = self._named(node, "point", "center")
-            centre = self._point(c) if c is not None else (0, 0, 0)
-            mesh = S.sphere(r, centre, to_world=tw)
+            mesh = S.icosphere(self._quantity(node, "radius", "len", 1.0), centre_of(), self._int(node, "tessellation", 32), to_world=tw)
+        elif t == "cylinder":
+            mesh = S.cylinder(pt("p0"), pt("p1"), self._quantity(node, "radius", "len", 1.0), self._int(node, "tessellation", 32), to_world=tw)
+        elif t == "lens":
+            mesh = S.lens(self._quantity(node, "radius", "len", 1.0), centre_of(), self._float(node, "R1", 0.0), self._float(node, "R2", 0.0),
+                          self._quantity(node, "thickness", "len", 0.0), self._int(node, "tessellation", 50), to_world=tw)
+        elif t in ("ply", "obj") and self.missing_meshes == "standin":
+            # SYNTHETIC: the mesh file is a Git-LFS stub; a procedural closed surface with the triangle budget and placement the scene gives it
+            # (standins: {shape id: dict(kind="blob"|"star", tris=..., radius=..., centre=...)}) takes its place and is listed in scene.standins
+            sid = node.attrib.get("id", "?")
+            spec = self.standin_specs.get(sid)
+            if spec is None: raise SceneXmlError(f'<shape type="{t}" id="{sid}">: no stand-in given for this mesh')
+            unit = self._quantity(node, "scale", "len", 1.0)
+            M = (tw if tw is not None else np.eye(4)) @ S.scale(unit)
+            if spec["kind"] == "blob":      # one or several lobes: (radius, centre, triangles)
+                lobes = spec.get("lobes") or [(spec["radius"], spec.get("centre", (0, 0, 0)), spec["tris"])]
+                parts = [S.blob(r, c, n, seed=spec.get("seed", 1) + 7 * i) for i, (r, c, n) in enumerate(lobes)]
+                pos = np.concatenate([m.positions for m in parts]); nrm = np.concatenate([m.normals for m in parts])
+                off = np.cumsum([0] + [len(m.positions) for m in parts[:-1]])
+                mesh = S.Mesh(pos, np.concatenate([m.indices + o for m, o in zip(parts, off)]), normals=nrm, to_world=M)
+            else: mesh = S.star_prism(spec.get("outer", 1.0), spec.get("inner", .55), spec.get("depth", 1.0), to_world=M)
+            fn = node.find("path")
+            self.standins.append(("mesh", fn.attrib.get("value") if fn is not None else sid, f'{spec["kind"]} of {len(mesh.indices)} triangles'))
         elif t in ("ply", "obj") and self.missing_meshes == "skip":
             fn = self._named(node, "string", "filename") or self._named(node, "path", "filename")
             self.skipped.append((node.attrib.get("id", "?"), fn.attrib.get("value") if fn is not None else "?"))
@@ -494,13 +557,15 @@ class _Loader:
             elif t not in ("uniform", "independent"): raise SceneXmlError(f"<sampler type={t!r}> is not supported")
         sc.xml_bsdfs = dict(self.bsdfs)             # materials by id, as <ref> resolves them
         sc.skipped_shapes = list(self.skipped)      # (id, file) of mesh shapes left out under missing_meshes="skip"
+        sc.standins = list(self.standins)           # (kind, file, what replaced it): every synthetic substitution made while loading
         return sc
 
 
-def load_scene(path, defines=None, lut=(2048, 1024), sensor_id=None, missing_meshes="error"):
+def load_scene(path, defines=None, lut=(2048, 1024), sensor_id=None, missing_meshes="error", standins=None, bitmap_standin=.5):
     """`wave_tracer render scene.xml -D k=v,...` front half: returns a scene.Scene (call .build() for the wtgpu_scene_desc tables).
-    missing_meshes="skip": ply/obj shapes (Git-LFS stubs in the reference tree) are left out and listed in scene.skipped_shapes."""
-    return _Loader(path, defines, missing_meshes).build(lut=lut, sensor_id=sensor_id)
+    missing_meshes="skip": ply/obj shapes (Git-LFS stubs in the reference tree) are left out and listed in scene.skipped_shapes;
+    missing_meshes="standin": they are replaced by the procedural surfaces `standins` describes per shape id (listed in scene.standins)."""
+    return _Loader(path, defines, missing_meshes, standins, bitmap_standin).build(lut=lut, sensor_id=sensor_id)
 
 
 def parse_defines(s):
