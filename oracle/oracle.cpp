@@ -486,3 +486,8 @@ void oracle_pmath(int fn, uint32_t n, const float* x, const float* y, float* out
 }
 
 } // extern "C"
+
+extern "C" void oracle_debug_cone_hist(int on, uint64_t out[96]) {
+    if (out) { for (int i = 0; i < 94; ++i) out[i] = ot::g_cone_hist[i].load(); out[94] = ot::g_cone_late[0].load(); out[95] = ot::g_cone_late[1].load(); }
+    if (on >= 0) { ot::g_cone_hist_on = on; if (on) { for (int i = 0; i < 96; ++i) ot::g_cone_hist[i] = 0; ot::g_cone_late[0] = ot::g_cone_late[1] = 0; } }
+}

@@ -55,6 +55,7 @@ void oracle_discrete_icdf(uint32_t n, const float* dcdf, uint32_t m, const float
 void oracle_gaussian_pdf(float sx, float sy, uint32_t n, const float* pts, float* out);
 void oracle_clip_triangles(uint32_t n, const float* tri, const float* zr, int* ntris, float* polygon, float* pieces);
 void oracle_gaussian_integrate_triangles(float sx, float sy, uint32_t n, const float* tri, float* out);
+void oracle_debug_cone_hist(int on, uint64_t out[96]);
 #ifdef __cplusplus
 }
 #endif

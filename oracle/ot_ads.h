@@ -4,6 +4,7 @@
 // /root/reference/src/ads/bvh8w.cpp and the work/record helpers of include/wt/ads/traversal_common.hpp,
 // reading the flattened tables of include/wtgpu.h (the tables are data, shared by oracle and product).
 #pragma once
+#include <atomic>
 #include "ot_math.h"
 #include "../include/wtgpu.h"
 #include <vector>
@@ -135,12 +136,19 @@ struct cone_record_t {
     bool empty() const { return tris.empty(); }
 };
 
+// diagnostic: histogram of cone-query sizes (log2 buckets): [0..31] queries by triangles TESTED, [32..63] queries by triangles ACCEPTED,
+// [64..95] triangles tested summed per tested-bucket.  Filled only while g_cone_hist_on (tools/cone_hist.py).
+inline std::atomic<uint64_t> g_cone_hist[96];
+inline std::atomic<int> g_cone_hist_on{0};
+inline std::atomic<uint64_t> g_cone_late[2];   // [0] queries whose closest distance still improved after 512 accepted triangles, [1] further improvements
+inline int cone_hist_bucket(uint64_t n) { int b = 0; while (n) { ++b; n >>= 1; } return b; }
 struct cone_work_t {
     std::vector<uint32_t> triangles;
     f_t intr_dist = inf;
     f_t z_search_range_scale = 1;
     bool front_face = false;
     range_t searchrange{ 0, inf };
+    int late = 0;
     range_t search_range(const elliptic_cone_t& cone) const {        // traversal_common.hpp:78-84
         const f_t dist = std::max(searchrange.min, intr_dist);
         const f_t z_dist = cone.axes(dist).x * z_search_range_scale;
@@ -159,7 +167,7 @@ inline bool cone_gather_tris(const ads_t& ads, const elliptic_cone_t& cone, rang
         if (intrs) {
             const f_t dist = intrs->dist;
             if (dist > range.max) continue;
-            if (dist < rec.intr_dist) { rec.intr_dist = dist; rec.front_face = front_face; }
+            if (dist < rec.intr_dist) { if (g_cone_hist_on.load(std::memory_order_relaxed) && rec.triangles.size() >= 512) g_cone_late[rec.late++ ? 1 : 0]++; rec.intr_dist = dist; rec.front_face = front_face; }
             found = true;
             rec.triangles.push_back(tuid);
         }
@@ -168,6 +176,7 @@ inline bool cone_gather_tris(const ads_t& ads, const elliptic_cone_t& cone, rang
 }
 
 inline cone_record_t intersect_cone(const ads_t& ads, const elliptic_cone_t& cone, range_t traversal_range, f_t z_scale, bool detect_edges, ads_counters_t* ctr = nullptr) {
+    const uint64_t tris_before = ctr ? ctr->tris : 0;
     cone_work_t work; work.searchrange = traversal_range; work.z_search_range_scale = z_scale;
     if (ctr) ctr->cone_casts++;
     range_t range = work.search_range(cone);
@@ -225,6 +234,10 @@ inline cone_record_t intersect_cone(const ads_t& ads, const elliptic_cone_t& con
         }
     }
 
+    if (ctr && g_cone_hist_on.load(std::memory_order_relaxed)) {
+        const uint64_t tested = ctr->tris - tris_before;
+        g_cone_hist[cone_hist_bucket(tested)]++; g_cone_hist[32 + cone_hist_bucket(work.triangles.size())]++; g_cone_hist[64 + cone_hist_bucket(tested)] += tested;
+    }
     // cone_work_to_intersection_record, traversal_common.hpp:116-149 (work tri dist is value-initialised to 0: nothing is culled)
     cone_record_t ret;
     ret.dist = work.intr_dist; ret.front_face = work.front_face;

@@ -381,3 +381,47 @@ def test_xml_scene_film_matches_oracle():
     l2, flux = _film_metrics(lgt, olgt)
     print("xml slit_bench: rel-L2 %.3e flux %.3e" % (l2, flux), st["segments"], ost["segments"])
     assert l2 <= L2_GATE and flux <= MEAN_GATE and _mean_rel(lgt, olgt) <= MEAN_GATE, (l2, flux)
+
+
+_TIER_CHECK = r"""
+import sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import numpy as np
+from wave_tracer_b200 import scenes, render, GpuScene
+which = sys.argv[1]
+if which == "cornell_box_bdpt": b = scenes.cornell_box(res=40, spp=2, dragon_tris=11520, bunny_tris=5120, lut=(512, 256)).build(table_size=256)
+elif which == "cornell_like_path": b = scenes.cornell_like(res=48, spp=4, fsd=True, n_sphere=48).build()
+else: b = scenes.etoile_like(res=64, spp=2, detail=3).build()
+gs = GpuScene(b, 0)
+out = {{}}
+for name, flags in (("team", 0), ("thread", 8)):
+    blk, lgt, st = render(b, gpu_scene=gs, flags=flags)
+    out[name] = {{k: int(st[k]) for k in ("samples", "segments", "ray_casts", "cone_casts", "shadow_casts", "nodes_visited", "tris_tested", "surface_interactions",
+                                          "fsd_interactions", "null_interactions", "splats", "capacity_overflows", "edges_fetched")}}
+    out[name]["film"] = [float(np.abs(blk).sum()), float(np.abs(lgt).sum())]
+    out[name + "_blk"], out[name + "_lgt"] = blk, lgt
+d = lambda x, y: float(np.abs(x - y).max() / max(1e-30, np.abs(y).max()))
+out["dblk"], out["dlgt"] = d(out.pop("team_blk"), out.pop("thread_blk")), d(out.pop("team_lgt"), out.pop("thread_lgt"))
+print("RESULT " + json.dumps(out))
+"""
+
+
+@pytest.mark.parametrize("scene", ["cornell_box_bdpt", "cornell_like_path", "etoile_path"])
+@pytest.mark.parametrize("tiers", [None, (0, 0), (8, 64), (8, 1 << 30)])
+def test_team_traversal_equals_thread_traversal(scene, tiers):
+    """The traversal tiers (eight lanes per beam -> a warp team -> a block team, gtrav.cuh / ctrav.cuh: lookahead windows, two-stage triangle tests,
+    in-order commit) take the same decisions as the one-thread-per-beam traversal that follows bvh8w.cpp literally: identical structural counters
+    INCLUDING the nodes visited and triangles tested, films equal up to the order of the f32 atomics.  Run in a fresh process per tier setting (the
+    hand-over thresholds are read once): default, everything to the block teams at once, low thresholds, warp teams only."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if tiers is not None: env["WT_BIG_TESTED"], env["WT_HUGE_TESTED"] = str(tiers[0]), str(tiers[1])
+    r = subprocess.run([sys.executable, "-c", _TIER_CHECK.format(root=root), scene], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    print("tiers %s %s: tris tested %d / %d nodes %d / %d, film diff %.2e %.2e" % (tiers, scene, out["team"]["tris_tested"], out["thread"]["tris_tested"],
+                                                                                   out["team"]["nodes_visited"], out["thread"]["nodes_visited"], out["dblk"], out["dlgt"]))
+    for k, v in out["thread"].items():
+        if k != "film": assert out["team"][k] == v, (k, out["team"][k], v)
+    assert out["dblk"] < 2e-4 and out["dlgt"] < 2e-4

@@ -717,6 +717,102 @@ WT_D void bd_resolve_hit_big(const DScene& sc, const Beam& beam, const TravOut& 
     if (sc.integrator.fsd) { bool eo = false; uint32_t need = 0u; h.n_edges = w_collect_edges(sc, tl, edges, sc.cap.edges, edge_bits, eo, need); if (eo) { h.overflow = true; h.need_edges = need; } }
 }
 
+
+// One BLOCK (256 threads) resolves one walker whose cone query returned a very long triangle list (all threads call with the same arguments;
+// every thread ends with the same BHit).  Closest triangle: strided scan + ordered (distance, list index) minimum over the block.  Gaussian
+// power: tiles of kHugeTile list entries -- each warp clips and integrates 32 triangles at a time into the tile's buffers (quadrature pieces by
+// the warp), then the first warp adds the tile's piece values IN LIST ORDER.  Edge set: first warp, scratch bitmap.  Bit-identical to bd_resolve_hit.
+constexpr uint32_t kHugeTile = 1024u;
+struct alignas(16) HugeShared { float v[3][kHugeTile]; uint8_t cnt[kHugeTile]; float rd[8]; uint32_t ri[8], rtu[8]; float rbx[8], rby[8]; float flux; };
+WT_D void bd_resolve_hit_block(const DScene& sc, const Beam& beam, const TravOut& tr, const TriList& tl, uint32_t* edges, uint32_t* edge_bits, BHit& h, HugeShared& sh) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
+    Range zr; bd_hit_init(h, beam, tr, zr);
+    if (tr.empty || h.ballistic) return;
+    const V3 dir = beam.env.d;
+    {   // find_closest_triangle (plt_bdpt_detail.hpp:362-390): the first entry, in list order, with the smallest hit distance
+        float bd = WT_INF, bbx = -1.f, bby = -1.f; uint32_t bi = 0xffffffffu, btu = WTGPU_INVALID_IDX;
+        for (uint32_t i = threadIdx.x; i < tl.n; i += blockDim.x) {
+            const uint32_t tu = tri_at(tl, i);
+            const Tri3 t = load_tri(sc, tu);
+            const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
+            const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+            if (rt.hit && rt.dist < h.pdist && rt.dist < bd) { bd = rt.dist; bi = i; btu = tu; bbx = rt.bx; bby = rt.by; }
+        }
+        float rd = bd; uint32_t ri = bi;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float od = __shfl_xor_sync(FULL, rd, o); const uint32_t oi = __shfl_xor_sync(FULL, ri, o);
+            if (oi != 0xffffffffu && (ri == 0xffffffffu || od < rd || (od == rd && oi < ri))) { rd = od; ri = oi; }
+        }
+        if (bi == ri) { sh.rd[warp] = rd; sh.ri[warp] = ri; sh.rtu[warp] = btu; sh.rbx[warp] = bbx; sh.rby[warp] = bby; }      // (ri == ~0: every lane writes the same "none")
+        __syncthreads();
+        float gd = WT_INF; uint32_t gi = 0xffffffffu; int gw = -1;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { const uint32_t oi = sh.ri[w]; const float od = sh.rd[w]; if (oi != 0xffffffffu && (gi == 0xffffffffu || od < gd || (od == gd && oi < gi))) { gd = od; gi = oi; gw = w; } }
+        if (gw >= 0) { h.primary = sh.rtu[gw]; h.pdist = gd; h.bx = sh.rbx[gw]; h.by = sh.rby[gw]; }
+        __syncthreads();
+        if (gw >= 0) return;
+    }
+    const Frame beam_frame = cone_frame(beam.env);
+    const G2 wf = wavefront_of(beam, h.dist);
+    const float csz = (zr.mx + zr.mn) / 2.f;
+    float flux = 0.f;
+    for (uint32_t t0 = 0u; t0 < tl.n; t0 += kHugeTile) {
+        const uint32_t tn = min(kHugeTile, tl.n - t0);
+        for (uint32_t c0 = warp * 32u; c0 < tn; c0 += blockDim.x) {       // this warp's 32-entry chunks of the tile
+            const uint32_t i = t0 + c0 + lane;
+            Clip cl; cl.tris = 0;
+            if (c0 + lane < tn) {
+                const Tri3 t = load_tri(sc, tri_at(tl, i));
+                if ((dot(t.n, -dir) > 0.f) == tr.cone.front)
+                    cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
+            }
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {       // piece k of every lane's triangle
+                int kind = G2_DONE; float val = 0.f; V2 pa = mk2(0.f, 0.f), pb = pa, pc = pa;
+                if (k < cl.tris) {
+                    V3 ct[3]; clip_tri(cl, k, ct);
+                    pa = cone_project_local(beam.env, ct[0], csz); pb = cone_project_local(beam.env, ct[1], csz); pc = cone_project_local(beam.env, ct[2], csz);
+                    kind = g2_classify(wf, pa, pb, pc, val);
+                    if (kind == G2_ANALYTIC) val = g2_analytic(sc, pa, pb, pc);
+                }
+                unsigned m = __ballot_sync(FULL, kind == G2_QUADRATURE);
+                while (m) {
+                    const int src = __ffs(m) - 1; m &= m - 1u;
+                    const V2 qa = mk2(__shfl_sync(FULL, pa.x, src), __shfl_sync(FULL, pa.y, src));
+                    const V2 qb = mk2(__shfl_sync(FULL, pb.x, src), __shfl_sync(FULL, pb.y, src));
+                    const V2 qc = mk2(__shfl_sync(FULL, pc.x, src), __shfl_sync(FULL, pc.y, src));
+                    const float r = g2_quadrature_warp(qa, qb, qc);
+                    if ((int)lane == src) val = r;
+                }
+                if (c0 + lane < tn) sh.v[k][c0 + lane] = val;
+            }
+            if (c0 + lane < tn) sh.cnt[c0 + lane] = (uint8_t)cl.tris;
+        }
+        __syncthreads();
+        if (warp == 0u) {       // ordered accumulation: entry t0, t0 + 1, ...; pieces 0, 1, 2 of each
+            for (uint32_t c0 = 0u; c0 < tn; c0 += 32u) {
+                const uint32_t j = c0 + lane;
+                const int c = j < tn ? (int)sh.cnt[j] : 0;
+                const float v0 = c > 0 ? sh.v[0][j] : 0.f, v1 = c > 1 ? sh.v[1][j] : 0.f, v2 = c > 2 ? sh.v[2][j] : 0.f;
+                unsigned rest = __ballot_sync(FULL, c > 0);
+                while (rest) {
+                    const int l = __ffs(rest) - 1; rest &= rest - 1u;
+                    const int cc = __shfl_sync(FULL, c, l);
+                    const float a0 = __shfl_sync(FULL, v0, l), a1 = __shfl_sync(FULL, v1, l), a2 = __shfl_sync(FULL, v2, l);
+                    flux += a0; if (cc > 1) flux += a1; if (cc > 2) flux += a2;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0u) sh.flux = flux;
+    __syncthreads();
+    h.flux = sh.flux;
+    if (sc.integrator.fsd) {
+        if (warp == 0u) { bool eo = false; uint32_t need = 0u; h.n_edges = w_collect_edges(sc, tl, edges, sc.cap.edges, edge_bits, eo, need); if (eo) { h.overflow = true; h.need_edges = need; } }
+    }
+}
+
 // continue_walk (plt_bdpt_detail.hpp:167-182)
 WT_D bool bd_continue_walk(BCtx& c, BWalk& data, Sampler& smp, bool do_RR) {
     const DScene& sc = *c.sc;
@@ -1177,7 +1273,7 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
     __shared__ GShared shm[128 / kGW];
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.r.sc;
-    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr, a.r.big_list, &a.r.ctr->n_big,
+    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr, a.r.big_save, &a.r.ctr->n_big, a.r.big_tested,
         [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
             const uint32_t wid = a.r.trav_list[i];
             BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
@@ -1187,18 +1283,18 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.r.trav_list[i]] = r; });
     flush_counters(a.r.ctr, ctr);
 }
-// the walkers k_bd_gtraverse handed over (cone queries over > kBigQuery triangles): one warp per walker (gtrav.cuh w_traverse_all)
+// the walkers k_bd_gtraverse handed over in the middle of a large cone query: one warp team per walker (ctrav.cuh), then one block team for the largest
 __global__ void __launch_bounds__(128, 4) k_bd_wtraverse(const BdArgs a) {
-    __shared__ GShared shm[4];
+    __shared__ TShared<32> shm[4];
     Counters ctr; counters_zero(ctr);
-    const DScene& sc = a.r.sc;
-    w_traverse_all(sc, a.r.ctr->n_big, a.r.big_list, &a.r.ctr->big_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr,
-        [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
-            const uint32_t wid = a.r.trav_list[i];
-            BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
-            env = w.beam.env; prev = w.prev_geo; lambda = wavenum_to_wavelen(w.beam.k);
-            tw = tri_writer(sc, a.trav_tris, wid);
-        },
+    t_traverse_all<32>(a.r.sc, a.r.ctr->n_big, a.r.big_save, &a.r.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.r.huge_save, &a.r.ctr->n_huge, a.r.huge_tested,
+        [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.r.trav_list[i]] = r; });
+    flush_counters(a.r.ctr, ctr);
+}
+__global__ void __launch_bounds__(256, 2) k_bd_ctraverse(const BdArgs a) {
+    __shared__ TShared<256> shm;
+    Counters ctr; counters_zero(ctr);
+    t_traverse_all<256>(a.r.sc, a.r.ctr->n_huge, a.r.huge_save, &a.r.ctr->huge_head, shm, ctr, nullptr, nullptr, 0u,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.r.trav_list[i]] = r; });
     flush_counters(a.r.ctr, ctr);
 }
@@ -1252,6 +1348,7 @@ __global__ void __launch_bounds__(128) k_bd_resolve_big(const BdArgs a, uint32_t
         if (i >= a.r.ctr->n_big_res) break;
         const uint32_t wid = a.r.trav_list[a.r.big_res_list[i]];
         const TravRec r = a.trav_rec[wid];
+        if (r.n_tris > kHugeList && !(r.flags & TR_OVERFLOW)) { if (lane == 0u) a.r.huge_res_list[atomicAdd(&a.r.ctr->n_huge_res, 1)] = a.r.big_res_list[i]; continue; }     // a very long list: a whole block
         TravOut tr; bd_trav_out(r, tr);
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
         BHit bh;
@@ -1260,6 +1357,31 @@ __global__ void __launch_bounds__(128) k_bd_resolve_big(const BdArgs a, uint32_t
         __syncwarp();
     }
     if (lane == 0u) { if (n_step) atomicAdd(&a.r.ctr->walker_steps, n_step); if (n_ovf) atomicAdd(&a.r.ctr->overflow, n_ovf); }
+}
+
+// the lists k_bd_resolve_big handed on (more than kHugeList triangles): one block per walker
+__global__ void __launch_bounds__(256) k_bd_resolve_huge(const BdArgs a, uint32_t bit_words) {
+    __shared__ HugeShared sh;
+    __shared__ int s_item;
+    const DScene& sc = a.r.sc;
+    uint32_t* bits = a.r.edge_bits + (size_t)blockIdx.x * bit_words;       // (one scratch bitmap per block: used by its first warp only)
+    unsigned long long n_step = 0, n_ovf = 0;
+    for (;;) {
+        if (threadIdx.x == 0u) s_item = atomicAdd(&a.r.ctr->huge_res_head, 1);
+        __syncthreads();
+        const int i = s_item;
+        __syncthreads();
+        if (i >= a.r.ctr->n_huge_res) break;
+        const uint32_t wid = a.r.trav_list[a.r.huge_res_list[i]];
+        const TravRec r = a.trav_rec[wid];
+        TravOut tr; bd_trav_out(r, tr);
+        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+        BHit bh;
+        bd_resolve_hit_block(sc, w.beam, tr, tri_list(sc, a.trav_tris, wid, r.n_tris, tr.cone.overflow), a.r.hit_edges + (size_t)wid * sc.cap.edges, bits, bh, sh);
+        if (threadIdx.x == 0u) { bd_store_hit(a, wid, bh); ++n_step; n_ovf += bh.overflow ? 1u : 0u; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0u) { if (n_step) atomicAdd(&a.r.ctr->walker_steps, n_step); if (n_ovf) atomicAdd(&a.r.ctr->overflow, n_ovf); }
 }
 
 __global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->trav_head = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; reset_iteration_lists(a.r.ctr); } }

@@ -414,6 +414,31 @@ WT_D ConePlane intersect_cone_plane(const Cone& cone, V3 n, float d, Range range
     return out;
 }
 
+// The rejections intersect_cone_tri (below) takes before its containment / plane / edge stages, as a predicate of their own: false = that
+// function returns +inf for these arguments (same arithmetic, same comparisons).  The team traversal (ctrav.cuh) runs it over a whole batch of
+// triangles and sends only the survivors through the full test, so the expensive stages run with full warps.
+WT_D bool cone_tri_maybe(const Cone& cone, const Frame& frame, V3 a, V3 b, V3 c, Range range) {
+    if (cone_is_ray(cone)) return true;
+    const V3 o = cone.o;
+    const V3 v0 = to_local(frame, a - o), v1 = to_local(frame, b - o), v2 = to_local(frame, c - o);
+    const float closest_z = min3f(v0.z, v1.z, v2.z), farthest_z = max3f(v0.z, v1.z, v2.z);
+    if (farthest_z < range.mn || closest_z > range.mx) return false;
+#ifndef WT_NO_CONE_QUICK_REJECT
+    if (cone.ta >= 0.f) {
+        const float r = fmaf(fminf(farthest_z, range.mx), cone.ta, cone.x0);
+        if (r > 0.f && r < WT_INF) {
+            const float u0 = v0.x, u1 = v1.x, u2 = v2.x, w0 = v0.y * cone.e, w1 = v1.y * cone.e, w2 = v2.y * cone.e;
+            const float ext = fmaxf(fmaxf(max3f(fabsf(u0), fabsf(u1), fabsf(u2)), max3f(fabsf(w0), fabsf(w1), fabsf(w2))), fmaxf(fabsf(closest_z), fabsf(farthest_z)));
+            const float bb = r + (1e-3f * r + 1e-5f * ext), bd = 1.41421356f * r + (2e-3f * r + 2e-5f * ext);
+            const float p0 = u0 + w0, p1 = u1 + w1, p2 = u2 + w2, q0 = u0 - w0, q1 = u1 - w1, q2 = u2 - w2;
+            if (min3f(u0, u1, u2) > bb || max3f(u0, u1, u2) < -bb || min3f(w0, w1, w2) > bb || max3f(w0, w1, w2) < -bb ||
+                min3f(p0, p1, p2) > bd || max3f(p0, p1, p2) < -bd || min3f(q0, q1, q2) > bd || max3f(q0, q1, q2) < -bd) return false;
+        }
+    }
+#endif
+    return true;
+}
+
 // cone-triangle closest distance (intersect/cone.hpp:550-626); returns +inf when there is no intersection
 WT_DN float intersect_cone_tri(const Cone& cone, const Frame& frame, V3 a, V3 b, V3 c, V3 n, Range range) {
     if (cone_is_ray(cone)) { const RayTri r = intersect_ray_tri(cone.o, cone.d, a, b, c, range); return r.hit ? r.dist : WT_INF; }

@@ -9,7 +9,8 @@
 //     prefix, the closest is found with a (distance, lane) min-reduction = the first minimal one in sequential order;
 //   * the stack lives in shared memory (1 KB per group); accepted triangles go straight to the beam's row of the result array in HBM, whose
 //     length is a run-time capacity (dtrav.cuh Caps) -- the count keeps running past it, so a too-short row is known exactly;
-//   * groups pull beams from the list with an atomic cursor, so a long beam delays only its own group;
+//   * groups pull beams from the list with an atomic cursor, so a long beam delays only its own group; a cone query that has tested more than
+//     TravTiers::big_tested triangles is handed over, state and stack, to the team traversal (ctrav.cuh);
 //   * the four groups of a warp run node steps freely but meet before every leaf step, where the expensive cone-triangle code runs.
 // Every decision is taken on the same values, in the same order, as the sequential code: results are bit-identical to dtrav.cuh.
 #pragma once
@@ -18,9 +19,7 @@ namespace wt {
 
 constexpr int kGW = 8;
 constexpr int kGStack = 128;
-struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; float key[kGW];
-    uint32_t bt0[4], bcnt[4]; float btmin[4];      // warp-per-beam mode: the leaves of the current cone batch
-};
+struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; float key[kGW]; };
 
 // what traverse() returns, as stored between the traversal kernel and the per-thread resolve kernel
 struct alignas(16) TravRec { uint32_t flags, ray_tuid; float ray_dist, bx, by, cone_dist; uint32_t n_tris; float region_depth, ox, oy, oz; uint32_t pad_; };
@@ -40,6 +39,17 @@ WT_D int g_argmin(const GLane& g, float v, bool valid) {
     return bl < 64 ? bl : -1;
 }
 
+// the same over a whole warp
+WT_D int g_argmin32(float v, bool valid, unsigned lane) {
+    float bv = valid ? v : WT_INF; int bl = valid ? (int)lane : 64;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (ol < 64 && (bl >= 64 || ov < bv || (ov == bv && ol < bl))) { bv = ov; bl = ol; }
+    }
+    return bl < 64 ? bl : -1;
+}
+
 // One group's traversal machine.  All members hold the same value in the 8 lanes of a group.
 struct GTrav {
     // beam
@@ -51,9 +61,15 @@ struct GTrav {
     Range qrange, crange;       // ray range / cone traversal range; current cone search range
     RayCull cull;               // range culling bounds of the current ray query (dtrav.cuh)
     RayHit rec; ConeResult res;
+    uint32_t qtested;           // triangles the current cone query has tested (hand-over trigger)
     TriWriter tw;               // where the current cone query's triangle list goes (dtrav.cuh TriList): the beam's row + extents of the spill arena
 };
-constexpr uint32_t kBigQuery = 512u;    // a cone query that has collected this many triangles is handed to the warp-per-query kernel (k_*_wtraverse)
+constexpr uint32_t kBigQuery = 32u;     // a triangle list longer than this is resolved by the warp-per-list resolve kernels (k_*_resolve_big) ...
+constexpr uint32_t kHugeList = 4096u;   // ... and one longer than this by a whole block (k_bd_resolve_huge)
+// A beam in the middle of a cone query, as handed from one traversal kernel to the next (ctrav.cuh): the whole machine state and the stack.
+struct alignas(16) TravSave { GTrav t; int item; int pad_[3]; float tmin[kGStack]; int32_t ptr[kGStack]; };
+// hand-over thresholds (triangles tested by the current cone query): group -> warp team, warp team -> block team
+struct TravTiers { uint32_t big_tested, huge_tested; };
 
 WT_D void g_start_ray(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, Range r, Counters& ctr) {
     t.mode = 1; t.qrange = r; t.cull = ray_cull(sc, r); t.rec.tuid = WTGPU_INVALID_IDX; t.rec.dist = WT_INF; t.rec.bx = t.rec.by = -1.f; t.rec.front = false;
@@ -62,7 +78,7 @@ WT_D void g_start_ray(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, R
     __syncwarp(g.gmask);
 }
 WT_D void g_start_cone(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, Range tr, Counters& ctr) {
-    t.mode = 2; t.qrange = tr; t.res.dist = WT_INF; t.res.front = false; t.res.n_tris = 0u; t.res.overflow = false; tw_begin(t.tw);
+    t.mode = 2; t.qtested = 0u; t.qrange = tr; t.res.dist = WT_INF; t.res.front = false; t.res.n_tris = 0u; t.res.overflow = false; tw_begin(t.tw);
     t.crange = cone_search_range(t.env, tr, t.res.dist, t.zs);
     t.s = 1;
     if (g.gl == 0u) { sh.tmin[0] = 0.f; sh.ptr[0] = sc.root_ptr; ctr.cone_casts++; }
@@ -93,6 +109,26 @@ WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float 
     t.s += __popc(km);
     __syncwarp(g.gmask);
 }
+// cone_cluster_intersect (bvh8w.cpp:187-230) for one child box: the AABB inflated by the cone radius at its farthest z, slab test against the
+// current search range; true = the child is pushed (with key tmin)
+WT_D bool cone_child_test(V3 ro, V3 rd, V3 inv, bool nx, bool ny, bool nz, float ta, float x0, Range cr, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float& tmin_out) {
+    float omnx = mnx - ro.x, omny = mny - ro.y, omnz = mnz - ro.z;
+    float omxx = mxx - ro.x, omxy = mxy - ro.y, omxz = mxz - ro.z;
+    const float bx = nx ? omnx : omxx, by = ny ? omny : omxy, bz = nz ? omnz : omxz;
+    const float ddb = fmaf(rd.z, bz, fmaf(rd.y, by, rd.x * bx));
+    const float maxz = fminf(fmaxf(ddb, 0.f), cr.mx);
+    const float enl = fmaf(maxz, ta, x0);
+    omnx -= enl; omny -= enl; omnz -= enl; omxx += enl; omxy += enl; omxz += enl;
+    const float dminx = (nx ? omxx : omnx) * inv.x, dminy = (ny ? omxy : omny) * inv.y, dminz = (nz ? omxz : omnz) * inv.z;
+    const float dmaxx = (nx ? omnx : omxx) * inv.x, dmaxy = (ny ? omny : omxy) * inv.y, dmaxz = (nz ? omnz : omxz) * inv.z;
+    float tmin = 0.f, tmax = dmaxx;
+    tmin = vmaxps(tmin, dminx); tmax = vminps(tmax, dmaxy);
+    tmin = vmaxps(tmin, dminy); tmax = vminps(tmax, dmaxz);
+    tmin = vmaxps(tmin, dminz);
+    tmin_out = tmin;
+    const bool ok = tmin <= tmax && tmax >= cr.mn && tmin <= cr.mx;
+    return ok && !(tmin >= cr.mx);
+}
 WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, int32_t ptr, Counters& ctr) {
     const wtgpu_node* __restrict__ n = sc.nodes + (ptr - 1);
     if (g.gl == 0u) ctr.nodes++;
@@ -109,21 +145,8 @@ WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, i
         const float rmax = vminps(vminps(vminps(t2x, t2y), t2z), t.rec.dist);
         push = rmin <= rmax && ch != 0 && ray_cull_keep(t.cull, rmin, rmax); key = rmin; cap = 64;
     } else {                // cone_cluster_intersect (bvh8w.cpp:187-230)
-        float omnx = mnx - ro.x, omny = mny - ro.y, omnz = mnz - ro.z;
-        float omxx = mxx - ro.x, omxy = mxy - ro.y, omxz = mxz - ro.z;
-        const float bx = t.nx ? omnx : omxx, by = t.ny ? omny : omxy, bz = t.nz ? omnz : omxz;
-        const float ddb = fmaf(rd.z, bz, fmaf(rd.y, by, rd.x * bx));
-        const float maxz = fminf(fmaxf(ddb, 0.f), t.crange.mx);
-        const float enl = fmaf(maxz, t.env.ta, t.env.x0);
-        omnx -= enl; omny -= enl; omnz -= enl; omxx += enl; omxy += enl; omxz += enl;
-        const float dminx = (t.nx ? omxx : omnx) * t.inv.x, dminy = (t.ny ? omxy : omny) * t.inv.y, dminz = (t.nz ? omxz : omnz) * t.inv.z;
-        const float dmaxx = (t.nx ? omnx : omxx) * t.inv.x, dmaxy = (t.ny ? omny : omxy) * t.inv.y, dmaxz = (t.nz ? omnz : omxz) * t.inv.z;
-        float tmin = 0.f, tmax = dmaxx;
-        tmin = vmaxps(tmin, dminx); tmax = vminps(tmax, dmaxy);
-        tmin = vmaxps(tmin, dminy); tmax = vminps(tmax, dmaxz);
-        tmin = vmaxps(tmin, dminz);
-        const bool ok = tmin <= tmax && tmax >= t.crange.mn && tmin <= t.crange.mx;
-        push = ok && ch != 0 && !(tmin >= t.crange.mx); key = tmin; cap = kGStack;
+        float tmin;
+        push = cone_child_test(ro, rd, t.inv, t.nx, t.ny, t.nz, t.env.ta, t.env.x0, t.crange, mnx, mny, mnz, mxx, mxy, mxz, tmin) && ch != 0; key = tmin; cap = kGStack;
     }
     g_push_sorted(g, sh, t, push, key, ch, cap, ctr);
 }
@@ -142,6 +165,7 @@ WT_D void g_leaf_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, u
         if (hit) while (t.s > 0 && sh.tmin[t.s - 1] >= t.rec.dist) --t.s;
     } else {                // gather_tris (bvh8w.cpp:123-185)
         bool found = false;
+        t.qtested += cnt;
         for (uint32_t base = 0; base < cnt; base += (uint32_t)kGW) {
             const uint32_t k = base + g.gl; const bool valid = k < cnt; const uint32_t tuid = t0 + k;
             float d = WT_INF; bool front = false;
@@ -239,7 +263,7 @@ WT_D bool g_query_done(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, 
 // SLOWER on the etoile-like scene and on double_slits, and again 6-9 % slower after the code-size work removed the instruction-fetch
 // stall (profiles/r01s3_phases.txt, session V): a group that reaches its leaf early idles through the others' node steps.)
 template <class Fetch, class Emit>
-WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* shm, bool force_rt, bool edge_query, Counters& ctr, uint32_t* big_list, int* n_big, Fetch&& fetch, Emit&& emit) {
+WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* shm, bool force_rt, bool edge_query, Counters& ctr, TravSave* big_save, int* n_big, uint32_t big_tested, Fetch&& fetch, Emit&& emit) {
     GLane g; g.gl = threadIdx.x & 7u; g.gshift = (threadIdx.x & 31u) & 24u; g.gmask = 0xffu << g.gshift;
     GShared& sh = shm[threadIdx.x / kGW];
     GTrav t; t.mode = 0; t.s = 0;
@@ -278,169 +302,18 @@ WT_D void g_traverse_all(const DScene& sc, int n_items, int* cursor, GShared* sh
         // phase 2: the groups of the warp do their leaf steps together
         if (leaf) {
             g_leaf_step(sc, g, sh, t, lt0, lcnt, ctr);
-            // a cone query over very many triangles: one group would walk it for milliseconds while the rest of the launch waits -- hand the
-            // beam to the warp-per-query kernel, which restarts it (same decisions, same list)
-            if (big_list && t.mode == 2 && t.res.n_tris > kBigQuery) {
-                if (g.gl == 0u) big_list[atomicAdd(n_big, 1)] = (uint32_t)item;
+            // a cone query over many triangles: one group would walk it for milliseconds while the rest of the launch waits -- the beam is
+            // handed, state and stack, to the team traversal (ctrav.cuh), which continues it from here (same decisions, same list)
+            if (big_save && t.mode == 2 && t.s > 0 && t.qtested > big_tested) {
+                int pos = 0;
+                if (g.gl == 0u) pos = atomicAdd(n_big, 1);
+                pos = g_shfl(g, pos, 0);
+                TravSave& sv = big_save[pos];
+                if (g.gl == 0u) { sv.t = t; sv.item = item; }
+                for (int i = (int)g.gl; i < t.s; i += kGW) { sv.tmin[i] = sh.tmin[i]; sv.ptr[i] = sh.ptr[i]; }
                 have = false; t.s = 0; t.mode = 0;
                 __syncwarp(g.gmask);
             }
-        }
-    }
-}
-
-// ---- the same machine driven by a WHOLE WARP per beam, for the beams g_traverse_all hands over.  Node steps use lanes 0-7 (one child each);
-// leaf steps use all 32 lanes: a ray-query leaf (<= 16 triangles) in one pass, and up to FOUR consecutive leaves of a cone query at a time.
-// The cone batch is speculative: every lane tests its triangle against the search range at the start of the batch; the leaves are then
-// committed in stack order, exactly as the sequential loop would (append, closest hit, range update, stack pruning), and if a commit
-// narrows the range the not-yet-committed leaves of the batch go back on the stack to be tested again against the new range -- so every
-// decision is taken on the same values in the same order, and the result is bit-identical.  (After the first few leaves of a query the range
-// no longer changes, so almost every batch commits whole.)
-WT_D int w_argmin(float v, bool valid, unsigned lane) {
-    float bv = valid ? v : WT_INF; int bl = valid ? (int)lane : 64;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-        if (ol < 64 && (bl >= 64 || ov < bv || (ov == bv && ol < bl))) { bv = ov; bl = ol; }
-    }
-    return bl < 64 ? bl : -1;
-}
-template <class Fetch, class Emit>
-WT_D void w_traverse_all(const DScene& sc, int n_items, const uint32_t* items, int* cursor, GShared* shm, bool force_rt, bool edge_query, Counters& ctr, Fetch&& fetch, Emit&& emit) {
-    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
-    GLane gw; gw.gl = lane; gw.gshift = 0u; gw.gmask = FULL;                    // the warp as one "group" for the set-up / query bookkeeping code
-    GLane g8; g8.gl = lane & 7u; g8.gshift = 0u; g8.gmask = 0xffu;              // lanes 0-7 for the node step
-    GShared& sh = shm[threadIdx.x >> 5];
-    GTrav t; t.mode = 0; t.s = 0;
-    for (;;) {
-        int i = 0;
-        if (lane == 0u) i = atomicAdd(cursor, 1);
-        i = __shfl_sync(FULL, i, 0);
-        if (i >= n_items) break;
-        const int item = (int)items[i];
-        { Cone env; Geo prev; float lambda; fetch(item, env, prev, lambda, t.tw); g_begin(sc, gw, sh, t, env, prev, lambda, force_rt, edge_query, ctr); }
-        for (;;) {
-            if (t.s == 0) {
-                TravRec out;
-                if (g_query_done(sc, gw, sh, t, out, ctr)) { emit(item, out, gw); __syncwarp(); break; }
-                continue;
-            }
-            const int32_t top = sh.ptr[t.s - 1];
-            uint32_t rt0 = 0u, rcnt = 0u; bool ray_leaf = false;
-            if (top >= 0) {
-                if (t.mode == 1) { const uint2 tr = __ldg(reinterpret_cast<const uint2*>(&sc.nodes[top - 1].tris_start)); if (tr.y <= 16u) { rt0 = tr.x; rcnt = tr.y; ray_leaf = true; if (lane == 0u) ctr.nodes++; } }
-                if (!ray_leaf) {
-                    --t.s;
-                    if (lane < 8u) g_node_step(sc, g8, sh, t, top, ctr);
-                    t.s = __shfl_sync(FULL, t.s, 0);
-                    __syncwarp();
-                    continue;
-                }
-            }
-            const V3 ro = t.env.o, rd = t.env.d;
-            if (t.mode == 1) {      // ray_gather over a leaf / a <= 16-triangle subtree
-                if (!ray_leaf) { const wtgpu_leaf lf = sc.leaves[-top - 1]; rt0 = lf.tris_ptr; rcnt = lf.count; }
-                --t.s;
-                bool hit = false;
-                for (uint32_t base = 0; base < rcnt; base += 32u) {
-                    const uint32_t k = base + lane; const bool valid = k < rcnt; const uint32_t tuid = rt0 + k;
-                    float z = -WT_INF, bx = 0.f, by = 0.f; bool front = false;
-                    if (valid) { const Tri3 tr = load_tri(sc, tuid); ctr.tris++; z = intersect_ray_tri_w(ro, rd, tr.a, tr.b, tr.c, t.qrange, bx, by); front = dot(tr.n, rd) <= 0.f; }
-                    const int w = w_argmin(z, valid && z != -WT_INF && z < t.rec.dist, lane);
-                    if (w >= 0) { t.rec.dist = __shfl_sync(FULL, z, w); t.rec.bx = __shfl_sync(FULL, bx, w); t.rec.by = __shfl_sync(FULL, by, w); t.rec.tuid = __shfl_sync(FULL, tuid, w); t.rec.front = __shfl_sync(FULL, front ? 1 : 0, w) != 0; hit = true; }
-                }
-                if (hit) while (t.s > 0 && sh.tmin[t.s - 1] >= t.rec.dist) --t.s;
-                continue;
-            }
-            // ---- cone query: a batch of up to four consecutive leaves from the top of the stack (a leaf of more than 8 triangles goes alone)
-            const int s0 = t.s;
-            int nb = 0;
-            if (lane == 0u) {
-                int sp = t.s;
-                while (nb < 4 && sp > 0 && sh.ptr[sp - 1] < 0) {
-                    const wtgpu_leaf lf = sc.leaves[-sh.ptr[sp - 1] - 1];
-                    if (lf.count > 8u && nb > 0) break;
-                    sh.bt0[nb] = lf.tris_ptr; sh.bcnt[nb] = lf.count; sh.btmin[nb] = sh.tmin[sp - 1]; ++nb; --sp;
-                    if (lf.count > 8u) break;
-                }
-            }
-            nb = __shfl_sync(FULL, nb, 0);
-            t.s = s0 - nb;
-            __syncwarp();
-            if (nb == 1 && sh.bcnt[0] > 8u) {     // the general leaf step, 32 triangles at a time (no speculation: one leaf)
-                const uint32_t lt0 = sh.bt0[0], lcnt = sh.bcnt[0];
-                bool found = false;
-                for (uint32_t base = 0; base < lcnt; base += 32u) {
-                    const uint32_t k = base + lane; const bool valid = k < lcnt; const uint32_t tuid = lt0 + k;
-                    float d = WT_INF; bool front = false;
-                    if (valid) { const Tri3 tr = load_tri(sc, tuid); ctr.tris++; d = intersect_cone_tri(t.env, t.frame, tr.a, tr.b, tr.c, tr.n, t.crange); front = dot(tr.n, -rd) > 0.f; }
-                    const bool acc = d < WT_INF && !(d > t.crange.mx);
-                    const unsigned m = __ballot_sync(FULL, acc);
-                    if (m) {
-                        found = true;
-                        const int w = w_argmin(d, acc && d < t.res.dist, lane);
-                        if (w >= 0) { t.res.dist = __shfl_sync(FULL, d, w); t.res.front = __shfl_sync(FULL, front ? 1 : 0, w) != 0; }
-                        const uint32_t upto = t.res.n_tris + (uint32_t)__popc(m);
-                        if (upto > t.tw.alloc_end && !t.tw.fail) {
-                            if (lane == 0u) tw_reserve(sc, t.tw, upto);
-                            t.tw.n_ext = __shfl_sync(FULL, t.tw.n_ext, 0); t.tw.alloc_end = __shfl_sync(FULL, t.tw.alloc_end, 0); t.tw.fail = __shfl_sync(FULL, t.tw.fail ? 1 : 0, 0) != 0;
-                            __syncwarp();
-                        }
-                        if (acc) tw_put(sc, t.tw, t.res.n_tris + (uint32_t)__popc(m & ((1u << lane) - 1u)), tuid);
-                        t.res.n_tris = upto;
-                        if (t.tw.fail) t.res.overflow = true;
-                    }
-                }
-                if (found) { t.crange = cone_search_range(t.env, t.qrange, t.res.dist, t.zs); while (t.s > 0 && sh.tmin[t.s - 1] >= t.crange.mx) --t.s; }
-                __syncwarp();
-                continue;
-            }
-            // lane l tests triangle (l & 7) of batch leaf (l >> 3) against the range at the start of the batch
-            const int bj = (int)(lane >> 3); const uint32_t bk = lane & 7u;
-            const bool valid = bj < nb && bk < sh.bcnt[bj & 3];
-            const uint32_t tuid = valid ? sh.bt0[bj & 3] + bk : 0u;
-            float d = WT_INF; bool front = false;
-            if (valid) { const Tri3 tr = load_tri(sc, tuid); d = intersect_cone_tri(t.env, t.frame, tr.a, tr.b, tr.c, tr.n, t.crange); front = dot(tr.n, -rd) > 0.f; }
-            const bool acc = d < WT_INF && !(d > t.crange.mx);
-            const unsigned am = __ballot_sync(FULL, acc);
-            // per-leaf closest accepted triangle: (distance, lane) minimum within each 8-lane segment = the first minimal one in leaf order
-            float ld = acc ? d : WT_INF; int ll = acc ? (int)lane : 64;
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                const float ov = __shfl_xor_sync(FULL, ld, o); const int ol = __shfl_xor_sync(FULL, ll, o);
-                if (ol < 64 && (ll >= 64 || ov < ld || (ov == ld && ol < ll))) { ld = ov; ll = ol; }
-            }
-            const Range r0 = t.crange;
-            int j = 0;
-            bool restart = false, prune_rest = false;
-            while (j < nb) {
-                if (lane == 0u) ctr.tris += sh.bcnt[j];         // leaf j is visited now (a leaf pruned or sent back below is not counted here)
-                prune_rest = false;
-                const unsigned mj = (am >> (8 * j)) & 0xffu;
-                if (!mj) { ++j; continue; }
-                // commit leaf j (gather_tris, bvh8w.cpp:123-185, then the range update and stack pruning that follow a leaf with hits)
-                const float dj = __shfl_sync(FULL, ld, 8 * j); const int lj = __shfl_sync(FULL, ll, 8 * j);
-                const bool fj = __shfl_sync(FULL, front ? 1 : 0, lj < 64 ? lj : 0) != 0;
-                if (lj < 64 && dj < t.res.dist) { t.res.dist = dj; t.res.front = fj; }
-                const uint32_t upto = t.res.n_tris + (uint32_t)__popc(mj);
-                if (upto > t.tw.alloc_end && !t.tw.fail) {
-                    if (lane == 0u) tw_reserve(sc, t.tw, upto);
-                    t.tw.n_ext = __shfl_sync(FULL, t.tw.n_ext, 0); t.tw.alloc_end = __shfl_sync(FULL, t.tw.alloc_end, 0); t.tw.fail = __shfl_sync(FULL, t.tw.fail ? 1 : 0, 0) != 0;
-                    __syncwarp();
-                }
-                if (acc && bj == j) tw_put(sc, t.tw, t.res.n_tris + (uint32_t)__popc(mj & ((1u << bk) - 1u)), tuid);
-                t.res.n_tris = upto;
-                if (t.tw.fail) t.res.overflow = true;
-                t.crange = cone_search_range(t.env, t.qrange, t.res.dist, t.zs);
-                int k = j + 1;
-                while (k < nb && sh.btmin[k] >= t.crange.mx) ++k;     // pruned from the top of the stack
-                j = k;
-                if (j == nb) { prune_rest = true; break; }            // the pruning continues into the stack proper
-                if (t.crange.mx != r0.mx || t.crange.mn != r0.mn) { restart = true; break; }       // the rest of the batch saw a stale range
-            }
-            if (restart) t.s = s0 - j;                  // leaves j.. go back on the stack (they are still there, in order) and are tested again
-            else if (prune_rest) while (t.s > 0 && sh.tmin[t.s - 1] >= t.crange.mx) --t.s;
-            __syncwarp();
         }
     }
 }

@@ -81,16 +81,20 @@ struct DevCounters {
     // capacity growth (dtrav.cuh Caps): the longest list a too-short row was asked to hold (0: every list fitted)
     unsigned int need_spill, need_edges, need_seg, need_ap, need_verts;
     unsigned int spill_head;            // bump cursor of the triangle-list arena (dtrav.cuh TriList); reset every iteration
-    int n_big, big_head, n_big_res, big_res_head;      // beams handed to the warp-per-beam traversal / resolve kernels this iteration; their work cursors
+    int n_big, big_head, n_big_res, big_res_head;      // beams handed to the team traversal (ctrav.cuh) / lists handed to the warp-per-list resolve kernels this iteration; their work cursors
+    int n_huge, huge_head;                             // beams the warp teams handed on to the block teams
+    int n_huge_res, huge_res_head;                     // lists the warp-per-list resolve handed on to the block-per-list resolve
     unsigned long long stack_drops;
 };
 WT_D void need_max(unsigned int* p, uint32_t v) { if (v > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(p, v); }
 
-namespace wt { struct TravRec; }
+namespace wt { struct TravRec; struct TravSave; }
 struct RenderArgs {
     DScene sc;
     wt::TravRec* trav_rec; uint32_t* trav_tris;      // results of traverse(), per slot; trav_tris: the first kTriRow triangle ids of the slot's cone-query list (dtrav.cuh TriList)
-    uint32_t* big_list; uint32_t* big_res_list;       // items (indices into trav_list) handed to the warp-per-beam kernels
+    wt::TravSave* big_save; wt::TravSave* huge_save;  // beams handed from the group traversal to the warp teams, and from those to the block teams (gtrav.cuh TravSave)
+    uint32_t big_tested, huge_tested;                 // the hand-over thresholds (triangles tested by the current cone query)
+    uint32_t* big_res_list; uint32_t* huge_res_list;  // items (indices into trav_list) handed to the warp-per-list / block-per-list resolve kernels
     uint32_t* edge_bits;                              // scratch bitmaps (one bit per edge of the scene) of the warp-per-beam resolve kernel, one per resident warp
     uint32_t* hit_edges;                              // sc.cap.edges edge ids per slot: the edges around the vertex (HitRec::n_edges of them)
     uint32_t* ap_edges; uint32_t it_parity;           // plt_path: 2 x pool rows of sc.cap.edges: UTD aperture edge lists (this iteration's row set: it_parity)
@@ -222,7 +226,7 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
 
 WT_D void reset_iteration_lists(DevCounters* c) {        // the triangle-list arena and the hand-over lists live for one iteration
     need_max(&c->need_spill, c->spill_head);
-    c->spill_head = 0u; c->n_big = 0; c->big_head = 0; c->n_big_res = 0; c->big_res_head = 0;
+    c->spill_head = 0u; c->n_big = 0; c->big_head = 0; c->n_big_res = 0; c->big_res_head = 0; c->n_huge = 0; c->huge_head = 0; c->n_huge_res = 0; c->huge_res_head = 0;
 }
 // the triangle-list writer / reader of path `slot` (rows of kTriRow entries + the slot's extent table)
 WT_D TriWriter tri_writer(const DScene& sc, uint32_t* trav_tris, uint32_t slot) { TriWriter w; w.row = trav_tris + (size_t)slot * kTriRow; w.ext = sc.spill_ext + (size_t)slot * kTriExt; tw_begin(w); return w; }
@@ -299,6 +303,7 @@ WT_D uint32_t w_collect_edges(const DScene& sc, const TriList& tl, uint32_t* edg
 }
 
 #include "gtrav.cuh"
+#include "ctrav.cuh"
 #include "dbdpt.cuh"
 
 __global__ void __launch_bounds__(128) k_traverse(const RenderArgs a) {
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs 
     __shared__ GShared shm[128 / kGW];
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.sc;
-    g_traverse_all(sc, a.ctr->n_trav, &a.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr, a.big_list, &a.ctr->n_big,
+    g_traverse_all(sc, a.ctr->n_trav, &a.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr, a.big_save, &a.ctr->n_big, a.big_tested,
         [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
             const uint32_t slot = a.trav_list[i];
             PathCore pc; soa_load(pc, a.core, a.pool, slot);
@@ -384,18 +389,18 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs 
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
     flush_counters(a.ctr, ctr);
 }
-// the beams k_gtraverse handed over (cone queries over > kBigQuery triangles): one warp per beam (gtrav.cuh w_traverse_all)
+// the beams k_gtraverse handed over in the middle of a large cone query: one warp team per beam (ctrav.cuh), then one block team for the largest
 __global__ void __launch_bounds__(128, 4) k_wtraverse(const RenderArgs a) {
-    __shared__ GShared shm[4];
+    __shared__ TShared<32> shm[4];
     Counters ctr; counters_zero(ctr);
-    const DScene& sc = a.sc;
-    w_traverse_all(sc, a.ctr->n_big, a.big_list, &a.ctr->big_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr,
-        [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
-            const uint32_t slot = a.trav_list[i];
-            PathCore pc; soa_load(pc, a.core, a.pool, slot);
-            env = pc.beam.env; prev = pc.prev_geo; lambda = wavenum_to_wavelen(pc.beam.k);
-            tw = tri_writer(sc, a.trav_tris, slot);
-        },
+    t_traverse_all<32>(a.sc, a.ctr->n_big, a.big_save, &a.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.huge_save, &a.ctr->n_huge, a.huge_tested,
+        [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
+    flush_counters(a.ctr, ctr);
+}
+__global__ void __launch_bounds__(256, 2) k_ctraverse(const RenderArgs a) {
+    __shared__ TShared<256> shm;
+    Counters ctr; counters_zero(ctr);
+    t_traverse_all<256>(a.sc, a.ctr->n_huge, a.huge_save, &a.ctr->huge_head, shm, ctr, nullptr, nullptr, 0u,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
     flush_counters(a.ctr, ctr);
 }
@@ -878,7 +883,8 @@ struct Pool {
     std::vector<void*> allocs;
     float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
     uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr, *trav_tris = nullptr, *hit_edges = nullptr, *ap_edges = nullptr;
-    uint32_t *spill = nullptr, *spill_ext = nullptr, *big_list = nullptr, *big_res_list = nullptr, *edge_bits = nullptr;
+    uint32_t *spill = nullptr, *spill_ext = nullptr, *big_res_list = nullptr, *edge_bits = nullptr;
+    wt::TravSave *big_save = nullptr, *huge_save = nullptr;
     TravRec* trav_rec = nullptr;
     DevCounters* ctr = nullptr;
     // plt_bdpt (P sample slots, 2P walkers)
@@ -1081,7 +1087,7 @@ static uint32_t bdpt_max_pairs(uint32_t verts, uint32_t max_depth) {     // stra
 }
 static size_t pool_bytes(const wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t parts, const Caps& c) {
     const size_t P = pool;
-    const size_t row = 4ull * (wt::kTriRow + wt::kTriExt) + 8ull, shared = (size_t)parts * (4ull * c.spill_words + 16ull * s->bit_words * s->big_blocks);      // triangle-list row + extent table + hand-over lists; per sub-pool: the arena, scratch bitmaps
+    const size_t row = 4ull * (wt::kTriRow + wt::kTriExt) + 8ull + 2ull * sizeof(wt::TravSave), shared = (size_t)parts * (4ull * c.spill_words + 16ull * s->bit_words * s->big_blocks);      // triangle-list row + extent table + hand-over lists; per sub-pool: the arena, scratch bitmaps
     if (kind == POOL_PATH) return shared + P * (16ull * (chunks_of<PathCore>() + chunks_of<PathFsd>() + chunks_of<HitRec>()) + sizeof(TravRec) + row + 12ull * c.edges + 16ull);
     if (kind == POOL_BDPT_MEGA) return shared + P * (4ull * c.arena_words + row + 4ull * c.edges);
     const size_t W2 = 2 * P;
@@ -1109,7 +1115,7 @@ static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t pa
         get(&q.key_count, 4ull * s->n_keys); get(&q.key_cursor, 4ull * s->n_keys);
         {   // triangle-list arena, extent tables and hand-over lists (one row per path / walker / thread); scratch edge bitmaps of the warp-per-beam resolve
             const size_t rows = kind == POOL_BDPT_WAVE ? 2 * P : P;
-            get(&q.spill, 4ull * c.spill_words); get(&q.spill_ext, 4ull * wt::kTriExt * rows); get(&q.big_list, 4ull * rows); get(&q.big_res_list, 4ull * rows);
+            get(&q.spill, 4ull * c.spill_words); get(&q.spill_ext, 4ull * wt::kTriExt * rows); get(&q.big_save, sizeof(wt::TravSave) * rows); get(&q.huge_save, sizeof(wt::TravSave) * rows); get(&q.big_res_list, 8ull * rows);
             get(&q.edge_bits, 16ull * s->bit_words * s->big_blocks);
             if (rc == WTGPU_OK) { cudaError_t e = cudaMemset(q.edge_bits, 0, 16ull * s->bit_words * s->big_blocks); if (e != cudaSuccess) { g_err = "cudaMemset(edge bitmaps)"; rc = WTGPU_E_CUDA; } }
         }
@@ -1165,6 +1171,9 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
     const bool nosort = (o->flags & WTGPU_RENDER_NO_SORT) != 0;
     const bool has_fsd = kind == POOL_BDPT_WAVE && s->integ.fsd != 0u && !s->sensor.ray_trace_only;
     const dim3 gBig(s->big_blocks);
+    // hand-over thresholds of the traversal tiers (gtrav.cuh TravTiers); WT_BIG_TESTED / WT_HUGE_TESTED override for A/B runs
+    static const wt::TravTiers tiers = []() { wt::TravTiers t; const char* b = getenv("WT_BIG_TESTED"); const char* h = getenv("WT_HUGE_TESTED");
+                                              t.big_tested = b ? (uint32_t)atoi(b) : 192u; t.huge_tested = h ? (uint32_t)atoi(h) : 6144u; return t; }();
 
     // the sub-pools start after whatever the caller queued on its stream
     CK(cudaEventRecord(s->ev_begin, user));
@@ -1176,7 +1185,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
         RenderArgs& a = args[k];
         a.sc = d; a.core = q.core; a.fsd = q.fsd; a.hit = q.hit; a.alive = q.alive; a.keys = q.keys; a.order = q.order;
         a.trav_rec = q.trav_rec; a.trav_tris = q.trav_tris; a.hit_edges = q.hit_edges; a.ap_edges = q.ap_edges; a.it_parity = 0u;
-        a.big_list = q.big_list; a.big_res_list = q.big_res_list; a.edge_bits = q.edge_bits;
+        a.big_save = q.big_save; a.huge_save = q.huge_save; a.big_tested = tiers.big_tested; a.huge_tested = tiers.huge_tested; a.big_res_list = q.big_res_list; a.huge_res_list = q.big_res_list + (kind == POOL_BDPT_WAVE ? 2 * (size_t)q.size : (size_t)q.size); a.edge_bits = q.edge_bits;
         a.key_count = q.key_count; a.key_cursor = q.key_cursor; a.trav_list = q.trav_list; a.ctr = q.ctr; a.film_block = dblock; a.film_light = dlight;
         a.pool = q.size; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
         a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
@@ -1219,8 +1228,8 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
             k_bd_generate<<<gP, blkT, 0, st>>>(b); ++launches; mark(q);
             if (use_thread_trav) { k_bd_traverse<<<gW, blkT, 0, st>>>(b); ++launches; }
             else {
-                k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_wtraverse<<<gC, blk, 0, st>>>(b);
-                k_bd_resolve<<<gW, blkT, 0, st>>>(b); k_bd_resolve_big<<<gBig, blk, 0, st>>>(b, s->bit_words); launches += 4;
+                k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_wtraverse<<<gC, blk, 0, st>>>(b); k_bd_ctraverse<<<dim3(n_sm * 2), dim3(256), 0, st>>>(b);
+                k_bd_resolve<<<gW, blkT, 0, st>>>(b); k_bd_resolve_big<<<gBig, blk, 0, st>>>(b, s->bit_words); k_bd_resolve_huge<<<dim3(std::min<uint32_t>(s->big_blocks, (uint32_t)n_sm * 2u)), dim3(256), 0, st>>>(b, s->bit_words); launches += 6;
             }
             mark(q);
             k_hist<<<gW, blkT, s->n_keys * 4, st>>>(b.r);
@@ -1245,8 +1254,8 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
             k_generate<<<grd, blkT, 0, st>>>(a); ++launches; mark(q);
             if (use_thread_trav) { k_traverse<<<grd, blkT, 0, st>>>(a); ++launches; }
             else {
-                k_gtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_wtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a);
-                k_resolve<<<grd, blkT, 0, st>>>(a); k_resolve_big<<<gBig, blk, 0, st>>>(a, s->bit_words); launches += 4;
+                k_gtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_wtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_ctraverse<<<dim3(n_sm * 2), dim3(256), 0, st>>>(a);
+                k_resolve<<<grd, blkT, 0, st>>>(a); k_resolve_big<<<gBig, blk, 0, st>>>(a, s->bit_words); launches += 5;
             }
             mark(q);
             if (nosort) {
