@@ -3,41 +3,55 @@
 //
 // A team of TEAM threads (one warp, or one 256-thread block) continues ONE beam at a time from the state the previous tier saved (TravSave:
 // machine state + stack; nothing is redone).  The team's first warp is the control warp: it runs the same machine as gtrav.cuh (g_begin /
-// g_query_done, ray queries, the sequential commit logic); the cone query's triangle work is done by the whole team in batches:
-//   L  lookahead: the top NW = TEAM/8 stack entries are looked at together, one 8-lane group each -- an internal node's eight children are tested
-//      against the current search range and ranked in pop order, NOT pushed; a leaf entry is itself.  The batch window is the leading run of
-//      "simple" entries: leaves, and nodes whose surviving children are all leaves (each <= 8 triangles).  A node on top of the stack that is
-//      not simple is expanded for real (that is simply the sequential algorithm's next step).
-//   T1 every triangle of the window's leaves (up to 8 TEAM of them) goes through the cheap rejections of the cone-triangle test
-//      (cone_tri_maybe: z range, separating axes); the survivors -- about one in seven -- are compacted;
+// g_query_done, ray queries, the sequential commit logic); the cone query's triangle work is done by the whole team in batches.
+//
+// The stack of the cone query lives in shared memory as Q (top = last entry).  A batch is built by LOOKAHEAD EXPANSION: the leading leaves on top
+// of Q move, in pop order, to the run R; then the first nodes below them (up to TEAM/8, one 8-lane group each) are expanded where they stand --
+// children tested against the current search range, ranked, written in pop order in place of the node, under a MARKER that keeps the node itself
+// -- and the step repeats until R holds enough leaves.  Expanding a node before the sequential algorithm reaches it is speculation on one thing
+// only: that the search range is still the same when it gets there (children, their order and their tmin depend on nothing else).  Then
+//   T1 every triangle of R's leaves (up to 8 TEAM of them) goes through the cheap rejections of the cone-triangle test (cone_tri_maybe: z range,
+//      separating axes); the survivors -- about one in seven -- are compacted;
 //   T2 the survivors go through the full test (intersect_cone_tri), one per thread: the expensive code runs with full warps;
-//   C  commit, in stack order, exactly what the sequential loop does leaf by leaf (bvh8w.cpp:123-185, 245-347): append the accepted triangles,
-//      closest hit, search-range update, unwinding of stale stack entries.  Everything in the batch was computed against the range at the start
-//      of the batch; if a commit NARROWS the range, the rest of the batch is discarded -- the not-yet-committed children of the entry being
-//      committed go onto the stack (that expansion was valid: the range had not changed when the sequential loop would have made it), later
-//      entries are still on the stack untouched -- and the next batch tests them again.  When no leaf of the batch improves the closest hit and
-//      no window entry is stale (the common case once the hit distance has settled), the whole batch commits with one parallel pass.
+//   C  commit, in pop order, exactly what the sequential loop does (bvh8w.cpp:123-185, 245-347): a marker = "node visited"; a leaf = append the
+//      accepted triangles, closest hit, search-range update, unwinding of stale entries.  If a commit NARROWS the range, everything after it was
+//      computed against a stale range: the rest of R goes back on top of Q and every marker still in Q is REVERTED (its children dropped, the
+//      node restored), which leaves exactly the sequential algorithm's stack; the next batch starts from there with the new range.  When no leaf of
+//      the batch improves the closest hit (the common case once the hit distance has settled) the whole batch commits in one parallel pass.
+// Entries that are stale (pushed under an older, wider range: tmin >= the current range's end) are never moved or expanded ahead of their turn:
+// whether the sequential loop visits or unwinds them depends on whether the leaf before them had hits, which is only known at commit.
+// The number of stack entries the sequential algorithm would hold is tracked per entry (ssz), so its 128-entry limit is honoured.
 // Every decision is taken on the same values, in the same order, as the sequential code: lists, distances and counters are identical.
 #pragma once
 
 namespace wt {
 
+enum : uint32_t { QK_LEAF = 0u, QK_NODE = 1u, QK_MARK = 2u };
+WT_D uint32_t q_info(uint32_t kind, uint32_t depth, uint32_t ssz) { return kind | (depth << 2) | (ssz << 8); }
+WT_D uint32_t q_kind(uint32_t i) { return i & 3u; }
+WT_D uint32_t q_depth(uint32_t i) { return (i >> 2) & 63u; }
+WT_D uint32_t q_ssz(uint32_t i) { return i >> 8; }
+
 template <int TEAM> struct alignas(16) TShared {
-    static constexpr int NW = TEAM / 8;
-    GShared g;                                  // the beam's stack (+ the ranked-push scratch of the control warp's node steps)
+    static constexpr int NW = TEAM / 8;                     // nodes expanded per round (one 8-lane group each)
+    static constexpr int QCAP = TEAM == 32 ? 256 : 1024;    // entries of Q (the sequential stack never exceeds kGStack; the rest is lookahead)
+    static constexpr int NL = TEAM;                         // leaves per batch
+    static constexpr int RCAP = 2 * TEAM;                   // entries of R (leaves + markers)
+    GShared g;                                              // ray queries' stack; scratch of real node steps
+    int32_t qptr[QCAP]; float qtmin[QCAP]; uint16_t qinfo[QCAP];
+    int32_t rptr[RCAP]; float rtmin[RCAP]; uint16_t rinfo[RCAP]; uint16_t rleaf[NL];       // R in pop order; rleaf: R index of batch leaf li
     Cone env; Frame frame; Range crange; V3 inv; int nx, ny, nz;       // the query, published by the control warp for the batch phases
-    int cmd, s, wlen, nl, nsurv;
-    int wn[NW], wfl[NW];                        // per window entry: children in pop order (1 for a leaf entry); flags: 1 internal, 2 has an internal child, 4 no entry, 8 a leaf of > 8 triangles
-    float wc_tmin[NW][8]; int32_t wc_ptr[NW][8]; uint32_t wc_t0[NW][8], wc_cnt[NW][8];
-    int lbase[NW];                              // first batch leaf of window entry w
-    uint32_t bt0[TEAM], bcnt[TEAM];             // batch leaves: triangle range
-    float dres[TEAM * 8]; uint16_t surv[TEAM * 8];
-    uint32_t lmask[TEAM], larg[TEAM]; float ldmin[TEAM];    // per batch leaf: accepted slots, first closest slot, its distance
+    int cmd, go, nsel, rn, nl, nsurv, big;
+    unsigned keep[QCAP / 32 + 1];                           // q_revert: keep flags per 32-entry chunk
+    int sel[NW];                                            // Q index of the nodes being expanded this round
+    int wn[NW]; float wc_tmin[NW][8]; int32_t wc_ptr[NW][8];
+    uint32_t bt0[NL], bcnt[NL];                             // batch leaves: triangle range
+    float dres[NL * 8]; uint16_t surv[NL * 8];
+    uint32_t lmask[NL], larg[NL]; float ldmin[NL];          // per batch leaf: accepted slots, first closest slot, its distance
 };
 template <int TEAM> WT_D void t_sync() { if (TEAM == 32) __syncwarp(); else __syncthreads(); }
 enum { TC_DONE = 0, TC_BATCH = 1 };
 
-WT_D void t_prune(GShared& sh, GTrav& t) { while (t.s > 0 && sh.tmin[t.s - 1] >= t.crange.mx) --t.s; }
 // lane-0 reservation of list storage up to `upto`, result broadcast over the control warp
 WT_D void t_reserve(const DScene& sc, GTrav& t, uint32_t upto, unsigned lane) {
     if (upto > t.tw.alloc_end && !t.tw.fail) {
@@ -46,11 +60,67 @@ WT_D void t_reserve(const DScene& sc, GTrav& t, uint32_t upto, unsigned lane) {
         __syncwarp();
     }
 }
+// Control warp (all lanes, same arguments).  Reverts every marker of Q[0, qs): its children are dropped, the node comes back -- Q becomes the
+// stack of the sequential algorithm.  An entry is the child of a marker still in Q exactly when some entry ABOVE it is shallower (its own
+// ancestors' markers are popped before it; everything else above it belongs to subtrees that precede it at the same or a greater depth), so:
+// pass 1, top down, a running minimum of the depths above each entry decides keep / drop; pass 2, bottom up, compacts.  Returns the new size.
+template <int TEAM> WT_D int q_revert(TShared<TEAM>& sh, int qs, unsigned lane) {
+    const unsigned FULL = 0xffffffffu;
+    __syncwarp();
+    if (qs <= 0) return 0;
+    uint32_t above = 64u;           // minimum depth of the entries above the chunk in hand
+    for (int hi = qs; hi > 0; hi -= 32) {
+        const int r = hi - 1 - (int)lane;           // lane 0 = the chunk's top entry
+        const uint32_t d = r >= 0 ? q_depth(sh.qinfo[r]) : 64u;
+        uint32_t incl = d;                          // minimum over this lane and the lanes above it (smaller lane index)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl = min(incl, u); }
+        uint32_t excl = __shfl_up_sync(FULL, incl, 1); if (lane == 0u) excl = 64u;
+        const bool keep = r >= 0 && !(min(above, excl) < d);
+        const unsigned km = __ballot_sync(FULL, keep);
+        if (lane == 0u) sh.keep[(hi - 1) >> 5] = km;          // bit l <-> entry hi - 1 - l
+        above = min(above, __shfl_sync(FULL, incl, 31));
+    }
+    __syncwarp();
+    int w = 0;
+    // the chunks were cut from the top: [hi - 32, hi) with hi = qs, qs - 32, ...; walk them bottom up
+    for (int hi = qs - ((qs - 1) / 32) * 32; hi <= qs; hi += 32) {
+        const unsigned km = sh.keep[(hi - 1) >> 5];
+        // ascending index within the chunk = descending lane: entry r = hi - 1 - l; position among the kept = number of kept entries with a smaller index = kept lanes above l
+        const int r = hi - 1 - (int)lane;
+        const bool keep = (km >> lane) & 1u;
+        int32_t p = 0; float tm = 0.f; uint32_t inf = 0u;
+        if (keep) { p = sh.qptr[r]; tm = sh.qtmin[r]; inf = sh.qinfo[r]; }
+        __syncwarp();
+        if (keep) {
+            const int at = w + __popc(km & ~((2u << lane) - 1u));          // kept lanes with a larger lane index = smaller entry index
+            if (q_kind(inf) == QK_MARK) inf = q_info(QK_NODE, q_depth(inf), q_ssz(inf));
+            sh.qptr[at] = p; sh.qtmin[at] = tm; sh.qinfo[at] = (uint16_t)inf;
+        }
+        w += __popc(km);
+        __syncwarp();
+    }
+    return w;
+}
+// the unwinding after a leaf with hits (bvh8w.cpp:262-267): stale entries leave the top of the stack (a marker stands for a node that was not stale)
+template <int TEAM> WT_D void q_prune(const TShared<TEAM>& sh, GTrav& t) { while (t.s > 0 && q_kind(sh.qinfo[t.s - 1]) != QK_MARK && sh.qtmin[t.s - 1] >= t.crange.mx) --t.s; }
+// the sequential stack in sh.g (as saved / as the group code leaves it) -> Q
+template <int TEAM> WT_D void q_from_stack(TShared<TEAM>& sh, int s, unsigned lane) {
+    for (int k = (int)lane; k < s; k += 32) { const int32_t p = sh.g.ptr[k]; sh.qptr[k] = p; sh.qtmin[k] = sh.g.tmin[k]; sh.qinfo[k] = (uint16_t)q_info(p < 0 ? QK_LEAF : QK_NODE, 0u, (uint32_t)k + 1u); }
+    __syncwarp();
+}
 
+#ifdef WT_TEAM_DEBUG
+#define TDBG(i, v) do { if (ctl && lane == 0u) d_[i] += (unsigned long long)(v); } while (0)
+#define TCLK(i) do { if (ctl && lane == 0u) { const long long c_ = clock64(); d_[i] += (unsigned long long)(c_ - clk_); clk_ = c_; } } while (0)
+#else
+#define TDBG(i, v) do { } while (0)
+#define TCLK(i) do { } while (0)
+#endif
 template <int TEAM, class Emit>
 WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, int* cursor, TShared<TEAM>& sh, Counters& ctr,
-                         TravSave* huge_save, int* n_huge, uint32_t huge_tested, Emit&& emit) {
-    constexpr int NW = TEAM / 8;
+                         TravSave* huge_save, int* n_huge, uint32_t huge_tested, unsigned long long* dbg, Emit&& emit) {
+    constexpr int NW = TShared<TEAM>::NW, QCAP = TShared<TEAM>::QCAP, NL = TShared<TEAM>::NL, RCAP = TShared<TEAM>::RCAP;
     const unsigned FULL = 0xffffffffu;
     const unsigned tid = threadIdx.x % (unsigned)TEAM, lane = threadIdx.x & 31u;
     const bool ctl = tid < 32u;
@@ -58,8 +128,12 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
     GLane g8; g8.gl = lane & 7u; g8.gshift = 0u; g8.gmask = 0xffu;                              // its lanes 0-7: real node steps
     GLane gg; gg.gl = lane & 7u; gg.gshift = lane & 24u; gg.gmask = 0xffu << gg.gshift;         // this thread's group of eight (lookahead)
     const int grp = (int)(tid >> 3);
-    GTrav t; t.mode = 0; t.s = 0;
+    GTrav t; t.mode = 0; t.s = 0;          // in a cone query t.s is the size of Q
+#ifdef WT_TEAM_DEBUG
+    unsigned long long d_[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; long long clk_ = clock64();      // 0 batches, 1 leaves, 2 rounds, 3 slow commits | cycles: 4 control, 5 lookahead, 6 tests, 7 commit
+#endif
     bool have = false; int item = 0;
+    int nl_cap = NL / 4;           // leaves per batch: small after the search range has changed (what follows such a leaf is thrown away), doubling while it holds
     for (;;) {
         // ---- control warp: the sequential machine, up to the next cone batch
         if (ctl) {
@@ -74,15 +148,17 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                     t = sv.t; item = sv.item;
                     for (int k = (int)lane; k < t.s; k += 32) { sh.g.tmin[k] = sv.tmin[k]; sh.g.ptr[k] = sv.ptr[k]; }
                     __syncwarp();
-                    have = true;
+                    q_from_stack(sh, t.s, lane);        // (items arrive in the middle of a cone query)
+                    have = true; nl_cap = NL / 4;
                 }
                 if (t.s == 0) {
                     TravRec out;
                     if (g_query_done(sc, gw, sh.g, t, out, ctr)) { emit(item, out, gw); have = false; __syncwarp(); }
+                    else if (t.mode == 2) q_from_stack(sh, t.s, lane);
                     continue;
                 }
-                const int32_t top = sh.g.ptr[t.s - 1];
                 if (t.mode == 1) {      // a ray query (ballistic segment): the whole of it in the control warp
+                    const int32_t top = sh.g.ptr[t.s - 1];
                     uint32_t rt0 = 0u, rcnt = 0u; bool ray_leaf = false;
                     if (top >= 0) {
                         const uint2 tr = __ldg(reinterpret_cast<const uint2*>(&sc.nodes[top - 1].tris_start));
@@ -111,12 +187,13 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                 }
                 // a cone query with work on its stack.  One that has grown very large goes to the next tier (a whole block per beam).
                 if (huge_save && t.qtested > huge_tested) {
+                    t.s = q_revert(sh, t.s, lane);
                     int pos = 0;
                     if (lane == 0u) pos = atomicAdd(n_huge, 1);
                     pos = __shfl_sync(FULL, pos, 0);
                     TravSave& sv = huge_save[pos];
                     if (lane == 0u) { sv.t = t; sv.item = item; }
-                    for (int k = (int)lane; k < t.s; k += 32) { sv.tmin[k] = sh.g.tmin[k]; sv.ptr[k] = sh.g.ptr[k]; }
+                    for (int k = (int)lane; k < t.s; k += 32) { sv.tmin[k] = sh.qtmin[k]; sv.ptr[k] = sh.qptr[k]; }
                     have = false; t.s = 0; t.mode = 0;
                     __syncwarp();
                     continue;
@@ -124,91 +201,149 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                 break;
             }
             if (lane == 0u) {
-                sh.cmd = cmd; sh.s = t.s; sh.nsurv = 0;
+                sh.cmd = cmd; sh.nsurv = 0; sh.rn = 0; sh.nl = 0; sh.big = 0x7fffffff;
                 if (cmd == TC_BATCH) { sh.env = t.env; sh.frame = t.frame; sh.crange = t.crange; sh.inv = t.inv; sh.nx = t.nx ? 1 : 0; sh.ny = t.ny ? 1 : 0; sh.nz = t.nz ? 1 : 0; }
             }
         }
         t_sync<TEAM>();
+        TCLK(4);
         if (sh.cmd == TC_DONE) break;
-        const int s0 = sh.s;
         const Cone env = sh.env; const Frame frame = sh.frame; const Range cr = sh.crange;
 
-        // ---- L: lookahead over the top NW stack entries, one group of eight lanes each
-        {
-            const int sidx = s0 - 1 - grp;
-            if (sidx >= 0) {
-                const int32_t ptr = sh.g.ptr[sidx];
-                if (ptr < 0) {
-                    if (gg.gl == 0u) {
-                        const wtgpu_leaf lf = sc.leaves[-ptr - 1];
-                        sh.wn[grp] = 1; sh.wfl[grp] = lf.count > 8u ? 8 : 0;
-                        sh.wc_tmin[grp][0] = sh.g.tmin[sidx]; sh.wc_ptr[grp][0] = ptr; sh.wc_t0[grp][0] = lf.tris_ptr; sh.wc_cnt[grp][0] = lf.count;
-                    }
-                } else {
-                    const wtgpu_node* __restrict__ n = sc.nodes + (ptr - 1);
-                    const float mnx = __ldg(&n->minx[gg.gl]), mny = __ldg(&n->miny[gg.gl]), mnz = __ldg(&n->minz[gg.gl]);
-                    const float mxx = __ldg(&n->maxx[gg.gl]), mxy = __ldg(&n->maxy[gg.gl]), mxz = __ldg(&n->maxz[gg.gl]);
-                    const int32_t ch = __ldg(&n->child[gg.gl]);
-                    float tmin;
-                    const bool push = cone_child_test(env.o, env.d, sh.inv, sh.nx != 0, sh.ny != 0, sh.nz != 0, env.ta, env.x0, cr, mnx, mny, mnz, mxx, mxy, mxz, tmin) && ch != 0;
-                    const unsigned m = g_ballot(gg, push);
-                    const int np = __popc(m);
-                    // rank in the order the insertion sort leaves the children on the stack (descending tmin, stable: bvh8w.cpp:44-57); pop order is the reverse
-                    const float key = push ? tmin : -WT_INF;
-                    int rank = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { const float kj = g_shfl(gg, key, j); rank += (kj > key || (kj == key && j < (int)gg.gl)) ? 1 : 0; }
-                    uint32_t big = 0u;
-                    if (push) {
-                        const int pi = np - 1 - rank;
-                        sh.wc_tmin[grp][pi] = tmin; sh.wc_ptr[grp][pi] = ch;
-                        if (ch < 0) { const wtgpu_leaf lf = sc.leaves[-ch - 1]; sh.wc_t0[grp][pi] = lf.tris_ptr; sh.wc_cnt[grp][pi] = lf.count; big = lf.count > 8u ? 1u : 0u; }
-                    }
-                    const unsigned deep = g_ballot(gg, push && ch > 0), bigm = g_ballot(gg, big != 0u);
-                    if (gg.gl == 0u) { sh.wn[grp] = np; sh.wfl[grp] = 1 | (deep ? 2 : 0) | (bigm ? 8 : 0); }
-                }
-            } else if (gg.gl == 0u) { sh.wn[grp] = 0; sh.wfl[grp] = 4; }
-        }
-        t_sync<TEAM>();
-
-        // ---- B: the window = the leading run of simple entries; its leaves in pop order
-        if (ctl) {
-            const int w = (int)lane;
-            const int fl = w < NW ? sh.wfl[w] : 4, wn = w < NW ? sh.wn[w] : 0;
-            const bool simple = !(fl & (2 | 4 | 8)) && (!(fl & 1) || (s0 - 1 - w) + wn <= kGStack);
-            const unsigned sm = __ballot_sync(FULL, simple);
-            const int wlen = sm == FULL ? 32 : __ffs(~sm) - 1;
-            const int cntw = w < wlen ? wn : 0;
-            int incl = cntw;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += u; }
-            const int nl = __shfl_sync(FULL, incl, 31);
-            if (w < wlen) { const int b = incl - cntw; sh.lbase[w] = b; for (int c = 0; c < cntw; ++c) { sh.bt0[b + c] = sh.wc_t0[w][c]; sh.bcnt[b + c] = sh.wc_cnt[w][c]; } }
-            if (lane == 0u) { sh.wlen = wlen; sh.nl = nl; }
-        }
-        t_sync<TEAM>();
-        const int wlen = sh.wlen, nl = sh.nl;
-
-        if (wlen == 0) {
-            // the top entry is not simple: the sequential algorithm's next step, by the control warp
+        // ---- lookahead: leading leaves / markers of Q -> R; the first nodes below them expanded in place; repeat
+        int rn = 0, nl = 0;         // (control warp) entries / leaves of R
+        int myk = -1;               // (control warp) which of the round's selected nodes this lane's entry is
+        for (int round = 0; ; ++round) {
             if (ctl) {
-                const int fl = sh.wfl[0];
-                if (fl & 1) {       // an internal node: expand it (the lookahead already holds its children when they fit the stack)
-                    const int np = sh.wn[0];
-                    if (s0 - 1 + np <= kGStack) {
-                        if (lane == 0u) ctr.nodes++;
-                        if ((int)lane < np) { const int at = s0 - 1 + (np - 1 - (int)lane); sh.g.tmin[at] = sh.wc_tmin[0][lane]; sh.g.ptr[at] = sh.wc_ptr[0][lane]; }
-                        t.s = s0 - 1 + np;
-                    } else {
-                        const int32_t top = sh.g.ptr[s0 - 1];
-                        t.s = s0 - 1;
-                        if (lane < 8u) g_node_step(sc, g8, sh.g, t, top, ctr);
-                        t.s = __shfl_sync(FULL, t.s, 0);
+                // (1) the leading run of Q moves to R.  A stale entry moves only when it is the very next thing the sequential loop pops (R empty).
+                bool room = true;
+                while (room && t.s > 0) {
+                    const int qi = t.s - 1 - (int)lane;
+                    uint32_t inf = QK_NODE; float tm = 0.f; int32_t p = 0;
+                    if (qi >= 0) { inf = sh.qinfo[qi]; tm = sh.qtmin[qi]; p = sh.qptr[qi]; }
+                    const uint32_t kd = q_kind(inf);
+                    const bool stale = kd != QK_MARK && tm >= cr.mx;
+                    const bool mov = qi >= 0 && kd != QK_NODE && !(stale && (lane > 0u || rn > 0));
+                    const unsigned mm = __ballot_sync(FULL, mov);
+                    int take = mm == FULL ? 32 : __ffs(~mm) - 1;                // leading lanes that move
+                    const unsigned lm = __ballot_sync(FULL, mov && kd == QK_LEAF);
+                    // capacity: R entries and batch leaves
+                    if (take > RCAP - rn) { take = RCAP - rn; room = false; }
+                    int nleaf = __popc(lm & (take >= 32 ? FULL : ((1u << take) - 1u)));
+                    while (nl + nleaf > nl_cap) { --take; room = false; nleaf = __popc(lm & ((1u << take) - 1u)); }
+                    if ((int)lane < take) {
+                        sh.rptr[rn + lane] = p; sh.rtmin[rn + lane] = tm; sh.rinfo[rn + lane] = (uint16_t)inf;
+                        if (kd == QK_LEAF) sh.rleaf[nl + __popc(lm & ((1u << lane) - 1u))] = (uint16_t)(rn + lane);
                     }
+                    rn += take; nl += nleaf; t.s -= take;
+                    if (take < 32) break;
+                }
+                // (2) the nodes to expand: the first NW eligible ones among the top 32 entries, up to the first entry that has to wait its turn
+                int nsel = 0; myk = -1;
+                const bool want = room && nl < (nl_cap * 3) / 4 && round < 6 && t.s > 0 && t.s + 9 * NW <= QCAP;
+                if (want) {
+                    const int qi = t.s - 1 - (int)lane;
+                    uint32_t inf = QK_LEAF; float tm = 0.f;
+                    if (qi >= 0) { inf = sh.qinfo[qi]; tm = sh.qtmin[qi]; }
+                    const uint32_t kd = q_kind(inf);
+                    const bool stale = kd != QK_MARK && tm >= cr.mx && (lane > 0u || rn > 0);
+                    const bool isnode = qi >= 0 && kd == QK_NODE;
+                    const bool stop = qi < 0 || stale || (isnode && q_ssz(inf) + 7u > (uint32_t)kGStack);
+                    const unsigned sm = __ballot_sync(FULL, stop);
+                    const unsigned before = sm ? ((1u << (__ffs(sm) - 1)) - 1u) : FULL;
+                    const unsigned nm = __ballot_sync(FULL, isnode) & before;
+                    const int k = __popc(nm & ((1u << lane) - 1u));
+                    if (((nm >> lane) & 1u) && k < NW) { sh.sel[k] = qi; myk = k; }
+                    nsel = min(__popc(nm), NW);
+                }
+                if (lane == 0u) { sh.nsel = nsel; sh.go = nsel > 0 ? 1 : 0; }
+            }
+            t_sync<TEAM>();
+            if (!sh.go) break;
+            TDBG(2, 1);
+            // (3) one group of eight lanes per selected node: children against the current range, ranked in pop order
+            if (grp < sh.nsel) {
+                const int32_t ptr = sh.qptr[sh.sel[grp]];
+                const wtgpu_node* __restrict__ n = sc.nodes + (ptr - 1);
+                const float mnx = __ldg(&n->minx[gg.gl]), mny = __ldg(&n->miny[gg.gl]), mnz = __ldg(&n->minz[gg.gl]);
+                const float mxx = __ldg(&n->maxx[gg.gl]), mxy = __ldg(&n->maxy[gg.gl]), mxz = __ldg(&n->maxz[gg.gl]);
+                const int32_t ch = __ldg(&n->child[gg.gl]);
+                float tmin;
+                const bool push = cone_child_test(env.o, env.d, sh.inv, sh.nx != 0, sh.ny != 0, sh.nz != 0, env.ta, env.x0, cr, mnx, mny, mnz, mxx, mxy, mxz, tmin) && ch != 0;
+                const unsigned m = g_ballot(gg, push);
+                const int np = __popc(m);
+                // rank in the order the insertion sort leaves the children on the stack (descending tmin, stable: bvh8w.cpp:44-57); pop order is the reverse
+                const float key = push ? tmin : -WT_INF;
+                int rank = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float kj = g_shfl(gg, key, j); rank += (kj > key || (kj == key && j < (int)gg.gl)) ? 1 : 0; }
+                if (push) { const int pi = np - 1 - rank; sh.wc_tmin[grp][pi] = tmin; sh.wc_ptr[grp][pi] = ch; }
+                if (gg.gl == 0u) sh.wn[grp] = np;
+            }
+            t_sync<TEAM>();
+            // (4) rewrite the top of Q: every selected node becomes [children in stack order ..., marker]
+            if (ctl) {
+                const int nsel = sh.nsel;
+                const int lowest = sh.sel[nsel - 1];            // the deepest selected entry: the region is [lowest, t.s)
+                const int qi = t.s - 1 - (int)lane;
+                const bool inreg = qi >= lowest;
+                uint32_t inf = 0u; float tm = 0.f; int32_t p = 0; const int k = inreg ? myk : -1;      // (this lane looked at the same entry when it selected)
+                if (inreg) { inf = sh.qinfo[qi]; tm = sh.qtmin[qi]; p = sh.qptr[qi]; }
+                const int np = k >= 0 ? sh.wn[k] : 0;
+                const int size = inreg ? (k >= 0 ? np + 1 : 1) : 0;
+                // entries deeper in the region (larger lane) come first in the new layout: offset = sum of the sizes of the lanes above this one
+                int incl = size;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_down_sync(FULL, incl, o); if ((int)lane + o < 32) incl += u; }
+                const int total = __shfl_sync(FULL, incl, 0);
+                const int at = lowest + incl - size;
+                __syncwarp();
+                if (inreg) {
+                    if (k < 0) { sh.qptr[at] = p; sh.qtmin[at] = tm; sh.qinfo[at] = (uint16_t)inf; }
+                    else {
+                        const uint32_t d = q_depth(inf), ssz = q_ssz(inf);
+                        for (int c = 0; c < np; ++c) {      // child with pop index c sits at at + (np - 1 - c); when it is on top the sequential stack holds ssz - 1 + (np - c) entries
+                            const int32_t cp = sh.wc_ptr[k][c];
+                            sh.qptr[at + np - 1 - c] = cp; sh.qtmin[at + np - 1 - c] = sh.wc_tmin[k][c];
+                            sh.qinfo[at + np - 1 - c] = (uint16_t)q_info(cp < 0 ? QK_LEAF : QK_NODE, min(d + 1u, 63u), ssz - 1u + (uint32_t)(np - c));
+                        }
+                        sh.qptr[at + np] = p; sh.qtmin[at + np] = tm; sh.qinfo[at + np] = (uint16_t)q_info(QK_MARK, d, ssz);
+                    }
+                }
+                t.s = lowest + total;
+                __syncwarp();
+            }
+        }
+        if (ctl && lane == 0u) { sh.rn = rn; sh.nl = nl; }
+        t_sync<TEAM>();
+        rn = sh.rn; nl = sh.nl;
+        TCLK(5); TDBG(0, 1); TDBG(1, nl);
+
+        // ---- B: the batch leaves' triangle ranges
+        for (int li = (int)tid; li < nl; li += TEAM) {
+            const wtgpu_leaf lf = sc.leaves[-sh.rptr[sh.rleaf[li]] - 1];
+            sh.bt0[li] = lf.tris_ptr; sh.bcnt[li] = lf.count;
+            if (lf.count > 8u) atomicMin(&sh.big, li);
+        }
+        t_sync<TEAM>();
+        if (rn == 0 || sh.big == 0) {
+            // nothing could be moved to R: the top of Q is a node that cannot be expanded in place (the sequential stack is nearly full, or Q
+            // is) -- or the first leaf holds more than eight triangles.  The sequential algorithm's next step, by the control warp, on the real stack.
+            if (ctl) {
+                // R goes back (nothing of it was committed), the markers are reverted
+                for (int e = rn - 1 - (int)lane; e >= 0; e -= 32) { const int at = t.s + (rn - 1 - e); sh.qptr[at] = sh.rptr[e]; sh.qtmin[at] = sh.rtmin[e]; sh.qinfo[at] = sh.rinfo[e]; }
+                t.s = q_revert(sh, t.s + rn, lane);
+                for (int k = (int)lane; k < t.s; k += 32) { sh.g.tmin[k] = sh.qtmin[k]; sh.g.ptr[k] = sh.qptr[k]; }
+                __syncwarp();
+                const int32_t top = sh.g.ptr[t.s - 1];
+                --t.s;
+                if (top >= 0) {
+                    if (lane < 8u) g_node_step(sc, g8, sh.g, t, top, ctr);
+                    t.s = __shfl_sync(FULL, t.s, 0);
                     __syncwarp();
-                } else {            // a leaf of more than eight triangles: the general leaf step, 32 triangles at a time
-                    const uint32_t lt0 = sh.wc_t0[0][0], lcnt = sh.wc_cnt[0][0];
-                    t.s = s0 - 1;
+                } else {            // the general leaf step, 32 triangles at a time
+                    const wtgpu_leaf lf = sc.leaves[-top - 1];
+                    const uint32_t lt0 = lf.tris_ptr, lcnt = lf.count;
                     t.qtested += lcnt;
                     bool found = false;
                     for (uint32_t base = 0; base < lcnt; base += 32u) {
@@ -228,11 +363,21 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                             if (t.tw.fail) t.res.overflow = true;
                         }
                     }
-                    if (found) { t.crange = cone_search_range(t.env, t.qrange, t.res.dist, t.zs); t_prune(sh.g, t); }
+                    if (found) { t.crange = cone_search_range(t.env, t.qrange, t.res.dist, t.zs); while (t.s > 0 && sh.g.tmin[t.s - 1] >= t.crange.mx) --t.s; }
                     __syncwarp();
                 }
+                q_from_stack(sh, t.s, lane);
             }
             continue;
+        }
+        if (sh.big < nl) {          // a leaf of more than eight triangles further down the run: the batch ends before it
+            if (ctl) {
+                const int cut = (int)sh.rleaf[sh.big];
+                for (int e = rn - 1 - (int)lane; e >= cut; e -= 32) { const int at = t.s + (rn - 1 - e); sh.qptr[at] = sh.rptr[e]; sh.qtmin[at] = sh.rtmin[e]; sh.qinfo[at] = sh.rinfo[e]; }
+                t.s += rn - cut;
+                __syncwarp();
+            }
+            nl = sh.big; rn = (int)sh.rleaf[sh.big];
         }
 
         // ---- T1: the cheap rejections for every triangle of the batch; survivors compacted
@@ -275,19 +420,26 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
         }
         t_sync<TEAM>();
 
-        // ---- C: commit in stack order (control warp)
+        TCLK(6);
+        // ---- C: commit R in pop order (control warp).  Leaves are committed in SEGMENTS that end at the first leaf improving the closest hit: up
+        // to there nothing the commit depends on changes, so the segment's accepted triangles are appended in one parallel pass; the improving
+        // leaf then moves the hit distance, and if that narrows the search range the rest of the batch is void (it saw the old range).
         if (ctl) {
-            // fast path: no leaf improves the closest hit (so the range cannot change) and no window entry below the top is stale (so the
-            // unwinding after a leaf with hits never removes one)
-            bool slow = false;
-            { const int w = (int)lane; if (__any_sync(FULL, w >= 1 && w < wlen && sh.g.tmin[s0 - 1 - w] >= t.crange.mx)) slow = true; }
-            for (int c0 = 0; c0 < nl && !slow; c0 += 32) { const int li = c0 + (int)lane; if (__any_sync(FULL, li < nl && sh.lmask[li] != 0u && sh.ldmin[li] < t.res.dist)) slow = true; }
-            if (!slow) {
-                uint32_t ntri = 0u, nnode = 0u;
-                for (int c0 = 0; c0 < nl; c0 += 32) {
+            int start = 0, e0 = 0;          // first uncommitted leaf / R entry
+            bool restarted = false;
+            uint32_t ntri = 0u;
+            for (;;) {
+                int first = nl;
+                for (int c0 = start; c0 < nl; c0 += 32) {
                     const int li = c0 + (int)lane;
-                    uint32_t m = li < nl ? sh.lmask[li] : 0u;
-                    ntri += li < nl ? sh.bcnt[li] : 0u;
+                    const unsigned im = __ballot_sync(FULL, li < nl && sh.lmask[li] != 0u && sh.ldmin[li] < t.res.dist);
+                    if (im) { first = c0 + __ffs(im) - 1; break; }
+                }
+                const int upto = first < nl ? first + 1 : nl;
+                for (int c0 = start; c0 < upto; c0 += 32) {
+                    const int li = c0 + (int)lane;
+                    uint32_t m = li < upto ? sh.lmask[li] : 0u;
+                    ntri += li < upto ? sh.bcnt[li] : 0u;
                     const uint32_t c = (uint32_t)__popc(m);
                     uint32_t incl = c;
 #pragma unroll
@@ -301,60 +453,41 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                         if (t.tw.fail) t.res.overflow = true;
                     }
                 }
-                { const int w = (int)lane; nnode = (w < wlen && (sh.wfl[w] & 1)) ? 1u : 0u; }
-                ctr.tris += ntri; ctr.nodes += nnode;
-                t.qtested += __reduce_add_sync(FULL, ntri);
-                const bool last_hit = sh.wn[wlen - 1] > 0 && sh.lmask[nl - 1] != 0u;
-                t.s = s0 - wlen;
-                if (last_hit) t_prune(sh.g, t);
-            } else {
-                // leaf by leaf.  last_hit: the last thing processed was a leaf with hits (the sequential loop unwinds stale entries right after it)
-                bool last_hit = false, restarted = false;
-                uint32_t ntri = 0u, nnode = 0u;
-                for (int w = 0; w < wlen && !restarted; ++w) {
-                    const int sidx = s0 - 1 - w;
-                    if (w > 0 && last_hit && sh.g.tmin[sidx] >= t.crange.mx) continue;      // unwound, unvisited (last_hit stays: the unwinding goes on)
-                    const int np = sh.wn[w];
-                    if (sh.wfl[w] & 1) { ++nnode; last_hit = false; }
-                    for (int c = 0; c < np; ++c) {
-                        const int li = sh.lbase[w] + c;
-                        ntri += sh.bcnt[li];
-                        const uint32_t m = sh.lmask[li];
-                        if (!m) { last_hit = false; continue; }
-                        const uint32_t upto = t.res.n_tris + (uint32_t)__popc(m);
-                        t_reserve(sc, t, upto, lane);
-                        if (lane < 8u && ((m >> lane) & 1u)) tw_put(sc, t.tw, t.res.n_tris + (uint32_t)__popc(m & ((1u << lane) - 1u)), sh.bt0[li] + lane);
-                        t.res.n_tris = upto;
-                        if (t.tw.fail) t.res.overflow = true;
-                        if (sh.ldmin[li] < t.res.dist) {
-                            t.res.dist = sh.ldmin[li];
-                            const Tri3 tr = load_tri(sc, sh.bt0[li] + sh.larg[li]);
-                            t.res.front = dot(tr.n, -t.env.d) > 0.f;
-                        }
-                        last_hit = true;
-                        const Range nr = cone_search_range(t.env, t.qrange, t.res.dist, t.zs);
-                        if (nr.mx != t.crange.mx || nr.mn != t.crange.mn) {
-                            // the rest of the batch saw a stale range: entries 0..w leave the stack, the uncommitted children of entry w go onto it
-                            // (in stack order = reverse pop order), the unwinding runs, and the next batch tests what is left against the new range
-                            t.crange = nr;
-                            int ns = sidx;
-                            __syncwarp();
-                            for (int cc = np - 1; cc > c; --cc) { if (lane == 0u) { sh.g.tmin[ns] = sh.wc_tmin[w][cc]; sh.g.ptr[ns] = sh.wc_ptr[w][cc]; } ++ns; }
-                            __syncwarp();
-                            t.s = ns;
-                            t_prune(sh.g, t);
-                            restarted = true;
-                            break;
-                        }
-                    }
+                const int e1 = first < nl ? (int)sh.rleaf[first] + 1 : rn;         // R entries [e0, e1) are done: e1 - e0 - (upto - start) of them are markers (nodes visited)
+                if (lane == 0u) ctr.nodes += (uint32_t)((e1 - e0) - (upto - start));
+                if (first >= nl) break;
+                t.res.dist = sh.ldmin[first];
+                { const Tri3 tr = load_tri(sc, sh.bt0[first] + sh.larg[first]); t.res.front = dot(tr.n, -t.env.d) > 0.f; }
+                const Range nr = cone_search_range(t.env, t.qrange, t.res.dist, t.zs);
+                if (nr.mx != t.crange.mx || nr.mn != t.crange.mn) {
+                    // the rest of R goes back on top of Q, the markers are reverted -- Q is the sequential stack again -- and the unwinding
+                    // that follows a leaf with hits runs with the new range
+                    TDBG(3, 1);
+                    t.crange = nr;
+                    const int e = e1 - 1, back = rn - e1;
+                    for (int x = rn - 1 - (int)lane; x > e; x -= 32) { const int at = t.s + (rn - 1 - x); sh.qptr[at] = sh.rptr[x]; sh.qtmin[at] = sh.rtmin[x]; sh.qinfo[at] = sh.rinfo[x]; }
+                    t.s = q_revert(sh, t.s + back, lane);
+                    q_prune(sh, t);
+                    restarted = true;
+                    nl_cap = max(NL / 16, 8);
+                    break;
                 }
-                if (lane == 0u) { ctr.tris += ntri; ctr.nodes += nnode; }
-                t.qtested += ntri;
-                if (!restarted) { t.s = s0 - wlen; if (last_hit) t_prune(sh.g, t); }
+                start = upto; e0 = e1;
+            }
+            ctr.tris += ntri;
+            t.qtested += __reduce_add_sync(FULL, ntri);
+            if (!restarted) {
+                const bool last_hit = nl > 0 && (int)sh.rleaf[nl - 1] == rn - 1 && sh.lmask[nl - 1] != 0u;      // the last thing popped was a leaf with hits
+                if (last_hit) q_prune(sh, t);
+                nl_cap = min(NL, nl_cap * 2);
             }
             __syncwarp();
         }
+        TCLK(7);
     }
+#ifdef WT_TEAM_DEBUG
+    if (ctl && lane == 0u) for (int i = 0; i < 8; ++i) atomicAdd(dbg + i, d_[i]);
+#endif
 }
 
 } // namespace wt

@@ -85,6 +85,7 @@ struct DevCounters {
     int n_huge, huge_head;                             // beams the warp teams handed on to the block teams
     int n_huge_res, huge_res_head;                     // lists the warp-per-list resolve handed on to the block-per-list resolve
     unsigned long long stack_drops;
+    unsigned long long dbg[16];         // -DWT_TEAM_DEBUG: team-traversal diagnostics (ctrav.cuh), printed by wtgpu_render when WT_DEBUG_TEAM is set
 };
 WT_D void need_max(unsigned int* p, uint32_t v) { if (v > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(p, v); }
 
@@ -393,14 +394,14 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs 
 __global__ void __launch_bounds__(128, 4) k_wtraverse(const RenderArgs a) {
     __shared__ TShared<32> shm[4];
     Counters ctr; counters_zero(ctr);
-    t_traverse_all<32>(a.sc, a.ctr->n_big, a.big_save, &a.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.huge_save, &a.ctr->n_huge, a.huge_tested,
+    t_traverse_all<32>(a.sc, a.ctr->n_big, a.big_save, &a.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.huge_save, &a.ctr->n_huge, a.huge_tested, a.ctr->dbg,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
     flush_counters(a.ctr, ctr);
 }
 __global__ void __launch_bounds__(256, 2) k_ctraverse(const RenderArgs a) {
     __shared__ TShared<256> shm;
     Counters ctr; counters_zero(ctr);
-    t_traverse_all<256>(a.sc, a.ctr->n_huge, a.huge_save, &a.ctr->huge_head, shm, ctr, nullptr, nullptr, 0u,
+    t_traverse_all<256>(a.sc, a.ctr->n_huge, a.huge_save, &a.ctr->huge_head, shm, ctr, nullptr, nullptr, 0u, a.ctr->dbg + 8,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
     flush_counters(a.ctr, ctr);
 }
@@ -1173,7 +1174,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
     const dim3 gBig(s->big_blocks);
     // hand-over thresholds of the traversal tiers (gtrav.cuh TravTiers); WT_BIG_TESTED / WT_HUGE_TESTED override for A/B runs
     static const wt::TravTiers tiers = []() { wt::TravTiers t; const char* b = getenv("WT_BIG_TESTED"); const char* h = getenv("WT_HUGE_TESTED");
-                                              t.big_tested = b ? (uint32_t)atoi(b) : 192u; t.huge_tested = h ? (uint32_t)atoi(h) : 6144u; return t; }();
+                                              t.big_tested = b ? (uint32_t)atoi(b) : 192u; t.huge_tested = h ? (uint32_t)atoi(h) : 3072u; return t; }();
 
     // the sub-pools start after whatever the caller queued on its stream
     CK(cudaEventRecord(s->ev_begin, user));
@@ -1320,7 +1321,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
         const DevCounters& c = *q.hctr;
         T.samples += c.samples; T.segments += c.segments; T.ray_casts += c.ray_casts; T.cone_casts += c.cone_casts; T.shadow_casts += c.shadow_casts; T.nodes += c.nodes; T.tris += c.tris;
         T.edges += c.edges; T.surface += c.surface; T.fsd += c.fsd; T.null_ += c.null_; T.splats += c.splats; T.overflow += c.overflow; T.shade_nodes += c.shade_nodes; T.shade_tris += c.shade_tris;
-        T.shaded += c.shaded; T.walker_steps += c.walker_steps; T.stack_drops += c.stack_drops;
+        T.shaded += c.shaded; T.walker_steps += c.walker_steps; T.stack_drops += c.stack_drops; for (int i = 0; i < 16; ++i) T.dbg[i] += c.dbg[i];
         for (int i = 0; i < 5; ++i) T.strategies[i] += c.strategies[i];
         T.need_spill = std::max(T.need_spill, std::max(c.need_spill, c.spill_head)); T.need_edges = std::max(T.need_edges, c.need_edges); T.need_seg = std::max(T.need_seg, c.need_seg);
         T.need_ap = std::max(T.need_ap, c.need_ap); T.need_verts = std::max(T.need_verts, c.need_verts);
@@ -1461,6 +1462,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         stats->gpu_ms = ms; stats->traverse_ms = t_trav; stats->shade_ms = t_shade; stats->generate_ms = t_gen; stats->sort_ms = t_sort; stats->connect_ms = t_conn;
         for (int c = 0; c < 5; ++c) stats->strategies[c] = hctr->strategies[c];
         stats->walker_steps = hctr->walker_steps;
+        if (getenv("WT_DEBUG_TEAM")) { fprintf(stderr, "team dbg:"); for (int i = 0; i < 16; ++i) fprintf(stderr, " %llu", hctr->dbg[i]); fprintf(stderr, "\n"); }
         stats->passes = passes; stats->stack_drops = hctr->stack_drops; stats->pool_used = pool; stats->subpools = parts;
         stats->cap_tris = s->caps.spill_words; stats->cap_edges = s->caps.edges; stats->cap_segments = s->caps.seg; stats->cap_apertures = s->caps.ap_walk; stats->cap_vertices = s->caps.verts;
     }
