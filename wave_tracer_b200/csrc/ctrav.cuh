@@ -240,7 +240,7 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                 }
                 // (2) the nodes to expand: the first NW eligible ones among the top 32 entries, up to the first entry that has to wait its turn
                 int nsel = 0; myk = -1;
-                const bool want = room && nl < (nl_cap * 3) / 4 && round < 6 && t.s > 0 && t.s + 9 * NW <= QCAP;
+                const bool want = room && nl < (nl_cap * 3) / 4 && round < 6 && t.s > 0 && t.s + rn + 9 * NW <= QCAP;       // (Q must be able to take R back: t.s + rn never exceeds QCAP)
                 if (want) {
                     const int qi = t.s - 1 - (int)lane;
                     uint32_t inf = QK_LEAF; float tm = 0.f;

@@ -132,6 +132,31 @@ WT_D float g2_quadrature_warp(V2 a, V2 b, V2 c) {
     if (cnt & 31u) flush(cnt & 31u);
     return ret * kInvTwoPi * sqrf(.002f);
 }
+// A warp's quadrature pieces (all 32 lanes call; `mine`: this lane holds one).  Under a beam much wider than the mesh's triangles EVERY piece takes the
+// quadrature branch with ~10^2 samples: then each lane sums its own (32 pieces side by side).  Only a piece with very many samples -- a sliver
+// across the whole 6-sigma window -- is worth the warp's joint evaluation, where the samples of ONE piece are spread over the lanes and the other
+// lanes' pieces wait.  Same sample sequence, same order of additions either way.
+constexpr float kQuadCoopSamples = 4096.f;
+WT_D float g2_quadrature_mixed(bool mine, V2 pa, V2 pb, V2 pc) {
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    float val = 0.f; bool big = false;
+    if (mine) {
+        const float L = 3.f, delta = .002f;
+        const float h = fminf(L, max3f(pa.y, pb.y, pc.y)) - fmaxf(-L, min3f(pa.y, pb.y, pc.y)), w = fminf(L, max3f(pa.x, pb.x, pc.x)) - fmaxf(-L, min3f(pa.x, pb.x, pc.x));
+        big = fmaxf(h, 0.f) * fmaxf(w, 0.f) * (.5f / (delta * delta)) > kQuadCoopSamples;
+        if (!big) val = g2_quadrature(pa, pb, pc);
+    }
+    unsigned m = __ballot_sync(FULL, mine && big);
+    while (m) {
+        const int src = __ffs(m) - 1; m &= m - 1u;
+        const V2 qa = mk2(__shfl_sync(FULL, pa.x, src), __shfl_sync(FULL, pa.y, src));
+        const V2 qb = mk2(__shfl_sync(FULL, pb.x, src), __shfl_sync(FULL, pb.y, src));
+        const V2 qc = mk2(__shfl_sync(FULL, pc.x, src), __shfl_sync(FULL, pc.y, src));
+        const float r = g2_quadrature_warp(qa, qb, qc);
+        if ((int)lane == src) val = r;
+    }
+    return val;
+}
 WT_NI float g2_analytic(const DScene& sc, V2 a, V2 b, V2 c) {
     const V2 t0 = b - a, t1 = c - a;         // T = mat2(t0, t1) columns
     const float detT = t0.x * t1.y - t1.x * t0.y;
@@ -644,173 +669,86 @@ WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, cons
                     add = true;
                 }
             }
-            unsigned m = __ballot_sync(0xffffffffu, kind == G2_QUADRATURE);
-            while (m) {
-                const int src = __ffs(m) - 1; m &= m - 1u;
-                const V2 qa = mk2(__shfl_sync(0xffffffffu, pa.x, src), __shfl_sync(0xffffffffu, pa.y, src));
-                const V2 qb = mk2(__shfl_sync(0xffffffffu, pb.x, src), __shfl_sync(0xffffffffu, pb.y, src));
-                const V2 qc = mk2(__shfl_sync(0xffffffffu, pc.x, src), __shfl_sync(0xffffffffu, pc.y, src));
-                const float r = g2_quadrature_warp(qa, qb, qc);
-                if ((int)lane == src) val = r;
-            }
+            { const float qv = g2_quadrature_mixed(kind == G2_QUADRATURE, pa, pb, pc); if (kind == G2_QUADRATURE) val = qv; }
             if (add) h.flux += val;
         }
     }
     if (flux_lane && sc.integrator.fsd) { bool eo = false; h.n_edges = collect_edges(sc, tl, edges, sc.cap.edges, eo); if (eo) { h.overflow = true; h.need_edges = 3u * tl.n; } }
 }
 
-// One WARP resolves one walker whose cone query returned a long triangle list (all lanes call with the same arguments; every lane ends with the
-// same BHit): closest triangle by an ordered warp minimum; the Gaussian power 32 triangles at a time -- lane l clips and integrates triangle
-// base + l (its <= 3 pieces; quadrature pieces by the whole warp), and the piece values are then added IN LIST ORDER; the edge set through
-// the scratch bitmap.  Bit-identical to bd_resolve_hit.
-WT_D void bd_resolve_hit_big(const DScene& sc, const Beam& beam, const TravOut& tr, const TriList& tl, uint32_t* edges, uint32_t* edge_bits, BHit& h) {
-    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
-    Range zr; bd_hit_init(h, beam, tr, zr);
-    if (tr.empty || h.ballistic) return;
+// ---- long triangle lists: one WARP per list (k_bd_resolve_big), and the Gaussian power of the lists that need it -- no triangle on the beam's
+// central ray -- as flat 32-triangle tasks over the whole GPU (k_bd_flux_chunks) whose piece values are then added IN LIST ORDER per list
+// (k_bd_flux_finish).  Under a beam much wider than the mesh's triangles a list holds 10^3-10^5 entries and nearly every clipped piece takes the
+// quadrature branch of integrate_triangle (~10^2 samples each, some 10^4): done inside one warp per list, a handful of lists decided the
+// duration of the launch.  Same values, same order of additions as bd_resolve_hit.
+
+// the clipped pieces of list entries [base, base + 32), one entry per lane (all 32 lanes call): values of pieces 0..2 and their number
+WT_D void bd_flux_chunk(const DScene& sc, const Beam& beam, bool front, const TriList& tl, Range zr, const Frame& beam_frame, const G2& wf, float csz, uint32_t base,
+                        float& v0, float& v1, float& v2, int& cnt) {
+    const unsigned lane = threadIdx.x & 31u;
     const V3 dir = beam.env.d;
-    w_find_closest(sc, tl, tr.origin, dir, zr, h.primary, h.pdist, h.bx, h.by);
-    if (h.primary != WTGPU_INVALID_IDX) return;
+    const uint32_t i = base + lane;
+    Clip cl; cl.tris = 0;
+    if (i < tl.n) {
+        const Tri3 t = load_tri(sc, tri_at(tl, i));
+        if ((dot(t.n, -dir) > 0.f) == front)
+            cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
+    }
+    v0 = v1 = v2 = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {       // piece k of every lane's triangle
+        int kind = G2_DONE; float val = 0.f; V2 pa = mk2(0.f, 0.f), pb = pa, pc = pa;
+        if (k < cl.tris) {
+            V3 ct[3]; clip_tri(cl, k, ct);
+            pa = cone_project_local(beam.env, ct[0], csz); pb = cone_project_local(beam.env, ct[1], csz); pc = cone_project_local(beam.env, ct[2], csz);
+            kind = g2_classify(wf, pa, pb, pc, val);
+            if (kind == G2_ANALYTIC) val = g2_analytic(sc, pa, pb, pc);
+        }
+        { const float qv = g2_quadrature_mixed(kind == G2_QUADRATURE, pa, pb, pc); if (kind == G2_QUADRATURE) val = qv; }
+        if (k == 0) v0 = val; else if (k == 1) v1 = val; else v2 = val;
+    }
+    cnt = cl.tris;
+}
+// ordered accumulation of one chunk: entry base, base + 1, ...; pieces 0, 1, 2 of each (all 32 lanes call; every lane returns the same sum)
+WT_D float bd_flux_add(float flux, float v0, float v1, float v2, int cnt) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned rest = __ballot_sync(FULL, cnt > 0);
+    while (rest) {
+        const int l = __ffs(rest) - 1; rest &= rest - 1u;
+        const int c = __shfl_sync(FULL, cnt, l);
+        const float a0 = __shfl_sync(FULL, v0, l), a1 = __shfl_sync(FULL, v1, l), a2 = __shfl_sync(FULL, v2, l);
+        flux += a0; if (c > 1) flux += a1; if (c > 2) flux += a2;
+    }
+    return flux;
+}
+// One warp resolves one walker (all lanes call with the same arguments; every lane ends with the same BHit).  First half: the closest triangle, found
+// by the flat search; returns true when there is none, i.e. the Gaussian power (and the edge set) are still to come.
+WT_D bool bd_resolve_closest_big(const DScene& sc, const Beam& beam, const TravOut& tr, const TriList& tl, unsigned long long best, BHit& h) {
+    Range zr; bd_hit_init(h, beam, tr, zr);
+    if (tr.empty || h.ballistic) return false;
+    if (best == ~0ull) return true;
+    // the winner of the flat search (k_bd_closest_chunks): its triangle once more, for the barycentrics
+    const uint32_t e = (uint32_t)best, tu = tri_at(tl, e);
+    const Tri3 t = load_tri(sc, tu);
+    const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
+    const RayTri rt = intersect_ray_tri(tr.origin, beam.env.d, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+    h.primary = tu; h.pdist = rt.dist; h.bx = rt.bx; h.by = rt.by;
+    return false;
+}
+// Second half, inside the warp (lists too short to be worth queueing, or no scratch left): the power chunk by chunk, the edge set through the scratch bitmap
+WT_D void bd_resolve_flux_big(const DScene& sc, const Beam& beam, const TravOut& tr, const TriList& tl, uint32_t* edges, uint32_t* edge_bits, BHit& h) {
+    const Range zr = mkr(h.dist, h.dist + tr.region_depth);
     const Frame beam_frame = cone_frame(beam.env);
     const G2 wf = wavefront_of(beam, h.dist);
     const float csz = (zr.mx + zr.mn) / 2.f;
     float flux = 0.f;
     for (uint32_t base = 0u; base < tl.n; base += 32u) {
-        const uint32_t i = base + lane;
-        Clip cl; cl.tris = 0;
-        if (i < tl.n) {
-            const Tri3 t = load_tri(sc, tri_at(tl, i));
-            if ((dot(t.n, -dir) > 0.f) == tr.cone.front)
-                cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
-        }
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-#pragma unroll 1
-        for (int k = 0; k < 3; ++k) {       // piece k of every lane's triangle
-            int kind = G2_DONE; float val = 0.f; V2 pa = mk2(0.f, 0.f), pb = pa, pc = pa;
-            if (k < cl.tris) {
-                V3 ct[3]; clip_tri(cl, k, ct);
-                pa = cone_project_local(beam.env, ct[0], csz); pb = cone_project_local(beam.env, ct[1], csz); pc = cone_project_local(beam.env, ct[2], csz);
-                kind = g2_classify(wf, pa, pb, pc, val);
-                if (kind == G2_ANALYTIC) val = g2_analytic(sc, pa, pb, pc);
-            }
-            unsigned m = __ballot_sync(FULL, kind == G2_QUADRATURE);
-            while (m) {
-                const int src = __ffs(m) - 1; m &= m - 1u;
-                const V2 qa = mk2(__shfl_sync(FULL, pa.x, src), __shfl_sync(FULL, pa.y, src));
-                const V2 qb = mk2(__shfl_sync(FULL, pb.x, src), __shfl_sync(FULL, pb.y, src));
-                const V2 qc = mk2(__shfl_sync(FULL, pc.x, src), __shfl_sync(FULL, pc.y, src));
-                const float r = g2_quadrature_warp(qa, qb, qc);
-                if ((int)lane == src) val = r;
-            }
-            if (k == 0) v0 = val; else if (k == 1) v1 = val; else v2 = val;
-        }
-        // ordered accumulation: triangle base, base + 1, ... ; pieces 0, 1, 2 of each
-        const unsigned any = __ballot_sync(FULL, cl.tris > 0);
-        unsigned rest = any;
-        while (rest) {
-            const int l = __ffs(rest) - 1; rest &= rest - 1u;
-            const int c = __shfl_sync(FULL, cl.tris, l);
-            const float a0 = __shfl_sync(FULL, v0, l), a1 = __shfl_sync(FULL, v1, l), a2 = __shfl_sync(FULL, v2, l);
-            flux += a0; if (c > 1) flux += a1; if (c > 2) flux += a2;
-        }
+        float v0, v1, v2; int cnt;
+        bd_flux_chunk(sc, beam, tr.cone.front, tl, zr, beam_frame, wf, csz, base, v0, v1, v2, cnt);
+        flux = bd_flux_add(flux, v0, v1, v2, cnt);
     }
     h.flux = flux;
     if (sc.integrator.fsd) { bool eo = false; uint32_t need = 0u; h.n_edges = w_collect_edges(sc, tl, edges, sc.cap.edges, edge_bits, eo, need); if (eo) { h.overflow = true; h.need_edges = need; } }
-}
-
-
-// One BLOCK (256 threads) resolves one walker whose cone query returned a very long triangle list (all threads call with the same arguments;
-// every thread ends with the same BHit).  Closest triangle: strided scan + ordered (distance, list index) minimum over the block.  Gaussian
-// power: tiles of kHugeTile list entries -- each warp clips and integrates 32 triangles at a time into the tile's buffers (quadrature pieces by
-// the warp), then the first warp adds the tile's piece values IN LIST ORDER.  Edge set: first warp, scratch bitmap.  Bit-identical to bd_resolve_hit.
-constexpr uint32_t kHugeTile = 1024u;
-struct alignas(16) HugeShared { float v[3][kHugeTile]; uint8_t cnt[kHugeTile]; float rd[8]; uint32_t ri[8], rtu[8]; float rbx[8], rby[8]; float flux; };
-WT_D void bd_resolve_hit_block(const DScene& sc, const Beam& beam, const TravOut& tr, const TriList& tl, uint32_t* edges, uint32_t* edge_bits, BHit& h, HugeShared& sh) {
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
-    Range zr; bd_hit_init(h, beam, tr, zr);
-    if (tr.empty || h.ballistic) return;
-    const V3 dir = beam.env.d;
-    {   // find_closest_triangle (plt_bdpt_detail.hpp:362-390): the first entry, in list order, with the smallest hit distance
-        float bd = WT_INF, bbx = -1.f, bby = -1.f; uint32_t bi = 0xffffffffu, btu = WTGPU_INVALID_IDX;
-        for (uint32_t i = threadIdx.x; i < tl.n; i += blockDim.x) {
-            const uint32_t tu = tri_at(tl, i);
-            const Tri3 t = load_tri(sc, tu);
-            const float tol = cone_intersection_tolerance(tr.origin, t.a, t.b, t.c);
-            const RayTri rt = intersect_ray_tri(tr.origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
-            if (rt.hit && rt.dist < h.pdist && rt.dist < bd) { bd = rt.dist; bi = i; btu = tu; bbx = rt.bx; bby = rt.by; }
-        }
-        float rd = bd; uint32_t ri = bi;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float od = __shfl_xor_sync(FULL, rd, o); const uint32_t oi = __shfl_xor_sync(FULL, ri, o);
-            if (oi != 0xffffffffu && (ri == 0xffffffffu || od < rd || (od == rd && oi < ri))) { rd = od; ri = oi; }
-        }
-        if (bi == ri) { sh.rd[warp] = rd; sh.ri[warp] = ri; sh.rtu[warp] = btu; sh.rbx[warp] = bbx; sh.rby[warp] = bby; }      // (ri == ~0: every lane writes the same "none")
-        __syncthreads();
-        float gd = WT_INF; uint32_t gi = 0xffffffffu; int gw = -1;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { const uint32_t oi = sh.ri[w]; const float od = sh.rd[w]; if (oi != 0xffffffffu && (gi == 0xffffffffu || od < gd || (od == gd && oi < gi))) { gd = od; gi = oi; gw = w; } }
-        if (gw >= 0) { h.primary = sh.rtu[gw]; h.pdist = gd; h.bx = sh.rbx[gw]; h.by = sh.rby[gw]; }
-        __syncthreads();
-        if (gw >= 0) return;
-    }
-    const Frame beam_frame = cone_frame(beam.env);
-    const G2 wf = wavefront_of(beam, h.dist);
-    const float csz = (zr.mx + zr.mn) / 2.f;
-    float flux = 0.f;
-    for (uint32_t t0 = 0u; t0 < tl.n; t0 += kHugeTile) {
-        const uint32_t tn = min(kHugeTile, tl.n - t0);
-        for (uint32_t c0 = warp * 32u; c0 < tn; c0 += blockDim.x) {       // this warp's 32-entry chunks of the tile
-            const uint32_t i = t0 + c0 + lane;
-            Clip cl; cl.tris = 0;
-            if (c0 + lane < tn) {
-                const Tri3 t = load_tri(sc, tri_at(tl, i));
-                if ((dot(t.n, -dir) > 0.f) == tr.cone.front)
-                    cl = clip_triangle_z(to_local(beam_frame, t.a - beam.env.o), to_local(beam_frame, t.b - beam.env.o), to_local(beam_frame, t.c - beam.env.o), zr);
-            }
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k) {       // piece k of every lane's triangle
-                int kind = G2_DONE; float val = 0.f; V2 pa = mk2(0.f, 0.f), pb = pa, pc = pa;
-                if (k < cl.tris) {
-                    V3 ct[3]; clip_tri(cl, k, ct);
-                    pa = cone_project_local(beam.env, ct[0], csz); pb = cone_project_local(beam.env, ct[1], csz); pc = cone_project_local(beam.env, ct[2], csz);
-                    kind = g2_classify(wf, pa, pb, pc, val);
-                    if (kind == G2_ANALYTIC) val = g2_analytic(sc, pa, pb, pc);
-                }
-                unsigned m = __ballot_sync(FULL, kind == G2_QUADRATURE);
-                while (m) {
-                    const int src = __ffs(m) - 1; m &= m - 1u;
-                    const V2 qa = mk2(__shfl_sync(FULL, pa.x, src), __shfl_sync(FULL, pa.y, src));
-                    const V2 qb = mk2(__shfl_sync(FULL, pb.x, src), __shfl_sync(FULL, pb.y, src));
-                    const V2 qc = mk2(__shfl_sync(FULL, pc.x, src), __shfl_sync(FULL, pc.y, src));
-                    const float r = g2_quadrature_warp(qa, qb, qc);
-                    if ((int)lane == src) val = r;
-                }
-                if (c0 + lane < tn) sh.v[k][c0 + lane] = val;
-            }
-            if (c0 + lane < tn) sh.cnt[c0 + lane] = (uint8_t)cl.tris;
-        }
-        __syncthreads();
-        if (warp == 0u) {       // ordered accumulation: entry t0, t0 + 1, ...; pieces 0, 1, 2 of each
-            for (uint32_t c0 = 0u; c0 < tn; c0 += 32u) {
-                const uint32_t j = c0 + lane;
-                const int c = j < tn ? (int)sh.cnt[j] : 0;
-                const float v0 = c > 0 ? sh.v[0][j] : 0.f, v1 = c > 1 ? sh.v[1][j] : 0.f, v2 = c > 2 ? sh.v[2][j] : 0.f;
-                unsigned rest = __ballot_sync(FULL, c > 0);
-                while (rest) {
-                    const int l = __ffs(rest) - 1; rest &= rest - 1u;
-                    const int cc = __shfl_sync(FULL, c, l);
-                    const float a0 = __shfl_sync(FULL, v0, l), a1 = __shfl_sync(FULL, v1, l), a2 = __shfl_sync(FULL, v2, l);
-                    flux += a0; if (cc > 1) flux += a1; if (cc > 2) flux += a2;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0u) sh.flux = flux;
-    __syncthreads();
-    h.flux = sh.flux;
-    if (sc.integrator.fsd) {
-        if (warp == 0u) { bool eo = false; uint32_t need = 0u; h.n_edges = w_collect_edges(sc, tl, edges, sc.cap.edges, edge_bits, eo, need); if (eo) { h.overflow = true; h.need_edges = need; } }
-    }
 }
 
 // continue_walk (plt_bdpt_detail.hpp:167-182)
@@ -880,7 +818,7 @@ WT_NI int bd_walk_step(BCtx& c, BWalk& data, Sampler& smp, const BHit& h, const 
         data.throughput *= w * bs.M.m[0];
         if (!data.fwd && bs.eta.re != 1.f) data.throughput /= sqrf(bs.eta.re);
     } else if (!h.ballistic && sc.integrator.fsd && h.n_edges) {       // sample_fraunhofer_fsd_interaction (:288-346)
-        if (data.n_ap >= sc.cap.ap_walk) { c.overflow = true; c.need_ap = max(c.need_ap, 2u * sc.cap.ap_walk); return BD_END; }
+        if (data.n_ap >= sc.cap.ap_walk) { c.overflow = true; c.need_ap = max(c.need_ap, sc.cap.ap_walk + 2u); return BD_END; }      // (how many more the walk would need is not known: two more)
         const int ai = (int)(data.ap0 + data.n_ap);
         const G2 wf = wavefront_of(beam, beam_dist);
         const uint32_t nseg = fraunhofer_build(sc, c.A, ai, beam_frame, beam.k, 1.f - h.flux, beam.env, edges, h.n_edges, wf, c.overflow, c.need_seg);
@@ -1313,6 +1251,47 @@ WT_D void bd_store_hit(const BdArgs& a, uint32_t wid, const BHit& bh) {
     a.r.keys[wid] = bd_hit_key(a.r.sc, bh, a.r.n_keys);
     if (bh.need_edges) need_max(&a.r.ctr->need_edges, bh.need_edges);
 }
+// ---- find_closest_triangle (plt_bdpt_detail.hpp:362-390) of a long list as flat tasks: a warp scans kClosestChunk consecutive entries and folds its
+// (distance, list index) minimum -- the first entry, in list order, with the smallest hit distance -- into the walker's 64-bit cell with one atomicMin.
+// Key: the distance's bits mapped so that unsigned order = float order, then the index.
+constexpr uint32_t kClosestChunk = 256u;
+WT_D unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }
+    return v;
+}
+WT_D unsigned long long closest_key(float d, uint32_t idx) { d = d + 0.f;      // (-0 -> +0: they compare equal in the sequential loop)
+     const uint32_t b = __float_as_uint(d); return ((unsigned long long)(b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u)) << 32) | idx; }
+__global__ void __launch_bounds__(128) k_bd_closest_chunks(const BdArgs a) {
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    const DScene& sc = a.r.sc;
+    for (;;) {
+        int i = 0;
+        if (lane == 0u) i = atomicAdd(&a.r.ctr->closest_task_head, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= a.r.ctr->n_closest_tasks) break;
+        const uint2 task = a.r.closest_tasks[i];
+        const uint32_t wid = a.r.trav_list[task.x];
+        const TravRec r = a.trav_rec[wid];
+        const TriList tl = tri_list(sc, a.trav_tris, wid, r.n_tris, (r.flags & TR_OVERFLOW) != 0u);
+        const V3 origin = mk3(r.ox, r.oy, r.oz);
+        // the beam's mean direction: floats 3..5 of BdWalker (beam.env = {o, d, ...}), i.e. chunk 0 .w and chunk 1 .xy
+        static_assert(offsetof(BdWalker, beam) == 0 && offsetof(Beam, env) == 0 && offsetof(Cone, d) == 12, "BdWalker layout");
+        const float4 c0 = a.walkers[wid], c1 = a.walkers[(size_t)2u * a.P + wid];
+        const V3 dir = mk3(c0.w, c1.x, c1.y);
+        const Range zr = mkr(r.cone_dist, r.cone_dist + r.region_depth);
+        unsigned long long best = ~0ull;
+        const uint32_t e0 = task.y * kClosestChunk, e1 = min(tl.n, e0 + kClosestChunk);
+        for (uint32_t e = e0 + lane; e < e1; e += 32u) {
+            const Tri3 t = load_tri(sc, tri_at(tl, e));
+            const float tol = cone_intersection_tolerance(origin, t.a, t.b, t.c);
+            const RayTri rt = intersect_ray_tri(origin, dir, t.a, t.b, t.c, mkr(zr.mn - tol, zr.mx + tol));
+            if (rt.hit && rt.dist < WT_INF) best = min(best, closest_key(rt.dist, e));
+        }
+        best = warp_min_u64(best);
+        if (lane == 0u && best != ~0ull) atomicMin(a.r.closest_best + wid, best);
+    }
+}
 __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     bool act = li < (uint32_t)a.r.ctr->n_trav;
@@ -1328,7 +1307,13 @@ __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
         const TravRec r = a.trav_rec[wid];
         bd_trav_out(r, tr);
         tl = tri_list(sc, a.trav_tris, wid, r.n_tris, tr.cone.overflow);
-        if (tl.n > kBigQuery && !tr.empty && !tr.ballistic) { a.r.big_res_list[atomicAdd(&a.r.ctr->n_big_res, 1)] = li; act = false; }    // a long list: to the warp-per-walker kernel
+        if (tl.n > kBigQuery && !tr.empty && !tr.ballistic) {      // a long list: its closest-triangle search as flat 256-entry tasks, the rest by a warp (k_bd_resolve_big)
+            a.r.big_res_list[atomicAdd(&a.r.ctr->n_big_res, 1)] = li; act = false;
+            a.r.closest_best[wid] = ~0ull;
+            const uint32_t nt = (tl.n + kClosestChunk - 1u) / kClosestChunk;
+            const uint32_t t0 = (uint32_t)atomicAdd(&a.r.ctr->n_closest_tasks, (int)nt);
+            for (uint32_t c = 0u; c < nt; ++c) a.r.closest_tasks[t0 + c] = make_uint2(li, c);
+        }
         else { soa_load(w, a.walkers, 2u * a.P, wid); edges = a.r.hit_edges + (size_t)wid * sc.cap.edges; }
     }
     bd_resolve_hit_warp(sc, act, w.beam, tr, tl, edges, bh);
@@ -1337,51 +1322,101 @@ __global__ void __launch_bounds__(128) k_bd_resolve(const BdArgs a) {
     count1(&a.r.ctr->walker_steps, act);
 }
 __global__ void __launch_bounds__(128) k_bd_resolve_big(const BdArgs a, uint32_t bit_words) {
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
     const DScene& sc = a.r.sc;
     uint32_t* bits = a.r.edge_bits + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * bit_words;
     unsigned long long n_step = 0, n_ovf = 0;
     for (;;) {
         int i = 0;
         if (lane == 0u) i = atomicAdd(&a.r.ctr->big_res_head, 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        i = __shfl_sync(FULL, i, 0);
         if (i >= a.r.ctr->n_big_res) break;
-        const uint32_t wid = a.r.trav_list[a.r.big_res_list[i]];
+        const uint32_t li = a.r.big_res_list[i], wid = a.r.trav_list[li];
         const TravRec r = a.trav_rec[wid];
-        if (r.n_tris > kHugeList && !(r.flags & TR_OVERFLOW)) { if (lane == 0u) a.r.huge_res_list[atomicAdd(&a.r.ctr->n_huge_res, 1)] = a.r.big_res_list[i]; continue; }     // a very long list: a whole block
         TravOut tr; bd_trav_out(r, tr);
         BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
+        const TriList tl = tri_list(sc, a.trav_tris, wid, r.n_tris, tr.cone.overflow);
         BHit bh;
-        bd_resolve_hit_big(sc, w.beam, tr, tri_list(sc, a.trav_tris, wid, r.n_tris, tr.cone.overflow), a.r.hit_edges + (size_t)wid * sc.cap.edges, bits, bh);
-        if (lane == 0u) { bd_store_hit(a, wid, bh); ++n_step; n_ovf += bh.overflow ? 1u : 0u; }
+        bool deferred = false; uint32_t sbase = 0u;
+        if (bd_resolve_closest_big(sc, w.beam, tr, tl, __ldcg(a.r.closest_best + wid), bh)) {
+            // the Gaussian power: the list is queued for the flat kernels -- scratch for the piece values (16 B per entry) is bump-allocated;
+            // none left -> computed here
+            if (a.r.flux_cap) {
+                if (lane == 0u) sbase = atomicAdd(&a.r.ctr->flux_scratch_head, tl.n);
+                sbase = __shfl_sync(FULL, sbase, 0);
+                deferred = sbase <= a.r.flux_cap && tl.n <= a.r.flux_cap - sbase;
+            }
+            if (!deferred) bd_resolve_flux_big(sc, w.beam, tr, tl, a.r.hit_edges + (size_t)wid * sc.cap.edges, bits, bh);
+        }
+        if (deferred) {       // queue the list: one item, ceil(n / 32) chunk tasks
+            const uint32_t nt = (tl.n + 31u) / 32u;
+            uint32_t it = 0u, t0 = 0u;
+            if (lane == 0u) { it = (uint32_t)atomicAdd(&a.r.ctr->n_flux_items, 1); t0 = (uint32_t)atomicAdd(&a.r.ctr->n_flux_tasks, (int)nt); a.r.flux_items[it] = make_uint2(li, sbase); }
+            it = __shfl_sync(FULL, it, 0); t0 = __shfl_sync(FULL, t0, 0);
+            for (uint32_t c = lane; c < nt; c += 32u) a.r.flux_tasks[t0 + c] = make_uint2(it, c);
+        } else if (lane == 0u) { bd_store_hit(a, wid, bh); ++n_step; n_ovf += bh.overflow ? 1u : 0u; }
         __syncwarp();
     }
     if (lane == 0u) { if (n_step) atomicAdd(&a.r.ctr->walker_steps, n_step); if (n_ovf) atomicAdd(&a.r.ctr->overflow, n_ovf); }
 }
-
-// the lists k_bd_resolve_big handed on (more than kHugeList triangles): one block per walker
-__global__ void __launch_bounds__(256) k_bd_resolve_huge(const BdArgs a, uint32_t bit_words) {
-    __shared__ HugeShared sh;
-    __shared__ int s_item;
+// what a flux task / item needs of its walker
+struct FluxCtx { Beam beam; TravOut tr; TriList tl; Range zr; Frame beam_frame; G2 wf; float csz; BHit h; uint32_t wid; };
+WT_D void bd_flux_ctx(const BdArgs& a, uint32_t li, FluxCtx& c) {
     const DScene& sc = a.r.sc;
-    uint32_t* bits = a.r.edge_bits + (size_t)blockIdx.x * bit_words;       // (one scratch bitmap per block: used by its first warp only)
+    c.wid = a.r.trav_list[li];
+    const TravRec r = a.trav_rec[c.wid];
+    bd_trav_out(r, c.tr);
+    BdWalker w; soa_load(w, a.walkers, 2u * a.P, c.wid);
+    c.beam = w.beam;
+    c.tl = tri_list(sc, a.trav_tris, c.wid, r.n_tris, c.tr.cone.overflow);
+    bd_hit_init(c.h, c.beam, c.tr, c.zr);
+    c.beam_frame = cone_frame(c.beam.env);
+    c.wf = wavefront_of(c.beam, c.h.dist);
+    c.csz = (c.zr.mx + c.zr.mn) / 2.f;
+}
+// flat tasks: the piece values of 32 consecutive entries of a queued list -> scratch
+__global__ void __launch_bounds__(128) k_bd_flux_chunks(const BdArgs a) {
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    const DScene& sc = a.r.sc;
+    for (;;) {
+        int i = 0;
+        if (lane == 0u) i = atomicAdd(&a.r.ctr->flux_task_head, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= a.r.ctr->n_flux_tasks) break;
+        const uint2 task = a.r.flux_tasks[i], item = a.r.flux_items[task.x];
+        FluxCtx c; bd_flux_ctx(a, item.x, c);
+        const uint32_t base = task.y * 32u;
+        float v0, v1, v2; int cnt;
+        bd_flux_chunk(sc, c.beam, c.tr.cone.front, c.tl, c.zr, c.beam_frame, c.wf, c.csz, base, v0, v1, v2, cnt);
+        if (base + lane < c.tl.n) a.r.flux_scratch[(size_t)item.y + base + lane] = make_float4(v0, v1, v2, __int_as_float(cnt));
+        __syncwarp();
+    }
+}
+// one warp per queued list: its piece values added in list order, the edge set, the hit record
+__global__ void __launch_bounds__(128) k_bd_flux_finish(const BdArgs a, uint32_t bit_words) {
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    const DScene& sc = a.r.sc;
+    uint32_t* bits = a.r.edge_bits + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * bit_words;
     unsigned long long n_step = 0, n_ovf = 0;
     for (;;) {
-        if (threadIdx.x == 0u) s_item = atomicAdd(&a.r.ctr->huge_res_head, 1);
-        __syncthreads();
-        const int i = s_item;
-        __syncthreads();
-        if (i >= a.r.ctr->n_huge_res) break;
-        const uint32_t wid = a.r.trav_list[a.r.huge_res_list[i]];
-        const TravRec r = a.trav_rec[wid];
-        TravOut tr; bd_trav_out(r, tr);
-        BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
-        BHit bh;
-        bd_resolve_hit_block(sc, w.beam, tr, tri_list(sc, a.trav_tris, wid, r.n_tris, tr.cone.overflow), a.r.hit_edges + (size_t)wid * sc.cap.edges, bits, bh, sh);
-        if (threadIdx.x == 0u) { bd_store_hit(a, wid, bh); ++n_step; n_ovf += bh.overflow ? 1u : 0u; }
-        __syncthreads();
+        int i = 0;
+        if (lane == 0u) i = atomicAdd(&a.r.ctr->flux_item_head, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= a.r.ctr->n_flux_items) break;
+        const uint2 item = a.r.flux_items[i];
+        FluxCtx c; bd_flux_ctx(a, item.x, c);
+        float flux = 0.f;
+        for (uint32_t base = 0u; base < c.tl.n; base += 32u) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (base + lane < c.tl.n) v = __ldcg(a.r.flux_scratch + (size_t)item.y + base + lane);
+            flux = bd_flux_add(flux, v.x, v.y, v.z, __float_as_int(v.w));
+        }
+        c.h.flux = flux;
+        if (sc.integrator.fsd) { bool eo = false; uint32_t need = 0u; c.h.n_edges = w_collect_edges(sc, c.tl, a.r.hit_edges + (size_t)c.wid * sc.cap.edges, sc.cap.edges, bits, eo, need); if (eo) { c.h.overflow = true; c.h.need_edges = need; } }
+        if (lane == 0u) { bd_store_hit(a, c.wid, c.h); ++n_step; n_ovf += c.h.overflow ? 1u : 0u; }
+        __syncwarp();
     }
-    if (threadIdx.x == 0u) { if (n_step) atomicAdd(&a.r.ctr->walker_steps, n_step); if (n_ovf) atomicAdd(&a.r.ctr->overflow, n_ovf); }
+    if (lane == 0u) { if (n_step) atomicAdd(&a.r.ctr->walker_steps, n_step); if (n_ovf) atomicAdd(&a.r.ctr->overflow, n_ovf); }
 }
 
 __global__ void k_bd_reset(const BdArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) { a.r.ctr->n_trav = 0; a.r.ctr->trav_head = 0; for (int c = 0; c < kPairClasses; ++c) a.r.ctr->n_pairs[c] = 0; a.r.ctr->n_fsd_list[a.fl_next] = 0; reset_iteration_lists(a.r.ctr); } }

@@ -64,8 +64,7 @@ struct GTrav {
     uint32_t qtested;           // triangles the current cone query has tested (hand-over trigger)
     TriWriter tw;               // where the current cone query's triangle list goes (dtrav.cuh TriList): the beam's row + extents of the spill arena
 };
-constexpr uint32_t kBigQuery = 32u;     // a triangle list longer than this is resolved by the warp-per-list resolve kernels (k_*_resolve_big) ...
-constexpr uint32_t kHugeList = 4096u;   // ... and one longer than this by a whole block (k_bd_resolve_huge)
+constexpr uint32_t kBigQuery = 32u;     // a triangle list longer than this is resolved by the warp-per-list resolve kernels (k_*_resolve_big)
 // A beam in the middle of a cone query, as handed from one traversal kernel to the next (ctrav.cuh): the whole machine state and the stack.
 struct alignas(16) TravSave { GTrav t; int item; int pad_[3]; float tmin[kGStack]; int32_t ptr[kGStack]; };
 // hand-over thresholds (triangles tested by the current cone query): group -> warp team, warp team -> block team

@@ -83,9 +83,11 @@ struct DevCounters {
     unsigned int spill_head;            // bump cursor of the triangle-list arena (dtrav.cuh TriList); reset every iteration
     int n_big, big_head, n_big_res, big_res_head;      // beams handed to the team traversal (ctrav.cuh) / lists handed to the warp-per-list resolve kernels this iteration; their work cursors
     int n_huge, huge_head;                             // beams the warp teams handed on to the block teams
-    int n_huge_res, huge_res_head;                     // lists the warp-per-list resolve handed on to the block-per-list resolve
+    int n_flux_items, flux_item_head, n_flux_tasks, flux_task_head;   // plt_bdpt: lists queued for the flat Gaussian-power kernels, their 32-entry chunk tasks; work cursors
+    unsigned int flux_scratch_head;                    // bump cursor of the piece-value scratch
+    int n_closest_tasks, closest_task_head;            // plt_bdpt: 256-entry tasks of the long lists' closest-triangle search; work cursor
     unsigned long long stack_drops;
-    unsigned long long dbg[16];         // -DWT_TEAM_DEBUG: team-traversal diagnostics (ctrav.cuh), printed by wtgpu_render when WT_DEBUG_TEAM is set
+    unsigned long long dbg[32];         // -DWT_TEAM_DEBUG: team-traversal diagnostics (ctrav.cuh), printed by wtgpu_render when WT_DEBUG_TEAM is set
 };
 WT_D void need_max(unsigned int* p, uint32_t v) { if (v > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(p, v); }
 
@@ -95,7 +97,9 @@ struct RenderArgs {
     wt::TravRec* trav_rec; uint32_t* trav_tris;      // results of traverse(), per slot; trav_tris: the first kTriRow triangle ids of the slot's cone-query list (dtrav.cuh TriList)
     wt::TravSave* big_save; wt::TravSave* huge_save;  // beams handed from the group traversal to the warp teams, and from those to the block teams (gtrav.cuh TravSave)
     uint32_t big_tested, huge_tested;                 // the hand-over thresholds (triangles tested by the current cone query)
-    uint32_t* big_res_list; uint32_t* huge_res_list;  // items (indices into trav_list) handed to the warp-per-list / block-per-list resolve kernels
+    uint32_t* big_res_list;                           // items (indices into trav_list) handed to the warp-per-list resolve kernels
+    uint2* closest_tasks; unsigned long long* closest_best;     // plt_bdpt: (list, chunk) tasks of the flat closest-triangle search; its result per walker (key of the winning entry)
+    uint2* flux_items; uint2* flux_tasks; float4* flux_scratch; uint32_t flux_cap;     // plt_bdpt: (item, scratch base) per queued list; (list, chunk) tasks; piece values; scratch entries
     uint32_t* edge_bits;                              // scratch bitmaps (one bit per edge of the scene) of the warp-per-beam resolve kernel, one per resident warp
     uint32_t* hit_edges;                              // sc.cap.edges edge ids per slot: the edges around the vertex (HitRec::n_edges of them)
     uint32_t* ap_edges; uint32_t it_parity;           // plt_path: 2 x pool rows of sc.cap.edges: UTD aperture edge lists (this iteration's row set: it_parity)
@@ -227,7 +231,7 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
 
 WT_D void reset_iteration_lists(DevCounters* c) {        // the triangle-list arena and the hand-over lists live for one iteration
     need_max(&c->need_spill, c->spill_head);
-    c->spill_head = 0u; c->n_big = 0; c->big_head = 0; c->n_big_res = 0; c->big_res_head = 0; c->n_huge = 0; c->huge_head = 0; c->n_huge_res = 0; c->huge_res_head = 0;
+    c->spill_head = 0u; c->n_big = 0; c->big_head = 0; c->n_big_res = 0; c->big_res_head = 0; c->n_huge = 0; c->huge_head = 0; c->n_flux_items = 0; c->flux_item_head = 0; c->n_flux_tasks = 0; c->flux_task_head = 0; c->flux_scratch_head = 0u; c->n_closest_tasks = 0; c->closest_task_head = 0;
 }
 // the triangle-list writer / reader of path `slot` (rows of kTriRow entries + the slot's extent table)
 WT_D TriWriter tri_writer(const DScene& sc, uint32_t* trav_tris, uint32_t slot) { TriWriter w; w.row = trav_tris + (size_t)slot * kTriRow; w.ext = sc.spill_ext + (size_t)slot * kTriExt; tw_begin(w); return w; }
@@ -841,7 +845,9 @@ struct BlockCache {
     size_t idle_bytes = 0;
 };
 BlockCache g_blocks;
-constexpr size_t kCacheMinBlock = 1ull << 20, kCacheMaxIdle = 48ull << 30;
+constexpr size_t kCacheMinBlock = 1ull << 20;
+// idle device blocks kept for the next scene handle / pool re-size (a fresh cudaMalloc of a 50 GB arena costs seconds): WT_CACHE_GB overrides the 112 GB default
+const size_t kCacheMaxIdle = []() { const char* e = getenv("WT_CACHE_GB"); return (size_t)(e ? atoi(e) : 112) << 30; }();
 cudaError_t wt_malloc_impl(void** p, size_t bytes) {
     int dev = 0; cudaGetDevice(&dev);
     {
@@ -885,6 +891,7 @@ struct Pool {
     float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
     uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr, *trav_tris = nullptr, *hit_edges = nullptr, *ap_edges = nullptr;
     uint32_t *spill = nullptr, *spill_ext = nullptr, *big_res_list = nullptr, *edge_bits = nullptr;
+    uint2 *flux_items = nullptr, *flux_tasks = nullptr, *closest_tasks = nullptr; unsigned long long* closest_best = nullptr; float4* flux_scratch = nullptr; uint32_t flux_cap = 0;
     wt::TravSave *big_save = nullptr, *huge_save = nullptr;
     TravRec* trav_rec = nullptr;
     DevCounters* ctr = nullptr;
@@ -1088,7 +1095,7 @@ static uint32_t bdpt_max_pairs(uint32_t verts, uint32_t max_depth) {     // stra
 }
 static size_t pool_bytes(const wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t parts, const Caps& c) {
     const size_t P = pool;
-    const size_t row = 4ull * (wt::kTriRow + wt::kTriExt) + 8ull + 2ull * sizeof(wt::TravSave), shared = (size_t)parts * (4ull * c.spill_words + 16ull * s->bit_words * s->big_blocks);      // triangle-list row + extent table + hand-over lists; per sub-pool: the arena, scratch bitmaps
+    const size_t row = 4ull * (wt::kTriRow + wt::kTriExt) + 8ull + 2ull * sizeof(wt::TravSave), shared = (size_t)parts * (4ull * c.spill_words + 16ull * s->bit_words * s->big_blocks + (kind == POOL_BDPT_WAVE ? 8ull * c.spill_words + (17ull << 20) : 0ull));      // triangle-list row + extent table + hand-over lists; per sub-pool: the arena, scratch bitmaps
     if (kind == POOL_PATH) return shared + P * (16ull * (chunks_of<PathCore>() + chunks_of<PathFsd>() + chunks_of<HitRec>()) + sizeof(TravRec) + row + 12ull * c.edges + 16ull);
     if (kind == POOL_BDPT_MEGA) return shared + P * (4ull * c.arena_words + row + 4ull * c.edges);
     const size_t W2 = 2 * P;
@@ -1116,7 +1123,9 @@ static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t pa
         get(&q.key_count, 4ull * s->n_keys); get(&q.key_cursor, 4ull * s->n_keys);
         {   // triangle-list arena, extent tables and hand-over lists (one row per path / walker / thread); scratch edge bitmaps of the warp-per-beam resolve
             const size_t rows = kind == POOL_BDPT_WAVE ? 2 * P : P;
-            get(&q.spill, 4ull * c.spill_words); get(&q.spill_ext, 4ull * wt::kTriExt * rows); get(&q.big_save, sizeof(wt::TravSave) * rows); get(&q.huge_save, sizeof(wt::TravSave) * rows); get(&q.big_res_list, 8ull * rows);
+            get(&q.spill, 4ull * c.spill_words); get(&q.spill_ext, 4ull * wt::kTriExt * rows); get(&q.big_save, sizeof(wt::TravSave) * rows); get(&q.huge_save, sizeof(wt::TravSave) * rows); get(&q.big_res_list, 4ull * rows);
+            if (kind == POOL_BDPT_WAVE) { q.flux_cap = c.spill_words / 2u + (1u << 20); get(&q.flux_items, 8ull * rows); get(&q.flux_tasks, 8ull * ((size_t)q.flux_cap / 32u + rows)); get(&q.flux_scratch, 16ull * q.flux_cap);
+                                          get(&q.closest_tasks, 8ull * ((size_t)c.spill_words / wt::kClosestChunk + 2 * rows)); get(&q.closest_best, 8ull * rows); }
             get(&q.edge_bits, 16ull * s->bit_words * s->big_blocks);
             if (rc == WTGPU_OK) { cudaError_t e = cudaMemset(q.edge_bits, 0, 16ull * s->bit_words * s->big_blocks); if (e != cudaSuccess) { g_err = "cudaMemset(edge bitmaps)"; rc = WTGPU_E_CUDA; } }
         }
@@ -1186,7 +1195,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
         RenderArgs& a = args[k];
         a.sc = d; a.core = q.core; a.fsd = q.fsd; a.hit = q.hit; a.alive = q.alive; a.keys = q.keys; a.order = q.order;
         a.trav_rec = q.trav_rec; a.trav_tris = q.trav_tris; a.hit_edges = q.hit_edges; a.ap_edges = q.ap_edges; a.it_parity = 0u;
-        a.big_save = q.big_save; a.huge_save = q.huge_save; a.big_tested = tiers.big_tested; a.huge_tested = tiers.huge_tested; a.big_res_list = q.big_res_list; a.huge_res_list = q.big_res_list + (kind == POOL_BDPT_WAVE ? 2 * (size_t)q.size : (size_t)q.size); a.edge_bits = q.edge_bits;
+        a.big_save = q.big_save; a.huge_save = q.huge_save; a.big_tested = tiers.big_tested; a.huge_tested = tiers.huge_tested; a.big_res_list = q.big_res_list; a.closest_tasks = q.closest_tasks; a.closest_best = q.closest_best; a.flux_items = q.flux_items; a.flux_tasks = q.flux_tasks; a.flux_scratch = q.flux_scratch; a.flux_cap = q.flux_cap; a.edge_bits = q.edge_bits;
         a.key_count = q.key_count; a.key_cursor = q.key_cursor; a.trav_list = q.trav_list; a.ctr = q.ctr; a.film_block = dblock; a.film_light = dlight;
         a.pool = q.size; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
         a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
@@ -1230,7 +1239,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
             if (use_thread_trav) { k_bd_traverse<<<gW, blkT, 0, st>>>(b); ++launches; }
             else {
                 k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_wtraverse<<<gC, blk, 0, st>>>(b); k_bd_ctraverse<<<dim3(n_sm * 2), dim3(256), 0, st>>>(b);
-                k_bd_resolve<<<gW, blkT, 0, st>>>(b); k_bd_resolve_big<<<gBig, blk, 0, st>>>(b, s->bit_words); k_bd_resolve_huge<<<dim3(std::min<uint32_t>(s->big_blocks, (uint32_t)n_sm * 2u)), dim3(256), 0, st>>>(b, s->bit_words); launches += 6;
+                k_bd_resolve<<<gW, blkT, 0, st>>>(b); k_bd_closest_chunks<<<gC, blk, 0, st>>>(b); k_bd_resolve_big<<<gBig, blk, 0, st>>>(b, s->bit_words); k_bd_flux_chunks<<<gC, blk, 0, st>>>(b); k_bd_flux_finish<<<gBig, blk, 0, st>>>(b, s->bit_words); launches += 8;
             }
             mark(q);
             k_hist<<<gW, blkT, s->n_keys * 4, st>>>(b.r);
@@ -1321,7 +1330,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
         const DevCounters& c = *q.hctr;
         T.samples += c.samples; T.segments += c.segments; T.ray_casts += c.ray_casts; T.cone_casts += c.cone_casts; T.shadow_casts += c.shadow_casts; T.nodes += c.nodes; T.tris += c.tris;
         T.edges += c.edges; T.surface += c.surface; T.fsd += c.fsd; T.null_ += c.null_; T.splats += c.splats; T.overflow += c.overflow; T.shade_nodes += c.shade_nodes; T.shade_tris += c.shade_tris;
-        T.shaded += c.shaded; T.walker_steps += c.walker_steps; T.stack_drops += c.stack_drops; for (int i = 0; i < 16; ++i) T.dbg[i] += c.dbg[i];
+        T.shaded += c.shaded; T.walker_steps += c.walker_steps; T.stack_drops += c.stack_drops; for (int i = 0; i < 32; ++i) T.dbg[i] += c.dbg[i];
         for (int i = 0; i < 5; ++i) T.strategies[i] += c.strategies[i];
         T.need_spill = std::max(T.need_spill, std::max(c.need_spill, c.spill_head)); T.need_edges = std::max(T.need_edges, c.need_edges); T.need_seg = std::max(T.need_seg, c.need_seg);
         T.need_ap = std::max(T.need_ap, c.need_ap); T.need_verts = std::max(T.need_verts, c.need_verts);
@@ -1399,6 +1408,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         if (!(s->pool == pool && s->pool_parts == parts && s->pool_kind == kind && caps_equal(s->pool_caps, s->caps))) {
             s->free_pool();
             size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+            { std::lock_guard<std::mutex> l(g_blocks.m); free_b += g_blocks.idle_bytes; }       // idle cached blocks are reclaimable (wt_malloc drops them when cudaMalloc fails)
             while (use_pool > 4096u && pool_bytes(s, kind, use_pool, parts, s->caps) > (size_t)(0.85 * (double)free_b)) use_pool = ((use_pool / 2u) + 127u) & ~127u;     // long rows: fewer paths in flight
         }
         int rc = ensure_pool(s, kind, use_pool, parts);
@@ -1414,7 +1424,8 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         // the triangle-list arena: the bump cursor kept counting past its end, so the largest demand of an iteration is known
         if (hctr->need_spill > nc.spill_words) nc.spill_words = (uint32_t)std::min<unsigned long long>(0xfff00000ull, (unsigned long long)hctr->need_spill + hctr->need_spill / 4u + (1u << 20));
         nc.edges = grow(nc.edges, hctr->need_edges); nc.seg = grow(nc.seg, hctr->need_seg);
-        nc.ap_walk = std::min(grow(nc.ap_walk, hctr->need_ap), std::max(s->integ.max_depth, 1u));
+        // (apertures are 4 KB each and every subpath reserves ap_walk of them: grown to the measured need, not in steps of 32)
+        if (hctr->need_ap > nc.ap_walk) nc.ap_walk = std::min(std::max(hctr->need_ap, nc.ap_walk + 1u), std::max(s->integ.max_depth, 1u));
         if (bdpt) nc.verts = std::min(grow(nc.verts, hctr->need_verts), s->integ.max_depth + 2u);
         caps_derive(nc);
         if (caps_equal(nc, s->caps) || passes >= 12u) {
@@ -1462,7 +1473,7 @@ int wtgpu_render(wtgpu_scene* s, const wtgpu_render_opts* o, float* film_block, 
         stats->gpu_ms = ms; stats->traverse_ms = t_trav; stats->shade_ms = t_shade; stats->generate_ms = t_gen; stats->sort_ms = t_sort; stats->connect_ms = t_conn;
         for (int c = 0; c < 5; ++c) stats->strategies[c] = hctr->strategies[c];
         stats->walker_steps = hctr->walker_steps;
-        if (getenv("WT_DEBUG_TEAM")) { fprintf(stderr, "team dbg:"); for (int i = 0; i < 16; ++i) fprintf(stderr, " %llu", hctr->dbg[i]); fprintf(stderr, "\n"); }
+        if (getenv("WT_DEBUG_TEAM")) { fprintf(stderr, "team dbg:"); for (int i = 0; i < 32; ++i) fprintf(stderr, " %llu", hctr->dbg[i]); fprintf(stderr, "\n"); }
         stats->passes = passes; stats->stack_drops = hctr->stack_drops; stats->pool_used = pool; stats->subpools = parts;
         stats->cap_tris = s->caps.spill_words; stats->cap_edges = s->caps.edges; stats->cap_segments = s->caps.seg; stats->cap_apertures = s->caps.ap_walk; stats->cap_vertices = s->caps.verts;
     }
