@@ -260,6 +260,7 @@ def main():
     # instrumented repeat of the first timed steps (same sample ranges): per-kernel device times and the counters the roofline's bytes come from
     n_inst = 0 if a.no_kernel_timing else min(a.steps, 2)
     if n_inst:
+        step(a.warmup, flags_inst)      # untimed: the pools are re-cut for one sub-pool here
         torch.cuda.synchronize()
         i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         i0.record()
