@@ -136,15 +136,26 @@ WT_D float g2_quadrature_warp(V2 a, V2 b, V2 c) {
 // quadrature branch with ~10^2 samples: then each lane sums its own (32 pieces side by side).  Only a piece with very many samples -- a sliver
 // across the whole 6-sigma window -- is worth the warp's joint evaluation, where the samples of ONE piece are spread over the lanes and the other
 // lanes' pieces wait.  Same sample sequence, same order of additions either way.
-constexpr float kQuadCoopSamples = 4096.f;
-WT_D float g2_quadrature_mixed(bool mine, V2 pa, V2 pb, V2 pc) {
+constexpr float kQuadCoopSamples = 4096.f, kQuadQueueSamples = 1024.f;
+// The flat Gaussian-power kernel goes one step further: a piece with more than ~10^3 samples becomes a task of its own (one warp per piece,
+// k_bd_quad_tasks), so that a 32-triangle chunk full of long slivers does not decide the duration of the launch.
+struct QuadQ { float4* tasks; int* n; int cap; };        // task = (a.xy, b.xy) (c.xy, destination index as two words)
+WT_D float g2_quadrature_mixed(bool mine, V2 pa, V2 pb, V2 pc, const QuadQ* q = nullptr, size_t dst = 0) {
     const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
     float val = 0.f; bool big = false;
     if (mine) {
         const float L = 3.f, delta = .002f;
         const float h = fminf(L, max3f(pa.y, pb.y, pc.y)) - fmaxf(-L, min3f(pa.y, pb.y, pc.y)), w = fminf(L, max3f(pa.x, pb.x, pc.x)) - fmaxf(-L, min3f(pa.x, pb.x, pc.x));
-        big = fmaxf(h, 0.f) * fmaxf(w, 0.f) * (.5f / (delta * delta)) > kQuadCoopSamples;
-        if (!big) val = g2_quadrature(pa, pb, pc);
+        const float est = fmaxf(h, 0.f) * fmaxf(w, 0.f) * (.5f / (delta * delta));
+        if (q && est > kQuadQueueSamples) {
+            const int at = atomicAdd(q->n, 1);
+            if (at < q->cap) {
+                q->tasks[2 * (size_t)at] = make_float4(pa.x, pa.y, pb.x, pb.y);
+                q->tasks[2 * (size_t)at + 1] = make_float4(pc.x, pc.y, __uint_as_float((uint32_t)dst), __uint_as_float((uint32_t)(dst >> 32)));
+                mine = false;       // (the task's warp writes the value)
+            }
+        }
+        if (mine) { big = est > kQuadCoopSamples; if (!big) val = g2_quadrature(pa, pb, pc); }
     }
     unsigned m = __ballot_sync(FULL, mine && big);
     while (m) {
@@ -684,7 +695,7 @@ WT_D void bd_resolve_hit_warp(const DScene& sc, bool act, const Beam& beam, cons
 
 // the clipped pieces of list entries [base, base + 32), one entry per lane (all 32 lanes call): values of pieces 0..2 and their number
 WT_D void bd_flux_chunk(const DScene& sc, const Beam& beam, bool front, const TriList& tl, Range zr, const Frame& beam_frame, const G2& wf, float csz, uint32_t base,
-                        float& v0, float& v1, float& v2, int& cnt) {
+                        float& v0, float& v1, float& v2, int& cnt, const QuadQ* q = nullptr, size_t dst = 0) {
     const unsigned lane = threadIdx.x & 31u;
     const V3 dir = beam.env.d;
     const uint32_t i = base + lane;
@@ -704,7 +715,7 @@ WT_D void bd_flux_chunk(const DScene& sc, const Beam& beam, bool front, const Tr
             kind = g2_classify(wf, pa, pb, pc, val);
             if (kind == G2_ANALYTIC) val = g2_analytic(sc, pa, pb, pc);
         }
-        { const float qv = g2_quadrature_mixed(kind == G2_QUADRATURE, pa, pb, pc); if (kind == G2_QUADRATURE) val = qv; }
+        { const float qv = g2_quadrature_mixed(kind == G2_QUADRATURE, pa, pb, pc, q, dst + (size_t)k); if (kind == G2_QUADRATURE) val = qv; }
         if (k == 0) v0 = val; else if (k == 1) v1 = val; else v2 = val;
     }
     cnt = cl.tris;
@@ -1387,8 +1398,25 @@ __global__ void __launch_bounds__(128) k_bd_flux_chunks(const BdArgs a) {
         FluxCtx c; bd_flux_ctx(a, item.x, c);
         const uint32_t base = task.y * 32u;
         float v0, v1, v2; int cnt;
-        bd_flux_chunk(sc, c.beam, c.tr.cone.front, c.tl, c.zr, c.beam_frame, c.wf, c.csz, base, v0, v1, v2, cnt);
+        const QuadQ qq = { a.r.quad_tasks, &a.r.ctr->n_quad_tasks, (int)a.r.quad_cap };
+        bd_flux_chunk(sc, c.beam, c.tr.cone.front, c.tl, c.zr, c.beam_frame, c.wf, c.csz, base, v0, v1, v2, cnt, &qq, ((size_t)item.y + base + lane) * 4u);
         if (base + lane < c.tl.n) a.r.flux_scratch[(size_t)item.y + base + lane] = make_float4(v0, v1, v2, __int_as_float(cnt));
+        __syncwarp();
+    }
+}
+// the long quadrature pieces k_bd_flux_chunks queued: one warp per piece, the value into its slot of the scratch
+__global__ void __launch_bounds__(128) k_bd_quad_tasks(const BdArgs a) {
+    const unsigned lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    const int n = min(a.r.ctr->n_quad_tasks, (int)a.r.quad_cap);
+    for (;;) {
+        int i = 0;
+        if (lane == 0u) i = atomicAdd(&a.r.ctr->quad_task_head, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= n) break;
+        const float4 t0 = a.r.quad_tasks[2 * (size_t)i], t1 = a.r.quad_tasks[2 * (size_t)i + 1];
+        const float v = g2_quadrature_warp(mk2(t0.x, t0.y), mk2(t0.z, t0.w), mk2(t1.x, t1.y));
+        const size_t dst = (size_t)__float_as_uint(t1.z) | ((size_t)__float_as_uint(t1.w) << 32);
+        if (lane == 0u) reinterpret_cast<float*>(a.r.flux_scratch)[dst] = v;
         __syncwarp();
     }
 }

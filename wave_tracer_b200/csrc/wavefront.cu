@@ -86,6 +86,7 @@ struct DevCounters {
     int n_flux_items, flux_item_head, n_flux_tasks, flux_task_head;   // plt_bdpt: lists queued for the flat Gaussian-power kernels, their 32-entry chunk tasks; work cursors
     unsigned int flux_scratch_head;                    // bump cursor of the piece-value scratch
     int n_closest_tasks, closest_task_head;            // plt_bdpt: 256-entry tasks of the long lists' closest-triangle search; work cursor
+    int n_quad_tasks, quad_task_head;                  // plt_bdpt: long quadrature pieces queued by the flat Gaussian-power kernel; work cursor
     unsigned long long stack_drops;
     unsigned long long dbg[32];         // -DWT_TEAM_DEBUG: team-traversal diagnostics (ctrav.cuh), printed by wtgpu_render when WT_DEBUG_TEAM is set
 };
@@ -99,7 +100,7 @@ struct RenderArgs {
     uint32_t big_tested, huge_tested;                 // the hand-over thresholds (triangles tested by the current cone query)
     uint32_t* big_res_list;                           // items (indices into trav_list) handed to the warp-per-list resolve kernels
     uint2* closest_tasks; unsigned long long* closest_best;     // plt_bdpt: (list, chunk) tasks of the flat closest-triangle search; its result per walker (key of the winning entry)
-    uint2* flux_items; uint2* flux_tasks; float4* flux_scratch; uint32_t flux_cap;     // plt_bdpt: (item, scratch base) per queued list; (list, chunk) tasks; piece values; scratch entries
+    uint2* flux_items; uint2* flux_tasks; float4* flux_scratch; uint32_t flux_cap; float4* quad_tasks; uint32_t quad_cap;     // plt_bdpt: (item, scratch base) per queued list; (list, chunk) tasks; piece values; scratch entries
     uint32_t* edge_bits;                              // scratch bitmaps (one bit per edge of the scene) of the warp-per-beam resolve kernel, one per resident warp
     uint32_t* hit_edges;                              // sc.cap.edges edge ids per slot: the edges around the vertex (HitRec::n_edges of them)
     uint32_t* ap_edges; uint32_t it_parity;           // plt_path: 2 x pool rows of sc.cap.edges: UTD aperture edge lists (this iteration's row set: it_parity)
@@ -231,7 +232,7 @@ WT_D void traverse(const DScene& sc, Cone env, const Geo& prev, float lambda, bo
 
 WT_D void reset_iteration_lists(DevCounters* c) {        // the triangle-list arena and the hand-over lists live for one iteration
     need_max(&c->need_spill, c->spill_head);
-    c->spill_head = 0u; c->n_big = 0; c->big_head = 0; c->n_big_res = 0; c->big_res_head = 0; c->n_huge = 0; c->huge_head = 0; c->n_flux_items = 0; c->flux_item_head = 0; c->n_flux_tasks = 0; c->flux_task_head = 0; c->flux_scratch_head = 0u; c->n_closest_tasks = 0; c->closest_task_head = 0;
+    c->spill_head = 0u; c->n_big = 0; c->big_head = 0; c->n_big_res = 0; c->big_res_head = 0; c->n_huge = 0; c->huge_head = 0; c->n_flux_items = 0; c->flux_item_head = 0; c->n_flux_tasks = 0; c->flux_task_head = 0; c->flux_scratch_head = 0u; c->n_closest_tasks = 0; c->closest_task_head = 0; c->n_quad_tasks = 0; c->quad_task_head = 0;
 }
 // the triangle-list writer / reader of path `slot` (rows of kTriRow entries + the slot's extent table)
 WT_D TriWriter tri_writer(const DScene& sc, uint32_t* trav_tris, uint32_t slot) { TriWriter w; w.row = trav_tris + (size_t)slot * kTriRow; w.ext = sc.spill_ext + (size_t)slot * kTriExt; tw_begin(w); return w; }
@@ -891,7 +892,7 @@ struct Pool {
     float4 *core = nullptr, *fsd = nullptr, *hit = nullptr;
     uint32_t *alive = nullptr, *keys = nullptr, *order = nullptr, *key_count = nullptr, *key_cursor = nullptr, *trav_list = nullptr, *trav_tris = nullptr, *hit_edges = nullptr, *ap_edges = nullptr;
     uint32_t *spill = nullptr, *spill_ext = nullptr, *big_res_list = nullptr, *edge_bits = nullptr;
-    uint2 *flux_items = nullptr, *flux_tasks = nullptr, *closest_tasks = nullptr; unsigned long long* closest_best = nullptr; float4* flux_scratch = nullptr; uint32_t flux_cap = 0;
+    uint2 *flux_items = nullptr, *flux_tasks = nullptr, *closest_tasks = nullptr; unsigned long long* closest_best = nullptr; float4* flux_scratch = nullptr; uint32_t flux_cap = 0; float4* quad_tasks = nullptr; uint32_t quad_cap = 0;
     wt::TravSave *big_save = nullptr, *huge_save = nullptr;
     TravRec* trav_rec = nullptr;
     DevCounters* ctr = nullptr;
@@ -1095,7 +1096,7 @@ static uint32_t bdpt_max_pairs(uint32_t verts, uint32_t max_depth) {     // stra
 }
 static size_t pool_bytes(const wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t parts, const Caps& c) {
     const size_t P = pool;
-    const size_t row = 4ull * (wt::kTriRow + wt::kTriExt) + 8ull + 2ull * sizeof(wt::TravSave), shared = (size_t)parts * (4ull * c.spill_words + 16ull * s->bit_words * s->big_blocks + (kind == POOL_BDPT_WAVE ? 8ull * c.spill_words + (17ull << 20) : 0ull));      // triangle-list row + extent table + hand-over lists; per sub-pool: the arena, scratch bitmaps
+    const size_t row = 4ull * (wt::kTriRow + wt::kTriExt) + 8ull + 2ull * sizeof(wt::TravSave), shared = (size_t)parts * (4ull * c.spill_words + 16ull * s->bit_words * s->big_blocks + (kind == POOL_BDPT_WAVE ? 9ull * c.spill_words + (20ull << 20) : 0ull));      // triangle-list row + extent table + hand-over lists; per sub-pool: the arena, scratch bitmaps
     if (kind == POOL_PATH) return shared + P * (16ull * (chunks_of<PathCore>() + chunks_of<PathFsd>() + chunks_of<HitRec>()) + sizeof(TravRec) + row + 12ull * c.edges + 16ull);
     if (kind == POOL_BDPT_MEGA) return shared + P * (4ull * c.arena_words + row + 4ull * c.edges);
     const size_t W2 = 2 * P;
@@ -1124,7 +1125,7 @@ static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t pa
         {   // triangle-list arena, extent tables and hand-over lists (one row per path / walker / thread); scratch edge bitmaps of the warp-per-beam resolve
             const size_t rows = kind == POOL_BDPT_WAVE ? 2 * P : P;
             get(&q.spill, 4ull * c.spill_words); get(&q.spill_ext, 4ull * wt::kTriExt * rows); get(&q.big_save, sizeof(wt::TravSave) * rows); get(&q.huge_save, sizeof(wt::TravSave) * rows); get(&q.big_res_list, 4ull * rows);
-            if (kind == POOL_BDPT_WAVE) { q.flux_cap = c.spill_words / 2u + (1u << 20); get(&q.flux_items, 8ull * rows); get(&q.flux_tasks, 8ull * ((size_t)q.flux_cap / 32u + rows)); get(&q.flux_scratch, 16ull * q.flux_cap);
+            if (kind == POOL_BDPT_WAVE) { q.flux_cap = c.spill_words / 2u + (1u << 20); get(&q.flux_items, 8ull * rows); get(&q.flux_tasks, 8ull * ((size_t)q.flux_cap / 32u + rows)); get(&q.flux_scratch, 16ull * q.flux_cap); q.quad_cap = q.flux_cap / 16u + 65536u; get(&q.quad_tasks, 32ull * q.quad_cap);
                                           get(&q.closest_tasks, 8ull * ((size_t)c.spill_words / wt::kClosestChunk + 2 * rows)); get(&q.closest_best, 8ull * rows); }
             get(&q.edge_bits, 16ull * s->bit_words * s->big_blocks);
             if (rc == WTGPU_OK) { cudaError_t e = cudaMemset(q.edge_bits, 0, 16ull * s->bit_words * s->big_blocks); if (e != cudaSuccess) { g_err = "cudaMemset(edge bitmaps)"; rc = WTGPU_E_CUDA; } }
@@ -1195,7 +1196,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
         RenderArgs& a = args[k];
         a.sc = d; a.core = q.core; a.fsd = q.fsd; a.hit = q.hit; a.alive = q.alive; a.keys = q.keys; a.order = q.order;
         a.trav_rec = q.trav_rec; a.trav_tris = q.trav_tris; a.hit_edges = q.hit_edges; a.ap_edges = q.ap_edges; a.it_parity = 0u;
-        a.big_save = q.big_save; a.huge_save = q.huge_save; a.big_tested = tiers.big_tested; a.huge_tested = tiers.huge_tested; a.big_res_list = q.big_res_list; a.closest_tasks = q.closest_tasks; a.closest_best = q.closest_best; a.flux_items = q.flux_items; a.flux_tasks = q.flux_tasks; a.flux_scratch = q.flux_scratch; a.flux_cap = q.flux_cap; a.edge_bits = q.edge_bits;
+        a.big_save = q.big_save; a.huge_save = q.huge_save; a.big_tested = tiers.big_tested; a.huge_tested = tiers.huge_tested; a.big_res_list = q.big_res_list; a.closest_tasks = q.closest_tasks; a.closest_best = q.closest_best; a.flux_items = q.flux_items; a.flux_tasks = q.flux_tasks; a.flux_scratch = q.flux_scratch; a.flux_cap = q.flux_cap; a.quad_tasks = q.quad_tasks; a.quad_cap = q.quad_cap; a.edge_bits = q.edge_bits;
         a.key_count = q.key_count; a.key_cursor = q.key_cursor; a.trav_list = q.trav_list; a.ctr = q.ctr; a.film_block = dblock; a.film_light = dlight;
         a.pool = q.size; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
         a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
@@ -1239,7 +1240,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
             if (use_thread_trav) { k_bd_traverse<<<gW, blkT, 0, st>>>(b); ++launches; }
             else {
                 k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_wtraverse<<<gC, blk, 0, st>>>(b); k_bd_ctraverse<<<dim3(n_sm * 2), dim3(256), 0, st>>>(b);
-                k_bd_resolve<<<gW, blkT, 0, st>>>(b); k_bd_closest_chunks<<<gC, blk, 0, st>>>(b); k_bd_resolve_big<<<gBig, blk, 0, st>>>(b, s->bit_words); k_bd_flux_chunks<<<gC, blk, 0, st>>>(b); k_bd_flux_finish<<<gBig, blk, 0, st>>>(b, s->bit_words); launches += 8;
+                k_bd_resolve<<<gW, blkT, 0, st>>>(b); k_bd_closest_chunks<<<gC, blk, 0, st>>>(b); k_bd_resolve_big<<<gBig, blk, 0, st>>>(b, s->bit_words); k_bd_flux_chunks<<<gC, blk, 0, st>>>(b); k_bd_quad_tasks<<<gC, blk, 0, st>>>(b); k_bd_flux_finish<<<gBig, blk, 0, st>>>(b, s->bit_words); launches += 9;
             }
             mark(q);
             k_hist<<<gW, blkT, s->n_keys * 4, st>>>(b.r);
