@@ -382,6 +382,11 @@ int wtgpu_set_capacities(wtgpu_scene* scene, const uint32_t in[5]);
 /* out[h][w][c] = block value/weight + light/spp ; host pointers */
 int wtgpu_develop(const wtgpu_sensor* sensor, uint32_t spp,
                   const float* film_block, const float* film_light, float* out);
+/* the same on the device (film_storage.hpp:256-291, 354-358: film develop of the block image + the light image): DEVICE pointers, queued on
+ * `stream` (a cudaStream_t, or null); one pass over the films, HBM-bound (12 B read + 4 B written per element).  What a multi-GPU render
+ * calls on rank 0 after the film reduce, so that only the developed image crosses PCIe. */
+int wtgpu_develop_device(const wtgpu_sensor* sensor, uint32_t spp,
+                         const float* d_film_block, const float* d_film_light, float* d_out, void* stream, int device);
 
 /* ---- unit-level entry points used by the parity tests (same kernels the renderer uses) ---- */
 typedef struct wtgpu_ray_query { float o[3], d[3]; float tmin, tmax; } wtgpu_ray_query;

@@ -425,3 +425,18 @@ def test_team_traversal_equals_thread_traversal(scene, tiers):
     for k, v in out["thread"].items():
         if k != "film": assert out["team"][k] == v, (k, out["team"][k], v)
     assert out["dblk"] < 2e-4 and out["dlgt"] < 2e-4
+
+
+def test_device_develop_equals_host_develop():
+    """wtgpu_develop_device (one HBM pass on the GPU, what the multi-GPU driver runs on rank 0 after the film reduce) against the host loop
+    wtgpu_develop: identical f32 arithmetic, bit for bit."""
+    import torch
+    from wave_tracer_b200.parallel import develop_on_device
+    b = scenes.cornell_like(res=64, spp=4, rgb=True).build()
+    gs = GpuScene(b, 0)
+    blk, lgt, st = render(b, spp=4, gpu_scene=gs)
+    host = np.zeros((b.height, b.width, b.channels), np.float32)
+    A.check(A.lib().wtgpu_develop(C.byref(b.desc.sensor), 4, blk.ctypes.data_as(C.c_void_p), lgt.ctypes.data_as(C.c_void_p), host.ctypes.data_as(C.c_void_p)), "develop")
+    dev = develop_on_device(gs, 4, torch.from_numpy(blk).cuda(), torch.from_numpy(lgt).cuda()).cpu().numpy()
+    assert np.array_equal(host.view(np.uint32), dev.view(np.uint32)) and np.abs(host).sum() > 0
+    gs.close()

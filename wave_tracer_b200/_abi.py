@@ -191,6 +191,7 @@ def lib():
     L.wtgpu_get_capacities.argtypes = [C.c_void_p, P(c_u32)]
     L.wtgpu_set_capacities.argtypes = [C.c_void_p, P(c_u32)]
     L.wtgpu_develop.argtypes = [P(Sensor), c_u32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.wtgpu_develop_device.argtypes = [P(Sensor), c_u32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.wtgpu_debug_intersect_rays.argtypes = [C.c_void_p, c_u32, P(RayQuery), P(RayHit)]
     L.wtgpu_debug_shadow_rays.argtypes = [C.c_void_p, c_u32, P(RayQuery), P(c_u32)]
     L.wtgpu_debug_intersect_cones.argtypes = [C.c_void_p, c_u32, P(ConeQuery), P(ConeHit)]
@@ -212,7 +213,7 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_trim", "wtgpu_render", "wtgpu_get_capacities", "wtgpu_set_capacities", "wtgpu_develop",
+EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_trim", "wtgpu_render", "wtgpu_get_capacities", "wtgpu_set_capacities", "wtgpu_develop", "wtgpu_develop_device",
                     "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_pmath", "wtgpu_debug_sobol", "wtgpu_debug_sizeof", "wthost_sobol_tables",
                     "wthost_ads_build", "wthost_ads_fill", "wthost_ads_destroy", "wthost_ads_sah_cost", "wthost_ads_max_depth"]
 

@@ -45,6 +45,7 @@ template <int TEAM> struct alignas(16) TShared {
     unsigned keep[QCAP / 32 + 1];                           // q_revert: keep flags per 32-entry chunk
     int sel[NW];                                            // Q index of the nodes being expanded this round
     int wn[NW]; float wc_tmin[NW][8]; int32_t wc_ptr[NW][8];
+    alignas(16) float nstage[NW][64];                                   // per expanding group: staging slot of its node record (gtrav.cuh g_stage_node)
     uint32_t bt0[NL], bcnt[NL];                             // batch leaves: triangle range
     float dres[NL * 8]; uint16_t surv[NL * 8];
     uint32_t lmask[NL], larg[NL]; float ldmin[NL];          // per batch leaf: accepted slots, first closest slot, its distance
@@ -119,7 +120,8 @@ template <int TEAM> WT_D void q_from_stack(TShared<TEAM>& sh, int s, unsigned la
 #endif
 template <int TEAM, class Emit>
 WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, int* cursor, TShared<TEAM>& sh, Counters& ctr,
-                         TravSave* huge_save, int* n_huge, uint32_t huge_tested, unsigned long long* dbg, Emit&& emit) {
+                         TravSave* huge_save, int* n_huge, TravTiers tiers, unsigned long long* dbg, Emit&& emit) {
+    const uint32_t huge_tested = tiers.huge_tested;
     constexpr int NW = TShared<TEAM>::NW, QCAP = TShared<TEAM>::QCAP, NL = TShared<TEAM>::NL, RCAP = TShared<TEAM>::RCAP;
     const unsigned FULL = 0xffffffffu;
     const unsigned tid = threadIdx.x % (unsigned)TEAM, lane = threadIdx.x & 31u;
@@ -133,7 +135,8 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
     unsigned long long d_[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; long long clk_ = clock64();      // 0 batches, 1 leaves, 2 rounds, 3 slow commits | cycles: 4 control, 5 lookahead, 6 tests, 7 commit
 #endif
     bool have = false; int item = 0;
-    int nl_cap = NL / 4;           // leaves per batch: small after the search range has changed (what follows such a leaf is thrown away), doubling while it holds
+    const int nl_init = max(NL / (int)max(tiers.init_div, 1u), 8), nl_restart = max(NL / (int)max(tiers.restart_div, 1u), 8);
+    int nl_cap = nl_init;           // leaves per batch: small after the search range has changed (what follows such a leaf is thrown away), doubling while it holds
     for (;;) {
         // ---- control warp: the sequential machine, up to the next cone batch
         if (ctl) {
@@ -149,7 +152,7 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                     for (int k = (int)lane; k < t.s; k += 32) { sh.g.tmin[k] = sv.tmin[k]; sh.g.ptr[k] = sv.ptr[k]; }
                     __syncwarp();
                     q_from_stack(sh, t.s, lane);        // (items arrive in the middle of a cone query)
-                    have = true; nl_cap = NL / 4;
+                    have = true; nl_cap = nl_init;
                 }
                 if (t.s == 0) {
                     TravRec out;
@@ -264,10 +267,8 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
             // (3) one group of eight lanes per selected node: children against the current range, ranked in pop order
             if (grp < sh.nsel) {
                 const int32_t ptr = sh.qptr[sh.sel[grp]];
-                const wtgpu_node* __restrict__ n = sc.nodes + (ptr - 1);
-                const float mnx = __ldg(&n->minx[gg.gl]), mny = __ldg(&n->miny[gg.gl]), mnz = __ldg(&n->minz[gg.gl]);
-                const float mxx = __ldg(&n->maxx[gg.gl]), mxy = __ldg(&n->maxy[gg.gl]), mxz = __ldg(&n->maxz[gg.gl]);
-                const int32_t ch = __ldg(&n->child[gg.gl]);
+                float mnx, mny, mnz, mxx, mxy, mxz; int32_t ch;
+                g_stage_node(sc, gg, sh.nstage[grp], ptr, mnx, mny, mnz, mxx, mxy, mxz, ch);
                 float tmin;
                 const bool push = cone_child_test(env.o, env.d, sh.inv, sh.nx != 0, sh.ny != 0, sh.nz != 0, env.ta, env.x0, cr, mnx, mny, mnz, mxx, mxy, mxz, tmin) && ch != 0;
                 const unsigned m = g_ballot(gg, push);
@@ -469,7 +470,7 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                     t.s = q_revert(sh, t.s + back, lane);
                     q_prune(sh, t);
                     restarted = true;
-                    nl_cap = max(NL / 16, 8);
+                    nl_cap = nl_restart;
                     break;
                 }
                 start = upto; e0 = e1;

@@ -1222,7 +1222,7 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
     __shared__ GShared shm[128 / kGW];
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.r.sc;
-    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr, a.r.big_save, &a.r.ctr->n_big, a.r.big_tested,
+    g_traverse_all(sc, a.r.ctr->n_trav, &a.r.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, false, ctr, a.r.big_save, &a.r.ctr->n_big, a.r.tiers.big_tested,
         [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
             const uint32_t wid = a.r.trav_list[i];
             BdWalker w; soa_load(w, a.walkers, 2u * a.P, wid);
@@ -1236,14 +1236,14 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
 __global__ void __launch_bounds__(128, 4) k_bd_wtraverse(const BdArgs a) {
     __shared__ TShared<32> shm[4];
     Counters ctr; counters_zero(ctr);
-    t_traverse_all<32>(a.r.sc, a.r.ctr->n_big, a.r.big_save, &a.r.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.r.huge_save, &a.r.ctr->n_huge, a.r.huge_tested, a.r.ctr->dbg,
+    t_traverse_all<32>(a.r.sc, a.r.ctr->n_big, a.r.big_save, &a.r.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.r.huge_save, &a.r.ctr->n_huge, a.r.tiers, a.r.ctr->dbg,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.r.trav_list[i]] = r; });
     flush_counters(a.r.ctr, ctr);
 }
 __global__ void __launch_bounds__(256, 2) k_bd_ctraverse(const BdArgs a) {
     __shared__ TShared<256> shm;
     Counters ctr; counters_zero(ctr);
-    t_traverse_all<256>(a.r.sc, a.r.ctr->n_huge, a.r.huge_save, &a.r.ctr->huge_head, shm, ctr, nullptr, nullptr, 0u, a.r.ctr->dbg + 8,
+    t_traverse_all<256>(a.r.sc, a.r.ctr->n_huge, a.r.huge_save, &a.r.ctr->huge_head, shm, ctr, nullptr, nullptr, a.r.tiers, a.r.ctr->dbg + 8,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.r.trav_list[i]] = r; });
     flush_counters(a.r.ctr, ctr);
 }

@@ -14,12 +14,13 @@
 //   * the four groups of a warp run node steps freely but meet before every leaf step, where the expensive cone-triangle code runs.
 // Every decision is taken on the same values, in the same order, as the sequential code: results are bit-identical to dtrav.cuh.
 #pragma once
+#include <cuda_pipeline.h>
 
 namespace wt {
 
 constexpr int kGW = 8;
 constexpr int kGStack = 128;
-struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; float key[kGW]; };
+struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; float key[kGW]; alignas(16) float node[64]; };     // node: staging slot of the 256-B node record in hand
 
 // what traverse() returns, as stored between the traversal kernel and the per-thread resolve kernel
 struct alignas(16) TravRec { uint32_t flags, ray_tuid; float ray_dist, bx, by, cone_dist; uint32_t n_tris; float region_depth, ox, oy, oz; uint32_t pad_; };
@@ -68,7 +69,7 @@ constexpr uint32_t kBigQuery = 32u;     // a triangle list longer than this is r
 // A beam in the middle of a cone query, as handed from one traversal kernel to the next (ctrav.cuh): the whole machine state and the stack.
 struct alignas(16) TravSave { GTrav t; int item; int pad_[3]; float tmin[kGStack]; int32_t ptr[kGStack]; };
 // hand-over thresholds (triangles tested by the current cone query): group -> warp team, warp team -> block team
-struct TravTiers { uint32_t big_tested, huge_tested; };
+// (TravTiers is declared in wavefront.cu ahead of RenderArgs: { big_tested, huge_tested, restart_div, init_div }) restart_div / init_div: the team batch after a range change / at the start is NL / div leaves
 
 WT_D void g_start_ray(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, Range r, Counters& ctr) {
     t.mode = 1; t.qrange = r; t.cull = ray_cull(sc, r); t.rec.tuid = WTGPU_INVALID_IDX; t.rec.dist = WT_INF; t.rec.bx = t.rec.by = -1.f; t.rec.front = false;
@@ -108,6 +109,27 @@ WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float 
     t.s += __popc(km);
     __syncwarp(g.gmask);
 }
+// The 256-B node record (eight rows of eight words: min x/y/z, max x/y/z, child pointers, triangle range) goes global -> shared memory with two
+// 16-B asynchronous copies per lane (LDGSTS: the group's eight lanes cover the record's two 128-B lines in one coalesced request each, no
+// registers in between); lane i then reads word i of each row.  `slot`: this group's 64-word staging slot.
+WT_D void g_stage_node(const DScene& sc, const GLane& g, float* slot, int32_t ptr, float& mnx, float& mny, float& mnz, float& mxx, float& mxy, float& mxz, int32_t& ch) {
+#ifdef WT_NO_NODE_STAGING      // A/B: seven 4-B loads per lane straight from global memory (round 1)
+    const wtgpu_node* __restrict__ n = sc.nodes + (ptr - 1);
+    mnx = __ldg(&n->minx[g.gl]); mny = __ldg(&n->miny[g.gl]); mnz = __ldg(&n->minz[g.gl]);
+    mxx = __ldg(&n->maxx[g.gl]); mxy = __ldg(&n->maxy[g.gl]); mxz = __ldg(&n->maxz[g.gl]);
+    ch = __ldg(&n->child[g.gl]);
+#else
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(sc.nodes + (ptr - 1)) + 2u * g.gl;
+    float4* dst = reinterpret_cast<float4*>(slot) + 2u * g.gl;
+    __pipeline_memcpy_async(dst, src, 16); __pipeline_memcpy_async(dst + 1, src + 1, 16);
+    __pipeline_commit(); __pipeline_wait_prior(0);
+    __syncwarp(g.gmask);
+    mnx = slot[0 * 8 + g.gl]; mny = slot[1 * 8 + g.gl]; mnz = slot[2 * 8 + g.gl];
+    mxx = slot[3 * 8 + g.gl]; mxy = slot[4 * 8 + g.gl]; mxz = slot[5 * 8 + g.gl];
+    ch = __float_as_int(slot[6 * 8 + g.gl]);
+    __syncwarp(g.gmask);
+#endif
+}
 // cone_cluster_intersect (bvh8w.cpp:187-230) for one child box: the AABB inflated by the cone radius at its farthest z, slab test against the
 // current search range; true = the child is pushed (with key tmin)
 WT_D bool cone_child_test(V3 ro, V3 rd, V3 inv, bool nx, bool ny, bool nz, float ta, float x0, Range cr, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float& tmin_out) {
@@ -129,11 +151,9 @@ WT_D bool cone_child_test(V3 ro, V3 rd, V3 inv, bool nx, bool ny, bool nz, float
     return ok && !(tmin >= cr.mx);
 }
 WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, int32_t ptr, Counters& ctr) {
-    const wtgpu_node* __restrict__ n = sc.nodes + (ptr - 1);
     if (g.gl == 0u) ctr.nodes++;
-    const float mnx = __ldg(&n->minx[g.gl]), mny = __ldg(&n->miny[g.gl]), mnz = __ldg(&n->minz[g.gl]);
-    const float mxx = __ldg(&n->maxx[g.gl]), mxy = __ldg(&n->maxy[g.gl]), mxz = __ldg(&n->maxz[g.gl]);
-    const int32_t ch = __ldg(&n->child[g.gl]);
+    float mnx, mny, mnz, mxx, mxy, mxz; int32_t ch;
+    g_stage_node(sc, g, sh.node, ptr, mnx, mny, mnz, mxx, mxy, mxz, ch);
     const V3 ro = t.env.o, rd = t.env.d;
     bool push; float key; int cap;       // (one copy of the ranked push for both query kinds: code size is what bounds this kernel)
     if (t.mode == 1) {      // intersect_ray_aabb_fast (intersect/ray.hpp:331-351), range {0, closest hit}

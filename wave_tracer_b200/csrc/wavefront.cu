@@ -92,12 +92,12 @@ struct DevCounters {
 };
 WT_D void need_max(unsigned int* p, uint32_t v) { if (v > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(p, v); }
 
-namespace wt { struct TravRec; struct TravSave; }
+namespace wt { struct TravRec; struct TravSave; struct TravTiers { uint32_t big_tested, huge_tested, restart_div, init_div; }; }
 struct RenderArgs {
     DScene sc;
     wt::TravRec* trav_rec; uint32_t* trav_tris;      // results of traverse(), per slot; trav_tris: the first kTriRow triangle ids of the slot's cone-query list (dtrav.cuh TriList)
     wt::TravSave* big_save; wt::TravSave* huge_save;  // beams handed from the group traversal to the warp teams, and from those to the block teams (gtrav.cuh TravSave)
-    uint32_t big_tested, huge_tested;                 // the hand-over thresholds (triangles tested by the current cone query)
+    wt::TravTiers tiers;                              // the hand-over thresholds (triangles tested by the current cone query) and team batch sizes
     uint32_t* big_res_list;                           // items (indices into trav_list) handed to the warp-per-list resolve kernels
     uint2* closest_tasks; unsigned long long* closest_best;     // plt_bdpt: (list, chunk) tasks of the flat closest-triangle search; its result per walker (key of the winning entry)
     uint2* flux_items; uint2* flux_tasks; float4* flux_scratch; uint32_t flux_cap; float4* quad_tasks; uint32_t quad_cap;     // plt_bdpt: (item, scratch base) per queued list; (list, chunk) tasks; piece values; scratch entries
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs 
     __shared__ GShared shm[128 / kGW];
     Counters ctr; counters_zero(ctr);
     const DScene& sc = a.sc;
-    g_traverse_all(sc, a.ctr->n_trav, &a.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr, a.big_save, &a.ctr->n_big, a.big_tested,
+    g_traverse_all(sc, a.ctr->n_trav, &a.ctr->trav_head, shm, sc.sensor.ray_trace_only != 0u, true, ctr, a.big_save, &a.ctr->n_big, a.tiers.big_tested,
         [&](int i, Cone& env, Geo& prev, float& lambda, TriWriter& tw) {
             const uint32_t slot = a.trav_list[i];
             PathCore pc; soa_load(pc, a.core, a.pool, slot);
@@ -399,14 +399,14 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs 
 __global__ void __launch_bounds__(128, 4) k_wtraverse(const RenderArgs a) {
     __shared__ TShared<32> shm[4];
     Counters ctr; counters_zero(ctr);
-    t_traverse_all<32>(a.sc, a.ctr->n_big, a.big_save, &a.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.huge_save, &a.ctr->n_huge, a.huge_tested, a.ctr->dbg,
+    t_traverse_all<32>(a.sc, a.ctr->n_big, a.big_save, &a.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.huge_save, &a.ctr->n_huge, a.tiers, a.ctr->dbg,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
     flush_counters(a.ctr, ctr);
 }
 __global__ void __launch_bounds__(256, 2) k_ctraverse(const RenderArgs a) {
     __shared__ TShared<256> shm;
     Counters ctr; counters_zero(ctr);
-    t_traverse_all<256>(a.sc, a.ctr->n_huge, a.huge_save, &a.ctr->huge_head, shm, ctr, nullptr, nullptr, 0u, a.ctr->dbg + 8,
+    t_traverse_all<256>(a.sc, a.ctr->n_huge, a.huge_save, &a.ctr->huge_head, shm, ctr, nullptr, nullptr, a.tiers, a.ctr->dbg + 8,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
     flush_counters(a.ctr, ctr);
 }
@@ -1159,6 +1159,15 @@ static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t pa
     return WTGPU_OK;
 }
 
+// film develop (film_storage.hpp:256-291, 354-358): value / weight of the block image + light image / spp
+__global__ void k_develop(const float2* __restrict__ block, const float* __restrict__ light, float* __restrict__ out, size_t n, float inv_spp) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (block) { const float2 b = __ldg(block + i); v = b.y > 0.f ? b.x / b.y : 0.f; }
+        if (light) v += __ldg(light + i) * inv_spp;
+        out[i] = v;
+    }
+}
 __global__ void k_film_add(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
 }
@@ -1184,7 +1193,8 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
     const dim3 gBig(s->big_blocks);
     // hand-over thresholds of the traversal tiers (gtrav.cuh TravTiers); WT_BIG_TESTED / WT_HUGE_TESTED override for A/B runs
     static const wt::TravTiers tiers = []() { wt::TravTiers t; const char* b = getenv("WT_BIG_TESTED"); const char* h = getenv("WT_HUGE_TESTED");
-                                              t.big_tested = b ? (uint32_t)atoi(b) : 192u; t.huge_tested = h ? (uint32_t)atoi(h) : 3072u; return t; }();
+                                              t.big_tested = b ? (uint32_t)atoi(b) : 192u; t.huge_tested = h ? (uint32_t)atoi(h) : 8000u;
+                                              const char* r = getenv("WT_RESTART_DIV"); const char* i = getenv("WT_INIT_DIV"); t.restart_div = r ? (uint32_t)atoi(r) : 16u; t.init_div = i ? (uint32_t)atoi(i) : 4u; return t; }();
 
     // the sub-pools start after whatever the caller queued on its stream
     CK(cudaEventRecord(s->ev_begin, user));
@@ -1196,7 +1206,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
         RenderArgs& a = args[k];
         a.sc = d; a.core = q.core; a.fsd = q.fsd; a.hit = q.hit; a.alive = q.alive; a.keys = q.keys; a.order = q.order;
         a.trav_rec = q.trav_rec; a.trav_tris = q.trav_tris; a.hit_edges = q.hit_edges; a.ap_edges = q.ap_edges; a.it_parity = 0u;
-        a.big_save = q.big_save; a.huge_save = q.huge_save; a.big_tested = tiers.big_tested; a.huge_tested = tiers.huge_tested; a.big_res_list = q.big_res_list; a.closest_tasks = q.closest_tasks; a.closest_best = q.closest_best; a.flux_items = q.flux_items; a.flux_tasks = q.flux_tasks; a.flux_scratch = q.flux_scratch; a.flux_cap = q.flux_cap; a.quad_tasks = q.quad_tasks; a.quad_cap = q.quad_cap; a.edge_bits = q.edge_bits;
+        a.big_save = q.big_save; a.huge_save = q.huge_save; a.tiers = tiers; a.big_res_list = q.big_res_list; a.closest_tasks = q.closest_tasks; a.closest_best = q.closest_best; a.flux_items = q.flux_items; a.flux_tasks = q.flux_tasks; a.flux_scratch = q.flux_scratch; a.flux_cap = q.flux_cap; a.quad_tasks = q.quad_tasks; a.quad_cap = q.quad_cap; a.edge_bits = q.edge_bits;
         a.key_count = q.key_count; a.key_cursor = q.key_cursor; a.trav_list = q.trav_list; a.ctr = q.ctr; a.film_block = dblock; a.film_light = dlight;
         a.pool = q.size; a.n_keys = s->n_keys; a.seed_lo = (uint32_t)o->seed; a.seed_hi = (uint32_t)(o->seed >> 32);
         a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
@@ -1509,6 +1519,16 @@ int wtgpu_develop(const wtgpu_sensor* sensor, uint32_t spp, const float* film_bl
         if (film_light) v += film_light[i] * sl;
         out[i] = v;
     }
+    return WTGPU_OK;
+}
+
+int wtgpu_develop_device(const wtgpu_sensor* sensor, uint32_t spp, const float* d_block, const float* d_light, float* d_out, void* stream, int device) {
+    if (!sensor || !d_out) { g_err = "null argument"; return WTGPU_E_INVALID; }
+    CK(cudaSetDevice(device));
+    const size_t n = (size_t)sensor->width * sensor->height * sensor->channels;
+    int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    k_develop<<<dim3(n_sm * 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(d_block), d_light, d_out, n, spp > 0 ? 1.f / (float)spp : 0.f);
+    CK(cudaGetLastError());
     return WTGPU_OK;
 }
 

@@ -52,3 +52,16 @@ def render_distributed(gpu_scene, spp, seed=0x5EED, pool_size=0, flags=0):
         raise err
     block, light = reduce_films(block, light)
     return block, light, st
+
+
+def develop_on_device(gpu_scene, spp, block, light):
+    """film develop (film_storage.hpp:256-291, 354-358) of device-resident films on their GPU (wtgpu_develop_device): returns a torch tensor
+    [H][W][C] -- on rank 0 after the reduce, so that only the developed image crosses PCIe."""
+    import ctypes as C
+    import torch
+    from . import _abi as A
+    b = gpu_scene.built
+    out = torch.empty((b.height, b.width, b.channels), dtype=torch.float32, device=block.device)
+    stream = torch.cuda.current_stream(block.device).cuda_stream
+    A.check(A.lib().wtgpu_develop_device(C.byref(b.desc.sensor), spp, block.data_ptr(), light.data_ptr(), out.data_ptr(), stream, gpu_scene.device), "wtgpu_develop_device")
+    return out
