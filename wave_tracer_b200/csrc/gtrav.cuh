@@ -109,11 +109,14 @@ WT_D void g_push_sorted(const GLane& g, GShared& sh, GTrav& t, bool push, float 
     t.s += __popc(km);
     __syncwarp(g.gmask);
 }
-// The 256-B node record (eight rows of eight words: min x/y/z, max x/y/z, child pointers, triangle range) goes global -> shared memory with two
-// 16-B asynchronous copies per lane (LDGSTS: the group's eight lanes cover the record's two 128-B lines in one coalesced request each, no
-// registers in between); lane i then reads word i of each row.  `slot`: this group's 64-word staging slot.
+// The 256-B node record (eight rows of eight words: min x/y/z, max x/y/z, child pointers, triangle range); lane i gets word i of each row.
+// -DWT_NODE_STAGING: the record goes global -> shared memory with two 16-B asynchronous copies per lane (LDGSTS: the group's eight lanes cover
+// the record's two 128-B lines in one coalesced request each) and is read back from the group's 64-word `slot`.  MEASURED SLOWER than the plain
+// loads on every workload (profiles/r02_ab_node_staging.log: cornell -3.5 %, etoile -1.5 %, double_slits -4 %, sponza -35 %): the copy has to be
+// waited for as a whole and costs a shared-memory round trip, whereas the seven sector loads are all in flight at once and feed the slab test
+// directly; the node table (4 MB) lives in L2 / L1 either way.  Kept as the A/B switch.
 WT_D void g_stage_node(const DScene& sc, const GLane& g, float* slot, int32_t ptr, float& mnx, float& mny, float& mnz, float& mxx, float& mxy, float& mxz, int32_t& ch) {
-#ifdef WT_NO_NODE_STAGING      // A/B: seven 4-B loads per lane straight from global memory (round 1)
+#ifndef WT_NODE_STAGING         // default: seven 4-B loads per lane straight from global memory (each a 32-B sector per group), consumed as they arrive
     const wtgpu_node* __restrict__ n = sc.nodes + (ptr - 1);
     mnx = __ldg(&n->minx[g.gl]); mny = __ldg(&n->miny[g.gl]); mnz = __ldg(&n->minz[g.gl]);
     mxx = __ldg(&n->maxx[g.gl]); mxy = __ldg(&n->maxy[g.gl]); mxz = __ldg(&n->maxz[g.gl]);
