@@ -149,6 +149,33 @@ def parity_record(workload, integrator, device):
             "gate": {"rel_l2": 1e-3, "mean_rel": 2e-4}}
 
 
+def short_record(workload, device, steps=2, warmup=2):
+    """A short device-timed run of another BASELINE workload (its own film size, pool and spp per step) with its parity record: embedded in the
+    default line as `other_workloads` so that one bench run states all four north_star / BASELINE configurations."""
+    import torch
+    from wave_tracer_b200 import GpuScene
+    wl = WORKLOADS[workload]
+    sc, integ, tsz = make_scene(workload, wl["res"], wl["spp"])
+    built = sc.build(table_size=tsz)
+    W, H, Cn = built.width, built.height, built.channels
+    gs = GpuScene(built, device)
+    dev = torch.device("cuda", device)
+    S = wl["spp_per_step"]
+    def step(i):
+        block = torch.zeros((H, W, Cn, 2), dtype=torch.float32, device=dev); light = torch.zeros((H, W, Cn), dtype=torch.float32, device=dev)
+        return gs.render_into(block.data_ptr(), light.data_ptr(), wl["spp"], 0x5EED, (i * S, i * S + S), None, True, wl["pool"], 0, torch.cuda.current_stream().cuda_stream)
+    for i in range(warmup): step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); stats = [step(warmup + i) for i in range(steps)]; e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    gs.close()
+    n = sum(s["samples"] for s in stats)
+    return {"workload": wl["name"], "integrator": integ, "film": [W, H, Cn], "triangles": int(built.desc.n_tris), "spp_per_step": S, "steps": steps, "warmup": warmup,
+            "value": n / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms / steps, "capacity_overflows": int(sum(s["capacity_overflows"] for s in stats)),
+            "parity": parity_record(workload, None, device)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +191,7 @@ def main():
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="N=1: do not append the short records of the other BASELINE workloads (config.other_workloads)")
     ap.add_argument("--no-sort", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true", help="do not record per-kernel CUDA events in the timed region (A/B of the instrumentation cost)")
     ap.add_argument("--flags", type=int, default=0, help="extra WTGPU_RENDER_* flags (A/B measurements)")
@@ -353,6 +381,9 @@ def main():
                "capacities": dict(zip(("cone_tris", "edges", "fraunhofer_segments", "apertures_per_subpath", "vertices_per_subpath"), gs.capacities())) | {"passes_in_timed_steps": max(s["passes"] for s in timed_stats), "pool_used": timed_stats[-1]["pool_used"], "subpools": timed_stats[-1].get("subpools")}}
         if world == 1 and not a.no_parity:
             out["parity"] = parity_record(a.workload, a.integrator, local)
+        if world == 1 and not a.no_other_workloads and a.res == wl["res"]:
+            gs.close()
+            out["other_workloads"] = [short_record(w, local) for w in WORKLOADS if w != a.workload]
         if world == 1 and not a.no_cpu_baseline:
             v, cores, sample = cpu_leg(built, 12.0)
             out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample, "build": "oracle/liboracle.so, g++ -O3 -march=x86-64-v3 -ffp-contract=off"}
