@@ -15,12 +15,27 @@ def _declared(header):
 
 
 def test_every_declared_symbol_is_exported():
-    L = A.lib()
-    names = _declared("wtgpu.h") | _declared("wthost.h")
-    assert len(names) >= 16
-    for n in sorted(names):
-        assert hasattr(L, n), f"{n} declared in include/ but not exported by libwt_b200.so"
-    assert set(A.EXPORTED_SYMBOLS) <= names
+    """wtgpu.h -> libwt_b200.so (the CUDA library), wthost.h -> libwt_host.so (host-only scene preparation)."""
+    L, H = A.lib(), A.host_lib()
+    gpu, host = _declared("wtgpu.h"), _declared("wthost.h")
+    assert len(gpu) >= 14 and len(host) >= 6
+    for n in sorted(gpu):
+        assert hasattr(L, n), f"{n} declared in include/wtgpu.h but not exported by libwt_b200.so"
+    for n in sorted(host):
+        assert hasattr(H, n), f"{n} declared in include/wthost.h but not exported by libwt_host.so"
+    assert set(A.EXPORTED_SYMBOLS) <= gpu and set(A.HOST_EXPORTED_SYMBOLS) <= host
+
+
+def test_host_library_is_host_only():
+    """libwt_host.so (what the CPU legs of bench.py build their scene tables with) links neither the CUDA runtime nor the CUDA library, and
+    building a scene does not load libwt_b200.so."""
+    import subprocess, sys
+    out = subprocess.run(["ldd", A.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "cudart" not in out and "libcuda" not in out and "libwt_b200" not in out, out
+    code = ("import sys; sys.path.insert(0, %r)\nfrom wave_tracer_b200 import scenes, _abi\nb = scenes.double_slits(res=32, spp=1).build()\n"
+            "assert b.desc.n_tris == 10 and _abi._lib is None\nassert 'libwt_b200' not in open('/proc/self/maps').read()\nprint('ok')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
 
 
 def test_struct_layouts_match():

@@ -198,9 +198,26 @@ def lib():
     L.wtgpu_debug_rng.argtypes = [c_u64, c_u32, c_u32, c_u32, P(c_f), C.c_int]
     L.wtgpu_debug_pmath.argtypes = [C.c_int, c_u32, P(c_f), P(c_f), P(c_f), C.c_int]
     L.wtgpu_debug_sobol.argtypes = [C.c_void_p, c_u64, c_u64, c_u32, P(c_u32), P(c_f)]
-    L.wthost_sobol_tables.argtypes = [P(SobolEntry), P(C.c_uint16), P(C.c_uint16)]
     L.wtgpu_debug_sizeof.argtypes = [C.c_int]
     L.wtgpu_debug_sizeof.restype = C.c_uint64
+    _lib = L
+    return L
+
+
+HOST_LIB_PATH = os.path.join(_HERE, "libwt_host.so")
+_host_lib = None
+
+
+def host_lib():
+    """Loads the host-only library (wthost_*: mesh -> triangles -> BVH -> edges, sobolld tables).  It contains no CUDA code and does not load the
+    CUDA library: the CPU legs of bench.py (`--impl reference`, cpu_baseline) build their scene tables with it and never map libwt_b200.so."""
+    global _host_lib
+    if _host_lib is not None:
+        return _host_lib
+    if not os.path.exists(HOST_LIB_PATH):
+        raise RuntimeError(f"wave_tracer_b200: native library {HOST_LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`.")
+    L = C.CDLL(HOST_LIB_PATH)
+    L.wthost_sobol_tables.argtypes = [P(SobolEntry), P(C.c_uint16), P(C.c_uint16)]
     L.wthost_ads_build.argtypes = [c_u32, P(MeshDesc), P(C.c_void_p)]
     L.wthost_ads_fill.argtypes = [C.c_void_p, P(SceneDesc)]
     L.wthost_ads_destroy.argtypes = [C.c_void_p]
@@ -209,13 +226,18 @@ def lib():
     L.wthost_ads_sah_cost.restype = c_dbl
     L.wthost_ads_max_depth.argtypes = [C.c_void_p]
     L.wthost_ads_max_depth.restype = c_u32
-    _lib = L
+    _host_lib = L
     return L
 
 
+def check_host(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"wthost: {what} failed with code {rc}")
+
+
 EXPORTED_SYMBOLS = ["wtgpu_device_count", "wtgpu_last_error", "wtgpu_scene_create", "wtgpu_scene_destroy", "wtgpu_trim", "wtgpu_render", "wtgpu_get_capacities", "wtgpu_set_capacities", "wtgpu_develop", "wtgpu_develop_device",
-                    "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_pmath", "wtgpu_debug_sobol", "wtgpu_debug_sizeof", "wthost_sobol_tables",
-                    "wthost_ads_build", "wthost_ads_fill", "wthost_ads_destroy", "wthost_ads_sah_cost", "wthost_ads_max_depth"]
+                    "wtgpu_debug_intersect_rays", "wtgpu_debug_shadow_rays", "wtgpu_debug_intersect_cones", "wtgpu_debug_rng", "wtgpu_debug_pmath", "wtgpu_debug_sobol", "wtgpu_debug_sizeof"]
+HOST_EXPORTED_SYMBOLS = ["wthost_sobol_tables", "wthost_ads_build", "wthost_ads_fill", "wthost_ads_destroy", "wthost_ads_sah_cost", "wthost_ads_max_depth"]
 
 
 def check(rc, what=""):

@@ -24,6 +24,14 @@
 // Every decision is taken on the same values, in the same order, as the sequential code: lists, distances and counters are identical.
 #pragma once
 
+// resident blocks per SM the team kernels are compiled for (register budget): warp teams 4 x 128 threads (128 registers), block teams 2 x 256
+#ifndef WT_WT_MINB
+#define WT_WT_MINB 4
+#endif
+#ifndef WT_CT_MINB
+#define WT_CT_MINB 2
+#endif
+
 namespace wt {
 
 enum : uint32_t { QK_LEAF = 0u, QK_NODE = 1u, QK_MARK = 2u };
@@ -45,7 +53,9 @@ template <int TEAM> struct alignas(16) TShared {
     unsigned keep[QCAP / 32 + 1];                           // q_revert: keep flags per 32-entry chunk
     int sel[NW];                                            // Q index of the nodes being expanded this round
     int wn[NW]; float wc_tmin[NW][8]; int32_t wc_ptr[NW][8];
-    alignas(16) float nstage[NW][64];                                   // per expanding group: staging slot of its node record (gtrav.cuh g_stage_node)
+#ifdef WT_NODE_STAGING
+    alignas(16) float nstage[NW][64];                       // per expanding group: staging slot of its node record (gtrav.cuh g_stage_node)
+#endif
     uint32_t bt0[NL], bcnt[NL];                             // batch leaves: triangle range
     float dres[NL * 8]; uint16_t surv[NL * 8];
     uint32_t lmask[NL], larg[NL]; float ldmin[NL];          // per batch leaf: accepted slots, first closest slot, its distance
@@ -268,7 +278,12 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
             if (grp < sh.nsel) {
                 const int32_t ptr = sh.qptr[sh.sel[grp]];
                 float mnx, mny, mnz, mxx, mxy, mxz; int32_t ch;
-                g_stage_node(sc, gg, sh.nstage[grp], ptr, mnx, mny, mnz, mxx, mxy, mxz, ch);
+#ifdef WT_NODE_STAGING
+                float* const nslot = sh.nstage[grp];
+#else
+                float* const nslot = nullptr;
+#endif
+                g_stage_node(sc, gg, nslot, ptr, mnx, mny, mnz, mxx, mxy, mxz, ch);
                 float tmin;
                 const bool push = cone_child_test(env.o, env.d, sh.inv, sh.nx != 0, sh.ny != 0, sh.nz != 0, env.ta, env.x0, cr, mnx, mny, mnz, mxx, mxy, mxz, tmin) && ch != 0;
                 const unsigned m = g_ballot(gg, push);

@@ -1233,14 +1233,14 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_bd_gtraverse(const BdArgs a
     flush_counters(a.r.ctr, ctr);
 }
 // the walkers k_bd_gtraverse handed over in the middle of a large cone query: one warp team per walker (ctrav.cuh), then one block team for the largest
-__global__ void __launch_bounds__(128, 4) k_bd_wtraverse(const BdArgs a) {
+__global__ void __launch_bounds__(128, WT_WT_MINB) k_bd_wtraverse(const BdArgs a) {
     __shared__ TShared<32> shm[4];
     Counters ctr; counters_zero(ctr);
     t_traverse_all<32>(a.r.sc, a.r.ctr->n_big, a.r.big_save, &a.r.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.r.huge_save, &a.r.ctr->n_huge, a.r.tiers, a.r.ctr->dbg,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.r.trav_list[i]] = r; });
     flush_counters(a.r.ctr, ctr);
 }
-__global__ void __launch_bounds__(256, 2) k_bd_ctraverse(const BdArgs a) {
+__global__ void __launch_bounds__(256, WT_CT_MINB) k_bd_ctraverse(const BdArgs a) {
     __shared__ TShared<256> shm;
     Counters ctr; counters_zero(ctr);
     t_traverse_all<256>(a.r.sc, a.r.ctr->n_huge, a.r.huge_save, &a.r.ctr->huge_head, shm, ctr, nullptr, nullptr, a.r.tiers, a.r.ctr->dbg + 8,

@@ -20,7 +20,11 @@ namespace wt {
 
 constexpr int kGW = 8;
 constexpr int kGStack = 128;
+#ifdef WT_NODE_STAGING
 struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; float key[kGW]; alignas(16) float node[64]; };     // node: staging slot of the 256-B node record in hand
+#else
+struct alignas(16) GShared { float tmin[kGStack]; int32_t ptr[kGStack]; float key[kGW]; float node[1]; };
+#endif
 
 // what traverse() returns, as stored between the traversal kernel and the per-thread resolve kernel
 struct alignas(16) TravRec { uint32_t flags, ray_tuid; float ray_dist, bx, by, cone_dist; uint32_t n_tris; float region_depth, ox, oy, oz; uint32_t pad_; };

@@ -12,7 +12,8 @@
 // Path state lives in HBM as structure-of-arrays of 16-B chunks (chunk c of slot s at base[c*pool + s]): every warp-level
 // state access is a run of fully coalesced 512-B transactions.
 #include "dfsd.cuh"
-#include "../../include/wthost.h"
+#include "sobol_tables.h"
+#include "../../include/wthost.h"      // (types only: wtgpu_debug_sizeof reports the layout of wthost_mesh_desc)
 
 #include <algorithm>
 #include <cstdio>
@@ -396,14 +397,14 @@ __global__ void __launch_bounds__(128, WT_GT_MINB) k_gtraverse(const RenderArgs 
     flush_counters(a.ctr, ctr);
 }
 // the beams k_gtraverse handed over in the middle of a large cone query: one warp team per beam (ctrav.cuh), then one block team for the largest
-__global__ void __launch_bounds__(128, 4) k_wtraverse(const RenderArgs a) {
+__global__ void __launch_bounds__(128, WT_WT_MINB) k_wtraverse(const RenderArgs a) {
     __shared__ TShared<32> shm[4];
     Counters ctr; counters_zero(ctr);
     t_traverse_all<32>(a.sc, a.ctr->n_big, a.big_save, &a.ctr->big_head, shm[threadIdx.x >> 5], ctr, a.huge_save, &a.ctr->n_huge, a.tiers, a.ctr->dbg,
         [&](int i, const TravRec& r, const GLane& g) { if (g.gl == 0u) a.trav_rec[a.trav_list[i]] = r; });
     flush_counters(a.ctr, ctr);
 }
-__global__ void __launch_bounds__(256, 2) k_ctraverse(const RenderArgs a) {
+__global__ void __launch_bounds__(256, WT_CT_MINB) k_ctraverse(const RenderArgs a) {
     __shared__ TShared<256> shm;
     Counters ctr; counters_zero(ctr);
     t_traverse_all<256>(a.sc, a.ctr->n_huge, a.huge_save, &a.ctr->huge_head, shm, ctr, nullptr, nullptr, a.tiers, a.ctr->dbg + 8,
@@ -945,42 +946,6 @@ struct wtgpu_scene {
 static void caps_derive(Caps& c) { c.ap_words = 16u + 9u * c.seg; c.arena_words = 2u * c.verts * wt::kVertWords + 2u * c.ap_walk * c.ap_words; }
 static bool caps_equal(const Caps& a, const Caps& b) { return a.spill_words == b.spill_words && a.edges == b.edges && a.seg == b.seg && a.ap_walk == b.ap_walk && a.verts == b.verts; }
 
-// Generator matrices of the sobolld sampler from the parsed table, as row masks for dsobol.cuh.
-// Direction numbers m_1..m_11 of a dimension are kept as base-3 digit vectors v[c][t] (digit t of m_{c+1}); the first s_j come from the
-// table, the rest from the recurrence over GF(3) of irreducible_gf3.hpp:103-118 written digit-wise:
-//     v[c][t] = v[c-deg][t] + sum_{j=1..deg} g_j * v[c-j][t-j]   (mod 3),   g_j = -a_{deg-j}  (the reference's convert_to_gf3 = {0,2,1}).
-// gen_mat (sobolld_sampler.hpp:140-154) then puts digit (c - r) of m_{c+1} at row r, column c (upper triangular).
-static bool sobol_build_tables(const wtgpu_sobol_entry* e, wt::SobolTables& t, std::string& why) {
-    const int M = (int)WTGPU_SOBOL_DIGITS;
-    memset(&t, 0, sizeof(t));
-    for (int dim = 0; dim < (int)WTGPU_SOBOL_DIMS; ++dim) {
-        const wtgpu_sobol_entry& en = e[dim + 1];       // entry 0 is skipped by the reference (sobolld_sampler.hpp:50-52: d+1)
-        const int deg = en.sj;
-        if (en.d == 0 || deg < 1 || deg + 1 > M) { why = "sobol table: bad entry " + std::to_string(dim + 1); return false; }
-        int poly[16] = { 0 };
-        { int a = en.aj; for (int i = 0; i <= deg; ++i) { poly[i] = a % 3; a /= 3; } if (a != 0 || poly[deg] == 0) { why = "sobol table: polynomial/degree mismatch in entry " + std::to_string(dim + 1); return false; } }
-        int v[WTGPU_SOBOL_DIGITS][WTGPU_SOBOL_DIGITS] = {};
-        for (int c = 0; c < deg; ++c) {
-            int m = en.mk[c], lim = 1; for (int q = 0; q <= c; ++q) lim *= 3;
-            if (m <= 0 || m >= lim) { why = "sobol table: direction number out of range in entry " + std::to_string(dim + 1); return false; }
-            for (int q = 0; q <= c; ++q) { v[c][q] = m % 3; m /= 3; }
-        }
-        for (int c = deg; c < M; ++c)
-            for (int q = 0; q <= c; ++q) {
-                int acc = v[c - deg][q];
-                for (int j = 1; j <= deg; ++j) if (q >= j) acc += ((3 - poly[deg - j]) % 3) * v[c - j][q - j];
-                v[c][q] = acc % 3;
-            }
-        for (int j = 0; j < M; ++j) {
-            const int r = M - 1 - j;                    // output digit j reads matrix row M-1-j (sobolld_sampler.hpp:170)
-            uint16_t o1 = 0, o2 = 0;
-            for (int c = r; c < M; ++c) { const int x = v[c][c - r]; if (x == 1) o1 |= (uint16_t)(1u << c); else if (x == 2) o2 |= (uint16_t)(1u << c); }
-            t.ones[dim][j] = o1; t.twos[dim][j] = o2;
-        }
-    }
-    return true;
-}
-
 template <class T> static int upload(wtgpu_scene* s, const T* src, size_t n, const T** dst) {
     void* p = nullptr;
     const size_t bytes = std::max<size_t>(1, n) * sizeof(T);
@@ -1050,7 +1015,7 @@ int wtgpu_scene_create(const wtgpu_scene_desc* desc, int device, wtgpu_scene** o
 #undef UP
     if (desc->sobol_table) {
         wt::SobolTables tb; std::string why;
-        if (!sobol_build_tables(desc->sobol_table, tb, why)) { g_err = why; delete s; return WTGPU_E_INVALID; }
+        if (!wt::sobol_build_tables(desc->sobol_table, tb.ones, tb.twos, why)) { g_err = why; delete s; return WTGPU_E_INVALID; }
         cudaError_t e_ = cudaMemcpyToSymbol(wt::c_sobol, &tb, sizeof(tb));
         if (e_ != cudaSuccess) { g_err = std::string("cudaMemcpyToSymbol(c_sobol): ") + cudaGetErrorString(e_); delete s; return WTGPU_E_CUDA; }
         s->has_sobol = true;
@@ -1249,7 +1214,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
             k_bd_generate<<<gP, blkT, 0, st>>>(b); ++launches; mark(q);
             if (use_thread_trav) { k_bd_traverse<<<gW, blkT, 0, st>>>(b); ++launches; }
             else {
-                k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_wtraverse<<<gC, blk, 0, st>>>(b); k_bd_ctraverse<<<dim3(n_sm * 2), dim3(256), 0, st>>>(b);
+                k_bd_gtraverse<<<gC, blk, 0, st>>>(b); k_bd_wtraverse<<<gC, blk, 0, st>>>(b); k_bd_ctraverse<<<dim3(n_sm * WT_CT_MINB), dim3(256), 0, st>>>(b);
                 k_bd_resolve<<<gW, blkT, 0, st>>>(b); k_bd_closest_chunks<<<gC, blk, 0, st>>>(b); k_bd_resolve_big<<<gBig, blk, 0, st>>>(b, s->bit_words); k_bd_flux_chunks<<<gC, blk, 0, st>>>(b); k_bd_quad_tasks<<<gC, blk, 0, st>>>(b); k_bd_flux_finish<<<gBig, blk, 0, st>>>(b, s->bit_words); launches += 9;
             }
             mark(q);
@@ -1275,7 +1240,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
             k_generate<<<grd, blkT, 0, st>>>(a); ++launches; mark(q);
             if (use_thread_trav) { k_traverse<<<grd, blkT, 0, st>>>(a); ++launches; }
             else {
-                k_gtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_wtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_ctraverse<<<dim3(n_sm * 2), dim3(256), 0, st>>>(a);
+                k_gtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_wtraverse<<<dim3(n_sm * 8), blk, 0, st>>>(a); k_ctraverse<<<dim3(n_sm * WT_CT_MINB), dim3(256), 0, st>>>(a);
                 k_resolve<<<grd, blkT, 0, st>>>(a); k_resolve_big<<<gBig, blk, 0, st>>>(a, s->bit_words); launches += 5;
             }
             mark(q);
@@ -1569,14 +1534,6 @@ int wtgpu_debug_intersect_cones(wtgpu_scene* s, uint32_t n, const wtgpu_cone_que
     wt_free(dq); wt_free(dh);
     return WTGPU_OK;
 }
-int wthost_sobol_tables(const wtgpu_sobol_entry* table, uint16_t* ones, uint16_t* twos) {
-    if (!table || !ones || !twos) { g_err = "null argument"; return WTGPU_E_INVALID; }
-    wt::SobolTables tb; std::string why;
-    if (!sobol_build_tables(table, tb, why)) { g_err = why; return WTGPU_E_INVALID; }
-    memcpy(ones, tb.ones, sizeof(tb.ones)); memcpy(twos, tb.twos, sizeof(tb.twos));
-    return WTGPU_OK;
-}
-
 int wtgpu_debug_sobol(wtgpu_scene* s, uint64_t seed, uint64_t g0, uint32_t n, uint32_t* out_num, float* out_val) {
     if (!s || !out_num || !out_val) { g_err = "null argument"; return WTGPU_E_INVALID; }
     if (!s->has_sobol) { g_err = "scene has no sobol table"; return WTGPU_E_INVALID; }

@@ -543,7 +543,7 @@ class BuiltScene:
         self.sampler = 0        # WTGPU_SAMPLER_*
     def __del__(self):
         try:
-            if self.ads is not None: A.lib().wthost_ads_destroy(self.ads)
+            if self.ads is not None: A.host_lib().wthost_ads_destroy(self.ads)
         except Exception:
             pass
     @property
@@ -591,7 +591,7 @@ class Scene:
         return float(min(ks)), float(max(ks))
 
     def build(self, table_size=256):
-        L = A.lib()
+        L = A.host_lib()
         out = BuiltScene()
         d = out.desc
         d.api_version = 1
@@ -669,9 +669,9 @@ class Scene:
                 m.emitter = len(emitters); emitters.append((em, si))
             out.keep.append(mesh)
         ads = C.c_void_p()
-        A.check(L.wthost_ads_build(len(self.shapes), meshes, C.byref(ads)), "wthost_ads_build")
+        A.check_host(L.wthost_ads_build(len(self.shapes), meshes, C.byref(ads)), "wthost_ads_build")
         out.ads = ads
-        A.check(L.wthost_ads_fill(ads, C.byref(d)), "wthost_ads_fill")
+        A.check_host(L.wthost_ads_fill(ads, C.byref(d)), "wthost_ads_fill")
         out.keep.append(meshes)
 
         wmin, wmax = np.array(d.world_min[:]), np.array(d.world_max[:])

@@ -110,5 +110,5 @@ def host_matrices(entries):
     """Row masks the product library derives from the table (wthost_sobol_tables): (ones, twos) as [47][11] lists."""
     arr = to_abi(entries)
     ones = (C.c_uint16 * (DIMS * DIGITS))(); twos = (C.c_uint16 * (DIMS * DIGITS))()
-    A.check(A.lib().wthost_sobol_tables(arr, ones, twos), "wthost_sobol_tables")
+    A.check_host(A.host_lib().wthost_sobol_tables(arr, ones, twos), "wthost_sobol_tables")
     return [list(ones[d * DIGITS:(d + 1) * DIGITS]) for d in range(DIMS)], [list(twos[d * DIGITS:(d + 1) * DIGITS]) for d in range(DIMS)]
