@@ -78,7 +78,7 @@ def load_table(path):
             v = [int(x) for x in line.split()]
             entries.append((v[0], v[1], v[2], v[3:3 + v[1]]))
             if len(entries) == ENTRIES: break
-    if len(entries) < ENTRIES or entries and entries[0][0] != entries[0][0]:
+    if len(entries) < ENTRIES:
         raise RuntimeError(f'Underflow in "{path}"')
     return entries
 
