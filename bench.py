@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
-    "cornell": dict(res=1440, spp=1024, spp_per_step=1, pool=1 << 20,
+    "cornell": dict(res=1440, spp=1024, spp_per_step=2, pool=1 << 20,
                     name="cornell-box/box res=1440 spp=1024 visible spectrum (film 1440x1440 RGB CIE/D55; plt_bdpt max_depth 16, RR, MIS, Fraunhofer FSD; box.xml restated element "
                          "for element; SYNTHETIC stand-ins for its three LFS-stub PLY meshes and one PNG: config.standins)"),
     "etoile": dict(res=720, spp=1024, spp_per_step=16, pool=1 << 20,
