@@ -906,11 +906,17 @@ struct Pool {
     cudaStream_t st = nullptr, st_fsd = nullptr; cudaEvent_t ev_iter = nullptr, ev_shade = nullptr, ev_samp = nullptr, ev_done = nullptr;
     std::vector<cudaEvent_t> evs; size_t n_ev = 0;     // per-kernel timing marks (WTGPU_RENDER_TIME_KERNELS)
     // state of the render in progress
-    uint64_t iters = 0; unsigned long long total = 0; bool in_flight = false, done = false;
+    uint64_t iters = 0; unsigned long long total = 0; bool done = false;
+    // iterations are queued ahead of the host's look at the counters (kPipeDepth in flight per sub-pool), so the GPU never waits for the host to
+    // react between two iterations; the iterations queued after the last useful one find nothing to do
+    static constexpr int kPipeDepth = 4;
+    DevCounters* hring[kPipeDepth] = {}; cudaEvent_t ev_ring[kPipeDepth] = {}; uint64_t submitted = 0, completed = 0; bool draining = false;
     void free_buffers() { for (void* p : allocs) wt_free(p); allocs.clear(); size = 0; }
     void destroy() {
         free_buffers();
         if (hctr) cudaFreeHost(hctr);
+        for (DevCounters* h : hring) if (h) cudaFreeHost(h);
+        for (cudaEvent_t e : ev_ring) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
         for (cudaEvent_t e : { ev_iter, ev_shade, ev_samp, ev_done }) if (e) cudaEventDestroy(e);
         if (st) cudaStreamDestroy(st);
@@ -1116,6 +1122,8 @@ static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t pa
                 cudaStreamCreateWithFlags(&q.st_fsd, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_iter, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&q.ev_shade, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_samp, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming) != cudaSuccess) { g_err = "creating the sub-pool's streams / events failed"; rc = WTGPU_E_CUDA; }
+            for (int r = 0; r < Pool::kPipeDepth && rc == WTGPU_OK; ++r)
+                if (cudaMallocHost(&q.hring[r], sizeof(DevCounters)) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_ring[r], cudaEventDisableTiming) != cudaSuccess) { g_err = "creating the sub-pool's counter ring failed"; rc = WTGPU_E_CUDA; }
         }
         if (rc != WTGPU_OK) { s->free_pool(); return rc; }
         q.size = psize;
@@ -1177,7 +1185,7 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
         a.tile_x0 = o->tile_x0; a.tile_y0 = o->tile_y0; a.tile_w = x1 - o->tile_x0; a.tile_h = y1 - o->tile_y0;
         a.sample_begin = o->sample_begin; a.n_samples = o->sample_end - o->sample_begin; a.total = total; a.part = k; a.n_parts = parts;
         q.total = total > k ? (total - k + parts - 1) / parts : 0ull;       // samples with id = k (mod parts)
-        q.iters = 0; q.in_flight = false; q.done = false; q.n_ev = 0;
+        q.iters = 0; q.done = false; q.n_ev = 0; q.submitted = q.completed = 0; q.draining = false;
         if (q.alive) CK(cudaMemsetAsync(q.alive, 0, 4ull * q.size, q.st));
         CK(cudaMemsetAsync(q.key_count, 0, 4ull * s->n_keys, q.st));
         CK(cudaMemsetAsync(q.ctr, 0, sizeof(DevCounters), q.st));
@@ -1256,17 +1264,21 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
             k_shade<<<grd, blkT, 0, st>>>(a); launches += 2; mark(q);
         }
         ++q.iters; ++iters_total;
-        CK(cudaMemcpyAsync(q.hctr, q.ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(q.ev_iter, st));
-        q.in_flight = true;
+        const int slot = (int)(q.submitted % (uint64_t)Pool::kPipeDepth);
+        CK(cudaMemcpyAsync(q.hring[slot], q.ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(q.ev_ring[slot], st));
+        ++q.submitted;
         return WTGPU_OK;
     };
 
+    static const int depth_env = []() { const char* e = getenv("WT_PIPE_DEPTH"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= Pool::kPipeDepth ? v : 2; }();      // measured: 2 = 4 (+5 % on sponza, double_slits, cornell over 1)
+    const uint64_t depth = kind == POOL_BDPT_MEGA ? 1u : (uint64_t)depth_env;      // (the one-launch driver renders everything in its first iteration)
     uint32_t remaining = 0;
     for (uint32_t k = 0; k < parts; ++k) {
-        if (s->pools[k].total == 0ull) { s->pools[k].done = true; continue; }
+        Pool& q = s->pools[k];
+        if (q.total == 0ull) { q.done = true; continue; }
         ++remaining;
-        const int rc = launch_iteration(k); if (rc != WTGPU_OK) return rc;
+        while (q.submitted - q.completed < depth) { const int rc = launch_iteration(k); if (rc != WTGPU_OK) return rc; }
     }
     uint32_t rr = 0;
     while (remaining) {
@@ -1274,18 +1286,24 @@ static int render_pass(wtgpu_scene* s, const wtgpu_render_opts* o, uint32_t kind
         for (uint32_t j = 0; j < parts; ++j) {
             const uint32_t k = (rr + j) % parts;
             Pool& q = s->pools[k];
-            if (!q.in_flight) continue;
-            const cudaError_t e = cudaEventQuery(q.ev_iter);
-            if (e == cudaErrorNotReady) continue;
-            CK(e);
-            q.in_flight = false; progressed = true;
-            const bool finished = kind == POOL_BDPT_MEGA || (q.hctr->next_sample >= q.total && q.hctr->live <= 0);
-            if (finished) { q.done = true; --remaining; continue; }
+            if (q.done) continue;
+            while (q.completed < q.submitted) {
+                const int slot = (int)(q.completed % (uint64_t)Pool::kPipeDepth);
+                const cudaError_t e = cudaEventQuery(q.ev_ring[slot]);
+                if (e == cudaErrorNotReady) break;
+                CK(e);
+                ++q.completed; progressed = true;
+                if (!q.draining && (kind == POOL_BDPT_MEGA || (q.hring[slot]->next_sample >= q.total && q.hring[slot]->live <= 0))) q.draining = true;
+            }
+            if (q.draining) { if (q.completed == q.submitted) { q.done = true; --remaining; } continue; }
             if (q.iters > 100000000ull) { g_err = "render did not converge"; return WTGPU_E_CUDA; }
-            const int rc = launch_iteration(k); if (rc != WTGPU_OK) return rc;
+            while (q.submitted - q.completed < depth) { const int rc = launch_iteration(k); if (rc != WTGPU_OK) return rc; }
         }
-        if (!progressed) {      // nothing ready: sleep on the next sub-pool in turn
-            for (uint32_t j = 0; j < parts; ++j) { const uint32_t k = (rr + j) % parts; if (s->pools[k].in_flight) { CK(cudaEventSynchronize(s->pools[k].ev_iter)); break; } }
+        if (!progressed) {      // nothing ready: sleep on the oldest iteration of the next sub-pool in turn
+            for (uint32_t j = 0; j < parts; ++j) {
+                const uint32_t k = (rr + j) % parts; Pool& q = s->pools[k];
+                if (!q.done && q.completed < q.submitted) { CK(cudaEventSynchronize(q.ev_ring[(int)(q.completed % (uint64_t)Pool::kPipeDepth)])); break; }
+            }
         }
         rr = (rr + 1u) % parts;
     }
