@@ -915,7 +915,7 @@ struct Pool {
     void destroy() {
         free_buffers();
         if (hctr) cudaFreeHost(hctr);
-        for (DevCounters* h : hring) if (h) cudaFreeHost(h);
+        if (hring[0]) cudaFreeHost(hring[0]);      // (one pinned block holds the ring)
         for (cudaEvent_t e : ev_ring) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
         for (cudaEvent_t e : { ev_iter, ev_shade, ev_samp, ev_done }) if (e) cudaEventDestroy(e);
@@ -1122,8 +1122,13 @@ static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t pa
                 cudaStreamCreateWithFlags(&q.st_fsd, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_iter, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&q.ev_shade, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_samp, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming) != cudaSuccess) { g_err = "creating the sub-pool's streams / events failed"; rc = WTGPU_E_CUDA; }
-            for (int r = 0; r < Pool::kPipeDepth && rc == WTGPU_OK; ++r)
-                if (cudaMallocHost(&q.hring[r], sizeof(DevCounters)) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_ring[r], cudaEventDisableTiming) != cudaSuccess) { g_err = "creating the sub-pool's counter ring failed"; rc = WTGPU_E_CUDA; }
+            if (rc == WTGPU_OK) {
+                if (cudaMallocHost(&q.hring[0], sizeof(DevCounters) * Pool::kPipeDepth) != cudaSuccess) { g_err = "creating the sub-pool's counter ring failed"; rc = WTGPU_E_CUDA; q.hring[0] = nullptr; }
+                for (int r = 0; r < Pool::kPipeDepth && rc == WTGPU_OK; ++r) {
+                    q.hring[r] = q.hring[0] + r;
+                    if (cudaEventCreateWithFlags(&q.ev_ring[r], cudaEventDisableTiming) != cudaSuccess) { g_err = "creating the sub-pool's counter ring failed"; rc = WTGPU_E_CUDA; }
+                }
+            }
         }
         if (rc != WTGPU_OK) { s->free_pool(); return rc; }
         q.size = psize;
