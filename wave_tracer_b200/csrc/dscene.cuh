@@ -362,7 +362,10 @@ WT_D V3 offseted_ray_origin(const DScene& sc, const Geo& g, V3 ro, V3 rd) {     
     return ro;
 }
 // integrator::shadow (traversal.hpp:319-333)
-WT_D bool shadow_between(const DScene& sc, const Geo& a, const Geo& b, Counters& ctr) {
+#ifndef WT_SHADOW_INLINE
+#define WT_SHADOW_INLINE __device__ __forceinline__
+#endif
+WT_SHADOW_INLINE bool shadow_between(const DScene& sc, const Geo& a, const Geo& b, Counters& ctr) {
     const V3 d0 = normalize(b.p - a.p);
     const V3 o = offseted_ray_origin(sc, a, a.p, d0);
     const V3 t = offseted_ray_origin(sc, b, b.p, -d0);

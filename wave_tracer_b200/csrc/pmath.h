@@ -24,8 +24,16 @@
 
 #if defined(__CUDACC__)
 #define PM_HD __host__ __device__ inline
+// the f32 entry points (sinf, expf, atan2f, ...): -DPM_API_NOINLINE keeps ONE copy of each per kernel instead of one per call site (code size:
+// the elementary functions were a quarter of k_shade's 700 KB of SASS).  Same arithmetic either way.
+#ifdef PM_API_NOINLINE
+#define PM_API __host__ __device__ __noinline__
+#else
+#define PM_API __host__ __device__ inline
+#endif
 #else
 #define PM_HD inline
+#define PM_API inline
 #endif
 
 namespace pm {
@@ -143,10 +151,10 @@ PM_HD void sincos_d(double x, double& s, double& c) {
     if (q & 2) s = -s;
     if ((q + 1) & 2) c = -c;
 }
-PM_HD float sinf(float x) { if (x == 0.f) return x; double s, c; sincos_d((double)x, s, c); return (float)s; }
-PM_HD float cosf(float x) { double s, c; sincos_d((double)x, s, c); return (float)c; }
-PM_HD void sincosf(float x, float* s, float* c) { double sd, cd; sincos_d((double)x, sd, cd); *s = x == 0.f ? x : (float)sd; *c = (float)cd; }
-PM_HD float tanf(float x) { if (x == 0.f) return x; double s, c; sincos_d((double)x, s, c); return (float)(s / c); }
+PM_API float sinf(float x) { if (x == 0.f) return x; double s, c; sincos_d((double)x, s, c); return (float)s; }
+PM_API float cosf(float x) { double s, c; sincos_d((double)x, s, c); return (float)c; }
+PM_API void sincosf(float x, float* s, float* c) { double sd, cd; sincos_d((double)x, sd, cd); *s = x == 0.f ? x : (float)sd; *c = (float)cd; }
+PM_API float tanf(float x) { if (x == 0.f) return x; double s, c; sincos_d((double)x, s, c); return (float)(s / c); }
 
 // ---- exp / log in binary64
 PM_HD double exp_d(double x) {          // |x| < ~700 ; relative error ~2e-16
@@ -194,20 +202,20 @@ PM_HD double log_d(double x) {          // x > 0 finite normal (every positive f
     const double ed = (double)e;
     return fma(ed, kLn2Hi, fma(ed, kLn2Lo, l));
 }
-PM_HD float expf(float x) {
+PM_API float expf(float x) {
     if (x != x) return x;
     if (x > 88.8f) return (float)pm_inf();
     if (x < -104.f) return 0.f;
     return (float)exp_d((double)x);
 }
-PM_HD float logf(float x) {
+PM_API float logf(float x) {
     if (x != x || x < 0.f) return (float)pm_nan();
     if (x == 0.f) return -(float)pm_inf();
     if (!(x < (float)pm_inf())) return x;
     if (x == 1.f) return 0.f;
     return (float)log_d((double)x);
 }
-PM_HD float powf(float x, float y) {
+PM_API float powf(float x, float y) {
     if (y == 0.f || x == 1.f) return 1.f;
     if (x != x || y != y) return (float)pm_nan();
     const bool yint = floorf(y) == y, yodd = yint && fabsf(y) < 16777216.f && (((long long)y) & 1ll);
@@ -259,16 +267,16 @@ PM_HD double atan2_d(double y, double x) {
     if (nx) a = (kPiD - a) + kPiLoD;
     return ny ? -a : a;
 }
-PM_HD float atan2f(float y, float x) {
+PM_API float atan2f(float y, float x) {
     if (y == 0.f && !(f2u(x) >> 31) && x == x) return y;            // +-0 for x >= +0
     return (float)atan2_d((double)y, (double)x);
 }
-PM_HD float acosf(float x) {
+PM_API float acosf(float x) {
     if (!(fabsf(x) <= 1.f)) return (float)pm_nan();
     const double xd = (double)x;
     return (float)atan2_d(sqrt((1.0 - xd) * (1.0 + xd)), xd);
 }
-PM_HD float hypotf(float a, float b) {
+PM_API float hypotf(float a, float b) {
     if (!(fabsf(a) < (float)pm_inf()) || !(fabsf(b) < (float)pm_inf())) return (a != a && fabsf(b) < (float)pm_inf()) || (b != b && fabsf(a) < (float)pm_inf()) || (a != a && b != b) ? (float)pm_nan() : (float)pm_inf();
     const double ad = (double)a, bd = (double)b;
     return (float)sqrt(fma(ad, ad, bd * bd));

@@ -914,8 +914,7 @@ struct Pool {
     void free_buffers() { for (void* p : allocs) wt_free(p); allocs.clear(); size = 0; }
     void destroy() {
         free_buffers();
-        if (hctr) cudaFreeHost(hctr);
-        if (hring[0]) cudaFreeHost(hring[0]);      // (one pinned block holds the ring)
+        if (hring[0]) cudaFreeHost(hring[0]);      // (one pinned block holds the ring and hctr)
         for (cudaEvent_t e : ev_ring) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
         for (cudaEvent_t e : { ev_iter, ev_shade, ev_samp, ev_done }) if (e) cudaEventDestroy(e);
@@ -1118,12 +1117,12 @@ static int ensure_pool(wtgpu_scene* s, uint32_t kind, uint32_t pool, uint32_t pa
             get(&q.bd_fsd_list, 12ull * W2); get(&q.bd_fsd_out, 32ull * W2);
         }
         if (rc == WTGPU_OK && !q.hctr) {
-            if (cudaMallocHost(&q.hctr, sizeof(DevCounters)) != cudaSuccess || cudaStreamCreateWithFlags(&q.st, cudaStreamNonBlocking) != cudaSuccess ||
+            if (cudaMallocHost(&q.hring[0], sizeof(DevCounters) * (Pool::kPipeDepth + 1)) != cudaSuccess || cudaStreamCreateWithFlags(&q.st, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaStreamCreateWithFlags(&q.st_fsd, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_iter, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&q.ev_shade, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&q.ev_samp, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming) != cudaSuccess) { g_err = "creating the sub-pool's streams / events failed"; rc = WTGPU_E_CUDA; }
             if (rc == WTGPU_OK) {
-                if (cudaMallocHost(&q.hring[0], sizeof(DevCounters) * Pool::kPipeDepth) != cudaSuccess) { g_err = "creating the sub-pool's counter ring failed"; rc = WTGPU_E_CUDA; q.hring[0] = nullptr; }
+                q.hctr = q.hring[0] + Pool::kPipeDepth;
                 for (int r = 0; r < Pool::kPipeDepth && rc == WTGPU_OK; ++r) {
                     q.hring[r] = q.hring[0] + r;
                     if (cudaEventCreateWithFlags(&q.ev_ring[r], cudaEventDisableTiming) != cudaSuccess) { g_err = "creating the sub-pool's counter ring failed"; rc = WTGPU_E_CUDA; }
