@@ -49,7 +49,7 @@ template <int TEAM> struct alignas(16) TShared {
     int32_t qptr[QCAP]; float qtmin[QCAP]; uint16_t qinfo[QCAP];
     int32_t rptr[RCAP]; float rtmin[RCAP]; uint16_t rinfo[RCAP]; uint16_t rleaf[NL];       // R in pop order; rleaf: R index of batch leaf li
     Cone env; Frame frame; Range crange; V3 inv; int nx, ny, nz;       // the query, published by the control warp for the batch phases
-    int cmd, go, nsel, rn, nl, nsurv, big;
+    int cmd, go, nsel, rn, nl, nsurv, big, ntri;
     unsigned keep[QCAP / 32 + 1];                           // q_revert: keep flags per 32-entry chunk
     int sel[NW];                                            // Q index of the nodes being expanded this round
     int wn[NW]; float wc_tmin[NW][8]; int32_t wc_ptr[NW][8];
@@ -57,7 +57,7 @@ template <int TEAM> struct alignas(16) TShared {
     alignas(16) float nstage[NW][64];                       // per expanding group: staging slot of its node record (gtrav.cuh g_stage_node)
 #endif
     uint32_t bt0[NL], bcnt[NL];                             // batch leaves: triangle range
-    float dres[NL * 8]; uint16_t surv[NL * 8];
+    float dres[NL * 8]; uint16_t surv[NL * 8]; uint16_t tslot[NL * 8];      // per triangle slot (leaf * 8 + k): test result; the slots that survived T1; the slots that hold a triangle
     uint32_t lmask[NL], larg[NL]; float ldmin[NL];          // per batch leaf: accepted slots, first closest slot, its distance
 };
 template <int TEAM> WT_D void t_sync() { if (TEAM == 32) __syncwarp(); else __syncthreads(); }
@@ -214,7 +214,7 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                 break;
             }
             if (lane == 0u) {
-                sh.cmd = cmd; sh.nsurv = 0; sh.rn = 0; sh.nl = 0; sh.big = 0x7fffffff;
+                sh.cmd = cmd; sh.nsurv = 0; sh.ntri = 0; sh.rn = 0; sh.nl = 0; sh.big = 0x7fffffff;
                 if (cmd == TC_BATCH) { sh.env = t.env; sh.frame = t.frame; sh.crange = t.crange; sh.inv = t.inv; sh.nx = t.nx ? 1 : 0; sh.ny = t.ny ? 1 : 0; sh.nz = t.nz ? 1 : 0; }
             }
         }
@@ -340,9 +340,14 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
             const wtgpu_leaf lf = sc.leaves[-sh.rptr[sh.rleaf[li]] - 1];
             sh.bt0[li] = lf.tris_ptr; sh.bcnt[li] = lf.count;
             if (lf.count > 8u) atomicMin(&sh.big, li);
+            else {      // the leaf's occupied slots join the batch's triangle list (any order: results are stored per slot)
+                const int at = atomicAdd(&sh.ntri, (int)lf.count);
+                for (uint32_t k = 0; k < lf.count; ++k) sh.tslot[at + (int)k] = (uint16_t)(li * 8 + (int)k);
+            }
         }
         t_sync<TEAM>();
-        if (rn == 0 || sh.big == 0) {
+        const int big = sh.big;     // (read by every thread before anything below can lead the control warp back to the top of the loop, where it is reset)
+        if (rn == 0 || big == 0) {
             // nothing could be moved to R: the top of Q is a node that cannot be expanded in place (the sequential stack is nearly full, or Q
             // is) -- or the first leaf holds more than eight triangles.  The sequential algorithm's next step, by the control warp, on the real stack.
             if (ctl) {
@@ -384,28 +389,32 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
                 }
                 q_from_stack(sh, t.s, lane);
             }
+            t_sync<TEAM>();         // (no thread is still deciding on `big` when the control warp starts the next step)
             continue;
         }
-        if (sh.big < nl) {          // a leaf of more than eight triangles further down the run: the batch ends before it
+        if (big < nl) {             // a leaf of more than eight triangles further down the run: the batch ends before it
             if (ctl) {
-                const int cut = (int)sh.rleaf[sh.big];
+                const int cut = (int)sh.rleaf[big];
                 for (int e = rn - 1 - (int)lane; e >= cut; e -= 32) { const int at = t.s + (rn - 1 - e); sh.qptr[at] = sh.rptr[e]; sh.qtmin[at] = sh.rtmin[e]; sh.qinfo[at] = sh.rinfo[e]; }
                 t.s += rn - cut;
                 __syncwarp();
             }
-            nl = sh.big; rn = (int)sh.rleaf[sh.big];
+            nl = big; rn = (int)sh.rleaf[big];
         }
 
         // ---- T1: the cheap rejections for every triangle of the batch; survivors compacted
         {
-            const int nslots = nl * 8;
-            for (int base = 0; base < nslots; base += TEAM) {
-                const int j = base + (int)tid;
-                bool maybe = false;
-                if (j < nslots) {
-                    const int li = j >> 3; const uint32_t k = (uint32_t)j & 7u;
-                    if (k < sh.bcnt[li]) { const Tri3 tr = load_tri(sc, sh.bt0[li] + k); maybe = cone_tri_maybe(env, frame, tr.a, tr.b, tr.c, cr); }
-                    sh.dres[j] = WT_INF;
+            const int ntri = sh.ntri;
+            for (int base = 0; base < ntri; base += TEAM) {
+                const int tq = base + (int)tid;
+                bool maybe = false; int j = 0;
+                if (tq < ntri) {
+                    j = (int)sh.tslot[tq];
+                    const int li = j >> 3;
+                    if (li < nl) {      // (a batch cut at a leaf of more than eight triangles: the leaves behind it wait)
+                        const Tri3 tr = load_tri(sc, sh.bt0[li] + ((uint32_t)j & 7u)); maybe = cone_tri_maybe(env, frame, tr.a, tr.b, tr.c, cr);
+                        sh.dres[j] = WT_INF;
+                    }
                 }
                 const unsigned m = __ballot_sync(FULL, maybe);
                 if (m) {
@@ -431,7 +440,7 @@ WT_D void t_traverse_all(const DScene& sc, int n_items, const TravSave* saves, i
         for (int li = (int)tid; li < nl; li += TEAM) {
             uint32_t m = 0u, arg = 0u; float dm = WT_INF;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const float d = sh.dres[li * 8 + k]; if (d < WT_INF && !(d > cr.mx)) { m |= 1u << k; if (d < dm) { dm = d; arg = (uint32_t)k; } } }
+            for (int k = 0; k < 8; ++k) { const float d = k < (int)sh.bcnt[li] ? sh.dres[li * 8 + k] : WT_INF; if (d < WT_INF && !(d > cr.mx)) { m |= 1u << k; if (d < dm) { dm = d; arg = (uint32_t)k; } } }
             sh.lmask[li] = m; sh.ldmin[li] = dm; sh.larg[li] = arg;
         }
         t_sync<TEAM>();
