@@ -491,3 +491,25 @@ extern "C" void oracle_debug_cone_hist(int on, uint64_t out[96]) {
     if (out) { for (int i = 0; i < 94; ++i) out[i] = ot::g_cone_hist[i].load(); out[94] = ot::g_cone_late[0].load(); out[95] = ot::g_cone_late[1].load(); }
     if (on >= 0) { ot::g_cone_hist_on = on; if (on) { for (int i = 0; i < 96; ++i) ot::g_cone_hist[i] = 0; ot::g_cone_late[0] = ot::g_cone_late[1] = 0; } }
 }
+
+// ---- frame_t (ot_math.h; include/wt/math/frame.hpp) for the pin against the reference's own header (oracle/ref_frame.cpp)
+static void frame_put(const ot::frame_t& f, float* o) { o[0] = f.t.x; o[1] = f.t.y; o[2] = f.t.z; o[3] = f.b.x; o[4] = f.b.y; o[5] = f.b.z; o[6] = f.n.x; o[7] = f.n.y; o[8] = f.n.z; }
+extern "C" void oracle_frame_orthogonal(uint32_t n, const float* nrm, float* out) { for (uint32_t i = 0; i < n; ++i) frame_put(ot::frame_t::build_orthogonal_frame({ nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2] }), out + 9 * i); }
+extern "C" void oracle_frame_shading(uint32_t n, const float* nrm, const float* dpdu, float* out) {
+    for (uint32_t i = 0; i < n; ++i) frame_put(ot::frame_t::build_shading_frame({ nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2] }, { dpdu[3 * i], dpdu[3 * i + 1], dpdu[3 * i + 2] }), out + 9 * i);
+}
+extern "C" void oracle_frame_xform(uint32_t n, const float* fr, const float* v, float* out) {      // same 21 values per item as ref_frame_xform
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* f = fr + 9 * i; const float* p = v + 3 * i; float* o = out + 21 * i;
+        const ot::frame_t F{ { f[0], f[1], f[2] }, { f[3], f[4], f[5] }, { f[6], f[7], f[8] } };
+        const ot::v3 a = F.to_local(ot::v3{ p[0], p[1], p[2] }), b = F.to_world(ot::v3{ p[0], p[1], p[2] });
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = b.x; o[4] = b.y; o[5] = b.z; o[6] = a.x; o[7] = a.y; o[8] = a.z; o[9] = b.x; o[10] = b.y; o[11] = b.z;
+        const ot::v2 e = F.to_local2(ot::v2{ p[0], p[1] }); o[12] = e.x; o[13] = e.y;
+        const ot::v3 g = F.to_world(ot::v2{ p[0], p[1] }); o[14] = g.x; o[15] = g.y; o[16] = g.z;
+        o[17] = a.x; o[18] = a.y; o[19] = a.z;
+        o[20] = F.handness();
+    }
+}
+extern "C" void oracle_rotation2(uint32_t n, const float* from, const float* to, float* out) {      // ot_math.h rotation_matrix (math/rotation.hpp:66-77), column-major like ref_rotation2
+    for (uint32_t i = 0; i < n; ++i) { const ot::mat2 R = ot::rotation_matrix(ot::v2{ from[2 * i], from[2 * i + 1] }, ot::v2{ to[2 * i], to[2 * i + 1] }); out[4 * i] = R.m[0][0]; out[4 * i + 1] = R.m[0][1]; out[4 * i + 2] = R.m[1][0]; out[4 * i + 3] = R.m[1][1]; }
+}

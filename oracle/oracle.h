@@ -56,6 +56,10 @@ void oracle_gaussian_pdf(float sx, float sy, uint32_t n, const float* pts, float
 void oracle_clip_triangles(uint32_t n, const float* tri, const float* zr, int* ntris, float* polygon, float* pieces);
 void oracle_gaussian_integrate_triangles(float sx, float sy, uint32_t n, const float* tri, float* out);
 void oracle_debug_cone_hist(int on, uint64_t out[96]);
+void oracle_frame_orthogonal(uint32_t n, const float* nrm, float* out);
+void oracle_frame_shading(uint32_t n, const float* nrm, const float* dpdu, float* out);
+void oracle_frame_xform(uint32_t n, const float* fr, const float* v, float* out);
+void oracle_rotation2(uint32_t n, const float* from, const float* to, float* out);
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,8 @@ struct vec3_t {
     f_t x{}, y{}, z{};
     constexpr vec3_t() = default;
     constexpr vec3_t(f_t x_, f_t y_, f_t z_) : x(x_), y(y_), z(z_) {}
+    constexpr f_t& operator[](std::size_t i) { return i == 0 ? x : i == 1 ? y : z; }
+    constexpr const f_t& operator[](std::size_t i) const { return i == 0 ? x : i == 1 ? y : z; }
 };
 constexpr vec3_t operator+(vec3_t a, vec3_t b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
 constexpr vec3_t operator-(vec3_t a, vec3_t b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
@@ -81,7 +83,13 @@ template <int N, typename T> using vec = vec2_t;
 template <typename T> using vec2 = vec2_t;
 template <typename T> using mat2 = mat2_t;
 template <typename T> using limits = std::numeric_limits<T>;
+#ifndef WT_SHIM_DISTINCT_PQ
 using pqvec2_t = vec2_t;
+#else
+// (ref_frame.cpp) math/frame.hpp overloads to_local / to_world on vectors of lengths vs plain vectors, so the two must be distinct types here too: a
+// pq vector is three numbers in metres; the arithmetic on it is the plain vectors' (mp-units adds no operation, only the unit)
+struct pqvec2_t { f_t x{}, y{}; constexpr pqvec2_t() = default; constexpr pqvec2_t(f_t x_, f_t y_) : x(x_), y(y_) {} };
+#endif
 using length_t = f_t;           // metres
 using angle_t = f_t;            // radians
 // mp-units semantics the pinned UTD code relies on: a wavenumber is held in 1/mm and lengths in m, so the dimensionless number k * l taken
@@ -92,7 +100,28 @@ constexpr wavenumber_length_t operator*(wavenumber_t k, length_t l) { return { k
 template <typename T> concept Angle = std::is_floating_point_v<T>;
 template <typename T> concept Wavenumber = std::is_same_v<T, wavenumber_t>;
 namespace u { constexpr f_t to_num(f_t v) { return v; } constexpr f_t to_num(wavenumber_length_t v) { return v.mm_per_m_scaled * f_t(1000); } }
+#ifndef WT_SHIM_DISTINCT_PQ
 using pqvec3_t = vec3_t;        // mp-units' vector of lengths: plain floats here
+#else
+struct pqvec3_t {
+    f_t x{}, y{}, z{};
+    constexpr pqvec3_t() = default;
+    constexpr pqvec3_t(f_t x_, f_t y_, f_t z_) : x(x_), y(y_), z(z_) {}
+    constexpr pqvec3_t(const vec3_t& v) : x(v.x), y(v.y), z(v.z) {}         // (a plain vector times a length, e.g. t * v.x with v.x in metres)
+};
+constexpr pqvec3_t operator-(const pqvec3_t& a, const vec3_t& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+struct dir2_t_tag {};
+#endif
+struct mat3_t {                          // glm::mat3, column-major: mat3(x0,y0,z0, x1,...) takes COLUMNS; m[i] is column i
+    vec3_t c[3];
+    constexpr mat3_t() : c{ { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } } {}
+    constexpr mat3_t(f_t x0, f_t y0, f_t z0, f_t x1, f_t y1, f_t z1, f_t x2, f_t y2, f_t z2) : c{ { x0, y0, z0 }, { x1, y1, z1 }, { x2, y2, z2 } } {}
+    constexpr vec3_t& operator[](std::size_t i) { return c[i]; }
+    constexpr const vec3_t& operator[](std::size_t i) const { return c[i]; }
+};
+constexpr mat3_t operator*(const mat3_t& a, f_t s) { mat3_t r; for (int i = 0; i < 3; ++i) r.c[i] = vec3_t{ a.c[i].x * s, a.c[i].y * s, a.c[i].z * s }; return r; }
+constexpr mat3_t operator+(const mat3_t& a, const mat3_t& b) { mat3_t r; for (int i = 0; i < 3; ++i) r.c[i] = vec3_t{ a.c[i].x + b.c[i].x, a.c[i].y + b.c[i].y, a.c[i].z + b.c[i].z }; return r; }
+constexpr vec3_t operator*(const mat3_t& m, const vec3_t& v) { return { m.c[0].x * v.x + m.c[1].x * v.y + m.c[2].x * v.z, m.c[0].y * v.x + m.c[1].y * v.y + m.c[2].y * v.z, m.c[0].z * v.x + m.c[1].z * v.y + m.c[2].z * v.z }; }
 // unit vector (include/wt/math/unit_vector/unit_vector.hpp): a vec3 with explicit construction from one
 struct dir3_t : vec3_t {
     constexpr dir3_t() = default;
@@ -129,6 +158,9 @@ template <typename T> constexpr T max(T a, T b, T c) noexcept { return std::max(
 inline bool isfinite(f_t v) noexcept { return std::isfinite(v); }
 inline f_t pow(f_t b, f_t e) noexcept { return std::pow(b, e); }
 inline f_t determinant(const mat2_t& m) noexcept { return m.c[0].x * m.c[1].y - m.c[1].x * m.c[0].y; }          // glm::determinant
+inline mat3_t outer(const vec3_t& c, const vec3_t& r) noexcept { mat3_t m; for (int i = 0; i < 3; ++i) m.c[i] = vec3_t{ c.x * r[i], c.y * r[i], c.z * r[i] }; return m; }     // glm::outerProduct
+inline mat3_t transpose(const mat3_t& a) noexcept { return mat3_t{ a.c[0].x, a.c[1].x, a.c[2].x, a.c[0].y, a.c[1].y, a.c[2].y, a.c[0].z, a.c[1].z, a.c[2].z }; }
+inline f_t determinant(const mat3_t& m) noexcept { return m.c[0].x * (m.c[1].y * m.c[2].z - m.c[2].y * m.c[1].z) - m.c[1].x * (m.c[0].y * m.c[2].z - m.c[2].y * m.c[0].z) + m.c[2].x * (m.c[0].y * m.c[1].z - m.c[1].y * m.c[0].z); }   // (only inside a debug assertion)
 inline mat2_t transpose(const mat2_t& m) noexcept { return mat2_t{ m.c[0].x, m.c[1].x, m.c[0].y, m.c[1].y }; }
 inline vec2_t iszero(vec2_t v) noexcept { return { f_t(v.x == 0), f_t(v.y == 0) }; }
 inline bool all(vec2_t v) noexcept { return v.x != 0 && v.y != 0; }
@@ -177,5 +209,14 @@ inline vec3_t cross(const vec3_t& x, const vec3_t& y) noexcept {                
     return { eft::diff_prod(x.y, y.z, x.z, y.y), eft::diff_prod(x.z, y.x, x.x, y.z), eft::diff_prod(x.x, y.y, x.y, y.x) };
 }
 inline dir3_t normalize(const vec3_t& v) noexcept { const f_t l = std::sqrt(dot(v, v)); return dir3_t{ v.x / l, v.y / l, v.z / l }; }
+#ifdef WT_SHIM_DISTINCT_PQ
+inline f_t dot(const pqvec2_t& a, const vec2_t& b) noexcept { return std::fma(a.y, b.y, a.x * b.x); }
+inline f_t dot(const pqvec3_t& a, const vec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
+inline f_t dot(const vec3_t& a, const pqvec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
+inline dir3_t normalize(const pqvec3_t& v) noexcept { const f_t l = std::sqrt(std::fma(v.z, v.z, std::fma(v.y, v.y, v.x * v.x))); return dir3_t{ v.x / l, v.y / l, v.z / l }; }
+struct bvec3_t { bool x, y, z; };
+inline bvec3_t iszero(const pqvec3_t& v) noexcept { return { v.x == 0, v.y == 0, v.z == 0 }; }
+inline bool all(const bvec3_t& b) noexcept { return b.x && b.y && b.z; }
+#endif
 }
 }

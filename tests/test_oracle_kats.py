@@ -695,3 +695,46 @@ def test_spectrum_distributions_equal_the_reference_code():
         R.ref_gaussian1d_integrate(sigma, n, P(mn), P(mx), P(a)); L.oracle_gaussian1d_integrate(sigma, n, P(mn), P(mx), P(b))
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), sigma
     assert abs(a[1] - 1.0) < 1e-6                    # sigma = 0: all the mass in the pixel that holds the sample
+
+
+REF_FRAME = os.path.join(os.path.dirname(REF_FSD_LUT), "libref_frame.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FRAME), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_frame_equals_the_reference_code():
+    """ot_math.h's frame_t (every beam, shading and cone frame of the path: SURVEY.md 8 rows a10, a16) against the REFERENCE'S OWN
+    include/wt/math/frame.hpp compiled unmodified (oracle/ref_frame.cpp; the shim gives vectors of lengths a type of their own, because
+    frame.hpp overloads on them): build_orthogonal_frame on 200 000 unit normals incl. the axes and the |n.x| == |n.y| tie, build_shading_frame
+    on 200 000 (n, dpdu) incl. dpdu == 0, dpdu nearly parallel to n and eight decades of |dpdu|, to_local / to_world for plain vectors, length
+    vectors, 2-vectors and unit vectors, handness -- all bit-identical."""
+    R = C.CDLL(REF_FRAME); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(23); n = 200000
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[:6] = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1]], np.float64)
+    t = rng.uniform(-1, 1, 1000); nrm[6:1006] = np.stack([t, t, np.sqrt(np.maximum(0, 1 - 2 * t * t))], 1)       # |n.x| == |n.y|
+    nrm[1006:2006] = np.stack([t, -t, np.sqrt(np.maximum(0, 1 - 2 * t * t))], 1)
+    nrm = np.ascontiguousarray(nrm, np.float32)
+    a = np.zeros((n, 9), np.float32); b = a.copy()
+    for lib, fn, out in ((R, "ref_frame_orthogonal", a), (L, "oracle_frame_orthogonal", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, nrm.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.allclose((a[2006:, 0:3] * a[2006:, 6:9]).sum(1), 0, atol=1e-6) and np.allclose(np.linalg.norm(a[2006:, 3:6], axis=1), 1, atol=1e-5)
+    dpdu = (rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-4, 4, size=(n, 1)))
+    dpdu[:2000] = 0
+    dpdu[2000:12000] = nrm[2000:12000] * rng.uniform(.1, 10, size=(10000, 1)) + rng.normal(size=(10000, 3)) * 1e-4       # nearly parallel to n
+    dpdu = np.ascontiguousarray(dpdu, np.float32)
+    for lib, fn, out in ((R, "ref_frame_shading", a), (L, "oracle_frame_shading", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp, fp]; f.restype = None; f(n, nrm.ctypes.data_as(fp), dpdu.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    fr = np.ascontiguousarray(a); v = np.ascontiguousarray(rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-3, 3, size=(n, 1)), np.float32)
+    x = np.zeros((n, 21), np.float32); y = x.copy()
+    for lib, fn, out in ((R, "ref_frame_xform", x), (L, "oracle_frame_xform", y)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp, fp]; f.restype = None; f(n, fr.ctypes.data_as(fp), v.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    # util::rotation_matrix(dir2_t, dir2_t) of math/rotation.hpp (the same TU): the rotation between the transverse frames of two beams
+    ang = rng.uniform(0, 2 * np.pi, size=(n, 2)); ang[:1000, 1] = ang[:1000, 0]; ang[1000:2000, 1] = ang[1000:2000, 0] + np.pi
+    f2 = np.ascontiguousarray(np.stack([np.cos(ang[:, 0]), np.sin(ang[:, 0])], 1), np.float32); t2 = np.ascontiguousarray(np.stack([np.cos(ang[:, 1]), np.sin(ang[:, 1])], 1), np.float32)
+    p = np.zeros((n, 4), np.float32); q = p.copy()
+    for lib, fn, out in ((R, "ref_rotation2", p), (L, "oracle_rotation2", q)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp, fp]; f.restype = None; f(n, f2.ctypes.data_as(fp), t2.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(p.view(np.uint32), q.view(np.uint32)) and np.allclose(p[:, 0] ** 2 + p[:, 1] ** 2, 1, atol=1e-5)
