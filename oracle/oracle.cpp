@@ -513,3 +513,27 @@ extern "C" void oracle_frame_xform(uint32_t n, const float* fr, const float* v, 
 extern "C" void oracle_rotation2(uint32_t n, const float* from, const float* to, float* out) {      // ot_math.h rotation_matrix (math/rotation.hpp:66-77), column-major like ref_rotation2
     for (uint32_t i = 0; i < n; ++i) { const ot::mat2 R = ot::rotation_matrix(ot::v2{ from[2 * i], from[2 * i + 1] }, ot::v2{ to[2 * i], to[2 * i + 1] }); out[4 * i] = R.m[0][0]; out[4 * i + 1] = R.m[0][1]; out[4 * i + 2] = R.m[1][0]; out[4 * i + 3] = R.m[1][1]; }
 }
+
+// ---- the edge tests of ot_math.h (include/wt/math/intersect/misc.hpp) for the pin against the reference's own header (oracle/ref_misc.cpp); same layouts
+extern "C" void oracle_edge_ellipsoid(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 18 * i;
+        const auto r = ot::intersect_edge_ellipsoid({ a[0], a[1], a[2] }, { a[3], a[4], a[5] }, { a[6], a[7], a[8] }, { a[9], a[10], a[11] }, { a[12], a[13], a[14] }, { a[15], a[16], a[17] });
+        out[2 * i] = r.t1; out[2 * i + 1] = r.t2;
+    }
+}
+extern "C" void oracle_edge_ellipse(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 6 * i; float* o = out + 14 * i;
+        const auto e = ot::intersect_edge_ellipse({ a[0], a[1] }, { a[2], a[3] }, a[4], a[5], false), l = ot::intersect_edge_ellipse({ a[0], a[1] }, { a[2], a[3] }, a[4], a[5], true);
+        o[0] = (float)e.points; o[1] = e.t1; o[2] = e.t2; o[3] = e.u1.x; o[4] = e.u1.y; o[5] = e.u2.x; o[6] = e.u2.y;
+        o[7] = (float)l.points; o[8] = l.t1; o[9] = l.t2; o[10] = l.u1.x; o[11] = l.u1.y; o[12] = l.u2.x; o[13] = l.u2.y;
+    }
+}
+extern "C" void oracle_edge_plane(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 12 * i; float* o = out + 4 * i;
+        const auto r = ot::intersect_edge_plane({ a[0], a[1], a[2] }, { a[3], a[4], a[5] }, { a[6], a[7], a[8] }, { a[9], a[10], a[11] });
+        o[0] = r ? 1.f : 0.f; o[1] = r ? r->x : 0.f; o[2] = r ? r->y : 0.f; o[3] = r ? r->z : 0.f;
+    }
+}

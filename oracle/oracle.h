@@ -60,6 +60,9 @@ void oracle_frame_orthogonal(uint32_t n, const float* nrm, float* out);
 void oracle_frame_shading(uint32_t n, const float* nrm, const float* dpdu, float* out);
 void oracle_frame_xform(uint32_t n, const float* fr, const float* v, float* out);
 void oracle_rotation2(uint32_t n, const float* from, const float* to, float* out);
+void oracle_edge_ellipsoid(uint32_t n, const float* in, float* out);
+void oracle_edge_ellipse(uint32_t n, const float* in, float* out);
+void oracle_edge_plane(uint32_t n, const float* in, float* out);
 #ifdef __cplusplus
 }
 #endif

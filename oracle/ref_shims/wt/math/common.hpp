@@ -89,6 +89,12 @@ using pqvec2_t = vec2_t;
 // (ref_frame.cpp) math/frame.hpp overloads to_local / to_world on vectors of lengths vs plain vectors, so the two must be distinct types here too: a
 // pq vector is three numbers in metres; the arithmetic on it is the plain vectors' (mp-units adds no operation, only the unit)
 struct pqvec2_t { f_t x{}, y{}; constexpr pqvec2_t() = default; constexpr pqvec2_t(f_t x_, f_t y_) : x(x_), y(y_) {} };
+constexpr pqvec2_t operator-(const pqvec2_t& a, const pqvec2_t& b) { return { a.x - b.x, a.y - b.y }; }
+constexpr pqvec2_t operator+(const pqvec2_t& a, const pqvec2_t& b) { return { a.x + b.x, a.y + b.y }; }
+constexpr pqvec2_t operator*(f_t s, const pqvec2_t& a) { return { s * a.x, s * a.y }; }
+constexpr vec2_t operator/(f_t s, const pqvec2_t& a) { return { s / a.x, s / a.y }; }                    // 1 / lengths
+constexpr vec2_t operator*(const pqvec2_t& a, const vec2_t& b) { return { a.x * b.x, a.y * b.y }; }      // lengths x (1 / lengths): numbers
+constexpr pqvec2_t operator*(const vec2_t& a, const pqvec2_t& b) { return { a.x * b.x, a.y * b.y }; }    // numbers x lengths
 #endif
 using length_t = f_t;           // metres
 using angle_t = f_t;            // radians
@@ -99,7 +105,7 @@ struct wavenumber_length_t { f_t mm_per_m_scaled; };
 constexpr wavenumber_length_t operator*(wavenumber_t k, length_t l) { return { k.per_mm * l }; }
 template <typename T> concept Angle = std::is_floating_point_v<T>;
 template <typename T> concept Wavenumber = std::is_same_v<T, wavenumber_t>;
-namespace u { constexpr f_t to_num(f_t v) { return v; } constexpr f_t to_num(wavenumber_length_t v) { return v.mm_per_m_scaled * f_t(1000); } }
+namespace u { constexpr vec2_t to_num(const vec2_t& v) { return v; } constexpr f_t to_num(f_t v) { return v; } constexpr f_t to_num(wavenumber_length_t v) { return v.mm_per_m_scaled * f_t(1000); } }
 #ifndef WT_SHIM_DISTINCT_PQ
 using pqvec3_t = vec3_t;        // mp-units' vector of lengths: plain floats here
 #else
@@ -110,6 +116,11 @@ struct pqvec3_t {
     constexpr pqvec3_t(const vec3_t& v) : x(v.x), y(v.y), z(v.z) {}         // (a plain vector times a length, e.g. t * v.x with v.x in metres)
 };
 constexpr pqvec3_t operator-(const pqvec3_t& a, const vec3_t& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+constexpr pqvec3_t operator-(const pqvec3_t& a, const pqvec3_t& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+constexpr pqvec3_t operator+(const pqvec3_t& a, const pqvec3_t& b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+constexpr pqvec3_t& operator-=(pqvec3_t& a, const pqvec3_t& b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; return a; }
+constexpr pqvec3_t operator*(f_t s, const pqvec3_t& a) { return { s * a.x, s * a.y, s * a.z }; }
+constexpr vec3_t operator/(const pqvec3_t& a, const pqvec3_t& b) { return { a.x / b.x, a.y / b.y, a.z / b.z }; }      // lengths / lengths: numbers
 struct dir2_t_tag {};
 #endif
 struct mat3_t {                          // glm::mat3, column-major: mat3(x0,y0,z0, x1,...) takes COLUMNS; m[i] is column i

@@ -738,3 +738,45 @@ def test_frame_equals_the_reference_code():
     for lib, fn, out in ((R, "ref_rotation2", p), (L, "oracle_rotation2", q)):
         f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp, fp]; f.restype = None; f(n, f2.ctypes.data_as(fp), t2.ctypes.data_as(fp), out.ctypes.data_as(fp))
     assert np.array_equal(p.view(np.uint32), q.view(np.uint32)) and np.allclose(p[:, 0] ** 2 + p[:, 1] ** 2, 1, atol=1e-5)
+
+
+REF_MISC = os.path.join(os.path.dirname(REF_FSD_LUT), "libref_misc.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MISC), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_edge_tests_equal_the_reference_code():
+    """ot_math.h's edge tests (the primitives under the UTD edge clipping against the beam's ellipsoid, the Gaussian-triangle
+    integral's edge / 3-sigma-disc test, clip_triangle_z and the cone-triangle test's near / far cap test) against the REFERENCE'S OWN
+    include/wt/math/intersect/misc.hpp compiled unmodified (oracle/ref_misc.cpp): intersect_edge_ellipsoid (t1, t2), intersect_edge_ellipse and
+    intersect_line_ellipse (point count, both parameters, both points), intersect_edge_plane (found / point) -- bit-identical on 200 000 cases
+    each: edges crossing, touching, inside and outside, degenerate (zero-length) edges, radii over six decades, planes through an end point."""
+    R = C.CDLL(REF_MISC); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(29); n = 200000
+    def both(name, inp, width):
+        a = np.zeros((n, width), np.float32); b = a.copy(); inp = np.ascontiguousarray(inp, np.float32)
+        for lib, fn, out in ((R, "ref_" + name, a), (L, "oracle_" + name, b)):
+            f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        return a, b
+    # edge - ellipsoid: random orthonormal (x, y), axes over four decades, edges around the ellipsoid
+    x = rng.normal(size=(n, 3)); x /= np.linalg.norm(x, axis=1, keepdims=True)
+    y = np.cross(x, rng.normal(size=(n, 3))); y /= np.linalg.norm(y, axis=1, keepdims=True)
+    axes = 10.0 ** rng.uniform(-2, 2, size=(n, 3)); centre = rng.normal(size=(n, 3)) * 3
+    p0 = centre + rng.normal(size=(n, 3)) * axes * rng.uniform(.2, 3, size=(n, 1)); p1 = centre + rng.normal(size=(n, 3)) * axes * rng.uniform(.2, 3, size=(n, 1))
+    p1[:500] = p0[:500]                                         # zero-length edges (a == 0)
+    a, b = both("edge_ellipsoid", np.concatenate([p0, p1, centre, x, y, axes], 1), 2)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and (a[:, 1] > a[:, 0]).sum() > n // 4
+    # edge / line - ellipse
+    r = 10.0 ** rng.uniform(-3, 3, size=(n, 2)); r[:50000, 1] = r[:50000, 0]      # circles (intersect_edge_circle) and ellipses
+    q0 = rng.normal(size=(n, 2)) * r * rng.uniform(.1, 3, size=(n, 1)); q1 = rng.normal(size=(n, 2)) * r * rng.uniform(.1, 3, size=(n, 1))
+    q1[:500] = q0[:500]
+    q0[500:1500] = np.stack([r[500:1500, 0], np.zeros(1000)], 1)                    # an end point on the ellipse
+    a, b = both("edge_ellipse", np.concatenate([q0, q1, r], 1), 14)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert set(np.unique(a[:, 0])) == {0.0, 1.0, 2.0} and (a[:, 7] == 2).sum() > n // 4
+    # edge - plane
+    nr = rng.normal(size=(n, 3)); nr /= np.linalg.norm(nr, axis=1, keepdims=True)
+    e0 = rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-2, 2, size=(n, 1)); e1 = rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-2, 2, size=(n, 1)); pp = rng.normal(size=(n, 3))
+    pp[:2000] = e0[:2000]                                       # the plane through an end point (d0 == 0)
+    e1[2000:3000] = e0[2000:3000] + np.cross(nr[2000:3000], rng.normal(size=(1000, 3)))      # edges parallel to the plane
+    a, b = both("edge_plane", np.concatenate([e0, e1, pp, nr], 1), 4)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and (a[:, 0] == 1).sum() > n // 10
