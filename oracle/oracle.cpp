@@ -537,3 +537,9 @@ extern "C" void oracle_edge_plane(uint32_t n, const float* in, float* out) {
         o[0] = r ? 1.f : 0.f; o[1] = r ? r->x : 0.f; o[2] = r ? r->y : 0.f; o[3] = r ? r->z : 0.f;
     }
 }
+extern "C" void oracle_point_in_triangle3(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) { const float* a = in + 12 * i; out[i] = ot::is_point_in_triangle({ a[0], a[1], a[2] }, { a[3], a[4], a[5] }, { a[6], a[7], a[8] }, { a[9], a[10], a[11] }) ? 1.f : 0.f; }
+}
+extern "C" void oracle_point_in_triangle2(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) { const float* a = in + 8 * i; out[i] = ot::g2d::point_in_triangle2({ a[0], a[1] }, { a[2], a[3] }, { a[4], a[5] }, { a[6], a[7] }) ? 1.f : 0.f; }
+}

@@ -33,6 +33,7 @@ constexpr vec2_t operator*(vec2_t v, f_t s) { return { v.x * s, v.y * s }; }
 constexpr vec2_t operator*(vec2_t a, vec2_t b) { return { a.x * b.x, a.y * b.y }; }
 constexpr vec2_t operator/(f_t s, vec2_t v) { return { s / v.x, s / v.y }; }
 constexpr vec2_t operator/(vec2_t v, f_t s) { return { v.x / s, v.y / s }; }
+constexpr vec2_t operator/(vec2_t a, vec2_t b) { return { a.x / b.x, a.y / b.y }; }
 constexpr vec2_t operator+(vec2_t a, vec2_t b) { return { a.x + b.x, a.y + b.y }; }
 constexpr vec2_t operator-(vec2_t a, vec2_t b) { return { a.x - b.x, a.y - b.y }; }
 constexpr vec2_t operator-(vec2_t a) { return { -a.x, -a.y }; }
@@ -104,6 +105,7 @@ struct wavenumber_t { f_t per_mm; };
 struct wavenumber_length_t { f_t mm_per_m_scaled; };
 constexpr wavenumber_length_t operator*(wavenumber_t k, length_t l) { return { k.per_mm * l }; }
 template <typename T> concept Angle = std::is_floating_point_v<T>;
+template <typename T> concept Length = std::is_floating_point_v<T>;      // a length is a plain f_t here
 template <typename T> concept Wavenumber = std::is_same_v<T, wavenumber_t>;
 namespace u { constexpr vec2_t to_num(const vec2_t& v) { return v; } constexpr f_t to_num(f_t v) { return v; } constexpr f_t to_num(wavenumber_length_t v) { return v.mm_per_m_scaled * f_t(1000); } }
 #ifndef WT_SHIM_DISTINCT_PQ
@@ -142,6 +144,7 @@ struct dir3_t : vec3_t {
 };
 
 namespace m {
+template <typename A, typename B, typename C> auto selectv(const A&, const B&, const C&);      // (named by never-instantiated wide templates)
 template <typename T> constexpr T pow(T base, std::size_t e) noexcept { T r = 1; for (std::size_t i = 0; i < e; ++i) r *= base; return r; }
 using std::ceil; using std::log; using std::abs;
 template <typename T> constexpr T min(T a, T b) noexcept { return std::min(a, b); }

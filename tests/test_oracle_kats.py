@@ -780,3 +780,16 @@ def test_edge_tests_equal_the_reference_code():
     e1[2000:3000] = e0[2000:3000] + np.cross(nr[2000:3000], rng.normal(size=(1000, 3)))      # edges parallel to the plane
     a, b = both("edge_plane", np.concatenate([e0, e1, pp, nr], 1), 4)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and (a[:, 0] == 1).sum() > n // 10
+    # is_point_in_triangle of math/util.hpp (the same TU): 3-D (points in the triangle's plane, as intersect_cone_tri calls it: inside, outside, on edges and
+    # vertices, slivers) and 2-D (the Gaussian-triangle integral's "origin inside" test)
+    A3 = rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-2, 2, size=(n, 1)); B3 = A3 + rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-3, 1, size=(n, 1)); C3 = A3 + rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-3, 1, size=(n, 1))
+    w = rng.uniform(-.3, 1.3, size=(n, 2)); w[:3000] = np.round(w[:3000] * 2) / 2                       # on edges / vertices
+    P3 = A3 + w[:, :1] * (B3 - A3) + w[:, 1:] * (C3 - A3)
+    a = np.zeros((n, 1), np.float32); b = a.copy(); inp = np.ascontiguousarray(np.concatenate([P3, A3, B3, C3], 1), np.float32)
+    for lib, fn, out in ((R, "ref_point_in_triangle3", a), (L, "oracle_point_in_triangle3", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(a, b) and .2 < a.mean() < .8
+    inp = np.ascontiguousarray(np.concatenate([P3[:, :2], A3[:, :2], B3[:, :2], C3[:, :2]], 1), np.float32)
+    for lib, fn, out in ((R, "ref_point_in_triangle2", a), (L, "oracle_point_in_triangle2", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(a, b) and .2 < a.mean() < .8
