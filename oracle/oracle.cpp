@@ -537,6 +537,39 @@ extern "C" void oracle_edge_plane(uint32_t n, const float* in, float* out) {
         o[0] = r ? 1.f : 0.f; o[1] = r ? r->x : 0.f; o[2] = r ? r->y : 0.f; o[3] = r ? r->z : 0.f;
     }
 }
+// the cone stages of intersect_cone_tri, laid out like oracle/ref_cone.cpp
+static ot::elliptic_cone_t kat_cone(const float* c) {
+    return ot::elliptic_cone_t::make_ecc(ot::ray_t{ { c[0], c[1], c[2] }, { c[3], c[4], c[5] } }, { c[6], c[7], c[8] }, c[9], c[10], c[11]);
+}
+extern "C" void oracle_cone_edge(uint32_t n, int in_local, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 20 * i; float* o = out + 10 * i;
+        const auto r = ot::intersect_cone_edge(kat_cone(a), { a[12], a[13], a[14] }, { a[15], a[16], a[17] }, { a[18], a[19] }, in_local != 0);
+        for (int k = 0; k < 10; ++k) o[k] = 0.f;
+        if (!r) continue;
+        o[0] = 1.f; o[1] = r->p0.x; o[2] = r->p0.y; o[3] = r->p0.z;
+        if (r->pts == 2) { o[4] = r->p1.x; o[5] = r->p1.y; o[6] = r->p1.z; }
+        o[7] = r->range.min; o[8] = r->range.max; o[9] = (float)r->pts;
+    }
+}
+extern "C" void oracle_cone_plane(uint32_t n, int in_local, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 18 * i; float* o = out + 9 * i;
+        const auto r = ot::intersect_cone_plane(kat_cone(a), { a[12], a[13], a[14] }, a[15], { a[16], a[17] }, in_local != 0);
+        for (int k = 0; k < 9; ++k) o[k] = 0.f;
+        if (r.range.empty()) continue;
+        o[0] = 1.f; o[1] = r.range.min; o[2] = r.range.max;
+        o[3] = r.near_.x; o[4] = r.near_.y; o[5] = r.near_.z; o[6] = r.far_.x; o[7] = r.far_.y; o[8] = r.far_.z;
+    }
+}
+extern "C" void oracle_cone_basics(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 13 * i; float* o = out + 5 * i;
+        const auto cone = kat_cone(a);
+        const auto ax = cone.axes(a[12]);
+        o[0] = ax.x; o[1] = ax.y; o[2] = cone.z_apex; o[3] = cone.e; o[4] = cone.one_over_e;
+    }
+}
 extern "C" void oracle_point_in_triangle3(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) { const float* a = in + 12 * i; out[i] = ot::is_point_in_triangle({ a[0], a[1], a[2] }, { a[3], a[4], a[5] }, { a[6], a[7], a[8] }, { a[9], a[10], a[11] }) ? 1.f : 0.f; }
 }

@@ -63,6 +63,9 @@ void oracle_rotation2(uint32_t n, const float* from, const float* to, float* out
 void oracle_edge_ellipsoid(uint32_t n, const float* in, float* out);
 void oracle_edge_ellipse(uint32_t n, const float* in, float* out);
 void oracle_edge_plane(uint32_t n, const float* in, float* out);
+void oracle_cone_edge(uint32_t n, int in_local, const float* in, float* out);
+void oracle_cone_plane(uint32_t n, int in_local, const float* in, float* out);
+void oracle_cone_basics(uint32_t n, const float* in, float* out);
 void oracle_point_in_triangle3(uint32_t n, const float* in, float* out);
 void oracle_point_in_triangle2(uint32_t n, const float* in, float* out);
 #ifdef __cplusplus

@@ -1,0 +1,57 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+// The scalar cone tests of the reference's include/wt/math/intersect/cone.hpp -- intersect_cone_edge (cone.hpp:38-128) and intersect_cone_plane
+// (cone.hpp:170-258), the two numerical stages of the cone-triangle test every cone query of the hot path runs per triangle -- together with
+// the reference's own include/wt/math/shapes/elliptic_cone.hpp, shapes/ray.hpp and intersect/ray.hpp, compiled from where they lie
+// -> oracle/_ref/libref_cone.so.  tests/test_oracle_kats.py compares them bit for bit with ot_math.h.
+// The rest of cone.hpp (cone-AABB on 8-wide AVX vectors, the 4-wide intersect_cone_tri) needs the reference's SIMD layer, which does not
+// compile against the shim; so the Makefile's `ref` target writes lines 1-271 of the header as they are (through test_cone_plane, plus the
+// closing brace of the namespace) to the git-ignored oracle/_ref/cone_scalar_part.hpp at build time and this TU includes that.  No reference
+// text is committed.
+#define WT_SHIM_DISTINCT_PQ
+#include <wt/util/assert.hpp>
+#include "_ref/cone_scalar_part.hpp"
+using namespace wt;
+namespace {
+// per cone: o[3] d[3] x[3] tan_alpha eccentricity x0  (the public constructor, elliptic_cone.hpp:64-78)
+inline elliptic_cone_t make_cone(const float* c) {
+    return elliptic_cone_t{ ray_t{ pqvec3_t{ c[0], c[1], c[2] }, dir3_t{ c[3], c[4], c[5] } }, dir3_t{ c[6], c[7], c[8] }, c[9], c[10], length_t(c[11]) };
+}
+template <bool in_local>
+inline void edge_one(const float* a, float* o) {
+    const auto cone = make_cone(a);
+    const auto r = intersect::intersect_cone_edge<in_local>(cone, pqvec3_t{ a[12], a[13], a[14] }, pqvec3_t{ a[15], a[16], a[17] }, pqrange_t<>{ a[18], a[19] });
+    for (int k = 0; k < 10; ++k) o[k] = 0.f;
+    if (!r) return;
+    o[0] = 1.f; o[1] = r->p0.x; o[2] = r->p0.y; o[3] = r->p0.z;
+    if (r->pts == 2) { o[4] = r->p1.x; o[5] = r->p1.y; o[6] = r->p1.z; }
+    o[7] = r->range.min; o[8] = r->range.max; o[9] = (float)r->pts;
+}
+template <bool in_local>
+inline void plane_one(const float* a, float* o) {
+    const auto cone = make_cone(a);
+    const auto r = intersect::intersect_cone_plane<in_local>(cone, dir3_t{ a[12], a[13], a[14] }, length_t(a[15]), pqrange_t<>{ a[16], a[17] });
+    for (int k = 0; k < 9; ++k) o[k] = 0.f;
+    if (r.range.empty()) return;
+    o[0] = 1.f; o[1] = r.range.min; o[2] = r.range.max;
+    o[3] = r.near.x; o[4] = r.near.y; o[5] = r.near.z; o[6] = r.far.x; o[7] = r.far.y; o[8] = r.far.z;
+}
+}
+extern "C" {
+// per item in: cone[12] p0[3] p1[3] range[2]; out: found p0[3] p1[3] (zero unless pts == 2) range[2] pts
+void ref_cone_edge(unsigned n, int in_local, const float* in, float* out) {
+    for (unsigned i = 0; i < n; ++i) { if (in_local) edge_one<true>(in + 20 * i, out + 10 * i); else edge_one<false>(in + 20 * i, out + 10 * i); }
+}
+// per item in: cone[12] n[3] d range[2]; out: found (range not empty) range[2] near[3] far[3]
+void ref_cone_plane(unsigned n, int in_local, const float* in, float* out) {
+    for (unsigned i = 0; i < n; ++i) { if (in_local) plane_one<true>(in + 18 * i, out + 9 * i); else plane_one<false>(in + 18 * i, out + 9 * i); }
+}
+// per item in: cone[12] z; out: axes x y, z_apex, e, one_over_e  (elliptic_cone.hpp: axes(), get_z_apex(), the eccentricity constructor)
+void ref_cone_basics(unsigned n, const float* in, float* out) {
+    for (unsigned i = 0; i < n; ++i) {
+        const float* a = in + 13 * i; float* o = out + 5 * i;
+        const auto cone = make_cone(a);
+        const auto ax = cone.axes(length_t(a[12]));
+        o[0] = ax.x; o[1] = ax.y; o[2] = cone.get_z_apex(); o[3] = cone.get_e(); o[4] = cone.get_one_over_e();
+    }
+}
+}

@@ -71,6 +71,8 @@ struct vec3_t {
     f_t x{}, y{}, z{};
     constexpr vec3_t() = default;
     constexpr vec3_t(f_t x_, f_t y_, f_t z_) : x(x_), y(y_), z(z_) {}
+    constexpr explicit vec3_t(f_t s) : x(s), y(s), z(s) {}
+    constexpr vec3_t(const vec2_t& v, f_t z_) : x(v.x), y(v.y), z(z_) {}
     constexpr f_t& operator[](std::size_t i) { return i == 0 ? x : i == 1 ? y : z; }
     constexpr const f_t& operator[](std::size_t i) const { return i == 0 ? x : i == 1 ? y : z; }
 };
@@ -89,7 +91,15 @@ using pqvec2_t = vec2_t;
 #else
 // (ref_frame.cpp) math/frame.hpp overloads to_local / to_world on vectors of lengths vs plain vectors, so the two must be distinct types here too: a
 // pq vector is three numbers in metres; the arithmetic on it is the plain vectors' (mp-units adds no operation, only the unit)
-struct pqvec2_t { f_t x{}, y{}; constexpr pqvec2_t() = default; constexpr pqvec2_t(f_t x_, f_t y_) : x(x_), y(y_) {} };
+struct pqvec3_t;
+struct pqvec2_t {
+    f_t x{}, y{};
+    constexpr pqvec2_t() = default;
+    constexpr pqvec2_t(f_t x_, f_t y_) : x(x_), y(y_) {}
+    constexpr pqvec2_t(const vec2_t& v) : x(v.x), y(v.y) {}            // (a plain vector times a length)
+    explicit inline pqvec2_t(const pqvec3_t& v);                        // the xy part
+};
+constexpr pqvec2_t operator*(const pqvec2_t& a, f_t s) { return { a.x * s, a.y * s }; }
 constexpr pqvec2_t operator-(const pqvec2_t& a, const pqvec2_t& b) { return { a.x - b.x, a.y - b.y }; }
 constexpr pqvec2_t operator+(const pqvec2_t& a, const pqvec2_t& b) { return { a.x + b.x, a.y + b.y }; }
 constexpr pqvec2_t operator*(f_t s, const pqvec2_t& a) { return { s * a.x, s * a.y }; }
@@ -107,20 +117,34 @@ constexpr wavenumber_length_t operator*(wavenumber_t k, length_t l) { return { k
 template <typename T> concept Angle = std::is_floating_point_v<T>;
 template <typename T> concept Length = std::is_floating_point_v<T>;      // a length is a plain f_t here
 template <typename T> concept Wavenumber = std::is_same_v<T, wavenumber_t>;
-namespace u { constexpr vec2_t to_num(const vec2_t& v) { return v; } constexpr f_t to_num(f_t v) { return v; } constexpr f_t to_num(wavenumber_length_t v) { return v.mm_per_m_scaled * f_t(1000); } }
+namespace u { constexpr f_t to_m(f_t v) { return v; } constexpr vec2_t to_num(const vec2_t& v) { return v; } constexpr f_t to_num(f_t v) { return v; } constexpr f_t to_num(wavenumber_length_t v) { return v.mm_per_m_scaled * f_t(1000); } }
 #ifndef WT_SHIM_DISTINCT_PQ
 using pqvec3_t = vec3_t;        // mp-units' vector of lengths: plain floats here
 #else
 struct pqvec3_t {
     f_t x{}, y{}, z{};
+    static constexpr pqvec3_t infinity() { return { std::numeric_limits<f_t>::infinity(), std::numeric_limits<f_t>::infinity(), std::numeric_limits<f_t>::infinity() }; }
     constexpr pqvec3_t() = default;
     constexpr pqvec3_t(f_t x_, f_t y_, f_t z_) : x(x_), y(y_), z(z_) {}
-    constexpr pqvec3_t(const vec3_t& v) : x(v.x), y(v.y), z(v.z) {}         // (a plain vector times a length, e.g. t * v.x with v.x in metres)
+    constexpr pqvec3_t(const vec3_t& v) : x(v.x), y(v.y), z(v.z) {}
+    constexpr pqvec3_t(const vec2_t& v, f_t z_) : x(v.x), y(v.y), z(z_) {}       // (lengths: a plain 2-vector times a length, and a z)         // (a plain vector times a length, e.g. t * v.x with v.x in metres)
 };
 constexpr pqvec3_t operator-(const pqvec3_t& a, const vec3_t& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
 constexpr pqvec3_t operator-(const pqvec3_t& a, const pqvec3_t& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
 constexpr pqvec3_t operator+(const pqvec3_t& a, const pqvec3_t& b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
 constexpr pqvec3_t& operator-=(pqvec3_t& a, const pqvec3_t& b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; return a; }
+inline pqvec2_t::pqvec2_t(const pqvec3_t& v) : x(v.x), y(v.y) {}
+constexpr pqvec3_t operator*(const pqvec3_t& a, const vec3_t& b) { return { a.x * b.x, a.y * b.y, a.z * b.z }; }
+constexpr pqvec3_t operator-(const pqvec3_t& a) { return { -a.x, -a.y, -a.z }; }
+constexpr pqvec3_t operator+(const pqvec3_t& a) { return a; }
+} namespace glm { struct bvec3_standin { bool x, y, z; }; } namespace wt {
+// boolean vectors and the glm-style select of the scalar ray-AABB entry point (math/intersect/ray.hpp:244-263; parsed, not under pin)
+struct vec3b_t { bool x, y, z; };
+} namespace glm { constexpr wt::vec3b_t equal(const wt::vec3_t& a, const wt::vec3_t& b) { return { a.x == b.x, a.y == b.y, a.z == b.z }; } } namespace wt {
+constexpr vec3b_t operator<(const vec3_t& a, const vec3_t& b) { return { a.x < b.x, a.y < b.y, a.z < b.z }; }
+constexpr bool operator<=(const pqvec3_t& a, const pqvec3_t& b) { return a.x <= b.x && a.y <= b.y && a.z <= b.z; }
+constexpr bool operator>=(const pqvec3_t& a, const pqvec3_t& b) { return a.x >= b.x && a.y >= b.y && a.z >= b.z; }
+constexpr pqvec3_t& operator+=(pqvec3_t& a, const pqvec3_t& b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
 constexpr pqvec3_t operator*(f_t s, const pqvec3_t& a) { return { s * a.x, s * a.y, s * a.z }; }
 constexpr vec3_t operator/(const pqvec3_t& a, const pqvec3_t& b) { return { a.x / b.x, a.y / b.y, a.z / b.z }; }      // lengths / lengths: numbers
 struct dir2_t_tag {};
@@ -143,7 +167,14 @@ struct dir3_t : vec3_t {
     constexpr dir3_t operator-() const { return dir3_t{ -x, -y, -z }; }
 };
 
+// mp-units' `zero`: compares with any quantity; quantities are plain f_t here
+struct zero_t { constexpr operator f_t() const noexcept { return 0; } };
+template <std::size_t W> struct bvec3_w_t;
+inline constexpr zero_t zero{};
+constexpr vec3_t operator/(f_t s, const vec3_t& v) { return { s / v.x, s / v.y, s / v.z }; }
 namespace m {
+inline f_t fma(f_t a, f_t b, f_t c) noexcept { return std::fma(a, b, c); }
+inline bool isnan(f_t v) noexcept { return std::isnan(v); }
 template <typename A, typename B, typename C> auto selectv(const A&, const B&, const C&);      // (named by never-instantiated wide templates)
 template <typename T> constexpr T pow(T base, std::size_t e) noexcept { T r = 1; for (std::size_t i = 0; i < e; ++i) r *= base; return r; }
 using std::ceil; using std::log; using std::abs;
@@ -181,6 +212,18 @@ inline bool all(vec2_t v) noexcept { return v.x != 0 && v.y != 0; }
 namespace eft {     // math/eft/eft.hpp: compensated a*b - c*d (Kahan), as ot_math.h restates it
 inline f_t diff_prod(f_t a, f_t b, f_t c, f_t d) noexcept { const f_t cd = c * d; const f_t r = std::fma(a, b, -cd); return r + std::fma(-c, d, cd); }
 inline f_t sum_prod(f_t a, f_t b, f_t c, f_t d) noexcept { return diff_prod(a, b, -c, d); }          // eft.hpp:153-159
+// eft.hpp:33-51,184-197 (Graillat / Menissier-Morain compensated dot product: two_prod by fma, two_sum, errors summed in order); the pinned
+// intersect_cone_edge calls it on 3-vectors for the `b` coefficient of its quadratic
+template <typename A, typename B> inline f_t dot(const A& v1, const B& v2) noexcept {
+    f_t d = 0, err = 0;
+    const f_t a[3] = { v1.x, v1.y, v1.z }, b[3] = { v2.x, v2.y, v2.z };
+    for (int i = 0; i < 3; ++i) {
+        const f_t prod = a[i] * b[i]; const f_t err1 = std::fma(a[i], b[i], -prod);
+        const f_t sum = d + prod; const f_t e1 = sum - d; const f_t e2 = sum - e1; const f_t err2 = (prod - e1) + (d - e2);
+        d = sum; err = err + err1 + err2;
+    }
+    return d + err;
+}
 }
 inline constexpr f_t inv_sqrt_two = f_t(1. / 1.41421356237309504880168872420969808);                   // math/defs.hpp:57
 inline constexpr f_t sqrt_pi_2 = f_t(1.253314137315500251207882642405522627), inv_sqrt_two_pi = f_t(0.398942280401432677939946059934381868);  // math/defs.hpp
@@ -224,6 +267,14 @@ inline vec3_t cross(const vec3_t& x, const vec3_t& y) noexcept {                
 }
 inline dir3_t normalize(const vec3_t& v) noexcept { const f_t l = std::sqrt(dot(v, v)); return dir3_t{ v.x / l, v.y / l, v.z / l }; }
 #ifdef WT_SHIM_DISTINCT_PQ
+inline f_t dot(const pqvec3_t& a, const pqvec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
+inline pqvec3_t cross(const vec3_t& x, const pqvec3_t& y) noexcept { return { eft::diff_prod(x.y, y.z, x.z, y.y), eft::diff_prod(x.z, y.x, x.x, y.z), eft::diff_prod(x.x, y.y, x.y, y.x) }; }
+inline pqvec3_t cross(const pqvec3_t& x, const pqvec3_t& y) noexcept { return { eft::diff_prod(x.y, y.z, x.z, y.y), eft::diff_prod(x.z, y.x, x.x, y.z), eft::diff_prod(x.x, y.y, x.y, y.x) }; }
+inline pqvec3_t cross(const pqvec3_t& x, const vec3_t& y) noexcept { return { eft::diff_prod(x.y, y.z, x.z, y.y), eft::diff_prod(x.z, y.x, x.x, y.z), eft::diff_prod(x.x, y.y, x.y, y.x) }; }
+inline pqvec3_t mix(const pqvec3_t& a, const pqvec3_t& b, const vec3b_t& s) noexcept { return { s.x ? b.x : a.x, s.y ? b.y : a.y, s.z ? b.z : a.z }; }
+inline pqvec3_t mix(const pqvec3_t& a, const pqvec3_t& b, bool s) noexcept { return s ? b : a; }
+inline f_t max_element(const pqvec3_t& v) noexcept { return std::max(v.x, std::max(v.y, v.z)); }
+inline f_t min_element(const pqvec3_t& v) noexcept { return std::min(v.x, std::min(v.y, v.z)); }
 inline f_t dot(const pqvec2_t& a, const vec2_t& b) noexcept { return std::fma(a.y, b.y, a.x * b.x); }
 inline f_t dot(const pqvec3_t& a, const vec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
 inline f_t dot(const vec3_t& a, const pqvec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }

@@ -793,3 +793,64 @@ def test_edge_tests_equal_the_reference_code():
     for lib, fn, out in ((R, "ref_point_in_triangle2", a), (L, "oracle_point_in_triangle2", b)):
         f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
     assert np.array_equal(a, b) and .2 < a.mean() < .8
+
+
+REF_CONE = os.path.join(os.path.dirname(REF_FSD_LUT), "libref_cone.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CONE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_cone_edge_and_plane_equal_the_reference_code():
+    """ot_math.h's intersect_cone_edge and intersect_cone_plane (the two numerical stages of the cone-triangle test every cone
+    query runs per candidate triangle, and of the cone-AABB test's edge stage) and elliptic_cone_t's constructor / axes() / apex against the
+    REFERENCE'S OWN include/wt/math/intersect/cone.hpp:38-258 and include/wt/math/shapes/elliptic_cone.hpp (oracle/ref_cone.cpp) -- bit-identical,
+    world-space and local-space variants, 200 000 cases each: cones from rays (tan_alpha = x0 = 0) to 45 degrees, eccentricities up to .999,
+    edges crossing / inside / outside / behind the apex / parallel to the axis / degenerate, clip ranges that cut the edge, planes facing and
+    grazing the cone."""
+    R = C.CDLL(REF_CONE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(31); n = 200000
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    x = np.cross(d, rng.normal(size=(n, 3))); x /= np.linalg.norm(x, axis=1, keepdims=True)
+    d = d.astype(np.float32); x = x.astype(np.float32)
+    o = rng.normal(size=(n, 3)) * 2
+    ta = 10.0 ** rng.uniform(-5, 0, size=n); x0 = 10.0 ** rng.uniform(-5, 0, size=n); ecc = rng.uniform(0, .999, size=n)
+    ecc[:40000] = 0                                                                   # circular cones
+    ta[:2000] = 0; x0[:2000] = 0                                                      # rays
+    ta[2000:6000] = 0                                                                 # cylinders (apex at -inf)
+    x0[6000:12000] = 0                                                                # pointed cones (apex at the origin)
+    cone = np.concatenate([o, d, x, ta[:, None], ecc[:, None], x0[:, None]], 1)
+    y = np.cross(d, x)
+    def world(l):
+        return o + l[:, :1] * x + l[:, 1:2] * y + l[:, 2:3] * d
+    def run(name, in_local, inp, width):
+        a = np.zeros((n, width), np.float32); b = a.copy(); inp = np.ascontiguousarray(inp, np.float32)
+        for lib, fn, out in ((R, "ref_" + name, a), (L, "oracle_" + name, b)):
+            f = getattr(lib, fn); f.argtypes = [C.c_uint32, C.c_int, fp, fp]; f.restype = None; f(n, in_local, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        return a, b
+    # edges in the cone's local frame, scaled to the cone's cross-section at their depth
+    z = rng.uniform(-1, 6, size=(n, 2)); rad = (ta[:, None] * np.abs(z) + x0[:, None])
+    l0 = np.concatenate([rng.normal(size=(n, 2)) * rad[:, :1] * rng.uniform(0, 3, size=(n, 1)), z[:, :1]], 1)
+    l1 = np.concatenate([rng.normal(size=(n, 2)) * rad[:, 1:] * rng.uniform(0, 3, size=(n, 1)), z[:, 1:]], 1)
+    l1[12000:13000] = l0[12000:13000]                                                 # zero-length edges
+    l1[13000:15000, :2] = l0[13000:15000, :2]                                         # parallel to the axis
+    l1[15000:17000, 2] = l0[15000:17000, 2]                                           # perpendicular to the axis
+    zr = np.sort(rng.uniform(-.5, 7, size=(n, 2)), axis=1); zr[:60000] = [0, np.inf]; zr[60000:70000, 0] = 0
+    for in_local, (q0, q1) in ((1, (l0, l1)), (0, (world(l0), world(l1)))):
+        a, b = run("cone_edge", in_local, np.concatenate([cone, q0, q1, zr], 1), 10)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert .15 < a[:, 0].mean() < .85 and (a[:, 9] == 2).sum() > n // 20 and (a[:, 9] == 1).sum() > n // 20
+    # planes: normals anywhere, offsets that put the plane in front of / behind / across the cone
+    nr = rng.normal(size=(n, 3)); nr /= np.linalg.norm(nr, axis=1, keepdims=True)
+    nr[20000:24000] = np.array([0, 0, 1.0])                                           # facing the axis (v_denom2 == 0 in local space)
+    nr[24000:28000, 2] = 0; nr[24000:28000] /= np.linalg.norm(nr[24000:28000], axis=1, keepdims=True)      # containing the axis direction
+    dd = rng.normal(size=n) * 3
+    for in_local in (1, 0):
+        nn = nr if in_local else (nr[:, :1] * x + nr[:, 1:2] * y + nr[:, 2:3] * d)
+        a, b = run("cone_plane", in_local, np.concatenate([cone, nn, dd[:, None], zr], 1), 9)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert .15 < a[:, 0].mean() < .95
+    # constructor / axes / apex
+    zz = rng.uniform(-1, 10, size=(n, 1))
+    a = np.zeros((n, 5), np.float32); b = a.copy(); inp = np.ascontiguousarray(np.concatenate([cone, zz], 1), np.float32)
+    for lib, fn, out in ((R, "ref_cone_basics", a), (L, "oracle_cone_basics", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
