@@ -562,6 +562,20 @@ extern "C" void oracle_cone_plane(uint32_t n, int in_local, const float* in, flo
         o[3] = r.near_.x; o[4] = r.near_.y; o[5] = r.near_.z; o[6] = r.far_.x; o[7] = r.far_.y; o[8] = r.far_.z;
     }
 }
+extern "C" void oracle_ray_tri(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 18 * i; float* o = out + 8 * i;
+        const ot::ray_t r{ { a[0], a[1], a[2] }, { a[3], a[4], a[5] } };
+        const ot::v3 A{ a[6], a[7], a[8] }, B{ a[9], a[10], a[11] }, Cc{ a[12], a[13], a[14] };
+        const ot::range_t range{ a[15], a[16] };
+        const auto h = ot::intersect_ray_tri(r, A, B, Cc, range);
+        o[0] = h ? 1.f : 0.f; o[1] = h ? h->dist : 0.f; o[2] = h ? h->bary.x : 0.f; o[3] = h ? h->bary.y : 0.f;
+        o[4] = ot::test_ray_tri(r, A, B, Cc, range) ? 1.f : 0.f;
+        o[5] = ot::test_ray_tri(r, A, B, Cc, range, a[17]) ? 1.f : 0.f;
+        const auto lp = ot::intersect_line_plane(A, B, Cc, r.d);
+        o[6] = lp ? 1.f : 0.f; o[7] = lp ? *lp : 0.f;
+    }
+}
 extern "C" void oracle_cone_basics(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 13 * i; float* o = out + 5 * i;

@@ -45,6 +45,22 @@ void ref_cone_edge(unsigned n, int in_local, const float* in, float* out) {
 void ref_cone_plane(unsigned n, int in_local, const float* in, float* out) {
     for (unsigned i = 0; i < n; ++i) { if (in_local) plane_one<true>(in + 18 * i, out + 9 * i); else plane_one<false>(in + 18 * i, out + 9 * i); }
 }
+// per item in: ro[3] rd[3] a[3] b[3] c[3] range[2] tol; out: found dist bary[2] (scalar intersect_ray_tri, ray.hpp:147-179: the ray degenerate of
+// intersect_cone_tri), test_ray_tri with tol = 0 and with tol (ray.hpp:56-76), then intersect_line_plane(a, b, c, rd) found / d (ray.hpp:30-49)
+void ref_ray_tri(unsigned n, const float* in, float* out) {
+    for (unsigned i = 0; i < n; ++i) {
+        const float* a = in + 18 * i; float* o = out + 8 * i;
+        const ray_t r{ pqvec3_t{ a[0], a[1], a[2] }, dir3_t{ a[3], a[4], a[5] } };
+        const pqvec3_t A{ a[6], a[7], a[8] }, B{ a[9], a[10], a[11] }, Cc{ a[12], a[13], a[14] };
+        const pqrange_t<> range{ a[15], a[16] };
+        const auto h = intersect::intersect_ray_tri(r, A, B, Cc, range);
+        o[0] = h ? 1.f : 0.f; o[1] = h ? (float)h->dist : 0.f; o[2] = h ? h->bary.uv.x : 0.f; o[3] = h ? h->bary.uv.y : 0.f;
+        o[4] = intersect::test_ray_tri(r, A, B, Cc, range) ? 1.f : 0.f;
+        o[5] = intersect::test_ray_tri(r, A, B, Cc, range, a[17]) ? 1.f : 0.f;
+        const auto lp = intersect::intersect_line_plane(A, B, Cc, r.d);
+        o[6] = lp ? 1.f : 0.f; o[7] = lp ? *lp : 0.f;
+    }
+}
 // per item in: cone[12] z; out: axes x y, z_apex, e, one_over_e  (elliptic_cone.hpp: axes(), get_z_apex(), the eccentricity constructor)
 void ref_cone_basics(unsigned n, const float* in, float* out) {
     for (unsigned i = 0; i < n; ++i) {

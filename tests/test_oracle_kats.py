@@ -854,3 +854,32 @@ def test_cone_edge_and_plane_equal_the_reference_code():
     for lib, fn, out in ((R, "ref_cone_basics", a), (L, "oracle_cone_basics", b)):
         f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CONE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_scalar_ray_tests_equal_the_reference_code():
+    """ot_math.h's scalar ray tests against the REFERENCE'S OWN include/wt/math/intersect/ray.hpp (compiled into oracle/_ref/libref_cone.so beneath
+    cone.hpp): intersect_ray_tri (ray.hpp:147-179: found, distance, both barycentrics -- the ray degenerate of intersect_cone_tri), test_ray_tri with
+    and without tolerance (ray.hpp:56-76: the cone test's axis shortcut) and intersect_line_plane (ray.hpp:30-49: the clip planes of
+    intersect_cone_edge) -- bit-identical on 200 000 cases: hits, misses, back faces, rays through edges and vertices, degenerate triangles,
+    rays in the triangle's plane, ranges cutting the hit.  (The 8-wide variants the BVH traversal evaluates per lane stay unpinned: AVX.)"""
+    R = C.CDLL(REF_CONE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(37); n = 200000
+    A = rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-2, 2, size=(n, 1)); B = A + rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-3, 1, size=(n, 1)); Cc = A + rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-3, 1, size=(n, 1))
+    Cc[:500] = B[:500]                                                                 # degenerate triangles (det == 0)
+    w = rng.uniform(-.2, .9, size=(n, 2)); w[500:4000] = np.round(w[500:4000] * 2) / 2   # through edges / vertices
+    P = A + w[:, :1] * (B - A) + w[:, 1:] * (Cc - A)
+    ro = P + rng.normal(size=(n, 3)) * np.linalg.norm(B - A, axis=1, keepdims=True) * rng.uniform(.1, 30, size=(n, 1))
+    rd = P - ro; t = np.linalg.norm(rd, axis=1, keepdims=True); rd /= t
+    rd[4000:6000] *= -1                                                                # pointing away
+    k = slice(6000, 8000); ro[k] = A[k] + 2 * (B[k] - A[k]) - (Cc[k] - A[k]); rd[k] = (Cc[k] - B[k]) / np.linalg.norm(Cc[k] - B[k], axis=1, keepdims=True)   # in the plane
+    zr = np.zeros((n, 2)); zr[:, 1] = np.inf
+    zr[100000:, 0] = (t[100000:, 0] * rng.uniform(0, 2, size=n - 100000)); zr[100000:, 1] = zr[100000:, 0] + t[100000:, 0] * rng.uniform(0, 2, size=n - 100000)
+    tol = 10.0 ** rng.uniform(-6, -1, size=(n, 1))
+    inp = np.ascontiguousarray(np.concatenate([ro, rd, A, B, Cc, zr, tol], 1), np.float32)
+    a = np.zeros((n, 8), np.float32); b = a.copy()
+    for lib, fn, out in ((R, "ref_ray_tri", a), (L, "oracle_ray_tri", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert .15 < a[:, 0].mean() < .7 and (a[:, 5] >= a[:, 4]).all() and (a[:, 5] > a[:, 4]).sum() > 20 and (a[:, 6] == 1).mean() > .9
+    assert np.array_equal(a[:, 0], a[:, 4]) or (a[:, 0] != a[:, 4]).mean() < 1e-3       # the two formulations decide alike but for rounding at the borders
