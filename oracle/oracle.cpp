@@ -562,6 +562,17 @@ extern "C" void oracle_cone_plane(uint32_t n, int in_local, const float* in, flo
         o[3] = r.near_.x; o[4] = r.near_.y; o[5] = r.near_.z; o[6] = r.far_.x; o[7] = r.far_.y; o[8] = r.far_.z;
     }
 }
+extern "C" void oracle_cone_tri(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 26 * i; float* o = out + 6 * i;
+        const auto cone = kat_cone(a);
+        const ot::v3 A{ a[12], a[13], a[14] }, B{ a[15], a[16], a[17] }, Cc{ a[18], a[19], a[20] };
+        const ot::range_t range{ a[24], a[25] };
+        const auto h = ot::intersect_cone_tri(cone, A, B, Cc, { a[21], a[22], a[23] }, range);
+        o[0] = h ? 1.f : 0.f; o[1] = h ? h->dist : 0.f; o[2] = h ? h->p.x : 0.f; o[3] = h ? h->p.y : 0.f; o[4] = h ? h->p.z : 0.f;
+        o[5] = ot::test_cone_tri(cone, A, B, Cc, range) ? 1.f : 0.f;
+    }
+}
 extern "C" void oracle_ray_tri(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 18 * i; float* o = out + 8 * i;

@@ -1,14 +1,17 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.
-// The scalar cone tests of the reference's include/wt/math/intersect/cone.hpp -- intersect_cone_edge (cone.hpp:38-128) and intersect_cone_plane
-// (cone.hpp:170-258), the two numerical stages of the cone-triangle test every cone query of the hot path runs per triangle -- together with
-// the reference's own include/wt/math/shapes/elliptic_cone.hpp, shapes/ray.hpp and intersect/ray.hpp, compiled from where they lie
-// -> oracle/_ref/libref_cone.so.  tests/test_oracle_kats.py compares them bit for bit with ot_math.h.
-// The rest of cone.hpp (cone-AABB on 8-wide AVX vectors, the 4-wide intersect_cone_tri) needs the reference's SIMD layer, which does not
-// compile against the shim; so the Makefile's `ref` target writes lines 1-271 of the header as they are (through test_cone_plane, plus the
-// closing brace of the namespace) to the git-ignored oracle/_ref/cone_scalar_part.hpp at build time and this TU includes that.  No reference
-// text is committed.
+// The cone tests of the reference's include/wt/math/intersect/cone.hpp -- intersect_cone_edge (cone.hpp:38-128), intersect_cone_plane (:170-258) and
+// the cone-triangle drivers test_cone_tri (:479-539) and intersect_cone_tri (:550-626), i.e. what every cone query of the hot path runs per triangle --
+// together with the reference's own include/wt/math/shapes/elliptic_cone.hpp, shapes/ray.hpp, intersect/ray.hpp (scalar entry points), intersect/misc.hpp,
+// math/util.hpp and math/frame.hpp, compiled from where they lie -> oracle/_ref/libref_cone.so.  tests/test_oracle_kats.py compares them bit for bit with
+// ot_math.h.
+// The middle of cone.hpp (:272-475, cone-AABB on 8-wide AVX vectors) needs the reference's SIMD layer, which does not compile against the shim; so the
+// Makefile's `ref` target writes lines 1-271 and 476-end of the header as they are to the git-ignored oracle/_ref/cone_scalar_part.hpp at build time
+// and this TU includes that.  No reference text is committed.  The 4-wide vector the triangle drivers stage the vertices in is the shim's array of lanes
+// (WT_SHIM_WIDE_LANES, ref_shims/wt/math/simd/wide_vector.hpp): one IEEE operation per AVX instruction.
 #define WT_SHIM_DISTINCT_PQ
+#define WT_SHIM_WIDE_LANES
 #include <wt/util/assert.hpp>
+#include "/root/reference/include/wt/math/util.hpp"
 #include "_ref/cone_scalar_part.hpp"
 using namespace wt;
 namespace {
@@ -44,6 +47,18 @@ void ref_cone_edge(unsigned n, int in_local, const float* in, float* out) {
 // per item in: cone[12] n[3] d range[2]; out: found (range not empty) range[2] near[3] far[3]
 void ref_cone_plane(unsigned n, int in_local, const float* in, float* out) {
     for (unsigned i = 0; i < n; ++i) { if (in_local) plane_one<true>(in + 18 * i, out + 9 * i); else plane_one<false>(in + 18 * i, out + 9 * i); }
+}
+// per item in: cone[12] a[3] b[3] c[3] n[3] range[2]; out: found dist p[3] (intersect_cone_tri, cone.hpp:550-626), test_cone_tri (cone.hpp:479-539)
+void ref_cone_tri(unsigned n, const float* in, float* out) {
+    for (unsigned i = 0; i < n; ++i) {
+        const float* a = in + 26 * i; float* o = out + 6 * i;
+        const auto cone = make_cone(a);
+        const pqvec3_t A{ a[12], a[13], a[14] }, B{ a[15], a[16], a[17] }, Cc{ a[18], a[19], a[20] };
+        const pqrange_t<> range{ a[24], a[25] };
+        const auto h = intersect::intersect_cone_tri(cone, A, B, Cc, dir3_t{ a[21], a[22], a[23] }, range);
+        o[0] = h ? 1.f : 0.f; o[1] = h ? (float)h->dist : 0.f; o[2] = h ? h->p.x : 0.f; o[3] = h ? h->p.y : 0.f; o[4] = h ? h->p.z : 0.f;
+        o[5] = intersect::test_cone_tri(cone, A, B, Cc, range) ? 1.f : 0.f;
+    }
 }
 // per item in: ro[3] rd[3] a[3] b[3] c[3] range[2] tol; out: found dist bary[2] (scalar intersect_ray_tri, ray.hpp:147-179: the ray degenerate of
 // intersect_cone_tri), test_ray_tri with tol = 0 and with tol (ray.hpp:56-76), then intersect_line_plane(a, b, c, rd) found / d (ray.hpp:30-49)

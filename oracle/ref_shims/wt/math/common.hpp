@@ -123,6 +123,7 @@ using pqvec3_t = vec3_t;        // mp-units' vector of lengths: plain floats her
 #else
 struct pqvec3_t {
     f_t x{}, y{}, z{};
+    static constexpr pqvec3_t zero() { return {}; }
     static constexpr pqvec3_t infinity() { return { std::numeric_limits<f_t>::infinity(), std::numeric_limits<f_t>::infinity(), std::numeric_limits<f_t>::infinity() }; }
     constexpr pqvec3_t() = default;
     constexpr pqvec3_t(f_t x_, f_t y_, f_t z_) : x(x_), y(y_), z(z_) {}

@@ -4,6 +4,9 @@
 #pragma once
 #include <limits>
 #include <wt/math/common.hpp>
+#ifdef WT_SHIM_WIDE_LANES
+#include <wt/math/simd/wide_vector.hpp>
+#endif
 namespace wt {
 template <typename T = f_t> struct range_t {
     T min, max;
@@ -11,6 +14,9 @@ template <typename T = f_t> struct range_t {
     constexpr bool empty() const noexcept { return !(min <= max); }
     constexpr bool overlaps(const range_t& o) const noexcept { return !(*this & o).empty(); }
     constexpr bool contains(T pt) const noexcept { return (pt < max && min < pt) || pt == min || pt == max; }
+#ifdef WT_SHIM_WIDE_LANES
+    template <std::size_t W> b_w_t<W> contains(const f_w_t<W>& pt) const noexcept { return (f_w_t<W>{ min } <= pt) && (f_w_t<W>{ max } >= pt); }      // range.hpp:89-99, inclusive ends
+#endif
     constexpr range_t operator&(const range_t& o) const noexcept { return { m::max(min, o.min), m::min(max, o.max) }; }
     constexpr bool operator==(const range_t& o) const noexcept { return (min == o.min && max == o.max) || (empty() && o.empty()); }
     constexpr bool operator!=(const range_t& o) const noexcept { return !(*this == o); }

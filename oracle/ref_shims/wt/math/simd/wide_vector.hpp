@@ -5,6 +5,7 @@
 #pragma once
 #include <cstddef>
 #include <wt/math/common.hpp>
+#ifndef WT_SHIM_WIDE_LANES
 namespace wt {
 template <std::size_t W> struct f_w_t;
 template <std::size_t W> struct b_w_t;
@@ -12,3 +13,70 @@ template <std::size_t W> struct length_w_t;
 template <std::size_t W> struct vec3_w_t;
 template <std::size_t W> struct pqvec3_w_t;
 }
+#else
+// WT_SHIM_WIDE_LANES (oracle/ref_cone.cpp only): the wide types as plain arrays of lanes, with exactly the members and operators that
+// frame_t::to_local(pqvec3_w_t) (frame.hpp:194-200), elliptic_cone_t::contains_local(pqvec3_w_t, range) (elliptic_cone.hpp:178-193) and the
+// scalar-entry cone-triangle tests (cone.hpp:479-626) use.  Each lane operation is the single IEEE operation the AVX instruction performs
+// (vsubps, vmulps, vaddps, vfmadd, vcmpps); the mixed-quantity dot product is the multiply + two fused multiply-adds of simd/math.hpp:536-541.
+#include <array>
+#include <cmath>
+namespace wt {
+template <std::size_t W> struct b_w_t {
+    bool v[W];
+    std::array<bool, W> to_bitmask() const noexcept { std::array<bool, W> r; for (std::size_t i = 0; i < W; ++i) r[i] = v[i]; return r; }
+};
+template <std::size_t W> inline b_w_t<W> operator&&(const b_w_t<W>& a, const b_w_t<W>& b) noexcept { b_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] && b.v[i]; return r; }
+template <std::size_t W> struct f_w_t {
+    f_t v[W];
+    f_w_t() = default;
+    explicit f_w_t(f_t s) noexcept { for (std::size_t i = 0; i < W; ++i) v[i] = s; }
+    template <int I> f_t reads() const noexcept { return v[I]; }
+    f_t read(int i) const noexcept { return v[i]; }
+};
+template <std::size_t W> struct length_w_t : f_w_t<W> {
+    length_w_t() = default;
+    explicit length_w_t(f_t s) noexcept : f_w_t<W>(s) {}
+    length_w_t(const f_w_t<W>& b) noexcept : f_w_t<W>(b) {}
+};
+template <std::size_t W> inline f_w_t<W> operator+(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
+template <std::size_t W> inline f_w_t<W> operator-(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] - b.v[i]; return r; }
+template <std::size_t W> inline f_w_t<W> operator*(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] * b.v[i]; return r; }
+template <std::size_t W> inline b_w_t<W> operator<=(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { b_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] <= b.v[i]; return r; }
+template <std::size_t W> inline b_w_t<W> operator>=(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { b_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] >= b.v[i]; return r; }
+template <std::size_t W> inline b_w_t<W> operator<(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { b_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] < b.v[i]; return r; }
+template <std::size_t W> inline b_w_t<W> operator>(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { b_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] > b.v[i]; return r; }
+template <std::size_t W> struct vec3_w_t {
+    f_w_t<W> c[3];
+    explicit vec3_w_t(const vec3_t& s) noexcept : c{ f_w_t<W>(s.x), f_w_t<W>(s.y), f_w_t<W>(s.z) } {}
+    const f_w_t<W>& x() const noexcept { return c[0]; }
+    const f_w_t<W>& y() const noexcept { return c[1]; }
+    const f_w_t<W>& z() const noexcept { return c[2]; }
+};
+template <std::size_t W> struct pqvec3_w_t {
+    length_w_t<W> c[3];
+    pqvec3_w_t() = default;
+    explicit pqvec3_w_t(const pqvec3_t& s) noexcept : c{ length_w_t<W>(s.x), length_w_t<W>(s.y), length_w_t<W>(s.z) } {}
+    pqvec3_w_t(const length_w_t<W>& x, const length_w_t<W>& y, const length_w_t<W>& z) noexcept : c{ x, y, z } {}
+    pqvec3_w_t(const pqvec3_t& p0, const pqvec3_t& p1, const pqvec3_t& p2, const pqvec3_t& p3) noexcept requires (W == 4) {
+        const pqvec3_t* p[4] = { &p0, &p1, &p2, &p3 };
+        for (int i = 0; i < 4; ++i) { c[0].v[i] = p[i]->x; c[1].v[i] = p[i]->y; c[2].v[i] = p[i]->z; }
+    }
+    const length_w_t<W>& x() const noexcept { return c[0]; }
+    const length_w_t<W>& y() const noexcept { return c[1]; }
+    const length_w_t<W>& z() const noexcept { return c[2]; }
+    template <int I> pqvec3_t reads() const noexcept { return pqvec3_t{ c[0].v[I], c[1].v[I], c[2].v[I] }; }
+    pqvec3_t read(int i) const noexcept { return pqvec3_t{ c[0].v[i], c[1].v[i], c[2].v[i] }; }
+};
+template <std::size_t W> inline pqvec3_w_t<W> operator-(const pqvec3_w_t<W>& a, const pqvec3_w_t<W>& b) noexcept { return pqvec3_w_t<W>{ a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2] }; }
+using pqvec3_w4_t = pqvec3_w_t<4>;
+namespace m {
+template <std::size_t W> inline f_w_t<W> fma(const f_w_t<W>& a, const f_w_t<W>& b, const f_w_t<W>& c) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = std::fma(a.v[i], b.v[i], c.v[i]); return r; }
+// simd/math.hpp:536-541 (quantities of different kinds: lengths . pure numbers)
+template <std::size_t W> inline f_w_t<W> dot(const pqvec3_w_t<W>& u, const vec3_w_t<W>& v) noexcept {
+    f_w_t<W> sum = u.x() * v.x();
+    sum = fma<W>(u.y(), v.y(), sum);
+    return fma<W>(u.z(), v.z(), sum);
+}
+}
+}
+#endif

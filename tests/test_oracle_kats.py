@@ -883,3 +883,42 @@ def test_scalar_ray_tests_equal_the_reference_code():
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert .15 < a[:, 0].mean() < .7 and (a[:, 5] >= a[:, 4]).all() and (a[:, 5] > a[:, 4]).sum() > 20 and (a[:, 6] == 1).mean() > .9
     assert np.array_equal(a[:, 0], a[:, 4]) or (a[:, 0] != a[:, 4]).mean() < 1e-3       # the two formulations decide alike but for rounding at the borders
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CONE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_cone_triangle_tests_equal_the_reference_code():
+    """ot_math.h's intersect_cone_tri and test_cone_tri -- THE per-triangle function of every cone query on the path -- against the
+    REFERENCE'S OWN drivers, include/wt/math/intersect/cone.hpp:479-626, compiled from where they lie over the reference's own cone-edge, cone-plane,
+    point-in-triangle, edge-plane, edge-ellipse, ray-triangle, frame_t::to_local and elliptic_cone_t::contains_local (oracle/ref_cone.cpp; the 4-wide
+    vector type the drivers stage the vertices in is the shim's array of lanes, one IEEE operation per AVX instruction).  Found / distance / point
+    and the boolean test, bit-identical on 300 000 cone-triangle pairs: triangles much smaller and much larger than the cone's section, in front,
+    behind, straddling the clip range, containing the axis, touching only by an edge, vertices inside; rays, cylinders, pointed and eccentric cones."""
+    R = C.CDLL(REF_CONE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(41); n = 300000
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    x = np.cross(d, rng.normal(size=(n, 3))); x /= np.linalg.norm(x, axis=1, keepdims=True)
+    d = d.astype(np.float32).astype(np.float64); x = x.astype(np.float32).astype(np.float64); y = np.cross(d, x)
+    o = rng.normal(size=(n, 3)) * 2
+    ta = 10.0 ** rng.uniform(-4, 0, size=n); x0 = 10.0 ** rng.uniform(-4, 0, size=n); ecc = rng.uniform(0, .99, size=n)
+    ecc[:60000] = 0; ta[:3000] = 0; x0[:3000] = 0; ta[3000:9000] = 0; x0[9000:18000] = 0
+    cone = np.concatenate([o, d, x, ta[:, None], ecc[:, None], x0[:, None]], 1)
+    z = rng.uniform(-.5, 6, size=(n, 1)); rad = ta[:, None] * np.abs(z) + x0[:, None]
+    centre = np.concatenate([rng.normal(size=(n, 2)) * rad * rng.uniform(0, 2.5, size=(n, 1)), z], 1)
+    size = rad * 10.0 ** rng.uniform(-1.5, 1.5, size=(n, 1))
+    size[:3000] = 10.0 ** rng.uniform(-2, 0, size=(3000, 1)); centre[:3000, :2] = rng.normal(size=(3000, 2)) * size[:3000] * .5      # rays: triangles around the axis
+    la, lb, lc = (centre + rng.normal(size=(n, 3)) * size for _ in range(3))
+    def world(l):
+        return o + l[:, :1] * x + l[:, 1:2] * y + l[:, 2:3] * d
+    A, B, Cc = world(la), world(lb), world(lc)
+    nr = np.cross(B - A, Cc - A); nr /= np.linalg.norm(nr, axis=1, keepdims=True)
+    zr = np.zeros((n, 2)); zr[:, 1] = np.inf
+    k = slice(150000, n); zr[k, 0] = rng.uniform(0, 5, size=n - 150000); zr[k, 1] = zr[k, 0] + 10.0 ** rng.uniform(-2, 1, size=n - 150000)
+    zr[150000:200000, 0] = 0
+    inp = np.ascontiguousarray(np.concatenate([cone, A, B, Cc, nr, zr], 1), np.float32)
+    a = np.zeros((n, 6), np.float32); b = a.copy()
+    for lib, fn, out in ((R, "ref_cone_tri", a), (L, "oracle_cone_tri", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    bad = np.flatnonzero((a.view(np.uint32) != b.view(np.uint32)).any(1))
+    assert bad.size == 0, (bad[:5], a[bad[:5]], b[bad[:5]])
+    assert .2 < a[:, 0].mean() < .8 and .2 < a[:, 5].mean() < .85
+    assert .2 < a[3000:, 0].mean() and a[:3000, 0].mean() > .1
