@@ -587,6 +587,22 @@ extern "C" void oracle_ray_tri(uint32_t n, const float* in, float* out) {
         o[6] = lp ? 1.f : 0.f; o[7] = lp ? *lp : 0.f;
     }
 }
+extern "C" void oracle_ray_tri_w(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 17 * i; const float* a0 = in + 17 * (i & ~7u); float* o = out + 4 * i;
+        const ot::range_t range{ a0[15], a0[16] };
+        const ot::v3 ro{ a[0], a[1], a[2] }, rd{ a[3], a[4], a[5] }, A{ a[6], a[7], a[8] }, B{ a[9], a[10], a[11] }, Cc{ a[12], a[13], a[14] };
+        const auto r = ot::intersect_ray_tri_w(ro, rd, A, B, Cc, range);
+        o[0] = r.result; o[1] = r.baryx; o[2] = r.baryy; o[3] = ot::test_ray_tri_w(ro, rd, A, B, Cc, range) ? 1.f : 0.f;
+    }
+}
+extern "C" void oracle_ray_aabb_fast(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 14 * i; const float* a0 = in + 14 * (i & ~7u); float* o = out + 3 * i;
+        const auto r = ot::ray_aabb_fast({ a[0], a[1], a[2] }, { a[3], a[4], a[5] }, { a[6], a[7], a[8] }, { a[9], a[10], a[11] }, { a0[12], a0[13] });
+        o[0] = r.mask ? 1.f : 0.f; o[1] = r.min; o[2] = r.max;
+    }
+}
 extern "C" void oracle_cone_basics(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 13 * i; float* o = out + 5 * i;

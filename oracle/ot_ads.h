@@ -66,6 +66,23 @@ inline bool ray_gather_tris(const ads_t& ads, const ray_t& ray, uint32_t t0, uin
     return intersects;
 }
 
+// intersect_ray_aabb_fast, one lane of the 8-wide form (intersect/ray.hpp:331-351).  The slabs are chosen by the SIGN BIT of 1/d (a blendv on
+// the raw bits); vmaxps / vminps return their second operand when the comparison is false -- also when either is NaN (0 * inf: origin on a slab
+// plane of an axis the ray is parallel to) -- and the four-argument forms pair up as (x, y), (z, range) (simd/math.hpp:333-356).
+struct ray_aabb_fast_t { bool mask; f_t min, max; };
+inline ray_aabb_fast_t ray_aabb_fast(v3 ro, v3 invd, v3 mn, v3 mx, range_t range) {
+    const bool nx = std::signbit(invd.x), ny = std::signbit(invd.y), nz = std::signbit(invd.z);
+    const f_t mnx = nx ? mx.x : mn.x, mxx = nx ? mn.x : mx.x;
+    const f_t mny = ny ? mx.y : mn.y, mxy = ny ? mn.y : mx.y;
+    const f_t mnz = nz ? mx.z : mn.z, mxz = nz ? mn.z : mx.z;
+    const f_t t1x = (mnx - ro.x) * invd.x, t1y = (mny - ro.y) * invd.y, t1z = (mnz - ro.z) * invd.z;
+    const f_t t2x = (mxx - ro.x) * invd.x, t2y = (mxy - ro.y) * invd.y, t2z = (mxz - ro.z) * invd.z;
+    auto vmax = [](f_t a, f_t b) { return a > b ? a : b; };
+    auto vmin = [](f_t a, f_t b) { return a < b ? a : b; };
+    const f_t rmin = vmax(vmax(t1x, t1y), vmax(t1z, range.min));
+    const f_t rmax = vmin(vmin(t2x, t2y), vmin(t2z, range.max));
+    return { rmin <= rmax, rmin, rmax };
+}
 template <bool shadow>
 inline bool ray_traverse(const ads_t& ads, const ray_t& ray, range_t range, ray_hit_t& rec, ads_counters_t* ctr) {
     constexpr int stack_size = 64;
@@ -91,18 +108,8 @@ inline bool ray_traverse(const ads_t& ads, const ray_t& ray, range_t range, ray_
             }
             const int begin = s;
             for (int i = 0; i < 8; ++i) {
-                // intersect_ray_aabb_fast (intersect/ray.hpp:331-351), range {0, record.triangle.dist}
-                const bool nx = std::signbit(ray.invd.x), ny = std::signbit(ray.invd.y), nz = std::signbit(ray.invd.z);
-                const f_t mnx = nx ? n.maxx[i] : n.minx[i], mxx = nx ? n.minx[i] : n.maxx[i];
-                const f_t mny = ny ? n.maxy[i] : n.miny[i], mxy = ny ? n.miny[i] : n.maxy[i];
-                const f_t mnz = nz ? n.maxz[i] : n.minz[i], mxz = nz ? n.minz[i] : n.maxz[i];
-                const f_t t1x = (mnx - ray.o.x) * ray.invd.x, t1y = (mny - ray.o.y) * ray.invd.y, t1z = (mnz - ray.o.z) * ray.invd.z;
-                const f_t t2x = (mxx - ray.o.x) * ray.invd.x, t2y = (mxy - ray.o.y) * ray.invd.y, t2z = (mxz - ray.o.z) * ray.invd.z;
-                // AVX max/min semantics: max(a,b) returns b if either is NaN
-                auto vmax = [](f_t a, f_t b) { return a > b ? a : b; };
-                auto vmin = [](f_t a, f_t b) { return a < b ? a : b; };
-                const f_t rmin = vmax(vmax(vmax(t1x, t1y), t1z), 0.f);
-                const f_t rmax = vmin(vmin(vmin(t2x, t2y), t2z), rec.dist);
+                const ray_aabb_fast_t hit = ray_aabb_fast(ray.o, ray.invd, { n.minx[i], n.miny[i], n.minz[i] }, { n.maxx[i], n.maxy[i], n.maxz[i] }, { 0.f, rec.dist });
+                const f_t rmin = hit.min, rmax = hit.max;
                 if (rmin <= rmax && n.child[i] != 0) stack[s++] = { rmin, n.child[i] };
             }
             stack_sorter(&stack[begin], s - begin);

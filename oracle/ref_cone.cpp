@@ -76,6 +76,36 @@ void ref_ray_tri(unsigned n, const float* in, float* out) {
         o[6] = lp ? 1.f : 0.f; o[7] = lp ? *lp : 0.f;
     }
 }
+// the 8-wide entry points of intersect/ray.hpp the BVH ray traversal evaluates (8 items per call, one per lane; n a multiple of 8).
+// per item in: ro[3] rd[3] a[3] b[3] c[3] range[2]; out: result (distance or -inf) baryx baryy (intersect_ray_tri<8>, ray.hpp:192-236), test_ray_tri<8> (:93-128)
+void ref_ray_tri_w8(unsigned n, const float* in, float* out) {
+    for (unsigned i = 0; i + 8 <= n; i += 8) {
+        const float* a0 = in + 17 * i;
+        const pqrange_t<> range{ a0[15], a0[16] };          // (the range of the first lane: the caller gives all 8 the same)
+        pqvec3_w_t<8> ro, A, B, Cc; vec3_w_t<8> rd;
+        for (int l = 0; l < 8; ++l) for (int k = 0; k < 3; ++k) {
+            const float* a = a0 + 17 * l;
+            ro.c[k].v[l] = a[k]; rd.c[k].v[l] = a[3 + k]; A.c[k].v[l] = a[6 + k]; B.c[k].v[l] = a[9 + k]; Cc.c[k].v[l] = a[12 + k];
+        }
+        const auto r = intersect::intersect_ray_tri<8>(ro, rd, A, B, Cc, range);
+        const auto t = intersect::test_ray_tri<8>(ro, rd, A, B, Cc, range);
+        for (int l = 0; l < 8; ++l) { float* o = out + 4 * (i + l); o[0] = r.result.v[l]; o[1] = r.baryx.v[l]; o[2] = r.baryy.v[l]; o[3] = t.v[l] ? 1.f : 0.f; }
+    }
+}
+// per item in: ro[3] rinvd[3] aabb_min[3] aabb_max[3] range[2]; out: mask min max (intersect_ray_aabb_fast<8>, ray.hpp:331-351)
+void ref_ray_aabb_fast_w8(unsigned n, const float* in, float* out) {
+    for (unsigned i = 0; i + 8 <= n; i += 8) {
+        const float* a0 = in + 14 * i;
+        const pqrange_t<> range{ a0[12], a0[13] };
+        pqvec3_w_t<8> ro, mn, mx; vec3_w_t<8> inv;
+        for (int l = 0; l < 8; ++l) for (int k = 0; k < 3; ++k) {
+            const float* a = a0 + 14 * l;
+            ro.c[k].v[l] = a[k]; inv.c[k].v[l] = a[3 + k]; mn.c[k].v[l] = a[6 + k]; mx.c[k].v[l] = a[9 + k];
+        }
+        const auto r = intersect::intersect_ray_aabb_fast<8>(ro, inv, mn, mx, range);
+        for (int l = 0; l < 8; ++l) { float* o = out + 3 * (i + l); o[0] = r.mask.v[l] ? 1.f : 0.f; o[1] = r.min.v[l]; o[2] = r.max.v[l]; }
+    }
+}
 // per item in: cone[12] z; out: axes x y, z_apex, e, one_over_e  (elliptic_cone.hpp: axes(), get_z_apex(), the eccentricity constructor)
 void ref_cone_basics(unsigned n, const float* in, float* out) {
     for (unsigned i = 0; i < n; ++i) {

@@ -922,3 +922,56 @@ def test_cone_triangle_tests_equal_the_reference_code():
     assert bad.size == 0, (bad[:5], a[bad[:5]], b[bad[:5]])
     assert .2 < a[:, 0].mean() < .8 and .2 < a[:, 5].mean() < .85
     assert .2 < a[3000:, 0].mean() and a[:3000, 0].mean() > .1
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CONE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_wide_ray_tests_equal_the_reference_code():
+    """What the BVH ray / shadow-ray traversal evaluates per triangle and per child box: the reference's 8-wide
+    intersect_ray_tri / test_ray_tri (intersect/ray.hpp:93-128, :192-236) and intersect_ray_aabb_fast (:331-351), compiled from where they lie
+    with the wide vectors as arrays of lanes (oracle/ref_cone.cpp), against the one-lane restatements in ot_math.h / ot_ads.h -- bit-identical:
+    200 000 ray-triangle pairs (distance or -inf, both barycentrics, the boolean test) and 400 000 ray-box pairs (mask, entry, exit), among them
+    axis-parallel rays (1/d = +-inf), origins ON a slab plane of such an axis (0 * inf = NaN, where the operand order of vmaxps / vminps and the
+    pairing of the four-argument max / min decide), origins inside the box, negative directions, boxes behind the ray, ranges ending before
+    the box."""
+    R = C.CDLL(REF_CONE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(43); n = 200000
+    def both(name, oname, inp, width, cnt):
+        a = np.zeros((cnt, width), np.float32); b = a.copy(); inp = np.ascontiguousarray(inp, np.float32)
+        for lib, fn, out in ((R, name, a), (L, oname, b)):
+            f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(cnt, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        return a, b
+    A = rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-2, 2, size=(n, 1)); B = A + rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-3, 1, size=(n, 1)); Cc = A + rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-3, 1, size=(n, 1))
+    Cc[:504] = B[:504]
+    w = rng.uniform(-.2, .9, size=(n, 2)); w[504:4000] = np.round(w[504:4000] * 2) / 2
+    P = A + w[:, :1] * (B - A) + w[:, 1:] * (Cc - A)
+    ro = P + rng.normal(size=(n, 3)) * np.linalg.norm(B - A, axis=1, keepdims=True) * rng.uniform(.1, 30, size=(n, 1))
+    rd = P - ro; t = np.linalg.norm(rd, axis=1, keepdims=True); rd /= t
+    rd[4000:6000] *= -1
+    zr = np.zeros((n, 2)); zr[:, 1] = np.inf
+    zr[100000:, 0] = np.repeat(t[100000::8, 0] * rng.uniform(0, 2, size=(n - 100000) // 8), 8); zr[100000:, 1] = zr[100000:, 0] + np.repeat(t[100000::8, 0] * rng.uniform(0, 2, size=(n - 100000) // 8), 8)
+    a, b = both("ref_ray_tri_w8", "oracle_ray_tri_w", np.concatenate([ro, rd, A, B, Cc, zr], 1), 4, n)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert .15 < np.isfinite(a[:, 0]).mean() < .7 and np.array_equal(np.isfinite(a[:, 0]), a[:, 3] == 1) or (np.isfinite(a[:, 0]) != (a[:, 3] == 1)).mean() < 1e-3
+    # boxes
+    n = 400000
+    c = rng.normal(size=(n, 3)) * 3; h = 10.0 ** rng.uniform(-2, 1, size=(n, 3)); mn = (c - h).astype(np.float32).astype(np.float64); mx = (c + h).astype(np.float32).astype(np.float64)
+    tgt = c + rng.uniform(-1.5, 1.5, size=(n, 3)) * h
+    ro = tgt + rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-1, 1.5, size=(n, 1)); ro[:40000] = c[:40000] + rng.uniform(-.9, .9, size=(40000, 3)) * h[:40000]       # inside
+    rd = tgt - ro; rd[:40000] = rng.normal(size=(40000, 3)); rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    rd[40000:60000] *= -1                                                              # boxes behind the ray
+    ax = rng.integers(0, 3, size=n); par = np.arange(n) % 4 == 1                       # a quarter: parallel to one axis ...
+    rd[par, ax[par]] = 0.0 * np.sign(rng.normal(size=par.sum()))                       # (+0 and -0)
+    par2 = np.arange(n) % 16 == 5; rd[par2, (ax[par2] + 1) % 3] = 0.0                  # ... some to two
+    on = np.arange(n) % 8 == 1                                                         # ... half of those with the origin ON a slab plane of that axis
+    side = rng.integers(0, 2, size=n)
+    ro = ro.astype(np.float32).astype(np.float64)
+    ro[on, ax[on]] = np.where(side[on] == 1, mx[on, ax[on]], mn[on, ax[on]])
+    on2 = np.arange(n) % 32 == 5; ro[on2, (ax[on2] + 1) % 3] = mn[on2, (ax[on2] + 1) % 3]
+    rd32 = rd.astype(np.float32)
+    with np.errstate(divide="ignore"):
+        inv = (np.float32(1) / rd32)
+    zr = np.zeros((n, 2)); zr[:, 1] = np.inf; zr[200000:, 1] = np.repeat(10.0 ** rng.uniform(-1, 1.5, size=(n - 200000) // 8), 8)
+    a, b = both("ref_ray_aabb_fast_w8", "oracle_ray_aabb_fast", np.concatenate([ro, inv, mn, mx, zr], 1), 3, n)
+    bad = np.flatnonzero((a.view(np.uint32) != b.view(np.uint32)).any(1))
+    assert bad.size == 0, (bad.size, bad[:5], a[bad[:5]], b[bad[:5]])
+    assert .2 < a[:, 0].mean() < .9 and np.isinf(inv).any(1).mean() > .2

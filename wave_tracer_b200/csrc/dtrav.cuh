@@ -176,8 +176,8 @@ WT_DN bool ray_traverse(const DScene& sc, V3 ro, V3 rd, Range range, RayHit& rec
                         const float t1x = ((nx ? amxx[i] : amnx[i]) - ro.x) * inv.x, t2x = ((nx ? amnx[i] : amxx[i]) - ro.x) * inv.x;
                         const float t1y = ((ny ? amxy[i] : amny[i]) - ro.y) * inv.y, t2y = ((ny ? amny[i] : amxy[i]) - ro.y) * inv.y;
                         const float t1z = ((nz ? amxz[i] : amnz[i]) - ro.z) * inv.z, t2z = ((nz ? amnz[i] : amxz[i]) - ro.z) * inv.z;
-                        const float rmin = vmaxps(vmaxps(vmaxps(t1x, t1y), t1z), 0.f);
-                        const float rmax = vminps(vminps(vminps(t2x, t2y), t2z), rec.dist);
+                        const float rmin = vmaxps(vmaxps(t1x, t1y), vmaxps(t1z, 0.f));        // (x, y), (z, range): simd/math.hpp:333-356 -- decides when a slab gives NaN
+                        const float rmax = vminps(vminps(t2x, t2y), vminps(t2z, rec.dist));
                         if (rmin <= rmax && ach[i] != 0 && ray_cull_keep(cull, rmin, rmax)) { if (s < 64) { stack[s].tmin = rmin; stack[s].ptr = ach[i]; ++s; } else ctr.stack_drops++; }
                     }
                 }

@@ -167,8 +167,8 @@ WT_D void g_node_step(const DScene& sc, const GLane& g, GShared& sh, GTrav& t, i
         const float t1x = ((t.nx ? mxx : mnx) - ro.x) * t.inv.x, t2x = ((t.nx ? mnx : mxx) - ro.x) * t.inv.x;
         const float t1y = ((t.ny ? mxy : mny) - ro.y) * t.inv.y, t2y = ((t.ny ? mny : mxy) - ro.y) * t.inv.y;
         const float t1z = ((t.nz ? mxz : mnz) - ro.z) * t.inv.z, t2z = ((t.nz ? mnz : mxz) - ro.z) * t.inv.z;
-        const float rmin = vmaxps(vmaxps(vmaxps(t1x, t1y), t1z), 0.f);
-        const float rmax = vminps(vminps(vminps(t2x, t2y), t2z), t.rec.dist);
+        const float rmin = vmaxps(vmaxps(t1x, t1y), vmaxps(t1z, 0.f));        // (x, y), (z, range): simd/math.hpp:333-356 -- decides when a slab gives NaN
+        const float rmax = vminps(vminps(t2x, t2y), vminps(t2z, t.rec.dist));
         push = rmin <= rmax && ch != 0 && ray_cull_keep(t.cull, rmin, rmax); key = rmin; cap = 64;
     } else {                // cone_cluster_intersect (bvh8w.cpp:187-230)
         float tmin;
