@@ -603,6 +603,23 @@ extern "C" void oracle_ray_aabb_fast(uint32_t n, const float* in, float* out) {
         o[0] = r.mask ? 1.f : 0.f; o[1] = r.min; o[2] = r.max;
     }
 }
+extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);
+        const auto cone = kat_cone(a0);
+        f_t tmin = 0;
+        const bool hit = ot::cone_cluster_lane(cone.o(), cone.d(), cone.r.invd, cone.tan_alpha, cone.x0, { a[12], a[13], a[14] }, { a[15], a[16], a[17] }, { a0[18], a0[19] }, tmin);
+        out[2 * i] = hit ? 1.f : 0.f; out[2 * i + 1] = tmin;
+    }
+}
+extern "C" void oracle_stack_sorter(uint32_t n, uint32_t run, float* io) {
+    std::vector<ot::stack_node_ptr_t> st(run);
+    for (uint32_t i = 0; i + run <= n; i += run) {
+        for (uint32_t k = 0; k < run; ++k) st[k] = { io[2 * (i + k)], (int32_t)io[2 * (i + k) + 1] };
+        ot::stack_sorter(st.data(), (int)run);
+        for (uint32_t k = 0; k < run; ++k) { io[2 * (i + k)] = st[k].min_range; io[2 * (i + k) + 1] = (float)st[k].ptr; }
+    }
+}
 extern "C" void oracle_cone_basics(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 13 * i; float* o = out + 5 * i;

@@ -69,6 +69,8 @@ void oracle_cone_tri(uint32_t n, const float* in, float* out);
 void oracle_ray_tri(uint32_t n, const float* in, float* out);
 void oracle_ray_tri_w(uint32_t n, const float* in, float* out);
 void oracle_ray_aabb_fast(uint32_t n, const float* in, float* out);
+void oracle_cone_cluster(uint32_t n, const float* in, float* out);
+void oracle_stack_sorter(uint32_t n, uint32_t run, float* io);
 void oracle_cone_basics(uint32_t n, const float* in, float* out);
 void oracle_point_in_triangle3(uint32_t n, const float* in, float* out);
 void oracle_point_in_triangle2(uint32_t n, const float* in, float* out);

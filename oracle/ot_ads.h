@@ -182,6 +182,33 @@ inline bool cone_gather_tris(const ads_t& ads, const elliptic_cone_t& cone, rang
     return found;
 }
 
+// cone_cluster_intersect, bvh8w.cpp:187-230, one lane: the box enlarged by the cone's radius at the box's farthest depth, slab-tested against the axis
+inline bool cone_cluster_lane(v3 ro, v3 rd, v3 rinvd, f_t ta, f_t ix, v3 mn, v3 mx, range_t range, f_t& tmin_out) {
+    f_t omnx = mn.x - ro.x, omny = mn.y - ro.y, omnz = mn.z - ro.z;
+    f_t omxx = mx.x - ro.x, omxy = mx.y - ro.y, omxz = mx.z - ro.z;
+    const bool sx = std::signbit(rinvd.x), sy = std::signbit(rinvd.y), sz = std::signbit(rinvd.z);
+    auto vmax = [](f_t a, f_t b) { return a > b ? a : b; };         // vmaxps / vminps: the second operand unless the comparison holds
+    auto vmin = [](f_t a, f_t b) { return a < b ? a : b; };
+    // b = selectv(max, min, sign(rinvd)): min where negative
+    const f_t bx = sx ? omnx : omxx, by = sy ? omny : omxy, bz = sz ? omnz : omxz;
+    const f_t dot_d_b = std::fma(rd.z, bz, std::fma(rd.y, by, rd.x * bx));
+    const f_t maxz = vmin(vmax(dot_d_b, 0.f), range.max);          // wide clamp, simd/math.hpp:358-367
+    const f_t enlr = std::fma(maxz, ta, ix);
+    omnx -= enlr; omny -= enlr; omnz -= enlr;
+    omxx += enlr; omxy += enlr; omxz += enlr;
+    const f_t aex = sx ? omxx : omnx, aey = sy ? omxy : omny, aez = sz ? omxz : omnz;
+    const f_t bex = sx ? omnx : omxx, bey = sy ? omny : omxy, bez = sz ? omnz : omxz;
+    const f_t dminx = aex * rinvd.x, dminy = aey * rinvd.y, dminz = aez * rinvd.z;
+    const f_t dmaxx = bex * rinvd.x, dmaxy = bey * rinvd.y, dmaxz = bez * rinvd.z;
+    f_t tmin = 0, tmax = dmaxx;
+    tmin = vmax(tmin, dminx);
+    tmax = vmin(tmax, dmaxy);
+    tmin = vmax(tmin, dminy);
+    tmax = vmin(tmax, dmaxz);
+    tmin = vmax(tmin, dminz);
+    tmin_out = tmin;
+    return tmin <= tmax && tmax >= range.min && tmin <= range.max;
+}
 inline cone_record_t intersect_cone(const ads_t& ads, const elliptic_cone_t& cone, range_t traversal_range, f_t z_scale, bool detect_edges, ads_counters_t* ctr = nullptr) {
     const uint64_t tris_before = ctr ? ctr->tris : 0;
     cone_work_t work; work.searchrange = traversal_range; work.z_search_range_scale = z_scale;
@@ -209,30 +236,8 @@ inline cone_record_t intersect_cone(const ads_t& ads, const elliptic_cone_t& con
             if (ctr) ctr->nodes++;
             const int begin = s;
             for (int i = 0; i < 8; ++i) {
-                // cone_cluster_intersect, bvh8w.cpp:187-230 (one lane)
-                f_t omnx = n.minx[i] - ro.x, omny = n.miny[i] - ro.y, omnz = n.minz[i] - ro.z;
-                f_t omxx = n.maxx[i] - ro.x, omxy = n.maxy[i] - ro.y, omxz = n.maxz[i] - ro.z;
-                const bool sx = std::signbit(rinvd.x), sy = std::signbit(rinvd.y), sz = std::signbit(rinvd.z);
-                // b = selectv(max, min, sign(rinvd)): min where negative
-                const f_t bx = sx ? omnx : omxx, by = sy ? omny : omxy, bz = sz ? omnz : omxz;
-                const f_t dot_d_b = std::fma(rd.z, bz, std::fma(rd.y, by, rd.x * bx));
-                const f_t maxz = std::min(std::max(dot_d_b, 0.f), range.max);
-                const f_t enlr = std::fma(maxz, ta, ix);
-                omnx -= enlr; omny -= enlr; omnz -= enlr;
-                omxx += enlr; omxy += enlr; omxz += enlr;
-                const f_t aex = sx ? omxx : omnx, aey = sy ? omxy : omny, aez = sz ? omxz : omnz;
-                const f_t bex = sx ? omnx : omxx, bey = sy ? omny : omxy, bez = sz ? omnz : omxz;
-                const f_t dminx = aex * rinvd.x, dminy = aey * rinvd.y, dminz = aez * rinvd.z;
-                const f_t dmaxx = bex * rinvd.x, dmaxy = bey * rinvd.y, dmaxz = bez * rinvd.z;
-                auto vmax = [](f_t a, f_t b) { return a > b ? a : b; };
-                auto vmin = [](f_t a, f_t b) { return a < b ? a : b; };
-                f_t tmin = 0, tmax = dmaxx;
-                tmin = vmax(tmin, dminx);
-                tmax = vmin(tmax, dmaxy);
-                tmin = vmax(tmin, dminy);
-                tmax = vmin(tmax, dmaxz);
-                tmin = vmax(tmin, dminz);
-                const bool result = tmin <= tmax && tmax >= range.min && tmin <= range.max;
+                f_t tmin;
+                const bool result = cone_cluster_lane(ro, rd, rinvd, ta, ix, { n.minx[i], n.miny[i], n.minz[i] }, { n.maxx[i], n.maxy[i], n.maxz[i] }, range, tmin);
                 if (!result || n.child[i] == 0) continue;
                 if (tmin >= range.max) continue;
                 stack[s++] = { tmin, n.child[i] };

@@ -39,6 +39,13 @@ inline void plane_one(const float* a, float* o) {
     o[3] = r.near.x; o[4] = r.near.y; o[5] = r.near.z; o[6] = r.far.x; o[7] = r.far.y; o[8] = r.far.z;
 }
 }
+// ---- the per-node test of the BVH cone traversal, src/ads/bvh8w.cpp:186-230 (cone_cluster_intersect) with its inputs (:107-121) and the child
+// stack's insertion sort (:44-57): the Makefile writes those line ranges of the .cpp, as they are, to oracle/_ref/bvh8w_cone_cluster_part.hpp.
+#include <bitset>
+#include <vector>
+namespace wt::ads { struct bvh8w_t; namespace bvh8w { struct bvh8w_aabbs_t { pqvec3_w_t<8> min, max; }; } }      // include/wt/ads/bvh8w/common.hpp:19-21
+using namespace wt::ads;
+#include "_ref/bvh8w_cone_cluster_part.hpp"
 extern "C" {
 // per item in: cone[12] p0[3] p1[3] range[2]; out: found p0[3] p1[3] (zero unless pts == 2) range[2] pts
 void ref_cone_edge(unsigned n, int in_local, const float* in, float* out) {
@@ -104,6 +111,28 @@ void ref_ray_aabb_fast_w8(unsigned n, const float* in, float* out) {
         }
         const auto r = intersect::intersect_ray_aabb_fast<8>(ro, inv, mn, mx, range);
         for (int l = 0; l < 8; ++l) { float* o = out + 3 * (i + l); o[0] = r.mask.v[l] ? 1.f : 0.f; o[1] = r.min.v[l]; o[2] = r.max.v[l]; }
+    }
+}
+// 8 boxes per call against ONE cone (that of the first lane's item).  per item in: cone[12] aabb_min[3] aabb_max[3] range[2]; out: hit tmin
+void ref_cone_cluster(unsigned n, const float* in, float* out) {
+    for (unsigned i = 0; i + 8 <= n; i += 8) {
+        const float* a0 = in + 20 * i;
+        const auto cone = make_cone(a0);
+        const pqrange_t<> range{ a0[18], a0[19] };
+        const cone_cluster_intersect_data_t data{ cone };
+        bvh8w::bvh8w_aabbs_t boxes;
+        for (int l = 0; l < 8; ++l) for (int k = 0; k < 3; ++k) { boxes.min.c[k].v[l] = a0[20 * l + 12 + k]; boxes.max.c[k].v[l] = a0[20 * l + 15 + k]; }
+        const auto r = cone_cluster_intersect(nullptr, range, data, boxes);
+        for (int l = 0; l < 8; ++l) { out[2 * (i + l)] = r.result_mask[l] ? 1.f : 0.f; out[2 * (i + l) + 1] = r.tmins.v[l]; }
+    }
+}
+// sorts runs of `run` (key, id) pairs in place with the reference's stack_sorter; in/out: n pairs of (min_range, ptr as float)
+void ref_stack_sorter(unsigned n, unsigned run, float* io) {
+    std::vector<stack_node_ptr_t> st(run);
+    for (unsigned i = 0; i + run <= n; i += run) {
+        for (unsigned k = 0; k < run; ++k) st[k] = { io[2 * (i + k)], (int32_t)io[2 * (i + k) + 1] };
+        stack_sorter(st.data(), (int)run);
+        for (unsigned k = 0; k < run; ++k) { io[2 * (i + k)] = st[k].min_range; io[2 * (i + k) + 1] = (float)st[k].ptr; }
     }
 }
 // per item in: cone[12] z; out: axes x y, z_apex, e, one_over_e  (elliptic_cone.hpp: axes(), get_z_apex(), the eccentricity constructor)

@@ -18,13 +18,13 @@ template <std::size_t W> struct pqvec3_w_t;
 // frame_t::to_local(pqvec3_w_t) (frame.hpp:194-200), elliptic_cone_t::contains_local(pqvec3_w_t, range) (elliptic_cone.hpp:178-193) and the
 // scalar-entry cone-triangle tests (cone.hpp:479-626) use.  Each lane operation is the single IEEE operation the AVX instruction performs
 // (vsubps, vmulps, vaddps, vfmadd, vcmpps); the mixed-quantity dot product is the multiply + two fused multiply-adds of simd/math.hpp:536-541.
-#include <array>
+#include <bitset>
 #include <cmath>
 #include <limits>
 namespace wt {
 template <std::size_t W> struct b_w_t {
     bool v[W];
-    std::array<bool, W> to_bitmask() const noexcept { std::array<bool, W> r; for (std::size_t i = 0; i < W; ++i) r[i] = v[i]; return r; }
+    std::bitset<W> to_bitmask() const noexcept { std::bitset<W> r; for (std::size_t i = 0; i < W; ++i) r[i] = v[i]; return r; }
 };
 template <std::size_t W> inline b_w_t<W> operator&&(const b_w_t<W>& a, const b_w_t<W>& b) noexcept { b_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] && b.v[i]; return r; }
 template <std::size_t W> inline b_w_t<W>& operator&=(b_w_t<W>& a, const b_w_t<W>& b) noexcept { for (std::size_t i = 0; i < W; ++i) a.v[i] = a.v[i] && b.v[i]; return a; }
@@ -66,6 +66,7 @@ template <std::size_t W> struct pqvec3_w_t {
     length_w_t<W> c[3];
     pqvec3_w_t() = default;
     explicit pqvec3_w_t(const pqvec3_t& s) noexcept : c{ length_w_t<W>(s.x), length_w_t<W>(s.y), length_w_t<W>(s.z) } {}
+    explicit pqvec3_w_t(const f_w_t<W>& s) noexcept : c{ s, s, s } {}                 // (a wide scalar to all three components: wide_vector.hpp:715)
     pqvec3_w_t(const length_w_t<W>& x, const length_w_t<W>& y, const length_w_t<W>& z) noexcept : c{ x, y, z } {}
     pqvec3_w_t(const pqvec3_t& p0, const pqvec3_t& p1, const pqvec3_t& p2, const pqvec3_t& p3) noexcept requires (W == 4) {
         const pqvec3_t* p[4] = { &p0, &p1, &p2, &p3 };
@@ -78,6 +79,7 @@ template <std::size_t W> struct pqvec3_w_t {
     pqvec3_t read(int i) const noexcept { return pqvec3_t{ c[0].v[i], c[1].v[i], c[2].v[i] }; }
 };
 template <std::size_t W> inline pqvec3_w_t<W> operator-(const pqvec3_w_t<W>& a, const pqvec3_w_t<W>& b) noexcept { return pqvec3_w_t<W>{ a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2] }; }
+template <std::size_t W> inline pqvec3_w_t<W> operator+(const pqvec3_w_t<W>& a, const pqvec3_w_t<W>& b) noexcept { return pqvec3_w_t<W>{ a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2] }; }
 template <std::size_t W> inline pqvec3_w_t<W> operator*(const pqvec3_w_t<W>& a, const vec3_w_t<W>& b) noexcept { return pqvec3_w_t<W>{ a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2] }; }
 // a mask made of the raw bits of a vector of numbers (wide_vector.hpp:225-228); blendv looks at the sign bit
 template <std::size_t W> struct bvec3_w_t {
@@ -85,6 +87,7 @@ template <std::size_t W> struct bvec3_w_t {
     explicit bvec3_w_t(const vec3_w_t<W>& s) noexcept { for (int k = 0; k < 3; ++k) for (std::size_t i = 0; i < W; ++i) c[k].v[i] = std::signbit(s.c[k].v[i]); }
 };
 using pqvec3_w4_t = pqvec3_w_t<4>;
+using pqvec3_w8_t = pqvec3_w_t<8>; using vec3_w8_t = vec3_w_t<8>; using f_w8_t = f_w_t<8>; using length_w8_t = length_w_t<8>; using bvec3_w8_t = bvec3_w_t<8>;
 namespace m {
 // simd/math.hpp:409-416 over vblendvps: b where the mask is set, else a
 template <std::size_t W> inline f_w_t<W> selectv(const f_w_t<W>& a, const f_w_t<W>& b, const b_w_t<W>& mask) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = mask.v[i] ? b.v[i] : a.v[i]; return r; }
@@ -93,8 +96,12 @@ template <std::size_t W> inline pqvec3_w_t<W> selectv(const pqvec3_w_t<W>& a, co
 // as (v1, v2), (v3, v4) (simd/math.hpp:333-356)
 template <std::size_t W> inline f_w_t<W> max(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] > b.v[i] ? a.v[i] : b.v[i]; return r; }
 template <std::size_t W> inline f_w_t<W> min(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] < b.v[i] ? a.v[i] : b.v[i]; return r; }
+template <std::size_t W> inline f_w_t<W> max(const length_w_t<W>& a, const length_w_t<W>& b) noexcept { return max<W>(static_cast<const f_w_t<W>&>(a), static_cast<const f_w_t<W>&>(b)); }
+template <std::size_t W> inline f_w_t<W> min(const length_w_t<W>& a, const length_w_t<W>& b) noexcept { return min<W>(static_cast<const f_w_t<W>&>(a), static_cast<const f_w_t<W>&>(b)); }
 template <std::size_t W> inline f_w_t<W> max(const f_w_t<W>& a, const f_w_t<W>& b, const f_w_t<W>& c, const f_w_t<W>& d) noexcept { return max<W>(max<W>(a, b), max<W>(c, d)); }
 template <std::size_t W> inline f_w_t<W> min(const f_w_t<W>& a, const f_w_t<W>& b, const f_w_t<W>& c, const f_w_t<W>& d) noexcept { return min<W>(min<W>(a, b), min<W>(c, d)); }
+// simd/math.hpp:358-367: min(max(v, lo), hi) on vmaxps / vminps
+template <std::size_t W> inline f_w_t<W> clamp(const f_w_t<W>& v, const f_w_t<W>& lo, const f_w_t<W>& hi) noexcept { return min<W>(max<W>(v, lo), hi); }
 template <std::size_t W> inline f_w_t<W> fms(const f_w_t<W>& a, const f_w_t<W>& b, const f_w_t<W>& c) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = std::fma(a.v[i], b.v[i], -c.v[i]); return r; }
 // simd/math.hpp:494-504 (eft::diff_prod on wide vectors) and :543-551 (cross)
 template <std::size_t W> inline f_w_t<W> diff_prod_w(const f_w_t<W>& a, const f_w_t<W>& b, const f_w_t<W>& c, const f_w_t<W>& d) noexcept { const auto cd = c * d; const auto diff = fms<W>(a, b, cd); const auto err = fms<W>(c, d, cd); return diff - err; }

@@ -975,3 +975,45 @@ def test_wide_ray_tests_equal_the_reference_code():
     bad = np.flatnonzero((a.view(np.uint32) != b.view(np.uint32)).any(1))
     assert bad.size == 0, (bad.size, bad[:5], a[bad[:5]], b[bad[:5]])
     assert .2 < a[:, 0].mean() < .9 and np.isinf(inv).any(1).mean() > .2
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CONE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_cone_node_test_and_stack_order_equal_the_reference_code():
+    """The per-node step of the BVH cone traversal: the reference's cone_cluster_intersect (src/ads/bvh8w.cpp:186-230) with its
+    per-cone inputs (:107-121) -- 8 child boxes against one cone: the box enlarged by the cone's radius at the box's farthest depth, slab test against
+    the axis, the three range conditions -- and the insertion sort that orders the pushed children (:44-57), compiled from the .cpp's own lines with
+    the wide vectors as arrays of lanes (oracle/ref_cone.cpp), against ot_ads.h's one-lane restatement: hit mask and tmin bit-identical on 400 000
+    cone-box pairs (boxes around, beside, behind and far beyond the cone; axis-parallel cones, 1/d = +-inf; ranges cutting the box), and the sorted order
+    identical -- ties included, the sort being stable in the direction the traversal pops -- on 50 000 runs of 8 keys with repeated and infinite keys."""
+    R = C.CDLL(REF_CONE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(47); n = 400000; g = n // 8
+    d = rng.normal(size=(g, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:4000] = np.eye(3)[rng.integers(0, 3, size=4000)] * np.sign(rng.normal(size=(4000, 1)))          # axis-parallel (two infinite reciprocals)
+    d[4000:8000, 0] = 0; d[4000:8000] /= np.linalg.norm(d[4000:8000], axis=1, keepdims=True)            # one
+    d = d.astype(np.float32).astype(np.float64)
+    x = np.cross(d, rng.normal(size=(g, 3))); x /= np.linalg.norm(x, axis=1, keepdims=True)
+    o = rng.normal(size=(g, 3)) * 2
+    ta = 10.0 ** rng.uniform(-4, 0, size=g); x0 = 10.0 ** rng.uniform(-4, 0, size=g); ecc = rng.uniform(0, .9, size=g)
+    ta[8000:9000] = 0; x0[9000:10000] = 0
+    cone = np.repeat(np.concatenate([o, d, x, ta[:, None], ecc[:, None], x0[:, None]], 1), 8, axis=0)
+    zr = np.zeros((g, 2)); zr[:, 1] = np.inf; zr[g // 2:, 0] = rng.uniform(0, 3, size=g - g // 2); zr[g // 2:, 1] = zr[g // 2:, 0] + 10.0 ** rng.uniform(-1, 1, size=g - g // 2)
+    zr = np.repeat(zr, 8, axis=0)
+    O = np.repeat(o, 8, axis=0); D = np.repeat(d, 8, axis=0)
+    z = rng.uniform(-2, 8, size=(n, 1)); rad = np.repeat(ta, 8)[:, None] * np.abs(z) + np.repeat(x0, 8)[:, None]
+    off = rng.normal(size=(n, 3)); off -= (off * D).sum(1, keepdims=True) * D
+    c = O + D * z + off * (rad + .3) * rng.uniform(0, 3, size=(n, 1))
+    h = 10.0 ** rng.uniform(-2, .5, size=(n, 3))
+    a = np.zeros((n, 2), np.float32); b = a.copy(); inp = np.ascontiguousarray(np.concatenate([cone, c - h, c + h, zr], 1), np.float32)
+    for lib, fn, out in ((R, "ref_cone_cluster", a), (L, "oracle_cone_cluster", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    bad = np.flatnonzero((a.view(np.uint32) != b.view(np.uint32)).any(1))
+    assert bad.size == 0, (bad.size, bad[:5], a[bad[:5]], b[bad[:5]])
+    assert .2 < a[:, 0].mean() < .9
+    # the child stack's sort
+    m = 50000 * 8
+    keys = rng.integers(0, 6, size=m).astype(np.float32) * np.float32(.25); keys[rng.random(m) < .05] = np.inf
+    io = np.ascontiguousarray(np.stack([keys, np.arange(m, dtype=np.float32) % 1024], 1), np.float32); io2 = io.copy()
+    for lib, fn, buf in ((R, "ref_stack_sorter", io), (L, "oracle_stack_sorter", io2)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, C.c_uint32, fp]; f.restype = None; f(m, 8, buf.ctypes.data_as(fp))
+    assert np.array_equal(io, io2)
+    k = io[:, 0].reshape(-1, 8); assert (k[:, :-1] >= k[:, 1:]).all()                  # farthest first: the nearest child is popped first
