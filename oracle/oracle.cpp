@@ -603,6 +603,17 @@ extern "C" void oracle_ray_aabb_fast(uint32_t n, const float* in, float* out) {
         o[0] = r.mask ? 1.f : 0.f; o[1] = r.min; o[2] = r.max;
     }
 }
+// per query in: o[3] d[3] x[3] tan_alpha eccentricity x0 tmin tmax z_scale; out as oracle/ref_traverse.cpp's ref_traverse_cones: the accepted triangles in
+// traversal order, their number, the closest distance, the face flag
+extern "C" void oracle_cone_work_lists(const wtgpu_scene_desc* desc, uint32_t n, const float* q, uint32_t cap, uint32_t* counts, uint32_t* tuids, float* dist, uint32_t* front) {
+    ads_t ads(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 15 * i;
+        const auto rec = intersect_cone(ads, kat_cone(c), { c[12], c[13] }, c[14], false);
+        counts[i] = (uint32_t)rec.tris.size(); dist[i] = rec.tris.empty() ? inf : rec.dist; front[i] = rec.front_face ? 1u : 0u;
+        for (uint32_t k = 0; k < cap; ++k) tuids[(size_t)i * cap + k] = k < rec.tris.size() ? rec.tris[k] : 0xffffffffu;
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

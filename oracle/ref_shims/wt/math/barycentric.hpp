@@ -4,7 +4,7 @@
 #include <optional>
 #include <wt/math/common.hpp>
 namespace wt {
-struct barycentric_t { vec2_t uv; constexpr explicit barycentric_t(vec2_t v) : uv(v) {} };
+struct barycentric_t { vec2_t uv{}; constexpr barycentric_t() = default; constexpr explicit barycentric_t(vec2_t v) : uv(v) {} };
 // Stand-in for include/wt/math/barycentric.hpp:109-129, needed only so that src/math/gaussian2d.cpp links: it serves the Dirac branch of
 // gaussian2d_t::integrate_triangle (sigma == 0), which no wavefront on the path reaches and which the pinning test does not exercise.
 inline std::optional<barycentric_t> barycentric_if_point_inside(const vec2_t& a, const vec2_t& b, const vec2_t& c, const vec2_t& p) noexcept {

@@ -54,9 +54,11 @@ template <std::size_t W> inline f_w_t<W> operator/(const f_w_t<W>& a, const f_w_
 template <std::size_t W> inline f_w_t<W> operator-(const f_w_t<W>& a) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = -a.v[i]; return r; }
 template <std::size_t W> inline b_w_t<W> operator!=(const f_w_t<W>& a, const f_w_t<W>& b) noexcept { b_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] != b.v[i]; return r; }
 template <std::size_t W> inline b_w_t<W> operator>=(const f_w_t<W>& a, zero_t) noexcept { b_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = a.v[i] >= f_t(0); return r; }
+namespace simd { struct unaligned_data_t {}; inline constexpr unaligned_data_t unaligned_data{}; }
 template <std::size_t W> struct vec3_w_t {
     f_w_t<W> c[3];
     vec3_w_t() = default;
+    vec3_w_t(const f_t* x, const f_t* y, const f_t* z, simd::unaligned_data_t) noexcept { for (std::size_t i = 0; i < W; ++i) { c[0].v[i] = x[i]; c[1].v[i] = y[i]; c[2].v[i] = z[i]; } }      // (W consecutive values per component)
     explicit vec3_w_t(const vec3_t& s) noexcept : c{ f_w_t<W>(s.x), f_w_t<W>(s.y), f_w_t<W>(s.z) } {}
     const f_w_t<W>& x() const noexcept { return c[0]; }
     const f_w_t<W>& y() const noexcept { return c[1]; }
@@ -68,6 +70,7 @@ template <std::size_t W> struct pqvec3_w_t {
     explicit pqvec3_w_t(const pqvec3_t& s) noexcept : c{ length_w_t<W>(s.x), length_w_t<W>(s.y), length_w_t<W>(s.z) } {}
     explicit pqvec3_w_t(const f_w_t<W>& s) noexcept : c{ s, s, s } {}                 // (a wide scalar to all three components: wide_vector.hpp:715)
     pqvec3_w_t(const length_w_t<W>& x, const length_w_t<W>& y, const length_w_t<W>& z) noexcept : c{ x, y, z } {}
+    pqvec3_w_t(const f_t* x, const f_t* y, const f_t* z, simd::unaligned_data_t) noexcept { for (std::size_t i = 0; i < W; ++i) { c[0].v[i] = x[i]; c[1].v[i] = y[i]; c[2].v[i] = z[i]; } }
     pqvec3_w_t(const pqvec3_t& p0, const pqvec3_t& p1, const pqvec3_t& p2, const pqvec3_t& p3) noexcept requires (W == 4) {
         const pqvec3_t* p[4] = { &p0, &p1, &p2, &p3 };
         for (int i = 0; i < 4; ++i) { c[0].v[i] = p[i]->x; c[1].v[i] = p[i]->y; c[2].v[i] = p[i]->z; }
@@ -87,7 +90,7 @@ template <std::size_t W> struct bvec3_w_t {
     explicit bvec3_w_t(const vec3_w_t<W>& s) noexcept { for (int k = 0; k < 3; ++k) for (std::size_t i = 0; i < W; ++i) c[k].v[i] = std::signbit(s.c[k].v[i]); }
 };
 using pqvec3_w4_t = pqvec3_w_t<4>;
-using pqvec3_w8_t = pqvec3_w_t<8>; using vec3_w8_t = vec3_w_t<8>; using f_w8_t = f_w_t<8>; using length_w8_t = length_w_t<8>; using bvec3_w8_t = bvec3_w_t<8>;
+using pqvec3_w8_t = pqvec3_w_t<8>; using vec3_w8_t = vec3_w_t<8>; using f_w8_t = f_w_t<8>; using length_w8_t = length_w_t<8>; using bvec3_w8_t = bvec3_w_t<8>; using b_w8_t = b_w_t<8>;
 namespace m {
 // simd/math.hpp:409-416 over vblendvps: b where the mask is set, else a
 template <std::size_t W> inline f_w_t<W> selectv(const f_w_t<W>& a, const f_w_t<W>& b, const b_w_t<W>& mask) noexcept { f_w_t<W> r; for (std::size_t i = 0; i < W; ++i) r.v[i] = mask.v[i] ? b.v[i] : a.v[i]; return r; }
@@ -120,6 +123,8 @@ template <std::size_t W, typename U, typename V> inline f_w_t<W> dot_w(const U& 
 template <std::size_t W> inline f_w_t<W> dot(const pqvec3_w_t<W>& u, const vec3_w_t<W>& v) noexcept { return dot_w<W>(u, v); }
 template <std::size_t W> inline f_w_t<W> dot(const vec3_w_t<W>& u, const pqvec3_w_t<W>& v) noexcept { return dot_w<W>(u, v); }
 template <std::size_t W> inline f_w_t<W> dot(const pqvec3_w_t<W>& u, const pqvec3_w_t<W>& v) noexcept { return dot_w<W>(u, v); }
+template <std::size_t W> inline f_w_t<W> dot(const vec3_w_t<W>& u, const vec3_w_t<W>& v) noexcept { return dot_w<W>(u, v); }
+template <std::size_t W> inline bool any(const b_w_t<W>& m) noexcept { for (std::size_t i = 0; i < W; ++i) if (m.v[i]) return true; return false; }
 }
 }
 #endif

@@ -1,0 +1,106 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+// The reference's BVH traversal loops themselves -- src/ads/bvh8w.cpp: the cone traversal (gather_tris :123-185, cone_cluster_intersect :186-230,
+// traverse :232-318: stack of 128, nearest child popped first, search range shrinking with every accepted triangle, unwinding), and the ray /
+// shadow-ray traversal (8-wide triangle clusters :64-100, gather_tris :394-452, ray_cluster_intersect :454-467, traverse :469-554: stack of 64,
+// nodes of <= 16 triangles treated as leaves) -- with the work records and search_range() of include/wt/ads/traversal_common.hpp:21-88, the
+// reference's own ads/common.hpp, ads/bvh8w/bvh8w_node.hpp, ads/bvh8w/common.hpp and, beneath them, everything oracle/ref_cone.cpp compiles
+// (cone / ray tests, elliptic_cone.hpp, frame.hpp ...) -> oracle/_ref/libref_traverse.so.  tests/test_oracle_kats.py runs it over the BVH the HOST
+// LAYER built for a scene and compares, per query, the accepted-triangle list IN TRAVERSAL ORDER, distances, barycentrics and faces with ot_ads.h.
+// bvh8w.cpp as a whole needs tinybvh, the scene tree and the statistics collectors; so the Makefile writes the line ranges named above, as they are,
+// to the git-ignored oracle/_ref/bvh8w_traverse_part.hpp / traversal_common_part.hpp at build time and this TU includes those.  What stands in here:
+// the tree container (arrays + the five accessors the loops call), ads_t::intersect_opts_t, and the statistics wrappers of ads_stats.hpp reduced to
+// their forwarding line.  Wide vectors are the shim's arrays of lanes (WT_SHIM_WIDE_LANES).
+#define WT_SHIM_DISTINCT_PQ
+#define WT_SHIM_WIDE_LANES
+#define RELEASE
+#include <wt/util/assert.hpp>
+#include <cstdint>
+#include <bitset>
+#include <vector>
+#include <cstring>
+#include "/root/reference/include/wt/math/util.hpp"
+#include "_ref/cone_scalar_part.hpp"
+#include <wt/ads/common.hpp>
+#include "/root/reference/include/wt/ads/bvh8w/bvh8w_node.hpp"
+#include "/root/reference/include/wt/ads/bvh8w/common.hpp"
+#include "../include/wtgpu.h"
+namespace wt::ads {
+class ads_t { public: struct intersect_opts_t { bool detect_edges = false, accumulate_edges = false, accumulate_triangles = false; f_t z_search_range_scale = 1; }; };      // ads.hpp:30-35
+struct vectorized_tri_data_t { std::vector<f_t> ax, ay, az, bx, by, bz, cx, cy, cz, nx, ny, nz; };
+class bvh8w_t : public ads_t {
+public:
+    std::vector<tri_t> tris; std::vector<bvh8w::node_t> nodes; std::vector<bvh8w::leaf_node_t> leaves; std::int32_t root = 0; vectorized_tri_data_t vt;
+    const tri_t& tri(tuid_t t) const noexcept { return tris[t.uid]; }
+    const bvh8w::node_t& node(idx_t i) const noexcept { return nodes[i]; }
+    const bvh8w::leaf_node_t& leaf_node(idx_t i) const noexcept { return leaves[i]; }
+    std::int32_t root_ptr() const noexcept { return root; }
+    const vectorized_tri_data_t& vectorized_tri_data() const noexcept { return vt; }
+};
+struct intersection_record_t;
+}
+namespace wt::ads_stats {       // ads_stats.hpp:148-201 without the counters
+static constexpr auto additional_ads_counters = false;
+inline void on_ray_aabb_8w_test() noexcept {}
+template <typename... Ts> inline auto intersect_ray_tri_8w(Ts&&... ts) noexcept { return intersect::intersect_ray_tri(std::forward<Ts>(ts)...); }
+template <typename... Ts> inline auto test_ray_tri_8w(Ts&&... ts) noexcept { return intersect::test_ray_tri(std::forward<Ts>(ts)...); }
+template <typename... Ts> inline std::optional<intersect::intersect_cone_tri_ret_t> intersect_cone_tri(Ts&&... ts) noexcept { return intersect::intersect_cone_tri(std::forward<Ts>(ts)...); }
+template <typename... Ts> inline bool test_cone_tri(Ts&&... ts) noexcept { return intersect::test_cone_tri(std::forward<Ts>(ts)...); }
+}
+#include "_ref/traversal_common_part.hpp"
+using namespace wt;
+using namespace wt::ads;
+#include "_ref/bvh8w_traverse_part.hpp"
+
+static bvh8w_t g_tree;
+extern "C" {
+// the host layer's BVH (include/wtgpu.h: 8-wide nodes, leaves, packed triangles) into the containers the loops read
+void ref_traverse_load(const wtgpu_scene_desc* d) {
+    bvh8w_t& t = g_tree;
+    t.tris.resize(d->n_tris); t.nodes.resize(d->n_nodes); t.leaves.resize(d->n_leaves); t.root = d->root_ptr;
+    auto& v = t.vt;
+    for (auto* a : { &v.ax, &v.ay, &v.az, &v.bx, &v.by, &v.bz, &v.cx, &v.cy, &v.cz, &v.nx, &v.ny, &v.nz }) a->assign(d->n_tris + 8, 0.f);
+    for (uint32_t i = 0; i < d->n_tris; ++i) {
+        const wtgpu_tri& s = d->tris[i];
+        t.tris[i].a = pqvec3_t{ s.ax, s.ay, s.az }; t.tris[i].b = pqvec3_t{ s.bx, s.by, s.bz }; t.tris[i].c = pqvec3_t{ s.cx, s.cy, s.cz }; t.tris[i].n = dir3_t{ s.nx, s.ny, s.nz };
+        v.ax[i] = s.ax; v.ay[i] = s.ay; v.az[i] = s.az; v.bx[i] = s.bx; v.by[i] = s.by; v.bz[i] = s.bz; v.cx[i] = s.cx; v.cy[i] = s.cy; v.cz[i] = s.cz; v.nx[i] = s.nx; v.ny[i] = s.ny; v.nz[i] = s.nz;
+    }
+    for (uint32_t i = 0; i < d->n_nodes; ++i) {
+        const wtgpu_node& s = d->nodes[i]; auto& n = t.nodes[i];
+        for (int l = 0; l < 8; ++l) {
+            n.min.c[0].v[l] = s.minx[l]; n.min.c[1].v[l] = s.miny[l]; n.min.c[2].v[l] = s.minz[l];
+            n.max.c[0].v[l] = s.maxx[l]; n.max.c[1].v[l] = s.maxy[l]; n.max.c[2].v[l] = s.maxz[l];
+            n.child_ptrs[l] = s.child[l];
+        }
+        n.tris_start = s.tris_start; n.tris_count = s.tris_count;
+    }
+    for (uint32_t i = 0; i < d->n_leaves; ++i) { t.leaves[i].tris_ptr = d->leaves[i].tris_ptr; t.leaves[i].count = d->leaves[i].count; }
+}
+// per query in: o[3] d[3] x[3] tan_alpha eccentricity x0 tmin tmax z_scale; out: the accepted triangles in traversal order (first `cap`), their number,
+// the closest distance, the face flag  (bvh8w_t::intersect(cone), bvh8w.cpp:320-331, before cone_work_to_intersection_record)
+void ref_traverse_cones(uint32_t n, const float* q, uint32_t cap, uint32_t* counts, uint32_t* tuids, float* dist, uint32_t* front) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 15 * i;
+        const elliptic_cone_t cone{ ray_t{ pqvec3_t{ c[0], c[1], c[2] }, dir3_t{ c[3], c[4], c[5] } }, dir3_t{ c[6], c[7], c[8] }, c[9], c[10], length_t(c[11]) };
+        ads_t::intersect_opts_t opts; opts.z_search_range_scale = c[14];
+        auto work = intersection_record_vec_work_t{ pqrange_t<>{ c[12], c[13] }, opts.z_search_range_scale };
+        int internal_nodes = 0, leaf_nodes = 0, subtrees = 0;
+        ::traverse<false>(&g_tree, cone, opts, work, internal_nodes, leaf_nodes, subtrees);
+        counts[i] = (uint32_t)work.triangles.size(); dist[i] = work.intr_dist; front[i] = work.front_face ? 1u : 0u;
+        for (uint32_t k = 0; k < cap; ++k) tuids[(size_t)i * cap + k] = k < work.triangles.size() ? (uint32_t)work.triangles[k].tuid.uid : 0xffffffffu;
+    }
+}
+// bvh8w_t::intersect(ray) / shadow(ray), bvh8w.cpp:556-603, before ray_work_to_intersection_record
+void ref_traverse_rays(uint32_t n, const wtgpu_ray_query* q, wtgpu_ray_hit* out, uint32_t* shadow) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const ray_t ray{ pqvec3_t{ q[i].o[0], q[i].o[1], q[i].o[2] }, dir3_t{ q[i].d[0], q[i].d[1], q[i].d[2] } };
+        const pqrange_t<> range{ q[i].tmin, q[i].tmax };
+        { intersection_record_ray_work_t work{ range }; int nodes = 0;
+          ::traverse<false>(&g_tree, ray, work, nodes);
+          const bool hit = m::isfinite(work.triangle.dist) && !(work.triangle.dist > range.max);
+          out[i].tuid = hit ? (uint32_t)work.triangle.tuid.uid : 0xffffffffu; out[i].dist = hit ? (float)work.triangle.dist : std::numeric_limits<float>::infinity();
+          out[i].bary[0] = hit ? work.intersection.bary.uv.x : -1.f; out[i].bary[1] = hit ? work.intersection.bary.uv.y : -1.f; out[i].front_face = hit && work.triangle.front_face; }
+        { intersection_record_ray_work_t work{ range }; int nodes = 0;
+          shadow[i] = ::traverse<true>(&g_tree, ray, work, nodes) ? 1u : 0u; }
+    }
+}
+}

@@ -1017,3 +1017,55 @@ def test_cone_node_test_and_stack_order_equal_the_reference_code():
         f = getattr(lib, fn); f.argtypes = [C.c_uint32, C.c_uint32, fp]; f.restype = None; f(m, 8, buf.ctypes.data_as(fp))
     assert np.array_equal(io, io2)
     k = io[:, 0].reshape(-1, 8); assert (k[:, :-1] >= k[:, 1:]).all()                  # farthest first: the nearest child is popped first
+
+
+REF_TRAVERSE = os.path.join(os.path.dirname(REF_FSD_LUT), "libref_traverse.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAVERSE), reason="oracle/_ref is built from /root/reference (this container only)")
+@pytest.mark.parametrize("scene", ["cornell", "etoile"])
+def test_bvh_traversal_equals_the_reference_code(scene):
+    """ot_ads.h's BVH traversals against the REFERENCE'S OWN loops (src/ads/bvh8w.cpp:123-318 cones, :382-554 rays and shadow rays, with
+    traversal_common.hpp's work records and search_range(); oracle/ref_traverse.cpp), run over the BVH the host layer built for the scene.
+    Cones: per query the list of accepted triangles IN TRAVERSAL ORDER (so: child order, stack sort, search-range shrinking after each leaf,
+    unwinding, the per-triangle cone test), its length, the closest distance (bits) and the face flag -- identical for every query.  Rays: hit
+    triangle, distance and barycentrics (bits), face flag; shadow rays: the boolean -- identical for every query."""
+    b = (scenes.cornell_like(res=16, spp=1, n_sphere=16) if scene == "cornell" else scenes.etoile_like(res=16, spp=1, n_buildings=60)).build()
+    R = C.CDLL(REF_TRAVERSE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float); up = C.POINTER(C.c_uint32)
+    R.ref_traverse_load.argtypes = [C.c_void_p]; R.ref_traverse_load.restype = None
+    R.ref_traverse_load(C.byref(b.desc))
+    # rays
+    n = 20000
+    q = _random_rays(b, n, 53)
+    for i in range(0, n, 5): q[i].tmax = float(np.float32(np.random.default_rng(i).uniform(.05, 1.5)) * np.linalg.norm(np.array(b.desc.world_max[:]) - np.array(b.desc.world_min[:])))
+    hr = (A.RayHit * n)(); ho = (A.RayHit * n)(); sr = (C.c_uint32 * n)(); so = (C.c_uint32 * n)()
+    R.ref_traverse_rays.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]; R.ref_traverse_rays.restype = None
+    R.ref_traverse_rays(n, q, hr, sr)
+    L.oracle_intersect_rays(C.byref(b.desc), n, q, ho); L.oracle_shadow_rays(C.byref(b.desc), n, q, so)
+    raw = lambda h: np.frombuffer(bytes(h), np.uint32).reshape(n, 5)
+    a, o = raw(hr), raw(ho)
+    bad = np.flatnonzero((a != o).any(1))
+    assert bad.size == 0, (bad.size, bad[:5], a[bad[:5]], o[bad[:5]])
+    assert (a[:, 0] != 0xFFFFFFFF).mean() > .4 and list(sr) == list(so) and 0 < sum(sr) < n
+    # cones, as the integrators cast them: thin beams and wide ones, circular and eccentric, with and without a far limit
+    n = 4000; rng = np.random.default_rng(59)
+    lo, hi = np.array(b.desc.world_min[:]), np.array(b.desc.world_max[:]); ext = np.linalg.norm(hi - lo)
+    o3 = lo + (hi - lo) * rng.uniform(0, 1, size=(n, 3)); t3 = lo + (hi - lo) * rng.uniform(0, 1, size=(n, 3))
+    d = t3 - o3; d /= np.linalg.norm(d, axis=1, keepdims=True); d = d.astype(np.float32).astype(np.float64)
+    x = np.cross(d, rng.normal(size=(n, 3))); x /= np.linalg.norm(x, axis=1, keepdims=True)
+    ta = 10.0 ** rng.uniform(-4, -1, size=n); x0 = ext * 10.0 ** rng.uniform(-5, -2, size=n); ecc = rng.uniform(0, .95, size=n); ecc[:1000] = 0
+    ta[:200] = 0; x0[:200] = 0                                                          # rays as cones
+    tmax = np.full(n, np.inf); tmax[2000:] = ext * rng.uniform(.05, 1, size=n - 2000)
+    zs = rng.choice([1.0, 2.0, 4.0], size=n)
+    cq = np.ascontiguousarray(np.concatenate([o3, d, x, ta[:, None], ecc[:, None], x0[:, None], np.zeros((n, 1)), tmax[:, None], zs[:, None]], 1), np.float32)
+    cap = 256
+    outs = []
+    for lib, fn, first in ((R, "ref_traverse_cones", ()), (L, "oracle_cone_work_lists", (C.byref(b.desc),))):
+        cnt = np.zeros(n, np.uint32); tu = np.zeros((n, cap), np.uint32); dist = np.zeros(n, np.float32); fr = np.zeros(n, np.uint32)
+        f = getattr(lib, fn); f.restype = None
+        f.argtypes = ([C.c_void_p] if first else []) + [C.c_uint32, fp, C.c_uint32, up, up, fp, up]
+        f(*first, n, cq.ctypes.data_as(fp), cap, cnt.ctypes.data_as(up), tu.ctypes.data_as(up), dist.ctypes.data_as(fp), fr.ctypes.data_as(up))
+        outs.append((cnt, tu, dist, fr))
+    (c1, t1, d1, f1), (c2, t2, d2, f2) = outs
+    assert np.array_equal(c1, c2) and np.array_equal(t1, t2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32)) and np.array_equal(f1, f2)
+    assert (c1 > 0).mean() > .5 and (c1 > 1).mean() > .1 and c1.max() > 8
