@@ -614,6 +614,24 @@ extern "C" void oracle_cone_work_lists(const wtgpu_scene_desc* desc, uint32_t n,
         for (uint32_t k = 0; k < cap; ++k) tuids[(size_t)i * cap + k] = k < rec.tris.size() ? rec.tris[k] : 0xffffffffu;
     }
 }
+static void kat_put_cone(const ot::elliptic_cone_t& c, float* o) {
+    o[0] = c.x().x; o[1] = c.x().y; o[2] = c.x().z; o[3] = c.x0; o[4] = c.e; o[5] = c.one_over_e; o[6] = c.tan_alpha; o[7] = c.z_apex;
+}
+extern "C" void oracle_cone_through_ellipse_n(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 16 * i; float* o = out + 9 * i;
+        f_t sid = 0;
+        const auto c = ot::elliptic_cone_t::cone_through_ellipse({ a[0], a[1], a[2] }, { a[3], a[4], a[5] }, { a[6], a[7], a[8] }, ot::ray_t{ { a[9], a[10], a[11] }, { a[12], a[13], a[14] } }, a[15], &sid);
+        kat_put_cone(c, o); o[8] = sid;
+    }
+}
+extern "C" void oracle_cone_through_ellipsoid_n(uint32_t n, const float* in, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 19 * i;
+        const ot::frame_t F{ { a[3], a[4], a[5] }, { a[6], a[7], a[8] }, { a[9], a[10], a[11] } };
+        kat_put_cone(ot::elliptic_cone_t::cone_through_ellipsoid({ a[0], a[1], a[2] }, F, ot::ray_t{ { a[12], a[13], a[14] }, { a[15], a[16], a[17] } }, a[18]), out + 8 * i);
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

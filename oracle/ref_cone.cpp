@@ -135,6 +135,28 @@ void ref_stack_sorter(unsigned n, unsigned run, float* io) {
         for (unsigned k = 0; k < run; ++k) { io[2 * (i + k)] = st[k].min_range; io[2 * (i + k) + 1] = (float)st[k].ptr; }
     }
 }
+// the beam re-fits of src/math/elliptic_cone.cpp (compiled from where it lies, linked into this library): out for both: x[3] x0 e one_over_e tan_alpha z_apex
+static void put_cone(const elliptic_cone_t& c, float* o) {
+    o[0] = c.x().x; o[1] = c.x().y; o[2] = c.x().z; o[3] = (float)c.x0(); o[4] = c.get_e(); o[5] = c.get_one_over_e(); o[6] = c.get_tan_alpha(); o[7] = (float)c.get_z_apex();
+}
+// per item in: x[3] y[3] n[3] ro[3] rd[3] tan_alpha; out: cone[8] self_intersection_distance  (elliptic_cone.cpp:19-84)
+void ref_cone_through_ellipse(unsigned n, const float* in, float* out) {
+    for (unsigned i = 0; i < n; ++i) {
+        const float* a = in + 16 * i; float* o = out + 9 * i;
+        length_t sid = 0;
+        const auto c = elliptic_cone_t::cone_through_ellipse(pqvec3_t{ a[0], a[1], a[2] }, pqvec3_t{ a[3], a[4], a[5] }, dir3_t{ a[6], a[7], a[8] },
+                                                             ray_t{ pqvec3_t{ a[9], a[10], a[11] }, dir3_t{ a[12], a[13], a[14] } }, a[15], &sid);
+        put_cone(c, o); o[8] = (float)sid;
+    }
+}
+// per item in: axes[3] frame t[3] b[3] n[3] ro[3] rd[3] tan_alpha; out: cone[8]  (elliptic_cone.cpp:86-145)
+void ref_cone_through_ellipsoid(unsigned n, const float* in, float* out) {
+    for (unsigned i = 0; i < n; ++i) {
+        const float* a = in + 19 * i;
+        const frame_t F{ dir3_t{ a[3], a[4], a[5] }, dir3_t{ a[6], a[7], a[8] }, dir3_t{ a[9], a[10], a[11] } };
+        put_cone(elliptic_cone_t::cone_through_ellipsoid(pqvec3_t{ a[0], a[1], a[2] }, F, ray_t{ pqvec3_t{ a[12], a[13], a[14] }, dir3_t{ a[15], a[16], a[17] } }, a[18]), out + 8 * i);
+    }
+}
 // per item in: cone[12] z; out: axes x y, z_apex, e, one_over_e  (elliptic_cone.hpp: axes(), get_z_apex(), the eccentricity constructor)
 void ref_cone_basics(unsigned n, const float* in, float* out) {
     for (unsigned i = 0; i < n; ++i) {

@@ -283,6 +283,7 @@ inline dir3_t normalize(const pqvec3_t& v) noexcept { const f_t l = std::sqrt(st
 struct bvec3_t { bool x, y, z; };
 inline bvec3_t iszero(const pqvec3_t& v) noexcept { return { v.x == 0, v.y == 0, v.z == 0 }; }
 inline bool all(const bvec3_t& b) noexcept { return b.x && b.y && b.z; }
+inline bvec3_t operator&&(const bvec3_t& a, const bvec3_t& b) noexcept { return { a.x && b.x, a.y && b.y, a.z && b.z }; }       // glm: componentwise
 #endif
 }
 }

@@ -1069,3 +1069,41 @@ def test_bvh_traversal_equals_the_reference_code(scene):
     (c1, t1, d1, f1), (c2, t2, d2, f2) = outs
     assert np.array_equal(c1, c2) and np.array_equal(t1, t2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32)) and np.array_equal(f1, f2)
     assert (c1 > 0).mean() > .5 and (c1 > 1).mean() > .1 and c1.max() > 8
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CONE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_cone_refits_equal_the_reference_code():
+    """ot_math.h's cone_through_ellipse and cone_through_ellipsoid (the re-fit of a beam's envelope through its footprint at every
+    interaction and restart) against the REFERENCE'S OWN src/math/elliptic_cone.cpp compiled from where it lies (over its own linalg.hpp SVD, frame.hpp
+    and intersect_cone_plane): the fitted cone's tangent, x0, e, 1/e, tan_alpha and apex, and the self-intersection distance -- bit-identical on
+    200 000 footprints each: axes over six decades, aspect ratios to 1000, circular footprints (sigma1 == sigma2), one or both axes zero, footprints
+    seen edge-on, ellipsoids with a vanishing axis."""
+    R = C.CDLL(REF_CONE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(61); n = 200000
+    def both(name, oname, inp, width):
+        a = np.zeros((n, width), np.float32); b = a.copy(); inp = np.ascontiguousarray(inp, np.float32)
+        for lib, fn, out in ((R, name, a), (L, oname, b)):
+            f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        return a, b
+    def unit(v): return v / np.linalg.norm(v, axis=1, keepdims=True)
+    nr = unit(rng.normal(size=(n, 3)))
+    tx = unit(np.cross(nr, rng.normal(size=(n, 3)))); ty = np.cross(nr, tx)
+    lx = 10.0 ** rng.uniform(-4, 2, size=(n, 1)); ly = lx * 10.0 ** rng.uniform(-3, 0, size=(n, 1)); ly[:20000] = lx[:20000]
+    ang = rng.uniform(0, 2 * np.pi, size=(n, 1))
+    x = (np.cos(ang) * tx + np.sin(ang) * ty) * lx; y = (-np.sin(ang) * tx + np.cos(ang) * ty) * ly
+    x[20000:21000] = 0; y[20000:21000] = 0; y[21000:23000] = 0                                      # degenerate footprints
+    rd = unit(nr * rng.uniform(.02, 1, size=(n, 1)) * np.sign(rng.normal(size=(n, 1))) + tx * rng.normal(size=(n, 1)) + ty * rng.normal(size=(n, 1)))
+    rd[23000:25000] = unit(tx[23000:25000] + 1e-4 * nr[23000:25000])                                 # edge-on
+    ro = rng.normal(size=(n, 3)) * 3; ta = 10.0 ** rng.uniform(-5, -.5, size=(n, 1)); ta[:5000] = 0
+    a, b = both("ref_cone_through_ellipse", "oracle_cone_through_ellipse_n", np.concatenate([x, y, nr, ro, rd, ta], 1), 9)
+    bad = np.flatnonzero((a.view(np.uint32) != b.view(np.uint32)).any(1))
+    assert bad.size == 0, (bad.size, bad[:5], a[bad[:5]], b[bad[:5]])
+    assert (a[:, 4] > 1.5).mean() > .5 and (a[:, 8] > 0).mean() > .3
+    axes = 10.0 ** rng.uniform(-4, 2, size=(n, 3)); axes[:20000, 1] = axes[:20000, 0]; axes[20000:30000, 2] = axes[20000:30000, 0] * 1e-6; axes[30000:31000, 2] = 0
+    ft = unit(rng.normal(size=(n, 3))); fb = unit(np.cross(ft, rng.normal(size=(n, 3)))); fn = np.cross(ft, fb)
+    ft, fb, fn = (v.astype(np.float32).astype(np.float64) for v in (ft, fb, fn))
+    rd = unit(rng.normal(size=(n, 3))); rd[31000:33000] = fn[31000:33000]; rd[33000:35000] = ft[33000:35000]
+    a, b = both("ref_cone_through_ellipsoid", "oracle_cone_through_ellipsoid_n", np.concatenate([axes, ft, fb, fn, ro, rd, ta], 1), 8)
+    bad = np.flatnonzero((a.view(np.uint32) != b.view(np.uint32)).any(1))
+    assert bad.size == 0, (bad.size, bad[:5], a[bad[:5]], b[bad[:5]])
+    assert (a[:, 4] > 1.5).mean() > .3
