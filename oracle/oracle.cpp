@@ -632,6 +632,33 @@ extern "C" void oracle_cone_through_ellipsoid_n(uint32_t n, const float* in, flo
         kat_put_cone(ot::elliptic_cone_t::cone_through_ellipsoid({ a[0], a[1], a[2] }, F, ot::ray_t{ { a[12], a[13], a[14] }, { a[15], a[16], a[17] } }, a[18]), out + 8 * i);
     }
 }
+// Mueller / Stokes algebra, laid out like oracle/ref_mueller.cpp
+extern "C" void oracle_mueller(uint32_t n, const float* in, float* out) {
+    auto load_m = [](const float* a) { ot::mueller_t M; for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) M.m[c][r] = a[4 * c + r]; return M; };
+    auto put_m = [](const ot::mueller_t& M, float* o) { for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) o[4 * c + r] = M.m[c][r]; };
+    auto load_f = [](const float* f) { return ot::frame_t{ { f[0], f[1], f[2] }, { f[3], f[4], f[5] }, { f[6], f[7], f[8] } }; };
+    auto put_s = [](const ot::stokes_t& s, float* o) { for (int i = 0; i < 4; ++i) o[i] = s.S[i]; };
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 89 * i; float* o = out + 144 * i;
+        const auto A = load_m(a), B = load_m(a + 16);
+        const ot::stokes_t S{ { a[32], a[33], a[34], a[35] } };
+        const ot::frame_t F1 = load_f(a + 36), F2 = load_f(a + 45), F3 = load_f(a + 54), F4 = load_f(a + 63);
+        const ot::v2 t1{ a[72], a[73] }, t2{ a[74], a[75] };
+        const c_t fs{ a[76], a[77] }, fp{ a[78], a[79] }, eta{ a[80], a[81] };
+        const ot::v3 w{ a[82], a[83], a[84] };
+        put_m(A * B, o); put_s(A * S, o + 16);
+        put_m(ot::mueller_t::rotation(t1, t2), o + 20);
+        put_m(ot::mueller_t::fresnel(fs, fp), o + 36);
+        put_m(ot::mueller_fresnel_reflection(eta, w), o + 52);
+        put_m(ot::mueller_fresnel_transmission(eta, w), o + 68);
+        put_m(ot::change_incident_frame(A, F1, F2), o + 84);
+        put_m(ot::change_exitant_frame(A, F1, F2), o + 100);
+        put_m(ot::compose(A, B, F1, F2), o + 116);
+        put_s(S.reorient(F1, F2), o + 132);
+        put_s(ot::mueller_apply(A, S, F1, F2), o + 136);
+        put_s(ot::mueller_apply(A, S, F1, F2, F3, F4), o + 140);
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

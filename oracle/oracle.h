@@ -72,6 +72,7 @@ void oracle_ray_aabb_fast(uint32_t n, const float* in, float* out);
 void oracle_cone_work_lists(const wtgpu_scene_desc* desc, uint32_t n, const float* q, uint32_t cap, uint32_t* counts, uint32_t* tuids, float* dist, uint32_t* front);
 void oracle_cone_through_ellipse_n(uint32_t n, const float* in, float* out);
 void oracle_cone_through_ellipsoid_n(uint32_t n, const float* in, float* out);
+void oracle_mueller(uint32_t n, const float* in, float* out);
 void oracle_cone_cluster(uint32_t n, const float* in, float* out);
 void oracle_stack_sorter(uint32_t n, uint32_t run, float* io);
 void oracle_cone_basics(uint32_t n, const float* in, float* out);

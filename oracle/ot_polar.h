@@ -98,6 +98,13 @@ inline mueller_t change_incident_frame(const mueller_t& M, const frame_t& oldf, 
     if (oldf.handness() != newf.handness()) R = R * mueller_t::handness_flip();
     return M * R;
 }
+// mueller.hpp:204-216
+inline mueller_t change_exitant_frame(const mueller_t& M, const frame_t& oldf, const frame_t& newf) {
+    const v3 tl = oldf.to_local(newf.t);
+    mueller_t R = mueller_t::rotation(v2{ tl.x, tl.y }, v2{ 1, 0 });
+    if (oldf.handness() != newf.handness()) R = R * mueller_t::handness_flip();
+    return R * M;
+}
 // mueller.hpp:402-415
 inline mueller_t compose(const mueller_t& M1, const mueller_t& M2, const frame_t& M1in, const frame_t& M2out) {
     const v3 tl = M1in.to_local(M2out.t);

@@ -24,6 +24,9 @@ struct vec2_t {
     f_t x{}, y{};
     constexpr vec2_t() = default;
     constexpr vec2_t(f_t x_, f_t y_) : x(x_), y(y_) {}
+#ifdef WT_SHIM_MAT4
+    template <typename V> requires requires(const V& v) { v.x; v.y; v.z; } explicit constexpr vec2_t(const V& v) : x(v.x), y(v.y) {}      // glm: the xy part of a 3-vector
+#endif
     constexpr vec2_t& operator/=(f_t s) { x /= s; y /= s; return *this; }
     constexpr f_t& operator[](std::size_t i) { return i == 0 ? x : y; }
     constexpr const f_t& operator[](std::size_t i) const { return i == 0 ? x : y; }
@@ -60,6 +63,7 @@ constexpr mat2_t operator*(const mat2_t& a, const mat2_t& b) {
              a.c[0].x * b.c[1].x + a.c[1].x * b.c[1].y, a.c[0].y * b.c[1].x + a.c[1].y * b.c[1].y };
 }
 constexpr mat2_t operator+(const mat2_t& a, const mat2_t& b) { return { a.c[0] + b.c[0], a.c[1] + b.c[1] }; }
+constexpr mat2_t operator-(const mat2_t& a, const mat2_t& b) { return { a.c[0].x - b.c[0].x, a.c[0].y - b.c[0].y, a.c[1].x - b.c[1].x, a.c[1].y - b.c[1].y }; }
 constexpr mat2_t operator*(const mat2_t& a, f_t s) { return { a.c[0] * s, a.c[1] * s }; }
 constexpr mat2_t operator*(f_t s, const mat2_t& a) { return { a.c[0] * s, a.c[1] * s }; }
 namespace u::ang { inline constexpr f_t rad = 1; }      // mp-units' radian: angles are plain f_t here
@@ -287,3 +291,56 @@ inline bvec3_t operator&&(const bvec3_t& a, const bvec3_t& b) noexcept { return 
 #endif
 }
 }
+
+#ifdef WT_SHIM_MAT4
+// WT_SHIM_MAT4 (oracle/ref_mueller.cpp only): glm's vec4 / column-major mat4 and the quantity-vector aliases, as far as
+// interaction/polarimetric/{stokes,mueller}.hpp use them.  glm semantics: mat4(s) = s on the diagonal; the 16-scalar constructor fills COLUMN by column;
+// m[i] is column i; mat * mat: column c of the result = sum_k a[k] * b[c][k] accumulated left to right (type_mat4x4.inl, no contraction);
+// mat4 +, scalar *, / are elementwise.  m::dot on 4-vectors is the fma chain of the reference's vecmath.hpp, like the 2- and 3-vector ones above.
+namespace wt {
+template <typename T> concept Quantity = std::is_arithmetic_v<T>;
+struct vec4q_t {
+    f_t x{}, y{}, z{}, w{};
+    constexpr vec4q_t() = default;
+    constexpr vec4q_t(f_t x_, f_t y_, f_t z_, f_t w_) : x(x_), y(y_), z(z_), w(w_) {}
+    constexpr f_t& operator[](std::size_t i) { return i == 0 ? x : i == 1 ? y : i == 2 ? z : w; }
+    constexpr const f_t& operator[](std::size_t i) const { return i == 0 ? x : i == 1 ? y : i == 2 ? z : w; }
+    constexpr bool operator==(const vec4q_t&) const = default;
+};
+constexpr vec4q_t operator*(const vec4q_t& a, f_t s) { return { a.x * s, a.y * s, a.z * s, a.w * s }; }
+constexpr vec4q_t operator*(f_t s, const vec4q_t& a) { return { s * a.x, s * a.y, s * a.z, s * a.w }; }
+constexpr vec4q_t operator/(const vec4q_t& a, f_t s) { return { a.x / s, a.y / s, a.z / s, a.w / s }; }
+constexpr vec4q_t operator+(const vec4q_t& a, const vec4q_t& b) { return { a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w }; }
+constexpr vec4q_t operator-(const vec4q_t& a, const vec4q_t& b) { return { a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w }; }
+template <typename T> concept ScalarOrUnit = std::is_arithmetic_v<T>;
+using QE_t = f_t; using QE_solid_angle_t = f_t; using QE_area_t = f_t; using QE_flux_t = f_t; using radiant_flux_t = f_t; using irradiance_t = f_t; using radiant_intensity_t = f_t; using radiance_t = f_t;
+using spectral_radiant_flux_t = f_t; using spectral_irradiance_t = f_t; using spectral_radiant_intensity_t = f_t; using spectral_radiance_t = f_t;      // quantities are plain f_t here
+template <Quantity Q> using qvec4 = vec4q_t;
+template <Quantity Q> using qvec3 = vec3_t;
+template <Quantity Q> using qvec2 = vec2_t;
+struct mat4_t {
+    vec4q_t c[4];
+    constexpr mat4_t() = default;
+    constexpr mat4_t(f_t s) : c{ { s, 0, 0, 0 }, { 0, s, 0, 0 }, { 0, 0, s, 0 }, { 0, 0, 0, s } } {}
+    constexpr mat4_t(f_t a0, f_t a1, f_t a2, f_t a3, f_t b0, f_t b1, f_t b2, f_t b3, f_t c0, f_t c1, f_t c2, f_t c3, f_t d0, f_t d1, f_t d2, f_t d3)
+        : c{ { a0, a1, a2, a3 }, { b0, b1, b2, b3 }, { c0, c1, c2, c3 }, { d0, d1, d2, d3 } } {}
+    constexpr vec4q_t& operator[](std::size_t i) { return c[i]; }
+    constexpr const vec4q_t& operator[](std::size_t i) const { return c[i]; }
+};
+constexpr mat4_t operator*(const mat4_t& a, f_t s) { mat4_t r; for (int i = 0; i < 4; ++i) r.c[i] = a.c[i] * s; return r; }
+constexpr mat4_t operator*(f_t s, const mat4_t& a) { mat4_t r; for (int i = 0; i < 4; ++i) r.c[i] = s * a.c[i]; return r; }
+constexpr mat4_t operator/(const mat4_t& a, f_t s) { mat4_t r; for (int i = 0; i < 4; ++i) r.c[i] = a.c[i] / s; return r; }
+constexpr mat4_t operator+(const mat4_t& a, const mat4_t& b) { mat4_t r; for (int i = 0; i < 4; ++i) r.c[i] = a.c[i] + b.c[i]; return r; }
+constexpr mat4_t operator*(const mat4_t& a, const mat4_t& b) { mat4_t r; for (int i = 0; i < 4; ++i) r.c[i] = a.c[0] * b.c[i].x + a.c[1] * b.c[i].y + a.c[2] * b.c[i].z + a.c[3] * b.c[i].w; return r; }
+namespace m {
+inline f_t dot(const vec4q_t& a, const vec4q_t& b) noexcept { return std::fma(a.w, b.w, std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x))); }
+inline bool isfinite(const vec4q_t& v) noexcept { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z) && std::isfinite(v.w); }
+inline bool isnan(const vec4q_t& v) noexcept { return std::isnan(v.x) || std::isnan(v.y) || std::isnan(v.z) || std::isnan(v.w); }
+inline bool isfinite(const mat4_t& a) noexcept { return isfinite(a.c[0]) && isfinite(a.c[1]) && isfinite(a.c[2]) && isfinite(a.c[3]); }
+inline bool isnan(const mat4_t& a) noexcept { return isnan(a.c[0]) || isnan(a.c[1]) || isnan(a.c[2]) || isnan(a.c[3]); }
+inline mat4_t transpose(const mat4_t& a) noexcept { mat4_t r; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.c[i][j] = a.c[j][i]; return r; }
+}
+}
+#include <format>
+template <> struct std::formatter<wt::mat4_t> : std::formatter<int> { auto format(const wt::mat4_t&, std::format_context& ctx) const { return ctx.out(); } };       // (never called)
+#endif

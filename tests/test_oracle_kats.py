@@ -1107,3 +1107,44 @@ def test_cone_refits_equal_the_reference_code():
     bad = np.flatnonzero((a.view(np.uint32) != b.view(np.uint32)).any(1))
     assert bad.size == 0, (bad.size, bad[:5], a[bad[:5]], b[bad[:5]])
     assert (a[:, 4] > 1.5).mean() > .3
+
+
+REF_MUELLER = os.path.join(os.path.dirname(REF_FSD_LUT), "libref_mueller.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MUELLER), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_mueller_stokes_equal_the_reference_code():
+    """ot_polar.h's Mueller / Stokes algebra (SURVEY.md 8 row a17 -- the row the survey flags for glm's column-major constructor and the explicit
+    transposes) against the REFERENCE'S OWN include/wt/interaction/polarimetric/mueller.hpp + stokes.hpp compiled unmodified (oracle/ref_mueller.cpp):
+    operator product, action on a Stokes vector, rotation(t1, t2), fresnel(fs, fp), fresnel_reflection / fresnel_transmission(eta, w) (over the
+    reference's own fresnel.hpp), change_incident_frame / change_exitant_frame and compose() with and without a handness flip, Stokes reorient,
+    and both frame-aware operator() forms (unpolarized short cut included) -- 144 numbers per case, bit-identical on 100 000 cases."""
+    R = C.CDLL(REF_MUELLER); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(67); n = 100000
+    def unit(v): return v / np.linalg.norm(v, axis=1, keepdims=True)
+    def frames(nrm):
+        t = unit(np.cross(nrm, rng.normal(size=(n, 3)))); b = np.cross(nrm, t)
+        b *= np.where(rng.random((n, 1)) < .3, -1.0, 1.0)                                       # left-handed frames
+        return np.concatenate([t, b, nrm], 1)
+    A_ = rng.normal(size=(n, 16)); B_ = rng.normal(size=(n, 16))
+    S = rng.normal(size=(n, 4)); S[:, 0] = np.abs(S[:, 0]) + np.linalg.norm(S[:, 1:], axis=1); S[:10000, 1:] = 0      # unpolarized
+    n1 = unit(rng.normal(size=(n, 3))).astype(np.float32).astype(np.float64); n2 = unit(rng.normal(size=(n, 3))).astype(np.float32).astype(np.float64)
+    F1, F2, F3, F4 = frames(n1), frames(n1), frames(n2), frames(n2)
+    F2[10000:11000] = F1[10000:11000]                                                         # identical frames (rotation by 0)
+    F2[11000:12000, 0:3] = -F1[11000:12000, 0:3]; F2[11000:12000, 3:6] = -F1[11000:12000, 3:6]   # rotation by pi
+    ang = rng.uniform(0, 2 * np.pi, size=(n, 2)); ang[:1000, 1] = ang[:1000, 0]
+    t1 = np.stack([np.cos(ang[:, 0]), np.sin(ang[:, 0])], 1); t2 = np.stack([np.cos(ang[:, 1]), np.sin(ang[:, 1])], 1)
+    fs = rng.normal(size=(n, 2)) * .7; fpp = rng.normal(size=(n, 2)) * .7
+    eta = np.stack([rng.uniform(.4, 3, size=n), np.where(rng.random(n) < .3, rng.uniform(0, 4, size=n), 0.0)], 1)
+    w = unit(rng.normal(size=(n, 3))); w[:, 2] = np.abs(w[:, 2]); w[:2000, 2] *= 1e-3; w = unit(w)      # grazing incidence among them
+    inp = np.ascontiguousarray(np.concatenate([A_, B_, S, F1, F2, F3, F4, t1, t2, fs, fpp, eta, w, np.zeros((n, 4))], 1), np.float32)
+    assert inp.shape[1] == 89
+    a = np.zeros((n, 144), np.float32); b = a.copy()
+    for lib, fn, out in ((R, "ref_mueller", a), (L, "oracle_mueller", b)):
+        f = getattr(lib, fn); f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, inp.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    names = ["A*B"] * 16 + ["A*S"] * 4 + ["rotation"] * 16 + ["fresnel"] * 16 + ["fresnel_reflection"] * 16 + ["fresnel_transmission"] * 16 + ["change_incident_frame"] * 16 + \
+        ["change_exitant_frame"] * 16 + ["compose"] * 16 + ["reorient"] * 4 + ["apply3"] * 4 + ["apply5"] * 4
+    ne = (a.view(np.uint32) != b.view(np.uint32)) & ~(np.isnan(a) & np.isnan(b))
+    bad = sorted({names[j] for j in np.flatnonzero(ne.any(0))})
+    assert not bad, (bad, int(ne.any(1).sum()))
+    assert np.isfinite(a[:, :52]).all() and np.abs(a[:, 132:]).max() > 0
