@@ -659,6 +659,21 @@ extern "C" void oracle_mueller(uint32_t n, const float* in, float* out) {
         put_s(ot::mueller_apply(A, S, F1, F2, F3, F4), o + 140);
     }
 }
+// integrator::traverse, laid out like oracle/ref_traverse.cpp's ref_integrator_traverse
+extern "C" void oracle_integrator_traverse(const wtgpu_scene_desc* desc, uint32_t n, const float* q, uint32_t cap, float* out, uint32_t* ntris, uint32_t* tris, uint32_t* nedges, uint32_t* edges) {
+    scene_t sc(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 16 * i; float* o = out + 12 * i;
+        const auto r = traverse(sc, kat_cone(c), c[12], c[13], c[14] != 0, c[15] != 0, nullptr);
+        const bool rt = r.ballistic && !r.empty;
+        o[0] = r.empty; o[1] = r.ballistic; o[2] = r.origin.x; o[3] = r.origin.y; o[4] = r.origin.z; o[5] = r.empty ? 0.f : r.distance(); o[6] = r.intersection_region_depth;
+        o[7] = !r.empty && (r.ballistic ? r.ray.front_face : r.cone.front_face); o[8] = rt; o[9] = rt ? r.ray.bary.x : 0.f; o[10] = rt ? r.ray.bary.y : 0.f; o[11] = 0;
+        std::vector<uint32_t> tl, el;
+        if (rt) tl.push_back(r.ray.tuid); else if (!r.empty) { tl = r.cone.tris; el = r.cone.edges; }
+        ntris[i] = (uint32_t)tl.size(); nedges[i] = (uint32_t)el.size();
+        for (uint32_t k = 0; k < cap; ++k) { tris[(size_t)i * cap + k] = k < tl.size() ? tl[k] : 0xffffffffu; edges[(size_t)i * cap + k] = k < el.size() ? el[k] : 0xffffffffu; }
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

@@ -141,6 +141,8 @@ constexpr pqvec3_t& operator-=(pqvec3_t& a, const pqvec3_t& b) { a.x -= b.x; a.y
 inline pqvec2_t::pqvec2_t(const pqvec3_t& v) : x(v.x), y(v.y) {}
 constexpr pqvec3_t operator*(const pqvec3_t& a, const vec3_t& b) { return { a.x * b.x, a.y * b.y, a.z * b.z }; }
 constexpr pqvec3_t operator-(const pqvec3_t& a) { return { -a.x, -a.y, -a.z }; }
+constexpr bool operator==(const pqvec3_t& a, const pqvec3_t& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+constexpr bool operator!=(const pqvec3_t& a, const pqvec3_t& b) { return !(a == b); }
 constexpr pqvec3_t operator+(const pqvec3_t& a) { return a; }
 } namespace glm { struct bvec3_standin { bool x, y, z; }; } namespace wt {
 // boolean vectors and the glm-style select of the scalar ray-AABB entry point (math/intersect/ray.hpp:244-263; parsed, not under pin)
@@ -281,6 +283,7 @@ inline pqvec3_t mix(const pqvec3_t& a, const pqvec3_t& b, bool s) noexcept { ret
 inline f_t max_element(const pqvec3_t& v) noexcept { return std::max(v.x, std::max(v.y, v.z)); }
 inline f_t min_element(const pqvec3_t& v) noexcept { return std::min(v.x, std::min(v.y, v.z)); }
 inline f_t dot(const pqvec2_t& a, const vec2_t& b) noexcept { return std::fma(a.y, b.y, a.x * b.x); }
+inline f_t length(const pqvec2_t& v) noexcept { return std::sqrt(std::fma(v.y, v.y, v.x * v.x)); }
 inline f_t dot(const pqvec3_t& a, const vec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
 inline f_t dot(const vec3_t& a, const pqvec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
 inline dir3_t normalize(const pqvec3_t& v) noexcept { const f_t l = std::sqrt(std::fma(v.z, v.z, std::fma(v.y, v.y, v.x * v.x))); return dir3_t{ v.x / l, v.y / l, v.z / l }; }

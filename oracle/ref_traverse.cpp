@@ -2,9 +2,11 @@
 // The reference's BVH traversal loops themselves -- src/ads/bvh8w.cpp: the cone traversal (gather_tris :123-185, cone_cluster_intersect :186-230,
 // traverse :232-318: stack of 128, nearest child popped first, search range shrinking with every accepted triangle, unwinding), and the ray /
 // shadow-ray traversal (8-wide triangle clusters :64-100, gather_tris :394-452, ray_cluster_intersect :454-467, traverse :469-554: stack of 64,
-// nodes of <= 16 triangles treated as leaves) -- with the work records and search_range() of include/wt/ads/traversal_common.hpp:21-88, the
+// nodes of <= 16 triangles treated as leaves) -- with the work records and search_range() of include/wt/ads/traversal_common.hpp:21-149, the
 // reference's own ads/common.hpp, ads/bvh8w/bvh8w_node.hpp, ads/bvh8w/common.hpp and, beneath them, everything oracle/ref_cone.cpp compiles
-// (cone / ray tests, elliptic_cone.hpp, frame.hpp ...) -> oracle/_ref/libref_traverse.so.  tests/test_oracle_kats.py runs it over the BVH the HOST
+// (cone / ray tests, elliptic_cone.hpp, frame.hpp ...), the reference's own ads/intersection_record.hpp, the record conversions of
+// traversal_common.hpp:90-149 (distance culling, edge sets) and, on top, the ballistic / diffusive state machine of include/wt/integrator/traversal.hpp:26-248
+// (calculate_min_ballistic_distance, max_ballistic_distance, traverse, traverse_shadow) -> oracle/_ref/libref_traverse.so.  tests/test_oracle_kats.py runs it over the BVH the HOST
 // LAYER built for a scene and compares, per query, the accepted-triangle list IN TRAVERSAL ORDER, distances, barycentrics and faces with ot_ads.h.
 // bvh8w.cpp as a whole needs tinybvh, the scene tree and the statistics collectors; so the Makefile writes the line ranges named above, as they are,
 // to the git-ignored oracle/_ref/bvh8w_traverse_part.hpp / traversal_common_part.hpp at build time and this TU includes those.  What stands in here:
@@ -24,8 +26,18 @@
 #include "/root/reference/include/wt/ads/bvh8w/bvh8w_node.hpp"
 #include "/root/reference/include/wt/ads/bvh8w/common.hpp"
 #include "../include/wtgpu.h"
+#include "/root/reference/include/wt/ads/intersection_record.hpp"
+#include "/root/reference/include/wt/util/unreachable.hpp"
+#include <set>
 namespace wt::ads {
-class ads_t { public: struct intersect_opts_t { bool detect_edges = false, accumulate_edges = false, accumulate_triangles = false; f_t z_search_range_scale = 1; }; };      // ads.hpp:30-35
+class ads_t {       // ads.hpp: the options (:30-35) and the four queries (:60-100) the integrators call
+public:
+    struct intersect_opts_t { bool detect_edges = false, accumulate_edges = false, accumulate_triangles = false; f_t z_search_range_scale = 1; };
+    virtual intersection_record_t intersect(const ray_t& ray, const pqrange_t<> range) const noexcept = 0;
+    virtual intersection_record_t intersect(const elliptic_cone_t& cone, const pqrange_t<> range, const intersect_opts_t& opts) const noexcept = 0;
+    virtual bool shadow(const ray_t& ray, const pqrange_t<> range) const noexcept = 0;
+    virtual bool shadow(const elliptic_cone_t& cone, const pqrange_t<> range) const noexcept = 0;
+};
 struct vectorized_tri_data_t { std::vector<f_t> ax, ay, az, bx, by, bz, cx, cy, cz, nx, ny, nz; };
 class bvh8w_t : public ads_t {
 public:
@@ -35,8 +47,11 @@ public:
     const bvh8w::leaf_node_t& leaf_node(idx_t i) const noexcept { return leaves[i]; }
     std::int32_t root_ptr() const noexcept { return root; }
     const vectorized_tri_data_t& vectorized_tri_data() const noexcept { return vt; }
+    intersection_record_t intersect(const ray_t& ray, const pqrange_t<> range) const noexcept override;
+    intersection_record_t intersect(const elliptic_cone_t& cone, const pqrange_t<> range, const intersect_opts_t& opts) const noexcept override;
+    bool shadow(const ray_t& ray, const pqrange_t<> range) const noexcept override;
+    bool shadow(const elliptic_cone_t& cone, const pqrange_t<> range) const noexcept override;
 };
-struct intersection_record_t;
 }
 namespace wt::ads_stats {       // ads_stats.hpp:148-201 without the counters
 static constexpr auto additional_ads_counters = false;
@@ -51,6 +66,34 @@ using namespace wt;
 using namespace wt::ads;
 #include "_ref/bvh8w_traverse_part.hpp"
 
+// the four bvh8w_t members (bvh8w.cpp:320-375, :556-603) without their statistics / timing lines
+intersection_record_t bvh8w_t::intersect(const elliptic_cone_t& cone, const pqrange_t<> traversal_range, const intersect_opts_t& opts) const noexcept {
+    auto work = intersection_record_vec_work_t{ traversal_range, opts.z_search_range_scale };
+    int internal_nodes = 0, leaf_nodes = 0, subtrees = 0;
+    ::traverse<false>(this, cone, opts, work, internal_nodes, leaf_nodes, subtrees);
+    return cone_work_to_intersection_record(*this, work, cone, opts);
+}
+bool bvh8w_t::shadow(const elliptic_cone_t& cone, const pqrange_t<> traversal_range) const noexcept {
+    if (traversal_range.empty()) return false;
+    auto work = intersection_record_vec_work_t{ traversal_range };
+    int internal_nodes = 0, leaf_nodes = 0, subtrees = 0;
+    ::traverse<true>(this, cone, { .detect_edges = false }, work, internal_nodes, leaf_nodes, subtrees);
+    return m::isfinite(work.intr_dist);
+}
+intersection_record_t bvh8w_t::intersect(const ray_t& ray, const pqrange_t<> traversal_range) const noexcept {
+    intersection_record_ray_work_t work{ traversal_range }; int nodes = 0;
+    ::traverse<false>(this, ray, work, nodes);
+    return ray_work_to_intersection_record(*this, work, traversal_range);
+}
+bool bvh8w_t::shadow(const ray_t& ray, const pqrange_t<> traversal_range) const noexcept {
+    if (traversal_range.empty()) return false;
+    intersection_record_ray_work_t work{ traversal_range }; int nodes = 0;
+    return ::traverse<true>(this, ray, work, nodes);
+}
+namespace wt::beam { struct beam_generic_t { static inline constexpr f_t major_axis_to_z_scale() noexcept { return 2; } }; }     // beam/beam_generic.hpp:50
+namespace wt { template <typename T> concept Wavelength = std::is_floating_point_v<T>; }
+#include "_ref/integrator_traversal_part.hpp"
+
 static bvh8w_t g_tree;
 extern "C" {
 // the host layer's BVH (include/wtgpu.h: 8-wide nodes, leaves, packed triangles) into the containers the loops read
@@ -62,6 +105,7 @@ void ref_traverse_load(const wtgpu_scene_desc* d) {
     for (uint32_t i = 0; i < d->n_tris; ++i) {
         const wtgpu_tri& s = d->tris[i];
         t.tris[i].a = pqvec3_t{ s.ax, s.ay, s.az }; t.tris[i].b = pqvec3_t{ s.bx, s.by, s.bz }; t.tris[i].c = pqvec3_t{ s.cx, s.cy, s.cz }; t.tris[i].n = dir3_t{ s.nx, s.ny, s.nz };
+        if (d->tri_meta) { const auto& mt = d->tri_meta[i]; t.tris[i].edge_ab = tuid_t{ mt.edge_ab }; t.tris[i].edge_bc = tuid_t{ mt.edge_bc }; t.tris[i].edge_ca = tuid_t{ mt.edge_ca }; }
         v.ax[i] = s.ax; v.ay[i] = s.ay; v.az[i] = s.az; v.bx[i] = s.bx; v.by[i] = s.by; v.bz[i] = s.bz; v.cx[i] = s.cx; v.cy[i] = s.cy; v.cz[i] = s.cz; v.nx[i] = s.nx; v.ny[i] = s.ny; v.nz[i] = s.nz;
     }
     for (uint32_t i = 0; i < d->n_nodes; ++i) {
@@ -87,6 +131,23 @@ void ref_traverse_cones(uint32_t n, const float* q, uint32_t cap, uint32_t* coun
         ::traverse<false>(&g_tree, cone, opts, work, internal_nodes, leaf_nodes, subtrees);
         counts[i] = (uint32_t)work.triangles.size(); dist[i] = work.intr_dist; front[i] = work.front_face ? 1u : 0u;
         for (uint32_t k = 0; k < cap; ++k) tuids[(size_t)i * cap + k] = k < work.triangles.size() ? (uint32_t)work.triangles[k].tuid.uid : 0xffffffffu;
+    }
+}
+// integrator::traverse (traversal.hpp:94-172).  per query in: o[3] d[3] x[3] tan_alpha eccentricity x0 lambda distance force_ray_tracing detect_edges = 16;
+// out per query: 12 floats (empty ballistic origin[3] distance depth front_face has_rt bary[2] pad) and the triangle / edge lists (counts + first `cap`)
+void ref_integrator_traverse(uint32_t n, const float* q, uint32_t cap, float* out, uint32_t* ntris, uint32_t* tris, uint32_t* nedges, uint32_t* edges) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 16 * i; float* o = out + 12 * i;
+        const elliptic_cone_t cone{ ray_t{ pqvec3_t{ c[0], c[1], c[2] }, dir3_t{ c[3], c[4], c[5] } }, dir3_t{ c[6], c[7], c[8] }, c[9], c[10], length_t(c[11]) };
+        const auto r = integrator::traverse(g_tree, cone, length_t(c[12]), length_t(c[13]), integrator::traversal_opts_t{ .force_ray_tracing = c[14] != 0, .detect_edges = c[15] != 0 });
+        const bool empty = r.record.empty();
+        o[0] = empty; o[1] = r.ballistic; o[2] = r.origin.x; o[3] = r.origin.y; o[4] = r.origin.z; o[5] = empty ? 0.f : (float)r.record.distance(); o[6] = r.intersection_region_depth;
+        o[7] = !empty && r.record.is_front_face(); o[8] = r.record.has_raytracing_intersection_record();
+        o[9] = o[8] ? r.record.get_raytracing_intersection_record().bary.uv.x : 0.f; o[10] = o[8] ? r.record.get_raytracing_intersection_record().bary.uv.y : 0.f; o[11] = 0;
+        uint32_t k = 0; for (const auto& t : r.record.triangles()) { if (k < cap) tris[(size_t)i * cap + k] = t.uid; ++k; }
+        ntris[i] = k; for (; k < cap; ++k) tris[(size_t)i * cap + k] = 0xffffffffu;
+        k = 0; for (const auto& e : r.record.edges()) { if (k < cap) edges[(size_t)i * cap + k] = e.uid; ++k; }
+        nedges[i] = k; for (; k < cap; ++k) edges[(size_t)i * cap + k] = 0xffffffffu;
     }
 }
 // bvh8w_t::intersect(ray) / shadow(ray), bvh8w.cpp:556-603, before ray_work_to_intersection_record

@@ -1148,3 +1148,42 @@ def test_mueller_stokes_equal_the_reference_code():
     bad = sorted({names[j] for j in np.flatnonzero(ne.any(0))})
     assert not bad, (bad, int(ne.any(1).sum()))
     assert np.isfinite(a[:, :52]).all() and np.abs(a[:, 132:]).max() > 0
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAVERSE), reason="oracle/_ref is built from /root/reference (this container only)")
+@pytest.mark.parametrize("scene", ["cornell", "etoile"])
+def test_ballistic_diffusive_traverse_equals_the_reference_code(scene):
+    """ot_integrator.h's traverse() -- the ballistic / diffusive state machine every path segment of both integrators runs --
+    against the REFERENCE'S OWN include/wt/integrator/traversal.hpp:22-248 (calculate_min_ballistic_distance, max_ballistic_distance, traverse) compiled
+    over the reference's own BVH loops, record conversions (distance culling, edge sets; traversal_common.hpp:90-149) and intersection_record.hpp
+    (oracle/ref_traverse.cpp), on the host layer's tree and edge table: per query empty / ballistic flags, origin, distance and region depth (bits),
+    face flag, barycentrics, the triangle list in order and the edge set -- identical for every query.  Wavelengths from 1e-6 to 1e-1 of the scene
+    (so hits on the 1st to 16th ballistic segment, diffusive restarts accepted and rejected), beams from rays to 6 degrees, with and without a
+    distance limit, forced ray tracing, edge detection on and off."""
+    b = (scenes.cornell_like(res=16, spp=1, n_sphere=16) if scene == "cornell" else scenes.etoile_like(res=16, spp=1, n_buildings=60)).build()
+    R = C.CDLL(REF_TRAVERSE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float); up = C.POINTER(C.c_uint32)
+    R.ref_traverse_load.argtypes = [C.c_void_p]; R.ref_traverse_load.restype = None
+    R.ref_traverse_load(C.byref(b.desc))
+    n = 6000; rng = np.random.default_rng(71)
+    lo, hi = np.array(b.desc.world_min[:]), np.array(b.desc.world_max[:]); ext = np.linalg.norm(hi - lo)
+    o3 = lo + (hi - lo) * rng.uniform(0, 1, size=(n, 3)); t3 = lo + (hi - lo) * rng.uniform(0, 1, size=(n, 3))
+    d = t3 - o3; d /= np.linalg.norm(d, axis=1, keepdims=True); d = d.astype(np.float32).astype(np.float64)
+    x = np.cross(d, rng.normal(size=(n, 3))); x /= np.linalg.norm(x, axis=1, keepdims=True)
+    ta = 10.0 ** rng.uniform(-4, -1, size=n); x0 = ext * 10.0 ** rng.uniform(-5, -2, size=n); ecc = rng.uniform(0, .95, size=n); ecc[:1500] = 0
+    ta[:300] = 0; x0[:300] = 0
+    lam = ext * 10.0 ** rng.uniform(-6, -1, size=n)
+    dist = np.full(n, np.inf); dist[3000:] = ext * rng.uniform(.02, 1, size=n - 3000)
+    frt = (rng.random(n) < .1).astype(np.float64); de = (rng.random(n) < .8).astype(np.float64)
+    q = np.ascontiguousarray(np.concatenate([o3, d, x, ta[:, None], ecc[:, None], x0[:, None], lam[:, None], dist[:, None], frt[:, None], de[:, None]], 1), np.float32)
+    cap = 256; outs = []
+    for lib, fn, first in ((R, "ref_integrator_traverse", ()), (L, "oracle_integrator_traverse", (C.byref(b.desc),))):
+        o = np.zeros((n, 12), np.float32); nt = np.zeros(n, np.uint32); tl = np.zeros((n, cap), np.uint32); ne = np.zeros(n, np.uint32); el = np.zeros((n, cap), np.uint32)
+        f = getattr(lib, fn); f.restype = None
+        f.argtypes = ([C.c_void_p] if first else []) + [C.c_uint32, fp, C.c_uint32, fp, up, up, up, up]
+        f(*first, n, q.ctypes.data_as(fp), cap, o.ctypes.data_as(fp), nt.ctypes.data_as(up), tl.ctypes.data_as(up), ne.ctypes.data_as(up), el.ctypes.data_as(up))
+        outs.append((o, nt, tl, ne, el))
+    (o1, nt1, tl1, ne1, el1), (o2, nt2, tl2, ne2, el2) = outs
+    bad = np.flatnonzero((o1.view(np.uint32) != o2.view(np.uint32)).any(1) | (nt1 != nt2) | (tl1 != tl2).any(1) | (ne1 != ne2) | (el1 != el2).any(1))
+    assert bad.size == 0, (bad.size, bad[:4], o1[bad[:4]], o2[bad[:4]], nt1[bad[:4]], nt2[bad[:4]], ne1[bad[:4]], ne2[bad[:4]])
+    hit = o1[:, 0] == 0
+    assert hit.mean() > .5 and (o1[hit, 1] == 1).sum() > n // 20 and (o1[hit, 1] == 0).sum() > n // 20 and ne1.max() > 0 and nt1.max() > 4
