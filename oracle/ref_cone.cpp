@@ -6,7 +6,7 @@
 // ot_math.h.
 // The middle of cone.hpp (:272-475, cone-AABB on 8-wide AVX vectors) needs the reference's SIMD layer, which does not compile against the shim; so the
 // Makefile's `ref` target writes lines 1-271 and 476-end of the header as they are to the git-ignored oracle/_ref/cone_scalar_part.hpp at build time
-// and this TU includes that.  No reference text is committed.  The 4-wide vector the triangle drivers stage the vertices in is the shim's array of lanes
+// and this TU includes that.  The cut is deleted again once the library is linked: no reference text is committed or left in the tree.  The 4-wide vector the triangle drivers stage the vertices in is the shim's array of lanes
 // (WT_SHIM_WIDE_LANES, ref_shims/wt/math/simd/wide_vector.hpp): one IEEE operation per AVX instruction.
 #define WT_SHIM_DISTINCT_PQ
 #define WT_SHIM_WIDE_LANES

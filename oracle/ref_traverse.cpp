@@ -9,7 +9,7 @@
 // (calculate_min_ballistic_distance, max_ballistic_distance, traverse, traverse_shadow) -> oracle/_ref/libref_traverse.so.  tests/test_oracle_kats.py runs it over the BVH the HOST
 // LAYER built for a scene and compares, per query, the accepted-triangle list IN TRAVERSAL ORDER, distances, barycentrics and faces with ot_ads.h.
 // bvh8w.cpp as a whole needs tinybvh, the scene tree and the statistics collectors; so the Makefile writes the line ranges named above, as they are,
-// to the git-ignored oracle/_ref/bvh8w_traverse_part.hpp / traversal_common_part.hpp at build time and this TU includes those.  What stands in here:
+// to the git-ignored oracle/_ref/bvh8w_traverse_part.hpp / traversal_common_part.hpp at build time (deleted again once the library is linked) and this TU includes those.  What stands in here:
 // the tree container (arrays + the five accessors the loops call), ads_t::intersect_opts_t, and the statistics wrappers of ads_stats.hpp reduced to
 // their forwarding line.  Wide vectors are the shim's arrays of lanes (WT_SHIM_WIDE_LANES).
 #define WT_SHIM_DISTINCT_PQ
