@@ -674,6 +674,20 @@ extern "C" void oracle_integrator_traverse(const wtgpu_scene_desc* desc, uint32_
         for (uint32_t k = 0; k < cap; ++k) { tris[(size_t)i * cap + k] = k < tl.size() ? tl[k] : 0xffffffffu; edges[(size_t)i * cap + k] = k < el.size() ? el[k] : 0xffffffffu; }
     }
 }
+// plt_path_t::find_closest_triangle, laid out like oracle/ref_traverse.cpp's ref_find_closest_triangle
+extern "C" void oracle_find_closest_triangle(const wtgpu_scene_desc* desc, uint32_t n, const float* q, float* out, uint32_t* tuid) {
+    scene_t sc(desc); film_t film(sc); path_stats_t st;
+    plt_path_t integ(sc, film, &st);
+    std::vector<uint32_t> list;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 10 * i;
+        list.clear(); for (uint32_t k = 0; k < (uint32_t)c[9]; ++k) list.push_back((uint32_t)c[8] + k);
+        const auto id = integ.find_closest_triangle(list, { c[6], c[7] }, { c[0], c[1], c[2] }, { c[3], c[4], c[5] });
+        const bool f = id.primary != WTGPU_INVALID_IDX;
+        tuid[i] = f ? id.primary : 0xffffffffu;
+        out[3 * i] = f ? id.dist : 0.f; out[3 * i + 1] = f ? id.bary.x : 0.f; out[3 * i + 2] = f ? id.bary.y : 0.f;
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

@@ -132,7 +132,8 @@ struct pqvec3_t {
     constexpr pqvec3_t() = default;
     constexpr pqvec3_t(f_t x_, f_t y_, f_t z_) : x(x_), y(y_), z(z_) {}
     constexpr pqvec3_t(const vec3_t& v) : x(v.x), y(v.y), z(v.z) {}
-    constexpr pqvec3_t(const vec2_t& v, f_t z_) : x(v.x), y(v.y), z(z_) {}       // (lengths: a plain 2-vector times a length, and a z)         // (a plain vector times a length, e.g. t * v.x with v.x in metres)
+    constexpr pqvec3_t(const vec2_t& v, f_t z_) : x(v.x), y(v.y), z(z_) {}
+    explicit constexpr pqvec3_t(f_t s) : x(s), y(s), z(s) {}       // (lengths: a plain 2-vector times a length, and a z)         // (a plain vector times a length, e.g. t * v.x with v.x in metres)
 };
 constexpr pqvec3_t operator-(const pqvec3_t& a, const vec3_t& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
 constexpr pqvec3_t operator-(const pqvec3_t& a, const pqvec3_t& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
@@ -281,6 +282,7 @@ inline pqvec3_t cross(const pqvec3_t& x, const vec3_t& y) noexcept { return { ef
 inline pqvec3_t mix(const pqvec3_t& a, const pqvec3_t& b, const vec3b_t& s) noexcept { return { s.x ? b.x : a.x, s.y ? b.y : a.y, s.z ? b.z : a.z }; }
 inline pqvec3_t mix(const pqvec3_t& a, const pqvec3_t& b, bool s) noexcept { return s ? b : a; }
 inline f_t max_element(const pqvec3_t& v) noexcept { return std::max(v.x, std::max(v.y, v.z)); }
+inline pqvec3_t abs(const pqvec3_t& v) noexcept { return { std::fabs(v.x), std::fabs(v.y), std::fabs(v.z) }; }
 inline f_t min_element(const pqvec3_t& v) noexcept { return std::min(v.x, std::min(v.y, v.z)); }
 inline f_t dot(const pqvec2_t& a, const vec2_t& b) noexcept { return std::fma(a.y, b.y, a.x * b.x); }
 inline f_t length(const pqvec2_t& v) noexcept { return std::sqrt(std::fma(v.y, v.y, v.x * v.x)); }

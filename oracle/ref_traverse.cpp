@@ -37,12 +37,13 @@ public:
     virtual intersection_record_t intersect(const elliptic_cone_t& cone, const pqrange_t<> range, const intersect_opts_t& opts) const noexcept = 0;
     virtual bool shadow(const ray_t& ray, const pqrange_t<> range) const noexcept = 0;
     virtual bool shadow(const elliptic_cone_t& cone, const pqrange_t<> range) const noexcept = 0;
+    virtual const tri_t& tri(tuid_t t) const noexcept = 0;
 };
 struct vectorized_tri_data_t { std::vector<f_t> ax, ay, az, bx, by, bz, cx, cy, cz, nx, ny, nz; };
 class bvh8w_t : public ads_t {
 public:
     std::vector<tri_t> tris; std::vector<bvh8w::node_t> nodes; std::vector<bvh8w::leaf_node_t> leaves; std::int32_t root = 0; vectorized_tri_data_t vt;
-    const tri_t& tri(tuid_t t) const noexcept { return tris[t.uid]; }
+    const tri_t& tri(tuid_t t) const noexcept override { return tris[t.uid]; }
     const bvh8w::node_t& node(idx_t i) const noexcept { return nodes[i]; }
     const bvh8w::leaf_node_t& leaf_node(idx_t i) const noexcept { return leaves[i]; }
     std::int32_t root_ptr() const noexcept { return root; }
@@ -90,11 +91,16 @@ bool bvh8w_t::shadow(const ray_t& ray, const pqrange_t<> traversal_range) const 
     intersection_record_ray_work_t work{ traversal_range }; int nodes = 0;
     return ::traverse<true>(this, ray, work, nodes);
 }
+static bvh8w_t g_tree;
 namespace wt::beam { struct beam_generic_t { static inline constexpr f_t major_axis_to_z_scale() noexcept { return 2; } }; }     // beam/beam_generic.hpp:50
 namespace wt { template <typename T> concept Wavelength = std::is_floating_point_v<T>; }
 #include "_ref/integrator_traversal_part.hpp"
+// the primary-triangle pick of plt_path::random_walk (plt_path_detail.hpp:244-276) over the reference's own cone_intersection_tolerance.hpp
+#include <optional>
+#include "/root/reference/include/wt/math/intersect/cone_intersection_tolerance.hpp"
+#include "_ref/plt_path_closest_part.hpp"
 
-static bvh8w_t g_tree;
+
 extern "C" {
 // the host layer's BVH (include/wtgpu.h: 8-wide nodes, leaves, packed triangles) into the containers the loops read
 void ref_traverse_load(const wtgpu_scene_desc* d) {
@@ -148,6 +154,19 @@ void ref_integrator_traverse(uint32_t n, const float* q, uint32_t cap, float* ou
         ntris[i] = k; for (; k < cap; ++k) tris[(size_t)i * cap + k] = 0xffffffffu;
         k = 0; for (const auto& e : r.record.edges()) { if (k < cap) edges[(size_t)i * cap + k] = e.uid; ++k; }
         nedges[i] = k; for (; k < cap; ++k) edges[(size_t)i * cap + k] = 0xffffffffu;
+    }
+}
+// find_closest_triangle (plt_path_detail.hpp:253-276).  per query in: origin[3] dir[3] zmin zmax first_tuid count; out: tuid (or ~0) dist bary[2]
+void ref_find_closest_triangle(uint32_t n, const float* q, float* out, uint32_t* tuid) {
+    std::vector<tuid_t> list;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 10 * i;
+        list.clear(); for (uint32_t k = 0; k < (uint32_t)c[9]; ++k) list.push_back(tuid_t{ (uint32_t)c[8] + k });
+        const intersection_record_t::triangles_accessor_t acc{ .s = list.data(), .e = list.data() + list.size() };
+        const auto id = find_closest_triangle(acc, g_tree, pqrange_t<>{ c[6], c[7] }, pqvec3_t{ c[0], c[1], c[2] }, dir3_t{ c[3], c[4], c[5] });
+        tuid[i] = id.primary ? (uint32_t)(id.primary - g_tree.tris.data()) : 0xffffffffu;
+        out[3 * i] = id.primary ? (float)id.primary_intersection_record.dist : 0.f;
+        out[3 * i + 1] = id.primary ? id.primary_intersection_record.bary.uv.x : 0.f; out[3 * i + 2] = id.primary ? id.primary_intersection_record.bary.uv.y : 0.f;
     }
 }
 // bvh8w_t::intersect(ray) / shadow(ray), bvh8w.cpp:556-603, before ray_work_to_intersection_record
