@@ -688,6 +688,19 @@ extern "C" void oracle_find_closest_triangle(const wtgpu_scene_desc* desc, uint3
         out[3 * i] = f ? id.dist : 0.f; out[3 * i + 1] = f ? id.bary.x : 0.f; out[3 * i + 2] = f ? id.bary.y : 0.f;
     }
 }
+// self-intersection offsets, laid out like oracle/ref_traverse.cpp's ref_edge_offsets
+extern "C" void oracle_edge_offsets(const wtgpu_scene_desc* desc, uint32_t n, const float* q, float* out) {
+    scene_t sc(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 7 * i; float* o = out + 6 * i;
+        const uint32_t ei = (uint32_t)c[0];
+        const ray_t ray{ { c[1], c[2], c[3] }, { c[4], c[5], c[6] } };
+        const v3 p = sc.offseted_ray_origin_edge(ei, ray);
+        const uint32_t t1 = desc->edges[ei].tri1;
+        const v3 err = scene_t::tri_fp_errors(sc.ads.tri_a(t1), sc.ads.tri_b(t1), sc.ads.tri_c(t1), ray.o);
+        o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = err.x; o[4] = err.y; o[5] = err.z;
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

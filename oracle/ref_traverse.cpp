@@ -99,6 +99,9 @@ namespace wt { template <typename T> concept Wavelength = std::is_floating_point
 #include <optional>
 #include "/root/reference/include/wt/math/intersect/cone_intersection_tolerance.hpp"
 #include "_ref/plt_path_closest_part.hpp"
+// self-intersection offsets: compute_intersection_triangle_fp_errors and intersection_edge_t::offseted_ray_origin (src/interaction/intersection.cpp:149-170, :187-211)
+#include "_ref/intersection_offset_part.hpp"
+static std::vector<edge_t> g_edges;
 
 
 extern "C" {
@@ -122,6 +125,12 @@ void ref_traverse_load(const wtgpu_scene_desc* d) {
             n.child_ptrs[l] = s.child[l];
         }
         n.tris_start = s.tris_start; n.tris_count = s.tris_count;
+    }
+    g_edges.assign(d->n_edges, edge_t{});
+    for (uint32_t i = 0; i < d->n_edges; ++i) {
+        const wtgpu_edge& s = d->edges[i]; edge_t& e = g_edges[i];
+        e.t1 = dir3_t{ s.t1[0], s.t1[1], s.t1[2] }; e.t2 = dir3_t{ s.t2[0], s.t2[1], s.t2[2] };
+        e.tri1 = &t.tris[s.tri1]; e.tri2 = s.tri2 != WTGPU_INVALID_IDX ? &t.tris[s.tri2] : nullptr;
     }
     for (uint32_t i = 0; i < d->n_leaves; ++i) { t.leaves[i].tris_ptr = d->leaves[i].tris_ptr; t.leaves[i].count = d->leaves[i].count; }
 }
@@ -154,6 +163,17 @@ void ref_integrator_traverse(uint32_t n, const float* q, uint32_t cap, float* ou
         ntris[i] = k; for (; k < cap; ++k) tris[(size_t)i * cap + k] = 0xffffffffu;
         k = 0; for (const auto& e : r.record.edges()) { if (k < cap) edges[(size_t)i * cap + k] = e.uid; ++k; }
         nedges[i] = k; for (; k < cap; ++k) edges[(size_t)i * cap + k] = 0xffffffffu;
+    }
+}
+// per query in: edge index, ray o[3] d[3]; out: the offset origin (intersection.cpp:187-211), then the fp error bound of the edge's first triangle (:149-170)
+void ref_edge_offsets(uint32_t n, const float* q, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 7 * i; float* o = out + 6 * i;
+        const edge_t& e = g_edges[(uint32_t)c[0]];
+        const ray_t ray{ pqvec3_t{ c[1], c[2], c[3] }, dir3_t{ c[4], c[5], c[6] } };
+        const auto p = intersection_edge_t{ &e, ray.o }.offseted_ray_origin(ray);
+        const auto err = compute_intersection_triangle_fp_errors(e.tri1->a, e.tri1->b, e.tri1->c, ray.o);
+        o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = err.x; o[4] = err.y; o[5] = err.z;
     }
 }
 // find_closest_triangle (plt_path_detail.hpp:253-276).  per query in: origin[3] dir[3] zmin zmax first_tuid count; out: tuid (or ~0) dist bary[2]

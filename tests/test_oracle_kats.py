@@ -1220,3 +1220,32 @@ def test_primary_triangle_pick_equals_the_reference_code():
     assert np.array_equal(t1, t2) and np.array_equal(o1.view(np.uint32), o2.view(np.uint32))
     found = t1 != 0xFFFFFFFF
     assert .3 < found.mean() < .95 and found[(kind == 1) | (kind == 2)].sum() > 50 and (~found[(kind == 1) | (kind == 2)]).sum() > 50
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAVERSE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_self_intersection_offsets_equal_the_reference_code():
+    """ot_scene.h's self-intersection offsets against the REFERENCE'S OWN src/interaction/intersection.cpp:149-170
+    (compute_intersection_triangle_fp_errors, the bound every offset origin of the path is built from) and :187-211
+    (intersection_edge_t::offseted_ray_origin: away from the wedge, open and closed edges, by the larger of the two faces' bounds), on the host
+    layer's edge table of the etoile-like scene: offset origin and error bound bit-identical on 50 000 (edge, ray) pairs, origins from on the edge
+    to a thousand scene sizes away."""
+    b = scenes.etoile_like(res=16, spp=1, n_buildings=60).build()
+    R = C.CDLL(REF_TRAVERSE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float)
+    R.ref_traverse_load.argtypes = [C.c_void_p]; R.ref_traverse_load.restype = None
+    R.ref_traverse_load(C.byref(b.desc))
+    ne = b.desc.n_edges; assert ne > 100
+    n = 50000; rng = np.random.default_rng(79)
+    lo, hi = np.array(b.desc.world_min[:]), np.array(b.desc.world_max[:]); ext = np.linalg.norm(hi - lo)
+    ei = rng.integers(0, ne, size=n)
+    ro = lo + (hi - lo) * rng.uniform(0, 1, size=(n, 3)) + rng.normal(size=(n, 3)) * ext * 10.0 ** rng.uniform(-3, 3, size=(n, 1))
+    E = np.frombuffer((C.c_uint8 * (96 * ne)).from_address(C.addressof(b.desc.edges.contents)), np.float32).reshape(ne, 24)
+    ro[:10000] = E[ei[:10000], 0:3] + rng.uniform(0, 1, size=(10000, 1)) * (E[ei[:10000], 3:6] - E[ei[:10000], 0:3])      # on the edge
+    rd = rng.normal(size=(n, 3)); rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    q = np.ascontiguousarray(np.concatenate([ei[:, None].astype(np.float64), ro, rd], 1), np.float32)
+    a = np.zeros((n, 6), np.float32); o = a.copy()
+    f = R.ref_edge_offsets; f.argtypes = [C.c_uint32, fp, fp]; f.restype = None; f(n, q.ctypes.data_as(fp), a.ctypes.data_as(fp))
+    g = L.oracle_edge_offsets; g.argtypes = [C.c_void_p, C.c_uint32, fp, fp]; g.restype = None; g(C.byref(b.desc), n, q.ctypes.data_as(fp), o.ctypes.data_as(fp))
+    assert np.array_equal(a.view(np.uint32), o.view(np.uint32))
+    assert (np.linalg.norm(a[:, :3] - q[:, 1:4], axis=1) > 0).mean() > .9
+    open_edges = np.frombuffer((C.c_uint8 * (96 * ne)).from_address(C.addressof(b.desc.edges.contents)), np.uint32).reshape(ne, 24)[:, 23] == 0xFFFFFFFF
+    assert 0 <= open_edges.sum() <= ne
