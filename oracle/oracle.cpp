@@ -701,6 +701,24 @@ extern "C" void oracle_edge_offsets(const wtgpu_scene_desc* desc, uint32_t n, co
         o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = err.x; o[4] = err.y; o[5] = err.z;
     }
 }
+// plt_bdpt_t::find_closest_triangle, laid out like oracle/ref_traverse.cpp's ref_bd_find_closest_triangle
+extern "C" void oracle_bd_find_closest_triangle(const wtgpu_scene_desc* desc, uint32_t n, const float* q, float* out, uint32_t* tuid) {
+    scene_t sc(desc); film_t film(sc); bdpt_stats_t st;
+    plt_bdpt_t integ(sc, film, &st);
+    std::vector<uint32_t> list;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 28 * i; float* o = out + 4 * i;
+        list.clear(); for (uint32_t k = 0; k < (uint32_t)c[9]; ++k) list.push_back((uint32_t)c[8] + k);
+        const v3 dir{ c[3], c[4], c[5] };
+        const frame_t bf{ { c[10], c[11], c[12] }, { c[13], c[14], c[15] }, dir };
+        const auto env = elliptic_cone_t::make_ecc(ray_t{ { c[16], c[17], c[18] }, dir }, { c[19], c[20], c[21] }, c[22], c[23], c[24]);
+        const wavefront_t wf(v2{ c[25], c[26] });
+        const auto id = integ.find_closest_triangle(list, { c[6], c[7] }, { c[0], c[1], c[2] }, dir, bf, env, wf, c[27] != 0);
+        const bool f = id.primary != WTGPU_INVALID_IDX;
+        tuid[i] = f ? id.primary : 0xffffffffu;
+        o[0] = f ? id.dist : 0.f; o[1] = f ? id.bary.x : 0.f; o[2] = f ? id.bary.y : 0.f; o[3] = id.integrated_radiant_flux;
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

@@ -143,6 +143,7 @@ struct wavefront_t {
         gaussian2d_t g(v2{ fp.x / beam_cross_section_envelope, fp.y / beam_cross_section_envelope });
         dist = g.is_dirac() ? gaussian2d_t(v2{ 0, 0 }) : g;
     }
+    explicit wavefront_t(v2 sigma) { gaussian2d_t g(sigma); dist = g.is_dirac() ? gaussian2d_t(v2{ 0, 0 }) : g; }      // (for the pins: a wavefront of given standard deviations)
     v2 envelope() const { return dist.sigma * beam_cross_section_envelope; }
     f_t amplitude_magnitude(v2 x) const { return std::sqrt(dist.pdf(x)); }
     f_t integrate_triangle(v2 a, v2 b, v2 c) const { return dist.integrate_triangle(a, b, c); }

@@ -27,6 +27,9 @@ struct vec2_t {
 #ifdef WT_SHIM_MAT4
     template <typename V> requires requires(const V& v) { v.x; v.y; v.z; } explicit constexpr vec2_t(const V& v) : x(v.x), y(v.y) {}      // glm: the xy part of a 3-vector
 #endif
+#ifdef WT_SHIM_DISTINCT_PQ
+    template <typename V> requires (requires(const V& v) { v.x; v.y; } && !requires(const V& v) { v.z; } && !std::is_same_v<V, vec2_t>) explicit constexpr vec2_t(const V& v) : x(v.x), y(v.y) {}      // numbers out of a 2-vector of lengths (divided by the unit)
+#endif
     constexpr vec2_t& operator/=(f_t s) { x /= s; y /= s; return *this; }
     constexpr f_t& operator[](std::size_t i) { return i == 0 ? x : y; }
     constexpr const f_t& operator[](std::size_t i) const { return i == 0 ? x : y; }
@@ -104,6 +107,8 @@ struct pqvec2_t {
     explicit inline pqvec2_t(const pqvec3_t& v);                        // the xy part
 };
 constexpr pqvec2_t operator*(const pqvec2_t& a, f_t s) { return { a.x * s, a.y * s }; }
+constexpr pqvec2_t operator/(const pqvec2_t& a, f_t s) { return { a.x / s, a.y / s }; }
+constexpr vec2_t to_vec2(const pqvec2_t& a) { return { a.x, a.y }; }
 constexpr pqvec2_t operator-(const pqvec2_t& a, const pqvec2_t& b) { return { a.x - b.x, a.y - b.y }; }
 constexpr pqvec2_t operator+(const pqvec2_t& a, const pqvec2_t& b) { return { a.x + b.x, a.y + b.y }; }
 constexpr pqvec2_t operator*(f_t s, const pqvec2_t& a) { return { s * a.x, s * a.y }; }
@@ -119,7 +124,8 @@ struct wavenumber_t { f_t per_mm; };
 struct wavenumber_length_t { f_t mm_per_m_scaled; };
 constexpr wavenumber_length_t operator*(wavenumber_t k, length_t l) { return { k.per_mm * l }; }
 template <typename T> concept Angle = std::is_floating_point_v<T>;
-template <typename T> concept Length = std::is_floating_point_v<T>;      // a length is a plain f_t here
+template <typename T> concept Length = std::is_floating_point_v<T>;
+template <typename T> concept Area = std::is_floating_point_v<T>;      // a length is a plain f_t here
 template <typename T> concept Wavenumber = std::is_same_v<T, wavenumber_t>;
 namespace u { constexpr f_t to_m(f_t v) { return v; } constexpr vec2_t to_num(const vec2_t& v) { return v; } constexpr f_t to_num(f_t v) { return v; } constexpr f_t to_num(wavenumber_length_t v) { return v.mm_per_m_scaled * f_t(1000); } }
 #ifndef WT_SHIM_DISTINCT_PQ
@@ -233,6 +239,7 @@ template <typename A, typename B> inline f_t dot(const A& v1, const B& v2) noexc
     return d + err;
 }
 }
+inline constexpr f_t sqrt_two = f_t(1.41421356237309504880168872420969808);
 inline constexpr f_t inv_sqrt_two = f_t(1. / 1.41421356237309504880168872420969808);                   // math/defs.hpp:57
 inline constexpr f_t sqrt_pi_2 = f_t(1.253314137315500251207882642405522627), inv_sqrt_two_pi = f_t(0.398942280401432677939946059934381868);  // math/defs.hpp
 inline f_t round(f_t v) noexcept { return std::round(v); }                                      // common.hpp:104-106 glm::round

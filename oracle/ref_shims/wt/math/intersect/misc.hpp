@@ -2,6 +2,10 @@
 // is written over mp-units quantities), restated on plain floats: only the `points` count is used by src/math/gaussian2d.cpp; and
 // intersect_edge_plane (:163-180), which math/intersect/clip.hpp calls.
 #pragma once
+#ifdef WT_SHIM_DISTINCT_PQ
+// (the builds in which vectors of lengths are a type of their own compile the reference's own header)
+#include "/root/reference/include/wt/math/intersect/misc.hpp"
+#else
 #include <optional>
 #include <utility>
 #include <wt/math/common.hpp>
@@ -33,3 +37,4 @@ inline std::optional<pqvec3_t> intersect_edge_plane(const pqvec3_t& p0, const pq
     return std::nullopt;
 }
 }
+#endif

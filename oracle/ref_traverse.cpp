@@ -98,7 +98,17 @@ namespace wt { template <typename T> concept Wavelength = std::is_floating_point
 // the primary-triangle pick of plt_path::random_walk (plt_path_detail.hpp:244-276) over the reference's own cone_intersection_tolerance.hpp
 #include <optional>
 #include "/root/reference/include/wt/math/intersect/cone_intersection_tolerance.hpp"
+namespace ref_plt_path { using namespace wt; using namespace wt::ads;
 #include "_ref/plt_path_closest_part.hpp"
+}
+// ... and plt_bdpt's (plt_bdpt_detail.hpp:351-419): the same pick, then -- when no triangle lies under the point -- the beam's Gaussian integrated over the
+// front- or back-facing triangles of the list, clipped to the interaction depth and projected onto the cross-section at its centre, summed in list order;
+// over the reference's own clip.hpp, gaussian_wavefront.hpp, elliptic_cone_t::project_local and src/math/gaussian2d.cpp (oracle/ref_gaussian2d_lanes.cpp)
+#include "/root/reference/include/wt/math/intersect/clip.hpp"
+#include "/root/reference/include/wt/beam/gaussian_wavefront.hpp"
+namespace ref_plt_bdpt { using namespace wt; using namespace wt::ads;
+#include "_ref/plt_bdpt_closest_part.hpp"
+}
 // self-intersection offsets: compute_intersection_triangle_fp_errors and intersection_edge_t::offseted_ray_origin (src/interaction/intersection.cpp:149-170, :187-211)
 #include "_ref/intersection_offset_part.hpp"
 static std::vector<edge_t> g_edges;
@@ -165,6 +175,24 @@ void ref_integrator_traverse(uint32_t n, const float* q, uint32_t cap, float* ou
         nedges[i] = k; for (; k < cap; ++k) edges[(size_t)i * cap + k] = 0xffffffffu;
     }
 }
+// plt_bdpt's find_closest_triangle.  per query in: origin[3] dir[3] zmin zmax first_tuid count | beam frame t[3] b[3] (n = dir) | envelope o[3] x[3] tan_alpha
+// eccentricity x0 (d = dir) | wavefront sigma x y | integrate_front_facing = 28; out: tuid (or ~0), dist bary[2] integrated_radiant_flux
+void ref_bd_find_closest_triangle(uint32_t n, const float* q, float* out, uint32_t* tuid) {
+    std::vector<tuid_t> list;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 28 * i; float* o = out + 4 * i;
+        list.clear(); for (uint32_t k = 0; k < (uint32_t)c[9]; ++k) list.push_back(tuid_t{ (uint32_t)c[8] + k });
+        const intersection_record_t::triangles_accessor_t acc{ .s = list.data(), .e = list.data() + list.size() };
+        const dir3_t dir{ c[3], c[4], c[5] };
+        const frame_t bf{ dir3_t{ c[10], c[11], c[12] }, dir3_t{ c[13], c[14], c[15] }, dir };
+        const elliptic_cone_t env{ ray_t{ pqvec3_t{ c[16], c[17], c[18] }, dir }, dir3_t{ c[19], c[20], c[21] }, c[22], c[23], length_t(c[24]) };
+        const beam::gaussian_wavefront_t wf{ gaussian2d_t{ vec2_t{ c[25], c[26] } } };
+        const auto id = ref_plt_bdpt::find_closest_triangle(acc, g_tree, pqrange_t<>{ c[6], c[7] }, pqvec3_t{ c[0], c[1], c[2] }, dir, bf, env, wf, true, c[27] != 0);
+        tuid[i] = id.primary ? (uint32_t)(id.primary - g_tree.tris.data()) : 0xffffffffu;
+        o[0] = id.primary ? (float)id.primary_intersection_record.dist : 0.f; o[1] = id.primary ? id.primary_intersection_record.bary.uv.x : 0.f; o[2] = id.primary ? id.primary_intersection_record.bary.uv.y : 0.f;
+        o[3] = id.integrated_radiant_flux;
+    }
+}
 // per query in: edge index, ray o[3] d[3]; out: the offset origin (intersection.cpp:187-211), then the fp error bound of the edge's first triangle (:149-170)
 void ref_edge_offsets(uint32_t n, const float* q, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
@@ -183,7 +211,7 @@ void ref_find_closest_triangle(uint32_t n, const float* q, float* out, uint32_t*
         const float* c = q + 10 * i;
         list.clear(); for (uint32_t k = 0; k < (uint32_t)c[9]; ++k) list.push_back(tuid_t{ (uint32_t)c[8] + k });
         const intersection_record_t::triangles_accessor_t acc{ .s = list.data(), .e = list.data() + list.size() };
-        const auto id = find_closest_triangle(acc, g_tree, pqrange_t<>{ c[6], c[7] }, pqvec3_t{ c[0], c[1], c[2] }, dir3_t{ c[3], c[4], c[5] });
+        const auto id = ref_plt_path::find_closest_triangle(acc, g_tree, pqrange_t<>{ c[6], c[7] }, pqvec3_t{ c[0], c[1], c[2] }, dir3_t{ c[3], c[4], c[5] });
         tuid[i] = id.primary ? (uint32_t)(id.primary - g_tree.tris.data()) : 0xffffffffu;
         out[3 * i] = id.primary ? (float)id.primary_intersection_record.dist : 0.f;
         out[3 * i + 1] = id.primary ? id.primary_intersection_record.bary.uv.x : 0.f; out[3 * i + 2] = id.primary ? id.primary_intersection_record.bary.uv.y : 0.f;

@@ -1249,3 +1249,47 @@ def test_self_intersection_offsets_equal_the_reference_code():
     assert (np.linalg.norm(a[:, :3] - q[:, 1:4], axis=1) > 0).mean() > .9
     open_edges = np.frombuffer((C.c_uint8 * (96 * ne)).from_address(C.addressof(b.desc.edges.contents)), np.uint32).reshape(ne, 24)[:, 23] == 0xFFFFFFFF
     assert 0 <= open_edges.sum() <= ne
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAVERSE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_bdpt_closest_triangle_and_gaussian_power_equal_the_reference_code():
+    """plt_bdpt_t::find_closest_triangle of ot_bdpt.h -- what the bench's dominant kernels (k_bd_resolve and its flat-resolve successors) compute per
+    diffusive vertex: the primary-triangle pick and, when no triangle lies under the point, the beam's Gaussian power over the front- or back-facing
+    triangles of the cone query's list, each clipped to the interaction depth, projected onto the cross-section at its centre and integrated, summed in
+    f32 IN LIST ORDER -- against the REFERENCE'S OWN plt_bdpt_detail.hpp:352-419 compiled over its own clip.hpp,
+    gaussian_wavefront.hpp, elliptic_cone_t::project_local, cone_intersection_tolerance.hpp and src/math/gaussian2d.cpp (oracle/ref_traverse.cpp):
+    chosen triangle, distance, barycentrics and the integrated flux bit-identical on 30 000 vertices over lists of 1-48 triangles of the cornell-like
+    scene, beams from a tenth of a triangle to many triangles wide, depth ranges cutting through the triangles."""
+    b = scenes.cornell_like(res=16, spp=1, n_sphere=16).build()
+    R = C.CDLL(REF_TRAVERSE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float); up = C.POINTER(C.c_uint32)
+    R.ref_traverse_load.argtypes = [C.c_void_p]; R.ref_traverse_load.restype = None
+    R.ref_traverse_load(C.byref(b.desc))
+    nt = b.desc.n_tris; T = np.frombuffer((C.c_float * (12 * nt)).from_address(C.addressof(b.desc.tris.contents)), np.float32).reshape(nt, 12)
+    n = 30000; rng = np.random.default_rng(83)
+    cnt = rng.integers(1, 49, size=n); first = rng.integers(0, nt - 48, size=n); pick = first + rng.integers(0, cnt)
+    A3, B3, C3 = T[pick, 0:3].astype(np.float64), T[pick, 4:7].astype(np.float64), T[pick, 8:11].astype(np.float64)
+    size = np.linalg.norm(B3 - A3, axis=1) + np.linalg.norm(C3 - A3, axis=1)
+    w = rng.uniform(-.6, 1.2, size=(n, 2)); P = A3 + w[:, :1] * (B3 - A3) + w[:, 1:] * (C3 - A3)      # most points beside the triangle: the integration branch
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True); d = d.astype(np.float32).astype(np.float64)
+    z = size * 10.0 ** rng.uniform(-.5, 1.5, size=n)
+    o = P - d * z[:, None]
+    t = np.cross(d, rng.normal(size=(n, 3))); t /= np.linalg.norm(t, axis=1, keepdims=True); t = t.astype(np.float32).astype(np.float64); bb = np.cross(d, t)
+    ta = 10.0 ** rng.uniform(-3, -1, size=n); x0 = size * 10.0 ** rng.uniform(-2, 0, size=n); ecc = rng.uniform(0, .9, size=n)
+    rad = ta * z + x0
+    sig = np.stack([rad / 3, rad / 3 * np.sqrt(1 - ecc ** 2)], 1)
+    depth = 2 * rad * rng.uniform(.2, 3, size=n)
+    zmin = z - depth * rng.uniform(0, 1, size=n); zmax = zmin + depth
+    iff = (rng.random(n) < .5).astype(np.float64)
+    q = np.ascontiguousarray(np.concatenate([o, d, zmin[:, None], zmax[:, None], first[:, None], cnt[:, None], t, bb, o, t, ta[:, None], ecc[:, None], x0[:, None], sig, iff[:, None]], 1), np.float32)
+    assert q.shape[1] == 28
+    outs = []
+    for lib, fn, firstarg in ((R, "ref_bd_find_closest_triangle", ()), (L, "oracle_bd_find_closest_triangle", (C.byref(b.desc),))):
+        out = np.zeros((n, 4), np.float32); tu = np.zeros(n, np.uint32)
+        f = getattr(lib, fn); f.restype = None; f.argtypes = ([C.c_void_p] if firstarg else []) + [C.c_uint32, fp, fp, up]
+        f(*firstarg, n, q.ctypes.data_as(fp), out.ctypes.data_as(fp), tu.ctypes.data_as(up))
+        outs.append((out, tu))
+    (o1, t1), (o2, t2) = outs
+    bad = np.flatnonzero((t1 != t2) | (o1.view(np.uint32) != o2.view(np.uint32)).any(1))
+    assert bad.size == 0, (bad.size, bad[:5], o1[bad[:5]], o2[bad[:5]], t1[bad[:5]], t2[bad[:5]])
+    found = t1 != 0xFFFFFFFF
+    assert .1 < found.mean() < .8 and (o1[~found, 3] > 0).mean() > .3 and (o1[~found, 3] > 1e-3).sum() > 500
