@@ -11,7 +11,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with `pytest -m gpu` on a B200)")
     # oracle/_ref: the pieces of the reference that compile from where they lie (this container only).  Built before collection, because the
     # pinning tests are skipped when the libraries are absent (as they are on the GPU box, where /root/reference does not exist).
-    if os.path.isdir("/root/reference/include/wt") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_distributions.so")):
+    if os.path.isdir("/root/reference/include/wt") and not all(os.path.exists(os.path.join(ROOT, "oracle", "_ref", f)) for f in ("libref_distributions.so", "libref_traverse.so", "libref_mueller.so")):
         import subprocess
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"], check=False)
 
