@@ -719,6 +719,26 @@ extern "C" void oracle_bd_find_closest_triangle(const wtgpu_scene_desc* desc, ui
         o[0] = f ? id.dist : 0.f; o[1] = f ? id.bary.x : 0.f; o[2] = f ? id.bary.y : 0.f; o[3] = id.integrated_radiant_flux;
     }
 }
+// fraunhofer_fsd_t's constructor, laid out like oracle/ref_traverse.cpp's ref_ffsd_aperture
+extern "C" void oracle_ffsd_aperture(const wtgpu_scene_desc* desc, uint32_t n, const float* q, uint32_t cap, uint32_t* counts, float* summary, float* edges) {
+    scene_t sc(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 27 * i;
+        const auto beam = kat_cone(c);
+        const frame_t fr{ { c[12], c[13], c[14] }, { c[15], c[16], c[17] }, { c[18], c[19], c[20] } };
+        const wavefront_t wf(v2{ c[23], c[24] });
+        std::vector<uint32_t> es; for (uint32_t k = 0; k < (uint32_t)c[26]; ++k) es.push_back((uint32_t)c[25] + k);
+        const fraunhofer_fsd_t f(sc, nullptr, fr, c[21], c[22], beam, es, wf);
+        const auto& ap = f.ap;
+        counts[i] = (uint32_t)ap.edges.size();
+        summary[4 * i] = ap.recp_I; summary[4 * i + 1] = ap.psi02; summary[4 * i + 2] = ap.P0; summary[4 * i + 3] = ap.P0_pdf;
+        for (uint32_t k = 0; k < cap; ++k) {
+            float* o = edges + ((size_t)i * cap + k) * 9;
+            if (k < ap.edges.size()) { const auto& e = ap.edges[k]; o[0] = e.e.x; o[1] = e.e.y; o[2] = e.v.x; o[3] = e.v.y; o[4] = e.a_b.real(); o[5] = e.a_b.imag(); o[6] = e.iab_2.real(); o[7] = e.iab_2.imag(); o[8] = ap.edge_pdfs[k]; }
+            else for (int j = 0; j < 9; ++j) o[j] = 0.f;
+        }
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

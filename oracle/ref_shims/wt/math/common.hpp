@@ -109,6 +109,7 @@ struct pqvec2_t {
 constexpr pqvec2_t operator*(const pqvec2_t& a, f_t s) { return { a.x * s, a.y * s }; }
 constexpr pqvec2_t operator/(const pqvec2_t& a, f_t s) { return { a.x / s, a.y / s }; }
 constexpr vec2_t to_vec2(const pqvec2_t& a) { return { a.x, a.y }; }
+constexpr vec2_t operator/(const pqvec2_t& a, const pqvec2_t& b) { return { a.x / b.x, a.y / b.y }; }      // lengths / lengths: numbers
 constexpr pqvec2_t operator-(const pqvec2_t& a, const pqvec2_t& b) { return { a.x - b.x, a.y - b.y }; }
 constexpr pqvec2_t operator+(const pqvec2_t& a, const pqvec2_t& b) { return { a.x + b.x, a.y + b.y }; }
 constexpr pqvec2_t operator*(f_t s, const pqvec2_t& a) { return { s * a.x, s * a.y }; }
@@ -293,6 +294,8 @@ inline pqvec3_t abs(const pqvec3_t& v) noexcept { return { std::fabs(v.x), std::
 inline f_t min_element(const pqvec3_t& v) noexcept { return std::min(v.x, std::min(v.y, v.z)); }
 inline f_t dot(const pqvec2_t& a, const vec2_t& b) noexcept { return std::fma(a.y, b.y, a.x * b.x); }
 inline f_t length(const pqvec2_t& v) noexcept { return std::sqrt(std::fma(v.y, v.y, v.x * v.x)); }
+inline f_t max_element(const pqvec2_t& v) noexcept { return std::max(v.x, v.y); }
+inline pqvec2_t mix(const pqvec2_t& a, const pqvec2_t& b, f_t x) noexcept { if (x == f_t(0)) return a; if (x == f_t(1)) return b; return { a.x * (f_t(1) - x) + b.x * x, a.y * (f_t(1) - x) + b.y * x }; }      // as the 2-vector of numbers above
 inline f_t dot(const pqvec3_t& a, const vec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
 inline f_t dot(const vec3_t& a, const pqvec3_t& b) noexcept { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
 inline dir3_t normalize(const pqvec3_t& v) noexcept { const f_t l = std::sqrt(std::fma(v.z, v.z, std::fma(v.y, v.y, v.x * v.x))); return dir3_t{ v.x / l, v.y / l, v.z / l }; }
@@ -303,6 +306,20 @@ inline bvec3_t operator&&(const bvec3_t& a, const bvec3_t& b) noexcept { return 
 #endif
 }
 }
+
+#ifdef WT_SHIM_MM_UNIT
+// WT_SHIM_MM_UNIT (oracle/ref_traverse.cpp only): `f_t(1) * u::mm`, the unit the Fraunhofer aperture is expressed in.  Lengths are plain floats in METRES
+// here; a length held in millimetres is a type of its own, and the two places the pinned constructor uses it follow mp-units: a length in metres divided
+// by one in millimetres is a number carrying the unit ratio m/mm, converted to a plain number by the exact factor 1000 (one f32 product after the
+// quotient of the numerical values); a wavenumber in 1/mm times a length in mm is a plain number (no factor).
+namespace wt {
+struct length_mm_t { f_t mm; };
+namespace u { struct mm_unit_t {}; inline constexpr mm_unit_t mm{}; }
+constexpr length_mm_t operator*(f_t v, u::mm_unit_t) { return { v }; }
+constexpr vec2_t operator/(const pqvec2_t& a, const length_mm_t& b) { return { a.x / b.mm * f_t(1000), a.y / b.mm * f_t(1000) }; }
+constexpr f_t operator*(const wavenumber_t& k, const length_mm_t& l) { return k.per_mm * l.mm; }
+}
+#endif
 
 #ifdef WT_SHIM_MAT4
 // WT_SHIM_MAT4 (oracle/ref_mueller.cpp only): glm's vec4 / column-major mat4 and the quantity-vector aliases, as far as

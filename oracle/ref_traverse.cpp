@@ -14,6 +14,7 @@
 // their forwarding line.  Wide vectors are the shim's arrays of lanes (WT_SHIM_WIDE_LANES).
 #define WT_SHIM_DISTINCT_PQ
 #define WT_SHIM_WIDE_LANES
+#define WT_SHIM_MM_UNIT
 #define RELEASE
 #include <wt/util/assert.hpp>
 #include <cstdint>
@@ -38,12 +39,14 @@ public:
     virtual bool shadow(const ray_t& ray, const pqrange_t<> range) const noexcept = 0;
     virtual bool shadow(const elliptic_cone_t& cone, const pqrange_t<> range) const noexcept = 0;
     virtual const tri_t& tri(tuid_t t) const noexcept = 0;
+    virtual const edge_t& edge(tuid_t e) const noexcept = 0;
 };
 struct vectorized_tri_data_t { std::vector<f_t> ax, ay, az, bx, by, bz, cx, cy, cz, nx, ny, nz; };
 class bvh8w_t : public ads_t {
 public:
-    std::vector<tri_t> tris; std::vector<bvh8w::node_t> nodes; std::vector<bvh8w::leaf_node_t> leaves; std::int32_t root = 0; vectorized_tri_data_t vt;
+    std::vector<tri_t> tris; std::vector<bvh8w::node_t> nodes; std::vector<bvh8w::leaf_node_t> leaves; std::int32_t root = 0; vectorized_tri_data_t vt; std::vector<edge_t> edges;
     const tri_t& tri(tuid_t t) const noexcept override { return tris[t.uid]; }
+    const edge_t& edge(tuid_t e) const noexcept override { return edges[e.uid]; }
     const bvh8w::node_t& node(idx_t i) const noexcept { return nodes[i]; }
     const bvh8w::leaf_node_t& leaf_node(idx_t i) const noexcept { return leaves[i]; }
     std::int32_t root_ptr() const noexcept { return root; }
@@ -109,9 +112,25 @@ namespace ref_plt_path { using namespace wt; using namespace wt::ads;
 namespace ref_plt_bdpt { using namespace wt; using namespace wt::ads;
 #include "_ref/plt_bdpt_closest_part.hpp"
 }
+// the Fraunhofer aperture of plt_bdpt's diffusive vertices: the constructor of fraunhofer::free_space_diffraction_t, src/interaction/fsd/fraunhofer/
+// free_space_diffraction.cpp:18-129 (silhouette edges of the cone query's edge set, clamped to the beam's 3-sigma ellipse, cut into segments of a third of
+// its radius, each weighted by Pj; the 0-th order lobe from eight samples of the aperture's spectrum), over the reference's own fsd.hpp, fsd_sampler.hpp,
+// gaussian_wavefront.hpp, intersect_edge_ellipse and is_point_in_ellipsoid.  The class is declared here with the members the constructor touches
+// (free_space_diffraction.hpp:30-60 pulls in sampler/density.hpp, written directly over mp-units).
+#include "/root/reference/include/wt/interaction/fsd/fraunhofer/fsd.hpp"
+#include "/root/reference/include/wt/interaction/fsd/fraunhofer/fsd_sampler.hpp"
+namespace wt::fraunhofer {
+class free_space_diffraction_t {
+public:
+    static constexpr auto fsd_unit = f_t(1) * u::mm;
+    fsd::fsd_aperture_t aperture; wavenumber_t k; frame_t frame; const fsd_sampler::fsd_sampler_t* fsd_sampler;
+    free_space_diffraction_t(const ads::ads_t* ads, const fsd_sampler::fsd_sampler_t* fsd_sampler, const frame_t& frame, wavenumber_t k, f_t totalPower,
+                             const elliptic_cone_t& beam, const ads::intersection_record_t::edges_container_t& edges, const beam::gaussian_wavefront_t& wave_function) noexcept;
+};
+}
+#include "_ref/ffsd_ctor_part.hpp"
 // self-intersection offsets: compute_intersection_triangle_fp_errors and intersection_edge_t::offseted_ray_origin (src/interaction/intersection.cpp:149-170, :187-211)
 #include "_ref/intersection_offset_part.hpp"
-static std::vector<edge_t> g_edges;
 
 
 extern "C" {
@@ -136,10 +155,12 @@ void ref_traverse_load(const wtgpu_scene_desc* d) {
         }
         n.tris_start = s.tris_start; n.tris_count = s.tris_count;
     }
-    g_edges.assign(d->n_edges, edge_t{});
+    auto& g_edges = t.edges; g_edges.assign(d->n_edges, edge_t{});
     for (uint32_t i = 0; i < d->n_edges; ++i) {
         const wtgpu_edge& s = d->edges[i]; edge_t& e = g_edges[i];
         e.t1 = dir3_t{ s.t1[0], s.t1[1], s.t1[2] }; e.t2 = dir3_t{ s.t2[0], s.t2[1], s.t2[2] };
+        e.a = pqvec3_t{ s.a[0], s.a[1], s.a[2] }; e.b = pqvec3_t{ s.b[0], s.b[1], s.b[2] }; e.e = dir3_t{ s.e[0], s.e[1], s.e[2] };
+        e.n1 = dir3_t{ s.n1[0], s.n1[1], s.n1[2] }; e.n2 = dir3_t{ s.n2[0], s.n2[1], s.n2[2] }; e.alpha = s.alpha;
         e.tri1 = &t.tris[s.tri1]; e.tri2 = s.tri2 != WTGPU_INVALID_IDX ? &t.tris[s.tri2] : nullptr;
     }
     for (uint32_t i = 0; i < d->n_leaves; ++i) { t.leaves[i].tris_ptr = d->leaves[i].tris_ptr; t.leaves[i].count = d->leaves[i].count; }
@@ -193,11 +214,31 @@ void ref_bd_find_closest_triangle(uint32_t n, const float* q, float* out, uint32
         o[3] = id.integrated_radiant_flux;
     }
 }
+// per query in: beam o[3] d[3] x[3] tan_alpha eccentricity x0 | frame t[3] b[3] n[3] | k [1/mm] total_power | wavefront sigma x y | first edge, count = 27
+// out: counts[i] = aperture edges; summary[4] = recp_I psi02 P0 P0_pdf; the first `cap` edges x 9 (e[2] v[2] a_b re im iab_2 re im pdf)
+void ref_ffsd_aperture(uint32_t n, const float* q, uint32_t cap, uint32_t* counts, float* summary, float* edges) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 27 * i;
+        const elliptic_cone_t beam{ ray_t{ pqvec3_t{ c[0], c[1], c[2] }, dir3_t{ c[3], c[4], c[5] } }, dir3_t{ c[6], c[7], c[8] }, c[9], c[10], length_t(c[11]) };
+        const frame_t fr{ dir3_t{ c[12], c[13], c[14] }, dir3_t{ c[15], c[16], c[17] }, dir3_t{ c[18], c[19], c[20] } };
+        const beam::gaussian_wavefront_t wf{ gaussian2d_t{ vec2_t{ c[23], c[24] } } };
+        std::set<tuid_t> es; for (uint32_t k = 0; k < (uint32_t)c[26]; ++k) es.insert(tuid_t{ (uint32_t)c[25] + k });
+        const fraunhofer::free_space_diffraction_t f(&g_tree, nullptr, fr, wavenumber_t{ c[21] }, c[22], beam, es, wf);
+        const auto& ap = f.aperture;
+        counts[i] = (uint32_t)ap.edges.size();
+        summary[4 * i] = ap.recp_I; summary[4 * i + 1] = ap.psi02; summary[4 * i + 2] = ap.P0; summary[4 * i + 3] = ap.P0_pdf;
+        for (uint32_t k = 0; k < cap; ++k) {
+            float* o = edges + ((size_t)i * cap + k) * 9;
+            if (k < ap.edges.size()) { const auto& e = ap.edges[k]; o[0] = e.e.x; o[1] = e.e.y; o[2] = e.v.x; o[3] = e.v.y; o[4] = e.a_b.real(); o[5] = e.a_b.imag(); o[6] = e.iab_2.real(); o[7] = e.iab_2.imag(); o[8] = ap.edge_pdfs[k]; }
+            else for (int j = 0; j < 9; ++j) o[j] = 0.f;
+        }
+    }
+}
 // per query in: edge index, ray o[3] d[3]; out: the offset origin (intersection.cpp:187-211), then the fp error bound of the edge's first triangle (:149-170)
 void ref_edge_offsets(uint32_t n, const float* q, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* c = q + 7 * i; float* o = out + 6 * i;
-        const edge_t& e = g_edges[(uint32_t)c[0]];
+        const edge_t& e = g_tree.edges[(uint32_t)c[0]];
         const ray_t ray{ pqvec3_t{ c[1], c[2], c[3] }, dir3_t{ c[4], c[5], c[6] } };
         const auto p = intersection_edge_t{ &e, ray.o }.offseted_ray_origin(ray);
         const auto err = compute_intersection_triangle_fp_errors(e.tri1->a, e.tri1->b, e.tri1->c, ray.o);

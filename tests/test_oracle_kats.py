@@ -1293,3 +1293,44 @@ def test_bdpt_closest_triangle_and_gaussian_power_equal_the_reference_code():
     assert bad.size == 0, (bad.size, bad[:5], o1[bad[:5]], o2[bad[:5]], t1[bad[:5]], t2[bad[:5]])
     found = t1 != 0xFFFFFFFF
     assert .1 < found.mean() < .8 and (o1[~found, 3] > 0).mean() > .3 and (o1[~found, 3] > 1e-3).sum() > 500
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAVERSE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_fraunhofer_aperture_construction_equals_the_reference_code():
+    """ot_bdpt.h's fraunhofer_fsd_t constructor -- the aperture plt_bdpt builds at every diffusive vertex with free-space diffraction (SURVEY.md 8 row a15;
+    on the device the aperture-walk kernels) -- against the REFERENCE'S OWN src/interaction/fsd/fraunhofer/free_space_diffraction.cpp:18-129 compiled
+    over its own fsd.hpp (Pj, ASF_unclamped, P0), gaussian_wavefront.hpp, intersect_edge_ellipse and is_point_in_ellipsoid (oracle/ref_traverse.cpp), on
+    the host layer's edge table of the etoile-like scene: number of aperture segments, every segment (edge vector, mid point, both amplitude terms) and
+    its selection probability, psi0^2, P0, the 0-th order lobe's probability and 1 / I -- bit-identical on 20 000 vertices: beams from much narrower to
+    much wider than the edges (1 to dozens of segments per edge), edges inside, crossing and outside the 3-sigma ellipse, silhouette and
+    non-silhouette edges, zero incident power."""
+    b = scenes.etoile_like(res=16, spp=1, n_buildings=60).build()
+    R = C.CDLL(REF_TRAVERSE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float); up = C.POINTER(C.c_uint32)
+    R.ref_traverse_load.argtypes = [C.c_void_p]; R.ref_traverse_load.restype = None
+    R.ref_traverse_load(C.byref(b.desc))
+    ne = b.desc.n_edges
+    E = np.frombuffer((C.c_uint8 * (96 * ne)).from_address(C.addressof(b.desc.edges.contents)), np.float32).reshape(ne, 24)
+    n = 20000; rng = np.random.default_rng(89)
+    cnt = rng.integers(1, 9, size=n); first = rng.integers(0, ne - 8, size=n); pick = first + rng.integers(0, cnt)
+    ea, eb = E[pick, 0:3].astype(np.float64), E[pick, 3:6].astype(np.float64); elen = np.linalg.norm(eb - ea, axis=1)
+    P = ea + rng.uniform(-.2, 1.2, size=(n, 1)) * (eb - ea)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True); d = d.astype(np.float32).astype(np.float64)
+    t = np.cross(d, rng.normal(size=(n, 3))); t /= np.linalg.norm(t, axis=1, keepdims=True); t = t.astype(np.float32).astype(np.float64); bb = np.cross(d, t)
+    z = elen * 10.0 ** rng.uniform(-.5, 1.5, size=n)
+    rad = elen * 10.0 ** rng.uniform(-1.3, 1, size=n)
+    o = P - d * z[:, None] + (t * rng.normal(size=(n, 1)) + bb * rng.normal(size=(n, 1))) * rad[:, None] * rng.uniform(0, 1.5, size=(n, 1))
+    org = o + d * z[:, None]                                                            # the cone's origin for the aperture is the interaction centre
+    ecc = rng.uniform(0, .9, size=n); sig = np.stack([rad / 3, rad / 3 * np.sqrt(1 - ecc ** 2)], 1)
+    k = 10.0 ** rng.uniform(-1, 4, size=n); power = rng.uniform(0, 2, size=n); power[:500] = 0
+    q = np.ascontiguousarray(np.concatenate([org, d, t, np.full((n, 1), 1e-3), ecc[:, None], rad[:, None], t, bb, d, k[:, None], power[:, None], sig, first[:, None], cnt[:, None]], 1), np.float32)
+    assert q.shape[1] == 27
+    cap = 96; outs = []
+    for lib, fn, firstarg in ((R, "ref_ffsd_aperture", ()), (L, "oracle_ffsd_aperture", (C.byref(b.desc),))):
+        cn = np.zeros(n, np.uint32); sm = np.zeros((n, 4), np.float32); ed = np.zeros((n, cap, 9), np.float32)
+        f = getattr(lib, fn); f.restype = None; f.argtypes = ([C.c_void_p] if firstarg else []) + [C.c_uint32, fp, C.c_uint32, up, fp, fp]
+        f(*firstarg, n, q.ctypes.data_as(fp), cap, cn.ctypes.data_as(up), sm.ctypes.data_as(fp), ed.ctypes.data_as(fp))
+        outs.append((cn, sm, ed))
+    (c1, s1, e1), (c2, s2, e2) = outs
+    bad = np.flatnonzero((c1 != c2) | (s1.view(np.uint32) != s2.view(np.uint32)).any(1) | (e1.view(np.uint32) != e2.view(np.uint32)).any((1, 2)))
+    assert bad.size == 0, (bad.size, bad[:4], c1[bad[:4]], c2[bad[:4]], s1[bad[:4]], s2[bad[:4]])
+    assert (c1 > 0).mean() > .3 and c1.max() > 12 and (c1 == 0).sum() > 100
