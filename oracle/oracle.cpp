@@ -739,6 +739,33 @@ extern "C" void oracle_ffsd_aperture(const wtgpu_scene_desc* desc, uint32_t n, c
         }
     }
 }
+// fsd_t::build + f(), laid out like oracle/ref_traverse.cpp's ref_utd_fsd
+extern "C" void oracle_utd_fsd(const wtgpu_scene_desc* desc, uint32_t n, const float* q, uint32_t cap, uint32_t* nap, float* ap, uint32_t* nf, float* fo) {
+    scene_t sc(desc);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 28 * i;
+        const frame_t fr{ { c[3], c[4], c[5] }, { c[6], c[7], c[8] }, { c[9], c[10], c[11] } };
+        std::vector<uint32_t> es; for (uint32_t k = 0; k < (uint32_t)c[21]; ++k) es.push_back((uint32_t)c[20] + k);
+        const fsd_t f = fsd_t::build(sc, { c[0], c[1], c[2] }, fr, { c[12], c[13], c[14] }, { c[15], c[16], c[17] }, c[18], es);
+        nap[i] = (uint32_t)f.edges.size();
+        for (uint32_t k = 0; k < cap; ++k) {
+            float* o = ap + ((size_t)i * cap + k) * 15; for (int j = 0; j < 15; ++j) o[j] = 0.f;
+            if (k >= f.edges.size()) continue;
+            const auto& e = f.edges[k];
+            o[0] = e.v.x; o[1] = e.v.y; o[2] = e.v.z; o[3] = e.l; o[4] = e.nff.x; o[5] = e.nff.y; o[6] = e.nff.z; o[7] = e.tff.x; o[8] = e.tff.y; o[9] = e.tff.z;
+            o[10] = e.nbf.x; o[11] = e.nbf.y; o[12] = e.nbf.z; o[13] = e.alpha; o[14] = (float)e.ads_edge_idx;
+        }
+        const auto r = f.f({ c[22], c[23], c[24] }, { c[25], c[26], c[27] });
+        nf[i] = (uint32_t)r.size();
+        for (uint32_t k = 0; k < cap; ++k) {
+            float* o = fo + ((size_t)i * cap + k) * 10; for (int j = 0; j < 10; ++j) o[j] = 0.f;
+            if (k >= r.size()) continue;
+            const auto& d = r[k];
+            o[0] = (float)d.edge_idx; o[1] = d.p.x; o[2] = d.p.y; o[3] = d.p.z; o[4] = d.ri; o[5] = d.ro;
+            o[6] = d.utd.Ds.real(); o[7] = d.utd.Ds.imag(); o[8] = d.utd.Dh.real(); o[9] = d.utd.Dh.imag();
+        }
+    }
+}
 extern "C" void oracle_cone_cluster(uint32_t n, const float* in, float* out) {
     for (uint32_t i = 0; i < n; ++i) {
         const float* a = in + 20 * i; const float* a0 = in + 20 * (i & ~7u);

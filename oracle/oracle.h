@@ -78,6 +78,7 @@ void oracle_find_closest_triangle(const wtgpu_scene_desc* desc, uint32_t n, cons
 void oracle_edge_offsets(const wtgpu_scene_desc* desc, uint32_t n, const float* q, float* out);
 void oracle_bd_find_closest_triangle(const wtgpu_scene_desc* desc, uint32_t n, const float* q, float* out, uint32_t* tuid);
 void oracle_ffsd_aperture(const wtgpu_scene_desc* desc, uint32_t n, const float* q, uint32_t cap, uint32_t* counts, float* summary, float* edges);
+void oracle_utd_fsd(const wtgpu_scene_desc* desc, uint32_t n, const float* q, uint32_t cap, uint32_t* nap, float* ap, uint32_t* nf, float* fo);
 void oracle_cone_cluster(uint32_t n, const float* in, float* out);
 void oracle_stack_sorter(uint32_t n, uint32_t run, float* io);
 void oracle_cone_basics(uint32_t n, const float* in, float* out);

@@ -161,6 +161,7 @@ constexpr bool operator<=(const pqvec3_t& a, const pqvec3_t& b) { return a.x <= 
 constexpr bool operator>=(const pqvec3_t& a, const pqvec3_t& b) { return a.x >= b.x && a.y >= b.y && a.z >= b.z; }
 constexpr pqvec3_t& operator+=(pqvec3_t& a, const pqvec3_t& b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
 constexpr pqvec3_t operator*(f_t s, const pqvec3_t& a) { return { s * a.x, s * a.y, s * a.z }; }
+constexpr pqvec3_t operator/(const pqvec3_t& a, f_t s) { return { a.x / s, a.y / s, a.z / s }; }       // (by a number, or by a length: see dir3_t's constructor below)
 constexpr vec3_t operator/(const pqvec3_t& a, const pqvec3_t& b) { return { a.x / b.x, a.y / b.y, a.z / b.z }; }      // lengths / lengths: numbers
 struct dir2_t_tag {};
 #endif
@@ -179,6 +180,9 @@ struct dir3_t : vec3_t {
     constexpr dir3_t() = default;
     constexpr dir3_t(f_t x_, f_t y_, f_t z_) : vec3_t(x_, y_, z_) {}
     constexpr explicit dir3_t(const vec3_t& v) : vec3_t(v) {}
+#ifdef WT_SHIM_DISTINCT_PQ
+    constexpr explicit dir3_t(const pqvec3_t& v) : vec3_t{ v.x, v.y, v.z } {}      // a vector of lengths divided by its length (plain floats cannot tell: the quotient arrives as lengths)
+#endif
     constexpr dir3_t operator-() const { return dir3_t{ -x, -y, -z }; }
 };
 
@@ -186,6 +190,7 @@ struct dir3_t : vec3_t {
 struct zero_t { constexpr operator f_t() const noexcept { return 0; } };
 template <std::size_t W> struct bvec3_w_t;
 inline constexpr zero_t zero{};
+template <typename T> requires std::is_same_v<T, c_t> inline bool operator==(const T& a, zero_t) noexcept { return a.real() == f_t(0) && a.imag() == f_t(0); }
 constexpr vec3_t operator/(f_t s, const vec3_t& v) { return { s / v.x, s / v.y, s / v.z }; }
 namespace m {
 inline f_t fma(f_t a, f_t b, f_t c) noexcept { return std::fma(a, b, c); }
@@ -291,6 +296,10 @@ inline pqvec3_t mix(const pqvec3_t& a, const pqvec3_t& b, const vec3b_t& s) noex
 inline pqvec3_t mix(const pqvec3_t& a, const pqvec3_t& b, bool s) noexcept { return s ? b : a; }
 inline f_t max_element(const pqvec3_t& v) noexcept { return std::max(v.x, std::max(v.y, v.z)); }
 inline pqvec3_t abs(const pqvec3_t& v) noexcept { return { std::fabs(v.x), std::fabs(v.y), std::fabs(v.z) }; }
+inline f_t length2(const pqvec3_t& v) noexcept { return std::fma(v.z, v.z, std::fma(v.y, v.y, v.x * v.x)); }
+inline f_t length(const pqvec3_t& v) noexcept { return std::sqrt(length2(v)); }
+inline bool isfinite(const pqvec3_t& v) noexcept { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); }
+inline pqvec3_t mix(const pqvec3_t& a, const pqvec3_t& b, f_t x) noexcept { if (x == f_t(0)) return a; if (x == f_t(1)) return b; return { a.x * (f_t(1) - x) + b.x * x, a.y * (f_t(1) - x) + b.y * x, a.z * (f_t(1) - x) + b.z * x }; }
 inline f_t min_element(const pqvec3_t& v) noexcept { return std::min(v.x, std::min(v.y, v.z)); }
 inline f_t dot(const pqvec2_t& a, const vec2_t& b) noexcept { return std::fma(a.y, b.y, a.x * b.x); }
 inline f_t length(const pqvec2_t& v) noexcept { return std::sqrt(std::fma(v.y, v.y, v.x * v.x)); }

@@ -112,6 +112,27 @@ namespace ref_plt_path { using namespace wt; using namespace wt::ads;
 namespace ref_plt_bdpt { using namespace wt; using namespace wt::ads;
 #include "_ref/plt_bdpt_closest_part.hpp"
 }
+// the UTD aperture of plt_path's diffusive vertices and its evaluation: the constructor and f() of wt::free_space_diffraction_t, src/interaction/fsd/
+// free_space_diffraction.cpp:17-81 and :199-240 (front-face choice per wedge, edges clamped to the interaction region's ellipsoid, Fermat point per
+// edge, wedge-side rejection, UTD coefficients), over the reference's own utd.hpp / fsd/common.hpp and intersect_edge_ellipsoid.  The class is declared
+// here with the members those two functions touch (free_space_diffraction.hpp:28-75 pulls in sampler/density.hpp, written directly over mp-units); sample()
+// and pdf() need its angle-density types and are not part of the pin.  libcerf's cerfc is supplied by the test (ref_traverse_set_cerfc), as for libref_utd.so.
+#include "/root/reference/include/wt/interaction/fsd/utd.hpp"
+extern "C" { ref_cerfc_fn ref_cerfc_hook = nullptr; void ref_traverse_set_cerfc(ref_cerfc_fn f) { ref_cerfc_hook = f; } }
+namespace wt {
+class free_space_diffraction_t {
+public:
+    utd::fsd_aperture_t aperture; pqvec3_t interaction_wp;
+    struct diffracting_edge_t { utd::UTD_ret_t utd; ads::tuid_t edge_idx; pqvec3_t p; dir3_t wi, wo; length_t ri, ro; };
+    using eval_ret_t = std::vector<diffracting_edge_t>;
+    free_space_diffraction_t(const ads::ads_t* ads, const pqvec3_t& interaction_wp, const frame_t& interaction_region_frame, const pqvec3_t& interaction_region_size,
+                             const dir3_t& wi, wavenumber_t k, const ads::intersection_record_t::edges_container_t& edges) noexcept;
+    eval_ret_t f(const pqvec3_t& src, const pqvec3_t& dst) const noexcept;
+};
+}
+namespace wt {
+#include "_ref/utd_fsd_part.hpp"
+}
 // the Fraunhofer aperture of plt_bdpt's diffusive vertices: the constructor of fraunhofer::free_space_diffraction_t, src/interaction/fsd/fraunhofer/
 // free_space_diffraction.cpp:18-129 (silhouette edges of the cone query's edge set, clamped to the beam's 3-sigma ellipse, cut into segments of a third of
 // its radius, each weighted by Pj; the 0-th order lobe from eight samples of the aperture's spectrum), over the reference's own fsd.hpp, fsd_sampler.hpp,
@@ -128,7 +149,9 @@ public:
                              const elliptic_cone_t& beam, const ads::intersection_record_t::edges_container_t& edges, const beam::gaussian_wavefront_t& wave_function) noexcept;
 };
 }
+namespace wt::fraunhofer {
 #include "_ref/ffsd_ctor_part.hpp"
+}
 // self-intersection offsets: compute_intersection_triangle_fp_errors and intersection_edge_t::offseted_ray_origin (src/interaction/intersection.cpp:149-170, :187-211)
 #include "_ref/intersection_offset_part.hpp"
 
@@ -231,6 +254,34 @@ void ref_ffsd_aperture(uint32_t n, const float* q, uint32_t cap, uint32_t* count
             float* o = edges + ((size_t)i * cap + k) * 9;
             if (k < ap.edges.size()) { const auto& e = ap.edges[k]; o[0] = e.e.x; o[1] = e.e.y; o[2] = e.v.x; o[3] = e.v.y; o[4] = e.a_b.real(); o[5] = e.a_b.imag(); o[6] = e.iab_2.real(); o[7] = e.iab_2.imag(); o[8] = ap.edge_pdfs[k]; }
             else for (int j = 0; j < 9; ++j) o[j] = 0.f;
+        }
+    }
+}
+// per query in: interaction_wp[3] | region frame t[3] b[3] n[3] | region size[3] | wi[3] | k [1/mm] | first edge, count | src[3] dst[3] = 28
+// out: nap[i] aperture wedges, the first `cap` x 15 (v[3] l nff[3] tff[3] nbf[3] alpha idx); nf[i] diffracting edges of f(src, dst), the first `cap` x 10
+// (idx p[3] ri ro Ds re im Dh re im)
+void ref_utd_fsd(uint32_t n, const float* q, uint32_t cap, uint32_t* nap, float* ap, uint32_t* nf, float* fo) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 28 * i;
+        const frame_t fr{ dir3_t{ c[3], c[4], c[5] }, dir3_t{ c[6], c[7], c[8] }, dir3_t{ c[9], c[10], c[11] } };
+        std::set<tuid_t> es; for (uint32_t k = 0; k < (uint32_t)c[21]; ++k) es.insert(tuid_t{ (uint32_t)c[20] + k });
+        const wt::free_space_diffraction_t f(&g_tree, pqvec3_t{ c[0], c[1], c[2] }, fr, pqvec3_t{ c[12], c[13], c[14] }, dir3_t{ c[15], c[16], c[17] }, wavenumber_t{ c[18] }, es);
+        nap[i] = (uint32_t)f.aperture.edges.size();
+        for (uint32_t k = 0; k < cap; ++k) {
+            float* o = ap + ((size_t)i * cap + k) * 15; for (int j = 0; j < 15; ++j) o[j] = 0.f;
+            if (k >= f.aperture.edges.size()) continue;
+            const auto& e = f.aperture.edges[k];
+            o[0] = e.v.x; o[1] = e.v.y; o[2] = e.v.z; o[3] = (float)e.l; o[4] = e.nff.x; o[5] = e.nff.y; o[6] = e.nff.z; o[7] = e.tff.x; o[8] = e.tff.y; o[9] = e.tff.z;
+            o[10] = e.nbf.x; o[11] = e.nbf.y; o[12] = e.nbf.z; o[13] = (float)e.alpha; o[14] = (float)e.ads_edge_idx.uid;
+        }
+        const auto r = f.f(pqvec3_t{ c[22], c[23], c[24] }, pqvec3_t{ c[25], c[26], c[27] });
+        nf[i] = (uint32_t)r.size();
+        for (uint32_t k = 0; k < cap; ++k) {
+            float* o = fo + ((size_t)i * cap + k) * 10; for (int j = 0; j < 10; ++j) o[j] = 0.f;
+            if (k >= r.size()) continue;
+            const auto& d = r[k];
+            o[0] = (float)d.edge_idx.uid; o[1] = d.p.x; o[2] = d.p.y; o[3] = d.p.z; o[4] = (float)d.ri; o[5] = (float)d.ro;
+            o[6] = d.utd.Ds.real(); o[7] = d.utd.Ds.imag(); o[8] = d.utd.Dh.real(); o[9] = d.utd.Dh.imag();
         }
     }
 }

@@ -1334,3 +1334,51 @@ def test_fraunhofer_aperture_construction_equals_the_reference_code():
     bad = np.flatnonzero((c1 != c2) | (s1.view(np.uint32) != s2.view(np.uint32)).any(1) | (e1.view(np.uint32) != e2.view(np.uint32)).any((1, 2)))
     assert bad.size == 0, (bad.size, bad[:4], c1[bad[:4]], c2[bad[:4]], s1[bad[:4]], s2[bad[:4]])
     assert (c1 > 0).mean() > .3 and c1.max() > 12 and (c1 == 0).sum() > 100
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAVERSE), reason="oracle/_ref is built from /root/reference (this container only)")
+def test_utd_aperture_and_evaluation_equal_the_reference_code():
+    """ot_integrator.h's fsd_t (plt_path's UTD free-space diffraction) against the REFERENCE'S OWN
+    src/interaction/fsd/free_space_diffraction.cpp -- the constructor (:22-82: front face per wedge, rejection of light from inside the wedge, edges
+    clamped to the interaction region's ellipsoid, mid point and length) and f(src, dst) (:195-240: Fermat point per wedge, wedge-side rejection, ri / ro,
+    UTD coefficients) -- compiled over its own utd.hpp and intersect_edge_ellipsoid (oracle/ref_traverse.cpp), on the host layer's edge table of the
+    etoile-like scene: the aperture (every wedge's v, l, nff, tff, nbf, alpha, edge id) and the diffracting edges' ids, points and distances
+    bit-identical; Ds / Dh to 2e-5 of their magnitude (the reference calls libcerf, supplied here from scipy; the oracle its own series) -- 20 000
+    vertices, regions from smaller than an edge to unbounded."""
+    import scipy.special as sp
+    b = scenes.etoile_like(res=16, spp=1, n_buildings=60).build()
+    R = C.CDLL(REF_TRAVERSE); L = _oracle.lib_glibc(); fp = C.POINTER(C.c_float); up = C.POINTER(C.c_uint32)
+    CB = C.CFUNCTYPE(None, C.c_double, C.c_double, C.POINTER(C.c_double))
+    def cerfc(re, im, out):
+        v = sp.erfc(complex(re, im)); out[0] = v.real; out[1] = v.imag
+    cb = CB(cerfc); R.ref_traverse_set_cerfc.argtypes = [CB]; R.ref_traverse_set_cerfc(cb)
+    R.ref_traverse_load.argtypes = [C.c_void_p]; R.ref_traverse_load.restype = None
+    R.ref_traverse_load(C.byref(b.desc))
+    ne = b.desc.n_edges
+    E = np.frombuffer((C.c_uint8 * (96 * ne)).from_address(C.addressof(b.desc.edges.contents)), np.float32).reshape(ne, 24)
+    n = 20000; rng = np.random.default_rng(97)
+    cnt = rng.integers(1, 9, size=n); first = rng.integers(0, ne - 8, size=n); pick = first + rng.integers(0, cnt)
+    ea, eb = E[pick, 0:3].astype(np.float64), E[pick, 3:6].astype(np.float64); elen = np.linalg.norm(eb - ea, axis=1)
+    P = ea + rng.uniform(0, 1, size=(n, 1)) * (eb - ea)
+    wi = rng.normal(size=(n, 3)); wi /= np.linalg.norm(wi, axis=1, keepdims=True); wi = wi.astype(np.float32).astype(np.float64)
+    t = np.cross(wi, rng.normal(size=(n, 3))); t /= np.linalg.norm(t, axis=1, keepdims=True); t = t.astype(np.float32).astype(np.float64); bb = np.cross(wi, t)
+    size = elen[:, None] * 10.0 ** rng.uniform(-1, 1, size=(n, 3)); size[:2000] = np.inf
+    wp = P + rng.normal(size=(n, 3)) * size.clip(max=1e3).min(1, keepdims=True) * .3
+    k = 10.0 ** rng.uniform(-1, 3, size=(n, 1))
+    src = wp + wi * elen[:, None] * 10.0 ** rng.uniform(0, 2, size=(n, 1))
+    wo = rng.normal(size=(n, 3)); wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    dst = wp + wo * elen[:, None] * 10.0 ** rng.uniform(0, 2, size=(n, 1))
+    q = np.ascontiguousarray(np.concatenate([wp, t, bb, wi, size, wi, k, np.zeros((n, 1)), first[:, None], cnt[:, None], src, dst], 1), np.float32)
+    assert q.shape[1] == 28
+    cap = 8; outs = []
+    for lib, fn, firstarg in ((R, "ref_utd_fsd", ()), (L, "oracle_utd_fsd", (C.byref(b.desc),))):
+        na = np.zeros(n, np.uint32); ap = np.zeros((n, cap, 15), np.float32); nf = np.zeros(n, np.uint32); fo = np.zeros((n, cap, 10), np.float32)
+        f = getattr(lib, fn); f.restype = None; f.argtypes = ([C.c_void_p] if firstarg else []) + [C.c_uint32, fp, C.c_uint32, up, fp, up, fp]
+        f(*firstarg, n, q.ctypes.data_as(fp), cap, na.ctypes.data_as(up), ap.ctypes.data_as(fp), nf.ctypes.data_as(up), fo.ctypes.data_as(fp))
+        outs.append((na, ap, nf, fo))
+    (na1, ap1, nf1, fo1), (na2, ap2, nf2, fo2) = outs
+    assert np.array_equal(na1, na2) and np.array_equal(ap1.view(np.uint32), ap2.view(np.uint32))
+    assert np.array_equal(nf1, nf2) and np.array_equal(fo1[..., :6].view(np.uint32), fo2[..., :6].view(np.uint32))
+    mag = np.abs(fo1[..., 6:]).max(-1, keepdims=True) + 1e-30
+    assert (np.abs(fo1[..., 6:] - fo2[..., 6:]) / mag).max() < 2e-5
+    assert (na1 > 0).mean() > .5 and nf1.sum() > 1500 and na1.max() >= 4
