@@ -6,7 +6,9 @@
 // reference's own ads/common.hpp, ads/bvh8w/bvh8w_node.hpp, ads/bvh8w/common.hpp and, beneath them, everything oracle/ref_cone.cpp compiles
 // (cone / ray tests, elliptic_cone.hpp, frame.hpp ...), the reference's own ads/intersection_record.hpp, the record conversions of
 // traversal_common.hpp:90-149 (distance culling, edge sets) and, on top, the ballistic / diffusive state machine of include/wt/integrator/traversal.hpp:26-248
-// (calculate_min_ballistic_distance, max_ballistic_distance, traverse, traverse_shadow) -> oracle/_ref/libref_traverse.so.  tests/test_oracle_kats.py runs it over the BVH the HOST
+// (calculate_min_ballistic_distance, max_ballistic_distance, traverse, traverse_shadow) and, cut the same way further down in this file: both integrators' find_closest_triangle (plt_path_detail.hpp:244-276, plt_bdpt_detail.hpp:352-419), the self-intersection offsets of
+// src/interaction/intersection.cpp, and the apertures of the two diffraction models (src/interaction/fsd/free_space_diffraction.cpp, fsd/fraunhofer/free_space_diffraction.cpp)
+// -> oracle/_ref/libref_traverse.so.  tests/test_oracle_kats.py runs it over the BVH the HOST
 // LAYER built for a scene and compares, per query, the accepted-triangle list IN TRAVERSAL ORDER, distances, barycentrics and faces with ot_ads.h.
 // bvh8w.cpp as a whole needs tinybvh, the scene tree and the statistics collectors; so the Makefile writes the line ranges named above, as they are,
 // to the git-ignored oracle/_ref/bvh8w_traverse_part.hpp / traversal_common_part.hpp at build time (deleted again once the library is linked) and this TU includes those.  What stands in here:
