@@ -249,7 +249,8 @@ inline constexpr f_t sqrt_two = f_t(1.41421356237309504880168872420969808);
 inline constexpr f_t inv_sqrt_two = f_t(1. / 1.41421356237309504880168872420969808);                   // math/defs.hpp:57
 inline constexpr f_t sqrt_pi_2 = f_t(1.253314137315500251207882642405522627), inv_sqrt_two_pi = f_t(0.398942280401432677939946059934381868);  // math/defs.hpp
 inline f_t round(f_t v) noexcept { return std::round(v); }                                      // common.hpp:104-106 glm::round
-inline f_t atan2(f_t y, f_t x) noexcept { return std::atan2(y, x); }                            // quantity/math.hpp:213-216
+inline f_t atan2(f_t y, f_t x) noexcept { return std::atan2(y, x); }
+inline f_t acos(f_t v) noexcept { return std::acos(v); }                            // quantity/math.hpp:213-216
 inline f_t cot(f_t a) noexcept { return f_t(1) / std::tan(a); }                                 // quantity/math.hpp:199-202
 inline f_t mod(f_t a, f_t b) noexcept { return a - b * std::floor(a / b); }                      // quantity/math.hpp:84-88 glm::mod
 inline bool isfinite(const c_t& v) noexcept { return std::isfinite(v.real()) && std::isfinite(v.imag()); }

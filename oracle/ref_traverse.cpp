@@ -114,6 +114,12 @@ namespace ref_plt_path { using namespace wt; using namespace wt::ads;
 namespace ref_plt_bdpt { using namespace wt; using namespace wt::ads;
 #include "_ref/plt_bdpt_closest_part.hpp"
 }
+// the geometry of an edge record -- wedge normals pointing outwards, in-face tangents, opening angle, the 160-degree cut -- as the reference derives it from
+// the two triangles sharing the edge: edge_for, include/wt/ads/edge_classification.hpp:31-86.  Pins the edge table the HOST LAYER builds (libwt_host.so).
+#include <atomic>
+namespace wt::ads::construction {
+#include "_ref/edge_for_part.hpp"
+}
 // the UTD aperture of plt_path's diffusive vertices and its evaluation: the constructor and f() of wt::free_space_diffraction_t, src/interaction/fsd/
 // free_space_diffraction.cpp:17-81 and :199-240 (front-face choice per wedge, edges clamped to the interaction region's ellipsoid, Fermat point per
 // edge, wedge-side rejection, UTD coefficients), over the reference's own utd.hpp / fsd/common.hpp and intersect_edge_ellipsoid.  The class is declared
@@ -285,6 +291,24 @@ void ref_utd_fsd(uint32_t n, const float* q, uint32_t cap, uint32_t* nap, float*
             o[0] = (float)d.edge_idx.uid; o[1] = d.p.x; o[2] = d.p.y; o[3] = d.p.z; o[4] = (float)d.ri; o[5] = (float)d.ro;
             o[6] = d.utd.Ds.real(); o[7] = d.utd.Ds.imag(); o[8] = d.utd.Dh.real(); o[9] = d.utd.Dh.imag();
         }
+    }
+}
+// per item in: tri1 a[3] b[3] c[3] n[3] | has tri2 | tri2 a[3] b[3] c[3] n[3] | edge a[3] b[3] | c1[3] c2[3] = 37
+// out: found, e[3] n1[3] t1[3] n2[3] t2[3] alpha, inconsistent-normals flag = 18
+void ref_edge_for(uint32_t n, const float* q, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c = q + 37 * i; float* o = out + 18 * i;
+        auto load = [](const float* t) { tri_t r{}; r.a = pqvec3_t{ t[0], t[1], t[2] }; r.b = pqvec3_t{ t[3], t[4], t[5] }; r.c = pqvec3_t{ t[6], t[7], t[8] }; r.n = dir3_t{ t[9], t[10], t[11] }; return r; };
+        const tri_t t1 = load(c), t2 = load(c + 13);
+        const bool has2 = c[12] != 0;
+        const pqvec3_t a{ c[25], c[26], c[27] }, b{ c[28], c[29], c[30] }, c1{ c[31], c[32], c[33] }, c2{ c[34], c[35], c[36] };
+        std::atomic<bool> inconsistent{ false };
+        const auto e = construction::edge_for(&t1, has2 ? &t2 : nullptr, tuid_t{ 0 }, tuid_t{ 1 }, a, b, c1, has2 ? &c2 : nullptr, inconsistent);
+        for (int j = 0; j < 18; ++j) o[j] = 0.f;
+        o[17] = inconsistent ? 1.f : 0.f;
+        if (!e) continue;
+        o[0] = 1.f; o[1] = e->e.x; o[2] = e->e.y; o[3] = e->e.z; o[4] = e->n1.x; o[5] = e->n1.y; o[6] = e->n1.z; o[7] = e->t1.x; o[8] = e->t1.y; o[9] = e->t1.z;
+        o[10] = e->n2.x; o[11] = e->n2.y; o[12] = e->n2.z; o[13] = e->t2.x; o[14] = e->t2.y; o[15] = e->t2.z; o[16] = (float)e->alpha;
     }
 }
 // per query in: edge index, ray o[3] d[3]; out: the offset origin (intersection.cpp:187-211), then the fp error bound of the edge's first triangle (:149-170)

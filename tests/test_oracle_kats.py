@@ -1382,3 +1382,39 @@ def test_utd_aperture_and_evaluation_equal_the_reference_code():
     mag = np.abs(fo1[..., 6:]).max(-1, keepdims=True) + 1e-30
     assert (np.abs(fo1[..., 6:] - fo2[..., 6:]) / mag).max() < 2e-5
     assert (na1 > 0).mean() > .5 and nf1.sum() > 1500 and na1.max() >= 4
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAVERSE), reason="oracle/_ref is built from /root/reference (this container only)")
+@pytest.mark.parametrize("scene", ["etoile", "cornell"])
+def test_host_edge_table_equals_the_reference_code(scene):
+    """The edge table the HOST LAYER builds (libwt_host.so, host_ads.cpp: what both diffraction models and the edge offsets read) against the
+    REFERENCE'S OWN edge_for (include/wt/ads/edge_classification.hpp:31-86, oracle/ref_traverse.cpp): for every edge of the scene -- from its two
+    triangles, its end points and the opposite vertices -- the reference finds an edge, and e, n1, t1, n2, t2 and the opening angle are bit-identical
+    with the table's record (wedge normals flipped outwards on concave wedges, tangents pointing into their faces, open edges)."""
+    b = (scenes.etoile_like(res=16, spp=1, n_buildings=60) if scene == "etoile" else scenes.cornell_like(res=16, spp=1, n_sphere=12)).build()
+    R = C.CDLL(REF_TRAVERSE); fp = C.POINTER(C.c_float)
+    ne, nt = b.desc.n_edges, b.desc.n_tris
+    raw = np.frombuffer((C.c_uint8 * (96 * ne)).from_address(C.addressof(b.desc.edges.contents)), np.uint8).reshape(ne, 96)
+    E = raw.view(np.float32).reshape(ne, 24); EI = raw.view(np.uint32).reshape(ne, 24)
+    T = np.frombuffer((C.c_float * (12 * nt)).from_address(C.addressof(b.desc.tris.contents)), np.float32).reshape(nt, 12)
+    tri1 = EI[:, 22]; tri2 = EI[:, 23]; has2 = tri2 != 0xFFFFFFFF; t2i = np.where(has2, tri2, 0)
+    def verts(t): return T[t, 0:3], T[t, 4:7], T[t, 8:11], np.stack([T[t, 3], T[t, 7], T[t, 11]], 1)
+    ea, eb = E[:, 0:3], E[:, 3:6]
+    def opposite(t, valid):
+        a, bb, c, _ = verts(t)
+        is_a = lambda v: (v.view(np.uint32) == ea.view(np.uint32)).all(1) | (v.view(np.uint32) == eb.view(np.uint32)).all(1)
+        ma, mb, mc = is_a(np.ascontiguousarray(a)), is_a(np.ascontiguousarray(bb)), is_a(np.ascontiguousarray(c))
+        assert ((ma.astype(int) + mb + mc) == 2)[valid].all()                            # exactly two of the three vertices are the edge's end points
+        return np.where(~ma[:, None], a, np.where(~mb[:, None], bb, c))
+    ea = np.ascontiguousarray(ea); eb = np.ascontiguousarray(eb)
+    c1 = opposite(tri1, np.ones(ne, bool)); c2 = opposite(t2i, has2)
+    a1, b1, cc1, n1 = verts(tri1); a2, b2, cc2, n2 = verts(t2i)
+    q = np.ascontiguousarray(np.concatenate([a1, b1, cc1, n1, has2[:, None].astype(np.float32), a2, b2, cc2, n2, ea, eb, c1, np.where(has2[:, None], c2, 0)], 1), np.float32)
+    assert q.shape[1] == 37
+    out = np.zeros((ne, 18), np.float32)
+    R.ref_edge_for.argtypes = [C.c_uint32, fp, fp]; R.ref_edge_for.restype = None; R.ref_edge_for(ne, q.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert (out[:, 0] == 1).all() and (out[:, 17] == 0).all()
+    host = np.concatenate([E[:, 6:9], E[:, 9:12], E[:, 12:15], E[:, 15:18], E[:, 18:21], E[:, 21:22]], 1)          # e n1 t1 n2 t2 alpha
+    bad = np.flatnonzero((np.ascontiguousarray(host).view(np.uint32) != np.ascontiguousarray(out[:, 1:17]).view(np.uint32)).any(1))
+    assert bad.size == 0, (bad.size, ne, bad[:4], host[bad[:4]], out[bad[:4], 1:17])
+    assert ne > 20

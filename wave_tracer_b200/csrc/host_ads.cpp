@@ -281,28 +281,35 @@ inline vkey key_of(f3 p) {
 
 struct atri_t { f3 a, b, c, n; uint32_t e_ab = WTGPU_INVALID_IDX, e_bc = WTGPU_INVALID_IDX, e_ca = WTGPU_INVALID_IDX; };
 
-// reference: edge_classification.hpp:31-95 (edge_for)
+// the reference's vector algebra (include/wt/math/vecmath.hpp:21-66) for edge_for below: dot = product + fused multiply-adds in component order, cross by
+// compensated products, normalize = division by the length.  (The CPU test suite compares the table with the reference's own edge_for bit for bit:
+// test_host_edge_table_equals_the_reference_code.)
+inline float dot_r(f3 a, f3 b) { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
+inline f3 cross_r(f3 x, f3 y) { return { diff_prod(x.y, y.z, x.z, y.y), diff_prod(x.z, y.x, x.x, y.z), diff_prod(x.x, y.y, x.y, y.x) }; }
+inline f3 normalize_r(f3 a) { const float l = std::sqrt(dot_r(a, a)); return { a.x / l, a.y / l, a.z / l }; }
+
+// reference: edge_classification.hpp:31-86 (edge_for)
 bool edge_for(const atri_t* t1, const atri_t* t2, uint32_t tuid1, uint32_t tuid2,
               f3 a, f3 b, f3 c1, const f3* c2, wtgpu_edge& out) {
     f3 n1 = t1->n;
     f3 n2 = t2 ? t2->n : -n1;
-    const f3 e = normalizef(b - a);
-    const f3 m = (a + b) * .5f;
+    const f3 e = normalize_r(b - a);
+    const f3 m = { (a.x + b.x) / 2.f, (a.y + b.y) / 2.f, (a.z + b.z) / 2.f };
     f3 tt1 = { 0, 0, 1 }, tt2 = { 0, 0, 1 };
     if (t2) {
-        const bool concave1 = dotf(n1, *c2 - m) > 0;
-        const bool concave2 = dotf(n2, c1 - m) > 0;
+        const bool concave1 = dot_r(n1, *c2 - m) > 0;
+        const bool concave2 = dot_r(n2, c1 - m) > 0;
         if (concave1 != concave2) return false;     // inconsistent normals
         if (concave1 && concave2) { n1 = -n1; n2 = -n2; }
-        tt2 = crossf(n2, e);
-        if (dotf(tt2, *c2 - m) < 0) tt2 = -tt2;
+        tt2 = cross_r(n2, e);
+        if (dot_r(tt2, *c2 - m) < 0) tt2 = -tt2;
     }
-    tt1 = crossf(n1, e);
-    if (dotf(tt1, c1 - m) < 0) tt1 = -tt1;
+    tt1 = cross_r(n1, e);
+    if (dot_r(tt1, c1 - m) < 0) tt1 = -tt1;
     if (!t2) tt2 = tt1;
 
     const float pi = 3.14159265358979323846f;
-    const float d = std::min(1.f, std::max(-1.f, dotf(n1, n2)));
+    const float d = std::min(1.f, std::max(-1.f, dot_r(n1, n2)));
     const float alpha = std::max(0.f, pi - std::acos(d));
     if (alpha > 160.f / 180.f * pi) return false;
 
